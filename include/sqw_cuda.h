@@ -1,0 +1,320 @@
+/*
+ * sqw_cuda.h — C ABI of the B200 (sm_100a) world-drawing path for Square-Wheel.
+ *
+ * This is the drop-in boundary.  The reference has no FFI of its own; its public
+ * renderer surface is
+ *     Renderer::new / prepare_frame::<ColorT> / draw_frame::<ColorT>   (src/square_wheel/renderer.rs:24,61,106)
+ *     Postprocessor::get_hdr_buffer / perform_postprocessing           (src/square_wheel/postprocessor.rs:56,68)
+ * and those five signatures stay as they are.  What is replaced are four internal seams:
+ *
+ *   S0 load      texture / lightmap ownership     map_materials_processor.rs:29, partial_renderer.rs:56
+ *   S1 surfaces  body of build_polygons_surfaces  partial_renderer.rs:1682-1831 (-> surfaces.rs:66,95,854)
+ *   S2 raster    perform_rasterization            partial_renderer.rs:1192-1283 (-> rasterizer.rs:35,731)
+ *   S3 post      perform_postprocessing           postprocessor.rs:68-204
+ *   readback     `pixels: &mut [ColorT]` argument of draw_frame / perform_postprocessing
+ *
+ * Conventions
+ *   - plain C types only; every struct below is `#[repr(C)]`-compatible and has a fixed size (checked with
+ *     static asserts in the implementation).
+ *   - the library COPIES whatever it is given; the caller keeps ownership of all host memory.
+ *   - every entry returns SQW_OK (0) or a negative error code and never unwinds across the boundary
+ *     (the reference aborts on panic, src/Cargo.toml:8); sqw_last_error() gives the text.
+ *   - a context may be used from any ONE thread at a time (the reference calls prepare_frame from an
+ *     arbitrary rayon worker, host.rs:438-449); every entry does its own cudaSetDevice.
+ *   - pixel formats: Color32 = A<<24|R<<16|G<<8|B (common/color.rs:16-24),
+ *                    Color64 = A<<48|R<<32|G<<16|B (common/color.rs:139-147).
+ *   - numerics follow the PORTABLE branch of fast_math.rs (:370-725): exact 1/x and 1/sqrt, mul+add instead
+ *     of fma, truncating float->int.
+ */
+#ifndef SQW_CUDA_H
+#define SQW_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SQW_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------------------------------------- */
+#define SQW_OK 0
+#define SQW_ERR_INVALID_ARGUMENT (-1)
+#define SQW_ERR_CUDA (-2)
+#define SQW_ERR_OUT_OF_MEMORY (-3)
+#define SQW_ERR_NO_DEVICE (-4)
+
+typedef struct sqw_ctx sqw_ctx;   /* one per map replica on one GPU (Renderer::new)                     */
+typedef struct sqw_view sqw_view; /* one render target + scratch (a PartialRenderer, partial_renderer.rs:15) */
+
+/* ---- S0: static data ---------------------------------------------------------------------------------- */
+
+/* Image element kinds.  One "image" is one mip of one texture. */
+#define SQW_IMAGE_TEXTURE_ELEMENT 0 /* textures.rs:20-27  TextureElement {Color32 diffuse; i8x4 normal.xyz,roughness} 8 B */
+#define SQW_IMAGE_COLOR32 1         /* TextureLite = image::Image (common/image.rs:3-8), skybox 32-bit sides   4 B */
+#define SQW_IMAGE_COLOR64 2         /* SkyboxSideTexture<Color64> (textures.rs:82-87)                           8 B */
+
+/* bsp_map_compact.rs:142-156.  LightmapElement is [f32;3]; the directional element is 10 floats. */
+typedef struct sqw_directional_lightmap_element
+{
+	float ambient_light[3];
+	float light_direction_vector_scaled[3];
+	float directional_light_deviation;
+	float directional_light_color[3];
+} sqw_directional_lightmap_element;
+
+typedef struct sqw_map_desc
+{
+	const float* lightmaps_data; /* [num_lightmap_elements][3], de-quantised (bsp_map_save_load.rs:208-221) */
+	const sqw_directional_lightmap_element* directional_lightmaps_data; /* same count, or NULL */
+	uint64_t num_lightmap_elements;
+	uint32_t max_images; /* capacity of the image table (0 = default 4096) */
+	uint32_t reserved;
+} sqw_map_desc;
+
+/* Create a context on CUDA device `device` and upload the static map data.  Replaces the ownership half of
+ * Renderer::new (renderer.rs:24).  `external_stream` may be a cudaStream_t the caller wants all work of this
+ * context to be issued on (pass NULL for a private non-blocking stream). */
+int sqw_create(sqw_ctx** out_ctx, int device, const sqw_map_desc* map, void* external_stream);
+void sqw_destroy(sqw_ctx* ctx);
+const char* sqw_last_error(const sqw_ctx* ctx); /* ctx may be NULL: error of the last failed sqw_create */
+int sqw_abi_version(void);
+
+/* Upload one image (one mip).  Returns the image id (>= 0) or a negative error.
+ * Replaces texture ownership in MapMaterialsProcessor::new (map_materials_processor.rs:29-167). */
+int sqw_upload_image(sqw_ctx* ctx, int kind, uint32_t width, uint32_t height, const void* pixels);
+/* Replace the pixels of an existing image (animated textures, map_materials_processor.rs:295-302). */
+int sqw_update_image(sqw_ctx* ctx, int image_id, const void* pixels);
+
+/* ---- views (render targets) ---------------------------------------------------------------------------- */
+
+/* color_bits: 32 (Color32 framebuffer, LDR path host.rs:416) or 64 (Color64 HDR buffer, postprocessor.rs:56). */
+int sqw_view_create(sqw_ctx* ctx, sqw_view** out_view, uint32_t width, uint32_t height, int color_bits);
+void sqw_view_destroy(sqw_view* view);
+
+/* ---- S1: surfaces --------------------------------------------------------------------------------------- */
+
+#define SQW_SURF_HAS_NORMAL_MAP 1u        /* Texture::has_normal_map        textures.rs:14 */
+#define SQW_SURF_HAS_NON_ONE_ROUGHNESS 2u /* Texture::has_non_one_roughness textures.rs:15 */
+#define SQW_SURF_IS_METAL 4u              /* Texture::is_metal              textures.rs:16 */
+#define SQW_SURF_DIRECTIONAL_LIGHTMAP 8u  /* use_directional_lightmap       partial_renderer.rs:1676 */
+#define SQW_SURF_APPLY_DIFFUSE 16u        /* apply_diffuse_layer            partial_renderer.rs:1700 */
+#define SQW_SURF_EMISSIVE 32u             /* get_emissive_texture is Some   partial_renderer.rs:1801 */
+
+#define SQW_MAX_POLYGON_LIGHTS 6 /* partial_renderer.rs:1666 */
+#define SQW_NO_LIGHTMAP_SCALE 31 /* surfaces.rs:429 */
+
+/* One call of build_surface_{simple,directional}_lightmap (+ mix_surface_with_texture for the emissive layer),
+ * i.e. the arguments assembled in partial_renderer.rs:1682-1819.  128 bytes. */
+typedef struct sqw_surface_job
+{
+	float basis_u[3];      /* PolygonBasisVecs (surfaces.rs:7-14), already scaled for the mip and shift-corrected */
+	float basis_v[3];      /* (partial_renderer.rs:1736-1740) */
+	float basis_start[3];
+	float basis_normal[3];
+	uint32_t surface_size[2];
+	int32_t tc_start[2];            /* surface_tc_min + texture shift >> mip (partial_renderer.rs:1690-1693) */
+	uint32_t texture_image;         /* image id of the TextureElement mip */
+	uint32_t flags;                 /* SQW_SURF_* */
+	uint32_t lightmap_size[2];      /* lightmap.rs:11 */
+	uint32_t lightmap_scale_log2;   /* LIGHTMAP_SCALE_LOG2 - mip; ignored when lightmap_offset == 0 */
+	uint32_t lightmap_tc_shift[2];  /* partial_renderer.rs:1744-1752 */
+	uint32_t lightmap_offset;       /* Polygon::lightmap_data_offset; 0 = no lightmap */
+	uint32_t num_lights;            /* <= SQW_MAX_POLYGON_LIGHTS */
+	uint16_t lights[SQW_MAX_POLYGON_LIGHTS]; /* indices into the lights array of the call */
+	uint32_t emissive_image;        /* COLOR32 image id of the emissive mip (if SQW_SURF_EMISSIVE) */
+	float emissive_light[3];        /* emissive_texture.1 */
+	uint32_t surface_pixels_offset; /* in pixels of the view's colour type (DrawPolygonData, renderer_structs.rs:86) */
+	uint32_t reserved;
+} sqw_surface_job;
+
+#define SQW_SHADOW_NONE 0
+#define SQW_SHADOW_CUBE 1
+#define SQW_SHADOW_PROJECTOR 2
+
+/* DynamicLightWithShadow (light.rs:4-11) with the shadow map flattened to an offset into the call's
+ * shadow_maps array.  Cube maps store their six sides consecutively (size*size floats each, side order of
+ * light.rs:13-22).  80 bytes. */
+typedef struct sqw_light
+{
+	float position[3];
+	float radius;
+	float inv_square_radius;
+	float color[3];
+	uint32_t shadow_type; /* SQW_SHADOW_* */
+	uint32_t shadow_map_size;
+	uint32_t shadow_map_offset; /* in floats */
+	float basis_x[3];           /* ProjectorShadowMap (light.rs:55-62) */
+	float basis_y[3];
+	float basis_z[3];
+} sqw_light;
+
+/* Build all surfaces of one view.  Replaces the body of PartialRenderer::build_polygons_surfaces.
+ * Surfaces stay device-resident in the view's surface pool at job.surface_pixels_offset.
+ * total_surface_pixels = num_visible_surfaces_pixels (partial_renderer.rs:1449): the pool grows to hold it. */
+int sqw_build_surfaces(
+	sqw_view* view,
+	const sqw_surface_job* jobs,
+	uint32_t num_jobs,
+	const sqw_light* lights,
+	uint32_t num_lights,
+	const float* shadow_maps,
+	uint64_t shadow_maps_len,
+	const float cam_pos[3],
+	uint64_t total_surface_pixels);
+
+/* ---- S2: rasterisation ---------------------------------------------------------------------------------- */
+
+#define SQW_CMD_POLYGON 0  /* Rasterizer::fill_polygon  rasterizer.rs:35  */
+#define SQW_CMD_TRIANGLE 1 /* Rasterizer::fill_triangle rasterizer.rs:731 */
+
+#define SQW_BLEND_NONE 0 /* common/material.rs:101-116 */
+#define SQW_BLEND_AVERAGE 1
+#define SQW_BLEND_ADDITIVE 2
+#define SQW_BLEND_ALPHA_TEST 3
+#define SQW_BLEND_ALPHA_BLEND 4
+
+#define SQW_TC_FULL_PERSPECTIVE 0 /* rasterizer.rs:4-10 */
+#define SQW_TC_LINE_Z_CORRECTION 1
+#define SQW_TC_AFFINE 2
+
+#define SQW_TEX_SURFACE 0 /* view surface pool, tex_ref = pixel offset (get_polygon_surface_data, partial_renderer.rs:3777) */
+#define SQW_TEX_IMAGE 1   /* image table, tex_ref = image id (sky side, model/decal/sprite TextureLite mip) */
+#define SQW_TEX_VIEW 2    /* colour buffer of another view of the same ctx, tex_ref = view index (portal textures, partial_renderer.rs:3720) */
+
+/* PolygonPointProjected (rasterizer.rs:1484-1489): 16.16 fixed point. */
+typedef struct sqw_polygon_point
+{
+	int32_t x, y;
+} sqw_polygon_point;
+
+/* TrianglePointProjected (rasterizer.rs:1491-1498). 28 bytes. */
+typedef struct sqw_triangle_point
+{
+	int32_t x, y;
+	int32_t tc[2];
+	int32_t light[3];
+} sqw_triangle_point;
+
+/* One recorded Rasterizer::fill_polygon / fill_triangle call, in submission (painter's) order. 64 bytes.
+ * The host still does project_and_clip_polygon, mode selection and the z_scale renormalisation
+ * (draw_polygon, partial_renderer.rs:4011-4142); the command carries the final arguments. */
+typedef struct sqw_draw_cmd
+{
+	uint8_t kind;     /* SQW_CMD_* */
+	uint8_t blend;    /* SQW_BLEND_* */
+	uint8_t tc_mode;  /* SQW_TC_* (polygons) */
+	uint8_t tex_kind; /* SQW_TEX_* */
+	uint32_t num_vertices;  /* polygons: 3..24; triangles: 3 */
+	uint32_t vertex_offset; /* element index into polygon_points / triangle_points */
+	uint32_t tex_ref;
+	int32_t tex_size[2]; /* TextureInfo (rasterizer.rs:1500-1503) */
+	float depth_eq[3];   /* DepthEquation {d_inv_z_dx, d_inv_z_dy, k} (equations.rs:5-11) */
+	float tc_eq[6];      /* TexCoordEquation {d_tc_dx[2], d_tc_dy[2], k[2]} (equations.rs:14-19) */
+	uint32_t reserved;
+} sqw_draw_cmd;
+
+/* Draw a command list into the view's colour buffer with the clip rect of the single-threaded reference
+ * (whole surface, partial_renderer.rs:1207-1233).  clear_color: NULL = keep the buffer, else the buffer is
+ * first filled with this raw pixel value (draw_background, partial_renderer.rs:249-256; 4 or 8 bytes are read). */
+int sqw_draw(
+	sqw_view* view,
+	const sqw_draw_cmd* cmds,
+	uint32_t num_cmds,
+	const sqw_polygon_point* polygon_points,
+	uint32_t num_polygon_points,
+	const sqw_triangle_point* triangle_points,
+	uint32_t num_triangle_points,
+	const void* clear_color);
+
+/* ---- S3: post-processing --------------------------------------------------------------------------------- */
+
+/* Arguments of perform_postprocessing plus the PostprocessorConfig fields it reads (postprocessor_config.rs:5-93). */
+typedef struct sqw_post_params
+{
+	float exposure;          /* Postprocessor::current_exposure (postprocessor.rs:15) */
+	float color_modulate[3]; /* FrameInfo::color_modulate */
+	float bloom_sigma;       /* 0 disables bloom (postprocessor.rs:86) */
+	float bloom_scale;
+	uint32_t bloom_buffer_scale_log2; /* clamped to [1,3] (postprocessor.rs:731-734) */
+	uint32_t linear_bloom_filter;
+} sqw_post_params;
+
+/* Tonemap (+bloom) the 64-bit view into 32-bit pixels.  dst may be NULL (picture stays on the device, see
+ * sqw_read_pixels32).  dst_pitch is in pixels (SurfaceInfo::pitch).  avg_color_out = [B,G,R] average colour in
+ * ColorVec lane order (postprocessor.rs:176-179 or :840-843) so the host can keep running update_exposure. */
+int sqw_postprocess(sqw_view* view, const sqw_post_params* params, uint32_t* dst, size_t dst_pitch, float avg_color_out[3]);
+
+/* ---- readback --------------------------------------------------------------------------------------------- */
+
+/* Copy the view's colour buffer (4 or 8 bytes per pixel) to host; dst_pitch in pixels. Synchronises. */
+int sqw_read_pixels(sqw_view* view, void* dst, size_t dst_pitch);
+/* Upload host pixels (4 or 8 bytes per pixel) into the view's colour buffer; src_pitch in pixels.  This is the
+ * write half of Postprocessor::get_hdr_buffer (postprocessor.rs:56): a host that only replaces S3 renders into its
+ * own buffer and hands it over here. */
+int sqw_write_pixels(sqw_view* view, const void* src, size_t src_pitch);
+/* Copy the post-processed 32-bit picture of a 64-bit view. Synchronises. */
+int sqw_read_pixels32(sqw_view* view, uint32_t* dst, size_t dst_pitch);
+/* Copy `count` pixels of the surface pool starting at `offset` (both in pixels) — test/inspection hook. */
+int sqw_read_surfaces(sqw_view* view, void* dst, uint64_t offset, uint64_t count);
+/* Wait for everything issued for this view. */
+int sqw_view_synchronize(sqw_view* view);
+
+/* ---- recorded frames (batched views) -------------------------------------------------------- */
+/* A recorded frame holds device copies of one view's job list, command list and post params so that it can be
+ * replayed without host->device traffic.  This is what the view-batch workload and the device-resident bench
+ * number use; sqw_build_surfaces / sqw_draw / sqw_postprocess above are "record + submit one stage". */
+typedef struct sqw_frame sqw_frame;
+
+int sqw_frame_create(sqw_view* view, sqw_frame** out_frame);
+void sqw_frame_destroy(sqw_frame* frame);
+int sqw_frame_set_surfaces(
+	sqw_frame* frame,
+	const sqw_surface_job* jobs,
+	uint32_t num_jobs,
+	const sqw_light* lights,
+	uint32_t num_lights,
+	const float* shadow_maps,
+	uint64_t shadow_maps_len,
+	const float cam_pos[3],
+	uint64_t total_surface_pixels);
+int sqw_frame_set_draw(
+	sqw_frame* frame,
+	const sqw_draw_cmd* cmds,
+	uint32_t num_cmds,
+	const sqw_polygon_point* polygon_points,
+	uint32_t num_polygon_points,
+	const sqw_triangle_point* triangle_points,
+	uint32_t num_triangle_points,
+	const void* clear_color);
+int sqw_frame_set_post(sqw_frame* frame, const sqw_post_params* params);
+/* Launch surfaces -> raster -> post for the recorded frame on the context's stream (asynchronous).
+ * stages: bit0 surfaces, bit1 raster, bit2 post. */
+#define SQW_STAGE_SURFACES 1u
+#define SQW_STAGE_RASTER 2u
+#define SQW_STAGE_POST 4u
+#define SQW_STAGE_ALL 7u
+int sqw_frame_submit(sqw_frame* frame, uint32_t stages);
+
+/* Statistics of the last submit of this frame (units of the texels/s metric and of the roofline). */
+typedef struct sqw_frame_stats
+{
+	uint64_t surface_texels;      /* S   = sum of surface_size[0]*surface_size[1] */
+	uint64_t emissive_texels;     /* S_e */
+	uint64_t lightmap_bytes;      /* L   */
+	uint64_t num_spans;           /* rows of all commands */
+	uint32_t num_kernel_launches; /* kernels launched by one submit */
+	uint32_t num_surface_variants;
+	uint32_t num_tiles;
+	uint32_t reserved;
+} sqw_frame_stats;
+int sqw_frame_get_stats(const sqw_frame* frame, sqw_frame_stats* out);
+
+/* Average colour produced by the last post stage of this view (synchronises). */
+int sqw_view_get_average_color(sqw_view* view, float avg_color_out[3]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SQW_CUDA_H */

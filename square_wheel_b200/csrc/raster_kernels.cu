@@ -1,0 +1,851 @@
+// Stage 2 — span rasteriser on sm_100a.
+//
+// Replaces Rasterizer::fill_polygon / fill_triangle (src/square_wheel/rasterizer.rs:35-1292) as driven by
+// PartialRenderer::perform_rasterization (partial_renderer.rs:1192-1283) with the single-threaded reference's
+// clip rect (the whole surface).
+//
+// The reference is an incremental integer DDA painted back to front without a depth buffer.  To reproduce its
+// pixels bit for bit on a GPU the incremental state is turned into closed forms with the same wrap-around
+// arithmetic, and the painter's order is kept per pixel:
+//
+//   raster_setup_kernel   one THREAD per (command, scan-line): re-walks the polygon edges (or the triangle
+//                         halves) to the trapezoid that owns the line, evaluates x_left/x_right for that line as
+//                         x0 + n*dx_dy (mod 2^32, exactly the value the reference reaches after n additions) and
+//                         does the per-line set-up of the reference's inner loops (i64 equations, span end-point
+//                         clamps, the i32 divisions) -> one 48-byte SpanRec.
+//   raster_bin_kernel     one CTA per 8-row band: order-preserving compaction (ballot + popc prefix) of the
+//                         commands whose row range touches the band.
+//   raster_tile_kernel    one CTA per 128x8 tile, one warp per row, 4 consecutive pixels per lane kept in
+//                         registers; the warp walks the band's command list in submission order, filters it
+//                         32 commands at a time against the tile, loads the SpanRec of its row (warp-uniform,
+//                         one L1 transaction) and applies texel fetch + blend to the covered pixels.  The tile
+//                         is written once with 128-bit stores — every framebuffer byte is written exactly once
+//                         per frame no matter how much overdraw the painter's order has.
+//
+// Bound: HBM/L2 — per covered pixel one texel gather (C bytes, L2-resident surfaces) and per tile one C-byte
+// store; the full-perspective mode adds one u32 divide per pixel (rasterizer.rs:430).
+#include "sqw_device.cuh"
+#include "sqw_internal.h"
+
+namespace sqw
+{
+namespace
+{
+
+// rasterizer.rs:1573-1580
+constexpr int TC_SHIFT = 24;
+constexpr int INV_Z_SHIFT = 29;
+constexpr int INV_Z_PRE_SHIFT = 8;
+constexpr int Z_CALC_SHIFT = 31;
+constexpr int TC_FINAL_SHIFT = TC_SHIFT + Z_CALC_SHIFT - INV_Z_SHIFT + INV_Z_PRE_SHIFT; // 34
+constexpr float TC_SCALE = 16777216.0f;
+constexpr float INV_Z_SCALE = 536870912.0f;
+
+__device__ __forceinline__ int64_t min64(int64_t a, int64_t b) { return a < b ? a : b; }
+__device__ __forceinline__ int64_t max64(int64_t a, int64_t b) { return a > b ? a : b; }
+
+struct PolygonSide
+{
+	Fixed16 x_start, dx_dy;
+};
+
+struct Eq64
+{
+	int64_t d_inv_z_dx, d_inv_z_dy, inv_z_k;
+	int64_t d_tc_dx[2], d_tc_dy[2], tc_k[2];
+};
+__device__ __forceinline__ Eq64 make_eq(const sqw_draw_cmd& c) // rasterizer.rs:287-310 / :472-495
+{
+	Eq64 e;
+	const float dzx = c.depth_eq[0], dzy = c.depth_eq[1], dzk = c.depth_eq[2];
+	e.d_inv_z_dx = f32_to_i64_trunc(INV_Z_SCALE * dzx);
+	e.d_inv_z_dy = f32_to_i64_trunc(INV_Z_SCALE * dzy);
+	e.inv_z_k = f32_to_i64_trunc(INV_Z_SCALE * (dzk + (dzx + dzy) * 0.5f));
+#pragma unroll
+	for (int i = 0; i < 2; ++i)
+	{
+		const float tx = c.tc_eq[i], ty = c.tc_eq[2 + i], tk = c.tc_eq[4 + i];
+		e.d_tc_dx[i] = f32_to_i64_trunc(TC_SCALE * tx);
+		e.d_tc_dy[i] = f32_to_i64_trunc(TC_SCALE * ty);
+		e.tc_k[i] = f32_to_i64_trunc(TC_SCALE * (tk + (tx + ty) * 0.5f));
+	}
+	return e;
+}
+
+__device__ __forceinline__ void write_empty(SpanRec* out)
+{
+	uint4* o = reinterpret_cast<uint4*>(out);
+	o[0] = make_uint4(0, 0, 0, 0);
+	o[1] = make_uint4(0, 0, 0, 0);
+	o[2] = make_uint4(0, 0, 0, 0);
+}
+
+// One scan-line `row` of one trapezoid [y_start, y_end) of a polygon: the body of the `for y_int` loop of
+// fill_polygon_part / _line_z_corrected / _affine up to (not including) the pixel loop.
+__device__ void polygon_part_line(
+	const sqw_draw_cmd& c, const CmdDev& cd, int32_t row, int32_t y_start_int, Fixed16 y_start, Fixed16 y_end, PolygonSide left_side, PolygonSide right_side,
+	int32_t clip_w, SpanRec* out)
+{
+	const int32_t n = row - y_start_int;
+	const Fixed16 y_start_delta = wsub(wadd(int_to_fixed16(y_start_int), SQW_FIXED16_HALF), y_start);
+	// x_left after n additions of dx_dy (rasterizer.rs:319-320, :448-449)
+	const Fixed16 x_left = wadd(wadd(wadd(left_side.x_start, fixed16_mul(y_start_delta, left_side.dx_dy)), SQW_FIXED16_HALF), wmul(n, left_side.dx_dy));
+	const Fixed16 x_right = wadd(wadd(wadd(right_side.x_start, fixed16_mul(y_start_delta, right_side.dx_dy)), SQW_FIXED16_HALF), wmul(n, right_side.dx_dy));
+	const int32_t x_start_int = max(fixed16_floor_to_int(x_left), 0);
+	const int32_t x_end_int = min(fixed16_floor_to_int(x_right), clip_w);
+	if (x_start_int >= x_end_int)
+	{
+		write_empty(out);
+		return;
+	}
+
+	SpanRec r;
+	r.x0 = (int16_t)x_start_int;
+	r.x1 = (int16_t)x_end_int;
+#pragma unroll
+	for (int i = 0; i < 11; ++i)
+		r.v[i] = 0;
+
+	const int64_t span_start_x = x_start_int;
+	const int64_t span_end_x = x_end_int - 1;
+	const int32_t span_length_minus_one = (x_end_int - 1) - x_start_int;
+
+	if (cd.tc_mode == SQW_TC_AFFINE)
+	{
+		// rasterizer.rs:597-703
+		const float dzx = c.depth_eq[0], dzy = c.depth_eq[1], dzk = c.depth_eq[2];
+		const float y_start_f32 = fixed16_to_f32(y_start);
+		const float y_end_f32 = fixed16_to_f32(y_end);
+		const Fixed16 y_delta = wsub(y_end, y_start);
+		const float x_start_left = fixed16_to_f32(left_side.x_start);
+		const float x_end_left = fixed16_to_f32(wadd(left_side.x_start, fixed16_mul(y_delta, left_side.dx_dy)));
+		const float x_start_right = fixed16_to_f32(right_side.x_start);
+		const float x_end_right = fixed16_to_f32(wadd(right_side.x_start, fixed16_mul(y_delta, right_side.dx_dy)));
+		const float z_start_left = 1.0f / (dzx * x_start_left + dzy * y_start_f32 + dzk);
+		const float z_end_left = 1.0f / (dzx * x_end_left + dzy * y_end_f32 + dzk);
+		const float z_start_right = 1.0f / (dzx * x_start_right + dzy * y_start_f32 + dzk);
+		const float z_end_right = 1.0f / (dzx * x_end_right + dzy * y_end_f32 + dzk);
+		const Fixed16 y_delta_for_tc = max(y_delta, SQW_FIXED16_ONE);
+		const Fixed16 x_delta_for_tc = max(wsub(x_right, x_left), SQW_FIXED16_ONE);
+#pragma unroll
+		for (int i = 0; i < 2; ++i)
+		{
+			const Fixed16 max_tc = wsub(int_to_fixed16(c.tex_size[i]), 1);
+			const float tx = c.tc_eq[i], ty = c.tc_eq[2 + i], tk = c.tc_eq[4 + i];
+			const Fixed16 tc_start_left = min(max(f32_to_fixed16_unchecked(z_start_left * (x_start_left * tx + y_start_f32 * ty + tk)), 0), max_tc);
+			const Fixed16 tc_end_left = min(max(f32_to_fixed16_unchecked(z_end_left * (x_end_left * tx + y_end_f32 * ty + tk)), 0), max_tc);
+			const Fixed16 tc_start_right = min(max(f32_to_fixed16_unchecked(z_start_right * (x_start_right * tx + y_start_f32 * ty + tk)), 0), max_tc);
+			const Fixed16 tc_end_right = min(max(f32_to_fixed16_unchecked(z_end_right * (x_end_right * tx + y_end_f32 * ty + tk)), 0), max_tc);
+			const Fixed16 d_tc_left = fixed16_div(wsub(tc_end_left, tc_start_left), y_delta_for_tc);
+			const Fixed16 d_tc_right = fixed16_div(wsub(tc_end_right, tc_start_right), y_delta_for_tc);
+			// :680-681 + n row steps (:724-727)
+			const Fixed16 tc_left = wadd(wadd(tc_start_left, fixed16_mul(y_start_delta, d_tc_left)), wmul(n, d_tc_left));
+			const Fixed16 tc_right = wadd(wadd(tc_start_right, fixed16_mul(y_start_delta, d_tc_right)), wmul(n, d_tc_right));
+			r.v[2 + i] = tc_left;
+			r.v[4 + i] = fixed16_div(wsub(tc_right, tc_left), x_delta_for_tc);
+		}
+	}
+	else
+	{
+		const Eq64 e = make_eq(c);
+		const int64_t line_inv_z = (int64_t)row * e.d_inv_z_dy + e.inv_z_k; // :321 + n * d_inv_z_dy (:450)
+		const int64_t line_tc[2] = {(int64_t)row * e.d_tc_dy[0] + e.tc_k[0], (int64_t)row * e.d_tc_dy[1] + e.tc_k[1]};
+		const int64_t inv_z_min = 1 << INV_Z_PRE_SHIFT;
+		const int64_t inv_z_max = 1 << 29;
+		if (cd.tc_mode == SQW_TC_FULL_PERSPECTIVE)
+		{
+			// :345-422
+			const int32_t span_inv_z_start = (int32_t)max64(inv_z_min, min64(span_start_x * e.d_inv_z_dx + line_inv_z, inv_z_max));
+			const int32_t span_inv_z_end = (int32_t)max64(inv_z_min, min64(span_end_x * e.d_inv_z_dx + line_inv_z, inv_z_max));
+			const int32_t span_d_inv_z = span_length_minus_one > 0 ? (span_inv_z_end - span_inv_z_start) / span_length_minus_one : 0;
+			r.v[0] = span_inv_z_start;
+			r.v[1] = span_d_inv_z;
+#pragma unroll
+			for (int i = 0; i < 2; ++i)
+			{
+				const int tc_max_shift = INV_Z_SHIFT - TC_SHIFT;
+				const int64_t tc_max_max = 1 << 29;
+				const int64_t span_inv_z_corrected = (int64_t)(span_inv_z_start - (1 << INV_Z_PRE_SHIFT));
+				const int64_t tc_max_start = max64(0, min64(((span_inv_z_corrected * (int64_t)c.tex_size[i]) >> tc_max_shift) - 1, tc_max_max));
+				const int32_t span_tc_start = (int32_t)max64(0, min64(span_start_x * e.d_tc_dx[i] + line_tc[i], tc_max_start));
+				if (span_length_minus_one > 0)
+				{
+					const int64_t tc_max_end = max64(
+						0, min64((((span_inv_z_corrected + (int64_t)wmul(span_d_inv_z, span_length_minus_one)) * (int64_t)c.tex_size[i]) >> tc_max_shift) - 1, tc_max_max));
+					const int32_t span_tc_end = (int32_t)max64(0, min64(span_end_x * e.d_tc_dx[i] + line_tc[i], tc_max_end));
+					const int32_t d = (span_tc_end - span_tc_start) / span_length_minus_one;
+					r.v[4 + i] = d;
+					r.v[2 + i] = span_tc_end > span_tc_start ? span_tc_start : wsub(span_tc_end, wmul(d, span_length_minus_one));
+				}
+				else
+					r.v[2 + i] = span_tc_start;
+			}
+		}
+		else
+		{
+			// line-z corrected, :532-556
+			const uint32_t span_inv_z_start = (uint32_t)min64(max64(span_start_x * e.d_inv_z_dx + line_inv_z, inv_z_min), inv_z_max);
+			const uint32_t span_inv_z_end = (uint32_t)min64(max64(span_end_x * e.d_inv_z_dx + line_inv_z, inv_z_min), inv_z_max);
+			const uint64_t span_z_start = (1u << Z_CALC_SHIFT) / (span_inv_z_start >> INV_Z_PRE_SHIFT);
+			const uint64_t span_z_end = (1u << Z_CALC_SHIFT) / (span_inv_z_end >> INV_Z_PRE_SHIFT);
+#pragma unroll
+			for (int i = 0; i < 2; ++i)
+			{
+				const uint64_t tc_start = (uint64_t)max64(line_tc[i] + span_start_x * e.d_tc_dx[i], 0);
+				const uint64_t tc_end = (uint64_t)max64(line_tc[i] + span_end_x * e.d_tc_dx[i], 0);
+				const uint64_t max_tc = ((uint64_t)(int64_t)c.tex_size[i] << 16) - 1;
+				uint64_t a = (span_z_start * tc_start) >> (TC_FINAL_SHIFT - 16);
+				uint64_t b = (span_z_end * tc_end) >> (TC_FINAL_SHIFT - 16);
+				const int32_t tc_mul_z_start = (int32_t)(a < max_tc ? a : max_tc);
+				const int32_t tc_mul_z_end = (int32_t)(b < max_tc ? b : max_tc);
+				r.v[2 + i] = tc_mul_z_start;
+				if (span_length_minus_one > 0)
+					r.v[4 + i] = (tc_mul_z_end - tc_mul_z_start) / span_length_minus_one;
+			}
+		}
+	}
+	uint4* o = reinterpret_cast<uint4*>(out);
+	const uint4* s = reinterpret_cast<const uint4*>(&r);
+	o[0] = s[0];
+	o[1] = s[1];
+	o[2] = s[2];
+}
+
+// Edge walk of fill_polygon_impl_2_static_params (rasterizer.rs:160-270), stopped at the trapezoid owning `row`.
+__device__ void setup_polygon_line(const sqw_draw_cmd& c, const CmdDev& cd, const sqw_polygon_point* __restrict__ vertices, int32_t row, int32_t clip_w, int32_t clip_h, SpanRec* out)
+{
+	const uint32_t num_vertices = c.num_vertices;
+	uint32_t lower_vertex_index = 0;
+	Fixed16 min_y = vertices[0].y;
+	for (uint32_t index = 1; index < num_vertices; ++index)
+	{
+		const Fixed16 y = vertices[index].y;
+		if (y < min_y)
+		{
+			min_y = y;
+			lower_vertex_index = index;
+		}
+	}
+
+	uint32_t left_index = lower_vertex_index;
+	uint32_t right_index = lower_vertex_index;
+	Fixed16 cur_y = min_y;
+	for (;;)
+	{
+		uint32_t next_left_index = left_index + num_vertices - 1;
+		if (next_left_index >= num_vertices)
+			next_left_index -= num_vertices;
+		uint32_t next_right_index = right_index + 1;
+		if (next_right_index >= num_vertices)
+			next_right_index -= num_vertices;
+
+		const sqw_polygon_point left_vertex = vertices[left_index];
+		const sqw_polygon_point next_left_vertex = vertices[next_left_index];
+		const sqw_polygon_point right_vertex = vertices[right_index];
+		const sqw_polygon_point next_right_vertex = vertices[next_right_index];
+
+		const Fixed16 dy_left = wsub(next_left_vertex.y, left_vertex.y);
+		const Fixed16 dy_right = wsub(next_right_vertex.y, right_vertex.y);
+		const Fixed16 next_y = min(next_left_vertex.y, next_right_vertex.y);
+
+		const int32_t y_start_int = max(fixed16_round_to_int(cur_y), 0);
+		const int32_t y_end_int = min(fixed16_round_to_int(next_y), clip_h);
+		const bool owns_row = row >= y_start_int && row < y_end_int;
+
+		if (dy_left > SQW_FIXED16_HALF && dy_right > SQW_FIXED16_HALF)
+		{
+			if (owns_row)
+			{
+				const Fixed16 dx_dy_left = fixed16_div(wsub(next_left_vertex.x, left_vertex.x), dy_left);
+				const Fixed16 dx_dy_right = fixed16_div(wsub(next_right_vertex.x, right_vertex.x), dy_right);
+				PolygonSide l, r;
+				l.x_start = wadd(left_vertex.x, fixed16_mul(dx_dy_left, wsub(cur_y, left_vertex.y)));
+				l.dx_dy = dx_dy_left;
+				r.x_start = wadd(right_vertex.x, fixed16_mul(dx_dy_right, wsub(cur_y, right_vertex.y)));
+				r.dx_dy = dx_dy_right;
+				polygon_part_line(c, cd, row, y_start_int, cur_y, next_y, l, r, clip_w, out);
+				return;
+			}
+		}
+		else if (dy_left > 0 && dy_right > 0)
+		{
+			const int32_t cur_y_int = fixed16_round_to_int(cur_y);
+			const int32_t next_y_int = fixed16_round_to_int(next_y);
+			if (cur_y_int < next_y_int && owns_row)
+			{
+				// thin trapezoid: a single line evaluated at its centre (:226-252)
+				const Fixed16 thin_line_y = wadd(int_to_fixed16(cur_y_int), SQW_FIXED16_HALF);
+				PolygonSide l, r;
+				l.x_start = wadd(left_vertex.x, fixed16_mul_div(wsub(thin_line_y, left_vertex.y), wsub(next_left_vertex.x, left_vertex.x), dy_left));
+				l.dx_dy = 0;
+				r.x_start = wadd(right_vertex.x, fixed16_mul_div(wsub(thin_line_y, right_vertex.y), wsub(next_right_vertex.x, right_vertex.x), dy_right));
+				r.dx_dy = 0;
+				polygon_part_line(c, cd, row, y_start_int, cur_y, next_y, l, r, clip_w, out);
+				return;
+			}
+		}
+
+		if (next_left_index == next_right_index)
+			break;
+		if (next_right_vertex.y < next_left_vertex.y)
+			right_index = next_right_index;
+		else
+			left_index = next_left_index;
+		cur_y = next_y;
+	}
+	write_empty(out);
+}
+
+// fill_triangle_part (rasterizer.rs:984-1215) for the line `row`.
+__device__ void triangle_part_line(
+	const sqw_draw_cmd& c, int32_t row, Fixed16 y_start, Fixed16 y_end, PolygonSide left_side, PolygonSide right_side, const Fixed16 tc_start_left[2],
+	const Fixed16 d_tc_dy_left_in[2], const Fixed16 d_tc_dx_in[2], const Fixed16 light_start_left[3], const Fixed16 d_light_left_in[3],
+	const Fixed16 d_light_dx_in[3], int32_t clip_w, int32_t clip_h, SpanRec* out)
+{
+	const int32_t y_start_int = max(fixed16_round_to_int(y_start), 0);
+	const int32_t n = row - y_start_int;
+
+	const Fixed16 y_start_delta = wsub(wadd(int_to_fixed16(y_start_int), SQW_FIXED16_HALF), y_start);
+	const Fixed16 x_left0 = wadd(wadd(left_side.x_start, fixed16_mul(y_start_delta, left_side.dx_dy)), SQW_FIXED16_HALF);
+	const Fixed16 x_right0 = wadd(wadd(right_side.x_start, fixed16_mul(y_start_delta, right_side.dx_dy)), SQW_FIXED16_HALF);
+
+	const Fixed16 y_end_delta = wsub(y_end, wadd(y_start, y_start_delta));
+	const Fixed16 d_x_lower = max(wsub(x_right0, x_left0), 0);
+	const Fixed16 x_upper_left = wadd(x_left0, fixed16_mul(y_end_delta, left_side.dx_dy));
+	const Fixed16 x_upper_right = wadd(x_right0, fixed16_mul(y_end_delta, right_side.dx_dy));
+	const Fixed16 d_x_upper = max(wsub(x_upper_right, x_upper_left), 0);
+
+	const Fixed16 x_left = wadd(x_left0, wmul(n, left_side.dx_dy));
+	const Fixed16 x_right = wadd(x_right0, wmul(n, right_side.dx_dy));
+	const int32_t x_start_int = max(fixed16_floor_to_int(x_left), 0);
+	const int32_t x_end_int = min(fixed16_floor_to_int(x_right), clip_w);
+	if (x_start_int >= x_end_int)
+	{
+		write_empty(out);
+		return;
+	}
+	const Fixed16 x_start_delta = wsub(wadd(int_to_fixed16(x_start_int), SQW_FIXED16_ONE), x_left); // :1202
+
+	SpanRec r;
+	r.x0 = (int16_t)x_start_int;
+	r.x1 = (int16_t)x_end_int;
+	r.v[10] = 0;
+
+	// :1018-1138 texture coordinate range correction
+#pragma unroll
+	for (int i = 0; i < 2; ++i)
+	{
+		Fixed16 d_tc_dy_left = d_tc_dy_left_in[i];
+		Fixed16 d_tc_dx = d_tc_dx_in[i];
+		const Fixed16 max_tc = wsub(int_to_fixed16(c.tex_size[i]), 1);
+		Fixed16 tc_left = min(max(wadd(tc_start_left[i], fixed16_mul(y_start_delta, d_tc_dy_left)), 0), max_tc);
+		{
+			const Fixed16 tc_lower_delta = fixed16_mul(d_tc_dx, d_x_lower);
+			if (tc_lower_delta > max_tc)
+			{
+				tc_left = 0;
+				d_tc_dx = fixed16_div(max_tc, d_x_lower);
+			}
+			else if (tc_lower_delta < -max_tc)
+			{
+				tc_left = max_tc;
+				d_tc_dx = fixed16_div(-max_tc, d_x_lower);
+			}
+			else
+			{
+				const Fixed16 tc_lower_right = wadd(tc_left, tc_lower_delta);
+				if (tc_lower_right > max_tc)
+					tc_left = wsub(tc_left, wsub(tc_lower_right, max_tc));
+				else if (tc_lower_right < 0)
+					tc_left = wsub(tc_left, tc_lower_right);
+			}
+		}
+		{
+			Fixed16 tc_upper_left = min(max(wadd(tc_left, fixed16_mul(y_end_delta, d_tc_dy_left)), 0), max_tc);
+			const Fixed16 tc_upper_delta = fixed16_mul(d_tc_dx, d_x_upper);
+			if (tc_upper_delta > max_tc)
+			{
+				tc_upper_left = 0;
+				d_tc_dx = fixed16_div(max_tc, d_x_upper);
+			}
+			else if (tc_upper_delta < -max_tc)
+			{
+				tc_upper_left = max_tc;
+				d_tc_dx = fixed16_div(-max_tc, d_x_upper);
+			}
+			else
+			{
+				const Fixed16 tc_upper_right = wadd(tc_upper_left, tc_upper_delta);
+				if (tc_upper_right > max_tc)
+					tc_upper_left = wsub(tc_upper_left, wsub(tc_upper_right, max_tc));
+				else if (tc_upper_right < 0)
+					tc_upper_left = wsub(tc_upper_left, tc_upper_right);
+			}
+			d_tc_dy_left = y_end_delta > 0 ? fixed16_div(wsub(tc_upper_left, tc_left), y_end_delta) : 0;
+
+			const Fixed16 tc_upper_left2 = wadd(tc_left, fixed16_mul(y_end_delta, d_tc_dy_left));
+			const Fixed16 tc_upper_delta2 = fixed16_mul(d_tc_dx, d_x_upper);
+			const Fixed16 tc_upper_right2 = wadd(tc_upper_left2, tc_upper_delta2);
+			if (tc_upper_right2 < 0)
+				d_tc_dx = d_x_upper > 0 ? fixed16_div(-tc_upper_left2, d_x_upper) : 0;
+			else if (tc_upper_right2 > max_tc)
+				d_tc_dx = d_x_upper > 0 ? fixed16_div(wsub(max_tc, tc_upper_left2), d_x_upper) : 0;
+		}
+		const Fixed16 tc_left_row = wadd(tc_left, wmul(n, d_tc_dy_left));                 // :1285 applied n times
+		r.v[0 + i] = wadd(tc_left_row, fixed16_mul(x_start_delta, d_tc_dx));                 // :1205-1208
+		r.v[2 + i] = d_tc_dx;
+	}
+
+	// :1140-1192 light underflow correction
+#pragma unroll
+	for (int i = 0; i < 3; ++i)
+	{
+		Fixed16 d_light_left = d_light_left_in[i];
+		Fixed16 d_light_dx = d_light_dx_in[i];
+		Fixed16 light_left = max(wadd(light_start_left[i], fixed16_mul(y_start_delta, d_light_left)), 0);
+		const Fixed16 light_lower_right = wadd(light_left, fixed16_mul(d_x_lower, d_light_dx));
+		if (light_lower_right < 0)
+			light_left = wsub(light_left, light_lower_right);
+		{
+			Fixed16 light_upper_left = max(wadd(light_left, fixed16_mul(y_end_delta, d_light_left)), 0);
+			const Fixed16 light_upper_right = wadd(light_upper_left, fixed16_mul(d_x_upper, d_light_dx));
+			if (light_upper_right < 0)
+				light_upper_left = wsub(light_upper_left, light_upper_right);
+			d_light_left = y_end_delta > 0 ? fixed16_div(wsub(light_upper_left, light_left), y_end_delta) : 0;
+
+			const Fixed16 light_upper_left2 = wadd(light_left, fixed16_mul(y_end_delta, d_light_left));
+			const Fixed16 light_upper_right2 = wadd(light_upper_left2, fixed16_mul(d_x_upper, d_light_dx));
+			if (light_upper_right2 < 0)
+				d_light_dx = d_x_upper > 0 ? fixed16_div(-light_upper_left2, d_x_upper) : 0;
+		}
+		const Fixed16 light_left_row = wadd(light_left, wmul(n, d_light_left));            // :1289 applied n times
+		r.v[4 + i] = wadd(light_left_row, fixed16_mul(x_start_delta, d_light_dx));           // :1210-1214
+		r.v[7 + i] = d_light_dx;
+	}
+
+	uint4* o = reinterpret_cast<uint4*>(out);
+	const uint4* s = reinterpret_cast<const uint4*>(&r);
+	o[0] = s[0];
+	o[1] = s[1];
+	o[2] = s[2];
+}
+
+// fill_triangle_impl (rasterizer.rs:765-966) reduced to the half that owns `row`.
+__device__ void setup_triangle_line(const sqw_draw_cmd& c, const sqw_triangle_point* __restrict__ vertices, int32_t row, int32_t clip_w, int32_t clip_h, SpanRec* out)
+{
+	const sqw_triangle_point v0 = vertices[0], v1 = vertices[1], v2 = vertices[2];
+	int upper_index, lower_index;
+	if (v0.y >= v1.y && v0.y >= v2.y)
+	{
+		upper_index = 0;
+		lower_index = v1.y < v2.y ? 1 : 2;
+	}
+	else if (v1.y >= v0.y && v1.y >= v2.y)
+	{
+		upper_index = 1;
+		lower_index = v0.y < v2.y ? 0 : 2;
+	}
+	else
+	{
+		upper_index = 2;
+		lower_index = v0.y < v1.y ? 0 : 1;
+	}
+	const int middle_index = 3 - upper_index - lower_index;
+	const sqw_triangle_point upper_vertex = upper_index == 0 ? v0 : (upper_index == 1 ? v1 : v2);
+	const sqw_triangle_point lower_vertex = lower_index == 0 ? v0 : (lower_index == 1 ? v1 : v2);
+	const sqw_triangle_point middle_vertex = middle_index == 0 ? v0 : (middle_index == 1 ? v1 : v2);
+
+	const Fixed16 long_edge_dy = max(wsub(upper_vertex.y, lower_vertex.y), SQW_FIXED16_HALF);
+	const Fixed16 lower_part_dy = max(wsub(middle_vertex.y, lower_vertex.y), SQW_FIXED16_HALF);
+	const Fixed16 upper_part_dy = max(wsub(upper_vertex.y, middle_vertex.y), SQW_FIXED16_HALF);
+
+	const Fixed16 long_edge_dx_dy = fixed16_div(wsub(upper_vertex.x, lower_vertex.x), long_edge_dy);
+	const Fixed16 long_edge_x_in_middle = wadd(lower_vertex.x, fixed16_mul(long_edge_dx_dy, wsub(middle_vertex.y, lower_vertex.y)));
+	const Fixed16 lower_part_dx_dy = fixed16_div(wsub(middle_vertex.x, lower_vertex.x), lower_part_dy);
+	const Fixed16 upper_part_dx_dy = fixed16_div(wsub(upper_vertex.x, middle_vertex.x), upper_part_dy);
+
+	Fixed16 long_edge_d_tc_dy[2], long_edge_tc_in_middle[2], d_tc_dy_lower[2], d_tc_dy_upper[2];
+#pragma unroll
+	for (int i = 0; i < 2; ++i)
+	{
+		long_edge_d_tc_dy[i] = fixed16_div(wsub(upper_vertex.tc[i], lower_vertex.tc[i]), long_edge_dy);
+		long_edge_tc_in_middle[i] = wadd(lower_vertex.tc[i], fixed16_mul(long_edge_d_tc_dy[i], lower_part_dy));
+		d_tc_dy_lower[i] = fixed16_div(wsub(middle_vertex.tc[i], lower_vertex.tc[i]), lower_part_dy);
+		d_tc_dy_upper[i] = fixed16_div(wsub(upper_vertex.tc[i], middle_vertex.tc[i]), upper_part_dy);
+	}
+	Fixed16 long_edge_d_light_dy[3], long_edge_light_in_middle[3], d_light_dy_lower[3], d_light_dy_upper[3];
+#pragma unroll
+	for (int i = 0; i < 3; ++i)
+	{
+		long_edge_d_light_dy[i] = fixed16_div(wsub(upper_vertex.light[i], lower_vertex.light[i]), long_edge_dy);
+		long_edge_light_in_middle[i] = wadd(lower_vertex.light[i], fixed16_mul(long_edge_d_light_dy[i], lower_part_dy));
+		d_light_dy_lower[i] = fixed16_div(wsub(middle_vertex.light[i], lower_vertex.light[i]), lower_part_dy);
+		d_light_dy_upper[i] = fixed16_div(wsub(upper_vertex.light[i], middle_vertex.light[i]), upper_part_dy);
+	}
+
+	// Which half owns the row?  (fill_triangle_part returns early when its clipped row range is empty, :1000-1005)
+	const int32_t lo0 = max(fixed16_round_to_int(lower_vertex.y), 0), lo1 = min(fixed16_round_to_int(middle_vertex.y), clip_h);
+	const int32_t up0 = max(fixed16_round_to_int(middle_vertex.y), 0), up1 = min(fixed16_round_to_int(upper_vertex.y), clip_h);
+	const bool in_lower = row >= lo0 && row < lo1;
+	const bool in_upper = row >= up0 && row < up1;
+	if (!in_lower && !in_upper)
+	{
+		write_empty(out);
+		return;
+	}
+
+	Fixed16 d_tc_dx[2], d_light_dx[3];
+	PolygonSide l, r;
+	if (long_edge_x_in_middle >= middle_vertex.x)
+	{
+		const Fixed16 middle_dx = max(wsub(long_edge_x_in_middle, middle_vertex.x), SQW_FIXED16_HALF);
+#pragma unroll
+		for (int i = 0; i < 2; ++i)
+			d_tc_dx[i] = fixed16_div(wsub(long_edge_tc_in_middle[i], middle_vertex.tc[i]), middle_dx);
+#pragma unroll
+		for (int i = 0; i < 3; ++i)
+			d_light_dx[i] = fixed16_div(wsub(long_edge_light_in_middle[i], middle_vertex.light[i]), middle_dx);
+		if (in_lower)
+		{
+			l.x_start = lower_vertex.x;
+			l.dx_dy = lower_part_dx_dy;
+			r.x_start = lower_vertex.x;
+			r.dx_dy = long_edge_dx_dy;
+			triangle_part_line(c, row, lower_vertex.y, middle_vertex.y, l, r, lower_vertex.tc, d_tc_dy_lower, d_tc_dx, lower_vertex.light, d_light_dy_lower, d_light_dx, clip_w, clip_h, out);
+		}
+		else
+		{
+			l.x_start = middle_vertex.x;
+			l.dx_dy = upper_part_dx_dy;
+			r.x_start = long_edge_x_in_middle;
+			r.dx_dy = long_edge_dx_dy;
+			triangle_part_line(c, row, middle_vertex.y, upper_vertex.y, l, r, middle_vertex.tc, d_tc_dy_upper, d_tc_dx, middle_vertex.light, d_light_dy_upper, d_light_dx, clip_w, clip_h, out);
+		}
+	}
+	else
+	{
+		const Fixed16 middle_dx = max(wsub(middle_vertex.x, long_edge_x_in_middle), SQW_FIXED16_HALF);
+#pragma unroll
+		for (int i = 0; i < 2; ++i)
+			d_tc_dx[i] = fixed16_div(wsub(middle_vertex.tc[i], long_edge_tc_in_middle[i]), middle_dx);
+#pragma unroll
+		for (int i = 0; i < 3; ++i)
+			d_light_dx[i] = fixed16_div(wsub(middle_vertex.light[i], long_edge_light_in_middle[i]), middle_dx);
+		if (in_lower)
+		{
+			l.x_start = lower_vertex.x;
+			l.dx_dy = long_edge_dx_dy;
+			r.x_start = lower_vertex.x;
+			r.dx_dy = lower_part_dx_dy;
+			triangle_part_line(c, row, lower_vertex.y, middle_vertex.y, l, r, lower_vertex.tc, long_edge_d_tc_dy, d_tc_dx, lower_vertex.light, long_edge_d_light_dy, d_light_dx, clip_w, clip_h, out);
+		}
+		else
+		{
+			l.x_start = long_edge_x_in_middle;
+			l.dx_dy = long_edge_dx_dy;
+			r.x_start = middle_vertex.x;
+			r.dx_dy = upper_part_dx_dy;
+			triangle_part_line(c, row, middle_vertex.y, upper_vertex.y, l, r, long_edge_tc_in_middle, long_edge_d_tc_dy, d_tc_dx, long_edge_light_in_middle, long_edge_d_light_dy, d_light_dx, clip_w, clip_h, out);
+		}
+	}
+}
+
+__global__ void __launch_bounds__(128) raster_setup_kernel(
+	const sqw_draw_cmd* __restrict__ cmds, const CmdDev* __restrict__ cmd_dev, uint32_t num_cmds, const sqw_polygon_point* __restrict__ polygon_points,
+	const sqw_triangle_point* __restrict__ triangle_points, const uint32_t* __restrict__ cmd_span_base, uint32_t total_spans, SpanRec* __restrict__ spans,
+	int32_t clip_w, int32_t clip_h)
+{
+	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= total_spans)
+		return;
+	// Owning command: last index with cmd_span_base[i] <= s.
+	uint32_t lo = 0, hi = num_cmds; // invariant: base[lo] <= s < base[hi]
+	while (hi - lo > 1)
+	{
+		const uint32_t mid = (lo + hi) >> 1;
+		if (__ldg(cmd_span_base + mid) <= s)
+			lo = mid;
+		else
+			hi = mid;
+	}
+	const CmdDev cd = cmd_dev[lo];
+	const sqw_draw_cmd c = cmds[lo];
+	const int32_t row = (int32_t)cd.y0 + (int32_t)(s - cd.span_base);
+	if (cd.kind == SQW_CMD_POLYGON)
+		setup_polygon_line(c, cd, polygon_points + c.vertex_offset, row, clip_w, clip_h, spans + s);
+	else
+		setup_triangle_line(c, triangle_points + c.vertex_offset, row, clip_w, clip_h, spans + s);
+}
+
+// ---- binning -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) raster_bin_kernel(const CmdDev* __restrict__ cmd_dev, uint32_t num_cmds, const uint32_t* __restrict__ band_offsets, uint32_t* __restrict__ band_lists)
+{
+	__shared__ uint32_t s_warp_counts[8];
+	__shared__ uint32_t s_running;
+	const int band = blockIdx.x;
+	const int32_t band_y0 = band * SQW_TILE_H, band_y1 = band_y0 + SQW_TILE_H;
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	if (threadIdx.x == 0)
+		s_running = band_offsets[band];
+	__syncthreads();
+	for (uint32_t base = 0; base < num_cmds; base += 256)
+	{
+		const uint32_t i = base + threadIdx.x;
+		bool hit = false;
+		if (i < num_cmds)
+		{
+			const uint2 w = __ldg(reinterpret_cast<const uint2*>(cmd_dev + i)); // y0,y1,bx0,bx1
+			const int32_t y0 = (int16_t)(w.x & 0xFFFF), y1 = (int16_t)(w.x >> 16);
+			hit = y0 < y1 && y0 < band_y1 && y1 > band_y0;
+		}
+		const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, hit);
+		if (lane == 0)
+			s_warp_counts[warp] = __popc(ballot);
+		__syncthreads();
+		uint32_t offset = s_running;
+		for (int w = 0; w < warp; ++w)
+			offset += s_warp_counts[w];
+		if (hit)
+			band_lists[offset + __popc(ballot & ((1u << lane) - 1))] = i;
+		__syncthreads();
+		if (threadIdx.x == 0)
+		{
+			uint32_t t = 0;
+			for (int w = 0; w < 8; ++w)
+				t += s_warp_counts[w];
+			s_running += t;
+		}
+		__syncthreads();
+	}
+}
+
+// ---- tile kernel ----------------------------------------------------------------------------------------------
+template <class C>
+__device__ __forceinline__ typename C::Raw fetch_texel(const void* tex, uint32_t address)
+{
+	return __ldg(static_cast<const typename C::Raw*>(tex) + address);
+}
+
+template <class C>
+__global__ void __launch_bounds__(SQW_RASTER_THREADS) raster_tile_kernel(
+	const CmdDev* __restrict__ cmd_dev, const SpanRec* __restrict__ spans, const uint32_t* __restrict__ band_lists, const uint32_t* __restrict__ band_offsets,
+	const char* __restrict__ surfaces_base, typename C::Raw* __restrict__ color_buffer, int32_t width, int32_t height, int32_t pitch, int clear,
+	typename C::Raw clear_color)
+{
+	typedef typename C::Raw Raw;
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int band = blockIdx.y;
+	const int32_t row = band * SQW_TILE_H + warp;
+	if (row >= height)
+		return;
+	const int32_t tile_x0 = blockIdx.x * SQW_TILE_W;
+	const int32_t tile_x1 = min(tile_x0 + SQW_TILE_W, width);
+	const int32_t px0 = tile_x0 + lane * 4;
+
+	Raw* const dst = color_buffer + (size_t)row * pitch + px0;
+	Raw px[4];
+	const bool vec_ok = (px0 + 4 <= width) && ((pitch & 3) == 0);
+	if (clear)
+	{
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+			px[i] = clear_color;
+	}
+	else
+	{
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+			px[i] = (px0 + i < width) ? dst[i] : 0;
+	}
+
+	const uint32_t list_begin = band_offsets[band], list_end = band_offsets[band + 1];
+	for (uint32_t base = list_begin; base < list_end; base += 32)
+	{
+		uint32_t ci = 0;
+		bool hit = false;
+		if (base + lane < list_end)
+		{
+			ci = __ldg(band_lists + base + lane);
+			const uint2 w = __ldg(reinterpret_cast<const uint2*>(cmd_dev + ci));
+			const int32_t y0 = (int16_t)(w.x & 0xFFFF), y1 = (int16_t)(w.x >> 16);
+			const int32_t bx0 = (int16_t)(w.y & 0xFFFF), bx1 = (int16_t)(w.y >> 16);
+			hit = row >= y0 && row < y1 && bx0 < tile_x1 && bx1 > tile_x0;
+		}
+		uint32_t mask = __ballot_sync(0xFFFFFFFFu, hit);
+		while (mask)
+		{
+			const int bit = __ffs(mask) - 1;
+			mask &= mask - 1;
+			const uint32_t cmd_index = __shfl_sync(0xFFFFFFFFu, ci, bit);
+			const CmdDev* cdp = cmd_dev + cmd_index;
+			const uint4 c0 = __ldg(reinterpret_cast<const uint4*>(cdp));     // y0,y1,bx0,bx1 | span_base | kind.. | (pad)
+			const uint4 c1 = __ldg(reinterpret_cast<const uint4*>(cdp) + 1); // texture ptr | tex_width | tex_height
+			const int32_t y0 = (int16_t)(c0.x & 0xFFFF);
+			const uint32_t span_base = c0.z;
+			const uint32_t kind = c0.w & 0xFF, blend = (c0.w >> 8) & 0xFF, tc_mode = (c0.w >> 16) & 0xFF, tex64 = (c0.w >> 24) & 1;
+			// bit 1 of the last flag byte: `texture` is a byte offset into the view's surface pool (the pool may be
+			// re-allocated between recording and submission, so surface references stay relative).
+			const uint64_t tex_bits = (uint64_t)c1.x | ((uint64_t)c1.y << 32);
+			const void* const tex = ((c0.w >> 25) & 1) ? static_cast<const void*>(surfaces_base + tex_bits) : reinterpret_cast<const void*>(tex_bits);
+			const uint32_t tex_width = c1.z;
+
+			const uint4* sp = reinterpret_cast<const uint4*>(spans + span_base + (uint32_t)(row - y0));
+			const uint4 s0 = __ldg(sp);
+			const int32_t x0 = (int16_t)(s0.x & 0xFFFF), x1 = (int16_t)(s0.x >> 16);
+			if (x0 >= x1 || x0 >= tile_x1 || x1 <= tile_x0)
+				continue;
+			const uint4 s1 = __ldg(sp + 1);
+			const uint4 s2 = __ldg(sp + 2);
+			// v[0..2] = s0.y,z,w ; v[3..6] = s1 ; v[7..10] = s2
+
+			if (kind == SQW_CMD_POLYGON)
+			{
+				const int32_t tc0 = (int32_t)s0.w, tc1 = (int32_t)s1.x, dtc0 = (int32_t)s1.y, dtc1 = (int32_t)s1.z;
+				if (tc_mode == SQW_TC_FULL_PERSPECTIVE)
+				{
+					const int32_t inv_z0 = (int32_t)s0.y, d_inv_z = (int32_t)s0.z;
+#pragma unroll
+					for (int i = 0; i < 4; ++i)
+					{
+						const int32_t x = px0 + i;
+						if (x >= x0 && x < x1)
+						{
+							const int32_t k = x - x0;
+							const uint32_t span_inv_z = (uint32_t)wadd(inv_z0, wmul(k, d_inv_z));
+							const uint32_t z = (1u << Z_CALC_SHIFT) / (span_inv_z >> INV_Z_PRE_SHIFT); // rasterizer.rs:430
+							const uint64_t t0 = (uint64_t)(int64_t)wadd(tc0, wmul(k, dtc0));
+							const uint64_t t1 = (uint64_t)(int64_t)wadd(tc1, wmul(k, dtc1));
+							const uint32_t u = (uint32_t)(((uint64_t)z * t0) >> TC_FINAL_SHIFT);
+							const uint32_t v = (uint32_t)(((uint64_t)z * t1) >> TC_FINAL_SHIFT);
+							px[i] = blend_pixel<C>(blend, px[i], fetch_texel<C>(tex, u + v * tex_width));
+						}
+					}
+				}
+				else
+				{
+#pragma unroll
+					for (int i = 0; i < 4; ++i)
+					{
+						const int32_t x = px0 + i;
+						if (x >= x0 && x < x1)
+						{
+							const int32_t k = x - x0;
+							const uint32_t u = (uint32_t)(wadd(tc0, wmul(k, dtc0)) >> 16);
+							const uint32_t v = (uint32_t)(wadd(tc1, wmul(k, dtc1)) >> 16);
+							px[i] = blend_pixel<C>(blend, px[i], fetch_texel<C>(tex, u + v * tex_width));
+						}
+					}
+				}
+			}
+			else
+			{
+				// fill_triangle_part pixel loop (rasterizer.rs:1223-1279)
+				const int32_t tc0 = (int32_t)s0.y, tc1 = (int32_t)s0.z, dtc0 = (int32_t)s0.w, dtc1 = (int32_t)s1.x;
+				const int32_t l0 = (int32_t)s1.y, l1 = (int32_t)s1.z, l2 = (int32_t)s1.w;
+				const int32_t dl0 = (int32_t)s2.x, dl1 = (int32_t)s2.y, dl2 = (int32_t)s2.z;
+#pragma unroll
+				for (int i = 0; i < 4; ++i)
+				{
+					const int32_t x = px0 + i;
+					if (x >= x0 && x < x1)
+					{
+						const int32_t k = x - x0;
+						const uint32_t u = (uint32_t)(wadd(tc0, wmul(k, dtc0)) >> 16);
+						const uint32_t v = (uint32_t)(wadd(tc1, wmul(k, dtc1)) >> 16);
+						// line_light = from_color_i32x3([l0,l1,l2]) -> lanes [B,G,R,A] = [l2,l1,l0,0]
+						const ColorVecI light = cvi(wadd(l2, wmul(k, dl2)), wadd(l1, wmul(k, dl1)), wadd(l0, wmul(k, dl0)), 0);
+						ColorVecI texel_vec;
+						int32_t alpha;
+						bool alpha_pass;
+						if (tex64)
+						{
+							const uint64_t t = __ldg(static_cast<const uint64_t*>(tex) + (u + v * tex_width));
+							texel_vec = cvi_from_color64(t);
+							alpha = Color64::get_alpha(t);
+							alpha_pass = Color64::test_alpha(t);
+						}
+						else
+						{
+							const uint32_t t = __ldg(static_cast<const uint32_t*>(tex) + (u + v * tex_width));
+							texel_vec = cvi_from_color32(t);
+							alpha = Color32::get_alpha(t);
+							alpha_pass = Color32::test_alpha(t);
+						}
+						const ColorVecI lighted = cvi_shr<16>(cvi_mul(texel_vec, light));
+						const Raw src = C::from_veci(lighted);
+						switch (blend)
+						{
+						case SQW_BLEND_NONE: px[i] = src; break;
+						case SQW_BLEND_AVERAGE: px[i] = C::average(px[i], src); break;
+						case SQW_BLEND_ADDITIVE: px[i] = C::saturated_sum(px[i], src); break;
+						case SQW_BLEND_ALPHA_TEST:
+							if (alpha_pass)
+								px[i] = src;
+							break;
+						default:
+							px[i] = C::from_veci(cvi_shr<8>(cvi_add(cvi_mul_scalar(C::to_veci(px[i]), 255 - alpha), cvi_mul_scalar(lighted, alpha))));
+							break;
+						}
+					}
+				}
+			}
+		}
+	}
+
+	if (vec_ok)
+	{
+		if (sizeof(Raw) == 8)
+		{
+			uint4* d = reinterpret_cast<uint4*>(dst);
+			d[0] = make_uint4((uint32_t)px[0], (uint32_t)((uint64_t)px[0] >> 32), (uint32_t)px[1], (uint32_t)((uint64_t)px[1] >> 32));
+			d[1] = make_uint4((uint32_t)px[2], (uint32_t)((uint64_t)px[2] >> 32), (uint32_t)px[3], (uint32_t)((uint64_t)px[3] >> 32));
+		}
+		else
+		{
+			*reinterpret_cast<uint4*>(dst) = make_uint4((uint32_t)px[0], (uint32_t)px[1], (uint32_t)px[2], (uint32_t)px[3]);
+		}
+	}
+	else
+	{
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+			if (px0 + i < width)
+				dst[i] = px[i];
+	}
+}
+
+} // namespace
+
+cudaError_t launch_raster_setup(const RasterLaunch& l, cudaStream_t stream)
+{
+	if (l.total_spans == 0)
+		return cudaSuccess;
+	const uint32_t blocks = (l.total_spans + 127) / 128;
+	raster_setup_kernel<<<blocks, 128, 0, stream>>>(
+		l.cmds, l.cmd_dev, l.num_cmds, l.polygon_points, l.triangle_points, l.cmd_span_base, l.total_spans, l.spans, l.width, l.height);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_raster_bin(const RasterLaunch& l, cudaStream_t stream)
+{
+	if (l.num_cmds == 0 || l.num_bands == 0)
+		return cudaSuccess;
+	raster_bin_kernel<<<l.num_bands, 256, 0, stream>>>(l.cmd_dev, l.num_cmds, l.band_offsets, l.band_lists);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_raster_tiles(const RasterLaunch& l, cudaStream_t stream)
+{
+	if (l.num_bands == 0)
+		return cudaSuccess;
+	const dim3 grid((uint32_t)((l.width + SQW_TILE_W - 1) / SQW_TILE_W), l.num_bands);
+	if (l.color64)
+		raster_tile_kernel<Color64><<<grid, SQW_RASTER_THREADS, 0, stream>>>(
+			l.cmd_dev, l.spans, l.band_lists, l.band_offsets, static_cast<const char*>(l.surfaces_base), static_cast<uint64_t*>(l.color_buffer), l.width, l.height, l.pitch, l.clear, (uint64_t)l.clear_color);
+	else
+		raster_tile_kernel<Color32><<<grid, SQW_RASTER_THREADS, 0, stream>>>(
+			l.cmd_dev, l.spans, l.band_lists, l.band_offsets, static_cast<const char*>(l.surfaces_base), static_cast<uint32_t*>(l.color_buffer), l.width, l.height, l.pitch, l.clear, (uint32_t)l.clear_color);
+	return cudaGetLastError();
+}
+
+} // namespace sqw

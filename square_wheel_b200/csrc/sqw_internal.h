@@ -1,0 +1,131 @@
+// Internal structures shared by the C-ABI implementation (sqw_api.cu) and the kernels.
+#pragma once
+#include "../../include/sqw_cuda.h"
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sqw
+{
+
+// Device image table entry (one mip of one texture), filled by sqw_upload_image.
+struct ImageDev
+{
+	const void* pixels;
+	uint32_t width, height;
+};
+
+// ---- stage 1 ------------------------------------------------------------------------------------------------
+// One CTA of surface_build_kernel processes one band: SURF_BAND_ROWS rows of one job.
+#define SQW_SURF_BAND_ROWS 16
+#define SQW_SURF_THREADS 256
+struct SurfaceBand
+{
+	uint32_t job;
+	uint32_t row0;
+};
+
+// Surface kernel variant = (colour width, directional lightmap, dynamic lights, normal map, specular type);
+// mirrors the const-generic dispatch chain of surfaces.rs:124-423.
+struct SurfaceVariant
+{
+	uint8_t color64;
+	uint8_t directional;
+	uint8_t dynamic_lights;
+	uint8_t normal_map;
+	uint8_t specular; // 0 none, 1 dielectric, 2 metal
+	uint8_t emissive_only; // job without diffuse layer: only mix_surface_with_texture(BlendingMode::None)
+};
+
+struct SurfaceLaunch
+{
+	const sqw_surface_job* jobs;   // device
+	const SurfaceBand* bands;      // device, this variant's slice
+	uint32_t num_bands;
+	const ImageDev* images;        // device
+	const float* lightmaps;        // device
+	const sqw_directional_lightmap_element* directional_lightmaps; // device
+	const sqw_light* lights;       // device
+	const float* shadow_maps;      // device
+	float cam_pos[3];
+	void* surfaces;                // device pool base
+};
+cudaError_t launch_surface_build(const SurfaceVariant& v, const SurfaceLaunch& l, cudaStream_t stream);
+
+// ---- stage 2 ------------------------------------------------------------------------------------------------
+#define SQW_TILE_W 128
+#define SQW_TILE_H 8
+#define SQW_RASTER_THREADS 256 /* 8 warps: each warp owns one row of the tile, each lane 4 consecutive pixels */
+
+// Per-command data prepared by the host part of sqw_frame_set_draw (row range, conservative column range,
+// span-table offset, resolved texture pointer).  32 bytes.
+struct CmdDev
+{
+	int16_t y0, y1;   // row range [y0, y1) inside the clip rect (rows that can own a span)
+	int16_t bx0, bx1; // conservative pixel column range [bx0, bx1)
+	uint32_t span_base;
+	uint8_t kind, blend, tc_mode, tex_flags; // tex_flags bit0: texture elements are 8 bytes (else 4); bit1: `texture` is a byte offset into the surface pool
+	const void* texture;
+	int32_t tex_width;
+	int32_t tex_height;
+};
+static_assert(sizeof(CmdDev) == 32, "CmdDev must be 32 bytes");
+
+// One scan-line of one command: everything fill_polygon_part* / fill_triangle_part derive per line before the
+// pixel loop.  48 bytes, written by raster_setup_kernel, read (warp-uniform) by raster_tile_kernel.
+//   polygon, full perspective: v[0] = span_inv_z, v[1] = span_d_inv_z, v[2..3] = span_tc, v[4..5] = span_d_tc   (rasterizer.rs:345-422)
+//   polygon, line-z / affine : v[2..3] = tc (16.16), v[4..5] = d_tc                                           (:540-556, :697-703)
+//   triangle                 : v[0..1] = line_tc, v[2..3] = d_tc_dx, v[4..6] = line_light, v[7..9] = d_light_dx (:1205-1214)
+struct SpanRec
+{
+	int16_t x0, x1; // pixel span [x0, x1); x0 >= x1 means empty
+	int32_t v[11];
+};
+static_assert(sizeof(SpanRec) == 48, "SpanRec must be 48 bytes");
+
+struct RasterLaunch
+{
+	const sqw_draw_cmd* cmds; // device copy of the submitted commands
+	const CmdDev* cmd_dev;    // device
+	uint32_t num_cmds;
+	const sqw_polygon_point* polygon_points;
+	const sqw_triangle_point* triangle_points;
+	SpanRec* spans;                // device, total_spans entries
+	const uint32_t* cmd_span_base; // device, num_cmds + 1 (exclusive prefix of row counts)
+	uint32_t total_spans;
+	uint32_t* band_lists;         // device, ordered command indices per band
+	const uint32_t* band_offsets; // device, num_bands + 1
+	uint32_t num_bands;
+	int32_t width, height, pitch;
+	void* color_buffer;
+	const void* surfaces_base; // view surface pool (CmdDev::texture is relative to it when flag bit 1 is set)
+	int color64;
+	int clear;
+	uint64_t clear_color;
+};
+cudaError_t launch_raster_setup(const RasterLaunch& l, cudaStream_t stream);
+cudaError_t launch_raster_bin(const RasterLaunch& l, cudaStream_t stream);
+cudaError_t launch_raster_tiles(const RasterLaunch& l, cudaStream_t stream);
+
+// ---- stage 3 ------------------------------------------------------------------------------------------------
+struct PostLaunch
+{
+	const uint64_t* hdr;
+	uint32_t width, height;
+	uint32_t* dst; // device, pitch = width
+	float inv_scale_bgr[3];
+	unsigned long long* color_sums; // device, 3 x u64 (B, G, R)
+	// bloom
+	uint64_t* bloom0;
+	uint64_t* bloom1;
+	uint32_t bloom_w, bloom_h, bloom_scale_log2;
+	int32_t blur_radius;
+	int32_t kernel_h[33];
+	int32_t kernel_v[33];
+	int linear;
+};
+cudaError_t launch_tonemap(const PostLaunch& l, cudaStream_t stream);
+cudaError_t launch_bloom_downscale(const PostLaunch& l, cudaStream_t stream);
+cudaError_t launch_bloom_blur(const PostLaunch& l, cudaStream_t stream);
+cudaError_t launch_tonemap_bloom(const PostLaunch& l, cudaStream_t stream);
+
+} // namespace sqw

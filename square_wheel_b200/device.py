@@ -1,0 +1,221 @@
+"""Thin object wrappers over the C-ABI (include/sqw_cuda.h): Context (one map replica on one GPU), View (one render
+target), Frame (one recorded frame).  All compute happens inside libsqw_cuda.so; these classes only marshal numpy
+arrays into the plain-pointer calls."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _native as N
+
+
+class SqwError(RuntimeError):
+    pass
+
+
+def _as(a, dtype):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=dtype) if not (isinstance(a, np.ndarray) and a.dtype == dtype and a.flags["C_CONTIGUOUS"]) else a
+    return a
+
+
+class Context:
+    """sqw_ctx: replaces the data-ownership half of Renderer::new (src/square_wheel/renderer.rs:24)."""
+
+    def __init__(self, lightmaps: Optional[np.ndarray], directional_lightmaps: Optional[np.ndarray], device: int = 0, stream: int = 0, max_images: int = 0):
+        self._lib = N.load_cuda_library()
+        self._handle = C.c_void_p()
+        lm = _as(lightmaps, np.float32)
+        dlm = _as(directional_lightmaps, N.directional_lightmap_dtype)
+        n = 0
+        if lm is not None:
+            n = lm.size // 3
+        if dlm is not None:
+            if lm is not None and dlm.size != n:
+                raise ValueError("lightmap arrays must have the same element count")
+            n = dlm.size
+        desc = N.MapDesc(N.ptr(lm), N.ptr(dlm), n, max_images, 0)
+        rc = self._lib.sqw_create(C.byref(self._handle), device, C.byref(desc), C.c_void_p(stream) if stream else None)
+        if rc != N.SQW_OK:
+            raise SqwError(f"sqw_create failed ({rc}): {self._lib.sqw_last_error(None).decode()}")
+        self.device = device
+        self.images = []  # (kind, w, h)
+
+    def _check(self, rc: int, what: str):
+        if rc < 0:
+            raise SqwError(f"{what} failed ({rc}): {self._lib.sqw_last_error(self._handle).decode()}")
+        return rc
+
+    def upload_image(self, kind: int, pixels: np.ndarray) -> int:
+        """pixels: 2-D array [height, width] of texture_element_dtype / uint32 / uint64."""
+        dt = {N.IMAGE_TEXTURE_ELEMENT: N.texture_element_dtype, N.IMAGE_COLOR32: np.uint32, N.IMAGE_COLOR64: np.uint64}[kind]
+        p = _as(pixels, dt)
+        h, w = p.shape
+        image_id = self._check(self._lib.sqw_upload_image(self._handle, kind, w, h, N.ptr(p)), "sqw_upload_image")
+        self.images.append((kind, w, h))
+        return image_id
+
+    def update_image(self, image_id: int, pixels: np.ndarray):
+        self._check(self._lib.sqw_update_image(self._handle, image_id, N.ptr(np.ascontiguousarray(pixels))), "sqw_update_image")
+
+    def create_view(self, width: int, height: int, color_bits: int) -> "View":
+        return View(self, width, height, color_bits)
+
+    def close(self):
+        if self._handle:
+            self._lib.sqw_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class View:
+    """sqw_view: one render target + per-view scratch (a PartialRenderer, partial_renderer.rs:15-50)."""
+
+    def __init__(self, ctx: Context, width: int, height: int, color_bits: int):
+        self.ctx = ctx
+        self._lib = ctx._lib
+        self._handle = C.c_void_p()
+        ctx._check(self._lib.sqw_view_create(ctx._handle, C.byref(self._handle), width, height, color_bits), "sqw_view_create")
+        self.width, self.height, self.color_bits = width, height, color_bits
+        self.pixel_dtype = np.uint32 if color_bits == 32 else np.uint64
+
+    # ---- immediate-mode stage calls (S1, S2, S3 of SURVEY.md §8b) ----
+    def build_surfaces(self, jobs, lights=None, shadow_maps=None, cam_pos=(0.0, 0.0, 0.0), total_surface_pixels: Optional[int] = None):
+        jobs = _as(jobs, N.surface_job_dtype)
+        lights = _as(lights, N.light_dtype) if lights is not None else np.zeros(0, N.light_dtype)
+        sm = _as(shadow_maps, np.float32) if shadow_maps is not None else np.zeros(0, np.float32)
+        cp = np.asarray(cam_pos, np.float32)
+        if total_surface_pixels is None:
+            total_surface_pixels = required_surface_pixels(jobs)
+        self.ctx._check(
+            self._lib.sqw_build_surfaces(self._handle, N.ptr(jobs), len(jobs), N.ptr(lights), len(lights), N.ptr(sm), sm.size, N.ptr(cp), total_surface_pixels),
+            "sqw_build_surfaces",
+        )
+
+    def draw(self, cmds, polygon_points=None, triangle_points=None, clear_color: Optional[int] = None):
+        cmds = _as(cmds, N.draw_cmd_dtype)
+        pp = _as(polygon_points, N.polygon_point_dtype) if polygon_points is not None else np.zeros(0, N.polygon_point_dtype)
+        tp = _as(triangle_points, N.triangle_point_dtype) if triangle_points is not None else np.zeros(0, N.triangle_point_dtype)
+        cc = np.array([clear_color], np.uint64) if clear_color is not None else None
+        self.ctx._check(self._lib.sqw_draw(self._handle, N.ptr(cmds), len(cmds), N.ptr(pp), len(pp), N.ptr(tp), len(tp), N.ptr(cc)), "sqw_draw")
+
+    def postprocess(self, params: N.PostParams, read_back: bool = True):
+        """Returns (pixels or None, average colour [B, G, R])."""
+        dst = np.empty((self.height, self.width), np.uint32) if read_back else None
+        avg = np.zeros(3, np.float32)
+        self.ctx._check(self._lib.sqw_postprocess(self._handle, C.byref(params), N.ptr(dst), self.width, N.ptr(avg)), "sqw_postprocess")
+        return dst, avg
+
+    # ---- readback ----
+    def read_pixels(self) -> np.ndarray:
+        out = np.empty((self.height, self.width), self.pixel_dtype)
+        self.ctx._check(self._lib.sqw_read_pixels(self._handle, N.ptr(out), self.width), "sqw_read_pixels")
+        return out
+
+    def write_pixels(self, pixels: np.ndarray):
+        px = _as(pixels, self.pixel_dtype)
+        assert px.shape == (self.height, self.width)
+        self.ctx._check(self._lib.sqw_write_pixels(self._handle, N.ptr(px), self.width), "sqw_write_pixels")
+
+    def read_pixels32(self) -> np.ndarray:
+        out = np.empty((self.height, self.width), np.uint32)
+        self.ctx._check(self._lib.sqw_read_pixels32(self._handle, N.ptr(out), self.width), "sqw_read_pixels32")
+        return out
+
+    def read_surfaces(self, offset: int, count: int) -> np.ndarray:
+        out = np.empty(count, self.pixel_dtype)
+        self.ctx._check(self._lib.sqw_read_surfaces(self._handle, N.ptr(out), offset, count), "sqw_read_surfaces")
+        return out
+
+    def average_color(self) -> np.ndarray:
+        avg = np.zeros(3, np.float32)
+        self.ctx._check(self._lib.sqw_view_get_average_color(self._handle, N.ptr(avg)), "sqw_view_get_average_color")
+        return avg
+
+    def synchronize(self):
+        self.ctx._check(self._lib.sqw_view_synchronize(self._handle), "sqw_view_synchronize")
+
+    def create_frame(self) -> "Frame":
+        return Frame(self)
+
+    def close(self):
+        if self._handle and self.ctx._handle:
+            self._lib.sqw_view_destroy(self._handle)
+        self._handle = C.c_void_p()
+
+
+class Frame:
+    """sqw_frame: device copies of one view's job list, command list and post params (SURVEY.md §8e batched views)."""
+
+    def __init__(self, view: View):
+        self.view = view
+        self._lib = view._lib
+        self._handle = C.c_void_p()
+        view.ctx._check(self._lib.sqw_frame_create(view._handle, C.byref(self._handle)), "sqw_frame_create")
+        self.h2d_bytes = 0
+
+    def set_surfaces(self, jobs, lights=None, shadow_maps=None, cam_pos=(0.0, 0.0, 0.0), total_surface_pixels: Optional[int] = None):
+        jobs = _as(jobs, N.surface_job_dtype)
+        lights = _as(lights, N.light_dtype) if lights is not None else np.zeros(0, N.light_dtype)
+        sm = _as(shadow_maps, np.float32) if shadow_maps is not None else np.zeros(0, np.float32)
+        cp = np.asarray(cam_pos, np.float32)
+        if total_surface_pixels is None:
+            total_surface_pixels = required_surface_pixels(jobs)
+        self.view.ctx._check(
+            self._lib.sqw_frame_set_surfaces(self._handle, N.ptr(jobs), len(jobs), N.ptr(lights), len(lights), N.ptr(sm), sm.size, N.ptr(cp), total_surface_pixels),
+            "sqw_frame_set_surfaces",
+        )
+        self.h2d_bytes += jobs.nbytes + lights.nbytes + sm.nbytes
+
+    def set_draw(self, cmds, polygon_points=None, triangle_points=None, clear_color: Optional[int] = None):
+        cmds = _as(cmds, N.draw_cmd_dtype)
+        pp = _as(polygon_points, N.polygon_point_dtype) if polygon_points is not None else np.zeros(0, N.polygon_point_dtype)
+        tp = _as(triangle_points, N.triangle_point_dtype) if triangle_points is not None else np.zeros(0, N.triangle_point_dtype)
+        cc = np.array([clear_color], np.uint64) if clear_color is not None else None
+        self.view.ctx._check(
+            self._lib.sqw_frame_set_draw(self._handle, N.ptr(cmds), len(cmds), N.ptr(pp), len(pp), N.ptr(tp), len(tp), N.ptr(cc)), "sqw_frame_set_draw"
+        )
+        self.h2d_bytes += cmds.nbytes + pp.nbytes + tp.nbytes
+
+    def set_post(self, params: N.PostParams):
+        self.view.ctx._check(self._lib.sqw_frame_set_post(self._handle, C.byref(params)), "sqw_frame_set_post")
+
+    def submit(self, stages: int = N.STAGE_ALL):
+        self.view.ctx._check(self._lib.sqw_frame_submit(self._handle, stages), "sqw_frame_submit")
+
+    def stats(self) -> N.FrameStats:
+        st = N.FrameStats()
+        self.view.ctx._check(self._lib.sqw_frame_get_stats(self._handle, C.byref(st)), "sqw_frame_get_stats")
+        return st
+
+    def close(self):
+        if self._handle and self.view._handle and self.view.ctx._handle:
+            self._lib.sqw_frame_destroy(self._handle)
+        self._handle = C.c_void_p()
+
+
+def required_surface_pixels(jobs: np.ndarray) -> int:
+    if len(jobs) == 0:
+        return 0
+    sizes = jobs["surface_size"].astype(np.int64)
+    return int((jobs["surface_pixels_offset"].astype(np.int64) + sizes[:, 0] * sizes[:, 1]).max())
+
+
+def make_post_params(exposure=1.0, color_modulate=(1.0, 1.0, 1.0), bloom_sigma=0.0, bloom_scale=0.25, bloom_buffer_scale_log2=1, linear_bloom_filter=False) -> N.PostParams:
+    """Defaults follow postprocessor_config.rs:5-93 except bloom_sigma (1.0 there; 0 = tonemap only)."""
+    p = N.PostParams()
+    p.exposure = exposure
+    p.color_modulate = (C.c_float * 3)(*color_modulate)
+    p.bloom_sigma = bloom_sigma
+    p.bloom_scale = bloom_scale
+    p.bloom_buffer_scale_log2 = bloom_buffer_scale_log2
+    p.linear_bloom_filter = 1 if linear_bloom_filter else 0
+    return p

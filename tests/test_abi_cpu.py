@@ -1,0 +1,65 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol include/sqw_cuda.h declares,
+struct layouts match, and without a GPU it fails loudly instead of falling back to the CPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from square_wheel_b200 import _native as N
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    text = open(os.path.join(ROOT, "include", "sqw_cuda.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sqw_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as g
+
+    g.build_cuda()
+    lib = C.CDLL(N.CUDA_LIB_PATH)
+    declared = _declared_functions()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/sqw_cuda.h but not exported"
+    bound = {s[0] for s in N.CUDA_SYMBOLS}
+    assert set(declared) == bound, f"python binding out of sync: {set(declared) ^ bound}"
+    assert lib.sqw_abi_version() == 1
+
+
+def test_struct_sizes_match_header():
+    text = open(os.path.join(ROOT, "square_wheel_b200", "csrc", "sqw_api.cu")).read()
+    sizes = dict(re.findall(r"static_assert\(sizeof\((\w+)\) == (\d+)", text))
+    assert int(sizes["sqw_surface_job"]) == N.surface_job_dtype.itemsize
+    assert int(sizes["sqw_light"]) == N.light_dtype.itemsize
+    assert int(sizes["sqw_draw_cmd"]) == N.draw_cmd_dtype.itemsize
+    assert int(sizes["sqw_triangle_point"]) == N.triangle_point_dtype.itemsize
+    assert int(sizes["sqw_directional_lightmap_element"]) == N.directional_lightmap_dtype.itemsize
+    assert int(sizes["sqw_post_params"]) == C.sizeof(N.PostParams)
+
+
+def test_no_cpu_fallback_without_device():
+    """On a box without a CUDA device the product path must fail loudly (SQW_ERR_NO_DEVICE), never compute on the CPU."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from square_wheel_b200.device import Context, SqwError
+
+    with pytest.raises(SqwError, match="no CUDA device"):
+        Context(np.zeros((4, 3), np.float32), None)
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under square_wheel_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "square_wheel_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")) or f == "Makefile":
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "liboracle" not in src and "import oracle" not in src and "oracle/" not in src and "oracle_" not in src, f"{f} references the oracle"
