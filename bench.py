@@ -1,0 +1,444 @@
+#!/usr/bin/env python
+"""Benchmark of the world-drawing hot path (surface building -> span rasterisation -> tonemapping).
+
+    python bench.py --gpus N --steps K --warmup W            this repo's CUDA path (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...   the reference's CPU implementation of the same path
+                                                             (oracle restatement, all host threads; rank 0 only)
+
+Workload (BASELINE.json configs[1]): the demo-map stand-in (seeded synthetic map) at 3840x2160,
+directional lightmaps + normal mapping + dielectric/metal specular, 64-bit HDR framebuffer + tonemapping.  One STEP = one
+batch of FRAMES_PER_STEP consecutive camera poses of the fixed 64-pose fly-through.  Prints one JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+FRAMES_PER_STEP = 16
+NUM_POSES = 64
+WIDTH, HEIGHT = 3840, 2160
+SCENE_KW = dict(seed=2, grid=(24, 24, 5), cell_size=(160.0, 160.0, 128.0), num_rooms=26, num_materials=24, texture_size_log2=8, max_polygon_size=64.0, material_mode=0, emissive_fraction=0.15)
+METRIC = "4k_hdr_frames_per_sec"
+UNIT = "frames/s"
+
+
+def workload_config(extra=None):
+    cfg = {
+        "workload": "configs[1]: demo-map stand-in (synthetic seed 2, 24x24x5 cells, 13k polygons, 24 materials 256^2) 3840x2160, directional lightmaps + normal maps + specular, Color64 HDR + tonemap (bloom off)",
+        "resolution": [WIDTH, HEIGHT],
+        "frames_per_step": FRAMES_PER_STEP,
+        "camera_path": f"{NUM_POSES}-pose Catmull-Rom loop, fov 0.375*pi",
+        "l2_policy": "inputs larger than L2: each frame streams >0.4 GB (surface pool + 66 MB HDR buffer + 33 MB picture) through a 126 MB L2",
+        "map": "synthetic stand-in: demo2.sqwm cannot be produced here (no rustc for map_compiler/lightmapper, textures not shipped)",
+    }
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, gpu_index):
+        self.samples = []
+        self.proc = None
+        self.gpu_index = gpu_index
+        self.thread = None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True
+            )
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 7:
+                self.samples.append(parts)
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm = []
+        smax = 0
+        reasons = set()
+        for p in self.samples:
+            try:
+                sm.append(float(p[0]))
+                smax = max(smax, float(p[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def prepare_host_frames(scene, poses, use_directional=True):
+    from square_wheel_b200 import scene as S
+
+    hr = S.HostRenderer(scene, use_directional_lightmaps=use_directional)
+    t0 = time.perf_counter()
+    frames = [hr.build_frame(WIDTH, HEIGHT, p) for p in poses]
+    host_ms = (time.perf_counter() - t0) * 1e3 / max(len(poses), 1)
+    hr.close()
+    return frames, host_ms
+
+
+def algorithmic_bytes(hf_stats, color_bytes=8):
+    """BASELINE.md 'Algorithmic bytes per frame': B1 = S(8+C) + Se(4+2C) + L; B2 = 2 P C (one texel gathered + one pixel written per
+    final pixel, overdraw not counted); B3 = P(8+4)."""
+    S, Se, L = hf_stats
+    P = WIDTH * HEIGHT
+    b1 = S * (8 + color_bytes) + Se * (4 + 2 * color_bytes) + L
+    b2 = 2 * P * color_bytes
+    b3 = P * 12
+    return b1, b2, b3
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU restatement (oracle port) of the same three stages with all host threads, on a bounded sample of the
+    workload per step.  Only rank 0 works."""
+    if rank != 0:
+        return
+    import oracle
+    from square_wheel_b200 import scene as S
+    from square_wheel_b200.device import make_post_params
+
+    sample_frames = 2
+    cores = os.cpu_count() or 1
+    scene = S.Scene(**SCENE_KW)
+    poses = scene.camera_path(NUM_POSES)
+    need = (args.steps + args.warmup) * sample_frames
+    idx = [(i * (FRAMES_PER_STEP // sample_frames)) % NUM_POSES for i in range(need)]
+    frames, _ = prepare_host_frames(scene, [poses[i] for i in idx])
+    post = make_post_params(exposure=1.0)
+
+    def one_frame(hf):
+        surf = oracle.build_surfaces(64, hf.jobs, None, None, hf.cam_pos, scene.images, scene.lightmaps, scene.directional_lightmaps, hf.total_surface_pixels, num_threads=cores)
+        fb = np.zeros((HEIGHT, WIDTH), np.uint64)
+        if hf.needs_clear:
+            oracle.fill(fb, S.BACKGROUND_COLOR64)
+        oracle.draw(64, fb, hf.cmds, hf.polygon_points, None, surf, scene.images, num_threads=cores)
+        oracle.postprocess(fb, post, num_threads=cores)
+
+    k = 0
+    for _ in range(args.warmup):
+        for _ in range(sample_frames):
+            one_frame(frames[k])
+            k += 1
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for _ in range(sample_frames):
+            one_frame(frames[k])
+            k += 1
+    dt = time.perf_counter() - t0
+    fps = args.steps * sample_frames / dt
+    sample = f"{sample_frames} of the {FRAMES_PER_STEP} frames of each step (every {FRAMES_PER_STEP // sample_frames}th pose), all three stages, {cores} threads"
+    line = {
+        "impl": "reference",
+        "metric": METRIC,
+        "value": fps,
+        "unit": UNIT,
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f32+i32/i64 (Color64 u16x4 pixels)",
+        "data": "synthetic",
+        "config": workload_config({"reference_impl": "C++ restatement of Square-Wheel @4820f17 (oracle/), not the Rust binary (no rustc in the image)"}),
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_cuda(args, rank, local_rank, world):
+    import torch
+
+    from square_wheel_b200 import _native as N
+    from square_wheel_b200 import scene as S
+    from square_wheel_b200.device import Context, make_post_params
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the world-drawing path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    # ---- scene + host preparation (the part of the renderer that stays on the host) ----
+    scene = S.Scene(**SCENE_KW)
+    poses = scene.camera_path(NUM_POSES)
+    # independent camera views are partitioned across GPUs: rank r starts its loop at a different phase of the fly-through
+    order = [(i + rank * (NUM_POSES // max(world, 1))) % NUM_POSES for i in range(NUM_POSES)]
+    host_frames, host_ms = prepare_host_frames(scene, [poses[i] for i in order])
+
+    stream = torch.cuda.current_stream()
+    ctx = Context(scene.lightmaps, scene.directional_lightmaps, device=local_rank, stream=stream.cuda_stream)
+    scene.upload(ctx)
+    view = ctx.create_view(WIDTH, HEIGHT, 64)
+    post = make_post_params(exposure=1.0)
+
+    # recorded frames: device-resident job / command lists (inputs resident in HBM for `value`)
+    max_surface = max(hf.total_surface_pixels for hf in host_frames)
+    recorded = []
+    for hf in host_frames:
+        f = view.create_frame()
+        f.set_surfaces(hf.jobs, None, None, hf.cam_pos, max_surface)
+        f.set_draw(hf.cmds, hf.polygon_points, None, clear_color=S.BACKGROUND_COLOR64 if hf.needs_clear else None)
+        f.set_post(post)
+        recorded.append(f)
+    view.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run_steps(n_steps, start):
+        k = start
+        for _ in range(n_steps):
+            for _ in range(FRAMES_PER_STEP):
+                recorded[k % NUM_POSES].submit(N.STAGE_ALL)
+                k += 1
+        return k
+
+    # ---- device-resident timing: W warm-up steps, then exactly K steps between events ----
+    k = run_steps(args.warmup, 0)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    k_end = run_steps(args.steps, k)
+    e1.record(stream)
+    barrier()
+    elapsed_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([elapsed_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    frames_timed = args.steps * FRAMES_PER_STEP
+    fps = world * frames_timed / (elapsed_ms * 1e-3)
+
+    # statistics of the timed frames (units of texels/s and of the roofline)
+    st_S = st_Se = st_L = st_spans = 0
+    launches = 0
+    for i in range(k, k_end):
+        st = recorded[i % NUM_POSES].stats()
+        st_S += st.surface_texels
+        st_Se += st.emissive_texels
+        st_L += st.lightmap_bytes
+        st_spans += st.num_spans
+        launches += st.num_kernel_launches
+    per_frame = (st_S / frames_timed, st_Se / frames_timed, st_L / frames_timed)
+
+    # ---- per-kernel durations: same K steps again with CUDA events around every launch on the launching stream ----
+    barrier()
+    ctx.profile_begin()
+    run_steps(args.steps, k)
+    kt = ctx.profile_end()
+    b1, b2, b3 = algorithmic_bytes(per_frame)
+    stage_bytes = {"surface_build": b1, "raster_tile": b2, "tonemap": b3}
+    peak, peak_src = load_peaks()
+    kernels = {}
+    total_kernel_ms = sum(v[0] for v in kt.values())
+    for name, (ms, n) in kt.items():
+        if n == 0:
+            continue
+        kernels[name] = {"ms_per_frame": ms / frames_timed, "launches_per_frame": n / frames_timed, "share": ms / total_kernel_ms}
+        if name in stage_bytes:
+            gbs = stage_bytes[name] / (ms / frames_timed * 1e-3) / 1e9
+            kernels[name].update({"algorithmic_bytes_per_frame": stage_bytes[name], "achieved_gbs": gbs, "frac_of_measured_peak": gbs / peak})
+    dominant = max(kernels, key=lambda n: kernels[n]["ms_per_frame"])
+    dom = kernels[dominant]
+    roofline = {
+        "kernel": dominant,
+        "bound": "hbm",
+        "achieved": dom.get("achieved_gbs"),
+        "peak": peak,
+        "peak_source": peak_src,
+        "unit": "GB/s",
+        "frac": dom.get("frac_of_measured_peak"),
+        "traffic": None,
+        "per_launch": "one frame (all launches of this kernel in one frame)",
+        "algorithmic_bytes": dom.get("algorithmic_bytes_per_frame"),
+        "ms": dom["ms_per_frame"],
+        "kernels": kernels,
+        "frame_bytes_total": b1 + b2 + b3,
+        "frame_gbs_total": (b1 + b2 + b3) / (elapsed_ms * 1e-3 / frames_timed) / 1e9,
+        "frame_frac_total": (b1 + b2 + b3) / (elapsed_ms * 1e-3 / frames_timed) / 1e9 / peak,
+    }
+
+    # ---- end to end through the C-ABI with HOST buffers: per frame H2D of job + command lists, D2H of the 32-bit picture ----
+    pinned = torch.empty((HEIGHT, WIDTH), dtype=torch.int32, pin_memory=True)
+    frame_e2e = view.create_frame()
+    lib = ctx._lib
+
+    def e2e_steps(n_steps, start):
+        kk = start
+        h2d = 0
+        for _ in range(n_steps):
+            for _ in range(FRAMES_PER_STEP):
+                hf = host_frames[kk % NUM_POSES]
+                before = frame_e2e.h2d_bytes
+                frame_e2e.set_surfaces(hf.jobs, None, None, hf.cam_pos, max_surface)
+                frame_e2e.set_draw(hf.cmds, hf.polygon_points, None, clear_color=S.BACKGROUND_COLOR64 if hf.needs_clear else None)
+                frame_e2e.set_post(post)
+                frame_e2e.submit(N.STAGE_ALL)
+                rc = lib.sqw_read_pixels32(view._handle, pinned.data_ptr(), WIDTH)  # synchronises: the picture is in host memory
+                assert rc == 0
+                h2d += frame_e2e.h2d_bytes - before
+                kk += 1
+        return kk, h2d
+
+    e2e_steps(1, 0)
+    barrier()
+    t0 = time.perf_counter()
+    _, h2d_total = e2e_steps(args.steps, k)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_fps = world * frames_timed / e2e_s
+    e2e = {
+        "value": e2e_fps,
+        "unit": UNIT,
+        "h2d_bytes_per_step": int(h2d_total / args.steps),
+        "d2h_bytes_per_step": WIDTH * HEIGHT * 4 * FRAMES_PER_STEP,
+        "note": "per frame: sqw_frame_set_surfaces + set_draw (pageable host lists) + submit + sqw_read_pixels32 into pinned host memory; host visibility/BSP traversal (stays host in the reference too) is outside",
+    }
+
+    # ---- CPU baseline on this box's host cores (rank 0, N=1 only): bounded sample of the same workload ----
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle
+
+        cores = os.cpu_count() or 1
+        sample = [host_frames[i] for i in (0, 21, 42)]
+        t0 = time.perf_counter()
+        stage_s = [0.0, 0.0, 0.0]
+        for hf in sample:
+            t = time.perf_counter()
+            surf = oracle.build_surfaces(64, hf.jobs, None, None, hf.cam_pos, scene.images, scene.lightmaps, scene.directional_lightmaps, hf.total_surface_pixels, num_threads=cores)
+            stage_s[0] += time.perf_counter() - t
+            fb = np.zeros((HEIGHT, WIDTH), np.uint64)
+            if hf.needs_clear:
+                oracle.fill(fb, S.BACKGROUND_COLOR64)
+            t = time.perf_counter()
+            oracle.draw(64, fb, hf.cmds, hf.polygon_points, None, surf, scene.images, num_threads=cores)
+            stage_s[1] += time.perf_counter() - t
+            t = time.perf_counter()
+            oracle.postprocess(fb, post, num_threads=cores)
+            stage_s[2] += time.perf_counter() - t
+        dt = sum(stage_s)
+        cpu_baseline = {
+            "value": len(sample) / dt,
+            "unit": UNIT,
+            "cores": cores,
+            "kind": "port",
+            "sample": f"{len(sample)} frames of the workload (poses 0, 21, 42), {cores} threads: surfaces parallel-for over polygons, raster split_rect, tonemap row ranges",
+            "stage_ms_per_frame": {"surfaces": stage_s[0] / len(sample) * 1e3, "rasterization": stage_s[1] / len(sample) * 1e3, "tonemapping": stage_s[2] / len(sample) * 1e3},
+            "wall_s": time.perf_counter() - t0,
+            "note": "C++ restatement of Square-Wheel @4820f17, not the Rust binary",
+        }
+
+    if rank == 0:
+        line = {
+            "metric": METRIC,
+            "value": fps,
+            "unit": UNIT,
+            "n_gpus": world,
+            "steps": args.steps,
+            "warmup": args.warmup,
+            "ms_per_step": elapsed_ms / args.steps,
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "f32+i32/i64 (Color64 u16x4 pixels)",
+            "data": "synthetic",
+            "config": workload_config(
+                {
+                    "parallelism": f"view-batch x{world} (independent camera views per GPU, no collective on the hot path)",
+                    "surface_texels_per_frame": per_frame[0],
+                    "surface_texels_per_sec": world * st_S / (elapsed_ms * 1e-3),
+                    "spans_per_frame": st_spans / frames_timed,
+                    "visible_polygons_per_frame": float(np.mean([len(h.jobs) for h in host_frames])),
+                    "draw_commands_per_frame": float(np.mean([len(h.cmds) for h in host_frames])),
+                    "host_prepare_ms_per_frame": host_ms,
+                    "scene": {f[0]: int(getattr(scene.info, f[0])) for f in scene.info._fields_},
+                }
+            ),
+            "clocks": clocks,
+            "e2e": e2e,
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_cuda(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -311,6 +311,27 @@ typedef struct sqw_frame_stats
 } sqw_frame_stats;
 int sqw_frame_get_stats(const sqw_frame* frame, sqw_frame_stats* out);
 
+/* ---- per-kernel timing (measurement support) ---------------------------------------------------------------- */
+/* Between sqw_profile_begin and sqw_profile_end every kernel launch of this context is bracketed by CUDA events on the
+ * context's stream (the reference's PerformanceCounter::run_with_measure around each stage, performance_counter.rs:39).
+ * sqw_profile_end synchronises and returns the accumulated device time and launch count per kernel kind. */
+#define SQW_KERNEL_SURFACE_BUILD 0
+#define SQW_KERNEL_RASTER_SETUP 1
+#define SQW_KERNEL_RASTER_BIN 2
+#define SQW_KERNEL_RASTER_TILE 3
+#define SQW_KERNEL_TONEMAP 4
+#define SQW_KERNEL_BLOOM_DOWNSCALE 5
+#define SQW_KERNEL_BLOOM_BLUR 6
+#define SQW_KERNEL_TONEMAP_BLOOM 7
+#define SQW_NUM_KERNEL_KINDS 8
+typedef struct sqw_kernel_times
+{
+	double ms[SQW_NUM_KERNEL_KINDS];
+	uint64_t launches[SQW_NUM_KERNEL_KINDS];
+} sqw_kernel_times;
+int sqw_profile_begin(sqw_ctx* ctx);
+int sqw_profile_end(sqw_ctx* ctx, sqw_kernel_times* out);
+
 /* Average colour produced by the last post stage of this view (synchronises). */
 int sqw_view_get_average_color(sqw_view* view, float avg_color_out[3]);
 

@@ -138,6 +138,12 @@ class FrameStats(C.Structure):
     ]
 
 
+class KernelTimes(C.Structure):
+    _fields_ = [("ms", C.c_double * 8), ("launches", C.c_uint64 * 8)]
+
+
+KERNEL_NAMES = ["surface_build", "raster_setup", "raster_bin", "raster_tile", "tonemap", "bloom_downscale", "bloom_blur", "tonemap_bloom"]
+
 # Every symbol include/sqw_cuda.h declares: (name, restype, argtypes)
 _VP = C.c_void_p
 CUDA_SYMBOLS = [
@@ -165,6 +171,8 @@ CUDA_SYMBOLS = [
     ("sqw_frame_submit", C.c_int, [_VP, C.c_uint32]),
     ("sqw_frame_get_stats", C.c_int, [_VP, C.POINTER(FrameStats)]),
     ("sqw_view_get_average_color", C.c_int, [_VP, _VP]),
+    ("sqw_profile_begin", C.c_int, [_VP]),
+    ("sqw_profile_end", C.c_int, [_VP, C.POINTER(KernelTimes)]),
 ]
 
 _cuda_lib = None

@@ -82,7 +82,54 @@ struct sqw_ctx
 	uint32_t max_images = 0;
 	std::vector<sqw_view*> views;
 	std::string last_error;
+	// per-kernel timing (sqw_profile_begin / _end)
+	bool profiling = false;
+	struct TimedLaunch
+	{
+		cudaEvent_t start, stop;
+		int kind;
+	};
+	std::vector<TimedLaunch> timed;
+	std::vector<cudaEvent_t> event_pool;
+	cudaEvent_t get_event()
+	{
+		if (!event_pool.empty())
+		{
+			cudaEvent_t e = event_pool.back();
+			event_pool.pop_back();
+			return e;
+		}
+		cudaEvent_t e = nullptr;
+		cudaEventCreate(&e);
+		return e;
+	}
 };
+
+namespace
+{
+// RAII bracket around one kernel launch when profiling is on.
+struct LaunchTimer
+{
+	sqw_ctx* ctx;
+	sqw_ctx::TimedLaunch t{};
+	LaunchTimer(sqw_ctx* c, int kind) : ctx(c)
+	{
+		if (!ctx->profiling)
+			return;
+		t.kind = kind;
+		t.start = ctx->get_event();
+		t.stop = ctx->get_event();
+		cudaEventRecord(t.start, ctx->stream);
+	}
+	~LaunchTimer()
+	{
+		if (!ctx->profiling)
+			return;
+		cudaEventRecord(t.stop, ctx->stream);
+		ctx->timed.push_back(t);
+	}
+};
+} // namespace
 
 struct sqw_view
 {
@@ -271,6 +318,13 @@ void sqw_destroy(sqw_ctx* ctx)
 		cudaFree(ctx->d_lightmaps);
 	if (ctx->d_directional_lightmaps)
 		cudaFree(ctx->d_directional_lightmaps);
+	for (auto& t : ctx->timed)
+	{
+		cudaEventDestroy(t.start);
+		cudaEventDestroy(t.stop);
+	}
+	for (cudaEvent_t e : ctx->event_pool)
+		cudaEventDestroy(e);
 	if (ctx->own_stream && ctx->stream)
 		cudaStreamDestroy(ctx->stream);
 	delete ctx;
@@ -728,7 +782,10 @@ int sqw_frame_submit(sqw_frame* f, uint32_t stages)
 		{
 			l.bands = static_cast<const SurfaceBand*>(f->d_bands.ptr) + g.band_offset;
 			l.num_bands = g.num_bands;
-			SQW_CUDA(ctx, launch_surface_build(g.variant, l, s));
+			{
+				LaunchTimer timer(ctx, SQW_KERNEL_SURFACE_BUILD);
+				SQW_CUDA(ctx, launch_surface_build(g.variant, l, s));
+			}
 			++launches;
 		}
 	}
@@ -757,16 +814,19 @@ int sqw_frame_submit(sqw_frame* f, uint32_t stages)
 		l.clear_color = f->clear_color;
 		if (f->total_spans)
 		{
+			LaunchTimer timer(ctx, SQW_KERNEL_RASTER_SETUP);
 			SQW_CUDA(ctx, launch_raster_setup(l, s));
 			++launches;
 		}
 		if (f->num_cmds)
 		{
+			LaunchTimer timer(ctx, SQW_KERNEL_RASTER_BIN);
 			SQW_CUDA(ctx, launch_raster_bin(l, s));
 			++launches;
 		}
 		if (f->num_cmds || f->clear)
 		{
+			LaunchTimer timer(ctx, SQW_KERNEL_RASTER_TILE);
 			SQW_CUDA(ctx, launch_raster_tiles(l, s));
 			++launches;
 		}
@@ -809,25 +869,74 @@ int sqw_frame_submit(sqw_frame* f, uint32_t stages)
 				l.kernel_v[i] = (int32_t)(kernel[i] * p.bloom_scale * 16384.0f); // :906
 			}
 			l.blur_radius = radius;
-			SQW_CUDA(ctx, launch_bloom_downscale(l, s));
+			{
+				LaunchTimer timer(ctx, SQW_KERNEL_BLOOM_DOWNSCALE);
+				SQW_CUDA(ctx, launch_bloom_downscale(l, s));
+			}
 			++launches;
 			if (radius > 0)
 			{
+				LaunchTimer timer(ctx, SQW_KERNEL_BLOOM_BLUR);
 				SQW_CUDA(ctx, launch_bloom_blur(l, s));
 				launches += 2;
 			}
-			SQW_CUDA(ctx, launch_tonemap_bloom(l, s));
+			{
+				LaunchTimer timer(ctx, SQW_KERNEL_TONEMAP_BLOOM);
+				SQW_CUDA(ctx, launch_tonemap_bloom(l, s));
+			}
 			++launches;
 			view->sums_divisor = (uint64_t)l.bloom_w * l.bloom_h;
 		}
 		else
 		{
-			SQW_CUDA(ctx, launch_tonemap(l, s));
+			{
+				LaunchTimer timer(ctx, SQW_KERNEL_TONEMAP);
+				SQW_CUDA(ctx, launch_tonemap(l, s));
+			}
 			++launches;
 			view->sums_divisor = (uint64_t)view->width * view->height;
 		}
 	}
 	f->stats.num_kernel_launches = launches;
+	return SQW_OK;
+}
+
+int sqw_profile_begin(sqw_ctx* ctx)
+{
+	if (!ctx)
+		return SQW_ERR_INVALID_ARGUMENT;
+	SQW_CUDA(ctx, cudaSetDevice(ctx->device));
+	SQW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	for (auto& t : ctx->timed)
+	{
+		ctx->event_pool.push_back(t.start);
+		ctx->event_pool.push_back(t.stop);
+	}
+	ctx->timed.clear();
+	ctx->profiling = true;
+	return SQW_OK;
+}
+
+int sqw_profile_end(sqw_ctx* ctx, sqw_kernel_times* out)
+{
+	if (!ctx || !out)
+		return SQW_ERR_INVALID_ARGUMENT;
+	SQW_CUDA(ctx, cudaSetDevice(ctx->device));
+	ctx->profiling = false;
+	SQW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	std::memset(out, 0, sizeof(*out));
+	for (auto& t : ctx->timed)
+	{
+		float ms = 0.0f;
+		if (cudaEventElapsedTime(&ms, t.start, t.stop) == cudaSuccess && t.kind >= 0 && t.kind < SQW_NUM_KERNEL_KINDS)
+		{
+			out->ms[t.kind] += ms;
+			out->launches[t.kind] += 1;
+		}
+		ctx->event_pool.push_back(t.start);
+		ctx->event_pool.push_back(t.stop);
+	}
+	ctx->timed.clear();
 	return SQW_OK;
 }
 

@@ -64,6 +64,15 @@ class Context:
     def create_view(self, width: int, height: int, color_bits: int) -> "View":
         return View(self, width, height, color_bits)
 
+    def profile_begin(self):
+        self._check(self._lib.sqw_profile_begin(self._handle), "sqw_profile_begin")
+
+    def profile_end(self) -> dict:
+        """{kernel name: (total ms, launches)} for everything launched since profile_begin."""
+        kt = N.KernelTimes()
+        self._check(self._lib.sqw_profile_end(self._handle, C.byref(kt)), "sqw_profile_end")
+        return {name: (kt.ms[i], int(kt.launches[i])) for i, name in enumerate(N.KERNEL_NAMES)}
+
     def close(self):
         if self._handle:
             self._lib.sqw_destroy(self._handle)

@@ -1,0 +1,180 @@
+// C API of the host-side library (libsqw_host.so) for the head-less drivers (tests, bench, Python mirror).
+// This library contains NO pixel work: it plays the part of the reference's Rust host around the C-ABI seams
+// (scene description, visibility, surface preparation, BSP traversal).
+#include "renderer.hpp"
+#include <cstring>
+#include <new>
+
+using namespace sqwh;
+
+extern "C"
+{
+
+struct sqwh_scene_params // mirrors sqwh::SceneParams (plain C layout for ctypes)
+{
+	uint32_t seed;
+	uint32_t grid[3];
+	float cell_size[3];
+	uint32_t num_rooms;
+	uint32_t num_materials;
+	uint32_t texture_size_log2;
+	float max_polygon_size;
+	uint32_t material_mode;
+	float emissive_fraction;
+};
+
+struct sqwh_scene_info
+{
+	uint32_t num_nodes, num_leafs, num_polygons, num_portals, num_vertices, num_materials, num_images, num_waypoints;
+	uint64_t num_lightmap_elements;
+};
+
+struct sqwh_renderer_config
+{
+	uint32_t use_directional_lightmaps;
+	float textures_mip_bias;
+	uint32_t clear_background;
+	uint32_t invert_polygons_order;
+};
+
+struct sqwh_frame_info
+{
+	uint32_t num_jobs, num_cmds, num_polygon_points, needs_background_clear;
+	uint64_t total_surface_pixels;
+	uint32_t num_visible_leafs, num_visible_polygons;
+	uint32_t mode_counts[3];
+	float cam_pos[3];
+	uint32_t reserved;
+};
+
+void sqwh_default_scene_params(sqwh_scene_params* p)
+{
+	const SceneParams d;
+	p->seed = d.seed;
+	for (int i = 0; i < 3; ++i)
+	{
+		p->grid[i] = d.grid[i];
+		p->cell_size[i] = d.cell_size[i];
+	}
+	p->num_rooms = d.num_rooms;
+	p->num_materials = d.num_materials;
+	p->texture_size_log2 = d.texture_size_log2;
+	p->max_polygon_size = d.max_polygon_size;
+	p->material_mode = d.material_mode;
+	p->emissive_fraction = d.emissive_fraction;
+}
+
+Scene* sqwh_scene_create(const sqwh_scene_params* p)
+{
+	if (!p || p->grid[0] == 0 || p->grid[1] == 0 || p->grid[2] == 0 || p->num_materials == 0 || p->texture_size_log2 < 4 || p->texture_size_log2 > 11)
+		return nullptr;
+	SceneParams sp;
+	sp.seed = p->seed;
+	for (int i = 0; i < 3; ++i)
+	{
+		sp.grid[i] = p->grid[i];
+		sp.cell_size[i] = p->cell_size[i];
+	}
+	sp.num_rooms = p->num_rooms;
+	sp.num_materials = p->num_materials;
+	sp.texture_size_log2 = p->texture_size_log2;
+	sp.max_polygon_size = p->max_polygon_size;
+	sp.material_mode = p->material_mode;
+	sp.emissive_fraction = p->emissive_fraction;
+	Scene* s = new (std::nothrow) Scene();
+	if (!s)
+		return nullptr;
+	generate_scene(sp, *s);
+	return s;
+}
+void sqwh_scene_destroy(Scene* s) { delete s; }
+
+void sqwh_scene_get_info(const Scene* s, sqwh_scene_info* out)
+{
+	out->num_nodes = (uint32_t)s->map.nodes.size();
+	out->num_leafs = (uint32_t)s->map.leafs.size();
+	out->num_polygons = (uint32_t)s->map.polygons.size();
+	out->num_portals = (uint32_t)s->map.portals.size();
+	out->num_vertices = (uint32_t)s->map.vertices.size();
+	out->num_materials = (uint32_t)s->materials.size();
+	out->num_images = (uint32_t)s->images.size();
+	out->num_waypoints = (uint32_t)s->camera_waypoints.size();
+	out->num_lightmap_elements = s->map.directional_lightmaps_data.size();
+}
+const void* sqwh_scene_image(const Scene* s, uint32_t index, int32_t* kind, uint32_t* width, uint32_t* height)
+{
+	if (index >= s->images.size())
+		return nullptr;
+	const HostImage& img = s->images[index];
+	*kind = img.kind;
+	*width = img.width;
+	*height = img.height;
+	return img.pixels.data();
+}
+const float* sqwh_scene_lightmaps(const Scene* s) { return s->map.lightmaps_data.data(); }
+const sqw_directional_lightmap_element* sqwh_scene_directional_lightmaps(const Scene* s) { return s->map.directional_lightmaps_data.data(); }
+const Polygon* sqwh_scene_polygons(const Scene* s) { return s->map.polygons.data(); }
+const Vec3f* sqwh_scene_vertices(const Scene* s) { return s->map.vertices.data(); }
+
+// out: num_frames x {position[3], azimuth, elevation}
+uint32_t sqwh_scene_camera_path(const Scene* s, uint32_t num_frames, uint32_t jitter_seed, float* out)
+{
+	std::vector<CameraPose> path;
+	make_camera_path(*s, num_frames, jitter_seed, path);
+	for (size_t i = 0; i < path.size(); ++i)
+	{
+		out[i * 5 + 0] = path[i].position.x;
+		out[i * 5 + 1] = path[i].position.y;
+		out[i * 5 + 2] = path[i].position.z;
+		out[i * 5 + 3] = path[i].azimuth;
+		out[i * 5 + 4] = path[i].elevation;
+	}
+	return (uint32_t)path.size();
+}
+
+Renderer* sqwh_renderer_create(const Scene* s, const sqwh_renderer_config* cfg)
+{
+	RendererConfig c;
+	if (cfg)
+	{
+		c.use_directional_lightmaps = cfg->use_directional_lightmaps != 0;
+		c.textures_mip_bias = cfg->textures_mip_bias;
+		c.clear_background = cfg->clear_background != 0;
+		c.invert_polygons_order = cfg->invert_polygons_order != 0;
+	}
+	return new (std::nothrow) Renderer(*s, c);
+}
+void sqwh_renderer_destroy(Renderer* r) { delete r; }
+
+// pose: {position[3], azimuth, elevation}; fov: vertical field of view in radians (game_map.rs:865 uses 0.375 * pi)
+void sqwh_renderer_prepare_frame(Renderer* r, uint32_t width, uint32_t height, const float* pose, float fov)
+{
+	CameraPose p;
+	p.position = {pose[0], pose[1], pose[2]};
+	p.azimuth = pose[3];
+	p.elevation = pose[4];
+	r->prepare_frame(width, height, p, fov);
+}
+void sqwh_renderer_draw_frame(Renderer* r) { r->draw_frame(); }
+
+void sqwh_renderer_frame_info(const Renderer* r, sqwh_frame_info* out)
+{
+	std::memset(out, 0, sizeof(*out));
+	out->num_jobs = (uint32_t)r->jobs().size();
+	out->num_cmds = (uint32_t)r->cmds().size();
+	out->num_polygon_points = (uint32_t)r->polygon_points().size();
+	out->needs_background_clear = r->needs_background_clear() ? 1 : 0;
+	out->total_surface_pixels = r->total_surface_pixels();
+	out->num_visible_leafs = r->stats().num_visible_leafs;
+	out->num_visible_polygons = r->stats().num_visible_polygons;
+	for (int i = 0; i < 3; ++i)
+		out->mode_counts[i] = r->stats().mode_counts[i];
+	out->cam_pos[0] = r->camera_matrices().position.x;
+	out->cam_pos[1] = r->camera_matrices().position.y;
+	out->cam_pos[2] = r->camera_matrices().position.z;
+}
+const sqw_surface_job* sqwh_renderer_jobs(const Renderer* r) { return r->jobs().data(); }
+const sqw_draw_cmd* sqwh_renderer_cmds(const Renderer* r) { return r->cmds().data(); }
+const sqw_polygon_point* sqwh_renderer_polygon_points(const Renderer* r) { return r->polygon_points().data(); }
+
+} // extern "C"

@@ -1,0 +1,128 @@
+// In-memory map (BSPMap, src/common/bsp_map_compact.rs:7-35), materials and textures of the host-side mirror, plus the
+// seeded synthetic map generator that stands in for map_compiler + lightmapper output (the compiled demo
+// map and its textures are not shipped and the Rust tools cannot be built here).
+#pragma once
+#include "../../include/sqw_cuda.h"
+#include "math.hpp"
+#include <string>
+#include <vector>
+
+namespace sqwh
+{
+
+constexpr uint32_t FIRST_LEAF_INDEX = 1u << 31; // bsp_map_compact.rs:46
+constexpr uint32_t MAX_BSP_TREE_DEPTH = 128;
+constexpr uint32_t LIGHTMAP_SCALE_LOG2 = 4; // common/lightmap.rs:4
+constexpr uint32_t LIGHTMAP_SCALE = 1u << LIGHTMAP_SCALE_LOG2;
+constexpr uint32_t MAX_MIP = 4; // textures.rs:6
+constexpr uint32_t NUM_MIPS = MAX_MIP + 1;
+
+struct BSPNode // bsp_map_compact.rs:37-44 (24 bytes)
+{
+	uint32_t children[2];
+	Plane plane;
+};
+struct BSPLeaf // :48-56
+{
+	uint32_t first_polygon, num_polygons, first_leaf_portal, num_leaf_portals;
+};
+struct Polygon // :58-75 (80 bytes)
+{
+	uint32_t first_vertex, num_vertices;
+	Plane plane;
+	Plane tex_coord_equation[2];
+	int32_t tex_coord_min[2];
+	int32_t tex_coord_max[2];
+	uint32_t lightmap_data_offset;
+	uint32_t texture;
+};
+static_assert(sizeof(Polygon) == 80, "Polygon layout (.sqwm lump 2)");
+struct Portal // :77-85
+{
+	uint32_t leafs[2];
+	Plane plane;
+	uint32_t first_vertex, num_vertices;
+};
+
+struct BSPMap
+{
+	std::vector<BSPNode> nodes; // last node is the root
+	std::vector<BSPLeaf> leafs;
+	std::vector<Polygon> polygons;
+	std::vector<Portal> portals;
+	std::vector<uint32_t> leafs_portals;
+	std::vector<Vec3f> vertices;
+	std::vector<float> lightmaps_data; // [n][3]
+	std::vector<sqw_directional_lightmap_element> directional_lightmaps_data;
+	uint32_t root_node() const { return nodes.empty() ? FIRST_LEAF_INDEX : (uint32_t)nodes.size() - 1; } // :289-292
+};
+
+inline uint32_t get_lightmap_size(int32_t tc_min, int32_t tc_max) // common/lightmap.rs:19-27
+{
+	return (uint32_t)(((tc_max + (int32_t)(LIGHTMAP_SCALE - 1)) >> LIGHTMAP_SCALE_LOG2) - (tc_min >> LIGHTMAP_SCALE_LOG2) + 1);
+}
+
+// Host image (one mip).  kind = SQW_IMAGE_*; pixels are TextureElement (8 B) or Color32 (4 B) or Color64 (8 B).
+struct HostImage
+{
+	int kind = 0;
+	uint32_t width = 0, height = 0;
+	std::vector<uint8_t> pixels;
+};
+
+// The subset of common/material.rs:7-98 the world-drawing path reads.
+struct Material
+{
+	bool draw = true;
+	bool light = true;
+	bool has_diffuse = true;
+	int blending_mode = SQW_BLEND_NONE;
+	bool has_normal_map = false, has_non_one_roughness = false, is_metal = false; // Texture flags (textures.rs:14-16)
+	uint32_t texture_images[NUM_MIPS] = {0, 0, 0, 0, 0};                          // image ids of the TextureElement mips
+	bool has_emissive = false;
+	uint32_t emissive_images[NUM_MIPS] = {0, 0, 0, 0, 0};
+	float emissive_light[3] = {0, 0, 0};
+	int32_t texture_shift[2] = {0, 0}; // MapMaterialsProcessor::get_texture_shift (scrolling), 0 when animations are off
+	bool is_skybox = false;
+};
+
+struct SceneParams
+{
+	uint32_t seed = 1;
+	uint32_t grid[3] = {12, 12, 3};
+	float cell_size[3] = {256.0f, 256.0f, 192.0f};
+	uint32_t num_rooms = 7;
+	uint32_t num_materials = 16;
+	uint32_t texture_size_log2 = 8; // 256 x 256 world textures (demo/export_textures.py:27)
+	float max_polygon_size = 128.0f; // split so that a lightmap stays <= 17 texels per side (bsp_builder.rs:1282)
+	uint32_t material_mode = 0;      // 0: mix per demo_materials.json (normal map + dielectric/metal specular), 1: plain (no normal map, roughness 1)
+	float emissive_fraction = 0.15f;
+};
+
+struct Scene
+{
+	SceneParams params;
+	BSPMap map;
+	std::vector<Material> materials;
+	std::vector<HostImage> images; // image id = index; the caller uploads them in this order
+	std::vector<Vec3f> camera_waypoints; // centres of the cells the fly-through visits
+	std::vector<uint8_t> solid;          // grid occupancy
+	bool is_solid(int x, int y, int z) const;
+	Vec3f cell_center(int x, int y, int z) const;
+};
+
+void generate_scene(const SceneParams& params, Scene& out);
+
+// 64-pose (or n-pose) Catmull-Rom fly-through of SURVEY.md §8(d): position + azimuth + elevation per frame.
+struct CameraPose
+{
+	Vec3f position;
+	float azimuth, elevation;
+};
+void make_camera_path(const Scene& scene, uint32_t num_frames, uint32_t jitter_seed, std::vector<CameraPose>& out);
+
+// textures.rs:309-365 / :388-421
+void build_texture_mip(HostImage& mip, const HostImage& prev);
+void build_texture_lite_mip(HostImage& mip, const HostImage& prev);
+
+} // namespace sqwh

@@ -1,0 +1,851 @@
+// Host-side mirror of the renderer front end (see renderer.hpp).  Each function cites the reference code it follows.
+#include "renderer.hpp"
+#include <algorithm>
+#include <cstring>
+
+namespace sqwh
+{
+
+constexpr size_t MAX_VERTICES = 24; // renderer_utils.rs:4
+constexpr float Z_NEAR = 1.0f;      // renderer_utils.rs:7
+
+// ---- common/clipping_polygon.rs ------------------------------------------------------------------------------------
+namespace
+{
+inline bool axis_valid(const ClipAxis& a) { return a.min < a.max; }
+inline bool axis_contains(const ClipAxis& a, const ClipAxis& o) { return o.min >= a.min && o.max <= a.max; }
+inline void axis_extend(ClipAxis& a, const ClipAxis& o)
+{
+	if (o.min < a.min)
+		a.min = o.min;
+	if (o.max > a.max)
+		a.max = o.max;
+}
+inline void axis_extend_point(ClipAxis& a, float p)
+{
+	if (p < a.min)
+		a.min = p;
+	if (p > a.max)
+		a.max = p;
+}
+inline void axis_intersect(ClipAxis& a, const ClipAxis& o)
+{
+	if (o.min > a.min)
+		a.min = o.min;
+	if (o.max < a.max)
+		a.max = o.max;
+}
+} // namespace
+
+ClippingPolygon ClippingPolygon::from_box(float min_x, float min_y, float max_x, float max_y)
+{
+	ClippingPolygon c;
+	c.x = {min_x, max_x};
+	c.y = {min_y, max_y};
+	c.x_plus_y = {min_x + min_y, max_x + max_y};
+	c.x_minus_y = {min_x - max_y, max_x - min_y};
+	return c;
+}
+ClippingPolygon ClippingPolygon::from_point(Vec2f p)
+{
+	ClippingPolygon c;
+	c.x = {p.x, p.x};
+	c.y = {p.y, p.y};
+	c.x_plus_y = {p.x + p.y, p.x + p.y};
+	c.x_minus_y = {p.x - p.y, p.x - p.y};
+	return c;
+}
+bool ClippingPolygon::is_valid_and_non_empty() const { return axis_valid(x) && axis_valid(y) && axis_valid(x_plus_y) && axis_valid(x_minus_y); }
+bool ClippingPolygon::contains(const ClippingPolygon& o) const
+{
+	return axis_contains(x, o.x) && axis_contains(y, o.y) && axis_contains(x_plus_y, o.x_plus_y) && axis_contains(x_minus_y, o.x_minus_y);
+}
+void ClippingPolygon::extend(const ClippingPolygon& o)
+{
+	axis_extend(x, o.x);
+	axis_extend(y, o.y);
+	axis_extend(x_plus_y, o.x_plus_y);
+	axis_extend(x_minus_y, o.x_minus_y);
+}
+void ClippingPolygon::extend_with_point(Vec2f p)
+{
+	axis_extend_point(x, p.x);
+	axis_extend_point(y, p.y);
+	axis_extend_point(x_plus_y, p.x + p.y);
+	axis_extend_point(x_minus_y, p.x - p.y);
+}
+void ClippingPolygon::intersect(const ClippingPolygon& o)
+{
+	axis_intersect(x, o.x);
+	axis_intersect(y, o.y);
+	axis_intersect(x_plus_y, o.x_plus_y);
+	axis_intersect(x_minus_y, o.x_minus_y);
+}
+void ClippingPolygon::get_clip_planes(Vec3f out[8]) const // clipping_polygon.rs:150-163
+{
+	out[0] = {-1.0f, 0.0f, -x.max};
+	out[1] = {1.0f, 0.0f, x.min};
+	out[2] = {0.0f, -1.0f, -y.max};
+	out[3] = {0.0f, 1.0f, y.min};
+	out[4] = {-1.0f, -1.0f, -x_plus_y.max};
+	out[5] = {1.0f, 1.0f, x_plus_y.min};
+	out[6] = {-1.0f, 1.0f, -x_minus_y.max};
+	out[7] = {1.0f, -1.0f, x_minus_y.min};
+}
+
+// ---- common/clipping.rs ------------------------------------------------------------------------------------------
+namespace
+{
+
+Vec3f get_line_z_intersection(Vec3f v0, Vec3f v1, float z) // clipping.rs:122-130
+{
+	const float dist0 = v0.z - z;
+	const float dist1 = v1.z - z;
+	const float dist_sum = v1.z - v0.z;
+	const float k0 = dist0 / dist_sum;
+	const float k1 = dist1 / dist_sum;
+	return v0 * k1 - v1 * k0;
+}
+
+size_t clip_3d_polygon_by_z_plane(const Vec3f* polygon, size_t n, float z_dist, Vec3f* out, size_t out_cap) // clipping.rs:4-57
+{
+	const Vec3f* prev_v = &polygon[n - 1];
+	size_t count = 0;
+	for (size_t i = 0; i < n; ++i)
+	{
+		const Vec3f* v = &polygon[i];
+		if (v->z > z_dist)
+		{
+			if (prev_v->z < z_dist)
+			{
+				out[count++] = get_line_z_intersection(*prev_v, *v, z_dist);
+				if (count == out_cap)
+					break;
+			}
+			out[count++] = *v;
+			if (count == out_cap)
+				break;
+		}
+		else if (v->z == z_dist)
+		{
+			out[count++] = *v;
+			if (count == out_cap)
+				break;
+		}
+		else if (prev_v->z > z_dist)
+		{
+			out[count++] = get_line_z_intersection(*prev_v, *v, z_dist);
+			if (count == out_cap)
+				break;
+		}
+		prev_v = v;
+	}
+	return count;
+}
+
+Vec2f get_line_line_intersection(Vec2f v0, Vec2f v1, Vec3f line) // clipping.rs:187-195
+{
+	const Vec2f l2{line.x, line.y};
+	const float dist0 = dot(v0, l2) - line.z;
+	const float dist1 = dot(v1, l2) - line.z;
+	const float dist_sum = dist1 - dist0;
+	const float k0 = dist0 / dist_sum;
+	const float k1 = dist1 / dist_sum;
+	return v0 * k1 - v1 * k0;
+}
+
+size_t clip_2d_polygon(const Vec2f* polygon, size_t n, Vec3f clip_line_equation, Vec2f* out, size_t out_cap) // clipping.rs:132-185
+{
+	const Vec2f l2{clip_line_equation.x, clip_line_equation.y};
+	const Vec2f* prev_v = &polygon[n - 1];
+	float prev_dist = dot(*prev_v, l2) - clip_line_equation.z;
+	size_t count = 0;
+	for (size_t i = 0; i < n; ++i)
+	{
+		const Vec2f* v = &polygon[i];
+		const float dist = dot(*v, l2) - clip_line_equation.z;
+		if (dist > 0.0f)
+		{
+			if (prev_dist < 0.0f)
+			{
+				out[count++] = get_line_line_intersection(*prev_v, *v, clip_line_equation);
+				if (count == out_cap)
+					break;
+			}
+			out[count++] = *v;
+			if (count == out_cap)
+				break;
+		}
+		else if (dist == 0.0f)
+		{
+			out[count++] = *v;
+			if (count == out_cap)
+				break;
+		}
+		else if (prev_dist > 0.0f)
+		{
+			out[count++] = get_line_line_intersection(*prev_v, *v, clip_line_equation);
+			if (count == out_cap)
+				break;
+		}
+		prev_v = v;
+		prev_dist = dist;
+	}
+	return count;
+}
+
+// renderer_utils.rs:10-58
+size_t project_and_clip_polygon(const Vec3f clip_planes[8], const Vec3f* vertices_transformed, size_t num_vertices, Vec2f* out_vertices)
+{
+	size_t vertex_count = std::min(num_vertices, MAX_VERTICES);
+	Vec3f z_clipped[MAX_VERTICES];
+	vertex_count = clip_3d_polygon_by_z_plane(vertices_transformed, vertex_count, Z_NEAR, z_clipped, MAX_VERTICES);
+	if (vertex_count < 3)
+		return vertex_count;
+	for (size_t i = 0; i < vertex_count; ++i)
+		out_vertices[i] = truncate(z_clipped[i]) / z_clipped[i].z;
+	Vec2f temp[MAX_VERTICES];
+	for (size_t i = 0; i < 4; ++i)
+	{
+		vertex_count = clip_2d_polygon(out_vertices, vertex_count, clip_planes[i * 2], temp, MAX_VERTICES);
+		if (vertex_count < 3)
+			return vertex_count;
+		vertex_count = clip_2d_polygon(temp, vertex_count, clip_planes[i * 2 + 1], out_vertices, MAX_VERTICES);
+		if (vertex_count < 3)
+			return vertex_count;
+	}
+	return vertex_count;
+}
+
+// equations.rs
+inline float sample_point(const float de[3], Vec2f p) { return de[0] * p.x + de[1] * p.y + de[2]; }
+
+// renderer_utils.rs:201-242
+uint32_t calculate_mip(const Vec2f* points, size_t n, const float de[3], const float te[6], float mip_bias)
+{
+	Vec2f mip_point = points[0];
+	float mip_point_inv_z = 0.0f;
+	for (size_t i = 0; i < n; ++i)
+	{
+		const float inv_z = sample_point(de, points[i]);
+		if (inv_z > mip_point_inv_z)
+		{
+			mip_point_inv_z = inv_z;
+			mip_point = points[i];
+		}
+	}
+	const float z_2 = 1.0f / (mip_point_inv_z * mip_point_inv_z);
+	const float z_4 = z_2 * z_2;
+	float d_tc_2[2];
+	for (int i = 0; i < 2; ++i)
+	{
+		// te layout: d_tc_dx[2], d_tc_dy[2], k[2]
+		const float d_tc_dx = te[i] * (de[2] + de[1] * mip_point.y) - (te[4 + i] + te[2 + i] * mip_point.y) * de[0];
+		const float d_tc_dy = te[2 + i] * (de[2] + de[0] * mip_point.x) - (te[4 + i] + te[i] * mip_point.x) * de[1];
+		d_tc_2[i] = (d_tc_dx * d_tc_dx + d_tc_dy * d_tc_dy) * z_4;
+	}
+	const float max_d_tc_2 = std::fmax(d_tc_2[0], d_tc_2[1]);
+	const float mip_f = std::log2(max_d_tc_2) * 0.5f + mip_bias;
+	float c = std::ceil(mip_f);
+	int32_t ci = (c != c) ? 0 : (c >= 2147483648.0f ? INT32_MAX : (c <= -2147483648.0f ? INT32_MIN : (int32_t)c)); // `as i32`
+	return (uint32_t)std::max(0, std::min(ci, (int32_t)MAX_MIP));
+}
+
+constexpr float TC_ERROR_THRESHOLD = 0.75f; // renderer_utils.rs:199
+
+// renderer_utils.rs:60-132
+bool affine_texture_coordinates_interpolation_may_be_used(const float de[3], const float te[6], Vec2f min_inv_z_point, Vec2f max_inv_z_point)
+{
+	const Vec2f edge = max_inv_z_point - min_inv_z_point;
+	const float edge_square_len = dot(edge, edge);
+	if (edge_square_len == 0.0f)
+		return true;
+	const float edge_len = std::sqrt(edge_square_len);
+	const Vec2f edge_vec_normalized = edge / edge_len;
+	const float inv_z_clamp = 1.0f / (float)(1 << 20);
+	const float min_point_inv_z = std::fmax(sample_point(de, min_inv_z_point), inv_z_clamp);
+	const float max_point_inv_z = std::fmax(sample_point(de, max_inv_z_point), inv_z_clamp);
+	const float depth_equation_projected_a = dot(Vec2f{de[0], de[1]}, edge_vec_normalized);
+	const float depth_equation_projected_b = min_point_inv_z;
+	if (std::fabs(depth_equation_projected_a) < 1.0e-10f)
+		return true;
+	const float depth_b_div_a = depth_equation_projected_b / depth_equation_projected_a;
+	const float max_diff_point = std::sqrt((0.0f + depth_b_div_a) * (edge_len + depth_b_div_a)) - depth_b_div_a;
+	const float max_diff_point_inv_z = depth_equation_projected_a * max_diff_point + depth_equation_projected_b;
+	for (int i = 0; i < 2; ++i)
+	{
+		const float min_point_tc = te[i] * min_inv_z_point.x + te[2 + i] * min_inv_z_point.y + te[4 + i];
+		const float max_point_tc = te[i] * max_inv_z_point.x + te[2 + i] * max_inv_z_point.y + te[4 + i];
+		const float tc_projected_a = dot(Vec2f{te[i], te[2 + i]}, edge_vec_normalized);
+		const float tc_projected_b = min_point_tc;
+		const float min_point_tc_z_mul = min_point_tc / min_point_inv_z;
+		const float max_point_tc_z_mul = max_point_tc / max_point_inv_z;
+		const float max_diff_point_tc_real = (tc_projected_a * max_diff_point + tc_projected_b) / max_diff_point_inv_z;
+		const float max_diff_point_tc_approximate = min_point_tc_z_mul + (max_point_tc_z_mul - min_point_tc_z_mul) * (max_diff_point - 0.0f) / (edge_len - 0.0f);
+		const float tc_abs_diff = std::fabs(max_diff_point_tc_real - max_diff_point_tc_approximate);
+		if (tc_abs_diff > TC_ERROR_THRESHOLD)
+			return false;
+	}
+	return true;
+}
+
+// renderer_utils.rs:134-197
+bool line_z_corrected_texture_coordinates_interpolation_may_be_used(const float de[3], const float te[6], Vec2f max_inv_z_point, float min_polygon_x, float max_polygon_x)
+{
+	if (max_polygon_x - min_polygon_x < 1.0f)
+		return true;
+	const float a = de[0];
+	const float b = de[1] * max_inv_z_point.y + de[2];
+	if (std::fabs(a) < 1.0e-10f)
+		return true;
+	const float depth_b_div_a = b / a;
+	const float max_diff_x = std::sqrt((min_polygon_x + depth_b_div_a) * (max_polygon_x + depth_b_div_a)) - depth_b_div_a;
+	const float max_diff_point_inv_z = a * max_diff_x + b;
+	const float inv_z_at_min_x = a * min_polygon_x + b;
+	const float inv_z_at_max_x = a * max_polygon_x + b;
+	const float almost_zero = 1e-20f;
+	if (inv_z_at_min_x <= almost_zero || inv_z_at_max_x <= almost_zero || max_diff_point_inv_z <= almost_zero)
+		return false;
+	for (int i = 0; i < 2; ++i)
+	{
+		const float ta = te[i];
+		const float tb = te[2 + i] * max_inv_z_point.y + te[4 + i];
+		const float tc_at_min_x = (ta * min_polygon_x + tb) / inv_z_at_min_x;
+		const float tc_at_max_x = (ta * max_polygon_x + tb) / inv_z_at_max_x;
+		const float max_diff_point_tc_real = (ta * max_diff_x + tb) / max_diff_point_inv_z;
+		const float max_diff_point_tc_approximate = tc_at_min_x + (tc_at_max_x - tc_at_min_x) * (max_diff_x - min_polygon_x) / (max_polygon_x - min_polygon_x);
+		const float tc_abs_diff = std::fabs(max_diff_point_tc_real - max_diff_point_tc_approximate);
+		if (tc_abs_diff > TC_ERROR_THRESHOLD)
+			return false;
+	}
+	return true;
+}
+
+inline int32_t f32_to_fixed16_unchecked(float x) // common/fixed_math.rs:36 (cvttss2si semantics)
+{
+	const float v = x * 65536.0f;
+	if (!(v > -2147483904.0f && v < 2147483648.0f))
+		return INT32_MIN;
+	return (int32_t)v;
+}
+
+// surfaces.rs:18-47 PolygonBasisVecs::form_plane_and_tex_coord_equation
+void basis_vecs_from_plane_and_tc(const Plane& plane, const Plane tc[2], DrawPolygonData& out)
+{
+	const Mat4f tex_coord_basis = Mat4f::from_cols(extend(tc[0].vec, tc[0].dist), extend(tc[1].vec, tc[1].dist), extend(plane.vec, -plane.dist), Vec4f{0, 0, 0, 1});
+	Mat4f inv;
+	if (!tex_coord_basis.transpose().invert(inv))
+	{
+		out.basis_u = {1, 0, 0};
+		out.basis_v = {0, 1, 0};
+		out.basis_start = {0, 0, 0};
+		out.basis_normal = {0, 0, 1};
+		return;
+	}
+	out.basis_u = truncate(inv.x);
+	out.basis_v = truncate(inv.y);
+	out.basis_start = truncate(inv.w);
+	const float min_positive_value = 1.0f / (float)(1 << 30);
+	out.basis_normal = plane.vec / std::fmax(magnitude(plane.vec), min_positive_value);
+}
+
+} // namespace
+
+// ---- Renderer ----------------------------------------------------------------------------------------------------------
+Renderer::Renderer(const Scene& scene, const RendererConfig& config) : scene_(scene), map_(scene.map), config_(config)
+{
+	// PartialRenderer::new (partial_renderer.rs:56-135)
+	polygons_data_.resize(map_.polygons.size());
+	for (size_t i = 0; i < map_.polygons.size(); ++i)
+		basis_vecs_from_plane_and_tc(map_.polygons[i].plane, map_.polygons[i].tex_coord_equation, polygons_data_[i]);
+	for (size_t leaf = 0; leaf < map_.leafs.size(); ++leaf)
+		for (uint32_t p = map_.leafs[leaf].first_polygon; p < map_.leafs[leaf].first_polygon + map_.leafs[leaf].num_polygons; ++p)
+			polygons_data_[p].parent_leaf = (uint32_t)leaf;
+	vertices_transformed_.resize(map_.vertices.size());
+	leafs_data_.resize(map_.leafs.size());
+	portals_data_.resize(map_.portals.size());
+}
+
+bool Renderer::leaf_bounds(uint32_t leaf, ClippingPolygon& out) const // map_visibility_calculator.rs:116-127
+{
+	const LeafData& d = leafs_data_[leaf];
+	if (d.visible_frame != visibility_frame_)
+		return false;
+	out = d.current_frame_bounds;
+	return true;
+}
+
+uint32_t Renderer::find_current_leaf() const // :134-156
+{
+	uint32_t index = map_.root_node();
+	const Vec4f w_row = camera_matrices_.planes_matrix.row(3);
+	for (;;)
+	{
+		if (index >= FIRST_LEAF_INDEX)
+			return index - FIRST_LEAF_INDEX;
+		const BSPNode& node = map_.nodes[index];
+		const float plane_transformed_w = dot(w_row, extend(node.plane.vec, -node.plane.dist));
+		index = plane_transformed_w >= 0.0f ? node.children[0] : node.children[1];
+	}
+}
+
+namespace
+{
+// map_visibility_calculator.rs:282-326 project_portal
+bool project_portal(const Portal& portal, const BSPMap& map, const Mat4f& view_matrix, ClippingPolygon& out)
+{
+	size_t vertex_count = std::min((size_t)portal.num_vertices, MAX_VERTICES);
+	Vec3f vt[MAX_VERTICES];
+	for (size_t i = 0; i < vertex_count; ++i)
+		vt[i] = view_matrix_transform_vertex(view_matrix, map.vertices[portal.first_vertex + i]);
+	Vec3f zc[MAX_VERTICES];
+	const float PORTAL_Z_NEAR = 1.0f / 4096.0f;
+	vertex_count = clip_3d_polygon_by_z_plane(vt, vertex_count, PORTAL_Z_NEAR, zc, MAX_VERTICES);
+	if (vertex_count < 3)
+		return false;
+	out = ClippingPolygon::from_point(truncate(zc[0]) / zc[0].z);
+	for (size_t i = 1; i < vertex_count; ++i)
+		out.extend_with_point(truncate(zc[i]) / zc[i].z);
+	return true;
+}
+} // namespace
+
+void Renderer::mark_reachable_leafs_iterative(const uint32_t* start_leafs, size_t num_start_leafs, const ClippingPolygon& start_bounds) // :158-264
+{
+	wave_cur_.clear();
+	wave_next_.clear();
+	for (size_t i = 0; i < num_start_leafs; ++i)
+	{
+		wave_cur_.push_back(start_leafs[i]);
+		leafs_data_[start_leafs[i]].current_frame_bounds = start_bounds;
+		leafs_data_[start_leafs[i]].visible_frame = visibility_frame_;
+	}
+	uint32_t depth = 0;
+	while (!wave_cur_.empty())
+	{
+		for (uint32_t leaf : wave_cur_)
+		{
+			const ClippingPolygon leaf_bounds_v = leafs_data_[leaf].current_frame_bounds;
+			const BSPLeaf& leaf_value = map_.leafs[leaf];
+			for (uint32_t k = leaf_value.first_leaf_portal; k < leaf_value.first_leaf_portal + leaf_value.num_leaf_portals; ++k)
+			{
+				const uint32_t portal = map_.leafs_portals[k];
+				const Portal& portal_value = map_.portals[portal];
+				const float portal_plane_pos = (camera_matrices_.planes_matrix * extend(portal_value.plane.vec, -portal_value.plane.dist)).w;
+				uint32_t next_leaf;
+				if (portal_value.leafs[0] == leaf)
+				{
+					if (portal_plane_pos <= 0.0f)
+						continue;
+					next_leaf = portal_value.leafs[1];
+				}
+				else
+				{
+					if (portal_plane_pos >= 0.0f)
+						continue;
+					next_leaf = portal_value.leafs[0];
+				}
+				PortalData& portal_data = portals_data_[portal];
+				if (portal_data.visible_frame != visibility_frame_)
+				{
+					portal_data.visible_frame = visibility_frame_;
+					portal_data.has_projection = project_portal(portal_value, map_, camera_matrices_.view_matrix, portal_data.current_frame_projection);
+				}
+				if (!portal_data.has_projection)
+					continue;
+				ClippingPolygon bounds_intersection = portal_data.current_frame_projection;
+				bounds_intersection.intersect(leaf_bounds_v);
+				if (!bounds_intersection.is_valid_and_non_empty())
+					continue;
+				LeafData& next_leaf_data = leafs_data_[next_leaf];
+				if (next_leaf_data.visible_frame != visibility_frame_)
+				{
+					next_leaf_data.visible_frame = visibility_frame_;
+					next_leaf_data.current_frame_bounds = bounds_intersection;
+				}
+				else
+				{
+					if (next_leaf_data.current_frame_bounds.contains(bounds_intersection))
+						continue;
+					next_leaf_data.current_frame_bounds.extend(bounds_intersection);
+				}
+				wave_next_.push_back(next_leaf);
+			}
+		}
+		wave_cur_.clear();
+		std::swap(wave_cur_, wave_next_);
+		if (++depth > 1024)
+			break;
+	}
+}
+
+bool Renderer::compute_is_inside_leaf_volume(uint32_t leaf_index) const // :266-280
+{
+	const BSPLeaf& leaf = map_.leafs[leaf_index];
+	for (uint32_t p = leaf.first_polygon; p < leaf.first_polygon + leaf.num_polygons; ++p)
+	{
+		const Polygon& polygon = map_.polygons[p];
+		if ((camera_matrices_.planes_matrix * extend(polygon.plane.vec, -polygon.plane.dist)).w < 0.0f)
+			return false;
+	}
+	return true;
+}
+
+void Renderer::update_visibility(const ClippingPolygon& frame_bounds) // :52-100
+{
+	++visibility_frame_;
+	const uint32_t current_leaf = find_current_leaf();
+	constexpr size_t MAX_START_LEAFS = 32;
+	uint32_t start_leafs[MAX_START_LEAFS];
+	start_leafs[0] = current_leaf;
+	size_t num_start_leafs = 1;
+	const BSPLeaf& leaf_value = map_.leafs[current_leaf];
+	for (uint32_t k = leaf_value.first_leaf_portal; k < leaf_value.first_leaf_portal + leaf_value.num_leaf_portals; ++k)
+	{
+		const Portal& portal_value = map_.portals[map_.leafs_portals[k]];
+		const float scaled_dist = dot(portal_value.plane.vec, camera_matrices_.position) - portal_value.plane.dist;
+		const float eps = Z_NEAR * 2.0f;
+		if (std::fabs(scaled_dist) <= eps * magnitude(portal_value.plane.vec))
+		{
+			const uint32_t next_leaf = portal_value.leafs[0] == current_leaf ? portal_value.leafs[1] : portal_value.leafs[0];
+			start_leafs[num_start_leafs++] = next_leaf;
+			if (num_start_leafs == MAX_START_LEAFS)
+				break;
+		}
+	}
+	mark_reachable_leafs_iterative(start_leafs, num_start_leafs, frame_bounds);
+	is_inside_leaf_volume_ = compute_is_inside_leaf_volume(current_leaf);
+}
+
+void Renderer::prepare_frame(uint32_t width, uint32_t height, const CameraPose& camera, float fov)
+{
+	width_ = width;
+	height_ = height;
+	camera_matrices_ = build_view_matrix(camera.position, camera.azimuth, camera.elevation, fov, (float)width, (float)height);
+	mip_bias_ = config_.textures_mip_bias; // update_mip_bias with dynamic_mip_bias = false (partial_renderer.rs:3786-3804)
+	++current_frame_;
+	stats_ = RendererDebugStats{};
+	update_visibility(ClippingPolygon::from_box(0.0f, 0.0f, (float)width, (float)height)); // partial_renderer.rs:173-190
+	prepare_polygons_surfaces();
+	build_surface_jobs();
+}
+
+void Renderer::prepare_polygons_surfaces() // partial_renderer.rs:1327-1449 (leaf polygons; submodels are not part of the synthetic maps)
+{
+	current_frame_visible_polygons_.clear();
+	num_visible_surfaces_pixels_ = 0;
+	for (size_t i = 0; i < map_.leafs.size(); ++i)
+	{
+		ClippingPolygon bounds;
+		if (!leaf_bounds((uint32_t)i, bounds))
+			continue;
+		++stats_.num_visible_leafs;
+		const BSPLeaf& leaf = map_.leafs[i];
+		Vec3f clip_planes[8];
+		bounds.get_clip_planes(clip_planes);
+		for (uint32_t p = leaf.first_polygon; p < leaf.first_polygon + leaf.num_polygons; ++p)
+			prepare_polygon_surface(clip_planes, p);
+	}
+	stats_.num_visible_polygons = (uint32_t)current_frame_visible_polygons_.size();
+	stats_.num_surfaces_pixels = num_visible_surfaces_pixels_;
+}
+
+void Renderer::prepare_polygon_surface(const Vec3f clip_planes[8], size_t polygon_index) // partial_renderer.rs:1464-1638
+{
+	DrawPolygonData& polygon_data = polygons_data_[polygon_index];
+	const Polygon& polygon = map_.polygons[polygon_index];
+
+	const Vec4f plane_transformed = camera_matrices_.planes_matrix * extend(polygon.plane.vec, -polygon.plane.dist);
+	if (plane_transformed.w <= 0.0f) // cull back faces
+		return;
+	const Material& material = scene_.materials[polygon.texture];
+	if (!material.draw)
+		return;
+
+	const Vec3f* polygon_vertices = &map_.vertices[polygon.first_vertex];
+	Vec3f* polygon_vertices_transformed = &vertices_transformed_[polygon.first_vertex];
+	for (uint32_t i = 0; i < polygon.num_vertices; ++i)
+		polygon_vertices_transformed[i] = view_matrix_transform_vertex(camera_matrices_.view_matrix, polygon_vertices[i]);
+
+	Vec2f vertices_2d[MAX_VERTICES];
+	const size_t vertex_count = project_and_clip_polygon(clip_planes, polygon_vertices_transformed, polygon.num_vertices, vertices_2d);
+	if (vertex_count < 3)
+		return;
+
+	// DepthEquation::from_transformed_plane_equation (equations.rs:22-31)
+	const float plane_transformed_w = -plane_transformed.w;
+	const float depth_equation[3] = {plane_transformed.x / plane_transformed_w, plane_transformed.y / plane_transformed_w, plane_transformed.z / plane_transformed_w};
+
+	const Vec4f tc_basis_transformed[2] = {
+		camera_matrices_.planes_matrix * extend(polygon.tex_coord_equation[0].vec, polygon.tex_coord_equation[0].dist),
+		camera_matrices_.planes_matrix * extend(polygon.tex_coord_equation[1].vec, polygon.tex_coord_equation[1].dist)};
+	// TexCoordEquation::from_depth_equation_and_transformed_tex_coord_equations (equations.rs:53-75)
+	float tc_equation[6];
+	for (int i = 0; i < 2; ++i)
+	{
+		tc_equation[i] = tc_basis_transformed[i].x + tc_basis_transformed[i].w * depth_equation[0];
+		tc_equation[2 + i] = tc_basis_transformed[i].y + tc_basis_transformed[i].w * depth_equation[1];
+		tc_equation[4 + i] = tc_basis_transformed[i].z + tc_basis_transformed[i].w * depth_equation[2];
+	}
+
+	const uint32_t mip = calculate_mip(vertices_2d, vertex_count, depth_equation, tc_equation, mip_bias_);
+	const float mip_scale = 1.0f / (float)(1 << mip);
+	float tc_equation_scaled[6];
+	for (int i = 0; i < 6; ++i)
+		tc_equation_scaled[i] = tc_equation[i] * mip_scale;
+
+	const float inf = (float)(1 << 29);
+	const float max_z = (float)(1 << 16);
+	float tc_min[2] = {inf, inf};
+	float tc_max[2] = {-inf, -inf};
+	for (size_t k = 0; k < vertex_count; ++k)
+	{
+		const Vec2f p = vertices_2d[k];
+		const float inv_z = std::fmax(sample_point(depth_equation, p), 1.0f / max_z);
+		const float z = 1.0f / inv_z;
+		for (int i = 0; i < 2; ++i)
+		{
+			const float tc = z * (tc_equation_scaled[i] * p.x + tc_equation_scaled[2 + i] * p.y + tc_equation_scaled[4 + i]);
+			if (tc < tc_min[i])
+				tc_min[i] = tc;
+			if (tc > tc_max[i])
+				tc_max[i] = tc;
+		}
+	}
+
+	int32_t surface_tc_min[2] = {0, 0};
+	int32_t surface_size[2] = {0, 0};
+	for (int i = 0; i < 2; ++i)
+	{
+		const float tc_reduce_eps = 1.0f / 32.0f;
+		tc_min[i] += tc_reduce_eps;
+		tc_max[i] -= tc_reduce_eps;
+		const int32_t round_mask = ~((int32_t)LIGHTMAP_SCALE - 1);
+		const int32_t tc_min_round_down = (polygon.tex_coord_min[i] & round_mask) >> mip;
+		const int32_t tc_max_round_up = ((polygon.tex_coord_max[i] + (int32_t)LIGHTMAP_SCALE - 1) & round_mask) >> mip;
+		int32_t tc_min_int = std::max((int32_t)std::floor(std::fmax(tc_min[i], -inf)), tc_min_round_down);
+		int32_t tc_max_int = std::min((int32_t)std::ceil(std::fmin(tc_max[i], inf)), tc_max_round_up);
+		if (tc_min_int >= tc_max_int)
+		{
+			tc_min_int = std::min(tc_min_int, tc_max_round_up - 1);
+			tc_max_int = tc_min_int + 1;
+		}
+		surface_tc_min[i] = tc_min_int;
+		surface_size[i] = tc_max_int - tc_min_int;
+	}
+
+	const size_t surface_pixels_offset = num_visible_surfaces_pixels_;
+	num_visible_surfaces_pixels_ += (size_t)(surface_size[0] * surface_size[1]);
+
+	polygon_data.visible_frame = current_frame_;
+	std::memcpy(polygon_data.depth_equation, depth_equation, sizeof(depth_equation));
+	std::memcpy(polygon_data.tex_coord_equation, tc_equation_scaled, sizeof(tc_equation_scaled));
+	polygon_data.surface_pixels_offset = surface_pixels_offset;
+	polygon_data.surface_size[0] = (uint32_t)surface_size[0];
+	polygon_data.surface_size[1] = (uint32_t)surface_size[1];
+	polygon_data.mip = mip;
+	polygon_data.surface_tc_min[0] = surface_tc_min[0];
+	polygon_data.surface_tc_min[1] = surface_tc_min[1];
+	for (int i = 0; i < 2; ++i) // :1629-1635 shift of the tc equation to the surface rect
+	{
+		const float tcm = (float)surface_tc_min[i];
+		polygon_data.tex_coord_equation[i] -= tcm * depth_equation[0];
+		polygon_data.tex_coord_equation[2 + i] -= tcm * depth_equation[1];
+		polygon_data.tex_coord_equation[4 + i] -= tcm * depth_equation[2];
+	}
+	current_frame_visible_polygons_.push_back((uint32_t)polygon_index);
+}
+
+void Renderer::build_surface_jobs() // the closure of build_polygons_surfaces (partial_renderer.rs:1682-1819) turned into job records
+{
+	jobs_.clear();
+	jobs_.reserve(current_frame_visible_polygons_.size());
+	const bool use_directional_lightmap = config_.use_directional_lightmaps && !map_.directional_lightmaps_data.empty();
+	for (uint32_t polygon_index : current_frame_visible_polygons_)
+	{
+		const Polygon& polygon = map_.polygons[polygon_index];
+		const DrawPolygonData& polygon_data = polygons_data_[polygon_index];
+		const Material& material = scene_.materials[polygon.texture];
+		sqw_surface_job j;
+		std::memset(&j, 0, sizeof(j));
+		const int32_t extra_shift_mip_compensated[2] = {material.texture_shift[0] >> polygon_data.mip, material.texture_shift[1] >> polygon_data.mip};
+		j.surface_size[0] = polygon_data.surface_size[0];
+		j.surface_size[1] = polygon_data.surface_size[1];
+		j.tc_start[0] = polygon_data.surface_tc_min[0] + extra_shift_mip_compensated[0];
+		j.tc_start[1] = polygon_data.surface_tc_min[1] + extra_shift_mip_compensated[1];
+		j.surface_pixels_offset = (uint32_t)polygon_data.surface_pixels_offset;
+		const bool apply_diffuse_layer = material.light && material.has_diffuse;
+		if (apply_diffuse_layer)
+		{
+			j.flags |= SQW_SURF_APPLY_DIFFUSE;
+			// get_basis_vecs_for_mip (surfaces.rs:49-63) + shift correction (partial_renderer.rs:1736-1740)
+			const float scale = (float)(1 << polygon_data.mip);
+			const Vec3f u = polygon_data.mip == 0 ? polygon_data.basis_u : polygon_data.basis_u * scale;
+			const Vec3f v = polygon_data.mip == 0 ? polygon_data.basis_v : polygon_data.basis_v * scale;
+			const Vec3f start = polygon_data.basis_start - (u * (float)extra_shift_mip_compensated[0] + v * (float)extra_shift_mip_compensated[1]);
+			const Vec3f nrm = polygon_data.basis_normal;
+			const float* src[4] = {&u.x, &v.x, &start.x, &nrm.x};
+			float* dst[4] = {j.basis_u, j.basis_v, j.basis_start, j.basis_normal};
+			for (int k = 0; k < 4; ++k)
+				std::memcpy(dst[k], src[k], 12);
+			j.texture_image = material.texture_images[polygon_data.mip];
+			if (material.has_normal_map)
+				j.flags |= SQW_SURF_HAS_NORMAL_MAP;
+			if (material.has_non_one_roughness)
+				j.flags |= SQW_SURF_HAS_NON_ONE_ROUGHNESS;
+			if (material.is_metal)
+				j.flags |= SQW_SURF_IS_METAL;
+			for (int i = 0; i < 2; ++i) // :1744-1752
+			{
+				const int32_t round_mask = ~((int32_t)LIGHTMAP_SCALE - 1);
+				const int32_t shift = polygon_data.surface_tc_min[i] - ((polygon.tex_coord_min[i] & round_mask) >> polygon_data.mip);
+				j.lightmap_tc_shift[i] = (uint32_t)shift;
+			}
+			j.lightmap_size[0] = get_lightmap_size(polygon.tex_coord_min[0], polygon.tex_coord_max[0]);
+			j.lightmap_size[1] = get_lightmap_size(polygon.tex_coord_min[1], polygon.tex_coord_max[1]);
+			j.lightmap_scale_log2 = LIGHTMAP_SCALE_LOG2 - polygon_data.mip;
+			j.lightmap_offset = polygon.lightmap_data_offset;
+			if (use_directional_lightmap)
+				j.flags |= SQW_SURF_DIRECTIONAL_LIGHTMAP;
+			j.num_lights = 0; // dynamic lights: FrameInfo::lights is empty for the fly-through workloads
+		}
+		if (material.has_emissive)
+		{
+			j.flags |= SQW_SURF_EMISSIVE;
+			j.emissive_image = material.emissive_images[polygon_data.mip];
+			std::memcpy(j.emissive_light, material.emissive_light, 12);
+		}
+		jobs_.push_back(j);
+	}
+}
+
+void Renderer::draw_frame() // PartialRenderer::draw_frame -> perform_rasterization, single-threaded branch (partial_renderer.rs:1207-1233)
+{
+	cmds_.clear();
+	polygon_points_.clear();
+	const ClippingPolygon viewport_clipping_polygon = ClippingPolygon::from_box(0.0f, 0.0f, (float)width_, (float)height_);
+	draw_tree(viewport_clipping_polygon);
+	stats_.num_draw_commands = (uint32_t)cmds_.size();
+}
+
+void Renderer::draw_tree(const ClippingPolygon& viewport_clipping_polygon) // partial_renderer.rs:2450-2517
+{
+	const Vec4f planes_matrix_w_row = camera_matrices_.planes_matrix.row(3);
+	uint32_t nodes_stack[MAX_BSP_TREE_DEPTH];
+	nodes_stack[0] = map_.root_node();
+	size_t num_nodes_on_stack = 1;
+	while (num_nodes_on_stack > 0)
+	{
+		const uint32_t node_index = nodes_stack[num_nodes_on_stack - 1];
+		if (node_index >= FIRST_LEAF_INDEX)
+		{
+			--num_nodes_on_stack;
+			const uint32_t leaf_index = node_index - FIRST_LEAF_INDEX;
+			ClippingPolygon bounds;
+			if (leaf_bounds(leaf_index, bounds))
+			{
+				bounds.intersect(viewport_clipping_polygon);
+				if (bounds.is_valid_and_non_empty())
+					draw_leaf(bounds, leaf_index);
+			}
+		}
+		else if (num_nodes_on_stack < MAX_BSP_TREE_DEPTH)
+		{
+			const BSPNode& node = map_.nodes[node_index];
+			const float plane_transformed_w = dot(planes_matrix_w_row, extend(node.plane.vec, -node.plane.dist));
+			uint32_t mask = plane_transformed_w >= 0.0f ? 1 : 0;
+			if (config_.invert_polygons_order)
+				mask ^= 1;
+			nodes_stack[num_nodes_on_stack - 1] = node.children[1 ^ mask];
+			nodes_stack[num_nodes_on_stack] = node.children[mask];
+			++num_nodes_on_stack;
+		}
+	}
+}
+
+void Renderer::draw_leaf(const ClippingPolygon& bounds, uint32_t leaf_index) // partial_renderer.rs:2519-2565 (leaf polygons)
+{
+	const BSPLeaf& leaf = map_.leafs[leaf_index];
+	Vec3f clip_planes[8];
+	bounds.get_clip_planes(clip_planes);
+	for (uint32_t polygon_index = leaf.first_polygon; polygon_index < leaf.first_polygon + leaf.num_polygons; ++polygon_index)
+	{
+		const Polygon& polygon = map_.polygons[polygon_index];
+		const DrawPolygonData& polygon_data = polygons_data_[polygon_index];
+		if (polygon_data.visible_frame != current_frame_)
+			continue;
+		draw_polygon(
+			clip_planes, &vertices_transformed_[polygon.first_vertex], polygon.num_vertices, polygon_data.depth_equation, polygon_data.tex_coord_equation,
+			polygon_data.surface_size, SQW_TEX_SURFACE, (uint32_t)polygon_data.surface_pixels_offset, scene_.materials[polygon.texture].blending_mode);
+	}
+}
+
+void Renderer::draw_polygon( // partial_renderer.rs:4011-4142, recording instead of rasterising
+	const Vec3f clip_planes[8], const Vec3f* vertices_transformed, size_t num_vertices, const float depth_equation[3], const float tex_coord_equation[6],
+	const uint32_t texture_size[2], uint8_t tex_kind, uint32_t tex_ref, int blending_mode)
+{
+	if (num_vertices < 3)
+		return;
+	Vec2f vertices_2d[MAX_VERTICES];
+	const size_t vertex_count = project_and_clip_polygon(clip_planes, vertices_transformed, num_vertices, vertices_2d);
+	if (vertex_count < 3)
+		return;
+
+	float min_inv_z = 1e24f, max_inv_z = -1e24f, min_x = 1e24f, max_x = -1e24f;
+	Vec2f min_inv_z_point = vertices_2d[0], max_inv_z_point = vertices_2d[0];
+	for (size_t i = 0; i < vertex_count; ++i)
+	{
+		const Vec2f point = vertices_2d[i];
+		const float inv_z = sample_point(depth_equation, point);
+		if (inv_z < min_inv_z)
+		{
+			min_inv_z = inv_z;
+			min_inv_z_point = point;
+		}
+		if (inv_z > max_inv_z)
+		{
+			max_inv_z = inv_z;
+			max_inv_z_point = point;
+		}
+		if (point.x < min_x)
+			min_x = point.x;
+		if (point.x > max_x)
+			max_x = point.x;
+	}
+
+	sqw_draw_cmd c;
+	std::memset(&c, 0, sizeof(c));
+	c.kind = SQW_CMD_POLYGON;
+	c.blend = (uint8_t)blending_mode;
+	c.tex_kind = tex_kind;
+	c.tex_ref = tex_ref;
+	c.tex_size[0] = (int32_t)texture_size[0];
+	c.tex_size[1] = (int32_t)texture_size[1];
+	c.num_vertices = (uint32_t)vertex_count;
+	c.vertex_offset = (uint32_t)polygon_points_.size();
+	for (size_t i = 0; i < vertex_count; ++i)
+		polygon_points_.push_back(sqw_polygon_point{f32_to_fixed16_unchecked(vertices_2d[i].x), f32_to_fixed16_unchecked(vertices_2d[i].y)});
+
+	if (affine_texture_coordinates_interpolation_may_be_used(depth_equation, tex_coord_equation, min_inv_z_point, max_inv_z_point))
+	{
+		c.tc_mode = SQW_TC_AFFINE;
+		std::memcpy(c.depth_eq, depth_equation, 12);
+		std::memcpy(c.tc_eq, tex_coord_equation, 24);
+	}
+	else
+	{
+		// power-of-two renormalisation (:4106-4109)
+		const float z_scale = std::exp2(-5.0f - std::ceil(std::log2(std::fmax(max_inv_z, 1.0f / (float)(1 << 20)))));
+		for (int i = 0; i < 3; ++i)
+			c.depth_eq[i] = depth_equation[i] * z_scale;
+		for (int i = 0; i < 6; ++i)
+			c.tc_eq[i] = tex_coord_equation[i] * z_scale;
+		c.tc_mode = line_z_corrected_texture_coordinates_interpolation_may_be_used(depth_equation, tex_coord_equation, max_inv_z_point, min_x, max_x)
+			? SQW_TC_LINE_Z_CORRECTION
+			: SQW_TC_FULL_PERSPECTIVE;
+	}
+	++stats_.mode_counts[c.tc_mode];
+	cmds_.push_back(c);
+}
+
+} // namespace sqwh

@@ -1,0 +1,139 @@
+// Host-side mirror of the reference's renderer front end: everything that "stays host" in SURVEY.md §8 (rows a1, a2, a5):
+// portal-flood visibility, polygon surface preparation, job list building, BSP traversal and polygon set-up — emitting
+// sqw_surface_job / sqw_draw_cmd lists for the C-ABI instead of calling the CPU kernels.
+//
+//   Renderer::prepare_frame  <->  Renderer::prepare_frame::<ColorT>  (src/square_wheel/renderer.rs:61)
+//                                 -> PartialRenderer::prepare_frame  (partial_renderer.rs:156)
+//   Renderer::draw_frame     <->  Renderer::draw_frame::<ColorT>     (renderer.rs:106)
+//                                 -> PartialRenderer::draw_frame / perform_rasterization (partial_renderer.rs:236, :1192)
+#pragma once
+#include "map.hpp"
+#include <vector>
+
+namespace sqwh
+{
+
+// common/clipping_polygon.rs
+struct ClipAxis
+{
+	float min = 0, max = 0;
+};
+struct ClippingPolygon
+{
+	ClipAxis x, y, x_plus_y, x_minus_y;
+	static ClippingPolygon from_box(float min_x, float min_y, float max_x, float max_y);
+	static ClippingPolygon from_point(Vec2f p);
+	bool is_valid_and_non_empty() const;
+	bool contains(const ClippingPolygon& o) const;
+	void extend(const ClippingPolygon& o);
+	void extend_with_point(Vec2f p);
+	void intersect(const ClippingPolygon& o);
+	void get_clip_planes(Vec3f out[8]) const;
+};
+
+// renderer_config.rs:5-31 (fields the path reads)
+struct RendererConfig
+{
+	bool use_directional_lightmaps = true;
+	float textures_mip_bias = 0.0f;
+	bool clear_background = true;
+	bool invert_polygons_order = false;
+};
+
+// renderer_structs.rs:75-91
+struct DrawPolygonData
+{
+	uint32_t parent_leaf = 0;
+	Vec3f basis_u, basis_v, basis_start, basis_normal; // PolygonBasisVecs for mip 0 (surfaces.rs:7-14)
+	uint32_t visible_frame = 0;
+	float depth_equation[3] = {0, 0, 0};
+	float tex_coord_equation[6] = {0, 0, 0, 0, 0, 0};
+	size_t surface_pixels_offset = 0;
+	uint32_t surface_size[2] = {0, 0};
+	uint32_t mip = 0;
+	int32_t surface_tc_min[2] = {0, 0};
+};
+
+// renderer_structs.rs:36-54 (units of the texels/s metric)
+struct RendererDebugStats
+{
+	uint32_t num_visible_leafs = 0;
+	uint32_t num_visible_polygons = 0;
+	uint64_t num_surfaces_pixels = 0;
+	uint32_t num_draw_commands = 0;
+	uint32_t mode_counts[3] = {0, 0, 0};
+};
+
+class Renderer
+{
+public:
+	Renderer(const Scene& scene, const RendererConfig& config);
+
+	// Visibility + surface preparation + job list.  color_bits only selects nothing here (the lists are colour-agnostic) but
+	// is kept for symmetry with prepare_frame::<ColorT>.
+	void prepare_frame(uint32_t width, uint32_t height, const CameraPose& camera, float fov);
+	// BSP traversal -> ordered draw commands for the frame prepared last.
+	void draw_frame();
+
+	const std::vector<sqw_surface_job>& jobs() const { return jobs_; }
+	uint64_t total_surface_pixels() const { return num_visible_surfaces_pixels_; }
+	const std::vector<sqw_draw_cmd>& cmds() const { return cmds_; }
+	const std::vector<sqw_polygon_point>& polygon_points() const { return polygon_points_; }
+	const CameraMatrices& camera_matrices() const { return camera_matrices_; }
+	bool needs_background_clear() const { return config_.clear_background && !is_inside_leaf_volume_; }
+	const RendererDebugStats& stats() const { return stats_; }
+
+private:
+	// map_visibility_calculator.rs
+	void update_visibility(const ClippingPolygon& frame_bounds);
+	uint32_t find_current_leaf() const;
+	void mark_reachable_leafs_iterative(const uint32_t* start_leafs, size_t num_start_leafs, const ClippingPolygon& start_bounds);
+	bool compute_is_inside_leaf_volume(uint32_t leaf_index) const;
+	bool leaf_bounds(uint32_t leaf, ClippingPolygon& out) const;
+	// partial_renderer.rs
+	void prepare_polygons_surfaces();
+	void prepare_polygon_surface(const Vec3f clip_planes[8], size_t polygon_index);
+	void build_surface_jobs();
+	void draw_tree(const ClippingPolygon& viewport_clipping_polygon);
+	void draw_leaf(const ClippingPolygon& bounds, uint32_t leaf_index);
+	void draw_polygon(
+		const Vec3f clip_planes[8], const Vec3f* vertices_transformed, size_t num_vertices, const float depth_equation[3], const float tex_coord_equation[6],
+		const uint32_t texture_size[2], uint8_t tex_kind, uint32_t tex_ref, int blending_mode);
+
+	const Scene& scene_;
+	const BSPMap& map_;
+	RendererConfig config_;
+	CameraMatrices camera_matrices_;
+	uint32_t width_ = 0, height_ = 0;
+	uint32_t current_frame_ = 0;
+	float mip_bias_ = 0;
+
+	struct LeafData
+	{
+		uint32_t visible_frame = 0;
+		ClippingPolygon current_frame_bounds;
+	};
+	struct PortalData
+	{
+		uint32_t visible_frame = 0;
+		bool has_projection = false;
+		ClippingPolygon current_frame_projection;
+	};
+	uint32_t visibility_frame_ = 0;
+	std::vector<LeafData> leafs_data_;
+	std::vector<PortalData> portals_data_;
+	std::vector<uint32_t> wave_cur_, wave_next_;
+	bool is_inside_leaf_volume_ = true;
+
+	std::vector<DrawPolygonData> polygons_data_;
+	std::vector<Vec3f> vertices_transformed_;
+	std::vector<uint32_t> current_frame_visible_polygons_;
+	uint64_t num_visible_surfaces_pixels_ = 0;
+
+	std::vector<sqw_surface_job> jobs_;
+	std::vector<sqw_draw_cmd> cmds_;
+	std::vector<sqw_polygon_point> polygon_points_;
+	RendererDebugStats stats_;
+};
+
+} // namespace sqwh

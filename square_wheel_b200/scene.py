@@ -1,0 +1,193 @@
+"""ctypes binding of libsqw_host.so — the C++ host-side mirror of the reference's renderer front end
+(square_wheel_b200/host/): synthetic map + materials + textures, camera paths, and the per-frame host work that
+"stays host" in SURVEY.md §8 (visibility, surface preparation, BSP traversal) producing job and command lists."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+import subprocess
+
+import numpy as np
+
+from . import _native as N
+
+_lib = None
+
+FOV_DEFAULT = 0.375 * math.pi  # test_game/game_map.rs:865
+
+
+class SceneParams(C.Structure):
+    _fields_ = [
+        ("seed", C.c_uint32),
+        ("grid", C.c_uint32 * 3),
+        ("cell_size", C.c_float * 3),
+        ("num_rooms", C.c_uint32),
+        ("num_materials", C.c_uint32),
+        ("texture_size_log2", C.c_uint32),
+        ("max_polygon_size", C.c_float),
+        ("material_mode", C.c_uint32),
+        ("emissive_fraction", C.c_float),
+    ]
+
+
+class SceneInfo(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("num_nodes", "num_leafs", "num_polygons", "num_portals", "num_vertices", "num_materials", "num_images", "num_waypoints")] + [
+        ("num_lightmap_elements", C.c_uint64)
+    ]
+
+
+class RendererConfig(C.Structure):
+    """renderer_config.rs:5-31 (the fields the path reads)."""
+
+    _fields_ = [("use_directional_lightmaps", C.c_uint32), ("textures_mip_bias", C.c_float), ("clear_background", C.c_uint32), ("invert_polygons_order", C.c_uint32)]
+
+
+class FrameInfo(C.Structure):
+    _fields_ = [
+        ("num_jobs", C.c_uint32),
+        ("num_cmds", C.c_uint32),
+        ("num_polygon_points", C.c_uint32),
+        ("needs_background_clear", C.c_uint32),
+        ("total_surface_pixels", C.c_uint64),
+        ("num_visible_leafs", C.c_uint32),
+        ("num_visible_polygons", C.c_uint32),
+        ("mode_counts", C.c_uint32 * 3),
+        ("cam_pos", C.c_float * 3),
+        ("reserved", C.c_uint32),
+    ]
+
+
+def build_host_library():
+    subprocess.run(["make", "-C", os.path.join(os.path.dirname(N.HOST_LIB_PATH), "host")], check=True, capture_output=True)
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(N.HOST_LIB_PATH):
+            build_host_library()
+        l = C.CDLL(N.HOST_LIB_PATH)
+        vp = C.c_void_p
+        l.sqwh_scene_create.restype = vp
+        l.sqwh_scene_create.argtypes = [C.POINTER(SceneParams)]
+        l.sqwh_scene_destroy.argtypes = [vp]
+        l.sqwh_scene_get_info.argtypes = [vp, C.POINTER(SceneInfo)]
+        l.sqwh_scene_image.restype = vp
+        l.sqwh_scene_image.argtypes = [vp, C.c_uint32, C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        l.sqwh_scene_lightmaps.restype = vp
+        l.sqwh_scene_lightmaps.argtypes = [vp]
+        l.sqwh_scene_directional_lightmaps.restype = vp
+        l.sqwh_scene_directional_lightmaps.argtypes = [vp]
+        l.sqwh_scene_camera_path.restype = C.c_uint32
+        l.sqwh_scene_camera_path.argtypes = [vp, C.c_uint32, C.c_uint32, vp]
+        l.sqwh_renderer_create.restype = vp
+        l.sqwh_renderer_create.argtypes = [vp, C.POINTER(RendererConfig)]
+        l.sqwh_renderer_destroy.argtypes = [vp]
+        l.sqwh_renderer_prepare_frame.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.c_float]
+        l.sqwh_renderer_draw_frame.argtypes = [vp]
+        l.sqwh_renderer_frame_info.argtypes = [vp, C.POINTER(FrameInfo)]
+        for name in ("sqwh_renderer_jobs", "sqwh_renderer_cmds", "sqwh_renderer_polygon_points"):
+            getattr(l, name).restype = vp
+            getattr(l, name).argtypes = [vp]
+        l.sqwh_default_scene_params.argtypes = [C.POINTER(SceneParams)]
+        _lib = l
+    return _lib
+
+
+def default_scene_params(**overrides) -> SceneParams:
+    p = SceneParams()
+    lib().sqwh_default_scene_params(C.byref(p))
+    for k, v in overrides.items():
+        if k in ("grid", "cell_size"):
+            arr = getattr(p, k)
+            for i in range(3):
+                arr[i] = v[i]
+        else:
+            setattr(p, k, v)
+    return p
+
+
+def _array_from(ptr, count, dtype):
+    if not ptr or count == 0:
+        return np.zeros(0, dtype)
+    buf = (C.c_char * (count * np.dtype(dtype).itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype, count=count).copy()
+
+
+class Scene:
+    """Synthetic stand-in for a compiled + lightmapped .sqwm map with its material textures."""
+
+    def __init__(self, params: SceneParams | None = None, **overrides):
+        self.params = params if params is not None else default_scene_params(**overrides)
+        self._lib = lib()
+        self._handle = self._lib.sqwh_scene_create(C.byref(self.params))
+        if not self._handle:
+            raise ValueError("bad scene parameters")
+        self.info = SceneInfo()
+        self._lib.sqwh_scene_get_info(self._handle, C.byref(self.info))
+        n = int(self.info.num_lightmap_elements)
+        self.lightmaps = _array_from(self._lib.sqwh_scene_lightmaps(self._handle), n * 3, np.float32).reshape(n, 3)
+        self.directional_lightmaps = _array_from(self._lib.sqwh_scene_directional_lightmaps(self._handle), n, N.directional_lightmap_dtype)
+        self.images = []  # (kind, ndarray[h, w]) in image-id order
+        kind, w, h = C.c_int32(), C.c_uint32(), C.c_uint32()
+        for i in range(self.info.num_images):
+            p = self._lib.sqwh_scene_image(self._handle, i, C.byref(kind), C.byref(w), C.byref(h))
+            dt = {N.IMAGE_TEXTURE_ELEMENT: N.texture_element_dtype, N.IMAGE_COLOR32: np.uint32, N.IMAGE_COLOR64: np.uint64}[kind.value]
+            self.images.append((kind.value, _array_from(p, w.value * h.value, dt).reshape(h.value, w.value)))
+
+    def camera_path(self, num_frames: int, jitter_seed: int = 0) -> np.ndarray:
+        """[num_frames, 5] = position xyz, azimuth, elevation (64-pose Catmull-Rom loop of SURVEY.md §8d)."""
+        out = np.zeros((num_frames, 5), np.float32)
+        n = self._lib.sqwh_scene_camera_path(self._handle, num_frames, jitter_seed, out.ctypes.data_as(C.c_void_p))
+        return out[:n]
+
+    def upload(self, ctx):
+        """Upload every image in image-id order (S0 of SURVEY.md §8b)."""
+        for i, (kind, px) in enumerate(self.images):
+            got = ctx.upload_image(kind, px)
+            assert got == i, "image ids must match the host library's numbering"
+
+    def close(self):
+        if self._handle:
+            self._lib.sqwh_scene_destroy(self._handle)
+            self._handle = None
+
+
+class HostFrame:
+    """Everything the host produced for one frame: the inputs of S1 and S2."""
+
+    def __init__(self, jobs, total_surface_pixels, cam_pos, cmds, polygon_points, needs_clear, info):
+        self.jobs, self.total_surface_pixels, self.cam_pos = jobs, total_surface_pixels, cam_pos
+        self.cmds, self.polygon_points, self.needs_clear, self.info = cmds, polygon_points, needs_clear, info
+
+
+class HostRenderer:
+    """C++ mirror of Renderer / PartialRenderer front end (renderer.rs:61,106; partial_renderer.rs:156,236)."""
+
+    def __init__(self, scene: Scene, use_directional_lightmaps=True, textures_mip_bias=0.0, clear_background=True):
+        self.scene = scene
+        self._lib = lib()
+        cfg = RendererConfig(1 if use_directional_lightmaps else 0, textures_mip_bias, 1 if clear_background else 0, 0)
+        self._handle = self._lib.sqwh_renderer_create(scene._handle, C.byref(cfg))
+
+    def build_frame(self, width: int, height: int, pose, fov: float = FOV_DEFAULT) -> HostFrame:
+        pose = np.ascontiguousarray(pose, np.float32)
+        self._lib.sqwh_renderer_prepare_frame(self._handle, width, height, pose.ctypes.data_as(C.c_void_p), fov)
+        self._lib.sqwh_renderer_draw_frame(self._handle)
+        fi = FrameInfo()
+        self._lib.sqwh_renderer_frame_info(self._handle, C.byref(fi))
+        jobs = _array_from(self._lib.sqwh_renderer_jobs(self._handle), fi.num_jobs, N.surface_job_dtype)
+        cmds = _array_from(self._lib.sqwh_renderer_cmds(self._handle), fi.num_cmds, N.draw_cmd_dtype)
+        pts = _array_from(self._lib.sqwh_renderer_polygon_points(self._handle), fi.num_polygon_points, N.polygon_point_dtype)
+        return HostFrame(jobs, int(fi.total_surface_pixels), np.array(list(fi.cam_pos), np.float32), cmds, pts, bool(fi.needs_background_clear), fi)
+
+    def close(self):
+        if self._handle:
+            self._lib.sqwh_renderer_destroy(self._handle)
+            self._handle = None
+
+
+# draw_background colour (partial_renderer.rs:253-256): ColorVec::from_color_f32x3(&[32.0, 16.0, 8.0]).into()
+BACKGROUND_COLOR32 = (32 << 16) | (16 << 8) | 8
+BACKGROUND_COLOR64 = (32 << 32) | (16 << 16) | 8

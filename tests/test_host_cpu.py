@@ -1,0 +1,75 @@
+"""CPU checks of the host-side mirror (C++ libsqw_host): map structure, visibility, job/command invariants that the
+reference guards with debug_assert!s, and the oracle running a whole frame from its output."""
+import numpy as np
+import pytest
+
+from square_wheel_b200 import _native as N
+from square_wheel_b200 import scene as S
+
+
+@pytest.fixture(scope="module")
+def scene():
+    sc = S.Scene(seed=5, texture_size_log2=6, num_materials=8)
+    yield sc
+    sc.close()
+
+
+def test_scene_is_deterministic():
+    a = S.Scene(seed=9, texture_size_log2=5, num_materials=4)
+    b = S.Scene(seed=9, texture_size_log2=5, num_materials=4)
+    c = S.Scene(seed=10, texture_size_log2=5, num_materials=4)
+    assert np.array_equal(a.directional_lightmaps, b.directional_lightmaps)
+    assert all(np.array_equal(x[1], y[1]) for x, y in zip(a.images, b.images))
+    assert a.info.num_polygons != c.info.num_polygons or not np.array_equal(a.lightmaps, c.lightmaps)
+    for s in (a, b, c):
+        s.close()
+
+
+def test_jobs_and_commands_respect_reference_invariants(scene):
+    r = S.HostRenderer(scene)
+    path = scene.camera_path(16)
+    total_cmds = 0
+    for pose in path:
+        hf = r.build_frame(640, 360, pose)
+        j = hf.jobs
+        assert len(j) > 0 and len(hf.cmds) > 0
+        # surface rectangles are a prefix sum (partial_renderer.rs:1617-1618): disjoint and dense
+        sizes = j["surface_size"].astype(np.int64)
+        offs = j["surface_pixels_offset"].astype(np.int64)
+        assert np.array_equal(offs, np.concatenate([[0], np.cumsum(sizes[:, 0] * sizes[:, 1])[:-1]]))
+        assert hf.total_surface_pixels == int((sizes[:, 0] * sizes[:, 1]).sum())
+        # lightmap fetches stay inside the polygon's lightmap (debug_assert surfaces.rs:482, :541)
+        lit = j["lightmap_offset"] != 0
+        sc = j["lightmap_scale_log2"].astype(np.int64)
+        for axis in (0, 1):
+            last = ((sizes[:, axis] - 1 + j["lightmap_tc_shift"][:, axis]) >> sc) + 1
+            assert np.all(last[lit] < j["lightmap_size"][:, axis][lit])
+        assert np.all(j["lightmap_size"][lit] <= 18)
+        # every command references the surface of exactly one job, with the job's size
+        assert np.all(hf.cmds["tex_kind"] == N.TEX_SURFACE)
+        by_offset = {int(o): tuple(s) for o, s in zip(offs, sizes)}
+        for c in hf.cmds:
+            assert by_offset[int(c["tex_ref"])] == tuple(int(x) for x in c["tex_size"])
+            assert 3 <= c["num_vertices"] <= 24
+        # projected vertices are inside the viewport (clipping by the leaf octagon) up to rounding
+        x = hf.polygon_points["x"] / 65536.0
+        y = hf.polygon_points["y"] / 65536.0
+        assert x.min() >= -1 and x.max() <= 641 and y.min() >= -1 and y.max() <= 361
+        total_cmds += len(hf.cmds)
+    assert total_cmds > 16 * 20
+    r.close()
+
+
+def test_oracle_renders_host_frame_without_gaps(scene, oracle_lib):
+    """A closed map seen from inside: every pixel is covered (no background shows through), and no debug assert fires."""
+    r = S.HostRenderer(scene)
+    W, H = 320, 180
+    for pose in scene.camera_path(6):
+        hf = r.build_frame(W, H, pose)
+        oracle_lib.reset_assert_failures()
+        surf = oracle_lib.build_surfaces(32, hf.jobs, None, None, hf.cam_pos, scene.images, scene.lightmaps, scene.directional_lightmaps, hf.total_surface_pixels)
+        fb = np.full((H, W), 0xDEADBEEF, np.uint32)
+        oracle_lib.draw(32, fb, hf.cmds, hf.polygon_points, None, surf, scene.images)
+        assert oracle_lib.assert_failures() == 0
+        assert np.count_nonzero(fb == 0xDEADBEEF) == 0
+    r.close()
