@@ -208,7 +208,10 @@ def run_cuda(args, rank, local_rank, world):
     order = [(i + rank * (NUM_POSES // max(world, 1))) % NUM_POSES for i in range(NUM_POSES)]
     host_frames, host_ms = prepare_host_frames(scene, [poses[i] for i in order])
 
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream: its handle is what the C-ABI launches on and what the torch events below are recorded on
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx = Context(scene.lightmaps, scene.directional_lightmaps, device=local_rank, stream=stream.cuda_stream)
     scene.upload(ctx)
     view = ctx.create_view(WIDTH, HEIGHT, 64)
@@ -239,11 +242,11 @@ def run_cuda(args, rank, local_rank, world):
         return k
 
     # ---- device-resident timing: W warm-up steps, then exactly K steps between events ----
-    k = run_steps(args.warmup, 0)
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    k = run_steps(args.warmup, 0)
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
@@ -251,7 +254,20 @@ def run_cuda(args, rank, local_rank, world):
     e1.record(stream)
     barrier()
     elapsed_ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = None
+    if rank == 0:
+        # The timed region of a short run is shorter than nvidia-smi's sampling period: keep the same load running (untimed)
+        # until the sampler has seen at least ~1.5 s of it, then take the median over the samples under load.
+        t_load = time.perf_counter()
+        n_before = len(sampler.samples)
+        while time.perf_counter() - t_load < 1.5 or len(sampler.samples) - n_before < 5:
+            run_steps(1, k)
+            torch.cuda.synchronize()
+            if time.perf_counter() - t_load > 6.0:
+                break
+        sampler.samples = sampler.samples[n_before:]
+        clocks = sampler.stop()
+        clocks["note"] = "sampled while the timed workload kept running (the timed region itself is shorter than the sampling period)"
     if dist is not None:
         t = torch.tensor([elapsed_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
