@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define SQW_ABI_VERSION 1
+#define SQW_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------------------------------------- */
 #define SQW_OK 0
@@ -70,8 +70,14 @@ typedef struct sqw_map_desc
 	const sqw_directional_lightmap_element* directional_lightmaps_data; /* same count, or NULL */
 	uint64_t num_lightmap_elements;
 	uint32_t max_images; /* capacity of the image table (0 = default 4096) */
-	uint32_t reserved;
+	uint32_t flags;      /* SQW_CTX_* */
 } sqw_map_desc;
+
+/* Every view of the context issues its work (uploads, kernels, read-backs) on a private CUDA stream, so frames of
+ * different views overlap on the GPU (the view-batch workload; the reference overlaps frame N's prepare
+ * with frame N-1's swap the same way, host.rs:438-449).  Work of ONE view stays in submission order.  Without the flag
+ * everything runs in order on the context's stream. */
+#define SQW_CTX_CONCURRENT_VIEWS 1u
 
 /* Create a context on CUDA device `device` and upload the static map data.  Replaces the ownership half of
  * Renderer::new (renderer.rs:24).  `external_stream` may be a cudaStream_t the caller wants all work of this
@@ -256,6 +262,11 @@ int sqw_read_pixels(sqw_view* view, void* dst, size_t dst_pitch);
 int sqw_write_pixels(sqw_view* view, const void* src, size_t src_pitch);
 /* Copy the post-processed 32-bit picture of a 64-bit view. Synchronises. */
 int sqw_read_pixels32(sqw_view* view, uint32_t* dst, size_t dst_pitch);
+/* Asynchronous variants: the copy is queued behind the view's rendering and completes by the next
+ * sqw_view_synchronize (or any synchronising call on the view).  dst should be page-locked memory, otherwise CUDA stages
+ * the copy.  With SQW_CTX_CONCURRENT_VIEWS the read-back of one view overlaps the rendering of the others. */
+int sqw_read_pixels_async(sqw_view* view, void* dst, size_t dst_pitch);
+int sqw_read_pixels32_async(sqw_view* view, uint32_t* dst, size_t dst_pitch);
 /* Copy `count` pixels of the surface pool starting at `offset` (both in pixels) — test/inspection hook. */
 int sqw_read_surfaces(sqw_view* view, void* dst, uint64_t offset, uint64_t count);
 /* Wait for everything issued for this view. */
@@ -297,6 +308,13 @@ int sqw_frame_set_post(sqw_frame* frame, const sqw_post_params* params);
 #define SQW_STAGE_ALL 7u
 int sqw_frame_submit(sqw_frame* frame, uint32_t stages);
 
+/* Fork / join between the context's stream and the private streams of its views (SQW_CTX_CONCURRENT_VIEWS; no-ops
+ * otherwise): frames submitted between the two calls start after everything queued on the context's stream before
+ * sqw_batch_begin, and work queued on the context's stream after sqw_batch_end starts after those frames.  A caller that
+ * passed its own stream to sqw_create brackets a batch of independent views with these (e.g. to time it with events). */
+int sqw_batch_begin(sqw_ctx* ctx);
+int sqw_batch_end(sqw_ctx* ctx);
+
 /* Statistics of the last submit of this frame (units of the texels/s metric and of the roofline). */
 typedef struct sqw_frame_stats
 {
@@ -317,13 +335,14 @@ int sqw_frame_get_stats(const sqw_frame* frame, sqw_frame_stats* out);
  * sqw_profile_end synchronises and returns the accumulated device time and launch count per kernel kind. */
 #define SQW_KERNEL_SURFACE_BUILD 0
 #define SQW_KERNEL_RASTER_SETUP 1
-#define SQW_KERNEL_RASTER_BIN 2
+#define SQW_KERNEL_RASTER_BIN 2 /* unused since binning runs as tail CTAs of the set-up grid */
 #define SQW_KERNEL_RASTER_TILE 3
 #define SQW_KERNEL_TONEMAP 4
 #define SQW_KERNEL_BLOOM_DOWNSCALE 5
 #define SQW_KERNEL_BLOOM_BLUR 6
 #define SQW_KERNEL_TONEMAP_BLOOM 7
-#define SQW_NUM_KERNEL_KINDS 8
+#define SQW_KERNEL_RASTER_TILE_TONEMAP 8 /* tile kernel with the fused tonemapping epilogue */
+#define SQW_NUM_KERNEL_KINDS 9
 typedef struct sqw_kernel_times
 {
 	double ms[SQW_NUM_KERNEL_KINDS];

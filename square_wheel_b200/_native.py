@@ -25,6 +25,7 @@ BLEND_NONE, BLEND_AVERAGE, BLEND_ADDITIVE, BLEND_ALPHA_TEST, BLEND_ALPHA_BLEND =
 TC_FULL_PERSPECTIVE, TC_LINE_Z_CORRECTION, TC_AFFINE = 0, 1, 2
 TEX_SURFACE, TEX_IMAGE, TEX_VIEW = 0, 1, 2
 STAGE_SURFACES, STAGE_RASTER, STAGE_POST, STAGE_ALL = 1, 2, 4, 7
+CTX_CONCURRENT_VIEWS = 1
 
 # ---- struct layouts as numpy dtypes (sizes asserted against the static_asserts in sqw_api.cu) ---------------
 surface_job_dtype = np.dtype(
@@ -107,7 +108,7 @@ class MapDesc(C.Structure):
         ("directional_lightmaps_data", C.c_void_p),
         ("num_lightmap_elements", C.c_uint64),
         ("max_images", C.c_uint32),
-        ("reserved", C.c_uint32),
+        ("flags", C.c_uint32),
     ]
 
 
@@ -139,10 +140,10 @@ class FrameStats(C.Structure):
 
 
 class KernelTimes(C.Structure):
-    _fields_ = [("ms", C.c_double * 8), ("launches", C.c_uint64 * 8)]
+    _fields_ = [("ms", C.c_double * 9), ("launches", C.c_uint64 * 9)]
 
 
-KERNEL_NAMES = ["surface_build", "raster_setup", "raster_bin", "raster_tile", "tonemap", "bloom_downscale", "bloom_blur", "tonemap_bloom"]
+KERNEL_NAMES = ["surface_build", "raster_setup", "raster_bin", "raster_tile", "tonemap", "bloom_downscale", "bloom_blur", "tonemap_bloom", "raster_tile_tonemap"]
 
 # Every symbol include/sqw_cuda.h declares: (name, restype, argtypes)
 _VP = C.c_void_p
@@ -160,6 +161,10 @@ CUDA_SYMBOLS = [
     ("sqw_postprocess", C.c_int, [_VP, C.POINTER(PostParams), _VP, C.c_size_t, _VP]),
     ("sqw_read_pixels", C.c_int, [_VP, _VP, C.c_size_t]),
     ("sqw_read_pixels32", C.c_int, [_VP, _VP, C.c_size_t]),
+    ("sqw_read_pixels_async", C.c_int, [_VP, _VP, C.c_size_t]),
+    ("sqw_read_pixels32_async", C.c_int, [_VP, _VP, C.c_size_t]),
+    ("sqw_batch_begin", C.c_int, [_VP]),
+    ("sqw_batch_end", C.c_int, [_VP]),
     ("sqw_write_pixels", C.c_int, [_VP, _VP, C.c_size_t]),
     ("sqw_read_surfaces", C.c_int, [_VP, _VP, C.c_uint64, C.c_uint64]),
     ("sqw_view_synchronize", C.c_int, [_VP]),

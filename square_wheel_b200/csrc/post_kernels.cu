@@ -19,17 +19,6 @@ namespace sqw
 namespace
 {
 
-// TonemappingFunction::do_it (:1019-1023) for the three colour lanes; the alpha lane is 0/0 or x/0 in the
-// reference and ends as 255 after `min(255.0)` in both of its implementations.
-__device__ __forceinline__ uint32_t tonemap_pixel(ColorVec c, float inv_scale_b, float inv_scale_g, float inv_scale_r)
-{
-	const float inv_255 = 1.0f / 255.0f;
-	const float b = __fdiv_rn(c.b, f32_mul_add(c.b, inv_255, inv_scale_b));
-	const float g = __fdiv_rn(c.g, f32_mul_add(c.g, inv_255, inv_scale_g));
-	const float r = __fdiv_rn(c.r, f32_mul_add(c.r, inv_255, inv_scale_r));
-	return f32_to_u_clamped(b, 255.0f) | (f32_to_u_clamped(g, 255.0f) << 8) | (f32_to_u_clamped(r, 255.0f) << 16) | 0xFF000000u;
-}
-
 __device__ __forceinline__ void block_sum3_atomic(unsigned long long b, unsigned long long g, unsigned long long r, unsigned long long* sums)
 {
 	__shared__ unsigned long long s_part[3][8];

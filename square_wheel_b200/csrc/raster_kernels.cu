@@ -13,8 +13,8 @@
 //                         x0 + n*dx_dy (mod 2^32, exactly the value the reference reaches after n additions) and
 //                         does the per-line set-up of the reference's inner loops (i64 equations, span end-point
 //                         clamps, the i32 divisions) -> one 48-byte SpanRec.
-//   raster_bin_kernel     one CTA per 8-row band: order-preserving compaction (ballot + popc prefix) of the
-//                         commands whose row range touches the band.
+//   (binning)             tail CTAs of the same grid, one per 8-row band: order-preserving compaction (ballot + popc
+//                         prefix) of the commands whose row range touches the band.
 //   raster_tile_kernel    one CTA per 128x8 tile, one warp per row, 4 consecutive pixels per lane kept in
 //                         registers; the warp walks the band's command list in submission order, filters it
 //                         32 commands at a time against the tile, loads the SpanRec of its row (warp-uniform,
@@ -26,6 +26,7 @@
 // store; the full-perspective mode adds one u32 divide per pixel (rasterizer.rs:430).
 #include "sqw_device.cuh"
 #include "sqw_internal.h"
+#include <algorithm>
 
 namespace sqw
 {
@@ -550,45 +551,20 @@ __device__ void setup_triangle_line(const sqw_draw_cmd& c, const sqw_triangle_po
 	}
 }
 
-__global__ void __launch_bounds__(128) raster_setup_kernel(
-	const sqw_draw_cmd* __restrict__ cmds, const CmdDev* __restrict__ cmd_dev, uint32_t num_cmds, const sqw_polygon_point* __restrict__ polygon_points,
-	const sqw_triangle_point* __restrict__ triangle_points, const uint32_t* __restrict__ cmd_span_base, uint32_t total_spans, SpanRec* __restrict__ spans,
-	int32_t clip_w, int32_t clip_h)
-{
-	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-	if (s >= total_spans)
-		return;
-	// Owning command: last index with cmd_span_base[i] <= s.
-	uint32_t lo = 0, hi = num_cmds; // invariant: base[lo] <= s < base[hi]
-	while (hi - lo > 1)
-	{
-		const uint32_t mid = (lo + hi) >> 1;
-		if (__ldg(cmd_span_base + mid) <= s)
-			lo = mid;
-		else
-			hi = mid;
-	}
-	const CmdDev cd = cmd_dev[lo];
-	const sqw_draw_cmd c = cmds[lo];
-	const int32_t row = (int32_t)cd.y0 + (int32_t)(s - cd.span_base);
-	if (cd.kind == SQW_CMD_POLYGON)
-		setup_polygon_line(c, cd, polygon_points + c.vertex_offset, row, clip_w, clip_h, spans + s);
-	else
-		setup_triangle_line(c, triangle_points + c.vertex_offset, row, clip_w, clip_h, spans + s);
-}
-
 // ---- binning -------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) raster_bin_kernel(const CmdDev* __restrict__ cmd_dev, uint32_t num_cmds, const uint32_t* __restrict__ band_offsets, uint32_t* __restrict__ band_lists)
+// One CTA per 8-row band: order-preserving compaction (ballot + popc prefix) of the commands whose row range touches
+// the band.  Runs as the tail CTAs of the set-up grid (the two jobs are independent; one launch instead of two).
+__device__ void bin_band(const CmdDev* __restrict__ cmd_dev, uint32_t num_cmds, const uint32_t* __restrict__ band_offsets, uint32_t* __restrict__ band_lists, int band)
 {
-	__shared__ uint32_t s_warp_counts[8];
+	constexpr int WARPS = SQW_SETUP_THREADS / 32;
+	__shared__ uint32_t s_warp_counts[WARPS];
 	__shared__ uint32_t s_running;
-	const int band = blockIdx.x;
 	const int32_t band_y0 = band * SQW_TILE_H, band_y1 = band_y0 + SQW_TILE_H;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	if (threadIdx.x == 0)
 		s_running = band_offsets[band];
 	__syncthreads();
-	for (uint32_t base = 0; base < num_cmds; base += 256)
+	for (uint32_t base = 0; base < num_cmds; base += SQW_SETUP_THREADS)
 	{
 		const uint32_t i = base + threadIdx.x;
 		bool hit = false;
@@ -611,12 +587,47 @@ __global__ void __launch_bounds__(256) raster_bin_kernel(const CmdDev* __restric
 		if (threadIdx.x == 0)
 		{
 			uint32_t t = 0;
-			for (int w = 0; w < 8; ++w)
+			for (int w = 0; w < WARPS; ++w)
 				t += s_warp_counts[w];
 			s_running += t;
 		}
 		__syncthreads();
 	}
+}
+
+__global__ void __launch_bounds__(SQW_SETUP_THREADS) raster_setup_kernel(
+	const sqw_draw_cmd* __restrict__ cmds, const CmdDev* __restrict__ cmd_dev, uint32_t num_cmds, const sqw_polygon_point* __restrict__ polygon_points,
+	const sqw_triangle_point* __restrict__ triangle_points, const uint32_t* __restrict__ cmd_span_base, uint32_t total_spans, SpanRec* __restrict__ spans,
+	int32_t clip_w, int32_t clip_h, uint32_t setup_blocks, const uint32_t* __restrict__ band_offsets, uint32_t* __restrict__ band_lists,
+	unsigned long long* __restrict__ sums_to_zero)
+{
+	if (blockIdx.x >= setup_blocks)
+	{
+		bin_band(cmd_dev, num_cmds, band_offsets, band_lists, (int)(blockIdx.x - setup_blocks));
+		return;
+	}
+	if (sums_to_zero && blockIdx.x == 0 && threadIdx.x < 3)
+		sums_to_zero[threadIdx.x] = 0; // colour sums of the fused tonemapping epilogue of the tile kernel that follows
+	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= total_spans)
+		return;
+	// Owning command: last index with cmd_span_base[i] <= s.
+	uint32_t lo = 0, hi = num_cmds; // invariant: base[lo] <= s < base[hi]
+	while (hi - lo > 1)
+	{
+		const uint32_t mid = (lo + hi) >> 1;
+		if (__ldg(cmd_span_base + mid) <= s)
+			lo = mid;
+		else
+			hi = mid;
+	}
+	const CmdDev cd = cmd_dev[lo];
+	const sqw_draw_cmd c = cmds[lo];
+	const int32_t row = (int32_t)cd.y0 + (int32_t)(s - cd.span_base);
+	if (cd.kind == SQW_CMD_POLYGON)
+		setup_polygon_line(c, cd, polygon_points + c.vertex_offset, row, clip_w, clip_h, spans + s);
+	else
+		setup_triangle_line(c, triangle_points + c.vertex_offset, row, clip_w, clip_h, spans + s);
 }
 
 // ---- tile kernel ----------------------------------------------------------------------------------------------
@@ -626,39 +637,45 @@ __device__ __forceinline__ typename C::Raw fetch_texel(const void* tex, uint32_t
 	return __ldg(static_cast<const typename C::Raw*>(tex) + address);
 }
 
-template <class C>
+// TONEMAP = true fuses Postprocessor::perform_tonemapping (postprocessor.rs:226-256) into the tile epilogue: the finished
+// HDR pixels are still in registers, so the 32-bit picture and the colour sums are produced without reading the 64-bit
+// buffer back (saves 8 of the 12 bytes per pixel of a separate tonemapping pass).
+template <class C, bool TONEMAP>
 __global__ void __launch_bounds__(SQW_RASTER_THREADS) raster_tile_kernel(
 	const CmdDev* __restrict__ cmd_dev, const SpanRec* __restrict__ spans, const uint32_t* __restrict__ band_lists, const uint32_t* __restrict__ band_offsets,
 	const char* __restrict__ surfaces_base, typename C::Raw* __restrict__ color_buffer, int32_t width, int32_t height, int32_t pitch, int clear,
-	typename C::Raw clear_color)
+	typename C::Raw clear_color, uint32_t* __restrict__ ldr, float isb, float isg, float isr, unsigned long long* __restrict__ sums)
 {
 	typedef typename C::Raw Raw;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int band = blockIdx.y;
 	const int32_t row = band * SQW_TILE_H + warp;
-	if (row >= height)
-		return;
+	const bool row_valid = row < height;
 	const int32_t tile_x0 = blockIdx.x * SQW_TILE_W;
 	const int32_t tile_x1 = min(tile_x0 + SQW_TILE_W, width);
 	const int32_t px0 = tile_x0 + lane * 4;
 
 	Raw* const dst = color_buffer + (size_t)row * pitch + px0;
 	Raw px[4];
-	const bool vec_ok = (px0 + 4 <= width) && ((pitch & 3) == 0);
+	// `have` bit i: px[i] holds the current value of the pixel.  The framebuffer is only read for pixels whose first
+	// covering command blends with the destination, and pixels no command touches are not written back: a frame whose
+	// polygons cover the screen (the usual case inside a map, partial_renderer.rs:249-256) never reads the buffer.
+	uint32_t have = 0;
+#pragma unroll
+	for (int i = 0; i < 4; ++i)
+		px[i] = clear_color;
 	if (clear)
-	{
-#pragma unroll
-		for (int i = 0; i < 4; ++i)
-			px[i] = clear_color;
-	}
-	else
-	{
-#pragma unroll
-		for (int i = 0; i < 4; ++i)
-			px[i] = (px0 + i < width) ? dst[i] : 0;
+		have = 0xF;
+	const bool vec_ok = (px0 + 4 <= width) && ((pitch & 3) == 0);
+
+#define SQW_NEED_DST(i)                       \
+	if (!(have & (1u << (i))))                \
+	{                                         \
+		px[i] = dst[i];                       \
+		have |= 1u << (i);                    \
 	}
 
-	const uint32_t list_begin = band_offsets[band], list_end = band_offsets[band + 1];
+	const uint32_t list_begin = row_valid ? band_offsets[band] : 0, list_end = row_valid ? band_offsets[band + 1] : 0;
 	for (uint32_t base = list_begin; base < list_end; base += 32)
 	{
 		uint32_t ci = 0;
@@ -679,60 +696,70 @@ __global__ void __launch_bounds__(SQW_RASTER_THREADS) raster_tile_kernel(
 			const uint32_t cmd_index = __shfl_sync(0xFFFFFFFFu, ci, bit);
 			const CmdDev* cdp = cmd_dev + cmd_index;
 			const uint4 c0 = __ldg(reinterpret_cast<const uint4*>(cdp));     // y0,y1,bx0,bx1 | span_base | kind.. | (pad)
-			const uint4 c1 = __ldg(reinterpret_cast<const uint4*>(cdp) + 1); // texture ptr | tex_width | tex_height
 			const int32_t y0 = (int16_t)(c0.x & 0xFFFF);
 			const uint32_t span_base = c0.z;
+			const uint4* sp = reinterpret_cast<const uint4*>(spans + span_base + (uint32_t)(row - y0));
+			const uint4 s0 = __ldg(sp);
+			const int32_t x0 = (int16_t)(s0.x & 0xFFFF), x1 = (int16_t)(s0.x >> 16);
+			if (x0 >= x1 || x0 >= tile_x1 || x1 <= tile_x0)
+				continue;
+			const uint4 c1 = __ldg(reinterpret_cast<const uint4*>(cdp) + 1); // texture ptr | tex_width | tex_height
 			const uint32_t kind = c0.w & 0xFF, blend = (c0.w >> 8) & 0xFF, tc_mode = (c0.w >> 16) & 0xFF, tex64 = (c0.w >> 24) & 1;
 			// bit 1 of the last flag byte: `texture` is a byte offset into the view's surface pool (the pool may be
 			// re-allocated between recording and submission, so surface references stay relative).
 			const uint64_t tex_bits = (uint64_t)c1.x | ((uint64_t)c1.y << 32);
 			const void* const tex = ((c0.w >> 25) & 1) ? static_cast<const void*>(surfaces_base + tex_bits) : reinterpret_cast<const void*>(tex_bits);
 			const uint32_t tex_width = c1.z;
-
-			const uint4* sp = reinterpret_cast<const uint4*>(spans + span_base + (uint32_t)(row - y0));
-			const uint4 s0 = __ldg(sp);
-			const int32_t x0 = (int16_t)(s0.x & 0xFFFF), x1 = (int16_t)(s0.x >> 16);
-			if (x0 >= x1 || x0 >= tile_x1 || x1 <= tile_x0)
-				continue;
 			const uint4 s1 = __ldg(sp + 1);
-			const uint4 s2 = __ldg(sp + 2);
 			// v[0..2] = s0.y,z,w ; v[3..6] = s1 ; v[7..10] = s2
+			// Blend modes that read the destination (rasterizer.rs:1511-1536); alpha test keeps it untouched when it fails.
+			const bool reads_dst = blend == SQW_BLEND_AVERAGE || blend == SQW_BLEND_ADDITIVE || blend == SQW_BLEND_ALPHA_BLEND;
 
 			if (kind == SQW_CMD_POLYGON)
 			{
 				const int32_t tc0 = (int32_t)s0.w, tc1 = (int32_t)s1.x, dtc0 = (int32_t)s1.y, dtc1 = (int32_t)s1.z;
-				if (tc_mode == SQW_TC_FULL_PERSPECTIVE)
-				{
-					const int32_t inv_z0 = (int32_t)s0.y, d_inv_z = (int32_t)s0.z;
+				const int32_t inv_z0 = (int32_t)s0.y, d_inv_z = (int32_t)s0.z;
+				const bool full = tc_mode == SQW_TC_FULL_PERSPECTIVE;
 #pragma unroll
-					for (int i = 0; i < 4; ++i)
+				for (int i = 0; i < 4; ++i)
+				{
+					const int32_t x = px0 + i;
+					if (x >= x0 && x < x1)
 					{
-						const int32_t x = px0 + i;
-						if (x >= x0 && x < x1)
+						const int32_t k = x - x0;
+						uint32_t u, v;
+						if (full)
 						{
-							const int32_t k = x - x0;
 							const uint32_t span_inv_z = (uint32_t)wadd(inv_z0, wmul(k, d_inv_z));
 							const uint32_t z = (1u << Z_CALC_SHIFT) / (span_inv_z >> INV_Z_PRE_SHIFT); // rasterizer.rs:430
 							const uint64_t t0 = (uint64_t)(int64_t)wadd(tc0, wmul(k, dtc0));
 							const uint64_t t1 = (uint64_t)(int64_t)wadd(tc1, wmul(k, dtc1));
-							const uint32_t u = (uint32_t)(((uint64_t)z * t0) >> TC_FINAL_SHIFT);
-							const uint32_t v = (uint32_t)(((uint64_t)z * t1) >> TC_FINAL_SHIFT);
-							px[i] = blend_pixel<C>(blend, px[i], fetch_texel<C>(tex, u + v * tex_width));
+							u = (uint32_t)(((uint64_t)z * t0) >> TC_FINAL_SHIFT);
+							v = (uint32_t)(((uint64_t)z * t1) >> TC_FINAL_SHIFT);
 						}
-					}
-				}
-				else
-				{
-#pragma unroll
-					for (int i = 0; i < 4; ++i)
-					{
-						const int32_t x = px0 + i;
-						if (x >= x0 && x < x1)
+						else
 						{
-							const int32_t k = x - x0;
-							const uint32_t u = (uint32_t)(wadd(tc0, wmul(k, dtc0)) >> 16);
-							const uint32_t v = (uint32_t)(wadd(tc1, wmul(k, dtc1)) >> 16);
-							px[i] = blend_pixel<C>(blend, px[i], fetch_texel<C>(tex, u + v * tex_width));
+							u = (uint32_t)(wadd(tc0, wmul(k, dtc0)) >> 16);
+							v = (uint32_t)(wadd(tc1, wmul(k, dtc1)) >> 16);
+						}
+						const Raw texel = fetch_texel<C>(tex, u + v * tex_width);
+						if (blend == SQW_BLEND_NONE)
+						{
+							px[i] = texel;
+							have |= 1u << i;
+						}
+						else if (blend == SQW_BLEND_ALPHA_TEST)
+						{
+							if (C::test_alpha(texel))
+							{
+								px[i] = texel;
+								have |= 1u << i;
+							}
+						}
+						else
+						{
+							SQW_NEED_DST(i)
+							px[i] = blend_pixel<C>(blend, px[i], texel);
 						}
 					}
 				}
@@ -740,6 +767,7 @@ __global__ void __launch_bounds__(SQW_RASTER_THREADS) raster_tile_kernel(
 			else
 			{
 				// fill_triangle_part pixel loop (rasterizer.rs:1223-1279)
+				const uint4 s2 = __ldg(sp + 2);
 				const int32_t tc0 = (int32_t)s0.y, tc1 = (int32_t)s0.z, dtc0 = (int32_t)s0.w, dtc1 = (int32_t)s1.x;
 				const int32_t l0 = (int32_t)s1.y, l1 = (int32_t)s1.z, l2 = (int32_t)s1.w;
 				const int32_t dl0 = (int32_t)s2.x, dl1 = (int32_t)s2.y, dl2 = (int32_t)s2.z;
@@ -773,14 +801,24 @@ __global__ void __launch_bounds__(SQW_RASTER_THREADS) raster_tile_kernel(
 						}
 						const ColorVecI lighted = cvi_shr<16>(cvi_mul(texel_vec, light));
 						const Raw src = C::from_veci(lighted);
+						if (reads_dst)
+						{
+							SQW_NEED_DST(i)
+						}
 						switch (blend)
 						{
-						case SQW_BLEND_NONE: px[i] = src; break;
+						case SQW_BLEND_NONE:
+							px[i] = src;
+							have |= 1u << i;
+							break;
 						case SQW_BLEND_AVERAGE: px[i] = C::average(px[i], src); break;
 						case SQW_BLEND_ADDITIVE: px[i] = C::saturated_sum(px[i], src); break;
 						case SQW_BLEND_ALPHA_TEST:
 							if (alpha_pass)
+							{
 								px[i] = src;
+								have |= 1u << i;
+							}
 							break;
 						default:
 							px[i] = C::from_veci(cvi_shr<8>(cvi_add(cvi_mul_scalar(C::to_veci(px[i]), 255 - alpha), cvi_mul_scalar(lighted, alpha))));
@@ -792,45 +830,99 @@ __global__ void __launch_bounds__(SQW_RASTER_THREADS) raster_tile_kernel(
 		}
 	}
 
-	if (vec_ok)
+	if (row_valid)
 	{
-		if (sizeof(Raw) == 8)
+		if (vec_ok && have == 0xF)
 		{
-			uint4* d = reinterpret_cast<uint4*>(dst);
-			d[0] = make_uint4((uint32_t)px[0], (uint32_t)((uint64_t)px[0] >> 32), (uint32_t)px[1], (uint32_t)((uint64_t)px[1] >> 32));
-			d[1] = make_uint4((uint32_t)px[2], (uint32_t)((uint64_t)px[2] >> 32), (uint32_t)px[3], (uint32_t)((uint64_t)px[3] >> 32));
+			if (sizeof(Raw) == 8)
+			{
+				uint4* d = reinterpret_cast<uint4*>(dst);
+				d[0] = make_uint4((uint32_t)px[0], (uint32_t)((uint64_t)px[0] >> 32), (uint32_t)px[1], (uint32_t)((uint64_t)px[1] >> 32));
+				d[1] = make_uint4((uint32_t)px[2], (uint32_t)((uint64_t)px[2] >> 32), (uint32_t)px[3], (uint32_t)((uint64_t)px[3] >> 32));
+			}
+			else
+			{
+				*reinterpret_cast<uint4*>(dst) = make_uint4((uint32_t)px[0], (uint32_t)px[1], (uint32_t)px[2], (uint32_t)px[3]);
+			}
 		}
 		else
 		{
-			*reinterpret_cast<uint4*>(dst) = make_uint4((uint32_t)px[0], (uint32_t)px[1], (uint32_t)px[2], (uint32_t)px[3]);
+#pragma unroll
+			for (int i = 0; i < 4; ++i)
+				if (px0 + i < width && (have & (1u << i)))
+					dst[i] = px[i];
 		}
 	}
-	else
+
+	if (TONEMAP)
 	{
+		// sizeof(Raw) == 8 here (the host only fuses 64-bit views)
+		uint32_t sb = 0, sg = 0, sr = 0;
+		if (row_valid)
+		{
+			uint32_t out[4];
 #pragma unroll
-		for (int i = 0; i < 4; ++i)
-			if (px0 + i < width)
-				dst[i] = px[i];
+			for (int i = 0; i < 4; ++i)
+			{
+				out[i] = 0;
+				if (px0 + i < width)
+				{
+					SQW_NEED_DST(i) // untouched pixel: tonemap what the buffer holds
+					const uint64_t p = (uint64_t)px[i];
+					sb += (uint32_t)(p & 0xFFFF);
+					sg += (uint32_t)((p >> 16) & 0xFFFF);
+					sr += (uint32_t)((p >> 32) & 0xFFFF);
+					out[i] = tonemap_pixel(cv_from_color64(p), isb, isg, isr);
+				}
+			}
+			uint32_t* const o = ldr + (size_t)row * pitch + px0;
+			if (vec_ok)
+				__stcs(reinterpret_cast<uint4*>(o), make_uint4(out[0], out[1], out[2], out[3]));
+			else
+			{
+#pragma unroll
+				for (int i = 0; i < 4; ++i)
+					if (px0 + i < width)
+						o[i] = out[i];
+			}
+		}
+		// colour sums for update_exposure (postprocessor.rs:176-179): exact integers, 3 atomics per CTA
+		__shared__ uint32_t s_part[3][SQW_RASTER_THREADS / 32];
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1)
+		{
+			sb += __shfl_xor_sync(0xFFFFFFFFu, sb, o);
+			sg += __shfl_xor_sync(0xFFFFFFFFu, sg, o);
+			sr += __shfl_xor_sync(0xFFFFFFFFu, sr, o);
+		}
+		if (lane == 0)
+		{
+			s_part[0][warp] = sb;
+			s_part[1][warp] = sg;
+			s_part[2][warp] = sr;
+		}
+		__syncthreads();
+		if (threadIdx.x < 3)
+		{
+			unsigned long long t = 0;
+			for (int w = 0; w < SQW_RASTER_THREADS / 32; ++w)
+				t += s_part[threadIdx.x][w];
+			atomicAdd(sums + threadIdx.x, t);
+		}
 	}
+#undef SQW_NEED_DST
 }
 
 } // namespace
 
 cudaError_t launch_raster_setup(const RasterLaunch& l, cudaStream_t stream)
 {
-	if (l.total_spans == 0)
+	if (l.num_cmds == 0)
 		return cudaSuccess;
-	const uint32_t blocks = (l.total_spans + 127) / 128;
-	raster_setup_kernel<<<blocks, 128, 0, stream>>>(
-		l.cmds, l.cmd_dev, l.num_cmds, l.polygon_points, l.triangle_points, l.cmd_span_base, l.total_spans, l.spans, l.width, l.height);
-	return cudaGetLastError();
-}
-
-cudaError_t launch_raster_bin(const RasterLaunch& l, cudaStream_t stream)
-{
-	if (l.num_cmds == 0 || l.num_bands == 0)
-		return cudaSuccess;
-	raster_bin_kernel<<<l.num_bands, 256, 0, stream>>>(l.cmd_dev, l.num_cmds, l.band_offsets, l.band_lists);
+	const uint32_t setup_blocks = std::max<uint32_t>((l.total_spans + SQW_SETUP_THREADS - 1) / SQW_SETUP_THREADS, 1); // block 0 also zeroes the sums
+	raster_setup_kernel<<<setup_blocks + l.num_bands, SQW_SETUP_THREADS, 0, stream>>>(
+		l.cmds, l.cmd_dev, l.num_cmds, l.polygon_points, l.triangle_points, l.cmd_span_base, l.total_spans, l.spans, l.width, l.height, setup_blocks, l.band_offsets,
+		l.band_lists, l.zero_sums_in_setup ? l.color_sums : nullptr);
 	return cudaGetLastError();
 }
 
@@ -839,12 +931,16 @@ cudaError_t launch_raster_tiles(const RasterLaunch& l, cudaStream_t stream)
 	if (l.num_bands == 0)
 		return cudaSuccess;
 	const dim3 grid((uint32_t)((l.width + SQW_TILE_W - 1) / SQW_TILE_W), l.num_bands);
-	if (l.color64)
-		raster_tile_kernel<Color64><<<grid, SQW_RASTER_THREADS, 0, stream>>>(
-			l.cmd_dev, l.spans, l.band_lists, l.band_offsets, static_cast<const char*>(l.surfaces_base), static_cast<uint64_t*>(l.color_buffer), l.width, l.height, l.pitch, l.clear, (uint64_t)l.clear_color);
+#define SQW_TILE_ARGS(RAW) \
+	l.cmd_dev, l.spans, l.band_lists, l.band_offsets, static_cast<const char*>(l.surfaces_base), static_cast<RAW*>(l.color_buffer), l.width, l.height, l.pitch, l.clear, \
+		(RAW)l.clear_color, l.tonemap_dst, l.inv_scale_bgr[0], l.inv_scale_bgr[1], l.inv_scale_bgr[2], l.color_sums
+	if (l.color64 && l.tonemap_dst)
+		raster_tile_kernel<Color64, true><<<grid, SQW_RASTER_THREADS, 0, stream>>>(SQW_TILE_ARGS(uint64_t));
+	else if (l.color64)
+		raster_tile_kernel<Color64, false><<<grid, SQW_RASTER_THREADS, 0, stream>>>(SQW_TILE_ARGS(uint64_t));
 	else
-		raster_tile_kernel<Color32><<<grid, SQW_RASTER_THREADS, 0, stream>>>(
-			l.cmd_dev, l.spans, l.band_lists, l.band_offsets, static_cast<const char*>(l.surfaces_base), static_cast<uint32_t*>(l.color_buffer), l.width, l.height, l.pitch, l.clear, (uint32_t)l.clear_color);
+		raster_tile_kernel<Color32, false><<<grid, SQW_RASTER_THREADS, 0, stream>>>(SQW_TILE_ARGS(uint32_t));
+#undef SQW_TILE_ARGS
 	return cudaGetLastError();
 }
 

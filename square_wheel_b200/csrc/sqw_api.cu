@@ -60,6 +60,87 @@ struct DevBuf
 	}
 };
 
+// Host->device staging of one frame's lists: the caller's (pageable) arrays are packed into ONE page-locked buffer and sent
+// with ONE asynchronous copy; sections are 256-byte aligned inside a single grow-only device allocation.
+struct Arena
+{
+	char* h = nullptr;
+	size_t h_capacity = 0;
+	DevBuf d;
+	size_t used = 0;
+	cudaEvent_t copied = nullptr; // recorded after the copy: the staging buffer may be rewritten once it has fired
+	bool in_flight = false;
+
+	cudaError_t begin(size_t total_bytes)
+	{
+		if (in_flight)
+		{
+			cudaError_t e = cudaEventSynchronize(copied);
+			if (e != cudaSuccess)
+				return e;
+			in_flight = false;
+		}
+		used = 0;
+		if (total_bytes > h_capacity)
+		{
+			if (h)
+				cudaFreeHost(h);
+			h = nullptr;
+			h_capacity = 0;
+			const size_t rounded = (total_bytes + (total_bytes >> 2) + 4095) & ~size_t(4095);
+			cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&h), rounded, cudaHostAllocDefault);
+			if (e != cudaSuccess)
+			{
+				h = nullptr;
+				return e;
+			}
+			h_capacity = rounded;
+		}
+		return d.reserve(total_bytes);
+	}
+	static size_t padded(size_t bytes) { return (bytes + 255) & ~size_t(255); }
+	// returns the device address the section will have after commit()
+	void* push(const void* src, size_t bytes)
+	{
+		void* dev = static_cast<char*>(d.ptr) + used;
+		if (bytes)
+			std::memcpy(h + used, src, bytes);
+		used += padded(bytes);
+		return dev;
+	}
+	cudaError_t commit(cudaStream_t stream)
+	{
+		if (used == 0)
+			return cudaSuccess;
+		if (!copied)
+		{
+			cudaError_t e = cudaEventCreateWithFlags(&copied, cudaEventDisableTiming);
+			if (e != cudaSuccess)
+				return e;
+		}
+		cudaError_t e = cudaMemcpyAsync(d.ptr, h, used, cudaMemcpyHostToDevice, stream);
+		if (e != cudaSuccess)
+			return e;
+		in_flight = true;
+		return cudaEventRecord(copied, stream);
+	}
+	void release()
+	{
+		if (copied)
+		{
+			cudaEventSynchronize(copied);
+			cudaEventDestroy(copied);
+		}
+		copied = nullptr;
+		if (h)
+			cudaFreeHost(h);
+		h = nullptr;
+		h_capacity = 0;
+		d.release();
+		in_flight = false;
+	}
+};
+
 struct ImageHost
 {
 	void* pixels;
@@ -74,6 +155,8 @@ struct sqw_ctx
 	int device = 0;
 	cudaStream_t stream = nullptr;
 	bool own_stream = false;
+	bool concurrent_views = false; // SQW_CTX_CONCURRENT_VIEWS: every view issues its work on a private stream
+	cudaEvent_t batch_event = nullptr;
 	float* d_lightmaps = nullptr;
 	sqw_directional_lightmap_element* d_directional_lightmaps = nullptr;
 	uint64_t num_lightmap_elements = 0;
@@ -112,20 +195,21 @@ struct LaunchTimer
 {
 	sqw_ctx* ctx;
 	sqw_ctx::TimedLaunch t{};
-	LaunchTimer(sqw_ctx* c, int kind) : ctx(c)
+	cudaStream_t stream;
+	LaunchTimer(sqw_ctx* c, int kind, cudaStream_t s) : ctx(c), stream(s)
 	{
 		if (!ctx->profiling)
 			return;
 		t.kind = kind;
 		t.start = ctx->get_event();
 		t.stop = ctx->get_event();
-		cudaEventRecord(t.start, ctx->stream);
+		cudaEventRecord(t.start, stream);
 	}
 	~LaunchTimer()
 	{
 		if (!ctx->profiling)
 			return;
-		cudaEventRecord(t.stop, ctx->stream);
+		cudaEventRecord(t.stop, stream);
 		ctx->timed.push_back(t);
 	}
 };
@@ -137,6 +221,9 @@ struct sqw_view
 	uint32_t index = 0;
 	uint32_t width = 0, height = 0;
 	int color_bits = 0;
+	cudaStream_t stream = nullptr; // ctx->stream, or a private one (SQW_CTX_CONCURRENT_VIEWS)
+	bool own_stream = false;
+	cudaEvent_t done = nullptr; // recorded after every submit: other views that sample this one wait on it
 	void* d_color = nullptr;
 	uint32_t* d_ldr = nullptr; // post-processed picture (64-bit views)
 	DevBuf surfaces;
@@ -148,9 +235,9 @@ struct sqw_view
 	sqw_frame* immediate = nullptr;
 };
 
-struct SurfaceGroup
+struct SurfaceGroup // one kernel launch: all bands without / with dynamic lights
 {
-	SurfaceVariant variant;
+	bool dynamic_lights;
 	uint32_t band_offset, num_bands;
 };
 
@@ -158,13 +245,24 @@ struct sqw_frame
 {
 	sqw_view* view = nullptr;
 	// surfaces
-	DevBuf d_jobs, d_bands, d_lights, d_shadow_maps;
+	Arena surf_arena;
+	const sqw_surface_job* d_jobs = nullptr;
+	const SurfaceBand* d_bands = nullptr;
+	const sqw_light* d_lights = nullptr;
+	const float* d_shadow_maps = nullptr;
 	std::vector<SurfaceBand> h_bands;
 	std::vector<SurfaceGroup> groups;
 	float cam_pos[3] = {0, 0, 0};
 	bool has_surfaces = false;
 	// draw
-	DevBuf d_cmds, d_cmd_dev, d_polygon_points, d_triangle_points, d_cmd_span_base, d_band_offsets;
+	Arena draw_arena;
+	const sqw_draw_cmd* d_cmds = nullptr;
+	const CmdDev* d_cmd_dev = nullptr;
+	const sqw_polygon_point* d_polygon_points = nullptr;
+	const sqw_triangle_point* d_triangle_points = nullptr;
+	const uint32_t* d_cmd_span_base = nullptr;
+	const uint32_t* d_band_offsets = nullptr;
+	std::vector<uint32_t> sampled_views; // views referenced through SQW_TEX_VIEW
 	std::vector<CmdDev> h_cmd_dev;
 	std::vector<uint32_t> h_cmd_span_base, h_band_offsets;
 	uint32_t num_cmds = 0, total_spans = 0, num_bands = 0, total_band_entries = 0;
@@ -187,6 +285,14 @@ int fail(sqw_ctx* ctx, int code, const std::string& msg)
 	else
 		g_create_error = msg;
 	return code;
+}
+cudaError_t synchronize_all(sqw_ctx* ctx)
+{
+	cudaError_t e = cudaStreamSynchronize(ctx->stream);
+	for (sqw_view* v : ctx->views)
+		if (e == cudaSuccess && v && v->stream != ctx->stream)
+			e = cudaStreamSynchronize(v->stream);
+	return e;
 }
 int fail_cuda(sqw_ctx* ctx, cudaError_t e, const char* what)
 {
@@ -213,20 +319,11 @@ size_t image_element_size(int kind)
 
 inline int32_t fixed16_round_to_int_h(int32_t x) { return (int32_t)((uint32_t)x + 0x8000u) >> 16; }
 
-uint32_t variant_key(const SurfaceVariant& v) // bucket index: 24 lit variants + emissive-only
+uint32_t variant_bits(const SurfaceVariant& v) // SurfaceBand::variant
 {
 	if (v.emissive_only)
-		return 24;
-	return (uint32_t)v.directional * 12 + (uint32_t)v.dynamic_lights * 6 + (uint32_t)v.normal_map * 3 + (uint32_t)v.specular;
-}
-
-int upload(sqw_ctx* ctx, DevBuf& buf, const void* src, size_t bytes)
-{
-	if (bytes == 0)
-		return SQW_OK;
-	SQW_CUDA(ctx, buf.reserve(bytes));
-	SQW_CUDA(ctx, cudaMemcpyAsync(buf.ptr, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
-	return SQW_OK;
+		return 16;
+	return (uint32_t)v.directional | ((uint32_t)v.normal_map << 1) | ((uint32_t)v.specular << 2);
 }
 
 } // namespace
@@ -267,6 +364,7 @@ int sqw_create(sqw_ctx** out_ctx, int device, const sqw_map_desc* map, void* ext
 		}
 		ctx->own_stream = true;
 	}
+	ctx->concurrent_views = (map->flags & SQW_CTX_CONCURRENT_VIEWS) != 0;
 	ctx->max_images = map->max_images ? map->max_images : 4096;
 	ctx->num_lightmap_elements = map->num_lightmap_elements;
 	auto bail = [&](cudaError_t err, const char* what) {
@@ -325,6 +423,8 @@ void sqw_destroy(sqw_ctx* ctx)
 	}
 	for (cudaEvent_t e : ctx->event_pool)
 		cudaEventDestroy(e);
+	if (ctx->batch_event)
+		cudaEventDestroy(ctx->batch_event);
 	if (ctx->own_stream && ctx->stream)
 		cudaStreamDestroy(ctx->stream);
 	delete ctx;
@@ -360,6 +460,7 @@ int sqw_update_image(sqw_ctx* ctx, int image_id, const void* pixels)
 	if (!ctx || !pixels || image_id < 0 || (size_t)image_id >= ctx->images.size())
 		return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_update_image: bad argument");
 	SQW_CUDA(ctx, cudaSetDevice(ctx->device));
+	SQW_CUDA(ctx, synchronize_all(ctx)); // frames in flight on any view may still sample the old pixels
 	const ImageHost& img = ctx->images[(size_t)image_id];
 	SQW_CUDA(ctx, cudaMemcpyAsync(img.pixels, pixels, (size_t)img.width * img.height * image_element_size(img.kind), cudaMemcpyHostToDevice, ctx->stream));
 	SQW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -379,7 +480,19 @@ int sqw_view_create(sqw_ctx* ctx, sqw_view** out_view, uint32_t width, uint32_t 
 	v->height = height;
 	v->color_bits = color_bits;
 	const size_t px = (size_t)width * height;
-	cudaError_t e = cudaMalloc(&v->d_color, px * (color_bits / 8));
+	cudaError_t e = cudaSuccess;
+	v->stream = ctx->stream;
+	if (ctx->concurrent_views)
+	{
+		e = cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking);
+		v->own_stream = e == cudaSuccess;
+		if (e != cudaSuccess)
+			v->stream = ctx->stream;
+	}
+	if (e == cudaSuccess)
+		e = cudaEventCreateWithFlags(&v->done, cudaEventDisableTiming);
+	if (e == cudaSuccess)
+		e = cudaMalloc(&v->d_color, px * (color_bits / 8));
 	if (e == cudaSuccess)
 		e = cudaMemset(v->d_color, 0, px * (color_bits / 8));
 	if (e == cudaSuccess && color_bits == 64)
@@ -404,6 +517,7 @@ int sqw_view_create(sqw_ctx* ctx, sqw_view** out_view, uint32_t width, uint32_t 
 		sqw_view_destroy(v);
 		return rc;
 	}
+	cudaDeviceSynchronize(); // the clears above ran on the legacy stream; private streams do not order against it
 	v->index = (uint32_t)ctx->views.size();
 	ctx->views.push_back(v);
 	*out_view = v;
@@ -416,9 +530,14 @@ void sqw_view_destroy(sqw_view* view)
 		return;
 	sqw_ctx* ctx = view->ctx;
 	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(view->stream);
 	cudaStreamSynchronize(ctx->stream);
 	if (view->immediate)
 		sqw_frame_destroy(view->immediate);
+	if (view->done)
+		cudaEventDestroy(view->done);
+	if (view->own_stream)
+		cudaStreamDestroy(view->stream);
 	if (view->d_color)
 		cudaFree(view->d_color);
 	if (view->d_ldr)
@@ -458,11 +577,9 @@ void sqw_frame_destroy(sqw_frame* f)
 		return;
 	sqw_ctx* ctx = f->view->ctx;
 	cudaSetDevice(ctx->device);
-	cudaStreamSynchronize(ctx->stream);
-	DevBuf* bufs[] = {&f->d_jobs, &f->d_bands, &f->d_lights, &f->d_shadow_maps, &f->d_cmds, &f->d_cmd_dev, &f->d_polygon_points, &f->d_triangle_points,
-					  &f->d_cmd_span_base, &f->d_band_offsets};
-	for (DevBuf* b : bufs)
-		b->release();
+	cudaStreamSynchronize(f->view->stream);
+	f->surf_arena.release();
+	f->draw_arena.release();
 	if (f->view->immediate == f)
 		f->view->immediate = nullptr;
 	delete f;
@@ -480,7 +597,8 @@ int sqw_frame_set_surfaces(
 	const size_t C = (size_t)view->color_bits / 8;
 
 	// Validate and group jobs by kernel variant (the reference's const-generic dispatch, surfaces.rs:124-423).
-	std::vector<SurfaceBand> buckets[25];
+	std::vector<SurfaceBand> buckets[2]; // [0] no dynamic lights, [1] dynamic lights
+	uint32_t variants_seen = 0;
 	sqw_frame_stats& st = f->stats;
 	st.surface_texels = st.emissive_texels = st.lightmap_bytes = 0;
 	for (uint32_t i = 0; i < num_jobs; ++i)
@@ -527,47 +645,53 @@ int sqw_frame_set_surfaces(
 				st.lightmap_bytes += lm * (v.directional ? 40 : 12);
 			}
 		}
-		const uint32_t key = variant_key(v);
-		for (uint32_t row0 = 0; row0 < j.surface_size[1]; row0 += SQW_SURF_BAND_ROWS)
-			buckets[key].push_back(SurfaceBand{i, row0});
+		if (texels == 0)
+			continue;
+		const uint32_t vbits = variant_bits(v);
+		variants_seen |= 1u << (vbits + (v.dynamic_lights ? 12 : 0));
+		const uint32_t band_rows = std::min<uint32_t>(std::max<uint32_t>(SQW_SURF_BAND_TEXELS / j.surface_size[0], 1), SQW_SURF_MAX_BAND_ROWS);
+		for (uint32_t row0 = 0; row0 < j.surface_size[1]; row0 += band_rows)
+			buckets[v.dynamic_lights ? 1 : 0].push_back(SurfaceBand{i, row0, std::min(band_rows, j.surface_size[1] - row0), vbits});
 		st.surface_texels += texels;
 		if (emissive)
 			st.emissive_texels += texels;
 	}
 	f->h_bands.clear();
 	f->groups.clear();
-	for (uint32_t key = 0; key < 25; ++key)
+	for (uint32_t key = 0; key < 2; ++key)
 	{
 		if (buckets[key].empty())
 			continue;
+		// heaviest variants first so the tail of the grid is made of cheap bands
+		std::stable_sort(buckets[key].begin(), buckets[key].end(), [](const SurfaceBand& a, const SurfaceBand& b) { return (a.variant & 15u) > (b.variant & 15u); });
 		SurfaceGroup g{};
-		g.variant.color64 = view->color_bits == 64;
-		if (key == 24)
-			g.variant.emissive_only = 1;
-		else
-		{
-			g.variant.directional = (key / 12) & 1;
-			g.variant.dynamic_lights = (key / 6) & 1;
-			g.variant.normal_map = (key / 3) & 1;
-			g.variant.specular = key % 3;
-		}
+		g.dynamic_lights = key == 1;
 		g.band_offset = (uint32_t)f->h_bands.size();
 		g.num_bands = (uint32_t)buckets[key].size();
 		f->h_bands.insert(f->h_bands.end(), buckets[key].begin(), buckets[key].end());
 		f->groups.push_back(g);
 	}
-	st.num_surface_variants = (uint32_t)f->groups.size();
+	st.num_surface_variants = (uint32_t)__builtin_popcount(variants_seen);
 
-	SQW_CUDA(ctx, view->surfaces.reserve((size_t)total_surface_pixels * C + 16));
-	int rc;
-	if ((rc = upload(ctx, f->d_jobs, jobs, (size_t)num_jobs * sizeof(sqw_surface_job))) != SQW_OK)
-		return rc;
-	if ((rc = upload(ctx, f->d_bands, f->h_bands.data(), f->h_bands.size() * sizeof(SurfaceBand))) != SQW_OK)
-		return rc;
-	if ((rc = upload(ctx, f->d_lights, lights, (size_t)num_lights * sizeof(sqw_light))) != SQW_OK)
-		return rc;
-	if ((rc = upload(ctx, f->d_shadow_maps, shadow_maps, (size_t)shadow_maps_len * sizeof(float))) != SQW_OK)
-		return rc;
+	if ((size_t)total_surface_pixels * C + 16 > view->surfaces.capacity)
+	{
+		// growing frees the old pool: nothing queued on this view may still read it
+		SQW_CUDA(ctx, cudaStreamSynchronize(view->stream));
+		SQW_CUDA(ctx, view->surfaces.reserve((size_t)total_surface_pixels * C + 16));
+	}
+	{
+		Arena& a = f->surf_arena;
+		const size_t b_jobs = (size_t)num_jobs * sizeof(sqw_surface_job), b_bands = f->h_bands.size() * sizeof(SurfaceBand);
+		const size_t b_lights = (size_t)num_lights * sizeof(sqw_light), b_sm = (size_t)shadow_maps_len * sizeof(float);
+		if (b_sm && !shadow_maps)
+			return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_frame_set_surfaces: null shadow maps");
+		SQW_CUDA(ctx, a.begin(Arena::padded(b_jobs) + Arena::padded(b_bands) + Arena::padded(b_lights) + Arena::padded(b_sm)));
+		f->d_jobs = static_cast<const sqw_surface_job*>(a.push(jobs, b_jobs));
+		f->d_bands = static_cast<const SurfaceBand*>(a.push(f->h_bands.data(), b_bands));
+		f->d_lights = static_cast<const sqw_light*>(a.push(lights, b_lights));
+		f->d_shadow_maps = static_cast<const float*>(a.push(shadow_maps, b_sm));
+		SQW_CUDA(ctx, a.commit(view->stream));
+	}
 	f->cam_pos[0] = cam_pos[0];
 	f->cam_pos[1] = cam_pos[1];
 	f->cam_pos[2] = cam_pos[2];
@@ -589,6 +713,7 @@ int sqw_frame_set_draw(
 	const uint32_t num_bands = (uint32_t)((H + SQW_TILE_H - 1) / SQW_TILE_H);
 
 	f->h_cmd_dev.resize(num_cmds);
+	f->sampled_views.clear();
 	f->h_cmd_span_base.assign((size_t)num_cmds + 1, 0);
 	f->h_band_offsets.assign((size_t)num_bands + 1, 0);
 	uint64_t span_total = 0;
@@ -645,6 +770,8 @@ int sqw_frame_set_draw(
 					return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_frame_set_draw: view texture must match colour type and size");
 				d.texture = tv->d_color;
 				d.tex_flags = view->color_bits == 64 ? 1 : 0;
+				if (std::find(f->sampled_views.begin(), f->sampled_views.end(), c.tex_ref) == f->sampled_views.end())
+					f->sampled_views.push_back(c.tex_ref);
 			}
 			else
 				return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_frame_set_draw: bad tex_kind");
@@ -703,21 +830,26 @@ int sqw_frame_set_draw(
 	f->stats.num_spans = span_total;
 	f->stats.num_tiles = num_bands * (uint32_t)((W + SQW_TILE_W - 1) / SQW_TILE_W);
 
-	SQW_CUDA(ctx, view->spans.reserve((size_t)span_total * sizeof(SpanRec) + 64));
-	SQW_CUDA(ctx, view->band_lists.reserve((size_t)f->total_band_entries * 4 + 64));
-	int rc;
-	if ((rc = upload(ctx, f->d_cmds, cmds, (size_t)num_cmds * sizeof(sqw_draw_cmd))) != SQW_OK)
-		return rc;
-	if ((rc = upload(ctx, f->d_cmd_dev, f->h_cmd_dev.data(), (size_t)num_cmds * sizeof(CmdDev))) != SQW_OK)
-		return rc;
-	if ((rc = upload(ctx, f->d_polygon_points, polygon_points, (size_t)num_polygon_points * sizeof(sqw_polygon_point))) != SQW_OK)
-		return rc;
-	if ((rc = upload(ctx, f->d_triangle_points, triangle_points, (size_t)num_triangle_points * sizeof(sqw_triangle_point))) != SQW_OK)
-		return rc;
-	if ((rc = upload(ctx, f->d_cmd_span_base, f->h_cmd_span_base.data(), f->h_cmd_span_base.size() * 4)) != SQW_OK)
-		return rc;
-	if ((rc = upload(ctx, f->d_band_offsets, f->h_band_offsets.data(), f->h_band_offsets.size() * 4)) != SQW_OK)
-		return rc;
+	if ((size_t)span_total * sizeof(SpanRec) + 64 > view->spans.capacity || (size_t)f->total_band_entries * 4 + 64 > view->band_lists.capacity)
+	{
+		SQW_CUDA(ctx, cudaStreamSynchronize(view->stream)); // growing frees scratch a queued frame may still use
+		SQW_CUDA(ctx, view->spans.reserve((size_t)span_total * sizeof(SpanRec) + 64));
+		SQW_CUDA(ctx, view->band_lists.reserve((size_t)f->total_band_entries * 4 + 64));
+	}
+	{
+		Arena& a = f->draw_arena;
+		const size_t b_cmds = (size_t)num_cmds * sizeof(sqw_draw_cmd), b_dev = (size_t)num_cmds * sizeof(CmdDev);
+		const size_t b_pp = (size_t)num_polygon_points * sizeof(sqw_polygon_point), b_tp = (size_t)num_triangle_points * sizeof(sqw_triangle_point);
+		const size_t b_base = f->h_cmd_span_base.size() * 4, b_off = f->h_band_offsets.size() * 4;
+		SQW_CUDA(ctx, a.begin(Arena::padded(b_cmds) + Arena::padded(b_dev) + Arena::padded(b_pp) + Arena::padded(b_tp) + Arena::padded(b_base) + Arena::padded(b_off)));
+		f->d_cmds = static_cast<const sqw_draw_cmd*>(a.push(cmds, b_cmds));
+		f->d_cmd_dev = static_cast<const CmdDev*>(a.push(f->h_cmd_dev.data(), b_dev));
+		f->d_polygon_points = static_cast<const sqw_polygon_point*>(a.push(polygon_points, b_pp));
+		f->d_triangle_points = static_cast<const sqw_triangle_point*>(a.push(triangle_points, b_tp));
+		f->d_cmd_span_base = static_cast<const uint32_t*>(a.push(f->h_cmd_span_base.data(), b_base));
+		f->d_band_offsets = static_cast<const uint32_t*>(a.push(f->h_band_offsets.data(), b_off));
+		SQW_CUDA(ctx, a.commit(view->stream));
+	}
 	f->clear = clear_color != nullptr;
 	f->clear_color = 0;
 	if (clear_color)
@@ -762,47 +894,68 @@ int sqw_frame_submit(sqw_frame* f, uint32_t stages)
 	sqw_view* view = f->view;
 	sqw_ctx* ctx = view->ctx;
 	SQW_CUDA(ctx, cudaSetDevice(ctx->device));
-	cudaStream_t s = ctx->stream;
+	cudaStream_t s = view->stream;
 	uint32_t launches = 0;
 
-	if ((stages & SQW_STAGE_SURFACES) && f->has_surfaces)
+	const bool do_surfaces = (stages & SQW_STAGE_SURFACES) && f->has_surfaces;
+	const bool do_raster = (stages & SQW_STAGE_RASTER) && f->has_draw;
+	const bool do_post = (stages & SQW_STAGE_POST) && f->has_post;
+	// Tonemapping without bloom is fused into the tile kernel's epilogue (no second pass over the 64-bit buffer).
+	const bool fused_tonemap = do_raster && do_post && !(f->post.bloom_sigma > 0.0f);
+
+	float inv_scale_bgr[3] = {0, 0, 0};
+	if (do_post)
+	{
+		// TonemappingFunction::new (postprocessor.rs:1005-1017), ColorVec lanes [B, G, R]
+		const sqw_post_params& p = f->post;
+		inv_scale_bgr[0] = 1.0f / (p.exposure * p.color_modulate[2]);
+		inv_scale_bgr[1] = 1.0f / (p.exposure * p.color_modulate[1]);
+		inv_scale_bgr[2] = 1.0f / (p.exposure * p.color_modulate[0]);
+	}
+
+	if (do_surfaces)
 	{
 		SurfaceLaunch l{};
-		l.jobs = static_cast<const sqw_surface_job*>(f->d_jobs.ptr);
+		l.jobs = f->d_jobs;
 		l.images = ctx->d_images;
 		l.lightmaps = ctx->d_lightmaps;
 		l.directional_lightmaps = ctx->d_directional_lightmaps;
-		l.lights = static_cast<const sqw_light*>(f->d_lights.ptr);
-		l.shadow_maps = static_cast<const float*>(f->d_shadow_maps.ptr);
+		l.lights = f->d_lights;
+		l.shadow_maps = f->d_shadow_maps;
 		l.cam_pos[0] = f->cam_pos[0];
 		l.cam_pos[1] = f->cam_pos[1];
 		l.cam_pos[2] = f->cam_pos[2];
 		l.surfaces = view->surfaces.ptr;
 		for (const SurfaceGroup& g : f->groups)
 		{
-			l.bands = static_cast<const SurfaceBand*>(f->d_bands.ptr) + g.band_offset;
+			l.bands = f->d_bands + g.band_offset;
 			l.num_bands = g.num_bands;
 			{
-				LaunchTimer timer(ctx, SQW_KERNEL_SURFACE_BUILD);
-				SQW_CUDA(ctx, launch_surface_build(g.variant, l, s));
+				LaunchTimer timer(ctx, SQW_KERNEL_SURFACE_BUILD, s);
+				SQW_CUDA(ctx, launch_surface_build(view->color_bits == 64, g.dynamic_lights, l, s));
 			}
 			++launches;
 		}
 	}
 
-	if ((stages & SQW_STAGE_RASTER) && f->has_draw)
+	if (do_raster)
 	{
+		// portal / mirror textures: wait for the views this frame samples (they may run on other streams)
+		for (uint32_t vi : f->sampled_views)
+			if (vi < ctx->views.size() && ctx->views[vi] && ctx->views[vi]->stream != s)
+				SQW_CUDA(ctx, cudaStreamWaitEvent(s, ctx->views[vi]->done, 0));
+
 		RasterLaunch l{};
-		l.cmds = static_cast<const sqw_draw_cmd*>(f->d_cmds.ptr);
-		l.cmd_dev = static_cast<const CmdDev*>(f->d_cmd_dev.ptr);
+		l.cmds = f->d_cmds;
+		l.cmd_dev = f->d_cmd_dev;
 		l.num_cmds = f->num_cmds;
-		l.polygon_points = static_cast<const sqw_polygon_point*>(f->d_polygon_points.ptr);
-		l.triangle_points = static_cast<const sqw_triangle_point*>(f->d_triangle_points.ptr);
+		l.polygon_points = f->d_polygon_points;
+		l.triangle_points = f->d_triangle_points;
 		l.spans = static_cast<SpanRec*>(view->spans.ptr);
-		l.cmd_span_base = static_cast<const uint32_t*>(f->d_cmd_span_base.ptr);
+		l.cmd_span_base = f->d_cmd_span_base;
 		l.total_spans = f->total_spans;
 		l.band_lists = static_cast<uint32_t*>(view->band_lists.ptr);
-		l.band_offsets = static_cast<const uint32_t*>(f->d_band_offsets.ptr);
+		l.band_offsets = f->d_band_offsets;
 		l.num_bands = f->num_bands;
 		l.width = (int32_t)view->width;
 		l.height = (int32_t)view->height;
@@ -812,27 +965,33 @@ int sqw_frame_submit(sqw_frame* f, uint32_t stages)
 		l.color64 = view->color_bits == 64;
 		l.clear = f->clear;
 		l.clear_color = f->clear_color;
-		if (f->total_spans)
+		if (fused_tonemap)
 		{
-			LaunchTimer timer(ctx, SQW_KERNEL_RASTER_SETUP);
-			SQW_CUDA(ctx, launch_raster_setup(l, s));
-			++launches;
+			l.tonemap_dst = view->d_ldr;
+			l.inv_scale_bgr[0] = inv_scale_bgr[0];
+			l.inv_scale_bgr[1] = inv_scale_bgr[1];
+			l.inv_scale_bgr[2] = inv_scale_bgr[2];
+			l.color_sums = view->d_sums;
+			l.zero_sums_in_setup = f->num_cmds != 0;
+			if (!l.zero_sums_in_setup)
+				SQW_CUDA(ctx, cudaMemsetAsync(view->d_sums, 0, 3 * sizeof(unsigned long long), s));
+			view->sums_divisor = (uint64_t)view->width * view->height;
 		}
 		if (f->num_cmds)
 		{
-			LaunchTimer timer(ctx, SQW_KERNEL_RASTER_BIN);
-			SQW_CUDA(ctx, launch_raster_bin(l, s));
+			LaunchTimer timer(ctx, SQW_KERNEL_RASTER_SETUP, s);
+			SQW_CUDA(ctx, launch_raster_setup(l, s));
 			++launches;
 		}
-		if (f->num_cmds || f->clear)
+		if (f->num_cmds || f->clear || fused_tonemap)
 		{
-			LaunchTimer timer(ctx, SQW_KERNEL_RASTER_TILE);
+			LaunchTimer timer(ctx, fused_tonemap ? SQW_KERNEL_RASTER_TILE_TONEMAP : SQW_KERNEL_RASTER_TILE, s);
 			SQW_CUDA(ctx, launch_raster_tiles(l, s));
 			++launches;
 		}
 	}
 
-	if ((stages & SQW_STAGE_POST) && f->has_post)
+	if (do_post && !fused_tonemap)
 	{
 		const sqw_post_params& p = f->post;
 		PostLaunch l{};
@@ -840,10 +999,9 @@ int sqw_frame_submit(sqw_frame* f, uint32_t stages)
 		l.width = view->width;
 		l.height = view->height;
 		l.dst = view->d_ldr;
-		// TonemappingFunction::new (postprocessor.rs:1005-1017), ColorVec lanes [B, G, R]
-		l.inv_scale_bgr[0] = 1.0f / (p.exposure * p.color_modulate[2]);
-		l.inv_scale_bgr[1] = 1.0f / (p.exposure * p.color_modulate[1]);
-		l.inv_scale_bgr[2] = 1.0f / (p.exposure * p.color_modulate[0]);
+		l.inv_scale_bgr[0] = inv_scale_bgr[0];
+		l.inv_scale_bgr[1] = inv_scale_bgr[1];
+		l.inv_scale_bgr[2] = inv_scale_bgr[2];
 		l.color_sums = view->d_sums;
 		SQW_CUDA(ctx, cudaMemsetAsync(view->d_sums, 0, 3 * sizeof(unsigned long long), s));
 		if (p.bloom_sigma > 0.0f)
@@ -870,18 +1028,18 @@ int sqw_frame_submit(sqw_frame* f, uint32_t stages)
 			}
 			l.blur_radius = radius;
 			{
-				LaunchTimer timer(ctx, SQW_KERNEL_BLOOM_DOWNSCALE);
+				LaunchTimer timer(ctx, SQW_KERNEL_BLOOM_DOWNSCALE, s);
 				SQW_CUDA(ctx, launch_bloom_downscale(l, s));
 			}
 			++launches;
 			if (radius > 0)
 			{
-				LaunchTimer timer(ctx, SQW_KERNEL_BLOOM_BLUR);
+				LaunchTimer timer(ctx, SQW_KERNEL_BLOOM_BLUR, s);
 				SQW_CUDA(ctx, launch_bloom_blur(l, s));
 				launches += 2;
 			}
 			{
-				LaunchTimer timer(ctx, SQW_KERNEL_TONEMAP_BLOOM);
+				LaunchTimer timer(ctx, SQW_KERNEL_TONEMAP_BLOOM, s);
 				SQW_CUDA(ctx, launch_tonemap_bloom(l, s));
 			}
 			++launches;
@@ -890,14 +1048,52 @@ int sqw_frame_submit(sqw_frame* f, uint32_t stages)
 		else
 		{
 			{
-				LaunchTimer timer(ctx, SQW_KERNEL_TONEMAP);
+				LaunchTimer timer(ctx, SQW_KERNEL_TONEMAP, s);
 				SQW_CUDA(ctx, launch_tonemap(l, s));
 			}
 			++launches;
 			view->sums_divisor = (uint64_t)view->width * view->height;
 		}
 	}
+	if (ctx->concurrent_views)
+		SQW_CUDA(ctx, cudaEventRecord(view->done, s));
 	f->stats.num_kernel_launches = launches;
+	return SQW_OK;
+}
+
+// Fork / join between the context's stream and the private streams of its views (SQW_CTX_CONCURRENT_VIEWS): work
+// submitted between the two calls starts after everything queued on the context's stream before sqw_batch_begin, and
+// everything queued on the context's stream after sqw_batch_end starts after that work.  This is how a caller that
+// owns the context's stream (events, other libraries) brackets a batch of independent views.
+int sqw_batch_begin(sqw_ctx* ctx)
+{
+	if (!ctx)
+		return SQW_ERR_INVALID_ARGUMENT;
+	SQW_CUDA(ctx, cudaSetDevice(ctx->device));
+	if (!ctx->concurrent_views)
+		return SQW_OK;
+	if (!ctx->batch_event)
+		SQW_CUDA(ctx, cudaEventCreateWithFlags(&ctx->batch_event, cudaEventDisableTiming));
+	SQW_CUDA(ctx, cudaEventRecord(ctx->batch_event, ctx->stream));
+	for (sqw_view* v : ctx->views)
+		if (v && v->stream != ctx->stream)
+			SQW_CUDA(ctx, cudaStreamWaitEvent(v->stream, ctx->batch_event, 0));
+	return SQW_OK;
+}
+
+int sqw_batch_end(sqw_ctx* ctx)
+{
+	if (!ctx)
+		return SQW_ERR_INVALID_ARGUMENT;
+	SQW_CUDA(ctx, cudaSetDevice(ctx->device));
+	if (!ctx->concurrent_views)
+		return SQW_OK;
+	for (sqw_view* v : ctx->views)
+		if (v && v->stream != ctx->stream)
+		{
+			SQW_CUDA(ctx, cudaEventRecord(v->done, v->stream));
+			SQW_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, v->done, 0));
+		}
 	return SQW_OK;
 }
 
@@ -906,7 +1102,7 @@ int sqw_profile_begin(sqw_ctx* ctx)
 	if (!ctx)
 		return SQW_ERR_INVALID_ARGUMENT;
 	SQW_CUDA(ctx, cudaSetDevice(ctx->device));
-	SQW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	SQW_CUDA(ctx, synchronize_all(ctx));
 	for (auto& t : ctx->timed)
 	{
 		ctx->event_pool.push_back(t.start);
@@ -923,7 +1119,7 @@ int sqw_profile_end(sqw_ctx* ctx, sqw_kernel_times* out)
 		return SQW_ERR_INVALID_ARGUMENT;
 	SQW_CUDA(ctx, cudaSetDevice(ctx->device));
 	ctx->profiling = false;
-	SQW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	SQW_CUDA(ctx, synchronize_all(ctx));
 	std::memset(out, 0, sizeof(*out));
 	for (auto& t : ctx->timed)
 	{
@@ -997,8 +1193,8 @@ int sqw_view_get_average_color(sqw_view* view, float avg_color_out[3])
 	sqw_ctx* ctx = view->ctx;
 	SQW_CUDA(ctx, cudaSetDevice(ctx->device));
 	unsigned long long sums[3];
-	SQW_CUDA(ctx, cudaMemcpyAsync(sums, view->d_sums, sizeof(sums), cudaMemcpyDeviceToHost, ctx->stream));
-	SQW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	SQW_CUDA(ctx, cudaMemcpyAsync(sums, view->d_sums, sizeof(sums), cudaMemcpyDeviceToHost, view->stream));
+	SQW_CUDA(ctx, cudaStreamSynchronize(view->stream));
 	const float inv = 1.0f / (float)view->sums_divisor; // postprocessor.rs:176-179 / :840-843
 	for (int i = 0; i < 3; ++i)
 		avg_color_out[i] = (float)sums[i] * inv;
@@ -1036,8 +1232,8 @@ int sqw_read_pixels(sqw_view* view, void* dst, size_t dst_pitch)
 	sqw_ctx* ctx = view->ctx;
 	SQW_CUDA(ctx, cudaSetDevice(ctx->device));
 	const size_t C = (size_t)view->color_bits / 8;
-	SQW_CUDA(ctx, cudaMemcpy2DAsync(dst, dst_pitch * C, view->d_color, (size_t)view->width * C, (size_t)view->width * C, view->height, cudaMemcpyDeviceToHost, ctx->stream));
-	SQW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	SQW_CUDA(ctx, cudaMemcpy2DAsync(dst, dst_pitch * C, view->d_color, (size_t)view->width * C, (size_t)view->width * C, view->height, cudaMemcpyDeviceToHost, view->stream));
+	SQW_CUDA(ctx, cudaStreamSynchronize(view->stream));
 	return SQW_OK;
 }
 
@@ -1048,8 +1244,8 @@ int sqw_write_pixels(sqw_view* view, const void* src, size_t src_pitch)
 	sqw_ctx* ctx = view->ctx;
 	SQW_CUDA(ctx, cudaSetDevice(ctx->device));
 	const size_t C = (size_t)view->color_bits / 8;
-	SQW_CUDA(ctx, cudaMemcpy2DAsync(view->d_color, (size_t)view->width * C, src, src_pitch * C, (size_t)view->width * C, view->height, cudaMemcpyHostToDevice, ctx->stream));
-	SQW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	SQW_CUDA(ctx, cudaMemcpy2DAsync(view->d_color, (size_t)view->width * C, src, src_pitch * C, (size_t)view->width * C, view->height, cudaMemcpyHostToDevice, view->stream));
+	SQW_CUDA(ctx, cudaStreamSynchronize(view->stream));
 	return SQW_OK;
 }
 
@@ -1059,8 +1255,29 @@ int sqw_read_pixels32(sqw_view* view, uint32_t* dst, size_t dst_pitch)
 		return fail(view ? view->ctx : nullptr, SQW_ERR_INVALID_ARGUMENT, "sqw_read_pixels32: bad argument");
 	sqw_ctx* ctx = view->ctx;
 	SQW_CUDA(ctx, cudaSetDevice(ctx->device));
-	SQW_CUDA(ctx, cudaMemcpy2DAsync(dst, dst_pitch * 4, view->d_ldr, (size_t)view->width * 4, (size_t)view->width * 4, view->height, cudaMemcpyDeviceToHost, ctx->stream));
-	SQW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	SQW_CUDA(ctx, cudaMemcpy2DAsync(dst, dst_pitch * 4, view->d_ldr, (size_t)view->width * 4, (size_t)view->width * 4, view->height, cudaMemcpyDeviceToHost, view->stream));
+	SQW_CUDA(ctx, cudaStreamSynchronize(view->stream));
+	return SQW_OK;
+}
+
+int sqw_read_pixels32_async(sqw_view* view, uint32_t* dst, size_t dst_pitch)
+{
+	if (!view || !dst || dst_pitch < view->width || view->color_bits != 64)
+		return fail(view ? view->ctx : nullptr, SQW_ERR_INVALID_ARGUMENT, "sqw_read_pixels32_async: bad argument");
+	sqw_ctx* ctx = view->ctx;
+	SQW_CUDA(ctx, cudaSetDevice(ctx->device));
+	SQW_CUDA(ctx, cudaMemcpy2DAsync(dst, dst_pitch * 4, view->d_ldr, (size_t)view->width * 4, (size_t)view->width * 4, view->height, cudaMemcpyDeviceToHost, view->stream));
+	return SQW_OK;
+}
+
+int sqw_read_pixels_async(sqw_view* view, void* dst, size_t dst_pitch)
+{
+	if (!view || !dst || dst_pitch < view->width)
+		return fail(view ? view->ctx : nullptr, SQW_ERR_INVALID_ARGUMENT, "sqw_read_pixels_async: bad argument");
+	sqw_ctx* ctx = view->ctx;
+	SQW_CUDA(ctx, cudaSetDevice(ctx->device));
+	const size_t C = (size_t)view->color_bits / 8;
+	SQW_CUDA(ctx, cudaMemcpy2DAsync(dst, dst_pitch * C, view->d_color, (size_t)view->width * C, (size_t)view->width * C, view->height, cudaMemcpyDeviceToHost, view->stream));
 	return SQW_OK;
 }
 
@@ -1073,8 +1290,8 @@ int sqw_read_surfaces(sqw_view* view, void* dst, uint64_t offset, uint64_t count
 	if ((offset + count) * C > view->surfaces.capacity)
 		return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_read_surfaces: range outside the pool");
 	SQW_CUDA(ctx, cudaSetDevice(ctx->device));
-	SQW_CUDA(ctx, cudaMemcpyAsync(dst, static_cast<const char*>(view->surfaces.ptr) + offset * C, count * C, cudaMemcpyDeviceToHost, ctx->stream));
-	SQW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	SQW_CUDA(ctx, cudaMemcpyAsync(dst, static_cast<const char*>(view->surfaces.ptr) + offset * C, count * C, cudaMemcpyDeviceToHost, view->stream));
+	SQW_CUDA(ctx, cudaStreamSynchronize(view->stream));
 	return SQW_OK;
 }
 
@@ -1083,7 +1300,7 @@ int sqw_view_synchronize(sqw_view* view)
 	if (!view)
 		return SQW_ERR_INVALID_ARGUMENT;
 	SQW_CUDA(view->ctx, cudaSetDevice(view->ctx->device));
-	SQW_CUDA(view->ctx, cudaStreamSynchronize(view->ctx->stream));
+	SQW_CUDA(view->ctx, cudaStreamSynchronize(view->stream));
 	return SQW_OK;
 }
 

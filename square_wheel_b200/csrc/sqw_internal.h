@@ -15,13 +15,17 @@ struct ImageDev
 };
 
 // ---- stage 1 ------------------------------------------------------------------------------------------------
-// One CTA of surface_build_kernel processes one band: SURF_BAND_ROWS rows of one job.
-#define SQW_SURF_BAND_ROWS 16
+// One CTA of surface_build_kernel processes one band: up to SQW_SURF_MAX_BAND_ROWS consecutive rows of one job holding
+// about SQW_SURF_BAND_TEXELS texels.
+#define SQW_SURF_MAX_BAND_ROWS 32
+#define SQW_SURF_BAND_TEXELS 1024
 #define SQW_SURF_THREADS 256
 struct SurfaceBand
 {
 	uint32_t job;
 	uint32_t row0;
+	uint32_t num_rows; // 1..SQW_SURF_MAX_BAND_ROWS, never past the last row of the surface
+	uint32_t variant;  // bit0 directional lightmap, bit1 normal map, bits2-3 specular type, 16 = emissive-only
 };
 
 // Surface kernel variant = (colour width, directional lightmap, dynamic lights, normal map, specular type);
@@ -49,11 +53,13 @@ struct SurfaceLaunch
 	float cam_pos[3];
 	void* surfaces;                // device pool base
 };
-cudaError_t launch_surface_build(const SurfaceVariant& v, const SurfaceLaunch& l, cudaStream_t stream);
+// One grid for all bands of the launch; `dynamic_lights` selects the kernel built with the dynamic-light loop.
+cudaError_t launch_surface_build(bool color64, bool dynamic_lights, const SurfaceLaunch& l, cudaStream_t stream);
 
 // ---- stage 2 ------------------------------------------------------------------------------------------------
 #define SQW_TILE_W 128
 #define SQW_TILE_H 8
+#define SQW_SETUP_THREADS 128
 #define SQW_RASTER_THREADS 256 /* 8 warps: each warp owns one row of the tile, each lane 4 consecutive pixels */
 
 // Per-command data prepared by the host part of sqw_frame_set_draw (row range, conservative column range,
@@ -101,9 +107,14 @@ struct RasterLaunch
 	int color64;
 	int clear;
 	uint64_t clear_color;
+	// fused tonemapping epilogue (64-bit views, post stage without bloom): 32-bit picture, Reinhard scales, colour sums
+	uint32_t* tonemap_dst; // nullptr = not fused
+	float inv_scale_bgr[3];
+	unsigned long long* color_sums;
+	int zero_sums_in_setup; // the set-up kernel clears color_sums (saves a memset node per frame)
 };
+// span set-up + binning in one grid
 cudaError_t launch_raster_setup(const RasterLaunch& l, cudaStream_t stream);
-cudaError_t launch_raster_bin(const RasterLaunch& l, cudaStream_t stream);
 cudaError_t launch_raster_tiles(const RasterLaunch& l, cudaStream_t stream);
 
 // ---- stage 3 ------------------------------------------------------------------------------------------------

@@ -5,15 +5,19 @@
 // (partial_renderer.rs:1682-1819).
 //
 // Mapping to the GPU
-//   * one CTA (256 threads = 8 warps) builds one BAND = 16 consecutive rows of one surface job; a warp owns rows
-//     band_row0 + warp, + warp + 8; lanes stride over the texels of the row, so global stores of a warp are one
-//     contiguous 128 B (Color32) / 256 B (Color64) segment and texture loads are contiguous 256 B segments
-//     (8 B TextureElement per lane) that wrap at the texture border exactly like the reference's src_u counter.
-//   * the reference's per-row `line_lightmap` scratch (:477-502) lives in shared memory, one row per warp:
-//     lanes 0..18 interpolate the two lightmap rows, __syncwarp, then every lane interpolates along u.
+//   * one CTA (256 threads) builds one BAND = up to 32 consecutive rows of one surface job holding about
+//     SQW_SURF_BAND_TEXELS texels, so narrow (high-mip) and wide surfaces give every thread the same amount of work.
+//     The band's texels are numbered row-major and strided over the CTA: consecutive lanes take consecutive texels of a
+//     row, so global stores are contiguous 128 B (Color32) / 256 B (Color64) segments and texture loads are contiguous
+//     8 B-per-lane segments that wrap at the texture border exactly like the reference's src_u counter.
+//   * the reference's per-row `line_lightmap` scratch (:477-502) lives in shared memory, one line per band row; the
+//     CTA first interpolates the two lightmap rows of every band row cooperatively, then every thread interpolates
+//     along u for its texels.
 //   * the six const-generic parameters of the reference become template parameters (colour width, lightmap kind,
 //     dynamic lights, normal map, specular type); the lightmap scale stays a runtime value (it only feeds shifts).
-//     The host groups bands by variant and launches one grid per variant present in the frame.
+//     Every band carries its variant and ONE grid per frame (two when some polygons have dynamic lights: those
+//     variants need twice the registers) dispatches on it per CTA, so a frame's few hundred surfaces do not pay
+//     one launch latency per variant.
 //   * bound: HBM for the plain variants (8 B texel in, C bytes out), FP32/divide for specular + dynamic lights.
 //
 // Compiled with -fmad=false: the portable reference never fuses (fast_math.rs:737), and every 1/x, 1/sqrt is the
@@ -27,7 +31,6 @@ namespace
 {
 
 constexpr int MAX_LINE_LIGHTMAP = 19; // lightmap::MAX_LIGHTMAP_SIZE + 2 (surfaces.rs:466)
-constexpr int WARPS = SQW_SURF_THREADS / 32;
 
 constexpr float DIELECTRIC_ZERO_REFLECTIVITY = 0.04f;                                   // surfaces.rs:1152
 constexpr float DIELECTRIC_AVERAGE_REFLECTIVITY = DIELECTRIC_ZERO_REFLECTIVITY * 3.0f; // :1153
@@ -133,65 +136,68 @@ __device__ __forceinline__ typename C::Raw emissive_mix(uint32_t texel, ColorVec
 	return C::from_veci(m);
 }
 
+// rem_euclid (surfaces.rs:507-510) with the power-of-two shortcut (two's complement & mask == rem_euclid).
+__device__ __forceinline__ uint32_t wrap_coord(int32_t x, int32_t size, uint32_t pow2_mask)
+{
+	if (pow2_mask)
+		return (uint32_t)x & pow2_mask;
+	const int32_t m = x % size;
+	return (uint32_t)(m < 0 ? m + size : m);
+}
+__device__ __forceinline__ uint32_t pow2_mask_of(uint32_t size) { return (size & (size - 1)) == 0 ? size - 1 : 0; }
+
+typedef LmEl LineLightmap[MAX_LINE_LIGHTMAP + 1];
+
+// One band of one job: build_surface_impl_6_static_params (+ the emissive pass) for rows [band.row0, band.row0 + band.num_rows).
 template <class C, bool DIRECTIONAL, bool USE_DYNAMIC_LIGHTS, bool USE_NORMAL_MAP, int SPECULAR_TYPE, bool EMISSIVE_ONLY>
-__global__ void __launch_bounds__(SQW_SURF_THREADS) surface_build_kernel(
-	const sqw_surface_job* __restrict__ jobs, const SurfaceBand* __restrict__ bands, const ImageDev* __restrict__ images,
-	const float* __restrict__ lightmaps, const sqw_directional_lightmap_element* __restrict__ directional_lightmaps,
-	const sqw_light* __restrict__ lights, const float* __restrict__ shadow_maps, float cam_x, float cam_y, float cam_z,
-	typename C::Raw* __restrict__ surfaces)
+__device__ __forceinline__ void surface_band(
+	const sqw_surface_job& j, const SurfaceBand band, LineLightmap* line_lightmap, const ImageDev* __restrict__ images, const float* __restrict__ lightmaps,
+	const sqw_directional_lightmap_element* __restrict__ directional_lightmaps, const sqw_light* __restrict__ lights, const float* __restrict__ shadow_maps,
+	float cam_x, float cam_y, float cam_z, typename C::Raw* __restrict__ surfaces)
 {
 	typedef typename C::Raw Raw;
-	__shared__ LmEl s_line_lightmap[WARPS][MAX_LINE_LIGHTMAP + 1];
-	__shared__ sqw_surface_job s_job;
-
-	const SurfaceBand band = bands[blockIdx.x];
-	{
-		// Cooperative 136-byte job load into shared memory (34 words).
-		const uint32_t* src = reinterpret_cast<const uint32_t*>(jobs + band.job);
-		uint32_t* dst = reinterpret_cast<uint32_t*>(&s_job);
-		if (threadIdx.x < sizeof(sqw_surface_job) / 4)
-			dst[threadIdx.x] = src[threadIdx.x];
-	}
-	__syncthreads();
-	const sqw_surface_job& j = s_job;
-
-	const int warp = threadIdx.x >> 5;
-	const int lane = threadIdx.x & 31;
+	const uint32_t tid = threadIdx.x;
 	const uint32_t size_u = j.surface_size[0];
-	const uint32_t size_v = j.surface_size[1];
+	const uint32_t num_rows = band.num_rows;
+	const uint32_t total = num_rows * size_u;
 	Raw* const out = surfaces + j.surface_pixels_offset;
+	// (row, u) of this thread's first texel and its advance per stride of SQW_SURF_THREADS texels
+	const uint32_t step_rows = SQW_SURF_THREADS / size_u, step_u = SQW_SURF_THREADS % size_u;
+	uint32_t r = tid / size_u, dst_u = tid % size_u;
 
 	// Emissive layer (partial_renderer.rs:1801-1819): Additive over the diffuse layer, None when there is none.
 	const bool emissive = (j.flags & SQW_SURF_EMISSIVE) != 0;
 	ColorVecI emissive_light_vec = cvi(0, 0, 0, 0);
 	const uint32_t* emissive_pixels = nullptr;
-	uint32_t em_w = 1, em_h = 1;
+	uint32_t em_w = 1, em_h = 1, em_w_mask = 0, em_h_mask = 0;
+	int32_t em_u0 = 0;
 	if (emissive)
 	{
 		const ImageDev eimg = images[j.emissive_image];
 		emissive_pixels = static_cast<const uint32_t*>(eimg.pixels);
 		em_w = eimg.width;
 		em_h = eimg.height;
+		em_w_mask = pow2_mask_of(em_w);
+		em_h_mask = pow2_mask_of(em_h);
+		em_u0 = (int32_t)wrap_coord(j.tc_start[0], (int32_t)em_w, em_w_mask);
 		// surfaces.rs:911-914  light * 256 -> ColorVecI (`as i32`), lanes [B, G, R, 0]
 		emissive_light_vec = cvi(f32_as_i32(j.emissive_light[2] * 256.0f), f32_as_i32(j.emissive_light[1] * 256.0f), f32_as_i32(j.emissive_light[0] * 256.0f), 0);
 	}
 
 	if (EMISSIVE_ONLY)
 	{
-		for (uint32_t dst_v = band.row0 + warp; dst_v < min(band.row0 + SQW_SURF_BAND_ROWS, size_v); dst_v += WARPS)
+		for (uint32_t i = tid; i < total; i += SQW_SURF_THREADS)
 		{
-			int32_t src_v = (j.tc_start[1] + (int32_t)dst_v) % (int32_t)em_h;
-			if (src_v < 0)
-				src_v += (int32_t)em_h;
-			int32_t src_u0 = j.tc_start[0] % (int32_t)em_w;
-			if (src_u0 < 0)
-				src_u0 += (int32_t)em_w;
-			const uint32_t* src_line = emissive_pixels + (size_t)src_v * em_w;
-			Raw* dst_line = out + (size_t)dst_v * size_u;
-			for (uint32_t dst_u = lane; dst_u < size_u; dst_u += 32)
+			const uint32_t dst_v = band.row0 + r;
+			const uint32_t ev = wrap_coord(j.tc_start[1] + (int32_t)dst_v, (int32_t)em_h, em_h_mask);
+			const uint32_t eu = wrap_coord(em_u0 + (int32_t)dst_u, (int32_t)em_w, em_w_mask);
+			out[(size_t)dst_v * size_u + dst_u] = emissive_mix<C>(__ldg(emissive_pixels + (size_t)ev * em_w + eu), emissive_light_vec, false, 0);
+			r += step_rows;
+			dst_u += step_u;
+			if (dst_u >= size_u)
 			{
-				const uint32_t su = ((uint32_t)src_u0 + dst_u) % em_w;
-				dst_line[dst_u] = emissive_mix<C>(__ldg(src_line + su), emissive_light_vec, false, 0);
+				dst_u -= size_u;
+				++r;
 			}
 		}
 		return;
@@ -200,6 +206,7 @@ __global__ void __launch_bounds__(SQW_SURF_THREADS) surface_build_kernel(
 	const ImageDev timg = images[j.texture_image];
 	const uint2* const texture = static_cast<const uint2*>(timg.pixels);
 	const int32_t tex_w = (int32_t)timg.width, tex_h = (int32_t)timg.height;
+	const uint32_t tex_w_mask = pow2_mask_of(timg.width), tex_h_mask = pow2_mask_of(timg.height);
 
 	const Vec3 u_vec = v3(j.basis_u[0], j.basis_u[1], j.basis_u[2]);
 	const Vec3 v_vec = v3(j.basis_v[0], j.basis_v[1], j.basis_v[2]);
@@ -219,290 +226,302 @@ __global__ void __launch_bounds__(SQW_SURF_THREADS) surface_build_kernel(
 	const uint32_t lightmap_fetch_mask = (1u << (lm_scale_log2 & 31)) - 1;
 	const uint32_t lm_w = j.lightmap_size[0];
 
-	int32_t src_u0 = j.tc_start[0] % tex_w; // rem_euclid (:510)
-	if (src_u0 < 0)
-		src_u0 += tex_w;
-	int32_t em_u0 = 0;
-	if (emissive)
-	{
-		em_u0 = j.tc_start[0] % (int32_t)em_w;
-		if (em_u0 < 0)
-			em_u0 += (int32_t)em_w;
-	}
+	const int32_t src_u0 = (int32_t)wrap_coord(j.tc_start[0], tex_w, tex_w_mask); // rem_euclid (:510)
 
-	LmEl* const line_lightmap = s_line_lightmap[warp];
-
-	for (uint32_t dst_v = band.row0 + warp; dst_v < min(band.row0 + SQW_SURF_BAND_ROWS, size_v); dst_v += WARPS)
+	if (has_lightmap)
 	{
-		if (has_lightmap)
+		// :477-502 interpolate two lightmap rows into the line lightmap of every row of the band.
+		const uint32_t lm_cols = min(lm_w, (uint32_t)MAX_LINE_LIGHTMAP);
+		const uint32_t entries = num_rows * lm_cols;
+		for (uint32_t e = tid; e < entries; e += SQW_SURF_THREADS)
 		{
-			// :477-502 interpolate two lightmap rows into line_lightmap.
-			const uint32_t lightmap_base_v = dst_v + j.lightmap_tc_shift[1];
+			const uint32_t rr = e / lm_cols, x = e - rr * lm_cols;
+			const uint32_t lightmap_base_v = band.row0 + rr + j.lightmap_tc_shift[1];
 			const uint32_t lightmap_v = lightmap_base_v >> lm_scale_log2;
 			const float k = f32_mul_add((float)(lightmap_base_v & lightmap_fetch_mask), inv_lightmap_scale_f, k_shift);
 			const float omk = 1.0f - k;
 			const uint32_t base = lightmap_v * lm_w;
-			__syncwarp();
-			if (lane < min(lm_w, (uint32_t)MAX_LINE_LIGHTMAP))
+			float* d = reinterpret_cast<float*>(&line_lightmap[rr][x]);
+			if (DIRECTIONAL)
 			{
-				if (DIRECTIONAL)
-				{
-					const float* l0 = reinterpret_cast<const float*>(directional_lightmaps + (size_t)j.lightmap_offset + base + lane);
-					const float* l1 = l0 + (size_t)lm_w * 10;
-					float* d = reinterpret_cast<float*>(&line_lightmap[lane]);
+				const float* l0 = reinterpret_cast<const float*>(directional_lightmaps + (size_t)j.lightmap_offset + base + x);
+				const float* l1 = l0 + (size_t)lm_w * 10;
 #pragma unroll
-					for (int c = 0; c < 10; ++c)
-						d[c] = lm_mix(__ldg(l1 + c), __ldg(l0 + c), k, omk);
-				}
-				else
-				{
-					const float* l0 = lightmaps + ((size_t)j.lightmap_offset + base + lane) * 3;
-					const float* l1 = l0 + (size_t)lm_w * 3;
-					float* d = reinterpret_cast<float*>(&line_lightmap[lane]);
-#pragma unroll
-					for (int c = 0; c < 3; ++c)
-						d[c] = lm_mix(__ldg(l1 + c), __ldg(l0 + c), k, omk);
-				}
+				for (int c = 0; c < 10; ++c)
+					d[c] = lm_mix(__ldg(l1 + c), __ldg(l0 + c), k, omk);
 			}
-			__syncwarp();
-		}
-
-		Raw* const dst_line = out + (size_t)dst_v * size_u;
-		int32_t src_v = (j.tc_start[1] + (int32_t)dst_v) % tex_h; // :507
-		if (src_v < 0)
-			src_v += tex_h;
-		const uint2* const src_line = texture + (size_t)src_v * tex_w;
-		const uint32_t* em_line = nullptr;
-		if (emissive)
-		{
-			int32_t ev = (j.tc_start[1] + (int32_t)dst_v) % (int32_t)em_h;
-			if (ev < 0)
-				ev += (int32_t)em_h;
-			em_line = emissive_pixels + (size_t)ev * em_w;
-		}
-		const Vec3 start_pos_v = vec3_scalar_mul_add(v_vec, (float)dst_v, start_pos); // :512
-
-		for (uint32_t dst_u = lane; dst_u < size_u; dst_u += 32)
-		{
-			const Vec3 pos = vec3_scalar_mul_add(u_vec, (float)dst_u, start_pos_v); // :515
-
-			const uint32_t su = ((uint32_t)src_u0 + dst_u) % (uint32_t)tex_w; // the reference's wrapping src_u counter (:843-847)
-			const uint2 texel_value = __ldg(src_line + su);
-			const uint32_t diffuse = texel_value.x;
-			const int32_t packed = (int32_t)texel_value.y;
-
-			Vec3 texel_normal = v3(0.0f, 0.0f, 1.0f);
-			float texel_roughness = 0.0f;
-			if (USE_NORMAL_MAP)
+			else
 			{
-				// PackedNormalRoughness::unpack (textures.rs:42-58)
-				texel_normal.x = (float)((int32_t)((uint32_t)packed << 24) >> 24) * NORMAL_UNPACK_SCALE;
-				texel_normal.y = (float)((int32_t)((uint32_t)packed << 16) >> 24) * NORMAL_UNPACK_SCALE;
-				texel_normal.z = (float)((int32_t)((uint32_t)packed << 8) >> 24) * NORMAL_UNPACK_SCALE;
-				texel_roughness = (float)(packed >> 24) * NORMAL_UNPACK_SCALE;
-			}
-			else if (SPECULAR_TYPE != 0)
-				texel_roughness = (float)(packed >> 24) * NORMAL_UNPACK_SCALE; // unpack_roughness (textures.rs:60)
-
-			ColorVec total_light_albedo_modulated = cv(0.0f, 0.0f, 0.0f, 0.0f);
-			ColorVec total_light_direct = cv(0.0f, 0.0f, 0.0f, 0.0f);
-
-			if (has_lightmap)
-			{
-				const uint32_t lightmap_base_u = dst_u + j.lightmap_tc_shift[0];
-				const uint32_t lightmap_u = lightmap_base_u >> lm_scale_log2;
-				const float k = f32_mul_add((float)(lightmap_base_u & lightmap_fetch_mask), inv_lightmap_scale_f, k_shift);
-				const float omk = 1.0f - k;
-				const LmEl& l0 = line_lightmap[lightmap_u];
-				const LmEl& l1 = line_lightmap[lightmap_u + 1];
-				float constant_c[3];
+				const float* l0 = lightmaps + ((size_t)j.lightmap_offset + base + x) * 3;
+				const float* l1 = l0 + (size_t)lm_w * 3;
 #pragma unroll
 				for (int c = 0; c < 3; ++c)
-					constant_c[c] = lm_mix(l1.ambient[c], l0.ambient[c], k, omk);
-				Vec3 vs = v3(0.0f, 0.0f, 0.0f);
-				float deviation = 0.0f;
-				float dir_color_c[3] = {0.0f, 0.0f, 0.0f};
+					d[c] = lm_mix(__ldg(l1 + c), __ldg(l0 + c), k, omk);
+			}
+		}
+	}
+	__syncthreads();
+
+	for (uint32_t i = tid; i < total; i += SQW_SURF_THREADS)
+	{
+		const uint32_t dst_v = band.row0 + r;
+		const uint32_t src_v = wrap_coord(j.tc_start[1] + (int32_t)dst_v, tex_h, tex_h_mask); // :507
+		const Vec3 start_pos_v = vec3_scalar_mul_add(v_vec, (float)dst_v, start_pos);          // :512
+		const Vec3 pos = vec3_scalar_mul_add(u_vec, (float)dst_u, start_pos_v);                // :515
+		const uint32_t su = wrap_coord(src_u0 + (int32_t)dst_u, tex_w, tex_w_mask); // the reference's wrapping src_u counter (:843-847)
+		const uint32_t* em_line = nullptr;
+		if (emissive)
+			em_line = emissive_pixels + (size_t)wrap_coord(j.tc_start[1] + (int32_t)dst_v, (int32_t)em_h, em_h_mask) * em_w;
+		const uint2* const src_line = texture + (size_t)src_v * tex_w;
+		const uint2 texel_value = __ldg(src_line + su);
+		const uint32_t diffuse = texel_value.x;
+		const int32_t packed = (int32_t)texel_value.y;
+
+		Vec3 texel_normal = v3(0.0f, 0.0f, 1.0f);
+		float texel_roughness = 0.0f;
+		if (USE_NORMAL_MAP)
+		{
+			// PackedNormalRoughness::unpack (textures.rs:42-58)
+			texel_normal.x = (float)((int32_t)((uint32_t)packed << 24) >> 24) * NORMAL_UNPACK_SCALE;
+			texel_normal.y = (float)((int32_t)((uint32_t)packed << 16) >> 24) * NORMAL_UNPACK_SCALE;
+			texel_normal.z = (float)((int32_t)((uint32_t)packed << 8) >> 24) * NORMAL_UNPACK_SCALE;
+			texel_roughness = (float)(packed >> 24) * NORMAL_UNPACK_SCALE;
+		}
+		else if (SPECULAR_TYPE != 0)
+			texel_roughness = (float)(packed >> 24) * NORMAL_UNPACK_SCALE; // unpack_roughness (textures.rs:60)
+
+		ColorVec total_light_albedo_modulated = cv(0.0f, 0.0f, 0.0f, 0.0f);
+		ColorVec total_light_direct = cv(0.0f, 0.0f, 0.0f, 0.0f);
+
+		if (has_lightmap)
+		{
+			const uint32_t lightmap_base_u = dst_u + j.lightmap_tc_shift[0];
+			const uint32_t lightmap_u = lightmap_base_u >> lm_scale_log2;
+			const float k = f32_mul_add((float)(lightmap_base_u & lightmap_fetch_mask), inv_lightmap_scale_f, k_shift);
+			const float omk = 1.0f - k;
+			const LmEl& l0 = line_lightmap[r][lightmap_u];
+			const LmEl& l1 = line_lightmap[r][lightmap_u + 1];
+			float constant_c[3];
+#pragma unroll
+			for (int c = 0; c < 3; ++c)
+				constant_c[c] = lm_mix(l1.ambient[c], l0.ambient[c], k, omk);
+			Vec3 vs = v3(0.0f, 0.0f, 0.0f);
+			float deviation = 0.0f;
+			float dir_color_c[3] = {0.0f, 0.0f, 0.0f};
+			if (DIRECTIONAL)
+			{
+				vs = v3(lm_mix(l1.dir[0], l0.dir[0], k, omk), lm_mix(l1.dir[1], l0.dir[1], k, omk), lm_mix(l1.dir[2], l0.dir[2], k, omk));
+				deviation = lm_mix(l1.deviation, l0.deviation, k, omk);
+#pragma unroll
+				for (int c = 0; c < 3; ++c)
+					dir_color_c[c] = lm_mix(l1.color[c], l0.color[c], k, omk);
+			}
+			const ColorVec dir_color = cv_from_f32x3(dir_color_c);
+
+			if (SPECULAR_TYPE == 0)
+			{
+				total_light_albedo_modulated = cv(constant_c[2], constant_c[1], constant_c[0], 1.0f); // from_color_f32x3_with_one (:553)
 				if (DIRECTIONAL)
 				{
-					vs = v3(lm_mix(l1.dir[0], l0.dir[0], k, omk), lm_mix(l1.dir[1], l0.dir[1], k, omk), lm_mix(l1.dir[2], l0.dir[2], k, omk));
-					deviation = lm_mix(l1.deviation, l0.deviation, k, omk);
-#pragma unroll
-					for (int c = 0; c < 3; ++c)
-						dir_color_c[c] = lm_mix(l1.color[c], l0.color[c], k, omk);
-				}
-				const ColorVec dir_color = cv_from_f32x3(dir_color_c);
-
-				if (SPECULAR_TYPE == 0)
-				{
-					total_light_albedo_modulated = cv(constant_c[2], constant_c[1], constant_c[0], 1.0f); // from_color_f32x3_with_one (:553)
-					if (DIRECTIONAL)
-					{
-						const float dot = USE_NORMAL_MAP ? fmaxf(vec3_dot(vs, texel_normal), 0.0f) : vs.z;
-						total_light_albedo_modulated = cv_mul_scalar_add(dir_color, dot, total_light_albedo_modulated);
-					}
-				}
-				else
-				{
-					const Vec3 normal = texel_normal; // unit_z when there is no normal map (:575-582)
-					const Vec3 vec_to_camera = cam_pos - pos;
-					const Vec3 vtc_ts = v3(vec3_dot(vec_to_camera, u_vec_normalized), vec3_dot(vec_to_camera, v_vec_normalized), vec3_dot(vec_to_camera, basis_normal));
-					const float vec_to_camera_normal_dot = vec3_dot(vtc_ts, normal);
-					const Vec3 vec_to_camera_reflected = normal * (2.0f * vec_to_camera_normal_dot) - vtc_ts;
-					const float vec_to_camera_len2 = fmaxf(vec3_len2(vec_to_camera_reflected), SQW_MIN_POSITIVE_VALUE);
-					const float angle_cos = fmaxf(vec_to_camera_normal_dot * inv_sqrt_fast(vec_to_camera_len2), 0.0f);
-					const float fresnel_factor_base = get_fresnel_factor_base(angle_cos);
-					const float specular_k =
-						SPECULAR_TYPE == 1 ? get_specular_k_dielectric(fresnel_factor_base, texel_roughness) : get_specular_k_metal(fresnel_factor_base, texel_roughness);
-					const float one_minus_specular_k = 1.0f - specular_k;
-
-					const ColorVec constant_component = cv_from_f32x3(constant_c);
-					total_light_albedo_modulated = cv_scalar_mul(constant_component, one_minus_specular_k);
-					total_light_direct = cv_scalar_mul(constant_component, specular_k);
-					total_light_albedo_modulated.a = 1.0f; // :621
-
-					if (DIRECTIONAL)
-					{
-						const float direction_vec_len2 = vec3_len2(vs);
-						const float direction_vec_len = direction_vec_len2 * inv_sqrt_fast(direction_vec_len2);
-						const float refl_light_angle_cos = vec3_dot(vec_to_camera_reflected, vs) * inv_sqrt_fast(vec_to_camera_len2 * direction_vec_len2);
-						const float inv_roughness_corrected = fmaxf(inv_fast(texel_roughness + deviation), 0.75f); // :633
-						const float specular_intensity = get_specular_intensity(refl_light_angle_cos, inv_roughness_corrected);
-						if (SPECULAR_TYPE == 1)
-						{
-							const float diffuse_intensity = fmaxf(vec3_dot(vs, texel_normal), 0.0f);
-							total_light_albedo_modulated = cv_mul_scalar_add(dir_color, diffuse_intensity * one_minus_specular_k, total_light_albedo_modulated);
-							total_light_direct = cv_mul_scalar_add(dir_color, specular_intensity * specular_k * direction_vec_len, total_light_direct);
-						}
-						else
-						{
-							const float scale = specular_intensity * direction_vec_len;
-							total_light_albedo_modulated = cv_mul_scalar_add(dir_color, one_minus_specular_k * scale, total_light_albedo_modulated);
-							total_light_direct = cv_mul_scalar_add(dir_color, specular_k * scale, total_light_direct);
-						}
-					}
+					const float dot = USE_NORMAL_MAP ? fmaxf(vec3_dot(vs, texel_normal), 0.0f) : vs.z;
+					total_light_albedo_modulated = cv_mul_scalar_add(dir_color, dot, total_light_albedo_modulated);
 				}
 			}
-
-			if (USE_DYNAMIC_LIGHTS)
+			else
 			{
-				Vec3 normal;
-				if (USE_NORMAL_MAP)
-				{
-					normal = v3( // :686-702
-						f32_mul_add(texel_normal.x, u_vec_normalized.x, f32_mul_add(texel_normal.y, v_vec_normalized.x, texel_normal.z * basis_normal.x)),
-						f32_mul_add(texel_normal.x, u_vec_normalized.y, f32_mul_add(texel_normal.y, v_vec_normalized.y, texel_normal.z * basis_normal.y)),
-						f32_mul_add(texel_normal.x, u_vec_normalized.z, f32_mul_add(texel_normal.y, v_vec_normalized.z, texel_normal.z * basis_normal.z)));
-				}
-				else
-					normal = basis_normal;
+				const Vec3 normal = texel_normal; // unit_z when there is no normal map (:575-582)
+				const Vec3 vec_to_camera = cam_pos - pos;
+				const Vec3 vtc_ts = v3(vec3_dot(vec_to_camera, u_vec_normalized), vec3_dot(vec_to_camera, v_vec_normalized), vec3_dot(vec_to_camera, basis_normal));
+				const float vec_to_camera_normal_dot = vec3_dot(vtc_ts, normal);
+				const Vec3 vec_to_camera_reflected = normal * (2.0f * vec_to_camera_normal_dot) - vtc_ts;
+				const float vec_to_camera_len2 = fmaxf(vec3_len2(vec_to_camera_reflected), SQW_MIN_POSITIVE_VALUE);
+				const float angle_cos = fmaxf(vec_to_camera_normal_dot * inv_sqrt_fast(vec_to_camera_len2), 0.0f);
+				const float fresnel_factor_base = get_fresnel_factor_base(angle_cos);
+				const float specular_k =
+					SPECULAR_TYPE == 1 ? get_specular_k_dielectric(fresnel_factor_base, texel_roughness) : get_specular_k_metal(fresnel_factor_base, texel_roughness);
+				const float one_minus_specular_k = 1.0f - specular_k;
 
-				Vec3 vec_to_camera_reflected = v3(0.0f, 0.0f, 0.0f);
-				float vec_to_camera_len2 = SQW_MIN_POSITIVE_VALUE;
-				float specular_k = 0.0f;
-				float inv_roughness = 0.0f;
-				if (SPECULAR_TYPE != 0)
-				{
-					const Vec3 vec_to_camera = cam_pos - pos;
-					const float vec_to_camera_normal_dot = vec3_dot(vec_to_camera, normal);
-					vec_to_camera_reflected = normal * (2.0f * vec_to_camera_normal_dot) - vec_to_camera;
-					vec_to_camera_len2 = fmaxf(vec3_len2(vec_to_camera_reflected), SQW_MIN_POSITIVE_VALUE);
-					const float angle_cos = fmaxf(vec_to_camera_normal_dot * inv_sqrt_fast(vec_to_camera_len2), 0.0f);
-					const float fresnel_factor_base = get_fresnel_factor_base(angle_cos);
-					specular_k =
-						SPECULAR_TYPE == 1 ? get_specular_k_dielectric(fresnel_factor_base, texel_roughness) : get_specular_k_metal(fresnel_factor_base, texel_roughness);
-					inv_roughness = inv_fast(texel_roughness);
-				}
+				const ColorVec constant_component = cv_from_f32x3(constant_c);
+				total_light_albedo_modulated = cv_scalar_mul(constant_component, one_minus_specular_k);
+				total_light_direct = cv_scalar_mul(constant_component, specular_k);
+				total_light_albedo_modulated.a = 1.0f; // :621
 
-				const uint32_t num_lights = min(j.num_lights, (uint32_t)SQW_MAX_POLYGON_LIGHTS);
-				for (uint32_t li = 0; li < num_lights; ++li)
+				if (DIRECTIONAL)
 				{
-					const sqw_light& light = lights[j.lights[li]];
-					const Vec3 vec_to_light = v3(light.position[0], light.position[1], light.position[2]) - pos;
-					const float shadow_factor = get_light_shadow_factor(light, shadow_maps, vec_to_light);
-					const float vec_to_light_len2 = fmaxf(vec3_len2(vec_to_light), SQW_MIN_POSITIVE_VALUE);
-					const float distance_factor = fmaxf(inv_fast(vec_to_light_len2) - light.inv_square_radius, 0.0f);
-					const float shadow_distance_factor = shadow_factor * distance_factor;
-					const float diffuse_intensity = SPECULAR_TYPE == 2 ? 0.0f : fmaxf(vec3_dot(normal, vec_to_light) * inv_sqrt_fast(vec_to_light_len2), 0.0f);
-					float specular_intensity = 0.0f;
-					if (SPECULAR_TYPE != 0)
+					const float direction_vec_len2 = vec3_len2(vs);
+					const float direction_vec_len = direction_vec_len2 * inv_sqrt_fast(direction_vec_len2);
+					const float refl_light_angle_cos = vec3_dot(vec_to_camera_reflected, vs) * inv_sqrt_fast(vec_to_camera_len2 * direction_vec_len2);
+					const float inv_roughness_corrected = fmaxf(inv_fast(texel_roughness + deviation), 0.75f); // :633
+					const float specular_intensity = get_specular_intensity(refl_light_angle_cos, inv_roughness_corrected);
+					if (SPECULAR_TYPE == 1)
 					{
-						const float c = vec3_dot(vec_to_camera_reflected, vec_to_light) * inv_sqrt_fast(vec_to_camera_len2 * vec_to_light_len2);
-						specular_intensity = get_specular_intensity(c, inv_roughness);
-					}
-					const ColorVec light_color = cv_from_f32x3(light.color);
-					if (SPECULAR_TYPE == 0)
-						total_light_albedo_modulated = cv_mul_scalar_add(light_color, diffuse_intensity * shadow_distance_factor, total_light_albedo_modulated);
-					else if (SPECULAR_TYPE == 1)
-					{
-						total_light_albedo_modulated =
-							cv_mul_scalar_add(light_color, diffuse_intensity * (1.0f - specular_k) * shadow_distance_factor, total_light_albedo_modulated);
-						total_light_direct = cv_mul_scalar_add(light_color, specular_intensity * specular_k * shadow_distance_factor, total_light_direct);
+						const float diffuse_intensity = fmaxf(vec3_dot(vs, texel_normal), 0.0f);
+						total_light_albedo_modulated = cv_mul_scalar_add(dir_color, diffuse_intensity * one_minus_specular_k, total_light_albedo_modulated);
+						total_light_direct = cv_mul_scalar_add(dir_color, specular_intensity * specular_k * direction_vec_len, total_light_direct);
 					}
 					else
 					{
-						const float sisdf = specular_intensity * shadow_distance_factor;
-						total_light_albedo_modulated = cv_mul_scalar_add(light_color, (1.0f - specular_k) * sisdf, total_light_albedo_modulated);
-						total_light_direct = cv_mul_scalar_add(light_color, specular_k * sisdf, total_light_direct);
+						const float scale = specular_intensity * direction_vec_len;
+						total_light_albedo_modulated = cv_mul_scalar_add(dir_color, one_minus_specular_k * scale, total_light_albedo_modulated);
+						total_light_direct = cv_mul_scalar_add(dir_color, specular_k * scale, total_light_direct);
 					}
 				}
 			}
+		}
 
-			ColorVec result_color = cv_mul(cv_from_color32(diffuse), total_light_albedo_modulated); // :833
-			if (SPECULAR_TYPE != 0)
-				result_color = cv_mul_scalar_add(total_light_direct, 255.0f, result_color);
-			Raw result = C::from_vec(result_color);
-
-			if (emissive)
+		if (USE_DYNAMIC_LIGHTS)
+		{
+			Vec3 normal;
+			if (USE_NORMAL_MAP)
 			{
-				const uint32_t eu = ((uint32_t)em_u0 + dst_u) % em_w;
-				result = emissive_mix<C>(__ldg(em_line + eu), emissive_light_vec, true, result);
+				normal = v3( // :686-702
+					f32_mul_add(texel_normal.x, u_vec_normalized.x, f32_mul_add(texel_normal.y, v_vec_normalized.x, texel_normal.z * basis_normal.x)),
+					f32_mul_add(texel_normal.x, u_vec_normalized.y, f32_mul_add(texel_normal.y, v_vec_normalized.y, texel_normal.z * basis_normal.y)),
+					f32_mul_add(texel_normal.x, u_vec_normalized.z, f32_mul_add(texel_normal.y, v_vec_normalized.z, texel_normal.z * basis_normal.z)));
 			}
-			dst_line[dst_u] = result;
+			else
+				normal = basis_normal;
+
+			Vec3 vec_to_camera_reflected = v3(0.0f, 0.0f, 0.0f);
+			float vec_to_camera_len2 = SQW_MIN_POSITIVE_VALUE;
+			float specular_k = 0.0f;
+			float inv_roughness = 0.0f;
+			if (SPECULAR_TYPE != 0)
+			{
+				const Vec3 vec_to_camera = cam_pos - pos;
+				const float vec_to_camera_normal_dot = vec3_dot(vec_to_camera, normal);
+				vec_to_camera_reflected = normal * (2.0f * vec_to_camera_normal_dot) - vec_to_camera;
+				vec_to_camera_len2 = fmaxf(vec3_len2(vec_to_camera_reflected), SQW_MIN_POSITIVE_VALUE);
+				const float angle_cos = fmaxf(vec_to_camera_normal_dot * inv_sqrt_fast(vec_to_camera_len2), 0.0f);
+				const float fresnel_factor_base = get_fresnel_factor_base(angle_cos);
+				specular_k =
+					SPECULAR_TYPE == 1 ? get_specular_k_dielectric(fresnel_factor_base, texel_roughness) : get_specular_k_metal(fresnel_factor_base, texel_roughness);
+				inv_roughness = inv_fast(texel_roughness);
+			}
+
+			const uint32_t num_lights = min(j.num_lights, (uint32_t)SQW_MAX_POLYGON_LIGHTS);
+			for (uint32_t li = 0; li < num_lights; ++li)
+			{
+				const sqw_light& light = lights[j.lights[li]];
+				const Vec3 vec_to_light = v3(light.position[0], light.position[1], light.position[2]) - pos;
+				const float shadow_factor = get_light_shadow_factor(light, shadow_maps, vec_to_light);
+				const float vec_to_light_len2 = fmaxf(vec3_len2(vec_to_light), SQW_MIN_POSITIVE_VALUE);
+				const float distance_factor = fmaxf(inv_fast(vec_to_light_len2) - light.inv_square_radius, 0.0f);
+				const float shadow_distance_factor = shadow_factor * distance_factor;
+				const float diffuse_intensity = SPECULAR_TYPE == 2 ? 0.0f : fmaxf(vec3_dot(normal, vec_to_light) * inv_sqrt_fast(vec_to_light_len2), 0.0f);
+				float specular_intensity = 0.0f;
+				if (SPECULAR_TYPE != 0)
+				{
+					const float c = vec3_dot(vec_to_camera_reflected, vec_to_light) * inv_sqrt_fast(vec_to_camera_len2 * vec_to_light_len2);
+					specular_intensity = get_specular_intensity(c, inv_roughness);
+				}
+				const ColorVec light_color = cv_from_f32x3(light.color);
+				if (SPECULAR_TYPE == 0)
+					total_light_albedo_modulated = cv_mul_scalar_add(light_color, diffuse_intensity * shadow_distance_factor, total_light_albedo_modulated);
+				else if (SPECULAR_TYPE == 1)
+				{
+					total_light_albedo_modulated =
+						cv_mul_scalar_add(light_color, diffuse_intensity * (1.0f - specular_k) * shadow_distance_factor, total_light_albedo_modulated);
+					total_light_direct = cv_mul_scalar_add(light_color, specular_intensity * specular_k * shadow_distance_factor, total_light_direct);
+				}
+				else
+				{
+					const float sisdf = specular_intensity * shadow_distance_factor;
+					total_light_albedo_modulated = cv_mul_scalar_add(light_color, (1.0f - specular_k) * sisdf, total_light_albedo_modulated);
+					total_light_direct = cv_mul_scalar_add(light_color, specular_k * sisdf, total_light_direct);
+				}
+			}
+		}
+
+		ColorVec result_color = cv_mul(cv_from_color32(diffuse), total_light_albedo_modulated); // :833
+		if (SPECULAR_TYPE != 0)
+			result_color = cv_mul_scalar_add(total_light_direct, 255.0f, result_color);
+		Raw result = C::from_vec(result_color);
+
+		if (emissive)
+		{
+			const uint32_t eu = wrap_coord(em_u0 + (int32_t)dst_u, (int32_t)em_w, em_w_mask);
+			result = emissive_mix<C>(__ldg(em_line + eu), emissive_light_vec, true, result);
+		}
+		out[(size_t)dst_v * size_u + dst_u] = result;
+
+		r += step_rows;
+		dst_u += step_u;
+		if (dst_u >= size_u)
+		{
+			dst_u -= size_u;
+			++r;
 		}
 	}
 }
 
-template <class C, bool DIRECTIONAL, bool DYN, bool NM, int SPEC, bool EMONLY>
+// Variant byte of a band: bit0 directional lightmap, bit1 normal map, bits2-3 specular type, bit4 emissive-only.
+template <class C, bool DYN>
+__global__ void __launch_bounds__(SQW_SURF_THREADS) surface_build_kernel(
+	const sqw_surface_job* __restrict__ jobs, const SurfaceBand* __restrict__ bands, const ImageDev* __restrict__ images,
+	const float* __restrict__ lightmaps, const sqw_directional_lightmap_element* __restrict__ directional_lightmaps,
+	const sqw_light* __restrict__ lights, const float* __restrict__ shadow_maps, float cam_x, float cam_y, float cam_z,
+	typename C::Raw* __restrict__ surfaces)
+{
+	__shared__ LineLightmap s_line_lightmap[SQW_SURF_MAX_BAND_ROWS];
+	__shared__ sqw_surface_job s_job;
+
+	const SurfaceBand band = bands[blockIdx.x];
+	{
+		// Cooperative 136-byte job load into shared memory (34 words).
+		const uint32_t* src = reinterpret_cast<const uint32_t*>(jobs + band.job);
+		uint32_t* dst = reinterpret_cast<uint32_t*>(&s_job);
+		if (threadIdx.x < sizeof(sqw_surface_job) / 4)
+			dst[threadIdx.x] = src[threadIdx.x];
+	}
+	__syncthreads();
+
+#define SQW_BAND_CASE(DIR, NM, SPEC)                                                                                                                       \
+	case ((DIR) | ((NM) << 1) | ((SPEC) << 2)):                                                                                                            \
+		surface_band<C, (DIR) != 0, DYN, (NM) != 0, SPEC, false>(                                                                                          \
+			s_job, band, s_line_lightmap, images, lightmaps, directional_lightmaps, lights, shadow_maps, cam_x, cam_y, cam_z, surfaces);                   \
+		break;
+	switch (band.variant)
+	{
+		SQW_BAND_CASE(0, 0, 0)
+		SQW_BAND_CASE(0, 0, 1)
+		SQW_BAND_CASE(0, 0, 2)
+		SQW_BAND_CASE(0, 1, 0)
+		SQW_BAND_CASE(0, 1, 1)
+		SQW_BAND_CASE(0, 1, 2)
+		SQW_BAND_CASE(1, 0, 0)
+		SQW_BAND_CASE(1, 0, 1)
+		SQW_BAND_CASE(1, 0, 2)
+		SQW_BAND_CASE(1, 1, 0)
+		SQW_BAND_CASE(1, 1, 1)
+		SQW_BAND_CASE(1, 1, 2)
+	default:
+		if (!DYN)
+			surface_band<C, false, false, false, 0, true>(
+				s_job, band, s_line_lightmap, images, lightmaps, directional_lightmaps, lights, shadow_maps, cam_x, cam_y, cam_z, surfaces);
+		break;
+	}
+#undef SQW_BAND_CASE
+}
+
+template <class C, bool DYN>
 cudaError_t launch_one(const SurfaceLaunch& l, cudaStream_t stream)
 {
-	surface_build_kernel<C, DIRECTIONAL, DYN, NM, SPEC, EMONLY><<<l.num_bands, SQW_SURF_THREADS, 0, stream>>>(
+	surface_build_kernel<C, DYN><<<l.num_bands, SQW_SURF_THREADS, 0, stream>>>(
 		l.jobs, l.bands, l.images, l.lightmaps, l.directional_lightmaps, l.lights, l.shadow_maps, l.cam_pos[0], l.cam_pos[1], l.cam_pos[2],
 		static_cast<typename C::Raw*>(l.surfaces));
 	return cudaGetLastError();
 }
 
-template <class C, bool DIRECTIONAL, bool DYN, bool NM>
-cudaError_t launch_spec(int spec, const SurfaceLaunch& l, cudaStream_t s)
-{
-	switch (spec)
-	{
-	case 0: return launch_one<C, DIRECTIONAL, DYN, NM, 0, false>(l, s);
-	case 1: return launch_one<C, DIRECTIONAL, DYN, NM, 1, false>(l, s);
-	default: return launch_one<C, DIRECTIONAL, DYN, NM, 2, false>(l, s);
-	}
-}
-template <class C, bool DIRECTIONAL>
-cudaError_t launch_dyn_nm(const SurfaceVariant& v, const SurfaceLaunch& l, cudaStream_t s)
-{
-	if (v.dynamic_lights)
-		return v.normal_map ? launch_spec<C, DIRECTIONAL, true, true>(v.specular, l, s) : launch_spec<C, DIRECTIONAL, true, false>(v.specular, l, s);
-	return v.normal_map ? launch_spec<C, DIRECTIONAL, false, true>(v.specular, l, s) : launch_spec<C, DIRECTIONAL, false, false>(v.specular, l, s);
-}
-template <class C>
-cudaError_t launch_color(const SurfaceVariant& v, const SurfaceLaunch& l, cudaStream_t s)
-{
-	if (v.emissive_only)
-		return launch_one<C, false, false, false, 0, true>(l, s);
-	return v.directional ? launch_dyn_nm<C, true>(v, l, s) : launch_dyn_nm<C, false>(v, l, s);
-}
-
 } // namespace
 
-cudaError_t launch_surface_build(const SurfaceVariant& v, const SurfaceLaunch& l, cudaStream_t stream)
+cudaError_t launch_surface_build(bool color64, bool dynamic_lights, const SurfaceLaunch& l, cudaStream_t stream)
 {
 	if (l.num_bands == 0)
 		return cudaSuccess;
-	return v.color64 ? launch_color<Color64>(v, l, stream) : launch_color<Color32>(v, l, stream);
+	if (color64)
+		return dynamic_lights ? launch_one<Color64, true>(l, stream) : launch_one<Color64, false>(l, stream);
+	return dynamic_lights ? launch_one<Color32, true>(l, stream) : launch_one<Color32, false>(l, stream);
 }
 
 } // namespace sqw

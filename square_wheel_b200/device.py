@@ -25,7 +25,7 @@ def _as(a, dtype):
 class Context:
     """sqw_ctx: replaces the data-ownership half of Renderer::new (src/square_wheel/renderer.rs:24)."""
 
-    def __init__(self, lightmaps: Optional[np.ndarray], directional_lightmaps: Optional[np.ndarray], device: int = 0, stream: int = 0, max_images: int = 0):
+    def __init__(self, lightmaps: Optional[np.ndarray], directional_lightmaps: Optional[np.ndarray], device: int = 0, stream: int = 0, max_images: int = 0, concurrent_views: bool = False):
         self._lib = N.load_cuda_library()
         self._handle = C.c_void_p()
         lm = _as(lightmaps, np.float32)
@@ -37,7 +37,7 @@ class Context:
             if lm is not None and dlm.size != n:
                 raise ValueError("lightmap arrays must have the same element count")
             n = dlm.size
-        desc = N.MapDesc(N.ptr(lm), N.ptr(dlm), n, max_images, 0)
+        desc = N.MapDesc(N.ptr(lm), N.ptr(dlm), n, max_images, N.CTX_CONCURRENT_VIEWS if concurrent_views else 0)
         rc = self._lib.sqw_create(C.byref(self._handle), device, C.byref(desc), C.c_void_p(stream) if stream else None)
         if rc != N.SQW_OK:
             raise SqwError(f"sqw_create failed ({rc}): {self._lib.sqw_last_error(None).decode()}")
@@ -63,6 +63,14 @@ class Context:
 
     def create_view(self, width: int, height: int, color_bits: int) -> "View":
         return View(self, width, height, color_bits)
+
+    def batch_begin(self):
+        """Fork the views' private streams from the context's stream (concurrent_views)."""
+        self._check(self._lib.sqw_batch_begin(self._handle), "sqw_batch_begin")
+
+    def batch_end(self):
+        """Join the views' private streams back into the context's stream."""
+        self._check(self._lib.sqw_batch_end(self._handle), "sqw_batch_end")
 
     def profile_begin(self):
         self._check(self._lib.sqw_profile_begin(self._handle), "sqw_profile_begin")
@@ -138,6 +146,13 @@ class View:
         out = np.empty((self.height, self.width), np.uint32)
         self.ctx._check(self._lib.sqw_read_pixels32(self._handle, N.ptr(out), self.width), "sqw_read_pixels32")
         return out
+
+    def read_pixels32_async(self, dst_ptr: int, dst_pitch: int):
+        """Queue the copy of the post-processed picture into (page-locked) host memory at dst_ptr; complete after synchronize()."""
+        self.ctx._check(self._lib.sqw_read_pixels32_async(self._handle, C.c_void_p(dst_ptr), dst_pitch), "sqw_read_pixels32_async")
+
+    def read_pixels_async(self, dst_ptr: int, dst_pitch: int):
+        self.ctx._check(self._lib.sqw_read_pixels_async(self._handle, C.c_void_p(dst_ptr), dst_pitch), "sqw_read_pixels_async")
 
     def read_surfaces(self, offset: int, count: int) -> np.ndarray:
         out = np.empty(count, self.pixel_dtype)

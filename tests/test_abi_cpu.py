@@ -29,7 +29,8 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/sqw_cuda.h but not exported"
     bound = {s[0] for s in N.CUDA_SYMBOLS}
     assert set(declared) == bound, f"python binding out of sync: {set(declared) ^ bound}"
-    assert lib.sqw_abi_version() == 1
+    header = open(HEADER).read() if 'HEADER' in globals() else open(os.path.join(os.path.dirname(__file__), '..', 'include', 'sqw_cuda.h')).read()
+    assert lib.sqw_abi_version() == int(re.search(r'#define SQW_ABI_VERSION (\d+)', header).group(1))
 
 
 def test_struct_sizes_match_header():
