@@ -42,7 +42,7 @@ __device__ __forceinline__ void block_sum3_atomic(unsigned long long b, unsigned
 		unsigned long long t = 0;
 		for (int w = 0; w < (int)(blockDim.x >> 5); ++w)
 			t += s_part[threadIdx.x][w];
-		atomicAdd(sums + threadIdx.x, t);
+		atomicAdd(sums + (blockIdx.x % SQW_SUM_SLOTS) * 4 + threadIdx.x, t);
 	}
 }
 

@@ -27,6 +27,7 @@
 #include "sqw_device.cuh"
 #include "sqw_internal.h"
 #include <algorithm>
+#include <cstdlib>
 
 namespace sqw
 {
@@ -598,16 +599,31 @@ __device__ void bin_band(const CmdDev* __restrict__ cmd_dev, uint32_t num_cmds, 
 __global__ void __launch_bounds__(SQW_SETUP_THREADS) raster_setup_kernel(
 	const sqw_draw_cmd* __restrict__ cmds, const CmdDev* __restrict__ cmd_dev, uint32_t num_cmds, const sqw_polygon_point* __restrict__ polygon_points,
 	const sqw_triangle_point* __restrict__ triangle_points, const uint32_t* __restrict__ cmd_span_base, uint32_t total_spans, SpanRec* __restrict__ spans,
-	int32_t clip_w, int32_t clip_h, uint32_t setup_blocks, const uint32_t* __restrict__ band_offsets, uint32_t* __restrict__ band_lists,
-	unsigned long long* __restrict__ sums_to_zero)
+	int32_t clip_w, int32_t clip_h, uint32_t setup_blocks, const uint32_t* __restrict__ band_offsets, uint32_t* __restrict__ band_lists, uint32_t num_bands,
+	unsigned long long* __restrict__ sums_to_zero, uint8_t* __restrict__ tonemap_lut, float isb, float isg, float isr)
 {
+	if (blockIdx.x >= setup_blocks + num_bands)
+	{
+		// Tonemapping table of the fused tile epilogue: TonemappingFunction::do_it (postprocessor.rs:1019-1023) of every
+		// channel value below SQW_TONEMAP_LUT_SIZE, computed with the same IEEE operations as tonemap_pixel.
+		const uint32_t idx = (blockIdx.x - setup_blocks - num_bands) * SQW_SETUP_THREADS + threadIdx.x;
+		if (idx < 3 * SQW_TONEMAP_LUT_SIZE)
+		{
+			const uint32_t ch = idx / SQW_TONEMAP_LUT_SIZE;
+			const float c = (float)(idx % SQW_TONEMAP_LUT_SIZE);
+			const float inv_scale = ch == 0 ? isb : (ch == 1 ? isg : isr);
+			tonemap_lut[idx] = (uint8_t)f32_to_u_clamped(__fdiv_rn(c, f32_mul_add(c, 1.0f / 255.0f, inv_scale)), 255.0f);
+		}
+		return;
+	}
 	if (blockIdx.x >= setup_blocks)
 	{
 		bin_band(cmd_dev, num_cmds, band_offsets, band_lists, (int)(blockIdx.x - setup_blocks));
 		return;
 	}
-	if (sums_to_zero && blockIdx.x == 0 && threadIdx.x < 3)
-		sums_to_zero[threadIdx.x] = 0; // colour sums of the fused tonemapping epilogue of the tile kernel that follows
+	if (sums_to_zero && blockIdx.x == 0) // colour sums of the fused tonemapping epilogue of the tile kernel that follows
+		for (uint32_t i = threadIdx.x; i < SQW_SUM_WORDS; i += SQW_SETUP_THREADS)
+			sums_to_zero[i] = 0;
 	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
 	if (s >= total_spans)
 		return;
@@ -637,144 +653,266 @@ __device__ __forceinline__ typename C::Raw fetch_texel(const void* tex, uint32_t
 	return __ldg(static_cast<const typename C::Raw*>(tex) + address);
 }
 
-// TONEMAP = true fuses Postprocessor::perform_tonemapping (postprocessor.rs:226-256) into the tile epilogue: the finished
+#define SQW_NEED_DST(i)                       \
+	if (!(have & (1u << (i))))                \
+	{                                         \
+		px[i] = dst[SQW_PX_OFS(i)];           \
+		have |= 1u << (i);                    \
+	}
+
+// TONEMAP != 0 fuses Postprocessor::perform_tonemapping (postprocessor.rs:226-256) into the tile epilogue: the finished
 // HDR pixels are still in registers, so the 32-bit picture and the colour sums are produced without reading the 64-bit
 // buffer back (saves 8 of the 12 bytes per pixel of a separate tonemapping pass).
-template <class C, bool TONEMAP>
-__global__ void __launch_bounds__(SQW_RASTER_THREADS) raster_tile_kernel(
+//
+// Work distribution inside the 128x8 tile: warp w owns the 32x4 pixel block (w & 3, w >> 2) and lane l the four
+// consecutive pixels ((l & 7) * 4 .. + 3) of block row l >> 3.  A compact footprint meets far fewer polygon edges than
+// a 128x1 strip, so fewer commands are evaluated with lanes idle, and every global store is still a full 256-byte run.
+//   phase A  all 256 threads test one candidate of the band list each against the tile's column range and compact the
+//            survivors IN LIST ORDER (ballot + popc prefix across warps) into shared memory, texture pointer resolved;
+//   phase B  the span records of 32 listed commands x 8 band rows are fetched by all 256 threads at once into shared
+//            memory (one memory latency per tile instead of one per command), then every warp walks the list:
+//            warp-uniform reject against its 32x4 block, span record of the lane's row from shared memory, pixels.
+//            Only the texel gathers of a covering command go to global memory.
+template <class C, int TONEMAP>
+__global__ void __launch_bounds__(SQW_RASTER_THREADS, SQW_TILE_CTAS_PER_SM) raster_tile_kernel(
 	const CmdDev* __restrict__ cmd_dev, const SpanRec* __restrict__ spans, const uint32_t* __restrict__ band_lists, const uint32_t* __restrict__ band_offsets,
 	const char* __restrict__ surfaces_base, typename C::Raw* __restrict__ color_buffer, int32_t width, int32_t height, int32_t pitch, int clear,
-	typename C::Raw clear_color, uint32_t* __restrict__ ldr, float isb, float isg, float isr, unsigned long long* __restrict__ sums)
+	typename C::Raw clear_color, uint32_t* __restrict__ ldr, float isb, float isg, float isr, unsigned long long* __restrict__ sums,
+	const uint8_t* __restrict__ tonemap_lut, uint32_t tiles_x, uint32_t num_tiles)
 {
 	typedef typename C::Raw Raw;
+	constexpr int WARPS = SQW_RASTER_THREADS / 32;
+	__shared__ uint4 s_cmd[2][SQW_RASTER_THREADS]; // [0] CmdDev words 0-3, [1] {texture pointer, tex_width, tex_height}
+	__shared__ uint32_t s_warp_counts[WARPS];
+	__shared__ uint4 s_span[3][SQW_TILE_STAGE_HITS][SQW_TILE_H]; // SpanRec words of (staged command, band row)
+	// Per-channel tonemapping table (exact results for channel values < SQW_TONEMAP_LUT_SIZE, built by the set-up grid of
+	// this frame): three byte look-ups replace three IEEE divides for all but very bright pixels.
+	__shared__ __align__(16) uint8_t s_lut[TONEMAP ? 3 * SQW_TONEMAP_LUT_SIZE : 16];
+	if (TONEMAP)
+	{
+		const uint4* src = reinterpret_cast<const uint4*>(tonemap_lut);
+		uint4* d = reinterpret_cast<uint4*>(s_lut);
+		for (uint32_t i = threadIdx.x; i < 3 * SQW_TONEMAP_LUT_SIZE / 16; i += SQW_RASTER_THREADS)
+			d[i] = __ldg(src + i);
+	}
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int band = blockIdx.y;
-	const int32_t row = band * SQW_TILE_H + warp;
-	const bool row_valid = row < height;
-	const int32_t tile_x0 = blockIdx.x * SQW_TILE_W;
+	uint32_t sb = 0, sg = 0, sr = 0; // colour sums of the fused tonemapping (all tiles of this CTA)
+	if (TONEMAP)
+		__syncthreads(); // s_lut is complete
+
+	// Persistent CTAs: the grid is sized to what the GPU holds at once and every CTA strides over the tiles, so the
+	// per-CTA costs (tonemapping table, sum reduction, launch) are paid a few hundred times per frame, not once per tile.
+	for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+	{
+	const int band = (int)(tile / tiles_x);
+	const int32_t tile_x0 = (int32_t)(tile % tiles_x) * SQW_TILE_W;
 	const int32_t tile_x1 = min(tile_x0 + SQW_TILE_W, width);
-	const int32_t px0 = tile_x0 + lane * 4;
+	const int32_t band_y0 = band * SQW_TILE_H, band_y1 = min(band_y0 + SQW_TILE_H, height);
+	// this warp's block and this lane's pixels
+	const int32_t blk_x0 = tile_x0 + (warp & 3) * 32, blk_x1 = blk_x0 + 32;
+	const int32_t blk_y0 = band_y0 + (warp >> 2) * 4, blk_y1 = min(blk_y0 + 4, height);
+	const int32_t row = blk_y0 + (lane >> 3);
+	const bool row_valid = row < height;
+	// The lane's four pixels are two PAIRS, 16 pixels apart: x = px0 + {0, 1, 16, 17}.  That way the 8 lanes of a block row
+	// write 8 consecutive 16-byte chunks per store instruction (whole 32-byte sectors, 128 contiguous bytes per row)
+	// instead of half-sectors with a 32-byte stride.
+	const int32_t px0 = blk_x0 + (lane & 7) * 2;
+#define SQW_PX_OFS(i) (((i) & 1) + 16 * ((i) >> 1))
 
 	Raw* const dst = color_buffer + (size_t)row * pitch + px0;
 	Raw px[4];
 	// `have` bit i: px[i] holds the current value of the pixel.  The framebuffer is only read for pixels whose first
 	// covering command blends with the destination, and pixels no command touches are not written back: a frame whose
 	// polygons cover the screen (the usual case inside a map, partial_renderer.rs:249-256) never reads the buffer.
-	uint32_t have = 0;
+	uint32_t have = clear ? 0xFu : 0u;
 #pragma unroll
 	for (int i = 0; i < 4; ++i)
 		px[i] = clear_color;
-	if (clear)
-		have = 0xF;
-	const bool vec_ok = (px0 + 4 <= width) && ((pitch & 3) == 0);
+	const bool vec_ok = (blk_x1 <= width) && ((pitch & 1) == 0);
 
-#define SQW_NEED_DST(i)                       \
-	if (!(have & (1u << (i))))                \
-	{                                         \
-		px[i] = dst[i];                       \
-		have |= 1u << (i);                    \
-	}
-
-	const uint32_t list_begin = row_valid ? band_offsets[band] : 0, list_end = row_valid ? band_offsets[band + 1] : 0;
-	for (uint32_t base = list_begin; base < list_end; base += 32)
+	const uint32_t list_begin = band_offsets[band], list_end = band_offsets[band + 1];
+	for (uint32_t base = list_begin; base < list_end; base += SQW_RASTER_THREADS)
 	{
-		uint32_t ci = 0;
+		// ---- phase A: tile list ----
 		bool hit = false;
-		if (base + lane < list_end)
+		uint4 c0 = make_uint4(0, 0, 0, 0);
+		const uint4* cdp = nullptr;
+		if (base + threadIdx.x < list_end)
 		{
-			ci = __ldg(band_lists + base + lane);
-			const uint2 w = __ldg(reinterpret_cast<const uint2*>(cmd_dev + ci));
-			const int32_t y0 = (int16_t)(w.x & 0xFFFF), y1 = (int16_t)(w.x >> 16);
-			const int32_t bx0 = (int16_t)(w.y & 0xFFFF), bx1 = (int16_t)(w.y >> 16);
-			hit = row >= y0 && row < y1 && bx0 < tile_x1 && bx1 > tile_x0;
+			cdp = reinterpret_cast<const uint4*>(cmd_dev + __ldg(band_lists + base + threadIdx.x));
+			c0 = __ldg(cdp); // y0,y1 | bx0,bx1 | span_base | kind, blend, tc_mode, tex_flags
+			const int32_t y0 = (int16_t)(c0.x & 0xFFFF), y1 = (int16_t)(c0.x >> 16);
+			const int32_t bx0 = (int16_t)(c0.y & 0xFFFF), bx1 = (int16_t)(c0.y >> 16);
+			hit = y0 < band_y1 && y1 > band_y0 && bx0 < tile_x1 && bx1 > tile_x0;
 		}
-		uint32_t mask = __ballot_sync(0xFFFFFFFFu, hit);
-		while (mask)
+		const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, hit);
+		if (lane == 0)
+			s_warp_counts[warp] = __popc(ballot);
+		__syncthreads();
+		uint32_t slot = __popc(ballot & ((1u << lane) - 1)), num_hits = 0;
+#pragma unroll
+		for (int w = 0; w < WARPS; ++w)
 		{
-			const int bit = __ffs(mask) - 1;
-			mask &= mask - 1;
-			const uint32_t cmd_index = __shfl_sync(0xFFFFFFFFu, ci, bit);
-			const CmdDev* cdp = cmd_dev + cmd_index;
-			const uint4 c0 = __ldg(reinterpret_cast<const uint4*>(cdp));     // y0,y1,bx0,bx1 | span_base | kind.. | (pad)
-			const int32_t y0 = (int16_t)(c0.x & 0xFFFF);
-			const uint32_t span_base = c0.z;
-			const uint4* sp = reinterpret_cast<const uint4*>(spans + span_base + (uint32_t)(row - y0));
-			const uint4 s0 = __ldg(sp);
-			const int32_t x0 = (int16_t)(s0.x & 0xFFFF), x1 = (int16_t)(s0.x >> 16);
-			if (x0 >= x1 || x0 >= tile_x1 || x1 <= tile_x0)
-				continue;
-			const uint4 c1 = __ldg(reinterpret_cast<const uint4*>(cdp) + 1); // texture ptr | tex_width | tex_height
-			const uint32_t kind = c0.w & 0xFF, blend = (c0.w >> 8) & 0xFF, tc_mode = (c0.w >> 16) & 0xFF, tex64 = (c0.w >> 24) & 1;
+			const uint32_t n = s_warp_counts[w];
+			if (w < warp)
+				slot += n;
+			num_hits += n;
+		}
+		if (hit)
+		{
+			uint4 c1 = __ldg(cdp + 1); // texture ptr | tex_width | tex_height
 			// bit 1 of the last flag byte: `texture` is a byte offset into the view's surface pool (the pool may be
 			// re-allocated between recording and submission, so surface references stay relative).
-			const uint64_t tex_bits = (uint64_t)c1.x | ((uint64_t)c1.y << 32);
-			const void* const tex = ((c0.w >> 25) & 1) ? static_cast<const void*>(surfaces_base + tex_bits) : reinterpret_cast<const void*>(tex_bits);
-			const uint32_t tex_width = c1.z;
-			const uint4 s1 = __ldg(sp + 1);
-			// v[0..2] = s0.y,z,w ; v[3..6] = s1 ; v[7..10] = s2
+			if ((c0.w >> 25) & 1)
+			{
+				const uint64_t t = (uint64_t)reinterpret_cast<uintptr_t>(surfaces_base) + ((uint64_t)c1.x | ((uint64_t)c1.y << 32));
+				c1.x = (uint32_t)t;
+				c1.y = (uint32_t)(t >> 32);
+			}
+			s_cmd[0][slot] = c0;
+			s_cmd[1][slot] = c1;
+		}
+		__syncthreads();
+
+		// ---- phase B: walk the tile list in submission order, SQW_TILE_STAGE_HITS commands at a time ----
+		for (uint32_t h0 = 0; h0 < num_hits; h0 += SQW_TILE_STAGE_HITS)
+		{
+			// Stage the span records of these commands for the 8 rows of the band: one (command, row) pair per thread, all
+			// loads independent, so the whole tile pays ONE memory latency for its span records.
+			{
+				const uint32_t hs = threadIdx.x >> 3, rs = threadIdx.x & 7;
+				if (h0 + hs < num_hits)
+				{
+					const uint4 w0 = s_cmd[0][h0 + hs];
+					const int32_t y0 = (int16_t)(w0.x & 0xFFFF), y1 = (int16_t)(w0.x >> 16);
+					const int32_t srow = band_y0 + (int32_t)rs;
+					uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, r2 = r0;
+					if (srow >= y0 && srow < y1)
+					{
+						const uint4* sp = reinterpret_cast<const uint4*>(spans + w0.z + (uint32_t)(srow - y0));
+						r0 = __ldg(sp);
+						r1 = __ldg(sp + 1);
+						if ((w0.w & 0xFF) == SQW_CMD_TRIANGLE)
+							r2 = __ldg(sp + 2);
+					}
+					s_span[0][hs][rs] = r0;
+					s_span[1][hs][rs] = r1;
+					s_span[2][hs][rs] = r2;
+				}
+			}
+			__syncthreads();
+			const uint32_t h1 = min(num_hits - h0, (uint32_t)SQW_TILE_STAGE_HITS);
+			const int rb = (warp >> 2) * 4 + (lane >> 3); // this lane's row inside the band
+			for (uint32_t hh = 0; hh < h1; ++hh)
+			{
+			const uint32_t h = h0 + hh;
+			const uint4 w0 = s_cmd[0][h];
+			const int32_t y0 = (int16_t)(w0.x & 0xFFFF), y1 = (int16_t)(w0.x >> 16);
+			const int32_t bx0 = (int16_t)(w0.y & 0xFFFF), bx1 = (int16_t)(w0.y >> 16);
+			if (y0 >= blk_y1 || y1 <= blk_y0 || bx0 >= blk_x1 || bx1 <= blk_x0)
+				continue; // warp-uniform
+			const uint4 r0 = s_span[0][hh][rb];
+			const int32_t x0 = (int16_t)(r0.x & 0xFFFF), x1 = (int16_t)(r0.x >> 16);
+			const bool covered = x0 < x1 && ((x0 < px0 + 2 && x1 > px0) || (x0 < px0 + 18 && x1 > px0 + 16));
+			if (!__any_sync(0xFFFFFFFFu, covered))
+				continue;
+			const uint4 w1 = s_cmd[1][h];
+			const uint4 r1 = s_span[1][hh][rb];
+			const uint32_t kind = w0.w & 0xFF, blend = (w0.w >> 8) & 0xFF, tc_mode = (w0.w >> 16) & 0xFF, tex64 = (w0.w >> 24) & 1;
+			const void* const tex = reinterpret_cast<const void*>((uint64_t)w1.x | ((uint64_t)w1.y << 32));
+			const uint32_t tex_width = w1.z;
+			// v[0..2] = r0.y,z,w ; v[3..6] = r1 ; v[7..10] = r2
 			// Blend modes that read the destination (rasterizer.rs:1511-1536); alpha test keeps it untouched when it fails.
 			const bool reads_dst = blend == SQW_BLEND_AVERAGE || blend == SQW_BLEND_ADDITIVE || blend == SQW_BLEND_ALPHA_BLEND;
 
 			if (kind == SQW_CMD_POLYGON)
 			{
-				const int32_t tc0 = (int32_t)s0.w, tc1 = (int32_t)s1.x, dtc0 = (int32_t)s1.y, dtc1 = (int32_t)s1.z;
-				const int32_t inv_z0 = (int32_t)s0.y, d_inv_z = (int32_t)s0.z;
-				const bool full = tc_mode == SQW_TC_FULL_PERSPECTIVE;
+				const int32_t tc0 = (int32_t)r0.w, tc1 = (int32_t)r1.x, dtc0 = (int32_t)r1.y, dtc1 = (int32_t)r1.z;
+				const int32_t inv_z0 = (int32_t)r0.y, d_inv_z = (int32_t)r0.z;
+				// The four pixels of the lane are evaluated WITHOUT branches (addresses of uncovered pixels are computed from
+				// wrapped garbage and never dereferenced), so the four dependent chains — one u32 divide each in the full
+				// perspective mode — interleave and the four texel gathers are in flight together.
+				bool in[4];
+				uint32_t address[4];
+				if (tc_mode == SQW_TC_FULL_PERSPECTIVE)
+				{
+#pragma unroll
+					for (int i = 0; i < 4; ++i)
+					{
+						const int32_t x = px0 + SQW_PX_OFS(i);
+						in[i] = x >= x0 && x < x1;
+						const int32_t k = x - x0;
+						const uint32_t span_inv_z = (uint32_t)wadd(inv_z0, wmul(k, d_inv_z));
+						const uint32_t z = (1u << Z_CALC_SHIFT) / max(span_inv_z >> INV_Z_PRE_SHIFT, 1u); // rasterizer.rs:430 (covered pixels: >= 1 by the span clamp)
+						const uint64_t t0 = (uint64_t)(int64_t)wadd(tc0, wmul(k, dtc0));
+						const uint64_t t1 = (uint64_t)(int64_t)wadd(tc1, wmul(k, dtc1));
+						const uint32_t u = (uint32_t)(((uint64_t)z * t0) >> TC_FINAL_SHIFT);
+						const uint32_t v = (uint32_t)(((uint64_t)z * t1) >> TC_FINAL_SHIFT);
+						address[i] = u + v * tex_width;
+					}
+				}
+				else
+				{
+#pragma unroll
+					for (int i = 0; i < 4; ++i)
+					{
+						const int32_t x = px0 + SQW_PX_OFS(i);
+						in[i] = x >= x0 && x < x1;
+						const int32_t k = x - x0;
+						const uint32_t u = (uint32_t)(wadd(tc0, wmul(k, dtc0)) >> 16);
+						const uint32_t v = (uint32_t)(wadd(tc1, wmul(k, dtc1)) >> 16);
+						address[i] = u + v * tex_width;
+					}
+				}
+				Raw texel[4];
 #pragma unroll
 				for (int i = 0; i < 4; ++i)
 				{
-					const int32_t x = px0 + i;
-					if (x >= x0 && x < x1)
+					texel[i] = 0;
+					if (in[i])
+						texel[i] = fetch_texel<C>(tex, address[i]);
+				}
+				if (blend == SQW_BLEND_NONE)
+				{
+#pragma unroll
+					for (int i = 0; i < 4; ++i)
 					{
-						const int32_t k = x - x0;
-						uint32_t u, v;
-						if (full)
-						{
-							const uint32_t span_inv_z = (uint32_t)wadd(inv_z0, wmul(k, d_inv_z));
-							const uint32_t z = (1u << Z_CALC_SHIFT) / (span_inv_z >> INV_Z_PRE_SHIFT); // rasterizer.rs:430
-							const uint64_t t0 = (uint64_t)(int64_t)wadd(tc0, wmul(k, dtc0));
-							const uint64_t t1 = (uint64_t)(int64_t)wadd(tc1, wmul(k, dtc1));
-							u = (uint32_t)(((uint64_t)z * t0) >> TC_FINAL_SHIFT);
-							v = (uint32_t)(((uint64_t)z * t1) >> TC_FINAL_SHIFT);
-						}
-						else
-						{
-							u = (uint32_t)(wadd(tc0, wmul(k, dtc0)) >> 16);
-							v = (uint32_t)(wadd(tc1, wmul(k, dtc1)) >> 16);
-						}
-						const Raw texel = fetch_texel<C>(tex, u + v * tex_width);
-						if (blend == SQW_BLEND_NONE)
-						{
-							px[i] = texel;
-							have |= 1u << i;
-						}
-						else if (blend == SQW_BLEND_ALPHA_TEST)
-						{
-							if (C::test_alpha(texel))
-							{
-								px[i] = texel;
-								have |= 1u << i;
-							}
-						}
-						else
+						px[i] = in[i] ? texel[i] : px[i];
+						have |= in[i] ? (1u << i) : 0u;
+					}
+				}
+				else if (blend == SQW_BLEND_ALPHA_TEST)
+				{
+#pragma unroll
+					for (int i = 0; i < 4; ++i)
+					{
+						const bool pass = in[i] && C::test_alpha(texel[i]);
+						px[i] = pass ? texel[i] : px[i];
+						have |= pass ? (1u << i) : 0u;
+					}
+				}
+				else
+				{
+#pragma unroll
+					for (int i = 0; i < 4; ++i)
+						if (in[i])
 						{
 							SQW_NEED_DST(i)
-							px[i] = blend_pixel<C>(blend, px[i], texel);
+							px[i] = blend_pixel<C>(blend, px[i], texel[i]);
 						}
-					}
 				}
 			}
 			else
 			{
 				// fill_triangle_part pixel loop (rasterizer.rs:1223-1279)
-				const uint4 s2 = __ldg(sp + 2);
-				const int32_t tc0 = (int32_t)s0.y, tc1 = (int32_t)s0.z, dtc0 = (int32_t)s0.w, dtc1 = (int32_t)s1.x;
-				const int32_t l0 = (int32_t)s1.y, l1 = (int32_t)s1.z, l2 = (int32_t)s1.w;
-				const int32_t dl0 = (int32_t)s2.x, dl1 = (int32_t)s2.y, dl2 = (int32_t)s2.z;
+				const uint4 r2 = s_span[2][hh][rb];
+				const int32_t tc0 = (int32_t)r0.y, tc1 = (int32_t)r0.z, dtc0 = (int32_t)r0.w, dtc1 = (int32_t)r1.x;
+				const int32_t l0 = (int32_t)r1.y, l1 = (int32_t)r1.z, l2 = (int32_t)r1.w;
+				const int32_t dl0 = (int32_t)r2.x, dl1 = (int32_t)r2.y, dl2 = (int32_t)r2.z;
 #pragma unroll
 				for (int i = 0; i < 4; ++i)
 				{
-					const int32_t x = px0 + i;
+					const int32_t x = px0 + SQW_PX_OFS(i);
 					if (x >= x0 && x < x1)
 					{
 						const int32_t k = x - x0;
@@ -827,7 +965,11 @@ __global__ void __launch_bounds__(SQW_RASTER_THREADS) raster_tile_kernel(
 					}
 				}
 			}
+			}
+			__syncthreads(); // the span stage (and, after the last group, the tile list) is rewritten next
 		}
+		if (num_hits == 0)
+			__syncthreads(); // s_warp_counts is rewritten by the next pass
 	}
 
 	if (row_valid)
@@ -836,28 +978,27 @@ __global__ void __launch_bounds__(SQW_RASTER_THREADS) raster_tile_kernel(
 		{
 			if (sizeof(Raw) == 8)
 			{
-				uint4* d = reinterpret_cast<uint4*>(dst);
-				d[0] = make_uint4((uint32_t)px[0], (uint32_t)((uint64_t)px[0] >> 32), (uint32_t)px[1], (uint32_t)((uint64_t)px[1] >> 32));
-				d[1] = make_uint4((uint32_t)px[2], (uint32_t)((uint64_t)px[2] >> 32), (uint32_t)px[3], (uint32_t)((uint64_t)px[3] >> 32));
+				*reinterpret_cast<uint4*>(dst) = make_uint4((uint32_t)px[0], (uint32_t)((uint64_t)px[0] >> 32), (uint32_t)px[1], (uint32_t)((uint64_t)px[1] >> 32));
+				*reinterpret_cast<uint4*>(dst + 16) = make_uint4((uint32_t)px[2], (uint32_t)((uint64_t)px[2] >> 32), (uint32_t)px[3], (uint32_t)((uint64_t)px[3] >> 32));
 			}
 			else
 			{
-				*reinterpret_cast<uint4*>(dst) = make_uint4((uint32_t)px[0], (uint32_t)px[1], (uint32_t)px[2], (uint32_t)px[3]);
+				*reinterpret_cast<uint2*>(dst) = make_uint2((uint32_t)px[0], (uint32_t)px[1]);
+				*reinterpret_cast<uint2*>(dst + 16) = make_uint2((uint32_t)px[2], (uint32_t)px[3]);
 			}
 		}
 		else
 		{
 #pragma unroll
 			for (int i = 0; i < 4; ++i)
-				if (px0 + i < width && (have & (1u << i)))
-					dst[i] = px[i];
+				if (px0 + SQW_PX_OFS(i) < width && (have & (1u << i)))
+					dst[SQW_PX_OFS(i)] = px[i];
 		}
 	}
 
 	if (TONEMAP)
 	{
 		// sizeof(Raw) == 8 here (the host only fuses 64-bit views)
-		uint32_t sb = 0, sg = 0, sr = 0;
 		if (row_valid)
 		{
 			uint32_t out[4];
@@ -865,64 +1006,81 @@ __global__ void __launch_bounds__(SQW_RASTER_THREADS) raster_tile_kernel(
 			for (int i = 0; i < 4; ++i)
 			{
 				out[i] = 0;
-				if (px0 + i < width)
+				if (px0 + SQW_PX_OFS(i) < width)
 				{
 					SQW_NEED_DST(i) // untouched pixel: tonemap what the buffer holds
 					const uint64_t p = (uint64_t)px[i];
-					sb += (uint32_t)(p & 0xFFFF);
-					sg += (uint32_t)((p >> 16) & 0xFFFF);
-					sr += (uint32_t)((p >> 32) & 0xFFFF);
-					out[i] = tonemap_pixel(cv_from_color64(p), isb, isg, isr);
+					const uint32_t cb = (uint32_t)(p & 0xFFFF), cg = (uint32_t)((p >> 16) & 0xFFFF), cr = (uint32_t)((p >> 32) & 0xFFFF);
+					sb += cb;
+					sg += cg;
+					sr += cr;
+					if ((cb | cg | cr) < SQW_TONEMAP_LUT_SIZE)
+						out[i] = (uint32_t)s_lut[cb] | ((uint32_t)s_lut[SQW_TONEMAP_LUT_SIZE + cg] << 8) | ((uint32_t)s_lut[2 * SQW_TONEMAP_LUT_SIZE + cr] << 16) | 0xFF000000u;
+					else
+						out[i] = tonemap_pixel(cv_from_color64(p), isb, isg, isr);
 				}
 			}
 			uint32_t* const o = ldr + (size_t)row * pitch + px0;
 			if (vec_ok)
-				__stcs(reinterpret_cast<uint4*>(o), make_uint4(out[0], out[1], out[2], out[3]));
+			{
+				__stcs(reinterpret_cast<uint2*>(o), make_uint2(out[0], out[1]));
+				__stcs(reinterpret_cast<uint2*>(o + 16), make_uint2(out[2], out[3]));
+			}
 			else
 			{
 #pragma unroll
 				for (int i = 0; i < 4; ++i)
-					if (px0 + i < width)
-						o[i] = out[i];
+					if (px0 + SQW_PX_OFS(i) < width)
+						o[SQW_PX_OFS(i)] = out[i];
 			}
 		}
-		// colour sums for update_exposure (postprocessor.rs:176-179): exact integers, 3 atomics per CTA
-		__shared__ uint32_t s_part[3][SQW_RASTER_THREADS / 32];
+	}
+	} // tile loop
+
+	if (TONEMAP)
+	{
+		// colour sums for update_exposure (postprocessor.rs:176-179): exact integers, 3 atomics per CTA.  A lane adds at most
+		// 4 x 65535 per tile and a CTA handles a few dozen tiles, so 32-bit partial sums cannot overflow before the warp reduction.
+		__shared__ unsigned long long s_part[3][WARPS];
+		unsigned long long wb = sb, wg = sg, wr = sr;
 #pragma unroll
 		for (int o = 16; o > 0; o >>= 1)
 		{
-			sb += __shfl_xor_sync(0xFFFFFFFFu, sb, o);
-			sg += __shfl_xor_sync(0xFFFFFFFFu, sg, o);
-			sr += __shfl_xor_sync(0xFFFFFFFFu, sr, o);
+			wb += __shfl_xor_sync(0xFFFFFFFFu, wb, o);
+			wg += __shfl_xor_sync(0xFFFFFFFFu, wg, o);
+			wr += __shfl_xor_sync(0xFFFFFFFFu, wr, o);
 		}
 		if (lane == 0)
 		{
-			s_part[0][warp] = sb;
-			s_part[1][warp] = sg;
-			s_part[2][warp] = sr;
+			s_part[0][warp] = wb;
+			s_part[1][warp] = wg;
+			s_part[2][warp] = wr;
 		}
 		__syncthreads();
 		if (threadIdx.x < 3)
 		{
 			unsigned long long t = 0;
-			for (int w = 0; w < SQW_RASTER_THREADS / 32; ++w)
+			for (int w = 0; w < WARPS; ++w)
 				t += s_part[threadIdx.x][w];
-			atomicAdd(sums + threadIdx.x, t);
+			atomicAdd(sums + (blockIdx.x % SQW_SUM_SLOTS) * 4 + threadIdx.x, t);
 		}
 	}
-#undef SQW_NEED_DST
 }
+#undef SQW_NEED_DST
+#undef SQW_PX_OFS
 
 } // namespace
 
 cudaError_t launch_raster_setup(const RasterLaunch& l, cudaStream_t stream)
 {
-	if (l.num_cmds == 0)
+	if (l.num_cmds == 0 && !l.tonemap_dst)
 		return cudaSuccess;
 	const uint32_t setup_blocks = std::max<uint32_t>((l.total_spans + SQW_SETUP_THREADS - 1) / SQW_SETUP_THREADS, 1); // block 0 also zeroes the sums
-	raster_setup_kernel<<<setup_blocks + l.num_bands, SQW_SETUP_THREADS, 0, stream>>>(
+	const uint32_t bin_blocks = l.num_cmds ? l.num_bands : 0;
+	const uint32_t lut_blocks = l.tonemap_dst ? (3 * SQW_TONEMAP_LUT_SIZE + SQW_SETUP_THREADS - 1) / SQW_SETUP_THREADS : 0;
+	raster_setup_kernel<<<setup_blocks + bin_blocks + lut_blocks, SQW_SETUP_THREADS, 0, stream>>>(
 		l.cmds, l.cmd_dev, l.num_cmds, l.polygon_points, l.triangle_points, l.cmd_span_base, l.total_spans, l.spans, l.width, l.height, setup_blocks, l.band_offsets,
-		l.band_lists, l.zero_sums_in_setup ? l.color_sums : nullptr);
+		l.band_lists, bin_blocks, l.tonemap_dst ? l.color_sums : nullptr, l.tonemap_lut, l.inv_scale_bgr[0], l.inv_scale_bgr[1], l.inv_scale_bgr[2]);
 	return cudaGetLastError();
 }
 
@@ -930,16 +1088,26 @@ cudaError_t launch_raster_tiles(const RasterLaunch& l, cudaStream_t stream)
 {
 	if (l.num_bands == 0)
 		return cudaSuccess;
-	const dim3 grid((uint32_t)((l.width + SQW_TILE_W - 1) / SQW_TILE_W), l.num_bands);
+	const uint32_t tiles_x = (uint32_t)((l.width + SQW_TILE_W - 1) / SQW_TILE_W), num_tiles = tiles_x * l.num_bands;
+	// persistent grid: resident CTAs per SM (registers and shared memory allow 4) x SM count
+	static int sm_count = 0;
+	if (sm_count == 0)
+	{
+		int dev = 0;
+		cudaGetDevice(&dev);
+		if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0)
+			sm_count = 148;
+	}
+	const uint32_t grid = std::min<uint32_t>(num_tiles, (uint32_t)sm_count * SQW_TILE_CTAS_PER_SM);
 #define SQW_TILE_ARGS(RAW) \
 	l.cmd_dev, l.spans, l.band_lists, l.band_offsets, static_cast<const char*>(l.surfaces_base), static_cast<RAW*>(l.color_buffer), l.width, l.height, l.pitch, l.clear, \
-		(RAW)l.clear_color, l.tonemap_dst, l.inv_scale_bgr[0], l.inv_scale_bgr[1], l.inv_scale_bgr[2], l.color_sums
+		(RAW)l.clear_color, l.tonemap_dst, l.inv_scale_bgr[0], l.inv_scale_bgr[1], l.inv_scale_bgr[2], l.color_sums, l.tonemap_lut, tiles_x, num_tiles
 	if (l.color64 && l.tonemap_dst)
-		raster_tile_kernel<Color64, true><<<grid, SQW_RASTER_THREADS, 0, stream>>>(SQW_TILE_ARGS(uint64_t));
+		raster_tile_kernel<Color64, 1><<<grid, SQW_RASTER_THREADS, 0, stream>>>(SQW_TILE_ARGS(uint64_t));
 	else if (l.color64)
-		raster_tile_kernel<Color64, false><<<grid, SQW_RASTER_THREADS, 0, stream>>>(SQW_TILE_ARGS(uint64_t));
+		raster_tile_kernel<Color64, 0><<<grid, SQW_RASTER_THREADS, 0, stream>>>(SQW_TILE_ARGS(uint64_t));
 	else
-		raster_tile_kernel<Color32, false><<<grid, SQW_RASTER_THREADS, 0, stream>>>(SQW_TILE_ARGS(uint32_t));
+		raster_tile_kernel<Color32, 0><<<grid, SQW_RASTER_THREADS, 0, stream>>>(SQW_TILE_ARGS(uint32_t));
 #undef SQW_TILE_ARGS
 	return cudaGetLastError();
 }

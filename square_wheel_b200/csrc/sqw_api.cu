@@ -87,7 +87,8 @@ struct Arena
 				cudaFreeHost(h);
 			h = nullptr;
 			h_capacity = 0;
-			const size_t rounded = (total_bytes + (total_bytes >> 2) + 4095) & ~size_t(4095);
+			// page-locked allocations are slow and synchronise the device: grow geometrically from a floor of 1 MiB
+			const size_t rounded = std::max<size_t>((2 * total_bytes + 4095) & ~size_t(4095), size_t(1) << 20);
 			cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&h), rounded, cudaHostAllocDefault);
 			if (e != cudaSuccess)
 			{
@@ -96,7 +97,7 @@ struct Arena
 			}
 			h_capacity = rounded;
 		}
-		return d.reserve(total_bytes);
+		return d.reserve(std::max<size_t>(total_bytes, h_capacity / 2));
 	}
 	static size_t padded(size_t bytes) { return (bytes + 255) & ~size_t(255); }
 	// returns the device address the section will have after commit()
@@ -230,7 +231,8 @@ struct sqw_view
 	DevBuf spans;
 	DevBuf band_lists;
 	uint64_t* d_bloom[2] = {nullptr, nullptr};
-	unsigned long long* d_sums = nullptr; // 3 x u64
+	uint8_t* d_tonemap_lut = nullptr;     // 3 x SQW_TONEMAP_LUT_SIZE (64-bit views)
+	unsigned long long* d_sums = nullptr; // SQW_SUM_SLOTS x {B, G, R, pad}
 	uint64_t sums_divisor = 1;
 	sqw_frame* immediate = nullptr;
 };
@@ -505,10 +507,12 @@ int sqw_view_create(sqw_ctx* ctx, sqw_view** out_view, uint32_t width, uint32_t 
 		if (e == cudaSuccess)
 			e = cudaMalloc(&v->d_bloom[1], bpx * 8);
 	}
+	if (e == cudaSuccess && color_bits == 64)
+		e = cudaMalloc(&v->d_tonemap_lut, 3 * SQW_TONEMAP_LUT_SIZE);
 	if (e == cudaSuccess)
-		e = cudaMalloc(&v->d_sums, 3 * sizeof(unsigned long long));
+		e = cudaMalloc(&v->d_sums, SQW_SUM_WORDS * sizeof(unsigned long long));
 	if (e == cudaSuccess)
-		e = cudaMemset(v->d_sums, 0, 3 * sizeof(unsigned long long));
+		e = cudaMemset(v->d_sums, 0, SQW_SUM_WORDS * sizeof(unsigned long long));
 	if (e != cudaSuccess)
 	{
 		int rc = fail_cuda(ctx, e, "sqw_view_create: device allocation");
@@ -550,6 +554,8 @@ void sqw_view_destroy(sqw_view* view)
 			cudaFree(b);
 	if (view->d_sums)
 		cudaFree(view->d_sums);
+	if (view->d_tonemap_lut)
+		cudaFree(view->d_tonemap_lut);
 	// keep indices of the other views stable: leave a hole
 	for (auto& p : ctx->views)
 		if (p == view)
@@ -971,13 +977,11 @@ int sqw_frame_submit(sqw_frame* f, uint32_t stages)
 			l.inv_scale_bgr[0] = inv_scale_bgr[0];
 			l.inv_scale_bgr[1] = inv_scale_bgr[1];
 			l.inv_scale_bgr[2] = inv_scale_bgr[2];
-			l.color_sums = view->d_sums;
-			l.zero_sums_in_setup = f->num_cmds != 0;
-			if (!l.zero_sums_in_setup)
-				SQW_CUDA(ctx, cudaMemsetAsync(view->d_sums, 0, 3 * sizeof(unsigned long long), s));
+			l.color_sums = view->d_sums; // zeroed by the set-up grid
+			l.tonemap_lut = view->d_tonemap_lut;
 			view->sums_divisor = (uint64_t)view->width * view->height;
 		}
-		if (f->num_cmds)
+		if (f->num_cmds || fused_tonemap)
 		{
 			LaunchTimer timer(ctx, SQW_KERNEL_RASTER_SETUP, s);
 			SQW_CUDA(ctx, launch_raster_setup(l, s));
@@ -1003,7 +1007,7 @@ int sqw_frame_submit(sqw_frame* f, uint32_t stages)
 		l.inv_scale_bgr[1] = inv_scale_bgr[1];
 		l.inv_scale_bgr[2] = inv_scale_bgr[2];
 		l.color_sums = view->d_sums;
-		SQW_CUDA(ctx, cudaMemsetAsync(view->d_sums, 0, 3 * sizeof(unsigned long long), s));
+		SQW_CUDA(ctx, cudaMemsetAsync(view->d_sums, 0, SQW_SUM_WORDS * sizeof(unsigned long long), s));
 		if (p.bloom_sigma > 0.0f)
 		{
 			// perform_bloom (postprocessor.rs:729-789)
@@ -1192,12 +1196,17 @@ int sqw_view_get_average_color(sqw_view* view, float avg_color_out[3])
 		return SQW_ERR_INVALID_ARGUMENT;
 	sqw_ctx* ctx = view->ctx;
 	SQW_CUDA(ctx, cudaSetDevice(ctx->device));
-	unsigned long long sums[3];
-	SQW_CUDA(ctx, cudaMemcpyAsync(sums, view->d_sums, sizeof(sums), cudaMemcpyDeviceToHost, view->stream));
+	unsigned long long slots[SQW_SUM_WORDS];
+	SQW_CUDA(ctx, cudaMemcpyAsync(slots, view->d_sums, sizeof(slots), cudaMemcpyDeviceToHost, view->stream));
 	SQW_CUDA(ctx, cudaStreamSynchronize(view->stream));
 	const float inv = 1.0f / (float)view->sums_divisor; // postprocessor.rs:176-179 / :840-843
 	for (int i = 0; i < 3; ++i)
-		avg_color_out[i] = (float)sums[i] * inv;
+	{
+		unsigned long long sum = 0;
+		for (int slot = 0; slot < SQW_SUM_SLOTS; ++slot)
+			sum += slots[slot * 4 + i];
+		avg_color_out[i] = (float)sum * inv;
+	}
 	return SQW_OK;
 }
 

@@ -244,4 +244,5 @@ __device__ __forceinline__ uint32_t tonemap_pixel(ColorVec c, float inv_scale_b,
 	return f32_to_u_clamped(b, 255.0f) | (f32_to_u_clamped(g, 255.0f) << 8) | (f32_to_u_clamped(r, 255.0f) << 16) | 0xFF000000u;
 }
 
+
 } // namespace sqw

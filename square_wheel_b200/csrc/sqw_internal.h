@@ -59,8 +59,16 @@ cudaError_t launch_surface_build(bool color64, bool dynamic_lights, const Surfac
 // ---- stage 2 ------------------------------------------------------------------------------------------------
 #define SQW_TILE_W 128
 #define SQW_TILE_H 8
+// Colour sums (average colour for update_exposure) are accumulated with atomics into SQW_SUM_SLOTS separate 32-byte slots
+// {B, G, R, pad} chosen by CTA index — thousands of same-address atomics would serialise in one L2 slice — and added
+// up on the host when the average is read.
+#define SQW_SUM_SLOTS 64
+#define SQW_SUM_WORDS (SQW_SUM_SLOTS * 4)
 #define SQW_SETUP_THREADS 128
-#define SQW_RASTER_THREADS 256 /* 8 warps: each warp owns one row of the tile, each lane 4 consecutive pixels */
+#define SQW_TONEMAP_LUT_SIZE 4096 /* channel values below this (16 x LDR white) are tonemapped by table look-up */
+#define SQW_TILE_STAGE_HITS (256 / SQW_TILE_H) /* commands whose span records are staged in shared memory at a time */
+#define SQW_RASTER_THREADS 256
+#define SQW_TILE_CTAS_PER_SM 4 /* resident CTAs of the persistent tile kernel per SM (register and shared-memory budget) */ /* 8 warps: each warp owns one row of the tile, each lane 4 consecutive pixels */
 
 // Per-command data prepared by the host part of sqw_frame_set_draw (row range, conservative column range,
 // span-table offset, resolved texture pointer).  32 bytes.
@@ -111,7 +119,7 @@ struct RasterLaunch
 	uint32_t* tonemap_dst; // nullptr = not fused
 	float inv_scale_bgr[3];
 	unsigned long long* color_sums;
-	int zero_sums_in_setup; // the set-up kernel clears color_sums (saves a memset node per frame)
+	uint8_t* tonemap_lut; // device, 3 x SQW_TONEMAP_LUT_SIZE bytes (B, G, R), rebuilt by the set-up grid of every fused frame
 };
 // span set-up + binning in one grid
 cudaError_t launch_raster_setup(const RasterLaunch& l, cudaStream_t stream);
