@@ -8,7 +8,7 @@
 // pixels bit for bit on a GPU the incremental state is turned into closed forms with the same wrap-around
 // arithmetic, and the painter's order is kept per pixel:
 //
-//   raster_setup_kernel   one THREAD per (command, scan-line): re-walks the polygon edges (or the triangle
+//   raster_setup_kernel   one THREAD per (command, scan-line), one warp per 32 scan-lines of one command: re-walks the polygon edges (or the triangle
 //                         halves) to the trapezoid that owns the line, evaluates x_left/x_right for that line as
 //                         x0 + n*dx_dy (mod 2^32, exactly the value the reference reaches after n additions) and
 //                         does the per-line set-up of the reference's inner loops (i64 equations, span end-point
@@ -598,7 +598,7 @@ __device__ void bin_band(const CmdDev* __restrict__ cmd_dev, uint32_t num_cmds, 
 
 __global__ void __launch_bounds__(SQW_SETUP_THREADS) raster_setup_kernel(
 	const sqw_draw_cmd* __restrict__ cmds, const CmdDev* __restrict__ cmd_dev, uint32_t num_cmds, const sqw_polygon_point* __restrict__ polygon_points,
-	const sqw_triangle_point* __restrict__ triangle_points, const uint32_t* __restrict__ cmd_span_base, uint32_t total_spans, SpanRec* __restrict__ spans,
+	const sqw_triangle_point* __restrict__ triangle_points, const uint2* __restrict__ chunks, uint32_t num_chunks, SpanRec* __restrict__ spans,
 	int32_t clip_w, int32_t clip_h, uint32_t setup_blocks, const uint32_t* __restrict__ band_offsets, uint32_t* __restrict__ band_lists, uint32_t num_bands,
 	unsigned long long* __restrict__ sums_to_zero, uint8_t* __restrict__ tonemap_lut, float isb, float isg, float isr)
 {
@@ -624,21 +624,18 @@ __global__ void __launch_bounds__(SQW_SETUP_THREADS) raster_setup_kernel(
 	if (sums_to_zero && blockIdx.x == 0) // colour sums of the fused tonemapping epilogue of the tile kernel that follows
 		for (uint32_t i = threadIdx.x; i < SQW_SUM_WORDS; i += SQW_SETUP_THREADS)
 			sums_to_zero[i] = 0;
-	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-	if (s >= total_spans)
+	// One warp per chunk = up to 32 consecutive scan-lines of one command (chunk list built by the host while it computes
+	// the row ranges): the command and its vertices are warp-uniform, so their loads are broadcasts served by one L1 line.
+	const uint32_t chunk = blockIdx.x * (SQW_SETUP_THREADS / 32) + (threadIdx.x >> 5);
+	if (chunk >= num_chunks)
 		return;
-	// Owning command: last index with cmd_span_base[i] <= s.
-	uint32_t lo = 0, hi = num_cmds; // invariant: base[lo] <= s < base[hi]
-	while (hi - lo > 1)
-	{
-		const uint32_t mid = (lo + hi) >> 1;
-		if (__ldg(cmd_span_base + mid) <= s)
-			lo = mid;
-		else
-			hi = mid;
-	}
-	const CmdDev cd = cmd_dev[lo];
-	const sqw_draw_cmd c = cmds[lo];
+	const uint2 ch = __ldg(chunks + chunk); // {command index, first row of the chunk relative to the command's y0}
+	const CmdDev cd = cmd_dev[ch.x];
+	const uint32_t r = ch.y + (threadIdx.x & 31);
+	if (r >= (uint32_t)((int32_t)cd.y1 - (int32_t)cd.y0))
+		return;
+	const sqw_draw_cmd c = cmds[ch.x];
+	const uint32_t s = cd.span_base + r;
 	const int32_t row = (int32_t)cd.y0 + (int32_t)(s - cd.span_base);
 	if (cd.kind == SQW_CMD_POLYGON)
 		setup_polygon_line(c, cd, polygon_points + c.vertex_offset, row, clip_w, clip_h, spans + s);
@@ -1075,11 +1072,12 @@ cudaError_t launch_raster_setup(const RasterLaunch& l, cudaStream_t stream)
 {
 	if (l.num_cmds == 0 && !l.tonemap_dst)
 		return cudaSuccess;
-	const uint32_t setup_blocks = std::max<uint32_t>((l.total_spans + SQW_SETUP_THREADS - 1) / SQW_SETUP_THREADS, 1); // block 0 also zeroes the sums
+	const uint32_t chunks_per_block = SQW_SETUP_THREADS / 32;
+	const uint32_t setup_blocks = std::max<uint32_t>((l.num_chunks + chunks_per_block - 1) / chunks_per_block, 1); // block 0 also zeroes the sums
 	const uint32_t bin_blocks = l.num_cmds ? l.num_bands : 0;
 	const uint32_t lut_blocks = l.tonemap_dst ? (3 * SQW_TONEMAP_LUT_SIZE + SQW_SETUP_THREADS - 1) / SQW_SETUP_THREADS : 0;
 	raster_setup_kernel<<<setup_blocks + bin_blocks + lut_blocks, SQW_SETUP_THREADS, 0, stream>>>(
-		l.cmds, l.cmd_dev, l.num_cmds, l.polygon_points, l.triangle_points, l.cmd_span_base, l.total_spans, l.spans, l.width, l.height, setup_blocks, l.band_offsets,
+		l.cmds, l.cmd_dev, l.num_cmds, l.polygon_points, l.triangle_points, l.chunks, l.num_chunks, l.spans, l.width, l.height, setup_blocks, l.band_offsets,
 		l.band_lists, bin_blocks, l.tonemap_dst ? l.color_sums : nullptr, l.tonemap_lut, l.inv_scale_bgr[0], l.inv_scale_bgr[1], l.inv_scale_bgr[2]);
 	return cudaGetLastError();
 }

@@ -262,11 +262,12 @@ struct sqw_frame
 	const CmdDev* d_cmd_dev = nullptr;
 	const sqw_polygon_point* d_polygon_points = nullptr;
 	const sqw_triangle_point* d_triangle_points = nullptr;
-	const uint32_t* d_cmd_span_base = nullptr;
+	const uint2* d_chunks = nullptr;
 	const uint32_t* d_band_offsets = nullptr;
 	std::vector<uint32_t> sampled_views; // views referenced through SQW_TEX_VIEW
 	std::vector<CmdDev> h_cmd_dev;
-	std::vector<uint32_t> h_cmd_span_base, h_band_offsets;
+	std::vector<uint2> h_chunks;
+	std::vector<uint32_t> h_band_offsets;
 	uint32_t num_cmds = 0, total_spans = 0, num_bands = 0, total_band_entries = 0;
 	bool clear = false;
 	uint64_t clear_color = 0;
@@ -720,7 +721,7 @@ int sqw_frame_set_draw(
 
 	f->h_cmd_dev.resize(num_cmds);
 	f->sampled_views.clear();
-	f->h_cmd_span_base.assign((size_t)num_cmds + 1, 0);
+	f->h_chunks.clear();
 	f->h_band_offsets.assign((size_t)num_bands + 1, 0);
 	uint64_t span_total = 0;
 	for (uint32_t i = 0; i < num_cmds; ++i)
@@ -818,7 +819,8 @@ int sqw_frame_set_draw(
 		d.bx0 = (int16_t)bx0;
 		d.bx1 = (int16_t)bx1;
 		d.span_base = (uint32_t)span_total;
-		f->h_cmd_span_base[i] = (uint32_t)span_total;
+		for (int32_t r0 = 0; r0 < y1 - y0; r0 += 32)
+			f->h_chunks.push_back(make_uint2(i, (uint32_t)r0));
 		span_total += (uint64_t)(y1 - y0);
 		if (span_total > 0xFFFFFFFFull)
 			return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_frame_set_draw: too many scan-lines");
@@ -826,7 +828,6 @@ int sqw_frame_set_draw(
 			for (int32_t b = y0 / SQW_TILE_H; b <= (y1 - 1) / SQW_TILE_H; ++b)
 				f->h_band_offsets[(size_t)b + 1]++;
 	}
-	f->h_cmd_span_base[num_cmds] = (uint32_t)span_total;
 	for (uint32_t b = 0; b < num_bands; ++b)
 		f->h_band_offsets[(size_t)b + 1] += f->h_band_offsets[b];
 	f->num_cmds = num_cmds;
@@ -846,13 +847,13 @@ int sqw_frame_set_draw(
 		Arena& a = f->draw_arena;
 		const size_t b_cmds = (size_t)num_cmds * sizeof(sqw_draw_cmd), b_dev = (size_t)num_cmds * sizeof(CmdDev);
 		const size_t b_pp = (size_t)num_polygon_points * sizeof(sqw_polygon_point), b_tp = (size_t)num_triangle_points * sizeof(sqw_triangle_point);
-		const size_t b_base = f->h_cmd_span_base.size() * 4, b_off = f->h_band_offsets.size() * 4;
+		const size_t b_base = f->h_chunks.size() * sizeof(uint2), b_off = f->h_band_offsets.size() * 4;
 		SQW_CUDA(ctx, a.begin(Arena::padded(b_cmds) + Arena::padded(b_dev) + Arena::padded(b_pp) + Arena::padded(b_tp) + Arena::padded(b_base) + Arena::padded(b_off)));
 		f->d_cmds = static_cast<const sqw_draw_cmd*>(a.push(cmds, b_cmds));
 		f->d_cmd_dev = static_cast<const CmdDev*>(a.push(f->h_cmd_dev.data(), b_dev));
 		f->d_polygon_points = static_cast<const sqw_polygon_point*>(a.push(polygon_points, b_pp));
 		f->d_triangle_points = static_cast<const sqw_triangle_point*>(a.push(triangle_points, b_tp));
-		f->d_cmd_span_base = static_cast<const uint32_t*>(a.push(f->h_cmd_span_base.data(), b_base));
+		f->d_chunks = static_cast<const uint2*>(a.push(f->h_chunks.data(), b_base));
 		f->d_band_offsets = static_cast<const uint32_t*>(a.push(f->h_band_offsets.data(), b_off));
 		SQW_CUDA(ctx, a.commit(view->stream));
 	}
@@ -958,7 +959,8 @@ int sqw_frame_submit(sqw_frame* f, uint32_t stages)
 		l.polygon_points = f->d_polygon_points;
 		l.triangle_points = f->d_triangle_points;
 		l.spans = static_cast<SpanRec*>(view->spans.ptr);
-		l.cmd_span_base = f->d_cmd_span_base;
+		l.chunks = f->d_chunks;
+		l.num_chunks = (uint32_t)f->h_chunks.size();
 		l.total_spans = f->total_spans;
 		l.band_lists = static_cast<uint32_t*>(view->band_lists.ptr);
 		l.band_offsets = f->d_band_offsets;

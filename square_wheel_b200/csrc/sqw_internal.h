@@ -104,7 +104,8 @@ struct RasterLaunch
 	const sqw_polygon_point* polygon_points;
 	const sqw_triangle_point* triangle_points;
 	SpanRec* spans;                // device, total_spans entries
-	const uint32_t* cmd_span_base; // device, num_cmds + 1 (exclusive prefix of row counts)
+	const uint2* chunks; // device: {command index, first row relative to the command's y0} per 32 scan-lines of a command
+	uint32_t num_chunks;
 	uint32_t total_spans;
 	uint32_t* band_lists;         // device, ordered command indices per band
 	const uint32_t* band_offsets; // device, num_bands + 1

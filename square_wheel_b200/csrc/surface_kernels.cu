@@ -457,7 +457,7 @@ __device__ __forceinline__ void surface_band(
 
 // Variant byte of a band: bit0 directional lightmap, bit1 normal map, bits2-3 specular type, bit4 emissive-only.
 template <class C, bool DYN>
-__global__ void __launch_bounds__(SQW_SURF_THREADS) surface_build_kernel(
+__global__ void __launch_bounds__(SQW_SURF_THREADS, DYN ? 3 : 4) surface_build_kernel(
 	const sqw_surface_job* __restrict__ jobs, const SurfaceBand* __restrict__ bands, const ImageDev* __restrict__ images,
 	const float* __restrict__ lightmaps, const sqw_directional_lightmap_element* __restrict__ directional_lightmaps,
 	const sqw_light* __restrict__ lights, const float* __restrict__ shadow_maps, float cam_x, float cam_y, float cam_z,
