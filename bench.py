@@ -205,9 +205,14 @@ def run_cuda(args, rank, local_rank, world):
     # ---- scene + host preparation (the part of the renderer that stays on the host) ----
     scene = S.Scene(**SCENE_KW)
     poses = scene.camera_path(NUM_POSES)
-    # independent camera views are partitioned across GPUs: rank r starts its loop at a different phase of the fly-through
-    order = [(i + rank * (NUM_POSES // max(world, 1))) % NUM_POSES for i in range(NUM_POSES)]
-    host_frames, host_ms = prepare_host_frames(scene, [poses[i] for i in order])
+    # Independent camera views are partitioned across GPUs: the batch is the 64-pose path resampled x world
+    # (seeded jitter), rank r renders the contiguous block partition_views() gives it -> 64 views per GPU (weak scaling).
+    from square_wheel_b200 import batch as B
+
+    all_poses = poses if world == 1 else B.resample_camera_path(poses, world)
+    mine = B.partition_views(len(all_poses), world, rank)
+    assert len(mine) == NUM_POSES
+    host_frames, host_ms = prepare_host_frames(scene, [all_poses[i] for i in mine])
 
     # a real (non-default) stream: its handle is what the C-ABI launches on and what the torch events below are recorded on
     stream = torch.cuda.Stream(device=local_rank)
@@ -277,10 +282,7 @@ def run_cuda(args, rank, local_rank, world):
         sampler.samples = sampler.samples[n_before:]
         clocks = sampler.stop()
         clocks["note"] = "sampled while the timed workload kept running (the timed region itself is shorter than the sampling period)"
-    if dist is not None:
-        t = torch.tensor([elapsed_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
+    elapsed_ms = B.max_over_ranks(elapsed_ms, dist, "cuda")
     frames_timed = args.steps * FRAMES_PER_STEP
     fps = world * frames_timed / (elapsed_ms * 1e-3)
 
@@ -369,10 +371,7 @@ def run_cuda(args, rank, local_rank, world):
     _, h2d_total = e2e_steps(args.steps, k)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    if dist is not None:
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    e2e_s = B.max_over_ranks(e2e_s, dist, "cuda")
     e2e_fps = world * frames_timed / e2e_s
     e2e = {
         "value": e2e_fps,

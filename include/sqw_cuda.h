@@ -99,6 +99,13 @@ int sqw_update_image(sqw_ctx* ctx, int image_id, const void* pixels);
 int sqw_view_create(sqw_ctx* ctx, sqw_view** out_view, uint32_t width, uint32_t height, int color_bits);
 void sqw_view_destroy(sqw_view* view);
 
+/* Change the logical size of a view within the size it was created with (portal textures change resolution from frame
+ * to frame, partial_renderer.rs:2130-2182, while the reference's pixel pool only ever grows, :2163-2176).  The pitch of the
+ * colour buffer becomes `width`.  Contents are undefined afterwards. */
+int sqw_view_set_size(sqw_view* view, uint32_t width, uint32_t height);
+/* Index of the view in its context: the value to put into sqw_draw_cmd::tex_ref with SQW_TEX_VIEW. */
+int sqw_view_index(const sqw_view* view);
+
 /* ---- S1: surfaces --------------------------------------------------------------------------------------- */
 
 #define SQW_SURF_HAS_NORMAL_MAP 1u        /* Texture::has_normal_map        textures.rs:14 */
@@ -169,6 +176,39 @@ int sqw_build_surfaces(
 	uint64_t shadow_maps_len,
 	const float cam_pos[3],
 	uint64_t total_surface_pixels);
+
+/* mix_surface_with_texture (surfaces.rs:854-971) applied to the whole colour buffer of a view that serves as a portal /
+ * mirror texture: overlay of the portal's glass texture with its blending mode and light (partial_renderer.rs:2212-2271).
+ * image_id: SQW_IMAGE_COLOR32 mip of the overlay; surface_tc_min = PortalInfo::tc_min; blending_mode = SQW_BLEND_*
+ * (declared below). */
+int sqw_view_mix_texture(sqw_view* view, uint32_t image_id, const int32_t surface_tc_min[2], int blending_mode, const float light[3]);
+
+/* ---- shadow maps --------------------------------------------------------------- */
+/* The depth rasteriser that fills the shadow maps the surface stage samples: DepthRasterizer::fill_polygon
+ * (rasterizer.rs:1295-1474) as driven by DepthRenderer::draw_map (depth_renderer.rs:47-67) from
+ * PartialRenderer::build_shadow_maps (partial_renderer.rs:524-590).  The host keeps doing the visibility flood, culling,
+ * clipping and the biased depth equation (depth_renderer.rs:214-286) per light / cube side and records the fill calls. */
+#define SQW_DEPTH_MAP_CLEAR 1u            /* fill the map with clear_value first (the reference keeps stale texels where nothing is drawn) */
+#define SQW_DEPTH_MAP_PROJECTOR_CIRCLE 2u /* make_shadow_map_circle afterwards (light.rs:133-157; square maps) */
+
+typedef struct sqw_depth_map /* 32 bytes */
+{
+	uint32_t offset; /* in floats into the frame's shadow map array (sqw_light::shadow_map_offset + side * size * size) */
+	uint32_t width, height;
+	uint32_t first_cmd, num_cmds; /* its commands: consecutive, in submission order */
+	uint32_t flags;               /* SQW_DEPTH_MAP_* */
+	float clear_value;
+	uint32_t reserved;
+} sqw_depth_map;
+
+typedef struct sqw_depth_cmd /* one DepthRasterizer::fill_polygon::<DEPTH_TEST> call, 32 bytes */
+{
+	uint32_t num_vertices;  /* 3..24 */
+	uint32_t vertex_offset; /* into polygon_points of the call */
+	uint32_t depth_test;    /* 0: overwrite (world polygons, back to front); 1: max with the stored value (submodels) */
+	float depth_eq[3];      /* DepthEquation with the bias and scale of depth_renderer.rs:226-237 applied */
+	uint32_t reserved[2];
+} sqw_depth_cmd;
 
 /* ---- S2: rasterisation ---------------------------------------------------------------------------------- */
 
@@ -300,12 +340,26 @@ int sqw_frame_set_draw(
 	uint32_t num_triangle_points,
 	const void* clear_color);
 int sqw_frame_set_post(sqw_frame* frame, const sqw_post_params* params);
+/* Record the shadow-map fills of the frame.  They run (SQW_STAGE_SHADOW_MAPS) before the surface stage and write into the
+ * frame's shadow map array: call sqw_frame_set_surfaces with shadow_maps = NULL and shadow_maps_len = the array length to
+ * have that array live on the device only (no upload), or with host data to pre-fill it. */
+int sqw_frame_set_shadow_map_draw(
+	sqw_frame* frame,
+	const sqw_depth_map* maps,
+	uint32_t num_maps,
+	const sqw_depth_cmd* cmds,
+	uint32_t num_cmds,
+	const sqw_polygon_point* polygon_points,
+	uint32_t num_polygon_points);
+/* Copy `count` floats of the frame's shadow map array starting at `offset` (test / inspection hook; synchronises). */
+int sqw_frame_read_shadow_maps(sqw_frame* frame, float* dst, uint64_t offset, uint64_t count);
 /* Launch surfaces -> raster -> post for the recorded frame on the context's stream (asynchronous).
  * stages: bit0 surfaces, bit1 raster, bit2 post. */
 #define SQW_STAGE_SURFACES 1u
 #define SQW_STAGE_RASTER 2u
 #define SQW_STAGE_POST 4u
-#define SQW_STAGE_ALL 7u
+#define SQW_STAGE_SHADOW_MAPS 8u /* runs first */
+#define SQW_STAGE_ALL 15u
 int sqw_frame_submit(sqw_frame* frame, uint32_t stages);
 
 /* Fork / join between the context's stream and the private streams of its views (SQW_CTX_CONCURRENT_VIEWS; no-ops
@@ -342,7 +396,10 @@ int sqw_frame_get_stats(const sqw_frame* frame, sqw_frame_stats* out);
 #define SQW_KERNEL_BLOOM_BLUR 6
 #define SQW_KERNEL_TONEMAP_BLOOM 7
 #define SQW_KERNEL_RASTER_TILE_TONEMAP 8 /* tile kernel with the fused tonemapping epilogue */
-#define SQW_NUM_KERNEL_KINDS 9
+#define SQW_KERNEL_MIX_TEXTURE 9
+#define SQW_KERNEL_DEPTH_SETUP 10
+#define SQW_KERNEL_DEPTH_RESOLVE 11
+#define SQW_NUM_KERNEL_KINDS 12
 typedef struct sqw_kernel_times
 {
 	double ms[SQW_NUM_KERNEL_KINDS];

@@ -110,6 +110,16 @@ def draw(color_bits, framebuffer, cmds, polygon_points, triangle_points, surface
     return framebuffer
 
 
+def draw_shadow_maps(shadow_maps, maps, cmds, polygon_points):
+    """DepthRasterizer::fill_polygon for every recorded fill call, map by map, into `shadow_maps` (float32, in place)."""
+    maps = np.ascontiguousarray(maps)
+    cmds = np.ascontiguousarray(cmds)
+    pp = np.ascontiguousarray(polygon_points)
+    rc = lib().oracle_draw_shadow_maps(_p(shadow_maps), _p(maps), C.c_uint32(len(maps)), _p(cmds), C.c_uint32(len(cmds)), _p(pp))
+    assert rc == 0
+    return shadow_maps
+
+
 def fill(framebuffer, raw_color):
     lib().oracle_fill(C.c_int(32 if framebuffer.dtype == np.uint32 else 64), _p(framebuffer), C.c_uint64(framebuffer.size), C.c_uint64(raw_color))
 

@@ -24,7 +24,8 @@ CMD_POLYGON, CMD_TRIANGLE = 0, 1
 BLEND_NONE, BLEND_AVERAGE, BLEND_ADDITIVE, BLEND_ALPHA_TEST, BLEND_ALPHA_BLEND = range(5)
 TC_FULL_PERSPECTIVE, TC_LINE_Z_CORRECTION, TC_AFFINE = 0, 1, 2
 TEX_SURFACE, TEX_IMAGE, TEX_VIEW = 0, 1, 2
-STAGE_SURFACES, STAGE_RASTER, STAGE_POST, STAGE_ALL = 1, 2, 4, 7
+STAGE_SURFACES, STAGE_RASTER, STAGE_POST, STAGE_SHADOW_MAPS, STAGE_ALL = 1, 2, 4, 8, 15
+DEPTH_MAP_CLEAR, DEPTH_MAP_PROJECTOR_CIRCLE = 1, 2
 CTX_CONCURRENT_VIEWS = 1
 
 # ---- struct layouts as numpy dtypes (sizes asserted against the static_asserts in sqw_api.cu) ---------------
@@ -102,6 +103,14 @@ assert directional_lightmap_dtype.itemsize == 40
 texture_element_dtype = np.dtype([("diffuse", "<u4"), ("packed_normal_roughness", "<i4")])
 
 
+depth_map_dtype = np.dtype(
+    [("offset", "<u4"), ("width", "<u4"), ("height", "<u4"), ("first_cmd", "<u4"), ("num_cmds", "<u4"), ("flags", "<u4"), ("clear_value", "<f4"), ("reserved", "<u4")]
+)
+assert depth_map_dtype.itemsize == 32
+depth_cmd_dtype = np.dtype([("num_vertices", "<u4"), ("vertex_offset", "<u4"), ("depth_test", "<u4"), ("depth_eq", "<f4", (3,)), ("reserved", "<u4", (2,))])
+assert depth_cmd_dtype.itemsize == 32
+
+
 class MapDesc(C.Structure):
     _fields_ = [
         ("lightmaps_data", C.c_void_p),
@@ -140,10 +149,10 @@ class FrameStats(C.Structure):
 
 
 class KernelTimes(C.Structure):
-    _fields_ = [("ms", C.c_double * 9), ("launches", C.c_uint64 * 9)]
+    _fields_ = [("ms", C.c_double * 12), ("launches", C.c_uint64 * 12)]
 
 
-KERNEL_NAMES = ["surface_build", "raster_setup", "raster_bin", "raster_tile", "tonemap", "bloom_downscale", "bloom_blur", "tonemap_bloom", "raster_tile_tonemap"]
+KERNEL_NAMES = ["surface_build", "raster_setup", "raster_bin", "raster_tile", "tonemap", "bloom_downscale", "bloom_blur", "tonemap_bloom", "raster_tile_tonemap", "mix_texture", "depth_setup", "depth_resolve"]
 
 # Every symbol include/sqw_cuda.h declares: (name, restype, argtypes)
 _VP = C.c_void_p
@@ -163,6 +172,11 @@ CUDA_SYMBOLS = [
     ("sqw_read_pixels32", C.c_int, [_VP, _VP, C.c_size_t]),
     ("sqw_read_pixels_async", C.c_int, [_VP, _VP, C.c_size_t]),
     ("sqw_read_pixels32_async", C.c_int, [_VP, _VP, C.c_size_t]),
+    ("sqw_view_set_size", C.c_int, [_VP, C.c_uint32, C.c_uint32]),
+    ("sqw_view_index", C.c_int, [_VP]),
+    ("sqw_view_mix_texture", C.c_int, [_VP, C.c_uint32, _VP, C.c_int, _VP]),
+    ("sqw_frame_set_shadow_map_draw", C.c_int, [_VP, _VP, C.c_uint32, _VP, C.c_uint32, _VP, C.c_uint32]),
+    ("sqw_frame_read_shadow_maps", C.c_int, [_VP, _VP, C.c_uint64, C.c_uint64]),
     ("sqw_batch_begin", C.c_int, [_VP]),
     ("sqw_batch_end", C.c_int, [_VP]),
     ("sqw_write_pixels", C.c_int, [_VP, _VP, C.c_size_t]),

@@ -26,6 +26,7 @@
 // store; the full-perspective mode adds one u32 divide per pixel (rasterizer.rs:430).
 #include "sqw_device.cuh"
 #include "sqw_internal.h"
+#include "sqw_raster_walk.cuh"
 #include <algorithm>
 #include <cstdlib>
 
@@ -45,11 +46,6 @@ constexpr float INV_Z_SCALE = 536870912.0f;
 
 __device__ __forceinline__ int64_t min64(int64_t a, int64_t b) { return a < b ? a : b; }
 __device__ __forceinline__ int64_t max64(int64_t a, int64_t b) { return a > b ? a : b; }
-
-struct PolygonSide
-{
-	Fixed16 x_start, dx_dy;
-};
 
 struct Eq64
 {
@@ -213,89 +209,14 @@ __device__ void polygon_part_line(
 	o[2] = s[2];
 }
 
-// Edge walk of fill_polygon_impl_2_static_params (rasterizer.rs:160-270), stopped at the trapezoid owning `row`.
+// fill_polygon_impl_2_static_params (rasterizer.rs:160-270) for the line `row`: the edge walk lives in sqw_raster_walk.cuh.
 __device__ void setup_polygon_line(const sqw_draw_cmd& c, const CmdDev& cd, const sqw_polygon_point* __restrict__ vertices, int32_t row, int32_t clip_w, int32_t clip_h, SpanRec* out)
 {
-	const uint32_t num_vertices = c.num_vertices;
-	uint32_t lower_vertex_index = 0;
-	Fixed16 min_y = vertices[0].y;
-	for (uint32_t index = 1; index < num_vertices; ++index)
-	{
-		const Fixed16 y = vertices[index].y;
-		if (y < min_y)
-		{
-			min_y = y;
-			lower_vertex_index = index;
-		}
-	}
-
-	uint32_t left_index = lower_vertex_index;
-	uint32_t right_index = lower_vertex_index;
-	Fixed16 cur_y = min_y;
-	for (;;)
-	{
-		uint32_t next_left_index = left_index + num_vertices - 1;
-		if (next_left_index >= num_vertices)
-			next_left_index -= num_vertices;
-		uint32_t next_right_index = right_index + 1;
-		if (next_right_index >= num_vertices)
-			next_right_index -= num_vertices;
-
-		const sqw_polygon_point left_vertex = vertices[left_index];
-		const sqw_polygon_point next_left_vertex = vertices[next_left_index];
-		const sqw_polygon_point right_vertex = vertices[right_index];
-		const sqw_polygon_point next_right_vertex = vertices[next_right_index];
-
-		const Fixed16 dy_left = wsub(next_left_vertex.y, left_vertex.y);
-		const Fixed16 dy_right = wsub(next_right_vertex.y, right_vertex.y);
-		const Fixed16 next_y = min(next_left_vertex.y, next_right_vertex.y);
-
-		const int32_t y_start_int = max(fixed16_round_to_int(cur_y), 0);
-		const int32_t y_end_int = min(fixed16_round_to_int(next_y), clip_h);
-		const bool owns_row = row >= y_start_int && row < y_end_int;
-
-		if (dy_left > SQW_FIXED16_HALF && dy_right > SQW_FIXED16_HALF)
-		{
-			if (owns_row)
-			{
-				const Fixed16 dx_dy_left = fixed16_div(wsub(next_left_vertex.x, left_vertex.x), dy_left);
-				const Fixed16 dx_dy_right = fixed16_div(wsub(next_right_vertex.x, right_vertex.x), dy_right);
-				PolygonSide l, r;
-				l.x_start = wadd(left_vertex.x, fixed16_mul(dx_dy_left, wsub(cur_y, left_vertex.y)));
-				l.dx_dy = dx_dy_left;
-				r.x_start = wadd(right_vertex.x, fixed16_mul(dx_dy_right, wsub(cur_y, right_vertex.y)));
-				r.dx_dy = dx_dy_right;
-				polygon_part_line(c, cd, row, y_start_int, cur_y, next_y, l, r, clip_w, out);
-				return;
-			}
-		}
-		else if (dy_left > 0 && dy_right > 0)
-		{
-			const int32_t cur_y_int = fixed16_round_to_int(cur_y);
-			const int32_t next_y_int = fixed16_round_to_int(next_y);
-			if (cur_y_int < next_y_int && owns_row)
-			{
-				// thin trapezoid: a single line evaluated at its centre (:226-252)
-				const Fixed16 thin_line_y = wadd(int_to_fixed16(cur_y_int), SQW_FIXED16_HALF);
-				PolygonSide l, r;
-				l.x_start = wadd(left_vertex.x, fixed16_mul_div(wsub(thin_line_y, left_vertex.y), wsub(next_left_vertex.x, left_vertex.x), dy_left));
-				l.dx_dy = 0;
-				r.x_start = wadd(right_vertex.x, fixed16_mul_div(wsub(thin_line_y, right_vertex.y), wsub(next_right_vertex.x, right_vertex.x), dy_right));
-				r.dx_dy = 0;
-				polygon_part_line(c, cd, row, y_start_int, cur_y, next_y, l, r, clip_w, out);
-				return;
-			}
-		}
-
-		if (next_left_index == next_right_index)
-			break;
-		if (next_right_vertex.y < next_left_vertex.y)
-			right_index = next_right_index;
-		else
-			left_index = next_left_index;
-		cur_y = next_y;
-	}
-	write_empty(out);
+	PolygonPart part;
+	if (find_polygon_part(vertices, c.num_vertices, row, clip_h, part))
+		polygon_part_line(c, cd, row, part.y_start_int, part.y_start, part.y_end, part.left, part.right, clip_w, out);
+	else
+		write_empty(out);
 }
 
 // fill_triangle_part (rasterizer.rs:984-1215) for the line `row`.

@@ -18,6 +18,8 @@ static_assert(sizeof(sqw_polygon_point) == 8, "sqw_polygon_point layout");
 static_assert(sizeof(sqw_triangle_point) == 28, "sqw_triangle_point layout");
 static_assert(sizeof(sqw_directional_lightmap_element) == 40, "sqw_directional_lightmap_element layout");
 static_assert(sizeof(sqw_post_params) == 32, "sqw_post_params layout");
+static_assert(sizeof(sqw_depth_map) == 32, "sqw_depth_map layout");
+static_assert(sizeof(sqw_depth_cmd) == 32, "sqw_depth_cmd layout");
 
 namespace
 {
@@ -220,7 +222,8 @@ struct sqw_view
 {
 	sqw_ctx* ctx = nullptr;
 	uint32_t index = 0;
-	uint32_t width = 0, height = 0;
+	uint32_t width = 0, height = 0;             // logical size (sqw_view_set_size)
+	uint32_t alloc_width = 0, alloc_height = 0; // size the buffers were allocated for
 	int color_bits = 0;
 	cudaStream_t stream = nullptr; // ctx->stream, or a private one (SQW_CTX_CONCURRENT_VIEWS)
 	bool own_stream = false;
@@ -256,6 +259,23 @@ struct sqw_frame
 	std::vector<SurfaceGroup> groups;
 	float cam_pos[3] = {0, 0, 0};
 	bool has_surfaces = false;
+	DevBuf d_shadow_dev; // device-only shadow map array (sqw_frame_set_surfaces with shadow_maps == NULL)
+	float* d_shadow_maps_rw = nullptr;
+	uint64_t shadow_maps_len = 0;
+	// shadow map fills
+	Arena depth_arena;
+	DevBuf d_depth_spans;
+	const sqw_depth_cmd* d_depth_cmds = nullptr;
+	const DepthCmdDev* d_depth_cmd_dev = nullptr;
+	const sqw_polygon_point* d_depth_points = nullptr;
+	const sqw_depth_map* d_depth_maps = nullptr;
+	const uint2* d_depth_chunks = nullptr;
+	const uint2* d_depth_row_chunks = nullptr;
+	uint32_t num_depth_chunks = 0, num_depth_row_chunks = 0;
+	uint64_t depth_max_end = 0;
+	bool has_depth = false;
+	std::vector<DepthCmdDev> h_depth_cmd_dev;
+	std::vector<uint2> h_depth_chunks, h_depth_row_chunks;
 	// draw
 	Arena draw_arena;
 	const sqw_draw_cmd* d_cmds = nullptr;
@@ -269,6 +289,7 @@ struct sqw_frame
 	std::vector<uint2> h_chunks;
 	std::vector<uint32_t> h_band_offsets;
 	uint32_t num_cmds = 0, total_spans = 0, num_bands = 0, total_band_entries = 0;
+	uint32_t draw_width = 0, draw_height = 0; // view size the command list was prepared for
 	bool clear = false;
 	uint64_t clear_color = 0;
 	bool has_draw = false;
@@ -479,8 +500,8 @@ int sqw_view_create(sqw_ctx* ctx, sqw_view** out_view, uint32_t width, uint32_t 
 	if (!v)
 		return fail(ctx, SQW_ERR_OUT_OF_MEMORY, "sqw_view_create: host allocation failed");
 	v->ctx = ctx;
-	v->width = width;
-	v->height = height;
+	v->width = v->alloc_width = width;
+	v->height = v->alloc_height = height;
 	v->color_bits = color_bits;
 	const size_t px = (size_t)width * height;
 	cudaError_t e = cudaSuccess;
@@ -566,6 +587,38 @@ void sqw_view_destroy(sqw_view* view)
 	delete view;
 }
 
+int sqw_view_set_size(sqw_view* view, uint32_t width, uint32_t height)
+{
+	if (!view)
+		return SQW_ERR_INVALID_ARGUMENT;
+	if (width == 0 || height == 0 || (uint64_t)width * height > (uint64_t)view->alloc_width * view->alloc_height)
+		return fail(view->ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_view_set_size: larger than the size the view was created with");
+	// frames already queued for this view keep the geometry they were submitted with (kernel arguments are by value)
+	view->width = width;
+	view->height = height;
+	return SQW_OK;
+}
+
+int sqw_view_index(const sqw_view* view) { return view ? (int)view->index : SQW_ERR_INVALID_ARGUMENT; }
+
+int sqw_view_mix_texture(sqw_view* view, uint32_t image_id, const int32_t surface_tc_min[2], int blending_mode, const float light[3])
+{
+	if (!view || !surface_tc_min || !light)
+		return SQW_ERR_INVALID_ARGUMENT;
+	sqw_ctx* ctx = view->ctx;
+	if (image_id >= ctx->images.size() || ctx->images[image_id].kind != SQW_IMAGE_COLOR32 || blending_mode < 0 || blending_mode > SQW_BLEND_ALPHA_BLEND)
+		return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_view_mix_texture: bad overlay image or blending mode");
+	SQW_CUDA(ctx, cudaSetDevice(ctx->device));
+	const ImageHost& img = ctx->images[image_id];
+	{
+		LaunchTimer timer(ctx, SQW_KERNEL_MIX_TEXTURE, view->stream);
+		SQW_CUDA(ctx, launch_mix_texture(view->color_bits == 64, view->d_color, view->width, view->height, surface_tc_min, img.pixels, img.width, img.height, blending_mode, light, view->stream));
+	}
+	if (ctx->concurrent_views)
+		SQW_CUDA(ctx, cudaEventRecord(view->done, view->stream));
+	return SQW_OK;
+}
+
 int sqw_frame_create(sqw_view* view, sqw_frame** out_frame)
 {
 	if (!view || !out_frame)
@@ -587,6 +640,9 @@ void sqw_frame_destroy(sqw_frame* f)
 	cudaStreamSynchronize(f->view->stream);
 	f->surf_arena.release();
 	f->draw_arena.release();
+	f->depth_arena.release();
+	f->d_depth_spans.release();
+	f->d_shadow_dev.release();
 	if (f->view->immediate == f)
 		f->view->immediate = nullptr;
 	delete f;
@@ -690,13 +746,19 @@ int sqw_frame_set_surfaces(
 		Arena& a = f->surf_arena;
 		const size_t b_jobs = (size_t)num_jobs * sizeof(sqw_surface_job), b_bands = f->h_bands.size() * sizeof(SurfaceBand);
 		const size_t b_lights = (size_t)num_lights * sizeof(sqw_light), b_sm = (size_t)shadow_maps_len * sizeof(float);
-		if (b_sm && !shadow_maps)
-			return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_frame_set_surfaces: null shadow maps");
-		SQW_CUDA(ctx, a.begin(Arena::padded(b_jobs) + Arena::padded(b_bands) + Arena::padded(b_lights) + Arena::padded(b_sm)));
+		const size_t b_sm_upload = shadow_maps ? b_sm : 0; // NULL: the array lives on the device only (filled by the shadow map stage)
+		if (b_sm && !shadow_maps && b_sm + 16 > f->d_shadow_dev.capacity)
+		{
+			SQW_CUDA(ctx, cudaStreamSynchronize(view->stream));
+			SQW_CUDA(ctx, f->d_shadow_dev.reserve(b_sm + 16));
+		}
+		SQW_CUDA(ctx, a.begin(Arena::padded(b_jobs) + Arena::padded(b_bands) + Arena::padded(b_lights) + Arena::padded(b_sm_upload)));
 		f->d_jobs = static_cast<const sqw_surface_job*>(a.push(jobs, b_jobs));
 		f->d_bands = static_cast<const SurfaceBand*>(a.push(f->h_bands.data(), b_bands));
 		f->d_lights = static_cast<const sqw_light*>(a.push(lights, b_lights));
-		f->d_shadow_maps = static_cast<const float*>(a.push(shadow_maps, b_sm));
+		f->d_shadow_maps_rw = shadow_maps ? static_cast<float*>(a.push(shadow_maps, b_sm)) : static_cast<float*>(f->d_shadow_dev.ptr);
+		f->d_shadow_maps = f->d_shadow_maps_rw;
+		f->shadow_maps_len = shadow_maps_len;
 		SQW_CUDA(ctx, a.commit(view->stream));
 	}
 	f->cam_pos[0] = cam_pos[0];
@@ -831,6 +893,8 @@ int sqw_frame_set_draw(
 	for (uint32_t b = 0; b < num_bands; ++b)
 		f->h_band_offsets[(size_t)b + 1] += f->h_band_offsets[b];
 	f->num_cmds = num_cmds;
+	f->draw_width = view->width;
+	f->draw_height = view->height;
 	f->total_spans = (uint32_t)span_total;
 	f->num_bands = num_bands;
 	f->total_band_entries = f->h_band_offsets[num_bands];
@@ -862,6 +926,92 @@ int sqw_frame_set_draw(
 	if (clear_color)
 		std::memcpy(&f->clear_color, clear_color, C);
 	f->has_draw = true;
+	return SQW_OK;
+}
+
+int sqw_frame_set_shadow_map_draw(
+	sqw_frame* f, const sqw_depth_map* maps, uint32_t num_maps, const sqw_depth_cmd* cmds, uint32_t num_cmds, const sqw_polygon_point* points, uint32_t num_points)
+{
+	if (!f || (num_maps && !maps) || (num_cmds && (!cmds || !points)))
+		return fail(f ? f->view->ctx : nullptr, SQW_ERR_INVALID_ARGUMENT, "sqw_frame_set_shadow_map_draw: null argument");
+	sqw_view* view = f->view;
+	sqw_ctx* ctx = view->ctx;
+	SQW_CUDA(ctx, cudaSetDevice(ctx->device));
+	f->h_depth_cmd_dev.assign(num_cmds, DepthCmdDev{0, 0, 0, 0, 0});
+	f->h_depth_chunks.clear();
+	f->h_depth_row_chunks.clear();
+	std::vector<uint8_t> cmd_seen(num_cmds, 0);
+	uint64_t span_total = 0, max_end = 0;
+	for (uint32_t m = 0; m < num_maps; ++m)
+	{
+		const sqw_depth_map& map = maps[m];
+		if (map.width == 0 || map.height == 0 || map.width > 16384 || map.height > 16384 || (uint64_t)map.first_cmd + map.num_cmds > num_cmds)
+			return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_frame_set_shadow_map_draw: bad map");
+		max_end = std::max<uint64_t>(max_end, (uint64_t)map.offset + (uint64_t)map.width * map.height);
+		for (uint32_t r0 = 0; r0 < map.height; r0 += 32)
+			f->h_depth_row_chunks.push_back(make_uint2(m, r0));
+		for (uint32_t ci = map.first_cmd; ci < map.first_cmd + map.num_cmds; ++ci)
+		{
+			const sqw_depth_cmd& c = cmds[ci];
+			if (cmd_seen[ci] || c.num_vertices < 3 || c.num_vertices > 64 || (uint64_t)c.vertex_offset + c.num_vertices > num_points)
+				return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_frame_set_shadow_map_draw: bad fill call (or one shared by two maps)");
+			cmd_seen[ci] = 1;
+			int32_t min_y = INT32_MAX, max_y = INT32_MIN;
+			for (uint32_t k = 0; k < c.num_vertices; ++k)
+			{
+				min_y = std::min(min_y, points[c.vertex_offset + k].y);
+				max_y = std::max(max_y, points[c.vertex_offset + k].y);
+			}
+			int32_t y0 = std::max(fixed16_round_to_int_h(min_y), 0);
+			int32_t y1 = std::min(fixed16_round_to_int_h(max_y), (int32_t)map.height);
+			if (y0 >= y1)
+				y0 = y1 = 0;
+			DepthCmdDev& d = f->h_depth_cmd_dev[ci];
+			d.y0 = (int16_t)y0;
+			d.y1 = (int16_t)y1;
+			d.span_base = (uint32_t)span_total;
+			d.map = m;
+			d.depth_test = c.depth_test ? 1u : 0u;
+			for (int32_t r0 = 0; r0 < y1 - y0; r0 += 32)
+				f->h_depth_chunks.push_back(make_uint2(ci, (uint32_t)r0));
+			span_total += (uint64_t)(y1 - y0);
+			if (span_total > 0xFFFFFFFFull)
+				return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_frame_set_shadow_map_draw: too many scan-lines");
+		}
+	}
+	if ((size_t)span_total * sizeof(DepthSpan) + 64 > f->d_depth_spans.capacity)
+	{
+		SQW_CUDA(ctx, cudaStreamSynchronize(view->stream));
+		SQW_CUDA(ctx, f->d_depth_spans.reserve((size_t)span_total * sizeof(DepthSpan) + 64));
+	}
+	Arena& a = f->depth_arena;
+	const size_t b_cmds = (size_t)num_cmds * sizeof(sqw_depth_cmd), b_dev = (size_t)num_cmds * sizeof(DepthCmdDev), b_pts = (size_t)num_points * sizeof(sqw_polygon_point);
+	const size_t b_maps = (size_t)num_maps * sizeof(sqw_depth_map), b_ch = f->h_depth_chunks.size() * sizeof(uint2), b_rch = f->h_depth_row_chunks.size() * sizeof(uint2);
+	SQW_CUDA(ctx, a.begin(Arena::padded(b_cmds) + Arena::padded(b_dev) + Arena::padded(b_pts) + Arena::padded(b_maps) + Arena::padded(b_ch) + Arena::padded(b_rch)));
+	f->d_depth_cmds = static_cast<const sqw_depth_cmd*>(a.push(cmds, b_cmds));
+	f->d_depth_cmd_dev = static_cast<const DepthCmdDev*>(a.push(f->h_depth_cmd_dev.data(), b_dev));
+	f->d_depth_points = static_cast<const sqw_polygon_point*>(a.push(points, b_pts));
+	f->d_depth_maps = static_cast<const sqw_depth_map*>(a.push(maps, b_maps));
+	f->d_depth_chunks = static_cast<const uint2*>(a.push(f->h_depth_chunks.data(), b_ch));
+	f->d_depth_row_chunks = static_cast<const uint2*>(a.push(f->h_depth_row_chunks.data(), b_rch));
+	SQW_CUDA(ctx, a.commit(view->stream));
+	f->num_depth_chunks = (uint32_t)f->h_depth_chunks.size();
+	f->num_depth_row_chunks = (uint32_t)f->h_depth_row_chunks.size();
+	f->depth_max_end = max_end;
+	f->has_depth = num_maps != 0;
+	return SQW_OK;
+}
+
+int sqw_frame_read_shadow_maps(sqw_frame* f, float* dst, uint64_t offset, uint64_t count)
+{
+	if (!f || !dst)
+		return SQW_ERR_INVALID_ARGUMENT;
+	sqw_ctx* ctx = f->view->ctx;
+	if (!f->d_shadow_maps_rw || offset + count > f->shadow_maps_len)
+		return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_frame_read_shadow_maps: range outside the frame's shadow map array");
+	SQW_CUDA(ctx, cudaSetDevice(ctx->device));
+	SQW_CUDA(ctx, cudaMemcpyAsync(dst, f->d_shadow_maps_rw + offset, count * sizeof(float), cudaMemcpyDeviceToHost, f->view->stream));
+	SQW_CUDA(ctx, cudaStreamSynchronize(f->view->stream));
 	return SQW_OK;
 }
 
@@ -920,6 +1070,34 @@ int sqw_frame_submit(sqw_frame* f, uint32_t stages)
 		inv_scale_bgr[2] = 1.0f / (p.exposure * p.color_modulate[0]);
 	}
 
+	if ((stages & SQW_STAGE_SHADOW_MAPS) && f->has_depth)
+	{
+		if (!f->d_shadow_maps_rw || f->depth_max_end > f->shadow_maps_len)
+			return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_frame_submit: shadow map fills write outside the frame's shadow map array (set the surfaces first)");
+		DepthLaunch l{};
+		l.cmds = f->d_depth_cmds;
+		l.cmd_dev = f->d_depth_cmd_dev;
+		l.points = f->d_depth_points;
+		l.maps = f->d_depth_maps;
+		l.chunks = f->d_depth_chunks;
+		l.num_chunks = f->num_depth_chunks;
+		l.row_chunks = f->d_depth_row_chunks;
+		l.num_row_chunks = f->num_depth_row_chunks;
+		l.spans = static_cast<DepthSpan*>(f->d_depth_spans.ptr);
+		l.shadow_maps = f->d_shadow_maps_rw;
+		if (l.num_chunks)
+		{
+			LaunchTimer timer(ctx, SQW_KERNEL_DEPTH_SETUP, s);
+			SQW_CUDA(ctx, launch_depth_setup(l, s));
+			++launches;
+		}
+		{
+			LaunchTimer timer(ctx, SQW_KERNEL_DEPTH_RESOLVE, s);
+			SQW_CUDA(ctx, launch_depth_resolve(l, s));
+			++launches;
+		}
+	}
+
 	if (do_surfaces)
 	{
 		SurfaceLaunch l{};
@@ -945,6 +1123,8 @@ int sqw_frame_submit(sqw_frame* f, uint32_t stages)
 		}
 	}
 
+	if (do_raster && (f->draw_width != view->width || f->draw_height != view->height))
+		return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_frame_submit: the view was resized after the command list was set");
 	if (do_raster)
 	{
 		// portal / mirror textures: wait for the views this frame samples (they may run on other streams)

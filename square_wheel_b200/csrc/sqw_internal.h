@@ -56,6 +56,10 @@ struct SurfaceLaunch
 // One grid for all bands of the launch; `dynamic_lights` selects the kernel built with the dynamic-light loop.
 cudaError_t launch_surface_build(bool color64, bool dynamic_lights, const SurfaceLaunch& l, cudaStream_t stream);
 
+cudaError_t launch_mix_texture(
+	bool color64, void* surface, uint32_t size_u, uint32_t size_v, const int32_t tc_min[2], const void* texture, uint32_t tex_w, uint32_t tex_h, int blending_mode,
+	const float light[3], cudaStream_t stream);
+
 // ---- stage 2 ------------------------------------------------------------------------------------------------
 #define SQW_TILE_W 128
 #define SQW_TILE_H 8
@@ -125,6 +129,37 @@ struct RasterLaunch
 // span set-up + binning in one grid
 cudaError_t launch_raster_setup(const RasterLaunch& l, cudaStream_t stream);
 cudaError_t launch_raster_tiles(const RasterLaunch& l, cudaStream_t stream);
+
+// ---- shadow maps ----------------------------------------------------------------------------------------------
+struct DepthCmdDev // per fill call, prepared by sqw_frame_set_shadow_map_draw. 16 bytes
+{
+	int16_t y0, y1; // rows [y0, y1) of its map that can own a span
+	uint32_t span_base;
+	uint32_t map;
+	uint32_t depth_test;
+};
+struct DepthSpan // one scan-line of one fill call. 16 bytes
+{
+	int16_t x0, x1;   // pixel span [x0, x1)
+	float inv_z;      // value written to pixel x0 (rasterizer.rs:1456)
+	float d_inv_z_dx; // added after every pixel (:1463)
+	uint32_t pad;
+};
+struct DepthLaunch
+{
+	const sqw_depth_cmd* cmds;
+	const DepthCmdDev* cmd_dev;
+	const sqw_polygon_point* points;
+	const sqw_depth_map* maps;
+	const uint2* chunks; // {command, first row relative to y0} per 32 scan-lines of a command
+	uint32_t num_chunks;
+	const uint2* row_chunks; // {map, first row} per 32 rows of a map
+	uint32_t num_row_chunks;
+	DepthSpan* spans;
+	float* shadow_maps;
+};
+cudaError_t launch_depth_setup(const DepthLaunch& l, cudaStream_t stream);
+cudaError_t launch_depth_resolve(const DepthLaunch& l, cudaStream_t stream);
 
 // ---- stage 3 ------------------------------------------------------------------------------------------------
 struct PostLaunch

@@ -24,6 +24,8 @@
 // IEEE-rounded one (fast_math.rs:376-384) so results are bit-identical to the CPU restatement.
 #include "sqw_device.cuh"
 #include "sqw_internal.h"
+#include <algorithm>
+#include <climits>
 
 namespace sqw
 {
@@ -504,6 +506,44 @@ __global__ void __launch_bounds__(SQW_SURF_THREADS, DYN ? 3 : 4) surface_build_k
 #undef SQW_BAND_CASE
 }
 
+// mix_surface_with_texture_impl (surfaces.rs:903-971) with any of the five blending modes: the overlay of a portal /
+// mirror glass texture on a rendered portal texture (partial_renderer.rs:2261-2271).  One thread per texel, consecutive
+// threads on consecutive texels of a row (coalesced read-modify-write of the surface, wrapped reads of the overlay).
+template <class C>
+__global__ void __launch_bounds__(256) mix_texture_kernel(
+	typename C::Raw* __restrict__ surface, uint32_t size_u, uint32_t size_v, int32_t tc_min_u, int32_t tc_min_v, const uint32_t* __restrict__ texture, uint32_t tex_w,
+	uint32_t tex_h, int blending_mode, int32_t light_b, int32_t light_g, int32_t light_r)
+{
+	const uint32_t tex_w_mask = pow2_mask_of(tex_w), tex_h_mask = pow2_mask_of(tex_h);
+	const ColorVecI light_vec = cvi(light_b, light_g, light_r, 0);
+	const uint64_t total = (uint64_t)size_u * size_v;
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x)
+	{
+		const uint32_t dst_v = (uint32_t)(i / size_u), dst_u = (uint32_t)(i - (uint64_t)dst_v * size_u);
+		const uint32_t src_v = wrap_coord(tc_min_v + (int32_t)dst_v, (int32_t)tex_h, tex_h_mask);
+		const uint32_t src_u = wrap_coord(tc_min_u + (int32_t)dst_u, (int32_t)tex_w, tex_w_mask);
+		const uint32_t texel_value = __ldg(texture + (size_t)src_v * tex_w + src_u);
+		const ColorVecI m = cvi_shr<8>(cvi_mul(cvi_from_color32(texel_value), light_vec));
+		typename C::Raw& dst = surface[i];
+		switch (blending_mode)
+		{
+		case SQW_BLEND_NONE: dst = C::from_veci(m); break;
+		case SQW_BLEND_AVERAGE: dst = C::from_veci(cvi_shr<1>(cvi_add(m, C::to_veci(dst)))); break;
+		case SQW_BLEND_ADDITIVE: dst = C::from_veci(cvi_add(m, C::to_veci(dst))); break;
+		case SQW_BLEND_ALPHA_TEST:
+			if (Color32::test_alpha(texel_value))
+				dst = C::from_veci(m);
+			break;
+		default:
+		{
+			const int32_t alpha = Color32::get_alpha(texel_value);
+			dst = C::from_veci(cvi_shr<8>(cvi_add(cvi_mul_scalar(m, alpha), cvi_mul_scalar(C::to_veci(dst), 255 - alpha))));
+			break;
+		}
+		}
+	}
+}
+
 template <class C, bool DYN>
 cudaError_t launch_one(const SurfaceLaunch& l, cudaStream_t stream)
 {
@@ -522,6 +562,34 @@ cudaError_t launch_surface_build(bool color64, bool dynamic_lights, const Surfac
 	if (color64)
 		return dynamic_lights ? launch_one<Color64, true>(l, stream) : launch_one<Color64, false>(l, stream);
 	return dynamic_lights ? launch_one<Color32, true>(l, stream) : launch_one<Color32, false>(l, stream);
+}
+
+cudaError_t launch_mix_texture(
+	bool color64, void* surface, uint32_t size_u, uint32_t size_v, const int32_t tc_min[2], const void* texture, uint32_t tex_w, uint32_t tex_h, int blending_mode,
+	const float light[3], cudaStream_t stream)
+{
+	const uint64_t total = (uint64_t)size_u * size_v;
+	if (total == 0)
+		return cudaSuccess;
+	// surfaces.rs:911-914  light * 256 -> ColorVecI (`as i32`: saturating, NaN -> 0), lanes [B, G, R, 0]
+	auto as_i32 = [](float x) -> int32_t {
+		if (!(x == x))
+			return 0;
+		if (x >= 2147483648.0f)
+			return INT32_MAX;
+		if (x <= -2147483648.0f)
+			return INT32_MIN;
+		return (int32_t)x;
+	};
+	const int32_t lb = as_i32(light[2] * 256.0f), lg = as_i32(light[1] * 256.0f), lr = as_i32(light[0] * 256.0f);
+	const uint32_t blocks = (uint32_t)std::min<uint64_t>((total + 255) / 256, 148ull * 8);
+	if (color64)
+		mix_texture_kernel<Color64><<<blocks, 256, 0, stream>>>(
+			static_cast<uint64_t*>(surface), size_u, size_v, tc_min[0], tc_min[1], static_cast<const uint32_t*>(texture), tex_w, tex_h, blending_mode, lb, lg, lr);
+	else
+		mix_texture_kernel<Color32><<<blocks, 256, 0, stream>>>(
+			static_cast<uint32_t*>(surface), size_u, size_v, tc_min[0], tc_min[1], static_cast<const uint32_t*>(texture), tex_w, tex_h, blending_mode, lb, lg, lr);
+	return cudaGetLastError();
 }
 
 } // namespace sqw

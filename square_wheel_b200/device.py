@@ -131,6 +131,21 @@ class View:
         self.ctx._check(self._lib.sqw_postprocess(self._handle, C.byref(params), N.ptr(dst), self.width, N.ptr(avg)), "sqw_postprocess")
         return dst, avg
 
+    def set_size(self, width: int, height: int):
+        """Logical size within the allocated one (portal textures, partial_renderer.rs:2130-2182)."""
+        self.ctx._check(self._lib.sqw_view_set_size(self._handle, width, height), "sqw_view_set_size")
+        self.width, self.height = width, height
+
+    @property
+    def index(self) -> int:
+        return self.ctx._check(self._lib.sqw_view_index(self._handle), "sqw_view_index")
+
+    def mix_texture(self, image_id: int, surface_tc_min, blending_mode: int, light):
+        """mix_surface_with_texture over the whole colour buffer (portal / mirror glass overlay, surfaces.rs:854)."""
+        tc = np.asarray(surface_tc_min, np.int32)
+        li = np.asarray(light, np.float32)
+        self.ctx._check(self._lib.sqw_view_mix_texture(self._handle, image_id, N.ptr(tc), blending_mode, N.ptr(li)), "sqw_view_mix_texture")
+
     # ---- readback ----
     def read_pixels(self) -> np.ndarray:
         out = np.empty((self.height, self.width), self.pixel_dtype)
@@ -186,15 +201,18 @@ class Frame:
         view.ctx._check(self._lib.sqw_frame_create(view._handle, C.byref(self._handle)), "sqw_frame_create")
         self.h2d_bytes = 0
 
-    def set_surfaces(self, jobs, lights=None, shadow_maps=None, cam_pos=(0.0, 0.0, 0.0), total_surface_pixels: Optional[int] = None):
+    def set_surfaces(self, jobs, lights=None, shadow_maps=None, cam_pos=(0.0, 0.0, 0.0), total_surface_pixels: Optional[int] = None, device_shadow_maps_len: int = 0):
+        """device_shadow_maps_len > 0 (with shadow_maps=None): the shadow map array lives on the device only and is filled by
+        the shadow map stage (set_shadow_map_draw)."""
         jobs = _as(jobs, N.surface_job_dtype)
         lights = _as(lights, N.light_dtype) if lights is not None else np.zeros(0, N.light_dtype)
         sm = _as(shadow_maps, np.float32) if shadow_maps is not None else np.zeros(0, np.float32)
         cp = np.asarray(cam_pos, np.float32)
         if total_surface_pixels is None:
             total_surface_pixels = required_surface_pixels(jobs)
+        sm_ptr, sm_len = (N.ptr(sm), sm.size) if shadow_maps is not None or device_shadow_maps_len == 0 else (None, device_shadow_maps_len)
         self.view.ctx._check(
-            self._lib.sqw_frame_set_surfaces(self._handle, N.ptr(jobs), len(jobs), N.ptr(lights), len(lights), N.ptr(sm), sm.size, N.ptr(cp), total_surface_pixels),
+            self._lib.sqw_frame_set_surfaces(self._handle, N.ptr(jobs), len(jobs), N.ptr(lights), len(lights), sm_ptr, sm_len, N.ptr(cp), total_surface_pixels),
             "sqw_frame_set_surfaces",
         )
         self.h2d_bytes += jobs.nbytes + lights.nbytes + sm.nbytes
@@ -208,6 +226,21 @@ class Frame:
             self._lib.sqw_frame_set_draw(self._handle, N.ptr(cmds), len(cmds), N.ptr(pp), len(pp), N.ptr(tp), len(tp), N.ptr(cc)), "sqw_frame_set_draw"
         )
         self.h2d_bytes += cmds.nbytes + pp.nbytes + tp.nbytes
+
+    def set_shadow_map_draw(self, maps, cmds, polygon_points):
+        """Record the shadow-map fills (DepthRasterizer::fill_polygon calls, rasterizer.rs:1314) of the frame."""
+        maps = _as(maps, N.depth_map_dtype)
+        cmds = _as(cmds, N.depth_cmd_dtype)
+        pp = _as(polygon_points, N.polygon_point_dtype) if polygon_points is not None else np.zeros(0, N.polygon_point_dtype)
+        self.view.ctx._check(
+            self._lib.sqw_frame_set_shadow_map_draw(self._handle, N.ptr(maps), len(maps), N.ptr(cmds), len(cmds), N.ptr(pp), len(pp)), "sqw_frame_set_shadow_map_draw"
+        )
+        self.h2d_bytes += maps.nbytes + cmds.nbytes + pp.nbytes
+
+    def read_shadow_maps(self, offset: int, count: int) -> np.ndarray:
+        out = np.empty(count, np.float32)
+        self.view.ctx._check(self._lib.sqw_frame_read_shadow_maps(self._handle, N.ptr(out), offset, count), "sqw_frame_read_shadow_maps")
+        return out
 
     def set_post(self, params: N.PostParams):
         self.view.ctx._check(self._lib.sqw_frame_set_post(self._handle, C.byref(params)), "sqw_frame_set_post")

@@ -248,3 +248,25 @@ def test_known_answer_digests(oracle_lib):
     oracle_lib.reset_assert_failures()
     got = kat_cases(oracle_lib)
     assert got == golden["digests"], {k: (got[k], golden["digests"].get(k)) for k in got if got[k] != golden["digests"].get(k)}
+
+
+def test_depth_rasterizer_closed_forms(oracle_lib):
+    """DepthRasterizer (rasterizer.rs:1295-1474): a screen-filling polygon with a constant depth equation writes that constant
+    everywhere; DEPTH_TEST keeps the larger inverse depth; the projector circle mask is symmetric and leaves the centre alone."""
+    from square_wheel_b200 import _native as N
+
+    w = h = 32
+    pts = np.array([(-65536, -65536), ((w + 1) << 16, -65536), ((w + 1) << 16, (h + 1) << 16), (-65536, (h + 1) << 16)], N.polygon_point_dtype)
+    maps = np.zeros(1, N.depth_map_dtype)
+    maps[0] = (0, w, h, 0, 2, N.DEPTH_MAP_CLEAR | N.DEPTH_MAP_PROJECTOR_CIRCLE, 0.0, 0)
+    cmds = np.zeros(2, N.depth_cmd_dtype)
+    cmds["num_vertices"] = 4
+    cmds[0]["depth_eq"] = (0.0, 0.0, 0.25)
+    cmds[1]["depth_eq"] = (1.0 / 64.0, 0.0, 0.0)  # inv_z = (x + 0.5) / 64: larger than 0.25 for x >= 16
+    cmds[1]["depth_test"] = 1
+    out = oracle_lib.draw_shadow_maps(np.full(w * h, -1.0, np.float32), maps, cmds, pts).reshape(h, w)
+    row = out[h // 2]
+    assert np.all(row[:16] == 0.25)
+    assert np.allclose(row[16:], (np.arange(16, 32) + 0.5) / 64.0, rtol=1e-6)
+    assert out[0, 0] == np.float32(1.0e24) and out[0, w - 1] == np.float32(1.0e24) and out[h - 1, 0] == np.float32(1.0e24)
+    assert np.array_equal(out == np.float32(1.0e24), (out == np.float32(1.0e24))[:, ::-1])

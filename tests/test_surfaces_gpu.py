@@ -103,3 +103,32 @@ def test_bad_jobs_are_rejected(assets):
             view.build_surfaces(j, None, None, (0, 0, 0), 64 * 64)
     finally:
         view.close()
+
+
+@pytest.mark.parametrize("color_bits", [32, 64])
+def test_view_mix_texture_all_blending_modes(assets, oracle_lib, color_bits):
+    """mix_surface_with_texture (surfaces.rs:854-971) as the portal / mirror glass overlay (partial_renderer.rs:2261-2271): every
+    blending mode, wrapped negative texture coordinates, a view resized below its allocated size, bit-exact."""
+    ctx = assets.device_context()
+    r = synth.rng(77 + color_bits)
+    view = ctx.create_view(200, 120, color_bits)
+    dt = np.uint32 if color_bits == 32 else np.uint64
+    for k, (w, h) in enumerate([(200, 120), (131, 57), (64, 64), (17, 9), (1, 1)]):
+        view.set_size(w, h)
+        for mode in range(5):
+            if color_bits == 32:
+                base = r.integers(0, 2**32, size=(h, w), dtype=np.uint64).astype(np.uint32)
+            else:
+                base = (r.integers(0, 4096, size=(h, w, 4), dtype=np.uint64) << (np.arange(4, dtype=np.uint64) * 16)).sum(axis=2).astype(np.uint64)
+            view.write_pixels(base)
+            tc_min = [int(r.integers(-300, 300)), int(r.integers(-300, 300))]
+            light = r.uniform(0.0, 3.0, 3).astype(np.float32)
+            image = assets.lite_ids[(k + mode) % len(assets.lite_ids)]
+            view.mix_texture(image, tc_min, mode, light)
+            got = view.read_pixels()
+            want = base.copy().reshape(-1)
+            oracle_lib.mix_surface_with_texture(color_bits, want, [w, h], tc_min, assets.images[image][1], mode, light)
+            assert_pixels_equal(got, want.reshape(h, w).astype(dt), f"mix {w}x{h} mode {mode}")
+    with pytest.raises(Exception):
+        view.set_size(201, 120)
+    view.close()
