@@ -35,6 +35,7 @@ struct sqwh_renderer_config
 	float textures_mip_bias;
 	uint32_t clear_background;
 	uint32_t invert_polygons_order;
+	float shadows_quality;
 };
 
 struct sqwh_frame_info
@@ -44,7 +45,20 @@ struct sqwh_frame_info
 	uint32_t num_visible_leafs, num_visible_polygons;
 	uint32_t mode_counts[3];
 	float cam_pos[3];
-	uint32_t reserved;
+	uint32_t num_lights;
+	uint32_t num_depth_maps, num_depth_cmds, num_depth_points;
+	uint32_t num_triangle_points;
+	uint64_t shadow_maps_len;
+};
+
+struct sqwh_dynamic_light // frame_info.rs:149-168
+{
+	float position[3];
+	float radius;
+	float color[3];
+	uint32_t shadow_type; // SQW_SHADOW_*
+	float rotation[4];    // quaternion s, x, y, z (Projector)
+	float fov;            // radians (Projector)
 };
 
 void sqwh_default_scene_params(sqwh_scene_params* p)
@@ -141,6 +155,7 @@ Renderer* sqwh_renderer_create(const Scene* s, const sqwh_renderer_config* cfg)
 		c.textures_mip_bias = cfg->textures_mip_bias;
 		c.clear_background = cfg->clear_background != 0;
 		c.invert_polygons_order = cfg->invert_polygons_order != 0;
+		c.shadows_quality = cfg->shadows_quality;
 	}
 	return new (std::nothrow) Renderer(*s, c);
 }
@@ -157,6 +172,22 @@ void sqwh_renderer_prepare_frame(Renderer* r, uint32_t width, uint32_t height, c
 }
 void sqwh_renderer_draw_frame(Renderer* r) { r->draw_frame(); }
 
+// FrameInfo::lights of the next prepare_frame
+void sqwh_renderer_set_lights(Renderer* r, const sqwh_dynamic_light* lights, uint32_t n)
+{
+	std::vector<DynamicLight> v(n);
+	for (uint32_t i = 0; i < n; ++i)
+	{
+		v[i].position = {lights[i].position[0], lights[i].position[1], lights[i].position[2]};
+		v[i].radius = lights[i].radius;
+		std::memcpy(v[i].color, lights[i].color, 12);
+		v[i].shadow_type = lights[i].shadow_type;
+		v[i].rotation = Quaternion{lights[i].rotation[0], {lights[i].rotation[1], lights[i].rotation[2], lights[i].rotation[3]}};
+		v[i].fov = lights[i].fov;
+	}
+	r->set_lights(v.data(), v.size());
+}
+
 void sqwh_renderer_frame_info(const Renderer* r, sqwh_frame_info* out)
 {
 	std::memset(out, 0, sizeof(*out));
@@ -172,7 +203,16 @@ void sqwh_renderer_frame_info(const Renderer* r, sqwh_frame_info* out)
 	out->cam_pos[0] = r->camera_matrices().position.x;
 	out->cam_pos[1] = r->camera_matrices().position.y;
 	out->cam_pos[2] = r->camera_matrices().position.z;
+	out->num_lights = (uint32_t)r->lights().size();
+	out->num_depth_maps = (uint32_t)r->depth_maps().size();
+	out->num_depth_cmds = (uint32_t)r->depth_cmds().size();
+	out->num_depth_points = (uint32_t)r->depth_points().size();
+	out->shadow_maps_len = r->shadow_maps_len();
 }
+const sqw_light* sqwh_renderer_lights(const Renderer* r) { return r->lights().data(); }
+const sqw_depth_map* sqwh_renderer_depth_maps(const Renderer* r) { return r->depth_maps().data(); }
+const sqw_depth_cmd* sqwh_renderer_depth_cmds(const Renderer* r) { return r->depth_cmds().data(); }
+const sqw_polygon_point* sqwh_renderer_depth_points(const Renderer* r) { return r->depth_points().data(); }
 const sqw_surface_job* sqwh_renderer_jobs(const Renderer* r) { return r->jobs().data(); }
 const sqw_draw_cmd* sqwh_renderer_cmds(const Renderer* r) { return r->cmds().data(); }
 const sqw_polygon_point* sqwh_renderer_polygon_points(const Renderer* r) { return r->polygon_points().data(); }

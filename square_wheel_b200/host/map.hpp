@@ -75,6 +75,7 @@ struct Material
 {
 	bool draw = true;
 	bool light = true;
+	bool shadow = true; // casts shadows in shadow maps (material.rs `shadow`, depth_renderer.rs:31)
 	bool has_diffuse = true;
 	int blending_mode = SQW_BLEND_NONE;
 	bool has_normal_map = false, has_non_one_roughness = false, is_metal = false; // Texture flags (textures.rs:14-16)

@@ -352,7 +352,8 @@ void basis_vecs_from_plane_and_tc(const Plane& plane, const Plane tc[2], DrawPol
 } // namespace
 
 // ---- Renderer ----------------------------------------------------------------------------------------------------------
-Renderer::Renderer(const Scene& scene, const RendererConfig& config) : scene_(scene), map_(scene.map), config_(config)
+Renderer::Renderer(const Scene& scene, const RendererConfig& config)
+	: scene_(scene), map_(scene.map), config_(config), visibility_(scene.map), shadow_visibility_(scene.map)
 {
 	// PartialRenderer::new (partial_renderer.rs:56-135)
 	polygons_data_.resize(map_.polygons.size());
@@ -362,11 +363,16 @@ Renderer::Renderer(const Scene& scene, const RendererConfig& config) : scene_(sc
 		for (uint32_t p = map_.leafs[leaf].first_polygon; p < map_.leafs[leaf].first_polygon + map_.leafs[leaf].num_polygons; ++p)
 			polygons_data_[p].parent_leaf = (uint32_t)leaf;
 	vertices_transformed_.resize(map_.vertices.size());
+	leaf_lights_.resize(map_.leafs.size());
+}
+
+VisibilityCalculator::VisibilityCalculator(const BSPMap& map) : map_(map)
+{
 	leafs_data_.resize(map_.leafs.size());
 	portals_data_.resize(map_.portals.size());
 }
 
-bool Renderer::leaf_bounds(uint32_t leaf, ClippingPolygon& out) const // map_visibility_calculator.rs:116-127
+bool VisibilityCalculator::leaf_bounds(uint32_t leaf, ClippingPolygon& out) const // map_visibility_calculator.rs:116-127
 {
 	const LeafData& d = leafs_data_[leaf];
 	if (d.visible_frame != visibility_frame_)
@@ -375,7 +381,7 @@ bool Renderer::leaf_bounds(uint32_t leaf, ClippingPolygon& out) const // map_vis
 	return true;
 }
 
-uint32_t Renderer::find_current_leaf() const // :134-156
+uint32_t VisibilityCalculator::find_current_leaf() const // :134-156
 {
 	uint32_t index = map_.root_node();
 	const Vec4f w_row = camera_matrices_.planes_matrix.row(3);
@@ -410,7 +416,7 @@ bool project_portal(const Portal& portal, const BSPMap& map, const Mat4f& view_m
 }
 } // namespace
 
-void Renderer::mark_reachable_leafs_iterative(const uint32_t* start_leafs, size_t num_start_leafs, const ClippingPolygon& start_bounds) // :158-264
+void VisibilityCalculator::mark_reachable_leafs_iterative(const uint32_t* start_leafs, size_t num_start_leafs, const ClippingPolygon& start_bounds) // :158-264
 {
 	wave_cur_.clear();
 	wave_next_.clear();
@@ -479,7 +485,7 @@ void Renderer::mark_reachable_leafs_iterative(const uint32_t* start_leafs, size_
 	}
 }
 
-bool Renderer::compute_is_inside_leaf_volume(uint32_t leaf_index) const // :266-280
+bool VisibilityCalculator::compute_is_inside_leaf_volume(uint32_t leaf_index) const // :266-280
 {
 	const BSPLeaf& leaf = map_.leafs[leaf_index];
 	for (uint32_t p = leaf.first_polygon; p < leaf.first_polygon + leaf.num_polygons; ++p)
@@ -491,8 +497,9 @@ bool Renderer::compute_is_inside_leaf_volume(uint32_t leaf_index) const // :266-
 	return true;
 }
 
-void Renderer::update_visibility(const ClippingPolygon& frame_bounds) // :52-100
+void VisibilityCalculator::update_visibility(const CameraMatrices& camera_matrices, const ClippingPolygon& frame_bounds) // :52-100
 {
+	camera_matrices_ = camera_matrices;
 	++visibility_frame_;
 	const uint32_t current_leaf = find_current_leaf();
 	constexpr size_t MAX_START_LEAFS = 32;
@@ -517,6 +524,310 @@ void Renderer::update_visibility(const ClippingPolygon& frame_bounds) // :52-100
 	is_inside_leaf_volume_ = compute_is_inside_leaf_volume(current_leaf);
 }
 
+// ---- dynamic lights (dynamic_objects_index.rs, partial_renderer.rs:398-590, depth_renderer.rs) ------------------------------
+namespace
+{
+inline Vec3f quaternion_rotate_vector(Quaternion q, Vec3f v) // cgmath Quaternion::rotate_vector
+{
+	const Vec3f t = cross(q.v, v) * 2.0f;
+	return v + t * q.s + cross(q.v, t);
+}
+inline Mat4f get_object_matrix(Vec3f position, Quaternion rotation) // common/matrix.rs:112-118
+{
+	return Mat4f::from_translation(position) * mat4_from_quaternion(rotation);
+}
+// light.rs:86-130 get_cube_map_side_matrix
+Mat4f get_cube_map_side_matrix(uint32_t side)
+{
+	Mat4f mat = Mat4f::identity();
+	const Vec4f ux{1, 0, 0, 0}, uy{0, 1, 0, 0}, uz{0, 0, 1, 0};
+	auto neg = [](Vec4f v) { return Vec4f{-v.x, -v.y, -v.z, -v.w}; };
+	switch (side)
+	{
+	case 0: mat.x = uz; mat.y = neg(ux); mat.z = neg(uy); break;      // XPlus
+	case 1: mat.x = neg(uz); mat.y = ux; mat.z = neg(uy); break;      // XMinus
+	case 2: mat.x = ux; mat.y = uz; mat.z = neg(uy); break;           // YPlus
+	case 3: mat.x = neg(ux); mat.y = neg(uz); mat.z = neg(uy); break; // YMinus
+	case 4: mat.x = ux; mat.y = uy; mat.z = uz; break;                // ZPlus
+	default: mat.x = ux; mat.y = neg(uy); mat.z = neg(uz); break;     // ZMinus
+	}
+	return mat;
+}
+// common/matrix.rs:49-78 build_view_matrix_with_full_rotation
+CameraMatrices build_view_matrix_with_full_rotation(Vec3f position, Quaternion rotation, float fov, float viewport_width, float viewport_height)
+{
+	const float inv_half_fov_tan = 1.0f / std::tan(fov * 0.5f);
+	const float aspect = viewport_width / viewport_height;
+	Mat4f basis_change = Mat4f::identity();
+	basis_change.x = {0, 0, 1, 0};
+	basis_change.y = {-1, 0, 0, 0};
+	basis_change.z = {0, -1, 0, 0};
+	return complete_view_matrix(position, basis_change * mat4_from_quaternion(rotation.conjugate()), Vec2f{inv_half_fov_tan / aspect, inv_half_fov_tan}, viewport_width, viewport_height);
+}
+} // namespace
+
+void Renderer::position_object_sphere_r(uint32_t id, Vec3f center, float radius, uint32_t node_index) // dynamic_objects_index.rs:211-243
+{
+	if (node_index >= FIRST_LEAF_INDEX)
+	{
+		const uint32_t leaf_index = node_index - FIRST_LEAF_INDEX;
+		leaf_lights_[leaf_index].push_back(id);
+		light_leafs_[id].push_back(leaf_index);
+		return;
+	}
+	const BSPNode& node = map_.nodes[node_index];
+	const float scaled_radius = radius * magnitude(node.plane.vec);
+	const float scaled_dist = dot(center, node.plane.vec);
+	if (scaled_dist + scaled_radius >= node.plane.dist)
+		position_object_sphere_r(id, center, radius, node.children[0]);
+	if (scaled_dist - scaled_radius <= node.plane.dist)
+		position_object_sphere_r(id, center, radius, node.children[1]);
+}
+
+void Renderer::position_object_convex_hull_r(uint32_t id, const Vec3f* vertices, size_t n, uint32_t node_index) // :176-209
+{
+	if (node_index >= FIRST_LEAF_INDEX)
+	{
+		const uint32_t leaf_index = node_index - FIRST_LEAF_INDEX;
+		leaf_lights_[leaf_index].push_back(id);
+		light_leafs_[id].push_back(leaf_index);
+		return;
+	}
+	const BSPNode& node = map_.nodes[node_index];
+	size_t vertices_front = 0;
+	for (size_t i = 0; i < n; ++i)
+		if (dot(node.plane.vec, vertices[i]) > node.plane.dist)
+			++vertices_front;
+	if (vertices_front > 0)
+		position_object_convex_hull_r(id, vertices, n, node.children[0]);
+	if (vertices_front < n)
+		position_object_convex_hull_r(id, vertices, n, node.children[1]);
+}
+
+void Renderer::position_dynamic_lights() // dynamic_objects_index.rs:112-141
+{
+	for (auto& l : leaf_lights_)
+		l.clear();
+	light_leafs_.assign(frame_lights_.size(), {});
+	for (size_t index = 0; index < frame_lights_.size(); ++index)
+	{
+		const DynamicLight& light = frame_lights_[index];
+		if (light.shadow_type == SQW_SHADOW_PROJECTOR)
+		{
+			const Mat4f matrix = get_object_matrix(light.position, light.rotation);
+			const float half_width = light.radius * std::tan(light.fov * 0.5f);
+			const Vec3f local[5] = {{0, 0, 0}, {light.radius, half_width, half_width}, {light.radius, half_width, -half_width}, {light.radius, -half_width, half_width}, {light.radius, -half_width, -half_width}};
+			Vec3f vt[5];
+			for (int i = 0; i < 5; ++i)
+				vt[i] = truncate(matrix * extend(local[i], 1.0f));
+			position_object_convex_hull_r((uint32_t)index, vt, 5, map_.root_node());
+		}
+		else
+			position_object_sphere_r((uint32_t)index, light.position, light.radius, map_.root_node());
+	}
+}
+
+void Renderer::prepare_dynamic_lights() // partial_renderer.rs:398-522
+{
+	dynamic_lights_info_.assign(frame_lights_.size(), DynamicLightInfo{});
+	size_t shadow_map_data_offset = 0;
+	for (size_t index = 0; index < frame_lights_.size(); ++index)
+	{
+		const DynamicLight& light = frame_lights_[index];
+		DynamicLightInfo& light_info = dynamic_lights_info_[index];
+		for (uint32_t leaf_index : light_leafs_[index])
+		{
+			ClippingPolygon b;
+			if (visibility_.leaf_bounds(leaf_index, b))
+			{
+				light_info.visible = true;
+				break;
+			}
+		}
+		if (!light_info.visible)
+			continue;
+		size_t shadow_map_data_size = 0;
+		if (light.shadow_type == SQW_SHADOW_CUBE)
+		{
+			const float dist_from_camera = magnitude(camera_matrices_.position - light.position);
+			const float dist_to_closest_point = dist_from_camera - light.radius;
+			const uint32_t min_shadow_map_size = 64, max_shadow_map_size = 256;
+			if (dist_to_closest_point <= 0.0f)
+				light_info.shadow_map_size = max_shadow_map_size;
+			else
+			{
+				const float target_size = 128.0f * light.radius / dist_to_closest_point;
+				const uint32_t shift = std::min((uint32_t)std::fmax(std::log2(target_size) + config_.shadows_quality, 0.0f), 30u);
+				light_info.shadow_map_size = std::max(std::min(1u << shift, max_shadow_map_size), min_shadow_map_size);
+			}
+			shadow_map_data_size = (size_t)light_info.shadow_map_size * light_info.shadow_map_size * 6;
+		}
+		else if (light.shadow_type == SQW_SHADOW_PROJECTOR)
+		{
+			const uint32_t min_shadow_map_size = 32, max_shadow_map_size = 1024;
+			const float h = light.radius * std::tan(light.fov * 0.5f);
+			const Mat4f light_matrix = get_object_matrix(light.position, light.rotation);
+			float closest_square_dist = 1.0e24f;
+			const Vec3f corners[5] = {{light.radius, 0, 0}, {light.radius, h, h}, {light.radius, h, -h}, {light.radius, -h, h}, {light.radius, -h, -h}};
+			for (const Vec3f& v : corners)
+			{
+				const Vec3f d = camera_matrices_.position - truncate(light_matrix * extend(v, 1.0f));
+				closest_square_dist = std::fmin(closest_square_dist, dot(d, d));
+			}
+			const float target_size = 1024.0f * h / std::sqrt(closest_square_dist);
+			const uint32_t shift = std::min((uint32_t)std::fmax(std::log2(target_size) + config_.shadows_quality, 0.0f), 30u);
+			light_info.shadow_map_size = std::max(std::min(1u << shift, max_shadow_map_size), min_shadow_map_size);
+			shadow_map_data_size = (size_t)light_info.shadow_map_size * light_info.shadow_map_size;
+		}
+		light_info.shadow_map_data_offset = shadow_map_data_offset;
+		shadow_map_data_offset += shadow_map_data_size;
+	}
+	shadow_maps_len_ = shadow_map_data_offset;
+
+	// create_dynamic_light_with_shadow (renderer_structs.rs:228-308) flattened into the C-ABI record
+	lights_.assign(frame_lights_.size(), sqw_light{});
+	for (size_t index = 0; index < frame_lights_.size(); ++index)
+	{
+		const DynamicLight& light = frame_lights_[index];
+		const DynamicLightInfo& light_info = dynamic_lights_info_[index];
+		sqw_light& l = lights_[index];
+		std::memcpy(l.position, &light.position.x, 12);
+		l.radius = light.radius;
+		l.inv_square_radius = 1.0f / (light.radius * light.radius);
+		std::memcpy(l.color, light.color, 12);
+		// An invisible light is in no visible leaf, so no visible polygon can select it (the reference gives it a dummy map).
+		l.shadow_type = light_info.visible ? light.shadow_type : (uint32_t)SQW_SHADOW_NONE;
+		l.shadow_map_size = light_info.shadow_map_size;
+		l.shadow_map_offset = (uint32_t)light_info.shadow_map_data_offset;
+		if (light.shadow_type == SQW_SHADOW_PROJECTOR)
+		{
+			const float inv_half_fov_tan = 1.0f / std::tan(light.fov * 0.5f);
+			const Vec3f bx = quaternion_rotate_vector(light.rotation, Vec3f{0, 1, 0}) * inv_half_fov_tan;
+			const Vec3f by = quaternion_rotate_vector(light.rotation, Vec3f{0, 0, 1}) * inv_half_fov_tan;
+			const Vec3f bz = quaternion_rotate_vector(light.rotation, Vec3f{-1, 0, 0});
+			std::memcpy(l.basis_x, &bx.x, 12);
+			std::memcpy(l.basis_y, &by.x, 12);
+			std::memcpy(l.basis_z, &bz.x, 12);
+		}
+	}
+}
+
+void Renderer::build_shadow_maps() // partial_renderer.rs:524-590: records the fills instead of rasterising on the CPU
+{
+	depth_maps_.clear();
+	depth_cmds_.clear();
+	depth_points_.clear();
+	for (size_t index = 0; index < frame_lights_.size(); ++index)
+	{
+		const DynamicLight& light = frame_lights_[index];
+		const DynamicLightInfo& light_info = dynamic_lights_info_[index];
+		if (!light_info.visible)
+			continue;
+		const uint32_t size = light_info.shadow_map_size;
+		if (light.shadow_type == SQW_SHADOW_CUBE)
+		{
+			for (uint32_t side = 0; side < 6; ++side)
+			{
+				const CameraMatrices m = complete_view_matrix(light.position, get_cube_map_side_matrix(side), Vec2f{1.0f, 1.0f}, (float)size, (float)size); // light.rs:72-84
+				depth_draw_map((uint32_t)light_info.shadow_map_data_offset + side * size * size, size, SQW_DEPTH_MAP_CLEAR, m);
+			}
+		}
+		else if (light.shadow_type == SQW_SHADOW_PROJECTOR)
+		{
+			const CameraMatrices m = build_view_matrix_with_full_rotation(light.position, light.rotation, light.fov, (float)size, (float)size); // light.rs:62-70
+			depth_draw_map((uint32_t)light_info.shadow_map_data_offset, size, SQW_DEPTH_MAP_CLEAR | SQW_DEPTH_MAP_PROJECTOR_CIRCLE, m);
+		}
+	}
+}
+
+// DepthRenderer::draw_map (depth_renderer.rs:47-117): visibility from the light, BSP walk back to front, one fill per polygon.
+// The reference does not clear the map (stale texels stay where no polygon lands); the recorded map is cleared to 0 first,
+// which is what a first frame sees (shadow_maps_data is created zeroed, partial_renderer.rs:518-521).
+void Renderer::depth_draw_map(uint32_t offset, uint32_t size, uint32_t flags, const CameraMatrices& depth_matrices)
+{
+	sqw_depth_map map;
+	std::memset(&map, 0, sizeof(map));
+	map.offset = offset;
+	map.width = map.height = size;
+	map.first_cmd = (uint32_t)depth_cmds_.size();
+	map.flags = flags;
+	map.clear_value = 0.0f;
+
+	shadow_visibility_.update_visibility(depth_matrices, ClippingPolygon::from_box(0.0f, 0.0f, (float)size, (float)size));
+	const Vec4f planes_matrix_w_row = depth_matrices.planes_matrix.row(3);
+	uint32_t nodes_stack[MAX_BSP_TREE_DEPTH];
+	nodes_stack[0] = map_.root_node();
+	size_t num_nodes_on_stack = 1;
+	while (num_nodes_on_stack > 0)
+	{
+		const uint32_t node_index = nodes_stack[num_nodes_on_stack - 1];
+		if (node_index >= FIRST_LEAF_INDEX)
+		{
+			--num_nodes_on_stack;
+			const uint32_t leaf_index = node_index - FIRST_LEAF_INDEX;
+			ClippingPolygon bounds;
+			if (shadow_visibility_.leaf_bounds(leaf_index, bounds))
+			{
+				const BSPLeaf& leaf = map_.leafs[leaf_index];
+				Vec3f clip_planes[8];
+				bounds.get_clip_planes(clip_planes);
+				for (uint32_t p = leaf.first_polygon; p < leaf.first_polygon + leaf.num_polygons; ++p)
+					depth_draw_polygon(depth_matrices, clip_planes, p, false); // back to front, no depth test (:133-137)
+			}
+		}
+		else if (num_nodes_on_stack < MAX_BSP_TREE_DEPTH)
+		{
+			const BSPNode& node = map_.nodes[node_index];
+			const float plane_transformed_w = dot(planes_matrix_w_row, extend(node.plane.vec, -node.plane.dist));
+			const uint32_t mask = plane_transformed_w >= 0.0f ? 1 : 0;
+			nodes_stack[num_nodes_on_stack - 1] = node.children[1 ^ mask];
+			nodes_stack[num_nodes_on_stack] = node.children[mask];
+			++num_nodes_on_stack;
+		}
+	}
+	map.num_cmds = (uint32_t)depth_cmds_.size() - map.first_cmd;
+	depth_maps_.push_back(map);
+}
+
+void Renderer::depth_draw_polygon(const CameraMatrices& m, const Vec3f clip_planes[8], uint32_t polygon_index, bool depth_test) // depth_renderer.rs:204-286
+{
+	const Polygon& polygon = map_.polygons[polygon_index];
+	const Material& material = scene_.materials[polygon.texture];
+	if (!(material.shadow && material.blending_mode == SQW_BLEND_NONE)) // materials_shadow_table (:21-37)
+		return;
+	const Vec4f plane_transformed = m.planes_matrix * extend(polygon.plane.vec, -polygon.plane.dist);
+	if (plane_transformed.w <= 0.0f)
+		return;
+	const float plane_transformed_w = -plane_transformed.w;
+	const float d_inv_z_dx = plane_transformed.x / plane_transformed_w;
+	const float d_inv_z_dy = plane_transformed.y / plane_transformed_w;
+	const float DEPTH_BIAS_CONST = -1.0f / (float)(1 << 20);
+	const float DEPTH_BIAS_SLOPE = -1.0f;
+	const float DEPTH_EQUATION_SCALE = 1.0f - 1.0f / 1024.0f;
+	sqw_depth_cmd c;
+	std::memset(&c, 0, sizeof(c));
+	c.depth_eq[0] = DEPTH_EQUATION_SCALE * d_inv_z_dx;
+	c.depth_eq[1] = DEPTH_EQUATION_SCALE * d_inv_z_dy;
+	c.depth_eq[2] = DEPTH_EQUATION_SCALE * (plane_transformed.z / plane_transformed_w + DEPTH_BIAS_CONST + DEPTH_BIAS_SLOPE * (std::fabs(d_inv_z_dx) + std::fabs(d_inv_z_dy)));
+	c.depth_test = depth_test ? 1 : 0;
+
+	Vec3f vertices_transformed[MAX_VERTICES];
+	const size_t vertex_count = std::min((size_t)polygon.num_vertices, MAX_VERTICES);
+	for (size_t i = 0; i < vertex_count; ++i)
+		vertices_transformed[i] = view_matrix_transform_vertex(m.view_matrix, map_.vertices[polygon.first_vertex + i]);
+	if (vertex_count < 3)
+		return;
+	Vec2f vertices_2d[MAX_VERTICES];
+	const size_t n = project_and_clip_polygon(clip_planes, vertices_transformed, vertex_count, vertices_2d);
+	if (n < 3)
+		return;
+	c.num_vertices = (uint32_t)n;
+	c.vertex_offset = (uint32_t)depth_points_.size();
+	for (size_t i = 0; i < n; ++i)
+		depth_points_.push_back(sqw_polygon_point{f32_to_fixed16_unchecked(vertices_2d[i].x), f32_to_fixed16_unchecked(vertices_2d[i].y)});
+	depth_cmds_.push_back(c);
+}
+
 void Renderer::prepare_frame(uint32_t width, uint32_t height, const CameraPose& camera, float fov)
 {
 	width_ = width;
@@ -525,9 +836,12 @@ void Renderer::prepare_frame(uint32_t width, uint32_t height, const CameraPose& 
 	mip_bias_ = config_.textures_mip_bias; // update_mip_bias with dynamic_mip_bias = false (partial_renderer.rs:3786-3804)
 	++current_frame_;
 	stats_ = RendererDebugStats{};
-	update_visibility(ClippingPolygon::from_box(0.0f, 0.0f, (float)width, (float)height)); // partial_renderer.rs:173-190
-	prepare_polygons_surfaces();
-	build_surface_jobs();
+	visibility_.update_visibility(camera_matrices_, ClippingPolygon::from_box(0.0f, 0.0f, (float)width, (float)height)); // partial_renderer.rs:173-190
+	position_dynamic_lights();   // renderer.rs:88 (DynamicObjectsIndex)
+	prepare_dynamic_lights();    // partial_renderer.rs:192
+	build_shadow_maps();         // :194
+	prepare_polygons_surfaces(); // :214
+	build_surface_jobs();        // :221
 }
 
 void Renderer::prepare_polygons_surfaces() // partial_renderer.rs:1327-1449 (leaf polygons; submodels are not part of the synthetic maps)
@@ -537,7 +851,7 @@ void Renderer::prepare_polygons_surfaces() // partial_renderer.rs:1327-1449 (lea
 	for (size_t i = 0; i < map_.leafs.size(); ++i)
 	{
 		ClippingPolygon bounds;
-		if (!leaf_bounds((uint32_t)i, bounds))
+		if (!visibility_.leaf_bounds((uint32_t)i, bounds))
 			continue;
 		++stats_.num_visible_leafs;
 		const BSPLeaf& leaf = map_.leafs[i];
@@ -656,6 +970,53 @@ void Renderer::prepare_polygon_surface(const Vec3f clip_planes[8], size_t polygo
 	current_frame_visible_polygons_.push_back((uint32_t)polygon_index);
 }
 
+namespace
+{
+// partial_renderer.rs:3877-3985
+bool polygon_is_affected_by_light(const Polygon& polygon, const DrawPolygonData& basis_vecs, const sqw_light& light)
+{
+	const Vec3f light_position{light.position[0], light.position[1], light.position[2]};
+	const Vec3f vec_from_light_position_to_tc_start_point = light_position - basis_vecs.basis_start;
+	const float signed_distance_to_polygon_plane = dot(vec_from_light_position_to_tc_start_point, basis_vecs.basis_normal);
+	if (signed_distance_to_polygon_plane <= 0.0f)
+		return false;
+	const float square_radius_at_polygon_plane = light.radius * light.radius - signed_distance_to_polygon_plane * signed_distance_to_polygon_plane;
+	if (square_radius_at_polygon_plane <= 0.0f)
+		return false;
+	if (light.shadow_type == SQW_SHADOW_PROJECTOR)
+	{
+		const Vec3f u0 = basis_vecs.basis_u * (float)polygon.tex_coord_min[0], u1 = basis_vecs.basis_u * (float)polygon.tex_coord_max[0];
+		const Vec3f v0 = basis_vecs.basis_v * (float)polygon.tex_coord_min[1], v1 = basis_vecs.basis_v * (float)polygon.tex_coord_max[1];
+		const Vec3f vertices[4] = {basis_vecs.basis_start + u0 + v0, basis_vecs.basis_start + u0 + v1, basis_vecs.basis_start + u1 + v0, basis_vecs.basis_start + u1 + v1};
+		const Vec3f bx{light.basis_x[0], light.basis_x[1], light.basis_x[2]}, by{light.basis_y[0], light.basis_y[1], light.basis_y[2]}, bz{light.basis_z[0], light.basis_z[1], light.basis_z[2]};
+		const Vec3f plane_vecs[5] = {bz, bz - bx, bz + bx, bz - by, bz + by};
+		for (const Vec3f& plane_vec : plane_vecs)
+		{
+			const float dist = dot(plane_vec, light_position);
+			int vertices_front = 0;
+			for (const Vec3f& vertex : vertices)
+				if (dot(plane_vec, vertex) >= dist)
+					++vertices_front;
+			if (vertices_front >= 4)
+				return false;
+		}
+		return true;
+	}
+	// texture coordinates of the projection of the light onto the polygon plane: rows of inverse(cols(u, v, n))
+	const Vec3f u = basis_vecs.basis_u, v = basis_vecs.basis_v, n = basis_vecs.basis_normal;
+	const float det = dot(u, cross(v, n));
+	if (det == 0.0f || !std::isfinite(det))
+		return false;
+	const Vec3f mat_x = cross(v, n) / det, mat_y = cross(n, u) / det; // (M^-1)^T columns x, y
+	const float tc_u = dot(vec_from_light_position_to_tc_start_point, mat_x), tc_v = dot(vec_from_light_position_to_tc_start_point, mat_y);
+	const float radius_at_polygon_plane = std::sqrt(square_radius_at_polygon_plane);
+	const float u_radius = radius_at_polygon_plane * (1.0f / std::sqrt(dot(u, u)));
+	const float v_radius = radius_at_polygon_plane * (1.0f / std::sqrt(dot(v, v)));
+	return !(tc_u + u_radius < (float)polygon.tex_coord_min[0] || tc_v + v_radius < (float)polygon.tex_coord_min[1] || tc_u - u_radius > (float)polygon.tex_coord_max[0] ||
+			 tc_v - v_radius > (float)polygon.tex_coord_max[1]);
+}
+} // namespace
+
 void Renderer::build_surface_jobs() // the closure of build_polygons_surfaces (partial_renderer.rs:1682-1819) turned into job records
 {
 	jobs_.clear();
@@ -707,7 +1068,16 @@ void Renderer::build_surface_jobs() // the closure of build_polygons_surfaces (p
 			j.lightmap_offset = polygon.lightmap_data_offset;
 			if (use_directional_lightmap)
 				j.flags |= SQW_SURF_DIRECTIONAL_LIGHTMAP;
-			j.num_lights = 0; // dynamic lights: FrameInfo::lights is empty for the fly-through workloads
+			// lights of the polygon's leaf that reach it, at most MAX_POLYGON_LIGHTS (partial_renderer.rs:1705-1734)
+			for (uint32_t light_index : leaf_lights_[polygon_data.parent_leaf])
+			{
+				if (polygon_is_affected_by_light(polygon, polygon_data, lights_[light_index]))
+				{
+					j.lights[j.num_lights++] = (uint16_t)light_index;
+					if (j.num_lights == SQW_MAX_POLYGON_LIGHTS)
+						break;
+				}
+			}
 		}
 		if (material.has_emissive)
 		{
@@ -742,7 +1112,7 @@ void Renderer::draw_tree(const ClippingPolygon& viewport_clipping_polygon) // pa
 			--num_nodes_on_stack;
 			const uint32_t leaf_index = node_index - FIRST_LEAF_INDEX;
 			ClippingPolygon bounds;
-			if (leaf_bounds(leaf_index, bounds))
+			if (visibility_.leaf_bounds(leaf_index, bounds))
 			{
 				bounds.intersect(viewport_clipping_polygon);
 				if (bounds.is_valid_and_non_empty())

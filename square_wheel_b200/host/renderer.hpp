@@ -36,6 +36,7 @@ struct RendererConfig
 {
 	bool use_directional_lightmaps = true;
 	float textures_mip_bias = 0.0f;
+	float shadows_quality = 0.0f;
 	bool clear_background = true;
 	bool invert_polygons_order = false;
 };
@@ -64,6 +65,59 @@ struct RendererDebugStats
 	uint32_t mode_counts[3] = {0, 0, 0};
 };
 
+// frame_info.rs:149-168
+struct DynamicLight
+{
+	Vec3f position;
+	float radius = 0;
+	float color[3] = {0, 0, 0};
+	uint32_t shadow_type = SQW_SHADOW_NONE; // SQW_SHADOW_*
+	Quaternion rotation;                    // Projector only
+	float fov = 0;                          // Projector only, radians
+};
+
+// renderer_structs.rs:207-213
+struct DynamicLightInfo
+{
+	bool visible = false;
+	uint32_t shadow_map_size = 0;
+	size_t shadow_map_data_offset = 0;
+};
+
+// map_visibility_calculator.rs: portal-flood visibility from one view point.  The renderer owns one for the camera and one
+// for the shadow-map views (DepthRenderer::visibility_calculator, depth_renderer.rs:11).
+class VisibilityCalculator
+{
+public:
+	explicit VisibilityCalculator(const BSPMap& map);
+	void update_visibility(const CameraMatrices& camera_matrices, const ClippingPolygon& frame_bounds);
+	bool leaf_bounds(uint32_t leaf, ClippingPolygon& out) const; // get_current_frame_leaf_bounds
+	bool is_inside_leaf_volume() const { return is_inside_leaf_volume_; }
+
+private:
+	uint32_t find_current_leaf() const;
+	void mark_reachable_leafs_iterative(const uint32_t* start_leafs, size_t num_start_leafs, const ClippingPolygon& start_bounds);
+	bool compute_is_inside_leaf_volume(uint32_t leaf_index) const;
+	struct LeafData
+	{
+		uint32_t visible_frame = 0;
+		ClippingPolygon current_frame_bounds;
+	};
+	struct PortalData
+	{
+		uint32_t visible_frame = 0;
+		bool has_projection = false;
+		ClippingPolygon current_frame_projection;
+	};
+	const BSPMap& map_;
+	CameraMatrices camera_matrices_;
+	uint32_t visibility_frame_ = 0;
+	std::vector<LeafData> leafs_data_;
+	std::vector<PortalData> portals_data_;
+	std::vector<uint32_t> wave_cur_, wave_next_;
+	bool is_inside_leaf_volume_ = true;
+};
+
 class Renderer
 {
 public:
@@ -80,16 +134,25 @@ public:
 	const std::vector<sqw_draw_cmd>& cmds() const { return cmds_; }
 	const std::vector<sqw_polygon_point>& polygon_points() const { return polygon_points_; }
 	const CameraMatrices& camera_matrices() const { return camera_matrices_; }
-	bool needs_background_clear() const { return config_.clear_background && !is_inside_leaf_volume_; }
+	bool needs_background_clear() const { return config_.clear_background && !visibility_.is_inside_leaf_volume(); }
+	// FrameInfo::lights for the next prepare_frame (frame_info.rs:24)
+	void set_lights(const DynamicLight* lights, size_t n) { frame_lights_.assign(lights, lights + n); }
+	const std::vector<sqw_light>& lights() const { return lights_; }
+	const std::vector<sqw_depth_map>& depth_maps() const { return depth_maps_; }
+	const std::vector<sqw_depth_cmd>& depth_cmds() const { return depth_cmds_; }
+	const std::vector<sqw_polygon_point>& depth_points() const { return depth_points_; }
+	uint64_t shadow_maps_len() const { return shadow_maps_len_; }
 	const RendererDebugStats& stats() const { return stats_; }
 
 private:
-	// map_visibility_calculator.rs
-	void update_visibility(const ClippingPolygon& frame_bounds);
-	uint32_t find_current_leaf() const;
-	void mark_reachable_leafs_iterative(const uint32_t* start_leafs, size_t num_start_leafs, const ClippingPolygon& start_bounds);
-	bool compute_is_inside_leaf_volume(uint32_t leaf_index) const;
-	bool leaf_bounds(uint32_t leaf, ClippingPolygon& out) const;
+	// dynamic_objects_index.rs / partial_renderer.rs:398-590 / depth_renderer.rs
+	void position_dynamic_lights();
+	void position_object_sphere_r(uint32_t id, Vec3f center, float radius, uint32_t node_index);
+	void position_object_convex_hull_r(uint32_t id, const Vec3f* vertices, size_t n, uint32_t node_index);
+	void prepare_dynamic_lights();
+	void build_shadow_maps();
+	void depth_draw_map(uint32_t offset, uint32_t size, uint32_t flags, const CameraMatrices& depth_matrices);
+	void depth_draw_polygon(const CameraMatrices& m, const Vec3f clip_planes[8], uint32_t polygon_index, bool depth_test);
 	// partial_renderer.rs
 	void prepare_polygons_surfaces();
 	void prepare_polygon_surface(const Vec3f clip_planes[8], size_t polygon_index);
@@ -108,22 +171,19 @@ private:
 	uint32_t current_frame_ = 0;
 	float mip_bias_ = 0;
 
-	struct LeafData
-	{
-		uint32_t visible_frame = 0;
-		ClippingPolygon current_frame_bounds;
-	};
-	struct PortalData
-	{
-		uint32_t visible_frame = 0;
-		bool has_projection = false;
-		ClippingPolygon current_frame_projection;
-	};
-	uint32_t visibility_frame_ = 0;
-	std::vector<LeafData> leafs_data_;
-	std::vector<PortalData> portals_data_;
-	std::vector<uint32_t> wave_cur_, wave_next_;
-	bool is_inside_leaf_volume_ = true;
+	VisibilityCalculator visibility_;
+	VisibilityCalculator shadow_visibility_;
+
+	// FrameInfo::lights and what prepare_dynamic_lights / build_shadow_maps derive from them
+	std::vector<DynamicLight> frame_lights_;
+	std::vector<DynamicLightInfo> dynamic_lights_info_;
+	std::vector<std::vector<uint32_t>> leaf_lights_;  // DynamicObjectsIndex::get_leaf_objects
+	std::vector<std::vector<uint32_t>> light_leafs_;  // DynamicObjectsIndex::get_object_leafs
+	std::vector<sqw_light> lights_;
+	std::vector<sqw_depth_map> depth_maps_;
+	std::vector<sqw_depth_cmd> depth_cmds_;
+	std::vector<sqw_polygon_point> depth_points_;
+	uint64_t shadow_maps_len_ = 0;
 
 	std::vector<DrawPolygonData> polygons_data_;
 	std::vector<Vec3f> vertices_transformed_;

@@ -17,6 +17,7 @@ import numpy as np
 
 from . import _native as N
 from .device import Context, Frame, View, make_post_params
+from ._native import STAGE_SHADOW_MAPS as N_STAGE_SHADOW_MAPS, STAGE_SURFACES as N_STAGE_SURFACES
 from .scene import BACKGROUND_COLOR32, BACKGROUND_COLOR64, FOV_DEFAULT, HostFrame, HostRenderer, Scene
 
 
@@ -40,6 +41,7 @@ class FrameInfo:
     pose: np.ndarray
     fov: float = FOV_DEFAULT
     color_modulate: tuple = (1.0, 1.0, 1.0)
+    lights: Optional[np.ndarray] = None  # FrameInfo::lights (frame_info.rs:24) as scene.dynamic_light_dtype records
 
 
 @dataclass
@@ -49,6 +51,7 @@ class RendererConfig:
     use_directional_lightmaps: bool = True
     textures_mip_bias: float = 0.0
     clear_background: bool = True
+    shadows_quality: float = 0.0
 
 
 class Renderer:
@@ -58,8 +61,9 @@ class Renderer:
         self.config = config or RendererConfig()
         self.ctx = Context(scene.lightmaps, scene.directional_lightmaps, device=device, stream=stream)
         scene.upload(self.ctx)
-        self.host = HostRenderer(scene, self.config.use_directional_lightmaps, self.config.textures_mip_bias, self.config.clear_background)
+        self.host = HostRenderer(scene, self.config.use_directional_lightmaps, self.config.textures_mip_bias, self.config.clear_background, self.config.shadows_quality)
         self._views = {}
+        self._frames = {}
         self._host_frame: Optional[HostFrame] = None
         self._view: Optional[View] = None
 
@@ -71,10 +75,18 @@ class Renderer:
 
     def prepare_frame(self, surface_info: SurfaceInfo, frame_info: FrameInfo, color_bits: int = 64):
         """prepare_frame::<ColorT> (renderer.rs:61): host preparation, then surface building on the GPU (seam S1)."""
-        hf = self.host.build_frame(surface_info.width, surface_info.height, frame_info.pose, frame_info.fov)
+        hf = self.host.build_frame(surface_info.width, surface_info.height, frame_info.pose, frame_info.fov, frame_info.lights)
         view = self._get_view(surface_info, color_bits)
-        view.build_surfaces(hf.jobs, None, None, hf.cam_pos, hf.total_surface_pixels)
-        self._host_frame, self._view = hf, view
+        key = (surface_info.width, surface_info.height, color_bits)
+        if key not in self._frames:
+            self._frames[key] = view.create_frame()
+        frame = self._frames[key]
+        has_lights = hf.lights is not None and len(hf.lights) > 0
+        frame.set_surfaces(hf.jobs, hf.lights if has_lights else None, None, hf.cam_pos, hf.total_surface_pixels, device_shadow_maps_len=hf.shadow_maps_len if has_lights else 0)
+        # build_shadow_maps (partial_renderer.rs:194); an empty list clears what an earlier frame recorded
+        frame.set_shadow_map_draw(hf.depth_maps, hf.depth_cmds, hf.depth_points)
+        frame.submit(N_STAGE_SHADOW_MAPS | N_STAGE_SURFACES)
+        self._host_frame, self._view, self._frame = hf, view, frame
         return hf
 
     def draw_frame(self, pixels: Optional[np.ndarray] = None):
@@ -90,6 +102,8 @@ class Renderer:
         return view
 
     def close(self):
+        for f in self._frames.values():
+            f.close()
         for v in self._views.values():
             v.close()
         self.host.close()

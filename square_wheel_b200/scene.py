@@ -40,7 +40,13 @@ class SceneInfo(C.Structure):
 class RendererConfig(C.Structure):
     """renderer_config.rs:5-31 (the fields the path reads)."""
 
-    _fields_ = [("use_directional_lightmaps", C.c_uint32), ("textures_mip_bias", C.c_float), ("clear_background", C.c_uint32), ("invert_polygons_order", C.c_uint32)]
+    _fields_ = [
+        ("use_directional_lightmaps", C.c_uint32),
+        ("textures_mip_bias", C.c_float),
+        ("clear_background", C.c_uint32),
+        ("invert_polygons_order", C.c_uint32),
+        ("shadows_quality", C.c_float),
+    ]
 
 
 class FrameInfo(C.Structure):
@@ -54,8 +60,20 @@ class FrameInfo(C.Structure):
         ("num_visible_polygons", C.c_uint32),
         ("mode_counts", C.c_uint32 * 3),
         ("cam_pos", C.c_float * 3),
-        ("reserved", C.c_uint32),
+        ("num_lights", C.c_uint32),
+        ("num_depth_maps", C.c_uint32),
+        ("num_depth_cmds", C.c_uint32),
+        ("num_depth_points", C.c_uint32),
+        ("num_triangle_points", C.c_uint32),
+        ("shadow_maps_len", C.c_uint64),
     ]
+
+
+# frame_info.rs:149-168 DynamicLight (rotation = quaternion s, x, y, z and fov only matter for projector shadows)
+dynamic_light_dtype = np.dtype(
+    [("position", "<f4", (3,)), ("radius", "<f4"), ("color", "<f4", (3,)), ("shadow_type", "<u4"), ("rotation", "<f4", (4,)), ("fov", "<f4")]
+)
+assert dynamic_light_dtype.itemsize == 52
 
 
 def build_host_library():
@@ -87,7 +105,11 @@ def lib() -> C.CDLL:
         l.sqwh_renderer_prepare_frame.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.c_float]
         l.sqwh_renderer_draw_frame.argtypes = [vp]
         l.sqwh_renderer_frame_info.argtypes = [vp, C.POINTER(FrameInfo)]
-        for name in ("sqwh_renderer_jobs", "sqwh_renderer_cmds", "sqwh_renderer_polygon_points"):
+        l.sqwh_renderer_set_lights.argtypes = [vp, vp, C.c_uint32]
+        for name in (
+            "sqwh_renderer_jobs", "sqwh_renderer_cmds", "sqwh_renderer_polygon_points", "sqwh_renderer_lights", "sqwh_renderer_depth_maps", "sqwh_renderer_depth_cmds",
+            "sqwh_renderer_depth_points",
+        ):
             getattr(l, name).restype = vp
             getattr(l, name).argtypes = [vp]
         l.sqwh_default_scene_params.argtypes = [C.POINTER(SceneParams)]
@@ -157,22 +179,37 @@ class Scene:
 class HostFrame:
     """Everything the host produced for one frame: the inputs of S1 and S2."""
 
-    def __init__(self, jobs, total_surface_pixels, cam_pos, cmds, polygon_points, needs_clear, info):
+    def __init__(self, jobs, total_surface_pixels, cam_pos, cmds, polygon_points, needs_clear, info, lights=None, depth_maps=None, depth_cmds=None, depth_points=None, shadow_maps_len=0):
         self.jobs, self.total_surface_pixels, self.cam_pos = jobs, total_surface_pixels, cam_pos
         self.cmds, self.polygon_points, self.needs_clear, self.info = cmds, polygon_points, needs_clear, info
+        # dynamic lights of the frame and the shadow-map fills that feed them (empty without FrameInfo::lights)
+        self.lights, self.depth_maps, self.depth_cmds, self.depth_points, self.shadow_maps_len = lights, depth_maps, depth_cmds, depth_points, shadow_maps_len
+
+    def record(self, frame, clear_color=None, post=None):
+        """Hand everything to one recorded device frame (sqw_frame_set_*)."""
+        has_lights = self.lights is not None and len(self.lights) > 0
+        frame.set_surfaces(self.jobs, self.lights if has_lights else None, None, self.cam_pos, self.total_surface_pixels, device_shadow_maps_len=self.shadow_maps_len if has_lights else 0)
+        if self.depth_maps is not None:
+            frame.set_shadow_map_draw(self.depth_maps, self.depth_cmds, self.depth_points)  # an empty list clears an earlier recording
+        frame.set_draw(self.cmds, self.polygon_points, None, clear_color=clear_color)
+        if post is not None:
+            frame.set_post(post)
 
 
 class HostRenderer:
     """C++ mirror of Renderer / PartialRenderer front end (renderer.rs:61,106; partial_renderer.rs:156,236)."""
 
-    def __init__(self, scene: Scene, use_directional_lightmaps=True, textures_mip_bias=0.0, clear_background=True):
+    def __init__(self, scene: Scene, use_directional_lightmaps=True, textures_mip_bias=0.0, clear_background=True, shadows_quality=0.0):
         self.scene = scene
         self._lib = lib()
-        cfg = RendererConfig(1 if use_directional_lightmaps else 0, textures_mip_bias, 1 if clear_background else 0, 0)
+        cfg = RendererConfig(1 if use_directional_lightmaps else 0, textures_mip_bias, 1 if clear_background else 0, 0, shadows_quality)
         self._handle = self._lib.sqwh_renderer_create(scene._handle, C.byref(cfg))
 
-    def build_frame(self, width: int, height: int, pose, fov: float = FOV_DEFAULT) -> HostFrame:
+    def build_frame(self, width: int, height: int, pose, fov: float = FOV_DEFAULT, lights=None) -> HostFrame:
+        """lights: FrameInfo::lights as an array of dynamic_light_dtype (or None)."""
         pose = np.ascontiguousarray(pose, np.float32)
+        lt = np.ascontiguousarray(lights, dynamic_light_dtype) if lights is not None else np.zeros(0, dynamic_light_dtype)
+        self._lib.sqwh_renderer_set_lights(self._handle, lt.ctypes.data_as(C.c_void_p), len(lt))
         self._lib.sqwh_renderer_prepare_frame(self._handle, width, height, pose.ctypes.data_as(C.c_void_p), fov)
         self._lib.sqwh_renderer_draw_frame(self._handle)
         fi = FrameInfo()
@@ -180,7 +217,13 @@ class HostRenderer:
         jobs = _array_from(self._lib.sqwh_renderer_jobs(self._handle), fi.num_jobs, N.surface_job_dtype)
         cmds = _array_from(self._lib.sqwh_renderer_cmds(self._handle), fi.num_cmds, N.draw_cmd_dtype)
         pts = _array_from(self._lib.sqwh_renderer_polygon_points(self._handle), fi.num_polygon_points, N.polygon_point_dtype)
-        return HostFrame(jobs, int(fi.total_surface_pixels), np.array(list(fi.cam_pos), np.float32), cmds, pts, bool(fi.needs_background_clear), fi)
+        out_lights = _array_from(self._lib.sqwh_renderer_lights(self._handle), fi.num_lights, N.light_dtype)
+        dmaps = _array_from(self._lib.sqwh_renderer_depth_maps(self._handle), fi.num_depth_maps, N.depth_map_dtype)
+        dcmds = _array_from(self._lib.sqwh_renderer_depth_cmds(self._handle), fi.num_depth_cmds, N.depth_cmd_dtype)
+        dpts = _array_from(self._lib.sqwh_renderer_depth_points(self._handle), fi.num_depth_points, N.polygon_point_dtype)
+        return HostFrame(
+            jobs, int(fi.total_surface_pixels), np.array(list(fi.cam_pos), np.float32), cmds, pts, bool(fi.needs_background_clear), fi, out_lights, dmaps, dcmds, dpts, int(fi.shadow_maps_len)
+        )
 
     def close(self):
         if self._handle:

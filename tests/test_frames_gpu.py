@@ -107,3 +107,53 @@ def test_4k_frame_properties(scene, oracle_lib):
         assert_pixels_equal(first[y0 + 1 : y1], fb[y0 + 1 : y1], "4K strip")
     finally:
         r.close()
+
+
+def _lights_along_path(path, n, seed):
+    r = np.random.default_rng(seed)
+    lights = np.zeros(n, S.dynamic_light_dtype)
+    for i in range(n):
+        lights[i]["position"] = path[(i * 5) % len(path)][:3] + r.uniform(-30.0, 30.0, 3)
+        lights[i]["radius"] = (128.0, 256.0, 512.0)[i % 3]
+        lights[i]["color"] = r.uniform(4000.0, 60000.0, 3)
+        lights[i]["shadow_type"] = (N.SHADOW_NONE, N.SHADOW_CUBE, N.SHADOW_PROJECTOR)[i % 3]
+        # projector looking along a random horizontal direction (rotation about z), 0.2*pi opening like the test game's flashlight
+        a = r.uniform(0, 2 * np.pi)
+        lights[i]["rotation"] = (np.cos(a / 2), 0.0, 0.0, np.sin(a / 2))
+        lights[i]["fov"] = 0.2 * np.pi
+    return lights
+
+
+@pytest.mark.parametrize("color_bits", [32, 64])
+def test_config2_dynamic_lights_with_gpu_shadow_maps(scene, oracle_lib, color_bits):
+    """configs[2] in miniature: 8 dynamic lights (none / cube / projector shadows).  The host records the shadow-map fills
+    (DepthRenderer::draw_map per cube side / projector) and the light lists per polygon; shadow maps, surfaces and the picture
+    are produced on the GPU and must equal the oracle's, which renders its own shadow maps from the same fill list."""
+    W, H = 640, 360
+    r = Renderer(scene, RendererConfig(use_directional_lightmaps=True))
+    try:
+        path = scene.camera_path(64)
+        lights = _lights_along_path(path, 8, 3)
+        lit_jobs = 0
+        for k in (0, 11, 26, 40):
+            hf = r.prepare_frame(SurfaceInfo(W, H), FrameInfo(path[k], lights=lights), color_bits=color_bits)
+            pixels = np.zeros((H, W), np.uint32 if color_bits == 32 else np.uint64)
+            r.draw_frame(pixels)
+            lit_jobs += int((hf.jobs["num_lights"] > 0).sum())
+            sm = np.zeros(max(hf.shadow_maps_len, 1), np.float32)
+            if len(hf.depth_maps):
+                oracle_lib.draw_shadow_maps(sm, hf.depth_maps, hf.depth_cmds, hf.depth_points)
+                got_sm = r._frame.read_shadow_maps(0, hf.shadow_maps_len)
+                assert got_sm.view(np.uint32).tolist() == sm[: hf.shadow_maps_len].view(np.uint32).tolist(), f"frame {k} shadow maps"
+            oracle_lib.reset_assert_failures()
+            surf = oracle_lib.build_surfaces(color_bits, hf.jobs, hf.lights, sm, hf.cam_pos, scene.images, scene.lightmaps, scene.directional_lightmaps, hf.total_surface_pixels)
+            fb = np.zeros((H, W), pixels.dtype)
+            if hf.needs_clear:
+                oracle_lib.fill(fb, S.BACKGROUND_COLOR64 if color_bits == 64 else S.BACKGROUND_COLOR32)
+            oracle_lib.draw(color_bits, fb, hf.cmds, hf.polygon_points, None, surf, scene.images)
+            assert oracle_lib.assert_failures() == 0
+            assert_pixels_equal(r._view.read_surfaces(0, hf.total_surface_pixels), surf, f"frame {k} surfaces")
+            assert_pixels_equal(pixels, fb, f"frame {k} picture")
+        assert lit_jobs > 20  # the lights really reach visible polygons
+    finally:
+        r.close()
