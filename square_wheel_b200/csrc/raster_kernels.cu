@@ -474,27 +474,41 @@ __device__ void setup_triangle_line(const sqw_draw_cmd& c, const sqw_triangle_po
 }
 
 // ---- binning -------------------------------------------------------------------------------------------------
-// One CTA per 8-row band: order-preserving compaction (ballot + popc prefix) of the commands whose row range touches
-// the band.  Runs as the tail CTAs of the set-up grid (the two jobs are independent; one launch instead of two).
-__device__ void bin_band(const CmdDev* __restrict__ cmd_dev, uint32_t num_cmds, const uint32_t* __restrict__ band_offsets, uint32_t* __restrict__ band_lists, int band)
+// One CTA per 8-row band, two steps:
+//   1. order-preserving compaction (ballot + popc prefix) of the commands whose row range touches the band -> band list
+//      (kept in shared memory, spilled to band_lists beyond SQW_BIN_CACHE entries);
+//   2. every warp takes some of the band's 128-pixel columns and compacts, again in order, the band list entries whose
+//      conservative column range touches the column into that tile's list.  Tile (band, col) owns the N slots starting at
+//      band_offsets[band] * tiles_x + col * N (N = band list length), so no global prefix sum is needed; tile_desc gets
+//      {first slot, count}.  The tile kernel then reads ready-made ordered lists and never synchronises its CTA.
+// Runs as the tail CTAs of the set-up grid (the two jobs are independent; one launch instead of two).
+#define SQW_BIN_CACHE 1024
+__device__ void bin_band(
+	const CmdDev* __restrict__ cmd_dev, uint32_t num_cmds, const uint32_t* __restrict__ band_offsets, uint32_t* band_lists, uint32_t* __restrict__ tile_lists,
+	uint2* __restrict__ tile_desc, uint32_t tiles_x, int band)
 {
 	constexpr int WARPS = SQW_SETUP_THREADS / 32;
 	__shared__ uint32_t s_warp_counts[WARPS];
 	__shared__ uint32_t s_running;
+	__shared__ uint32_t s_idx[SQW_BIN_CACHE];
+	__shared__ uint32_t s_bx[SQW_BIN_CACHE];
 	const int32_t band_y0 = band * SQW_TILE_H, band_y1 = band_y0 + SQW_TILE_H;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const uint32_t band_begin = band_offsets[band];
 	if (threadIdx.x == 0)
-		s_running = band_offsets[band];
+		s_running = band_begin;
 	__syncthreads();
 	for (uint32_t base = 0; base < num_cmds; base += SQW_SETUP_THREADS)
 	{
 		const uint32_t i = base + threadIdx.x;
 		bool hit = false;
+		uint32_t bx = 0;
 		if (i < num_cmds)
 		{
 			const uint2 w = __ldg(reinterpret_cast<const uint2*>(cmd_dev + i)); // y0,y1,bx0,bx1
 			const int32_t y0 = (int16_t)(w.x & 0xFFFF), y1 = (int16_t)(w.x >> 16);
 			hit = y0 < y1 && y0 < band_y1 && y1 > band_y0;
+			bx = w.y;
 		}
 		const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, hit);
 		if (lane == 0)
@@ -504,7 +518,15 @@ __device__ void bin_band(const CmdDev* __restrict__ cmd_dev, uint32_t num_cmds, 
 		for (int w = 0; w < warp; ++w)
 			offset += s_warp_counts[w];
 		if (hit)
-			band_lists[offset + __popc(ballot & ((1u << lane) - 1))] = i;
+		{
+			const uint32_t pos = offset + __popc(ballot & ((1u << lane) - 1));
+			band_lists[pos] = i;
+			if (pos - band_begin < SQW_BIN_CACHE)
+			{
+				s_idx[pos - band_begin] = i;
+				s_bx[pos - band_begin] = bx;
+			}
+		}
 		__syncthreads();
 		if (threadIdx.x == 0)
 		{
@@ -515,12 +537,48 @@ __device__ void bin_band(const CmdDev* __restrict__ cmd_dev, uint32_t num_cmds, 
 		}
 		__syncthreads();
 	}
+	const uint32_t n = s_running - band_begin; // == band_offsets[band + 1] - band_begin (the host counted with the same test)
+	for (uint32_t col = (uint32_t)warp; col < tiles_x; col += WARPS)
+	{
+		const int32_t col_x0 = (int32_t)col * SQW_TILE_W, col_x1 = col_x0 + SQW_TILE_W;
+		const uint32_t list_start = band_begin * tiles_x + col * n;
+		uint32_t count = 0;
+		for (uint32_t base = 0; base < n; base += 32)
+		{
+			const uint32_t e = base + (uint32_t)lane;
+			bool hit = false;
+			uint32_t idx = 0;
+			if (e < n)
+			{
+				uint32_t bx;
+				if (e < SQW_BIN_CACHE)
+				{
+					idx = s_idx[e];
+					bx = s_bx[e];
+				}
+				else
+				{
+					idx = band_lists[band_begin + e]; // written above by this CTA: plain load, not the read-only path
+					bx = __ldg(reinterpret_cast<const uint32_t*>(cmd_dev + idx) + 1);
+				}
+				const int32_t bx0 = (int16_t)(bx & 0xFFFF), bx1 = (int16_t)(bx >> 16);
+				hit = bx0 < col_x1 && bx1 > col_x0;
+			}
+			const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, hit);
+			if (hit)
+				tile_lists[list_start + count + __popc(ballot & ((1u << lane) - 1))] = idx;
+			count += __popc(ballot);
+		}
+		if (lane == 0)
+			tile_desc[(uint32_t)band * tiles_x + col] = make_uint2(list_start, count);
+	}
 }
 
 __global__ void __launch_bounds__(SQW_SETUP_THREADS) raster_setup_kernel(
 	const sqw_draw_cmd* __restrict__ cmds, const CmdDev* __restrict__ cmd_dev, uint32_t num_cmds, const sqw_polygon_point* __restrict__ polygon_points,
 	const sqw_triangle_point* __restrict__ triangle_points, const uint2* __restrict__ chunks, uint32_t num_chunks, SpanRec* __restrict__ spans,
-	int32_t clip_w, int32_t clip_h, uint32_t setup_blocks, const uint32_t* __restrict__ band_offsets, uint32_t* __restrict__ band_lists, uint32_t num_bands,
+	int32_t clip_w, int32_t clip_h, uint32_t setup_blocks, const uint32_t* __restrict__ band_offsets, uint32_t* band_lists, uint32_t* __restrict__ tile_lists,
+	uint2* __restrict__ tile_desc, uint32_t tiles_x, uint32_t num_bands,
 	unsigned long long* __restrict__ sums_to_zero, uint8_t* __restrict__ tonemap_lut, float isb, float isg, float isr)
 {
 	if (blockIdx.x >= setup_blocks + num_bands)
@@ -539,7 +597,7 @@ __global__ void __launch_bounds__(SQW_SETUP_THREADS) raster_setup_kernel(
 	}
 	if (blockIdx.x >= setup_blocks)
 	{
-		bin_band(cmd_dev, num_cmds, band_offsets, band_lists, (int)(blockIdx.x - setup_blocks));
+		bin_band(cmd_dev, num_cmds, band_offsets, band_lists, tile_lists, tile_desc, tiles_x, (int)(blockIdx.x - setup_blocks));
 		return;
 	}
 	if (sums_to_zero && blockIdx.x == 0) // colour sums of the fused tonemapping epilogue of the tile kernel that follows
@@ -582,27 +640,27 @@ __device__ __forceinline__ typename C::Raw fetch_texel(const void* tex, uint32_t
 // HDR pixels are still in registers, so the 32-bit picture and the colour sums are produced without reading the 64-bit
 // buffer back (saves 8 of the 12 bytes per pixel of a separate tonemapping pass).
 //
-// Work distribution inside the 128x8 tile: warp w owns the 32x4 pixel block (w & 3, w >> 2) and lane l the four
-// consecutive pixels ((l & 7) * 4 .. + 3) of block row l >> 3.  A compact footprint meets far fewer polygon edges than
-// a 128x1 strip, so fewer commands are evaluated with lanes idle, and every global store is still a full 256-byte run.
-//   phase A  all 256 threads test one candidate of the band list each against the tile's column range and compact the
-//            survivors IN LIST ORDER (ballot + popc prefix across warps) into shared memory, texture pointer resolved;
-//   phase B  the span records of 32 listed commands x 8 band rows are fetched by all 256 threads at once into shared
-//            memory (one memory latency per tile instead of one per command), then every warp walks the list:
-//            warp-uniform reject against its 32x4 block, span record of the lane's row from shared memory, pixels.
-//            Only the texel gathers of a covering command go to global memory.
+// Warp-autonomous tiles.  A CTA walks 128x8 tiles (persistent grid), warp w owns the 32x4 pixel block (w & 3, w >> 2) of
+// the tile and lane l four pixels of block row l >> 3.  A compact footprint meets far fewer polygon edges than a 128x1
+// strip, and every global store is still a run of whole 32-byte sectors.  Nothing in the tile loop synchronises the CTA:
+//   list     the ordered command list of the tile comes ready-made from the binning CTAs of the set-up grid; a lane takes
+//            one entry, rejects it against the warp's block and the survivors are compacted IN LIST ORDER (ballot + popc)
+//            into the warp's slice of shared memory, texture pointer resolved.  The descriptor and the first 32 entries
+//            of the NEXT tile are fetched while the current one is evaluated.
+//   spans    the span records of 8 listed commands x 4 block rows are fetched by the 32 lanes at once into the warp's
+//            slice of shared memory (one memory latency per 8 commands), then the warp walks them in order: span record
+//            of the lane's row from shared memory, pixels.  Only the texel gathers go to global memory.
 template <class C, int TONEMAP>
 __global__ void __launch_bounds__(SQW_RASTER_THREADS, SQW_TILE_CTAS_PER_SM) raster_tile_kernel(
-	const CmdDev* __restrict__ cmd_dev, const SpanRec* __restrict__ spans, const uint32_t* __restrict__ band_lists, const uint32_t* __restrict__ band_offsets,
+	const CmdDev* __restrict__ cmd_dev, const SpanRec* __restrict__ spans, const uint32_t* __restrict__ tile_lists, const uint2* __restrict__ tile_desc,
 	const char* __restrict__ surfaces_base, typename C::Raw* __restrict__ color_buffer, int32_t width, int32_t height, int32_t pitch, int clear,
 	typename C::Raw clear_color, uint32_t* __restrict__ ldr, float isb, float isg, float isr, unsigned long long* __restrict__ sums,
 	const uint8_t* __restrict__ tonemap_lut, uint32_t tiles_x, uint32_t num_tiles)
 {
 	typedef typename C::Raw Raw;
 	constexpr int WARPS = SQW_RASTER_THREADS / 32;
-	__shared__ uint4 s_cmd[2][SQW_RASTER_THREADS]; // [0] CmdDev words 0-3, [1] {texture pointer, tex_width, tex_height}
-	__shared__ uint32_t s_warp_counts[WARPS];
-	__shared__ uint4 s_span[3][SQW_TILE_STAGE_HITS][SQW_TILE_H]; // SpanRec words of (staged command, band row)
+	__shared__ uint4 s_cmd_all[WARPS][2][32];                       // per warp: [0] CmdDev words 0-3, [1] {texture pointer, tex_width, tex_height}
+	__shared__ uint4 s_span_all[WARPS][3][SQW_TILE_STAGE_HITS][4]; // per warp: SpanRec words of (staged command, block row)
 	// Per-channel tonemapping table (exact results for channel values < SQW_TONEMAP_LUT_SIZE, built by the set-up grid of
 	// this frame): three byte look-ups replace three IEEE divides for all but very bright pixels.
 	__shared__ __align__(16) uint8_t s_lut[TONEMAP ? 3 * SQW_TONEMAP_LUT_SIZE : 16];
@@ -614,18 +672,31 @@ __global__ void __launch_bounds__(SQW_RASTER_THREADS, SQW_TILE_CTAS_PER_SM) rast
 			d[i] = __ldg(src + i);
 	}
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	uint4(*const s_cmd)[32] = s_cmd_all[warp];
+	uint4(*const s_span)[SQW_TILE_STAGE_HITS][4] = s_span_all[warp];
 	uint32_t sb = 0, sg = 0, sr = 0; // colour sums of the fused tonemapping (all tiles of this CTA)
 	if (TONEMAP)
-		__syncthreads(); // s_lut is complete
+		__syncthreads(); // s_lut is complete (the only CTA-wide barrier before the final sum reduction)
 
 	// Persistent CTAs: the grid is sized to what the GPU holds at once and every CTA strides over the tiles, so the
 	// per-CTA costs (tonemapping table, sum reduction, launch) are paid a few hundred times per frame, not once per tile.
+	uint2 desc_next = make_uint2(0, 0);
+	uint32_t idx_next = 0;
+	if (blockIdx.x < num_tiles)
+	{
+		desc_next = __ldg(tile_desc + blockIdx.x);
+		if ((uint32_t)lane < desc_next.y)
+			idx_next = __ldg(tile_lists + desc_next.x + lane);
+	}
 	for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
 	{
+	const uint2 desc = desc_next; // {first entry in tile_lists, number of entries}
+	uint32_t idx = idx_next;
+	if (tile + gridDim.x < num_tiles)
+		desc_next = __ldg(tile_desc + tile + gridDim.x);
 	const int band = (int)(tile / tiles_x);
 	const int32_t tile_x0 = (int32_t)(tile % tiles_x) * SQW_TILE_W;
-	const int32_t tile_x1 = min(tile_x0 + SQW_TILE_W, width);
-	const int32_t band_y0 = band * SQW_TILE_H, band_y1 = min(band_y0 + SQW_TILE_H, height);
+	const int32_t band_y0 = band * SQW_TILE_H;
 	// this warp's block and this lane's pixels
 	const int32_t blk_x0 = tile_x0 + (warp & 3) * 32, blk_x1 = blk_x0 + 32;
 	const int32_t blk_y0 = band_y0 + (warp >> 2) * 4, blk_y1 = min(blk_y0 + 4, height);
@@ -648,34 +719,27 @@ __global__ void __launch_bounds__(SQW_RASTER_THREADS, SQW_TILE_CTAS_PER_SM) rast
 		px[i] = clear_color;
 	const bool vec_ok = (blk_x1 <= width) && ((pitch & 1) == 0);
 
-	const uint32_t list_begin = band_offsets[band], list_end = band_offsets[band + 1];
-	for (uint32_t base = list_begin; base < list_end; base += SQW_RASTER_THREADS)
+	if (blk_x0 < width && blk_y0 < height) // (warp-uniform) blocks outside the picture have nothing to do
+	for (uint32_t base = 0; base < desc.y; base += 32)
 	{
-		// ---- phase A: tile list ----
+		// ---- the warp's list: entries of the tile list that can touch this 32x4 block, in order ----
+		if (base)
+			idx = (base + lane < desc.y) ? __ldg(tile_lists + desc.x + base + lane) : 0u;
 		bool hit = false;
 		uint4 c0 = make_uint4(0, 0, 0, 0);
 		const uint4* cdp = nullptr;
-		if (base + threadIdx.x < list_end)
+		if (base + lane < desc.y)
 		{
-			cdp = reinterpret_cast<const uint4*>(cmd_dev + __ldg(band_lists + base + threadIdx.x));
+			cdp = reinterpret_cast<const uint4*>(cmd_dev + idx);
 			c0 = __ldg(cdp); // y0,y1 | bx0,bx1 | span_base | kind, blend, tc_mode, tex_flags
 			const int32_t y0 = (int16_t)(c0.x & 0xFFFF), y1 = (int16_t)(c0.x >> 16);
 			const int32_t bx0 = (int16_t)(c0.y & 0xFFFF), bx1 = (int16_t)(c0.y >> 16);
-			hit = y0 < band_y1 && y1 > band_y0 && bx0 < tile_x1 && bx1 > tile_x0;
+			hit = y0 < blk_y1 && y1 > blk_y0 && bx0 < blk_x1 && bx1 > blk_x0;
 		}
 		const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, hit);
-		if (lane == 0)
-			s_warp_counts[warp] = __popc(ballot);
-		__syncthreads();
-		uint32_t slot = __popc(ballot & ((1u << lane) - 1)), num_hits = 0;
-#pragma unroll
-		for (int w = 0; w < WARPS; ++w)
-		{
-			const uint32_t n = s_warp_counts[w];
-			if (w < warp)
-				slot += n;
-			num_hits += n;
-		}
+		if (ballot == 0)
+			continue;
+		const uint32_t num_hits = __popc(ballot);
 		if (hit)
 		{
 			uint4 c1 = __ldg(cdp + 1); // texture ptr | tex_width | tex_height
@@ -687,23 +751,24 @@ __global__ void __launch_bounds__(SQW_RASTER_THREADS, SQW_TILE_CTAS_PER_SM) rast
 				c1.x = (uint32_t)t;
 				c1.y = (uint32_t)(t >> 32);
 			}
+			const uint32_t slot = __popc(ballot & ((1u << lane) - 1));
 			s_cmd[0][slot] = c0;
 			s_cmd[1][slot] = c1;
 		}
-		__syncthreads();
+		__syncwarp();
 
-		// ---- phase B: walk the tile list in submission order, SQW_TILE_STAGE_HITS commands at a time ----
+		// ---- walk the warp's list in submission order, SQW_TILE_STAGE_HITS commands at a time ----
 		for (uint32_t h0 = 0; h0 < num_hits; h0 += SQW_TILE_STAGE_HITS)
 		{
-			// Stage the span records of these commands for the 8 rows of the band: one (command, row) pair per thread, all
-			// loads independent, so the whole tile pays ONE memory latency for its span records.
+			// Stage the span records of these commands for the 4 rows of the block: one (command, row) pair per lane, all
+			// loads independent, so the warp pays ONE memory latency for the span records of 8 commands.
 			{
-				const uint32_t hs = threadIdx.x >> 3, rs = threadIdx.x & 7;
+				const uint32_t hs = (uint32_t)lane >> 2, rs = (uint32_t)lane & 3;
 				if (h0 + hs < num_hits)
 				{
 					const uint4 w0 = s_cmd[0][h0 + hs];
 					const int32_t y0 = (int16_t)(w0.x & 0xFFFF), y1 = (int16_t)(w0.x >> 16);
-					const int32_t srow = band_y0 + (int32_t)rs;
+					const int32_t srow = blk_y0 + (int32_t)rs;
 					uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, r2 = r0;
 					if (srow >= y0 && srow < y1)
 					{
@@ -718,17 +783,13 @@ __global__ void __launch_bounds__(SQW_RASTER_THREADS, SQW_TILE_CTAS_PER_SM) rast
 					s_span[2][hs][rs] = r2;
 				}
 			}
-			__syncthreads();
+			__syncwarp();
 			const uint32_t h1 = min(num_hits - h0, (uint32_t)SQW_TILE_STAGE_HITS);
-			const int rb = (warp >> 2) * 4 + (lane >> 3); // this lane's row inside the band
+			const int rb = lane >> 3; // this lane's row inside the block
 			for (uint32_t hh = 0; hh < h1; ++hh)
 			{
 			const uint32_t h = h0 + hh;
 			const uint4 w0 = s_cmd[0][h];
-			const int32_t y0 = (int16_t)(w0.x & 0xFFFF), y1 = (int16_t)(w0.x >> 16);
-			const int32_t bx0 = (int16_t)(w0.y & 0xFFFF), bx1 = (int16_t)(w0.y >> 16);
-			if (y0 >= blk_y1 || y1 <= blk_y0 || bx0 >= blk_x1 || bx1 <= blk_x0)
-				continue; // warp-uniform
 			const uint4 r0 = s_span[0][hh][rb];
 			const int32_t x0 = (int16_t)(r0.x & 0xFFFF), x1 = (int16_t)(r0.x >> 16);
 			const bool covered = x0 < x1 && ((x0 < px0 + 2 && x1 > px0) || (x0 < px0 + 18 && x1 > px0 + 16));
@@ -884,11 +945,12 @@ __global__ void __launch_bounds__(SQW_RASTER_THREADS, SQW_TILE_CTAS_PER_SM) rast
 				}
 			}
 			}
-			__syncthreads(); // the span stage (and, after the last group, the tile list) is rewritten next
+			__syncwarp(); // the span stage (and, after the last group, the warp's list) is rewritten next
 		}
-		if (num_hits == 0)
-			__syncthreads(); // s_warp_counts is rewritten by the next pass
 	}
+
+	// first entries of the next tile's list: the latency overlaps the epilogue below
+	idx_next = ((uint32_t)lane < desc_next.y && tile + gridDim.x < num_tiles) ? __ldg(tile_lists + desc_next.x + lane) : 0u;
 
 	if (row_valid)
 	{
@@ -991,15 +1053,15 @@ __global__ void __launch_bounds__(SQW_RASTER_THREADS, SQW_TILE_CTAS_PER_SM) rast
 
 cudaError_t launch_raster_setup(const RasterLaunch& l, cudaStream_t stream)
 {
-	if (l.num_cmds == 0 && !l.tonemap_dst)
+	if (l.num_bands == 0)
 		return cudaSuccess;
 	const uint32_t chunks_per_block = SQW_SETUP_THREADS / 32;
 	const uint32_t setup_blocks = std::max<uint32_t>((l.num_chunks + chunks_per_block - 1) / chunks_per_block, 1); // block 0 also zeroes the sums
-	const uint32_t bin_blocks = l.num_cmds ? l.num_bands : 0;
+	const uint32_t bin_blocks = l.num_bands; // also with an empty command list: the tile kernel reads every tile descriptor
 	const uint32_t lut_blocks = l.tonemap_dst ? (3 * SQW_TONEMAP_LUT_SIZE + SQW_SETUP_THREADS - 1) / SQW_SETUP_THREADS : 0;
 	raster_setup_kernel<<<setup_blocks + bin_blocks + lut_blocks, SQW_SETUP_THREADS, 0, stream>>>(
 		l.cmds, l.cmd_dev, l.num_cmds, l.polygon_points, l.triangle_points, l.chunks, l.num_chunks, l.spans, l.width, l.height, setup_blocks, l.band_offsets,
-		l.band_lists, bin_blocks, l.tonemap_dst ? l.color_sums : nullptr, l.tonemap_lut, l.inv_scale_bgr[0], l.inv_scale_bgr[1], l.inv_scale_bgr[2]);
+		l.band_lists, l.tile_lists, l.tile_desc, (uint32_t)((l.width + SQW_TILE_W - 1) / SQW_TILE_W), bin_blocks, l.tonemap_dst ? l.color_sums : nullptr, l.tonemap_lut, l.inv_scale_bgr[0], l.inv_scale_bgr[1], l.inv_scale_bgr[2]);
 	return cudaGetLastError();
 }
 
@@ -1019,7 +1081,7 @@ cudaError_t launch_raster_tiles(const RasterLaunch& l, cudaStream_t stream)
 	}
 	const uint32_t grid = std::min<uint32_t>(num_tiles, (uint32_t)sm_count * SQW_TILE_CTAS_PER_SM);
 #define SQW_TILE_ARGS(RAW) \
-	l.cmd_dev, l.spans, l.band_lists, l.band_offsets, static_cast<const char*>(l.surfaces_base), static_cast<RAW*>(l.color_buffer), l.width, l.height, l.pitch, l.clear, \
+	l.cmd_dev, l.spans, l.tile_lists, l.tile_desc, static_cast<const char*>(l.surfaces_base), static_cast<RAW*>(l.color_buffer), l.width, l.height, l.pitch, l.clear, \
 		(RAW)l.clear_color, l.tonemap_dst, l.inv_scale_bgr[0], l.inv_scale_bgr[1], l.inv_scale_bgr[2], l.color_sums, l.tonemap_lut, tiles_x, num_tiles
 	if (l.color64 && l.tonemap_dst)
 		raster_tile_kernel<Color64, 1><<<grid, SQW_RASTER_THREADS, 0, stream>>>(SQW_TILE_ARGS(uint64_t));

@@ -768,6 +768,20 @@ int sqw_frame_set_surfaces(
 	return SQW_OK;
 }
 
+// Layout of sqw_view::band_lists (scratch of the binning CTAs of one draw): [band lists][tile lists][tile descriptors].
+static size_t bin_tile_lists_offset(uint32_t band_entries)
+{
+	return ((size_t)band_entries * 4 + 63) & ~(size_t)63;
+}
+static size_t bin_tile_desc_offset(uint32_t band_entries, uint32_t tiles_x)
+{
+	return bin_tile_lists_offset(band_entries) + (((size_t)band_entries * tiles_x * 4 + 63) & ~(size_t)63);
+}
+static size_t bin_scratch_bytes(uint32_t band_entries, uint32_t tiles_x, uint32_t num_bands)
+{
+	return bin_tile_desc_offset(band_entries, tiles_x) + (size_t)num_bands * tiles_x * sizeof(uint2) + 64;
+}
+
 int sqw_frame_set_draw(
 	sqw_frame* f, const sqw_draw_cmd* cmds, uint32_t num_cmds, const sqw_polygon_point* polygon_points, uint32_t num_polygon_points,
 	const sqw_triangle_point* triangle_points, uint32_t num_triangle_points, const void* clear_color)
@@ -901,11 +915,16 @@ int sqw_frame_set_draw(
 	f->stats.num_spans = span_total;
 	f->stats.num_tiles = num_bands * (uint32_t)((W + SQW_TILE_W - 1) / SQW_TILE_W);
 
-	if ((size_t)span_total * sizeof(SpanRec) + 64 > view->spans.capacity || (size_t)f->total_band_entries * 4 + 64 > view->band_lists.capacity)
+	// Scratch of the binning CTAs: band lists, then the tile lists (tiles_x slots per band entry), then the tile descriptors.
+	const uint64_t tiles_x = (uint64_t)((W + SQW_TILE_W - 1) / SQW_TILE_W);
+	if ((uint64_t)f->total_band_entries * tiles_x > 0xFFFFFFFFull)
+		return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_frame_set_draw: too many commands per band");
+	const size_t bin_bytes = bin_scratch_bytes(f->total_band_entries, (uint32_t)tiles_x, num_bands);
+	if ((size_t)span_total * sizeof(SpanRec) + 64 > view->spans.capacity || bin_bytes > view->band_lists.capacity)
 	{
 		SQW_CUDA(ctx, cudaStreamSynchronize(view->stream)); // growing frees scratch a queued frame may still use
 		SQW_CUDA(ctx, view->spans.reserve((size_t)span_total * sizeof(SpanRec) + 64));
-		SQW_CUDA(ctx, view->band_lists.reserve((size_t)f->total_band_entries * 4 + 64));
+		SQW_CUDA(ctx, view->band_lists.reserve(bin_bytes));
 	}
 	{
 		Arena& a = f->draw_arena;
@@ -1142,7 +1161,13 @@ int sqw_frame_submit(sqw_frame* f, uint32_t stages)
 		l.chunks = f->d_chunks;
 		l.num_chunks = (uint32_t)f->h_chunks.size();
 		l.total_spans = f->total_spans;
-		l.band_lists = static_cast<uint32_t*>(view->band_lists.ptr);
+		{
+			const uint32_t tiles_x = (view->width + SQW_TILE_W - 1) / SQW_TILE_W;
+			char* const base = static_cast<char*>(view->band_lists.ptr);
+			l.band_lists = reinterpret_cast<uint32_t*>(base);
+			l.tile_lists = reinterpret_cast<uint32_t*>(base + bin_tile_lists_offset(f->total_band_entries));
+			l.tile_desc = reinterpret_cast<uint2*>(base + bin_tile_desc_offset(f->total_band_entries, tiles_x));
+		}
 		l.band_offsets = f->d_band_offsets;
 		l.num_bands = f->num_bands;
 		l.width = (int32_t)view->width;

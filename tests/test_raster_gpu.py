@@ -140,3 +140,24 @@ def test_surface_textures_and_empty_list(assets, oracle_lib):
     fb = np.zeros((H, W), np.uint64)
     oracle_lib.draw(64, fb, cmds, pts, None, surf, assets.images)
     assert_pixels_equal(got, fb, "surface-textured polygons")
+
+
+def test_crowded_bands(assets, oracle_lib):
+    """Thousands of small triangles on a small target: more than 1024 commands per 8-row band (the binning CTAs spill their
+    band list to global memory) and tile lists far longer than one 32-entry chunk; order must still be the submission order."""
+    r = synth.rng(5150)
+    ctx = assets.device_context()
+    W, H = 300, 40
+    n = 3000
+    tex = [assets.lite_ids[int(r.integers(0, len(assets.lite_ids)))] for _ in range(n)]
+    cmds, pts = synth.make_triangle_scene(r, W, H, n, [assets.image_size(t) for t in tex], blends=(0, 0, 1, 2, 3, 4), max_extent=60.0)
+    cmds["tex_ref"] = tex
+    view = ctx.create_view(W, H, 64)
+    try:
+        view.draw(cmds, None, pts, clear_color=0)
+        got = view.read_pixels()
+    finally:
+        view.close()
+    fb = np.zeros((H, W), np.uint64)
+    oracle_lib.draw(64, fb, cmds, None, pts, None, assets.images)
+    assert_pixels_equal(got, fb, "crowded bands")
