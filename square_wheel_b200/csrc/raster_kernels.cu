@@ -480,12 +480,12 @@ __device__ void setup_triangle_line(const sqw_draw_cmd& c, const sqw_triangle_po
 //   2. every warp takes some of the band's 128-pixel columns and compacts, again in order, the band list entries whose
 //      conservative column range touches the column into that tile's list.  Tile (band, col) owns the N slots starting at
 //      band_offsets[band] * tiles_x + col * N (N = band list length), so no global prefix sum is needed; tile_desc gets
-//      {first slot, count}.  The tile kernel then reads ready-made ordered lists and never synchronises its CTA.
+//      {first slot, count, tile origin}.  The tile kernel then reads ready-made ordered lists and never synchronises its CTA.
 // Runs as the tail CTAs of the set-up grid (the two jobs are independent; one launch instead of two).
 #define SQW_BIN_CACHE 1024
 __device__ void bin_band(
 	const CmdDev* __restrict__ cmd_dev, uint32_t num_cmds, const uint32_t* __restrict__ band_offsets, uint32_t* band_lists, uint32_t* __restrict__ tile_lists,
-	uint2* __restrict__ tile_desc, uint32_t tiles_x, int band)
+	uint4* __restrict__ tile_desc, uint32_t tiles_x, int band)
 {
 	constexpr int WARPS = SQW_SETUP_THREADS / 32;
 	__shared__ uint32_t s_warp_counts[WARPS];
@@ -570,7 +570,7 @@ __device__ void bin_band(
 			count += __popc(ballot);
 		}
 		if (lane == 0)
-			tile_desc[(uint32_t)band * tiles_x + col] = make_uint2(list_start, count);
+			tile_desc[(uint32_t)band * tiles_x + col] = make_uint4(list_start, count, (uint32_t)col_x0 | ((uint32_t)band_y0 << 16), 0u);
 	}
 }
 
@@ -578,7 +578,7 @@ __global__ void __launch_bounds__(SQW_SETUP_THREADS) raster_setup_kernel(
 	const sqw_draw_cmd* __restrict__ cmds, const CmdDev* __restrict__ cmd_dev, uint32_t num_cmds, const sqw_polygon_point* __restrict__ polygon_points,
 	const sqw_triangle_point* __restrict__ triangle_points, const uint2* __restrict__ chunks, uint32_t num_chunks, SpanRec* __restrict__ spans,
 	int32_t clip_w, int32_t clip_h, uint32_t setup_blocks, const uint32_t* __restrict__ band_offsets, uint32_t* band_lists, uint32_t* __restrict__ tile_lists,
-	uint2* __restrict__ tile_desc, uint32_t tiles_x, uint32_t num_bands,
+	uint4* __restrict__ tile_desc, uint32_t tiles_x, uint32_t num_bands,
 	unsigned long long* __restrict__ sums_to_zero, uint8_t* __restrict__ tonemap_lut, float isb, float isg, float isr)
 {
 	if (blockIdx.x >= setup_blocks + num_bands)
@@ -629,6 +629,7 @@ __device__ __forceinline__ typename C::Raw fetch_texel(const void* tex, uint32_t
 	return __ldg(static_cast<const typename C::Raw*>(tex) + address);
 }
 
+#define SQW_PX_OFS(i) (((i) & 1) + 16 * ((i) >> 1))
 #define SQW_NEED_DST(i)                       \
 	if (!(have & (1u << (i))))                \
 	{                                         \
@@ -636,31 +637,268 @@ __device__ __forceinline__ typename C::Raw fetch_texel(const void* tex, uint32_t
 		have |= 1u << (i);                    \
 	}
 
+// One command on the four pixels x = px0 + {0, 1, 16, 17} of one row: the pixel loops of fill_polygon_part*
+// (rasterizer.rs:424-445, :558-572, :705-719) or fill_triangle_part (:1223-1279) and write_into_framebuffer (:1511-1536).
+//   w0 = CmdDev words {y0,y1 | bx0,bx1 | span_base | kind, blend, tc_mode, tex_flags}; r0..r2 = the SpanRec of the row.
+// `have` bit i: px[i] holds the current value of the pixel; the framebuffer (dst) is only read for pixels whose first
+// covering command blends with the destination.
+template <class C>
+__device__ __forceinline__ void shade_quad(
+	const uint4 w0, const void* const tex, const uint32_t tex_width, const uint4 r0, const uint4 r1, const uint4 r2, const int32_t px0,
+	const typename C::Raw* __restrict__ const dst, typename C::Raw (&px)[4], uint32_t& have)
+{
+	typedef typename C::Raw Raw;
+	const int32_t x0 = (int16_t)(r0.x & 0xFFFF), x1 = (int16_t)(r0.x >> 16);
+	const uint32_t kind = w0.w & 0xFF, blend = (w0.w >> 8) & 0xFF, tc_mode = (w0.w >> 16) & 0xFF, tex64 = (w0.w >> 24) & 1;
+	// Blend modes that read the destination (rasterizer.rs:1511-1536); alpha test keeps it untouched when it fails.
+	const bool reads_dst = blend == SQW_BLEND_AVERAGE || blend == SQW_BLEND_ADDITIVE || blend == SQW_BLEND_ALPHA_BLEND;
+
+	if (kind == SQW_CMD_POLYGON)
+	{
+		const int32_t tc0 = (int32_t)r0.w, tc1 = (int32_t)r1.x, dtc0 = (int32_t)r1.y, dtc1 = (int32_t)r1.z;
+		const int32_t inv_z0 = (int32_t)r0.y, d_inv_z = (int32_t)r0.z;
+		// The four pixels of the lane are evaluated WITHOUT branches (addresses of uncovered pixels are computed from
+		// wrapped garbage and never dereferenced), so the four dependent chains — one u32 divide each in the full
+		// perspective mode — interleave and the four texel gathers are in flight together.
+		bool in[4];
+		uint32_t address[4];
+		if (tc_mode == SQW_TC_FULL_PERSPECTIVE)
+		{
+#pragma unroll
+			for (int i = 0; i < 4; ++i)
+			{
+				const int32_t x = px0 + SQW_PX_OFS(i);
+				in[i] = x >= x0 && x < x1;
+				const int32_t k = x - x0;
+				const uint32_t span_inv_z = (uint32_t)wadd(inv_z0, wmul(k, d_inv_z));
+				const uint32_t z = (1u << Z_CALC_SHIFT) / max(span_inv_z >> INV_Z_PRE_SHIFT, 1u); // rasterizer.rs:430 (covered pixels: >= 1 by the span clamp)
+				const uint64_t t0 = (uint64_t)(int64_t)wadd(tc0, wmul(k, dtc0));
+				const uint64_t t1 = (uint64_t)(int64_t)wadd(tc1, wmul(k, dtc1));
+				const uint32_t u = (uint32_t)(((uint64_t)z * t0) >> TC_FINAL_SHIFT);
+				const uint32_t v = (uint32_t)(((uint64_t)z * t1) >> TC_FINAL_SHIFT);
+				address[i] = u + v * tex_width;
+			}
+		}
+		else
+		{
+#pragma unroll
+			for (int i = 0; i < 4; ++i)
+			{
+				const int32_t x = px0 + SQW_PX_OFS(i);
+				in[i] = x >= x0 && x < x1;
+				const int32_t k = x - x0;
+				const uint32_t u = (uint32_t)(wadd(tc0, wmul(k, dtc0)) >> 16);
+				const uint32_t v = (uint32_t)(wadd(tc1, wmul(k, dtc1)) >> 16);
+				address[i] = u + v * tex_width;
+			}
+		}
+		Raw texel[4];
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+		{
+			texel[i] = 0;
+			if (in[i])
+				texel[i] = fetch_texel<C>(tex, address[i]);
+		}
+		if (blend == SQW_BLEND_NONE)
+		{
+#pragma unroll
+			for (int i = 0; i < 4; ++i)
+			{
+				px[i] = in[i] ? texel[i] : px[i];
+				have |= in[i] ? (1u << i) : 0u;
+			}
+		}
+		else if (blend == SQW_BLEND_ALPHA_TEST)
+		{
+#pragma unroll
+			for (int i = 0; i < 4; ++i)
+			{
+				const bool pass = in[i] && C::test_alpha(texel[i]);
+				px[i] = pass ? texel[i] : px[i];
+				have |= pass ? (1u << i) : 0u;
+			}
+		}
+		else
+		{
+#pragma unroll
+			for (int i = 0; i < 4; ++i)
+				if (in[i])
+				{
+					SQW_NEED_DST(i)
+					px[i] = blend_pixel<C>(blend, px[i], texel[i]);
+				}
+		}
+	}
+	else
+	{
+		// fill_triangle_part pixel loop (rasterizer.rs:1223-1279)
+		const int32_t tc0 = (int32_t)r0.y, tc1 = (int32_t)r0.z, dtc0 = (int32_t)r0.w, dtc1 = (int32_t)r1.x;
+		const int32_t l0 = (int32_t)r1.y, l1 = (int32_t)r1.z, l2 = (int32_t)r1.w;
+		const int32_t dl0 = (int32_t)r2.x, dl1 = (int32_t)r2.y, dl2 = (int32_t)r2.z;
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+		{
+			const int32_t x = px0 + SQW_PX_OFS(i);
+			if (x >= x0 && x < x1)
+			{
+				const int32_t k = x - x0;
+				const uint32_t u = (uint32_t)(wadd(tc0, wmul(k, dtc0)) >> 16);
+				const uint32_t v = (uint32_t)(wadd(tc1, wmul(k, dtc1)) >> 16);
+				// line_light = from_color_i32x3([l0,l1,l2]) -> lanes [B,G,R,A] = [l2,l1,l0,0]
+				const ColorVecI light = cvi(wadd(l2, wmul(k, dl2)), wadd(l1, wmul(k, dl1)), wadd(l0, wmul(k, dl0)), 0);
+				ColorVecI texel_vec;
+				int32_t alpha;
+				bool alpha_pass;
+				if (tex64)
+				{
+					const uint64_t t = __ldg(static_cast<const uint64_t*>(tex) + (u + v * tex_width));
+					texel_vec = cvi_from_color64(t);
+					alpha = Color64::get_alpha(t);
+					alpha_pass = Color64::test_alpha(t);
+				}
+				else
+				{
+					const uint32_t t = __ldg(static_cast<const uint32_t*>(tex) + (u + v * tex_width));
+					texel_vec = cvi_from_color32(t);
+					alpha = Color32::get_alpha(t);
+					alpha_pass = Color32::test_alpha(t);
+				}
+				const ColorVecI lighted = cvi_shr<16>(cvi_mul(texel_vec, light));
+				const Raw src = C::from_veci(lighted);
+				if (reads_dst)
+				{
+					SQW_NEED_DST(i)
+				}
+				switch (blend)
+				{
+				case SQW_BLEND_NONE:
+					px[i] = src;
+					have |= 1u << i;
+					break;
+				case SQW_BLEND_AVERAGE: px[i] = C::average(px[i], src); break;
+				case SQW_BLEND_ADDITIVE: px[i] = C::saturated_sum(px[i], src); break;
+				case SQW_BLEND_ALPHA_TEST:
+					if (alpha_pass)
+					{
+						px[i] = src;
+						have |= 1u << i;
+					}
+					break;
+				default:
+					px[i] = C::from_veci(cvi_shr<8>(cvi_add(cvi_mul_scalar(C::to_veci(px[i]), 255 - alpha), cvi_mul_scalar(lighted, alpha))));
+					break;
+				}
+			}
+		}
+	}
+}
+
+// The finished quad of one row: one 128-bit store per pixel pair, and with TONEMAP the 32-bit picture and colour sums.
+template <class C, int TONEMAP>
+__device__ __forceinline__ void finish_quad(
+	typename C::Raw (&px)[4], uint32_t have, const int32_t px0, const int32_t width, const bool vec_ok, typename C::Raw* __restrict__ const dst,
+	uint32_t* __restrict__ const o, const uint8_t* const s_lut, const float isb, const float isg, const float isr, uint32_t& sb, uint32_t& sg, uint32_t& sr)
+{
+	typedef typename C::Raw Raw;
+	if (vec_ok && have == 0xF)
+	{
+		// the usual case: all four pixels are final and inside the picture
+		if (sizeof(Raw) == 8)
+		{
+			*reinterpret_cast<uint4*>(dst) = make_uint4((uint32_t)px[0], (uint32_t)((uint64_t)px[0] >> 32), (uint32_t)px[1], (uint32_t)((uint64_t)px[1] >> 32));
+			*reinterpret_cast<uint4*>(dst + 16) = make_uint4((uint32_t)px[2], (uint32_t)((uint64_t)px[2] >> 32), (uint32_t)px[3], (uint32_t)((uint64_t)px[3] >> 32));
+		}
+		else
+		{
+			*reinterpret_cast<uint2*>(dst) = make_uint2((uint32_t)px[0], (uint32_t)px[1]);
+			*reinterpret_cast<uint2*>(dst + 16) = make_uint2((uint32_t)px[2], (uint32_t)px[3]);
+		}
+		if (TONEMAP)
+		{
+			// sizeof(Raw) == 8 here (the host only fuses 64-bit views)
+			uint32_t out[4];
+			const uint64_t any = (uint64_t)px[0] | (uint64_t)px[1] | (uint64_t)px[2] | (uint64_t)px[3];
+			uint32_t cb[4], cg[4], cr[4];
+#pragma unroll
+			for (int i = 0; i < 4; ++i)
+			{
+				const uint64_t p = (uint64_t)px[i];
+				cb[i] = (uint32_t)(p & 0xFFFF);
+				cg[i] = (uint32_t)((p >> 16) & 0xFFFF);
+				cr[i] = (uint32_t)((p >> 32) & 0xFFFF);
+				sb += cb[i];
+				sg += cg[i];
+				sr += cr[i];
+			}
+			// one test for the twelve channels: no B, G or R bit at or above SQW_TONEMAP_LUT_SIZE
+			if ((any & (0x0000FFFFFFFFFFFFull & ~(0x0001000100010001ull * (SQW_TONEMAP_LUT_SIZE - 1)))) == 0)
+			{
+#pragma unroll
+				for (int i = 0; i < 4; ++i)
+					out[i] = (uint32_t)s_lut[cb[i]] | ((uint32_t)s_lut[SQW_TONEMAP_LUT_SIZE + cg[i]] << 8) | ((uint32_t)s_lut[2 * SQW_TONEMAP_LUT_SIZE + cr[i]] << 16) | 0xFF000000u;
+			}
+			else
+			{
+#pragma unroll
+				for (int i = 0; i < 4; ++i)
+					out[i] = tonemap_pixel(cv_from_color64((uint64_t)px[i]), isb, isg, isr);
+			}
+			__stcs(reinterpret_cast<uint2*>(o), make_uint2(out[0], out[1]));
+			__stcs(reinterpret_cast<uint2*>(o + 16), make_uint2(out[2], out[3]));
+		}
+	}
+	else
+	{
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+			if (px0 + SQW_PX_OFS(i) < width && (have & (1u << i)))
+				dst[SQW_PX_OFS(i)] = px[i];
+		if (TONEMAP)
+		{
+#pragma unroll
+			for (int i = 0; i < 4; ++i)
+				if (px0 + SQW_PX_OFS(i) < width)
+				{
+					SQW_NEED_DST(i) // untouched pixel: tonemap what the buffer holds
+					const uint64_t p = (uint64_t)px[i];
+					sb += (uint32_t)(p & 0xFFFF);
+					sg += (uint32_t)((p >> 16) & 0xFFFF);
+					sr += (uint32_t)((p >> 32) & 0xFFFF);
+					o[SQW_PX_OFS(i)] = tonemap_pixel(cv_from_color64(p), isb, isg, isr);
+				}
+		}
+	}
+}
+
 // TONEMAP != 0 fuses Postprocessor::perform_tonemapping (postprocessor.rs:226-256) into the tile epilogue: the finished
 // HDR pixels are still in registers, so the 32-bit picture and the colour sums are produced without reading the 64-bit
 // buffer back (saves 8 of the 12 bytes per pixel of a separate tonemapping pass).
 //
-// Warp-autonomous tiles.  A CTA walks 128x8 tiles (persistent grid), warp w owns the 32x4 pixel block (w & 3, w >> 2) of
-// the tile and lane l four pixels of block row l >> 3.  A compact footprint meets far fewer polygon edges than a 128x1
-// strip, and every global store is still a run of whole 32-byte sectors.  Nothing in the tile loop synchronises the CTA:
+// Warp-autonomous tiles.  A CTA of 4 warps walks 128x8 tiles (persistent grid); warp w owns the 32x8 pixel block w of the
+// tile and lane l eight pixels: four of block row l >> 3 and four of row 4 + (l >> 3), all kept in registers until the
+// tile is finished, so each framebuffer byte is written once per frame however much overdraw the painter's order has.
+// A compact footprint meets far fewer polygon edges than a 128x1 strip, and every global store is still a run of whole
+// 32-byte sectors.  Nothing in the tile loop synchronises the CTA:
 //   list     the ordered command list of the tile comes ready-made from the binning CTAs of the set-up grid; a lane takes
 //            one entry, rejects it against the warp's block and the survivors are compacted IN LIST ORDER (ballot + popc)
 //            into the warp's slice of shared memory, texture pointer resolved.  The descriptor and the first 32 entries
 //            of the NEXT tile are fetched while the current one is evaluated.
-//   spans    the span records of 8 listed commands x 4 block rows are fetched by the 32 lanes at once into the warp's
-//            slice of shared memory (one memory latency per 8 commands), then the warp walks them in order: span record
-//            of the lane's row from shared memory, pixels.  Only the texel gathers go to global memory.
+//   spans    the span records of 4 listed commands x 8 block rows are fetched by the 32 lanes at once into the warp's
+//            slice of shared memory (one memory latency per 4 commands), then the warp walks them in order: span records
+//            of the lane's two rows from shared memory, pixels.  Only the texel gathers go to global memory.
 template <class C, int TONEMAP>
 __global__ void __launch_bounds__(SQW_RASTER_THREADS, SQW_TILE_CTAS_PER_SM) raster_tile_kernel(
-	const CmdDev* __restrict__ cmd_dev, const SpanRec* __restrict__ spans, const uint32_t* __restrict__ tile_lists, const uint2* __restrict__ tile_desc,
+	const CmdDev* __restrict__ cmd_dev, const SpanRec* __restrict__ spans, const uint32_t* __restrict__ tile_lists, const uint4* __restrict__ tile_desc,
 	const char* __restrict__ surfaces_base, typename C::Raw* __restrict__ color_buffer, int32_t width, int32_t height, int32_t pitch, int clear,
 	typename C::Raw clear_color, uint32_t* __restrict__ ldr, float isb, float isg, float isr, unsigned long long* __restrict__ sums,
-	const uint8_t* __restrict__ tonemap_lut, uint32_t tiles_x, uint32_t num_tiles)
+	const uint8_t* __restrict__ tonemap_lut, uint32_t num_tiles)
 {
 	typedef typename C::Raw Raw;
 	constexpr int WARPS = SQW_RASTER_THREADS / 32;
-	__shared__ uint4 s_cmd_all[WARPS][2][32];                       // per warp: [0] CmdDev words 0-3, [1] {texture pointer, tex_width, tex_height}
-	__shared__ uint4 s_span_all[WARPS][3][SQW_TILE_STAGE_HITS][4]; // per warp: SpanRec words of (staged command, block row)
+	static_assert(WARPS * 32 == SQW_TILE_W && SQW_TILE_H == 8 && SQW_TILE_STAGE_HITS * SQW_TILE_H == 32, "tile geometry");
+	__shared__ uint4 s_cmd_all[WARPS][2][32];                                // per warp: [0] CmdDev words 0-3, [1] {texture pointer, tex_width, tex_height}
+	__shared__ uint4 s_span_all[WARPS][3][SQW_TILE_STAGE_HITS][SQW_TILE_H]; // per warp: SpanRec words of (staged command, block row)
 	// Per-channel tonemapping table (exact results for channel values < SQW_TONEMAP_LUT_SIZE, built by the set-up grid of
 	// this frame): three byte look-ups replace three IEEE divides for all but very bright pixels.
 	__shared__ __align__(16) uint8_t s_lut[TONEMAP ? 3 * SQW_TONEMAP_LUT_SIZE : 16];
@@ -673,14 +911,14 @@ __global__ void __launch_bounds__(SQW_RASTER_THREADS, SQW_TILE_CTAS_PER_SM) rast
 	}
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	uint4(*const s_cmd)[32] = s_cmd_all[warp];
-	uint4(*const s_span)[SQW_TILE_STAGE_HITS][4] = s_span_all[warp];
+	uint4(*const s_span)[SQW_TILE_STAGE_HITS][SQW_TILE_H] = s_span_all[warp];
 	uint32_t sb = 0, sg = 0, sr = 0; // colour sums of the fused tonemapping (all tiles of this CTA)
 	if (TONEMAP)
 		__syncthreads(); // s_lut is complete (the only CTA-wide barrier before the final sum reduction)
 
 	// Persistent CTAs: the grid is sized to what the GPU holds at once and every CTA strides over the tiles, so the
 	// per-CTA costs (tonemapping table, sum reduction, launch) are paid a few hundred times per frame, not once per tile.
-	uint2 desc_next = make_uint2(0, 0);
+	uint4 desc_next = make_uint4(0, 0, 0, 0);
 	uint32_t idx_next = 0;
 	if (blockIdx.x < num_tiles)
 	{
@@ -688,41 +926,37 @@ __global__ void __launch_bounds__(SQW_RASTER_THREADS, SQW_TILE_CTAS_PER_SM) rast
 		if ((uint32_t)lane < desc_next.y)
 			idx_next = __ldg(tile_lists + desc_next.x + lane);
 	}
+	const int ra = lane >> 3, rb = 4 + (lane >> 3); // this lane's two rows inside the block
 	for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
 	{
-	const uint2 desc = desc_next; // {first entry in tile_lists, number of entries}
+	const uint4 desc = desc_next; // {first entry in tile_lists, number of entries, tile_x0 | band_y0 << 16, -}
 	uint32_t idx = idx_next;
 	if (tile + gridDim.x < num_tiles)
 		desc_next = __ldg(tile_desc + tile + gridDim.x);
-	const int band = (int)(tile / tiles_x);
-	const int32_t tile_x0 = (int32_t)(tile % tiles_x) * SQW_TILE_W;
-	const int32_t band_y0 = band * SQW_TILE_H;
 	// this warp's block and this lane's pixels
-	const int32_t blk_x0 = tile_x0 + (warp & 3) * 32, blk_x1 = blk_x0 + 32;
-	const int32_t blk_y0 = band_y0 + (warp >> 2) * 4, blk_y1 = min(blk_y0 + 4, height);
-	const int32_t row = blk_y0 + (lane >> 3);
-	const bool row_valid = row < height;
-	// The lane's four pixels are two PAIRS, 16 pixels apart: x = px0 + {0, 1, 16, 17}.  That way the 8 lanes of a block row
-	// write 8 consecutive 16-byte chunks per store instruction (whole 32-byte sectors, 128 contiguous bytes per row)
-	// instead of half-sectors with a 32-byte stride.
+	const int32_t blk_x0 = (int32_t)(desc.z & 0xFFFF) + warp * 32, blk_x1 = blk_x0 + 32;
+	const int32_t blk_y0 = (int32_t)(desc.z >> 16), blk_y1 = min(blk_y0 + SQW_TILE_H, height);
+	const int32_t row_a = blk_y0 + ra, row_b = blk_y0 + rb;
+	// The lane's four pixels of a row are two PAIRS, 16 pixels apart: x = px0 + {0, 1, 16, 17}.  That way the 8 lanes of a
+	// block row write 8 consecutive 16-byte chunks per store instruction (whole 32-byte sectors, 128 contiguous bytes per
+	// row) instead of half-sectors with a 32-byte stride.
 	const int32_t px0 = blk_x0 + (lane & 7) * 2;
-#define SQW_PX_OFS(i) (((i) & 1) + 16 * ((i) >> 1))
-
-	Raw* const dst = color_buffer + (size_t)row * pitch + px0;
-	Raw px[4];
+	const uint32_t pix_a = (uint32_t)row_a * (uint32_t)pitch + (uint32_t)px0; // < 2^32: the view size is limited to 16384^2
+	const uint32_t pix_b = pix_a + 4u * (uint32_t)pitch;
+	Raw px_a[4], px_b[4];
 	// `have` bit i: px[i] holds the current value of the pixel.  The framebuffer is only read for pixels whose first
 	// covering command blends with the destination, and pixels no command touches are not written back: a frame whose
 	// polygons cover the screen (the usual case inside a map, partial_renderer.rs:249-256) never reads the buffer.
-	uint32_t have = clear ? 0xFu : 0u;
+	uint32_t have_a = clear ? 0xFu : 0u, have_b = have_a;
 #pragma unroll
 	for (int i = 0; i < 4; ++i)
-		px[i] = clear_color;
+		px_a[i] = px_b[i] = clear_color;
 	const bool vec_ok = (blk_x1 <= width) && ((pitch & 1) == 0);
 
-	if (blk_x0 < width && blk_y0 < height) // (warp-uniform) blocks outside the picture have nothing to do
+	if (blk_x0 < width) // (warp-uniform) blocks outside the picture have nothing to do
 	for (uint32_t base = 0; base < desc.y; base += 32)
 	{
-		// ---- the warp's list: entries of the tile list that can touch this 32x4 block, in order ----
+		// ---- the warp's list: entries of the tile list that can touch this 32x8 block, in order ----
 		if (base)
 			idx = (base + lane < desc.y) ? __ldg(tile_lists + desc.x + base + lane) : 0u;
 		bool hit = false;
@@ -732,9 +966,8 @@ __global__ void __launch_bounds__(SQW_RASTER_THREADS, SQW_TILE_CTAS_PER_SM) rast
 		{
 			cdp = reinterpret_cast<const uint4*>(cmd_dev + idx);
 			c0 = __ldg(cdp); // y0,y1 | bx0,bx1 | span_base | kind, blend, tc_mode, tex_flags
-			const int32_t y0 = (int16_t)(c0.x & 0xFFFF), y1 = (int16_t)(c0.x >> 16);
 			const int32_t bx0 = (int16_t)(c0.y & 0xFFFF), bx1 = (int16_t)(c0.y >> 16);
-			hit = y0 < blk_y1 && y1 > blk_y0 && bx0 < blk_x1 && bx1 > blk_x0;
+			hit = bx0 < blk_x1 && bx1 > blk_x0; // the row range was tested by the binning CTA (block rows = band rows)
 		}
 		const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, hit);
 		if (ballot == 0)
@@ -760,10 +993,10 @@ __global__ void __launch_bounds__(SQW_RASTER_THREADS, SQW_TILE_CTAS_PER_SM) rast
 		// ---- walk the warp's list in submission order, SQW_TILE_STAGE_HITS commands at a time ----
 		for (uint32_t h0 = 0; h0 < num_hits; h0 += SQW_TILE_STAGE_HITS)
 		{
-			// Stage the span records of these commands for the 4 rows of the block: one (command, row) pair per lane, all
-			// loads independent, so the warp pays ONE memory latency for the span records of 8 commands.
+			// Stage the span records of these commands for the 8 rows of the block: one (command, row) pair per lane, all
+			// loads independent, so the warp pays ONE memory latency for the span records of 4 commands.
 			{
-				const uint32_t hs = (uint32_t)lane >> 2, rs = (uint32_t)lane & 3;
+				const uint32_t hs = (uint32_t)lane >> 3, rs = (uint32_t)lane & 7;
 				if (h0 + hs < num_hits)
 				{
 					const uint4 w0 = s_cmd[0][h0 + hs];
@@ -785,165 +1018,23 @@ __global__ void __launch_bounds__(SQW_RASTER_THREADS, SQW_TILE_CTAS_PER_SM) rast
 			}
 			__syncwarp();
 			const uint32_t h1 = min(num_hits - h0, (uint32_t)SQW_TILE_STAGE_HITS);
-			const int rb = lane >> 3; // this lane's row inside the block
 			for (uint32_t hh = 0; hh < h1; ++hh)
 			{
-			const uint32_t h = h0 + hh;
-			const uint4 w0 = s_cmd[0][h];
-			const uint4 r0 = s_span[0][hh][rb];
-			const int32_t x0 = (int16_t)(r0.x & 0xFFFF), x1 = (int16_t)(r0.x >> 16);
-			const bool covered = x0 < x1 && ((x0 < px0 + 2 && x1 > px0) || (x0 < px0 + 18 && x1 > px0 + 16));
-			if (!__any_sync(0xFFFFFFFFu, covered))
-				continue;
-			const uint4 w1 = s_cmd[1][h];
-			const uint4 r1 = s_span[1][hh][rb];
-			const uint32_t kind = w0.w & 0xFF, blend = (w0.w >> 8) & 0xFF, tc_mode = (w0.w >> 16) & 0xFF, tex64 = (w0.w >> 24) & 1;
-			const void* const tex = reinterpret_cast<const void*>((uint64_t)w1.x | ((uint64_t)w1.y << 32));
-			const uint32_t tex_width = w1.z;
-			// v[0..2] = r0.y,z,w ; v[3..6] = r1 ; v[7..10] = r2
-			// Blend modes that read the destination (rasterizer.rs:1511-1536); alpha test keeps it untouched when it fails.
-			const bool reads_dst = blend == SQW_BLEND_AVERAGE || blend == SQW_BLEND_ADDITIVE || blend == SQW_BLEND_ALPHA_BLEND;
-
-			if (kind == SQW_CMD_POLYGON)
-			{
-				const int32_t tc0 = (int32_t)r0.w, tc1 = (int32_t)r1.x, dtc0 = (int32_t)r1.y, dtc1 = (int32_t)r1.z;
-				const int32_t inv_z0 = (int32_t)r0.y, d_inv_z = (int32_t)r0.z;
-				// The four pixels of the lane are evaluated WITHOUT branches (addresses of uncovered pixels are computed from
-				// wrapped garbage and never dereferenced), so the four dependent chains — one u32 divide each in the full
-				// perspective mode — interleave and the four texel gathers are in flight together.
-				bool in[4];
-				uint32_t address[4];
-				if (tc_mode == SQW_TC_FULL_PERSPECTIVE)
-				{
-#pragma unroll
-					for (int i = 0; i < 4; ++i)
-					{
-						const int32_t x = px0 + SQW_PX_OFS(i);
-						in[i] = x >= x0 && x < x1;
-						const int32_t k = x - x0;
-						const uint32_t span_inv_z = (uint32_t)wadd(inv_z0, wmul(k, d_inv_z));
-						const uint32_t z = (1u << Z_CALC_SHIFT) / max(span_inv_z >> INV_Z_PRE_SHIFT, 1u); // rasterizer.rs:430 (covered pixels: >= 1 by the span clamp)
-						const uint64_t t0 = (uint64_t)(int64_t)wadd(tc0, wmul(k, dtc0));
-						const uint64_t t1 = (uint64_t)(int64_t)wadd(tc1, wmul(k, dtc1));
-						const uint32_t u = (uint32_t)(((uint64_t)z * t0) >> TC_FINAL_SHIFT);
-						const uint32_t v = (uint32_t)(((uint64_t)z * t1) >> TC_FINAL_SHIFT);
-						address[i] = u + v * tex_width;
-					}
-				}
-				else
-				{
-#pragma unroll
-					for (int i = 0; i < 4; ++i)
-					{
-						const int32_t x = px0 + SQW_PX_OFS(i);
-						in[i] = x >= x0 && x < x1;
-						const int32_t k = x - x0;
-						const uint32_t u = (uint32_t)(wadd(tc0, wmul(k, dtc0)) >> 16);
-						const uint32_t v = (uint32_t)(wadd(tc1, wmul(k, dtc1)) >> 16);
-						address[i] = u + v * tex_width;
-					}
-				}
-				Raw texel[4];
-#pragma unroll
-				for (int i = 0; i < 4; ++i)
-				{
-					texel[i] = 0;
-					if (in[i])
-						texel[i] = fetch_texel<C>(tex, address[i]);
-				}
-				if (blend == SQW_BLEND_NONE)
-				{
-#pragma unroll
-					for (int i = 0; i < 4; ++i)
-					{
-						px[i] = in[i] ? texel[i] : px[i];
-						have |= in[i] ? (1u << i) : 0u;
-					}
-				}
-				else if (blend == SQW_BLEND_ALPHA_TEST)
-				{
-#pragma unroll
-					for (int i = 0; i < 4; ++i)
-					{
-						const bool pass = in[i] && C::test_alpha(texel[i]);
-						px[i] = pass ? texel[i] : px[i];
-						have |= pass ? (1u << i) : 0u;
-					}
-				}
-				else
-				{
-#pragma unroll
-					for (int i = 0; i < 4; ++i)
-						if (in[i])
-						{
-							SQW_NEED_DST(i)
-							px[i] = blend_pixel<C>(blend, px[i], texel[i]);
-						}
-				}
-			}
-			else
-			{
-				// fill_triangle_part pixel loop (rasterizer.rs:1223-1279)
-				const uint4 r2 = s_span[2][hh][rb];
-				const int32_t tc0 = (int32_t)r0.y, tc1 = (int32_t)r0.z, dtc0 = (int32_t)r0.w, dtc1 = (int32_t)r1.x;
-				const int32_t l0 = (int32_t)r1.y, l1 = (int32_t)r1.z, l2 = (int32_t)r1.w;
-				const int32_t dl0 = (int32_t)r2.x, dl1 = (int32_t)r2.y, dl2 = (int32_t)r2.z;
-#pragma unroll
-				for (int i = 0; i < 4; ++i)
-				{
-					const int32_t x = px0 + SQW_PX_OFS(i);
-					if (x >= x0 && x < x1)
-					{
-						const int32_t k = x - x0;
-						const uint32_t u = (uint32_t)(wadd(tc0, wmul(k, dtc0)) >> 16);
-						const uint32_t v = (uint32_t)(wadd(tc1, wmul(k, dtc1)) >> 16);
-						// line_light = from_color_i32x3([l0,l1,l2]) -> lanes [B,G,R,A] = [l2,l1,l0,0]
-						const ColorVecI light = cvi(wadd(l2, wmul(k, dl2)), wadd(l1, wmul(k, dl1)), wadd(l0, wmul(k, dl0)), 0);
-						ColorVecI texel_vec;
-						int32_t alpha;
-						bool alpha_pass;
-						if (tex64)
-						{
-							const uint64_t t = __ldg(static_cast<const uint64_t*>(tex) + (u + v * tex_width));
-							texel_vec = cvi_from_color64(t);
-							alpha = Color64::get_alpha(t);
-							alpha_pass = Color64::test_alpha(t);
-						}
-						else
-						{
-							const uint32_t t = __ldg(static_cast<const uint32_t*>(tex) + (u + v * tex_width));
-							texel_vec = cvi_from_color32(t);
-							alpha = Color32::get_alpha(t);
-							alpha_pass = Color32::test_alpha(t);
-						}
-						const ColorVecI lighted = cvi_shr<16>(cvi_mul(texel_vec, light));
-						const Raw src = C::from_veci(lighted);
-						if (reads_dst)
-						{
-							SQW_NEED_DST(i)
-						}
-						switch (blend)
-						{
-						case SQW_BLEND_NONE:
-							px[i] = src;
-							have |= 1u << i;
-							break;
-						case SQW_BLEND_AVERAGE: px[i] = C::average(px[i], src); break;
-						case SQW_BLEND_ADDITIVE: px[i] = C::saturated_sum(px[i], src); break;
-						case SQW_BLEND_ALPHA_TEST:
-							if (alpha_pass)
-							{
-								px[i] = src;
-								have |= 1u << i;
-							}
-							break;
-						default:
-							px[i] = C::from_veci(cvi_shr<8>(cvi_add(cvi_mul_scalar(C::to_veci(px[i]), 255 - alpha), cvi_mul_scalar(lighted, alpha))));
-							break;
-						}
-					}
-				}
-			}
+				const uint4 ra0 = s_span[0][hh][ra], rb0 = s_span[0][hh][rb];
+				const int32_t ax0 = (int16_t)(ra0.x & 0xFFFF), ax1 = (int16_t)(ra0.x >> 16);
+				const int32_t bx0 = (int16_t)(rb0.x & 0xFFFF), bx1 = (int16_t)(rb0.x >> 16);
+				const bool cov_a = (ax0 < px0 + 2 && ax1 > px0) || (ax0 < px0 + 18 && ax1 > px0 + 16);
+				const bool cov_b = (bx0 < px0 + 2 && bx1 > px0) || (bx0 < px0 + 18 && bx1 > px0 + 16);
+				const uint32_t any_a = __ballot_sync(0xFFFFFFFFu, cov_a), any_b = __ballot_sync(0xFFFFFFFFu, cov_b);
+				if ((any_a | any_b) == 0)
+					continue;
+				const uint4 w0 = s_cmd[0][h0 + hh];
+				const uint4 w1 = s_cmd[1][h0 + hh];
+				const void* const tex = reinterpret_cast<const void*>((uint64_t)w1.x | ((uint64_t)w1.y << 32));
+				if (any_a) // (warp-uniform)
+					shade_quad<C>(w0, tex, w1.z, ra0, s_span[1][hh][ra], s_span[2][hh][ra], px0, color_buffer + pix_a, px_a, have_a);
+				if (any_b)
+					shade_quad<C>(w0, tex, w1.z, rb0, s_span[1][hh][rb], s_span[2][hh][rb], px0, color_buffer + pix_b, px_b, have_b);
 			}
 			__syncwarp(); // the span stage (and, after the last group, the warp's list) is rewritten next
 		}
@@ -952,75 +1043,17 @@ __global__ void __launch_bounds__(SQW_RASTER_THREADS, SQW_TILE_CTAS_PER_SM) rast
 	// first entries of the next tile's list: the latency overlaps the epilogue below
 	idx_next = ((uint32_t)lane < desc_next.y && tile + gridDim.x < num_tiles) ? __ldg(tile_lists + desc_next.x + lane) : 0u;
 
-	if (row_valid)
-	{
-		if (vec_ok && have == 0xF)
-		{
-			if (sizeof(Raw) == 8)
-			{
-				*reinterpret_cast<uint4*>(dst) = make_uint4((uint32_t)px[0], (uint32_t)((uint64_t)px[0] >> 32), (uint32_t)px[1], (uint32_t)((uint64_t)px[1] >> 32));
-				*reinterpret_cast<uint4*>(dst + 16) = make_uint4((uint32_t)px[2], (uint32_t)((uint64_t)px[2] >> 32), (uint32_t)px[3], (uint32_t)((uint64_t)px[3] >> 32));
-			}
-			else
-			{
-				*reinterpret_cast<uint2*>(dst) = make_uint2((uint32_t)px[0], (uint32_t)px[1]);
-				*reinterpret_cast<uint2*>(dst + 16) = make_uint2((uint32_t)px[2], (uint32_t)px[3]);
-			}
-		}
-		else
-		{
-#pragma unroll
-			for (int i = 0; i < 4; ++i)
-				if (px0 + SQW_PX_OFS(i) < width && (have & (1u << i)))
-					dst[SQW_PX_OFS(i)] = px[i];
-		}
-	}
-
-	if (TONEMAP)
-	{
-		// sizeof(Raw) == 8 here (the host only fuses 64-bit views)
-		if (row_valid)
-		{
-			uint32_t out[4];
-#pragma unroll
-			for (int i = 0; i < 4; ++i)
-			{
-				out[i] = 0;
-				if (px0 + SQW_PX_OFS(i) < width)
-				{
-					SQW_NEED_DST(i) // untouched pixel: tonemap what the buffer holds
-					const uint64_t p = (uint64_t)px[i];
-					const uint32_t cb = (uint32_t)(p & 0xFFFF), cg = (uint32_t)((p >> 16) & 0xFFFF), cr = (uint32_t)((p >> 32) & 0xFFFF);
-					sb += cb;
-					sg += cg;
-					sr += cr;
-					if ((cb | cg | cr) < SQW_TONEMAP_LUT_SIZE)
-						out[i] = (uint32_t)s_lut[cb] | ((uint32_t)s_lut[SQW_TONEMAP_LUT_SIZE + cg] << 8) | ((uint32_t)s_lut[2 * SQW_TONEMAP_LUT_SIZE + cr] << 16) | 0xFF000000u;
-					else
-						out[i] = tonemap_pixel(cv_from_color64(p), isb, isg, isr);
-				}
-			}
-			uint32_t* const o = ldr + (size_t)row * pitch + px0;
-			if (vec_ok)
-			{
-				__stcs(reinterpret_cast<uint2*>(o), make_uint2(out[0], out[1]));
-				__stcs(reinterpret_cast<uint2*>(o + 16), make_uint2(out[2], out[3]));
-			}
-			else
-			{
-#pragma unroll
-				for (int i = 0; i < 4; ++i)
-					if (px0 + SQW_PX_OFS(i) < width)
-						o[SQW_PX_OFS(i)] = out[i];
-			}
-		}
-	}
+	if (row_a < height)
+		finish_quad<C, TONEMAP>(px_a, have_a, px0, width, vec_ok, color_buffer + pix_a, ldr + pix_a, s_lut, isb, isg, isr, sb, sg, sr);
+	if (row_b < height)
+		finish_quad<C, TONEMAP>(px_b, have_b, px0, width, vec_ok, color_buffer + pix_b, ldr + pix_b, s_lut, isb, isg, isr, sb, sg, sr);
+	(void)blk_y1;
 	} // tile loop
 
 	if (TONEMAP)
 	{
 		// colour sums for update_exposure (postprocessor.rs:176-179): exact integers, 3 atomics per CTA.  A lane adds at most
-		// 4 x 65535 per tile and a CTA handles a few dozen tiles, so 32-bit partial sums cannot overflow before the warp reduction.
+		// 8 x 65535 per tile and a CTA handles a few dozen tiles, so 32-bit partial sums cannot overflow before the warp reduction.
 		__shared__ unsigned long long s_part[3][WARPS];
 		unsigned long long wb = sb, wg = sg, wr = sr;
 #pragma unroll
@@ -1048,6 +1081,7 @@ __global__ void __launch_bounds__(SQW_RASTER_THREADS, SQW_TILE_CTAS_PER_SM) rast
 }
 #undef SQW_NEED_DST
 #undef SQW_PX_OFS
+
 
 } // namespace
 
@@ -1079,10 +1113,14 @@ cudaError_t launch_raster_tiles(const RasterLaunch& l, cudaStream_t stream)
 		if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0)
 			sm_count = 148;
 	}
+#ifdef SQW_TILE_NONPERSISTENT
+	const uint32_t grid = num_tiles;
+#else
 	const uint32_t grid = std::min<uint32_t>(num_tiles, (uint32_t)sm_count * SQW_TILE_CTAS_PER_SM);
+#endif
 #define SQW_TILE_ARGS(RAW) \
 	l.cmd_dev, l.spans, l.tile_lists, l.tile_desc, static_cast<const char*>(l.surfaces_base), static_cast<RAW*>(l.color_buffer), l.width, l.height, l.pitch, l.clear, \
-		(RAW)l.clear_color, l.tonemap_dst, l.inv_scale_bgr[0], l.inv_scale_bgr[1], l.inv_scale_bgr[2], l.color_sums, l.tonemap_lut, tiles_x, num_tiles
+		(RAW)l.clear_color, l.tonemap_dst, l.inv_scale_bgr[0], l.inv_scale_bgr[1], l.inv_scale_bgr[2], l.color_sums, l.tonemap_lut, num_tiles
 	if (l.color64 && l.tonemap_dst)
 		raster_tile_kernel<Color64, 1><<<grid, SQW_RASTER_THREADS, 0, stream>>>(SQW_TILE_ARGS(uint64_t));
 	else if (l.color64)

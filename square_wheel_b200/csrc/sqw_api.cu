@@ -779,7 +779,7 @@ static size_t bin_tile_desc_offset(uint32_t band_entries, uint32_t tiles_x)
 }
 static size_t bin_scratch_bytes(uint32_t band_entries, uint32_t tiles_x, uint32_t num_bands)
 {
-	return bin_tile_desc_offset(band_entries, tiles_x) + (size_t)num_bands * tiles_x * sizeof(uint2) + 64;
+	return bin_tile_desc_offset(band_entries, tiles_x) + (size_t)num_bands * tiles_x * sizeof(uint4) + 64;
 }
 
 int sqw_frame_set_draw(
@@ -1166,7 +1166,7 @@ int sqw_frame_submit(sqw_frame* f, uint32_t stages)
 			char* const base = static_cast<char*>(view->band_lists.ptr);
 			l.band_lists = reinterpret_cast<uint32_t*>(base);
 			l.tile_lists = reinterpret_cast<uint32_t*>(base + bin_tile_lists_offset(f->total_band_entries));
-			l.tile_desc = reinterpret_cast<uint2*>(base + bin_tile_desc_offset(f->total_band_entries, tiles_x));
+			l.tile_desc = reinterpret_cast<uint4*>(base + bin_tile_desc_offset(f->total_band_entries, tiles_x));
 		}
 		l.band_offsets = f->d_band_offsets;
 		l.num_bands = f->num_bands;
@@ -1188,7 +1188,7 @@ int sqw_frame_submit(sqw_frame* f, uint32_t stages)
 			l.tonemap_lut = view->d_tonemap_lut;
 			view->sums_divisor = (uint64_t)view->width * view->height;
 		}
-		if (f->num_cmds || fused_tonemap)
+		if (f->num_cmds || f->clear || fused_tonemap) // the binning CTAs also write the (empty) tile lists of a clear-only draw
 		{
 			LaunchTimer timer(ctx, SQW_KERNEL_RASTER_SETUP, s);
 			SQW_CUDA(ctx, launch_raster_setup(l, s));

@@ -70,9 +70,11 @@ cudaError_t launch_mix_texture(
 #define SQW_SUM_WORDS (SQW_SUM_SLOTS * 4)
 #define SQW_SETUP_THREADS 128
 #define SQW_TONEMAP_LUT_SIZE 4096 /* channel values below this (16 x LDR white) are tonemapped by table look-up */
-#define SQW_TILE_STAGE_HITS 8 /* commands whose span records a warp stages in shared memory at a time (x 4 block rows = 32 lanes) */
-#define SQW_RASTER_THREADS 256
-#define SQW_TILE_CTAS_PER_SM 4 /* resident CTAs of the persistent tile kernel per SM (register and shared-memory budget) */ /* 8 warps: each warp owns one row of the tile, each lane 4 consecutive pixels */
+#define SQW_TILE_STAGE_HITS 4 /* commands whose span records a warp stages in shared memory at a time (x 8 block rows = 32 lanes) */
+#define SQW_RASTER_THREADS 128 /* 4 warps, each owning a 32x8 pixel block of the 128x8 tile */
+#ifndef SQW_TILE_CTAS_PER_SM
+#define SQW_TILE_CTAS_PER_SM 5 /* resident CTAs of the persistent tile kernel per SM (register and shared-memory budget) */
+#endif
 
 // Per-command data prepared by the host part of sqw_frame_set_draw (row range, conservative column range,
 // span-table offset, resolved texture pointer).  32 bytes.
@@ -115,7 +117,7 @@ struct RasterLaunch
 	const uint32_t* band_offsets; // device, num_bands + 1
 	uint32_t* tile_lists;         // device, ordered command indices per 128x8 tile: tile (band, col) owns the slots
 	                              // [band_offsets[band] * tiles_x + col * N, + N), N = band list length
-	uint2* tile_desc;             // device, {first slot, count} per tile, written by the binning CTAs
+	uint4* tile_desc;             // device, {first slot, count, x0 | y0 << 16, -} per tile, written by the binning CTAs
 	uint32_t num_bands;
 	int32_t width, height, pitch;
 	void* color_buffer;
