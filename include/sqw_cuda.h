@@ -408,6 +408,11 @@ typedef struct sqw_kernel_times
 int sqw_profile_begin(sqw_ctx* ctx);
 int sqw_profile_end(sqw_ctx* ctx, sqw_kernel_times* out);
 
+/* Device self-test of the arithmetic shortcuts the kernels take (synchronises): exhaustive comparison of the reciprocal-based
+ * `2^31 / (inv_z >> 8)` of the full-perspective pixel loop (rasterizer.rs:430) with the plain u32 division for every
+ * divisor below 2^24.  SQW_OK, or SQW_ERR_CUDA with the mismatch count in sqw_last_error(). */
+int sqw_self_test(sqw_ctx* ctx);
+
 /* Average colour produced by the last post stage of this view (synchronises). */
 int sqw_view_get_average_color(sqw_view* view, float avg_color_out[3]);
 

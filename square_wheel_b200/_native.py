@@ -192,6 +192,7 @@ CUDA_SYMBOLS = [
     ("sqw_view_get_average_color", C.c_int, [_VP, _VP]),
     ("sqw_profile_begin", C.c_int, [_VP]),
     ("sqw_profile_end", C.c_int, [_VP, C.POINTER(KernelTimes)]),
+    ("sqw_self_test", C.c_int, [_VP]),
 ]
 
 _cuda_lib = None

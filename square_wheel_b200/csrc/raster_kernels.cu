@@ -623,6 +623,30 @@ __global__ void __launch_bounds__(SQW_SETUP_THREADS) raster_setup_kernel(
 }
 
 // ---- tile kernel ----------------------------------------------------------------------------------------------
+// z = 2^31 / d exactly as the u32 division of rasterizer.rs:430, for d in [1, 2^24) (inv_z >> 8 of a 32-bit value), in 13
+// instructions instead of the ~20 of the generic u32 division: two correction steps from the hardware reciprocal.
+//   q0 = trunc(2^31 * rcp(d) * (1 - 2^-21)) never exceeds the quotient and misses it by less than 2^11 + 1, so the
+//   remainder 2^31 - q0*d is below 2^11*d + 2d: its quotient by d (same reciprocal, same downward bias) is at most one short.
+// sqw_self_test compares it with the plain division for every d.
+__device__ __forceinline__ uint32_t z_from_inv_z(uint32_t d)
+{
+	float r;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__uint2float_rz(d))); // d < 2^24: the conversion is exact
+	r = __fmul_rz(r, 0x1.fffffp-1f);                                        // (1 - 2^-21): biased low, never above 1/d
+	const uint32_t q0 = __float2uint_rz(__fmul_rz(r, 2147483648.0f));
+	const uint32_t rem0 = (1u << Z_CALC_SHIFT) - q0 * d;
+	const uint32_t k = __float2uint_rz(__fmul_rz(__uint2float_rz(rem0), r));
+	const uint32_t rem1 = rem0 - k * d;
+	return q0 + k + (rem1 >= d ? 1u : 0u);
+}
+
+__global__ void z_from_inv_z_test_kernel(unsigned long long* mismatches)
+{
+	const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+	if (d >= 1 && d < (1u << 24) && z_from_inv_z(d) != (1u << Z_CALC_SHIFT) / d)
+		atomicAdd(mismatches, 1ull);
+}
+
 template <class C>
 __device__ __forceinline__ typename C::Raw fetch_texel(const void* tex, uint32_t address)
 {
@@ -671,7 +695,7 @@ __device__ __forceinline__ void shade_quad(
 				in[i] = x >= x0 && x < x1;
 				const int32_t k = x - x0;
 				const uint32_t span_inv_z = (uint32_t)wadd(inv_z0, wmul(k, d_inv_z));
-				const uint32_t z = (1u << Z_CALC_SHIFT) / max(span_inv_z >> INV_Z_PRE_SHIFT, 1u); // rasterizer.rs:430 (covered pixels: >= 1 by the span clamp)
+				const uint32_t z = z_from_inv_z(max(span_inv_z >> INV_Z_PRE_SHIFT, 1u)); // rasterizer.rs:430 (covered pixels: >= 1 by the span clamp)
 				const uint64_t t0 = (uint64_t)(int64_t)wadd(tc0, wmul(k, dtc0));
 				const uint64_t t1 = (uint64_t)(int64_t)wadd(tc1, wmul(k, dtc1));
 				const uint32_t u = (uint32_t)(((uint64_t)z * t0) >> TC_FINAL_SHIFT);
@@ -902,19 +926,20 @@ __global__ void __launch_bounds__(SQW_RASTER_THREADS, SQW_TILE_CTAS_PER_SM) rast
 	// Per-channel tonemapping table (exact results for channel values < SQW_TONEMAP_LUT_SIZE, built by the set-up grid of
 	// this frame): three byte look-ups replace three IEEE divides for all but very bright pixels.
 	__shared__ __align__(16) uint8_t s_lut[TONEMAP ? 3 * SQW_TONEMAP_LUT_SIZE : 16];
+	// The table is copied with asynchronous copies (LDGSTS): the first tile's list, span records and texels are fetched and
+	// evaluated while it arrives; the CTA waits for it once, before its first tonemapping epilogue.
 	if (TONEMAP)
 	{
-		const uint4* src = reinterpret_cast<const uint4*>(tonemap_lut);
-		uint4* d = reinterpret_cast<uint4*>(s_lut);
+		const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_lut);
 		for (uint32_t i = threadIdx.x; i < 3 * SQW_TONEMAP_LUT_SIZE / 16; i += SQW_RASTER_THREADS)
-			d[i] = __ldg(src + i);
+			asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 16), "l"(tonemap_lut + (size_t)i * 16) : "memory");
+		asm volatile("cp.async.commit_group;" ::: "memory");
 	}
+	bool lut_pending = TONEMAP != 0;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	uint4(*const s_cmd)[32] = s_cmd_all[warp];
 	uint4(*const s_span)[SQW_TILE_STAGE_HITS][SQW_TILE_H] = s_span_all[warp];
-	uint32_t sb = 0, sg = 0, sr = 0; // colour sums of the fused tonemapping (all tiles of this CTA)
-	if (TONEMAP)
-		__syncthreads(); // s_lut is complete (the only CTA-wide barrier before the final sum reduction)
+	uint32_t sb = 0, sg = 0, sr = 0; // colour sums of the fused tonemapping (all tiles of this warp)
 
 	// Persistent CTAs: the grid is sized to what the GPU holds at once and every CTA strides over the tiles, so the
 	// per-CTA costs (tonemapping table, sum reduction, launch) are paid a few hundred times per frame, not once per tile.
@@ -1043,6 +1068,12 @@ __global__ void __launch_bounds__(SQW_RASTER_THREADS, SQW_TILE_CTAS_PER_SM) rast
 	// first entries of the next tile's list: the latency overlaps the epilogue below
 	idx_next = ((uint32_t)lane < desc_next.y && tile + gridDim.x < num_tiles) ? __ldg(tile_lists + desc_next.x + lane) : 0u;
 
+	if (lut_pending) // (CTA-uniform: first tile of the CTA) the only CTA-wide barrier of the kernel
+	{
+		asm volatile("cp.async.wait_all;" ::: "memory");
+		__syncthreads();
+		lut_pending = false;
+	}
 	if (row_a < height)
 		finish_quad<C, TONEMAP>(px_a, have_a, px0, width, vec_ok, color_buffer + pix_a, ldr + pix_a, s_lut, isb, isg, isr, sb, sg, sr);
 	if (row_b < height)
@@ -1052,9 +1083,9 @@ __global__ void __launch_bounds__(SQW_RASTER_THREADS, SQW_TILE_CTAS_PER_SM) rast
 
 	if (TONEMAP)
 	{
-		// colour sums for update_exposure (postprocessor.rs:176-179): exact integers, 3 atomics per CTA.  A lane adds at most
-		// 8 x 65535 per tile and a CTA handles a few dozen tiles, so 32-bit partial sums cannot overflow before the warp reduction.
-		__shared__ unsigned long long s_part[3][WARPS];
+		// colour sums for update_exposure (postprocessor.rs:176-179): exact integers, 3 atomics per warp (no CTA barrier: a
+		// warp that is done leaves).  A lane adds at most 8 x 65535 per tile and a warp handles a few dozen tiles, so 32-bit
+		// partial sums cannot overflow before the warp reduction.
 		unsigned long long wb = sb, wg = sg, wr = sr;
 #pragma unroll
 		for (int o = 16; o > 0; o >>= 1)
@@ -1063,20 +1094,8 @@ __global__ void __launch_bounds__(SQW_RASTER_THREADS, SQW_TILE_CTAS_PER_SM) rast
 			wg += __shfl_xor_sync(0xFFFFFFFFu, wg, o);
 			wr += __shfl_xor_sync(0xFFFFFFFFu, wr, o);
 		}
-		if (lane == 0)
-		{
-			s_part[0][warp] = wb;
-			s_part[1][warp] = wg;
-			s_part[2][warp] = wr;
-		}
-		__syncthreads();
-		if (threadIdx.x < 3)
-		{
-			unsigned long long t = 0;
-			for (int w = 0; w < WARPS; ++w)
-				t += s_part[threadIdx.x][w];
-			atomicAdd(sums + (blockIdx.x % SQW_SUM_SLOTS) * 4 + threadIdx.x, t);
-		}
+		if (lane < 3)
+			atomicAdd(sums + ((blockIdx.x * WARPS + warp) % SQW_SUM_SLOTS) * 4 + lane, lane == 0 ? wb : (lane == 1 ? wg : wr));
 	}
 }
 #undef SQW_NEED_DST
@@ -1096,6 +1115,12 @@ cudaError_t launch_raster_setup(const RasterLaunch& l, cudaStream_t stream)
 	raster_setup_kernel<<<setup_blocks + bin_blocks + lut_blocks, SQW_SETUP_THREADS, 0, stream>>>(
 		l.cmds, l.cmd_dev, l.num_cmds, l.polygon_points, l.triangle_points, l.chunks, l.num_chunks, l.spans, l.width, l.height, setup_blocks, l.band_offsets,
 		l.band_lists, l.tile_lists, l.tile_desc, (uint32_t)((l.width + SQW_TILE_W - 1) / SQW_TILE_W), bin_blocks, l.tonemap_dst ? l.color_sums : nullptr, l.tonemap_lut, l.inv_scale_bgr[0], l.inv_scale_bgr[1], l.inv_scale_bgr[2]);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_z_from_inv_z_test(unsigned long long* mismatches, cudaStream_t stream)
+{
+	z_from_inv_z_test_kernel<<<(1u << 24) / 256, 256, 0, stream>>>(mismatches);
 	return cudaGetLastError();
 }
 

@@ -1324,6 +1324,28 @@ int sqw_profile_begin(sqw_ctx* ctx)
 	return SQW_OK;
 }
 
+int sqw_self_test(sqw_ctx* ctx)
+{
+	if (!ctx)
+		return SQW_ERR_INVALID_ARGUMENT;
+	SQW_CUDA(ctx, cudaSetDevice(ctx->device));
+	unsigned long long* d_mismatches = nullptr;
+	SQW_CUDA(ctx, cudaMalloc(&d_mismatches, sizeof(unsigned long long)));
+	unsigned long long mismatches = ~0ull;
+	cudaError_t e = cudaMemsetAsync(d_mismatches, 0, sizeof(unsigned long long), ctx->stream);
+	if (e == cudaSuccess)
+		e = launch_z_from_inv_z_test(d_mismatches, ctx->stream);
+	if (e == cudaSuccess)
+		e = cudaMemcpyAsync(&mismatches, d_mismatches, sizeof(mismatches), cudaMemcpyDeviceToHost, ctx->stream);
+	if (e == cudaSuccess)
+		e = cudaStreamSynchronize(ctx->stream);
+	cudaFree(d_mismatches);
+	SQW_CUDA(ctx, e);
+	if (mismatches != 0)
+		return fail(ctx, SQW_ERR_CUDA, "sqw_self_test: z_from_inv_z differs from the u32 division for " + std::to_string(mismatches) + " divisors");
+	return SQW_OK;
+}
+
 int sqw_profile_end(sqw_ctx* ctx, sqw_kernel_times* out)
 {
 	if (!ctx || !out)

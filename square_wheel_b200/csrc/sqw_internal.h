@@ -134,6 +134,8 @@ struct RasterLaunch
 // span set-up + binning in one grid
 cudaError_t launch_raster_setup(const RasterLaunch& l, cudaStream_t stream);
 cudaError_t launch_raster_tiles(const RasterLaunch& l, cudaStream_t stream);
+// exhaustive check of z_from_inv_z; *mismatches (device) must be zeroed by the caller
+cudaError_t launch_z_from_inv_z_test(unsigned long long* mismatches, cudaStream_t stream);
 
 // ---- shadow maps ----------------------------------------------------------------------------------------------
 struct DepthCmdDev // per fill call, prepared by sqw_frame_set_shadow_map_draw. 16 bytes

@@ -81,6 +81,10 @@ class Context:
         self._check(self._lib.sqw_profile_end(self._handle, C.byref(kt)), "sqw_profile_end")
         return {name: (kt.ms[i], int(kt.launches[i])) for i, name in enumerate(N.KERNEL_NAMES)}
 
+    def self_test(self):
+        """Exhaustive device check of the arithmetic shortcuts of the kernels (sqw_self_test); raises SqwError on a mismatch."""
+        self._check(self._lib.sqw_self_test(self._handle), "sqw_self_test")
+
     def close(self):
         if self._handle:
             self._lib.sqw_destroy(self._handle)

@@ -161,3 +161,9 @@ def test_crowded_bands(assets, oracle_lib):
     fb = np.zeros((H, W), np.uint64)
     oracle_lib.draw(64, fb, cmds, None, pts, None, assets.images)
     assert_pixels_equal(got, fb, "crowded bands")
+
+
+def test_device_self_test(assets):
+    """sqw_self_test: the reciprocal-based z = 2^31 / (inv_z >> 8) of the full-perspective pixel loop equals the u32 division
+    of rasterizer.rs:430 for every divisor below 2^24 (checked exhaustively on the device)."""
+    assets.device_context().self_test()
