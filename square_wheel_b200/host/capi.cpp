@@ -21,12 +21,15 @@ struct sqwh_scene_params // mirrors sqwh::SceneParams (plain C layout for ctypes
 	float max_polygon_size;
 	uint32_t material_mode;
 	float emissive_fraction;
+	uint32_t num_models;
+	uint32_t model_detail;
 };
 
 struct sqwh_scene_info
 {
 	uint32_t num_nodes, num_leafs, num_polygons, num_portals, num_vertices, num_materials, num_images, num_waypoints;
 	uint64_t num_lightmap_elements;
+	uint32_t num_models, reserved;
 };
 
 struct sqwh_renderer_config
@@ -49,6 +52,28 @@ struct sqwh_frame_info
 	uint32_t num_depth_maps, num_depth_cmds, num_depth_points;
 	uint32_t num_triangle_points;
 	uint64_t shadow_maps_len;
+};
+
+struct sqwh_model_entity // frame_info.rs:55-69 (ModelEntity) in plain C layout
+{
+	float position[3];
+	float rotation[4];    // quaternion s, x, y, z
+	uint32_t frames[2];   // AnimationPoint
+	float lerp;
+	uint32_t model;       // index of the scene's model fixture
+	uint32_t skin;        // index of the scene's skin (TextureLiteWithMips)
+	uint32_t blending_mode;
+	uint32_t lighting;    // 0 Default, 1 ConstantLight, 2 AdvancedLight
+	float light[3];       // ConstantLight value / AdvancedLight::light_add
+	float grid_light_scale;
+	float light_position[3];
+	uint32_t flags;       // 1 VIEW_MODEL, 2 ONLY_THIRD_PERSON_VIEW
+};
+
+struct sqwh_model_info
+{
+	uint32_t num_frames, num_meshes, num_vertices, num_triangles, kind, num_bones;
+	float bbox_min[3], bbox_max[3]; // union over all frames
 };
 
 struct sqwh_dynamic_light // frame_info.rs:149-168
@@ -76,6 +101,8 @@ void sqwh_default_scene_params(sqwh_scene_params* p)
 	p->max_polygon_size = d.max_polygon_size;
 	p->material_mode = d.material_mode;
 	p->emissive_fraction = d.emissive_fraction;
+	p->num_models = d.num_models;
+	p->model_detail = d.model_detail;
 }
 
 Scene* sqwh_scene_create(const sqwh_scene_params* p)
@@ -95,6 +122,8 @@ Scene* sqwh_scene_create(const sqwh_scene_params* p)
 	sp.max_polygon_size = p->max_polygon_size;
 	sp.material_mode = p->material_mode;
 	sp.emissive_fraction = p->emissive_fraction;
+	sp.num_models = p->num_models;
+	sp.model_detail = p->model_detail;
 	Scene* s = new (std::nothrow) Scene();
 	if (!s)
 		return nullptr;
@@ -114,6 +143,8 @@ void sqwh_scene_get_info(const Scene* s, sqwh_scene_info* out)
 	out->num_images = (uint32_t)s->images.size();
 	out->num_waypoints = (uint32_t)s->camera_waypoints.size();
 	out->num_lightmap_elements = s->map.directional_lightmaps_data.size();
+	out->num_models = (uint32_t)s->models.size();
+	out->reserved = 0;
 }
 const void* sqwh_scene_image(const Scene* s, uint32_t index, int32_t* kind, uint32_t* width, uint32_t* height)
 {
@@ -188,6 +219,61 @@ void sqwh_renderer_set_lights(Renderer* r, const sqwh_dynamic_light* lights, uin
 	r->set_lights(v.data(), v.size());
 }
 
+// FrameInfo::model_entities of the next prepare_frame.  Returns 0, or -1 when an entity refers to a missing model / skin / frame.
+int sqwh_renderer_set_models(Renderer* r, const Scene* s, const sqwh_model_entity* models, uint32_t n)
+{
+	std::vector<ModelEntity> v(n);
+	for (uint32_t i = 0; i < n; ++i)
+	{
+		const sqwh_model_entity& m = models[i];
+		if (m.model >= s->models.size() || m.skin >= s->model_skins.size() || m.blending_mode > SQW_BLEND_ALPHA_BLEND || m.lighting > MODEL_LIGHTING_ADVANCED)
+			return -1;
+		const size_t num_frames = s->models[m.model].frames_info.size();
+		if (m.frames[0] >= num_frames || m.frames[1] >= num_frames)
+			return -1;
+		v[i].position = {m.position[0], m.position[1], m.position[2]};
+		v[i].rotation = Quaternion{m.rotation[0], {m.rotation[1], m.rotation[2], m.rotation[3]}};
+		v[i].frames[0] = m.frames[0];
+		v[i].frames[1] = m.frames[1];
+		v[i].lerp = m.lerp;
+		v[i].model = m.model;
+		for (uint32_t k = 0; k < NUM_MIPS; ++k)
+			v[i].texture_images[k] = s->model_skins[m.skin][k];
+		v[i].blending_mode = (int)m.blending_mode;
+		v[i].lighting = (ModelLightingKind)m.lighting;
+		std::memcpy(v[i].light, m.light, 12);
+		v[i].grid_light_scale = m.grid_light_scale;
+		v[i].light_position = {m.light_position[0], m.light_position[1], m.light_position[2]};
+		v[i].flags = m.flags;
+	}
+	r->set_models(v.data(), v.size());
+	return 0;
+}
+
+int sqwh_scene_model_info(const Scene* s, uint32_t index, sqwh_model_info* out)
+{
+	if (index >= s->models.size())
+		return -1;
+	const TriangleModel& m = s->models[index];
+	std::memset(out, 0, sizeof(*out));
+	out->num_frames = (uint32_t)m.frames_info.size();
+	out->num_meshes = (uint32_t)m.meshes.size();
+	out->num_bones = (uint32_t)m.bones.size();
+	for (const TriangleModelMesh& mesh : m.meshes)
+	{
+		out->num_vertices += (uint32_t)mesh.num_vertices();
+		out->num_triangles += (uint32_t)mesh.triangles.size();
+		out->kind = mesh.kind;
+	}
+	BBox b = m.frames_info[0];
+	for (const BBox& f : m.frames_info)
+		b.extend(f);
+	const float mn[3] = {b.min.x, b.min.y, b.min.z}, mx[3] = {b.max.x, b.max.y, b.max.z};
+	std::memcpy(out->bbox_min, mn, 12);
+	std::memcpy(out->bbox_max, mx, 12);
+	return 0;
+}
+
 void sqwh_renderer_frame_info(const Renderer* r, sqwh_frame_info* out)
 {
 	std::memset(out, 0, sizeof(*out));
@@ -207,6 +293,7 @@ void sqwh_renderer_frame_info(const Renderer* r, sqwh_frame_info* out)
 	out->num_depth_maps = (uint32_t)r->depth_maps().size();
 	out->num_depth_cmds = (uint32_t)r->depth_cmds().size();
 	out->num_depth_points = (uint32_t)r->depth_points().size();
+	out->num_triangle_points = (uint32_t)r->triangle_points().size();
 	out->shadow_maps_len = r->shadow_maps_len();
 }
 const sqw_light* sqwh_renderer_lights(const Renderer* r) { return r->lights().data(); }
@@ -216,5 +303,6 @@ const sqw_polygon_point* sqwh_renderer_depth_points(const Renderer* r) { return 
 const sqw_surface_job* sqwh_renderer_jobs(const Renderer* r) { return r->jobs().data(); }
 const sqw_draw_cmd* sqwh_renderer_cmds(const Renderer* r) { return r->cmds().data(); }
 const sqw_polygon_point* sqwh_renderer_polygon_points(const Renderer* r) { return r->polygon_points().data(); }
+const sqw_triangle_point* sqwh_renderer_triangle_points(const Renderer* r) { return r->triangle_points().data(); }
 
 } // extern "C"

@@ -765,12 +765,63 @@ struct Builder
 
 } // namespace
 
+namespace
+{
+// Model skin (TextureLite): coloured panels with seams, every fourth skin with transparent holes (alpha 0) for the alpha-test
+// and alpha-blend modes.  64 x 64 with 4 more mips (TextureLiteWithMips, textures.rs:367-386).
+void make_model_skin(Pcg32& rng, uint32_t size, bool with_holes, HostImage& out)
+{
+	out.kind = SQW_IMAGE_COLOR32;
+	out.width = out.height = size;
+	out.pixels.resize((size_t)size * size * 4);
+	uint32_t* px = reinterpret_cast<uint32_t*>(out.pixels.data());
+	const uint32_t cells = 8;
+	std::vector<float> lat(cells * cells);
+	for (float& v : lat)
+		v = rng.uniform();
+	const float base[3] = {rng.uniform(0.35f, 1.0f), rng.uniform(0.35f, 1.0f), rng.uniform(0.35f, 1.0f)};
+	for (uint32_t y = 0; y < size; ++y)
+		for (uint32_t x = 0; x < size; ++x)
+		{
+			const float n = value_noise(rng, lat, cells, ((float)x + 0.5f) / (float)size, ((float)y + 0.5f) / (float)size);
+			const bool seam = (x % (size / 4)) == 0 || (y % (size / 4)) == 0;
+			const float shade = seam ? 0.35f : 0.6f + 0.4f * n;
+			uint32_t rgb[3];
+			for (int c = 0; c < 3; ++c)
+				rgb[c] = (uint32_t)(base[c] * shade * 255.0f);
+			uint32_t alpha = 255;
+			if (with_holes)
+				alpha = n > 0.6f ? 0u : (n > 0.5f ? (uint32_t)(255.0f * (0.6f - n) * 10.0f) : 255u);
+			px[x + (size_t)y * size] = (alpha << 24) | (rgb[0] << 16) | (rgb[1] << 8) | rgb[2];
+		}
+}
+} // namespace
+
 void generate_scene(const SceneParams& params, Scene& out)
 {
 	out = Scene{};
 	out.params = params;
 	Builder b(out);
 	b.run();
+	// triangle-model fixtures and their skins (appended after the world images, so scenes without models keep their image ids)
+	Pcg32 rng(params.seed * 2654435761u + 99u);
+	for (uint32_t i = 0; i < params.num_models; ++i)
+	{
+		TriangleModel model;
+		generate_triangle_model(i % 3, params.seed + i, params.model_detail, model);
+		out.models.push_back(std::move(model));
+		HostImage mips[NUM_MIPS];
+		make_model_skin(rng, 64, (i % 4) == 3, mips[0]);
+		for (uint32_t k = 1; k < NUM_MIPS; ++k)
+			build_texture_lite_mip(mips[k], mips[k - 1]);
+		std::array<uint32_t, NUM_MIPS> ids;
+		for (uint32_t k = 0; k < NUM_MIPS; ++k)
+		{
+			ids[k] = (uint32_t)out.images.size();
+			out.images.push_back(std::move(mips[k]));
+		}
+		out.model_skins.push_back(ids);
+	}
 }
 
 void make_camera_path(const Scene& scene, uint32_t num_frames, uint32_t jitter_seed, std::vector<CameraPose>& out)

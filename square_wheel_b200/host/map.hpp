@@ -4,6 +4,7 @@
 #pragma once
 #include "../../include/sqw_cuda.h"
 #include "math.hpp"
+#include "model_data.hpp"
 #include <string>
 #include <vector>
 
@@ -98,6 +99,8 @@ struct SceneParams
 	float max_polygon_size = 128.0f; // split so that a lightmap stays <= 17 texels per side (bsp_builder.rs:1282)
 	uint32_t material_mode = 0;      // 0: mix per demo_materials.json (normal map + dielectric/metal specular), 1: plain (no normal map, roughness 1)
 	float emissive_fraction = 0.15f;
+	uint32_t num_models = 0;       // triangle-model fixtures to generate (models.hpp)
+	uint32_t model_detail = 10;    // rings of the lathe grids: a model has about 4 * detail^2 triangles
 };
 
 struct Scene
@@ -106,6 +109,10 @@ struct Scene
 	BSPMap map;
 	std::vector<Material> materials;
 	std::vector<HostImage> images; // image id = index; the caller uploads them in this order
+	// Triangle-model fixtures (SceneParams::num_models of them, kinds cycling NonAnimated / VertexAnimated / SkeletonAnimated)
+	// and their skins: TextureLiteWithMips as NUM_MIPS consecutive SQW_IMAGE_COLOR32 image ids per skin.
+	std::vector<TriangleModel> models;
+	std::vector<std::array<uint32_t, NUM_MIPS>> model_skins;
 	std::vector<Vec3f> camera_waypoints; // centres of the cells the fly-through visits
 	std::vector<uint8_t> solid;          // grid occupancy
 	bool is_solid(int x, int y, int z) const;

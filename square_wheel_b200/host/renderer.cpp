@@ -55,6 +55,13 @@ ClippingPolygon ClippingPolygon::from_point(Vec2f p)
 	c.x_minus_y = {p.x - p.y, p.x - p.y};
 	return c;
 }
+void ClippingPolygon::get_box_clip_planes(Vec3f out[4]) const // clipping_polygon.rs:154-162
+{
+	out[0] = {-1.0f, 0.0f, -x.max};
+	out[1] = {1.0f, 0.0f, x.min};
+	out[2] = {0.0f, -1.0f, -y.max};
+	out[3] = {0.0f, 1.0f, y.min};
+}
 bool ClippingPolygon::is_valid_and_non_empty() const { return axis_valid(x) && axis_valid(y) && axis_valid(x_plus_y) && axis_valid(x_minus_y); }
 bool ClippingPolygon::contains(const ClippingPolygon& o) const
 {
@@ -364,6 +371,34 @@ Renderer::Renderer(const Scene& scene, const RendererConfig& config)
 			polygons_data_[p].parent_leaf = (uint32_t)leaf;
 	vertices_transformed_.resize(map_.vertices.size());
 	leaf_lights_.resize(map_.leafs.size());
+	leaf_models_.resize(map_.leafs.size());
+	// get_leaf_clip_planes (renderer_structs.rs:167-226): portal and polygon planes of the leaf, normalised and deduplicated
+	leafs_planes_.resize(map_.leafs.size());
+	for (size_t leaf_index = 0; leaf_index < map_.leafs.size(); ++leaf_index)
+	{
+		const BSPLeaf& leaf = map_.leafs[leaf_index];
+		std::vector<Plane>& planes = leafs_planes_[leaf_index];
+		auto add_and_deduplicate_plane = [&](const Plane& plane) {
+			const float normal_length = magnitude(plane.vec);
+			if (normal_length < 0.00000000001f)
+				return;
+			const Plane plane_normalized = {plane.vec / normal_length, plane.dist / normal_length};
+			for (Plane& prev_plane : planes)
+				if (dot(plane_normalized.vec, prev_plane.vec) >= 1.0f - 1.0f / 256.0f)
+				{
+					prev_plane.dist = std::fmax(prev_plane.dist, plane_normalized.dist);
+					return;
+				}
+			planes.push_back(plane_normalized);
+		};
+		for (uint32_t i = leaf.first_leaf_portal; i < leaf.first_leaf_portal + leaf.num_leaf_portals; ++i)
+		{
+			const Portal& portal = map_.portals[map_.leafs_portals[i]];
+			add_and_deduplicate_plane(portal.leafs[0] == leaf_index ? portal.plane : Plane{-portal.plane.vec, -portal.plane.dist});
+		}
+		for (uint32_t p = leaf.first_polygon; p < leaf.first_polygon + leaf.num_polygons; ++p)
+			add_and_deduplicate_plane(map_.polygons[p].plane);
+	}
 }
 
 VisibilityCalculator::VisibilityCalculator(const BSPMap& map) : map_(map)
@@ -841,6 +876,9 @@ void Renderer::prepare_frame(uint32_t width, uint32_t height, const CameraPose& 
 	prepare_dynamic_lights();    // partial_renderer.rs:192
 	build_shadow_maps();         // :194
 	prepare_polygons_surfaces(); // :214
+	position_models();              // renderer.rs:84 (dynamic_models_index.position_models)
+	prepare_dynamic_models();       // partial_renderer.rs:209
+	build_dynamic_models_buffers(); // :227
 	build_surface_jobs();        // :221
 }
 
@@ -1093,6 +1131,7 @@ void Renderer::draw_frame() // PartialRenderer::draw_frame -> perform_rasterizat
 {
 	cmds_.clear();
 	polygon_points_.clear();
+	triangle_points_.clear();
 	const ClippingPolygon viewport_clipping_polygon = ClippingPolygon::from_box(0.0f, 0.0f, (float)width_, (float)height_);
 	draw_tree(viewport_clipping_polygon);
 	stats_.num_draw_commands = (uint32_t)cmds_.size();
@@ -1148,6 +1187,7 @@ void Renderer::draw_leaf(const ClippingPolygon& bounds, uint32_t leaf_index) // 
 			clip_planes, &vertices_transformed_[polygon.first_vertex], polygon.num_vertices, polygon_data.depth_equation, polygon_data.tex_coord_equation,
 			polygon_data.surface_size, SQW_TEX_SURFACE, (uint32_t)polygon_data.surface_pixels_offset, scene_.materials[polygon.texture].blending_mode);
 	}
+	draw_leaf_objects(bounds, leaf_index);
 }
 
 void Renderer::draw_polygon( // partial_renderer.rs:4011-4142, recording instead of rasterising
@@ -1216,6 +1256,416 @@ void Renderer::draw_polygon( // partial_renderer.rs:4011-4142, recording instead
 	}
 	++stats_.mode_counts[c.tc_mode];
 	cmds_.push_back(c);
+}
+
+
+// ---- triangle models ---------------------------------------------------------------------------------------------
+namespace
+{
+constexpr size_t MAX_LEAF_CLIP_PLANES = 20; // renderer_utils.rs:5
+
+inline int32_t f32_to_fixed16(float x) // fixed_math.rs:31-34: Rust `as` (saturating, NaN -> 0)
+{
+	const float v = x * 65536.0f;
+	if (!(v == v))
+		return 0;
+	if (v >= 2147483648.0f)
+		return INT32_MAX;
+	if (v <= -2147483648.0f)
+		return INT32_MIN;
+	return (int32_t)v;
+}
+
+// triangle_models_rendering.rs:213-273
+bool calculate_triangle_model_screen_polygon(const Vec3f v[8], ClippingPolygon& out)
+{
+	bool have = false;
+	int num_front_vertices = 0;
+	for (int i = 0; i < 8; ++i)
+		if (v[i].z > 0.0f)
+		{
+			++num_front_vertices;
+			const Vec2f point = truncate(v[i]) / v[i].z;
+			if (have)
+				out.extend_with_point(point);
+			else
+			{
+				out = ClippingPolygon::from_point(point);
+				have = true;
+			}
+		}
+	if (num_front_vertices == 8 || num_front_vertices == 0)
+		return have;
+	const float Z_NEAR_BBOX = 1.0f / 4096.0f;
+	for (int i = 0; i < 7; ++i)
+		for (int j = i + 1; j < 8; ++j)
+		{
+			if (v[i].z <= Z_NEAR_BBOX && v[j].z <= Z_NEAR_BBOX)
+				continue;
+			if (v[i].z >= Z_NEAR_BBOX && v[j].z >= Z_NEAR_BBOX)
+				continue;
+			const Vec3f p = get_line_z_intersection(v[i], v[j], Z_NEAR_BBOX);
+			out.extend_with_point(truncate(p) / p.z);
+		}
+	return true;
+}
+} // namespace
+
+void Renderer::position_model_convex_hull_r(uint32_t id, const Vec3f* vertices, size_t n, uint32_t node_index) // dynamic_objects_index.rs:172-209
+{
+	if (node_index >= FIRST_LEAF_INDEX)
+	{
+		const uint32_t leaf_index = node_index - FIRST_LEAF_INDEX;
+		leaf_models_[leaf_index].push_back(id);
+		model_leafs_[id].push_back(leaf_index);
+		return;
+	}
+	const BSPNode& node = map_.nodes[node_index];
+	size_t vertices_front = 0;
+	for (size_t i = 0; i < n; ++i)
+		if (dot(node.plane.vec, vertices[i]) > node.plane.dist)
+			++vertices_front;
+	if (vertices_front > 0)
+		position_model_convex_hull_r(id, vertices, n, node.children[0]);
+	if (vertices_front < n)
+		position_model_convex_hull_r(id, vertices, n, node.children[1]);
+}
+
+void Renderer::position_models() // dynamic_objects_index.rs:52-73
+{
+	for (auto& l : leaf_models_)
+		l.clear();
+	model_leafs_.assign(frame_models_.size(), {});
+	for (size_t index = 0; index < frame_models_.size(); ++index)
+	{
+		const ModelEntity& model = frame_models_[index];
+		if (model.flags & MODEL_FLAG_VIEW_MODEL)
+			continue;
+		const BBox bbox = get_current_triangle_model_bbox(scene_.models[model.model], model.frames);
+		const Mat4f matrix = get_object_matrix(model.position, model.rotation);
+		Vec3f corners[8];
+		bbox.get_corners_vertices(corners);
+		for (Vec3f& c : corners)
+			c = truncate(matrix * extend(c, 1.0f));
+		position_model_convex_hull_r((uint32_t)index, corners, 8, map_.root_node());
+	}
+}
+
+void Renderer::prepare_dynamic_models() // partial_renderer.rs:995-1120 (root view: is_third_person_view = false)
+{
+	visible_dynamic_meshes_list_.clear();
+	dynamic_model_to_dynamic_meshes_index_.assign(frame_models_.size(), DynamicModelInfo{});
+	size_t vertices_offset = 0, triangles_offset = 0;
+	for (size_t entity_index = 0; entity_index < frame_models_.size(); ++entity_index)
+	{
+		const ModelEntity& model = frame_models_[entity_index];
+		const TriangleModel& triangle_model = scene_.models[model.model];
+		DynamicModelInfo& info = dynamic_model_to_dynamic_meshes_index_[entity_index];
+		const Mat4f model_matrix = get_object_matrix(model.position, model.rotation);
+		const Mat4f model_view_matrix = camera_matrices_.view_matrix * model_matrix;
+		const BBox bbox = get_current_triangle_model_bbox(triangle_model, model.frames);
+		Vec3f bbox_vertices_transformed[8];
+		bbox.get_corners_vertices(bbox_vertices_transformed);
+		for (Vec3f& c : bbox_vertices_transformed)
+			c = view_matrix_transform_vertex(model_view_matrix, c);
+		ClippingPolygon clipping_polygon;
+		if (!calculate_triangle_model_screen_polygon(bbox_vertices_transformed, clipping_polygon))
+			continue; // behind the camera plane
+		if (model.flags & MODEL_FLAG_ONLY_THIRD_PERSON_VIEW)
+			continue;
+		bool visible = (model.flags & MODEL_FLAG_VIEW_MODEL) != 0;
+		for (uint32_t leaf_index : model_leafs_[entity_index])
+		{
+			ClippingPolygon leaf_clipping_polygon;
+			if (visibility_.leaf_bounds(leaf_index, leaf_clipping_polygon))
+			{
+				leaf_clipping_polygon.intersect(clipping_polygon);
+				if (leaf_clipping_polygon.is_valid_and_non_empty())
+				{
+					visible = true;
+					break;
+				}
+			}
+		}
+		if (!visible)
+			continue;
+		info.first_visible_mesh = (uint32_t)visible_dynamic_meshes_list_.size();
+		CameraMatrices model_camera_matrices;
+		model_camera_matrices.view_matrix = model_view_matrix;
+		Mat4f inv_t = Mat4f::identity();
+		model_matrix.transpose().invert(inv_t);
+		model_camera_matrices.planes_matrix = camera_matrices_.planes_matrix * inv_t;
+		model_camera_matrices.position = {0, 0, 0};
+		for (size_t mesh_index = 0; mesh_index < triangle_model.meshes.size(); ++mesh_index)
+		{
+			VisibleDynamicMeshInfo m;
+			m.entity_index = (uint32_t)entity_index;
+			m.mesh_index = (uint32_t)mesh_index;
+			m.vertices_offset = vertices_offset;
+			m.triangles_offset = triangles_offset;
+			std::memcpy(m.bbox_vertices_transformed, bbox_vertices_transformed, sizeof(bbox_vertices_transformed));
+			m.clipping_polygon = clipping_polygon;
+			m.model_matrix = model_matrix;
+			m.camera_matrices = model_camera_matrices;
+			visible_dynamic_meshes_list_.push_back(m);
+			vertices_offset += triangle_model.meshes[mesh_index].num_vertices();
+			triangles_offset += triangle_model.meshes[mesh_index].triangles.size();
+		}
+		info.num_visible_meshes = (uint32_t)triangle_model.meshes.size();
+	}
+	if (vertices_offset > dynamic_meshes_vertices_.size())
+		dynamic_meshes_vertices_.resize(vertices_offset);
+	if (triangles_offset > dynamic_meshes_triangles_.size())
+		dynamic_meshes_triangles_.resize(triangles_offset);
+	stats_.num_visible_meshes = (uint32_t)visible_dynamic_meshes_list_.size();
+}
+
+// get_model_light (triangle_models_rendering.rs:426-572).  Static part: the maps of this mirror carry no light grid, so
+// fetch_light_from_grid returns its zero element (:574-586); dynamic part: the eight bbox sample positions against every
+// dynamic light WITHOUT a shadow map.  Lights with cube / projector shadow maps need get_light_shadow_factor on shadow maps
+// that live on the device here (rendered by depth_kernels.cu) — they do not light models in this mirror.
+ModelLightData Renderer::get_model_light(const ModelEntity& model, const Mat4f& model_matrix) const
+{
+	LightGridElement static_light;
+	if (model.lighting == MODEL_LIGHTING_CONSTANT)
+	{
+		for (auto& side : static_light.light_cube)
+			std::memcpy(side, model.light, 12);
+	}
+	else if (model.lighting == MODEL_LIGHTING_ADVANCED)
+	{
+		for (auto& side : static_light.light_cube)
+			std::memcpy(side, model.light, 12); // + grid_light_scale * (zero grid light)
+	}
+	LightCube light_cube;
+	auto calculate_model_dynamic_light_cube = [&]() { // :494-537
+		const BBox bbox = get_current_triangle_model_bbox(scene_.models[model.model], model.frames);
+		const Vec3f bbox_center = bbox.get_center();
+		Vec3f sample_positions[8];
+		bbox.get_corners_vertices(sample_positions);
+		for (Vec3f& v : sample_positions)
+			v = truncate(model_matrix * extend((v + bbox_center) * 0.5f, 1.0f));
+		const Vec3f size = bbox.get_size();
+		const float min_square_distance = dot(size, size) * 0.25f;
+		for (const DynamicLight& light : frame_lights_)
+		{
+			if (light.shadow_type != SQW_SHADOW_NONE)
+				continue;
+			const float inv_square_radius = 1.0f / (light.radius * light.radius);
+			for (const Vec3f& position : sample_positions)
+			{
+				const Vec3f vec_to_light = light.position - position;
+				const float square_dist = std::fmax(dot(vec_to_light, vec_to_light), min_square_distance);
+				const float inv_square_dist = 1.0f / square_dist;
+				if (inv_square_dist < inv_square_radius)
+					continue;
+				const float scale = 1.0f * (inv_square_dist - inv_square_radius);
+				const float light_scaled[3] = {light.color[0] * scale, light.color[1] * scale, light.color[2] * scale};
+				light_cube.add_light_sample(vec_to_light, light_scaled);
+			}
+		}
+		light_cube.scale(1.0f / 8.0f);
+	};
+	switch (model.lighting)
+	{
+	case MODEL_LIGHTING_DEFAULT: calculate_model_dynamic_light_cube(); break;
+	case MODEL_LIGHTING_CONSTANT: light_cube.add_constant_light(model.light); break;
+	case MODEL_LIGHTING_ADVANCED:
+		calculate_model_dynamic_light_cube();
+		light_cube.scale(model.grid_light_scale);
+		light_cube.add_constant_light(model.light);
+		break;
+	}
+	return ModelLightData::from_two_light_grid_elements(static_light, light_cube.convert_into_light_grid_sample());
+}
+
+void Renderer::build_dynamic_models_buffers() // partial_renderer.rs:1122-1190
+{
+	for (VisibleDynamicMeshInfo& vm : visible_dynamic_meshes_list_)
+	{
+		const ModelEntity& model = frame_models_[vm.entity_index];
+		const TriangleModel& triangle_model = scene_.models[model.model];
+		const HostImage& mip0 = scene_.images[model.texture_images[0]];
+		const uint32_t size0[2] = {mip0.width, mip0.height};
+		vm.mip = calculate_triangle_model_texture_mip(vm.camera_matrices.view_matrix, get_current_triangle_model_bbox(triangle_model, model.frames), size0, mip_bias_);
+		const HostImage& texture = scene_.images[model.texture_images[vm.mip]];
+		const TriangleModelMesh& mesh = triangle_model.meshes[vm.mesh_index];
+		ModelVertex3d* dst_vertices = dynamic_meshes_vertices_.data() + vm.vertices_offset;
+		animate_and_transform_triangle_mesh_vertices(
+			triangle_model, mesh, model.frames, model.lerp, get_model_light(model, vm.model_matrix), vm.model_matrix, vm.camera_matrices.view_matrix,
+			Vec2f{(float)texture.width, (float)texture.height}, triangle_model.tc_shift, dst_vertices);
+		Triangle* dst_triangles = dynamic_meshes_triangles_.data() + vm.triangles_offset;
+		vm.num_visible_triangles = reject_triangle_model_back_faces(dst_vertices, mesh.triangles.data(), mesh.triangles.size(), dst_triangles);
+		sort_model_triangles(dst_vertices, dst_triangles, vm.num_visible_triangles);
+	}
+}
+
+// The tail of draw_leaf (partial_renderer.rs:2584-2790) for the object kinds of this mirror (triangle models).
+void Renderer::draw_leaf_objects(const ClippingPolygon& bounds, uint32_t leaf_index)
+{
+	const std::vector<uint32_t>& leaf_dynamic_models = leaf_models_[leaf_index];
+	if (leaf_dynamic_models.empty())
+		return;
+	Plane leaf_clip_planes[MAX_LEAF_CLIP_PLANES];
+	const std::vector<Plane>& world = leafs_planes_[leaf_index];
+	const size_t num_planes = std::min(MAX_LEAF_CLIP_PLANES, world.size());
+	for (size_t i = 0; i < num_planes; ++i)
+	{
+		const Vec4f t = camera_matrices_.planes_matrix * extend(world[i].vec, -world[i].dist);
+		leaf_clip_planes[i] = Plane{truncate(t), -t.w};
+	}
+	if (leaf_dynamic_models.size() == 1)
+	{
+		const DynamicModelInfo entry = dynamic_model_to_dynamic_meshes_index_[leaf_dynamic_models[0]];
+		for (uint32_t m = entry.first_visible_mesh; m < entry.first_visible_mesh + entry.num_visible_meshes; ++m)
+			draw_mesh(bounds, leaf_clip_planes, num_planes, m);
+		return;
+	}
+	objects_sorter_.clear();
+	for (uint32_t dynamic_model_index : leaf_dynamic_models)
+	{
+		const ModelEntity& model = frame_models_[dynamic_model_index];
+		const BBox bbox = model.has_ordering_custom_bbox ? model.ordering_custom_bbox : get_current_triangle_model_bbox(scene_.models[model.model], model.frames);
+		const DynamicModelInfo entry = dynamic_model_to_dynamic_meshes_index_[dynamic_model_index];
+		for (uint32_t m = entry.first_visible_mesh; m < entry.first_visible_mesh + entry.num_visible_meshes; ++m)
+			objects_sorter_.add_object(m, project_bbox(bbox, visible_dynamic_meshes_list_[m].camera_matrices));
+	}
+	objects_sorter_.sort_objects();
+	for (size_t i = 0; i < objects_sorter_.num_objects; ++i)
+		draw_mesh(bounds, leaf_clip_planes, num_planes, objects_sorter_.objects[i].first);
+}
+
+void Renderer::draw_mesh(const ClippingPolygon& clipping_polygon, const Plane* leaf_clip_planes, size_t num_leaf_clip_planes, size_t visible_mesh_index) // partial_renderer.rs:3525-3717
+{
+	const VisibleDynamicMeshInfo& vm = visible_dynamic_meshes_list_[visible_mesh_index];
+	{
+		ClippingPolygon mesh_clipping_polygon = vm.clipping_polygon;
+		mesh_clipping_polygon.intersect(clipping_polygon);
+		if (!mesh_clipping_polygon.is_valid_and_non_empty())
+			return;
+	}
+	const ModelEntity& model = frame_models_[vm.entity_index];
+	Plane clip_planes_3d[MAX_LEAF_CLIP_PLANES + 1];
+	size_t num_clip_planes_3d = 0;
+	const Plane near_z_plane = {{0.0f, 0.0f, 1.0f}, Z_NEAR};
+	for (size_t pi = 0; pi <= num_leaf_clip_planes; ++pi)
+	{
+		const Plane& clip_plane = pi == 0 ? near_z_plane : leaf_clip_planes[pi - 1];
+		int vertices_front = 0;
+		for (const Vec3f& v : vm.bbox_vertices_transformed)
+			if (dot(clip_plane.vec, v) >= clip_plane.dist)
+				++vertices_front;
+		if (vertices_front == 8)
+			continue;
+		if (vertices_front == 0)
+			return;
+		if (num_clip_planes_3d < MAX_LEAF_CLIP_PLANES) // the reference's fixed array holds MAX_LEAF_CLIP_PLANES entries
+			clip_planes_3d[num_clip_planes_3d++] = clip_plane;
+	}
+	Vec3f clip_planes_2d[4];
+	size_t num_clip_planes_2d = 0;
+	{
+		Vec3f mesh_planes[4], cur_planes[4];
+		vm.clipping_polygon.get_box_clip_planes(mesh_planes);
+		clipping_polygon.get_box_clip_planes(cur_planes);
+		for (int i = 0; i < 4; ++i)
+			if (cur_planes[i].z > mesh_planes[i].z)
+				clip_planes_2d[num_clip_planes_2d++] = cur_planes[i];
+	}
+	const uint32_t image_id = model.texture_images[vm.mip];
+	const HostImage& texture = scene_.images[image_id];
+	const ModelVertex3d* vertices_combined = dynamic_meshes_vertices_.data() + vm.vertices_offset;
+	const Triangle* triangles = dynamic_meshes_triangles_.data() + vm.triangles_offset;
+
+	auto emit = [&](const sqw_triangle_point pts[3]) {
+		sqw_draw_cmd c;
+		std::memset(&c, 0, sizeof(c));
+		c.kind = SQW_CMD_TRIANGLE;
+		c.blend = (uint8_t)model.blending_mode;
+		c.tex_kind = SQW_TEX_IMAGE;
+		c.tex_ref = image_id;
+		c.tex_size[0] = (int32_t)texture.width;
+		c.tex_size[1] = (int32_t)texture.height;
+		c.num_vertices = 3;
+		c.vertex_offset = (uint32_t)triangle_points_.size();
+		triangle_points_.insert(triangle_points_.end(), pts, pts + 3);
+		cmds_.push_back(c);
+		++stats_.num_triangles;
+	};
+	auto to_point = [](Vec2f pos, Vec2f tc, const float light[3]) {
+		sqw_triangle_point p;
+		p.x = f32_to_fixed16(pos.x);
+		p.y = f32_to_fixed16(pos.y);
+		p.tc[0] = f32_to_fixed16(tc.x);
+		p.tc[1] = f32_to_fixed16(tc.y);
+		for (int i = 0; i < 3; ++i)
+			p.light[i] = f32_to_fixed16(light[i]);
+		return p;
+	};
+
+	if (num_clip_planes_3d == 0 && num_clip_planes_2d == 0)
+	{
+		for (size_t t = 0; t < vm.num_visible_triangles; ++t)
+		{
+			sqw_triangle_point pts[3];
+			for (int k = 0; k < 3; ++k)
+			{
+				const ModelVertex3d& v = vertices_combined[triangles[t][k]];
+				pts[k] = to_point(truncate(v.pos) / v.pos.z, v.tc, v.light);
+			}
+			emit(pts);
+		}
+		return;
+	}
+	ModelVertex3d vertices_clipped0[MAX_VERTICES], vertices_clipped1[MAX_VERTICES];
+	ModelVertex2d vertices_projected0[MAX_VERTICES], vertices_projected1[MAX_VERTICES];
+	sqw_triangle_point vertices_fixed[MAX_VERTICES];
+	for (size_t t = 0; t < vm.num_visible_triangles; ++t)
+	{
+		ModelVertex3d *vc_src = vertices_clipped0, *vc_dst = vertices_clipped1;
+		for (int k = 0; k < 3; ++k)
+			vc_src[k] = vertices_combined[triangles[t][k]];
+		size_t num_vertices = 3;
+		bool rejected = false;
+		for (size_t pi = 0; pi < num_clip_planes_3d; ++pi)
+		{
+			num_vertices = clip_3d_model_polygon_by_plane(vc_src, num_vertices, clip_planes_3d[pi], vc_dst, MAX_VERTICES);
+			if (num_vertices < 3)
+			{
+				rejected = true;
+				break;
+			}
+			std::swap(vc_src, vc_dst);
+		}
+		if (rejected)
+			continue;
+		ModelVertex2d *vp_src = vertices_projected0, *vp_dst = vertices_projected1;
+		for (size_t k = 0; k < num_vertices; ++k)
+		{
+			vp_src[k].pos = truncate(vc_src[k].pos) / vc_src[k].pos.z;
+			vp_src[k].tc = vc_src[k].tc;
+			std::memcpy(vp_src[k].light, vc_src[k].light, 12);
+		}
+		for (size_t pi = 0; pi < num_clip_planes_2d; ++pi)
+		{
+			num_vertices = clip_2d_model_polygon(vp_src, num_vertices, clip_planes_2d[pi], vp_dst, MAX_VERTICES);
+			if (num_vertices < 3)
+			{
+				rejected = true;
+				break;
+			}
+			std::swap(vp_src, vp_dst);
+		}
+		if (rejected)
+			continue;
+		for (size_t k = 0; k < num_vertices; ++k)
+			vertices_fixed[k] = to_point(vp_src[k].pos, vp_src[k].tc, vp_src[k].light);
+		for (size_t k = 0; k + 2 < num_vertices; ++k)
+		{
+			const sqw_triangle_point pts[3] = {vertices_fixed[0], vertices_fixed[k + 1], vertices_fixed[k + 2]};
+			emit(pts);
+		}
+	}
 }
 
 } // namespace sqwh

@@ -8,6 +8,7 @@
 //                                 -> PartialRenderer::draw_frame / perform_rasterization (partial_renderer.rs:236, :1192)
 #pragma once
 #include "map.hpp"
+#include "models.hpp"
 #include <vector>
 
 namespace sqwh
@@ -25,6 +26,7 @@ struct ClippingPolygon
 	static ClippingPolygon from_point(Vec2f p);
 	bool is_valid_and_non_empty() const;
 	bool contains(const ClippingPolygon& o) const;
+	void get_box_clip_planes(Vec3f out[4]) const; // clipping_polygon.rs:154-162
 	void extend(const ClippingPolygon& o);
 	void extend_with_point(Vec2f p);
 	void intersect(const ClippingPolygon& o);
@@ -63,6 +65,8 @@ struct RendererDebugStats
 	uint64_t num_surfaces_pixels = 0;
 	uint32_t num_draw_commands = 0;
 	uint32_t mode_counts[3] = {0, 0, 0};
+	uint32_t num_visible_meshes = 0;
+	uint32_t num_triangles = 0; // SQW_CMD_TRIANGLE commands recorded
 };
 
 // frame_info.rs:149-168
@@ -137,6 +141,9 @@ public:
 	bool needs_background_clear() const { return config_.clear_background && !visibility_.is_inside_leaf_volume(); }
 	// FrameInfo::lights for the next prepare_frame (frame_info.rs:24)
 	void set_lights(const DynamicLight* lights, size_t n) { frame_lights_.assign(lights, lights + n); }
+	// FrameInfo::model_entities for the next prepare_frame (frame_info.rs:14)
+	void set_models(const ModelEntity* models, size_t n) { frame_models_.assign(models, models + n); }
+	const std::vector<sqw_triangle_point>& triangle_points() const { return triangle_points_; }
 	const std::vector<sqw_light>& lights() const { return lights_; }
 	const std::vector<sqw_depth_map>& depth_maps() const { return depth_maps_; }
 	const std::vector<sqw_depth_cmd>& depth_cmds() const { return depth_cmds_; }
@@ -153,6 +160,14 @@ private:
 	void build_shadow_maps();
 	void depth_draw_map(uint32_t offset, uint32_t size, uint32_t flags, const CameraMatrices& depth_matrices);
 	void depth_draw_polygon(const CameraMatrices& m, const Vec3f clip_planes[8], uint32_t polygon_index, bool depth_test);
+	// triangle models: dynamic_objects_index.rs:52-73, partial_renderer.rs:995-1190, :3525-3717, triangle_models_rendering.rs
+	void position_models();
+	void position_model_convex_hull_r(uint32_t id, const Vec3f* vertices, size_t n, uint32_t node_index);
+	void prepare_dynamic_models();
+	void build_dynamic_models_buffers();
+	ModelLightData get_model_light(const ModelEntity& model, const Mat4f& model_matrix) const;
+	void draw_leaf_objects(const ClippingPolygon& bounds, uint32_t leaf_index);
+	void draw_mesh(const ClippingPolygon& clipping_polygon, const Plane* leaf_clip_planes, size_t num_leaf_clip_planes, size_t visible_mesh_index);
 	// partial_renderer.rs
 	void prepare_polygons_surfaces();
 	void prepare_polygon_surface(const Vec3f clip_planes[8], size_t polygon_index);
@@ -184,6 +199,31 @@ private:
 	std::vector<sqw_depth_cmd> depth_cmds_;
 	std::vector<sqw_polygon_point> depth_points_;
 	uint64_t shadow_maps_len_ = 0;
+
+	// renderer_structs.rs:216-232 (VisibleDynamicMeshInfo) and the model buffers of PartialRenderer
+	struct VisibleDynamicMeshInfo
+	{
+		uint32_t entity_index = 0, mesh_index = 0;
+		size_t vertices_offset = 0, triangles_offset = 0, num_visible_triangles = 0;
+		Vec3f bbox_vertices_transformed[8];
+		ClippingPolygon clipping_polygon;
+		Mat4f model_matrix;
+		CameraMatrices camera_matrices;
+		uint32_t mip = 0;
+	};
+	struct DynamicModelInfo
+	{
+		uint32_t first_visible_mesh = 0, num_visible_meshes = 0;
+	};
+	std::vector<ModelEntity> frame_models_;
+	std::vector<std::vector<uint32_t>> leaf_models_, model_leafs_; // DynamicObjectsIndex for models
+	std::vector<std::vector<Plane>> leafs_planes_;                 // RenderersCommonData::leafs_planes (renderer.rs:49)
+	std::vector<VisibleDynamicMeshInfo> visible_dynamic_meshes_list_;
+	std::vector<DynamicModelInfo> dynamic_model_to_dynamic_meshes_index_;
+	std::vector<ModelVertex3d> dynamic_meshes_vertices_;
+	std::vector<Triangle> dynamic_meshes_triangles_;
+	std::vector<sqw_triangle_point> triangle_points_;
+	LeafObjectsSorter objects_sorter_;
 
 	std::vector<DrawPolygonData> polygons_data_;
 	std::vector<Vec3f> vertices_transformed_;

@@ -42,6 +42,7 @@ class FrameInfo:
     fov: float = FOV_DEFAULT
     color_modulate: tuple = (1.0, 1.0, 1.0)
     lights: Optional[np.ndarray] = None  # FrameInfo::lights (frame_info.rs:24) as scene.dynamic_light_dtype records
+    model_entities: Optional[np.ndarray] = None  # FrameInfo::model_entities (frame_info.rs:14) as scene.model_entity_dtype records
 
 
 @dataclass
@@ -75,7 +76,7 @@ class Renderer:
 
     def prepare_frame(self, surface_info: SurfaceInfo, frame_info: FrameInfo, color_bits: int = 64):
         """prepare_frame::<ColorT> (renderer.rs:61): host preparation, then surface building on the GPU (seam S1)."""
-        hf = self.host.build_frame(surface_info.width, surface_info.height, frame_info.pose, frame_info.fov, frame_info.lights)
+        hf = self.host.build_frame(surface_info.width, surface_info.height, frame_info.pose, frame_info.fov, frame_info.lights, frame_info.model_entities)
         view = self._get_view(surface_info, color_bits)
         key = (surface_info.width, surface_info.height, color_bits)
         if key not in self._frames:
@@ -96,7 +97,7 @@ class Renderer:
         clear = None
         if hf.needs_clear:  # draw_background (partial_renderer.rs:249-256)
             clear = BACKGROUND_COLOR64 if view.color_bits == 64 else BACKGROUND_COLOR32
-        view.draw(hf.cmds, hf.polygon_points, None, clear_color=clear)
+        view.draw(hf.cmds, hf.polygon_points, hf.triangle_points, clear_color=clear)
         if pixels is not None:
             pixels[:, : view.width] = view.read_pixels()
         return view

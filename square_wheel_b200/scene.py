@@ -28,12 +28,16 @@ class SceneParams(C.Structure):
         ("max_polygon_size", C.c_float),
         ("material_mode", C.c_uint32),
         ("emissive_fraction", C.c_float),
+        ("num_models", C.c_uint32),
+        ("model_detail", C.c_uint32),
     ]
 
 
 class SceneInfo(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("num_nodes", "num_leafs", "num_polygons", "num_portals", "num_vertices", "num_materials", "num_images", "num_waypoints")] + [
-        ("num_lightmap_elements", C.c_uint64)
+        ("num_lightmap_elements", C.c_uint64),
+        ("num_models", C.c_uint32),
+        ("reserved", C.c_uint32),
     ]
 
 
@@ -75,6 +79,20 @@ dynamic_light_dtype = np.dtype(
 )
 assert dynamic_light_dtype.itemsize == 52
 
+# frame_info.rs:55-69 ModelEntity (model / skin = indices of the scene's fixtures; rotation = quaternion s, x, y, z)
+model_entity_dtype = np.dtype(
+    [
+        ("position", "<f4", (3,)), ("rotation", "<f4", (4,)), ("frames", "<u4", (2,)), ("lerp", "<f4"), ("model", "<u4"), ("skin", "<u4"), ("blending_mode", "<u4"),
+        ("lighting", "<u4"), ("light", "<f4", (3,)), ("grid_light_scale", "<f4"), ("light_position", "<f4", (3,)), ("flags", "<u4"),
+    ]
+)
+assert model_entity_dtype.itemsize == 88
+MODEL_LIGHTING_DEFAULT, MODEL_LIGHTING_CONSTANT, MODEL_LIGHTING_ADVANCED = 0, 1, 2
+
+
+class ModelInfo(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("num_frames", "num_meshes", "num_vertices", "num_triangles", "kind", "num_bones")] + [("bbox_min", C.c_float * 3), ("bbox_max", C.c_float * 3)]
+
 
 def build_host_library():
     subprocess.run(["make", "-C", os.path.join(os.path.dirname(N.HOST_LIB_PATH), "host")], check=True, capture_output=True)
@@ -106,9 +124,13 @@ def lib() -> C.CDLL:
         l.sqwh_renderer_draw_frame.argtypes = [vp]
         l.sqwh_renderer_frame_info.argtypes = [vp, C.POINTER(FrameInfo)]
         l.sqwh_renderer_set_lights.argtypes = [vp, vp, C.c_uint32]
+        l.sqwh_renderer_set_models.restype = C.c_int
+        l.sqwh_renderer_set_models.argtypes = [vp, vp, vp, C.c_uint32]
+        l.sqwh_scene_model_info.restype = C.c_int
+        l.sqwh_scene_model_info.argtypes = [vp, C.c_uint32, C.POINTER(ModelInfo)]
         for name in (
             "sqwh_renderer_jobs", "sqwh_renderer_cmds", "sqwh_renderer_polygon_points", "sqwh_renderer_lights", "sqwh_renderer_depth_maps", "sqwh_renderer_depth_cmds",
-            "sqwh_renderer_depth_points",
+            "sqwh_renderer_depth_points", "sqwh_renderer_triangle_points",
         ):
             getattr(l, name).restype = vp
             getattr(l, name).argtypes = [vp]
@@ -158,6 +180,12 @@ class Scene:
             dt = {N.IMAGE_TEXTURE_ELEMENT: N.texture_element_dtype, N.IMAGE_COLOR32: np.uint32, N.IMAGE_COLOR64: np.uint64}[kind.value]
             self.images.append((kind.value, _array_from(p, w.value * h.value, dt).reshape(h.value, w.value)))
 
+    def model_info(self, index: int) -> ModelInfo:
+        mi = ModelInfo()
+        if self._lib.sqwh_scene_model_info(self._handle, index, C.byref(mi)) != 0:
+            raise IndexError(index)
+        return mi
+
     def camera_path(self, num_frames: int, jitter_seed: int = 0) -> np.ndarray:
         """[num_frames, 5] = position xyz, azimuth, elevation (64-pose Catmull-Rom loop of SURVEY.md §8d)."""
         out = np.zeros((num_frames, 5), np.float32)
@@ -179,9 +207,12 @@ class Scene:
 class HostFrame:
     """Everything the host produced for one frame: the inputs of S1 and S2."""
 
-    def __init__(self, jobs, total_surface_pixels, cam_pos, cmds, polygon_points, needs_clear, info, lights=None, depth_maps=None, depth_cmds=None, depth_points=None, shadow_maps_len=0):
+    def __init__(
+        self, jobs, total_surface_pixels, cam_pos, cmds, polygon_points, needs_clear, info, lights=None, depth_maps=None, depth_cmds=None, depth_points=None, shadow_maps_len=0, triangle_points=None
+    ):
         self.jobs, self.total_surface_pixels, self.cam_pos = jobs, total_surface_pixels, cam_pos
         self.cmds, self.polygon_points, self.needs_clear, self.info = cmds, polygon_points, needs_clear, info
+        self.triangle_points = triangle_points if triangle_points is not None and len(triangle_points) else None  # SQW_CMD_TRIANGLE vertices (models)
         # dynamic lights of the frame and the shadow-map fills that feed them (empty without FrameInfo::lights)
         self.lights, self.depth_maps, self.depth_cmds, self.depth_points, self.shadow_maps_len = lights, depth_maps, depth_cmds, depth_points, shadow_maps_len
 
@@ -191,7 +222,7 @@ class HostFrame:
         frame.set_surfaces(self.jobs, self.lights if has_lights else None, None, self.cam_pos, self.total_surface_pixels, device_shadow_maps_len=self.shadow_maps_len if has_lights else 0)
         if self.depth_maps is not None:
             frame.set_shadow_map_draw(self.depth_maps, self.depth_cmds, self.depth_points)  # an empty list clears an earlier recording
-        frame.set_draw(self.cmds, self.polygon_points, None, clear_color=clear_color)
+        frame.set_draw(self.cmds, self.polygon_points, self.triangle_points, clear_color=clear_color)
         if post is not None:
             frame.set_post(post)
 
@@ -205,11 +236,15 @@ class HostRenderer:
         cfg = RendererConfig(1 if use_directional_lightmaps else 0, textures_mip_bias, 1 if clear_background else 0, 0, shadows_quality)
         self._handle = self._lib.sqwh_renderer_create(scene._handle, C.byref(cfg))
 
-    def build_frame(self, width: int, height: int, pose, fov: float = FOV_DEFAULT, lights=None) -> HostFrame:
-        """lights: FrameInfo::lights as an array of dynamic_light_dtype (or None)."""
+    def build_frame(self, width: int, height: int, pose, fov: float = FOV_DEFAULT, lights=None, models=None) -> HostFrame:
+        """lights: FrameInfo::lights as an array of dynamic_light_dtype (or None); models: FrameInfo::model_entities as an array of
+        model_entity_dtype (or None)."""
         pose = np.ascontiguousarray(pose, np.float32)
         lt = np.ascontiguousarray(lights, dynamic_light_dtype) if lights is not None else np.zeros(0, dynamic_light_dtype)
         self._lib.sqwh_renderer_set_lights(self._handle, lt.ctypes.data_as(C.c_void_p), len(lt))
+        md = np.ascontiguousarray(models, model_entity_dtype) if models is not None else np.zeros(0, model_entity_dtype)
+        if self._lib.sqwh_renderer_set_models(self._handle, self.scene._handle, md.ctypes.data_as(C.c_void_p), len(md)) != 0:
+            raise ValueError("model entity refers to a missing model, skin or frame")
         self._lib.sqwh_renderer_prepare_frame(self._handle, width, height, pose.ctypes.data_as(C.c_void_p), fov)
         self._lib.sqwh_renderer_draw_frame(self._handle)
         fi = FrameInfo()
@@ -221,8 +256,9 @@ class HostRenderer:
         dmaps = _array_from(self._lib.sqwh_renderer_depth_maps(self._handle), fi.num_depth_maps, N.depth_map_dtype)
         dcmds = _array_from(self._lib.sqwh_renderer_depth_cmds(self._handle), fi.num_depth_cmds, N.depth_cmd_dtype)
         dpts = _array_from(self._lib.sqwh_renderer_depth_points(self._handle), fi.num_depth_points, N.polygon_point_dtype)
+        tpts = _array_from(self._lib.sqwh_renderer_triangle_points(self._handle), fi.num_triangle_points, N.triangle_point_dtype)
         return HostFrame(
-            jobs, int(fi.total_surface_pixels), np.array(list(fi.cam_pos), np.float32), cmds, pts, bool(fi.needs_background_clear), fi, out_lights, dmaps, dcmds, dpts, int(fi.shadow_maps_len)
+            jobs, int(fi.total_surface_pixels), np.array(list(fi.cam_pos), np.float32), cmds, pts, bool(fi.needs_background_clear), fi, out_lights, dmaps, dcmds, dpts, int(fi.shadow_maps_len), tpts
         )
 
     def close(self):

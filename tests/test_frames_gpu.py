@@ -157,3 +157,61 @@ def test_config2_dynamic_lights_with_gpu_shadow_maps(scene, oracle_lib, color_bi
         assert lit_jobs > 20  # the lights really reach visible polygons
     finally:
         r.close()
+
+
+def _models_ahead_of_camera(sc, pose, k, light_scale=0.7):
+    """One entity per model fixture, fanned out in front of the camera (forward = (-sin az, cos az, 0)), all blend modes and the
+    three ModelLighting kinds, animation frames advancing with k."""
+    n = int(sc.info.num_models)
+    models = np.zeros(n, S.model_entity_dtype)
+    az = float(pose[3])
+    for i in range(n):
+        a = az + (i - 0.5 * (n - 1)) * 0.2
+        models[i]["position"] = pose[:3] + (70.0 + 14.0 * i) * np.array([-np.sin(a), np.cos(a), 0.0], np.float32) + np.array([0.0, 0.0, -10.0 + 5.0 * (i % 3)], np.float32)
+        models[i]["rotation"] = (np.cos(0.3 * i + 0.1 * k), 0.0, np.sin(0.2 * i) * np.sin(0.3 * i + 0.1 * k), np.cos(0.2 * i) * np.sin(0.3 * i + 0.1 * k))
+        nf = sc.model_info(i).num_frames
+        models[i]["frames"] = (k % nf, (k + 1) % nf)
+        models[i]["lerp"] = (0.4, 0.0, 1.0, 0.75)[i % 4]
+        models[i]["model"] = i
+        models[i]["skin"] = i
+        models[i]["blending_mode"] = (N.BLEND_NONE, N.BLEND_NONE, N.BLEND_ALPHA_TEST, N.BLEND_ALPHA_BLEND, N.BLEND_AVERAGE, N.BLEND_ADDITIVE)[i % 6]
+        models[i]["lighting"] = (S.MODEL_LIGHTING_CONSTANT, S.MODEL_LIGHTING_DEFAULT, S.MODEL_LIGHTING_ADVANCED)[i % 3]
+        models[i]["light"] = (light_scale, light_scale * 0.8, light_scale * 0.6)
+        models[i]["grid_light_scale"] = 0.5
+        models[i]["light_position"] = models[i]["position"]
+    return models
+
+
+@pytest.mark.parametrize("color_bits", [32, 64])
+def test_config2_triangle_models(oracle_lib, color_bits):
+    """configs[2], the model part, in miniature: non-animated, vertex-animated (MD3-class) and skeleton-animated (IQM-class)
+    fixtures prepared by the host mirror (animation, light-cube lighting incl. shadow-less dynamic lights, back-face rejection,
+    depth sort, clipping by leaf and screen planes) arrive as thousands of small Gouraud triangles interleaved with the world
+    polygons in BSP order; the picture must equal the oracle's fed with the same lists."""
+    W, H = 640, 360
+    sc = S.Scene(seed=7, texture_size_log2=6, num_materials=8, num_models=8, model_detail=9)
+    r = Renderer(sc, RendererConfig(use_directional_lightmaps=True))
+    try:
+        path = sc.camera_path(64)
+        triangles = 0
+        for k in (0, 9, 31, 50):
+            lights = _lights_along_path(path, 4, 5)
+            lights["shadow_type"] = N.SHADOW_NONE
+            lights["position"] = path[k][:3] + np.array([[20, 30, 10], [-40, 60, 0], [10, 90, -20], [0, 10, 30]], np.float32)
+            models = _models_ahead_of_camera(sc, path[k], k)
+            hf = r.prepare_frame(SurfaceInfo(W, H), FrameInfo(path[k], lights=lights, model_entities=models), color_bits=color_bits)
+            pixels = np.zeros((H, W), np.uint32 if color_bits == 32 else np.uint64)
+            r.draw_frame(pixels)
+            triangles += int((hf.cmds["kind"] == N.CMD_TRIANGLE).sum())
+            oracle_lib.reset_assert_failures()
+            surf = oracle_lib.build_surfaces(color_bits, hf.jobs, hf.lights, None, hf.cam_pos, sc.images, sc.lightmaps, sc.directional_lightmaps, hf.total_surface_pixels)
+            fb = np.zeros((H, W), pixels.dtype)
+            if hf.needs_clear:
+                oracle_lib.fill(fb, S.BACKGROUND_COLOR64 if color_bits == 64 else S.BACKGROUND_COLOR32)
+            oracle_lib.draw(color_bits, fb, hf.cmds, hf.polygon_points, hf.triangle_points, surf, sc.images)
+            assert oracle_lib.assert_failures() == 0
+            assert_pixels_equal(pixels, fb, f"frame {k} picture with models")
+        assert triangles > 1500  # the models really are on screen
+    finally:
+        r.close()
+        sc.close()

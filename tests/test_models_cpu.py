@@ -1,0 +1,137 @@
+"""Host mirror of the triangle-model path (square_wheel_b200/host/models.cpp, Renderer::draw_mesh): invariants the reference's
+code guarantees (triangle_models_rendering.rs, partial_renderer.rs:3525-3717), checked on the command lists, and the oracle
+rasterising those lists without tripping its ported debug_assert!s."""
+import numpy as np
+import pytest
+
+from square_wheel_b200 import _native as N
+from square_wheel_b200 import scene as S
+
+
+@pytest.fixture(scope="module")
+def scene():
+    sc = S.Scene(seed=11, texture_size_log2=6, num_materials=6, num_models=6, model_detail=8)
+    yield sc
+    sc.close()
+
+
+def _entities(sc, pose, k, lighting=S.MODEL_LIGHTING_CONSTANT, distance=70.0):
+    n = int(sc.info.num_models)
+    m = np.zeros(n, S.model_entity_dtype)
+    az = float(pose[3])
+    for i in range(n):
+        a = az + (i - 0.5 * (n - 1)) * 0.2
+        m[i]["position"] = pose[:3] + (distance + 14.0 * i) * np.array([-np.sin(a), np.cos(a), 0.0], np.float32)
+        m[i]["rotation"] = (np.cos(0.2 * i), 0.0, 0.0, np.sin(0.2 * i))
+        nf = sc.model_info(i).num_frames
+        m[i]["frames"] = (k % nf, (k + 3) % nf)
+        m[i]["lerp"] = 0.3
+        m[i]["model"] = i
+        m[i]["skin"] = i
+        m[i]["lighting"] = lighting
+        m[i]["light"] = (0.5, 0.75, 1.0)
+    return m
+
+
+def test_model_fixtures_cover_the_three_vertex_data_kinds(scene):
+    kinds = [scene.model_info(i).kind for i in range(scene.info.num_models)]
+    assert kinds == [0, 1, 2, 0, 1, 2]  # NonAnimated, VertexAnimated, SkeletonAnimated (triangle_model.rs:64-75)
+    for i in range(scene.info.num_models):
+        mi = scene.model_info(i)
+        assert mi.num_triangles == 2 * 8 * 16 and mi.num_vertices == 9 * 17 and mi.num_vertices <= 65536  # VertexIndex = u16
+        assert mi.num_frames == (1 if mi.kind == 0 else 8)
+        assert mi.num_bones == (6 if mi.kind == 2 else 0)
+        assert all(lo < hi for lo, hi in zip(mi.bbox_min, mi.bbox_max))
+
+
+def test_bad_entities_are_rejected(scene):
+    hr = S.HostRenderer(scene)
+    try:
+        m = _entities(scene, scene.camera_path(4)[0], 0)
+        m[2]["frames"] = (99, 0)
+        with pytest.raises(ValueError):
+            hr.build_frame(320, 200, scene.camera_path(4)[0], models=m)
+        m = _entities(scene, scene.camera_path(4)[0], 0)
+        m[1]["model"] = 77
+        with pytest.raises(ValueError):
+            hr.build_frame(320, 200, scene.camera_path(4)[0], models=m)
+    finally:
+        hr.close()
+
+
+def test_triangle_commands_respect_reference_invariants(scene, oracle_lib):
+    W, H = 480, 270
+    hr = S.HostRenderer(scene)
+    try:
+        path = scene.camera_path(32)
+        total = 0
+        for k in (0, 7, 19):
+            without = hr.build_frame(W, H, path[k])
+            hf = hr.build_frame(W, H, path[k], models=_entities(scene, path[k], k))
+            tri = hf.cmds[hf.cmds["kind"] == N.CMD_TRIANGLE]
+            poly = hf.cmds[hf.cmds["kind"] == N.CMD_POLYGON]
+            # models only ADD commands: the world polygons and their order are untouched
+            assert poly.tobytes() == without.cmds.tobytes()
+            total += len(tri)
+            if len(tri) == 0:
+                continue
+            assert hf.triangle_points is not None and len(hf.triangle_points) == 3 * len(tri)
+            assert np.array_equal(tri["vertex_offset"], 3 * np.arange(len(tri), dtype=np.uint32))
+            assert np.all(tri["tex_kind"] == N.TEX_IMAGE)
+            # every triangle is clipped to the screen (leaf bounds are inside it) up to the 16.16 rounding of the clippers
+            x = hf.triangle_points["x"].astype(np.float64) / 65536.0
+            y = hf.triangle_points["y"].astype(np.float64) / 65536.0
+            assert x.min() > -1.0 and x.max() < W + 1.0 and y.min() > -1.0 and y.max() < H + 1.0
+            # ConstantLight (0.5, 0.75, 1.0) enters BOTH the static and the dynamic light-grid element of get_model_light
+            # (triangle_models_rendering.rs:459-462 and :541-546), so the cube sides are 2 * l and every vertex gets
+            # 2 * l * (|nx| + |ny| + |nz|) with 1 <= |n|_1 <= sqrt(3) for a unit normal (get_light_cube_light, light.rs:296-348) and the channel ratios survive
+            # (away from vertices produced by the clippers' linear interpolation the ratio is exact up to 16.16 truncation)
+            light = hf.triangle_points["light"].astype(np.float64) / 65536.0
+            assert light[:, 0].min() >= 1.0 * 0.999 and light[:, 0].max() <= 1.0 * 1.7330
+            np.testing.assert_allclose(light[:, 1] / light[:, 0], 1.5, atol=2e-3)
+            np.testing.assert_allclose(light[:, 2] / light[:, 0], 2.0, atol=2e-3)
+            # texture size = the chosen mip of a 64 x 64 skin
+            assert set(np.unique(tri["tex_size"][:, 0])) <= {64, 32, 16, 8, 4}
+            # the oracle rasterises the list without tripping a ported debug_assert!
+            fb = np.zeros((H, W), np.uint32)
+            oracle_lib.reset_assert_failures()
+            oracle_lib.draw(32, fb, tri, None, hf.triangle_points, None, scene.images)
+            assert oracle_lib.assert_failures() == 0
+            assert np.count_nonzero(fb) > 500
+        assert total > 1000
+    finally:
+        hr.close()
+
+
+def test_models_behind_the_camera_or_in_hidden_leafs_draw_nothing(scene):
+    hr = S.HostRenderer(scene)
+    try:
+        path = scene.camera_path(32)
+        behind = _entities(scene, path[3], 3, distance=-90.0)
+        hf = hr.build_frame(480, 270, path[3], models=behind)
+        assert int((hf.cmds["kind"] == N.CMD_TRIANGLE).sum()) == 0
+    finally:
+        hr.close()
+
+
+def test_default_lighting_uses_only_shadowless_dynamic_lights(scene):
+    """ModelLighting::Default without a light grid: black without lights, lit by a shadow-less light, and NOT lit by a light
+    whose shadow map lives on the device (documented limitation of the host mirror)."""
+    hr = S.HostRenderer(scene)
+    try:
+        path = scene.camera_path(32)
+        m = _entities(scene, path[5], 5, lighting=S.MODEL_LIGHTING_DEFAULT)
+        hf = hr.build_frame(480, 270, path[5], models=m)
+        assert hf.triangle_points is not None and np.all(hf.triangle_points["light"] == 0)
+        lights = np.zeros(1, S.dynamic_light_dtype)
+        lights[0]["position"] = path[5][:3]
+        lights[0]["radius"] = 512.0
+        lights[0]["color"] = (40000.0, 30000.0, 20000.0)
+        lights[0]["rotation"] = (1.0, 0.0, 0.0, 0.0)
+        hf = hr.build_frame(480, 270, path[5], lights=lights, models=m)
+        assert hf.triangle_points["light"].max() > 0
+        lights[0]["shadow_type"] = N.SHADOW_CUBE
+        hf = hr.build_frame(480, 270, path[5], lights=lights, models=m)
+        assert np.all(hf.triangle_points["light"] == 0)
+    finally:
+        hr.close()
