@@ -23,6 +23,8 @@ struct sqwh_scene_params // mirrors sqwh::SceneParams (plain C layout for ctypes
 	float emissive_fraction;
 	uint32_t num_models;
 	uint32_t model_detail;
+	uint32_t skybox;
+	uint32_t sky_size_log2;
 };
 
 struct sqwh_scene_info
@@ -103,6 +105,8 @@ void sqwh_default_scene_params(sqwh_scene_params* p)
 	p->emissive_fraction = d.emissive_fraction;
 	p->num_models = d.num_models;
 	p->model_detail = d.model_detail;
+	p->skybox = d.skybox;
+	p->sky_size_log2 = d.sky_size_log2;
 }
 
 Scene* sqwh_scene_create(const sqwh_scene_params* p)
@@ -124,6 +128,8 @@ Scene* sqwh_scene_create(const sqwh_scene_params* p)
 	sp.emissive_fraction = p->emissive_fraction;
 	sp.num_models = p->num_models;
 	sp.model_detail = p->model_detail;
+	sp.skybox = p->skybox;
+	sp.sky_size_log2 = p->sky_size_log2;
 	Scene* s = new (std::nothrow) Scene();
 	if (!s)
 		return nullptr;
@@ -201,7 +207,7 @@ void sqwh_renderer_prepare_frame(Renderer* r, uint32_t width, uint32_t height, c
 	p.elevation = pose[4];
 	r->prepare_frame(width, height, p, fov);
 }
-void sqwh_renderer_draw_frame(Renderer* r) { r->draw_frame(); }
+void sqwh_renderer_draw_frame(Renderer* r, int color_bits) { r->draw_frame(color_bits == 32 ? 32 : 64); }
 
 // FrameInfo::lights of the next prepare_frame
 void sqwh_renderer_set_lights(Renderer* r, const sqwh_dynamic_light* lights, uint32_t n)

@@ -797,12 +797,113 @@ void make_model_skin(Pcg32& rng, uint32_t size, bool with_holes, HostImage& out)
 }
 } // namespace
 
+namespace
+{
+// One side of the sky box in both colour widths (SkyboxSideTexture<ColorT>, textures.rs:82-87): a vertical gradient with
+// value-noise clouds and, on side +X, a sun disc far above LDR white in the 64-bit version (HDR unit: 255 = white).
+void make_sky_side(Pcg32& rng, uint32_t size, uint32_t side, HostImage& out32, HostImage& out64)
+{
+	out32.kind = SQW_IMAGE_COLOR32;
+	out64.kind = SQW_IMAGE_COLOR64;
+	out32.width = out32.height = out64.width = out64.height = size;
+	out32.pixels.resize((size_t)size * size * 4);
+	out64.pixels.resize((size_t)size * size * 8);
+	uint32_t* p32 = reinterpret_cast<uint32_t*>(out32.pixels.data());
+	uint64_t* p64 = reinterpret_cast<uint64_t*>(out64.pixels.data());
+	const uint32_t cells = 8;
+	std::vector<float> lat(cells * cells);
+	for (float& v : lat)
+		v = rng.uniform();
+	for (uint32_t y = 0; y < size; ++y)
+		for (uint32_t x = 0; x < size; ++x)
+		{
+			const float u = ((float)x + 0.5f) / (float)size, v = ((float)y + 0.5f) / (float)size;
+			const float cloud = value_noise(rng, lat, cells, u, v);
+			const float up = side == 5 ? 1.0f : (side == 4 ? 0.0f : 1.0f - v); // sides: v runs downwards (-Z basis of draw_skybox)
+			float rgb[3] = {0.25f + 0.35f * (1.0f - up), 0.45f + 0.3f * (1.0f - up), 0.95f};
+			const float c = cloud > 0.55f ? (cloud - 0.55f) / 0.45f : 0.0f;
+			for (float& ch : rgb)
+				ch = ch * (1.0f - c) + c;
+			float hdr_scale = 1.6f;
+			if (side == 1)
+			{
+				const float dx = u - 0.6f, dy = v - 0.3f;
+				if (dx * dx + dy * dy < 0.004f)
+				{
+					rgb[0] = rgb[1] = 1.0f;
+					rgb[2] = 0.85f;
+					hdr_scale = 24.0f;
+				}
+			}
+			uint32_t c8[3];
+			uint64_t c16[3];
+			for (int i = 0; i < 3; ++i)
+			{
+				c8[i] = (uint32_t)std::fmin(rgb[i] * 255.0f, 255.0f);
+				c16[i] = (uint64_t)std::fmin(rgb[i] * 255.0f * hdr_scale, 65535.0f);
+			}
+			p32[x + (size_t)y * size] = 0xFF000000u | (c8[0] << 16) | (c8[1] << 8) | c8[2];
+			p64[x + (size_t)y * size] = (c16[0] << 32) | (c16[1] << 16) | c16[2];
+		}
+}
+
+// 2x2 box filter of a Color64 image (the 64-bit twin of build_texture_lite_mip, textures.rs:388-421: channel average)
+void build_color64_mip(HostImage& mip, const HostImage& prev)
+{
+	mip.kind = SQW_IMAGE_COLOR64;
+	mip.width = prev.width >> 1;
+	mip.height = prev.height >> 1;
+	mip.pixels.resize((size_t)mip.width * mip.height * 8);
+	const uint64_t* src = reinterpret_cast<const uint64_t*>(prev.pixels.data());
+	uint64_t* dst = reinterpret_cast<uint64_t*>(mip.pixels.data());
+	for (uint32_t y = 0; y < mip.height; ++y)
+		for (uint32_t x = 0; x < mip.width; ++x)
+		{
+			uint64_t r = 0;
+			for (int ch = 0; ch < 4; ++ch)
+			{
+				uint64_t sum = 0;
+				for (int dy = 0; dy < 2; ++dy)
+					for (int dx = 0; dx < 2; ++dx)
+						sum += (src[x * 2 + dx + (size_t)(y * 2 + dy) * prev.width] >> (16 * ch)) & 0xFFFF;
+				r |= ((sum >> 2) & 0xFFFF) << (16 * ch);
+			}
+			dst[x + (size_t)y * mip.width] = r;
+		}
+}
+} // namespace
+
 void generate_scene(const SceneParams& params, Scene& out)
 {
 	out = Scene{};
 	out.params = params;
 	Builder b(out);
 	b.run();
+	if (params.skybox && out.materials.size() >= 4)
+	{
+		// appended after the world images, so scenes without a sky keep their image ids
+		Material& sky = out.materials[out.materials.size() / 4]; // the first ceiling material (Builder::pick_material)
+		sky.is_skybox = true;
+		Pcg32 sky_rng(params.seed * 40503u + 7u);
+		const uint32_t size = 1u << std::min(std::max(params.sky_size_log2, 5u), 10u);
+		for (uint32_t side = 0; side < 6; ++side)
+		{
+			HostImage m32[NUM_MIPS], m64[NUM_MIPS];
+			make_sky_side(sky_rng, size, side, m32[0], m64[0]);
+			for (uint32_t k = 1; k < NUM_MIPS; ++k)
+			{
+				build_texture_lite_mip(m32[k], m32[k - 1]);
+				build_color64_mip(m64[k], m64[k - 1]);
+			}
+			for (uint32_t k = 0; k < NUM_MIPS; ++k)
+			{
+				sky.skybox_images[0][side][k] = (uint32_t)out.images.size();
+				out.images.push_back(std::move(m32[k]));
+				sky.skybox_images[1][side][k] = (uint32_t)out.images.size();
+				out.images.push_back(std::move(m64[k]));
+			}
+		}
+	}
 	// triangle-model fixtures and their skins (appended after the world images, so scenes without models keep their image ids)
 	Pcg32 rng(params.seed * 2654435761u + 99u);
 	for (uint32_t i = 0; i < params.num_models; ++i)

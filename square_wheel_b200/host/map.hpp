@@ -85,7 +85,8 @@ struct Material
 	uint32_t emissive_images[NUM_MIPS] = {0, 0, 0, 0, 0};
 	float emissive_light[3] = {0, 0, 0};
 	int32_t texture_shift[2] = {0, 0}; // MapMaterialsProcessor::get_texture_shift (scrolling), 0 when animations are off
-	bool is_skybox = false;
+	bool is_skybox = false; // SpecialMaterialEffect::Skybox (material.rs:118-132): polygons are not drawn, they open a window onto the sky box
+	uint32_t skybox_images[2][6][NUM_MIPS] = {}; // SkyboxSideTexture<Color32> / <Color64> mips of the six sides (-X +X -Y +Y -Z +Z)
 };
 
 struct SceneParams
@@ -99,6 +100,8 @@ struct SceneParams
 	float max_polygon_size = 128.0f; // split so that a lightmap stays <= 17 texels per side (bsp_builder.rs:1282)
 	uint32_t material_mode = 0;      // 0: mix per demo_materials.json (normal map + dielectric/metal specular), 1: plain (no normal map, roughness 1)
 	float emissive_fraction = 0.15f;
+	uint32_t skybox = 0;           // 1: the first ceiling material becomes a sky box material (6 sides, 32- and 64-bit, 5 mips)
+	uint32_t sky_size_log2 = 7;    // side of a sky box texture
 	uint32_t num_models = 0;       // triangle-model fixtures to generate (models.hpp)
 	uint32_t model_detail = 10;    // rings of the lathe grids: a model has about 4 * detail^2 triangles
 };

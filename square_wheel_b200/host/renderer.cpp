@@ -886,6 +886,7 @@ void Renderer::prepare_polygons_surfaces() // partial_renderer.rs:1327-1449 (lea
 {
 	current_frame_visible_polygons_.clear();
 	num_visible_surfaces_pixels_ = 0;
+	has_current_sky_ = false; // :1336
 	for (size_t i = 0; i < map_.leafs.size(); ++i)
 	{
 		ClippingPolygon bounds;
@@ -923,6 +924,22 @@ void Renderer::prepare_polygon_surface(const Vec3f clip_planes[8], size_t polygo
 	const size_t vertex_count = project_and_clip_polygon(clip_planes, polygon_vertices_transformed, polygon.num_vertices, vertices_2d);
 	if (vertex_count < 3)
 		return;
+
+	if (material.is_skybox) // :1511-1529: sky polygons are not drawn, they only grow the window the sky box is seen through
+	{
+		ClippingPolygon polygon_bounds = ClippingPolygon::from_point(vertices_2d[0]);
+		for (size_t i = 1; i < vertex_count; ++i)
+			polygon_bounds.extend_with_point(vertices_2d[i]);
+		if (has_current_sky_)
+			current_sky_bounds_.extend(polygon_bounds);
+		else
+		{
+			has_current_sky_ = true;
+			current_sky_material_ = polygon.texture;
+			current_sky_bounds_ = polygon_bounds;
+		}
+		return;
+	}
 
 	// DepthEquation::from_transformed_plane_equation (equations.rs:22-31)
 	const float plane_transformed_w = -plane_transformed.w;
@@ -1127,14 +1144,87 @@ void Renderer::build_surface_jobs() // the closure of build_polygons_surfaces (p
 	}
 }
 
-void Renderer::draw_frame() // PartialRenderer::draw_frame -> perform_rasterization, single-threaded branch (partial_renderer.rs:1207-1233)
+void Renderer::draw_frame(int color_bits) // PartialRenderer::draw_frame -> perform_rasterization, single-threaded branch (partial_renderer.rs:1207-1233)
 {
 	cmds_.clear();
 	polygon_points_.clear();
 	triangle_points_.clear();
 	const ClippingPolygon viewport_clipping_polygon = ClippingPolygon::from_box(0.0f, 0.0f, (float)width_, (float)height_);
+	draw_skybox(viewport_clipping_polygon, color_bits); // perform_rasterization_for_viewport_part (:1296): sky first
 	draw_tree(viewport_clipping_polygon);
 	stats_.num_draw_commands = (uint32_t)cmds_.size();
+}
+
+void Renderer::draw_skybox(const ClippingPolygon& viewport_clipping_polygon, int color_bits) // partial_renderer.rs:2311-2448 (skybox_rotation = identity)
+{
+	if (!has_current_sky_)
+		return;
+	ClippingPolygon bounds = current_sky_bounds_;
+	bounds.intersect(viewport_clipping_polygon);
+	if (!bounds.is_valid_and_non_empty())
+		return;
+	const Material& material = scene_.materials[current_sky_material_];
+	if (!material.is_skybox)
+		return;
+	static const float BOX_VERTICES[8][3] = {{-1, -1, -1}, {-1, -1, 1}, {-1, 1, -1}, {-1, 1, 1}, {1, -1, -1}, {1, -1, 1}, {1, 1, -1}, {1, 1, 1}};
+	struct Side
+	{
+		int v[4];
+		Vec3f normal, u, w;
+	};
+	static const Side bbox_polygons[6] = {
+		{{0, 1, 3, 2}, {1, 0, 0}, {0, 1, 0}, {0, 0, -1}},   // -X
+		{{4, 6, 7, 5}, {-1, 0, 0}, {0, -1, 0}, {0, 0, -1}}, // +X
+		{{0, 4, 5, 1}, {0, 1, 0}, {-1, 0, 0}, {0, 0, -1}},  // -Y
+		{{2, 3, 7, 6}, {0, -1, 0}, {1, 0, 0}, {0, 0, -1}},  // +Y
+		{{0, 2, 6, 4}, {0, 0, 1}, {1, 0, 0}, {0, -1, 0}},   // -Z
+		{{1, 5, 7, 3}, {0, 0, -1}, {1, 0, 0}, {0, 1, 0}},   // +Z
+	};
+	const float side_plane_dist = -1.0f, side_tc_shift = 1.0f;
+	const Mat4f skybox_matrix = get_object_matrix(camera_matrices_.position, Quaternion{});
+	Mat4f skybox_matrix_inverse = Mat4f::identity();
+	skybox_matrix.transpose().invert(skybox_matrix_inverse);
+	const Mat4f skybox_view_matrix = camera_matrices_.view_matrix * skybox_matrix;
+	const Mat4f skybox_planes_matrix = camera_matrices_.planes_matrix * skybox_matrix_inverse;
+	const float SKY_SCALE = 16384.0f;
+	Vec3f box_vertices_transformed[8];
+	for (int i = 0; i < 8; ++i)
+		box_vertices_transformed[i] = view_matrix_transform_vertex(skybox_view_matrix, Vec3f{BOX_VERTICES[i][0], BOX_VERTICES[i][1], BOX_VERTICES[i][2]} * SKY_SCALE);
+	Vec3f clip_planes[8];
+	bounds.get_clip_planes(clip_planes);
+	const int w = color_bits == 64 ? 1 : 0;
+	for (int side = 0; side < 6; ++side)
+	{
+		const Side& polygon = bbox_polygons[side];
+		const HostImage& mip0 = scene_.images[material.skybox_images[w][side][0]];
+		if (mip0.width == 0)
+			continue;
+		const Vec3f vertices_transformed[4] = {box_vertices_transformed[polygon.v[0]], box_vertices_transformed[polygon.v[1]], box_vertices_transformed[polygon.v[2]], box_vertices_transformed[polygon.v[3]]};
+		const Vec4f plane_transformed = skybox_planes_matrix * extend(polygon.normal, -side_plane_dist);
+		const float plane_transformed_w = -plane_transformed.w;
+		const float depth_equation[3] = {plane_transformed.x / plane_transformed_w, plane_transformed.y / plane_transformed_w, plane_transformed.z / plane_transformed_w};
+		const float tc_equation_scale = (float)mip0.width * 0.5f;
+		const Vec4f tc_basis_transformed[2] = {skybox_planes_matrix * (extend(polygon.u, side_tc_shift) * tc_equation_scale), skybox_planes_matrix * (extend(polygon.w, side_tc_shift) * tc_equation_scale)};
+		float tc_equation[6];
+		for (int i = 0; i < 2; ++i)
+		{
+			tc_equation[i] = tc_basis_transformed[i].x + tc_basis_transformed[i].w * depth_equation[0];
+			tc_equation[2 + i] = tc_basis_transformed[i].y + tc_basis_transformed[i].w * depth_equation[1];
+			tc_equation[4 + i] = tc_basis_transformed[i].z + tc_basis_transformed[i].w * depth_equation[2];
+		}
+		Vec2f vertices_2d[MAX_VERTICES];
+		const size_t vertex_count = project_and_clip_polygon(clip_planes, vertices_transformed, 4, vertices_2d);
+		if (vertex_count < 3)
+			continue;
+		const uint32_t mip = calculate_mip(vertices_2d, vertex_count, depth_equation, tc_equation, mip_bias_);
+		float tc_equation_scaled[6];
+		for (int i = 0; i < 6; ++i)
+			tc_equation_scaled[i] = tc_equation[i] * (1.0f / (float)(1 << mip));
+		const uint32_t image_id = material.skybox_images[w][side][mip];
+		const HostImage& side_texture = scene_.images[image_id];
+		const uint32_t size[2] = {side_texture.width, side_texture.width};
+		draw_polygon(clip_planes, vertices_transformed, 4, depth_equation, tc_equation_scaled, size, SQW_TEX_IMAGE, image_id, SQW_BLEND_NONE);
+	}
 }
 
 void Renderer::draw_tree(const ClippingPolygon& viewport_clipping_polygon) // partial_renderer.rs:2450-2517

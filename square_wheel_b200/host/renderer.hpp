@@ -130,8 +130,9 @@ public:
 	// Visibility + surface preparation + job list.  color_bits only selects nothing here (the lists are colour-agnostic) but
 	// is kept for symmetry with prepare_frame::<ColorT>.
 	void prepare_frame(uint32_t width, uint32_t height, const CameraPose& camera, float fov);
-	// BSP traversal -> ordered draw commands for the frame prepared last.
-	void draw_frame();
+	// Sky box (if any polygon of a sky material is in view), then BSP traversal -> ordered draw commands for the frame prepared
+	// last.  color_bits picks the sky box textures of the target's colour type (SkyboxSideTexture<ColorT>).
+	void draw_frame(int color_bits = 64);
 
 	const std::vector<sqw_surface_job>& jobs() const { return jobs_; }
 	uint64_t total_surface_pixels() const { return num_visible_surfaces_pixels_; }
@@ -172,6 +173,7 @@ private:
 	void prepare_polygons_surfaces();
 	void prepare_polygon_surface(const Vec3f clip_planes[8], size_t polygon_index);
 	void build_surface_jobs();
+	void draw_skybox(const ClippingPolygon& viewport_clipping_polygon, int color_bits);
 	void draw_tree(const ClippingPolygon& viewport_clipping_polygon);
 	void draw_leaf(const ClippingPolygon& bounds, uint32_t leaf_index);
 	void draw_polygon(
@@ -224,6 +226,10 @@ private:
 	std::vector<Triangle> dynamic_meshes_triangles_;
 	std::vector<sqw_triangle_point> triangle_points_;
 	LeafObjectsSorter objects_sorter_;
+
+	bool has_current_sky_ = false; // PartialRenderer::current_sky (partial_renderer.rs:35)
+	uint32_t current_sky_material_ = 0;
+	ClippingPolygon current_sky_bounds_;
 
 	std::vector<DrawPolygonData> polygons_data_;
 	std::vector<Vec3f> vertices_transformed_;

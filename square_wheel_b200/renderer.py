@@ -76,7 +76,7 @@ class Renderer:
 
     def prepare_frame(self, surface_info: SurfaceInfo, frame_info: FrameInfo, color_bits: int = 64):
         """prepare_frame::<ColorT> (renderer.rs:61): host preparation, then surface building on the GPU (seam S1)."""
-        hf = self.host.build_frame(surface_info.width, surface_info.height, frame_info.pose, frame_info.fov, frame_info.lights, frame_info.model_entities)
+        hf = self.host.build_frame(surface_info.width, surface_info.height, frame_info.pose, frame_info.fov, frame_info.lights, frame_info.model_entities, color_bits)
         view = self._get_view(surface_info, color_bits)
         key = (surface_info.width, surface_info.height, color_bits)
         if key not in self._frames:

@@ -30,6 +30,8 @@ class SceneParams(C.Structure):
         ("emissive_fraction", C.c_float),
         ("num_models", C.c_uint32),
         ("model_detail", C.c_uint32),
+        ("skybox", C.c_uint32),
+        ("sky_size_log2", C.c_uint32),
     ]
 
 
@@ -121,7 +123,7 @@ def lib() -> C.CDLL:
         l.sqwh_renderer_create.argtypes = [vp, C.POINTER(RendererConfig)]
         l.sqwh_renderer_destroy.argtypes = [vp]
         l.sqwh_renderer_prepare_frame.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.c_float]
-        l.sqwh_renderer_draw_frame.argtypes = [vp]
+        l.sqwh_renderer_draw_frame.argtypes = [vp, C.c_int]
         l.sqwh_renderer_frame_info.argtypes = [vp, C.POINTER(FrameInfo)]
         l.sqwh_renderer_set_lights.argtypes = [vp, vp, C.c_uint32]
         l.sqwh_renderer_set_models.restype = C.c_int
@@ -236,9 +238,9 @@ class HostRenderer:
         cfg = RendererConfig(1 if use_directional_lightmaps else 0, textures_mip_bias, 1 if clear_background else 0, 0, shadows_quality)
         self._handle = self._lib.sqwh_renderer_create(scene._handle, C.byref(cfg))
 
-    def build_frame(self, width: int, height: int, pose, fov: float = FOV_DEFAULT, lights=None, models=None) -> HostFrame:
+    def build_frame(self, width: int, height: int, pose, fov: float = FOV_DEFAULT, lights=None, models=None, color_bits: int = 64) -> HostFrame:
         """lights: FrameInfo::lights as an array of dynamic_light_dtype (or None); models: FrameInfo::model_entities as an array of
-        model_entity_dtype (or None)."""
+        model_entity_dtype (or None); color_bits: colour type of the target (only picks the sky box textures, SkyboxSideTexture<ColorT>)."""
         pose = np.ascontiguousarray(pose, np.float32)
         lt = np.ascontiguousarray(lights, dynamic_light_dtype) if lights is not None else np.zeros(0, dynamic_light_dtype)
         self._lib.sqwh_renderer_set_lights(self._handle, lt.ctypes.data_as(C.c_void_p), len(lt))
@@ -246,7 +248,7 @@ class HostRenderer:
         if self._lib.sqwh_renderer_set_models(self._handle, self.scene._handle, md.ctypes.data_as(C.c_void_p), len(md)) != 0:
             raise ValueError("model entity refers to a missing model, skin or frame")
         self._lib.sqwh_renderer_prepare_frame(self._handle, width, height, pose.ctypes.data_as(C.c_void_p), fov)
-        self._lib.sqwh_renderer_draw_frame(self._handle)
+        self._lib.sqwh_renderer_draw_frame(self._handle, color_bits)
         fi = FrameInfo()
         self._lib.sqwh_renderer_frame_info(self._handle, C.byref(fi))
         jobs = _array_from(self._lib.sqwh_renderer_jobs(self._handle), fi.num_jobs, N.surface_job_dtype)

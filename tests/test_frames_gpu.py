@@ -215,3 +215,46 @@ def test_config2_triangle_models(oracle_lib, color_bits):
     finally:
         r.close()
         sc.close()
+
+
+@pytest.mark.parametrize("color_bits", [32, 64])
+def test_config3_skybox_and_blended_models(oracle_lib, color_bits):
+    """configs[3] in miniature: sky box seen through the window of the sky-material polygons (six sides, own mip chain, 32- and
+    64-bit SkyboxSideTexture, drawn before the BSP walk) plus alpha-tested / alpha-blended / average / additive models on top,
+    tonemapped with bloom in the 64-bit case (the 64-bit sky holds a sun disc far above LDR white)."""
+    W, H = 640, 360
+    sc = S.Scene(seed=7, texture_size_log2=6, num_materials=8, skybox=1, sky_size_log2=7, num_models=6, model_detail=8)
+    r = Renderer(sc, RendererConfig(use_directional_lightmaps=True))
+    post = Postprocessor(r, PostprocessorConfig(bloom_sigma=1.0)) if color_bits == 64 else None
+    try:
+        path = sc.camera_path(64)
+        sky_cmds = 0
+        for k in (25, 26, 40, 3):
+            pose = path[k].copy()
+            pose[4] += 0.5  # look up: the sky windows are ceilings
+            if post:
+                post.get_hdr_buffer((W, H))
+            models = _models_ahead_of_camera(sc, pose, k, light_scale=0.45)
+            hf = r.prepare_frame(SurfaceInfo(W, H), FrameInfo(pose, model_entities=models), color_bits=color_bits)
+            pixels = np.zeros((H, W), np.uint32 if color_bits == 32 else np.uint64)
+            view = r.draw_frame(pixels)
+            sky_cmds += int(((hf.cmds["kind"] == N.CMD_POLYGON) & (hf.cmds["tex_kind"] == N.TEX_IMAGE)).sum())
+            oracle_lib.reset_assert_failures()
+            surf = oracle_lib.build_surfaces(color_bits, hf.jobs, None, None, hf.cam_pos, sc.images, sc.lightmaps, sc.directional_lightmaps, hf.total_surface_pixels)
+            fb = np.zeros((H, W), pixels.dtype)
+            if hf.needs_clear:
+                oracle_lib.fill(fb, S.BACKGROUND_COLOR64 if color_bits == 64 else S.BACKGROUND_COLOR32)
+            oracle_lib.draw(color_bits, fb, hf.cmds, hf.polygon_points, hf.triangle_points, surf, sc.images)
+            assert oracle_lib.assert_failures() == 0
+            assert_pixels_equal(pixels, fb, f"frame {k} picture with sky")
+            if post:
+                ldr = np.zeros((H, W), np.uint32)
+                exposure = post.current_exposure
+                post.perform_postprocessing(ldr, SurfaceInfo(W, H), (1.0, 1.0, 1.0), 1.0 / 60.0)
+                p = make_post_params(exposure, (1.0, 1.0, 1.0), 1.0, 0.25, 1, False)
+                want_ldr, _, _ = oracle_lib.postprocess(fb, p)
+                assert_pixels_equal(ldr, want_ldr, f"frame {k} tonemapped picture with sky")
+        assert sky_cmds >= 4  # sky sides really were drawn
+    finally:
+        r.close()
+        sc.close()

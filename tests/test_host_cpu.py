@@ -73,3 +73,46 @@ def test_oracle_renders_host_frame_without_gaps(scene, oracle_lib):
         assert oracle_lib.assert_failures() == 0
         assert np.count_nonzero(fb == 0xDEADBEEF) == 0
     r.close()
+
+
+def test_skybox_polygons_become_a_window(oracle_lib):
+    """Sky-material polygons are not drawn (no surface job, no draw command); instead the sky box sides are the FIRST commands
+    of the frame, textured from images of the target's colour type, and the frame still has no gaps."""
+    from square_wheel_b200 import _native as N
+
+    sc = S.Scene(seed=7, texture_size_log2=6, num_materials=8, skybox=1, sky_size_log2=6)
+    plain = S.Scene(seed=7, texture_size_log2=6, num_materials=8)
+    hr, hr_plain = S.HostRenderer(sc), S.HostRenderer(plain)
+    try:
+        W, H = 320, 180
+        path = sc.camera_path(64)
+        seen = 0
+        for k in (25, 26, 3):
+            pose = path[k].copy()
+            pose[4] += 0.5
+            hf = hr.build_frame(W, H, pose, color_bits=32)
+            hp = hr_plain.build_frame(W, H, pose, color_bits=32)
+            sky = hf.cmds["tex_kind"] == N.TEX_IMAGE
+            n_sky = int(sky.sum())
+            if n_sky == 0:
+                continue
+            seen += 1
+            assert np.all(sky[:n_sky]) and not np.any(sky[n_sky:])  # drawn before the BSP walk (partial_renderer.rs:1296)
+            assert len(hf.jobs) < len(hp.jobs) and len(hf.cmds) - n_sky < len(hp.cmds)  # the sky polygons themselves are gone
+            for c in hf.cmds[:n_sky]:
+                kind, px = sc.images[int(c["tex_ref"])]
+                assert kind == N.IMAGE_COLOR32 and px.shape == (int(c["tex_size"][1]), int(c["tex_size"][0]))
+            h64 = hr.build_frame(W, H, pose, color_bits=64)
+            assert all(sc.images[int(c["tex_ref"])][0] == N.IMAGE_COLOR64 for c in h64.cmds[:n_sky])
+            surf = oracle_lib.build_surfaces(32, hf.jobs, None, None, hf.cam_pos, sc.images, sc.lightmaps, sc.directional_lightmaps, hf.total_surface_pixels)
+            fb = np.zeros((H, W), np.uint32)
+            oracle_lib.reset_assert_failures()
+            oracle_lib.draw(32, fb, hf.cmds, hf.polygon_points, None, surf, sc.images)
+            assert oracle_lib.assert_failures() == 0
+            assert int((fb == 0).sum()) == 0
+        assert seen >= 2
+    finally:
+        hr.close()
+        hr_plain.close()
+        sc.close()
+        plain.close()
