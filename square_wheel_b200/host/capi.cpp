@@ -72,6 +72,29 @@ struct sqwh_model_entity // frame_info.rs:55-69 (ModelEntity) in plain C layout
 	uint32_t flags;       // 1 VIEW_MODEL, 2 ONLY_THIRD_PERSON_VIEW
 };
 
+struct sqwh_sprite // frame_info.rs:125-138 (Sprite) in plain C layout
+{
+	float position[3];
+	float angle;
+	float radius;
+	uint32_t skin;          // index of the scene's skin (TextureLiteWithMips)
+	uint32_t blending_mode;
+	uint32_t orientation;   // SpriteOrientation 0..3
+	float light_scale;
+	float light_add[3];
+};
+
+struct sqwh_decal // frame_info.rs:112-123 (Decal) in plain C layout
+{
+	float position[3];
+	float rotation[4]; // quaternion s, x, y, z; the decal is projected along its -X axis
+	float scale[3];
+	uint32_t skin;     // index of the scene's skin (TextureLiteWithMips)
+	uint32_t blending_mode;
+	float lightmap_light_scale;
+	float light_add[3];
+};
+
 struct sqwh_model_info
 {
 	uint32_t num_frames, num_meshes, num_vertices, num_triangles, kind, num_bones;
@@ -253,6 +276,51 @@ int sqwh_renderer_set_models(Renderer* r, const Scene* s, const sqwh_model_entit
 		v[i].flags = m.flags;
 	}
 	r->set_models(v.data(), v.size());
+	return 0;
+}
+
+// FrameInfo::sprites of the next prepare_frame.  Returns 0, or -1 for a bad skin / mode.
+int sqwh_renderer_set_sprites(Renderer* r, const Scene* s, const sqwh_sprite* sprites, uint32_t n)
+{
+	std::vector<Sprite> v(n);
+	for (uint32_t i = 0; i < n; ++i)
+	{
+		const sqwh_sprite& sp = sprites[i];
+		if (sp.skin >= s->model_skins.size() || sp.blending_mode > SQW_BLEND_ALPHA_BLEND || sp.orientation > SPRITE_ALIGN_TO_Z_AXIS_FACING_TOWARDS_CAMERA || !(sp.radius > 0.0f))
+			return -1;
+		v[i].position = {sp.position[0], sp.position[1], sp.position[2]};
+		v[i].angle = sp.angle;
+		v[i].radius = sp.radius;
+		for (uint32_t k = 0; k < NUM_MIPS; ++k)
+			v[i].texture_images[k] = s->model_skins[sp.skin][k];
+		v[i].blending_mode = (int)sp.blending_mode;
+		v[i].orientation = (SpriteOrientation)sp.orientation;
+		v[i].light_scale = sp.light_scale;
+		std::memcpy(v[i].light_add, sp.light_add, 12);
+	}
+	r->set_sprites(v.data(), v.size());
+	return 0;
+}
+
+// FrameInfo::decals of the next prepare_frame.  Returns 0, or -1 for a bad skin / mode.
+int sqwh_renderer_set_decals(Renderer* r, const Scene* s, const sqwh_decal* decals, uint32_t n)
+{
+	std::vector<Decal> v(n);
+	for (uint32_t i = 0; i < n; ++i)
+	{
+		const sqwh_decal& d = decals[i];
+		if (d.skin >= s->model_skins.size() || d.blending_mode > SQW_BLEND_ALPHA_BLEND)
+			return -1;
+		v[i].position = {d.position[0], d.position[1], d.position[2]};
+		v[i].rotation = Quaternion{d.rotation[0], {d.rotation[1], d.rotation[2], d.rotation[3]}};
+		v[i].scale = {d.scale[0], d.scale[1], d.scale[2]};
+		for (uint32_t k = 0; k < NUM_MIPS; ++k)
+			v[i].texture_images[k] = s->model_skins[d.skin][k];
+		v[i].blending_mode = (int)d.blending_mode;
+		v[i].lightmap_light_scale = d.lightmap_light_scale;
+		std::memcpy(v[i].light_add, d.light_add, 12);
+	}
+	r->set_decals(v.data(), v.size());
 	return 0;
 }
 

@@ -76,6 +76,7 @@ struct Material
 {
 	bool draw = true;
 	bool light = true;
+	bool decals = true; // receives decals (material.rs `decals`, partial_renderer.rs:2814)
 	bool shadow = true; // casts shadows in shadow maps (material.rs `shadow`, depth_renderer.rs:31)
 	bool has_diffuse = true;
 	int blending_mode = SQW_BLEND_NONE;

@@ -49,6 +49,39 @@ struct ModelEntity
 	BBox ordering_custom_bbox;
 };
 
+// frame_info.rs:125-147
+enum SpriteOrientation : uint32_t
+{
+	SPRITE_PARALLEL_TO_CAMERA_PLANE = 0,
+	SPRITE_FACING_TOWARDS_CAMERA = 1,
+	SPRITE_ALIGN_TO_Z_AXIS_PARALLEL_TO_CAMERA_PLANE = 2,
+	SPRITE_ALIGN_TO_Z_AXIS_FACING_TOWARDS_CAMERA = 3,
+};
+struct Sprite
+{
+	Vec3f position;
+	float angle = 0.0f;
+	float radius = 1.0f;
+	uint32_t texture_images[NUM_MIPS] = {0, 0, 0, 0, 0}; // TextureLiteWithMips: SQW_IMAGE_COLOR32 image ids
+	int blending_mode = SQW_BLEND_NONE;
+	SpriteOrientation orientation = SPRITE_PARALLEL_TO_CAMERA_PLANE;
+	float light_scale = 0.0f;
+	float light_add[3] = {0, 0, 0};
+};
+constexpr uint32_t MAX_SPRITE_TESSELATION_LEVEL = 4; // renderer_structs.rs:164
+
+// frame_info.rs:112-123: the decal primitive is a cube with half-size 1, textured along its -X axis
+struct Decal
+{
+	Vec3f position;
+	Quaternion rotation;
+	Vec3f scale = {1, 1, 1};
+	uint32_t texture_images[NUM_MIPS] = {0, 0, 0, 0, 0}; // TextureLiteWithMips: SQW_IMAGE_COLOR32 image ids
+	int blending_mode = SQW_BLEND_NONE;
+	float lightmap_light_scale = 0.0f;
+	float light_add[3] = {0, 0, 0};
+};
+
 // bsp_map_compact.rs:179-189
 struct LightGridElement
 {

@@ -372,6 +372,8 @@ Renderer::Renderer(const Scene& scene, const RendererConfig& config)
 	vertices_transformed_.resize(map_.vertices.size());
 	leaf_lights_.resize(map_.leafs.size());
 	leaf_models_.resize(map_.leafs.size());
+	leaf_sprites_.resize(map_.leafs.size());
+	leaf_decals_.resize(map_.leafs.size());
 	// get_leaf_clip_planes (renderer_structs.rs:167-226): portal and polygon planes of the leaf, normalised and deduplicated
 	leafs_planes_.resize(map_.leafs.size());
 	for (size_t leaf_index = 0; leaf_index < map_.leafs.size(); ++leaf_index)
@@ -879,6 +881,10 @@ void Renderer::prepare_frame(uint32_t width, uint32_t height, const CameraPose& 
 	position_models();              // renderer.rs:84 (dynamic_models_index.position_models)
 	prepare_dynamic_models();       // partial_renderer.rs:209
 	build_dynamic_models_buffers(); // :227
+	position_decals();              // renderer.rs:85
+	prepare_decals();               // partial_renderer.rs:205
+	position_sprites();             // renderer.rs:86
+	prepare_sprites();              // partial_renderer.rs:207
 	build_surface_jobs();        // :221
 }
 
@@ -1277,6 +1283,11 @@ void Renderer::draw_leaf(const ClippingPolygon& bounds, uint32_t leaf_index) // 
 			clip_planes, &vertices_transformed_[polygon.first_vertex], polygon.num_vertices, polygon_data.depth_equation, polygon_data.tex_coord_equation,
 			polygon_data.surface_size, SQW_TEX_SURFACE, (uint32_t)polygon_data.surface_pixels_offset, scene_.materials[polygon.texture].blending_mode);
 	}
+	// decals after all leaf polygons (:2567-2582)
+	const std::vector<uint32_t>& leaf_decals = leaf_decals_[leaf_index];
+	if (!leaf_decals.empty())
+		for (uint32_t polygon_index = leaf.first_polygon; polygon_index < leaf.first_polygon + leaf.num_polygons; ++polygon_index)
+			draw_polygon_decals(clip_planes, polygon_index, leaf_decals);
 	draw_leaf_objects(bounds, leaf_index);
 }
 
@@ -1364,6 +1375,32 @@ inline int32_t f32_to_fixed16(float x) // fixed_math.rs:31-34: Rust `as` (satura
 	if (v <= -2147483648.0f)
 		return INT32_MIN;
 	return (int32_t)v;
+}
+
+inline int32_t f32_to_i32_saturating(float v) // Rust `as i32`
+{
+	if (!(v == v))
+		return 0;
+	if (v >= 2147483648.0f)
+		return INT32_MAX;
+	if (v <= -2147483648.0f)
+		return INT32_MIN;
+	return (int32_t)v;
+}
+
+inline void get_light_cube_light_host(const float light_cube[6][3], Vec3f n, float total_light[3]) // light.rs:296-348
+{
+	total_light[0] = total_light[1] = total_light[2] = 0.0f;
+	const float comp[3] = {n.x, n.y, n.z};
+	for (int axis = 0; axis < 3; ++axis)
+	{
+		if (comp[axis] <= 0.0f)
+			for (int i = 0; i < 3; ++i)
+				total_light[i] += light_cube[axis * 2][i] * (-comp[axis]);
+		else
+			for (int i = 0; i < 3; ++i)
+				total_light[i] += light_cube[axis * 2 + 1][i] * comp[axis];
+	}
 }
 
 // triangle_models_rendering.rs:213-273
@@ -1590,12 +1627,16 @@ void Renderer::build_dynamic_models_buffers() // partial_renderer.rs:1122-1190
 	}
 }
 
-// The tail of draw_leaf (partial_renderer.rs:2584-2790) for the object kinds of this mirror (triangle models).
+// The tail of draw_leaf (partial_renderer.rs:2584-2790) for the object kinds of this mirror (triangle models and sprites).
 void Renderer::draw_leaf_objects(const ClippingPolygon& bounds, uint32_t leaf_index)
 {
 	const std::vector<uint32_t>& leaf_dynamic_models = leaf_models_[leaf_index];
-	if (leaf_dynamic_models.empty())
+	const std::vector<uint32_t>& leaf_sprites = leaf_sprites_[leaf_index];
+	const size_t total_objects = leaf_dynamic_models.size() + leaf_sprites.size();
+	if (total_objects == 0)
 		return;
+	Vec3f clip_planes[8];
+	bounds.get_clip_planes(clip_planes);
 	Plane leaf_clip_planes[MAX_LEAF_CLIP_PLANES];
 	const std::vector<Plane>& world = leafs_planes_[leaf_index];
 	const size_t num_planes = std::min(MAX_LEAF_CLIP_PLANES, world.size());
@@ -1604,13 +1645,19 @@ void Renderer::draw_leaf_objects(const ClippingPolygon& bounds, uint32_t leaf_in
 		const Vec4f t = camera_matrices_.planes_matrix * extend(world[i].vec, -world[i].dist);
 		leaf_clip_planes[i] = Plane{truncate(t), -t.w};
 	}
-	if (leaf_dynamic_models.size() == 1)
+	if (total_objects == 1)
 	{
-		const DynamicModelInfo entry = dynamic_model_to_dynamic_meshes_index_[leaf_dynamic_models[0]];
-		for (uint32_t m = entry.first_visible_mesh; m < entry.first_visible_mesh + entry.num_visible_meshes; ++m)
-			draw_mesh(bounds, leaf_clip_planes, num_planes, m);
+		if (leaf_dynamic_models.size() == 1)
+		{
+			const DynamicModelInfo entry = dynamic_model_to_dynamic_meshes_index_[leaf_dynamic_models[0]];
+			for (uint32_t m = entry.first_visible_mesh; m < entry.first_visible_mesh + entry.num_visible_meshes; ++m)
+				draw_mesh(bounds, leaf_clip_planes, num_planes, m);
+		}
+		else
+			draw_sprite(clip_planes, leaf_clip_planes, num_planes, leaf_sprites[0]);
 		return;
 	}
+	const uint32_t SUBMODEL_INDEX_ADD = 65536, DYNAMIC_MESH_INDEX_ADD = SUBMODEL_INDEX_ADD + 65536, SPRITE_INDEX_ADD = DYNAMIC_MESH_INDEX_ADD + 65536;
 	objects_sorter_.clear();
 	for (uint32_t dynamic_model_index : leaf_dynamic_models)
 	{
@@ -1618,11 +1665,613 @@ void Renderer::draw_leaf_objects(const ClippingPolygon& bounds, uint32_t leaf_in
 		const BBox bbox = model.has_ordering_custom_bbox ? model.ordering_custom_bbox : get_current_triangle_model_bbox(scene_.models[model.model], model.frames);
 		const DynamicModelInfo entry = dynamic_model_to_dynamic_meshes_index_[dynamic_model_index];
 		for (uint32_t m = entry.first_visible_mesh; m < entry.first_visible_mesh + entry.num_visible_meshes; ++m)
-			objects_sorter_.add_object(m, project_bbox(bbox, visible_dynamic_meshes_list_[m].camera_matrices));
+			objects_sorter_.add_object(m + DYNAMIC_MESH_INDEX_ADD, project_bbox(bbox, visible_dynamic_meshes_list_[m].camera_matrices));
+	}
+	for (uint32_t sprite_index : leaf_sprites)
+	{
+		const Sprite& sprite = frame_sprites_[sprite_index];
+		const Vec3f extend_vec = {sprite.radius, sprite.radius, sprite.radius};
+		objects_sorter_.add_object(sprite_index + SPRITE_INDEX_ADD, project_bbox(BBox::from_min_max(sprite.position - extend_vec, sprite.position + extend_vec), camera_matrices_));
 	}
 	objects_sorter_.sort_objects();
 	for (size_t i = 0; i < objects_sorter_.num_objects; ++i)
-		draw_mesh(bounds, leaf_clip_planes, num_planes, objects_sorter_.objects[i].first);
+	{
+		const uint32_t object_index = objects_sorter_.objects[i].first;
+		if (object_index >= SPRITE_INDEX_ADD)
+			draw_sprite(clip_planes, leaf_clip_planes, num_planes, object_index - SPRITE_INDEX_ADD);
+		else
+			draw_mesh(bounds, leaf_clip_planes, num_planes, object_index - DYNAMIC_MESH_INDEX_ADD);
+	}
+}
+
+// ---- decals --------------------------------------------------------------------------------------------------
+namespace
+{
+Vec3f get_line_plane_intersection(Vec3f v0, Vec3f v1, const Plane& plane) // clipping.rs:187-195
+{
+	const float dist0 = dot(v0, plane.vec) - plane.dist;
+	const float dist1 = dot(v1, plane.vec) - plane.dist;
+	const float dist_sum = dist1 - dist0;
+	const float k0 = dist0 / dist_sum;
+	const float k1 = dist1 / dist_sum;
+	return v0 * k1 - v1 * k0;
+}
+
+size_t clip_3d_polygon_by_plane(const Vec3f* polygon, size_t n, const Plane& plane, Vec3f* out, size_t out_cap) // clipping.rs:53-103
+{
+	const Vec3f* prev_v = &polygon[n - 1];
+	float prev_dist = dot(plane.vec, *prev_v);
+	size_t count = 0;
+	for (size_t i = 0; i < n; ++i)
+	{
+		const Vec3f* v = &polygon[i];
+		const float dist = dot(plane.vec, *v);
+		if (dist > plane.dist)
+		{
+			if (prev_dist < plane.dist)
+			{
+				out[count++] = get_line_plane_intersection(*prev_v, *v, plane);
+				if (count == out_cap)
+					break;
+			}
+			out[count++] = *v;
+			if (count == out_cap)
+				break;
+		}
+		else if (dist == plane.dist)
+		{
+			out[count++] = *v;
+			if (count == out_cap)
+				break;
+		}
+		else if (prev_dist > plane.dist)
+		{
+			out[count++] = get_line_plane_intersection(*prev_v, *v, plane);
+			if (count == out_cap)
+				break;
+		}
+		prev_v = v;
+		prev_dist = dist;
+	}
+	return count;
+}
+} // namespace
+
+void Renderer::position_decal_convex_hull_r(uint32_t id, const Vec3f* vertices, size_t n, uint32_t node_index) // dynamic_objects_index.rs:172-209
+{
+	if (node_index >= FIRST_LEAF_INDEX)
+	{
+		const uint32_t leaf_index = node_index - FIRST_LEAF_INDEX;
+		leaf_decals_[leaf_index].push_back(id);
+		decal_leafs_[id].push_back(leaf_index);
+		return;
+	}
+	const BSPNode& node = map_.nodes[node_index];
+	size_t vertices_front = 0;
+	for (size_t i = 0; i < n; ++i)
+		if (dot(node.plane.vec, vertices[i]) > node.plane.dist)
+			++vertices_front;
+	if (vertices_front > 0)
+		position_decal_convex_hull_r(id, vertices, n, node.children[0]);
+	if (vertices_front < n)
+		position_decal_convex_hull_r(id, vertices, n, node.children[1]);
+}
+
+void Renderer::position_decals() // dynamic_objects_index.rs:76-91
+{
+	for (auto& l : leaf_decals_)
+		l.clear();
+	decal_leafs_.assign(frame_decals_.size(), {});
+	for (size_t index = 0; index < frame_decals_.size(); ++index)
+	{
+		const Decal& decal = frame_decals_[index];
+		const Mat4f matrix = get_object_matrix(decal.position, decal.rotation) * Mat4f::from_nonuniform_scale(decal.scale.x, decal.scale.y, decal.scale.z);
+		Vec3f corners[8];
+		BBox::from_min_max({-1, -1, -1}, {1, 1, 1}).get_corners_vertices(corners);
+		for (Vec3f& c : corners)
+			c = truncate(matrix * extend(c, 1.0f));
+		position_decal_convex_hull_r((uint32_t)index, corners, 8, map_.root_node());
+	}
+}
+
+void Renderer::prepare_decals() // partial_renderer.rs:665-737
+{
+	decals_info_.assign(frame_decals_.size(), DecalInfo{});
+	for (size_t i = 0; i < frame_decals_.size(); ++i)
+	{
+		const Decal& decal = frame_decals_[i];
+		const Mat4f decal_matrix = get_object_matrix(decal.position, decal.rotation) * Mat4f::from_nonuniform_scale(decal.scale.x, decal.scale.y, decal.scale.z);
+		Mat4f inv_t = Mat4f::identity();
+		decal_matrix.transpose().invert(inv_t);
+		decals_info_[i].camera_planes_matrix = camera_matrices_.planes_matrix * inv_t;
+		LightCube light_cube;
+		if (decal.lightmap_light_scale > 0.0f)
+		{
+			const float min_square_distance = dot(decal.scale, decal.scale) * 0.25f;
+			for (size_t li = 0; li < frame_lights_.size(); ++li)
+			{
+				const DynamicLight& light = frame_lights_[li];
+				// lights with shadow maps: see get_model_light (their maps live on the device)
+				if (!dynamic_lights_info_[li].visible || light.shadow_type != SQW_SHADOW_NONE)
+					continue;
+				const Vec3f vec_to_light = light.position - decal.position;
+				const float square_dist = std::fmax(dot(vec_to_light, vec_to_light), min_square_distance);
+				const float inv_square_dist = 1.0f / square_dist;
+				const float light_inv_square_radius = 1.0f / (light.radius * light.radius);
+				if (inv_square_dist < light_inv_square_radius)
+					continue;
+				const float scale = 1.0f * (inv_square_dist - light_inv_square_radius);
+				const float light_scaled[3] = {light.color[0] * scale, light.color[1] * scale, light.color[2] * scale};
+				light_cube.add_light_sample(vec_to_light, light_scaled);
+			}
+		}
+		decals_info_[i].dynamic_light = light_cube.convert_into_light_grid_sample();
+	}
+}
+
+void Renderer::get_polygon_lightmap_light(const Polygon& polygon, Vec2f lightmap_coord, float total_light[3]) const // partial_renderer.rs:3807-3875
+{
+	total_light[0] = total_light[1] = total_light[2] = 0.0f;
+	if (polygon.lightmap_data_offset == 0 || map_.lightmaps_data.empty())
+		return;
+	const float* polygon_lightmap_data = map_.lightmaps_data.data() + (size_t)polygon.lightmap_data_offset * 3;
+	const int32_t lightmap_coord_int[2] = {f32_to_i32_saturating(std::floor(lightmap_coord.x)), f32_to_i32_saturating(std::floor(lightmap_coord.y))};
+	const int32_t lightmap_size[2] = {(int32_t)get_lightmap_size(polygon.tex_coord_min[0], polygon.tex_coord_max[0]), (int32_t)get_lightmap_size(polygon.tex_coord_min[1], polygon.tex_coord_max[1])};
+	float total_factor = 0.0f;
+	for (int dy = 0; dy <= 1; ++dy)
+	{
+		const int64_t y = (int64_t)lightmap_coord_int[1] + dy;
+		if (y < 0 || y >= lightmap_size[1])
+			continue;
+		const float factor_y = 1.0f - std::fabs(lightmap_coord.y - (float)y);
+		for (int dx = 0; dx <= 1; ++dx)
+		{
+			const int64_t x = (int64_t)lightmap_coord_int[0] + dx;
+			if (x < 0 || x >= lightmap_size[0])
+				continue;
+			const float factor_x = 1.0f - std::fabs(lightmap_coord.x - (float)x);
+			const float* lightmap_light = polygon_lightmap_data + (size_t)(x + y * lightmap_size[0]) * 3;
+			const float cur_sample_factor = factor_x * factor_y;
+			for (int i = 0; i < 3; ++i)
+				total_light[i] += cur_sample_factor * lightmap_light[i];
+			total_factor += cur_sample_factor;
+		}
+	}
+	if (total_factor < 1.0f)
+	{
+		const float inv_total_factor = 1.0f / total_factor;
+		for (int i = 0; i < 3; ++i)
+			total_light[i] *= inv_total_factor;
+	}
+}
+
+struct Renderer::DecalDrawContext
+{
+	const Decal* decal;
+	const Polygon* polygon;
+	const float* depth_equation;
+	float tc_equation[6];
+	float polygon_lightmap_equation[6];
+	float polygon_lightmap_coord_shift[2];
+	uint32_t image_id;
+	float dynamic_light[3];
+};
+
+void Renderer::draw_polygon_decals(const Vec3f clip_planes[8], uint32_t polygon_index, const std::vector<uint32_t>& current_decals) // partial_renderer.rs:2794-2957
+{
+	const DrawPolygonData& polygon_data = polygons_data_[polygon_index];
+	if (polygon_data.visible_frame != current_frame_)
+		return;
+	const Polygon& polygon = map_.polygons[polygon_index];
+	if (!scene_.materials[polygon.texture].decals)
+		return;
+	static const float CUBE_SIDES[6][3] = {{-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1}};
+	static const float DECAL_TEXTURE_BASIS[2][4] = {{0.0f, -0.5f, 0.0f, 0.5f}, {0.0f, 0.0f, -0.5f, 0.5f}};
+	const float MAX_ANGLE_COS = 0.1f;
+	Vec3f vertices_clipped0[MAX_VERTICES], vertices_clipped1[MAX_VERTICES];
+	Vec2f vertices_projected[MAX_VERTICES];
+	for (uint32_t decal_index : current_decals)
+	{
+		const Decal& decal = frame_decals_[decal_index];
+		const DecalInfo& decal_info = decals_info_[decal_index];
+		const float decal_angle_cos = dot(polygon_data.basis_normal, quaternion_rotate_vector(decal.rotation, Vec3f{-1, 0, 0}));
+		if (decal_angle_cos < MAX_ANGLE_COS)
+			continue;
+		const Mat4f& decal_planes_matrix = decal_info.camera_planes_matrix;
+		const Vec3f* src_vertices = &vertices_transformed_[polygon.first_vertex];
+		Vec3f *vc_src = vertices_clipped0, *vc_dst = vertices_clipped1;
+		size_t num_vertices = std::min((size_t)polygon.num_vertices, MAX_VERTICES);
+		for (size_t i = 0; i < num_vertices; ++i)
+			vc_src[i] = src_vertices[i];
+		bool clipped_away = false;
+		for (const float* n : CUBE_SIDES)
+		{
+			const Vec4f plane_vec = decal_planes_matrix * Vec4f{n[0], n[1], n[2], 1.0f};
+			num_vertices = clip_3d_polygon_by_plane(vc_src, num_vertices, Plane{truncate(plane_vec), -plane_vec.w}, vc_dst, MAX_VERTICES);
+			if (num_vertices < 3)
+			{
+				clipped_away = true;
+				break;
+			}
+			std::swap(vc_src, vc_dst);
+		}
+		if (clipped_away)
+			continue;
+		num_vertices = project_and_clip_polygon(clip_planes, vc_src, num_vertices, vertices_projected);
+		if (num_vertices < 3)
+			continue;
+		const HostImage& texture = scene_.images[decal.texture_images[0]];
+		const Vec4f b0 = {DECAL_TEXTURE_BASIS[0][0], DECAL_TEXTURE_BASIS[0][1], DECAL_TEXTURE_BASIS[0][2], DECAL_TEXTURE_BASIS[0][3]};
+		const Vec4f b1 = {DECAL_TEXTURE_BASIS[1][0], DECAL_TEXTURE_BASIS[1][1], DECAL_TEXTURE_BASIS[1][2], DECAL_TEXTURE_BASIS[1][3]};
+		const Vec4f tc_basis_transformed[2] = {decal_planes_matrix * (b0 * (float)texture.width), decal_planes_matrix * (b1 * (float)texture.height)};
+		const float* depth_equation = polygon_data.depth_equation;
+		float tc_equation[6];
+		for (int i = 0; i < 2; ++i)
+		{
+			tc_equation[i] = tc_basis_transformed[i].x + tc_basis_transformed[i].w * depth_equation[0];
+			tc_equation[2 + i] = tc_basis_transformed[i].y + tc_basis_transformed[i].w * depth_equation[1];
+			tc_equation[4 + i] = tc_basis_transformed[i].z + tc_basis_transformed[i].w * depth_equation[2];
+		}
+		const uint32_t mip = calculate_mip(vertices_projected, num_vertices, depth_equation, tc_equation, mip_bias_);
+		DecalDrawContext ctx;
+		ctx.decal = &decal;
+		ctx.polygon = &polygon;
+		ctx.depth_equation = depth_equation;
+		ctx.image_id = decal.texture_images[mip];
+		for (int i = 0; i < 6; ++i)
+			ctx.tc_equation[i] = tc_equation[i] * (1.0f / (float)(1 << mip));
+		const float polygon_lightmap_coord_scale = (float)(1 << polygon_data.mip) / (float)LIGHTMAP_SCALE;
+		for (int i = 0; i < 2; ++i)
+			ctx.polygon_lightmap_coord_shift[i] = (float)polygon_data.surface_tc_min[i] * polygon_lightmap_coord_scale - (float)(polygon.tex_coord_min[i] >> LIGHTMAP_SCALE_LOG2);
+		for (int i = 0; i < 6; ++i)
+			ctx.polygon_lightmap_equation[i] = polygon_data.tex_coord_equation[i] * polygon_lightmap_coord_scale;
+		get_light_cube_light_host(decal_info.dynamic_light.light_cube, polygon_data.basis_normal, ctx.dynamic_light);
+		const float dynamic_light_dir_normal_dot = std::fmax(dot(polygon_data.basis_normal, decal_info.dynamic_light.light_direction_vector_scaled), 0.0f);
+		for (int i = 0; i < 3; ++i)
+			ctx.dynamic_light[i] += dynamic_light_dir_normal_dot * decal_info.dynamic_light.directional_light_color[i];
+		for (size_t t = 0; t + 2 < num_vertices; ++t)
+		{
+			const Vec2f points[3] = {vertices_projected[0], vertices_projected[t + 1], vertices_projected[t + 2]};
+			subdivide_and_draw_decal_triangle(ctx, points, 0);
+		}
+	}
+}
+
+void Renderer::subdivide_and_draw_decal_triangle(const DecalDrawContext& ctx, const Vec2f points[3], size_t recursion_depth) // partial_renderer.rs:2959-3096
+{
+	const float* depth_equation = ctx.depth_equation;
+	Vec2f min_inv_z_point = points[0], max_inv_z_point = points[0];
+	float min_inv_z = sample_point(depth_equation, points[0]), max_inv_z = min_inv_z;
+	for (int i = 1; i < 3; ++i)
+	{
+		const float inv_z = sample_point(depth_equation, points[i]);
+		if (inv_z < min_inv_z)
+		{
+			min_inv_z = inv_z;
+			min_inv_z_point = points[i];
+		}
+		if (inv_z > max_inv_z)
+		{
+			max_inv_z = inv_z;
+			max_inv_z_point = points[i];
+		}
+	}
+	const size_t max_recursion_depth = 2;
+	if (recursion_depth >= max_recursion_depth || affine_texture_coordinates_interpolation_may_be_used(depth_equation, ctx.tc_equation, min_inv_z_point, max_inv_z_point))
+	{
+		const Decal& decal = *ctx.decal;
+		const HostImage& texture = scene_.images[ctx.image_id];
+		const float tc_eps = 1.0f / 32.0f;
+		const float min_tc[2] = {tc_eps, tc_eps};
+		const float max_tc[2] = {(float)texture.width - tc_eps, (float)texture.height - tc_eps};
+		sqw_triangle_point vertices_fixed[3];
+		for (int k = 0; k < 3; ++k)
+		{
+			const Vec2f src = points[k];
+			const float z = 1.0f / sample_point(depth_equation, src);
+			float light[3] = {decal.light_add[0], decal.light_add[1], decal.light_add[2]};
+			if (decal.lightmap_light_scale > 0.0f)
+			{
+				const float* le = ctx.polygon_lightmap_equation;
+				const Vec2f lightmap_coord = {
+					z * (le[0] * src.x + le[2] * src.y + le[4]) + ctx.polygon_lightmap_coord_shift[0], z * (le[1] * src.x + le[3] * src.y + le[5]) + ctx.polygon_lightmap_coord_shift[1]};
+				float lightmap_light[3];
+				get_polygon_lightmap_light(*ctx.polygon, lightmap_coord, lightmap_light);
+				for (int i = 0; i < 3; ++i)
+				{
+					light[i] += lightmap_light[i] * decal.lightmap_light_scale;
+					light[i] += ctx.dynamic_light[i];
+				}
+			}
+			const float* te = ctx.tc_equation;
+			vertices_fixed[k].x = f32_to_fixed16(src.x);
+			vertices_fixed[k].y = f32_to_fixed16(src.y);
+			vertices_fixed[k].tc[0] = f32_to_fixed16(std::fmin(std::fmax(z * (te[0] * src.x + te[2] * src.y + te[4]), min_tc[0]), max_tc[0]));
+			vertices_fixed[k].tc[1] = f32_to_fixed16(std::fmin(std::fmax(z * (te[1] * src.x + te[3] * src.y + te[5]), min_tc[1]), max_tc[1]));
+			for (int i = 0; i < 3; ++i)
+				vertices_fixed[k].light[i] = f32_to_fixed16(light[i]);
+		}
+		sqw_draw_cmd c;
+		std::memset(&c, 0, sizeof(c));
+		c.kind = SQW_CMD_TRIANGLE;
+		c.blend = (uint8_t)decal.blending_mode;
+		c.tex_kind = SQW_TEX_IMAGE;
+		c.tex_ref = ctx.image_id;
+		c.tex_size[0] = (int32_t)texture.width;
+		c.tex_size[1] = (int32_t)texture.height;
+		c.num_vertices = 3;
+		c.vertex_offset = (uint32_t)triangle_points_.size();
+		triangle_points_.insert(triangle_points_.end(), vertices_fixed, vertices_fixed + 3);
+		cmds_.push_back(c);
+		++stats_.num_triangles;
+		++stats_.num_decal_triangles;
+		return;
+	}
+	const Vec2f center0 = (points[0] + points[1]) / 2.0f, center1 = (points[1] + points[2]) / 2.0f, center2 = (points[2] + points[0]) / 2.0f;
+	const Vec2f triangles[4][3] = {{points[0], center0, center2}, {points[1], center1, center0}, {points[2], center2, center1}, {center0, center1, center2}};
+	for (const auto& triangle : triangles)
+		subdivide_and_draw_decal_triangle(ctx, triangle, recursion_depth + 1);
+}
+
+// ---- sprites -------------------------------------------------------------------------------------------------
+void Renderer::position_sprite_sphere_r(uint32_t id, Vec3f center, float radius, uint32_t node_index) // dynamic_objects_index.rs:211-243
+{
+	if (node_index >= FIRST_LEAF_INDEX)
+	{
+		const uint32_t leaf_index = node_index - FIRST_LEAF_INDEX;
+		leaf_sprites_[leaf_index].push_back(id);
+		sprite_leafs_[id].push_back(leaf_index);
+		return;
+	}
+	const BSPNode& node = map_.nodes[node_index];
+	const float scaled_radius = radius * magnitude(node.plane.vec);
+	const float scaled_dist = dot(center, node.plane.vec);
+	if (scaled_dist + scaled_radius >= node.plane.dist)
+		position_sprite_sphere_r(id, center, radius, node.children[0]);
+	if (scaled_dist - scaled_radius <= node.plane.dist)
+		position_sprite_sphere_r(id, center, radius, node.children[1]);
+}
+
+void Renderer::position_sprites() // dynamic_objects_index.rs:93-106
+{
+	for (auto& l : leaf_sprites_)
+		l.clear();
+	sprite_leafs_.assign(frame_sprites_.size(), {});
+	for (size_t index = 0; index < frame_sprites_.size(); ++index)
+		position_sprite_sphere_r((uint32_t)index, frame_sprites_[index].position, frame_sprites_[index].radius, map_.root_node());
+}
+
+void Renderer::prepare_sprites() // partial_renderer.rs:740-990
+{
+	sprites_info_.assign(frame_sprites_.size(), SpriteInfo{});
+	if (frame_sprites_.empty())
+		return;
+	Mat4f view_matrix_inverse = Mat4f::identity();
+	camera_matrices_.view_matrix.invert(view_matrix_inverse);
+	const Vec3f u_vec_base_initial = truncate(view_matrix_inverse * Vec4f{1, 0, 0, 0});
+	const Vec3f u_vec_base = u_vec_base_initial / magnitude(u_vec_base_initial);
+	const Vec3f v_vec_base_initial = truncate(view_matrix_inverse * Vec4f{0, 1, 0, 0});
+	const Vec3f v_vec_base = v_vec_base_initial / magnitude(v_vec_base_initial);
+	const Vec3f camera_direction = cross(u_vec_base, v_vec_base);
+	const Vec3f unit_x = {1, 0, 0}, minus_unit_z = {0, 0, -1};
+	for (size_t sprite_index = 0; sprite_index < frame_sprites_.size(); ++sprite_index)
+	{
+		if (sprite_leafs_[sprite_index].empty())
+			continue;
+		const Sprite& sprite = frame_sprites_[sprite_index];
+		Vec3f u_vec_normalized = u_vec_base, v_vec_normalized = v_vec_base;
+		switch (sprite.orientation)
+		{
+		case SPRITE_PARALLEL_TO_CAMERA_PLANE: break;
+		case SPRITE_FACING_TOWARDS_CAMERA:
+		{
+			const Vec3f vec_to_camera = camera_matrices_.position - sprite.position;
+			const Vec3f plane_normal = vec_to_camera / std::fmax(magnitude(vec_to_camera), 0.001f);
+			const Vec3f u_vec_projected_to_plane = u_vec_base - plane_normal * dot(u_vec_base, plane_normal);
+			const float u_vec_projected_len = magnitude(u_vec_projected_to_plane);
+			u_vec_normalized = u_vec_projected_len < 0.0001f ? unit_x : u_vec_projected_to_plane / u_vec_projected_len;
+			v_vec_normalized = cross(u_vec_normalized, plane_normal);
+			break;
+		}
+		case SPRITE_ALIGN_TO_Z_AXIS_PARALLEL_TO_CAMERA_PLANE:
+		{
+			v_vec_normalized = minus_unit_z;
+			const Vec3f u_vec = cross(v_vec_normalized, camera_direction);
+			const float u_vec_len = magnitude(u_vec);
+			u_vec_normalized = u_vec_len < 0.0001f ? unit_x : u_vec / u_vec_len;
+			break;
+		}
+		case SPRITE_ALIGN_TO_Z_AXIS_FACING_TOWARDS_CAMERA:
+		{
+			const Vec3f vec_to_camera = camera_matrices_.position - sprite.position;
+			v_vec_normalized = minus_unit_z;
+			const Vec3f u_vec = cross(vec_to_camera, v_vec_normalized);
+			const float u_vec_len = magnitude(u_vec);
+			u_vec_normalized = u_vec_len < 0.0001f ? unit_x : u_vec / u_vec_len;
+			break;
+		}
+		}
+		if (sprite.angle != 0.0f)
+		{
+			const float c = std::cos(sprite.angle), sn = std::sin(sprite.angle);
+			const Vec3f u2 = u_vec_normalized * c - v_vec_normalized * sn, v2 = u_vec_normalized * sn + v_vec_normalized * c;
+			u_vec_normalized = u2;
+			v_vec_normalized = v2;
+		}
+		const HostImage& texture_mip0 = scene_.images[sprite.texture_images[0]];
+		const float ratio_h_w = (float)texture_mip0.height / (float)texture_mip0.width;
+		const float step_u = sprite.radius * (1.0f / std::sqrt(1.0f + ratio_h_w * ratio_h_w)); // inv_sqrt_fast, portable branch
+		const float ratio_w_h = (float)texture_mip0.width / (float)texture_mip0.height;
+		const float step_v = sprite.radius * (1.0f / std::sqrt(1.0f + ratio_w_h * ratio_w_h));
+		const Vec3f u_vec = u_vec_normalized * step_u, v_vec = v_vec_normalized * step_v;
+		const Vec3f vertices[4] = {sprite.position + u_vec + v_vec, sprite.position + u_vec - v_vec, sprite.position - u_vec - v_vec, sprite.position - u_vec + v_vec};
+		SpriteInfo& info = sprites_info_[sprite_index];
+		for (int i = 0; i < 4; ++i)
+			info.vertices_projected[i] = view_matrix_transform_vertex(camera_matrices_.view_matrix, vertices[i]);
+		const Vec3f* vp = info.vertices_projected;
+		if (vp[0].z > 0.0f && vp[1].z > 0.0f && vp[2].z > 0.0f && vp[3].z > 0.0f)
+		{
+			Vec2f points[4];
+			for (int i = 0; i < 4; ++i)
+				points[i] = truncate(vp[i]) / vp[i].z;
+			const Vec2f d0 = points[0] - points[2], d1 = points[1] - points[3];
+			const float shortest_diagonal_square_len = std::fmin(dot(d0, d0), dot(d1, d1));
+			if (shortest_diagonal_square_len <= 0.0f)
+				info.mip = MAX_MIP;
+			else
+			{
+				const float tc_diagonal_square_diff = (float)texture_mip0.width * (float)texture_mip0.width + (float)texture_mip0.height * (float)texture_mip0.height;
+				const float d_tc_2 = tc_diagonal_square_diff / shortest_diagonal_square_len;
+				const float mip_f = std::log2(d_tc_2) * 0.5f + mip_bias_;
+				const float m = std::fmax(std::round(mip_f), 0.0f); // f32::round: half away from zero, like std::round
+				info.mip = std::min<uint32_t>(m >= 4294967296.0f ? 0xFFFFFFFFu : (uint32_t)m, MAX_MIP);
+			}
+		}
+		else
+			info.mip = 0;
+		const float min_z = std::fmin(std::fmin(vp[0].z, vp[1].z), std::fmin(vp[2].z, vp[3].z));
+		const float max_z = std::fmax(std::fmax(vp[0].z, vp[1].z), std::fmax(vp[2].z, vp[3].z));
+		if (min_z <= 0.0f)
+			info.tesselation_level = MAX_SPRITE_TESSELATION_LEVEL;
+		else
+		{
+			const float t = std::fmax((max_z / min_z - 1.0f) * 4.0f, 1.0f);
+			info.tesselation_level = std::min<uint32_t>(t >= 4294967296.0f ? 0xFFFFFFFFu : (uint32_t)t, MAX_SPRITE_TESSELATION_LEVEL);
+		}
+		std::memcpy(info.light, sprite.light_add, 12);
+		if (sprite.light_scale > 0.0f)
+		{
+			// fetch_light_from_grid: zero without a light grid (see get_model_light); dynamic lights without shadow maps (:934-980)
+			const float dynamic_lights_scale = sprite.light_scale * 0.5f;
+			const float min_square_distance = sprite.radius * sprite.radius;
+			for (size_t li = 0; li < frame_lights_.size(); ++li)
+			{
+				const DynamicLight& light = frame_lights_[li];
+				if (!dynamic_lights_info_[li].visible || light.shadow_type != SQW_SHADOW_NONE)
+					continue;
+				const Vec3f vec_to_light = light.position - sprite.position;
+				const float inv_square_dist = 1.0f / std::fmax(dot(vec_to_light, vec_to_light), min_square_distance);
+				const float light_inv_square_radius = 1.0f / (light.radius * light.radius);
+				if (inv_square_dist < light_inv_square_radius)
+					continue;
+				const float scale = dynamic_lights_scale * 1.0f * (inv_square_dist - light_inv_square_radius);
+				for (int i = 0; i < 3; ++i)
+					info.light[i] += scale * light.color[i];
+			}
+		}
+		++stats_.num_visible_sprites;
+	}
+}
+
+void Renderer::emit_triangle_fan(const ModelVertex2d* vertices, size_t num_vertices, const float* constant_light, uint32_t image_id, int blending_mode)
+{
+	const HostImage& texture = scene_.images[image_id];
+	sqw_triangle_point fixed[MAX_VERTICES];
+	for (size_t k = 0; k < num_vertices; ++k)
+	{
+		const float* light = constant_light ? constant_light : vertices[k].light;
+		fixed[k].x = f32_to_fixed16(vertices[k].pos.x);
+		fixed[k].y = f32_to_fixed16(vertices[k].pos.y);
+		fixed[k].tc[0] = f32_to_fixed16(vertices[k].tc.x);
+		fixed[k].tc[1] = f32_to_fixed16(vertices[k].tc.y);
+		for (int i = 0; i < 3; ++i)
+			fixed[k].light[i] = f32_to_fixed16(light[i]);
+	}
+	for (size_t t = 0; t + 2 < num_vertices; ++t)
+	{
+		sqw_draw_cmd c;
+		std::memset(&c, 0, sizeof(c));
+		c.kind = SQW_CMD_TRIANGLE;
+		c.blend = (uint8_t)blending_mode;
+		c.tex_kind = SQW_TEX_IMAGE;
+		c.tex_ref = image_id;
+		c.tex_size[0] = (int32_t)texture.width;
+		c.tex_size[1] = (int32_t)texture.height;
+		c.num_vertices = 3;
+		c.vertex_offset = (uint32_t)triangle_points_.size();
+		triangle_points_.push_back(fixed[0]);
+		triangle_points_.push_back(fixed[t + 1]);
+		triangle_points_.push_back(fixed[t + 2]);
+		cmds_.push_back(c);
+		++stats_.num_triangles;
+	}
+}
+
+void Renderer::draw_sprite(const Vec3f clip_planes[8], const Plane* leaf_clip_planes, size_t num_leaf_clip_planes, uint32_t sprite_index) // partial_renderer.rs:3290-3523
+{
+	const Sprite& sprite = frame_sprites_[sprite_index];
+	const SpriteInfo& sprite_info = sprites_info_[sprite_index];
+	const uint32_t image_id = sprite.texture_images[sprite_info.mip];
+	const HostImage& texture_mip = scene_.images[image_id];
+	const float texture_size[2] = {(float)texture_mip.width, (float)texture_mip.height};
+	ModelVertex3d vertices_clipped0[MAX_VERTICES] = {}, vertices_clipped1[MAX_VERTICES] = {};
+	ModelVertex3d *vc_src = vertices_clipped0, *vc_dst = vertices_clipped1;
+	const float tc_reduce = 1.0f / 16.0f;
+	const Vec2f tcs[4] = {{texture_size[0] - tc_reduce, texture_size[1] - tc_reduce}, {texture_size[0] - tc_reduce, tc_reduce}, {tc_reduce, tc_reduce}, {tc_reduce, texture_size[1] - tc_reduce}};
+	for (int i = 0; i < 4; ++i)
+	{
+		vc_src[i].pos = sprite_info.vertices_projected[i];
+		vc_src[i].tc = tcs[i];
+		std::memcpy(vc_src[i].light, sprite_info.light, 12);
+	}
+	const Plane z_near_plane = {{0.0f, 0.0f, 1.0f}, Z_NEAR};
+	ModelVertex2d vertices_projected0[MAX_VERTICES], vertices_projected1[MAX_VERTICES];
+	// clip one convex polygon held in vc_src by the near plane, the leaf planes and the 8 screen-space planes, then emit its fan
+	auto clip_and_emit = [&](size_t num_vertices, const float* constant_light) {
+		for (size_t pi = 0; pi <= num_leaf_clip_planes; ++pi)
+		{
+			num_vertices = clip_3d_model_polygon_by_plane(vc_src, num_vertices, pi == 0 ? z_near_plane : leaf_clip_planes[pi - 1], vc_dst, MAX_VERTICES);
+			if (num_vertices < 3)
+				return;
+			std::swap(vc_src, vc_dst);
+		}
+		ModelVertex2d *vp_src = vertices_projected0, *vp_dst = vertices_projected1;
+		for (size_t k = 0; k < num_vertices; ++k)
+		{
+			vp_src[k].pos = truncate(vc_src[k].pos) / vc_src[k].pos.z;
+			vp_src[k].tc = vc_src[k].tc;
+			std::memcpy(vp_src[k].light, vc_src[k].light, 12);
+		}
+		for (int pi = 0; pi < 8; ++pi)
+		{
+			num_vertices = clip_2d_model_polygon(vp_src, num_vertices, clip_planes[pi], vp_dst, MAX_VERTICES);
+			if (num_vertices < 3)
+				return;
+			std::swap(vp_src, vp_dst);
+		}
+		emit_triangle_fan(vp_src, num_vertices, constant_light, image_id, sprite.blending_mode);
+	};
+	if (sprite_info.tesselation_level <= 1)
+	{
+		clip_and_emit(4, nullptr);
+		return;
+	}
+	// grid tesselation (:3405-3520): bilinear sub-quads, each clipped on its own; the light is the sprite's constant
+	ModelVertex3d tesselated_vertices[(MAX_SPRITE_TESSELATION_LEVEL + 1) * (MAX_SPRITE_TESSELATION_LEVEL + 1)] = {};
+	const uint32_t level = sprite_info.tesselation_level, num_vertices_in_row = level + 1;
+	const float inv_step = 1.0f / (float)level;
+	const ModelVertex3d corners[4] = {vc_src[0], vc_src[1], vc_src[2], vc_src[3]};
+	for (uint32_t y = 0; y < num_vertices_in_row; ++y)
+	{
+		const float y_mix = (float)y * inv_step;
+		for (uint32_t x = 0; x < num_vertices_in_row; ++x)
+		{
+			const float x_mix = (float)x * inv_step;
+			const float weights[4] = {x_mix * y_mix, (1.0f - x_mix) * y_mix, (1.0f - x_mix) * (1.0f - y_mix), x_mix * (1.0f - y_mix)};
+			ModelVertex3d& dst_v = tesselated_vertices[x + y * num_vertices_in_row];
+			dst_v.pos = corners[0].pos * weights[0] + corners[1].pos * weights[1] + corners[2].pos * weights[2] + corners[3].pos * weights[3];
+			dst_v.tc = corners[0].tc * weights[0] + corners[1].tc * weights[1] + corners[2].tc * weights[2] + corners[3].tc * weights[3];
+		}
+	}
+	for (uint32_t x = 0; x < level; ++x)
+		for (uint32_t y = 0; y < level; ++y)
+		{
+			vc_src[0] = tesselated_vertices[x + y * num_vertices_in_row];
+			vc_src[1] = tesselated_vertices[x + (y + 1) * num_vertices_in_row];
+			vc_src[2] = tesselated_vertices[1 + x + (y + 1) * num_vertices_in_row];
+			vc_src[3] = tesselated_vertices[1 + x + y * num_vertices_in_row];
+			clip_and_emit(4, sprite_info.light);
+		}
 }
 
 void Renderer::draw_mesh(const ClippingPolygon& clipping_polygon, const Plane* leaf_clip_planes, size_t num_leaf_clip_planes, size_t visible_mesh_index) // partial_renderer.rs:3525-3717

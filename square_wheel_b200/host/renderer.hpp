@@ -67,6 +67,8 @@ struct RendererDebugStats
 	uint32_t mode_counts[3] = {0, 0, 0};
 	uint32_t num_visible_meshes = 0;
 	uint32_t num_triangles = 0; // SQW_CMD_TRIANGLE commands recorded
+	uint32_t num_visible_sprites = 0;
+	uint32_t num_decal_triangles = 0;
 };
 
 // frame_info.rs:149-168
@@ -144,6 +146,10 @@ public:
 	void set_lights(const DynamicLight* lights, size_t n) { frame_lights_.assign(lights, lights + n); }
 	// FrameInfo::model_entities for the next prepare_frame (frame_info.rs:14)
 	void set_models(const ModelEntity* models, size_t n) { frame_models_.assign(models, models + n); }
+	// FrameInfo::decals for the next prepare_frame (frame_info.rs:16)
+	void set_decals(const Decal* decals, size_t n) { frame_decals_.assign(decals, decals + n); }
+	// FrameInfo::sprites for the next prepare_frame (frame_info.rs:17)
+	void set_sprites(const Sprite* sprites, size_t n) { frame_sprites_.assign(sprites, sprites + n); }
 	const std::vector<sqw_triangle_point>& triangle_points() const { return triangle_points_; }
 	const std::vector<sqw_light>& lights() const { return lights_; }
 	const std::vector<sqw_depth_map>& depth_maps() const { return depth_maps_; }
@@ -168,6 +174,20 @@ private:
 	void build_dynamic_models_buffers();
 	ModelLightData get_model_light(const ModelEntity& model, const Mat4f& model_matrix) const;
 	void draw_leaf_objects(const ClippingPolygon& bounds, uint32_t leaf_index);
+	// decals: dynamic_objects_index.rs:76-91, partial_renderer.rs:665-737, :2794-3096, :3807-3875
+	void position_decals();
+	void position_decal_convex_hull_r(uint32_t id, const Vec3f* vertices, size_t n, uint32_t node_index);
+	void prepare_decals();
+	void draw_polygon_decals(const Vec3f clip_planes[8], uint32_t polygon_index, const std::vector<uint32_t>& current_decals);
+	struct DecalDrawContext;
+	void subdivide_and_draw_decal_triangle(const DecalDrawContext& ctx, const Vec2f points[3], size_t recursion_depth);
+	void get_polygon_lightmap_light(const Polygon& polygon, Vec2f lightmap_coord, float out[3]) const;
+	// sprites: dynamic_objects_index.rs:93-106, partial_renderer.rs:740-990, :3290-3523
+	void position_sprites();
+	void position_sprite_sphere_r(uint32_t id, Vec3f center, float radius, uint32_t node_index);
+	void prepare_sprites();
+	void draw_sprite(const Vec3f clip_planes[8], const Plane* leaf_clip_planes, size_t num_leaf_clip_planes, uint32_t sprite_index);
+	void emit_triangle_fan(const ModelVertex2d* vertices, size_t num_vertices, const float* constant_light, uint32_t image_id, int blending_mode);
 	void draw_mesh(const ClippingPolygon& clipping_polygon, const Plane* leaf_clip_planes, size_t num_leaf_clip_planes, size_t visible_mesh_index);
 	// partial_renderer.rs
 	void prepare_polygons_surfaces();
@@ -224,6 +244,23 @@ private:
 	std::vector<DynamicModelInfo> dynamic_model_to_dynamic_meshes_index_;
 	std::vector<ModelVertex3d> dynamic_meshes_vertices_;
 	std::vector<Triangle> dynamic_meshes_triangles_;
+	struct SpriteInfo // renderer_structs.rs:199-205
+	{
+		Vec3f vertices_projected[4];
+		float light[3] = {0, 0, 0};
+		uint32_t mip = 0, tesselation_level = 0;
+	};
+	struct DecalInfo // renderer_structs.rs:191-197
+	{
+		Mat4f camera_planes_matrix;
+		LightGridElement dynamic_light;
+	};
+	std::vector<Decal> frame_decals_;
+	std::vector<std::vector<uint32_t>> leaf_decals_, decal_leafs_; // DynamicObjectsIndex for decals
+	std::vector<DecalInfo> decals_info_;
+	std::vector<Sprite> frame_sprites_;
+	std::vector<std::vector<uint32_t>> leaf_sprites_, sprite_leafs_; // DynamicObjectsIndex for sprites
+	std::vector<SpriteInfo> sprites_info_;
 	std::vector<sqw_triangle_point> triangle_points_;
 	LeafObjectsSorter objects_sorter_;
 

@@ -43,6 +43,8 @@ class FrameInfo:
     color_modulate: tuple = (1.0, 1.0, 1.0)
     lights: Optional[np.ndarray] = None  # FrameInfo::lights (frame_info.rs:24) as scene.dynamic_light_dtype records
     model_entities: Optional[np.ndarray] = None  # FrameInfo::model_entities (frame_info.rs:14) as scene.model_entity_dtype records
+    sprites: Optional[np.ndarray] = None  # FrameInfo::sprites (frame_info.rs:17) as scene.sprite_dtype records
+    decals: Optional[np.ndarray] = None  # FrameInfo::decals (frame_info.rs:16) as scene.decal_dtype records
 
 
 @dataclass
@@ -76,7 +78,7 @@ class Renderer:
 
     def prepare_frame(self, surface_info: SurfaceInfo, frame_info: FrameInfo, color_bits: int = 64):
         """prepare_frame::<ColorT> (renderer.rs:61): host preparation, then surface building on the GPU (seam S1)."""
-        hf = self.host.build_frame(surface_info.width, surface_info.height, frame_info.pose, frame_info.fov, frame_info.lights, frame_info.model_entities, color_bits)
+        hf = self.host.build_frame(surface_info.width, surface_info.height, frame_info.pose, frame_info.fov, frame_info.lights, frame_info.model_entities, color_bits, frame_info.sprites, frame_info.decals)
         view = self._get_view(surface_info, color_bits)
         key = (surface_info.width, surface_info.height, color_bits)
         if key not in self._frames:

@@ -91,6 +91,18 @@ model_entity_dtype = np.dtype(
 assert model_entity_dtype.itemsize == 88
 MODEL_LIGHTING_DEFAULT, MODEL_LIGHTING_CONSTANT, MODEL_LIGHTING_ADVANCED = 0, 1, 2
 
+# frame_info.rs:125-147 Sprite (skin = index of the scene's TextureLiteWithMips fixtures; orientation = SpriteOrientation 0..3)
+sprite_dtype = np.dtype(
+    [("position", "<f4", (3,)), ("angle", "<f4"), ("radius", "<f4"), ("skin", "<u4"), ("blending_mode", "<u4"), ("orientation", "<u4"), ("light_scale", "<f4"), ("light_add", "<f4", (3,))]
+)
+assert sprite_dtype.itemsize == 48
+
+# frame_info.rs:112-123 Decal: a unit cube placed by position / rotation / scale, projected along its -X axis onto the polygons inside
+decal_dtype = np.dtype(
+    [("position", "<f4", (3,)), ("rotation", "<f4", (4,)), ("scale", "<f4", (3,)), ("skin", "<u4"), ("blending_mode", "<u4"), ("lightmap_light_scale", "<f4"), ("light_add", "<f4", (3,))]
+)
+assert decal_dtype.itemsize == 64
+
 
 class ModelInfo(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("num_frames", "num_meshes", "num_vertices", "num_triangles", "kind", "num_bones")] + [("bbox_min", C.c_float * 3), ("bbox_max", C.c_float * 3)]
@@ -128,6 +140,10 @@ def lib() -> C.CDLL:
         l.sqwh_renderer_set_lights.argtypes = [vp, vp, C.c_uint32]
         l.sqwh_renderer_set_models.restype = C.c_int
         l.sqwh_renderer_set_models.argtypes = [vp, vp, vp, C.c_uint32]
+        l.sqwh_renderer_set_decals.restype = C.c_int
+        l.sqwh_renderer_set_decals.argtypes = [vp, vp, vp, C.c_uint32]
+        l.sqwh_renderer_set_sprites.restype = C.c_int
+        l.sqwh_renderer_set_sprites.argtypes = [vp, vp, vp, C.c_uint32]
         l.sqwh_scene_model_info.restype = C.c_int
         l.sqwh_scene_model_info.argtypes = [vp, C.c_uint32, C.POINTER(ModelInfo)]
         for name in (
@@ -238,15 +254,21 @@ class HostRenderer:
         cfg = RendererConfig(1 if use_directional_lightmaps else 0, textures_mip_bias, 1 if clear_background else 0, 0, shadows_quality)
         self._handle = self._lib.sqwh_renderer_create(scene._handle, C.byref(cfg))
 
-    def build_frame(self, width: int, height: int, pose, fov: float = FOV_DEFAULT, lights=None, models=None, color_bits: int = 64) -> HostFrame:
+    def build_frame(self, width: int, height: int, pose, fov: float = FOV_DEFAULT, lights=None, models=None, color_bits: int = 64, sprites=None, decals=None) -> HostFrame:
         """lights: FrameInfo::lights as an array of dynamic_light_dtype (or None); models: FrameInfo::model_entities as an array of
-        model_entity_dtype (or None); color_bits: colour type of the target (only picks the sky box textures, SkyboxSideTexture<ColorT>)."""
+        model_entity_dtype (or None); sprites / decals: FrameInfo::sprites / ::decals as arrays of sprite_dtype / decal_dtype (or None); color_bits: colour type of the target (only picks the sky box textures, SkyboxSideTexture<ColorT>)."""
         pose = np.ascontiguousarray(pose, np.float32)
         lt = np.ascontiguousarray(lights, dynamic_light_dtype) if lights is not None else np.zeros(0, dynamic_light_dtype)
         self._lib.sqwh_renderer_set_lights(self._handle, lt.ctypes.data_as(C.c_void_p), len(lt))
         md = np.ascontiguousarray(models, model_entity_dtype) if models is not None else np.zeros(0, model_entity_dtype)
         if self._lib.sqwh_renderer_set_models(self._handle, self.scene._handle, md.ctypes.data_as(C.c_void_p), len(md)) != 0:
             raise ValueError("model entity refers to a missing model, skin or frame")
+        dc = np.ascontiguousarray(decals, decal_dtype) if decals is not None else np.zeros(0, decal_dtype)
+        if self._lib.sqwh_renderer_set_decals(self._handle, self.scene._handle, dc.ctypes.data_as(C.c_void_p), len(dc)) != 0:
+            raise ValueError("decal refers to a missing skin or has a bad mode")
+        sp = np.ascontiguousarray(sprites, sprite_dtype) if sprites is not None else np.zeros(0, sprite_dtype)
+        if self._lib.sqwh_renderer_set_sprites(self._handle, self.scene._handle, sp.ctypes.data_as(C.c_void_p), len(sp)) != 0:
+            raise ValueError("sprite refers to a missing skin or has a bad mode / radius")
         self._lib.sqwh_renderer_prepare_frame(self._handle, width, height, pose.ctypes.data_as(C.c_void_p), fov)
         self._lib.sqwh_renderer_draw_frame(self._handle, color_bits)
         fi = FrameInfo()

@@ -66,3 +66,54 @@ def assert_pixels_equal(got, want, what=""):
     if bad.size:
         i = int(bad[0])
         raise AssertionError(f"{what}: {bad.size} of {got.size} elements differ; first at {i}: got {int(got.reshape(-1)[i]):#x} want {int(want.reshape(-1)[i]):#x}")
+
+
+# ---- FrameInfo fixtures for the host mirror (decals, sprites) ---------------------------------------------------
+def decal_rotation_for_normal(axis):
+    """Quaternion (s, x, y, z) turning +X onto -axis, so that the decal's -X axis — the direction its texture is projected
+    AGAINST, compared with the polygon normal in draw_polygon_decals (partial_renderer.rs:2838-2846) — equals `axis`."""
+    d = -np.asarray(axis, np.float64)
+    x = np.array([1.0, 0.0, 0.0])
+    c = float(np.dot(x, d))
+    if c > 0.9999:
+        return (1.0, 0.0, 0.0, 0.0)
+    if c < -0.9999:
+        return (0.0, 0.0, 0.0, 1.0)
+    v = np.cross(x, d)
+    s = np.sqrt((1.0 + c) * 2.0)
+    return (s / 2.0, v[0] / s, v[1] / s, v[2] / s)
+
+
+def scatter_decals(scene_module, pose, n, seed, num_skins=4):
+    """n decal boxes around the camera, projected onto floors, ceilings and the four wall directions, all blend modes, lit by
+    the polygon's lightmap (even indices) or by a constant (odd indices)."""
+    r = np.random.default_rng(seed)
+    dc = np.zeros(n, scene_module.decal_dtype)
+    axes = [(1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1)]
+    for i in range(n):
+        dc[i]["position"] = pose[:3] + r.uniform(-160.0, 160.0, 3) * np.array([1.0, 1.0, 0.3])
+        dc[i]["rotation"] = decal_rotation_for_normal(axes[i % 6])
+        dc[i]["scale"] = (200.0, r.uniform(15.0, 45.0), r.uniform(15.0, 45.0))
+        dc[i]["skin"] = i % num_skins
+        dc[i]["blending_mode"] = (0, 4, 3, 4, 1, 2)[i % 6]
+        dc[i]["lightmap_light_scale"] = 1.0 if i % 2 == 0 else 0.0
+        dc[i]["light_add"] = (0.0, 0.0, 0.0) if i % 2 == 0 else (0.9, 0.8, 0.7)
+    return dc
+
+
+def sprites_ahead_of_camera(scene_module, pose, n, num_skins=4, light_scale=0.0):
+    """n billboards fanned out in front of the camera (forward = (-sin az, cos az, 0)): the four SpriteOrientation kinds, with
+    and without in-plane rotation, all blend modes; near ones get tesselated (partial_renderer.rs:896-909)."""
+    sp = np.zeros(n, scene_module.sprite_dtype)
+    az = float(pose[3])
+    for i in range(n):
+        a = az + (i - 0.5 * (n - 1)) * 0.12
+        sp[i]["position"] = pose[:3] + (18.0 + 11.0 * i) * np.array([-np.sin(a), np.cos(a), 0.0]) + np.array([0.0, 0.0, (i % 3 - 1) * 8.0])
+        sp[i]["radius"] = 10.0 + 2.0 * i
+        sp[i]["skin"] = i % num_skins
+        sp[i]["orientation"] = i % 4
+        sp[i]["angle"] = 0.3 * i if i % 2 else 0.0
+        sp[i]["blending_mode"] = (0, 3, 4, 1, 2, 3, 4, 0)[i % 8]
+        sp[i]["light_scale"] = light_scale
+        sp[i]["light_add"] = (0.8, 0.7, 0.9)
+    return sp

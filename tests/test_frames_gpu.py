@@ -258,3 +258,42 @@ def test_config3_skybox_and_blended_models(oracle_lib, color_bits):
     finally:
         r.close()
         sc.close()
+
+
+@pytest.mark.parametrize("color_bits", [32, 64])
+def test_config3_decals_and_sprites(oracle_lib, color_bits):
+    """configs[3] in miniature, second half: decals (the polygons inside a decal box, clipped by its six planes, fan-triangulated
+    and subdivided until affine texturing is accurate, lit through the polygon's lightmap) and sprites (four orientations,
+    tesselated when close) — all blend modes, interleaved with world polygons and models in the reference's leaf order."""
+    from common import scatter_decals, sprites_ahead_of_camera
+
+    W, H = 640, 360
+    sc = S.Scene(seed=7, texture_size_log2=6, num_materials=8, num_models=4, model_detail=6)
+    r = Renderer(sc, RendererConfig(use_directional_lightmaps=True))
+    try:
+        path = sc.camera_path(64)
+        triangles = 0
+        for k in (0, 12, 33):
+            lights = _lights_along_path(path, 3, 9)
+            lights["shadow_type"] = N.SHADOW_NONE
+            lights["position"] = path[k][:3] + np.array([[20, 30, 10], [-40, 60, 0], [10, 90, -20]], np.float32)
+            fi = FrameInfo(
+                path[k], lights=lights, model_entities=_models_ahead_of_camera(sc, path[k], k)[:2], sprites=sprites_ahead_of_camera(S, path[k], 8, light_scale=0.5),
+                decals=scatter_decals(S, path[k], 48, k),
+            )
+            hf = r.prepare_frame(SurfaceInfo(W, H), fi, color_bits=color_bits)
+            pixels = np.zeros((H, W), np.uint32 if color_bits == 32 else np.uint64)
+            r.draw_frame(pixels)
+            triangles += int((hf.cmds["kind"] == N.CMD_TRIANGLE).sum())
+            oracle_lib.reset_assert_failures()
+            surf = oracle_lib.build_surfaces(color_bits, hf.jobs, hf.lights, None, hf.cam_pos, sc.images, sc.lightmaps, sc.directional_lightmaps, hf.total_surface_pixels)
+            fb = np.zeros((H, W), pixels.dtype)
+            if hf.needs_clear:
+                oracle_lib.fill(fb, S.BACKGROUND_COLOR64 if color_bits == 64 else S.BACKGROUND_COLOR32)
+            oracle_lib.draw(color_bits, fb, hf.cmds, hf.polygon_points, hf.triangle_points, surf, sc.images)
+            assert oracle_lib.assert_failures() == 0
+            assert_pixels_equal(pixels, fb, f"frame {k} picture with decals and sprites")
+        assert triangles > 300
+    finally:
+        r.close()
+        sc.close()

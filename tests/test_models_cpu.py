@@ -135,3 +135,51 @@ def test_default_lighting_uses_only_shadowless_dynamic_lights(scene):
         assert np.all(hf.triangle_points["light"] == 0)
     finally:
         hr.close()
+
+
+def test_sprites_and_decals_emit_clipped_lit_triangles(scene, oracle_lib):
+    """Sprites: a quad (2 triangles) or a tesselated grid, constant light = light_add (+ dynamic lights when light_scale > 0),
+    texture coordinates inside the chosen mip.  Decals: triangles only on polygons facing the decal, texture coordinates
+    clamped to [1/32, size - 1/32] (partial_renderer.rs:3004-3008), light = lightmap sample or light_add."""
+    from common import scatter_decals, sprites_ahead_of_camera
+
+    W, H = 480, 270
+    hr = S.HostRenderer(scene)
+    try:
+        path = scene.camera_path(32)
+        n_sprite = n_decal = 0
+        for k in (0, 7, 19):
+            base = hr.build_frame(W, H, path[k])
+            hs = hr.build_frame(W, H, path[k], sprites=sprites_ahead_of_camera(S, path[k], 8))
+            tri = hs.cmds[hs.cmds["kind"] == N.CMD_TRIANGLE]
+            assert hs.cmds[hs.cmds["kind"] == N.CMD_POLYGON].tobytes() == base.cmds.tobytes()
+            if len(tri):
+                n_sprite += len(tri)
+                light = hs.triangle_points["light"].astype(np.float64) / 65536.0
+                np.testing.assert_allclose(light, np.broadcast_to([0.8, 0.7, 0.9], light.shape), atol=2e-5)  # light_scale = 0: light_add only
+                tc = hs.triangle_points["tc"].astype(np.float64) / 65536.0
+                size = np.repeat(tri["tex_size"], 3, axis=0)
+                assert np.all(tc >= 1.0 / 16.0 - 1e-3) and np.all(tc <= size - 1.0 / 16.0 + 1e-3)  # tc_reduce (:3311)
+            hd = hr.build_frame(W, H, path[k], decals=scatter_decals(S, path[k], 48, k))
+            tri = hd.cmds[hd.cmds["kind"] == N.CMD_TRIANGLE]
+            assert hd.cmds[hd.cmds["kind"] == N.CMD_POLYGON].tobytes() == base.cmds.tobytes()
+            if len(tri):
+                n_decal += len(tri)
+                tc = hd.triangle_points["tc"].astype(np.float64) / 65536.0
+                size = np.repeat(tri["tex_size"], 3, axis=0)
+                assert np.all(tc >= 1.0 / 32.0 - 1e-4) and np.all(tc <= size - 1.0 / 32.0 + 1e-4)
+                x = hd.triangle_points["x"].astype(np.float64) / 65536.0
+                y = hd.triangle_points["y"].astype(np.float64) / 65536.0
+                assert x.min() > -1.0 and x.max() < W + 1.0 and y.min() > -1.0 and y.max() < H + 1.0
+                assert np.all(hd.triangle_points["light"] >= 0)
+                fb = np.zeros((H, W), np.uint32)
+                oracle_lib.reset_assert_failures()
+                oracle_lib.draw(32, fb, tri, None, hd.triangle_points, None, scene.images)
+                assert oracle_lib.assert_failures() == 0
+        assert n_sprite >= 16 and n_decal >= 40
+        with pytest.raises(ValueError):
+            bad = sprites_ahead_of_camera(S, path[0], 2)
+            bad[1]["radius"] = 0.0
+            hr.build_frame(W, H, path[0], sprites=bad)
+    finally:
+        hr.close()
