@@ -410,7 +410,8 @@ int sqw_profile_end(sqw_ctx* ctx, sqw_kernel_times* out);
 
 /* Device self-test of the arithmetic shortcuts the kernels take (synchronises): exhaustive comparison of the reciprocal-based
  * `2^31 / (inv_z >> 8)` of the full-perspective pixel loop (rasterizer.rs:430) with the plain u32 division for every
- * divisor below 2^24.  SQW_OK, or SQW_ERR_CUDA with the mismatch count in sqw_last_error(). */
+ * divisor below 2^24, and 2^26 hashed + edge-case operand pairs of the double-precision-assisted fixed16_div (fixed_math.rs:56)
+ * against the plain 64-bit division.  SQW_OK, or SQW_ERR_CUDA with the mismatch count in sqw_last_error(). */
 int sqw_self_test(sqw_ctx* ctx);
 
 /* Average colour produced by the last post stage of this view (synchronises). */

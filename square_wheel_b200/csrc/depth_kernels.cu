@@ -72,46 +72,70 @@ __global__ void __launch_bounds__(128) depth_setup_kernel(
 	spans[cd.span_base + r] = out;
 }
 
+// One WARP per shadow-map row (lane = pixel x mod 32, so a pixel always belongs to the same lane and the fills of a row
+// stay in submission order without any synchronisation).  The fills that own a span on the row are found 32 at a time
+// (one candidate per lane, ballot); each span is then replayed exactly like DepthRasterizer::fill_polygon's pixel loop
+// (rasterizer.rs:1455-1466): the running sum `inv_z += d_inv_z_dx` is carried ALONG the span by warp-uniform additions —
+// one per pixel, each lane keeping the value of its own pixel — so the float rounding sequence is the reference's, and
+// every store / max is a coalesced 128-byte row segment.
 __global__ void __launch_bounds__(128) depth_resolve_kernel(
 	const sqw_depth_cmd* __restrict__ cmds, const DepthCmdDev* __restrict__ cmd_dev, const sqw_depth_map* __restrict__ maps, const uint2* __restrict__ row_chunks,
 	uint32_t num_row_chunks, const DepthSpan* __restrict__ spans, float* __restrict__ shadow_maps)
 {
-	const uint32_t chunk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	const uint32_t warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	const uint32_t chunk = warp_global >> 5;
 	if (chunk >= num_row_chunks)
 		return;
-	const uint2 ch = __ldg(row_chunks + chunk); // {map, first row of the chunk}
+	const int lane = threadIdx.x & 31;
+	const uint2 ch = __ldg(row_chunks + chunk); // {map, first row of the 32-row chunk}
 	const sqw_depth_map map = maps[ch.x];
-	const int32_t row = (int32_t)(ch.y + (threadIdx.x & 31));
+	const int32_t row = (int32_t)(ch.y + (warp_global & 31));
 	if (row >= (int32_t)map.height)
 		return;
 	float* const line = shadow_maps + (size_t)map.offset + (size_t)row * map.width;
+	const int32_t width = (int32_t)map.width;
 	if (map.flags & SQW_DEPTH_MAP_CLEAR)
-		for (uint32_t x = 0; x < map.width; ++x)
+		for (int32_t x = lane; x < width; x += 32)
 			line[x] = map.clear_value;
 
-	for (uint32_t ci = map.first_cmd; ci < map.first_cmd + map.num_cmds; ++ci)
+	const uint32_t cmd_end = map.first_cmd + map.num_cmds;
+	for (uint32_t base = map.first_cmd; base < cmd_end; base += 32)
 	{
-		const DepthCmdDev cd = cmd_dev[ci];
-		if (row < (int32_t)cd.y0 || row >= (int32_t)cd.y1)
-			continue;
-		const DepthSpan s = spans[cd.span_base + (uint32_t)(row - (int32_t)cd.y0)];
-		if (s.x0 >= s.x1)
-			continue;
-		float inv_z = s.inv_z;
-		if (cd.depth_test)
+		const uint32_t ci = base + (uint32_t)lane;
+		DepthSpan s;
+		s.x0 = s.x1 = 0;
+		s.inv_z = s.d_inv_z_dx = 0.0f;
+		uint32_t depth_test = 0;
+		if (ci < cmd_end)
 		{
-			for (int32_t x = s.x0; x < s.x1; ++x)
+			const DepthCmdDev cd = cmd_dev[ci];
+			if (row >= (int32_t)cd.y0 && row < (int32_t)cd.y1)
 			{
-				line[x] = fmaxf(inv_z, line[x]); // f32::max (rasterizer.rs:1459)
-				inv_z = __fadd_rn(inv_z, s.d_inv_z_dx);
+				s = spans[cd.span_base + (uint32_t)(row - (int32_t)cd.y0)];
+				depth_test = cd.depth_test;
 			}
 		}
-		else
+		uint32_t pending = __ballot_sync(0xFFFFFFFFu, s.x0 < s.x1);
+		while (pending)
 		{
-			for (int32_t x = s.x0; x < s.x1; ++x)
+			const int src = __ffs(pending) - 1;
+			pending &= pending - 1;
+			const int32_t x0 = __shfl_sync(0xFFFFFFFFu, (int32_t)s.x0, src), x1 = __shfl_sync(0xFFFFFFFFu, (int32_t)s.x1, src);
+			const float d = __shfl_sync(0xFFFFFFFFu, s.d_inv_z_dx, src);
+			const uint32_t test = __shfl_sync(0xFFFFFFFFu, depth_test, src);
+			float v = __shfl_sync(0xFFFFFFFFu, s.inv_z, src); // value of pixel x0
+			for (int32_t cx = x0 & ~31; cx < x1; cx += 32)
 			{
-				line[x] = inv_z;
-				inv_z = __fadd_rn(inv_z, s.d_inv_z_dx);
+				const int32_t start = max(x0, cx), end = min(cx + 32, x1); // v = value of pixel `start`
+				const int32_t x = cx + lane;
+				float mine = 0.0f;
+				for (int32_t px = start; px < end; ++px) // warp-uniform trip count
+				{
+					mine = px == x ? v : mine;
+					v = __fadd_rn(v, d);
+				}
+				if (x >= start && x < end)
+					line[x] = test ? fmaxf(mine, line[x]) : mine; // f32::max when depth-tested (rasterizer.rs:1459)
 			}
 		}
 	}
@@ -119,12 +143,12 @@ __global__ void __launch_bounds__(128) depth_resolve_kernel(
 	if ((map.flags & SQW_DEPTH_MAP_PROJECTOR_CIRCLE) && map.width == map.height)
 	{
 		// make_shadow_map_circle (light.rs:133-157)
-		const int32_t size = (int32_t)map.width, radius = size / 2;
+		const int32_t size = width, radius = size / 2;
 		const int32_t dy = row - radius;
 		const int32_t dx = radius - min((int32_t)ceilf(__fsqrt_rn((float)max(radius * radius - dy * dy, 0))), radius);
-		for (int32_t x = 0; x < dx; ++x)
+		for (int32_t x = lane; x < dx; x += 32)
 			line[x] = 1.0e24f;
-		for (int32_t x = size - dx; x < size; ++x)
+		for (int32_t x = size - dx + lane; x < size; x += 32)
 			line[x] = 1.0e24f;
 	}
 }
@@ -143,7 +167,7 @@ cudaError_t launch_depth_resolve(const DepthLaunch& l, cudaStream_t stream)
 {
 	if (l.num_row_chunks == 0)
 		return cudaSuccess;
-	depth_resolve_kernel<<<(l.num_row_chunks + 3) / 4, 128, 0, stream>>>(l.cmds, l.cmd_dev, l.maps, l.row_chunks, l.num_row_chunks, l.spans, l.shadow_maps);
+	depth_resolve_kernel<<<l.num_row_chunks * 8, 128, 0, stream>>>(l.cmds, l.cmd_dev, l.maps, l.row_chunks, l.num_row_chunks, l.spans, l.shadow_maps);
 	return cudaGetLastError();
 }
 

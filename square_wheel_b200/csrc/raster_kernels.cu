@@ -495,48 +495,54 @@ __device__ void bin_band(
 	const int32_t band_y0 = band * SQW_TILE_H, band_y1 = band_y0 + SQW_TILE_H;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const uint32_t band_begin = band_offsets[band];
-	if (threadIdx.x == 0)
-		s_running = band_begin;
-	__syncthreads();
-	for (uint32_t base = 0; base < num_cmds; base += SQW_SETUP_THREADS)
+	// Every warp scans a contiguous quarter of the command list twice — count, then (after ONE barrier for the warp
+	// offsets) write — instead of the whole CTA synchronising three times per 128 commands.
+	const uint32_t per_warp = ((num_cmds + WARPS - 1) / WARPS + 31) & ~31u;
+	const uint32_t scan_begin = min((uint32_t)warp * per_warp, num_cmds), scan_end = min(scan_begin + per_warp, num_cmds);
+	auto touches = [&](uint32_t i, uint32_t& bx) {
+		const uint2 w = __ldg(reinterpret_cast<const uint2*>(cmd_dev + i)); // y0,y1,bx0,bx1
+		const int32_t y0 = (int16_t)(w.x & 0xFFFF), y1 = (int16_t)(w.x >> 16);
+		bx = w.y;
+		return y0 < y1 && y0 < band_y1 && y1 > band_y0;
+	};
+	uint32_t count = 0;
+	for (uint32_t base = scan_begin; base < scan_end; base += 32)
 	{
-		const uint32_t i = base + threadIdx.x;
-		bool hit = false;
-		uint32_t bx = 0;
-		if (i < num_cmds)
-		{
-			const uint2 w = __ldg(reinterpret_cast<const uint2*>(cmd_dev + i)); // y0,y1,bx0,bx1
-			const int32_t y0 = (int16_t)(w.x & 0xFFFF), y1 = (int16_t)(w.x >> 16);
-			hit = y0 < y1 && y0 < band_y1 && y1 > band_y0;
-			bx = w.y;
-		}
-		const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, hit);
-		if (lane == 0)
-			s_warp_counts[warp] = __popc(ballot);
-		__syncthreads();
-		uint32_t offset = s_running;
-		for (int w = 0; w < warp; ++w)
+		uint32_t bx;
+		const bool hit = base + lane < scan_end && touches(base + lane, bx);
+		count += __popc(__ballot_sync(0xFFFFFFFFu, hit));
+	}
+	if (lane == 0)
+		s_warp_counts[warp] = count;
+	__syncthreads();
+	uint32_t offset = band_begin, total = 0;
+	for (int w = 0; w < WARPS; ++w)
+	{
+		if (w < warp)
 			offset += s_warp_counts[w];
+		total += s_warp_counts[w];
+	}
+	for (uint32_t base = scan_begin; base < scan_end; base += 32)
+	{
+		uint32_t bx = 0;
+		const bool hit = base + lane < scan_end && touches(base + lane, bx);
+		const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, hit);
 		if (hit)
 		{
 			const uint32_t pos = offset + __popc(ballot & ((1u << lane) - 1));
-			band_lists[pos] = i;
+			band_lists[pos] = base + lane;
 			if (pos - band_begin < SQW_BIN_CACHE)
 			{
-				s_idx[pos - band_begin] = i;
+				s_idx[pos - band_begin] = base + lane;
 				s_bx[pos - band_begin] = bx;
 			}
 		}
-		__syncthreads();
-		if (threadIdx.x == 0)
-		{
-			uint32_t t = 0;
-			for (int w = 0; w < WARPS; ++w)
-				t += s_warp_counts[w];
-			s_running += t;
-		}
-		__syncthreads();
+		offset += __popc(ballot);
 	}
+	__syncthreads();
+	if (threadIdx.x == 0)
+		s_running = band_begin + total;
+	__syncthreads();
 	const uint32_t n = s_running - band_begin; // == band_offsets[band + 1] - band_begin (the host counted with the same test)
 	for (uint32_t col = (uint32_t)warp; col < tiles_x; col += WARPS)
 	{
@@ -638,6 +644,35 @@ __device__ __forceinline__ uint32_t z_from_inv_z(uint32_t d)
 	const uint32_t k = __float2uint_rz(__fmul_rz(__uint2float_rz(rem0), r));
 	const uint32_t rem1 = rem0 - k * d;
 	return q0 + k + (rem1 >= d ? 1u : 0u);
+}
+
+// 2^26 operand pairs for fixed16_div against the plain 64-bit division: a hash of the thread index picks both operands over the
+// whole i32 range, with every eighth pair forced onto the edges (0, +-1, +-2^15, +-2^16, INT_MIN, INT_MAX, equal magnitudes).
+__global__ void fixed16_div_test_kernel(unsigned long long* mismatches)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	uint32_t h = i * 2654435761u + 0x9E3779B9u;
+	h ^= h >> 16;
+	h *= 0x85EBCA6Bu;
+	h ^= h >> 13;
+	uint32_t g = (i ^ 0xA5A5A5A5u) * 0xC2B2AE35u;
+	g ^= g >> 15;
+	g *= 0x27D4EB2Fu;
+	g ^= g >> 16;
+	int32_t x = (int32_t)h, y = (int32_t)g;
+	const int32_t edges[12] = {0, 1, -1, 32768, -32768, 65536, -65536, INT32_MIN, INT32_MAX, 3, -3, 65535};
+	if ((i & 7) == 0)
+		x = edges[(i >> 3) % 12];
+	if ((i & 7) == 1)
+		y = edges[(i >> 3) % 12];
+	if ((i & 7) == 2)
+		y = (i & 8) ? x : -x;
+	if ((i & 15) == 3)
+		y >>= (h & 31); // small divisors: quotients far beyond 32 bits (the `as i32` wrap)
+	if (y == 0)
+		return;
+	if (fixed16_div(x, y) != fixed16_div_reference(x, y))
+		atomicAdd(mismatches, 1ull);
 }
 
 __global__ void z_from_inv_z_test_kernel(unsigned long long* mismatches)
@@ -1121,6 +1156,7 @@ cudaError_t launch_raster_setup(const RasterLaunch& l, cudaStream_t stream)
 cudaError_t launch_z_from_inv_z_test(unsigned long long* mismatches, cudaStream_t stream)
 {
 	z_from_inv_z_test_kernel<<<(1u << 24) / 256, 256, 0, stream>>>(mismatches);
+	fixed16_div_test_kernel<<<(1u << 26) / 256, 256, 0, stream>>>(mismatches);
 	return cudaGetLastError();
 }
 

@@ -28,9 +28,28 @@ __device__ __forceinline__ int32_t fixed16_round_to_int(Fixed16 x) { return wadd
 __device__ __forceinline__ int32_t fixed16_floor_to_int(Fixed16 x) { return x >> 16; }                     // :16
 __device__ __forceinline__ float fixed16_to_f32(Fixed16 x) { return (float)x / 65536.0f; }                 // :26
 __device__ __forceinline__ Fixed16 fixed16_mul(Fixed16 x, Fixed16 y) { return (int32_t)(((int64_t)x * (int64_t)y) >> 16); } // :41
-__device__ __forceinline__ Fixed16 fixed16_div(Fixed16 x, Fixed16 y) // :56
+// fixed16_div (:56): ((x as i64) << 16) / (y as i64), truncated toward zero, `as i32`.  The plain 64-bit integer division
+// (kept for sqw_self_test) costs well over a hundred instructions on the GPU and the triangle set-up needs two dozen of them
+// per scan-line chunk, so the product path divides the magnitudes in double precision — |x| * 2^16 < 2^48 is exact in a
+// double, the rounded quotient is off by less than 2^-4, so its truncation is within one of the true quotient — and
+// repairs the last unit with the exact integer remainder.
+__device__ __forceinline__ Fixed16 fixed16_div_reference(Fixed16 x, Fixed16 y)
 {
 	return (int32_t)((int64_t)((uint64_t)(int64_t)x << 16) / (int64_t)y);
+}
+__device__ __forceinline__ Fixed16 fixed16_div(Fixed16 x, Fixed16 y)
+{
+	if (y == 0)
+		return fixed16_div_reference(x, y); // undefined in the reference (it panics); whatever the device division yields
+	const uint64_t a = (uint64_t)(x < 0 ? -(int64_t)x : (int64_t)x) << 16;
+	const uint64_t b = (uint64_t)(y < 0 ? -(int64_t)y : (int64_t)y);
+	uint64_t q = (uint64_t)__double2ull_rz(__ddiv_rn(__ull2double_rn(a), __ull2double_rn(b)));
+	const int64_t r = (int64_t)(a - q * b);
+	if (r < 0)
+		--q;
+	else if ((uint64_t)r >= b)
+		++q;
+	return (int32_t)(((x < 0) != (y < 0)) ? -(int64_t)q : (int64_t)q);
 }
 __device__ __forceinline__ Fixed16 fixed16_mul_div(Fixed16 x, Fixed16 y, Fixed16 z) // :68
 {

@@ -1,0 +1,193 @@
+#!/usr/bin/env python
+"""Device-resident throughput and per-kernel times of the other BASELINE.json configs (bench.py measures configs[1]).
+
+    python tools/bench_configs.py [--frames 32] [--out profiles/rNN_configs.json]
+
+configs[0]  1280x720, simple lightmaps, 32-bit LDR (no post stage)
+configs[2]  synthetic stress: finely split map (tens of thousands of polygons in the map), mip bias -1, 16 dynamic lights
+            (12 plain, 2 cube, 2 projector shadow maps rendered on the GPU), 16 triangle models of ~2.9k triangles, 4K HDR
+configs[3]  sky box + 32 decals + 32 sprites + blended models, 4K HDR, tonemapping with the default bloom
+configs[4]  fly-through views at 1920x1080 with the configs[1] settings (the view-batch unit; bench.py --gpus N shards it)
+
+Same method as bench.py: recorded frames (inputs resident in HBM), 4 views in flight, CUDA events on the launching stream for
+the whole run, then the same frames again one at a time with sqw_profile events around every launch.  One GPU.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def lights_for(scene_mod, N, path, k, n):
+    r = np.random.default_rng(1000 + k)
+    lights = np.zeros(n, scene_mod.dynamic_light_dtype)
+    for i in range(n):
+        lights[i]["position"] = path[(k + i * 3) % len(path)][:3] + r.uniform(-40.0, 40.0, 3)
+        lights[i]["radius"] = (128.0, 256.0, 512.0)[i % 3]
+        lights[i]["color"] = r.uniform(4000.0, 60000.0, 3)
+        lights[i]["shadow_type"] = N.SHADOW_NONE if i < n - 4 else (N.SHADOW_CUBE if i < n - 2 else N.SHADOW_PROJECTOR)
+        a = r.uniform(0, 2 * np.pi)
+        lights[i]["rotation"] = (np.cos(a / 2), 0.0, 0.0, np.sin(a / 2))
+        lights[i]["fov"] = 0.2 * np.pi
+    return lights
+
+
+def models_for(scene_mod, sc, pose, k, n):
+    m = np.zeros(n, scene_mod.model_entity_dtype)
+    az = float(pose[3])
+    num_models = int(sc.info.num_models)
+    for i in range(n):
+        a = az + (i - 0.5 * (n - 1)) * 0.11
+        m[i]["position"] = pose[:3] + (60.0 + 17.0 * (i % 8)) * np.array([-np.sin(a), np.cos(a), 0.0]) + np.array([0.0, 0.0, -10.0 + 6.0 * (i % 4)])
+        m[i]["rotation"] = (np.cos(0.3 * i), 0.0, 0.0, np.sin(0.3 * i))
+        mi = i % num_models
+        nf = sc.model_info(mi).num_frames
+        m[i]["frames"] = (k % nf, (k + 1) % nf)
+        m[i]["lerp"] = 0.4
+        m[i]["model"] = mi
+        m[i]["skin"] = mi
+        m[i]["blending_mode"] = (0, 0, 3, 4)[i % 4]
+        m[i]["lighting"] = (scene_mod.MODEL_LIGHTING_CONSTANT, scene_mod.MODEL_LIGHTING_ADVANCED)[i % 2]
+        m[i]["light"] = (0.5, 0.45, 0.4)
+        m[i]["grid_light_scale"] = 0.5
+    return m
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=32)
+    ap.add_argument("--repeats", type=int, default=4)
+    ap.add_argument("--out", default=None)
+    args = ap.parse_args()
+
+    import torch
+
+    from common import scatter_decals, sprites_ahead_of_camera
+    from square_wheel_b200 import _native as N
+    from square_wheel_b200 import scene as S
+    from square_wheel_b200.device import Context, make_post_params
+
+    torch.cuda.set_device(0)
+    stream = torch.cuda.Stream(device=0)
+    torch.cuda.set_stream(stream)
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+
+    base_scene = dict(seed=2, grid=(24, 24, 5), cell_size=(160.0, 160.0, 128.0), num_rooms=26, num_materials=24, texture_size_log2=8, max_polygon_size=64.0, material_mode=0, emissive_fraction=0.15)
+    configs = {
+        "configs[0] 1280x720 simple lightmaps LDR": dict(scene=base_scene, size=(1280, 720), bits=32, directional=False, post=None),
+        "configs[2] stress 4K HDR: fine polygons, mip bias -1, 16 lights, 16 models": dict(
+            scene=dict(base_scene, max_polygon_size=20.0, num_models=6, model_detail=27), size=(3840, 2160), bits=64, directional=True, post=dict(), mip_bias=-1.0, lights=16, models=16
+        ),
+        "configs[3] sky + decals + sprites + blended models, 4K HDR + bloom": dict(
+            scene=dict(base_scene, skybox=1, sky_size_log2=9, num_models=6, model_detail=12), size=(3840, 2160), bits=64, directional=True, post=dict(bloom_sigma=1.0), models=6, sprites=32, decals=32,
+            look_up=0.35,
+        ),
+        "configs[4] view-batch unit: 1920x1080 HDR + tonemap": dict(scene=base_scene, size=(1920, 1080), bits=64, directional=True, post=dict()),
+    }
+    results = {}
+    for name, cfg in configs.items():
+        W, H = cfg["size"]
+        C = cfg["bits"] // 8
+        sc = S.Scene(**cfg["scene"])
+        hr = S.HostRenderer(sc, use_directional_lightmaps=cfg["directional"], textures_mip_bias=cfg.get("mip_bias", 0.0))
+        path = sc.camera_path(64)
+        frames = []
+        for i in range(args.frames):
+            k = (i * 64) // args.frames
+            pose = path[k].copy()
+            pose[4] += cfg.get("look_up", 0.0)
+            kw = {}
+            if cfg.get("lights"):
+                kw["lights"] = lights_for(S, N, path, k, cfg["lights"])
+            if cfg.get("models"):
+                kw["models"] = models_for(S, sc, pose, k, cfg["models"])
+            if cfg.get("sprites"):
+                kw["sprites"] = sprites_ahead_of_camera(S, pose, cfg["sprites"], num_skins=int(sc.info.num_models))
+            if cfg.get("decals"):
+                kw["decals"] = scatter_decals(S, pose, cfg["decals"], k, num_skins=int(sc.info.num_models))
+            frames.append(hr.build_frame(W, H, pose, color_bits=cfg["bits"], **kw))
+        hr.close()
+        ctx = Context(sc.lightmaps, sc.directional_lightmaps, device=0, stream=stream.cuda_stream, concurrent_views=True)
+        sc.upload(ctx)
+        views = [ctx.create_view(W, H, cfg["bits"]) for _ in range(4)]
+        post = make_post_params(exposure=1.0, **cfg["post"]) if cfg["post"] is not None else None
+        recorded = []
+        for i, hf in enumerate(frames):
+            f = views[i % 4].create_frame()
+            clear = None
+            if hf.needs_clear:
+                clear = S.BACKGROUND_COLOR64 if cfg["bits"] == 64 else S.BACKGROUND_COLOR32
+            hf.record(f, clear_color=clear, post=post)
+            recorded.append(f)
+        for v in views:
+            v.synchronize()
+
+        def run(serial=False):
+            ctx.batch_begin()
+            for f in recorded:
+                f.submit(N.STAGE_ALL)
+                if serial:
+                    f.view.synchronize()
+            ctx.batch_end()
+
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.repeats):
+            run()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        n = args.repeats * len(recorded)
+        ctx.profile_begin()
+        run(serial=True)
+        kt = ctx.profile_end()
+        st = [f.stats() for f in recorded]
+        S_tex = sum(s.surface_texels for s in st) / len(st)
+        Se = sum(s.emissive_texels for s in st) / len(st)
+        L = sum(s.lightmap_bytes for s in st) / len(st)
+        P = W * H
+        b1 = S_tex * (8 + C) + Se * (4 + 2 * C) + L
+        b2 = 2 * P * C + (4 * P if post is not None and not cfg["post"].get("bloom_sigma") else 0)
+        kernels = {k: {"us_per_frame": v[0] * 1e3 / len(recorded), "launches_per_frame": v[1] / len(recorded)} for k, v in kt.items() if v[1]}
+        for kname, b in (("surface_build", b1), ("raster_tile", b2), ("raster_tile_tonemap", b2)):
+            if kname in kernels:
+                gbs = b / (kernels[kname]["us_per_frame"] * 1e-6) / 1e9
+                kernels[kname].update(algorithmic_bytes_per_frame=b, achieved_gbs=gbs, frac_of_measured_peak=gbs / peak)
+        res = {
+            "resolution": [W, H], "color_bits": cfg["bits"], "frames_per_sec": n / (ms * 1e-3), "us_per_frame": ms * 1e3 / n, "frames": len(recorded),
+            "surface_texels_per_frame": S_tex, "surface_texels_per_sec": S_tex * n / (ms * 1e-3),
+            "draw_commands_per_frame": float(np.mean([len(hf.cmds) for hf in frames])),
+            "triangle_commands_per_frame": float(np.mean([(hf.cmds["kind"] == N.CMD_TRIANGLE).sum() for hf in frames])),
+            "surface_jobs_per_frame": float(np.mean([len(hf.jobs) for hf in frames])),
+            "spans_per_frame": float(np.mean([s.num_spans for s in st])),
+            "map_polygons": int(sc.info.num_polygons),
+            "kernels": kernels,
+        }
+        results[name] = res
+        print(name, json.dumps({k: (round(v, 2) if isinstance(v, float) else v) for k, v in res.items() if k != "kernels"}), flush=True)
+        for kname, kv in kernels.items():
+            print("   ", kname, {a: round(b, 3) if isinstance(b, float) else b for a, b in kv.items()}, flush=True)
+        for f in recorded:
+            f.close()
+        for v in views:
+            v.close()
+        ctx.close()
+        sc.close()
+    if args.out:
+        with open(args.out, "w") as fh:
+            json.dump({"hbm_peak_gbs": peak, "method": __doc__.split("Same method")[1].strip(), "configs": results}, fh, indent=1)
+
+
+if __name__ == "__main__":
+    main()
