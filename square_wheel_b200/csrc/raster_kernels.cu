@@ -219,40 +219,53 @@ __device__ void setup_polygon_line(const sqw_draw_cmd& c, const CmdDev& cd, cons
 		write_empty(out);
 }
 
-// fill_triangle_part (rasterizer.rs:984-1215) for the line `row`.
-__device__ void triangle_part_line(
-	const sqw_draw_cmd& c, int32_t row, Fixed16 y_start, Fixed16 y_end, PolygonSide left_side, PolygonSide right_side, const Fixed16 tc_start_left[2],
+// ---- triangles -----------------------------------------------------------------------------------------------
+// fill_triangle (rasterizer.rs:731-982) does almost all of its work once per triangle HALF, before the row loop: edge
+// slopes, texture-coordinate and light gradients (two dozen 16.16 divisions) and the range-correction block
+// (:1018-1192).  Only `x_left/x_right += dx_dy`, `tc_left += d_tc_dy_left`, `light_left += d_light_left` and the first
+// pixel offset depend on the row.  So the set-up is split the same way: raster_triangle_setup_kernel runs ONE THREAD
+// PER TRIANGLE and stores a TriRec (both halves, corrections applied); the per-row set-up in raster_setup_kernel reads
+// the half that owns its row (a warp-uniform 96-byte broadcast) and evaluates the closed forms of the row loop.
+struct TriPart // 96 bytes
+{
+	int32_t row0, row1;  // rows [row0, row1) this half owns (clipped)
+	int32_t y_start_int; // first row of the half's row loop (:1000)
+	Fixed16 x_left0, dx_dy_left, x_right0, dx_dy_right;
+	Fixed16 tc_left[2], d_tc_dy_left[2], d_tc_dx[2];
+	Fixed16 light_left[3], d_light_left[3], d_light_dx[3];
+	int32_t pad[2];
+};
+struct TriRec
+{
+	TriPart part[2]; // lower, upper
+};
+static_assert(sizeof(TriPart) == 96 && sizeof(TriRec) == SQW_TRI_REC_BYTES, "TriRec layout");
+
+// The row-independent part of fill_triangle_part (rasterizer.rs:984-1192).
+__device__ void triangle_part_setup(
+	const sqw_draw_cmd& c, Fixed16 y_start, Fixed16 y_end, PolygonSide left_side, PolygonSide right_side, const Fixed16 tc_start_left[2],
 	const Fixed16 d_tc_dy_left_in[2], const Fixed16 d_tc_dx_in[2], const Fixed16 light_start_left[3], const Fixed16 d_light_left_in[3],
-	const Fixed16 d_light_dx_in[3], int32_t clip_w, int32_t clip_h, SpanRec* out)
+	const Fixed16 d_light_dx_in[3], int32_t clip_h, TriPart& p)
 {
 	const int32_t y_start_int = max(fixed16_round_to_int(y_start), 0);
-	const int32_t n = row - y_start_int;
+	p.row0 = y_start_int;
+	p.row1 = min(fixed16_round_to_int(y_end), clip_h);
+	p.y_start_int = y_start_int;
+	p.pad[0] = p.pad[1] = 0;
 
 	const Fixed16 y_start_delta = wsub(wadd(int_to_fixed16(y_start_int), SQW_FIXED16_HALF), y_start);
 	const Fixed16 x_left0 = wadd(wadd(left_side.x_start, fixed16_mul(y_start_delta, left_side.dx_dy)), SQW_FIXED16_HALF);
 	const Fixed16 x_right0 = wadd(wadd(right_side.x_start, fixed16_mul(y_start_delta, right_side.dx_dy)), SQW_FIXED16_HALF);
+	p.x_left0 = x_left0;
+	p.dx_dy_left = left_side.dx_dy;
+	p.x_right0 = x_right0;
+	p.dx_dy_right = right_side.dx_dy;
 
 	const Fixed16 y_end_delta = wsub(y_end, wadd(y_start, y_start_delta));
 	const Fixed16 d_x_lower = max(wsub(x_right0, x_left0), 0);
 	const Fixed16 x_upper_left = wadd(x_left0, fixed16_mul(y_end_delta, left_side.dx_dy));
 	const Fixed16 x_upper_right = wadd(x_right0, fixed16_mul(y_end_delta, right_side.dx_dy));
 	const Fixed16 d_x_upper = max(wsub(x_upper_right, x_upper_left), 0);
-
-	const Fixed16 x_left = wadd(x_left0, wmul(n, left_side.dx_dy));
-	const Fixed16 x_right = wadd(x_right0, wmul(n, right_side.dx_dy));
-	const int32_t x_start_int = max(fixed16_floor_to_int(x_left), 0);
-	const int32_t x_end_int = min(fixed16_floor_to_int(x_right), clip_w);
-	if (x_start_int >= x_end_int)
-	{
-		write_empty(out);
-		return;
-	}
-	const Fixed16 x_start_delta = wsub(wadd(int_to_fixed16(x_start_int), SQW_FIXED16_ONE), x_left); // :1202
-
-	SpanRec r;
-	r.x0 = (int16_t)x_start_int;
-	r.x1 = (int16_t)x_end_int;
-	r.v[10] = 0;
 
 	// :1018-1138 texture coordinate range correction
 #pragma unroll
@@ -314,9 +327,9 @@ __device__ void triangle_part_line(
 			else if (tc_upper_right2 > max_tc)
 				d_tc_dx = d_x_upper > 0 ? fixed16_div(wsub(max_tc, tc_upper_left2), d_x_upper) : 0;
 		}
-		const Fixed16 tc_left_row = wadd(tc_left, wmul(n, d_tc_dy_left));                 // :1285 applied n times
-		r.v[0 + i] = wadd(tc_left_row, fixed16_mul(x_start_delta, d_tc_dx));                 // :1205-1208
-		r.v[2 + i] = d_tc_dx;
+		p.tc_left[i] = tc_left;
+		p.d_tc_dy_left[i] = d_tc_dy_left;
+		p.d_tc_dx[i] = d_tc_dx;
 	}
 
 	// :1140-1192 light underflow correction
@@ -341,11 +354,44 @@ __device__ void triangle_part_line(
 			if (light_upper_right2 < 0)
 				d_light_dx = d_x_upper > 0 ? fixed16_div(-light_upper_left2, d_x_upper) : 0;
 		}
-		const Fixed16 light_left_row = wadd(light_left, wmul(n, d_light_left));            // :1289 applied n times
-		r.v[4 + i] = wadd(light_left_row, fixed16_mul(x_start_delta, d_light_dx));           // :1210-1214
-		r.v[7 + i] = d_light_dx;
+		p.light_left[i] = light_left;
+		p.d_light_left[i] = d_light_left;
+		p.d_light_dx[i] = d_light_dx;
 	}
+}
 
+// The row loop of fill_triangle_part (rasterizer.rs:1194-1291) in closed form for the line `row` of the half `p`.
+__device__ __forceinline__ void triangle_row(const TriPart& p, int32_t row, int32_t clip_w, SpanRec* out)
+{
+	const int32_t n = row - p.y_start_int;
+	const Fixed16 x_left = wadd(p.x_left0, wmul(n, p.dx_dy_left));
+	const Fixed16 x_right = wadd(p.x_right0, wmul(n, p.dx_dy_right));
+	const int32_t x_start_int = max(fixed16_floor_to_int(x_left), 0);
+	const int32_t x_end_int = min(fixed16_floor_to_int(x_right), clip_w);
+	if (x_start_int >= x_end_int)
+	{
+		write_empty(out);
+		return;
+	}
+	const Fixed16 x_start_delta = wsub(wadd(int_to_fixed16(x_start_int), SQW_FIXED16_ONE), x_left); // :1202
+	SpanRec r;
+	r.x0 = (int16_t)x_start_int;
+	r.x1 = (int16_t)x_end_int;
+	r.v[10] = 0;
+#pragma unroll
+	for (int i = 0; i < 2; ++i)
+	{
+		const Fixed16 tc_left_row = wadd(p.tc_left[i], wmul(n, p.d_tc_dy_left[i]));  // :1285 applied n times
+		r.v[0 + i] = wadd(tc_left_row, fixed16_mul(x_start_delta, p.d_tc_dx[i]));      // :1205-1208
+		r.v[2 + i] = p.d_tc_dx[i];
+	}
+#pragma unroll
+	for (int i = 0; i < 3; ++i)
+	{
+		const Fixed16 light_left_row = wadd(p.light_left[i], wmul(n, p.d_light_left[i])); // :1289 applied n times
+		r.v[4 + i] = wadd(light_left_row, fixed16_mul(x_start_delta, p.d_light_dx[i]));     // :1210-1214
+		r.v[7 + i] = p.d_light_dx[i];
+	}
 	uint4* o = reinterpret_cast<uint4*>(out);
 	const uint4* s = reinterpret_cast<const uint4*>(&r);
 	o[0] = s[0];
@@ -353,8 +399,8 @@ __device__ void triangle_part_line(
 	o[2] = s[2];
 }
 
-// fill_triangle_impl (rasterizer.rs:765-966) reduced to the half that owns `row`.
-__device__ void setup_triangle_line(const sqw_draw_cmd& c, const sqw_triangle_point* __restrict__ vertices, int32_t row, int32_t clip_w, int32_t clip_h, SpanRec* out)
+// fill_triangle_impl (rasterizer.rs:765-966): both halves of one triangle.
+__device__ void triangle_command_setup(const sqw_draw_cmd& c, const sqw_triangle_point* __restrict__ vertices, int32_t clip_h, TriRec& rec)
 {
 	const sqw_triangle_point v0 = vertices[0], v1 = vertices[1], v2 = vertices[2];
 	int upper_index, lower_index;
@@ -406,17 +452,6 @@ __device__ void setup_triangle_line(const sqw_draw_cmd& c, const sqw_triangle_po
 		d_light_dy_upper[i] = fixed16_div(wsub(upper_vertex.light[i], middle_vertex.light[i]), upper_part_dy);
 	}
 
-	// Which half owns the row?  (fill_triangle_part returns early when its clipped row range is empty, :1000-1005)
-	const int32_t lo0 = max(fixed16_round_to_int(lower_vertex.y), 0), lo1 = min(fixed16_round_to_int(middle_vertex.y), clip_h);
-	const int32_t up0 = max(fixed16_round_to_int(middle_vertex.y), 0), up1 = min(fixed16_round_to_int(upper_vertex.y), clip_h);
-	const bool in_lower = row >= lo0 && row < lo1;
-	const bool in_upper = row >= up0 && row < up1;
-	if (!in_lower && !in_upper)
-	{
-		write_empty(out);
-		return;
-	}
-
 	Fixed16 d_tc_dx[2], d_light_dx[3];
 	PolygonSide l, r;
 	if (long_edge_x_in_middle >= middle_vertex.x)
@@ -428,22 +463,16 @@ __device__ void setup_triangle_line(const sqw_draw_cmd& c, const sqw_triangle_po
 #pragma unroll
 		for (int i = 0; i < 3; ++i)
 			d_light_dx[i] = fixed16_div(wsub(long_edge_light_in_middle[i], middle_vertex.light[i]), middle_dx);
-		if (in_lower)
-		{
-			l.x_start = lower_vertex.x;
-			l.dx_dy = lower_part_dx_dy;
-			r.x_start = lower_vertex.x;
-			r.dx_dy = long_edge_dx_dy;
-			triangle_part_line(c, row, lower_vertex.y, middle_vertex.y, l, r, lower_vertex.tc, d_tc_dy_lower, d_tc_dx, lower_vertex.light, d_light_dy_lower, d_light_dx, clip_w, clip_h, out);
-		}
-		else
-		{
-			l.x_start = middle_vertex.x;
-			l.dx_dy = upper_part_dx_dy;
-			r.x_start = long_edge_x_in_middle;
-			r.dx_dy = long_edge_dx_dy;
-			triangle_part_line(c, row, middle_vertex.y, upper_vertex.y, l, r, middle_vertex.tc, d_tc_dy_upper, d_tc_dx, middle_vertex.light, d_light_dy_upper, d_light_dx, clip_w, clip_h, out);
-		}
+		l.x_start = lower_vertex.x;
+		l.dx_dy = lower_part_dx_dy;
+		r.x_start = lower_vertex.x;
+		r.dx_dy = long_edge_dx_dy;
+		triangle_part_setup(c, lower_vertex.y, middle_vertex.y, l, r, lower_vertex.tc, d_tc_dy_lower, d_tc_dx, lower_vertex.light, d_light_dy_lower, d_light_dx, clip_h, rec.part[0]);
+		l.x_start = middle_vertex.x;
+		l.dx_dy = upper_part_dx_dy;
+		r.x_start = long_edge_x_in_middle;
+		r.dx_dy = long_edge_dx_dy;
+		triangle_part_setup(c, middle_vertex.y, upper_vertex.y, l, r, middle_vertex.tc, d_tc_dy_upper, d_tc_dx, middle_vertex.light, d_light_dy_upper, d_light_dx, clip_h, rec.part[1]);
 	}
 	else
 	{
@@ -454,23 +483,60 @@ __device__ void setup_triangle_line(const sqw_draw_cmd& c, const sqw_triangle_po
 #pragma unroll
 		for (int i = 0; i < 3; ++i)
 			d_light_dx[i] = fixed16_div(wsub(middle_vertex.light[i], long_edge_light_in_middle[i]), middle_dx);
-		if (in_lower)
-		{
-			l.x_start = lower_vertex.x;
-			l.dx_dy = long_edge_dx_dy;
-			r.x_start = lower_vertex.x;
-			r.dx_dy = lower_part_dx_dy;
-			triangle_part_line(c, row, lower_vertex.y, middle_vertex.y, l, r, lower_vertex.tc, long_edge_d_tc_dy, d_tc_dx, lower_vertex.light, long_edge_d_light_dy, d_light_dx, clip_w, clip_h, out);
-		}
-		else
-		{
-			l.x_start = long_edge_x_in_middle;
-			l.dx_dy = long_edge_dx_dy;
-			r.x_start = middle_vertex.x;
-			r.dx_dy = upper_part_dx_dy;
-			triangle_part_line(c, row, middle_vertex.y, upper_vertex.y, l, r, long_edge_tc_in_middle, long_edge_d_tc_dy, d_tc_dx, long_edge_light_in_middle, long_edge_d_light_dy, d_light_dx, clip_w, clip_h, out);
-		}
+		l.x_start = lower_vertex.x;
+		l.dx_dy = long_edge_dx_dy;
+		r.x_start = lower_vertex.x;
+		r.dx_dy = lower_part_dx_dy;
+		triangle_part_setup(c, lower_vertex.y, middle_vertex.y, l, r, lower_vertex.tc, long_edge_d_tc_dy, d_tc_dx, lower_vertex.light, long_edge_d_light_dy, d_light_dx, clip_h, rec.part[0]);
+		l.x_start = long_edge_x_in_middle;
+		l.dx_dy = long_edge_dx_dy;
+		r.x_start = middle_vertex.x;
+		r.dx_dy = upper_part_dx_dy;
+		triangle_part_setup(c, middle_vertex.y, upper_vertex.y, l, r, long_edge_tc_in_middle, long_edge_d_tc_dy, d_tc_dx, long_edge_light_in_middle, long_edge_d_light_dy, d_light_dx, clip_h, rec.part[1]);
 	}
+}
+
+// One thread per command: the TriRec of every triangle command (polygon commands leave their slot untouched).
+__global__ void __launch_bounds__(128) raster_triangle_setup_kernel(
+	const sqw_draw_cmd* __restrict__ cmds, uint32_t num_cmds, const sqw_triangle_point* __restrict__ triangle_points, int32_t clip_h, TriRec* __restrict__ tri_recs)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= num_cmds)
+		return;
+	const sqw_draw_cmd c = cmds[i];
+	if (c.kind != SQW_CMD_TRIANGLE)
+		return;
+	TriRec rec;
+	triangle_command_setup(c, triangle_points + c.vertex_offset, clip_h, rec);
+	uint4* o = reinterpret_cast<uint4*>(tri_recs + i);
+	const uint4* s4 = reinterpret_cast<const uint4*>(&rec);
+#pragma unroll
+	for (int k = 0; k < (int)(sizeof(TriRec) / 16); ++k)
+		o[k] = s4[k];
+}
+
+// The line `row` of a triangle command: the half that owns the row (fill_triangle_part returns early when its clipped
+// row range is empty, :1000-1005).
+__device__ __forceinline__ void setup_triangle_line(const TriRec* __restrict__ rec, int32_t row, int32_t clip_w, SpanRec* out)
+{
+	const uint4* src = reinterpret_cast<const uint4*>(rec);
+	const uint4 h0 = __ldg(src), h1 = __ldg(src + 6); // {row0, row1, ...} of the two halves
+	int part;
+	if (row >= (int32_t)h0.x && row < (int32_t)h0.y)
+		part = 0;
+	else if (row >= (int32_t)h1.x && row < (int32_t)h1.y)
+		part = 1;
+	else
+	{
+		write_empty(out);
+		return;
+	}
+	TriPart p;
+	uint4* d = reinterpret_cast<uint4*>(&p);
+#pragma unroll
+	for (int k = 0; k < 6; ++k)
+		d[k] = __ldg(src + part * 6 + k);
+	triangle_row(p, row, clip_w, out);
 }
 
 // ---- binning -------------------------------------------------------------------------------------------------
@@ -582,7 +648,7 @@ __device__ void bin_band(
 
 __global__ void __launch_bounds__(SQW_SETUP_THREADS) raster_setup_kernel(
 	const sqw_draw_cmd* __restrict__ cmds, const CmdDev* __restrict__ cmd_dev, uint32_t num_cmds, const sqw_polygon_point* __restrict__ polygon_points,
-	const sqw_triangle_point* __restrict__ triangle_points, const uint2* __restrict__ chunks, uint32_t num_chunks, SpanRec* __restrict__ spans,
+	const TriRec* __restrict__ tri_recs, const uint2* __restrict__ chunks, uint32_t num_chunks, SpanRec* __restrict__ spans,
 	int32_t clip_w, int32_t clip_h, uint32_t setup_blocks, const uint32_t* __restrict__ band_offsets, uint32_t* band_lists, uint32_t* __restrict__ tile_lists,
 	uint4* __restrict__ tile_desc, uint32_t tiles_x, uint32_t num_bands,
 	unsigned long long* __restrict__ sums_to_zero, uint8_t* __restrict__ tonemap_lut, float isb, float isg, float isr)
@@ -619,13 +685,15 @@ __global__ void __launch_bounds__(SQW_SETUP_THREADS) raster_setup_kernel(
 	const uint32_t r = ch.y + (threadIdx.x & 31);
 	if (r >= (uint32_t)((int32_t)cd.y1 - (int32_t)cd.y0))
 		return;
-	const sqw_draw_cmd c = cmds[ch.x];
 	const uint32_t s = cd.span_base + r;
 	const int32_t row = (int32_t)cd.y0 + (int32_t)(s - cd.span_base);
 	if (cd.kind == SQW_CMD_POLYGON)
+	{
+		const sqw_draw_cmd c = cmds[ch.x];
 		setup_polygon_line(c, cd, polygon_points + c.vertex_offset, row, clip_w, clip_h, spans + s);
+	}
 	else
-		setup_triangle_line(c, triangle_points + c.vertex_offset, row, clip_w, clip_h, spans + s);
+		setup_triangle_line(tri_recs + ch.x, row, clip_w, spans + s);
 }
 
 // ---- tile kernel ----------------------------------------------------------------------------------------------
@@ -1147,8 +1215,10 @@ cudaError_t launch_raster_setup(const RasterLaunch& l, cudaStream_t stream)
 	const uint32_t setup_blocks = std::max<uint32_t>((l.num_chunks + chunks_per_block - 1) / chunks_per_block, 1); // block 0 also zeroes the sums
 	const uint32_t bin_blocks = l.num_bands; // also with an empty command list: the tile kernel reads every tile descriptor
 	const uint32_t lut_blocks = l.tonemap_dst ? (3 * SQW_TONEMAP_LUT_SIZE + SQW_SETUP_THREADS - 1) / SQW_SETUP_THREADS : 0;
+	if (l.num_triangle_cmds)
+		raster_triangle_setup_kernel<<<(l.num_cmds + 127) / 128, 128, 0, stream>>>(l.cmds, l.num_cmds, l.triangle_points, l.height, static_cast<TriRec*>(l.tri_recs));
 	raster_setup_kernel<<<setup_blocks + bin_blocks + lut_blocks, SQW_SETUP_THREADS, 0, stream>>>(
-		l.cmds, l.cmd_dev, l.num_cmds, l.polygon_points, l.triangle_points, l.chunks, l.num_chunks, l.spans, l.width, l.height, setup_blocks, l.band_offsets,
+		l.cmds, l.cmd_dev, l.num_cmds, l.polygon_points, static_cast<const TriRec*>(l.tri_recs), l.chunks, l.num_chunks, l.spans, l.width, l.height, setup_blocks, l.band_offsets,
 		l.band_lists, l.tile_lists, l.tile_desc, (uint32_t)((l.width + SQW_TILE_W - 1) / SQW_TILE_W), bin_blocks, l.tonemap_dst ? l.color_sums : nullptr, l.tonemap_lut, l.inv_scale_bgr[0], l.inv_scale_bgr[1], l.inv_scale_bgr[2]);
 	return cudaGetLastError();
 }

@@ -233,6 +233,7 @@ struct sqw_view
 	DevBuf surfaces;
 	DevBuf spans;
 	DevBuf band_lists;
+	DevBuf tri_recs; // per-triangle set-up records of the draw being submitted (SQW_TRI_REC_BYTES per command)
 	uint64_t* d_bloom[2] = {nullptr, nullptr};
 	uint8_t* d_tonemap_lut = nullptr;     // 3 x SQW_TONEMAP_LUT_SIZE (64-bit views)
 	unsigned long long* d_sums = nullptr; // SQW_SUM_SLOTS x {B, G, R, pad}
@@ -286,9 +287,9 @@ struct sqw_frame
 	const uint32_t* d_band_offsets = nullptr;
 	std::vector<uint32_t> sampled_views; // views referenced through SQW_TEX_VIEW
 	std::vector<CmdDev> h_cmd_dev;
-	std::vector<uint2> h_chunks;
+	std::vector<uint2> h_chunks, h_chunks_tri;
 	std::vector<uint32_t> h_band_offsets;
-	uint32_t num_cmds = 0, total_spans = 0, num_bands = 0, total_band_entries = 0;
+	uint32_t num_cmds = 0, total_spans = 0, num_bands = 0, total_band_entries = 0, num_triangle_cmds = 0;
 	uint32_t draw_width = 0, draw_height = 0; // view size the command list was prepared for
 	bool clear = false;
 	uint64_t clear_color = 0;
@@ -571,6 +572,7 @@ void sqw_view_destroy(sqw_view* view)
 	view->surfaces.release();
 	view->spans.release();
 	view->band_lists.release();
+	view->tri_recs.release();
 	for (auto& b : view->d_bloom)
 		if (b)
 			cudaFree(b);
@@ -798,6 +800,7 @@ int sqw_frame_set_draw(
 	f->h_cmd_dev.resize(num_cmds);
 	f->sampled_views.clear();
 	f->h_chunks.clear();
+	f->h_chunks_tri.clear();
 	f->h_band_offsets.assign((size_t)num_bands + 1, 0);
 	uint64_t span_total = 0;
 	for (uint32_t i = 0; i < num_cmds; ++i)
@@ -895,8 +898,10 @@ int sqw_frame_set_draw(
 		d.bx0 = (int16_t)bx0;
 		d.bx1 = (int16_t)bx1;
 		d.span_base = (uint32_t)span_total;
+		// polygon chunks first, triangle chunks after them (h_chunks_tri is appended below): warps resident on an SM at the same
+		// time then mostly run the same half of the set-up code, which does not fit the instruction cache as a whole
 		for (int32_t r0 = 0; r0 < y1 - y0; r0 += 32)
-			f->h_chunks.push_back(make_uint2(i, (uint32_t)r0));
+			(c.kind == SQW_CMD_TRIANGLE ? f->h_chunks_tri : f->h_chunks).push_back(make_uint2(i, (uint32_t)r0));
 		span_total += (uint64_t)(y1 - y0);
 		if (span_total > 0xFFFFFFFFull)
 			return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_frame_set_draw: too many scan-lines");
@@ -904,9 +909,13 @@ int sqw_frame_set_draw(
 			for (int32_t b = y0 / SQW_TILE_H; b <= (y1 - 1) / SQW_TILE_H; ++b)
 				f->h_band_offsets[(size_t)b + 1]++;
 	}
+	f->h_chunks.insert(f->h_chunks.end(), f->h_chunks_tri.begin(), f->h_chunks_tri.end());
 	for (uint32_t b = 0; b < num_bands; ++b)
 		f->h_band_offsets[(size_t)b + 1] += f->h_band_offsets[b];
 	f->num_cmds = num_cmds;
+	f->num_triangle_cmds = 0;
+	for (uint32_t i = 0; i < num_cmds; ++i)
+		f->num_triangle_cmds += cmds[i].kind == SQW_CMD_TRIANGLE ? 1u : 0u;
 	f->draw_width = view->width;
 	f->draw_height = view->height;
 	f->total_spans = (uint32_t)span_total;
@@ -920,11 +929,14 @@ int sqw_frame_set_draw(
 	if ((uint64_t)f->total_band_entries * tiles_x > 0xFFFFFFFFull)
 		return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_frame_set_draw: too many commands per band");
 	const size_t bin_bytes = bin_scratch_bytes(f->total_band_entries, (uint32_t)tiles_x, num_bands);
-	if ((size_t)span_total * sizeof(SpanRec) + 64 > view->spans.capacity || bin_bytes > view->band_lists.capacity)
+	const size_t tri_bytes = f->num_triangle_cmds ? (size_t)num_cmds * SQW_TRI_REC_BYTES + 64 : 0;
+	if ((size_t)span_total * sizeof(SpanRec) + 64 > view->spans.capacity || bin_bytes > view->band_lists.capacity || tri_bytes > view->tri_recs.capacity)
 	{
 		SQW_CUDA(ctx, cudaStreamSynchronize(view->stream)); // growing frees scratch a queued frame may still use
 		SQW_CUDA(ctx, view->spans.reserve((size_t)span_total * sizeof(SpanRec) + 64));
 		SQW_CUDA(ctx, view->band_lists.reserve(bin_bytes));
+		if (tri_bytes)
+			SQW_CUDA(ctx, view->tri_recs.reserve(tri_bytes));
 	}
 	{
 		Arena& a = f->draw_arena;
@@ -1157,6 +1169,8 @@ int sqw_frame_submit(sqw_frame* f, uint32_t stages)
 		l.num_cmds = f->num_cmds;
 		l.polygon_points = f->d_polygon_points;
 		l.triangle_points = f->d_triangle_points;
+		l.tri_recs = view->tri_recs.ptr;
+		l.num_triangle_cmds = f->num_triangle_cmds;
 		l.spans = static_cast<SpanRec*>(view->spans.ptr);
 		l.chunks = f->d_chunks;
 		l.num_chunks = (uint32_t)f->h_chunks.size();
@@ -1192,7 +1206,7 @@ int sqw_frame_submit(sqw_frame* f, uint32_t stages)
 		{
 			LaunchTimer timer(ctx, SQW_KERNEL_RASTER_SETUP, s);
 			SQW_CUDA(ctx, launch_raster_setup(l, s));
-			++launches;
+			launches += f->num_triangle_cmds ? 2 : 1; // + the per-triangle set-up kernel
 		}
 		if (f->num_cmds || f->clear || fused_tonemap)
 		{

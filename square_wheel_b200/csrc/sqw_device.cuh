@@ -37,7 +37,8 @@ __device__ __forceinline__ Fixed16 fixed16_div_reference(Fixed16 x, Fixed16 y)
 {
 	return (int32_t)((int64_t)((uint64_t)(int64_t)x << 16) / (int64_t)y);
 }
-__device__ __forceinline__ Fixed16 fixed16_div(Fixed16 x, Fixed16 y)
+// __noinline__: the set-up kernel calls it some forty times; inlined, its code no longer fits the instruction cache
+static __device__ __noinline__ Fixed16 fixed16_div(Fixed16 x, Fixed16 y)
 {
 	if (y == 0)
 		return fixed16_div_reference(x, y); // undefined in the reference (it panics); whatever the device division yields

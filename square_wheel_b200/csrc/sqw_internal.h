@@ -69,6 +69,7 @@ cudaError_t launch_mix_texture(
 #define SQW_SUM_SLOTS 64
 #define SQW_SUM_WORDS (SQW_SUM_SLOTS * 4)
 #define SQW_SETUP_THREADS 128
+#define SQW_TRI_REC_BYTES 192 /* per-triangle set-up record (both halves), raster_kernels.cu */
 #define SQW_TONEMAP_LUT_SIZE 4096 /* channel values below this (16 x LDR white) are tonemapped by table look-up */
 #define SQW_TILE_STAGE_HITS 4 /* commands whose span records a warp stages in shared memory at a time (x 8 block rows = 32 lanes) */
 #define SQW_RASTER_THREADS 128 /* 4 warps, each owning a 32x8 pixel block of the 128x8 tile */
@@ -109,6 +110,8 @@ struct RasterLaunch
 	uint32_t num_cmds;
 	const sqw_polygon_point* polygon_points;
 	const sqw_triangle_point* triangle_points;
+	void* tri_recs;             // device, num_cmds x SQW_TRI_REC_BYTES: per-triangle set-up records (raster_triangle_setup_kernel)
+	uint32_t num_triangle_cmds; // 0: no triangle set-up launch
 	SpanRec* spans;                // device, total_spans entries
 	const uint2* chunks; // device: {command index, first row relative to the command's y0} per 32 scan-lines of a command
 	uint32_t num_chunks;

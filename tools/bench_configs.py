@@ -66,6 +66,7 @@ def main():
     ap.add_argument("--frames", type=int, default=32)
     ap.add_argument("--repeats", type=int, default=4)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--only", default=None, help="substring of the config name to run alone (for ncu captures)")
     args = ap.parse_args()
 
     import torch
@@ -94,6 +95,8 @@ def main():
     }
     results = {}
     for name, cfg in configs.items():
+        if args.only and args.only not in name:
+            continue
         W, H = cfg["size"]
         C = cfg["bits"] // 8
         sc = S.Scene(**cfg["scene"])
