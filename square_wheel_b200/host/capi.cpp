@@ -4,6 +4,7 @@
 #include "renderer.hpp"
 #include <cstring>
 #include <new>
+#include <string>
 
 using namespace sqwh;
 
@@ -25,6 +26,7 @@ struct sqwh_scene_params // mirrors sqwh::SceneParams (plain C layout for ctypes
 	uint32_t model_detail;
 	uint32_t skybox;
 	uint32_t sky_size_log2;
+	uint32_t light_grid;
 };
 
 struct sqwh_scene_info
@@ -130,6 +132,7 @@ void sqwh_default_scene_params(sqwh_scene_params* p)
 	p->model_detail = d.model_detail;
 	p->skybox = d.skybox;
 	p->sky_size_log2 = d.sky_size_log2;
+	p->light_grid = d.light_grid;
 }
 
 Scene* sqwh_scene_create(const sqwh_scene_params* p)
@@ -153,6 +156,7 @@ Scene* sqwh_scene_create(const sqwh_scene_params* p)
 	sp.model_detail = p->model_detail;
 	sp.skybox = p->skybox;
 	sp.sky_size_log2 = p->sky_size_log2;
+	sp.light_grid = p->light_grid;
 	Scene* s = new (std::nothrow) Scene();
 	if (!s)
 		return nullptr;
@@ -175,6 +179,27 @@ void sqwh_scene_get_info(const Scene* s, sqwh_scene_info* out)
 	out->num_models = (uint32_t)s->models.size();
 	out->reserved = 0;
 }
+// .sqwm v11 (bsp_map_save_load.rs): write the scene's map / replace the scene's map by a file's.  Return a MapFileResult
+// (0 ok, 1 i/o error, 2 not a map, 3 incompatible version), or 4 when the loaded map fails validate_map against the scene's
+// material table (the message is then in sqwh_last_map_error).  No Renderer may exist for the scene while its map is replaced.
+static std::string g_last_map_error;
+int sqwh_scene_save_map(const Scene* s, const char* path) { return (int)save_map(s->map, path); }
+int sqwh_scene_load_map(Scene* s, const char* path)
+{
+	BSPMap map;
+	const MapFileResult r = load_map(path, map);
+	if (r != MAP_FILE_OK)
+		return (int)r;
+	g_last_map_error = validate_map(map, s->materials.size());
+	if (!g_last_map_error.empty())
+		return 4;
+	s->map = std::move(map);
+	return 0;
+}
+const char* sqwh_last_map_error() { return g_last_map_error.c_str(); }
+uint32_t sqwh_scene_num_light_grid_samples(const Scene* s) { return (uint32_t)s->map.light_grid_samples.size(); }
+const char* sqwh_scene_texture_name(const Scene* s, uint32_t index) { return index < s->map.textures.size() ? s->map.textures[index].name : nullptr; }
+
 const void* sqwh_scene_image(const Scene* s, uint32_t index, int32_t* kind, uint32_t* width, uint32_t* height)
 {
 	if (index >= s->images.size())

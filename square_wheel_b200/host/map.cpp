@@ -8,6 +8,8 @@
 #include "map.hpp"
 #include <algorithm>
 #include <array>
+#include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -879,6 +881,60 @@ void generate_scene(const SceneParams& params, Scene& out)
 	out.params = params;
 	Builder b(out);
 	b.run();
+	// material names of the file format's texture table (bsp_map_compact.rs:137-139)
+	out.map.textures.resize(out.materials.size());
+	for (size_t i = 0; i < out.materials.size(); ++i)
+	{
+		std::memset(out.map.textures[i].name, 0, MAX_TEXTURE_NAME_LEN);
+		std::snprintf(out.map.textures[i].name, MAX_TEXTURE_NAME_LEN, "synthetic/material_%02u", (unsigned)i);
+	}
+	if (params.light_grid)
+	{
+		// Light grid fixture (lightmaps_builder.rs:299-330 layout): 64-unit cells over the whole grid volume, one column per
+		// (x, y) holding the samples of the non-solid z range; sample = a smooth seeded light cube + one directional component.
+		// Samples inside solid cells are the all-zero element, which fetch_light_from_grid skips (:644-647).
+		BSPMap& m = out.map;
+		const float cell = 64.0f;
+		const float extent[3] = {params.grid[0] * params.cell_size[0], params.grid[1] * params.cell_size[1], params.grid[2] * params.cell_size[2]};
+		for (int a = 0; a < 3; ++a)
+		{
+			m.light_grid_header.grid_cell_size[a] = cell;
+			m.light_grid_header.grid_start[a] = 0.5f * cell;
+			m.light_grid_header.grid_size[a] = std::max(1u, (uint32_t)(extent[a] / cell));
+		}
+		const uint32_t* gs = m.light_grid_header.grid_size;
+		m.light_grid_columns.resize((size_t)gs[0] * gs[1]);
+		for (uint32_t y = 0; y < gs[1]; ++y)
+			for (uint32_t x = 0; x < gs[0]; ++x)
+			{
+				LightGridColumn& col = m.light_grid_columns[x + (size_t)y * gs[0]];
+				col.start_z = 0;
+				col.first_sample = (uint32_t)m.light_grid_samples.size();
+				col.num_samples = gs[2];
+				for (uint32_t z = 0; z < gs[2]; ++z)
+				{
+					const Vec3f pos = {m.light_grid_header.grid_start[0] + x * cell, m.light_grid_header.grid_start[1] + y * cell, m.light_grid_header.grid_start[2] + z * cell};
+					LightGridElement e;
+					const int cx = (int)(pos.x / params.cell_size[0]), cy = (int)(pos.y / params.cell_size[1]), cz = (int)(pos.z / params.cell_size[2]);
+					if (!out.is_solid(cx, cy, cz))
+					{
+						const float w = 0.5f + 0.5f * std::sin(pos.x * 0.011f) * std::cos(pos.y * 0.013f);
+						for (int side = 0; side < 6; ++side)
+						{
+							const float up = side == 5 ? 1.6f : (side == 4 ? 0.5f : 1.0f); // brighter from above
+							e.light_cube[side][0] = 0.35f * up * (0.6f + 0.4f * w);
+							e.light_cube[side][1] = 0.32f * up;
+							e.light_cube[side][2] = 0.30f * up * (1.0f - 0.3f * w);
+						}
+						e.light_direction_vector_scaled = Vec3f{std::cos(pos.x * 0.02f), std::sin(pos.y * 0.02f), 0.7f} * 0.8f;
+						e.directional_light_color[0] = 0.9f;
+						e.directional_light_color[1] = 0.8f * (0.5f + 0.5f * w);
+						e.directional_light_color[2] = 0.6f;
+					}
+					m.light_grid_samples.push_back(e);
+				}
+			}
+	}
 	if (params.skybox && out.materials.size() >= 4)
 	{
 		// appended after the world images, so scenes without a sky keep their image ids

@@ -45,6 +45,46 @@ struct Portal // :77-85
 	uint32_t first_vertex, num_vertices;
 };
 
+struct Submodel // bsp_map_compact.rs:87-96
+{
+	uint32_t root_node, first_polygon, num_polygons;
+};
+struct SubmodelBSPNode // :98-107
+{
+	Plane plane;
+	uint32_t first_polygon, num_polygons;
+	uint32_t children[2];
+};
+struct Entity // :109-117
+{
+	uint32_t first_key_value_pair, num_key_value_pairs, submodel_index;
+};
+struct StringRef // :127-135
+{
+	uint16_t offset, size;
+};
+struct KeyValuePair // :119-125
+{
+	StringRef key, value;
+};
+constexpr size_t MAX_TEXTURE_NAME_LEN = 64; // :137
+struct TextureName
+{
+	char name[MAX_TEXTURE_NAME_LEN]; // NUL-padded material name
+};
+struct LightGridHeader // :158-167
+{
+	float grid_cell_size[3] = {0, 0, 0};
+	float grid_start[3] = {0, 0, 0};
+	uint32_t grid_size[3] = {0, 0, 0};
+};
+struct LightGridColumn // :169-177
+{
+	uint32_t start_z = 0, first_sample = 0, num_samples = 0;
+};
+static_assert(sizeof(BSPNode) == 24 && sizeof(BSPLeaf) == 16 && sizeof(Portal) == 32 && sizeof(Submodel) == 12 && sizeof(SubmodelBSPNode) == 32, ".sqwm lump element sizes");
+static_assert(sizeof(Entity) == 12 && sizeof(KeyValuePair) == 8 && sizeof(TextureName) == 64 && sizeof(LightGridHeader) == 36 && sizeof(LightGridColumn) == 12, ".sqwm lump element sizes");
+
 struct BSPMap
 {
 	std::vector<BSPNode> nodes; // last node is the root
@@ -53,10 +93,34 @@ struct BSPMap
 	std::vector<Portal> portals;
 	std::vector<uint32_t> leafs_portals;
 	std::vector<Vec3f> vertices;
+	std::vector<TextureName> textures;               // material names, indexed by Polygon::texture
+	std::vector<Submodel> submodels;                 // inline models (kept for the file format; the mirror does not draw them)
+	std::vector<SubmodelBSPNode> submodels_bsp_nodes;
+	std::vector<Entity> entities;
+	std::vector<KeyValuePair> key_value_pairs;
+	std::vector<uint8_t> strings_data;
+	LightGridHeader light_grid_header;
+	std::vector<LightGridColumn> light_grid_columns; // grid_size[0] x grid_size[1]
+	std::vector<LightGridElement> light_grid_samples;
 	std::vector<float> lightmaps_data; // [n][3]
 	std::vector<sqw_directional_lightmap_element> directional_lightmaps_data;
 	uint32_t root_node() const { return nodes.empty() ? FIRST_LEAF_INDEX : (uint32_t)nodes.size() - 1; } // :289-292
 };
+
+// .sqwm v11 (src/common/bsp_map_save_load.rs): "SqwM", version, 32 lumps {offset, element_size,
+// element_count}, raw little-endian #[repr(C)] elements; lightmaps, directional lightmaps and light grid samples are stored
+// quantised (lightmap_compression.rs) and are de-quantised f32 in memory.
+enum MapFileResult
+{
+	MAP_FILE_OK = 0,
+	MAP_FILE_IO_ERROR = 1,     // cannot open / short read or write
+	MAP_FILE_NOT_A_MAP = 2,    // bad id ("File is not a valid BSP map")
+	MAP_FILE_BAD_VERSION = 3,  // "Can't load incompatible map version"
+};
+MapFileResult save_map(const BSPMap& map, const char* file_path);
+MapFileResult load_map(const char* file_path, BSPMap& out);
+// The structural checks the renderer relies on (indices inside their arrays, lightmap ranges, root node): "" or what is wrong.
+std::string validate_map(const BSPMap& map, size_t num_materials);
 
 inline uint32_t get_lightmap_size(int32_t tc_min, int32_t tc_max) // common/lightmap.rs:19-27
 {
@@ -101,6 +165,7 @@ struct SceneParams
 	float max_polygon_size = 128.0f; // split so that a lightmap stays <= 17 texels per side (bsp_builder.rs:1282)
 	uint32_t material_mode = 0;      // 0: mix per demo_materials.json (normal map + dielectric/metal specular), 1: plain (no normal map, roughness 1)
 	float emissive_fraction = 0.15f;
+	uint32_t light_grid = 0;       // 1: generate a light grid (64-unit cells over the map) for model / sprite lighting
 	uint32_t skybox = 0;           // 1: the first ceiling material becomes a sky box material (6 sides, 32- and 64-bit, 5 mips)
 	uint32_t sky_size_log2 = 7;    // side of a sky box texture
 	uint32_t num_models = 0;       // triangle-model fixtures to generate (models.hpp)

@@ -93,4 +93,12 @@ struct TriangleModel
 //   kind 2: bending tentacle with a 6-bone chain (SkeletonAnimated, IQM-class).
 void generate_triangle_model(uint32_t kind, uint32_t seed, uint32_t detail, TriangleModel& out);
 
+// bsp_map_compact.rs:179-189
+struct LightGridElement
+{
+	float light_cube[6][3] = {};
+	Vec3f light_direction_vector_scaled = {0, 0, 0};
+	float directional_light_color[3] = {0, 0, 0};
+};
+
 } // namespace sqwh

@@ -82,14 +82,6 @@ struct Decal
 	float light_add[3] = {0, 0, 0};
 };
 
-// bsp_map_compact.rs:179-189
-struct LightGridElement
-{
-	float light_cube[6][3] = {};
-	Vec3f light_direction_vector_scaled = {0, 0, 0};
-	float directional_light_color[3] = {0, 0, 0};
-};
-
 // renderer_structs.rs:311-318 / triangle_models_rendering.rs:376-424
 struct ModelVertex3d
 {

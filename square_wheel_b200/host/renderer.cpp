@@ -1547,22 +1547,110 @@ void Renderer::prepare_dynamic_models() // partial_renderer.rs:995-1120 (root vi
 	stats_.num_visible_meshes = (uint32_t)visible_dynamic_meshes_list_.size();
 }
 
-// get_model_light (triangle_models_rendering.rs:426-572).  Static part: the maps of this mirror carry no light grid, so
-// fetch_light_from_grid returns its zero element (:574-586); dynamic part: the eight bbox sample positions against every
-// dynamic light WITHOUT a shadow map.  Lights with cube / projector shadow maps need get_light_shadow_factor on shadow maps
-// that live on the device here (rendered by depth_kernels.cu) — they do not light models in this mirror.
+// Trilinear fetch from the map's light grid with renormalisation over missing / all-zero samples.
+LightGridElement Renderer::fetch_light_from_grid(Vec3f pos) const // triangle_models_rendering.rs:574-699
+{
+	const LightGridElement zero_light;
+	const LightGridHeader& h = map_.light_grid_header;
+	if (h.grid_size[0] == 0 || h.grid_size[1] == 0 || h.grid_size[2] == 0 || h.grid_cell_size[0] == 0.0f || h.grid_cell_size[1] == 0.0f || h.grid_cell_size[2] == 0.0f ||
+		map_.light_grid_samples.empty() || map_.light_grid_columns.empty())
+		return zero_light;
+	const float grid_pos[3] = {(pos.x - h.grid_start[0]) / h.grid_cell_size[0], (pos.y - h.grid_start[1]) / h.grid_cell_size[1], (pos.z - h.grid_start[2]) / h.grid_cell_size[2]};
+	const int32_t grid_pos_i[3] = {f32_to_i32_saturating(std::floor(grid_pos[0])), f32_to_i32_saturating(std::floor(grid_pos[1])), f32_to_i32_saturating(std::floor(grid_pos[2]))};
+	auto is_zero = [](const LightGridElement& e) {
+		for (int s = 0; s < 6; ++s)
+			for (int c = 0; c < 3; ++c)
+				if (e.light_cube[s][c] != 0.0f)
+					return false;
+		return e.light_direction_vector_scaled.x == 0.0f && e.light_direction_vector_scaled.y == 0.0f && e.light_direction_vector_scaled.z == 0.0f &&
+			e.directional_light_color[0] == 0.0f && e.directional_light_color[1] == 0.0f && e.directional_light_color[2] == 0.0f;
+	};
+	LightGridElement total_light;
+	float total_factor = 0.0f;
+	for (int dx = 0; dx <= 1; ++dx)
+	{
+		const int64_t x = (int64_t)grid_pos_i[0] + dx;
+		if (x < 0 || x >= (int64_t)h.grid_size[0])
+			continue;
+		const float factor_x = 1.0f - std::fabs(grid_pos[0] - (float)x);
+		for (int dy = 0; dy <= 1; ++dy)
+		{
+			const int64_t y = (int64_t)grid_pos_i[1] + dy;
+			if (y < 0 || y >= (int64_t)h.grid_size[1])
+				continue;
+			const LightGridColumn& column = map_.light_grid_columns[(size_t)x + (size_t)y * h.grid_size[0]];
+			if (column.num_samples == 0)
+				continue;
+			const float factor_y = 1.0f - std::fabs(grid_pos[1] - (float)y);
+			for (int dz = 0; dz <= 1; ++dz)
+			{
+				const int64_t z = (int64_t)grid_pos_i[2] + dz;
+				if (z < 0 || z >= (int64_t)h.grid_size[2])
+					continue;
+				if ((uint64_t)z < column.start_z || (uint64_t)z >= (uint64_t)column.start_z + column.num_samples)
+					continue;
+				const size_t address = (size_t)column.first_sample + (size_t)(z - column.start_z);
+				if (address >= map_.light_grid_samples.size())
+					continue;
+				const LightGridElement& sample_value = map_.light_grid_samples[address];
+				if (is_zero(sample_value))
+					continue;
+				const float factor_z = 1.0f - std::fabs(grid_pos[2] - (float)z);
+				const float cur_sample_factor = factor_x * factor_y * factor_z;
+				for (int i = 0; i < 3; ++i)
+				{
+					for (int cube_side = 0; cube_side < 6; ++cube_side)
+						total_light.light_cube[cube_side][i] += sample_value.light_cube[cube_side][i] * cur_sample_factor;
+					total_light.directional_light_color[i] += sample_value.directional_light_color[i] * cur_sample_factor;
+				}
+				total_light.light_direction_vector_scaled = total_light.light_direction_vector_scaled + sample_value.light_direction_vector_scaled * cur_sample_factor;
+				total_factor += cur_sample_factor;
+			}
+		}
+	}
+	if (total_factor <= 0.0f)
+		return zero_light;
+	if (total_factor < 0.995f)
+	{
+		const float inv_total_factor = 1.0f / total_factor;
+		for (int i = 0; i < 3; ++i)
+		{
+			for (int cube_side = 0; cube_side < 6; ++cube_side)
+				total_light.light_cube[cube_side][i] *= inv_total_factor;
+			total_light.directional_light_color[i] *= inv_total_factor;
+		}
+		total_light.light_direction_vector_scaled = total_light.light_direction_vector_scaled * inv_total_factor;
+	}
+	return total_light;
+}
+
+// get_model_light (triangle_models_rendering.rs:426-572).  Static part: the light grid (get_model_static_light, :539-572);
+// dynamic part: the eight bbox sample positions against every dynamic light WITHOUT a shadow map.  Lights with cube /
+// projector shadow maps need get_light_shadow_factor on shadow maps that live on the device here (rendered by
+// depth_kernels.cu) — they do not light models in this mirror.
 ModelLightData Renderer::get_model_light(const ModelEntity& model, const Mat4f& model_matrix) const
 {
 	LightGridElement static_light;
-	if (model.lighting == MODEL_LIGHTING_CONSTANT)
+	if (model.lighting == MODEL_LIGHTING_DEFAULT)
+		static_light = fetch_light_from_grid(model.position);
+	else if (model.lighting == MODEL_LIGHTING_CONSTANT)
 	{
 		for (auto& side : static_light.light_cube)
 			std::memcpy(side, model.light, 12);
 	}
-	else if (model.lighting == MODEL_LIGHTING_ADVANCED)
+	else
 	{
 		for (auto& side : static_light.light_cube)
-			std::memcpy(side, model.light, 12); // + grid_light_scale * (zero grid light)
+			std::memcpy(side, model.light, 12);
+		if (model.grid_light_scale > 0.0f)
+		{
+			const LightGridElement grid_light = fetch_light_from_grid(model.light_position);
+			for (int i = 0; i < 6; ++i)
+				for (int j = 0; j < 3; ++j)
+					static_light.light_cube[i][j] += model.grid_light_scale * grid_light.light_cube[i][j];
+			static_light.light_direction_vector_scaled = grid_light.light_direction_vector_scaled * model.grid_light_scale;
+			std::memcpy(static_light.directional_light_color, grid_light.directional_light_color, 12);
+		}
 	}
 	LightCube light_cube;
 	auto calculate_model_dynamic_light_cube = [&]() { // :494-537
@@ -2141,7 +2229,15 @@ void Renderer::prepare_sprites() // partial_renderer.rs:740-990
 		std::memcpy(info.light, sprite.light_add, 12);
 		if (sprite.light_scale > 0.0f)
 		{
-			// fetch_light_from_grid: zero without a light grid (see get_model_light); dynamic lights without shadow maps (:934-980)
+			const LightGridElement grid_light = fetch_light_from_grid(sprite.position); // :915-932
+			const float cube_side_scale = sprite.light_scale / 6.0f;
+			for (const auto& cube_side : grid_light.light_cube)
+				for (int i = 0; i < 3; ++i)
+					info.light[i] += cube_side[i] * cube_side_scale;
+			const float directional_component_scale = sprite.light_scale * 0.5f * magnitude(grid_light.light_direction_vector_scaled);
+			for (int i = 0; i < 3; ++i)
+				info.light[i] += directional_component_scale * grid_light.directional_light_color[i];
+			// dynamic lights without shadow maps (:934-980; see get_model_light for the ones with)
 			const float dynamic_lights_scale = sprite.light_scale * 0.5f;
 			const float min_square_distance = sprite.radius * sprite.radius;
 			for (size_t li = 0; li < frame_lights_.size(); ++li)

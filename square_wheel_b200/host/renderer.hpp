@@ -173,6 +173,7 @@ private:
 	void prepare_dynamic_models();
 	void build_dynamic_models_buffers();
 	ModelLightData get_model_light(const ModelEntity& model, const Mat4f& model_matrix) const;
+	LightGridElement fetch_light_from_grid(Vec3f pos) const; // triangle_models_rendering.rs:574-699
 	void draw_leaf_objects(const ClippingPolygon& bounds, uint32_t leaf_index);
 	// decals: dynamic_objects_index.rs:76-91, partial_renderer.rs:665-737, :2794-3096, :3807-3875
 	void position_decals();

@@ -32,6 +32,7 @@ class SceneParams(C.Structure):
         ("model_detail", C.c_uint32),
         ("skybox", C.c_uint32),
         ("sky_size_log2", C.c_uint32),
+        ("light_grid", C.c_uint32),
     ]
 
 
@@ -144,6 +145,15 @@ def lib() -> C.CDLL:
         l.sqwh_renderer_set_decals.argtypes = [vp, vp, vp, C.c_uint32]
         l.sqwh_renderer_set_sprites.restype = C.c_int
         l.sqwh_renderer_set_sprites.argtypes = [vp, vp, vp, C.c_uint32]
+        l.sqwh_scene_save_map.restype = C.c_int
+        l.sqwh_scene_save_map.argtypes = [vp, C.c_char_p]
+        l.sqwh_scene_load_map.restype = C.c_int
+        l.sqwh_scene_load_map.argtypes = [vp, C.c_char_p]
+        l.sqwh_last_map_error.restype = C.c_char_p
+        l.sqwh_scene_num_light_grid_samples.restype = C.c_uint32
+        l.sqwh_scene_num_light_grid_samples.argtypes = [vp]
+        l.sqwh_scene_texture_name.restype = C.c_char_p
+        l.sqwh_scene_texture_name.argtypes = [vp, C.c_uint32]
         l.sqwh_scene_model_info.restype = C.c_int
         l.sqwh_scene_model_info.argtypes = [vp, C.c_uint32, C.POINTER(ModelInfo)]
         for name in (
@@ -186,6 +196,10 @@ class Scene:
         self._handle = self._lib.sqwh_scene_create(C.byref(self.params))
         if not self._handle:
             raise ValueError("bad scene parameters")
+        self._refresh()
+
+    def _refresh(self):
+        """(Re)read what the scene exposes to Python: counts, lightmaps, images."""
         self.info = SceneInfo()
         self._lib.sqwh_scene_get_info(self._handle, C.byref(self.info))
         n = int(self.info.num_lightmap_elements)
@@ -197,6 +211,31 @@ class Scene:
             p = self._lib.sqwh_scene_image(self._handle, i, C.byref(kind), C.byref(w), C.byref(h))
             dt = {N.IMAGE_TEXTURE_ELEMENT: N.texture_element_dtype, N.IMAGE_COLOR32: np.uint32, N.IMAGE_COLOR64: np.uint64}[kind.value]
             self.images.append((kind.value, _array_from(p, w.value * h.value, dt).reshape(h.value, w.value)))
+
+    MAP_FILE_ERRORS = {1: "i/o error", 2: "not a Square-Wheel map (bad id)", 3: "incompatible map version (expected 11)"}
+
+    def save_map(self, path: str):
+        """Write the map as .sqwm v11 (bsp_map_save_load.rs::save_map): lightmaps and light grid quantised like the reference."""
+        r = self._lib.sqwh_scene_save_map(self._handle, os.fsencode(path))
+        if r != 0:
+            raise OSError(f"save_map({path}): {self.MAP_FILE_ERRORS.get(r, r)}")
+
+    def load_map(self, path: str):
+        """Replace this scene's map by a .sqwm v11 file (bsp_map_save_load.rs::load_map), e.g. one compiled and lit by the
+        reference's map_compiler + lightmapper.  Materials, textures and models of the scene are kept: every polygon's texture
+        index must have a material.  Close renderers of this scene before calling."""
+        r = self._lib.sqwh_scene_load_map(self._handle, os.fsencode(path))
+        if r == 4:
+            raise ValueError(f"load_map({path}): {self._lib.sqwh_last_map_error().decode()}")
+        if r != 0:
+            raise OSError(f"load_map({path}): {self.MAP_FILE_ERRORS.get(r, r)}")
+        self._refresh()
+
+    def texture_name(self, index: int) -> str:
+        n = self._lib.sqwh_scene_texture_name(self._handle, index)
+        if n is None:
+            raise IndexError(index)
+        return n.decode()
 
     def model_info(self, index: int) -> ModelInfo:
         mi = ModelInfo()

@@ -297,3 +297,38 @@ def test_config3_decals_and_sprites(oracle_lib, color_bits):
     finally:
         r.close()
         sc.close()
+
+
+def test_frames_from_a_loaded_sqwm_map(oracle_lib, tmp_path):
+    """The data format on the input side of the path: a map written as .sqwm v11 (quantised lightmaps, light grid) and loaded
+    back renders bit-exactly against the oracle fed with the loaded lightmaps — models lit through the loaded light grid."""
+    W, H = 640, 360
+    kw = dict(seed=7, texture_size_log2=6, num_materials=8, light_grid=1, num_models=3, model_detail=8)
+    src = S.Scene(**kw)
+    path = str(tmp_path / "level.sqwm")
+    src.save_map(path)
+    src.close()
+    sc = S.Scene(**kw)
+    sc.load_map(path)
+    r = Renderer(sc, RendererConfig(use_directional_lightmaps=True))
+    try:
+        poses = sc.camera_path(64)
+        for k in (5, 30):
+            models = _models_ahead_of_camera(sc, poses[k], k)
+            models["lighting"] = S.MODEL_LIGHTING_DEFAULT
+            hf = r.prepare_frame(SurfaceInfo(W, H), FrameInfo(poses[k], model_entities=models), color_bits=64)
+            pixels = np.zeros((H, W), np.uint64)
+            r.draw_frame(pixels)
+            assert hf.triangle_points is not None and hf.triangle_points["light"].max() > 0  # the light grid lights the models
+            oracle_lib.reset_assert_failures()
+            surf = oracle_lib.build_surfaces(64, hf.jobs, None, None, hf.cam_pos, sc.images, sc.lightmaps, sc.directional_lightmaps, hf.total_surface_pixels)
+            fb = np.zeros((H, W), np.uint64)
+            if hf.needs_clear:
+                oracle_lib.fill(fb, S.BACKGROUND_COLOR64)
+            oracle_lib.draw(64, fb, hf.cmds, hf.polygon_points, hf.triangle_points, surf, sc.images)
+            assert oracle_lib.assert_failures() == 0
+            assert_pixels_equal(r._view.read_surfaces(0, hf.total_surface_pixels), surf, f"frame {k} surfaces from the loaded map")
+            assert_pixels_equal(pixels, fb, f"frame {k} picture from the loaded map")
+    finally:
+        r.close()
+        sc.close()
