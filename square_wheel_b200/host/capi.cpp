@@ -27,13 +27,14 @@ struct sqwh_scene_params // mirrors sqwh::SceneParams (plain C layout for ctypes
 	uint32_t skybox;
 	uint32_t sky_size_log2;
 	uint32_t light_grid;
+	uint32_t num_submodels;
 };
 
 struct sqwh_scene_info
 {
 	uint32_t num_nodes, num_leafs, num_polygons, num_portals, num_vertices, num_materials, num_images, num_waypoints;
 	uint64_t num_lightmap_elements;
-	uint32_t num_models, reserved;
+	uint32_t num_models, num_submodels;
 };
 
 struct sqwh_renderer_config
@@ -133,6 +134,7 @@ void sqwh_default_scene_params(sqwh_scene_params* p)
 	p->skybox = d.skybox;
 	p->sky_size_log2 = d.sky_size_log2;
 	p->light_grid = d.light_grid;
+	p->num_submodels = d.num_submodels;
 }
 
 Scene* sqwh_scene_create(const sqwh_scene_params* p)
@@ -157,6 +159,7 @@ Scene* sqwh_scene_create(const sqwh_scene_params* p)
 	sp.skybox = p->skybox;
 	sp.sky_size_log2 = p->sky_size_log2;
 	sp.light_grid = p->light_grid;
+	sp.num_submodels = p->num_submodels;
 	Scene* s = new (std::nothrow) Scene();
 	if (!s)
 		return nullptr;
@@ -177,7 +180,7 @@ void sqwh_scene_get_info(const Scene* s, sqwh_scene_info* out)
 	out->num_waypoints = (uint32_t)s->camera_waypoints.size();
 	out->num_lightmap_elements = s->map.directional_lightmaps_data.size();
 	out->num_models = (uint32_t)s->models.size();
-	out->reserved = 0;
+	out->num_submodels = (uint32_t)s->map.submodels.size();
 }
 // .sqwm v11 (bsp_map_save_load.rs): write the scene's map / replace the scene's map by a file's.  Return a MapFileResult
 // (0 ok, 1 i/o error, 2 not a map, 3 incompatible version), or 4 when the loaded map fails validate_map against the scene's
@@ -325,6 +328,36 @@ int sqwh_renderer_set_sprites(Renderer* r, const Scene* s, const sqwh_sprite* sp
 	}
 	r->set_sprites(v.data(), v.size());
 	return 0;
+}
+
+struct sqwh_submodel_entity // frame_info.rs:13 (SubmodelEntityOpt): present = 0 hides the submodel
+{
+	uint32_t present;
+	float position[3];
+	float rotation[4]; // quaternion s, x, y, z
+};
+// FrameInfo::submodel_entities of the next prepare_frame: one record per map submodel (n must equal the number of submodels).
+int sqwh_renderer_set_submodel_entities(Renderer* r, const sqwh_submodel_entity* e, uint32_t n)
+{
+	if (n != r->num_submodels())
+		return -1;
+	std::vector<Renderer::SubmodelEntity> v(n);
+	for (uint32_t i = 0; i < n; ++i)
+	{
+		v[i].present = e[i].present != 0;
+		v[i].position = {e[i].position[0], e[i].position[1], e[i].position[2]};
+		v[i].rotation = Quaternion{e[i].rotation[0], {e[i].rotation[1], e[i].rotation[2], e[i].rotation[3]}};
+	}
+	r->set_submodel_entities(v.data(), n);
+	return 0;
+}
+// bbox centre of a submodel = the position that leaves it where the map has it
+void sqwh_renderer_submodel_center(const Renderer* r, uint32_t index, float out[3])
+{
+	const Vec3f c = r->submodel_bbox(index).get_center();
+	out[0] = c.x;
+	out[1] = c.y;
+	out[2] = c.z;
 }
 
 // FrameInfo::decals of the next prepare_frame.  Returns 0, or -1 for a bad skin / mode.

@@ -761,7 +761,41 @@ struct Builder
 		}
 		build_bsp(all);
 		build_leaf_geometry();
+		build_submodels();
 		build_lightmaps();
+	}
+
+	// Inline models (bsp_map_compact.rs:87-107): axis-aligned crates standing beside the fly-through path, their polygons
+	// appended after all leaf polygons, one SubmodelBSPNode each (a convex solid needs no ordering between its faces).
+	void build_submodels()
+	{
+		BSPMap& m = s.map;
+		const size_t nw = s.camera_waypoints.size();
+		for (uint32_t k = 0; k < s.params.num_submodels && nw > 0; ++k)
+		{
+			const Vec3f c = s.camera_waypoints[(size_t)((uint64_t)k * nw / s.params.num_submodels) % nw];
+			const float half[3] = {rng.uniform(14.0f, 26.0f), rng.uniform(14.0f, 26.0f), rng.uniform(18.0f, 34.0f)};
+			const float side = (k & 1) ? 1.0f : -1.0f;
+			const Vec3f center = {c.x + side * 0.28f * s.params.cell_size[0], c.y - side * 0.22f * s.params.cell_size[1], c.z - 0.5f * s.params.cell_size[2] + half[2] + 6.0f};
+			const float lo[3] = {center.x - half[0], center.y - half[1], center.z - half[2]}, hi[3] = {center.x + half[0], center.y + half[1], center.z + half[2]};
+			Submodel sm;
+			sm.first_polygon = (uint32_t)m.polygons.size();
+			for (int axis = 0; axis < 3; ++axis)
+			{
+				const int ba = (axis + 1) % 3, ca = (axis + 2) % 3;
+				add_wall(1000003u + k, axis, hi[axis], +1, lo[ba], hi[ba], lo[ca], hi[ca]);
+				add_wall(1000003u + k, axis, lo[axis], -1, lo[ba], hi[ba], lo[ca], hi[ca]);
+			}
+			sm.num_polygons = (uint32_t)m.polygons.size() - sm.first_polygon;
+			sm.root_node = (uint32_t)m.submodels_bsp_nodes.size();
+			SubmodelBSPNode node;
+			node.plane = m.polygons[sm.first_polygon].plane;
+			node.first_polygon = sm.first_polygon;
+			node.num_polygons = sm.num_polygons;
+			node.children[0] = node.children[1] = 0xFFFFFFFFu; // >= number of nodes: no child
+			m.submodels_bsp_nodes.push_back(node);
+			m.submodels.push_back(sm);
+		}
 	}
 };
 

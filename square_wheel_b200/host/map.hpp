@@ -165,6 +165,7 @@ struct SceneParams
 	float max_polygon_size = 128.0f; // split so that a lightmap stays <= 17 texels per side (bsp_builder.rs:1282)
 	uint32_t material_mode = 0;      // 0: mix per demo_materials.json (normal map + dielectric/metal specular), 1: plain (no normal map, roughness 1)
 	float emissive_fraction = 0.15f;
+	uint32_t num_submodels = 0;    // inline models (crates beside the camera path), each a one-node submodel BSP of 6+ lit polygons
 	uint32_t light_grid = 0;       // 1: generate a light grid (64-unit cells over the map) for model / sprite lighting
 	uint32_t skybox = 0;           // 1: the first ceiling material becomes a sky box material (6 sides, 32- and 64-bit, 5 mips)
 	uint32_t sky_size_log2 = 7;    // side of a sky box texture

@@ -372,6 +372,30 @@ Renderer::Renderer(const Scene& scene, const RendererConfig& config)
 	vertices_transformed_.resize(map_.vertices.size());
 	leaf_lights_.resize(map_.leafs.size());
 	leaf_models_.resize(map_.leafs.size());
+	leaf_submodels_.resize(map_.leafs.size());
+	// InlineModelsIndex::new (inline_models_index.rs:162-186): bounding boxes of the submodels, extended a little; polygons know
+	// their submodel (DrawPolygonParent::Submodel, partial_renderer.rs:127-133)
+	submodels_bbox_.resize(map_.submodels.size());
+	submodel_leafs_.resize(map_.submodels.size());
+	submodels_info_.resize(map_.submodels.size());
+	submodel_entities_.resize(map_.submodels.size());
+	for (size_t i = 0; i < map_.submodels.size(); ++i)
+	{
+		const Submodel& submodel = map_.submodels[i];
+		const float inf = 1e24f;
+		BBox bbox = {{inf, inf, inf}, {-inf, -inf, -inf}};
+		for (uint32_t p = submodel.first_polygon; p < submodel.first_polygon + submodel.num_polygons; ++p)
+		{
+			polygons_data_[p].parent_submodel = (uint32_t)i;
+			for (uint32_t v = 0; v < map_.polygons[p].num_vertices; ++v)
+				bbox.extend_with_point(map_.vertices[map_.polygons[p].first_vertex + v]);
+		}
+		const Vec3f extend_vec = {0.25f, 0.25f, 0.25f};
+		bbox.max = bbox.max + extend_vec;
+		bbox.min = bbox.min - extend_vec;
+		submodels_bbox_[i] = bbox;
+		submodel_entities_[i].position = bbox.get_center();
+	}
 	leaf_sprites_.resize(map_.leafs.size());
 	leaf_decals_.resize(map_.leafs.size());
 	// get_leaf_clip_planes (renderer_structs.rs:167-226): portal and polygon planes of the leaf, normalised and deduplicated
@@ -822,6 +846,42 @@ void Renderer::depth_draw_map(uint32_t offset, uint32_t size, uint32_t flags, co
 			++num_nodes_on_stack;
 		}
 	}
+	// submodels atop of the static geometry, with depth test (depth_renderer.rs:64-66, :130-200)
+	for (size_t submodel_index = 0; submodel_index < map_.submodels.size(); ++submodel_index)
+	{
+		Mat4f model_matrix;
+		if (!get_submodel_matrix(submodel_index, model_matrix))
+			continue;
+		bool have_bounds = false;
+		ClippingPolygon bounds;
+		for (uint32_t leaf_index : submodel_leafs_[submodel_index])
+		{
+			ClippingPolygon leaf_bounds;
+			if (shadow_visibility_.leaf_bounds(leaf_index, leaf_bounds))
+			{
+				if (have_bounds)
+					bounds.extend(leaf_bounds);
+				else
+				{
+					bounds = leaf_bounds;
+					have_bounds = true;
+				}
+			}
+		}
+		if (!have_bounds)
+			continue;
+		Vec3f clip_planes[8];
+		bounds.get_clip_planes(clip_planes);
+		Mat4f model_matrix_inverse = Mat4f::identity();
+		model_matrix.transpose().invert(model_matrix_inverse);
+		CameraMatrices submodel_camera_matrices;
+		submodel_camera_matrices.view_matrix = depth_matrices.view_matrix * model_matrix;
+		submodel_camera_matrices.planes_matrix = depth_matrices.planes_matrix * model_matrix_inverse;
+		submodel_camera_matrices.position = depth_matrices.position;
+		const Submodel& submodel = map_.submodels[submodel_index];
+		for (uint32_t p = submodel.first_polygon; p < submodel.first_polygon + submodel.num_polygons; ++p)
+			depth_draw_polygon(submodel_camera_matrices, clip_planes, p, true);
+	}
 	map.num_cmds = (uint32_t)depth_cmds_.size() - map.first_cmd;
 	depth_maps_.push_back(map);
 }
@@ -876,7 +936,9 @@ void Renderer::prepare_frame(uint32_t width, uint32_t height, const CameraPose& 
 	visibility_.update_visibility(camera_matrices_, ClippingPolygon::from_box(0.0f, 0.0f, (float)width, (float)height)); // partial_renderer.rs:173-190
 	position_dynamic_lights();   // renderer.rs:88 (DynamicObjectsIndex)
 	prepare_dynamic_lights();    // partial_renderer.rs:192
+	position_submodels();        // renderer.rs:82 (inline_models_index.position_models)
 	build_shadow_maps();         // :194
+	prepare_submodels();         // :196
 	prepare_polygons_surfaces(); // :214
 	position_models();              // renderer.rs:84 (dynamic_models_index.position_models)
 	prepare_dynamic_models();       // partial_renderer.rs:209
@@ -903,13 +965,56 @@ void Renderer::prepare_polygons_surfaces() // partial_renderer.rs:1327-1449 (lea
 		Vec3f clip_planes[8];
 		bounds.get_clip_planes(clip_planes);
 		for (uint32_t p = leaf.first_polygon; p < leaf.first_polygon + leaf.num_polygons; ++p)
-			prepare_polygon_surface(clip_planes, p);
+			prepare_polygon_surface(camera_matrices_, clip_planes, p);
+	}
+	// surfaces of the submodels located in visible leafs (:1362-1447)
+	for (size_t index = 0; index < map_.submodels.size(); ++index)
+	{
+		const SubmodelInfo& info = submodels_info_[index];
+		if (!info.has_matrices)
+			continue;
+		bool have_bounds = false;
+		ClippingPolygon bounds;
+		for (uint32_t leaf_index : submodel_leafs_[index])
+		{
+			ClippingPolygon leaf_bounds;
+			if (visibility_.leaf_bounds(leaf_index, leaf_bounds))
+			{
+				if (have_bounds)
+					bounds.extend(leaf_bounds);
+				else
+				{
+					bounds = leaf_bounds;
+					have_bounds = true;
+				}
+			}
+		}
+		if (!have_bounds)
+			continue;
+		Vec3f clip_planes[8];
+		bounds.get_clip_planes(clip_planes);
+		const Submodel& submodel = map_.submodels[index];
+		for (uint32_t polygon_index = submodel.first_polygon; polygon_index < submodel.first_polygon + submodel.num_polygons; ++polygon_index)
+		{
+			prepare_polygon_surface(info.camera_matrices, clip_planes, polygon_index);
+			// visible: basis vectors in world space under the submodel's transformation, for specular and dynamic lighting
+			DrawPolygonData& polygon_data = polygons_data_[polygon_index];
+			if (polygon_data.visible_frame == current_frame_)
+			{
+				const Polygon& polygon = map_.polygons[polygon_index];
+				const Vec4f plane_transformed_vec = info.world_planes_matrix * extend(polygon.plane.vec, -polygon.plane.dist);
+				const Vec4f t0 = info.world_planes_matrix * extend(polygon.tex_coord_equation[0].vec, polygon.tex_coord_equation[0].dist);
+				const Vec4f t1 = info.world_planes_matrix * extend(polygon.tex_coord_equation[1].vec, polygon.tex_coord_equation[1].dist);
+				const Plane tc[2] = {Plane{truncate(t0), t0.w}, Plane{truncate(t1), t1.w}};
+				basis_vecs_from_plane_and_tc(Plane{truncate(plane_transformed_vec), -plane_transformed_vec.w}, tc, polygon_data);
+			}
+		}
 	}
 	stats_.num_visible_polygons = (uint32_t)current_frame_visible_polygons_.size();
 	stats_.num_surfaces_pixels = num_visible_surfaces_pixels_;
 }
 
-void Renderer::prepare_polygon_surface(const Vec3f clip_planes[8], size_t polygon_index) // partial_renderer.rs:1464-1638
+void Renderer::prepare_polygon_surface(const CameraMatrices& camera_matrices_, const Vec3f clip_planes[8], size_t polygon_index) // partial_renderer.rs:1464-1638
 {
 	DrawPolygonData& polygon_data = polygons_data_[polygon_index];
 	const Polygon& polygon = map_.polygons[polygon_index];
@@ -1130,7 +1235,9 @@ void Renderer::build_surface_jobs() // the closure of build_polygons_surfaces (p
 			if (use_directional_lightmap)
 				j.flags |= SQW_SURF_DIRECTIONAL_LIGHTMAP;
 			// lights of the polygon's leaf that reach it, at most MAX_POLYGON_LIGHTS (partial_renderer.rs:1705-1734)
-			for (uint32_t light_index : leaf_lights_[polygon_data.parent_leaf])
+			const std::vector<uint32_t>& lights_list =
+				polygon_data.parent_submodel < submodels_info_.size() ? submodels_info_[polygon_data.parent_submodel].dynamic_lights : leaf_lights_[polygon_data.parent_leaf];
+			for (uint32_t light_index : lights_list)
 			{
 				if (polygon_is_affected_by_light(polygon, polygon_data, lights_[light_index]))
 				{
@@ -1718,9 +1825,10 @@ void Renderer::build_dynamic_models_buffers() // partial_renderer.rs:1122-1190
 // The tail of draw_leaf (partial_renderer.rs:2584-2790) for the object kinds of this mirror (triangle models and sprites).
 void Renderer::draw_leaf_objects(const ClippingPolygon& bounds, uint32_t leaf_index)
 {
+	const std::vector<uint32_t>& leaf_submodels = leaf_submodels_[leaf_index];
 	const std::vector<uint32_t>& leaf_dynamic_models = leaf_models_[leaf_index];
 	const std::vector<uint32_t>& leaf_sprites = leaf_sprites_[leaf_index];
-	const size_t total_objects = leaf_dynamic_models.size() + leaf_sprites.size();
+	const size_t total_objects = leaf_submodels.size() + leaf_dynamic_models.size() + leaf_sprites.size();
 	if (total_objects == 0)
 		return;
 	Vec3f clip_planes[8];
@@ -1735,7 +1843,9 @@ void Renderer::draw_leaf_objects(const ClippingPolygon& bounds, uint32_t leaf_in
 	}
 	if (total_objects == 1)
 	{
-		if (leaf_dynamic_models.size() == 1)
+		if (leaf_submodels.size() == 1)
+			draw_submodel_in_leaf(clip_planes, leaf_clip_planes, num_planes, leaf_index, leaf_submodels[0]);
+		else if (leaf_dynamic_models.size() == 1)
 		{
 			const DynamicModelInfo entry = dynamic_model_to_dynamic_meshes_index_[leaf_dynamic_models[0]];
 			for (uint32_t m = entry.first_visible_mesh; m < entry.first_visible_mesh + entry.num_visible_meshes; ++m)
@@ -1747,6 +1857,17 @@ void Renderer::draw_leaf_objects(const ClippingPolygon& bounds, uint32_t leaf_in
 	}
 	const uint32_t SUBMODEL_INDEX_ADD = 65536, DYNAMIC_MESH_INDEX_ADD = SUBMODEL_INDEX_ADD + 65536, SPRITE_INDEX_ADD = DYNAMIC_MESH_INDEX_ADD + 65536;
 	objects_sorter_.clear();
+	for (uint32_t model_index : leaf_submodels)
+		if (submodels_info_[model_index].has_matrices)
+		{
+			// get_model_bbox_for_ordering (inline_models_index.rs:68-81): slightly reduced, to order touching models
+			BBox bbox = submodels_bbox_[model_index];
+			const Vec3f center = bbox.get_center();
+			const float eps = 1.0f;
+			bbox.max = {std::fmax(bbox.max.x - eps, center.x), std::fmax(bbox.max.y - eps, center.y), std::fmax(bbox.max.z - eps, center.z)};
+			bbox.min = {std::fmin(bbox.min.x + eps, center.x), std::fmin(bbox.min.y + eps, center.y), std::fmin(bbox.min.z + eps, center.z)};
+			objects_sorter_.add_object(model_index + SUBMODEL_INDEX_ADD, project_bbox(bbox, submodels_info_[model_index].camera_matrices));
+		}
 	for (uint32_t dynamic_model_index : leaf_dynamic_models)
 	{
 		const ModelEntity& model = frame_models_[dynamic_model_index];
@@ -1767,12 +1888,14 @@ void Renderer::draw_leaf_objects(const ClippingPolygon& bounds, uint32_t leaf_in
 		const uint32_t object_index = objects_sorter_.objects[i].first;
 		if (object_index >= SPRITE_INDEX_ADD)
 			draw_sprite(clip_planes, leaf_clip_planes, num_planes, object_index - SPRITE_INDEX_ADD);
-		else
+		else if (object_index >= DYNAMIC_MESH_INDEX_ADD)
 			draw_mesh(bounds, leaf_clip_planes, num_planes, object_index - DYNAMIC_MESH_INDEX_ADD);
+		else
+			draw_submodel_in_leaf(clip_planes, leaf_clip_planes, num_planes, leaf_index, object_index - SUBMODEL_INDEX_ADD);
 	}
 }
 
-// ---- decals --------------------------------------------------------------------------------------------------
+// common/clipping.rs: general-plane clipper shared by submodel polygons and decals
 namespace
 {
 Vec3f get_line_plane_intersection(Vec3f v0, Vec3f v1, const Plane& plane) // clipping.rs:187-195
@@ -1824,6 +1947,171 @@ size_t clip_3d_polygon_by_plane(const Vec3f* polygon, size_t n, const Plane& pla
 	return count;
 }
 } // namespace
+
+// ---- submodels (inline models) -----------------------------------------------------------------------------------
+void Renderer::set_submodel_entities(const SubmodelEntity* e, size_t n)
+{
+	for (size_t i = 0; i < submodel_entities_.size() && i < n; ++i)
+		submodel_entities_[i] = e[i];
+}
+
+bool Renderer::get_submodel_matrix(size_t index, Mat4f& out) const // inline_models_index.rs:188-196
+{
+	const SubmodelEntity& e = submodel_entities_[index];
+	if (!e.present)
+		return false;
+	const Vec3f center = submodels_bbox_[index].get_center();
+	out = Mat4f::from_translation(e.position) * mat4_from_quaternion(e.rotation) * Mat4f::from_translation(-center);
+	return true;
+}
+
+void Renderer::position_submodel_r(uint32_t model_index, const Vec3f bbox_vertices[8], uint32_t node_index) // inline_models_index.rs:128-158
+{
+	if (node_index >= FIRST_LEAF_INDEX)
+	{
+		const uint32_t leaf_index = node_index - FIRST_LEAF_INDEX;
+		leaf_submodels_[leaf_index].push_back(model_index);
+		submodel_leafs_[model_index].push_back(leaf_index);
+		return;
+	}
+	const BSPNode& node = map_.nodes[node_index];
+	size_t vertices_front = 0;
+	for (int i = 0; i < 8; ++i)
+		if (dot(node.plane.vec, bbox_vertices[i]) > node.plane.dist)
+			++vertices_front;
+	if (vertices_front > 0)
+		position_submodel_r(model_index, bbox_vertices, node.children[0]);
+	if (vertices_front < 8)
+		position_submodel_r(model_index, bbox_vertices, node.children[1]);
+}
+
+void Renderer::position_submodels() // InlineModelsIndex::position_models (every model repositioned every frame; same result)
+{
+	for (auto& l : leaf_submodels_)
+		l.clear();
+	for (size_t index = 0; index < map_.submodels.size(); ++index)
+	{
+		submodel_leafs_[index].clear();
+		Mat4f transform_matrix;
+		if (!get_submodel_matrix(index, transform_matrix))
+			continue;
+		Vec3f bbox_vertices[8];
+		submodels_bbox_[index].get_corners_vertices(bbox_vertices);
+		for (Vec3f& v : bbox_vertices)
+			v = truncate(transform_matrix * extend(v, 1.0f));
+		position_submodel_r((uint32_t)index, bbox_vertices, map_.root_node());
+	}
+}
+
+void Renderer::prepare_submodels() // partial_renderer.rs:593-660
+{
+	for (size_t index = 0; index < submodels_info_.size(); ++index)
+	{
+		SubmodelInfo& info = submodels_info_[index];
+		Mat4f model_matrix;
+		info.has_matrices = get_submodel_matrix(index, model_matrix);
+		info.dynamic_lights.clear();
+		if (!info.has_matrices)
+			continue;
+		Mat4f model_matrix_inverse = Mat4f::identity();
+		model_matrix.transpose().invert(model_matrix_inverse);
+		info.world_planes_matrix = model_matrix_inverse;
+		info.camera_matrices.view_matrix = camera_matrices_.view_matrix * model_matrix;
+		info.camera_matrices.planes_matrix = camera_matrices_.planes_matrix * model_matrix_inverse;
+		info.camera_matrices.position = camera_matrices_.position;
+		Vec3f v[8];
+		submodels_bbox_[index].get_corners_vertices(v);
+		for (Vec3f& c : v)
+			c = truncate(model_matrix * extend(c, 1.0f));
+		BBox bbox_world_space = BBox::from_point(v[0]);
+		for (int i = 1; i < 8; ++i)
+			bbox_world_space.extend_with_point(v[i]);
+		for (size_t li = 0; li < frame_lights_.size(); ++li)
+		{
+			const DynamicLight& light = frame_lights_[li];
+			if (!dynamic_lights_info_[li].visible)
+				continue;
+			if (light.position.x - light.radius > bbox_world_space.max.x || light.position.x + light.radius < bbox_world_space.min.x ||
+				light.position.y - light.radius > bbox_world_space.max.y || light.position.y + light.radius < bbox_world_space.min.y ||
+				light.position.z - light.radius > bbox_world_space.max.z || light.position.z + light.radius < bbox_world_space.min.z)
+				continue;
+			info.dynamic_lights.push_back((uint32_t)li);
+		}
+	}
+}
+
+void Renderer::draw_submodel_in_leaf(const Vec3f clip_planes[8], const Plane* leaf_clip_planes, size_t num_leaf_clip_planes, uint32_t leaf_index, uint32_t submodel_index) // :3098-3125
+{
+	const SubmodelInfo& info = submodels_info_[submodel_index];
+	if (!info.has_matrices)
+		return;
+	const uint32_t root = map_.submodels[submodel_index].root_node;
+	if (root < map_.submodels_bsp_nodes.size())
+		draw_submodel_bsp_node_r(info.camera_matrices.planes_matrix.row(3), clip_planes, leaf_clip_planes, num_leaf_clip_planes, leaf_index, root);
+}
+
+void Renderer::draw_submodel_bsp_node_r(
+	Vec4f submodel_planes_matrix_w, const Vec3f clip_planes[8], const Plane* leaf_clip_planes, size_t num_leaf_clip_planes, uint32_t leaf_index, uint32_t node_index) // :3127-3206
+{
+	const SubmodelBSPNode node = map_.submodels_bsp_nodes[node_index];
+	const float plane_transformed_w = dot(submodel_planes_matrix_w, extend(node.plane.vec, -node.plane.dist));
+	uint32_t mask = plane_transformed_w >= 0.0f ? 1 : 0;
+	if (config_.invert_polygons_order)
+		mask ^= 1;
+	const uint32_t c_b = node.children[mask], c_f = node.children[mask ^ 1];
+	const uint32_t num_nodes = (uint32_t)map_.submodels_bsp_nodes.size();
+	if (c_b < num_nodes)
+		draw_submodel_bsp_node_r(submodel_planes_matrix_w, clip_planes, leaf_clip_planes, num_leaf_clip_planes, leaf_index, c_b);
+	const std::vector<uint32_t>& leaf_decals = leaf_decals_[leaf_index];
+	for (uint32_t polygon_index = node.first_polygon; polygon_index < node.first_polygon + node.num_polygons; ++polygon_index)
+	{
+		draw_submodel_polygon(clip_planes, leaf_clip_planes, num_leaf_clip_planes, leaf_index, polygon_index);
+		if (!leaf_decals.empty())
+			draw_polygon_decals(clip_planes, polygon_index, leaf_decals);
+	}
+	if (c_f < num_nodes)
+		draw_submodel_bsp_node_r(submodel_planes_matrix_w, clip_planes, leaf_clip_planes, num_leaf_clip_planes, leaf_index, c_f);
+}
+
+void Renderer::draw_submodel_polygon(const Vec3f clip_planes[8], const Plane* leaf_clip_planes, size_t num_leaf_clip_planes, uint32_t leaf_index, uint32_t polygon_index) // :3208-3288
+{
+	const DrawPolygonData& polygon_data = polygons_data_[polygon_index];
+	if (polygon_data.visible_frame != current_frame_)
+		return;
+	const Polygon& polygon = map_.polygons[polygon_index];
+	Vec3f vertices_clipped[MAX_VERTICES], vertices_temp[MAX_VERTICES];
+	size_t vertex_count = std::min((size_t)polygon.num_vertices, MAX_VERTICES);
+	for (size_t i = 0; i < vertex_count; ++i)
+		vertices_clipped[i] = vertices_transformed_[polygon.first_vertex + i];
+	const std::vector<Plane>& leaf_clip_planes_world_space = leafs_planes_[leaf_index];
+	for (size_t pi = 0; pi < num_leaf_clip_planes && pi < leaf_clip_planes_world_space.size(); ++pi)
+	{
+		// polygons lying on a clip plane: decide in world space instead of clipping (:3234-3270)
+		const Plane& clip_plane_world_space = leaf_clip_planes_world_space[pi];
+		const float almost_one = 1.0f - 1.0f / 256.0f, dist_eps = 1.0f / 4.0f;
+		const float world_space_normals_dot = dot(polygon_data.basis_normal, clip_plane_world_space.vec);
+		if (world_space_normals_dot >= almost_one)
+		{
+			if (std::fabs(dot(clip_plane_world_space.vec, polygon_data.basis_start) - clip_plane_world_space.dist) <= dist_eps)
+				continue;
+		}
+		else if (world_space_normals_dot <= -almost_one)
+		{
+			if (std::fabs(dot(clip_plane_world_space.vec, polygon_data.basis_start) - clip_plane_world_space.dist) <= dist_eps)
+				return;
+		}
+		vertex_count = clip_3d_polygon_by_plane(vertices_clipped, vertex_count, leaf_clip_planes[pi], vertices_temp, MAX_VERTICES);
+		if (vertex_count < 3)
+			return;
+		for (size_t i = 0; i < vertex_count; ++i)
+			vertices_clipped[i] = vertices_temp[i];
+	}
+	draw_polygon(
+		clip_planes, vertices_clipped, vertex_count, polygon_data.depth_equation, polygon_data.tex_coord_equation, polygon_data.surface_size, SQW_TEX_SURFACE,
+		(uint32_t)polygon_data.surface_pixels_offset, scene_.materials[polygon.texture].blending_mode);
+}
+
+// ---- decals --------------------------------------------------------------------------------------------------
 
 void Renderer::position_decal_convex_hull_r(uint32_t id, const Vec3f* vertices, size_t n, uint32_t node_index) // dynamic_objects_index.rs:172-209
 {

@@ -47,6 +47,7 @@ struct RendererConfig
 struct DrawPolygonData
 {
 	uint32_t parent_leaf = 0;
+	uint32_t parent_submodel = 0xFFFFFFFFu; // DrawPolygonParent::Submodel(index) when < number of submodels (renderer_structs.rs:93-98)
 	Vec3f basis_u, basis_v, basis_start, basis_normal; // PolygonBasisVecs for mip 0 (surfaces.rs:7-14)
 	uint32_t visible_frame = 0;
 	float depth_equation[3] = {0, 0, 0};
@@ -146,6 +147,17 @@ public:
 	void set_lights(const DynamicLight* lights, size_t n) { frame_lights_.assign(lights, lights + n); }
 	// FrameInfo::model_entities for the next prepare_frame (frame_info.rs:14)
 	void set_models(const ModelEntity* models, size_t n) { frame_models_.assign(models, models + n); }
+	// FrameInfo::submodel_entities for the next prepare_frame (frame_info.rs:13): one optional entity per map submodel.  Before
+	// the first call every submodel stands where the map compiler left it (position = bbox centre, no rotation).
+	struct SubmodelEntity
+	{
+		bool present = true;
+		Vec3f position;
+		Quaternion rotation;
+	};
+	void set_submodel_entities(const SubmodelEntity* e, size_t n);
+	size_t num_submodels() const { return map_.submodels.size(); }
+	BBox submodel_bbox(size_t i) const { return submodels_bbox_[i]; }
 	// FrameInfo::decals for the next prepare_frame (frame_info.rs:16)
 	void set_decals(const Decal* decals, size_t n) { frame_decals_.assign(decals, decals + n); }
 	// FrameInfo::sprites for the next prepare_frame (frame_info.rs:17)
@@ -175,6 +187,15 @@ private:
 	ModelLightData get_model_light(const ModelEntity& model, const Mat4f& model_matrix) const;
 	LightGridElement fetch_light_from_grid(Vec3f pos) const; // triangle_models_rendering.rs:574-699
 	void draw_leaf_objects(const ClippingPolygon& bounds, uint32_t leaf_index);
+	// submodels: inline_models_index.rs, partial_renderer.rs:593-660, :1362-1447, :3098-3288, depth_renderer.rs:130-200
+	void position_submodels();
+	void position_submodel_r(uint32_t model_index, const Vec3f bbox_vertices[8], uint32_t node_index);
+	bool get_submodel_matrix(size_t index, Mat4f& out) const;
+	void prepare_submodels();
+	void draw_submodel_in_leaf(const Vec3f clip_planes[8], const Plane* leaf_clip_planes, size_t num_leaf_clip_planes, uint32_t leaf_index, uint32_t submodel_index);
+	void draw_submodel_bsp_node_r(
+		Vec4f submodel_planes_matrix_w, const Vec3f clip_planes[8], const Plane* leaf_clip_planes, size_t num_leaf_clip_planes, uint32_t leaf_index, uint32_t node_index);
+	void draw_submodel_polygon(const Vec3f clip_planes[8], const Plane* leaf_clip_planes, size_t num_leaf_clip_planes, uint32_t leaf_index, uint32_t polygon_index);
 	// decals: dynamic_objects_index.rs:76-91, partial_renderer.rs:665-737, :2794-3096, :3807-3875
 	void position_decals();
 	void position_decal_convex_hull_r(uint32_t id, const Vec3f* vertices, size_t n, uint32_t node_index);
@@ -192,7 +213,7 @@ private:
 	void draw_mesh(const ClippingPolygon& clipping_polygon, const Plane* leaf_clip_planes, size_t num_leaf_clip_planes, size_t visible_mesh_index);
 	// partial_renderer.rs
 	void prepare_polygons_surfaces();
-	void prepare_polygon_surface(const Vec3f clip_planes[8], size_t polygon_index);
+	void prepare_polygon_surface(const CameraMatrices& camera_matrices, const Vec3f clip_planes[8], size_t polygon_index);
 	void build_surface_jobs();
 	void draw_skybox(const ClippingPolygon& viewport_clipping_polygon, int color_bits);
 	void draw_tree(const ClippingPolygon& viewport_clipping_polygon);
@@ -251,6 +272,17 @@ private:
 		float light[3] = {0, 0, 0};
 		uint32_t mip = 0, tesselation_level = 0;
 	};
+	struct SubmodelInfo // renderer_structs.rs:170-189 (VisibleSubmodelInfo / VisibleSubmodelMatrices)
+	{
+		bool has_matrices = false;
+		Mat4f world_planes_matrix;
+		CameraMatrices camera_matrices;
+		std::vector<uint32_t> dynamic_lights;
+	};
+	std::vector<BBox> submodels_bbox_;          // InlineModelsIndex::models_info[i].bbox (extended by 1/4)
+	std::vector<SubmodelEntity> submodel_entities_;
+	std::vector<std::vector<uint32_t>> leaf_submodels_, submodel_leafs_;
+	std::vector<SubmodelInfo> submodels_info_;
 	struct DecalInfo // renderer_structs.rs:191-197
 	{
 		Mat4f camera_planes_matrix;

@@ -45,6 +45,7 @@ class FrameInfo:
     model_entities: Optional[np.ndarray] = None  # FrameInfo::model_entities (frame_info.rs:14) as scene.model_entity_dtype records
     sprites: Optional[np.ndarray] = None  # FrameInfo::sprites (frame_info.rs:17) as scene.sprite_dtype records
     decals: Optional[np.ndarray] = None  # FrameInfo::decals (frame_info.rs:16) as scene.decal_dtype records
+    submodel_entities: Optional[np.ndarray] = None  # FrameInfo::submodel_entities (frame_info.rs:13) as scene.submodel_entity_dtype records
 
 
 @dataclass
@@ -78,7 +79,7 @@ class Renderer:
 
     def prepare_frame(self, surface_info: SurfaceInfo, frame_info: FrameInfo, color_bits: int = 64):
         """prepare_frame::<ColorT> (renderer.rs:61): host preparation, then surface building on the GPU (seam S1)."""
-        hf = self.host.build_frame(surface_info.width, surface_info.height, frame_info.pose, frame_info.fov, frame_info.lights, frame_info.model_entities, color_bits, frame_info.sprites, frame_info.decals)
+        hf = self.host.build_frame(surface_info.width, surface_info.height, frame_info.pose, frame_info.fov, frame_info.lights, frame_info.model_entities, color_bits, frame_info.sprites, frame_info.decals, frame_info.submodel_entities)
         view = self._get_view(surface_info, color_bits)
         key = (surface_info.width, surface_info.height, color_bits)
         if key not in self._frames:

@@ -33,6 +33,7 @@ class SceneParams(C.Structure):
         ("skybox", C.c_uint32),
         ("sky_size_log2", C.c_uint32),
         ("light_grid", C.c_uint32),
+        ("num_submodels", C.c_uint32),
     ]
 
 
@@ -40,7 +41,7 @@ class SceneInfo(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("num_nodes", "num_leafs", "num_polygons", "num_portals", "num_vertices", "num_materials", "num_images", "num_waypoints")] + [
         ("num_lightmap_elements", C.c_uint64),
         ("num_models", C.c_uint32),
-        ("reserved", C.c_uint32),
+        ("num_submodels", C.c_uint32),
     ]
 
 
@@ -104,6 +105,10 @@ decal_dtype = np.dtype(
 )
 assert decal_dtype.itemsize == 64
 
+# frame_info.rs:13 SubmodelEntityOpt per map submodel: present = 0 hides it; position = where its bbox centre goes
+submodel_entity_dtype = np.dtype([("present", "<u4"), ("position", "<f4", (3,)), ("rotation", "<f4", (4,))])
+assert submodel_entity_dtype.itemsize == 32
+
 
 class ModelInfo(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("num_frames", "num_meshes", "num_vertices", "num_triangles", "kind", "num_bones")] + [("bbox_min", C.c_float * 3), ("bbox_max", C.c_float * 3)]
@@ -141,6 +146,9 @@ def lib() -> C.CDLL:
         l.sqwh_renderer_set_lights.argtypes = [vp, vp, C.c_uint32]
         l.sqwh_renderer_set_models.restype = C.c_int
         l.sqwh_renderer_set_models.argtypes = [vp, vp, vp, C.c_uint32]
+        l.sqwh_renderer_set_submodel_entities.restype = C.c_int
+        l.sqwh_renderer_set_submodel_entities.argtypes = [vp, vp, C.c_uint32]
+        l.sqwh_renderer_submodel_center.argtypes = [vp, C.c_uint32, vp]
         l.sqwh_renderer_set_decals.restype = C.c_int
         l.sqwh_renderer_set_decals.argtypes = [vp, vp, vp, C.c_uint32]
         l.sqwh_renderer_set_sprites.restype = C.c_int
@@ -293,15 +301,20 @@ class HostRenderer:
         cfg = RendererConfig(1 if use_directional_lightmaps else 0, textures_mip_bias, 1 if clear_background else 0, 0, shadows_quality)
         self._handle = self._lib.sqwh_renderer_create(scene._handle, C.byref(cfg))
 
-    def build_frame(self, width: int, height: int, pose, fov: float = FOV_DEFAULT, lights=None, models=None, color_bits: int = 64, sprites=None, decals=None) -> HostFrame:
+    def build_frame(self, width: int, height: int, pose, fov: float = FOV_DEFAULT, lights=None, models=None, color_bits: int = 64, sprites=None, decals=None, submodels=None) -> HostFrame:
         """lights: FrameInfo::lights as an array of dynamic_light_dtype (or None); models: FrameInfo::model_entities as an array of
-        model_entity_dtype (or None); sprites / decals: FrameInfo::sprites / ::decals as arrays of sprite_dtype / decal_dtype (or None); color_bits: colour type of the target (only picks the sky box textures, SkyboxSideTexture<ColorT>)."""
+        model_entity_dtype (or None); sprites / decals: FrameInfo::sprites / ::decals as arrays of sprite_dtype / decal_dtype (or None); submodels: FrameInfo::submodel_entities, one submodel_entity_dtype record per map submodel (None keeps the last ones;
+        initially every submodel stands where the map has it); color_bits: colour type of the target (only picks the sky box textures, SkyboxSideTexture<ColorT>)."""
         pose = np.ascontiguousarray(pose, np.float32)
         lt = np.ascontiguousarray(lights, dynamic_light_dtype) if lights is not None else np.zeros(0, dynamic_light_dtype)
         self._lib.sqwh_renderer_set_lights(self._handle, lt.ctypes.data_as(C.c_void_p), len(lt))
         md = np.ascontiguousarray(models, model_entity_dtype) if models is not None else np.zeros(0, model_entity_dtype)
         if self._lib.sqwh_renderer_set_models(self._handle, self.scene._handle, md.ctypes.data_as(C.c_void_p), len(md)) != 0:
             raise ValueError("model entity refers to a missing model, skin or frame")
+        if submodels is not None:
+            se = np.ascontiguousarray(submodels, submodel_entity_dtype)
+            if self._lib.sqwh_renderer_set_submodel_entities(self._handle, se.ctypes.data_as(C.c_void_p), len(se)) != 0:
+                raise ValueError("one submodel entity per map submodel is required")
         dc = np.ascontiguousarray(decals, decal_dtype) if decals is not None else np.zeros(0, decal_dtype)
         if self._lib.sqwh_renderer_set_decals(self._handle, self.scene._handle, dc.ctypes.data_as(C.c_void_p), len(dc)) != 0:
             raise ValueError("decal refers to a missing skin or has a bad mode")
@@ -323,6 +336,18 @@ class HostRenderer:
         return HostFrame(
             jobs, int(fi.total_surface_pixels), np.array(list(fi.cam_pos), np.float32), cmds, pts, bool(fi.needs_background_clear), fi, out_lights, dmaps, dcmds, dpts, int(fi.shadow_maps_len), tpts
         )
+
+    def default_submodel_entities(self) -> np.ndarray:
+        """Every submodel present, at the place the map has it (position = bbox centre, identity rotation)."""
+        n = int(self.scene.info.num_submodels)
+        e = np.zeros(n, submodel_entity_dtype)
+        c = np.zeros(3, np.float32)
+        for i in range(n):
+            self._lib.sqwh_renderer_submodel_center(self._handle, i, c.ctypes.data_as(C.c_void_p))
+            e[i]["present"] = 1
+            e[i]["position"] = c
+            e[i]["rotation"] = (1.0, 0.0, 0.0, 0.0)
+        return e
 
     def close(self):
         if self._handle:

@@ -332,3 +332,58 @@ def test_frames_from_a_loaded_sqwm_map(oracle_lib, tmp_path):
     finally:
         r.close()
         sc.close()
+
+
+@pytest.mark.parametrize("color_bits", [32, 64])
+def test_submodels_moved_rotated_lit_and_shadowing(oracle_lib, color_bits):
+    """Inline models (map submodels): surfaces prepared through the submodel's own camera matrices, basis vectors re-derived in
+    world space for specular and dynamic lights, polygons clipped by the leaf planes and drawn through the submodel BSP, sorted
+    with models and sprites inside a leaf, decals on their polygons, and depth-tested fills in the shadow maps."""
+    from common import scatter_decals, sprites_ahead_of_camera
+
+    W, H = 640, 360
+    sc = S.Scene(seed=7, texture_size_log2=6, num_materials=8, num_submodels=24, num_models=2, model_detail=6)
+    r = Renderer(sc, RendererConfig(use_directional_lightmaps=True))
+    try:
+        path = sc.camera_path(64)
+        base = r.host.default_submodel_entities()
+        submodel_jobs = 0
+        for n, k in enumerate((15, 16, 40, 2)):
+            ent = base.copy()
+            a = 0.3 * (n + 1)
+            ent["rotation"][:, 0] = np.cos(a / 2)
+            ent["rotation"][:, 3] = np.sin(a / 2)  # about z
+            ent["position"][:, 2] += 4.0 * n  # and lifted a little
+            ent["present"][n::5] = 0  # some are hidden
+            lights = _lights_along_path(path, 6, 21 + n)
+            lights["position"] = path[k][:3] + np.array([[30, 20, 10], [-40, 50, 0], [10, 80, -20], [0, 10, 30], [60, -20, 5], [-20, -30, 15]], np.float32)
+            fi = FrameInfo(
+                path[k], lights=lights, submodel_entities=ent, model_entities=_models_ahead_of_camera(sc, path[k], k), sprites=sprites_ahead_of_camera(S, path[k], 4, num_skins=2),
+                decals=scatter_decals(S, path[k], 24, k, num_skins=2),
+            )
+            hf = r.prepare_frame(SurfaceInfo(W, H), fi, color_bits=color_bits)
+            pixels = np.zeros((H, W), np.uint32 if color_bits == 32 else np.uint64)
+            r.draw_frame(pixels)
+            ent_none = base.copy()
+            ent_none["present"] = 0
+            sm = np.zeros(max(hf.shadow_maps_len, 1), np.float32)
+            if len(hf.depth_maps):
+                oracle_lib.draw_shadow_maps(sm, hf.depth_maps, hf.depth_cmds, hf.depth_points)
+                got_sm = r._frame.read_shadow_maps(0, hf.shadow_maps_len)
+                assert got_sm.view(np.uint32).tolist() == sm[: hf.shadow_maps_len].view(np.uint32).tolist(), f"frame {k} shadow maps"
+            oracle_lib.reset_assert_failures()
+            surf = oracle_lib.build_surfaces(color_bits, hf.jobs, hf.lights, sm, hf.cam_pos, sc.images, sc.lightmaps, sc.directional_lightmaps, hf.total_surface_pixels)
+            fb = np.zeros((H, W), pixels.dtype)
+            if hf.needs_clear:
+                oracle_lib.fill(fb, S.BACKGROUND_COLOR64 if color_bits == 64 else S.BACKGROUND_COLOR32)
+            oracle_lib.draw(color_bits, fb, hf.cmds, hf.polygon_points, hf.triangle_points, surf, sc.images)
+            assert oracle_lib.assert_failures() == 0
+            assert_pixels_equal(r._view.read_surfaces(0, hf.total_surface_pixels), surf, f"frame {k} surfaces with submodels")
+            assert_pixels_equal(pixels, fb, f"frame {k} picture with submodels")
+            jobs_with = len(hf.jobs)
+            hf0 = r.host.build_frame(W, H, path[k], lights=lights, submodels=ent_none, color_bits=color_bits)
+            submodel_jobs += jobs_with - len(hf0.jobs)
+        assert submodel_jobs >= 8  # submodel polygons really were built and drawn
+    finally:
+        r.close()
+        sc.close()

@@ -116,3 +116,52 @@ def test_skybox_polygons_become_a_window(oracle_lib):
         hr_plain.close()
         sc.close()
         plain.close()
+
+
+def test_submodels_follow_their_entities(oracle_lib):
+    """Inline models: hidden entities add nothing; present ones add surface jobs and polygon commands; moving an entity moves
+    its picture; depth-tested fills appear in the shadow-map lists; the oracle draws the frame without gaps or asserts."""
+    from square_wheel_b200 import _native as N
+
+    sc = S.Scene(seed=7, texture_size_log2=6, num_materials=8, num_submodels=24)
+    plain = S.Scene(seed=7, texture_size_log2=6, num_materials=8)
+    hr, hp = S.HostRenderer(sc), S.HostRenderer(plain)
+    try:
+        assert sc.info.num_submodels == 24 and sc.info.num_polygons > plain.info.num_polygons
+        W, H = 320, 180
+        pose = sc.camera_path(64)[15]
+        ent = hr.default_submodel_entities()
+        hidden = ent.copy()
+        hidden["present"] = 0
+        f_hidden = hr.build_frame(W, H, pose, submodels=hidden)
+        f_plain = hp.build_frame(W, H, pose)
+        assert len(f_hidden.jobs) == len(f_plain.jobs) and len(f_hidden.cmds) == len(f_plain.cmds)
+        f_shown = hr.build_frame(W, H, pose, submodels=ent)
+        assert len(f_shown.jobs) > len(f_hidden.jobs) and len(f_shown.cmds) > len(f_hidden.cmds)
+        moved = ent.copy()
+        moved["position"][:, 0] += 9.0
+        f_moved = hr.build_frame(W, H, pose, submodels=moved)
+        assert f_moved.polygon_points.tobytes() != f_shown.polygon_points.tobytes()
+        with pytest.raises(ValueError):
+            hr.build_frame(W, H, pose, submodels=ent[:3])
+        # shadow maps: submodel polygons are the depth-tested fills (depth_renderer.rs:64-66)
+        lights = np.zeros(1, S.dynamic_light_dtype)
+        lights[0]["position"] = pose[:3]
+        lights[0]["radius"] = 512.0
+        lights[0]["color"] = (30000.0, 30000.0, 30000.0)
+        lights[0]["shadow_type"] = N.SHADOW_CUBE
+        lights[0]["rotation"] = (1.0, 0.0, 0.0, 0.0)
+        f_lit = hr.build_frame(W, H, pose, lights=lights, submodels=ent)
+        assert len(f_lit.depth_cmds) and int(f_lit.depth_cmds["depth_test"].sum()) > 0
+        f_lit_hidden = hr.build_frame(W, H, pose, lights=lights, submodels=hidden)
+        assert int(f_lit_hidden.depth_cmds["depth_test"].sum()) == 0
+        surf = oracle_lib.build_surfaces(32, f_shown.jobs, None, None, f_shown.cam_pos, sc.images, sc.lightmaps, sc.directional_lightmaps, f_shown.total_surface_pixels)
+        fb = np.zeros((H, W), np.uint32)
+        oracle_lib.reset_assert_failures()
+        oracle_lib.draw(32, fb, f_shown.cmds, f_shown.polygon_points, None, surf, sc.images)
+        assert oracle_lib.assert_failures() == 0 and int((fb == 0).sum()) == 0
+    finally:
+        hr.close()
+        hp.close()
+        sc.close()
+        plain.close()
