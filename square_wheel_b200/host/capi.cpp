@@ -2,6 +2,7 @@
 // This library contains NO pixel work: it plays the part of the reference's Rust host around the C-ABI seams
 // (scene description, visibility, surface preparation, BSP traversal).
 #include "renderer.hpp"
+#include <algorithm>
 #include <cstring>
 #include <new>
 #include <string>
@@ -44,6 +45,7 @@ struct sqwh_renderer_config
 	uint32_t clear_background;
 	uint32_t invert_polygons_order;
 	float shadows_quality;
+	uint32_t portals_depth;
 };
 
 struct sqwh_frame_info
@@ -244,6 +246,7 @@ Renderer* sqwh_renderer_create(const Scene* s, const sqwh_renderer_config* cfg)
 		c.clear_background = cfg->clear_background != 0;
 		c.invert_polygons_order = cfg->invert_polygons_order != 0;
 		c.shadows_quality = cfg->shadows_quality;
+		c.portals_depth = std::min(cfg->portals_depth, 8u); // renderer.rs:33
 	}
 	return new (std::nothrow) Renderer(*s, c);
 }
@@ -329,6 +332,94 @@ int sqwh_renderer_set_sprites(Renderer* r, const Scene* s, const sqwh_sprite* sp
 	r->set_sprites(v.data(), v.size());
 	return 0;
 }
+
+#define SQWH_MAX_PORTAL_VERTICES 8
+struct sqwh_portal // frame_info.rs:171-205 (ViewPortal + ViewPortalTexture) in plain C layout
+{
+	uint32_t view;               // 0 CameraAtPosition, 1 Mirror, 2 ParallaxPortal
+	float camera_position[3];    // CameraAtPosition
+	float camera_rotation[4];    // quaternion s, x, y, z
+	float camera_fov;            // radians
+	float transform_matrix[16];  // ParallaxPortal, column-major
+	float plane[4];              // vec, dist
+	float tex_coord_equation[2][4];
+	uint32_t num_vertices;
+	float vertices[SQWH_MAX_PORTAL_VERTICES][3];
+	uint32_t blending_mode;
+	uint32_t has_texture;        // ViewPortalTexture present
+	uint32_t texture_skin;       // index of the scene's skin (TextureLiteWithMips)
+	uint32_t texture_blending_mode;
+	float texture_light_scale;
+	float texture_light_add[3];
+};
+struct sqwh_portal_info // renderer_structs.rs:234-243 + what the caller needs to finish the portal texture
+{
+	uint32_t resolution[2];      // 0 x 0: not visible this frame
+	int32_t tc_min[2];
+	uint32_t mip;
+	uint32_t has_texture, texture_image, texture_blending_mode; // overlay: SQW_IMAGE_COLOR32 image id of mip `mip`
+	float texture_light[3];
+};
+
+int sqwh_renderer_set_portals(Renderer* r, const Scene* s, const sqwh_portal* portals, uint32_t n)
+{
+	std::vector<ViewPortal> v(n);
+	for (uint32_t i = 0; i < n; ++i)
+	{
+		const sqwh_portal& p = portals[i];
+		if (p.view > PORTAL_VIEW_PARALLAX_PORTAL || p.num_vertices < 3 || p.num_vertices > SQWH_MAX_PORTAL_VERTICES || p.blending_mode > SQW_BLEND_ALPHA_BLEND ||
+			(p.has_texture && (p.texture_skin >= s->model_skins.size() || p.texture_blending_mode > SQW_BLEND_ALPHA_BLEND)))
+			return -1;
+		v[i].view = (PortalViewKind)p.view;
+		v[i].camera_position = {p.camera_position[0], p.camera_position[1], p.camera_position[2]};
+		v[i].camera_rotation = Quaternion{p.camera_rotation[0], {p.camera_rotation[1], p.camera_rotation[2], p.camera_rotation[3]}};
+		v[i].camera_fov = p.camera_fov;
+		const float* m = p.transform_matrix;
+		v[i].transform_matrix = Mat4f::from_cols({m[0], m[1], m[2], m[3]}, {m[4], m[5], m[6], m[7]}, {m[8], m[9], m[10], m[11]}, {m[12], m[13], m[14], m[15]});
+		v[i].plane = Plane{{p.plane[0], p.plane[1], p.plane[2]}, p.plane[3]};
+		for (int k = 0; k < 2; ++k)
+			v[i].tex_coord_equation[k] = Plane{{p.tex_coord_equation[k][0], p.tex_coord_equation[k][1], p.tex_coord_equation[k][2]}, p.tex_coord_equation[k][3]};
+		for (uint32_t k = 0; k < p.num_vertices; ++k)
+			v[i].vertices.push_back({p.vertices[k][0], p.vertices[k][1], p.vertices[k][2]});
+		v[i].blending_mode = (int)p.blending_mode;
+		v[i].has_texture = p.has_texture != 0;
+		if (v[i].has_texture)
+		{
+			for (uint32_t k = 0; k < NUM_MIPS; ++k)
+				v[i].texture_images[k] = s->model_skins[p.texture_skin][k];
+			v[i].texture_blending_mode = (int)p.texture_blending_mode;
+			v[i].texture_light_scale = p.texture_light_scale;
+			std::memcpy(v[i].texture_light_add, p.texture_light_add, 12);
+		}
+	}
+	r->set_portals(v.data(), v.size());
+	return 0;
+}
+uint32_t sqwh_renderer_num_portals(const Renderer* r) { return (uint32_t)r->portals_info().size(); }
+int sqwh_renderer_portal_info(const Renderer* r, uint32_t index, sqwh_portal_info* out)
+{
+	if (index >= r->portals_info().size())
+		return -1;
+	const PortalInfo& pi = r->portals_info()[index];
+	const ViewPortal& p = r->portals()[index];
+	std::memset(out, 0, sizeof(*out));
+	out->resolution[0] = pi.resolution[0];
+	out->resolution[1] = pi.resolution[1];
+	out->tc_min[0] = pi.tc_min[0];
+	out->tc_min[1] = pi.tc_min[1];
+	out->mip = pi.mip;
+	out->has_texture = p.has_texture ? 1 : 0;
+	if (p.has_texture)
+	{
+		out->texture_image = p.texture_images[pi.mip];
+		out->texture_blending_mode = (uint32_t)p.texture_blending_mode;
+		r->portal_texture_light(index, out->texture_light);
+	}
+	return 0;
+}
+// The nested view of portal `index` (build_view_portals_textures): prepares and records the child renderer's frame and returns the
+// child (read its lists with the usual getters before the next call), or NULL: portal invisible / depth limit (black texture).
+Renderer* sqwh_renderer_prepare_portal_view(Renderer* r, uint32_t index, int color_bits) { return r->prepare_portal_view(index, color_bits == 32 ? 32 : 64); }
 
 struct sqwh_submodel_entity // frame_info.rs:13 (SubmodelEntityOpt): present = 0 hides the submodel
 {

@@ -82,6 +82,40 @@ struct Decal
 	float light_add[3] = {0, 0, 0};
 };
 
+// frame_info.rs:171-205
+enum PortalViewKind : uint32_t
+{
+	PORTAL_VIEW_CAMERA_AT_POSITION = 0,
+	PORTAL_VIEW_MIRROR = 1,
+	PORTAL_VIEW_PARALLAX_PORTAL = 2,
+};
+struct ViewPortal
+{
+	PortalViewKind view = PORTAL_VIEW_MIRROR;
+	Vec3f camera_position;            // CameraAtPosition
+	Quaternion camera_rotation;
+	float camera_fov = 1.0f;          // radians
+	Mat4f transform_matrix = Mat4f::identity(); // ParallaxPortal
+	Plane plane;
+	Plane tex_coord_equation[2];
+	std::vector<Vec3f> vertices;
+	int blending_mode = SQW_BLEND_NONE;
+	bool has_texture = false;         // ViewPortalTexture
+	int texture_blending_mode = SQW_BLEND_AVERAGE;
+	uint32_t texture_images[NUM_MIPS] = {0, 0, 0, 0, 0};
+	float texture_light_scale = 0.0f;
+	float texture_light_add[3] = {1, 1, 1};
+};
+// renderer_structs.rs:234-243
+struct PortalInfo
+{
+	uint32_t resolution[2] = {0, 0}; // 0 area: not visible this frame
+	float depth_equation[3] = {0, 0, 0};
+	float tex_coord_equation[6] = {0, 0, 0, 0, 0, 0};
+	int32_t tc_min[2] = {0, 0};
+	uint32_t mip = 0;
+};
+
 // renderer_structs.rs:311-318 / triangle_models_rendering.rs:376-424
 struct ModelVertex3d
 {

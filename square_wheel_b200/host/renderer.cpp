@@ -397,6 +397,7 @@ Renderer::Renderer(const Scene& scene, const RendererConfig& config)
 		submodel_entities_[i].position = bbox.get_center();
 	}
 	leaf_sprites_.resize(map_.leafs.size());
+	leaf_portals_.resize(map_.leafs.size());
 	leaf_decals_.resize(map_.leafs.size());
 	// get_leaf_clip_planes (renderer_structs.rs:167-226): portal and polygon planes of the leaf, normalised and deduplicated
 	leafs_planes_.resize(map_.leafs.size());
@@ -583,6 +584,14 @@ void VisibilityCalculator::update_visibility(const CameraMatrices& camera_matric
 	}
 	mark_reachable_leafs_iterative(start_leafs, num_start_leafs, frame_bounds);
 	is_inside_leaf_volume_ = compute_is_inside_leaf_volume(current_leaf);
+}
+
+void VisibilityCalculator::update_visibility_with_start_leafs(const CameraMatrices& camera_matrices, const ClippingPolygon& frame_bounds, const uint32_t* start_leafs, size_t n) // :101-113
+{
+	camera_matrices_ = camera_matrices;
+	++visibility_frame_;
+	mark_reachable_leafs_iterative(start_leafs, n, frame_bounds);
+	is_inside_leaf_volume_ = true; // "Can't properly determine this."
 }
 
 // ---- dynamic lights (dynamic_objects_index.rs, partial_renderer.rs:398-590, depth_renderer.rs) ------------------------------
@@ -927,27 +936,39 @@ void Renderer::depth_draw_polygon(const CameraMatrices& m, const Vec3f clip_plan
 
 void Renderer::prepare_frame(uint32_t width, uint32_t height, const CameraPose& camera, float fov)
 {
+	prepare_frame_with_matrices(width, height, build_view_matrix(camera.position, camera.azimuth, camera.elevation, fov, (float)width, (float)height), false, nullptr, 0);
+}
+
+void Renderer::prepare_frame_with_matrices(uint32_t width, uint32_t height, const CameraMatrices& camera_matrices, bool is_third_person_view, const uint32_t* start_leafs, size_t num_start_leafs)
+{
 	width_ = width;
 	height_ = height;
-	camera_matrices_ = build_view_matrix(camera.position, camera.azimuth, camera.elevation, fov, (float)width, (float)height);
+	camera_matrices_ = camera_matrices;
+	is_third_person_view_ = is_third_person_view;
 	mip_bias_ = config_.textures_mip_bias; // update_mip_bias with dynamic_mip_bias = false (partial_renderer.rs:3786-3804)
 	++current_frame_;
 	stats_ = RendererDebugStats{};
-	visibility_.update_visibility(camera_matrices_, ClippingPolygon::from_box(0.0f, 0.0f, (float)width, (float)height)); // partial_renderer.rs:173-190
+	const ClippingPolygon frame_bounds = ClippingPolygon::from_box(0.0f, 0.0f, (float)width, (float)height); // partial_renderer.rs:173-190
+	if (start_leafs)
+		visibility_.update_visibility_with_start_leafs(camera_matrices_, frame_bounds, start_leafs, num_start_leafs);
+	else
+		visibility_.update_visibility(camera_matrices_, frame_bounds);
 	position_dynamic_lights();   // renderer.rs:88 (DynamicObjectsIndex)
 	prepare_dynamic_lights();    // partial_renderer.rs:192
 	position_submodels();        // renderer.rs:82 (inline_models_index.position_models)
 	build_shadow_maps();         // :194
 	prepare_submodels();         // :196
-	prepare_polygons_surfaces(); // :214
 	position_models();              // renderer.rs:84 (dynamic_models_index.position_models)
-	prepare_dynamic_models();       // partial_renderer.rs:209
-	build_dynamic_models_buffers(); // :227
+	prepare_dynamic_models();       // partial_renderer.rs:198-205
+	build_dynamic_models_buffers(); // :206
 	position_decals();              // renderer.rs:85
-	prepare_decals();               // partial_renderer.rs:205
+	prepare_decals();               // partial_renderer.rs:209
 	position_sprites();             // renderer.rs:86
-	prepare_sprites();              // partial_renderer.rs:207
+	prepare_sprites();              // partial_renderer.rs:211
+	prepare_polygons_surfaces(); // :214
 	build_surface_jobs();        // :221
+	position_portals();              // renderer.rs:90
+	prepare_view_portals_textures(); // partial_renderer.rs:230 (the nested views themselves: prepare_portal_view)
 }
 
 void Renderer::prepare_polygons_surfaces() // partial_renderer.rs:1327-1449 (leaf polygons; submodels are not part of the synthetic maps)
@@ -1605,7 +1626,9 @@ void Renderer::prepare_dynamic_models() // partial_renderer.rs:995-1120 (root vi
 		ClippingPolygon clipping_polygon;
 		if (!calculate_triangle_model_screen_polygon(bbox_vertices_transformed, clipping_polygon))
 			continue; // behind the camera plane
-		if (model.flags & MODEL_FLAG_ONLY_THIRD_PERSON_VIEW)
+		if ((model.flags & MODEL_FLAG_ONLY_THIRD_PERSON_VIEW) && !is_third_person_view_)
+			continue;
+		if ((model.flags & MODEL_FLAG_VIEW_MODEL) && is_third_person_view_)
 			continue;
 		bool visible = (model.flags & MODEL_FLAG_VIEW_MODEL) != 0;
 		for (uint32_t leaf_index : model_leafs_[entity_index])
@@ -1828,7 +1851,8 @@ void Renderer::draw_leaf_objects(const ClippingPolygon& bounds, uint32_t leaf_in
 	const std::vector<uint32_t>& leaf_submodels = leaf_submodels_[leaf_index];
 	const std::vector<uint32_t>& leaf_dynamic_models = leaf_models_[leaf_index];
 	const std::vector<uint32_t>& leaf_sprites = leaf_sprites_[leaf_index];
-	const size_t total_objects = leaf_submodels.size() + leaf_dynamic_models.size() + leaf_sprites.size();
+	const std::vector<uint32_t>& leaf_portals = leaf_portals_[leaf_index];
+	const size_t total_objects = leaf_submodels.size() + leaf_dynamic_models.size() + leaf_sprites.size() + leaf_portals.size();
 	if (total_objects == 0)
 		return;
 	Vec3f clip_planes[8];
@@ -1851,11 +1875,14 @@ void Renderer::draw_leaf_objects(const ClippingPolygon& bounds, uint32_t leaf_in
 			for (uint32_t m = entry.first_visible_mesh; m < entry.first_visible_mesh + entry.num_visible_meshes; ++m)
 				draw_mesh(bounds, leaf_clip_planes, num_planes, m);
 		}
-		else
+		else if (leaf_sprites.size() == 1)
 			draw_sprite(clip_planes, leaf_clip_planes, num_planes, leaf_sprites[0]);
+		else
+			draw_view_portal(clip_planes, leaf_clip_planes, num_planes, leaf_portals[0]);
 		return;
 	}
-	const uint32_t SUBMODEL_INDEX_ADD = 65536, DYNAMIC_MESH_INDEX_ADD = SUBMODEL_INDEX_ADD + 65536, SPRITE_INDEX_ADD = DYNAMIC_MESH_INDEX_ADD + 65536;
+	const uint32_t SUBMODEL_INDEX_ADD = 65536, DYNAMIC_MESH_INDEX_ADD = SUBMODEL_INDEX_ADD + 65536, SPRITE_INDEX_ADD = DYNAMIC_MESH_INDEX_ADD + 65536,
+				   PORTAL_INDEX_ADD = SPRITE_INDEX_ADD + 65536;
 	objects_sorter_.clear();
 	for (uint32_t model_index : leaf_submodels)
 		if (submodels_info_[model_index].has_matrices)
@@ -1882,11 +1909,21 @@ void Renderer::draw_leaf_objects(const ClippingPolygon& bounds, uint32_t leaf_in
 		const Vec3f extend_vec = {sprite.radius, sprite.radius, sprite.radius};
 		objects_sorter_.add_object(sprite_index + SPRITE_INDEX_ADD, project_bbox(BBox::from_min_max(sprite.position - extend_vec, sprite.position + extend_vec), camera_matrices_));
 	}
+	for (uint32_t portal_index : leaf_portals)
+	{
+		const ViewPortal& portal = frame_portals_[portal_index];
+		BBox bbox = BBox::from_point(portal.vertices[0]);
+		for (size_t v = 1; v < portal.vertices.size(); ++v)
+			bbox.extend_with_point(portal.vertices[v]);
+		objects_sorter_.add_object(portal_index + PORTAL_INDEX_ADD, project_bbox(bbox, camera_matrices_));
+	}
 	objects_sorter_.sort_objects();
 	for (size_t i = 0; i < objects_sorter_.num_objects; ++i)
 	{
 		const uint32_t object_index = objects_sorter_.objects[i].first;
-		if (object_index >= SPRITE_INDEX_ADD)
+		if (object_index >= PORTAL_INDEX_ADD)
+			draw_view_portal(clip_planes, leaf_clip_planes, num_planes, object_index - PORTAL_INDEX_ADD);
+		else if (object_index >= SPRITE_INDEX_ADD)
 			draw_sprite(clip_planes, leaf_clip_planes, num_planes, object_index - SPRITE_INDEX_ADD);
 		else if (object_index >= DYNAMIC_MESH_INDEX_ADD)
 			draw_mesh(bounds, leaf_clip_planes, num_planes, object_index - DYNAMIC_MESH_INDEX_ADD);
@@ -2387,6 +2424,292 @@ void Renderer::subdivide_and_draw_decal_triangle(const DecalDrawContext& ctx, co
 	const Vec2f triangles[4][3] = {{points[0], center0, center2}, {points[1], center1, center0}, {points[2], center2, center1}, {center0, center1, center2}};
 	for (const auto& triangle : triangles)
 		subdivide_and_draw_decal_triangle(ctx, triangle, recursion_depth + 1);
+}
+
+// ---- portals and mirrors -------------------------------------------------------------------------------------
+void Renderer::position_portal_convex_hull_r(uint32_t id, const Vec3f* vertices, size_t n, uint32_t node_index) // dynamic_objects_index.rs:172-209
+{
+	if (node_index >= FIRST_LEAF_INDEX)
+	{
+		const uint32_t leaf_index = node_index - FIRST_LEAF_INDEX;
+		leaf_portals_[leaf_index].push_back(id);
+		portal_leafs_[id].push_back(leaf_index);
+		return;
+	}
+	const BSPNode& node = map_.nodes[node_index];
+	size_t vertices_front = 0;
+	for (size_t i = 0; i < n; ++i)
+		if (dot(node.plane.vec, vertices[i]) > node.plane.dist)
+			++vertices_front;
+	if (vertices_front > 0)
+		position_portal_convex_hull_r(id, vertices, n, node.children[0]);
+	if (vertices_front < n)
+		position_portal_convex_hull_r(id, vertices, n, node.children[1]);
+}
+
+void Renderer::position_portals() // dynamic_objects_index.rs:143-157
+{
+	for (auto& l : leaf_portals_)
+		l.clear();
+	portal_leafs_.assign(frame_portals_.size(), {});
+	for (size_t index = 0; index < frame_portals_.size(); ++index)
+		position_portal_convex_hull_r((uint32_t)index, frame_portals_[index].vertices.data(), frame_portals_[index].vertices.size(), map_.root_node());
+}
+
+void Renderer::prepare_view_portals_textures() // partial_renderer.rs:1834-1996
+{
+	portals_info_.assign(frame_portals_.size(), PortalInfo{});
+	for (size_t portal_index = 0; portal_index < frame_portals_.size(); ++portal_index)
+	{
+		const ViewPortal& portal = frame_portals_[portal_index];
+		bool have_bounds = false;
+		ClippingPolygon bounds;
+		for (uint32_t leaf_index : portal_leafs_[portal_index])
+		{
+			ClippingPolygon leaf_bounds;
+			if (visibility_.leaf_bounds(leaf_index, leaf_bounds))
+			{
+				if (have_bounds)
+					bounds.extend(leaf_bounds);
+				else
+				{
+					bounds = leaf_bounds;
+					have_bounds = true;
+				}
+			}
+		}
+		if (!have_bounds)
+			continue; // in invisible leafs
+		Vec3f clip_planes[8];
+		bounds.get_clip_planes(clip_planes);
+		const Vec4f plane_transformed = camera_matrices_.planes_matrix * extend(portal.plane.vec, -portal.plane.dist);
+		if (plane_transformed.w <= 0.0f)
+			continue;
+		Vec3f vertices_3d[MAX_VERTICES];
+		const size_t n = std::min(MAX_VERTICES, portal.vertices.size());
+		if (n < 3)
+			continue;
+		for (size_t i = 0; i < n; ++i)
+			vertices_3d[i] = view_matrix_transform_vertex(camera_matrices_.view_matrix, portal.vertices[i]);
+		Vec2f vertices_2d[MAX_VERTICES];
+		const size_t vertex_count = project_and_clip_polygon(clip_planes, vertices_3d, n, vertices_2d);
+		if (vertex_count < 3)
+			continue; // fully clipped
+		const float inf = (float)(1 << 29);
+		float tc_min[2] = {inf, inf}, tc_max[2] = {-inf, -inf};
+		for (const Vec3f& vertex : portal.vertices)
+			for (int i = 0; i < 2; ++i)
+			{
+				const float tc = dot(portal.tex_coord_equation[i].vec, vertex) + portal.tex_coord_equation[i].dist;
+				tc_min[i] = tc < tc_min[i] ? tc : tc_min[i];
+				tc_max[i] = tc > tc_max[i] ? tc : tc_max[i];
+			}
+		for (int i = 0; i < 2; ++i)
+		{
+			const float tc_reduce_eps = 1.0f / 32.0f;
+			tc_min[i] += tc_reduce_eps;
+			tc_max[i] -= tc_reduce_eps;
+		}
+		PortalInfo info;
+		const float plane_transformed_w = -plane_transformed.w;
+		info.depth_equation[0] = plane_transformed.x / plane_transformed_w;
+		info.depth_equation[1] = plane_transformed.y / plane_transformed_w;
+		info.depth_equation[2] = plane_transformed.z / plane_transformed_w;
+		const Vec4f tc_basis_transformed[2] = {
+			camera_matrices_.planes_matrix * extend(portal.tex_coord_equation[0].vec, portal.tex_coord_equation[0].dist),
+			camera_matrices_.planes_matrix * extend(portal.tex_coord_equation[1].vec, portal.tex_coord_equation[1].dist)};
+		float tc_equation[6];
+		for (int i = 0; i < 2; ++i)
+		{
+			tc_equation[i] = tc_basis_transformed[i].x + tc_basis_transformed[i].w * info.depth_equation[0];
+			tc_equation[2 + i] = tc_basis_transformed[i].y + tc_basis_transformed[i].w * info.depth_equation[1];
+			tc_equation[4 + i] = tc_basis_transformed[i].z + tc_basis_transformed[i].w * info.depth_equation[2];
+		}
+		info.mip = calculate_mip(vertices_2d, vertex_count, info.depth_equation, tc_equation, mip_bias_);
+		const float mip_scale = 1.0f / (float)(1 << info.mip);
+		for (int i = 0; i < 6; ++i)
+			tc_equation[i] *= mip_scale;
+		int32_t tex_coord_max[2];
+		for (int i = 0; i < 2; ++i)
+		{
+			info.tc_min[i] = f32_to_i32_saturating(std::floor(tc_min[i]) * mip_scale);
+			tex_coord_max[i] = std::max(f32_to_i32_saturating(std::ceil(tc_max[i]) * mip_scale), info.tc_min[i] + 1);
+		}
+		for (int i = 0; i < 2; ++i) // shift to the surface rect
+		{
+			const float t = (float)info.tc_min[i];
+			tc_equation[i] -= t * info.depth_equation[0];
+			tc_equation[2 + i] -= t * info.depth_equation[1];
+			tc_equation[4 + i] -= t * info.depth_equation[2];
+		}
+		std::memcpy(info.tex_coord_equation, tc_equation, sizeof(tc_equation));
+		info.resolution[0] = (uint32_t)(tex_coord_max[0] - info.tc_min[0]);
+		info.resolution[1] = (uint32_t)(tex_coord_max[1] - info.tc_min[1]);
+		if (info.resolution[0] > 16384 || info.resolution[1] > 16384) // the device view limit; nothing sane asks for more
+			continue;
+		portals_info_[portal_index] = info;
+	}
+}
+
+Renderer* Renderer::prepare_portal_view(size_t portal_index, int color_bits) // partial_renderer.rs:2017-2225
+{
+	if (portal_index >= frame_portals_.size())
+		return nullptr;
+	const ViewPortal& portal = frame_portals_[portal_index];
+	const PortalInfo& portal_info = portals_info_[portal_index];
+	if (portal_info.resolution[0] * portal_info.resolution[1] == 0)
+		return nullptr;
+	if (config_.portals_depth == 0)
+		return nullptr; // "Portal/mirror depth limit reached": the texture is filled with black
+	if (!portal_renderer_)
+	{
+		RendererConfig child_config = config_;
+		child_config.portals_depth = config_.portals_depth - 1;
+		portal_renderer_.reset(new Renderer(scene_, child_config));
+	}
+	Renderer& renderer = *portal_renderer_;
+	// the nested renderer sees the same FrameWorldInfo
+	renderer.frame_lights_ = frame_lights_;
+	renderer.frame_models_ = frame_models_;
+	renderer.frame_sprites_ = frame_sprites_;
+	renderer.frame_decals_ = frame_decals_;
+	renderer.frame_portals_ = frame_portals_;
+	renderer.submodel_entities_ = submodel_entities_;
+
+	CameraMatrices portal_camera_matrices;
+	const uint32_t* start_leafs = nullptr;
+	size_t num_start_leafs = 0;
+	const float res_w = (float)portal_info.resolution[0], res_h = (float)portal_info.resolution[1];
+	auto tex_coord_space_matrices = [&](Vec3f eye, float dist_normalized, const Mat4f* post) {
+		// view matrix that maps the portal plane's texture space onto the texture's pixels, with the plane at Z_NEAR (:2069-2105)
+		const float normal_len = magnitude(portal.plane.vec);
+		const float mip_scale = 1.0f / (float)(1 << portal_info.mip);
+		const Mat4f tex_coord_basis = Mat4f::from_cols(
+										 extend(portal.tex_coord_equation[0].vec, portal.tex_coord_equation[0].dist) * mip_scale,
+										 extend(portal.tex_coord_equation[1].vec, portal.tex_coord_equation[1].dist) * mip_scale,
+										 extend(portal.plane.vec, -portal.plane.dist) * (mip_scale / normal_len), Vec4f{0.0f, 0.0f, 0.0f, 1.0f})
+										 .transpose();
+		const Vec3f eye_tc = truncate(tex_coord_basis * extend(eye, 1.0f));
+		const Mat4f translate = Mat4f::from_translation(-eye_tc);
+		Mat4f shift_to_viewport = Mat4f::identity();
+		shift_to_viewport.z.x = eye_tc.x - (float)portal_info.tc_min[0];
+		shift_to_viewport.z.y = eye_tc.y - (float)portal_info.tc_min[1];
+		const Mat4f z_scale = Mat4f::from_nonuniform_scale(Z_NEAR, Z_NEAR, Z_NEAR / (dist_normalized * mip_scale));
+		Mat4f m = shift_to_viewport * z_scale * translate * tex_coord_basis;
+		if (post)
+			m = m * *post;
+		CameraMatrices cm;
+		cm.view_matrix = m;
+		Mat4f inv = Mat4f::identity();
+		m.transpose().invert(inv);
+		cm.planes_matrix = inv;
+		return cm;
+	};
+	switch (portal.view)
+	{
+	case PORTAL_VIEW_CAMERA_AT_POSITION:
+		portal_camera_matrices = build_view_matrix_with_full_rotation(portal.camera_position, portal.camera_rotation, portal.camera_fov, res_w, res_h);
+		break;
+	case PORTAL_VIEW_MIRROR:
+	{
+		const float normal_square_len = dot(portal.plane.vec, portal.plane.vec);
+		const float normal_len = std::sqrt(normal_square_len);
+		const float dist = dot(portal.plane.vec, camera_matrices_.position) - portal.plane.dist;
+		const Vec3f position_reflected = camera_matrices_.position - portal.plane.vec * (2.0f * dist / normal_square_len);
+		portal_camera_matrices = tex_coord_space_matrices(position_reflected, dist / normal_len, nullptr);
+		portal_camera_matrices.position = position_reflected;
+		start_leafs = portal_leafs_[portal_index].data(); // start the visibility search where the mirror is
+		num_start_leafs = portal_leafs_[portal_index].size();
+		break;
+	}
+	case PORTAL_VIEW_PARALLAX_PORTAL:
+	{
+		Vec3f transformed[MAX_VERTICES];
+		const size_t n = std::min(portal.vertices.size(), MAX_VERTICES);
+		for (size_t i = 0; i < n; ++i)
+			transformed[i] = truncate(portal.transform_matrix * extend(portal.vertices[i], 1.0f));
+		transformed_portal_leafs_.clear();
+		// get_convex_hull_bsp_leafs (bsp_map_compact.rs:294-338)
+		std::vector<uint32_t> stack = {map_.root_node()};
+		while (!stack.empty())
+		{
+			const uint32_t node_index = stack.back();
+			stack.pop_back();
+			if (node_index >= FIRST_LEAF_INDEX)
+			{
+				transformed_portal_leafs_.push_back(node_index - FIRST_LEAF_INDEX);
+				continue;
+			}
+			const BSPNode& node = map_.nodes[node_index];
+			size_t vertices_front = 0;
+			for (size_t i = 0; i < n; ++i)
+				if (dot(node.plane.vec, transformed[i]) > node.plane.dist)
+					++vertices_front;
+			if (vertices_front < n)
+				stack.push_back(node.children[1]);
+			if (vertices_front > 0)
+				stack.push_back(node.children[0]); // popped first: the recursion's order
+		}
+		const float normal_len = magnitude(portal.plane.vec);
+		const float dist_normalized = (portal.plane.dist - dot(portal.plane.vec, camera_matrices_.position)) / normal_len;
+		Mat4f transform_inverse = Mat4f::identity();
+		portal.transform_matrix.invert(transform_inverse);
+		portal_camera_matrices = tex_coord_space_matrices(camera_matrices_.position, dist_normalized, &transform_inverse);
+		portal_camera_matrices.position = truncate(portal.transform_matrix * extend(camera_matrices_.position, 1.0f));
+		start_leafs = transformed_portal_leafs_.data();
+		num_start_leafs = transformed_portal_leafs_.size();
+		break;
+	}
+	}
+	renderer.prepare_frame_with_matrices(portal_info.resolution[0], portal_info.resolution[1], portal_camera_matrices, true, start_leafs, num_start_leafs);
+	renderer.draw_frame(color_bits);
+	return &renderer;
+}
+
+void Renderer::portal_texture_light(size_t portal_index, float out[3]) const // partial_renderer.rs:2241-2262
+{
+	const ViewPortal& portal = frame_portals_[portal_index];
+	const PortalInfo& portal_info = portals_info_[portal_index];
+	std::memcpy(out, portal.texture_light_add, 12);
+	if (!(portal.texture_light_scale > 0.0f))
+		return;
+	DrawPolygonData basis;
+	basis_vecs_from_plane_and_tc(portal.plane, portal.tex_coord_equation, basis);
+	const float scale = (float)(1 << portal_info.mip);
+	const Vec3f u = portal_info.mip == 0 ? basis.basis_u : basis.basis_u * scale, v = portal_info.mip == 0 ? basis.basis_v : basis.basis_v * scale;
+	const Vec3f polygon_center = basis.basis_start + u * ((float)portal_info.tc_min[0] + (float)portal_info.resolution[0] * 0.5f) + v * ((float)portal_info.tc_min[1] + (float)portal_info.resolution[1] * 0.5f);
+	const LightGridElement grid_light = fetch_light_from_grid(polygon_center);
+	float total_light[3];
+	get_light_cube_light_host(grid_light.light_cube, basis.basis_normal, total_light);
+	const float light_dir_dot = std::fmax(dot(basis.basis_normal, grid_light.light_direction_vector_scaled), 0.0f);
+	for (int i = 0; i < 3; ++i)
+	{
+		total_light[i] += grid_light.directional_light_color[i] * light_dir_dot;
+		out[i] = total_light[i] * portal.texture_light_scale + portal.texture_light_add[i];
+	}
+}
+
+void Renderer::draw_view_portal(const Vec3f clip_planes[8], const Plane* leaf_clip_planes, size_t num_leaf_clip_planes, uint32_t portal_index) // partial_renderer.rs:3720-3776
+{
+	const ViewPortal& portal = frame_portals_[portal_index];
+	const PortalInfo& portal_info = portals_info_[portal_index];
+	if (portal_info.resolution[0] * portal_info.resolution[1] == 0)
+		return;
+	Vec3f vertices_clipped[MAX_VERTICES], vertices_temp[MAX_VERTICES];
+	size_t vertex_count = std::min(portal.vertices.size(), MAX_VERTICES);
+	for (size_t i = 0; i < vertex_count; ++i)
+		vertices_clipped[i] = view_matrix_transform_vertex(camera_matrices_.view_matrix, portal.vertices[i]);
+	for (size_t pi = 0; pi < num_leaf_clip_planes; ++pi)
+	{
+		vertex_count = clip_3d_polygon_by_plane(vertices_clipped, vertex_count, leaf_clip_planes[pi], vertices_temp, MAX_VERTICES);
+		if (vertex_count < 3)
+			return;
+		for (size_t i = 0; i < vertex_count; ++i)
+			vertices_clipped[i] = vertices_temp[i];
+	}
+	// the texture is another render target: tex_ref = the PORTAL index, replaced by the caller with the device view it rendered
+	// the nested frame into (SQW_TEX_VIEW)
+	draw_polygon(clip_planes, vertices_clipped, vertex_count, portal_info.depth_equation, portal_info.tex_coord_equation, portal_info.resolution, SQW_TEX_VIEW, portal_index, portal.blending_mode);
 }
 
 // ---- sprites -------------------------------------------------------------------------------------------------

@@ -9,6 +9,7 @@
 #pragma once
 #include "map.hpp"
 #include "models.hpp"
+#include <memory>
 #include <vector>
 
 namespace sqwh
@@ -37,6 +38,7 @@ struct ClippingPolygon
 struct RendererConfig
 {
 	bool use_directional_lightmaps = true;
+	uint32_t portals_depth = 1; // renderer_config.rs `portals_depth`: nested renderers for portals / mirrors (renderer.rs:33 caps it at 8)
 	float textures_mip_bias = 0.0f;
 	float shadows_quality = 0.0f;
 	bool clear_background = true;
@@ -98,6 +100,8 @@ class VisibilityCalculator
 public:
 	explicit VisibilityCalculator(const BSPMap& map);
 	void update_visibility(const CameraMatrices& camera_matrices, const ClippingPolygon& frame_bounds);
+	// for portals / mirrors, whose camera can be far from where the search must start (map_visibility_calculator.rs:101-113)
+	void update_visibility_with_start_leafs(const CameraMatrices& camera_matrices, const ClippingPolygon& frame_bounds, const uint32_t* start_leafs, size_t n);
 	bool leaf_bounds(uint32_t leaf, ClippingPolygon& out) const; // get_current_frame_leaf_bounds
 	bool is_inside_leaf_volume() const { return is_inside_leaf_volume_; }
 
@@ -133,6 +137,8 @@ public:
 	// Visibility + surface preparation + job list.  color_bits only selects nothing here (the lists are colour-agnostic) but
 	// is kept for symmetry with prepare_frame::<ColorT>.
 	void prepare_frame(uint32_t width, uint32_t height, const CameraPose& camera, float fov);
+	// PartialRenderer::prepare_frame (partial_renderer.rs:156) with explicit matrices: what nested portal / mirror views use.
+	void prepare_frame_with_matrices(uint32_t width, uint32_t height, const CameraMatrices& camera_matrices, bool is_third_person_view, const uint32_t* start_leafs, size_t num_start_leafs);
 	// Sky box (if any polygon of a sky material is in view), then BSP traversal -> ordered draw commands for the frame prepared
 	// last.  color_bits picks the sky box textures of the target's colour type (SkyboxSideTexture<ColorT>).
 	void draw_frame(int color_bits = 64);
@@ -158,6 +164,16 @@ public:
 	void set_submodel_entities(const SubmodelEntity* e, size_t n);
 	size_t num_submodels() const { return map_.submodels.size(); }
 	BBox submodel_bbox(size_t i) const { return submodels_bbox_[i]; }
+	// FrameInfo::portals for the next prepare_frame (frame_info.rs:18)
+	void set_portals(const ViewPortal* portals, size_t n) { frame_portals_.assign(portals, portals + n); }
+	const std::vector<PortalInfo>& portals_info() const { return portals_info_; }
+	const std::vector<ViewPortal>& portals() const { return frame_portals_; }
+	// The nested view of portal i of the frame prepared last: build_view_portals_textures (partial_renderer.rs:2008-2225).  Prepares
+	// and records the child renderer's frame and returns it (valid until the next call), or nullptr when the portal is not visible
+	// or the depth limit is reached (the caller then fills the portal texture with black, :2038-2044).
+	Renderer* prepare_portal_view(size_t portal_index, int color_bits);
+	// light the portal's overlay texture is mixed with (:2227-2262)
+	void portal_texture_light(size_t portal_index, float out[3]) const;
 	// FrameInfo::decals for the next prepare_frame (frame_info.rs:16)
 	void set_decals(const Decal* decals, size_t n) { frame_decals_.assign(decals, decals + n); }
 	// FrameInfo::sprites for the next prepare_frame (frame_info.rs:17)
@@ -187,6 +203,11 @@ private:
 	ModelLightData get_model_light(const ModelEntity& model, const Mat4f& model_matrix) const;
 	LightGridElement fetch_light_from_grid(Vec3f pos) const; // triangle_models_rendering.rs:574-699
 	void draw_leaf_objects(const ClippingPolygon& bounds, uint32_t leaf_index);
+	// portals: dynamic_objects_index.rs:143-157, partial_renderer.rs:1834-1996, :3720-3776
+	void position_portals();
+	void position_portal_convex_hull_r(uint32_t id, const Vec3f* vertices, size_t n, uint32_t node_index);
+	void prepare_view_portals_textures();
+	void draw_view_portal(const Vec3f clip_planes[8], const Plane* leaf_clip_planes, size_t num_leaf_clip_planes, uint32_t portal_index);
 	// submodels: inline_models_index.rs, partial_renderer.rs:593-660, :1362-1447, :3098-3288, depth_renderer.rs:130-200
 	void position_submodels();
 	void position_submodel_r(uint32_t model_index, const Vec3f bbox_vertices[8], uint32_t node_index);
@@ -283,6 +304,12 @@ private:
 	std::vector<SubmodelEntity> submodel_entities_;
 	std::vector<std::vector<uint32_t>> leaf_submodels_, submodel_leafs_;
 	std::vector<SubmodelInfo> submodels_info_;
+	std::vector<ViewPortal> frame_portals_;
+	std::vector<std::vector<uint32_t>> leaf_portals_, portal_leafs_; // DynamicObjectsIndex for portals
+	std::vector<PortalInfo> portals_info_;
+	std::unique_ptr<Renderer> portal_renderer_; // PortalsRenderingData::renderer: the nested PartialRenderer, depth - 1
+	std::vector<uint32_t> transformed_portal_leafs_;
+	bool is_third_person_view_ = false;
 	struct DecalInfo // renderer_structs.rs:191-197
 	{
 		Mat4f camera_planes_matrix;

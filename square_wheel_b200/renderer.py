@@ -46,6 +46,7 @@ class FrameInfo:
     sprites: Optional[np.ndarray] = None  # FrameInfo::sprites (frame_info.rs:17) as scene.sprite_dtype records
     decals: Optional[np.ndarray] = None  # FrameInfo::decals (frame_info.rs:16) as scene.decal_dtype records
     submodel_entities: Optional[np.ndarray] = None  # FrameInfo::submodel_entities (frame_info.rs:13) as scene.submodel_entity_dtype records
+    portals: Optional[np.ndarray] = None  # FrameInfo::portals (frame_info.rs:18) as scene.portal_dtype records
 
 
 @dataclass
@@ -56,6 +57,10 @@ class RendererConfig:
     textures_mip_bias: float = 0.0
     clear_background: bool = True
     shadows_quality: float = 0.0
+    portals_depth: int = 1  # nested renderers for portals / mirrors (renderer.rs:33: at most 8)
+    # The reference never clears a portal texture: texels no nested polygon covers keep whatever an earlier frame left there.
+    # True makes them deterministic zeros (what the parity tests compare against).
+    clear_portal_textures: bool = False
 
 
 class Renderer:
@@ -65,9 +70,10 @@ class Renderer:
         self.config = config or RendererConfig()
         self.ctx = Context(scene.lightmaps, scene.directional_lightmaps, device=device, stream=stream)
         scene.upload(self.ctx)
-        self.host = HostRenderer(scene, self.config.use_directional_lightmaps, self.config.textures_mip_bias, self.config.clear_background, self.config.shadows_quality)
+        self.host = HostRenderer(scene, self.config.use_directional_lightmaps, self.config.textures_mip_bias, self.config.clear_background, self.config.shadows_quality, self.config.portals_depth)
         self._views = {}
         self._frames = {}
+        self._portal_views = {}  # (depth, slot) -> (View, Frame): render targets of the nested portal / mirror views
         self._host_frame: Optional[HostFrame] = None
         self._view: Optional[View] = None
 
@@ -79,7 +85,7 @@ class Renderer:
 
     def prepare_frame(self, surface_info: SurfaceInfo, frame_info: FrameInfo, color_bits: int = 64):
         """prepare_frame::<ColorT> (renderer.rs:61): host preparation, then surface building on the GPU (seam S1)."""
-        hf = self.host.build_frame(surface_info.width, surface_info.height, frame_info.pose, frame_info.fov, frame_info.lights, frame_info.model_entities, color_bits, frame_info.sprites, frame_info.decals, frame_info.submodel_entities)
+        hf = self.host.build_frame(surface_info.width, surface_info.height, frame_info.pose, frame_info.fov, frame_info.lights, frame_info.model_entities, color_bits, frame_info.sprites, frame_info.decals, frame_info.submodel_entities, frame_info.portals)
         view = self._get_view(surface_info, color_bits)
         key = (surface_info.width, surface_info.height, color_bits)
         if key not in self._frames:
@@ -90,8 +96,46 @@ class Renderer:
         # build_shadow_maps (partial_renderer.rs:194); an empty list clears what an earlier frame recorded
         frame.set_shadow_map_draw(hf.depth_maps, hf.depth_cmds, hf.depth_points)
         frame.submit(N_STAGE_SHADOW_MAPS | N_STAGE_SURFACES)
+        self._render_portals(hf, 1, color_bits)  # build_view_portals_textures (partial_renderer.rs:232)
         self._host_frame, self._view, self._frame = hf, view, frame
         return hf
+
+    def _render_portals(self, hf: HostFrame, depth: int, color_bits: int):
+        """build_view_portals_textures (partial_renderer.rs:2008-2282): every visible portal gets its own render target; the nested
+        frame is built and drawn into it (black at the depth limit), the portal's overlay texture is mixed in, and the polygon
+        commands of `hf` that show the portal are pointed at that target (SQW_TEX_VIEW)."""
+        for slot, node in enumerate(hf.portals):
+            w, h = node.resolution
+            key = (depth, slot, color_bits)
+            if key in self._portal_views and self._portal_views[key][2] < w * h:  # grown beyond what the target was allocated for
+                old_view, old_frame, _ = self._portal_views.pop(key)
+                old_frame.close()
+                old_view.close()
+            if key not in self._portal_views:
+                v = self.ctx.create_view(w, (h * 3 + 1) // 2, color_bits)  # sqw_view_set_size works within the allocated AREA
+                self._portal_views[key] = (v, v.create_frame(), w * ((h * 3 + 1) // 2))
+            view, frame, _ = self._portal_views[key]
+            if (view.width, view.height) != (w, h):
+                view.set_size(w, h)
+            child = node.frame
+            if child is None:
+                view.draw(np.zeros(0, N.draw_cmd_dtype), None, None, clear_color=0)
+            else:
+                self._render_portals(child, depth + 1, color_bits)
+                has_lights = child.lights is not None and len(child.lights) > 0
+                frame.set_surfaces(child.jobs, child.lights if has_lights else None, None, child.cam_pos, child.total_surface_pixels, device_shadow_maps_len=child.shadow_maps_len if has_lights else 0)
+                frame.set_shadow_map_draw(child.depth_maps, child.depth_cmds, child.depth_points)
+                frame.submit(N_STAGE_SHADOW_MAPS | N_STAGE_SURFACES)
+                clear = 0 if self.config.clear_portal_textures else None
+                if child.needs_clear:
+                    clear = BACKGROUND_COLOR64 if color_bits == 64 else BACKGROUND_COLOR32
+                view.draw(child.cmds, child.polygon_points, child.triangle_points, clear_color=clear)
+            if node.overlay is not None:
+                image, blend, light = node.overlay
+                view.mix_texture(image, node.tc_min, blend, light)
+            node.view = view
+            portal_cmds = (hf.cmds["tex_kind"] == N.TEX_VIEW) & (hf.cmds["kind"] == N.CMD_POLYGON) & (hf.cmds["tex_ref"] == node.index)
+            hf.cmds["tex_ref"][portal_cmds] = view.index
 
     def draw_frame(self, pixels: Optional[np.ndarray] = None):
         """draw_frame::<ColorT> (renderer.rs:106): rasterisation on the GPU (seam S2).  `pixels` ([h, pitch] uint32/uint64), when
@@ -108,6 +152,9 @@ class Renderer:
     def close(self):
         for f in self._frames.values():
             f.close()
+        for v, f, _ in self._portal_views.values():
+            f.close()
+            v.close()
         for v in self._views.values():
             v.close()
         self.host.close()

@@ -54,6 +54,7 @@ class RendererConfig(C.Structure):
         ("clear_background", C.c_uint32),
         ("invert_polygons_order", C.c_uint32),
         ("shadows_quality", C.c_float),
+        ("portals_depth", C.c_uint32),
     ]
 
 
@@ -109,6 +110,39 @@ assert decal_dtype.itemsize == 64
 submodel_entity_dtype = np.dtype([("present", "<u4"), ("position", "<f4", (3,)), ("rotation", "<f4", (4,))])
 assert submodel_entity_dtype.itemsize == 32
 
+# frame_info.rs:171-205 ViewPortal (+ ViewPortalTexture): view 0 CameraAtPosition / 1 Mirror / 2 ParallaxPortal; up to 8 vertices;
+# transform_matrix column-major; texture_skin = index of the scene's TextureLiteWithMips fixtures
+MAX_PORTAL_VERTICES = 8
+portal_dtype = np.dtype(
+    [
+        ("view", "<u4"), ("camera_position", "<f4", (3,)), ("camera_rotation", "<f4", (4,)), ("camera_fov", "<f4"), ("transform_matrix", "<f4", (16,)), ("plane", "<f4", (4,)),
+        ("tex_coord_equation", "<f4", (2, 4)), ("num_vertices", "<u4"), ("vertices", "<f4", (MAX_PORTAL_VERTICES, 3)), ("blending_mode", "<u4"), ("has_texture", "<u4"),
+        ("texture_skin", "<u4"), ("texture_blending_mode", "<u4"), ("texture_light_scale", "<f4"), ("texture_light_add", "<f4", (3,)),
+    ]
+)
+assert portal_dtype.itemsize == 280
+PORTAL_VIEW_CAMERA_AT_POSITION, PORTAL_VIEW_MIRROR, PORTAL_VIEW_PARALLAX_PORTAL = 0, 1, 2
+
+
+class PortalInfo(C.Structure):
+    _fields_ = [
+        ("resolution", C.c_uint32 * 2), ("tc_min", C.c_int32 * 2), ("mip", C.c_uint32), ("has_texture", C.c_uint32), ("texture_image", C.c_uint32),
+        ("texture_blending_mode", C.c_uint32), ("texture_light", C.c_float * 3),
+    ]
+
+
+class PortalView:
+    """One visible portal of a host frame: its texture geometry, the nested host frame that fills it (None at the depth limit:
+    the texture is black, partial_renderer.rs:2038-2044) and, once rendered, the device view that holds the texture."""
+
+    def __init__(self, index, info, frame):
+        self.index, self.frame = index, frame
+        self.resolution = (int(info.resolution[0]), int(info.resolution[1]))
+        self.tc_min = (int(info.tc_min[0]), int(info.tc_min[1]))
+        self.mip = int(info.mip)
+        self.overlay = (int(info.texture_image), int(info.texture_blending_mode), tuple(info.texture_light)) if info.has_texture else None
+        self.view = None  # device View, set by Renderer
+
 
 class ModelInfo(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("num_frames", "num_meshes", "num_vertices", "num_triangles", "kind", "num_bones")] + [("bbox_min", C.c_float * 3), ("bbox_max", C.c_float * 3)]
@@ -149,6 +183,14 @@ def lib() -> C.CDLL:
         l.sqwh_renderer_set_submodel_entities.restype = C.c_int
         l.sqwh_renderer_set_submodel_entities.argtypes = [vp, vp, C.c_uint32]
         l.sqwh_renderer_submodel_center.argtypes = [vp, C.c_uint32, vp]
+        l.sqwh_renderer_set_portals.restype = C.c_int
+        l.sqwh_renderer_set_portals.argtypes = [vp, vp, vp, C.c_uint32]
+        l.sqwh_renderer_num_portals.restype = C.c_uint32
+        l.sqwh_renderer_num_portals.argtypes = [vp]
+        l.sqwh_renderer_portal_info.restype = C.c_int
+        l.sqwh_renderer_portal_info.argtypes = [vp, C.c_uint32, C.POINTER(PortalInfo)]
+        l.sqwh_renderer_prepare_portal_view.restype = vp
+        l.sqwh_renderer_prepare_portal_view.argtypes = [vp, C.c_uint32, C.c_int]
         l.sqwh_renderer_set_decals.restype = C.c_int
         l.sqwh_renderer_set_decals.argtypes = [vp, vp, vp, C.c_uint32]
         l.sqwh_renderer_set_sprites.restype = C.c_int
@@ -278,6 +320,7 @@ class HostFrame:
         self.jobs, self.total_surface_pixels, self.cam_pos = jobs, total_surface_pixels, cam_pos
         self.cmds, self.polygon_points, self.needs_clear, self.info = cmds, polygon_points, needs_clear, info
         self.triangle_points = triangle_points if triangle_points is not None and len(triangle_points) else None  # SQW_CMD_TRIANGLE vertices (models)
+        self.portals = []  # PortalView per VISIBLE portal; polygon commands with tex_kind TEX_VIEW carry the portal index in tex_ref
         # dynamic lights of the frame and the shadow-map fills that feed them (empty without FrameInfo::lights)
         self.lights, self.depth_maps, self.depth_cmds, self.depth_points, self.shadow_maps_len = lights, depth_maps, depth_cmds, depth_points, shadow_maps_len
 
@@ -295,16 +338,17 @@ class HostFrame:
 class HostRenderer:
     """C++ mirror of Renderer / PartialRenderer front end (renderer.rs:61,106; partial_renderer.rs:156,236)."""
 
-    def __init__(self, scene: Scene, use_directional_lightmaps=True, textures_mip_bias=0.0, clear_background=True, shadows_quality=0.0):
+    def __init__(self, scene: Scene, use_directional_lightmaps=True, textures_mip_bias=0.0, clear_background=True, shadows_quality=0.0, portals_depth=1):
         self.scene = scene
         self._lib = lib()
-        cfg = RendererConfig(1 if use_directional_lightmaps else 0, textures_mip_bias, 1 if clear_background else 0, 0, shadows_quality)
+        cfg = RendererConfig(1 if use_directional_lightmaps else 0, textures_mip_bias, 1 if clear_background else 0, 0, shadows_quality, portals_depth)
         self._handle = self._lib.sqwh_renderer_create(scene._handle, C.byref(cfg))
 
-    def build_frame(self, width: int, height: int, pose, fov: float = FOV_DEFAULT, lights=None, models=None, color_bits: int = 64, sprites=None, decals=None, submodels=None) -> HostFrame:
+    def build_frame(self, width: int, height: int, pose, fov: float = FOV_DEFAULT, lights=None, models=None, color_bits: int = 64, sprites=None, decals=None, submodels=None, portals=None) -> HostFrame:
         """lights: FrameInfo::lights as an array of dynamic_light_dtype (or None); models: FrameInfo::model_entities as an array of
         model_entity_dtype (or None); sprites / decals: FrameInfo::sprites / ::decals as arrays of sprite_dtype / decal_dtype (or None); submodels: FrameInfo::submodel_entities, one submodel_entity_dtype record per map submodel (None keeps the last ones;
-        initially every submodel stands where the map has it); color_bits: colour type of the target (only picks the sky box textures, SkyboxSideTexture<ColorT>)."""
+        initially every submodel stands where the map has it); portals: FrameInfo::portals as an array of portal_dtype (or None) — the
+        nested views of the visible ones come back as HostFrame.portals; color_bits: colour type of the target (only picks the sky box textures, SkyboxSideTexture<ColorT>)."""
         pose = np.ascontiguousarray(pose, np.float32)
         lt = np.ascontiguousarray(lights, dynamic_light_dtype) if lights is not None else np.zeros(0, dynamic_light_dtype)
         self._lib.sqwh_renderer_set_lights(self._handle, lt.ctypes.data_as(C.c_void_p), len(lt))
@@ -321,8 +365,35 @@ class HostRenderer:
         sp = np.ascontiguousarray(sprites, sprite_dtype) if sprites is not None else np.zeros(0, sprite_dtype)
         if self._lib.sqwh_renderer_set_sprites(self._handle, self.scene._handle, sp.ctypes.data_as(C.c_void_p), len(sp)) != 0:
             raise ValueError("sprite refers to a missing skin or has a bad mode / radius")
+        pt = np.ascontiguousarray(portals, portal_dtype) if portals is not None else np.zeros(0, portal_dtype)
+        if self._lib.sqwh_renderer_set_portals(self._handle, self.scene._handle, pt.ctypes.data_as(C.c_void_p), len(pt)) != 0:
+            raise ValueError("bad portal (view kind, 3..8 vertices, blending mode, texture skin)")
         self._lib.sqwh_renderer_prepare_frame(self._handle, width, height, pose.ctypes.data_as(C.c_void_p), fov)
         self._lib.sqwh_renderer_draw_frame(self._handle, color_bits)
+        return self._collect(self._handle, color_bits)
+
+    def _collect(self, handle, color_bits: int) -> HostFrame:
+        """Copy the lists of the frame a (possibly nested) renderer prepared last, then — portal by portal, because a renderer
+        re-uses ONE nested renderer for all of its portals (partial_renderer.rs:2032) — prepare and collect the nested views."""
+        h = self._handle
+        self._handle = handle
+        try:
+            hf = self._collect_lists()
+        finally:
+            self._handle = h
+        info = PortalInfo()
+        for i in range(self._lib.sqwh_renderer_num_portals(handle)):
+            self._lib.sqwh_renderer_portal_info(handle, i, C.byref(info))
+            if info.resolution[0] * info.resolution[1] == 0:
+                continue
+            node = PortalView(i, info, None)
+            child = self._lib.sqwh_renderer_prepare_portal_view(handle, i, color_bits)
+            if child:
+                node.frame = self._collect(child, color_bits)
+            hf.portals.append(node)
+        return hf
+
+    def _collect_lists(self) -> HostFrame:
         fi = FrameInfo()
         self._lib.sqwh_renderer_frame_info(self._handle, C.byref(fi))
         jobs = _array_from(self._lib.sqwh_renderer_jobs(self._handle), fi.num_jobs, N.surface_job_dtype)

@@ -117,3 +117,82 @@ def sprites_ahead_of_camera(scene_module, pose, n, num_skins=4, light_scale=0.0)
         sp[i]["light_scale"] = light_scale
         sp[i]["light_add"] = (0.8, 0.7, 0.9)
     return sp
+
+
+def oracle_render_host_frame(oracle_lib, scene_module, sc, hf, width, height, color_bits, shadow_maps=None):
+    """The oracle's picture of a host frame, nested portal / mirror views included (build_view_portals_textures,
+    partial_renderer.rs:2008-2282): every visible portal's nested frame is rendered first (black at the depth limit), its overlay
+    texture mixed in, and the frame's TEX_VIEW commands sample those pictures.  Returns (surfaces, framebuffer).
+    `hf.cmds` may already carry device view indices in tex_ref (Renderer patches them): the mapping is rebuilt from hf.portals."""
+    dtype = np.uint32 if color_bits == 32 else np.uint64
+    view_textures = []
+    cmds = hf.cmds.copy()
+    for node in hf.portals:
+        w, h = node.resolution
+        if node.frame is None:
+            tex = np.zeros((h, w), dtype)
+        else:
+            _, tex = oracle_render_host_frame(oracle_lib, scene_module, sc, node.frame, w, h, color_bits)
+        if node.overlay is not None:
+            image, blend, light = node.overlay
+            oracle_lib.mix_surface_with_texture(color_bits, tex, (w, h), node.tc_min, sc.images[image][1], blend, light)
+        ref = node.view.index if node.view is not None else node.index
+        while len(view_textures) <= ref:
+            view_textures.append(None)
+        view_textures[ref] = tex
+    lights = hf.lights if hf.lights is not None and len(hf.lights) else None
+    sm = shadow_maps
+    if lights is not None and sm is None:
+        sm = np.zeros(max(hf.shadow_maps_len, 1), np.float32)
+        if hf.depth_maps is not None and len(hf.depth_maps):
+            oracle_lib.draw_shadow_maps(sm, hf.depth_maps, hf.depth_cmds, hf.depth_points)
+    surf = oracle_lib.build_surfaces(color_bits, hf.jobs, lights, sm, hf.cam_pos, sc.images, sc.lightmaps, sc.directional_lightmaps, hf.total_surface_pixels)
+    fb = np.zeros((height, width), dtype)
+    if hf.needs_clear:
+        oracle_lib.fill(fb, scene_module.BACKGROUND_COLOR64 if color_bits == 64 else scene_module.BACKGROUND_COLOR32)
+    oracle_lib.draw(color_bits, fb, cmds, hf.polygon_points, hf.triangle_points, surf, sc.images, view_textures=view_textures)
+    return surf, fb
+
+
+def wall_portals(scene_module, N, pose, overlay_skin=0, texels_per_unit=1.5):
+    """FrameInfo::portals fixture: three 60 x 50 unit quads on a vertical plane 90 units ahead of the camera, facing it — a
+    Mirror with an Average-blended overlay texture (a 'glass' material), a CameraAtPosition view and a ParallaxPortal that looks
+    into the space 140 units further ahead.  The tex-coord bases have the orientation the game gives them
+    (world_spawn.rs:372-381 / :407-415): mirrors (u x v) . n >= 0, parallax portals <= 0."""
+    az = float(pose[3])
+    fwd = np.array([-np.sin(az), np.cos(az), 0.0])
+    right = np.array([np.cos(az), np.sin(az), 0.0])
+    up = np.array([0.0, 0.0, 1.0])
+    p = np.zeros(3, scene_module.portal_dtype)
+    kinds = (scene_module.PORTAL_VIEW_MIRROR, scene_module.PORTAL_VIEW_CAMERA_AT_POSITION, scene_module.PORTAL_VIEW_PARALLAX_PORTAL)
+    for i, (off, kind) in enumerate(zip((-62.0, 0.0, 62.0), kinds)):
+        normal = -fwd
+        center = pose[:3] + fwd * 90.0 + right * off + up * (4.0 * i)
+        r = np.cross(up, normal)
+        r /= np.linalg.norm(r)
+        half_w, half_h = 30.0, 25.0
+        p[i]["view"] = kind
+        p[i]["plane"][:3] = normal
+        p[i]["plane"][3] = float(np.dot(normal, center))
+        tu, tv = r * texels_per_unit, -up * texels_per_unit
+        p[i]["tex_coord_equation"][0][:3] = tu
+        p[i]["tex_coord_equation"][0][3] = -float(np.dot(tu, center)) + half_w * texels_per_unit
+        p[i]["tex_coord_equation"][1][:3] = tv
+        p[i]["tex_coord_equation"][1][3] = -float(np.dot(tv, center)) + half_h * texels_per_unit
+        if kind == scene_module.PORTAL_VIEW_MIRROR:
+            p[i]["tex_coord_equation"][0] *= -1.0
+        p[i]["num_vertices"] = 4
+        p[i]["vertices"][:4] = [center - r * half_w - up * half_h, center - r * half_w + up * half_h, center + r * half_w + up * half_h, center + r * half_w - up * half_h]
+        p[i]["blending_mode"] = N.BLEND_NONE if i != 2 else N.BLEND_AVERAGE
+        p[i]["camera_position"] = pose[:3] + fwd * 20.0
+        a = az + np.pi / 2 + 0.5
+        p[i]["camera_rotation"] = (np.cos(a / 2), 0.0, 0.0, np.sin(a / 2))
+        p[i]["camera_fov"] = 1.2
+        shift = np.eye(4, dtype=np.float32)
+        shift[:3, 3] = fwd * 140.0
+        p[i]["transform_matrix"] = shift.T.reshape(16)  # column-major
+        p[i]["has_texture"] = 1 if i == 0 else 0
+        p[i]["texture_skin"] = overlay_skin
+        p[i]["texture_blending_mode"] = N.BLEND_AVERAGE
+        p[i]["texture_light_add"] = (0.8, 0.7, 0.9)
+    return p

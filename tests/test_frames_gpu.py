@@ -387,3 +387,41 @@ def test_submodels_moved_rotated_lit_and_shadowing(oracle_lib, color_bits):
     finally:
         r.close()
         sc.close()
+
+
+@pytest.mark.parametrize("color_bits,portals_depth", [(32, 1), (64, 2)])
+def test_config3_portals_and_mirrors(oracle_lib, color_bits, portals_depth):
+    """configs[3], last part: a mirror with a glass overlay (mix_surface_with_texture on the GPU), a camera portal and a blended
+    parallax portal.  Every nested view is its own device render target, built and drawn before the view that samples it
+    (SQW_TEX_VIEW), recursively up to portals_depth and black beyond; the whole tree must equal the oracle's."""
+    from common import oracle_render_host_frame, wall_portals
+
+    W, H = 640, 360
+    sc = S.Scene(seed=7, texture_size_log2=6, num_materials=8, num_models=2, model_detail=6, skybox=1, sky_size_log2=6)
+    r = Renderer(sc, RendererConfig(use_directional_lightmaps=True, portals_depth=portals_depth, clear_portal_textures=True))
+    try:
+        path = sc.camera_path(64)
+        nested = 0
+        for k in (0, 10, 33):
+            portals = wall_portals(S, N, path[k])
+            lights = _lights_along_path(path, 2, 31)
+            lights["shadow_type"] = N.SHADOW_NONE
+            lights["position"] = path[k][:3] + np.array([[20, 30, 10], [-30, 60, 0]], np.float32)
+            fi = FrameInfo(path[k], lights=lights, portals=portals, model_entities=_models_ahead_of_camera(sc, path[k], k))
+            hf = r.prepare_frame(SurfaceInfo(W, H), fi, color_bits=color_bits)
+            pixels = np.zeros((H, W), np.uint32 if color_bits == 32 else np.uint64)
+            r.draw_frame(pixels)
+            nested += sum(1 for n in hf.portals if n.frame is not None)
+            oracle_lib.reset_assert_failures()
+            _, fb = oracle_render_host_frame(oracle_lib, S, sc, hf, W, H, color_bits)
+            assert oracle_lib.assert_failures() == 0
+            for node in hf.portals:  # the nested render targets themselves
+                _, want = (None, np.zeros(node.resolution[::-1], pixels.dtype)) if node.frame is None else oracle_render_host_frame(oracle_lib, S, sc, node.frame, *node.resolution, color_bits)
+                if node.overlay is not None:
+                    oracle_lib.mix_surface_with_texture(color_bits, want, node.resolution, node.tc_min, sc.images[node.overlay[0]][1], node.overlay[1], node.overlay[2])
+                assert_pixels_equal(node.view.read_pixels(), want, f"frame {k} portal {node.index} texture")
+            assert_pixels_equal(pixels, fb, f"frame {k} picture with portals")
+        assert nested >= 4
+    finally:
+        r.close()
+        sc.close()

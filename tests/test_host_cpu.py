@@ -165,3 +165,47 @@ def test_submodels_follow_their_entities(oracle_lib):
         hp.close()
         sc.close()
         plain.close()
+
+
+def test_portals_and_mirrors_nest_host_frames(oracle_lib):
+    """FrameInfo::portals: every visible portal gets a texture rectangle, a nested host frame prepared with the portal's own
+    camera matrices (mirror: reflected eye, visibility started at the mirror's leafs), and a TEX_VIEW polygon command in the
+    outer frame; past portals_depth the nested frame is missing (black texture).  The oracle renders the whole tree."""
+    from common import oracle_render_host_frame, wall_portals
+    from square_wheel_b200 import _native as N
+
+    sc = S.Scene(seed=7, texture_size_log2=6, num_materials=8, num_models=2, model_detail=6)
+    try:
+        W, H = 320, 180
+        pose = sc.camera_path(64)[0]
+        portals = wall_portals(S, N, pose)
+        for depth in (0, 1, 2):
+            hr = S.HostRenderer(sc, portals_depth=depth)
+            try:
+                plain = hr.build_frame(W, H, pose, color_bits=32)
+                hf = hr.build_frame(W, H, pose, portals=portals, color_bits=32)
+                assert len(plain.portals) == 0 and int((plain.cmds["tex_kind"] == N.TEX_VIEW).sum()) == 0
+                assert len(hf.portals) >= 2
+                view_cmds = hf.cmds[hf.cmds["tex_kind"] == N.TEX_VIEW]
+                assert sorted(set(view_cmds["tex_ref"].tolist())) == sorted(n.index for n in hf.portals)
+                for node in hf.portals:
+                    assert 0 < node.resolution[0] <= 95 and 0 < node.resolution[1] <= 80  # 60 x 50 units at 1.5 texels per unit, mip >= 0
+                    cmd = view_cmds[view_cmds["tex_ref"] == node.index][0]
+                    assert tuple(cmd["tex_size"]) == node.resolution
+                    assert (node.frame is None) == (depth == 0)
+                    if node.frame is not None:
+                        assert len(node.frame.cmds) > 0
+                        # nested views see the portals too; at depth 1 their own nested frames are past the limit
+                        assert all((inner.frame is None) == (depth == 1) for inner in node.frame.portals)
+                    assert (node.overlay is not None) == (node.index == 0)
+                oracle_lib.reset_assert_failures()
+                _, fb = oracle_render_host_frame(oracle_lib, S, sc, hf, W, H, 32)
+                assert oracle_lib.assert_failures() == 0
+                if depth == 0:
+                    black = fb.copy()
+                else:
+                    assert int((fb != black).sum()) > 500  # the nested views really show something
+            finally:
+                hr.close()
+    finally:
+        sc.close()
