@@ -859,64 +859,105 @@ __device__ __forceinline__ void shade_quad(
 	}
 	else
 	{
-		// fill_triangle_part pixel loop (rasterizer.rs:1223-1279)
+		// fill_triangle_part pixel loop (rasterizer.rs:1223-1279), in three branch-free steps like the polygon path: the four
+		// texel addresses, the four gathers in flight together, then light and blend with the (warp-uniform) blend mode
+		// decided once outside the pixel loop.
 		const int32_t tc0 = (int32_t)r0.y, tc1 = (int32_t)r0.z, dtc0 = (int32_t)r0.w, dtc1 = (int32_t)r1.x;
 		const int32_t l0 = (int32_t)r1.y, l1 = (int32_t)r1.z, l2 = (int32_t)r1.w;
 		const int32_t dl0 = (int32_t)r2.x, dl1 = (int32_t)r2.y, dl2 = (int32_t)r2.z;
+		bool in[4];
+		uint32_t address[4];
 #pragma unroll
 		for (int i = 0; i < 4; ++i)
 		{
 			const int32_t x = px0 + SQW_PX_OFS(i);
-			if (x >= x0 && x < x1)
+			in[i] = x >= x0 && x < x1;
+			const int32_t k = x - x0;
+			const uint32_t u = (uint32_t)(wadd(tc0, wmul(k, dtc0)) >> 16);
+			const uint32_t v = (uint32_t)(wadd(tc1, wmul(k, dtc1)) >> 16);
+			address[i] = u + v * tex_width; // garbage for uncovered pixels, never dereferenced
+		}
+		ColorVecI texel_vec[4];
+		int32_t alpha[4];
+		bool alpha_pass[4];
+		if (tex64)
+		{
+			uint64_t t[4];
+#pragma unroll
+			for (int i = 0; i < 4; ++i)
 			{
-				const int32_t k = x - x0;
-				const uint32_t u = (uint32_t)(wadd(tc0, wmul(k, dtc0)) >> 16);
-				const uint32_t v = (uint32_t)(wadd(tc1, wmul(k, dtc1)) >> 16);
-				// line_light = from_color_i32x3([l0,l1,l2]) -> lanes [B,G,R,A] = [l2,l1,l0,0]
-				const ColorVecI light = cvi(wadd(l2, wmul(k, dl2)), wadd(l1, wmul(k, dl1)), wadd(l0, wmul(k, dl0)), 0);
-				ColorVecI texel_vec;
-				int32_t alpha;
-				bool alpha_pass;
-				if (tex64)
-				{
-					const uint64_t t = __ldg(static_cast<const uint64_t*>(tex) + (u + v * tex_width));
-					texel_vec = cvi_from_color64(t);
-					alpha = Color64::get_alpha(t);
-					alpha_pass = Color64::test_alpha(t);
-				}
-				else
-				{
-					const uint32_t t = __ldg(static_cast<const uint32_t*>(tex) + (u + v * tex_width));
-					texel_vec = cvi_from_color32(t);
-					alpha = Color32::get_alpha(t);
-					alpha_pass = Color32::test_alpha(t);
-				}
-				const ColorVecI lighted = cvi_shr<16>(cvi_mul(texel_vec, light));
-				const Raw src = C::from_veci(lighted);
-				if (reads_dst)
+				t[i] = 0;
+				if (in[i])
+					t[i] = __ldg(static_cast<const uint64_t*>(tex) + address[i]);
+			}
+#pragma unroll
+			for (int i = 0; i < 4; ++i)
+			{
+				texel_vec[i] = cvi_from_color64(t[i]);
+				alpha[i] = Color64::get_alpha(t[i]);
+				alpha_pass[i] = Color64::test_alpha(t[i]);
+			}
+		}
+		else
+		{
+			uint32_t t[4];
+#pragma unroll
+			for (int i = 0; i < 4; ++i)
+			{
+				t[i] = 0;
+				if (in[i])
+					t[i] = __ldg(static_cast<const uint32_t*>(tex) + address[i]);
+			}
+#pragma unroll
+			for (int i = 0; i < 4; ++i)
+			{
+				texel_vec[i] = cvi_from_color32(t[i]);
+				alpha[i] = Color32::get_alpha(t[i]);
+				alpha_pass[i] = Color32::test_alpha(t[i]);
+			}
+		}
+		ColorVecI lighted[4];
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+		{
+			const int32_t k = px0 + SQW_PX_OFS(i) - x0;
+			// line_light = from_color_i32x3([l0,l1,l2]) -> lanes [B,G,R,A] = [l2,l1,l0,0]
+			const ColorVecI light = cvi(wadd(l2, wmul(k, dl2)), wadd(l1, wmul(k, dl1)), wadd(l0, wmul(k, dl0)), 0);
+			lighted[i] = cvi_shr<16>(cvi_mul(texel_vec[i], light));
+		}
+		if (blend == SQW_BLEND_NONE)
+		{
+#pragma unroll
+			for (int i = 0; i < 4; ++i)
+			{
+				px[i] = in[i] ? C::from_veci(lighted[i]) : px[i];
+				have |= in[i] ? (1u << i) : 0u;
+			}
+		}
+		else if (blend == SQW_BLEND_ALPHA_TEST)
+		{
+#pragma unroll
+			for (int i = 0; i < 4; ++i)
+			{
+				const bool pass = in[i] && alpha_pass[i];
+				px[i] = pass ? C::from_veci(lighted[i]) : px[i];
+				have |= pass ? (1u << i) : 0u;
+			}
+		}
+		else
+		{
+#pragma unroll
+			for (int i = 0; i < 4; ++i)
+				if (in[i])
 				{
 					SQW_NEED_DST(i)
+					if (blend == SQW_BLEND_AVERAGE)
+						px[i] = C::average(px[i], C::from_veci(lighted[i]));
+					else if (blend == SQW_BLEND_ADDITIVE)
+						px[i] = C::saturated_sum(px[i], C::from_veci(lighted[i]));
+					else
+						px[i] = C::from_veci(cvi_shr<8>(cvi_add(cvi_mul_scalar(C::to_veci(px[i]), 255 - alpha[i]), cvi_mul_scalar(lighted[i], alpha[i]))));
 				}
-				switch (blend)
-				{
-				case SQW_BLEND_NONE:
-					px[i] = src;
-					have |= 1u << i;
-					break;
-				case SQW_BLEND_AVERAGE: px[i] = C::average(px[i], src); break;
-				case SQW_BLEND_ADDITIVE: px[i] = C::saturated_sum(px[i], src); break;
-				case SQW_BLEND_ALPHA_TEST:
-					if (alpha_pass)
-					{
-						px[i] = src;
-						have |= 1u << i;
-					}
-					break;
-				default:
-					px[i] = C::from_veci(cvi_shr<8>(cvi_add(cvi_mul_scalar(C::to_veci(px[i]), 255 - alpha), cvi_mul_scalar(lighted, alpha))));
-					break;
-				}
-			}
 		}
 	}
 }
