@@ -497,7 +497,7 @@ __device__ void triangle_command_setup(const sqw_draw_cmd& c, const sqw_triangle
 }
 
 // One thread per command: the TriRec of every triangle command (polygon commands leave their slot untouched).
-__global__ void __launch_bounds__(128) raster_triangle_setup_kernel(
+__global__ void __launch_bounds__(32) raster_triangle_setup_kernel(
 	const sqw_draw_cmd* __restrict__ cmds, uint32_t num_cmds, const sqw_triangle_point* __restrict__ triangle_points, int32_t clip_h, TriRec* __restrict__ tri_recs)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -571,12 +571,18 @@ __device__ void bin_band(
 		bx = w.y;
 		return y0 < y1 && y0 < band_y1 && y1 > band_y0;
 	};
+	// four independent loads per lane and iteration: the scan is a latency chain (one L2 round trip per step), not a bandwidth one
 	uint32_t count = 0;
-	for (uint32_t base = scan_begin; base < scan_end; base += 32)
+	for (uint32_t base = scan_begin; base < scan_end; base += 128)
 	{
-		uint32_t bx;
-		const bool hit = base + lane < scan_end && touches(base + lane, bx);
-		count += __popc(__ballot_sync(0xFFFFFFFFu, hit));
+		uint32_t bx[4];
+		bool hit[4];
+#pragma unroll
+		for (int k = 0; k < 4; ++k)
+			hit[k] = base + 32 * k + lane < scan_end && touches(base + 32 * k + lane, bx[k]);
+#pragma unroll
+		for (int k = 0; k < 4; ++k)
+			count += __popc(__ballot_sync(0xFFFFFFFFu, hit[k]));
 	}
 	if (lane == 0)
 		s_warp_counts[warp] = count;
@@ -588,22 +594,29 @@ __device__ void bin_band(
 			offset += s_warp_counts[w];
 		total += s_warp_counts[w];
 	}
-	for (uint32_t base = scan_begin; base < scan_end; base += 32)
+	for (uint32_t base = scan_begin; base < scan_end; base += 128)
 	{
-		uint32_t bx = 0;
-		const bool hit = base + lane < scan_end && touches(base + lane, bx);
-		const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, hit);
-		if (hit)
+		uint32_t bx[4] = {0, 0, 0, 0};
+		bool hit[4];
+#pragma unroll
+		for (int k = 0; k < 4; ++k)
+			hit[k] = base + 32 * k + lane < scan_end && touches(base + 32 * k + lane, bx[k]);
+#pragma unroll
+		for (int k = 0; k < 4; ++k)
 		{
-			const uint32_t pos = offset + __popc(ballot & ((1u << lane) - 1));
-			band_lists[pos] = base + lane;
-			if (pos - band_begin < SQW_BIN_CACHE)
+			const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, hit[k]);
+			if (hit[k])
 			{
-				s_idx[pos - band_begin] = base + lane;
-				s_bx[pos - band_begin] = bx;
+				const uint32_t pos = offset + __popc(ballot & ((1u << lane) - 1));
+				band_lists[pos] = base + 32 * k + lane;
+				if (pos - band_begin < SQW_BIN_CACHE)
+				{
+					s_idx[pos - band_begin] = base + 32 * k + lane;
+					s_bx[pos - band_begin] = bx[k];
+				}
 			}
+			offset += __popc(ballot);
 		}
-		offset += __popc(ballot);
 	}
 	__syncthreads();
 	if (threadIdx.x == 0)
@@ -653,11 +666,19 @@ __global__ void __launch_bounds__(SQW_SETUP_THREADS) raster_setup_kernel(
 	uint4* __restrict__ tile_desc, uint32_t tiles_x, uint32_t num_bands,
 	unsigned long long* __restrict__ sums_to_zero, uint8_t* __restrict__ tonemap_lut, float isb, float isg, float isr)
 {
-	if (blockIdx.x >= setup_blocks + num_bands)
+	// Grid order: binning CTAs FIRST (each is one long dependent chain over the whole command list — started last they were the
+	// tail of the kernel), then the tonemapping-table CTAs, then the span set-up CTAs.
+	if (blockIdx.x < num_bands)
+	{
+		bin_band(cmd_dev, num_cmds, band_offsets, band_lists, tile_lists, tile_desc, tiles_x, (int)blockIdx.x);
+		return;
+	}
+	const uint32_t lut_blocks = tonemap_lut ? (3 * SQW_TONEMAP_LUT_SIZE + SQW_SETUP_THREADS - 1) / SQW_SETUP_THREADS : 0;
+	if (blockIdx.x < num_bands + lut_blocks)
 	{
 		// Tonemapping table of the fused tile epilogue: TonemappingFunction::do_it (postprocessor.rs:1019-1023) of every
 		// channel value below SQW_TONEMAP_LUT_SIZE, computed with the same IEEE operations as tonemap_pixel.
-		const uint32_t idx = (blockIdx.x - setup_blocks - num_bands) * SQW_SETUP_THREADS + threadIdx.x;
+		const uint32_t idx = (blockIdx.x - num_bands) * SQW_SETUP_THREADS + threadIdx.x;
 		if (idx < 3 * SQW_TONEMAP_LUT_SIZE)
 		{
 			const uint32_t ch = idx / SQW_TONEMAP_LUT_SIZE;
@@ -667,17 +688,13 @@ __global__ void __launch_bounds__(SQW_SETUP_THREADS) raster_setup_kernel(
 		}
 		return;
 	}
-	if (blockIdx.x >= setup_blocks)
-	{
-		bin_band(cmd_dev, num_cmds, band_offsets, band_lists, tile_lists, tile_desc, tiles_x, (int)(blockIdx.x - setup_blocks));
-		return;
-	}
-	if (sums_to_zero && blockIdx.x == 0) // colour sums of the fused tonemapping epilogue of the tile kernel that follows
+	const uint32_t setup_block = blockIdx.x - num_bands - lut_blocks;
+	if (sums_to_zero && setup_block == 0) // colour sums of the fused tonemapping epilogue of the tile kernel that follows
 		for (uint32_t i = threadIdx.x; i < SQW_SUM_WORDS; i += SQW_SETUP_THREADS)
 			sums_to_zero[i] = 0;
 	// One warp per chunk = up to 32 consecutive scan-lines of one command (chunk list built by the host while it computes
 	// the row ranges): the command and its vertices are warp-uniform, so their loads are broadcasts served by one L1 line.
-	const uint32_t chunk = blockIdx.x * (SQW_SETUP_THREADS / 32) + (threadIdx.x >> 5);
+	const uint32_t chunk = setup_block * (SQW_SETUP_THREADS / 32) + (threadIdx.x >> 5);
 	if (chunk >= num_chunks)
 		return;
 	const uint2 ch = __ldg(chunks + chunk); // {command index, first row of the chunk relative to the command's y0}
@@ -1257,10 +1274,11 @@ cudaError_t launch_raster_setup(const RasterLaunch& l, cudaStream_t stream)
 	const uint32_t bin_blocks = l.num_bands; // also with an empty command list: the tile kernel reads every tile descriptor
 	const uint32_t lut_blocks = l.tonemap_dst ? (3 * SQW_TONEMAP_LUT_SIZE + SQW_SETUP_THREADS - 1) / SQW_SETUP_THREADS : 0;
 	if (l.num_triangle_cmds)
-		raster_triangle_setup_kernel<<<(l.num_cmds + 127) / 128, 128, 0, stream>>>(l.cmds, l.num_cmds, l.triangle_points, l.height, static_cast<TriRec*>(l.tri_recs));
+		raster_triangle_setup_kernel<<<(l.num_cmds + 31) / 32, 32, 0, stream>>> // one warp per CTA: a few hundred long serial chains spread over all SMs
+		(l.cmds, l.num_cmds, l.triangle_points, l.height, static_cast<TriRec*>(l.tri_recs));
 	raster_setup_kernel<<<setup_blocks + bin_blocks + lut_blocks, SQW_SETUP_THREADS, 0, stream>>>(
 		l.cmds, l.cmd_dev, l.num_cmds, l.polygon_points, static_cast<const TriRec*>(l.tri_recs), l.chunks, l.num_chunks, l.spans, l.width, l.height, setup_blocks, l.band_offsets,
-		l.band_lists, l.tile_lists, l.tile_desc, (uint32_t)((l.width + SQW_TILE_W - 1) / SQW_TILE_W), bin_blocks, l.tonemap_dst ? l.color_sums : nullptr, l.tonemap_lut, l.inv_scale_bgr[0], l.inv_scale_bgr[1], l.inv_scale_bgr[2]);
+		l.band_lists, l.tile_lists, l.tile_desc, (uint32_t)((l.width + SQW_TILE_W - 1) / SQW_TILE_W), bin_blocks, l.tonemap_dst ? l.color_sums : nullptr, l.tonemap_dst ? l.tonemap_lut : nullptr, l.inv_scale_bgr[0], l.inv_scale_bgr[1], l.inv_scale_bgr[2]);
 	return cudaGetLastError();
 }
 
