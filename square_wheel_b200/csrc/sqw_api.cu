@@ -4,6 +4,7 @@
 #include "sqw_internal.h"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -233,6 +234,9 @@ struct sqw_view
 	DevBuf surfaces;
 	DevBuf spans;
 	DevBuf band_lists;
+	// span set-up + binning of a frame run beside its surface building (they are independent; both feed the tile kernel)
+	cudaStream_t aux_stream = nullptr;
+	cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
 	DevBuf tri_recs; // per-triangle set-up records of the draw being submitted (SQW_TRI_REC_BYTES per command)
 	uint64_t* d_bloom[2] = {nullptr, nullptr};
 	uint8_t* d_tonemap_lut = nullptr;     // 3 x SQW_TONEMAP_LUT_SIZE (64-bit views)
@@ -517,6 +521,12 @@ int sqw_view_create(sqw_ctx* ctx, sqw_view** out_view, uint32_t width, uint32_t 
 	if (e == cudaSuccess)
 		e = cudaEventCreateWithFlags(&v->done, cudaEventDisableTiming);
 	if (e == cudaSuccess)
+		e = cudaStreamCreateWithFlags(&v->aux_stream, cudaStreamNonBlocking);
+	if (e == cudaSuccess)
+		e = cudaEventCreateWithFlags(&v->aux_fork, cudaEventDisableTiming);
+	if (e == cudaSuccess)
+		e = cudaEventCreateWithFlags(&v->aux_join, cudaEventDisableTiming);
+	if (e == cudaSuccess)
 		e = cudaMalloc(&v->d_color, px * (color_bits / 8));
 	if (e == cudaSuccess)
 		e = cudaMemset(v->d_color, 0, px * (color_bits / 8));
@@ -563,6 +573,15 @@ void sqw_view_destroy(sqw_view* view)
 		sqw_frame_destroy(view->immediate);
 	if (view->done)
 		cudaEventDestroy(view->done);
+	if (view->aux_stream)
+	{
+		cudaStreamSynchronize(view->aux_stream);
+		cudaStreamDestroy(view->aux_stream);
+	}
+	if (view->aux_fork)
+		cudaEventDestroy(view->aux_fork);
+	if (view->aux_join)
+		cudaEventDestroy(view->aux_join);
 	if (view->own_stream)
 		cudaStreamDestroy(view->stream);
 	if (view->d_color)
@@ -1129,6 +1148,78 @@ int sqw_frame_submit(sqw_frame* f, uint32_t stages)
 		}
 	}
 
+	if (do_raster && (f->draw_width != view->width || f->draw_height != view->height))
+		return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_frame_submit: the view was resized after the command list was set");
+	RasterLaunch rl{};
+	const bool raster_launches = do_raster && (f->num_cmds || f->clear || fused_tonemap); // the binning CTAs also write the (empty) tile lists of a clear-only draw
+	bool setup_forked = false;
+	if (do_raster)
+	{
+		
+		rl.cmds = f->d_cmds;
+		rl.cmd_dev = f->d_cmd_dev;
+		rl.num_cmds = f->num_cmds;
+		rl.polygon_points = f->d_polygon_points;
+		rl.triangle_points = f->d_triangle_points;
+		rl.tri_recs = view->tri_recs.ptr;
+		rl.num_triangle_cmds = f->num_triangle_cmds;
+		rl.spans = static_cast<SpanRec*>(view->spans.ptr);
+		rl.chunks = f->d_chunks;
+		rl.num_chunks = (uint32_t)f->h_chunks.size();
+		rl.total_spans = f->total_spans;
+		{
+			const uint32_t tiles_x = (view->width + SQW_TILE_W - 1) / SQW_TILE_W;
+			char* const base = static_cast<char*>(view->band_lists.ptr);
+			rl.band_lists = reinterpret_cast<uint32_t*>(base);
+			rl.tile_lists = reinterpret_cast<uint32_t*>(base + bin_tile_lists_offset(f->total_band_entries));
+			rl.tile_desc = reinterpret_cast<uint4*>(base + bin_tile_desc_offset(f->total_band_entries, tiles_x));
+		}
+		rl.band_offsets = f->d_band_offsets;
+		rl.num_bands = f->num_bands;
+		rl.width = (int32_t)view->width;
+		rl.height = (int32_t)view->height;
+		rl.pitch = (int32_t)view->width;
+		rl.color_buffer = view->d_color;
+		rl.surfaces_base = view->surfaces.ptr;
+		rl.color64 = view->color_bits == 64;
+		rl.clear = f->clear;
+		rl.clear_color = f->clear_color;
+		if (fused_tonemap)
+		{
+			rl.tonemap_dst = view->d_ldr;
+			rl.inv_scale_bgr[0] = inv_scale_bgr[0];
+			rl.inv_scale_bgr[1] = inv_scale_bgr[1];
+			rl.inv_scale_bgr[2] = inv_scale_bgr[2];
+			rl.color_sums = view->d_sums; // zeroed by the set-up grid
+			rl.tonemap_lut = view->d_tonemap_lut;
+			view->sums_divisor = (uint64_t)view->width * view->height;
+		}
+		// Span set-up + binning do not depend on the surfaces: when both stages are submitted together the set-up grid runs on the
+		// view's auxiliary stream BESIDE surface building and the tile kernel waits for both.  (Not while profiling: the
+		// per-kernel event times are then taken one kernel at a time.)
+		if (raster_launches)
+		{
+			cudaStream_t setup_stream = s;
+			// Only for single-stream contexts (one frame at a time: the fork shortens the frame); with SQW_CTX_CONCURRENT_VIEWS other
+			// views' kernels already fill the GPU and the extra events only cost.
+			static const bool no_fork = std::getenv("SQW_NO_SETUP_FORK") != nullptr; // A/B switch for measurements
+			if (do_surfaces && !ctx->profiling && !ctx->concurrent_views && !no_fork && view->aux_stream)
+			{
+				SQW_CUDA(ctx, cudaEventRecord(view->aux_fork, s));
+				SQW_CUDA(ctx, cudaStreamWaitEvent(view->aux_stream, view->aux_fork, 0));
+				setup_stream = view->aux_stream;
+				setup_forked = true;
+			}
+			{
+				LaunchTimer timer(ctx, SQW_KERNEL_RASTER_SETUP, setup_stream);
+				SQW_CUDA(ctx, launch_raster_setup(rl, setup_stream));
+			}
+			launches += f->num_triangle_cmds ? 2 : 1; // + the per-triangle set-up kernel
+			if (setup_forked)
+				SQW_CUDA(ctx, cudaEventRecord(view->aux_join, view->aux_stream));
+		}
+	}
+
 	if (do_surfaces)
 	{
 		SurfaceLaunch l{};
@@ -1154,64 +1245,18 @@ int sqw_frame_submit(sqw_frame* f, uint32_t stages)
 		}
 	}
 
-	if (do_raster && (f->draw_width != view->width || f->draw_height != view->height))
-		return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_frame_submit: the view was resized after the command list was set");
 	if (do_raster)
 	{
 		// portal / mirror textures: wait for the views this frame samples (they may run on other streams)
 		for (uint32_t vi : f->sampled_views)
 			if (vi < ctx->views.size() && ctx->views[vi] && ctx->views[vi]->stream != s)
 				SQW_CUDA(ctx, cudaStreamWaitEvent(s, ctx->views[vi]->done, 0));
-
-		RasterLaunch l{};
-		l.cmds = f->d_cmds;
-		l.cmd_dev = f->d_cmd_dev;
-		l.num_cmds = f->num_cmds;
-		l.polygon_points = f->d_polygon_points;
-		l.triangle_points = f->d_triangle_points;
-		l.tri_recs = view->tri_recs.ptr;
-		l.num_triangle_cmds = f->num_triangle_cmds;
-		l.spans = static_cast<SpanRec*>(view->spans.ptr);
-		l.chunks = f->d_chunks;
-		l.num_chunks = (uint32_t)f->h_chunks.size();
-		l.total_spans = f->total_spans;
-		{
-			const uint32_t tiles_x = (view->width + SQW_TILE_W - 1) / SQW_TILE_W;
-			char* const base = static_cast<char*>(view->band_lists.ptr);
-			l.band_lists = reinterpret_cast<uint32_t*>(base);
-			l.tile_lists = reinterpret_cast<uint32_t*>(base + bin_tile_lists_offset(f->total_band_entries));
-			l.tile_desc = reinterpret_cast<uint4*>(base + bin_tile_desc_offset(f->total_band_entries, tiles_x));
-		}
-		l.band_offsets = f->d_band_offsets;
-		l.num_bands = f->num_bands;
-		l.width = (int32_t)view->width;
-		l.height = (int32_t)view->height;
-		l.pitch = (int32_t)view->width;
-		l.color_buffer = view->d_color;
-		l.surfaces_base = view->surfaces.ptr;
-		l.color64 = view->color_bits == 64;
-		l.clear = f->clear;
-		l.clear_color = f->clear_color;
-		if (fused_tonemap)
-		{
-			l.tonemap_dst = view->d_ldr;
-			l.inv_scale_bgr[0] = inv_scale_bgr[0];
-			l.inv_scale_bgr[1] = inv_scale_bgr[1];
-			l.inv_scale_bgr[2] = inv_scale_bgr[2];
-			l.color_sums = view->d_sums; // zeroed by the set-up grid
-			l.tonemap_lut = view->d_tonemap_lut;
-			view->sums_divisor = (uint64_t)view->width * view->height;
-		}
-		if (f->num_cmds || f->clear || fused_tonemap) // the binning CTAs also write the (empty) tile lists of a clear-only draw
-		{
-			LaunchTimer timer(ctx, SQW_KERNEL_RASTER_SETUP, s);
-			SQW_CUDA(ctx, launch_raster_setup(l, s));
-			launches += f->num_triangle_cmds ? 2 : 1; // + the per-triangle set-up kernel
-		}
-		if (f->num_cmds || f->clear || fused_tonemap)
+		if (setup_forked)
+			SQW_CUDA(ctx, cudaStreamWaitEvent(s, view->aux_join, 0));
+		if (raster_launches)
 		{
 			LaunchTimer timer(ctx, fused_tonemap ? SQW_KERNEL_RASTER_TILE_TONEMAP : SQW_KERNEL_RASTER_TILE, s);
-			SQW_CUDA(ctx, launch_raster_tiles(l, s));
+			SQW_CUDA(ctx, launch_raster_tiles(rl, s));
 			++launches;
 		}
 	}
