@@ -1,5 +1,7 @@
 // Host-side mirror of the renderer front end (see renderer.hpp).  Each function cites the reference code it follows.
 #include "renderer.hpp"
+#include <atomic>
+#include <thread>
 #include <algorithm>
 #include <cstring>
 
@@ -1826,8 +1828,8 @@ ModelLightData Renderer::get_model_light(const ModelEntity& model, const Mat4f& 
 
 void Renderer::build_dynamic_models_buffers() // partial_renderer.rs:1122-1190
 {
-	for (VisibleDynamicMeshInfo& vm : visible_dynamic_meshes_list_)
-	{
+	// every mesh writes its own region of the vertex / triangle buffers: the reference runs this loop with rayon's par_iter_mut (:1181-1189)
+	auto process_mesh = [this](VisibleDynamicMeshInfo& vm) {
 		const ModelEntity& model = frame_models_[vm.entity_index];
 		const TriangleModel& triangle_model = scene_.models[model.model];
 		const HostImage& mip0 = scene_.images[model.texture_images[0]];
@@ -1842,7 +1844,26 @@ void Renderer::build_dynamic_models_buffers() // partial_renderer.rs:1122-1190
 		Triangle* dst_triangles = dynamic_meshes_triangles_.data() + vm.triangles_offset;
 		vm.num_visible_triangles = reject_triangle_model_back_faces(dst_vertices, mesh.triangles.data(), mesh.triangles.size(), dst_triangles);
 		sort_model_triangles(dst_vertices, dst_triangles, vm.num_visible_triangles);
+	};
+	const size_t num_meshes = visible_dynamic_meshes_list_.size();
+	const size_t num_threads = std::min<size_t>(std::min<size_t>(num_meshes, std::max(1u, std::thread::hardware_concurrency())), 8);
+	if (num_threads <= 1)
+	{
+		for (VisibleDynamicMeshInfo& vm : visible_dynamic_meshes_list_)
+			process_mesh(vm);
+		return;
 	}
+	std::atomic<size_t> next{0};
+	auto worker = [&]() {
+		for (size_t i = next.fetch_add(1); i < num_meshes; i = next.fetch_add(1))
+			process_mesh(visible_dynamic_meshes_list_[i]);
+	};
+	std::vector<std::thread> threads;
+	for (size_t t = 1; t < num_threads; ++t)
+		threads.emplace_back(worker);
+	worker();
+	for (std::thread& t : threads)
+		t.join();
 }
 
 // The tail of draw_leaf (partial_renderer.rs:2584-2790) for the object kinds of this mirror (triangle models and sprites).
