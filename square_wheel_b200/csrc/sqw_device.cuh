@@ -74,8 +74,9 @@ __device__ __forceinline__ Fixed16 f32_to_fixed16_unchecked(float x) { return f3
 // ---- fast_math.rs portable branch ---------------------------------------------------------------------------
 #define SQW_MIN_POSITIVE_VALUE (1.0f / 1073741824.0f) /* fast_math.rs:744 */
 
-__device__ __forceinline__ float inv_sqrt_fast(float x) { return __fdiv_rn(1.0f, __fsqrt_rn(x)); } // :376
-__device__ __forceinline__ float inv_fast(float x) { return __fdiv_rn(1.0f, x); }                  // :381
+// 1.0 / y correctly rounded IS the IEEE reciprocal: rcp.rn gives the same bits as div.rn(1, y) with a shorter sequence
+__device__ __forceinline__ float inv_sqrt_fast(float x) { return __frcp_rn(__fsqrt_rn(x)); } // :376
+__device__ __forceinline__ float inv_fast(float x) { return __frcp_rn(x); }                  // :381
 __device__ __forceinline__ float f32_mul_add(float x, float y, float z) { return __fadd_rn(__fmul_rn(x, y), z); } // :737
 
 struct Vec3
