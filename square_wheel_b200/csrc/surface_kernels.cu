@@ -139,12 +139,18 @@ __device__ __forceinline__ typename C::Raw emissive_mix(uint32_t texel, ColorVec
 }
 
 // rem_euclid (surfaces.rs:507-510) with the power-of-two shortcut (two's complement & mask == rem_euclid).
+// The general case is an out-of-line call on purpose: inlined, the compiler if-converts the branch and every texel pays the
+// ~30 instructions of the integer division even when all textures are powers of two (a tenth of the kernel's instructions).
+static __device__ __noinline__ uint32_t wrap_coord_general(int32_t x, int32_t size)
+{
+	const int32_t m = x % size;
+	return (uint32_t)(m < 0 ? m + size : m);
+}
 __device__ __forceinline__ uint32_t wrap_coord(int32_t x, int32_t size, uint32_t pow2_mask)
 {
 	if (pow2_mask)
 		return (uint32_t)x & pow2_mask;
-	const int32_t m = x % size;
-	return (uint32_t)(m < 0 ? m + size : m);
+	return wrap_coord_general(x, size);
 }
 __device__ __forceinline__ uint32_t pow2_mask_of(uint32_t size) { return (size & (size - 1)) == 0 ? size - 1 : 0; }
 
