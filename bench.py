@@ -24,7 +24,7 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-FRAMES_PER_STEP = 16
+FRAMES_PER_STEP = 64  # one step = one pass over the whole fixed camera path
 NUM_POSES = 64
 NUM_VIEWS = 4  # render targets in flight per GPU (independent camera views overlap on private streams)
 WIDTH, HEIGHT = 3840, 2160
@@ -135,7 +135,7 @@ def run_reference(args, rank, world):
     from square_wheel_b200 import scene as S
     from square_wheel_b200.device import make_post_params
 
-    sample_frames = 2
+    sample_frames = 4
     cores = os.cpu_count() or 1
     scene = S.Scene(**SCENE_KW)
     poses = scene.camera_path(NUM_POSES)
@@ -319,6 +319,14 @@ def run_cuda(args, rank, local_rank, world):
             gbs = stage_bytes[name] / (ms / frames_timed * 1e-3) / 1e9
             kernels[name].update({"algorithmic_bytes_per_frame": stage_bytes[name], "achieved_gbs": gbs, "frac_of_measured_peak": gbs / peak})
     dominant = max(kernels, key=lambda n: kernels[n]["ms_per_frame"])
+    # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (tools/ncu_traffic.py); null if absent
+    traffic = traffic_src = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        traffic = tj["kernels"][dominant]["traffic_bytes"]
+        traffic_src = "profiles/ncu_traffic.json (%s; %s)" % (tj.get("source"), tj.get("note"))
+    except (OSError, KeyError, ValueError):
+        pass
     dom = kernels[dominant]
     roofline = {
         "kernel": dominant,
@@ -328,7 +336,8 @@ def run_cuda(args, rank, local_rank, world):
         "peak_source": peak_src,
         "unit": "GB/s",
         "frac": dom.get("frac_of_measured_peak"),
-        "traffic": None,
+        "traffic": traffic,
+        "traffic_source": traffic_src,
         "per_launch": "one frame (all launches of this kernel in one frame)",
         "algorithmic_bytes": dom.get("algorithmic_bytes_per_frame"),
         "ms": dom["ms_per_frame"],

@@ -18,7 +18,9 @@ struct ImageDev
 // One CTA of surface_build_kernel processes one band: up to SQW_SURF_MAX_BAND_ROWS consecutive rows of one job holding
 // about SQW_SURF_BAND_TEXELS texels.
 #define SQW_SURF_MAX_BAND_ROWS 32
-#define SQW_SURF_BAND_TEXELS 1024
+#ifndef SQW_SURF_BAND_TEXELS
+#define SQW_SURF_BAND_TEXELS 2048
+#endif
 #define SQW_SURF_THREADS 256
 struct SurfaceBand
 {

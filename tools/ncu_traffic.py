@@ -1,0 +1,48 @@
+#!/usr/bin/env python
+"""DRAM traffic per launch of every kernel in an `ncu --set full` report -> profiles/ncu_traffic.json (read by bench.py for
+`roofline.traffic`).
+
+    python tools/ncu_traffic.py gpurun_out/prof_v7.ncu-rep profiles/ncu_traffic.json
+
+traffic = dram__bytes_read.sum + dram__bytes_write.sum, averaged over the captured launches of a kernel.  The capture runs
+with ncu's default cache control (caches flushed before every replay), so these are cold-cache numbers."""
+import collections
+import csv
+import io
+import json
+import subprocess
+import sys
+
+NAMES = {"surface_build_kernel": "surface_build", "raster_setup_kernel": "raster_setup", "raster_tile_kernel": "raster_tile", "tonemap_kernel": "tonemap"}
+UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+
+def main():
+    rep, out = sys.argv[1:3]
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum"],
+                         capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
+    hdr, units = rows[0], rows[1]
+    col = {h: i for i, h in enumerate(hdr)}
+    acc = collections.defaultdict(lambda: [0.0, 0.0, 0.0, 0])
+    for r in rows[2:]:
+        name = r[col["Kernel Name"]]
+        key = next((v for k, v in NAMES.items() if k in name), None)
+        if key is None:
+            continue
+        if key == "raster_tile" and "1>" in name.replace(" ", "").split("raster_tile_kernel")[1][:40]:
+            key = "raster_tile_tonemap"
+        a = acc[key]
+        for j, m in enumerate(["dram__bytes_read.sum", "dram__bytes_write.sum"]):
+            a[j] += float(r[col[m]].replace(",", "")) * UNIT.get(units[col[m]], 1.0)
+        a[2] += float(r[col["gpu__time_duration.sum"]].replace(",", "")) * {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(units[col["gpu__time_duration.sum"]], 1.0)
+        a[3] += 1
+    res = {"source": rep, "note": "ncu --set full, default cache control (cold caches), mean over the captured launches", "kernels": {}}
+    for k, (rd, wr, us, n) in acc.items():
+        res["kernels"][k] = {"launches": n, "dram_read_bytes": rd / n, "dram_write_bytes": wr / n, "traffic_bytes": (rd + wr) / n, "us_under_ncu": us / n}
+    json.dump(res, open(out, "w"), indent=1, sort_keys=True)
+    print(json.dumps(res["kernels"], indent=1))
+
+
+if __name__ == "__main__":
+    main()

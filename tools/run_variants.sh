@@ -3,6 +3,7 @@
 for so in build_variants/*.so; do
   cp $so square_wheel_b200/libsqw_cuda.so
   n=$(basename $so .so)
+  python -m pytest tests/test_surfaces_gpu.py tests/test_frames_gpu.py -x -q 2>&1 | tail -1
   python bench.py --steps 6 --warmup 3 --no-cpu-baseline > gpurun_out/bv_$n.json 2> gpurun_out/bv_$n.err || { echo "$n FAILED"; tail -3 gpurun_out/bv_$n.err; continue; }
   python - <<PY
 import json
