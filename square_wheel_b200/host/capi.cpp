@@ -3,6 +3,7 @@
 // (scene description, visibility, surface preparation, BSP traversal).
 #include "renderer.hpp"
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
 #include <new>
 #include <string>
@@ -527,5 +528,107 @@ const sqw_surface_job* sqwh_renderer_jobs(const Renderer* r) { return r->jobs().
 const sqw_draw_cmd* sqwh_renderer_cmds(const Renderer* r) { return r->cmds().data(); }
 const sqw_polygon_point* sqwh_renderer_polygon_points(const Renderer* r) { return r->polygon_points().data(); }
 const sqw_triangle_point* sqwh_renderer_triangle_points(const Renderer* r) { return r->triangle_points().data(); }
+
+// ---- triangle-model files (model_file.cpp: triangle_model_md3.rs / triangle_model_iqm.rs) ----------------------------------
+// Loads an .md3 / .iqm file (recognised by its magic) and appends it to the scene's models; returns the model index the
+// entities of sqwh_renderer_set_models refer to, or -1 with a message in err (when err_capacity > 0).
+static int append_loaded_model(Scene* s, bool ok, TriangleModel& m, const std::string& message, char* err, size_t err_capacity)
+{
+	if (!ok || m.meshes.empty() || m.frames_info.empty())
+	{
+		if (err && err_capacity)
+			std::snprintf(err, err_capacity, "%s", ok ? "model without meshes or frames" : message.c_str());
+		return -1;
+	}
+	s->models.push_back(std::move(m));
+	return (int)s->models.size() - 1;
+}
+int sqwh_scene_load_model_file(Scene* s, const char* path, char* err, size_t err_capacity)
+{
+	TriangleModel m;
+	std::string message;
+	const bool ok = load_model_file(path, m, &message);
+	return append_loaded_model(s, ok, m, message, err, err_capacity);
+}
+int sqwh_scene_load_model_memory(Scene* s, const void* data, size_t size, char* err, size_t err_capacity)
+{
+	TriangleModel m;
+	std::string message;
+	const bool ok = load_model(static_cast<const uint8_t*>(data), size, m, &message);
+	return append_loaded_model(s, ok, m, message, err, err_capacity);
+}
+
+// Raw arrays of a model for inspection (tests): returns the byte size of the array, copies it when it fits into `capacity`.
+//   what: 0 triangles u16[n][3] | 1 non-animated vertices f32[n][8] (position, normal, tc) | 2 vertex-animated constant f32[n][2]
+//         3 vertex-animated variable f32[frames*n][6] | 4 skeleton vertices {f32 tc[2], position[3], normal[3], u8 bone[4], weight[4]} (40 B)
+//         5 frame bones f32[frames*bones][16] (column-major) | 6 frame bounding boxes f32[frames][6] | 7 bone parents u32[bones]
+//         8 tc_shift f32[2] | 9 names: mesh name, material name, then bone names and animation names, each NUL-terminated
+//         10 animations {u32 start_frame, num_frames, f32 fps, u32 looped}[n]
+int64_t sqwh_scene_model_copy(const Scene* s, uint32_t index, uint32_t mesh_index, uint32_t what, void* out, uint64_t capacity)
+{
+	if (index >= s->models.size())
+		return -1;
+	const TriangleModel& m = s->models[index];
+	if (mesh_index >= m.meshes.size())
+		return -1;
+	const TriangleModelMesh& mesh = m.meshes[mesh_index];
+	std::vector<uint8_t> tmp;
+	const void* src = nullptr;
+	size_t bytes = 0;
+	auto pack_floats = [&](const std::vector<float>& f) {
+		tmp.resize(f.size() * 4);
+		if (!f.empty())
+			std::memcpy(tmp.data(), f.data(), tmp.size());
+		src = tmp.data();
+		bytes = tmp.size();
+	};
+	static_assert(sizeof(Triangle) == 6 && sizeof(VertexNonAnimated) == 32 && sizeof(VertexAnimatedVertexConstant) == 8 && sizeof(VertexAnimatedVertexVariable) == 24 &&
+					  sizeof(SkeletonAnimatedVertex) == 40 && sizeof(Mat4f) == 64 && sizeof(BBox) == 24,
+				  "model arrays are copied as they lie");
+	switch (what)
+	{
+	case 0: src = mesh.triangles.data(), bytes = mesh.triangles.size() * sizeof(Triangle); break;
+	case 1: src = mesh.non_animated.data(), bytes = mesh.non_animated.size() * sizeof(VertexNonAnimated); break;
+	case 2: src = mesh.constant.data(), bytes = mesh.constant.size() * sizeof(VertexAnimatedVertexConstant); break;
+	case 3: src = mesh.variable.data(), bytes = mesh.variable.size() * sizeof(VertexAnimatedVertexVariable); break;
+	case 4: src = mesh.skeleton.data(), bytes = mesh.skeleton.size() * sizeof(SkeletonAnimatedVertex); break;
+	case 5: src = m.frame_bones.data(), bytes = m.frame_bones.size() * sizeof(Mat4f); break;
+	case 6: src = m.frames_info.data(), bytes = m.frames_info.size() * sizeof(BBox); break;
+	case 7: src = m.bones.data(), bytes = m.bones.size() * 4; break;
+	case 8: pack_floats({m.tc_shift.x, m.tc_shift.y}); break;
+	case 9:
+	{
+		std::string all = mesh.name + '\0' + mesh.material_name + '\0';
+		for (const std::string& n : m.bone_names)
+			all += n + '\0';
+		for (const TriangleModelAnimation& a : m.animations)
+			all += a.name + '\0';
+		tmp.assign(all.begin(), all.end());
+		src = tmp.data();
+		bytes = tmp.size();
+		break;
+	}
+	case 10:
+	{
+		tmp.resize(m.animations.size() * 16);
+		for (size_t i = 0; i < m.animations.size(); ++i)
+		{
+			const TriangleModelAnimation& a = m.animations[i];
+			const uint32_t looped = a.looped ? 1u : 0u;
+			std::memcpy(&tmp[i * 16], &a.start_frame, 4);
+			std::memcpy(&tmp[i * 16 + 4], &a.num_frames, 4);
+			std::memcpy(&tmp[i * 16 + 8], &a.frames_per_second, 4);
+			std::memcpy(&tmp[i * 16 + 12], &looped, 4);
+		}
+		src = tmp.data();
+		bytes = tmp.size();
+		break;
+	}
+	default: return -1;
+	}
+	if (out && bytes <= capacity && bytes)
+		std::memcpy(out, src, bytes);
+	return (int64_t)bytes;
+}
 
 } // extern "C"

@@ -4,6 +4,7 @@
 #include "math.hpp"
 #include <array>
 #include <cmath>
+#include <string>
 #include <vector>
 
 namespace sqwh
@@ -70,6 +71,7 @@ enum VertexDataKind : uint32_t
 };
 struct TriangleModelMesh
 {
+	std::string name, material_name; // only file loaders fill these
 	std::vector<Triangle> triangles;
 	uint32_t num_frames = 1;
 	VertexDataKind kind = VERTEX_DATA_NON_ANIMATED;
@@ -79,8 +81,17 @@ struct TriangleModelMesh
 	std::vector<SkeletonAnimatedVertex> skeleton;
 	size_t num_vertices() const { return kind == VERTEX_DATA_NON_ANIMATED ? non_animated.size() : (kind == VERTEX_DATA_VERTEX_ANIMATED ? constant.size() : skeleton.size()); }
 };
+struct TriangleModelAnimation // triangle_model.rs:18-26
+{
+	std::string name;
+	uint32_t start_frame = 0, num_frames = 0;
+	float frames_per_second = 0.0f;
+	bool looped = false;
+};
 struct TriangleModel
 {
+	std::vector<TriangleModelAnimation> animations;
+	std::vector<std::string> bone_names; // TriangleModelBoneInfo::name (file loaders only)
 	std::vector<BBox> frames_info; // TriangleModelFrameInfo::bbox
 	std::vector<TriangleModelMesh> meshes;
 	std::vector<uint32_t> bones;     // TriangleModelBoneInfo::parent (>= bones.size(): none)
@@ -92,6 +103,13 @@ struct TriangleModel
 //   kind 0: static lamp-like solid of revolution (NonAnimated), kind 1: wobbling blob (VertexAnimated, MD3-class),
 //   kind 2: bending tentacle with a 6-bone chain (SkeletonAnimated, IQM-class).
 void generate_triangle_model(uint32_t kind, uint32_t seed, uint32_t detail, TriangleModel& out);
+
+// File loaders (model_file.cpp): triangle_model_md3.rs / triangle_model_iqm.rs on a byte image of the file.  false + message
+// where the reference returns Ok(None) or an io::Error.
+bool load_model_md3(const uint8_t* data, size_t size, TriangleModel& out, std::string* err);
+bool load_model_iqm(const uint8_t* data, size_t size, TriangleModel& out, std::string* err);
+bool load_model(const uint8_t* data, size_t size, TriangleModel& out, std::string* err); // by magic
+bool load_model_file(const char* path, TriangleModel& out, std::string* err);
 
 // bsp_map_compact.rs:179-189
 struct LightGridElement

@@ -206,6 +206,12 @@ def lib() -> C.CDLL:
         l.sqwh_scene_texture_name.argtypes = [vp, C.c_uint32]
         l.sqwh_scene_model_info.restype = C.c_int
         l.sqwh_scene_model_info.argtypes = [vp, C.c_uint32, C.POINTER(ModelInfo)]
+        l.sqwh_scene_load_model_file.restype = C.c_int
+        l.sqwh_scene_load_model_file.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_size_t]
+        l.sqwh_scene_load_model_memory.restype = C.c_int
+        l.sqwh_scene_load_model_memory.argtypes = [vp, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
+        l.sqwh_scene_model_copy.restype = C.c_int64
+        l.sqwh_scene_model_copy.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, C.c_uint64]
         for name in (
             "sqwh_renderer_jobs", "sqwh_renderer_cmds", "sqwh_renderer_polygon_points", "sqwh_renderer_lights", "sqwh_renderer_depth_maps", "sqwh_renderer_depth_cmds",
             "sqwh_renderer_depth_points", "sqwh_renderer_triangle_points",
@@ -292,6 +298,46 @@ class Scene:
         if self._lib.sqwh_scene_model_info(self._handle, index, C.byref(mi)) != 0:
             raise IndexError(index)
         return mi
+
+    def load_model(self, source) -> int:
+        """Append a triangle model from an .md3 / .iqm file (path) or from the bytes of one (triangle_model_md3.rs::load_model_md3,
+        triangle_model_iqm.rs::load_model_iqm; recognised by its magic).  Returns the model index for model_entity_dtype["model"].
+        Raises ValueError with the loader's message where the reference returns Ok(None) / an io::Error."""
+        err = C.create_string_buffer(256)
+        if isinstance(source, (bytes, bytearray, memoryview)):
+            data = bytes(source)
+            r = self._lib.sqwh_scene_load_model_memory(self._handle, data, len(data), err, len(err))
+        else:
+            r = self._lib.sqwh_scene_load_model_file(self._handle, os.fsencode(source), err, len(err))
+        if r < 0:
+            raise ValueError(f"load_model: {err.value.decode(errors='replace')}")
+        self._lib.sqwh_scene_get_info(self._handle, C.byref(self.info))
+        return r
+
+    _MODEL_ARRAYS = {
+        "triangles": (0, np.dtype("<u2"), 3), "non_animated": (1, np.dtype("<f4"), 8), "constant": (2, np.dtype("<f4"), 2), "variable": (3, np.dtype("<f4"), 6),
+        "skeleton": (4, np.dtype([("tex_coord", "<f4", (2,)), ("position", "<f4", (3,)), ("normal", "<f4", (3,)), ("bone_index", "u1", (4,)), ("weight", "u1", (4,))]), None),
+        "frame_bones": (5, np.dtype("<f4"), 16), "frames_bbox": (6, np.dtype("<f4"), 6), "bone_parents": (7, np.dtype("<u4"), None), "tc_shift": (8, np.dtype("<f4"), None),
+        "animations": (10, np.dtype([("start_frame", "<u4"), ("num_frames", "<u4"), ("frames_per_second", "<f4"), ("looped", "<u4")]), None),
+    }
+
+    def model_arrays(self, index: int, mesh: int = 0) -> dict:
+        """The arrays of a model as the loaders / generators left them (frame_bones: [frames * bones, 16] column-major 4x4)."""
+        out = {}
+        for name, (what, dt, cols) in self._MODEL_ARRAYS.items():
+            n = self._lib.sqwh_scene_model_copy(self._handle, index, mesh, what, None, 0)
+            if n < 0:
+                raise IndexError((index, mesh))
+            buf = np.zeros(n, np.uint8)
+            self._lib.sqwh_scene_model_copy(self._handle, index, mesh, what, buf.ctypes.data_as(C.c_void_p), n)
+            a = buf.view(dt)
+            out[name] = a.reshape(-1, cols) if cols else a
+        n = self._lib.sqwh_scene_model_copy(self._handle, index, mesh, 9, None, 0)
+        buf = np.zeros(max(n, 1), np.uint8)
+        self._lib.sqwh_scene_model_copy(self._handle, index, mesh, 9, buf.ctypes.data_as(C.c_void_p), n)
+        names = bytes(buf[:n]).split(b"\0")[:-1] if n else []
+        out["names"] = [x.decode(errors="replace") for x in names]
+        return out
 
     def camera_path(self, num_frames: int, jitter_seed: int = 0) -> np.ndarray:
         """[num_frames, 5] = position xyz, azimuth, elevation (64-pose Catmull-Rom loop of SURVEY.md §8d)."""

@@ -218,6 +218,55 @@ def test_config2_triangle_models(oracle_lib, color_bits):
 
 
 @pytest.mark.parametrize("color_bits", [32, 64])
+def test_models_loaded_from_md3_and_iqm_files(oracle_lib, color_bits):
+    """triangle models that come from files (triangle_model_md3.rs / triangle_model_iqm.rs loaders of the host mirror,
+    fed with files written by tests/model_files.py) go through the same animation / lighting / clipping / sorting mirror and the GPU
+    rasteriser as the seeded fixtures: pictures equal the oracle's, frame pairs and lerp factors varying."""
+    import model_files as MF
+
+    W, H = 480, 270
+    sc = S.Scene(seed=9, texture_size_log2=6, num_materials=8, num_models=2, model_detail=4)
+    rng = np.random.default_rng(41)
+    i_md3 = sc.load_model(MF.barrel_md3_file(rng, num_frames=3))
+    i_iqm = sc.load_model(MF.tube_iqm_file(rng, rings=9, segments=10, num_joints=4, num_frames=6)[1])
+    r = Renderer(sc, RendererConfig(use_directional_lightmaps=True))
+    try:
+        path = sc.camera_path(32)
+        triangles = 0
+        for k in (2, 11, 20):
+            pose = path[k]
+            fwd = np.array([-np.sin(pose[3]), np.cos(pose[3]), 0.0], np.float32)
+            side = np.array([np.cos(pose[3]), np.sin(pose[3]), 0.0], np.float32)
+            models = np.zeros(2, S.model_entity_dtype)
+            for m, (mi, nf) in enumerate(((i_md3, 3), (i_iqm, 6))):
+                models[m]["position"] = pose[:3] + 55.0 * fwd + (18.0 * m - 9.0) * side + np.array([0, 0, -18.0], np.float32)
+                models[m]["rotation"] = (np.cos(0.2 * k), 0.0, 0.0, np.sin(0.2 * k))
+                models[m]["frames"] = (k % nf, (k + 1) % nf)
+                models[m]["lerp"] = (0.3, 1.0, 0.0)[k % 3]
+                models[m]["model"] = mi
+                models[m]["skin"] = m
+                models[m]["blending_mode"] = (N.BLEND_NONE, N.BLEND_ALPHA_BLEND)[(m + k) % 2]
+                models[m]["lighting"] = (S.MODEL_LIGHTING_CONSTANT, S.MODEL_LIGHTING_DEFAULT)[m]
+                models[m]["light"] = (0.9, 0.8, 0.7)
+            hf = r.prepare_frame(SurfaceInfo(W, H), FrameInfo(pose, model_entities=models), color_bits=color_bits)
+            pixels = np.zeros((H, W), np.uint32 if color_bits == 32 else np.uint64)
+            r.draw_frame(pixels)
+            triangles += int((hf.cmds["kind"] == N.CMD_TRIANGLE).sum())
+            oracle_lib.reset_assert_failures()
+            surf = oracle_lib.build_surfaces(color_bits, hf.jobs, hf.lights, None, hf.cam_pos, sc.images, sc.lightmaps, sc.directional_lightmaps, hf.total_surface_pixels)
+            fb = np.zeros((H, W), pixels.dtype)
+            if hf.needs_clear:
+                oracle_lib.fill(fb, S.BACKGROUND_COLOR64 if color_bits == 64 else S.BACKGROUND_COLOR32)
+            oracle_lib.draw(color_bits, fb, hf.cmds, hf.polygon_points, hf.triangle_points, surf, sc.images)
+            assert oracle_lib.assert_failures() == 0
+            assert_pixels_equal(pixels, fb, f"frame {k} picture with file models")
+        assert triangles > 150  # the loaded models really are on screen
+    finally:
+        r.close()
+        sc.close()
+
+
+@pytest.mark.parametrize("color_bits", [32, 64])
 def test_config3_skybox_and_blended_models(oracle_lib, color_bits):
     """configs[3] in miniature: sky box seen through the window of the sky-material polygons (six sides, own mip chain, 32- and
     64-bit SkyboxSideTexture, drawn before the BSP walk) plus alpha-tested / alpha-blended / average / additive models on top,
