@@ -82,11 +82,15 @@ __global__ void __launch_bounds__(256) bloom_downscale_kernel(
 	constexpr int S = 1 << S_LOG2;
 	constexpr int32_t average_scaler = (1 << 8) / (S * S); // :799
 	unsigned long long sb = 0, sg = 0, sr = 0;
-	const uint64_t total = (uint64_t)bw * bh;
-	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride)
+	const uint32_t chunks_per_row = (bw + 255u) >> 8;
+	const uint32_t num_chunks = chunks_per_row * bh;
+	for (uint32_t chunk = blockIdx.x; chunk < num_chunks; chunk += gridDim.x)
 	{
-		const uint32_t dst_x = (uint32_t)(i % bw), dst_y = (uint32_t)(i / bw);
+		const uint32_t dst_y = chunk / chunks_per_row;
+		const uint32_t dst_x = ((chunk - dst_y * chunks_per_row) << 8) + threadIdx.x;
+		if (dst_x >= bw)
+			continue;
+		const size_t i = (size_t)dst_y * bw + dst_x;
 		ColorVecI sum = cvi(0, 0, 0, 0);
 #pragma unroll
 		for (int dy = 0; dy < S; ++dy)
@@ -114,19 +118,25 @@ struct BlurKernel
 template <bool HORIZONTAL>
 __global__ void __launch_bounds__(256) bloom_blur_kernel(const uint64_t* __restrict__ src, uint64_t* __restrict__ dst, int32_t bw, int32_t bh, int32_t radius, BlurKernel kernel)
 {
-	const uint64_t total = (uint64_t)bw * bh;
-	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride)
+	// work item = 256 consecutive pixels of one row (32-bit index arithmetic, one division per item instead of one 64-bit
+	// division per pixel)
+	const uint32_t chunks_per_row = ((uint32_t)bw + 255u) >> 8;
+	const uint32_t num_chunks = chunks_per_row * (uint32_t)bh;
+	for (uint32_t chunk = blockIdx.x; chunk < num_chunks; chunk += gridDim.x)
 	{
-		const int32_t x = (int32_t)(i % (uint32_t)bw), y = (int32_t)(i / (uint32_t)bw);
-		ColorVecI sum = cvi_mul_scalar(cvi_from_color64(__ldg(src + i)), kernel.w[radius]);
+		const int32_t y = (int32_t)(chunk / chunks_per_row);
+		const int32_t x = (int32_t)((chunk - (uint32_t)y * chunks_per_row) << 8) + (int32_t)threadIdx.x;
+		if (x >= bw)
+			continue;
+		const uint64_t* const row = src + (size_t)y * bw;
+		ColorVecI sum = cvi_mul_scalar(cvi_from_color64(__ldg(row + x)), kernel.w[radius]);
 		for (int32_t d = 1; d <= radius; ++d)
 		{
 			uint64_t a, b;
 			if (HORIZONTAL)
 			{
-				a = __ldg(src + (size_t)y * bw + max(x - d, 0));
-				b = __ldg(src + (size_t)y * bw + min(x + d, bw - 1));
+				a = __ldg(row + max(x - d, 0));
+				b = __ldg(row + min(x + d, bw - 1));
 			}
 			else
 			{
@@ -136,108 +146,143 @@ __global__ void __launch_bounds__(256) bloom_blur_kernel(const uint64_t* __restr
 			const ColorVecI two_sum = cvi_add(cvi_from_color64(a), cvi_from_color64(b));
 			sum = cvi_add(sum, cvi_mul_scalar(two_sum, kernel.w[d + radius]));
 		}
-		dst[i] = Color64::from_veci(cvi_shr<14>(sum));
+		dst[(size_t)y * bw + x] = Color64::from_veci(cvi_shr<14>(sum));
 	}
 }
 
 __device__ __forceinline__ ColorVec bloom_at(const uint64_t* __restrict__ bloom0, uint32_t bw, uint32_t x, uint32_t y) { return cv_from_color64(__ldg(bloom0 + (size_t)y * bw + x)); }
 
-// One thread per output pixel.  Region classification reproduces the loop nests of the reference exactly:
+// Region classification reproduces the loop nests of the reference exactly:
 //   nearest (:346-462): bloom texel = (min(x / S, bw - 1), min(y / S, bh - 1)), sum = bloom + hdr.
 //   linear  (:464-726): x < S/2 -> left border, x >= (bw-1)*S + S/2 -> right border, else between texels
 //                       sx = (x - S/2) / S and sx + 1 with mix_factors[(x - S/2) % S]; same for y; the order of
 //                       the mul_scalar_add chain is the reference's.
 template <int S_LOG2, bool LINEAR>
+__device__ __forceinline__ ColorVec bloom_sum(const ColorVec c, const uint32_t x, const uint32_t y, const uint64_t* __restrict__ bloom0, const uint32_t bw, const uint32_t bh)
+{
+	constexpr uint32_t S = 1u << S_LOG2;
+	ColorVec sum;
+	if (!LINEAR)
+	{
+		const uint32_t sx = min(x >> S_LOG2, bw - 1), sy = min(y >> S_LOG2, bh - 1);
+		sum = cv_add(bloom_at(bloom0, bw, sx, sy), c);
+	}
+	else
+	{
+		const uint32_t right_border_begin_x = (bw - 1) * S + S / 2;
+		const uint32_t upper_border_begin_y = (bh - 1) * S + S / 2;
+		// x classification
+		int xr; // 0 left border, 1 main, 2 right border
+		uint32_t sx = 0;
+		float xm = 0.0f;
+		if (x < S / 2)
+			xr = 0;
+		else if (x >= right_border_begin_x)
+		{
+			xr = 2;
+			sx = bw - 1;
+		}
+		else
+		{
+			xr = 1;
+			sx = (x - S / 2) >> S_LOG2;
+			const uint32_t dx = (x - S / 2) & (S - 1);
+			xm = (float)((S + 1) & 1) / (2.0f * (float)S) + (float)dx / (float)S; // :477
+		}
+		int yr;
+		uint32_t sy = 0;
+		float ym = 0.0f;
+		if (y < S / 2)
+			yr = 0;
+		else if (y >= upper_border_begin_y)
+		{
+			yr = 2;
+			sy = bh - 1;
+		}
+		else
+		{
+			yr = 1;
+			sy = (y - S / 2) >> S_LOG2;
+			const uint32_t dy = (y - S / 2) & (S - 1);
+			ym = (float)((S + 1) & 1) / (2.0f * (float)S) + (float)dy / (float)S;
+		}
+
+		if (yr != 1)
+		{
+			if (xr != 1)
+				sum = cv_add(bloom_at(bloom0, bw, sx, sy), c); // corners (:672-725)
+			else
+			{
+				// lower / upper border (:488-522, :632-669)
+				const ColorVec b00 = bloom_at(bloom0, bw, sx, sy), b10 = bloom_at(bloom0, bw, sx + 1, sy);
+				sum = cv_mul_scalar_add(b00, 1.0f - xm, cv_mul_scalar_add(b10, xm, c));
+			}
+		}
+		else
+		{
+			const float oym = 1.0f - ym;
+			if (xr != 1)
+			{
+				// left / right border (:536-556, :609-629)
+				const ColorVec b00 = bloom_at(bloom0, bw, sx, sy), b01 = bloom_at(bloom0, bw, sx, sy + 1);
+				const ColorVec bs = cv_mul_scalar_add(b00, oym, cv_scalar_mul(b01, ym));
+				sum = cv_add(bs, c);
+			}
+			else
+			{
+				// main image (:558-607)
+				const ColorVec b00 = bloom_at(bloom0, bw, sx, sy), b01 = bloom_at(bloom0, bw, sx, sy + 1);
+				const ColorVec b10 = bloom_at(bloom0, bw, sx + 1, sy), b11 = bloom_at(bloom0, bw, sx + 1, sy + 1);
+				const ColorVec left = cv_mul_scalar_add(b00, oym, cv_scalar_mul(b01, ym));
+				const ColorVec right = cv_mul_scalar_add(b10, oym, cv_scalar_mul(b11, ym));
+				sum = cv_mul_scalar_add(left, 1.0f - xm, cv_mul_scalar_add(right, xm, c));
+			}
+		}
+	}
+	return sum;
+}
+
+// Work item = one run of consecutive pixels of one row (32-bit index arithmetic, the row classification uniform per item).
+// Rows whose width is a multiple of four (every usual resolution) take FOUR pixels per thread: two 128-bit loads of the HDR
+// buffer in flight per thread and one 128-bit store of the picture; neighbouring pixels share their bloom texels through L1.
+template <int S_LOG2, bool LINEAR>
 __global__ void __launch_bounds__(256) tonemap_bloom_kernel(
 	const uint64_t* __restrict__ hdr, uint32_t* __restrict__ dst, uint32_t w, uint32_t h, const uint64_t* __restrict__ bloom0, uint32_t bw, uint32_t bh, float isb,
 	float isg, float isr)
 {
-	constexpr uint32_t S = 1u << S_LOG2;
-	const uint64_t total = (uint64_t)w * h;
-	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride)
+	if ((w & 3u) == 0)
 	{
-		const uint32_t x = (uint32_t)(i % w), y = (uint32_t)(i / w);
-		const ColorVec c = cv_from_color64(__ldcs(hdr + i));
-		ColorVec sum;
-		if (!LINEAR)
+		const uint32_t quads_per_row = w >> 2;
+		const uint32_t chunks_per_row = (quads_per_row + 255u) >> 8;
+		const uint32_t num_chunks = chunks_per_row * h;
+		for (uint32_t chunk = blockIdx.x; chunk < num_chunks; chunk += gridDim.x)
 		{
-			const uint32_t sx = min(x >> S_LOG2, bw - 1), sy = min(y >> S_LOG2, bh - 1);
-			sum = cv_add(bloom_at(bloom0, bw, sx, sy), c);
+			const uint32_t y = chunk / chunks_per_row;
+			const uint32_t q = ((chunk - y * chunks_per_row) << 8) + threadIdx.x;
+			if (q >= quads_per_row)
+				continue;
+			const uint32_t x = q << 2;
+			const size_t i = (size_t)y * w + x; // a multiple of four: 32-byte aligned in hdr, 16-byte aligned in dst
+			const uint4 v0 = __ldcs(reinterpret_cast<const uint4*>(hdr + i)), v1 = __ldcs(reinterpret_cast<const uint4*>(hdr + i) + 1);
+			const uint64_t p[4] = {(uint64_t)v0.x | ((uint64_t)v0.y << 32), (uint64_t)v0.z | ((uint64_t)v0.w << 32), (uint64_t)v1.x | ((uint64_t)v1.y << 32), (uint64_t)v1.z | ((uint64_t)v1.w << 32)};
+			uint32_t out[4];
+#pragma unroll
+			for (int k = 0; k < 4; ++k)
+				out[k] = tonemap_pixel(bloom_sum<S_LOG2, LINEAR>(cv_from_color64(p[k]), x + k, y, bloom0, bw, bh), isb, isg, isr);
+			__stcs(reinterpret_cast<uint4*>(dst + i), make_uint4(out[0], out[1], out[2], out[3]));
 		}
-		else
-		{
-			const uint32_t right_border_begin_x = (bw - 1) * S + S / 2;
-			const uint32_t upper_border_begin_y = (bh - 1) * S + S / 2;
-			// x classification
-			int xr; // 0 left border, 1 main, 2 right border
-			uint32_t sx = 0;
-			float xm = 0.0f;
-			if (x < S / 2)
-				xr = 0;
-			else if (x >= right_border_begin_x)
-			{
-				xr = 2;
-				sx = bw - 1;
-			}
-			else
-			{
-				xr = 1;
-				sx = (x - S / 2) >> S_LOG2;
-				const uint32_t dx = (x - S / 2) & (S - 1);
-				xm = (float)((S + 1) & 1) / (2.0f * (float)S) + (float)dx / (float)S; // :477
-			}
-			int yr;
-			uint32_t sy = 0;
-			float ym = 0.0f;
-			if (y < S / 2)
-				yr = 0;
-			else if (y >= upper_border_begin_y)
-			{
-				yr = 2;
-				sy = bh - 1;
-			}
-			else
-			{
-				yr = 1;
-				sy = (y - S / 2) >> S_LOG2;
-				const uint32_t dy = (y - S / 2) & (S - 1);
-				ym = (float)((S + 1) & 1) / (2.0f * (float)S) + (float)dy / (float)S;
-			}
-
-			if (yr != 1)
-			{
-				if (xr != 1)
-					sum = cv_add(bloom_at(bloom0, bw, sx, sy), c); // corners (:672-725)
-				else
-				{
-					// lower / upper border (:488-522, :632-669)
-					const ColorVec b00 = bloom_at(bloom0, bw, sx, sy), b10 = bloom_at(bloom0, bw, sx + 1, sy);
-					sum = cv_mul_scalar_add(b00, 1.0f - xm, cv_mul_scalar_add(b10, xm, c));
-				}
-			}
-			else
-			{
-				const float oym = 1.0f - ym;
-				if (xr != 1)
-				{
-					// left / right border (:536-556, :609-629)
-					const ColorVec b00 = bloom_at(bloom0, bw, sx, sy), b01 = bloom_at(bloom0, bw, sx, sy + 1);
-					const ColorVec bs = cv_mul_scalar_add(b00, oym, cv_scalar_mul(b01, ym));
-					sum = cv_add(bs, c);
-				}
-				else
-				{
-					// main image (:558-607)
-					const ColorVec b00 = bloom_at(bloom0, bw, sx, sy), b01 = bloom_at(bloom0, bw, sx, sy + 1);
-					const ColorVec b10 = bloom_at(bloom0, bw, sx + 1, sy), b11 = bloom_at(bloom0, bw, sx + 1, sy + 1);
-					const ColorVec left = cv_mul_scalar_add(b00, oym, cv_scalar_mul(b01, ym));
-					const ColorVec right = cv_mul_scalar_add(b10, oym, cv_scalar_mul(b11, ym));
-					sum = cv_mul_scalar_add(left, 1.0f - xm, cv_mul_scalar_add(right, xm, c));
-				}
-			}
-		}
-		__stcs(dst + i, tonemap_pixel(sum, isb, isg, isr));
+		return;
+	}
+	const uint32_t chunks_per_row = (w + 255u) >> 8;
+	const uint32_t num_chunks = chunks_per_row * h;
+	for (uint32_t chunk = blockIdx.x; chunk < num_chunks; chunk += gridDim.x)
+	{
+		const uint32_t y = chunk / chunks_per_row;
+		const uint32_t x = ((chunk - y * chunks_per_row) << 8) + threadIdx.x;
+		if (x >= w)
+			continue;
+		const size_t i = (size_t)y * w + x;
+		__stcs(dst + i, tonemap_pixel(bloom_sum<S_LOG2, LINEAR>(cv_from_color64(__ldcs(hdr + i)), x, y, bloom0, bw, bh), isb, isg, isr));
 	}
 }
 
