@@ -1,0 +1,39 @@
+"""bench.py contract checks that need no GPU: the reference arm prints the agreed JSON line, the CUDA arm refuses to run without a
+device (there is no CPU fallback to fall into)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(*args):
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True, cwd=ROOT, timeout=600)
+
+
+def test_reference_arm_prints_the_contract_line():
+    r = _run("--impl", "reference", "--steps", "1", "--warmup", "1")
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1  # ONE JSON line
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "4k_hdr_frames_per_sec" and d["unit"] == "frames/s"
+    assert d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 1 and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["value"] > 0 and d["ms_per_step"] > 0
+    assert "configs[1]" in d["config"]["workload"] and d["config"]["resolution"] == [3840, 2160]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "frames" in cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_cuda_arm_refuses_to_run_without_a_device():
+    import torch
+
+    if torch.cuda.is_available():
+        import pytest
+
+        pytest.skip("a GPU is present")
+    r = _run("--steps", "1", "--warmup", "3", "--no-cpu-baseline")
+    assert r.returncode != 0
+    assert "no CPU fallback" in r.stderr and r.stdout.strip() == ""
