@@ -183,7 +183,7 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 def run_cuda(args, rank, local_rank, world):
@@ -458,13 +458,35 @@ def run_cuda(args, rank, local_rank, world):
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
         }
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def keep_stdout_for_the_result():
+    """Native libraries write to file descriptor 1 (NCCL prints its version there when NCCL_DEBUG asks for it): point fd 1 at
+    stderr for the whole run and keep the original stdout for the ONE JSON line."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit_line(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    keep_stdout_for_the_result()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)
