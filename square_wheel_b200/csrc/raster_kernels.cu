@@ -541,8 +541,8 @@ __device__ __forceinline__ void setup_triangle_line(const TriRec* __restrict__ r
 
 // ---- binning -------------------------------------------------------------------------------------------------
 // One CTA per 8-row band, two steps:
-//   1. order-preserving compaction (ballot + popc prefix) of the commands whose row range touches the band -> band list
-//      (kept in shared memory, spilled to band_lists beyond SQW_BIN_CACHE entries);
+//   1. the ordered list of the commands whose row range touches the band is built by the HOST (sqw_frame_set_draw walks those
+//      row ranges anyway); the CTA stages it in shared memory (read from band_lists beyond SQW_BIN_CACHE entries);
 //   2. every warp takes some of the band's 128-pixel columns and compacts, again in order, the band list entries whose
 //      conservative column range touches the column into that tile's list.  Tile (band, col) owns the N slots starting at
 //      band_offsets[band] * tiles_x + col * N (N = band list length), so no global prefix sum is needed; tile_desc gets
@@ -550,79 +550,26 @@ __device__ __forceinline__ void setup_triangle_line(const TriRec* __restrict__ r
 // Runs as the tail CTAs of the set-up grid (the two jobs are independent; one launch instead of two).
 #define SQW_BIN_CACHE 1024
 __device__ void bin_band(
-	const CmdDev* __restrict__ cmd_dev, uint32_t num_cmds, const uint32_t* __restrict__ band_offsets, uint32_t* band_lists, uint32_t* __restrict__ tile_lists,
+	const CmdDev* __restrict__ cmd_dev, uint32_t num_cmds, const uint32_t* __restrict__ band_offsets, const uint32_t* __restrict__ band_lists, uint32_t* __restrict__ tile_lists,
 	uint4* __restrict__ tile_desc, uint32_t tiles_x, int band)
 {
 	constexpr int WARPS = SQW_SETUP_THREADS / 32;
-	__shared__ uint32_t s_warp_counts[WARPS];
-	__shared__ uint32_t s_running;
 	__shared__ uint32_t s_idx[SQW_BIN_CACHE];
 	__shared__ uint32_t s_bx[SQW_BIN_CACHE];
-	const int32_t band_y0 = band * SQW_TILE_H, band_y1 = band_y0 + SQW_TILE_H;
+	const int32_t band_y0 = band * SQW_TILE_H;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const uint32_t band_begin = band_offsets[band];
-	// Every warp scans a contiguous quarter of the command list twice — count, then (after ONE barrier for the warp
-	// offsets) write — instead of the whole CTA synchronising three times per 128 commands.
-	const uint32_t per_warp = ((num_cmds + WARPS - 1) / WARPS + 31) & ~31u;
-	const uint32_t scan_begin = min((uint32_t)warp * per_warp, num_cmds), scan_end = min(scan_begin + per_warp, num_cmds);
-	auto touches = [&](uint32_t i, uint32_t& bx) {
-		const uint2 w = __ldg(reinterpret_cast<const uint2*>(cmd_dev + i)); // y0,y1,bx0,bx1
-		const int32_t y0 = (int16_t)(w.x & 0xFFFF), y1 = (int16_t)(w.x >> 16);
-		bx = w.y;
-		return y0 < y1 && y0 < band_y1 && y1 > band_y0;
-	};
-	// four independent loads per lane and iteration: the scan is a latency chain (one L2 round trip per step), not a bandwidth one
-	uint32_t count = 0;
-	for (uint32_t base = scan_begin; base < scan_end; base += 128)
+	const uint32_t band_begin = __ldg(band_offsets + band);
+	const uint32_t n = __ldg(band_offsets + band + 1) - band_begin;
+	// 1. the band's ordered command list comes from the host (it walks every command's row range anyway to size the lists): stage
+	//    the indices and the conservative column ranges of up to SQW_BIN_CACHE entries in shared memory — two dependent loads
+	//    per entry, all entries independent of each other.
+	for (uint32_t e = threadIdx.x; e < min(n, (uint32_t)SQW_BIN_CACHE); e += SQW_SETUP_THREADS)
 	{
-		uint32_t bx[4];
-		bool hit[4];
-#pragma unroll
-		for (int k = 0; k < 4; ++k)
-			hit[k] = base + 32 * k + lane < scan_end && touches(base + 32 * k + lane, bx[k]);
-#pragma unroll
-		for (int k = 0; k < 4; ++k)
-			count += __popc(__ballot_sync(0xFFFFFFFFu, hit[k]));
-	}
-	if (lane == 0)
-		s_warp_counts[warp] = count;
-	__syncthreads();
-	uint32_t offset = band_begin, total = 0;
-	for (int w = 0; w < WARPS; ++w)
-	{
-		if (w < warp)
-			offset += s_warp_counts[w];
-		total += s_warp_counts[w];
-	}
-	for (uint32_t base = scan_begin; base < scan_end; base += 128)
-	{
-		uint32_t bx[4] = {0, 0, 0, 0};
-		bool hit[4];
-#pragma unroll
-		for (int k = 0; k < 4; ++k)
-			hit[k] = base + 32 * k + lane < scan_end && touches(base + 32 * k + lane, bx[k]);
-#pragma unroll
-		for (int k = 0; k < 4; ++k)
-		{
-			const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, hit[k]);
-			if (hit[k])
-			{
-				const uint32_t pos = offset + __popc(ballot & ((1u << lane) - 1));
-				band_lists[pos] = base + 32 * k + lane;
-				if (pos - band_begin < SQW_BIN_CACHE)
-				{
-					s_idx[pos - band_begin] = base + 32 * k + lane;
-					s_bx[pos - band_begin] = bx[k];
-				}
-			}
-			offset += __popc(ballot);
-		}
+		const uint32_t idx = __ldg(band_lists + band_begin + e);
+		s_idx[e] = idx;
+		s_bx[e] = __ldg(reinterpret_cast<const uint32_t*>(cmd_dev + idx) + 1);
 	}
 	__syncthreads();
-	if (threadIdx.x == 0)
-		s_running = band_begin + total;
-	__syncthreads();
-	const uint32_t n = s_running - band_begin; // == band_offsets[band + 1] - band_begin (the host counted with the same test)
 	for (uint32_t col = (uint32_t)warp; col < tiles_x; col += WARPS)
 	{
 		const int32_t col_x0 = (int32_t)col * SQW_TILE_W, col_x1 = col_x0 + SQW_TILE_W;
@@ -643,7 +590,7 @@ __device__ void bin_band(
 				}
 				else
 				{
-					idx = band_lists[band_begin + e]; // written above by this CTA: plain load, not the read-only path
+					idx = __ldg(band_lists + band_begin + e);
 					bx = __ldg(reinterpret_cast<const uint32_t*>(cmd_dev + idx) + 1);
 				}
 				const int32_t bx0 = (int16_t)(bx & 0xFFFF), bx1 = (int16_t)(bx >> 16);
@@ -662,7 +609,7 @@ __device__ void bin_band(
 __global__ void __launch_bounds__(SQW_SETUP_THREADS) raster_setup_kernel(
 	const sqw_draw_cmd* __restrict__ cmds, const CmdDev* __restrict__ cmd_dev, uint32_t num_cmds, const sqw_polygon_point* __restrict__ polygon_points,
 	const TriRec* __restrict__ tri_recs, const uint2* __restrict__ chunks, uint32_t num_chunks, SpanRec* __restrict__ spans,
-	int32_t clip_w, int32_t clip_h, uint32_t setup_blocks, const uint32_t* __restrict__ band_offsets, uint32_t* band_lists, uint32_t* __restrict__ tile_lists,
+	int32_t clip_w, int32_t clip_h, uint32_t setup_blocks, const uint32_t* __restrict__ band_offsets, const uint32_t* __restrict__ band_lists, uint32_t* __restrict__ tile_lists,
 	uint4* __restrict__ tile_desc, uint32_t tiles_x, uint32_t num_bands,
 	unsigned long long* __restrict__ sums_to_zero, uint8_t* __restrict__ tonemap_lut, float isb, float isg, float isr)
 {

@@ -289,6 +289,8 @@ struct sqw_frame
 	const sqw_triangle_point* d_triangle_points = nullptr;
 	const uint2* d_chunks = nullptr;
 	const uint32_t* d_band_offsets = nullptr;
+	const uint32_t* d_band_list = nullptr; // ordered command indices per band, band b at [band_offsets[b], band_offsets[b + 1])
+	std::vector<uint32_t> h_band_list, h_band_cursor;
 	std::vector<uint32_t> sampled_views; // views referenced through SQW_TEX_VIEW
 	std::vector<CmdDev> h_cmd_dev;
 	std::vector<uint2> h_chunks, h_chunks_tri;
@@ -940,6 +942,16 @@ int sqw_frame_set_draw(
 	f->total_spans = (uint32_t)span_total;
 	f->num_bands = num_bands;
 	f->total_band_entries = f->h_band_offsets[num_bands];
+	// The bands' ordered command lists (the binning CTAs used to scan the whole command list per band for them).
+	f->h_band_list.resize(f->total_band_entries);
+	f->h_band_cursor.assign(f->h_band_offsets.begin(), f->h_band_offsets.end() - 1);
+	for (uint32_t i = 0; i < num_cmds; ++i)
+	{
+		const CmdDev& d = f->h_cmd_dev[i];
+		if (d.y0 < d.y1)
+			for (int32_t b = d.y0 / SQW_TILE_H; b <= (d.y1 - 1) / SQW_TILE_H; ++b)
+				f->h_band_list[f->h_band_cursor[(size_t)b]++] = i;
+	}
 	f->stats.num_spans = span_total;
 	f->stats.num_tiles = num_bands * (uint32_t)((W + SQW_TILE_W - 1) / SQW_TILE_W);
 
@@ -961,14 +973,15 @@ int sqw_frame_set_draw(
 		Arena& a = f->draw_arena;
 		const size_t b_cmds = (size_t)num_cmds * sizeof(sqw_draw_cmd), b_dev = (size_t)num_cmds * sizeof(CmdDev);
 		const size_t b_pp = (size_t)num_polygon_points * sizeof(sqw_polygon_point), b_tp = (size_t)num_triangle_points * sizeof(sqw_triangle_point);
-		const size_t b_base = f->h_chunks.size() * sizeof(uint2), b_off = f->h_band_offsets.size() * 4;
-		SQW_CUDA(ctx, a.begin(Arena::padded(b_cmds) + Arena::padded(b_dev) + Arena::padded(b_pp) + Arena::padded(b_tp) + Arena::padded(b_base) + Arena::padded(b_off)));
+		const size_t b_base = f->h_chunks.size() * sizeof(uint2), b_off = f->h_band_offsets.size() * 4, b_list = f->h_band_list.size() * 4;
+		SQW_CUDA(ctx, a.begin(Arena::padded(b_cmds) + Arena::padded(b_dev) + Arena::padded(b_pp) + Arena::padded(b_tp) + Arena::padded(b_base) + Arena::padded(b_off) + Arena::padded(b_list)));
 		f->d_cmds = static_cast<const sqw_draw_cmd*>(a.push(cmds, b_cmds));
 		f->d_cmd_dev = static_cast<const CmdDev*>(a.push(f->h_cmd_dev.data(), b_dev));
 		f->d_polygon_points = static_cast<const sqw_polygon_point*>(a.push(polygon_points, b_pp));
 		f->d_triangle_points = static_cast<const sqw_triangle_point*>(a.push(triangle_points, b_tp));
 		f->d_chunks = static_cast<const uint2*>(a.push(f->h_chunks.data(), b_base));
 		f->d_band_offsets = static_cast<const uint32_t*>(a.push(f->h_band_offsets.data(), b_off));
+		f->d_band_list = static_cast<const uint32_t*>(a.push(f->h_band_list.data(), b_list));
 		SQW_CUDA(ctx, a.commit(view->stream));
 	}
 	f->clear = clear_color != nullptr;
@@ -1170,7 +1183,7 @@ int sqw_frame_submit(sqw_frame* f, uint32_t stages)
 		{
 			const uint32_t tiles_x = (view->width + SQW_TILE_W - 1) / SQW_TILE_W;
 			char* const base = static_cast<char*>(view->band_lists.ptr);
-			rl.band_lists = reinterpret_cast<uint32_t*>(base);
+			rl.band_lists = f->d_band_list;
 			rl.tile_lists = reinterpret_cast<uint32_t*>(base + bin_tile_lists_offset(f->total_band_entries));
 			rl.tile_desc = reinterpret_cast<uint4*>(base + bin_tile_desc_offset(f->total_band_entries, tiles_x));
 		}

@@ -118,7 +118,7 @@ struct RasterLaunch
 	const uint2* chunks; // device: {command index, first row relative to the command's y0} per 32 scan-lines of a command
 	uint32_t num_chunks;
 	uint32_t total_spans;
-	uint32_t* band_lists;         // device, ordered command indices per band
+	const uint32_t* band_lists;   // device, ordered command indices per band (built by sqw_frame_set_draw)
 	const uint32_t* band_offsets; // device, num_bands + 1
 	uint32_t* tile_lists;         // device, ordered command indices per 128x8 tile: tile (band, col) owns the slots
 	                              // [band_offsets[band] * tiles_x + col * N, + N), N = band list length
