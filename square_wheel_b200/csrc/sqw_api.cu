@@ -4,6 +4,7 @@
 #include "sqw_internal.h"
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -160,6 +161,7 @@ struct sqw_ctx
 	cudaStream_t stream = nullptr;
 	bool own_stream = false;
 	bool concurrent_views = false; // SQW_CTX_CONCURRENT_VIEWS: every view issues its work on a private stream
+	size_t l2_persist_bytes = 0;   // > 0: the views' surface pools are marked L2-persisting on their streams (sqw_create)
 	cudaEvent_t batch_event = nullptr;
 	float* d_lightmaps = nullptr;
 	sqw_directional_lightmap_element* d_directional_lightmaps = nullptr;
@@ -396,6 +398,20 @@ int sqw_create(sqw_ctx** out_ctx, int device, const sqw_map_desc* map, void* ext
 		ctx->own_stream = true;
 	}
 	ctx->concurrent_views = (map->flags & SQW_CTX_CONCURRENT_VIEWS) != 0;
+	{
+		// A view's surface pool is written by the surface kernel and gathered by the tile kernel a moment later, while the other
+		// views in flight stream ~100 MB of pixels each through the 126 MB L2.  Marking the pools L2-persisting on their streams
+		// (a 24 MB carve-out of the device's L2; 16-48 MB measured alike, 64 MB and more hurt the pixel stores) keeps them on chip:
+		// +2.3 % frames/s at four 4K views in flight.  SQW_L2_PERSIST_MB overrides the size, 0 turns it off.  The limit is device-wide.
+		const char* mb = std::getenv("SQW_L2_PERSIST_MB");
+		int max_persist = 0;
+		cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
+		const size_t want = std::min<size_t>((size_t)(mb ? std::atol(mb) : 24) << 20, (size_t)std::max(max_persist, 0));
+		if (want && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess)
+			ctx->l2_persist_bytes = want;
+		else
+			cudaGetLastError(); // not supported here: carry on without it
+	}
 	ctx->max_images = map->max_images ? map->max_images : 4096;
 	ctx->num_lightmap_elements = map->num_lightmap_elements;
 	auto bail = [&](cudaError_t err, const char* what) {
@@ -438,6 +454,8 @@ void sqw_destroy(sqw_ctx* ctx)
 		cudaStreamSynchronize(ctx->stream);
 	while (!ctx->views.empty())
 		sqw_view_destroy(ctx->views.back());
+	if (ctx->l2_persist_bytes)
+		cudaCtxResetPersistingL2Cache();
 	for (auto& img : ctx->images)
 		if (img.pixels)
 			cudaFree(img.pixels);
@@ -764,6 +782,18 @@ int sqw_frame_set_surfaces(
 		// growing frees the old pool: nothing queued on this view may still read it
 		SQW_CUDA(ctx, cudaStreamSynchronize(view->stream));
 		SQW_CUDA(ctx, view->surfaces.reserve((size_t)total_surface_pixels * C + 16));
+		if (ctx->l2_persist_bytes && (view->own_stream || ctx->own_stream)) // never touch the attributes of a caller's stream
+		{
+			int max_window = 0;
+			cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
+			cudaStreamAttrValue attr{};
+			attr.accessPolicyWindow.base_ptr = view->surfaces.ptr;
+			attr.accessPolicyWindow.num_bytes = std::min<size_t>(view->surfaces.capacity, (size_t)max_window);
+			attr.accessPolicyWindow.hitRatio = 1.0f;
+			attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+			attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+			SQW_CUDA(ctx, cudaStreamSetAttribute(view->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+		}
 	}
 	{
 		Arena& a = f->surf_arena;
