@@ -42,6 +42,38 @@ def test_surface_variants_bit_exact(assets, oracle_lib, color_bits, directional,
     assert_pixels_equal(got, want, f"surfaces c{color_bits} dir{directional} lights{with_lights}")
 
 
+@pytest.mark.parametrize("color_bits", [32, 64])
+def test_non_power_of_two_textures(oracle_lib, color_bits):
+    """Texture and emissive images whose sizes are not powers of two take the general rem_euclid wrap (surfaces.rs:507-510, :843-847;
+    an out-of-line integer division in the kernel) instead of the mask shortcut; negative and huge tc_start included."""
+    from common import Assets
+
+    a = Assets(seed=23, num_lightmap_elements=20000, tex_sizes=(24, 40))
+    r = synth.rng(77)
+    for (w, h) in ((20, 12), (7, 33)):
+        a.lite_ids.append(len(a.images))
+        a.images.append((N.IMAGE_COLOR32, synth.make_lite_texture(r, w, h)))
+    ctx = a.device_context()
+    try:
+        jobs, total, lm_needed = synth.make_surface_jobs(r, 96, a.texture_ids, a.texture_flags, emissive_images=a.lite_ids[-2:], directional=True, lights=0, max_size=80)
+        assert lm_needed <= len(a.lightmaps)
+        jobs["tc_start"][::3] = r.integers(-100000, -1, (len(jobs[::3]), 2))
+        jobs["tc_start"][1::3] = r.integers(1 << 20, 1 << 24, (len(jobs[1::3]), 2))
+        cam = r.uniform(-300, 300, 3).astype(np.float32)
+        view = ctx.create_view(64, 64, color_bits)
+        try:
+            view.build_surfaces(jobs, None, None, cam, total)
+            got = view.read_surfaces(0, total)
+        finally:
+            view.close()
+        oracle_lib.reset_assert_failures()
+        want = oracle_lib.build_surfaces(color_bits, jobs, None, None, cam, a.images, a.lightmaps, a.directional_lightmaps, total)
+        assert oracle_lib.assert_failures() == 0
+        assert_pixels_equal(got, want, f"non power-of-two textures c{color_bits}")
+    finally:
+        ctx.close()
+
+
 def test_large_surfaces_and_wrap(assets, oracle_lib):
     """Maximum lit surface size (272 x 272 at mip 0, lightmap 18 x 18), negative tc_start, texture smaller than surface."""
     r = synth.rng(5)
