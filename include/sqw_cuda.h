@@ -82,9 +82,10 @@ typedef struct sqw_map_desc
 /* Create a context on CUDA device `device` and upload the static map data.  Replaces the ownership half of
  * Renderer::new (renderer.rs:24).  `external_stream` may be a cudaStream_t the caller wants all work of this
  * context to be issued on (pass NULL for a private non-blocking stream).
- * Side effect: sets the device-wide cudaLimitPersistingL2CacheSize to 24 MB (environment SQW_L2_PERSIST_MB overrides, 0 = leave
- * it alone) and marks the views' surface pools L2-persisting on the streams the library owns, so that a view's surfaces survive in
- * L2 between its surface kernel and its tile kernel while other views stream their pixels; reset by sqw_destroy. */
+ * Side effect: sets the device-wide cudaLimitPersistingL2CacheSize to 48 MB (environment SQW_L2_PERSIST_MB overrides, 0 = leave
+ * it alone) and marks the views' per-frame scratch (surface pool, span table, tile lists: one block per view) L2-persisting on the
+ * streams the library owns, so that what one kernel of a frame hands to the next survives in L2 while other views stream their
+ * pixels; reset by sqw_destroy. */
 int sqw_create(sqw_ctx** out_ctx, int device, const sqw_map_desc* map, void* external_stream);
 void sqw_destroy(sqw_ctx* ctx);
 const char* sqw_last_error(const sqw_ctx* ctx); /* ctx may be NULL: error of the last failed sqw_create */

@@ -33,10 +33,13 @@ struct DevBuf
 {
 	void* ptr = nullptr;
 	size_t capacity = 0;
+	bool slice = false; // part of a larger allocation owned by someone else (sqw_view::scratch_base): never freed or grown here
 	cudaError_t reserve(size_t bytes)
 	{
 		if (bytes <= capacity)
 			return cudaSuccess;
+		if (slice)
+			return cudaErrorInvalidValue;
 		if (ptr)
 		{
 			cudaError_t e = cudaFree(ptr);
@@ -57,7 +60,7 @@ struct DevBuf
 	}
 	void release()
 	{
-		if (ptr)
+		if (ptr && !slice)
 			cudaFree(ptr);
 		ptr = nullptr;
 		capacity = 0;
@@ -161,7 +164,7 @@ struct sqw_ctx
 	cudaStream_t stream = nullptr;
 	bool own_stream = false;
 	bool concurrent_views = false; // SQW_CTX_CONCURRENT_VIEWS: every view issues its work on a private stream
-	size_t l2_persist_bytes = 0;   // > 0: the views' surface pools are marked L2-persisting on their streams (sqw_create)
+	size_t l2_persist_bytes = 0;   // > 0: the views' scratch blocks are marked L2-persisting on their streams (sqw_create)
 	cudaEvent_t batch_event = nullptr;
 	float* d_lightmaps = nullptr;
 	sqw_directional_lightmap_element* d_directional_lightmaps = nullptr;
@@ -233,6 +236,11 @@ struct sqw_view
 	cudaEvent_t done = nullptr; // recorded after every submit: other views that sample this one wait on it
 	void* d_color = nullptr;
 	uint32_t* d_ldr = nullptr; // post-processed picture (64-bit views)
+	// Per-frame scratch of the view — surface pool, span table, band / tile lists, triangle records — lives in ONE allocation
+	// (scratch_base, sections in this order) so that a single L2 access-policy window on the view's stream covers everything a
+	// frame's kernels hand to each other; the four DevBufs below are non-owning slices of it (view_scratch_reserve).
+	char* scratch_base = nullptr;
+	size_t scratch_total = 0;
 	DevBuf surfaces;
 	DevBuf spans;
 	DevBuf band_lists;
@@ -339,6 +347,68 @@ int fail_cuda(sqw_ctx* ctx, cudaError_t e, const char* what)
 			return fail_cuda((ctx), e__, #call); \
 	} while (0)
 
+// Grow one section of the view's scratch block (0 surfaces, 1 spans, 2 band / tile lists, 3 triangle records).  The caller has
+// synchronised the view's stream (a queued frame may still use the old block).  The other sections keep their contents (the
+// surface pool of sqw_build_surfaces must survive the sqw_draw that follows).  Re-points the access-policy window of the view's
+// own stream at the whole block: the surface kernel's stores, the set-up grid's span records and tile lists all stay in the L2
+// carve-out (sqw_create) until the tile kernel has consumed them, whatever the other views in flight stream through L2 meanwhile.
+cudaError_t view_scratch_reserve(sqw_view* view, int section, size_t bytes)
+{
+	DevBuf* const parts[4] = {&view->surfaces, &view->spans, &view->band_lists, &view->tri_recs};
+	if (bytes <= parts[section]->capacity)
+		return cudaSuccess;
+	size_t cap[4], total = 0;
+	for (int i = 0; i < 4; ++i)
+	{
+		cap[i] = parts[i]->capacity;
+		if (i == section)
+			cap[i] = (bytes + (bytes >> 2) + 255) & ~size_t(255);
+		total += cap[i];
+	}
+	char* block = nullptr;
+	cudaError_t e = cudaMalloc(&block, total);
+	if (e != cudaSuccess)
+		return e;
+	size_t off = 0;
+	for (int i = 0; i < 4 && e == cudaSuccess; ++i)
+	{
+		if (i != section && parts[i]->capacity)
+			e = cudaMemcpy(block + off, parts[i]->ptr, parts[i]->capacity, cudaMemcpyDeviceToDevice);
+		off += cap[i];
+	}
+	if (e != cudaSuccess)
+	{
+		cudaFree(block);
+		return e;
+	}
+	if (view->scratch_base)
+		cudaFree(view->scratch_base);
+	view->scratch_base = block;
+	view->scratch_total = total;
+	off = 0;
+	for (int i = 0; i < 4; ++i)
+	{
+		parts[i]->ptr = cap[i] ? block + off : nullptr;
+		parts[i]->capacity = cap[i];
+		parts[i]->slice = true;
+		off += cap[i];
+	}
+	sqw_ctx* ctx = view->ctx;
+	if (ctx->l2_persist_bytes && (view->own_stream || ctx->own_stream)) // never touch the attributes of a caller's stream
+	{
+		int max_window = 0;
+		cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
+		cudaStreamAttrValue attr{};
+		attr.accessPolicyWindow.base_ptr = block;
+		attr.accessPolicyWindow.num_bytes = std::min<size_t>(total, (size_t)std::max(max_window, 0));
+		attr.accessPolicyWindow.hitRatio = 1.0f;
+		attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+		attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+		e = cudaStreamSetAttribute(view->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+	}
+	return e;
+}
+
 size_t image_element_size(int kind)
 {
 	switch (kind)
@@ -399,14 +469,15 @@ int sqw_create(sqw_ctx** out_ctx, int device, const sqw_map_desc* map, void* ext
 	}
 	ctx->concurrent_views = (map->flags & SQW_CTX_CONCURRENT_VIEWS) != 0;
 	{
-		// A view's surface pool is written by the surface kernel and gathered by the tile kernel a moment later, while the other
-		// views in flight stream ~100 MB of pixels each through the 126 MB L2.  Marking the pools L2-persisting on their streams
-		// (a 24 MB carve-out of the device's L2; 16-48 MB measured alike, 64 MB and more hurt the pixel stores) keeps them on chip:
-		// +2.3 % frames/s at four 4K views in flight.  SQW_L2_PERSIST_MB overrides the size, 0 turns it off.  The limit is device-wide.
+		// A view's scratch — surface pool, span table, tile lists — is written by one kernel of a frame and read by the next a moment
+		// later, while the other views in flight stream ~100 MB of pixels each through the 126 MB L2.  Marking the views' scratch
+		// blocks L2-persisting on their streams (view_scratch_reserve) keeps them on chip: 17.7k -> 19.0k frames/s at four 4K views
+		// in flight with a 48 MB carve-out (about the four views' working sets; 40-56 MB measured alike, 64 MB and more slow the pixel
+		// stores down).  SQW_L2_PERSIST_MB overrides the size, 0 turns it off.  The limit is device-wide.
 		const char* mb = std::getenv("SQW_L2_PERSIST_MB");
 		int max_persist = 0;
 		cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
-		const size_t want = std::min<size_t>((size_t)(mb ? std::atol(mb) : 24) << 20, (size_t)std::max(max_persist, 0));
+		const size_t want = std::min<size_t>((size_t)(mb ? std::atol(mb) : 48) << 20, (size_t)std::max(max_persist, 0));
 		if (want && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess)
 			ctx->l2_persist_bytes = want;
 		else
@@ -608,10 +679,8 @@ void sqw_view_destroy(sqw_view* view)
 		cudaFree(view->d_color);
 	if (view->d_ldr)
 		cudaFree(view->d_ldr);
-	view->surfaces.release();
-	view->spans.release();
-	view->band_lists.release();
-	view->tri_recs.release();
+	if (view->scratch_base)
+		cudaFree(view->scratch_base); // the four sections are slices of it
 	for (auto& b : view->d_bloom)
 		if (b)
 			cudaFree(b);
@@ -781,19 +850,7 @@ int sqw_frame_set_surfaces(
 	{
 		// growing frees the old pool: nothing queued on this view may still read it
 		SQW_CUDA(ctx, cudaStreamSynchronize(view->stream));
-		SQW_CUDA(ctx, view->surfaces.reserve((size_t)total_surface_pixels * C + 16));
-		if (ctx->l2_persist_bytes && (view->own_stream || ctx->own_stream)) // never touch the attributes of a caller's stream
-		{
-			int max_window = 0;
-			cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
-			cudaStreamAttrValue attr{};
-			attr.accessPolicyWindow.base_ptr = view->surfaces.ptr;
-			attr.accessPolicyWindow.num_bytes = std::min<size_t>(view->surfaces.capacity, (size_t)max_window);
-			attr.accessPolicyWindow.hitRatio = 1.0f;
-			attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-			attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-			SQW_CUDA(ctx, cudaStreamSetAttribute(view->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
-		}
+		SQW_CUDA(ctx, view_scratch_reserve(view, 0, (size_t)total_surface_pixels * C + 16));
 	}
 	{
 		Arena& a = f->surf_arena;
@@ -994,10 +1051,10 @@ int sqw_frame_set_draw(
 	if ((size_t)span_total * sizeof(SpanRec) + 64 > view->spans.capacity || bin_bytes > view->band_lists.capacity || tri_bytes > view->tri_recs.capacity)
 	{
 		SQW_CUDA(ctx, cudaStreamSynchronize(view->stream)); // growing frees scratch a queued frame may still use
-		SQW_CUDA(ctx, view->spans.reserve((size_t)span_total * sizeof(SpanRec) + 64));
-		SQW_CUDA(ctx, view->band_lists.reserve(bin_bytes));
+		SQW_CUDA(ctx, view_scratch_reserve(view, 1, (size_t)span_total * sizeof(SpanRec) + 64));
+		SQW_CUDA(ctx, view_scratch_reserve(view, 2, bin_bytes));
 		if (tri_bytes)
-			SQW_CUDA(ctx, view->tri_recs.reserve(tri_bytes));
+			SQW_CUDA(ctx, view_scratch_reserve(view, 3, tri_bytes));
 	}
 	{
 		Arena& a = f->draw_arena;
