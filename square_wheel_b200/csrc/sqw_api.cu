@@ -625,8 +625,9 @@ int sqw_view_create(sqw_ctx* ctx, sqw_view** out_view, uint32_t width, uint32_t 
 		e = cudaMalloc(&v->d_ldr, px * 4);
 	if (e == cudaSuccess && color_bits == 64)
 	{
-		// bloom buffers at the largest size (scale 2)
-		const size_t bpx = (size_t)(width / 2) * (height / 2) + 1;
+		// bloom buffers at the largest size (scale 2) of ANY shape sqw_view_set_size accepts: it bounds the area, and
+		// (w / 2) * (h / 2) <= w * h / 4 for every shape of that area (1921 x 1081 -> 2076 x 1000 needs more than (1921 / 2) * (1081 / 2))
+		const size_t bpx = ((size_t)width * height + 3) / 4 + 1;
 		e = cudaMalloc(&v->d_bloom[0], bpx * 8);
 		if (e == cudaSuccess)
 			e = cudaMalloc(&v->d_bloom[1], bpx * 8);
@@ -768,6 +769,21 @@ int sqw_frame_set_surfaces(
 	sqw_ctx* ctx = view->ctx;
 	SQW_CUDA(ctx, cudaSetDevice(ctx->device));
 	const size_t C = (size_t)view->color_bits / 8;
+
+	// Every shadow map a light points at must lie inside the frame's shadow map array: the kernel fetches
+	// sm[offset + side * size^2 + u + v * size] (light.rs:196-294) without a bound of its own.
+	for (uint32_t l = 0; l < num_lights; ++l)
+	{
+		const sqw_light& li = lights[l];
+		if (li.shadow_type == SQW_SHADOW_NONE)
+			continue;
+		if (li.shadow_type != SQW_SHADOW_CUBE && li.shadow_type != SQW_SHADOW_PROJECTOR)
+			return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_frame_set_surfaces: unknown shadow type");
+		const uint64_t sides = li.shadow_type == SQW_SHADOW_CUBE ? 6 : 1;
+		const uint64_t end = (uint64_t)li.shadow_map_offset + sides * (uint64_t)li.shadow_map_size * li.shadow_map_size;
+		if (li.shadow_map_size == 0 || end > shadow_maps_len)
+			return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_frame_set_surfaces: a light's shadow map lies outside the shadow map array");
+	}
 
 	// Validate and group jobs by kernel variant (the reference's const-generic dispatch, surfaces.rs:124-423).
 	std::vector<SurfaceBand> buckets[2]; // [0] no dynamic lights, [1] dynamic lights

@@ -1,0 +1,253 @@
+"""Parity of the path bench.py times: ONE submission of all stages with bloom off, where Postprocessor::perform_tonemapping
+(postprocessor.rs:226-256) is fused into the epilogue of the tile kernel (raster_tile_kernel<Color64, 1>, csrc/raster_kernels.cu):
+the per-frame tonemapping table in shared memory, the exact IEEE fallback for channels beyond the table, the path that tonemaps
+pixels no command touched (frames without clear), the slotted colour sums behind get_average_color and both read-back calls.
+
+Every case goes sqw_frame_set_surfaces / set_draw / set_post(bloom_sigma = 0) -> sqw_frame_submit(SQW_STAGE_ALL) and compares the
+64-bit picture, the 32-bit picture (synchronous and asynchronous read-back) and the average colour with oracle.draw ->
+oracle.postprocess on the same lists."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import synth
+from common import Assets, assert_pixels_equal
+from square_wheel_b200 import _native as N
+from square_wheel_b200 import scene as S
+from square_wheel_b200.device import make_post_params
+
+pytestmark = pytest.mark.gpu
+
+LUT = 4096  # SQW_TONEMAP_LUT_SIZE: channel values below it come from the table, the others from the IEEE formula
+
+
+@pytest.fixture(scope="module")
+def assets():
+    a = Assets(seed=41, num_lightmap_elements=20000, tex_sizes=(32,))
+    r = synth.rng(4141)
+    # Color64 polygon textures whose channels straddle the table limit inside every quad of pixels: uniform up to 3 x LUT, plus one
+    # that is entirely below and one entirely above
+    a.hdr_ids = []
+    for (w, h, lo, hi) in ((64, 64, 0, 3 * LUT), (32, 48, 0, LUT), (16, 16, LUT, 65536), (128, 32, LUT - 8, LUT + 8)):
+        px = r.integers(lo, hi, (h, w, 4), dtype=np.uint64)
+        px[..., 3] = r.integers(0, 256, (h, w), dtype=np.uint64)
+        a.hdr_ids.append(len(a.images))
+        a.images.append((N.IMAGE_COLOR64, (px[..., 3] << np.uint64(48)) | (px[..., 0] << np.uint64(32)) | (px[..., 1] << np.uint64(16)) | px[..., 2]))
+    return a
+
+
+def _read_async(view):
+    """sqw_read_pixels32_async into page-locked memory (what bench.py's e2e leg does), then the view's synchronize."""
+    import torch
+
+    buf = torch.empty((view.height, view.width), dtype=torch.int32, pin_memory=True)
+    buf.fill_(0x5A5A5A5A)
+    view.read_pixels32_async(buf.data_ptr(), view.width)
+    view.synchronize()
+    return buf.numpy().view(np.uint32).copy()
+
+
+def _check_fused(view, frame, fb_want, post, what, stats_launches=None):
+    frame.submit(N.STAGE_ALL)
+    got_hdr = view.read_pixels()
+    got_ldr = view.read_pixels32()
+    got_ldr_async = _read_async(view)
+    got_avg = view.average_color()
+    import oracle
+
+    want_ldr, want_avg, _ = oracle.postprocess(fb_want, post)
+    assert_pixels_equal(got_hdr, fb_want, f"{what}: 64-bit picture")
+    assert_pixels_equal(got_ldr & 0xFFFFFF, want_ldr & 0xFFFFFF, f"{what}: tonemapped picture")
+    assert_pixels_equal(got_ldr_async, got_ldr, f"{what}: asynchronous read-back")
+    # exact integer sums on the GPU, f32 row sums in the reference (it only feeds update_exposure)
+    np.testing.assert_allclose(got_avg, want_avg, rtol=1e-5, atol=1e-3)
+    st = frame.stats()
+    if stats_launches is not None:
+        assert st.num_kernel_launches == stats_launches, f"{what}: {st.num_kernel_launches} launches: the fused path is raster set-up + tile kernel (+ surfaces)"
+
+
+@pytest.mark.parametrize("size", [(333, 201), (257, 129), (128, 8), (129, 9), (1, 1), (640, 360)])
+@pytest.mark.parametrize("clear", [True, False])
+def test_fused_tonemap_polygons(assets, oracle_lib, size, clear):
+    """Polygons with HDR textures, all five blend modes and three tc modes, widths that are odd / not a multiple of the 128-pixel
+    tile (`vec_ok` false in the last tile column) and heights that are not a multiple of the 8-row band.  clear=False: the
+    view holds an earlier picture, pixels no command covers are tonemapped from what the buffer holds."""
+    W, H = size
+    r = synth.rng(700 + W + (1 if clear else 0))
+    ctx = assets.device_context()
+    n = 60 if W > 8 else 3
+    tex = [assets.hdr_ids[int(r.integers(0, len(assets.hdr_ids)))] for _ in range(n)]
+    cmds, pts = synth.make_polygon_scene(r, max(W, 64), max(H, 64), n, [assets.image_size(t) for t in tex], blends=(0, 0, 0, 1, 2, 3, 4))
+    cmds["tex_kind"] = N.TEX_IMAGE
+    cmds["tex_ref"] = tex
+    before = synth.make_hdr_image(r, W, H)
+    clear_color = 0x00FF123400560789
+    post = make_post_params(exposure=0.6, color_modulate=(1.1, 0.8, 1.3))
+    view = ctx.create_view(W, H, 64)
+    frame = view.create_frame()
+    try:
+        view.write_pixels(before)
+        frame.set_draw(cmds, pts, None, clear_color=clear_color if clear else None)
+        frame.set_post(post)
+        fb = before.copy()
+        if clear:
+            oracle_lib.fill(fb, clear_color)
+        oracle_lib.reset_assert_failures()
+        oracle_lib.draw(64, fb, cmds, pts, None, None, assets.images)
+        assert oracle_lib.assert_failures() == 0
+        if not clear and W > 8:
+            assert (fb == before).any() and (fb != before).any()  # covered and uncovered pixels both exist
+        _check_fused(view, frame, fb, post, f"fused {size} clear={clear}", stats_launches=1 + 1)
+        # a second submission of the recorded frame (what bench.py replays): same picture when it clears, and for a frame
+        # without clear the blends read what the first one left behind
+        if not clear:
+            oracle_lib.draw(64, fb, cmds, pts, None, None, assets.images)
+        _check_fused(view, frame, fb, post, f"fused {size} clear={clear}, replay")
+    finally:
+        frame.close()
+        view.close()
+
+
+@pytest.mark.parametrize("exposure,modulate", [(1.0, (1.0, 1.0, 1.0)), (0.05, (1.0, 1.0, 1.0)), (9.0, (0.3, 1.0, 2.5))])
+def test_fused_tonemap_table_limit_in_one_quad(assets, oracle_lib, exposure, modulate):
+    """A flat polygon whose texture hops over the table limit from texel to texel: neighbouring pixels of one lane's quad
+    fall on both sides of it (the `any >= LUT` switch of finish_quad), for exposures that put the Reinhard curve anywhere."""
+    W, H = 512, 64
+    ctx = assets.device_context()
+    tw, th = 512, 64
+    xx = np.arange(tw, dtype=np.uint64)[None, :] + np.zeros((th, 1), np.uint64)
+    yy = np.arange(th, dtype=np.uint64)[:, None] + np.zeros((1, tw), np.uint64)
+    blue = np.uint64(LUT - 6) + (xx * np.uint64(7) + yy * np.uint64(3)) % np.uint64(13)  # hops over the limit every pixel or two
+    green = xx * np.uint64(16) + yy  # 0 .. 8255: one crossing per row
+    red = np.uint64(LUT + 6) - (xx * np.uint64(5) + yy) % np.uint64(13)
+    tex = (np.uint64(255) << np.uint64(48)) | (red << np.uint64(32)) | (green << np.uint64(16)) | blue
+    image = ctx.upload_image(N.IMAGE_COLOR64, tex)
+    cmds = np.zeros(1, N.draw_cmd_dtype)
+    cmds[0]["kind"] = N.CMD_POLYGON
+    cmds[0]["tc_mode"] = N.TC_AFFINE
+    cmds[0]["num_vertices"] = 4
+    cmds[0]["tex_size"] = (tw, th)
+    cmds[0]["tex_kind"] = N.TEX_IMAGE
+    cmds[0]["tex_ref"] = image
+    cmds[0]["depth_eq"] = (0.0, 0.0, 1.0 / 64.0)  # z = 64 everywhere
+    cmds[0]["tc_eq"] = (1.0 / 64.0, 0.0, 0.0, 1.0 / 64.0, 0.0, 0.0)  # u = x, v = y
+    pts = np.array([(0, 0), (W << 16, 0), (W << 16, H << 16), (0, H << 16)], N.polygon_point_dtype)
+    post = make_post_params(exposure=exposure, color_modulate=modulate)
+    images = list(assets.images) + [(N.IMAGE_COLOR64, tex)]
+    assert len(images) == image + 1
+    view = ctx.create_view(W, H, 64)
+    frame = view.create_frame()
+    try:
+        frame.set_draw(cmds, pts, None, clear_color=0)
+        frame.set_post(post)
+        fb = np.zeros((H, W), np.uint64)
+        oracle_lib.draw(64, fb, cmds, pts, None, None, images)
+        b = (fb & np.uint64(0xFFFF)).astype(np.int64)
+        quads = b.reshape(H, W // 2, 2)
+        assert ((quads.min(-1) < LUT) & (quads.max(-1) >= LUT)).mean() > 0.25  # the switch happens inside many pixel pairs
+        _check_fused(view, frame, fb, post, f"table limit, exposure {exposure}")
+    finally:
+        frame.close()
+        view.close()
+        assets.images.append((N.IMAGE_COLOR64, tex))  # keep the fixture's image table in step with the context
+
+
+def test_fused_tonemap_surfaces_and_triangles(assets, oracle_lib):
+    """All three stages in one submission (what smoke() and bench.py do): surfaces with emissive layers, polygons sampling
+    them, Gouraud triangles on top, bloom off."""
+    r = synth.rng(4242)
+    ctx = assets.device_context()
+    W, H = 410, 230
+    lights, sm = synth.make_lights(r, 6)
+    jobs, total, _ = synth.make_surface_jobs(r, 40, assets.texture_ids, assets.texture_flags, emissive_images=assets.lite_ids, directional=True, lights=len(lights), max_size=64)
+    jobs["flags"] |= N.SURF_APPLY_DIFFUSE
+    cam = np.array([5.0, -20.0, 12.0], np.float32)
+    sizes = [tuple(int(x) for x in j["surface_size"]) for j in jobs]
+    pc, pp = synth.make_polygon_scene(r, W, H, len(jobs), sizes, blends=(0, 0, 4))
+    pc["tex_kind"] = N.TEX_SURFACE
+    pc["tex_ref"] = jobs["surface_pixels_offset"]
+    nt = 200
+    ttex = [assets.lite_ids[int(r.integers(0, len(assets.lite_ids)))] for _ in range(nt)]
+    tc, tp = synth.make_triangle_scene(r, W, H, nt, [assets.image_size(t) for t in ttex], blends=(0, 1, 2, 3, 4), max_extent=70.0)
+    tc["tex_ref"] = ttex
+    cmds = np.concatenate([pc, tc])
+    post = make_post_params(exposure=1.7, color_modulate=(0.9, 1.0, 1.2))
+    view = ctx.create_view(W, H, 64)
+    frame = view.create_frame()
+    try:
+        frame.set_surfaces(jobs, lights, sm, cam, total)
+        frame.set_draw(cmds, pp, tp, clear_color=0)
+        frame.set_post(post)
+        surf = oracle_lib.build_surfaces(64, jobs, lights, sm, cam, assets.images, assets.lightmaps, assets.directional_lightmaps, total)
+        fb = np.zeros((H, W), np.uint64)
+        oracle_lib.draw(64, fb, cmds, pp, tp, surf, assets.images)
+        _check_fused(view, frame, fb, post, "surfaces + polygons + triangles")
+        assert_pixels_equal(view.read_surfaces(0, total), surf, "surfaces of the fused frame")
+    finally:
+        frame.close()
+        view.close()
+
+
+def test_fused_tonemap_bench_scene_4k(oracle_lib):
+    """The frames bench.py times: its scene (SCENE_KW, seed 2, 256^2 textures), its resolution, its recorded-frame replay with
+    several views in flight on private streams — every pixel of the 64-bit and the 32-bit picture against the oracle."""
+    import bench
+    from square_wheel_b200.device import Context
+
+    W, H = bench.WIDTH, bench.HEIGHT
+    sc = S.Scene(**bench.SCENE_KW)
+    ctx = Context(sc.lightmaps, sc.directional_lightmaps, device=0, concurrent_views=True)
+    views, frames = [], []
+    try:
+        sc.upload(ctx)
+        poses = sc.camera_path(bench.NUM_POSES)
+        picks = (0, 21, 42, 63)
+        first_ldr = {}
+        hr = S.HostRenderer(sc, use_directional_lightmaps=True)
+        hfs = [hr.build_frame(W, H, poses[k]) for k in picks]
+        hr.close()
+        post = make_post_params(exposure=1.0)
+        max_surface = max(hf.total_surface_pixels for hf in hfs)
+        views = [ctx.create_view(W, H, 64) for _ in range(2)]
+        for i, hf in enumerate(hfs):
+            f = views[i % 2].create_frame()
+            f.set_surfaces(hf.jobs, None, None, hf.cam_pos, max_surface)
+            f.set_draw(hf.cmds, hf.polygon_points, None, clear_color=S.BACKGROUND_COLOR64 if hf.needs_clear else None)
+            f.set_post(post)
+            frames.append(f)
+        # two rounds over the recorded frames like bench.py's steps (views alternate, the later frame of a view wins)
+        for rnd in range(2):
+            for pair in ((0, 1), (2, 3)):
+                ctx.batch_begin()
+                for i in pair:
+                    frames[i].submit(N.STAGE_ALL)
+                ctx.batch_end()
+                for i in pair:
+                    hf, view = hfs[i], views[i % 2]
+                    got_hdr = view.read_pixels()
+                    got_ldr = view.read_pixels32()
+                    got_avg = view.average_color()
+                    if rnd == 1:
+                        continue  # the second round is compared through the first one's pictures below
+                    surf = oracle_lib.build_surfaces(64, hf.jobs, None, None, hf.cam_pos, sc.images, sc.lightmaps, sc.directional_lightmaps, hf.total_surface_pixels, num_threads=4)
+                    fb = np.zeros((H, W), np.uint64)
+                    if hf.needs_clear:
+                        oracle_lib.fill(fb, S.BACKGROUND_COLOR64)
+                    oracle_lib.draw(64, fb, hf.cmds, hf.polygon_points, None, surf, sc.images)
+                    want_ldr, want_avg, _ = oracle_lib.postprocess(fb, post, num_threads=4)
+                    assert_pixels_equal(view.read_surfaces(0, hf.total_surface_pixels), surf, f"pose {picks[i]} surfaces")
+                    assert_pixels_equal(got_hdr, fb, f"pose {picks[i]} 64-bit picture")
+                    assert_pixels_equal(got_ldr & 0xFFFFFF, want_ldr & 0xFFFFFF, f"pose {picks[i]} tonemapped picture")
+                    np.testing.assert_allclose(got_avg, want_avg, rtol=1e-5, atol=1e-3)
+                    first_ldr[i] = got_ldr
+                if rnd == 1:
+                    for i in pair:
+                        assert_pixels_equal(views[i % 2].read_pixels32(), first_ldr[i], f"pose {picks[i]} replay")
+    finally:
+        for f in frames:
+            f.close()
+        for v in views:
+            v.close()
+        ctx.close()
+        sc.close()

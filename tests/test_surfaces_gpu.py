@@ -164,3 +164,52 @@ def test_view_mix_texture_all_blending_modes(assets, oracle_lib, color_bits):
     with pytest.raises(Exception):
         view.set_size(201, 120)
     view.close()
+
+
+def test_shadow_map_references_are_validated(assets):
+    """A light whose shadow map lies outside the frame's shadow map array is refused on the host (the kernel fetches
+    sm[offset + side * size^2 + u + v * size] unchecked, surface_kernels.cu cube / projector fetch): truncated array, zero size,
+    offset past the end, shadow type set with no array at all, unknown shadow type."""
+    from square_wheel_b200.device import SqwError
+
+    r = synth.rng(515)
+    ctx = assets.device_context()
+    lights, sm = synth.make_lights(r, 6)
+    jobs, total, _ = synth.make_surface_jobs(r, 8, assets.texture_ids, assets.texture_flags, directional=True, lights=len(lights), max_size=32)
+    cam = np.zeros(3, np.float32)
+    view = ctx.create_view(32, 32, 64)
+    try:
+        view.build_surfaces(jobs, lights, sm, cam, total)  # the valid set passes
+        with pytest.raises(SqwError):
+            view.build_surfaces(jobs, lights, sm[:-1], cam, total)
+        with pytest.raises(SqwError):
+            view.build_surfaces(jobs, lights, None, cam, total)
+        for field, value in (("shadow_map_size", 0), ("shadow_map_offset", len(sm)), ("shadow_map_size", 1 << 15), ("shadow_type", 7)):
+            bad = lights.copy()
+            bad[1][field] = value  # light 1 has a cube shadow map
+            with pytest.raises(SqwError):
+                view.build_surfaces(jobs, bad, sm, cam, total)
+        view.build_surfaces(jobs, lights, sm, cam, total)  # and the view still works afterwards
+    finally:
+        view.close()
+
+
+def test_view_reshape_keeps_bloom_inside_its_buffers(assets, oracle_lib):
+    """sqw_view_set_size bounds the AREA: 1921 x 1081 reshaped to 2076 x 1000 needs more half-resolution bloom texels than
+    (1921 / 2) * (1081 / 2); the buffers are sized for any shape of the allocated area (checked small: 61 x 33 -> 66 x 30)."""
+    from square_wheel_b200.device import make_post_params
+
+    r = synth.rng(616)
+    ctx = assets.device_context()
+    view = ctx.create_view(61, 33, 64)
+    try:
+        assert (66 // 2) * (30 // 2) > (61 // 2) * (33 // 2) and 66 * 30 <= 61 * 33
+        view.set_size(66, 30)
+        hdr = synth.make_hdr_image(r, 66, 30)
+        view.write_pixels(hdr)
+        p = make_post_params(exposure=1.1, bloom_sigma=3.0, bloom_buffer_scale_log2=1)
+        got, _ = view.postprocess(p)
+        want, _, _ = oracle_lib.postprocess(hdr, p)
+        assert_pixels_equal(got, want, "bloom on a reshaped view")
+    finally:
+        view.close()

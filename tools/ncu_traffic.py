@@ -14,17 +14,25 @@ import subprocess
 import sys
 
 NAMES = {"surface_build_kernel": "surface_build", "raster_setup_kernel": "raster_setup", "raster_tile_kernel": "raster_tile", "tonemap_kernel": "tonemap"}
+# issue / occupancy figures bench.py copies into `roofline` next to the traffic (the tile kernel is issue-bound, not DRAM-bound)
+EXTRA = {
+    "issue_active_pct": "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "warps_active_pct": "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "warp_instructions": "smsp__inst_executed.sum",
+    "registers": "launch__registers_per_thread",
+}
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
 
 def main():
     rep, out = sys.argv[1:3]
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum"],
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum," + ",".join(EXTRA.values())],
                          capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     hdr, units = rows[0], rows[1]
     col = {h: i for i, h in enumerate(hdr)}
     acc = collections.defaultdict(lambda: [0.0, 0.0, 0.0, 0])
+    extra = collections.defaultdict(lambda: collections.defaultdict(float))
     for r in rows[2:]:
         name = r[col["Kernel Name"]]
         key = next((v for k, v in NAMES.items() if k in name), None)
@@ -37,9 +45,17 @@ def main():
             a[j] += float(r[col[m]].replace(",", "")) * UNIT.get(units[col[m]], 1.0)
         a[2] += float(r[col["gpu__time_duration.sum"]].replace(",", "")) * {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(units[col["gpu__time_duration.sum"]], 1.0)
         a[3] += 1
+        for k, m in EXTRA.items():
+            if m in col:
+                try:
+                    extra[key][k] += float(r[col[m]].replace(",", ""))
+                except ValueError:
+                    pass
     res = {"source": rep, "note": "ncu --set full, default cache control (cold caches), mean over the captured launches", "kernels": {}}
     for k, (rd, wr, us, n) in acc.items():
         res["kernels"][k] = {"launches": n, "dram_read_bytes": rd / n, "dram_write_bytes": wr / n, "traffic_bytes": (rd + wr) / n, "us_under_ncu": us / n}
+        for kk, v in extra[k].items():
+            res["kernels"][k][kk] = v / n
     json.dump(res, open(out, "w"), indent=1, sort_keys=True)
     print(json.dumps(res["kernels"], indent=1))
 
