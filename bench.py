@@ -277,7 +277,7 @@ def run_cuda(args, rank, local_rank, world):
         # until the sampler has seen at least ~1.5 s of it, then take the median over the samples under load.
         t_load = time.perf_counter()
         n_before = len(sampler.samples)
-        while time.perf_counter() - t_load < 1.5 or len(sampler.samples) - n_before < 5:
+        while (time.perf_counter() - t_load < 1.5 or len(sampler.samples) - n_before < 5) and not args.kernels_only:
             run_steps(1, k)
             torch.cuda.synchronize()
             if time.perf_counter() - t_load > 6.0:
@@ -395,12 +395,13 @@ def run_cuda(args, rank, local_rank, world):
             v.synchronize()  # every picture of the step is in host memory
         return kk, h2d
 
-    e2e_steps(1, 0)
+    e2e_n = 0 if args.kernels_only else args.steps
+    e2e_steps(min(e2e_n, 1), 0)
     barrier()
     t0 = time.perf_counter()
-    _, h2d_total = e2e_steps(args.steps, k)
+    _, h2d_total = e2e_steps(e2e_n, k)
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    e2e_s = max(time.perf_counter() - t0, 1e-9)
     e2e_s = B.max_over_ranks(e2e_s, dist, "cuda")
     e2e_fps = world * frames_timed / e2e_s
     e2e = {
@@ -413,7 +414,7 @@ def run_cuda(args, rank, local_rank, world):
 
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only): bounded sample of the same workload ----
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.kernels_only:
         import oracle
 
         cores = os.cpu_count() or 1
@@ -514,6 +515,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernels-only", action="store_true", help="development: device-resident timing and per-kernel times only (no e2e leg, no CPU baseline)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -556,6 +556,7 @@ __device__ void bin_band(
 	constexpr int WARPS = SQW_SETUP_THREADS / 32;
 	__shared__ uint32_t s_idx[SQW_BIN_CACHE];
 	__shared__ uint32_t s_bx[SQW_BIN_CACHE];
+	__shared__ uint8_t s_cx[SQW_BIN_CACHE]; // 1: the command is not an opaque polygon (triangle, or a blend that reads the destination / the texel's alpha)
 	const int32_t band_y0 = band * SQW_TILE_H;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const uint32_t band_begin = __ldg(band_offsets + band);
@@ -568,6 +569,7 @@ __device__ void bin_band(
 		const uint32_t idx = __ldg(band_lists + band_begin + e);
 		s_idx[e] = idx;
 		s_bx[e] = __ldg(reinterpret_cast<const uint32_t*>(cmd_dev + idx) + 1);
+		s_cx[e] = (__ldg(reinterpret_cast<const uint32_t*>(cmd_dev + idx) + 3) & 0xFFFFu) != (uint32_t)SQW_CMD_POLYGON; // kind | blend << 8
 	}
 	__syncthreads();
 	for (uint32_t col = (uint32_t)warp; col < tiles_x; col += WARPS)
@@ -575,10 +577,11 @@ __device__ void bin_band(
 		const int32_t col_x0 = (int32_t)col * SQW_TILE_W, col_x1 = col_x0 + SQW_TILE_W;
 		const uint32_t list_start = band_begin * tiles_x + col * n;
 		uint32_t count = 0;
+		bool complex = false;
 		for (uint32_t base = 0; base < n; base += 32)
 		{
 			const uint32_t e = base + (uint32_t)lane;
-			bool hit = false;
+			bool hit = false, cx = false;
 			uint32_t idx = 0;
 			if (e < n)
 			{
@@ -587,22 +590,27 @@ __device__ void bin_band(
 				{
 					idx = s_idx[e];
 					bx = s_bx[e];
+					cx = s_cx[e] != 0;
 				}
 				else
 				{
 					idx = __ldg(band_lists + band_begin + e);
 					bx = __ldg(reinterpret_cast<const uint32_t*>(cmd_dev + idx) + 1);
+					cx = (__ldg(reinterpret_cast<const uint32_t*>(cmd_dev + idx) + 3) & 0xFFFFu) != (uint32_t)SQW_CMD_POLYGON;
 				}
 				const int32_t bx0 = (int16_t)(bx & 0xFFFF), bx1 = (int16_t)(bx >> 16);
 				hit = bx0 < col_x1 && bx1 > col_x0;
 			}
 			const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, hit);
+			complex |= __any_sync(0xFFFFFFFFu, hit && cx);
 			if (hit)
 				tile_lists[list_start + count + __popc(ballot & ((1u << lane) - 1))] = idx;
 			count += __popc(ballot);
 		}
+		// .w: tile class.  SQW_TILE_CLASS_OPAQUE = every command of the tile is a polygon drawn with BlendingMode::None: only the LAST
+		// command covering a pixel shows, which raster_tile_opaque_kernel exploits; everything else goes to raster_tile_kernel.
 		if (lane == 0)
-			tile_desc[(uint32_t)band * tiles_x + col] = make_uint4(list_start, count, (uint32_t)col_x0 | ((uint32_t)band_y0 << 16), 0u);
+			tile_desc[(uint32_t)band * tiles_x + col] = make_uint4(list_start, count, (uint32_t)col_x0 | ((uint32_t)band_y0 << 16), complex ? SQW_TILE_CLASS_GENERAL : SQW_TILE_CLASS_OPAQUE);
 	}
 }
 
@@ -1064,6 +1072,11 @@ __global__ void __launch_bounds__(SQW_RASTER_THREADS, SQW_TILE_CTAS_PER_SM) rast
 	uint32_t idx = idx_next;
 	if (tile + gridDim.x < num_tiles)
 		desc_next = __ldg(tile_desc + tile + gridDim.x);
+	if (desc.w == SQW_TILE_CLASS_OPAQUE) // (CTA-uniform) rendered by raster_tile_opaque_kernel
+	{
+		idx_next = ((uint32_t)lane < desc_next.y && tile + gridDim.x < num_tiles) ? __ldg(tile_lists + desc_next.x + lane) : 0u;
+		continue;
+	}
 	// this warp's block and this lane's pixels
 	const int32_t blk_x0 = (int32_t)(desc.z & 0xFFFF) + warp * 32, blk_x1 = blk_x0 + 32;
 	const int32_t blk_y0 = (int32_t)(desc.z >> 16), blk_y1 = min(blk_y0 + SQW_TILE_H, height);
@@ -1204,6 +1217,440 @@ __global__ void __launch_bounds__(SQW_RASTER_THREADS, SQW_TILE_CTAS_PER_SM) rast
 			atomicAdd(sums + ((blockIdx.x * WARPS + warp) % SQW_SUM_SLOTS) * 4 + lane, lane == 0 ? wb : (lane == 1 ? wg : wr));
 	}
 }
+
+// ---- opaque-polygon tile kernel ---------------------------------------------------------------------------------
+// Tiles whose every command is a polygon drawn with BlendingMode::None (class SQW_TILE_CLASS_OPAQUE; all world geometry of a
+// frame without translucent surfaces) need no painter's loop: write_into_framebuffer overwrites (rasterizer.rs:1516), so a pixel
+// shows the LAST command of the list that covers it, whatever lay below.  The kernel therefore works in two passes per 32x8 block:
+//   winners   walks the block's commands in order and only compares the lane's eight pixel positions with the span [x0, x1) of
+//             their row: three integer instructions per (pixel, command);
+//   resolve   evaluates the reference's pixel loop (rasterizer.rs:424-445 / :558-572 / :705-719) ONCE per pixel, for the winning
+//             command, and issues the eight texel gathers of the lane together.
+// Shading cost no longer depends on how many commands touch a block (1.7 on average at 4K in the stand-in map: most of them
+// only clip a corner of it) nor on overdraw.
+// Memory latency is taken off the critical path by a software pipeline over the tiles of a warp: while tile i is evaluated the
+// descriptor of tile i + 4, the list of i + 3 and the command records of i + 2 are in flight in registers, and the span records
+// of tile i + 1 travel to shared memory with asynchronous copies (LDGSTS, zero-filled for rows a command does not own) into
+// the other half of the warp's double buffer.  Warps are autonomous (two 128x8 tiles per CTA of eight warps, no barrier in
+// the tile loop); only the tonemapping table is shared by the CTA.
+struct OpaqueStage // one warp, one pipeline stage: 2208 bytes
+{
+	uint4 span[SQW_OPAQUE_STAGE_HITS][SQW_TILE_H][2]; // SpanRec words 0-7 of (hit, block row)
+	uint4 cmd[SQW_OPAQUE_STAGE_HITS];                   // texture pointer (2 words) | tex_width + (tc_mode << 24) | span_base
+	uint32_t rows[SQW_OPAQUE_STAGE_HITS];               // y0 | y1 << 16
+};
+#define SQW_NO_WINNER 0xFFu
+
+__device__ __forceinline__ void cp_async_16_zfill(void* smem_dst, const void* gmem_src, bool valid)
+{
+	const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
+	const int src_size = valid ? 16 : 0; // 0: nothing is read, the 16 bytes are filled with zeros
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem_src), "r"(src_size) : "memory");
+}
+
+// Compaction of one 32-entry piece of a tile list for one warp: entries whose column range meets the warp's block, in list
+// order, slots [first_slot, first_slot + SQW_OPAQUE_STAGE_HITS) go to the stage.  Returns the number of hits (bits 0-30).
+__device__ __forceinline__ uint32_t opaque_stage_commands(
+	OpaqueStage& st, const uint4 c0, const uint4 c1_in, const bool entry_valid, const int32_t blk_x0, const char* __restrict__ const surfaces_base, const uint32_t first_slot, const int lane)
+{
+	const int32_t bx0 = (int16_t)(c0.y & 0xFFFF), bx1 = (int16_t)(c0.y >> 16);
+	const bool hit = entry_valid && bx0 < blk_x0 + 32 && bx1 > blk_x0; // the row range was tested by the binning CTA (block rows = band rows)
+	const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, hit);
+	const uint32_t slot = __popc(ballot & ((1u << lane) - 1)) - first_slot; // (wraps for slots before first_slot)
+	if (hit && slot < SQW_OPAQUE_STAGE_HITS)
+	{
+		uint4 c1 = c1_in;
+		if ((c0.w >> 25) & 1) // `texture` is a byte offset into the view's surface pool
+		{
+			const uint64_t t = (uint64_t)reinterpret_cast<uintptr_t>(surfaces_base) + ((uint64_t)c1.x | ((uint64_t)c1.y << 32));
+			c1.x = (uint32_t)t;
+			c1.y = (uint32_t)(t >> 32);
+		}
+		st.cmd[slot] = make_uint4(c1.x, c1.y, (c1.z & 0xFFFFFFu) | (((c0.w >> 16) & 0xFFu) << 24), c0.z);
+		st.rows[slot] = c0.x;
+	}
+	// bit 31: some staged command uses the full-perspective pixel loop (the resolve pass then evaluates the division)
+	const bool full = hit && slot < SQW_OPAQUE_STAGE_HITS && ((c0.w >> 16) & 0xFFu) == SQW_TC_FULL_PERSPECTIVE;
+	return __popc(ballot) | (__any_sync(0xFFFFFFFFu, full) ? 0x80000000u : 0u);
+}
+
+// Asynchronous copies of the span records of the staged commands (after a __syncwarp that follows opaque_stage_commands).
+__device__ __forceinline__ void opaque_stage_spans(OpaqueStage& st, const uint32_t num_staged, const int32_t blk_y0, const SpanRec* __restrict__ const spans, const int lane)
+{
+#pragma unroll
+	for (int j = 0; j < SQW_OPAQUE_STAGE_HITS * SQW_TILE_H / 32; ++j)
+	{
+		const uint32_t p = (uint32_t)lane + 32u * j, h = p >> 3, r = p & 7;
+		if (h < num_staged)
+		{
+			const uint32_t rows = st.rows[h];
+			const int32_t y0 = (int16_t)(rows & 0xFFFF), y1 = (int16_t)(rows >> 16);
+			const int32_t srow = blk_y0 + (int32_t)r;
+			const bool ok = srow >= y0 && srow < y1;
+			const uint4* src = reinterpret_cast<const uint4*>(spans + st.cmd[h].w + (ok ? (uint32_t)(srow - y0) : 0u));
+			cp_async_16_zfill(&st.span[h][r][0], src, ok);
+			cp_async_16_zfill(&st.span[h][r][1], src + 1, ok);
+		}
+	}
+}
+
+// Address of the texel the reference's pixel loop fetches for pixel x of a span (polygon commands), as straight-line code:
+// the eight pixels of a lane are independent dependency chains that the scheduler interleaves, so nothing here may branch.
+// FULL = some lane of the warp has a full-perspective winner among these pixels: the division is then evaluated for every pixel
+// and the result selected by the winner's mode (line-z corrected and affine spans step in 16.16, rasterizer.rs:558-572, :705-719).
+template <class C, bool FULL>
+__device__ __forceinline__ const typename C::Raw* opaque_texel_address(const uint4 r0, const uint4 r1, const uint4 cm, const int32_t x)
+{
+	const int32_t k = x - (int32_t)(int16_t)(r0.x & 0xFFFF);
+	const int32_t t0 = wadd((int32_t)r0.w, wmul(k, (int32_t)r1.y)), t1 = wadd((int32_t)r1.x, wmul(k, (int32_t)r1.z));
+	uint32_t u = (uint32_t)(t0 >> 16), v = (uint32_t)(t1 >> 16);
+	if (FULL)
+	{
+		const uint32_t span_inv_z = (uint32_t)wadd((int32_t)r0.y, wmul(k, (int32_t)r0.z));
+		const uint32_t z = z_from_inv_z(span_inv_z >> INV_Z_PRE_SHIFT); // rasterizer.rs:430; >= 1 inside a full-perspective span by the clamp of the set-up
+		// tc = (z as u64 * span_tc as u64) >> 34 (:431-434).  span_tc never leaves [0, tc_max] inside a span (both span ends are
+		// clamped to it and the steps are truncated towards zero), so the sign extension of the reference's cast is a no-op
+		// and the product is the unsigned 32 x 32 -> 64 one: its high word shifted by two.
+		static_assert(TC_FINAL_SHIFT == 34, "tc shift");
+		const bool full = (cm.z >> 24) == SQW_TC_FULL_PERSPECTIVE;
+		u = full ? __umulhi(z, (uint32_t)t0) >> 2 : u;
+		v = full ? __umulhi(z, (uint32_t)t1) >> 2 : v;
+	}
+	const typename C::Raw* const tex = reinterpret_cast<const typename C::Raw*>((uint64_t)cm.x | ((uint64_t)cm.y << 32));
+	return tex + (u + v * (cm.z & 0xFFFFFFu));
+}
+
+// Lane layout of the opaque kernel: a lane owns FOUR CONSECUTIVE pixels of block row lane >> 3 and of row 4 + (lane >> 3):
+// x = px0 + {0, 1, 2, 3}, px0 = block x + 4 * (lane & 7).  A quad is one 256-bit store of 64-bit pixels (STG.256, new with
+// sm_100) and one 128-bit store of the 32-bit picture; 8 lanes write 256 contiguous bytes of a row.
+//
+// Winners of the lane's eight pixels among the staged commands [0, nh), then one texel gather per pixel that has one.
+template <class C>
+__device__ __forceinline__ void opaque_chunk(
+	const OpaqueStage& st, const uint32_t nh, const bool any_full, const int ra, const int rb, const int32_t px0, typename C::Raw (&px_a)[4], typename C::Raw (&px_b)[4],
+	uint32_t& have_a, uint32_t& have_b)
+{
+	typedef typename C::Raw Raw;
+	uint32_t wa[4], wb[4];
+#pragma unroll
+	for (int i = 0; i < 4; ++i)
+		wa[i] = wb[i] = SQW_NO_WINNER;
+	for (uint32_t h = 0; h < nh; ++h)
+	{
+		const uint32_t xa = st.span[h][ra][0].x, xb = st.span[h][rb][0].x;
+		const int32_t a0 = (int16_t)(xa & 0xFFFF), b0 = (int16_t)(xb & 0xFFFF);
+		const uint32_t alen = (uint32_t)max((int32_t)(int16_t)(xa >> 16) - a0, 0), blen = (uint32_t)max((int32_t)(int16_t)(xb >> 16) - b0, 0);
+		const int32_t da = px0 - a0, db = px0 - b0;
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+		{
+			wa[i] = (uint32_t)(da + i) < alen ? h : wa[i];
+			wb[i] = (uint32_t)(db + i) < blen ? h : wb[i];
+		}
+	}
+	// Records of the winners, straight from the stage (slot 0 stands in for pixels without a winner: its record exists and the
+	// gather is predicated off).  No branch between the pixels: eight independent chains for the scheduler to interleave.
+	uint32_t valid = 0;
+	const Raw* pa[4];
+	const Raw* pb[4];
+#pragma unroll
+	for (int i = 0; i < 4; ++i)
+	{
+		valid |= (wa[i] != SQW_NO_WINNER ? 1u : 0u) << i;
+		valid |= (wb[i] != SQW_NO_WINNER ? 16u : 0u) << i;
+	}
+	if (any_full) // (warp-uniform) some staged command is drawn with full perspective correction
+	{
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+		{
+			const uint32_t sa = wa[i] == SQW_NO_WINNER ? 0u : wa[i], sb = wb[i] == SQW_NO_WINNER ? 0u : wb[i];
+			pa[i] = opaque_texel_address<C, true>(st.span[sa][ra][0], st.span[sa][ra][1], st.cmd[sa], px0 + i);
+			pb[i] = opaque_texel_address<C, true>(st.span[sb][rb][0], st.span[sb][rb][1], st.cmd[sb], px0 + i);
+		}
+	}
+	else
+	{
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+		{
+			const uint32_t sa = wa[i] == SQW_NO_WINNER ? 0u : wa[i], sb = wb[i] == SQW_NO_WINNER ? 0u : wb[i];
+			pa[i] = opaque_texel_address<C, false>(st.span[sa][ra][0], st.span[sa][ra][1], st.cmd[sa], px0 + i);
+			pb[i] = opaque_texel_address<C, false>(st.span[sb][rb][0], st.span[sb][rb][1], st.cmd[sb], px0 + i);
+		}
+	}
+	// the eight gathers of the lane are in flight together
+	Raw ta[4], tb[4];
+#pragma unroll
+	for (int i = 0; i < 4; ++i)
+	{
+		ta[i] = tb[i] = 0;
+		if (valid & (1u << i))
+			ta[i] = __ldg(pa[i]);
+		if (valid & (16u << i))
+			tb[i] = __ldg(pb[i]);
+	}
+#pragma unroll
+	for (int i = 0; i < 4; ++i)
+	{
+		px_a[i] = (valid & (1u << i)) ? ta[i] : px_a[i];
+		px_b[i] = (valid & (16u << i)) ? tb[i] : px_b[i];
+	}
+	have_a |= valid & 0xFu;
+	have_b |= valid >> 4;
+}
+
+// The finished quad of one row (four consecutive pixels): one 256-bit store of the 64-bit pixels (128-bit for 32-bit ones), and
+// with TONEMAP one 128-bit store of the 32-bit picture plus the colour sums.  Same arithmetic as finish_quad.
+template <class C, int TONEMAP>
+__device__ __forceinline__ void opaque_finish_quad(
+	typename C::Raw (&px)[4], uint32_t have, const int32_t px0, const int32_t width, const bool vec_ok, typename C::Raw* __restrict__ const dst,
+	uint32_t* __restrict__ const o, const uint8_t* const s_lut, const float isb, const float isg, const float isr, uint32_t& sb, uint32_t& sg, uint32_t& sr)
+{
+	typedef typename C::Raw Raw;
+	if (vec_ok && have == 0xF)
+	{
+		if (sizeof(Raw) == 8)
+			asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "l"((uint64_t)px[0]), "l"((uint64_t)px[1]), "l"((uint64_t)px[2]), "l"((uint64_t)px[3]) : "memory");
+		else
+			*reinterpret_cast<uint4*>(dst) = make_uint4((uint32_t)px[0], (uint32_t)px[1], (uint32_t)px[2], (uint32_t)px[3]);
+		if (TONEMAP)
+		{
+			uint32_t out[4];
+			const uint64_t any = (uint64_t)px[0] | (uint64_t)px[1] | (uint64_t)px[2] | (uint64_t)px[3];
+			uint32_t cb[4], cg[4], cr[4];
+#pragma unroll
+			for (int i = 0; i < 4; ++i)
+			{
+				const uint64_t p = (uint64_t)px[i];
+				cb[i] = (uint32_t)(p & 0xFFFF);
+				cg[i] = (uint32_t)((p >> 16) & 0xFFFF);
+				cr[i] = (uint32_t)((p >> 32) & 0xFFFF);
+				sb += cb[i];
+				sg += cg[i];
+				sr += cr[i];
+			}
+			if ((any & (0x0000FFFFFFFFFFFFull & ~(0x0001000100010001ull * (SQW_TONEMAP_LUT_SIZE - 1)))) == 0)
+			{
+#pragma unroll
+				for (int i = 0; i < 4; ++i)
+					out[i] = (uint32_t)s_lut[cb[i]] | ((uint32_t)s_lut[SQW_TONEMAP_LUT_SIZE + cg[i]] << 8) | ((uint32_t)s_lut[2 * SQW_TONEMAP_LUT_SIZE + cr[i]] << 16) | 0xFF000000u;
+			}
+			else
+			{
+#pragma unroll
+				for (int i = 0; i < 4; ++i)
+					out[i] = tonemap_pixel(cv_from_color64((uint64_t)px[i]), isb, isg, isr);
+			}
+			__stcs(reinterpret_cast<uint4*>(o), make_uint4(out[0], out[1], out[2], out[3]));
+		}
+	}
+	else
+	{
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+			if (px0 + i < width && (have & (1u << i)))
+				dst[i] = px[i];
+		if (TONEMAP)
+		{
+#pragma unroll
+			for (int i = 0; i < 4; ++i)
+				if (px0 + i < width)
+				{
+					if (!(have & (1u << i)))
+						px[i] = dst[i]; // untouched pixel: tonemap what the buffer holds
+					const uint64_t p = (uint64_t)px[i];
+					sb += (uint32_t)(p & 0xFFFF);
+					sg += (uint32_t)((p >> 16) & 0xFFFF);
+					sr += (uint32_t)((p >> 32) & 0xFFFF);
+					o[i] = tonemap_pixel(cv_from_color64(p), isb, isg, isr);
+				}
+		}
+	}
+}
+
+template <class C, int TONEMAP>
+__global__ void __launch_bounds__(SQW_OPAQUE_WARPS * 32, SQW_OPAQUE_CTAS_PER_SM) raster_tile_opaque_kernel(
+	const CmdDev* __restrict__ cmd_dev, const SpanRec* __restrict__ spans, const uint32_t* __restrict__ tile_lists, const uint4* __restrict__ tile_desc,
+	const char* __restrict__ surfaces_base, typename C::Raw* __restrict__ color_buffer, int32_t width, int32_t height, int32_t pitch, int clear,
+	typename C::Raw clear_color, uint32_t* __restrict__ ldr, float isb, float isg, float isr, unsigned long long* __restrict__ sums,
+	const uint8_t* __restrict__ tonemap_lut, uint32_t num_tiles)
+{
+	typedef typename C::Raw Raw;
+	constexpr int THREADS = SQW_OPAQUE_WARPS * 32;
+	constexpr uint32_t K = SQW_OPAQUE_STAGE_HITS;
+	static_assert(SQW_OPAQUE_WARPS % 4 == 0 && SQW_TILE_W == 128 && SQW_TILE_H == 8 && (K * SQW_TILE_H) % 32 == 0, "tile geometry");
+	__shared__ OpaqueStage s_stage_all[SQW_OPAQUE_WARPS][2];
+	__shared__ __align__(16) uint8_t s_lut[TONEMAP ? 3 * SQW_TONEMAP_LUT_SIZE : 16];
+	if (TONEMAP)
+	{
+		const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_lut);
+		for (uint32_t i = threadIdx.x; i < 3 * SQW_TONEMAP_LUT_SIZE / 16; i += THREADS)
+			asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 16), "l"(tonemap_lut + (size_t)i * 16) : "memory");
+		asm volatile("cp.async.commit_group;" ::: "memory");
+	}
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	OpaqueStage(&stage)[2] = s_stage_all[warp];
+	uint32_t sb = 0, sg = 0, sr = 0;
+	const int ra = lane >> 3, rb = 4 + (lane >> 3);
+	const int32_t lane_x = (warp & 3) * 32 + (lane & 7) * 4; // first pixel of the lane relative to the tile
+	const bool pitch_vec = (pitch & 3) == 0; // rows start on 32-byte boundaries: the quad stores are aligned
+
+	// Tiles of this warp: the tile group (four warps) g of CTA b takes tiles (b * G + g) + n * (gridDim.x * G).
+	constexpr uint32_t G = SQW_OPAQUE_WARPS / 4;
+	const uint32_t tile_first = blockIdx.x * G + (uint32_t)(warp >> 2), tile_stride = gridDim.x * G;
+
+	// ---- pipeline registers ----
+	// A tile travels through four loads, one per iteration of the loop below: descriptor -> first 32 list entries -> their
+	// command records -> span records (shared memory).  `inf*` = the descriptor fields the later steps need:
+	// origin (x0 | y0 << 16) in .x; list length, or ~0 for a tile that is absent / of the other class in .y.
+	auto load_desc = [&](uint32_t tile) { return tile < num_tiles ? __ldg(tile_desc + tile) : make_uint4(0, 0, 0, SQW_TILE_CLASS_GENERAL); };
+	auto desc_info = [&](const uint4 d, uint32_t tile) { return make_uint2(d.z, (tile < num_tiles && d.w == SQW_TILE_CLASS_OPAQUE) ? d.y : 0xFFFFFFFFu); };
+	auto load_idx = [&](const uint4 d, const uint2 inf) { return (inf.y != 0xFFFFFFFFu && (uint32_t)lane < inf.y) ? __ldg(tile_lists + d.x + lane) : 0xFFFFFFFFu; };
+	uint4 c0n = make_uint4(0, 0, 0, 0), c1n = c0n; // command records of the entries of tile i + 2 (one entry per lane)
+	bool c_valid = false;
+	auto load_cmds = [&](uint32_t idx) {
+		c_valid = idx != 0xFFFFFFFFu;
+		if (c_valid)
+		{
+			const uint4* cdp = reinterpret_cast<const uint4*>(cmd_dev + idx);
+			c0n = __ldg(cdp);
+			c1n = __ldg(cdp + 1);
+		}
+	};
+	// hits of a tile's first list piece -> stage buffer + asynchronous span copies; returns the hit count
+	auto stage_tile = [&](OpaqueStage& st, const uint2 inf) -> uint32_t {
+		uint32_t nh = 0;
+		if (inf.y != 0xFFFFFFFFu) // (warp-uniform)
+		{
+			const int32_t blk_x0 = (int32_t)(inf.x & 0xFFFF) + (warp & 3) * 32;
+			nh = opaque_stage_commands(st, c0n, c1n, c_valid, blk_x0, surfaces_base, 0, lane);
+			__syncwarp();
+			opaque_stage_spans(st, min(nh & 0x7FFFFFFFu, K), (int32_t)(inf.x >> 16), spans, lane);
+		}
+		asm volatile("cp.async.commit_group;" ::: "memory");
+		return nh;
+	};
+
+	// ---- prologue: fill the pipeline for tiles 0 .. 3 of this warp ----
+	uint32_t tile = tile_first;
+	uint4 d0 = load_desc(tile), d1 = load_desc(tile + tile_stride), d2 = load_desc(tile + 2 * tile_stride), d3 = load_desc(tile + 3 * tile_stride);
+	uint2 inf0 = desc_info(d0, tile), inf1 = desc_info(d1, tile + tile_stride), inf2 = desc_info(d2, tile + 2 * tile_stride), inf3 = desc_info(d3, tile + 3 * tile_stride);
+	uint32_t idx0 = load_idx(d0, inf0), idx1 = load_idx(d1, inf1), idxn = load_idx(d2, inf2);
+	load_cmds(idx0);
+	uint32_t nh0 = stage_tile(stage[0], inf0);
+	load_cmds(idx1);
+	// from here on: c0n/c1n belong to tile + 1, idxn to tile + 2, dn to tile + 3
+	uint4 dn = d3;
+	uint2 infn = inf3;
+	if (TONEMAP)
+	{
+		// the table (and the first tile's span records) have arrived; the only CTA-wide barrier of the kernel
+		asm volatile("cp.async.wait_all;" ::: "memory");
+		__syncthreads();
+	}
+
+	for (uint32_t it = 0; tile < num_tiles; tile += tile_stride, ++it)
+	{
+		OpaqueStage& st = stage[it & 1];
+		// (A) tile + 1: hits -> other stage buffer, span records on their way
+		const uint32_t nh1 = stage_tile(stage[(it & 1) ^ 1], inf1);
+		// (B) tile + 2: command records of its list entries
+		load_cmds(idxn);
+		// (C) tile + 3: first 32 list entries
+		idxn = load_idx(dn, infn);
+		const uint2 inf3_new = infn;
+		// (D) tile + 4: descriptor
+		dn = load_desc(tile + 4 * tile_stride);
+		infn = desc_info(dn, tile + 4 * tile_stride);
+		// (E) the span records of this tile have landed (everything but the group committed in (A))
+		asm volatile("cp.async.wait_group 1;" ::: "memory");
+		__syncwarp();
+
+		if (inf0.y != 0xFFFFFFFFu) // (warp-uniform) a tile of this kernel's class
+		{
+			const int32_t blk_x0 = (int32_t)(inf0.x & 0xFFFF) + (warp & 3) * 32;
+			const int32_t blk_y0 = (int32_t)(inf0.x >> 16);
+			const int32_t row_a = blk_y0 + ra, row_b = blk_y0 + rb;
+			const int32_t px0 = (int32_t)(inf0.x & 0xFFFF) + lane_x;
+			const uint32_t pix_a = (uint32_t)row_a * (uint32_t)pitch + (uint32_t)px0;
+			const uint32_t pix_b = pix_a + 4u * (uint32_t)pitch;
+			Raw px_a[4], px_b[4];
+			uint32_t have_a = clear ? 0xFu : 0u, have_b = have_a;
+#pragma unroll
+			for (int i = 0; i < 4; ++i)
+				px_a[i] = px_b[i] = clear_color;
+			const bool vec_ok = (blk_x0 + 32 <= width) && pitch_vec;
+			if (blk_x0 < width) // (warp-uniform)
+			{
+				if (inf0.y <= 32 && (nh0 & 0x7FFFFFFFu) <= K)
+				{
+					if (nh0)
+						opaque_chunk<C>(st, nh0 & 0x7FFFFFFFu, (nh0 >> 31) != 0, ra, rb, px0, px_a, px_b, have_a, have_b);
+				}
+				else
+				{
+					// Rare: a list longer than one piece, or more hits than a stage holds (far, finely tessellated geometry).  The
+					// same two passes, chunk by chunk in list order (a later chunk's winners replace earlier ones), staged
+					// synchronously into this tile's stage buffer.
+					const uint32_t list_start = __ldg(&tile_desc[tile].x);
+					for (uint32_t base = 0; base < inf0.y; base += 32)
+					{
+						const bool valid = base + lane < inf0.y;
+						uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
+						if (valid)
+						{
+							const uint4* cdp = reinterpret_cast<const uint4*>(cmd_dev + __ldg(tile_lists + list_start + base + lane));
+							c0 = __ldg(cdp);
+							c1 = __ldg(cdp + 1);
+						}
+						uint32_t nh = 1;
+						for (uint32_t first = 0; first < nh; first += K)
+						{
+							__syncwarp();
+							const uint32_t nhf = opaque_stage_commands(st, c0, c1, valid, blk_x0, surfaces_base, first, lane);
+							nh = nhf & 0x7FFFFFFFu;
+							if (first >= nh)
+								break;
+							__syncwarp();
+							const uint32_t n = min(nh - first, K);
+							opaque_stage_spans(st, n, blk_y0, spans, lane);
+							asm volatile("cp.async.commit_group;" ::: "memory");
+							asm volatile("cp.async.wait_all;" ::: "memory");
+							__syncwarp();
+							opaque_chunk<C>(st, n, (nhf >> 31) != 0, ra, rb, px0, px_a, px_b, have_a, have_b);
+						}
+					}
+				}
+			}
+			if (row_a < height)
+				opaque_finish_quad<C, TONEMAP>(px_a, have_a, px0, width, vec_ok, color_buffer + pix_a, ldr + pix_a, s_lut, isb, isg, isr, sb, sg, sr);
+			if (row_b < height)
+				opaque_finish_quad<C, TONEMAP>(px_b, have_b, px0, width, vec_ok, color_buffer + pix_b, ldr + pix_b, s_lut, isb, isg, isr, sb, sg, sr);
+		}
+		__syncwarp(); // this stage buffer is rewritten by step (A) of the next iteration but one; the other one by the next
+		inf0 = inf1;
+		inf1 = inf2;
+		inf2 = inf3_new;
+		nh0 = nh1;
+	}
+	asm volatile("cp.async.wait_all;" ::: "memory"); // nothing may still be writing this CTA's shared memory when it retires
+
+	if (TONEMAP)
+	{
+		unsigned long long wb = sb, wg = sg, wr = sr;
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1)
+		{
+			wb += __shfl_xor_sync(0xFFFFFFFFu, wb, o);
+			wg += __shfl_xor_sync(0xFFFFFFFFu, wg, o);
+			wr += __shfl_xor_sync(0xFFFFFFFFu, wr, o);
+		}
+		if (lane < 3 && (wb | wg | wr))
+			atomicAdd(sums + ((blockIdx.x * SQW_OPAQUE_WARPS + warp) % SQW_SUM_SLOTS) * 4 + lane, lane == 0 ? wb : (lane == 1 ? wg : wr));
+	}
+}
+#undef SQW_NO_WINNER
 #undef SQW_NEED_DST
 #undef SQW_PX_OFS
 
@@ -1256,6 +1703,20 @@ cudaError_t launch_raster_tiles(const RasterLaunch& l, cudaStream_t stream)
 #define SQW_TILE_ARGS(RAW) \
 	l.cmd_dev, l.spans, l.tile_lists, l.tile_desc, static_cast<const char*>(l.surfaces_base), static_cast<RAW*>(l.color_buffer), l.width, l.height, l.pitch, l.clear, \
 		(RAW)l.clear_color, l.tonemap_dst, l.inv_scale_bgr[0], l.inv_scale_bgr[1], l.inv_scale_bgr[2], l.color_sums, l.tonemap_lut, num_tiles
+	// Tiles of class SQW_TILE_CLASS_OPAQUE (only polygons with BlendingMode::None: all of them in a frame of plain world geometry).
+	{
+		constexpr uint32_t G = SQW_OPAQUE_WARPS / 4;
+		const uint32_t ogrid = std::min<uint32_t>((num_tiles + G - 1) / G, (uint32_t)sm_count * SQW_OPAQUE_CTAS_PER_SM);
+		if (l.color64 && l.tonemap_dst)
+			raster_tile_opaque_kernel<Color64, 1><<<ogrid, SQW_OPAQUE_WARPS * 32, 0, stream>>>(SQW_TILE_ARGS(uint64_t));
+		else if (l.color64)
+			raster_tile_opaque_kernel<Color64, 0><<<ogrid, SQW_OPAQUE_WARPS * 32, 0, stream>>>(SQW_TILE_ARGS(uint64_t));
+		else
+			raster_tile_opaque_kernel<Color32, 0><<<ogrid, SQW_OPAQUE_WARPS * 32, 0, stream>>>(SQW_TILE_ARGS(uint32_t));
+		if (l.num_general_cmds == 0)
+			return cudaGetLastError();
+	}
+	// The other tiles: triangles, blended and alpha-tested polygons (the kernel skips the opaque class).
 	if (l.color64 && l.tonemap_dst)
 		raster_tile_kernel<Color64, 1><<<grid, SQW_RASTER_THREADS, 0, stream>>>(SQW_TILE_ARGS(uint64_t));
 	else if (l.color64)

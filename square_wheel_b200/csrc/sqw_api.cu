@@ -305,7 +305,7 @@ struct sqw_frame
 	std::vector<CmdDev> h_cmd_dev;
 	std::vector<uint2> h_chunks, h_chunks_tri;
 	std::vector<uint32_t> h_band_offsets;
-	uint32_t num_cmds = 0, total_spans = 0, num_bands = 0, total_band_entries = 0, num_triangle_cmds = 0;
+	uint32_t num_cmds = 0, total_spans = 0, num_bands = 0, total_band_entries = 0, num_triangle_cmds = 0, num_general_cmds = 0;
 	uint32_t draw_width = 0, draw_height = 0; // view size the command list was prepared for
 	bool clear = false;
 	uint64_t clear_color = 0;
@@ -1038,8 +1038,12 @@ int sqw_frame_set_draw(
 		f->h_band_offsets[(size_t)b + 1] += f->h_band_offsets[b];
 	f->num_cmds = num_cmds;
 	f->num_triangle_cmds = 0;
+	f->num_general_cmds = 0; // commands that are not opaque polygons: their tiles go to the general tile kernel
 	for (uint32_t i = 0; i < num_cmds; ++i)
+	{
 		f->num_triangle_cmds += cmds[i].kind == SQW_CMD_TRIANGLE ? 1u : 0u;
+		f->num_general_cmds += (cmds[i].kind != SQW_CMD_POLYGON || cmds[i].blend != SQW_BLEND_NONE) ? 1u : 0u;
+	}
 	f->draw_width = view->width;
 	f->draw_height = view->height;
 	f->total_spans = (uint32_t)span_total;
@@ -1279,6 +1283,7 @@ int sqw_frame_submit(sqw_frame* f, uint32_t stages)
 		rl.triangle_points = f->d_triangle_points;
 		rl.tri_recs = view->tri_recs.ptr;
 		rl.num_triangle_cmds = f->num_triangle_cmds;
+		rl.num_general_cmds = f->num_general_cmds;
 		rl.spans = static_cast<SpanRec*>(view->spans.ptr);
 		rl.chunks = f->d_chunks;
 		rl.num_chunks = (uint32_t)f->h_chunks.size();
@@ -1373,7 +1378,7 @@ int sqw_frame_submit(sqw_frame* f, uint32_t stages)
 		{
 			LaunchTimer timer(ctx, fused_tonemap ? SQW_KERNEL_RASTER_TILE_TONEMAP : SQW_KERNEL_RASTER_TILE, s);
 			SQW_CUDA(ctx, launch_raster_tiles(rl, s));
-			++launches;
+			launches += f->num_general_cmds ? 2 : 1; // opaque-polygon tile kernel (+ the general one when some tile needs it)
 		}
 	}
 

@@ -75,6 +75,14 @@ cudaError_t launch_mix_texture(
 #define SQW_TONEMAP_LUT_SIZE 4096 /* channel values below this (16 x LDR white) are tonemapped by table look-up */
 #define SQW_TILE_STAGE_HITS 4 /* commands whose span records a warp stages in shared memory at a time (x 8 block rows = 32 lanes) */
 #define SQW_RASTER_THREADS 128 /* 4 warps, each owning a 32x8 pixel block of the 128x8 tile */
+// Tile classes (tile_desc.w, written by the binning CTAs): which of the two tile kernels renders the tile.
+#define SQW_TILE_CLASS_GENERAL 0u /* raster_tile_kernel: any command mix, painter's order per pixel */
+#define SQW_TILE_CLASS_OPAQUE 1u  /* raster_tile_opaque_kernel: only polygons with BlendingMode::None */
+#define SQW_OPAQUE_STAGE_HITS 8   /* commands whose span records a warp of the opaque tile kernel stages at a time */
+#define SQW_OPAQUE_WARPS 8        /* warps per CTA of the opaque tile kernel: two 128x8 tiles side by side */
+#ifndef SQW_OPAQUE_CTAS_PER_SM
+#define SQW_OPAQUE_CTAS_PER_SM 2
+#endif
 #ifndef SQW_TILE_CTAS_PER_SM
 #define SQW_TILE_CTAS_PER_SM 5 /* resident CTAs of the persistent tile kernel per SM (register and shared-memory budget) */
 #endif
@@ -135,6 +143,9 @@ struct RasterLaunch
 	float inv_scale_bgr[3];
 	unsigned long long* color_sums;
 	uint8_t* tonemap_lut; // device, 3 x SQW_TONEMAP_LUT_SIZE bytes (B, G, R), rebuilt by the set-up grid of every fused frame
+	// number of commands that are not opaque polygons (triangles, blended / alpha-tested polygons): 0 = every tile is of class
+	// SQW_TILE_CLASS_OPAQUE and the general tile kernel is not launched
+	uint32_t num_general_cmds;
 };
 // span set-up + binning in one grid
 cudaError_t launch_raster_setup(const RasterLaunch& l, cudaStream_t stream);

@@ -64,21 +64,24 @@ def _check_fused(view, frame, fb_want, post, what, stats_launches=None):
     np.testing.assert_allclose(got_avg, want_avg, rtol=1e-5, atol=1e-3)
     st = frame.stats()
     if stats_launches is not None:
-        assert st.num_kernel_launches == stats_launches, f"{what}: {st.num_kernel_launches} launches: the fused path is raster set-up + tile kernel (+ surfaces)"
+        assert st.num_kernel_launches == stats_launches, f"{what}: {st.num_kernel_launches} launches: the fused path is raster set-up + opaque tile kernel (+ general tile kernel) (+ surfaces)"
 
 
 @pytest.mark.parametrize("size", [(333, 201), (257, 129), (128, 8), (129, 9), (1, 1), (640, 360)])
 @pytest.mark.parametrize("clear", [True, False])
-def test_fused_tonemap_polygons(assets, oracle_lib, size, clear):
+@pytest.mark.parametrize("opaque_only", [True, False])
+def test_fused_tonemap_polygons(assets, oracle_lib, size, clear, opaque_only):
     """Polygons with HDR textures, all five blend modes and three tc modes, widths that are odd / not a multiple of the 128-pixel
     tile (`vec_ok` false in the last tile column) and heights that are not a multiple of the 8-row band.  clear=False: the
-    view holds an earlier picture, pixels no command covers are tonemapped from what the buffer holds."""
+    view holds an earlier picture, pixels no command covers are tonemapped from what the buffer holds.  opaque_only: every
+    polygon uses BlendingMode::None, so all tiles take raster_tile_opaque_kernel (the frames bench.py times); otherwise the blended
+    ones send their tiles to the general raster_tile_kernel and the two kernels share the picture."""
     W, H = size
     r = synth.rng(700 + W + (1 if clear else 0))
     ctx = assets.device_context()
     n = 60 if W > 8 else 3
     tex = [assets.hdr_ids[int(r.integers(0, len(assets.hdr_ids)))] for _ in range(n)]
-    cmds, pts = synth.make_polygon_scene(r, max(W, 64), max(H, 64), n, [assets.image_size(t) for t in tex], blends=(0, 0, 0, 1, 2, 3, 4))
+    cmds, pts = synth.make_polygon_scene(r, max(W, 64), max(H, 64), n, [assets.image_size(t) for t in tex], blends=(0,) if opaque_only else (0, 0, 0, 1, 2, 3, 4))
     cmds["tex_kind"] = N.TEX_IMAGE
     cmds["tex_ref"] = tex
     before = synth.make_hdr_image(r, W, H)
@@ -98,7 +101,7 @@ def test_fused_tonemap_polygons(assets, oracle_lib, size, clear):
         assert oracle_lib.assert_failures() == 0
         if not clear and W > 8:
             assert (fb == before).any() and (fb != before).any()  # covered and uncovered pixels both exist
-        _check_fused(view, frame, fb, post, f"fused {size} clear={clear}", stats_launches=1 + 1)
+        _check_fused(view, frame, fb, post, f"fused {size} clear={clear}", stats_launches=2 if opaque_only else 3)
         # a second submission of the recorded frame (what bench.py replays): same picture when it clears, and for a frame
         # without clear the blends read what the first one left behind
         if not clear:

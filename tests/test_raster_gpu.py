@@ -167,3 +167,54 @@ def test_device_self_test(assets):
     """sqw_self_test: the reciprocal-based z = 2^31 / (inv_z >> 8) of the full-perspective pixel loop equals the u32 division
     of rasterizer.rs:430 for every divisor below 2^24 (checked exhaustively on the device)."""
     assets.device_context().self_test()
+
+
+@pytest.mark.parametrize("color_bits", [32, 64])
+@pytest.mark.parametrize("clear", [True, False])
+def test_opaque_polygon_tiles_crowded(assets, oracle_lib, color_bits, clear):
+    """Hundreds of small polygons drawn with BlendingMode::None on a small target: every tile is of the opaque class
+    (raster_tile_opaque_kernel: last covering command wins), tile lists are longer than one 32-entry piece and blocks are hit by
+    more commands than one stage holds (the chunked path), three tc modes mixed, odd size.  Without clear the uncovered pixels
+    keep what the buffer held."""
+    r = synth.rng(8800 + color_bits + (1 if clear else 0))
+    ctx = assets.device_context()
+    W, H = 301, 45
+    n = 700
+    if color_bits == 32:
+        ids = [assets.lite_ids[2]] * 3 + [assets.lite_ids[0]]  # mostly the 8x8 texture: small polygons
+    else:
+        ids = [assets.sky64_ids[1]] * 3 + [assets.sky64_ids[0]]
+    tex = [ids[int(r.integers(0, len(ids)))] for _ in range(n)]
+    cmds, pts = synth.make_polygon_scene(r, W, H, n, [assets.image_size(t) for t in tex], blends=(0,))
+    cmds["tex_kind"] = N.TEX_IMAGE
+    cmds["tex_ref"] = tex
+    dtype = np.uint32 if color_bits == 32 else np.uint64
+    before = r.integers(1, 2**31, (H, W), dtype=np.uint64).astype(dtype)
+    clear_color = 0x0012345600654321 if color_bits == 64 else 0x80402010
+    view = ctx.create_view(W, H, color_bits)
+    try:
+        view.write_pixels(before)
+        view.draw(cmds, pts, None, clear_color=clear_color if clear else None)
+        got = view.read_pixels()
+    finally:
+        view.close()
+    fb = before.copy()
+    if clear:
+        oracle_lib.fill(fb, clear_color)
+    oracle_lib.reset_assert_failures()
+    oracle_lib.draw(color_bits, fb, cmds, pts, None, None, assets.images)
+    assert oracle_lib.assert_failures() == 0
+    # the case really is crowded: some 128x8 tile sees more than 32 commands and some 32x8 block more than 8
+    x = pts["x"].astype(np.float64) / 65536.0
+    y = pts["y"].astype(np.float64) / 65536.0
+    blocks = np.zeros(((H + 7) // 8, (W + 31) // 32), np.int32)
+    tiles = np.zeros(((H + 7) // 8, (W + 127) // 128), np.int32)
+    for c in cmds:
+        o, k = int(c["vertex_offset"]), int(c["num_vertices"])
+        x0, x1 = max(int(np.floor(x[o : o + k].min())), 0), min(int(np.ceil(x[o : o + k].max())), W - 1)
+        y0, y1 = max(int(np.floor(y[o : o + k].min())), 0), min(int(np.ceil(y[o : o + k].max())), H - 1)
+        if x1 >= x0 and y1 >= y0:
+            blocks[y0 // 8 : y1 // 8 + 1, x0 // 32 : x1 // 32 + 1] += 1
+            tiles[y0 // 8 : y1 // 8 + 1, x0 // 128 : x1 // 128 + 1] += 1
+    assert tiles.max() > 40 and blocks.max() > 12
+    assert_pixels_equal(got, fb, f"crowded opaque tiles c{color_bits} clear={clear}")
