@@ -686,6 +686,21 @@ __device__ __forceinline__ uint32_t z_from_inv_z(uint32_t d)
 	return q0 + k + (rem1 >= d ? 1u : 0u);
 }
 
+// The same for d >= 2^11, where the first quotient misses by at most one: q - q0 < 2^31 / d * (2^-21 + 2^-22) + 1 < 2, so one
+// correction step is enough (7 instructions fewer per pixel).  A polygon's largest inv_z is normalised into [2^23, 2^24)
+// (draw_polygon, partial_renderer.rs:4106-4109), so d >= 2^11 whenever the depth range inside it is below 16 : 1; the opaque
+// tile kernel checks the bound per warp and falls back to z_from_inv_z.  sqw_self_test compares it for every d >= 2^11.
+#define SQW_Z_ONE_STEP_MIN_D 2048u
+__device__ __forceinline__ uint32_t z_from_inv_z_one_step(uint32_t d)
+{
+	float r;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__uint2float_rz(d)));
+	r = __fmul_rz(r, 0x1.fffffp-1f);
+	const uint32_t q0 = __float2uint_rz(__fmul_rz(r, 2147483648.0f));
+	const uint32_t rem0 = (1u << Z_CALC_SHIFT) - q0 * d;
+	return q0 + (rem0 >= d ? 1u : 0u);
+}
+
 // 2^26 operand pairs for fixed16_div against the plain 64-bit division: a hash of the thread index picks both operands over the
 // whole i32 range, with every eighth pair forced onto the edges (0, +-1, +-2^15, +-2^16, INT_MIN, INT_MAX, equal magnitudes).
 __global__ void fixed16_div_test_kernel(unsigned long long* mismatches)
@@ -719,6 +734,8 @@ __global__ void z_from_inv_z_test_kernel(unsigned long long* mismatches)
 {
 	const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
 	if (d >= 1 && d < (1u << 24) && z_from_inv_z(d) != (1u << Z_CALC_SHIFT) / d)
+		atomicAdd(mismatches, 1ull);
+	if (d >= SQW_Z_ONE_STEP_MIN_D && d < (1u << 24) && z_from_inv_z_one_step(d) != (1u << Z_CALC_SHIFT) / d)
 		atomicAdd(mismatches, 1ull);
 }
 
@@ -1233,11 +1250,11 @@ __global__ void __launch_bounds__(SQW_RASTER_THREADS, SQW_TILE_CTAS_PER_SM) rast
 // of tile i + 1 travel to shared memory with asynchronous copies (LDGSTS, zero-filled for rows a command does not own) into
 // the other half of the warp's double buffer.  Warps are autonomous (two 128x8 tiles per CTA of eight warps, no barrier in
 // the tile loop); only the tonemapping table is shared by the CTA.
-struct OpaqueStage // one warp, one pipeline stage: 2208 bytes
+struct OpaqueStage // one warp, one pipeline stage: 2240 bytes
 {
 	uint4 span[SQW_OPAQUE_STAGE_HITS][SQW_TILE_H][2]; // SpanRec words 0-7 of (hit, block row)
-	uint4 cmd[SQW_OPAQUE_STAGE_HITS];                   // texture pointer (2 words) | tex_width + (tc_mode << 24) | span_base
-	uint32_t rows[SQW_OPAQUE_STAGE_HITS];               // y0 | y1 << 16
+	uint4 cmd[SQW_OPAQUE_STAGE_HITS];                   // texture pointer (2 words) | tex_width | tc_mode
+	uint2 rows[SQW_OPAQUE_STAGE_HITS];                  // y0 | y1 << 16, span_base
 };
 #define SQW_NO_WINNER 0xFFu
 
@@ -1249,7 +1266,7 @@ __device__ __forceinline__ void cp_async_16_zfill(void* smem_dst, const void* gm
 }
 
 // Compaction of one 32-entry piece of a tile list for one warp: entries whose column range meets the warp's block, in list
-// order, slots [first_slot, first_slot + SQW_OPAQUE_STAGE_HITS) go to the stage.  Returns the number of hits (bits 0-30).
+// order, slots [first_slot, first_slot + SQW_OPAQUE_STAGE_HITS) go to the stage.  Returns the number of hits (bits 0-29) and two flags.
 __device__ __forceinline__ uint32_t opaque_stage_commands(
 	OpaqueStage& st, const uint4 c0, const uint4 c1_in, const bool entry_valid, const int32_t blk_x0, const char* __restrict__ const surfaces_base, const uint32_t first_slot, const int lane)
 {
@@ -1266,12 +1283,14 @@ __device__ __forceinline__ uint32_t opaque_stage_commands(
 			c1.x = (uint32_t)t;
 			c1.y = (uint32_t)(t >> 32);
 		}
-		st.cmd[slot] = make_uint4(c1.x, c1.y, (c1.z & 0xFFFFFFu) | (((c0.w >> 16) & 0xFFu) << 24), c0.z);
-		st.rows[slot] = c0.x;
+		st.cmd[slot] = make_uint4(c1.x, c1.y, c1.z, (c0.w >> 16) & 0xFFu);
+		st.rows[slot] = make_uint2(c0.x, c0.z);
 	}
-	// bit 31: some staged command uses the full-perspective pixel loop (the resolve pass then evaluates the division)
+	// bit 31: some staged command uses the full-perspective pixel loop (the resolve pass then evaluates the division);
+	// bit 30: one of those may meet divisors below SQW_Z_ONE_STEP_MIN_D (no SQW_CMDF_Z_ONE_STEP flag): general division
 	const bool full = hit && slot < SQW_OPAQUE_STAGE_HITS && ((c0.w >> 16) & 0xFFu) == SQW_TC_FULL_PERSPECTIVE;
-	return __popc(ballot) | (__any_sync(0xFFFFFFFFu, full) ? 0x80000000u : 0u);
+	const bool slow = full && !((c0.w >> 24) & SQW_CMDF_Z_ONE_STEP);
+	return __popc(ballot) | (__any_sync(0xFFFFFFFFu, full) ? 0x80000000u : 0u) | (__any_sync(0xFFFFFFFFu, slow) ? 0x40000000u : 0u);
 }
 
 // Asynchronous copies of the span records of the staged commands (after a __syncwarp that follows opaque_stage_commands).
@@ -1283,11 +1302,11 @@ __device__ __forceinline__ void opaque_stage_spans(OpaqueStage& st, const uint32
 		const uint32_t p = (uint32_t)lane + 32u * j, h = p >> 3, r = p & 7;
 		if (h < num_staged)
 		{
-			const uint32_t rows = st.rows[h];
-			const int32_t y0 = (int16_t)(rows & 0xFFFF), y1 = (int16_t)(rows >> 16);
+			const uint2 rows = st.rows[h];
+			const int32_t y0 = (int16_t)(rows.x & 0xFFFF), y1 = (int16_t)(rows.x >> 16);
 			const int32_t srow = blk_y0 + (int32_t)r;
 			const bool ok = srow >= y0 && srow < y1;
-			const uint4* src = reinterpret_cast<const uint4*>(spans + st.cmd[h].w + (ok ? (uint32_t)(srow - y0) : 0u));
+			const uint4* src = reinterpret_cast<const uint4*>(spans + rows.y + (ok ? (uint32_t)(srow - y0) : 0u));
 			cp_async_16_zfill(&st.span[h][r][0], src, ok);
 			cp_async_16_zfill(&st.span[h][r][1], src + 1, ok);
 		}
@@ -1298,7 +1317,7 @@ __device__ __forceinline__ void opaque_stage_spans(OpaqueStage& st, const uint32
 // the eight pixels of a lane are independent dependency chains that the scheduler interleaves, so nothing here may branch.
 // FULL = some lane of the warp has a full-perspective winner among these pixels: the division is then evaluated for every pixel
 // and the result selected by the winner's mode (line-z corrected and affine spans step in 16.16, rasterizer.rs:558-572, :705-719).
-template <class C, bool FULL>
+template <class C, int FULL>
 __device__ __forceinline__ const typename C::Raw* opaque_texel_address(const uint4 r0, const uint4 r1, const uint4 cm, const int32_t x)
 {
 	const int32_t k = x - (int32_t)(int16_t)(r0.x & 0xFFFF);
@@ -1307,17 +1326,54 @@ __device__ __forceinline__ const typename C::Raw* opaque_texel_address(const uin
 	if (FULL)
 	{
 		const uint32_t span_inv_z = (uint32_t)wadd((int32_t)r0.y, wmul(k, (int32_t)r0.z));
-		const uint32_t z = z_from_inv_z(span_inv_z >> INV_Z_PRE_SHIFT); // rasterizer.rs:430; >= 1 inside a full-perspective span by the clamp of the set-up
+		// rasterizer.rs:430; the divisor is >= 1 inside a full-perspective span by the clamp of the set-up
+		const uint32_t z = FULL == 1 ? z_from_inv_z_one_step(span_inv_z >> INV_Z_PRE_SHIFT) : z_from_inv_z(span_inv_z >> INV_Z_PRE_SHIFT);
+#ifdef SQW_DEBUG_Z_ONE_STEP
+		// validation build: a flagged command met a divisor the one-step form does not cover (the host's bound would be wrong)
+		if (FULL == 1 && cm.w == SQW_TC_FULL_PERSPECTIVE && k >= 0 && x < (int32_t)(int16_t)(r0.x >> 16) && z != z_from_inv_z(span_inv_z >> INV_Z_PRE_SHIFT))
+			__trap(); // (pixels outside the span have no winner here: their address is never used)
+#endif
 		// tc = (z as u64 * span_tc as u64) >> 34 (:431-434).  span_tc never leaves [0, tc_max] inside a span (both span ends are
 		// clamped to it and the steps are truncated towards zero), so the sign extension of the reference's cast is a no-op
 		// and the product is the unsigned 32 x 32 -> 64 one: its high word shifted by two.
 		static_assert(TC_FINAL_SHIFT == 34, "tc shift");
-		const bool full = (cm.z >> 24) == SQW_TC_FULL_PERSPECTIVE;
+		const bool full = cm.w == SQW_TC_FULL_PERSPECTIVE;
 		u = full ? __umulhi(z, (uint32_t)t0) >> 2 : u;
 		v = full ? __umulhi(z, (uint32_t)t1) >> 2 : v;
 	}
 	const typename C::Raw* const tex = reinterpret_cast<const typename C::Raw*>((uint64_t)cm.x | ((uint64_t)cm.y << 32));
-	return tex + (u + v * (cm.z & 0xFFFFFFu));
+	return tex + (u + v * cm.z);
+}
+
+// 128-bit shared-memory load under a predicate, never a branch: a reload that no lane needs costs an issue slot but no
+// shared-memory wavefront (a 128-bit load costs four, broadcast or not: the load/store pipe is what bounds this kernel).
+__device__ __forceinline__ void lds128_if(const bool pred, const void* smem_src, uint4& v)
+{
+	const uint32_t src = (uint32_t)__cvta_generic_to_shared(smem_src);
+	asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %4, 0;\n\t@p ld.shared.v4.u32 {%0, %1, %2, %3}, [%5];\n\t}" : "+r"(v.x), "+r"(v.y), "+r"(v.z), "+r"(v.w) : "r"((uint32_t)pred), "r"(src));
+}
+
+// Texel addresses of the lane's four consecutive pixels of one row.  Neighbouring pixels nearly always share their winner, so
+// the winner's records (span record of the row, command) are loaded once and only reloaded — under a predicate — where the
+// winner changes inside the quad (lanes on a polygon edge).  Pixels without a winner keep the previous record; their gather is
+// predicated off by the caller.  Straight-line code: the pixels are independent chains for the scheduler to interleave.
+template <class C, int FULL>
+__device__ __forceinline__ void opaque_resolve_quad(const OpaqueStage& st, const uint32_t (&w)[4], const int row, const int32_t px0, const typename C::Raw* (&p)[4])
+{
+	uint32_t sprev = w[0] == SQW_NO_WINNER ? 0u : w[0];
+	uint4 r0 = st.span[sprev][row][0], r1 = st.span[sprev][row][1], cm = st.cmd[sprev];
+	p[0] = opaque_texel_address<C, FULL>(r0, r1, cm, px0);
+#pragma unroll
+	for (int i = 1; i < 4; ++i)
+	{
+		const uint32_t si = w[i] == SQW_NO_WINNER ? sprev : w[i];
+		const bool reload = si != sprev;
+		lds128_if(reload, &st.span[si][row][0], r0);
+		lds128_if(reload, &st.span[si][row][1], r1);
+		lds128_if(reload, &st.cmd[si], cm);
+		sprev = si;
+		p[i] = opaque_texel_address<C, FULL>(r0, r1, cm, px0 + i);
+	}
 }
 
 // Lane layout of the opaque kernel: a lane owns FOUR CONSECUTIVE pixels of block row lane >> 3 and of row 4 + (lane >> 3):
@@ -1327,7 +1383,7 @@ __device__ __forceinline__ const typename C::Raw* opaque_texel_address(const uin
 // Winners of the lane's eight pixels among the staged commands [0, nh), then one texel gather per pixel that has one.
 template <class C>
 __device__ __forceinline__ void opaque_chunk(
-	const OpaqueStage& st, const uint32_t nh, const bool any_full, const int ra, const int rb, const int32_t px0, typename C::Raw (&px_a)[4], typename C::Raw (&px_b)[4],
+	const OpaqueStage& st, const uint32_t nh, const bool any_full, const bool one_step, const int ra, const int rb, const int32_t px0, typename C::Raw (&px_a)[4], typename C::Raw (&px_b)[4],
 	uint32_t& have_a, uint32_t& have_b)
 {
 	typedef typename C::Raw Raw;
@@ -1348,8 +1404,6 @@ __device__ __forceinline__ void opaque_chunk(
 			wb[i] = (uint32_t)(db + i) < blen ? h : wb[i];
 		}
 	}
-	// Records of the winners, straight from the stage (slot 0 stands in for pixels without a winner: its record exists and the
-	// gather is predicated off).  No branch between the pixels: eight independent chains for the scheduler to interleave.
 	uint32_t valid = 0;
 	const Raw* pa[4];
 	const Raw* pb[4];
@@ -1361,23 +1415,21 @@ __device__ __forceinline__ void opaque_chunk(
 	}
 	if (any_full) // (warp-uniform) some staged command is drawn with full perspective correction
 	{
-#pragma unroll
-		for (int i = 0; i < 4; ++i)
+		if (one_step) // (warp-uniform) every staged full-perspective command keeps its divisors >= SQW_Z_ONE_STEP_MIN_D (CmdDev flag, set by the host)
 		{
-			const uint32_t sa = wa[i] == SQW_NO_WINNER ? 0u : wa[i], sb = wb[i] == SQW_NO_WINNER ? 0u : wb[i];
-			pa[i] = opaque_texel_address<C, true>(st.span[sa][ra][0], st.span[sa][ra][1], st.cmd[sa], px0 + i);
-			pb[i] = opaque_texel_address<C, true>(st.span[sb][rb][0], st.span[sb][rb][1], st.cmd[sb], px0 + i);
+			opaque_resolve_quad<C, 1>(st, wa, ra, px0, pa);
+			opaque_resolve_quad<C, 1>(st, wb, rb, px0, pb);
+		}
+		else
+		{
+			opaque_resolve_quad<C, 2>(st, wa, ra, px0, pa);
+			opaque_resolve_quad<C, 2>(st, wb, rb, px0, pb);
 		}
 	}
 	else
 	{
-#pragma unroll
-		for (int i = 0; i < 4; ++i)
-		{
-			const uint32_t sa = wa[i] == SQW_NO_WINNER ? 0u : wa[i], sb = wb[i] == SQW_NO_WINNER ? 0u : wb[i];
-			pa[i] = opaque_texel_address<C, false>(st.span[sa][ra][0], st.span[sa][ra][1], st.cmd[sa], px0 + i);
-			pb[i] = opaque_texel_address<C, false>(st.span[sb][rb][0], st.span[sb][rb][1], st.cmd[sb], px0 + i);
-		}
+		opaque_resolve_quad<C, 0>(st, wa, ra, px0, pa);
+		opaque_resolve_quad<C, 0>(st, wb, rb, px0, pb);
 	}
 	// the eight gathers of the lane are in flight together
 	Raw ta[4], tb[4];
@@ -1526,7 +1578,7 @@ __global__ void __launch_bounds__(SQW_OPAQUE_WARPS * 32, SQW_OPAQUE_CTAS_PER_SM)
 			const int32_t blk_x0 = (int32_t)(inf.x & 0xFFFF) + (warp & 3) * 32;
 			nh = opaque_stage_commands(st, c0n, c1n, c_valid, blk_x0, surfaces_base, 0, lane);
 			__syncwarp();
-			opaque_stage_spans(st, min(nh & 0x7FFFFFFFu, K), (int32_t)(inf.x >> 16), spans, lane);
+			opaque_stage_spans(st, min(nh & 0x3FFFFFFFu, K), (int32_t)(inf.x >> 16), spans, lane);
 		}
 		asm volatile("cp.async.commit_group;" ::: "memory");
 		return nh;
@@ -1583,10 +1635,10 @@ __global__ void __launch_bounds__(SQW_OPAQUE_WARPS * 32, SQW_OPAQUE_CTAS_PER_SM)
 			const bool vec_ok = (blk_x0 + 32 <= width) && pitch_vec;
 			if (blk_x0 < width) // (warp-uniform)
 			{
-				if (inf0.y <= 32 && (nh0 & 0x7FFFFFFFu) <= K)
+				if (inf0.y <= 32 && (nh0 & 0x3FFFFFFFu) <= K)
 				{
 					if (nh0)
-						opaque_chunk<C>(st, nh0 & 0x7FFFFFFFu, (nh0 >> 31) != 0, ra, rb, px0, px_a, px_b, have_a, have_b);
+						opaque_chunk<C>(st, nh0 & 0x3FFFFFFFu, (nh0 >> 31) != 0, !((nh0 >> 30) & 1), ra, rb, px0, px_a, px_b, have_a, have_b);
 				}
 				else
 				{
@@ -1609,7 +1661,7 @@ __global__ void __launch_bounds__(SQW_OPAQUE_WARPS * 32, SQW_OPAQUE_CTAS_PER_SM)
 						{
 							__syncwarp();
 							const uint32_t nhf = opaque_stage_commands(st, c0, c1, valid, blk_x0, surfaces_base, first, lane);
-							nh = nhf & 0x7FFFFFFFu;
+							nh = nhf & 0x3FFFFFFFu;
 							if (first >= nh)
 								break;
 							__syncwarp();
@@ -1618,7 +1670,7 @@ __global__ void __launch_bounds__(SQW_OPAQUE_WARPS * 32, SQW_OPAQUE_CTAS_PER_SM)
 							asm volatile("cp.async.commit_group;" ::: "memory");
 							asm volatile("cp.async.wait_all;" ::: "memory");
 							__syncwarp();
-							opaque_chunk<C>(st, n, (nhf >> 31) != 0, ra, rb, px0, px_a, px_b, have_a, have_b);
+							opaque_chunk<C>(st, n, (nhf >> 31) != 0, !((nhf >> 30) & 1), ra, rb, px0, px_a, px_b, have_a, have_b);
 						}
 					}
 				}

@@ -953,13 +953,30 @@ int sqw_frame_set_draw(
 				min_y = std::min(min_y, p.y);
 				max_y = std::max(max_y, p.y);
 			}
+			// Smallest inv_z of the polygon (it is linear, so a vertex has it), lowered by two pixels of gradient for the pixel-centre
+			// offsets and the rounding of the span ends, in the rasteriser's 2^29 scale (rasterizer.rs:287-310): when even half of it
+			// stays above 2^11 << 8, every per-pixel divisor inv_z >> 8 of the full-perspective loop is >= 2^11 and the opaque tile
+			// kernel may use its one-step division.
+			uint8_t z_flag = 0;
+			if (c.tc_mode == SQW_TC_FULL_PERSPECTIVE)
+			{
+				double min_iz = 1e300;
+				for (uint32_t k = 0; k < c.num_vertices; ++k)
+				{
+					const sqw_polygon_point& p = polygon_points[c.vertex_offset + k];
+					min_iz = std::min(min_iz, (double)c.depth_eq[0] * (p.x / 65536.0) + (double)c.depth_eq[1] * (p.y / 65536.0) + (double)c.depth_eq[2]);
+				}
+				min_iz -= 2.0 * (std::fabs((double)c.depth_eq[0]) + std::fabs((double)c.depth_eq[1]));
+				if (min_iz * 536870912.0 * 0.5 >= 2048.0 * 256.0)
+					z_flag = SQW_CMDF_Z_ONE_STEP;
+			}
 			// polygon textures have the framebuffer's colour type (rasterizer.rs:41)
 			if (c.tex_kind == SQW_TEX_SURFACE)
 			{
 				if ((uint64_t)c.tex_ref + tex_elems > view->surfaces.capacity / C)
 					return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_frame_set_draw: surface reference outside the pool (build surfaces first)");
 				d.texture = reinterpret_cast<const void*>((uintptr_t)c.tex_ref * C);
-				d.tex_flags = (view->color_bits == 64 ? 1 : 0) | 2;
+				d.tex_flags = (view->color_bits == 64 ? 1 : 0) | 2 | z_flag;
 			}
 			else if (c.tex_kind == SQW_TEX_IMAGE)
 			{
@@ -969,7 +986,7 @@ int sqw_frame_set_draw(
 				if (img.kind != (view->color_bits == 64 ? SQW_IMAGE_COLOR64 : SQW_IMAGE_COLOR32) || tex_elems > (uint64_t)img.width * img.height)
 					return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_frame_set_draw: polygon image must match the view colour type and size");
 				d.texture = img.pixels;
-				d.tex_flags = view->color_bits == 64 ? 1 : 0;
+				d.tex_flags = (view->color_bits == 64 ? 1 : 0) | z_flag;
 			}
 			else if (c.tex_kind == SQW_TEX_VIEW)
 			{
@@ -979,7 +996,7 @@ int sqw_frame_set_draw(
 				if (tv->color_bits != view->color_bits || tex_elems > (uint64_t)tv->width * tv->height)
 					return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_frame_set_draw: view texture must match colour type and size");
 				d.texture = tv->d_color;
-				d.tex_flags = view->color_bits == 64 ? 1 : 0;
+				d.tex_flags = (view->color_bits == 64 ? 1 : 0) | z_flag;
 				if (std::find(f->sampled_views.begin(), f->sampled_views.end(), c.tex_ref) == f->sampled_views.end())
 					f->sampled_views.push_back(c.tex_ref);
 			}

@@ -78,8 +78,14 @@ cudaError_t launch_mix_texture(
 // Tile classes (tile_desc.w, written by the binning CTAs): which of the two tile kernels renders the tile.
 #define SQW_TILE_CLASS_GENERAL 0u /* raster_tile_kernel: any command mix, painter's order per pixel */
 #define SQW_TILE_CLASS_OPAQUE 1u  /* raster_tile_opaque_kernel: only polygons with BlendingMode::None */
-#define SQW_OPAQUE_STAGE_HITS 8   /* commands whose span records a warp of the opaque tile kernel stages at a time */
-#define SQW_OPAQUE_WARPS 8        /* warps per CTA of the opaque tile kernel: two 128x8 tiles side by side */
+#ifndef SQW_OPAQUE_STAGE_HITS
+#define SQW_OPAQUE_STAGE_HITS 8
+#endif
+//   /* commands whose span records a warp of the opaque tile kernel stages at a time */
+#ifndef SQW_OPAQUE_WARPS
+#define SQW_OPAQUE_WARPS 8
+#endif
+//        /* warps per CTA of the opaque tile kernel: two 128x8 tiles side by side */
 #ifndef SQW_OPAQUE_CTAS_PER_SM
 #define SQW_OPAQUE_CTAS_PER_SM 2
 #endif
@@ -87,6 +93,7 @@ cudaError_t launch_mix_texture(
 #define SQW_TILE_CTAS_PER_SM 5 /* resident CTAs of the persistent tile kernel per SM (register and shared-memory budget) */
 #endif
 
+#define SQW_CMDF_Z_ONE_STEP 4u
 // Per-command data prepared by the host part of sqw_frame_set_draw (row range, conservative column range,
 // span-table offset, resolved texture pointer).  32 bytes.
 struct CmdDev
@@ -94,7 +101,8 @@ struct CmdDev
 	int16_t y0, y1;   // row range [y0, y1) inside the clip rect (rows that can own a span)
 	int16_t bx0, bx1; // conservative pixel column range [bx0, bx1)
 	uint32_t span_base;
-	uint8_t kind, blend, tc_mode, tex_flags; // tex_flags bit0: texture elements are 8 bytes (else 4); bit1: `texture` is a byte offset into the surface pool
+	uint8_t kind, blend, tc_mode, tex_flags; // tex_flags bit0: texture elements are 8 bytes (else 4); bit1: `texture` is a byte offset into the surface pool;
+	                                         // bit2 (SQW_CMDF_Z_ONE_STEP): full-perspective polygon whose inv_z >> 8 stays >= 2^11 at every pixel
 	const void* texture;
 	int32_t tex_width;
 	int32_t tex_height;
