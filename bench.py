@@ -129,45 +129,76 @@ def algorithmic_bytes(hf_stats, color_bytes=8, blended_pixels=0):
     return b1, b2, b3
 
 
+class CpuRenderer:
+    """The CPU arm: the oracle restatement driven the way the reference drives its renderer — buffers allocated once and reused for
+    every frame (surface pool partial_renderer.rs:1454-1462, HDR buffer postprocessor.rs:56, window surface), one persistent thread
+    pool (oracle_pool.h, standing in for the global rayon pool), the numerics of the reference's RELEASE build (fast_math.rs:6-368:
+    rcpss / rsqrtss / FMA, src/build_release.sh:2) compiled with -O3 -march=native on the machine that runs it."""
+
+    def __init__(self, scene, frames, cores):
+        import oracle
+
+        self.oracle, self.scene, self.cores = oracle, scene, cores
+        try:
+            oracle.lib("sse_native")
+            self.numerics = "sse_native"
+        except Exception:  # no compiler on this machine: the portable x86-64-v3 build that travelled with the repo
+            self.numerics = "sse"
+        self.surfaces = np.zeros(max(hf.total_surface_pixels for hf in frames), np.uint64)
+        self.hdr = np.zeros((HEIGHT, WIDTH), np.uint64)
+        self.ldr = np.zeros((HEIGHT, WIDTH), np.uint32)
+        self.stage_s = [0.0, 0.0, 0.0]
+
+    def frame(self, hf, post):
+        from square_wheel_b200 import scene as S
+
+        o, sc = self.oracle, self.scene
+        t0 = time.perf_counter()
+        o.build_surfaces(64, hf.jobs, None, None, hf.cam_pos, sc.images, sc.lightmaps, sc.directional_lightmaps, hf.total_surface_pixels, out=self.surfaces, num_threads=self.cores, numerics=self.numerics)
+        t1 = time.perf_counter()
+        if hf.needs_clear:
+            o.fill(self.hdr, S.BACKGROUND_COLOR64)
+        o.draw(64, self.hdr, hf.cmds, hf.polygon_points, None, self.surfaces, sc.images, num_threads=self.cores, numerics=self.numerics)
+        t2 = time.perf_counter()
+        o.postprocess(self.hdr, post, num_threads=self.cores, dst=self.ldr, numerics=self.numerics)
+        t3 = time.perf_counter()
+        self.stage_s[0] += t1 - t0
+        self.stage_s[1] += t2 - t1
+        self.stage_s[2] += t3 - t2
+
+    def describe(self):
+        return (
+            f"C++ restatement of Square-Wheel @4820f17 (oracle/, numerics '{self.numerics}': the release build's rcpss / rsqrtss / FMA branch, -O3 -march=native), "
+            "not the Rust binary (no rustc in the image); persistent surface / HDR / picture buffers and one persistent thread pool"
+        )
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the CPU restatement (oracle port) of the same three stages with all host threads, on a bounded sample of the
-    workload per step.  Only rank 0 works."""
+    """--impl reference: the CPU restatement (oracle port) of the same three stages with all host threads.  One step = the same 64
+    frames the CUDA arm renders per step.  Only rank 0 works."""
     if rank != 0:
         return
-    import oracle
     from square_wheel_b200 import scene as S
     from square_wheel_b200.device import make_post_params
 
-    sample_frames = 16
     cores = os.cpu_count() or 1
     scene = S.Scene(**SCENE_KW)
     poses = scene.camera_path(NUM_POSES)
-    need = (args.steps + args.warmup) * sample_frames
-    idx = [(i * (FRAMES_PER_STEP // sample_frames)) % NUM_POSES for i in range(need)]
-    frames, _ = prepare_host_frames(scene, [poses[i] for i in idx])
+    frames, _ = prepare_host_frames(scene, poses)
     post = make_post_params(exposure=1.0)
-
-    def one_frame(hf):
-        surf = oracle.build_surfaces(64, hf.jobs, None, None, hf.cam_pos, scene.images, scene.lightmaps, scene.directional_lightmaps, hf.total_surface_pixels, num_threads=cores)
-        fb = np.zeros((HEIGHT, WIDTH), np.uint64)
-        if hf.needs_clear:
-            oracle.fill(fb, S.BACKGROUND_COLOR64)
-        oracle.draw(64, fb, hf.cmds, hf.polygon_points, None, surf, scene.images, num_threads=cores)
-        oracle.postprocess(fb, post, num_threads=cores)
-
-    k = 0
-    for _ in range(args.warmup):
-        for _ in range(sample_frames):
-            one_frame(frames[k])
-            k += 1
+    cpu = CpuRenderer(scene, frames, cores)
+    for _ in range(max(args.warmup, 1)):
+        for hf in frames[:: max(1, FRAMES_PER_STEP // 16)]:  # untimed: page faults of the buffers, pool start-up, caches
+            cpu.frame(hf, post)
+    cpu.stage_s = [0.0, 0.0, 0.0]
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        for _ in range(sample_frames):
-            one_frame(frames[k])
-            k += 1
+        for hf in frames:
+            cpu.frame(hf, post)
     dt = time.perf_counter() - t0
-    fps = args.steps * sample_frames / dt
-    sample = f"{sample_frames} of the {FRAMES_PER_STEP} frames of each step (every {FRAMES_PER_STEP // sample_frames}th pose), all three stages, {cores} threads"
+    n = args.steps * len(frames)
+    fps = n / dt
+    sample = f"all {FRAMES_PER_STEP} frames of each step, all three stages, {cores} threads (warm-up: every 4th pose per warm-up step)"
     line = {
         "impl": "reference",
         "metric": METRIC,
@@ -182,8 +213,12 @@ def run_reference(args, rank, world):
         "vs_baseline": None,
         "dtype": "f32+i32/i64 (Color64 u16x4 pixels)",
         "data": "synthetic",
-        "config": workload_config({"reference_impl": "C++ restatement of Square-Wheel @4820f17 (oracle/), not the Rust binary (no rustc in the image)"}),
-        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(),
+        "reference_impl": cpu.describe(),
+        "cpu_baseline": {
+            "value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+            "stage_ms_per_frame": {k: v / n * 1e3 for k, v in zip(("surfaces", "rasterization", "tonemapping"), cpu.stage_s)},
+        },
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit_line(line)
@@ -306,6 +341,27 @@ def run_cuda(args, rank, local_rank, world):
     ctx.profile_begin()
     run_steps(args.steps, k, serial=True)
     kt = ctx.profile_end()
+    # ---- the same K steps with SQW_CTX_FAST_SURFACE_NUMERICS (surface building with hardware rcp / rsqrt and FMA: the numerics class
+    # of the reference's release build; tests/test_surfaces_gpu.py bounds it).  Reported beside the bit-exact headline, never as it.
+    ctx.set_fast_surface_numerics(True)
+    run_steps(1, k)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(stream)
+    run_steps(args.steps, k)
+    f1.record(stream)
+    barrier()
+    fast_ms = B.max_over_ranks(f0.elapsed_time(f1), dist, "cuda")
+    ctx.profile_begin()
+    run_steps(1, k, serial=True)
+    kt_fast = ctx.profile_end()
+    ctx.set_fast_surface_numerics(False)
+    fast_numerics = {
+        "value": world * args.steps * FRAMES_PER_STEP / (fast_ms * 1e-3),
+        "unit": UNIT,
+        "surface_build_us_per_frame": kt_fast["surface_build"][0] / FRAMES_PER_STEP * 1e3,
+        "note": "SQW_CTX_FAST_SURFACE_NUMERICS: stage 1 with MUFU.RCP / MUFU.RSQ / FFMA (the reference release build's rcpss / rsqrtss / FMA class, fast_math.rs:6-368); within 2 HDR units / 1e-3 of the bit-exact surfaces (tests/test_surfaces_gpu.py); stages 2 and 3 unchanged",
+    }
     b1, b2, b3 = algorithmic_bytes(per_frame)
     # The fused tile + tonemap kernel has two accountings, both reported: the LITERAL unfused contract B2 + B3 (what the reference's
     # two passes move), and the FUSED MINIMUM — bytes the fused kernel cannot avoid: surface texels read (S C), the 64-bit pixel
@@ -415,37 +471,24 @@ def run_cuda(args, rank, local_rank, world):
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only): bounded sample of the same workload ----
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.kernels_only:
-        import oracle
-
         cores = os.cpu_count() or 1
-        sample = list(host_frames)  # one whole step: every pose of the camera path once (~1.2 s wall, ~18 CPU-seconds on 16 threads)
-        for hf in sample[:2]:  # untimed warm-up (thread pool, page faults of the 66 MB frame buffer)
-            oracle.postprocess(np.zeros((HEIGHT, WIDTH), np.uint64), post, num_threads=cores)
+        cpu = CpuRenderer(scene, host_frames, cores)
+        for hf in host_frames[::8]:  # untimed warm-up (thread pool, page faults of the persistent buffers)
+            cpu.frame(hf, post)
+        cpu.stage_s = [0.0, 0.0, 0.0]
         t0 = time.perf_counter()
-        stage_s = [0.0, 0.0, 0.0]
-        for hf in sample:
-            t = time.perf_counter()
-            surf = oracle.build_surfaces(64, hf.jobs, None, None, hf.cam_pos, scene.images, scene.lightmaps, scene.directional_lightmaps, hf.total_surface_pixels, num_threads=cores)
-            stage_s[0] += time.perf_counter() - t
-            fb = np.zeros((HEIGHT, WIDTH), np.uint64)
-            if hf.needs_clear:
-                oracle.fill(fb, S.BACKGROUND_COLOR64)
-            t = time.perf_counter()
-            oracle.draw(64, fb, hf.cmds, hf.polygon_points, None, surf, scene.images, num_threads=cores)
-            stage_s[1] += time.perf_counter() - t
-            t = time.perf_counter()
-            oracle.postprocess(fb, post, num_threads=cores)
-            stage_s[2] += time.perf_counter() - t
-        dt = sum(stage_s)
+        for hf in host_frames:
+            cpu.frame(hf, post)
+        dt = time.perf_counter() - t0
         cpu_baseline = {
-            "value": len(sample) / dt,
+            "value": len(host_frames) / dt,
             "unit": UNIT,
             "cores": cores,
             "kind": "port",
-            "sample": f"one step = all {len(sample)} frames of the camera path, {cores} threads: surfaces parallel-for over polygons, raster split_rect, tonemap row ranges",
-            "stage_ms_per_frame": {"surfaces": stage_s[0] / len(sample) * 1e3, "rasterization": stage_s[1] / len(sample) * 1e3, "tonemapping": stage_s[2] / len(sample) * 1e3},
-            "wall_s": time.perf_counter() - t0,
-            "note": "C++ restatement of Square-Wheel @4820f17, not the Rust binary",
+            "sample": f"one step = all {len(host_frames)} frames of the camera path, {cores} threads: surfaces parallel-for over polygons, raster split_rect, tonemap row ranges",
+            "stage_ms_per_frame": {k: v / len(host_frames) * 1e3 for k, v in zip(("surfaces", "rasterization", "tonemapping"), cpu.stage_s)},
+            "wall_s": dt,
+            "note": cpu.describe(),
         }
 
     if rank == 0:
@@ -478,6 +521,7 @@ def run_cuda(args, rank, local_rank, world):
             "e2e": e2e,
             "gpu_launches": launches,
             "roofline": roofline,
+            "fast_surface_numerics": fast_numerics,
             "cpu_baseline": cpu_baseline,
         }
         emit_line(line)

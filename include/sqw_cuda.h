@@ -78,6 +78,13 @@ typedef struct sqw_map_desc
  * with frame N-1's swap the same way, host.rs:438-449).  Work of ONE view stays in submission order.  Without the flag
  * everything runs in order on the context's stream. */
 #define SQW_CTX_CONCURRENT_VIEWS 1u
+/* Surface building (stage 1) uses the numerics CLASS of the reference's release build instead of its portable branch: hardware
+ * reciprocal and reciprocal square root for inv_fast / inv_sqrt_fast and fused multiply-add for f32_mul_add (fast_math.rs:13-22,
+ * :729-733; the release build is compiled for haswell, src/build_release.sh:2, where those are rcpss / rsqrtss / vfmadd).  Without
+ * the flag every stage is bit-exact against the portable branch (fast_math.rs:370-725).  With it, surfaces differ from both
+ * reference builds by no more than those builds differ from each other (north_star's +-1 LSB of the final 8-bit picture);
+ * stages 2 and 3 are not affected. */
+#define SQW_CTX_FAST_SURFACE_NUMERICS 2u
 
 /* Create a context on CUDA device `device` and upload the static map data.  Replaces the ownership half of
  * Renderer::new (renderer.rs:24).  `external_stream` may be a cudaStream_t the caller wants all work of this
@@ -417,6 +424,10 @@ int sqw_profile_end(sqw_ctx* ctx, sqw_kernel_times* out);
  * divisor below 2^24, and 2^26 hashed + edge-case operand pairs of the double-precision-assisted fixed16_div (fixed_math.rs:56)
  * against the plain 64-bit division.  SQW_OK, or SQW_ERR_CUDA with the mismatch count in sqw_last_error(). */
 int sqw_self_test(sqw_ctx* ctx);
+
+/* Switch SQW_CTX_FAST_SURFACE_NUMERICS on or off for frames submitted from now on (the flag of sqw_create is the initial
+ * state).  Lets one context serve a bit-exact consumer and a throughput consumer, and bench.py time both on the same data. */
+int sqw_set_fast_surface_numerics(sqw_ctx* ctx, int enable);
 
 /* Average colour produced by the last post stage of this view (synchronises). */
 int sqw_view_get_average_color(sqw_view* view, float avg_color_out[3]);

@@ -11,7 +11,16 @@
 // Numerics: the PORTABLE branch of src/square_wheel/fast_math.rs (:370-725) is normative:
 //   inv_fast = 1/x, inv_sqrt_fast = 1/sqrt(x), f32_mul_add = x*y+z (two roundings), float->int truncates.
 // Build with -ffp-contract=off so the compiler never fuses what the reference keeps separate.
+//
+// -DORACLE_NUMERICS_SSE (liboracle_sse.so) restates the OTHER branch, fast_math.rs:6-368 — what the reference's shipping build
+// executes (-Ctarget-cpu=haswell, src/build_release.sh:2): rcpss / rsqrtss approximations, cvtps2dq round-to-nearest-even
+// conversions, fused multiply-add, pavgb / pavgw rounding-up averages.  It is the yardstick for north_star's tolerance
+// (+-1 LSB per 8-bit channel, 1e-3 relative on HDR values) and the build timed as the CPU baseline.  rcpss / rsqrtss results are
+// implementation-defined (they differ between CPU vendors), which is why this mode bounds a tolerance and is not bit-normative.
 #pragma once
+#ifdef ORACLE_NUMERICS_SSE
+#include <immintrin.h>
+#endif
 
 #include "../include/sqw_cuda.h"
 #include <algorithm>
@@ -66,9 +75,17 @@ inline Fixed16 f32_to_fixed16_unchecked(float x) { return f32_to_i32_trunc(x * (
 // ---- fast_math.rs portable branch ------------------------------------------------------------------------------
 constexpr float MIN_POSITIVE_VALUE = 1.0f / (float)(1 << 30); // fast_math.rs:744
 
+#ifdef ORACLE_NUMERICS_SSE
+inline float inv_sqrt_fast(float x) { return _mm_cvtss_f32(_mm_rsqrt_ss(_mm_set1_ps(x))); } // fast_math.rs:13
+inline float inv_fast(float x) { return _mm_cvtss_f32(_mm_rcp_ss(_mm_set1_ps(x))); }        // :19
+inline float f32_mul_add(float x, float y, float z) { return _mm_cvtss_f32(_mm_fmadd_ss(_mm_set_ss(x), _mm_set_ss(y), _mm_set_ss(z))); } // :731 (target_feature = "fma")
+// cvtps2dq of one lane: round to nearest even (MXCSR default), out of range -> INT_MIN
+inline int32_t f32_to_i32_round(float x) { return _mm_cvtss_si32(_mm_set_ss(x)); }
+#else
 inline float inv_sqrt_fast(float x) { return 1.0f / std::sqrt(x); } // :376
 inline float inv_fast(float x) { return 1.0f / x; }                 // :381
 inline float f32_mul_add(float x, float y, float z) { return x * y + z; } // :737
+#endif
 // Rust f32::max / min: if one operand is NaN the other is returned.
 inline float fmax_(float a, float b) { return std::fmax(a, b); }
 inline float fmin_(float a, float b) { return std::fmin(a, b); }
@@ -122,7 +139,11 @@ inline ColorVec cv_div(ColorVec a, ColorVec b) { return {{a.v[0] / b.v[0], a.v[1
 inline uint32_t f32_to_u_clamped(float x, float maxv)
 {
 	float m = fmin_(x, maxv);
+#ifdef ORACLE_NUMERICS_SSE
+	return m > 0.0f ? (uint32_t)f32_to_i32_round(m) : 0u; // _mm_min_ps + _mm_cvtps_epi32 (fast_math.rs:131-160)
+#else
 	return m > 0.0f ? (uint32_t)m : 0u;
+#endif
 }
 inline uint32_t cv_into_color32(ColorVec c)
 {
@@ -152,6 +173,9 @@ inline ColorVecI cvi_from_i32x3(const int32_t c[3]) { return {{c[2], c[1], c[0],
 inline ColorVecI cvi_from_f32x3(const float c[3]) // :623  `as i32` (saturating truncation)
 {
 	auto cv = [](float x) -> int32_t {
+#ifdef ORACLE_NUMERICS_SSE
+		return f32_to_i32_round(x); // _mm_cvtps_epi32 (fast_math.rs:289)
+#endif
 		if (x != x)
 			return 0;
 		if (x >= 2147483648.0f)
@@ -193,7 +217,11 @@ struct Color32
 	static Raw from_vec(ColorVec c) { return cv_into_color32(c); }
 	static Raw from_veci(ColorVecI c) { return cvi_into_color32(c); }
 	static ColorVecI to_veci(Raw c) { return cvi_from_color32(c); }
+#ifdef ORACLE_NUMERICS_SSE
+	static Raw average(Raw a, Raw b) { return (Raw)_mm_cvtsi128_si32(_mm_avg_epu8(_mm_cvtsi32_si128((int)a), _mm_cvtsi32_si128((int)b))); } // fast_math.rs:43 (rounds up)
+#else
 	static Raw average(Raw a, Raw b) { return (((a ^ b) & 0xFEFEFEFEu) >> 1) + (a & b); } // color.rs:46
+#endif
 	static Raw saturated_sum(Raw a, Raw b) // fast_math.rs:386
 	{
 		Raw r = 0;
@@ -213,7 +241,11 @@ struct Color64
 	static Raw from_vec(ColorVec c) { return cv_into_color64(c); }
 	static Raw from_veci(ColorVecI c) { return cvi_into_color64(c); }
 	static ColorVecI to_veci(Raw c) { return cvi_from_color64(c); }
+#ifdef ORACLE_NUMERICS_SSE
+	static Raw average(Raw a, Raw b) { return (Raw)_mm_cvtsi128_si64(_mm_avg_epu16(_mm_cvtsi64_si128((long long)a), _mm_cvtsi64_si128((long long)b))); } // fast_math.rs:54
+#else
 	static Raw average(Raw a, Raw b) { return (((a ^ b) & 0xFFFEFFFEFFFEFFFEull) >> 1) + (a & b); } // color.rs:163
+#endif
 	static Raw saturated_sum(Raw a, Raw b) // fast_math.rs:397
 	{
 		Raw r = 0;

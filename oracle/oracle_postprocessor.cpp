@@ -2,7 +2,7 @@
 //
 // Restatement of src/square_wheel/postprocessor.rs (stage 3: tonemapping + bloom + average colour).
 #include "oracle_common.h"
-#include <thread>
+#include "oracle_pool.h"
 #include <vector>
 
 namespace oracle
@@ -56,6 +56,35 @@ struct Post
 	// :226-256
 	ColorVec perform_tonemapping(size_t y_start, size_t y_end, const TonemappingFunction& f) const
 	{
+#ifdef ORACLE_NUMERICS_SSE
+		// The release build's ColorVec IS an __m128 (fast_math.rs:95-98): the loop below is postprocessor.rs:226-256 with the same
+		// intrinsics per pixel — from_color64 (:123-132), add, mul_add = vfmadd (:208), div (:213), into_color32 = min + cvtps2dq +
+		// pshufb (:134-146).  Lane for lane the same IEEE operations as the scalar statement of this mode further down.
+		{
+			const __m128 inv_scale = _mm_loadu_ps(f.inv_scale_vec.v), inv_255 = _mm_loadu_ps(f.inv_255_vec.v);
+			const __m128 max_val = _mm_set1_ps(255.0f);
+			const __m128i shuffle_mask = _mm_set_epi8(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 12, 8, 4, 0);
+			__m128 colors_sum = _mm_setzero_ps();
+			for (size_t y = y_start; y < y_end; ++y)
+			{
+				__m128 line_colors_sum = _mm_setzero_ps();
+				const uint64_t* src_line = hdr_buffer + y * hdr_size[0];
+				uint32_t* dst_line = pixels + y * pitch;
+				for (size_t x = 0; x < hdr_size[0]; ++x)
+				{
+					const __m128 c = _mm_cvtepi32_ps(_mm_cvtepu16_epi32(_mm_cvtsi64_si128((long long)src_line[x])));
+					line_colors_sum = _mm_add_ps(line_colors_sum, c);
+					const __m128 mapped = _mm_div_ps(c, _mm_fmadd_ps(c, inv_255, inv_scale));
+					const __m128i values_32bit = _mm_cvtps_epi32(_mm_min_ps(mapped, max_val));
+					dst_line[x] = (uint32_t)_mm_cvtsi128_si32(_mm_shuffle_epi8(values_32bit, shuffle_mask));
+				}
+				colors_sum = _mm_add_ps(colors_sum, line_colors_sum);
+			}
+			ColorVec r;
+			_mm_storeu_ps(r.v, colors_sum);
+			return r;
+		}
+#endif
 		ColorVec colors_sum = cv_zero();
 		for (size_t y = y_start; y < y_end; ++y)
 		{
@@ -359,11 +388,8 @@ extern "C" int oracle_postprocess(
 			run(0, p.bloom_size[1]);
 		else
 		{
-			std::vector<std::thread> threads; // :127-145
-			for (int i = 0; i < nt; ++i)
-				threads.emplace_back(run, p.bloom_size[1] * (size_t)i / (size_t)nt, p.bloom_size[1] * (size_t)(i + 1) / (size_t)nt);
-			for (auto& t : threads)
-				t.join();
+			// :127-145
+			ThreadPool::instance().parallel_for((uint32_t)nt, nt, [&](uint32_t i) { run(p.bloom_size[1] * (size_t)i / (size_t)nt, p.bloom_size[1] * (size_t)(i + 1) / (size_t)nt); });
 		}
 		if (bloom_out)
 			std::memcpy(bloom_out, p.bloom_buffers[0].data(), p.bloom_buffers[0].size() * sizeof(uint64_t));
@@ -376,11 +402,7 @@ extern "C" int oracle_postprocess(
 		else
 		{
 			std::vector<ColorVec> sums((size_t)nt, cv_zero()); // :156-174
-			std::vector<std::thread> threads;
-			for (int i = 0; i < nt; ++i)
-				threads.emplace_back([&, i]() { sums[(size_t)i] = p.perform_tonemapping((size_t)height * (size_t)i / (size_t)nt, (size_t)height * (size_t)(i + 1) / (size_t)nt, f); });
-			for (auto& t : threads)
-				t.join();
+			ThreadPool::instance().parallel_for((uint32_t)nt, nt, [&](uint32_t i) { sums[(size_t)i] = p.perform_tonemapping((size_t)height * (size_t)i / (size_t)nt, (size_t)height * (size_t)(i + 1) / (size_t)nt, f); });
 			for (auto& s : sums)
 				colors_sum = cv_add(colors_sum, s);
 		}

@@ -5,7 +5,7 @@
 // thread/rect split of PartialRenderer::perform_rasterization (partial_renderer.rs:1192-1283, rect_splitting.rs).
 // Compiled with -fwrapv: Rust release builds wrap on signed overflow and so does this file.
 #include "oracle_common.h"
-#include <thread>
+#include "oracle_pool.h"
 #include <vector>
 
 namespace oracle
@@ -822,11 +822,10 @@ void run_draw(const DrawCall& d, int num_threads)
 	// whole command list (the reference walks the whole BSP per thread).
 	std::vector<RectF> rects;
 	split_rect_r(RectF{0.0f, 0.0f, (float)d.width, (float)d.height}, (uint32_t)std::min(num_threads, 64), rects);
-	std::vector<std::thread> threads;
-	for (const RectF& rc : rects)
-		threads.emplace_back([&d, rc]() { run_cmds<C>(d, ClipRect{(int32_t)rc.min_x, (int32_t)rc.min_y, (int32_t)rc.max_x, (int32_t)rc.max_y}); });
-	for (auto& t : threads)
-		t.join();
+	ThreadPool::instance().parallel_for((uint32_t)rects.size(), num_threads, [&](uint32_t i) {
+		const RectF& rc = rects[i];
+		run_cmds<C>(d, ClipRect{(int32_t)rc.min_x, (int32_t)rc.min_y, (int32_t)rc.max_x, (int32_t)rc.max_y});
+	});
 }
 
 } // namespace

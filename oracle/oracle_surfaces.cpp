@@ -4,7 +4,7 @@
 // src/square_wheel/light.rs, portable numerics.
 #include "oracle_common.h"
 #include <atomic>
-#include <thread>
+#include "oracle_pool.h"
 #include <vector>
 
 namespace oracle
@@ -587,23 +587,13 @@ void run_jobs(const SurfacesCall& c, int num_threads)
 			run_job<C>(c, c.jobs[i]);
 		return;
 	}
-	// rayon par_iter over visible polygons (partial_renderer.rs:1822-1831): dynamic work distribution.
-	std::atomic<uint32_t> next{0};
-	std::vector<std::thread> threads;
-	for (int t = 0; t < num_threads; ++t)
-		threads.emplace_back([&]() {
-			for (;;)
-			{
-				uint32_t i = next.fetch_add(8);
-				if (i >= c.num_jobs)
-					break;
-				uint32_t e = std::min(i + 8, c.num_jobs);
-				for (; i < e; ++i)
-					run_job<C>(c, c.jobs[i]);
-			}
-		});
-	for (auto& t : threads)
-		t.join();
+	// rayon par_iter over visible polygons (partial_renderer.rs:1822-1831): dynamic work distribution over the persistent pool.
+	const uint32_t chunk = 8;
+	ThreadPool::instance().parallel_for((c.num_jobs + chunk - 1) / chunk, num_threads, [&](uint32_t t) {
+		const uint32_t e = std::min((t + 1) * chunk, c.num_jobs);
+		for (uint32_t i = t * chunk; i < e; ++i)
+			run_job<C>(c, c.jobs[i]);
+	});
 }
 
 } // namespace

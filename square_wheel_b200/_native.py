@@ -27,6 +27,7 @@ TEX_SURFACE, TEX_IMAGE, TEX_VIEW = 0, 1, 2
 STAGE_SURFACES, STAGE_RASTER, STAGE_POST, STAGE_SHADOW_MAPS, STAGE_ALL = 1, 2, 4, 8, 15
 DEPTH_MAP_CLEAR, DEPTH_MAP_PROJECTOR_CIRCLE = 1, 2
 CTX_CONCURRENT_VIEWS = 1
+CTX_FAST_SURFACE_NUMERICS = 2
 
 # ---- struct layouts as numpy dtypes (sizes asserted against the static_asserts in sqw_api.cu) ---------------
 surface_job_dtype = np.dtype(
@@ -193,6 +194,7 @@ CUDA_SYMBOLS = [
     ("sqw_profile_begin", C.c_int, [_VP]),
     ("sqw_profile_end", C.c_int, [_VP, C.POINTER(KernelTimes)]),
     ("sqw_self_test", C.c_int, [_VP]),
+    ("sqw_set_fast_surface_numerics", C.c_int, [_VP, C.c_int]),
 ]
 
 _cuda_lib = None

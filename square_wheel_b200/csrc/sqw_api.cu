@@ -164,6 +164,7 @@ struct sqw_ctx
 	cudaStream_t stream = nullptr;
 	bool own_stream = false;
 	bool concurrent_views = false; // SQW_CTX_CONCURRENT_VIEWS: every view issues its work on a private stream
+	bool fast_surface_numerics = false; // SQW_CTX_FAST_SURFACE_NUMERICS
 	size_t l2_persist_bytes = 0;   // > 0: the views' scratch blocks are marked L2-persisting on their streams (sqw_create)
 	cudaEvent_t batch_event = nullptr;
 	float* d_lightmaps = nullptr;
@@ -468,6 +469,7 @@ int sqw_create(sqw_ctx** out_ctx, int device, const sqw_map_desc* map, void* ext
 		ctx->own_stream = true;
 	}
 	ctx->concurrent_views = (map->flags & SQW_CTX_CONCURRENT_VIEWS) != 0;
+	ctx->fast_surface_numerics = (map->flags & SQW_CTX_FAST_SURFACE_NUMERICS) != 0;
 	{
 		// A view's scratch — surface pool, span table, tile lists — is written by one kernel of a frame and read by the next a moment
 		// later, while the other views in flight stream ~100 MB of pixels each through the 126 MB L2.  Marking the views' scratch
@@ -1377,7 +1379,7 @@ int sqw_frame_submit(sqw_frame* f, uint32_t stages)
 			l.num_bands = g.num_bands;
 			{
 				LaunchTimer timer(ctx, SQW_KERNEL_SURFACE_BUILD, s);
-				SQW_CUDA(ctx, launch_surface_build(view->color_bits == 64, g.dynamic_lights, l, s));
+				SQW_CUDA(ctx, (ctx->fast_surface_numerics ? launch_surface_build_fast : launch_surface_build)(view->color_bits == 64, g.dynamic_lights, l, s));
 			}
 			++launches;
 		}
@@ -1518,6 +1520,14 @@ int sqw_profile_begin(sqw_ctx* ctx)
 	}
 	ctx->timed.clear();
 	ctx->profiling = true;
+	return SQW_OK;
+}
+
+int sqw_set_fast_surface_numerics(sqw_ctx* ctx, int enable)
+{
+	if (!ctx)
+		return SQW_ERR_INVALID_ARGUMENT;
+	ctx->fast_surface_numerics = enable != 0;
 	return SQW_OK;
 }
 

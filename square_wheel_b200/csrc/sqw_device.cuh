@@ -74,10 +74,29 @@ __device__ __forceinline__ Fixed16 f32_to_fixed16_unchecked(float x) { return f3
 // ---- fast_math.rs portable branch ---------------------------------------------------------------------------
 #define SQW_MIN_POSITIVE_VALUE (1.0f / 1073741824.0f) /* fast_math.rs:744 */
 
+#if defined(SQW_NUMERICS_FAST) && SQW_NUMERICS_FAST
+// The numerics CLASS of the reference's release build (fast_math.rs:13-22 rcpss / rsqrtss, :729-733 fused multiply-add): MUFU.RCP /
+// MUFU.RSQ (1 ulp; rcpss / rsqrtss promise 1.5 * 2^-12) and FFMA.  Only the translation unit of the fast surface kernels
+// (surface_kernels_fast.cu, SQW_CTX_FAST_SURFACE_NUMERICS) is compiled this way.
+__device__ __forceinline__ float inv_sqrt_fast(float x)
+{
+	float r;
+	asm("rsqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+	return r;
+}
+__device__ __forceinline__ float inv_fast(float x)
+{
+	float r;
+	asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+	return r;
+}
+__device__ __forceinline__ float f32_mul_add(float x, float y, float z) { return __fmaf_rn(x, y, z); }
+#else
 // 1.0 / y correctly rounded IS the IEEE reciprocal: rcp.rn gives the same bits as div.rn(1, y) with a shorter sequence
 __device__ __forceinline__ float inv_sqrt_fast(float x) { return __frcp_rn(__fsqrt_rn(x)); } // :376
 __device__ __forceinline__ float inv_fast(float x) { return __frcp_rn(x); }                  // :381
 __device__ __forceinline__ float f32_mul_add(float x, float y, float z) { return __fadd_rn(__fmul_rn(x, y), z); } // :737
+#endif
 
 struct Vec3
 {

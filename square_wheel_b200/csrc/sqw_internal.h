@@ -57,6 +57,8 @@ struct SurfaceLaunch
 };
 // One grid for all bands of the launch; `dynamic_lights` selects the kernel built with the dynamic-light loop.
 cudaError_t launch_surface_build(bool color64, bool dynamic_lights, const SurfaceLaunch& l, cudaStream_t stream);
+// the same kernels built with hardware rcp / rsqrt and FMA (surface_kernels_fast.cu, SQW_CTX_FAST_SURFACE_NUMERICS)
+cudaError_t launch_surface_build_fast(bool color64, bool dynamic_lights, const SurfaceLaunch& l, cudaStream_t stream);
 
 cudaError_t launch_mix_texture(
 	bool color64, void* surface, uint32_t size_u, uint32_t size_v, const int32_t tc_min[2], const void* texture, uint32_t tex_w, uint32_t tex_h, int blending_mode,

@@ -561,7 +561,13 @@ cudaError_t launch_one(const SurfaceLaunch& l, cudaStream_t stream)
 
 } // namespace
 
+// This file is compiled twice: as is (portable numerics, bit-exact) and through surface_kernels_fast.cu with SQW_NUMERICS_FAST
+// (sqw_device.cuh), which exports the second entry point.
+#if defined(SQW_NUMERICS_FAST) && SQW_NUMERICS_FAST
+cudaError_t launch_surface_build_fast(bool color64, bool dynamic_lights, const SurfaceLaunch& l, cudaStream_t stream)
+#else
 cudaError_t launch_surface_build(bool color64, bool dynamic_lights, const SurfaceLaunch& l, cudaStream_t stream)
+#endif
 {
 	if (l.num_bands == 0)
 		return cudaSuccess;
@@ -570,6 +576,7 @@ cudaError_t launch_surface_build(bool color64, bool dynamic_lights, const Surfac
 	return dynamic_lights ? launch_one<Color32, true>(l, stream) : launch_one<Color32, false>(l, stream);
 }
 
+#if !(defined(SQW_NUMERICS_FAST) && SQW_NUMERICS_FAST)
 cudaError_t launch_mix_texture(
 	bool color64, void* surface, uint32_t size_u, uint32_t size_v, const int32_t tc_min[2], const void* texture, uint32_t tex_w, uint32_t tex_h, int blending_mode,
 	const float light[3], cudaStream_t stream)
@@ -597,5 +604,6 @@ cudaError_t launch_mix_texture(
 			static_cast<uint32_t*>(surface), size_u, size_v, tc_min[0], tc_min[1], static_cast<const uint32_t*>(texture), tex_w, tex_h, blending_mode, lb, lg, lr);
 	return cudaGetLastError();
 }
+#endif
 
 } // namespace sqw

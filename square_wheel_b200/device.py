@@ -25,7 +25,10 @@ def _as(a, dtype):
 class Context:
     """sqw_ctx: replaces the data-ownership half of Renderer::new (src/square_wheel/renderer.rs:24)."""
 
-    def __init__(self, lightmaps: Optional[np.ndarray], directional_lightmaps: Optional[np.ndarray], device: int = 0, stream: int = 0, max_images: int = 0, concurrent_views: bool = False):
+    def __init__(
+        self, lightmaps: Optional[np.ndarray], directional_lightmaps: Optional[np.ndarray], device: int = 0, stream: int = 0, max_images: int = 0, concurrent_views: bool = False,
+        fast_surface_numerics: bool = False,
+    ):
         self._lib = N.load_cuda_library()
         self._handle = C.c_void_p()
         lm = _as(lightmaps, np.float32)
@@ -37,7 +40,8 @@ class Context:
             if lm is not None and dlm.size != n:
                 raise ValueError("lightmap arrays must have the same element count")
             n = dlm.size
-        desc = N.MapDesc(N.ptr(lm), N.ptr(dlm), n, max_images, N.CTX_CONCURRENT_VIEWS if concurrent_views else 0)
+        flags = (N.CTX_CONCURRENT_VIEWS if concurrent_views else 0) | (N.CTX_FAST_SURFACE_NUMERICS if fast_surface_numerics else 0)
+        desc = N.MapDesc(N.ptr(lm), N.ptr(dlm), n, max_images, flags)
         rc = self._lib.sqw_create(C.byref(self._handle), device, C.byref(desc), C.c_void_p(stream) if stream else None)
         if rc != N.SQW_OK:
             raise SqwError(f"sqw_create failed ({rc}): {self._lib.sqw_last_error(None).decode()}")
@@ -80,6 +84,10 @@ class Context:
         kt = N.KernelTimes()
         self._check(self._lib.sqw_profile_end(self._handle, C.byref(kt)), "sqw_profile_end")
         return {name: (kt.ms[i], int(kt.launches[i])) for i, name in enumerate(N.KERNEL_NAMES)}
+
+    def set_fast_surface_numerics(self, enable: bool):
+        """SQW_CTX_FAST_SURFACE_NUMERICS for the frames submitted from now on (sqw_set_fast_surface_numerics)."""
+        self._check(self._lib.sqw_set_fast_surface_numerics(self._handle, 1 if enable else 0), "sqw_set_fast_surface_numerics")
 
     def self_test(self):
         """Exhaustive device check of the arithmetic shortcuts of the kernels (sqw_self_test); raises SqwError on a mismatch."""

@@ -270,3 +270,72 @@ def test_depth_rasterizer_closed_forms(oracle_lib):
     assert np.allclose(row[16:], (np.arange(16, 32) + 0.5) / 64.0, rtol=1e-6)
     assert out[0, 0] == np.float32(1.0e24) and out[0, w - 1] == np.float32(1.0e24) and out[h - 1, 0] == np.float32(1.0e24)
     assert np.array_equal(out == np.float32(1.0e24), (out == np.float32(1.0e24))[:, ::-1])
+
+
+# ---- the second numerics mode: the branch of fast_math.rs the reference's release build runs (liboracle_sse.so) ----------------
+def test_sse_tonemapping_is_the_release_builds_formula(oracle_lib):
+    """numerics="sse": perform_tonemapping with the release build's operations (fast_math.rs:123-146, :208-213): ONE fused
+    multiply-add c * (1/255) + 1/(exposure * modulate), an IEEE division, min(255), cvtps2dq (round to nearest EVEN).  Checked
+    against that formula evaluated in numpy (products of a 16-bit integer and an f32 are exact in f64, so the f64 sum rounded to
+    f32 is the fused result up to a double rounding that random data does not hit more than a handful of times)."""
+    r = synth.rng(4321)
+    hdr = synth.make_hdr_image(r, 257, 63)
+    exposure, modulate = 0.7, (1.0, 0.9, 1.2)
+    p = make_post_params(exposure=exposure, color_modulate=modulate)
+    got, avg, _ = oracle_lib.postprocess(hdr, p, numerics="sse")
+    c = channels64(hdr)[..., :3].astype(np.float64)  # B, G, R
+    inv_scale = np.array([np.float32(1.0) / (np.float32(exposure) * np.float32(m)) for m in modulate[::-1]], np.float32)
+    den = (c * np.float64(np.float32(1.0) / np.float32(255.0)) + inv_scale.astype(np.float64)).astype(np.float32)
+    mapped = np.minimum((c.astype(np.float32) / den).astype(np.float32), np.float32(255.0))
+    want = np.rint(mapped.astype(np.float64)).astype(np.int64)  # rint = round half to even, like cvtps2dq
+    d = np.abs(channels32(got)[..., :3] - want)
+    assert d.max() <= 1 and (d != 0).mean() < 1e-4
+    assert (channels32(got)[..., 3] == 255).all()  # alpha lane: x / 0 -> inf or NaN -> min_ps(., 255) = 255
+    # the portable branch truncates instead: the two builds differ by at most one LSB of the picture
+    port, avg_p, _ = oracle_lib.postprocess(hdr, p)
+    assert np.abs(channels32(got)[..., :3] - channels32(port)[..., :3]).max() <= 1
+    np.testing.assert_allclose(avg, avg_p, rtol=1e-6)
+
+
+@pytest.mark.parametrize("directional", [False, True])
+def test_sse_surfaces_stay_within_the_spread_of_the_two_builds(oracle_lib, directional):
+    """What north_star's tolerance means in the reference's own terms: the release build (rcpss / rsqrtss with 1.5 * 2^-12 relative
+    error, FMA, rounding conversions) against the portable build on static surfaces — a few HDR units (255 = LDR white), a few
+    1e-3 relative on bright texels.  This is the bound the fast GPU surface kernels are tested against."""
+    a = Assets(seed=11, num_lightmap_elements=60000)
+    r = synth.rng(77 + directional)
+    jobs, total, need = synth.make_surface_jobs(r, 200, a.texture_ids, a.texture_flags, emissive_images=a.lite_ids, directional=directional, lights=0, max_size=96)
+    assert need <= len(a.lightmaps)
+    cam = np.array([10.0, 20.0, 30.0], np.float32)
+    p = channels64(oracle_lib.build_surfaces(64, jobs, None, None, cam, a.images, a.lightmaps, a.directional_lightmaps, total))[..., :3]
+    q = channels64(oracle_lib.build_surfaces(64, jobs, None, None, cam, a.images, a.lightmaps, a.directional_lightmaps, total, numerics="sse"))[..., :3]
+    d = np.abs(p - q)
+    assert d.max() <= 4
+    assert (d > 1).mean() < 0.05
+    big = p >= 1024
+    assert (d[big] <= 3e-3 * p[big]).all()
+    assert (p != q).mean() > 0.3  # and it IS a different build: most texels round differently
+
+
+def test_sse_average_blend_rounds_up(oracle_lib):
+    """BlendingMode::Average in the release build is pavgb / pavgw, (a + b + 1) >> 1 per channel (fast_math.rs:43-63); the
+    portable branch rounds down (color.rs:46-49).  One polygon over a constant background shows the difference."""
+    a = Assets(seed=5, num_lightmap_elements=16, tex_sizes=(16,))
+    W, H = 64, 32
+    tex = np.zeros((8, 8), np.uint64)
+    tex[:] = (np.uint64(255) << np.uint64(48)) | (np.uint64(7) << np.uint64(32)) | (np.uint64(4) << np.uint64(16)) | np.uint64(1)
+    images = list(a.images) + [(N.IMAGE_COLOR64, tex)]
+    cmds = np.zeros(1, N.draw_cmd_dtype)
+    cmds[0]["kind"], cmds[0]["blend"], cmds[0]["tc_mode"], cmds[0]["num_vertices"] = N.CMD_POLYGON, N.BLEND_AVERAGE, N.TC_AFFINE, 4
+    cmds[0]["tex_size"], cmds[0]["tex_kind"], cmds[0]["tex_ref"] = (8, 8), N.TEX_IMAGE, len(images) - 1
+    cmds[0]["depth_eq"] = (0.0, 0.0, 1.0)
+    cmds[0]["tc_eq"] = (0.1, 0.0, 0.0, 0.1, 0.0, 0.0)
+    pts = np.array([(0, 0), (W << 16, 0), (W << 16, H << 16), (0, H << 16)], N.polygon_point_dtype)
+    bg = (np.uint64(9) << np.uint64(32)) | (np.uint64(2) << np.uint64(16)) | np.uint64(4)
+    out = {}
+    for mode in ("portable", "sse"):
+        fb = np.full((H, W), bg, np.uint64)
+        oracle_lib.draw(64, fb, cmds, pts, None, None, images, numerics=mode)
+        out[mode] = channels64(fb)[H // 2, W // 2, :3].tolist()
+    assert out["portable"] == [(1 + 4) // 2, (4 + 2) // 2, (7 + 9) // 2]
+    assert out["sse"] == [(1 + 4 + 1) // 2, (4 + 2 + 1) // 2, (7 + 9 + 1) // 2]

@@ -213,3 +213,52 @@ def test_view_reshape_keeps_bloom_inside_its_buffers(assets, oracle_lib):
         assert_pixels_equal(got, want, "bloom on a reshaped view")
     finally:
         view.close()
+
+
+def _channels64(x):
+    return np.stack([(x >> np.uint64(s)) & np.uint64(0xFFFF) for s in (0, 16, 32)], -1).astype(np.int64)
+
+
+@pytest.mark.parametrize("directional", [False, True])
+@pytest.mark.parametrize("with_lights", [False, True])
+def test_fast_surface_numerics_within_the_reference_builds_spread(assets, oracle_lib, directional, with_lights):
+    """SQW_CTX_FAST_SURFACE_NUMERICS: hardware reciprocal / reciprocal square root and fused multiply-add, the numerics CLASS of
+    the reference's release build (fast_math.rs:6-368).  The tolerance is north_star's, made concrete by the reference itself:
+    its two builds (oracle numerics "portable" = fast_math.rs:370-725 and "sse" = :6-368, rcpss / rsqrtss / FMA / cvtps2dq)
+    differ from each other by up to 3 HDR units (255 = LDR white) and 2e-3 relative on static surfaces, more where an
+    approximate reciprocal flips a shadow-map comparison.  The fast kernels must stay within
+
+        |gpu - portable| <= 2 units or 1e-3 relative           for every channel of surfaces without dynamic lights,
+        the same for all but 1e-3 of the channels               with dynamic lights (shadow-map comparisons flip in both builds too),
+
+    and must be no further from the SSE build than the portable build is.  Every variant (normal map x specular kind x lightmap
+    scale x emissive) appears in the job list."""
+    from square_wheel_b200.device import Context
+
+    r = synth.rng(900 + 7 * directional + 13 * with_lights)
+    ctx = Context(assets.lightmaps, assets.directional_lightmaps, device=0, fast_surface_numerics=True)
+    try:
+        for i, (kind, px) in enumerate(assets.images):
+            assert ctx.upload_image(kind, px) == i
+        lights, sm = synth.make_lights(r, 9) if with_lights else (np.zeros(0, N.light_dtype), np.zeros(0, np.float32))
+        jobs, total, _ = synth.make_surface_jobs(
+            r, 200, assets.texture_ids, assets.texture_flags, emissive_images=assets.lite_ids, directional=directional, lights=len(lights), max_size=96
+        )
+        cam = r.uniform(-300, 300, 3).astype(np.float32)
+        view = ctx.create_view(64, 64, 64)
+        view.build_surfaces(jobs, lights, sm, cam, total)
+        got = _channels64(view.read_surfaces(0, total))
+        view.close()
+    finally:
+        ctx.close()
+    portable = _channels64(oracle_lib.build_surfaces(64, jobs, lights, sm, cam, assets.images, assets.lightmaps, assets.directional_lightmaps, total))
+    sse = _channels64(oracle_lib.build_surfaces(64, jobs, lights, sm, cam, assets.images, assets.lightmaps, assets.directional_lightmaps, total, numerics="sse"))
+    d = np.abs(got - portable)
+    ok = (d <= 2) | (d <= 1e-3 * portable)
+    bad = 1.0 - ok.mean()
+    assert bad <= (1e-3 if with_lights else 0.0), f"{bad:.2e} of the channels outside 2 units / 1e-3 (max {d.max()})"
+    assert (d == 0).mean() > 0.9  # and most texels are simply equal: only rcp / rsqrt / FMA roundings differ
+    # distance to the release-build restatement: not worse than the portable build's own distance to it
+    d_sse, d_ref = np.abs(got - sse), np.abs(portable - sse)
+    assert d_sse.mean() <= d_ref.mean() * 1.05 + 1e-3
+    assert (d_sse > 3).mean() <= (d_ref > 3).mean() + (1e-3 if with_lights else 1e-5)
