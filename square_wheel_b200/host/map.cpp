@@ -81,7 +81,9 @@ float value_noise(Pcg32&, const std::vector<float>& lattice, uint32_t cells, flo
 	return (a * (1 - tx) + b * tx) * (1 - ty) + (c * (1 - tx) + d * tx) * ty;
 }
 
-void make_world_texture(Pcg32& rng, uint32_t size, bool normal_map, bool roughness_map, float base_roughness, HostImage& out)
+// alpha_mode: 0 opaque; 1 smooth translucency (noise, 48..208: alpha_blend / stained_glass of demo_materials.json); 2 a grid of
+// holes (alpha 0 inside the tiles, 255 on the bars: alpha_grid)
+void make_world_texture(Pcg32& rng, uint32_t size, bool normal_map, bool roughness_map, float base_roughness, HostImage& out, int alpha_mode = 0)
 {
 	out.kind = SQW_IMAGE_TEXTURE_ELEMENT;
 	out.width = out.height = size;
@@ -114,7 +116,12 @@ void make_world_texture(Pcg32& rng, uint32_t size, bool normal_map, bool roughne
 				float val = (base[c] + tint[c] * (n - 0.5f) * 2.0f) * (0.55f + 0.45f * g) * (0.75f + 0.5f * n);
 				rgb[c] = (uint32_t)std::fmin(std::fmax(val * 255.0f, 0.0f), 255.0f);
 			}
-			px[x + (size_t)y * size].diffuse = 0xFF000000u | (rgb[0] << 16) | (rgb[1] << 8) | rgb[2];
+			uint32_t alpha = 255;
+			if (alpha_mode == 1)
+				alpha = (uint32_t)std::fmin(std::fmax(48.0f + 160.0f * n, 0.0f), 255.0f);
+			else if (alpha_mode == 2)
+				alpha = edge < 4.0f * groove ? 255u : 0u;
+			px[x + (size_t)y * size].diffuse = (alpha << 24) | (rgb[0] << 16) | (rgb[1] << 8) | rgb[2];
 		}
 	const float bump = rng.uniform(1.5f, 5.0f);
 	for (uint32_t y = 0; y < size; ++y)
@@ -712,16 +719,30 @@ struct Builder
 		for (uint32_t mi = 0; mi < s.params.num_materials; ++mi)
 		{
 			Material& mat = s.materials[mi];
-			if (s.params.material_mode == 0)
+			if (s.params.material_mode == 0 || s.params.material_mode == 2)
 			{
 				// demo_materials.json: everything has a normal map; roughness < 1 for most; a quarter are metals
 				mat.has_normal_map = true;
 				mat.has_non_one_roughness = (mi % 4) != 3;
 				mat.is_metal = (mi % 4) == 1;
 			}
+			int alpha_mode = 0;
+			if (s.params.material_mode == 2)
+			{
+				// BASELINE configs[3]: a third of the world materials are translucent or alpha-tested like alpha_blend / alpha_grid /
+				// stained_glass of demo_materials.json (material.rs:101-116); they neither cast shadows nor hide what lies behind
+				switch (mi % 12)
+				{
+				case 2: mat.blending_mode = SQW_BLEND_ALPHA_BLEND; alpha_mode = 1; break;
+				case 5: mat.blending_mode = SQW_BLEND_ALPHA_TEST; alpha_mode = 2; break;
+				case 8: mat.blending_mode = SQW_BLEND_AVERAGE; break;
+				case 11: mat.blending_mode = SQW_BLEND_ADDITIVE; break;
+				default: break;
+				}
+			}
 			const float base_roughness = mat.has_non_one_roughness ? rng.uniform(0.15f, 0.7f) : 1.0f;
 			HostImage mips[NUM_MIPS];
-			make_world_texture(rng, size, mat.has_normal_map, mat.has_non_one_roughness, base_roughness, mips[0]);
+			make_world_texture(rng, size, mat.has_normal_map, mat.has_non_one_roughness, base_roughness, mips[0], alpha_mode);
 			for (uint32_t k = 1; k < NUM_MIPS; ++k)
 				build_texture_mip(mips[k], mips[k - 1]);
 			for (uint32_t k = 0; k < NUM_MIPS; ++k)

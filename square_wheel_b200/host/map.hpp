@@ -163,7 +163,7 @@ struct SceneParams
 	uint32_t num_materials = 16;
 	uint32_t texture_size_log2 = 8; // 256 x 256 world textures (demo/export_textures.py:27)
 	float max_polygon_size = 128.0f; // split so that a lightmap stays <= 17 texels per side (bsp_builder.rs:1282)
-	uint32_t material_mode = 0;      // 0: mix per demo_materials.json (normal map + dielectric/metal specular), 1: plain (no normal map, roughness 1)
+	uint32_t material_mode = 0;      // 0: mix per demo_materials.json (normal map + dielectric/metal specular), 1: plain (no normal map, roughness 1), 2: as 0 plus translucent / alpha-tested / average / additive materials
 	float emissive_fraction = 0.15f;
 	uint32_t num_submodels = 0;    // inline models (crates beside the camera path), each a one-node submodel BSP of 6+ lit polygons
 	uint32_t light_grid = 0;       // 1: generate a light grid (64-unit cells over the map) for model / sprite lighting

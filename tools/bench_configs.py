@@ -61,6 +61,75 @@ def models_for(scene_mod, sc, pose, k, n):
     return m
 
 
+def portals_for(scene_mod, N, pose, num_skins):
+    """BASELINE configs[3]: 2 mirrors + 1 camera portal + 1 parallax portal on a wall ahead of the camera (the fixture of the parity
+    tests plus a second mirror above the first)."""
+    from common import wall_portals
+
+    p3 = wall_portals(scene_mod, N, pose, overlay_skin=0)
+    p = np.zeros(4, scene_mod.portal_dtype)
+    p[:3] = p3
+    p[3] = p3[0]
+    up = np.array([0.0, 0.0, 56.0], np.float32)
+    p[3]["vertices"][:4] += up
+    p[3]["plane"][3] += float(np.dot(p3[0]["plane"][:3], up))
+    p[3]["tex_coord_equation"][1][3] -= float(np.dot(p3[0]["tex_coord_equation"][1][:3], up))
+    p[3]["has_texture"] = 0
+    return p
+
+
+class FrameTree:
+    """A recorded frame with its nested portal / mirror frames (build_view_portals_textures, partial_renderer.rs:2008-2282): every
+    visible portal owns a render target; submit() replays nested frames first (depth-first), mixes the glass overlays in and then
+    submits the frame that samples them.  Nothing synchronises with the host."""
+
+    def __init__(self, ctx, view, hf, color_bits, clear_color, post, S, N):
+        self.view, self.N = view, N
+        self.children = []  # (FrameTree of the nested view, overlay or None, tc_min)
+        self.owned_views = []
+        for node in hf.portals:
+            w, h = node.resolution
+            v = ctx.create_view(w, h, color_bits)
+            self.owned_views.append(v)
+            if node.frame is None:
+                child = None  # past the depth limit: black
+            else:
+                cc = (S.BACKGROUND_COLOR64 if color_bits == 64 else S.BACKGROUND_COLOR32) if node.frame.needs_clear else 0
+                child = FrameTree(ctx, v, node.frame, color_bits, cc, None, S, N)
+            self.children.append((child, v, node.overlay, node.tc_min))
+            sel = (hf.cmds["tex_kind"] == N.TEX_VIEW) & (hf.cmds["kind"] == N.CMD_POLYGON) & (hf.cmds["tex_ref"] == node.index)
+            hf.cmds["tex_ref"][sel] = v.index
+        self.frame = view.create_frame()
+        hf.record(self.frame, clear_color=clear_color, post=post)
+        self.empty = np.zeros(0, N.draw_cmd_dtype)
+
+    def submit(self, stages):
+        N = self.N
+        for child, v, overlay, tc_min in self.children:
+            if child is None:
+                v.draw(self.empty, None, None, clear_color=0)
+            else:
+                child.submit(N.STAGE_SHADOW_MAPS | N.STAGE_SURFACES | N.STAGE_RASTER)
+            if overlay is not None:
+                image, blend, light = overlay
+                v.mix_texture(image, tc_min, blend, light)
+        self.frame.submit(stages)
+
+    def stats(self):
+        return self.frame.stats()
+
+    def num_nested(self):
+        return sum(1 + (c.num_nested() if c is not None else 0) for c, _, _, _ in self.children)
+
+    def close(self):
+        for child, v, _, _ in self.children:
+            if child is not None:
+                child.close()
+        self.frame.close()
+        for v in self.owned_views:
+            v.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=32)
@@ -84,11 +153,18 @@ def main():
     base_scene = dict(seed=2, grid=(24, 24, 5), cell_size=(160.0, 160.0, 128.0), num_rooms=26, num_materials=24, texture_size_log2=8, max_polygon_size=64.0, material_mode=0, emissive_fraction=0.15)
     configs = {
         "configs[0] 1280x720 simple lightmaps LDR": dict(scene=base_scene, size=(1280, 720), bits=32, directional=False, post=None),
-        "configs[2] stress 4K HDR: fine polygons, mip bias -1, 16 lights, 16 models": dict(
-            scene=dict(base_scene, max_polygon_size=20.0, num_models=6, model_detail=27), size=(3840, 2160), bits=64, directional=True, post=dict(), mip_bias=-1.0, lights=16, models=16
+        # ~20k visible polygons per frame on average (7.5-unit polygons: 0.75 M polygons in the map), mip bias -1 => mip 0
+        "configs[2] stress 4K HDR: ~20k visible polygons, mip bias -1, 16 lights, 16 models": dict(
+            scene=dict(base_scene, max_polygon_size=7.5, num_models=6, model_detail=27), size=(3840, 2160), bits=64, directional=True, post=dict(), mip_bias=-1.0, lights=16, models=16
         ),
-        "configs[3] sky + decals + sprites + blended models, 4K HDR + bloom": dict(
-            scene=dict(base_scene, skybox=1, sky_size_log2=9, num_models=6, model_detail=12), size=(3840, 2160), bits=64, directional=True, post=dict(bloom_sigma=1.0), models=6, sprites=32, decals=32,
+        # translucent / alpha-tested / average / additive WORLD materials (material_mode 2), 32 decals, 32 sprites, sky box (6 x 512^2),
+        # 2 mirrors + camera portal + parallax portal at portals_depth 2, blended models, 4K HDR (variant with the default bloom below)
+        "configs[3] translucent + alpha-tested world, decals, sprites, sky, portals + mirrors (depth 2), 4K HDR + tonemap": dict(
+            scene=dict(base_scene, material_mode=2, skybox=1, sky_size_log2=9, num_models=6, model_detail=12), size=(3840, 2160), bits=64, directional=True, post=dict(), models=6, sprites=32, decals=32,
+            look_up=0.35, portals=True, portals_depth=2,
+        ),
+        "configs[3] same without portals, with the default bloom": dict(
+            scene=dict(base_scene, material_mode=2, skybox=1, sky_size_log2=9, num_models=6, model_detail=12), size=(3840, 2160), bits=64, directional=True, post=dict(bloom_sigma=1.0), models=6, sprites=32, decals=32,
             look_up=0.35,
         ),
         "configs[4] view-batch unit: 1920x1080 HDR + tonemap": dict(scene=base_scene, size=(1920, 1080), bits=64, directional=True, post=dict()),
@@ -100,7 +176,7 @@ def main():
         W, H = cfg["size"]
         C = cfg["bits"] // 8
         sc = S.Scene(**cfg["scene"])
-        hr = S.HostRenderer(sc, use_directional_lightmaps=cfg["directional"], textures_mip_bias=cfg.get("mip_bias", 0.0))
+        hr = S.HostRenderer(sc, use_directional_lightmaps=cfg["directional"], textures_mip_bias=cfg.get("mip_bias", 0.0), portals_depth=cfg.get("portals_depth", 1))
         path = sc.camera_path(64)
         frames = []
         for i in range(args.frames):
@@ -116,6 +192,8 @@ def main():
                 kw["sprites"] = sprites_ahead_of_camera(S, pose, cfg["sprites"], num_skins=int(sc.info.num_models))
             if cfg.get("decals"):
                 kw["decals"] = scatter_decals(S, pose, cfg["decals"], k, num_skins=int(sc.info.num_models))
+            if cfg.get("portals"):
+                kw["portals"] = portals_for(S, N, pose, int(sc.info.num_models))
             frames.append(hr.build_frame(W, H, pose, color_bits=cfg["bits"], **kw))
         hr.close()
         ctx = Context(sc.lightmaps, sc.directional_lightmaps, device=0, stream=stream.cuda_stream, concurrent_views=True)
@@ -124,12 +202,10 @@ def main():
         post = make_post_params(exposure=1.0, **cfg["post"]) if cfg["post"] is not None else None
         recorded = []
         for i, hf in enumerate(frames):
-            f = views[i % 4].create_frame()
             clear = None
             if hf.needs_clear:
                 clear = S.BACKGROUND_COLOR64 if cfg["bits"] == 64 else S.BACKGROUND_COLOR32
-            hf.record(f, clear_color=clear, post=post)
-            recorded.append(f)
+            recorded.append(FrameTree(ctx, views[i % 4], hf, cfg["bits"], clear, post, S, N))
         for v in views:
             v.synchronize()
 
@@ -138,7 +214,7 @@ def main():
             for f in recorded:
                 f.submit(N.STAGE_ALL)
                 if serial:
-                    f.view.synchronize()
+                    torch.cuda.synchronize()
             ctx.batch_end()
 
         for _ in range(3):
@@ -161,7 +237,7 @@ def main():
         L = sum(s.lightmap_bytes for s in st) / len(st)
         P = W * H
         b1 = S_tex * (8 + C) + Se * (4 + 2 * C) + L
-        b2 = 2 * P * C + (4 * P if post is not None and not cfg["post"].get("bloom_sigma") else 0)
+        b2 = P * C + S_tex * C + (4 * P if post is not None and not cfg["post"].get("bloom_sigma") else 0)  # P C + S C (+ the picture when tonemapping is fused)
         kernels = {k: {"us_per_frame": v[0] * 1e3 / len(recorded), "launches_per_frame": v[1] / len(recorded)} for k, v in kt.items() if v[1]}
         for kname, b in (("surface_build", b1), ("raster_tile", b2), ("raster_tile_tonemap", b2)):
             if kname in kernels:
@@ -175,6 +251,8 @@ def main():
             "surface_jobs_per_frame": float(np.mean([len(hf.jobs) for hf in frames])),
             "spans_per_frame": float(np.mean([s.num_spans for s in st])),
             "map_polygons": int(sc.info.num_polygons),
+            "nested_portal_views_per_frame": float(np.mean([f.num_nested() for f in recorded])),
+            "blended_world_commands_per_frame": float(np.mean([((hf.cmds["kind"] == N.CMD_POLYGON) & (hf.cmds["blend"] != 0)).sum() for hf in frames])),
             "kernels": kernels,
         }
         results[name] = res
