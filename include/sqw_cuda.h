@@ -410,7 +410,8 @@ int sqw_frame_get_stats(const sqw_frame* frame, sqw_frame_stats* out);
 #define SQW_KERNEL_MIX_TEXTURE 9
 #define SQW_KERNEL_DEPTH_SETUP 10
 #define SQW_KERNEL_DEPTH_RESOLVE 11
-#define SQW_NUM_KERNEL_KINDS 12
+#define SQW_KERNEL_MODELS_PREPARE 12 /* model_bones + model_vertices + model_triangles kernels of one sqw_models_prepare */
+#define SQW_NUM_KERNEL_KINDS 13
 typedef struct sqw_kernel_times
 {
 	double ms[SQW_NUM_KERNEL_KINDS];
@@ -423,6 +424,60 @@ int sqw_profile_end(sqw_ctx* ctx, sqw_kernel_times* out);
  * `2^31 / (inv_z >> 8)` of the full-perspective pixel loop (rasterizer.rs:430) with the plain u32 division for every
  * divisor below 2^24, and 2^26 hashed + edge-case operand pairs of the double-precision-assisted fixed16_div (fixed_math.rs:56)
  * against the plain 64-bit division.  SQW_OK, or SQW_ERR_CUDA with the mismatch count in sqw_last_error(). */
+/* ---- triangle-model preparation on the GPU ----------------------------------------------------------
+ * Replaces the body of PartialRenderer::build_dynamic_models_buffers (partial_renderer.rs:1122-1190): per visible mesh,
+ * animate_and_transform_triangle_mesh_vertices (triangle_models_rendering.rs:7-203), reject_triangle_model_back_faces (:327-345)
+ * and sort_model_triangles (:347-364).  Meshes are uploaded once (S0); per frame the host hands one sqw_model_instance per
+ * visible mesh (matrices, animation point, light cube: per-MODEL scalar work that stays on the host). */
+#define SQW_MESH_NON_ANIMATED 0      /* VertexData::NonAnimated      (triangle_model.rs:66) */
+#define SQW_MESH_VERTEX_ANIMATED 1   /* VertexData::VertexAnimated   (MD3) */
+#define SQW_MESH_SKELETON_ANIMATED 2 /* VertexData::SkeletonAnimated (IQM) */
+typedef struct sqw_model_mesh
+{
+	uint32_t kind; /* SQW_MESH_* */
+	uint32_t num_vertices, num_triangles, num_frames, num_bones;
+	uint32_t reserved;
+	/* NON_ANIMATED: [num_vertices] x {position[3], normal[3], tex_coord[2]} f32 (VertexNonAnimated);
+	 * VERTEX_ANIMATED: [num_frames][num_vertices] x {position[3], normal[3]} f32 (VertexAnimatedVertexVariable);
+	 * SKELETON_ANIMATED: [num_vertices] x {tex_coord[2], position[3], normal[3] f32, bone_index[4], weight[4] u8} = 40 bytes */
+	const void* vertices;
+	const float* tex_coords;      /* VERTEX_ANIMATED: [num_vertices][2] (VertexAnimatedVertexConstant), else NULL */
+	const uint16_t* triangles;    /* [num_triangles][3] */
+	const uint32_t* bone_parents; /* SKELETON_ANIMATED: [num_bones], >= num_bones = no parent; bones sorted in hierarchy order */
+	const float* frame_bones;     /* SKELETON_ANIMATED: [num_frames][num_bones][16] column-major 4x4, or NULL (no animation) */
+} sqw_model_mesh;
+typedef struct sqw_model_instance
+{
+	uint32_t mesh;      /* id returned by sqw_upload_model_mesh */
+	uint32_t frames[2]; /* AnimationPoint (frame_info.rs:71-77) */
+	float lerp;
+	float model_matrix[16];      /* column-major */
+	float model_view_matrix[16]; /* VisibleDynamicMeshInfo::camera_matrices.view_matrix */
+	float tc_scale[2];           /* size of the texture mip chosen for the model */
+	float tc_shift[2];           /* TriangleModel::tc_shift */
+	float light_cube[6][3];      /* ModelLightData (triangle_models_rendering.rs:684-699) */
+	float light_vector_scaled[2][3];
+	float light_color[2][3];
+	uint32_t vertex_offset;   /* first output vertex (in vertices) */
+	uint32_t triangle_offset; /* first output triangle; the instance owns num_triangles slots of its mesh */
+	uint32_t bone_offset;     /* filled by the library */
+	uint32_t sort_offset;     /* filled by the library */
+} sqw_model_instance;
+typedef struct sqw_model_vertex /* ModelVertex3d (renderer_structs.rs:311-318) */
+{
+	float pos[3];
+	float tc[2];
+	float light[3];
+} sqw_model_vertex;
+/* Upload one mesh; returns its id (>= 0) or an error.  The library copies. */
+int sqw_upload_model_mesh(sqw_ctx* ctx, const sqw_model_mesh* mesh);
+/* Prepare every instance on the view's stream: transformed, lit vertices at vertex_offset, front-facing triangles sorted back to
+ * front (largest z first; equal keys keep the mesh order) at triangle_offset, their count per instance. */
+int sqw_models_prepare(sqw_view* view, const sqw_model_instance* instances, uint32_t num_instances);
+/* Read the results of the last sqw_models_prepare back (parity tests; a host that still clips and emits the triangles itself).
+ * Any pointer may be NULL.  counts: [num_instances]. */
+int sqw_models_read(sqw_view* view, sqw_model_vertex* vertices, uint64_t num_vertices, uint16_t* triangles, uint64_t num_triangles, uint32_t* counts, uint32_t num_instances);
+
 int sqw_self_test(sqw_ctx* ctx);
 
 /* Switch SQW_CTX_FAST_SURFACE_NUMERICS on or off for frames submitted from now on (the flag of sqw_create is the initial

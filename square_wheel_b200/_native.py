@@ -112,6 +112,25 @@ depth_cmd_dtype = np.dtype([("num_vertices", "<u4"), ("vertex_offset", "<u4"), (
 assert depth_cmd_dtype.itemsize == 32
 
 
+class ModelMesh(C.Structure):  # sqw_model_mesh
+    _fields_ = [
+        ("kind", C.c_uint32), ("num_vertices", C.c_uint32), ("num_triangles", C.c_uint32), ("num_frames", C.c_uint32), ("num_bones", C.c_uint32), ("reserved", C.c_uint32),
+        ("vertices", C.c_void_p), ("tex_coords", C.c_void_p), ("triangles", C.c_void_p), ("bone_parents", C.c_void_p), ("frame_bones", C.c_void_p),
+    ]
+
+
+MESH_NON_ANIMATED, MESH_VERTEX_ANIMATED, MESH_SKELETON_ANIMATED = 0, 1, 2
+model_instance_dtype = np.dtype(
+    [
+        ("mesh", "<u4"), ("frames", "<u4", 2), ("lerp", "<f4"), ("model_matrix", "<f4", 16), ("model_view_matrix", "<f4", 16), ("tc_scale", "<f4", 2), ("tc_shift", "<f4", 2),
+        ("light_cube", "<f4", (6, 3)), ("light_vector_scaled", "<f4", (2, 3)), ("light_color", "<f4", (2, 3)),
+        ("vertex_offset", "<u4"), ("triangle_offset", "<u4"), ("bone_offset", "<u4"), ("sort_offset", "<u4"),
+    ]
+)
+assert model_instance_dtype.itemsize == 296
+model_vertex_dtype = np.dtype([("pos", "<f4", 3), ("tc", "<f4", 2), ("light", "<f4", 3)])
+
+
 class MapDesc(C.Structure):
     _fields_ = [
         ("lightmaps_data", C.c_void_p),
@@ -150,10 +169,10 @@ class FrameStats(C.Structure):
 
 
 class KernelTimes(C.Structure):
-    _fields_ = [("ms", C.c_double * 12), ("launches", C.c_uint64 * 12)]
+    _fields_ = [("ms", C.c_double * 13), ("launches", C.c_uint64 * 13)]
 
 
-KERNEL_NAMES = ["surface_build", "raster_setup", "raster_bin", "raster_tile", "tonemap", "bloom_downscale", "bloom_blur", "tonemap_bloom", "raster_tile_tonemap", "mix_texture", "depth_setup", "depth_resolve"]
+KERNEL_NAMES = ["surface_build", "raster_setup", "raster_bin", "raster_tile", "tonemap", "bloom_downscale", "bloom_blur", "tonemap_bloom", "raster_tile_tonemap", "mix_texture", "depth_setup", "depth_resolve", "models_prepare"]
 
 # Every symbol include/sqw_cuda.h declares: (name, restype, argtypes)
 _VP = C.c_void_p
@@ -195,6 +214,9 @@ CUDA_SYMBOLS = [
     ("sqw_profile_end", C.c_int, [_VP, C.POINTER(KernelTimes)]),
     ("sqw_self_test", C.c_int, [_VP]),
     ("sqw_set_fast_surface_numerics", C.c_int, [_VP, C.c_int]),
+    ("sqw_upload_model_mesh", C.c_int, [_VP, _VP]),
+    ("sqw_models_prepare", C.c_int, [_VP, _VP, C.c_uint32]),
+    ("sqw_models_read", C.c_int, [_VP, _VP, C.c_uint64, _VP, C.c_uint64, _VP, C.c_uint32]),
 ]
 
 _cuda_lib = None

@@ -18,6 +18,7 @@ static_assert(sizeof(sqw_light) == 80, "sqw_light layout");
 static_assert(sizeof(sqw_draw_cmd) == 64, "sqw_draw_cmd layout");
 static_assert(sizeof(sqw_polygon_point) == 8, "sqw_polygon_point layout");
 static_assert(sizeof(sqw_triangle_point) == 28, "sqw_triangle_point layout");
+static_assert(sizeof(sqw_model_instance) == 296 && sizeof(sqw_model_vertex) == 32, "sqw_model_instance / sqw_model_vertex layout");
 static_assert(sizeof(sqw_directional_lightmap_element) == 40, "sqw_directional_lightmap_element layout");
 static_assert(sizeof(sqw_post_params) == 32, "sqw_post_params layout");
 static_assert(sizeof(sqw_depth_map) == 32, "sqw_depth_map layout");
@@ -174,6 +175,11 @@ struct sqw_ctx
 	ImageDev* d_images = nullptr;
 	uint32_t max_images = 0;
 	std::vector<sqw_view*> views;
+	// triangle-model meshes (sqw_upload_model_mesh): host-side descriptors with DEVICE pointers + the device table
+	std::vector<sqw::ModelMeshDev> meshes;
+	std::vector<void*> mesh_allocations;
+	sqw::ModelMeshDev* d_meshes = nullptr;
+	size_t d_meshes_capacity = 0;
 	std::string last_error;
 	// per-kernel timing (sqw_profile_begin / _end)
 	bool profiling = false;
@@ -254,6 +260,10 @@ struct sqw_view
 	unsigned long long* d_sums = nullptr; // SQW_SUM_SLOTS x {B, G, R, pad}
 	uint64_t sums_divisor = 1;
 	sqw_frame* immediate = nullptr;
+	// results and scratch of sqw_models_prepare
+	DevBuf model_instances, model_vertices, model_triangles, model_counts, model_bones, model_sort;
+	uint32_t model_num_instances = 0;
+	uint64_t model_num_vertices = 0, model_num_triangles = 0;
 };
 
 struct SurfaceGroup // one kernel launch: all bands without / with dynamic lights
@@ -534,6 +544,10 @@ void sqw_destroy(sqw_ctx* ctx)
 			cudaFree(img.pixels);
 	if (ctx->d_images)
 		cudaFree(ctx->d_images);
+	for (void* p : ctx->mesh_allocations)
+		cudaFree(p);
+	if (ctx->d_meshes)
+		cudaFree(ctx->d_meshes);
 	if (ctx->d_lightmaps)
 		cudaFree(ctx->d_lightmaps);
 	if (ctx->d_directional_lightmaps)
@@ -691,6 +705,8 @@ void sqw_view_destroy(sqw_view* view)
 		cudaFree(view->d_sums);
 	if (view->d_tonemap_lut)
 		cudaFree(view->d_tonemap_lut);
+	for (DevBuf* b : {&view->model_instances, &view->model_vertices, &view->model_triangles, &view->model_counts, &view->model_bones, &view->model_sort})
+		b->release();
 	// keep indices of the other views stable: leave a hole
 	for (auto& p : ctx->views)
 		if (p == view)
@@ -1520,6 +1536,146 @@ int sqw_profile_begin(sqw_ctx* ctx)
 	}
 	ctx->timed.clear();
 	ctx->profiling = true;
+	return SQW_OK;
+}
+
+int sqw_upload_model_mesh(sqw_ctx* ctx, const sqw_model_mesh* mesh)
+{
+	if (!ctx || !mesh)
+		return SQW_ERR_INVALID_ARGUMENT;
+	if (mesh->kind > SQW_MESH_SKELETON_ANIMATED || mesh->num_vertices == 0 || mesh->num_vertices > 65536 || !mesh->vertices || (mesh->num_triangles && !mesh->triangles) ||
+		mesh->num_frames == 0 || (mesh->kind == SQW_MESH_VERTEX_ANIMATED && !mesh->tex_coords) ||
+		(mesh->kind == SQW_MESH_SKELETON_ANIMATED && mesh->frame_bones && (mesh->num_bones == 0 || !mesh->bone_parents)))
+		return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_upload_model_mesh: bad mesh description");
+	for (uint32_t i = 0; i < mesh->num_triangles * 3; ++i)
+		if (mesh->triangles[i] >= mesh->num_vertices)
+			return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_upload_model_mesh: triangle refers to a vertex outside the mesh");
+	SQW_CUDA(ctx, cudaSetDevice(ctx->device));
+	sqw::ModelMeshDev d{};
+	d.kind = mesh->kind;
+	d.num_vertices = mesh->num_vertices;
+	d.num_triangles = mesh->num_triangles;
+	d.num_frames = mesh->num_frames;
+	d.num_bones = mesh->kind == SQW_MESH_SKELETON_ANIMATED ? mesh->num_bones : 0;
+	auto upload = [&](const void* src, size_t bytes, const void** dst) -> cudaError_t {
+		*dst = nullptr;
+		if (!src || bytes == 0)
+			return cudaSuccess;
+		void* p = nullptr;
+		cudaError_t e = cudaMalloc(&p, bytes);
+		if (e != cudaSuccess)
+			return e;
+		ctx->mesh_allocations.push_back(p);
+		*dst = p;
+		return cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice);
+	};
+	const size_t nv = mesh->num_vertices;
+	const size_t vbytes = mesh->kind == SQW_MESH_NON_ANIMATED ? nv * 32 : (mesh->kind == SQW_MESH_VERTEX_ANIMATED ? (size_t)mesh->num_frames * nv * 24 : nv * 40);
+	SQW_CUDA(ctx, upload(mesh->vertices, vbytes, &d.vertices));
+	SQW_CUDA(ctx, upload(mesh->kind == SQW_MESH_VERTEX_ANIMATED ? mesh->tex_coords : nullptr, nv * 8, reinterpret_cast<const void**>(&d.tex_coords)));
+	SQW_CUDA(ctx, upload(mesh->triangles, (size_t)mesh->num_triangles * 6, reinterpret_cast<const void**>(&d.triangles)));
+	if (mesh->kind == SQW_MESH_SKELETON_ANIMATED && mesh->frame_bones)
+	{
+		SQW_CUDA(ctx, upload(mesh->bone_parents, (size_t)mesh->num_bones * 4, reinterpret_cast<const void**>(&d.bone_parents)));
+		SQW_CUDA(ctx, upload(mesh->frame_bones, (size_t)mesh->num_frames * mesh->num_bones * 64, reinterpret_cast<const void**>(&d.frame_bones)));
+	}
+	ctx->meshes.push_back(d);
+	// the device table is rebuilt (uploads happen at load time)
+	if (ctx->meshes.size() > ctx->d_meshes_capacity)
+	{
+		if (ctx->d_meshes)
+			cudaFree(ctx->d_meshes);
+		ctx->d_meshes_capacity = std::max<size_t>(64, ctx->meshes.size() * 2);
+		SQW_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_meshes), ctx->d_meshes_capacity * sizeof(sqw::ModelMeshDev)));
+	}
+	SQW_CUDA(ctx, cudaMemcpy(ctx->d_meshes, ctx->meshes.data(), ctx->meshes.size() * sizeof(sqw::ModelMeshDev), cudaMemcpyHostToDevice));
+	return (int)ctx->meshes.size() - 1;
+}
+
+int sqw_models_prepare(sqw_view* view, const sqw_model_instance* instances, uint32_t num_instances)
+{
+	if (!view || (num_instances && !instances))
+		return SQW_ERR_INVALID_ARGUMENT;
+	sqw_ctx* ctx = view->ctx;
+	SQW_CUDA(ctx, cudaSetDevice(ctx->device));
+	std::vector<sqw_model_instance> inst(instances, instances + num_instances);
+	uint64_t num_vertices = 0, num_triangles = 0, bones = 0, sort_slots = 0;
+	uint32_t max_vertices = 0, max_bones = 0;
+	for (sqw_model_instance& in : inst)
+	{
+		if (in.mesh >= ctx->meshes.size())
+			return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_models_prepare: unknown mesh");
+		const sqw::ModelMeshDev& m = ctx->meshes[in.mesh];
+		if (in.frames[0] >= m.num_frames || in.frames[1] >= m.num_frames)
+			return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_models_prepare: animation frame outside the mesh");
+		num_vertices = std::max<uint64_t>(num_vertices, (uint64_t)in.vertex_offset + m.num_vertices);
+		num_triangles = std::max<uint64_t>(num_triangles, (uint64_t)in.triangle_offset + m.num_triangles);
+		max_vertices = std::max(max_vertices, m.num_vertices);
+		in.bone_offset = (uint32_t)bones;
+		if (m.kind == SQW_MESH_SKELETON_ANIMATED && m.frame_bones)
+		{
+			bones += std::min<uint32_t>(m.num_bones, 255u);
+			max_bones = std::max(max_bones, m.num_bones);
+		}
+		uint32_t n = 1;
+		while (n < m.num_triangles)
+			n <<= 1;
+		in.sort_offset = (uint32_t)sort_slots;
+		sort_slots += n;
+	}
+	if (num_vertices > (1ull << 30) || num_triangles > (1ull << 30) || sort_slots > (1ull << 31))
+		return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_models_prepare: too many vertices / triangles");
+	cudaStream_t s = view->stream;
+	const size_t need[6] = {inst.size() * sizeof(sqw_model_instance) + 16, (size_t)num_vertices * 32 + 16, (size_t)num_triangles * 6 + 16, (size_t)num_instances * 4 + 16,
+							(size_t)bones * 25 * 4 + 16, (size_t)sort_slots * 8 + 16};
+	DevBuf* bufs[6] = {&view->model_instances, &view->model_vertices, &view->model_triangles, &view->model_counts, &view->model_bones, &view->model_sort};
+	for (int i = 0; i < 6; ++i)
+		if (need[i] > bufs[i]->capacity)
+		{
+			SQW_CUDA(ctx, cudaStreamSynchronize(s)); // growing frees the old buffer
+			SQW_CUDA(ctx, bufs[i]->reserve(need[i]));
+		}
+	view->model_num_instances = num_instances;
+	view->model_num_vertices = num_vertices;
+	view->model_num_triangles = num_triangles;
+	if (num_instances == 0)
+		return SQW_OK;
+	SQW_CUDA(ctx, cudaMemcpyAsync(view->model_instances.ptr, inst.data(), inst.size() * sizeof(sqw_model_instance), cudaMemcpyHostToDevice, s));
+	SQW_CUDA(ctx, cudaStreamSynchronize(s)); // `inst` is a local staging copy
+	sqw::ModelLaunch l{};
+	l.instances = static_cast<const sqw_model_instance*>(view->model_instances.ptr);
+	l.meshes = ctx->d_meshes;
+	l.num_instances = num_instances;
+	l.max_vertices = max_vertices;
+	l.max_bones = max_bones;
+	l.bone_scratch = static_cast<float*>(view->model_bones.ptr);
+	l.sort_scratch = static_cast<unsigned long long*>(view->model_sort.ptr);
+	l.vertices = static_cast<float*>(view->model_vertices.ptr);
+	l.triangles = static_cast<uint16_t*>(view->model_triangles.ptr);
+	l.counts = static_cast<uint32_t*>(view->model_counts.ptr);
+	{
+		LaunchTimer timer(ctx, SQW_KERNEL_MODELS_PREPARE, s);
+		SQW_CUDA(ctx, sqw::launch_models_prepare(l, s));
+	}
+	return SQW_OK;
+}
+
+int sqw_models_read(sqw_view* view, sqw_model_vertex* vertices, uint64_t num_vertices, uint16_t* triangles, uint64_t num_triangles, uint32_t* counts, uint32_t num_instances)
+{
+	if (!view)
+		return SQW_ERR_INVALID_ARGUMENT;
+	sqw_ctx* ctx = view->ctx;
+	if (num_vertices > view->model_num_vertices || num_triangles > view->model_num_triangles || num_instances > view->model_num_instances)
+		return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_models_read: more than the last sqw_models_prepare produced");
+	SQW_CUDA(ctx, cudaSetDevice(ctx->device));
+	cudaStream_t s = view->stream;
+	if (vertices && num_vertices)
+		SQW_CUDA(ctx, cudaMemcpyAsync(vertices, view->model_vertices.ptr, (size_t)num_vertices * 32, cudaMemcpyDeviceToHost, s));
+	if (triangles && num_triangles)
+		SQW_CUDA(ctx, cudaMemcpyAsync(triangles, view->model_triangles.ptr, (size_t)num_triangles * 6, cudaMemcpyDeviceToHost, s));
+	if (counts && num_instances)
+		SQW_CUDA(ctx, cudaMemcpyAsync(counts, view->model_counts.ptr, (size_t)num_instances * 4, cudaMemcpyDeviceToHost, s));
+	SQW_CUDA(ctx, cudaStreamSynchronize(s));
 	return SQW_OK;
 }
 

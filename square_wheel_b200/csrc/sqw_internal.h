@@ -163,6 +163,31 @@ cudaError_t launch_raster_tiles(const RasterLaunch& l, cudaStream_t stream);
 // exhaustive check of z_from_inv_z; *mismatches (device) must be zeroed by the caller
 cudaError_t launch_z_from_inv_z_test(unsigned long long* mismatches, cudaStream_t stream);
 
+// ---- triangle models (model_kernels.cu) -----------------------------------------------------------------------------
+struct ModelMeshDev // device copy of one sqw_model_mesh
+{
+	uint32_t kind, num_vertices, num_triangles, num_frames, num_bones, pad;
+	const void* vertices;
+	const float* tex_coords;
+	const uint16_t* triangles;
+	const uint32_t* bone_parents;
+	const float* frame_bones;
+};
+struct ModelLaunch
+{
+	const sqw_model_instance* instances; // device
+	const ModelMeshDev* meshes;          // device table
+	uint32_t num_instances;
+	uint32_t max_vertices; // largest mesh among the instances (grid size)
+	uint32_t max_bones;    // 0: no skeleton-animated instance
+	float* bone_scratch;   // 25 floats per (instance, bone)
+	unsigned long long* sort_scratch;
+	float* vertices;       // out: 8 floats per vertex
+	uint16_t* triangles;   // out
+	uint32_t* counts;      // out
+};
+cudaError_t launch_models_prepare(const ModelLaunch& l, cudaStream_t stream);
+
 // ---- shadow maps ----------------------------------------------------------------------------------------------
 struct DepthCmdDev // per fill call, prepared by sqw_frame_set_shadow_map_draw. 16 bytes
 {

@@ -85,6 +85,34 @@ class Context:
         self._check(self._lib.sqw_profile_end(self._handle, C.byref(kt)), "sqw_profile_end")
         return {name: (kt.ms[i], int(kt.launches[i])) for i, name in enumerate(N.KERNEL_NAMES)}
 
+    def upload_model_mesh(self, arrays: dict) -> int:
+        """One mesh of a triangle model as Scene.model_arrays() returns it (sqw_upload_model_mesh).  Returns the mesh id."""
+        tri = np.ascontiguousarray(arrays["triangles"], np.uint16)
+        m = N.ModelMesh()
+        keep = [tri]
+        if len(arrays["non_animated"]):
+            v = np.ascontiguousarray(arrays["non_animated"], np.float32)
+            m.kind, m.num_vertices, m.num_frames = N.MESH_NON_ANIMATED, len(v), 1
+        elif len(arrays["constant"]):
+            tc = np.ascontiguousarray(arrays["constant"], np.float32)
+            v = np.ascontiguousarray(arrays["variable"], np.float32)
+            m.kind, m.num_vertices, m.num_frames = N.MESH_VERTEX_ANIMATED, len(tc), len(v) // len(tc)
+            m.tex_coords = tc.ctypes.data
+            keep.append(tc)
+        else:
+            v = np.ascontiguousarray(arrays["skeleton"])
+            assert v.dtype.itemsize == 40
+            parents = np.ascontiguousarray(arrays["bone_parents"], np.uint32)
+            fb = np.ascontiguousarray(arrays["frame_bones"], np.float32)
+            m.kind, m.num_vertices, m.num_bones = N.MESH_SKELETON_ANIMATED, len(v), len(parents)
+            m.num_frames = max(len(fb) // max(len(parents), 1), 1) if len(fb) else 1
+            if len(fb):
+                m.bone_parents, m.frame_bones = parents.ctypes.data, fb.ctypes.data
+            keep += [parents, fb]
+        keep.append(v)
+        m.vertices, m.triangles, m.num_triangles = v.ctypes.data, tri.ctypes.data, len(tri)
+        return self._check(self._lib.sqw_upload_model_mesh(self._handle, C.byref(m)), "sqw_upload_model_mesh")
+
     def set_fast_surface_numerics(self, enable: bool):
         """SQW_CTX_FAST_SURFACE_NUMERICS for the frames submitted from now on (sqw_set_fast_surface_numerics)."""
         self._check(self._lib.sqw_set_fast_surface_numerics(self._handle, 1 if enable else 0), "sqw_set_fast_surface_numerics")
@@ -185,6 +213,19 @@ class View:
         out = np.empty(count, self.pixel_dtype)
         self.ctx._check(self._lib.sqw_read_surfaces(self._handle, N.ptr(out), offset, count), "sqw_read_surfaces")
         return out
+
+    def models_prepare(self, instances: np.ndarray):
+        """build_dynamic_models_buffers on the GPU (sqw_models_prepare): animation, transform, lighting, back-face rejection, sort."""
+        inst = _as(instances, N.model_instance_dtype)
+        self.ctx._check(self._lib.sqw_models_prepare(self._handle, N.ptr(inst), len(inst)), "sqw_models_prepare")
+
+    def models_read(self, num_vertices: int, num_triangles: int, num_instances: int):
+        """(vertices [model_vertex_dtype], triangles [n, 3] uint16, visible-triangle counts) of the last models_prepare."""
+        v = np.zeros(num_vertices, N.model_vertex_dtype)
+        t = np.zeros((num_triangles, 3), np.uint16)
+        c = np.zeros(num_instances, np.uint32)
+        self.ctx._check(self._lib.sqw_models_read(self._handle, N.ptr(v), num_vertices, N.ptr(t), num_triangles, N.ptr(c), num_instances), "sqw_models_read")
+        return v, t, c
 
     def average_color(self) -> np.ndarray:
         avg = np.zeros(3, np.float32)

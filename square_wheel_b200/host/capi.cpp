@@ -474,6 +474,34 @@ int sqwh_renderer_set_decals(Renderer* r, const Scene* s, const sqwh_decal* deca
 	return 0;
 }
 
+// build_dynamic_models_buffers of the frame prepared last: records (Renderer::DynamicMeshExport, 304 bytes), vertices (8 f32 each)
+// and sorted triangles (3 u16 each) of this mirror.  NULL buffers: only the counts are returned.
+int sqwh_renderer_dynamic_meshes(const Renderer* r, void* records, uint32_t capacity, float* vertices, uint64_t vertices_capacity, uint16_t* triangles, uint64_t triangles_capacity, uint64_t counts_out[3])
+{
+	if (!r)
+		return -1;
+	static_assert(sizeof(Renderer::DynamicMeshExport) == 304, "DynamicMeshExport layout");
+	const size_t n = r->export_dynamic_meshes(nullptr, 0);
+	(void)n;
+	std::vector<Renderer::DynamicMeshExport> all(4096);
+	const size_t count = r->export_dynamic_meshes(all.data(), all.size());
+	const auto& v = r->dynamic_meshes_vertices();
+	const auto& t = r->dynamic_meshes_triangles();
+	if (counts_out)
+	{
+		counts_out[0] = count;
+		counts_out[1] = v.size();
+		counts_out[2] = t.size();
+	}
+	if (records)
+		std::memcpy(records, all.data(), std::min<size_t>(count, capacity) * sizeof(Renderer::DynamicMeshExport));
+	if (vertices)
+		std::memcpy(vertices, v.data(), std::min<uint64_t>(v.size(), vertices_capacity) * sizeof(ModelVertex3d));
+	if (triangles)
+		std::memcpy(triangles, t.data(), std::min<uint64_t>(t.size(), triangles_capacity) * sizeof(Triangle));
+	return (int)count;
+}
+
 int sqwh_scene_model_info(const Scene* s, uint32_t index, sqwh_model_info* out)
 {
 	if (index >= s->models.size())

@@ -1826,6 +1826,47 @@ ModelLightData Renderer::get_model_light(const ModelEntity& model, const Mat4f& 
 	return ModelLightData::from_two_light_grid_elements(static_light, light_cube.convert_into_light_grid_sample());
 }
 
+size_t Renderer::export_dynamic_meshes(DynamicMeshExport* out, size_t capacity) const
+{
+	size_t n = 0;
+	for (const VisibleDynamicMeshInfo& vm : visible_dynamic_meshes_list_)
+	{
+		if (n >= capacity)
+			break;
+		const ModelEntity& model = frame_models_[vm.entity_index];
+		const TriangleModel& triangle_model = scene_.models[model.model];
+		const TriangleModelMesh& mesh = triangle_model.meshes[vm.mesh_index];
+		const HostImage& texture = scene_.images[model.texture_images[vm.mip]];
+		DynamicMeshExport& e = out[n++];
+		e.model = model.model;
+		e.mesh = vm.mesh_index;
+		e.frames[0] = model.frames[0];
+		e.frames[1] = model.frames[1];
+		e.lerp = model.lerp;
+		std::memcpy(e.model_matrix, &vm.model_matrix, 64);
+		std::memcpy(e.model_view_matrix, &vm.camera_matrices.view_matrix, 64);
+		e.tc_scale[0] = (float)texture.width;
+		e.tc_scale[1] = (float)texture.height;
+		e.tc_shift[0] = triangle_model.tc_shift.x;
+		e.tc_shift[1] = triangle_model.tc_shift.y;
+		const ModelLightData light = get_model_light(model, vm.model_matrix);
+		std::memcpy(e.light_cube, light.light_cube, sizeof(e.light_cube));
+		for (int d = 0; d < 2; ++d)
+		{
+			e.light_vector_scaled[d][0] = light.vector_scaled[d].x;
+			e.light_vector_scaled[d][1] = light.vector_scaled[d].y;
+			e.light_vector_scaled[d][2] = light.vector_scaled[d].z;
+			std::memcpy(e.light_color[d], light.color[d], 12);
+		}
+		e.vertices_offset = (uint32_t)vm.vertices_offset;
+		e.num_vertices = (uint32_t)mesh.num_vertices();
+		e.triangles_offset = (uint32_t)vm.triangles_offset;
+		e.num_triangles = (uint32_t)mesh.triangles.size();
+		e.num_visible_triangles = (uint32_t)vm.num_visible_triangles;
+	}
+	return n;
+}
+
 void Renderer::build_dynamic_models_buffers() // partial_renderer.rs:1122-1190
 {
 	// every mesh writes its own region of the vertex / triangle buffers: the reference runs this loop with rayon's par_iter_mut (:1181-1189)

@@ -185,6 +185,21 @@ public:
 	const std::vector<sqw_polygon_point>& depth_points() const { return depth_points_; }
 	uint64_t shadow_maps_len() const { return shadow_maps_len_; }
 	const RendererDebugStats& stats() const { return stats_; }
+	// Inputs and results of build_dynamic_models_buffers (partial_renderer.rs:1122-1190) for the frame prepared last, one record
+	// per visible mesh: what the GPU model-preparation kernels (csrc/model_kernels.cu, sqw_models_prepare) consume, and this
+	// mirror's own vertices / sorted triangles for the parity tests.
+	struct DynamicMeshExport
+	{
+		uint32_t model, mesh, frames[2];
+		float lerp;
+		float model_matrix[16], model_view_matrix[16]; // column-major
+		float tc_scale[2], tc_shift[2];
+		float light_cube[6][3], light_vector_scaled[2][3], light_color[2][3]; // ModelLightData
+		uint32_t vertices_offset, num_vertices, triangles_offset, num_triangles, num_visible_triangles;
+	};
+	size_t export_dynamic_meshes(DynamicMeshExport* out, size_t capacity) const;
+	const std::vector<ModelVertex3d>& dynamic_meshes_vertices() const { return dynamic_meshes_vertices_; }
+	const std::vector<Triangle>& dynamic_meshes_triangles() const { return dynamic_meshes_triangles_; }
 
 private:
 	// dynamic_objects_index.rs / partial_renderer.rs:398-590 / depth_renderer.rs

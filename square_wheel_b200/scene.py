@@ -37,6 +37,17 @@ class SceneParams(C.Structure):
     ]
 
 
+# Renderer::DynamicMeshExport (host/renderer.hpp)
+dynamic_mesh_dtype = np.dtype(
+    [
+        ("model", "<u4"), ("mesh", "<u4"), ("frames", "<u4", 2), ("lerp", "<f4"), ("model_matrix", "<f4", 16), ("model_view_matrix", "<f4", 16), ("tc_scale", "<f4", 2),
+        ("tc_shift", "<f4", 2), ("light_cube", "<f4", (6, 3)), ("light_vector_scaled", "<f4", (2, 3)), ("light_color", "<f4", (2, 3)),
+        ("vertices_offset", "<u4"), ("num_vertices", "<u4"), ("triangles_offset", "<u4"), ("num_triangles", "<u4"), ("num_visible_triangles", "<u4"),
+    ]
+)
+assert dynamic_mesh_dtype.itemsize == 304
+
+
 class SceneInfo(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("num_nodes", "num_leafs", "num_polygons", "num_portals", "num_vertices", "num_materials", "num_images", "num_waypoints")] + [
         ("num_lightmap_elements", C.c_uint64),
@@ -178,6 +189,8 @@ def lib() -> C.CDLL:
         l.sqwh_renderer_draw_frame.argtypes = [vp, C.c_int]
         l.sqwh_renderer_frame_info.argtypes = [vp, C.POINTER(FrameInfo)]
         l.sqwh_renderer_set_lights.argtypes = [vp, vp, C.c_uint32]
+        l.sqwh_renderer_dynamic_meshes.restype = C.c_int
+        l.sqwh_renderer_dynamic_meshes.argtypes = [vp, vp, C.c_uint32, vp, C.c_uint64, vp, C.c_uint64, C.POINTER(C.c_uint64)]
         l.sqwh_renderer_set_models.restype = C.c_int
         l.sqwh_renderer_set_models.argtypes = [vp, vp, vp, C.c_uint32]
         l.sqwh_renderer_set_submodel_entities.restype = C.c_int
@@ -453,6 +466,20 @@ class HostRenderer:
         return HostFrame(
             jobs, int(fi.total_surface_pixels), np.array(list(fi.cam_pos), np.float32), cmds, pts, bool(fi.needs_background_clear), fi, out_lights, dmaps, dcmds, dpts, int(fi.shadow_maps_len), tpts
         )
+
+    def dynamic_meshes(self):
+        """build_dynamic_models_buffers (partial_renderer.rs:1122-1190) of the frame built last: (records, vertices, triangles) —
+        one dynamic_mesh_dtype record per visible mesh with everything the GPU model-preparation kernels take as input
+        (sqw_model_instance fields) and this mirror's own results: lit camera-space vertices and sorted front-facing triangles."""
+        counts = (C.c_uint64 * 3)()
+        self._lib.sqwh_renderer_dynamic_meshes(self._handle, None, 0, None, 0, None, 0, counts)
+        rec = np.zeros(int(counts[0]), dynamic_mesh_dtype)
+        v = np.zeros(int(counts[1]), np.dtype([("pos", "<f4", 3), ("tc", "<f4", 2), ("light", "<f4", 3)]))
+        t = np.zeros((int(counts[2]), 3), np.uint16)
+        self._lib.sqwh_renderer_dynamic_meshes(
+            self._handle, rec.ctypes.data_as(C.c_void_p), len(rec), v.ctypes.data_as(C.c_void_p), len(v), t.ctypes.data_as(C.c_void_p), len(t), counts
+        )
+        return rec, v, t
 
     def default_submodel_entities(self) -> np.ndarray:
         """Every submodel present, at the place the map has it (position = bbox centre, identity rotation)."""

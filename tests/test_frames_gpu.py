@@ -474,3 +474,37 @@ def test_config3_portals_and_mirrors(oracle_lib, color_bits, portals_depth):
     finally:
         r.close()
         sc.close()
+
+
+@pytest.mark.parametrize("color_bits", [32, 64])
+def test_config3_translucent_and_alpha_tested_world_materials(oracle_lib, color_bits):
+    """configs[3], the world part: a third of the map's materials are alpha-blended, alpha-tested (a grid of holes), averaged or
+    additive (material.rs:101-116, demo_materials.json alpha_blend / alpha_grid / stained_glass), so the BSP walk interleaves
+    blended polygons with opaque ones: tiles of both classes (opaque-polygon kernel / general kernel) share every frame."""
+    W, H = 640, 360
+    sc = S.Scene(seed=5, texture_size_log2=6, num_materials=24, material_mode=2)
+    r = Renderer(sc, RendererConfig(use_directional_lightmaps=True))
+    try:
+        path = sc.camera_path(64)
+        blended = 0
+        # The reference clears the picture only when the camera is outside the map (partial_renderer.rs:253): inside it, a blended
+        # wall facing the void blends with what the PREVIOUS frame left in the buffer.  The oracle's buffer is carried from frame
+        # to frame the same way (both start from zeros).
+        fb = np.zeros((H, W), np.uint32 if color_bits == 32 else np.uint64)
+        for k in (2, 17, 33, 58):
+            hf = r.prepare_frame(SurfaceInfo(W, H), FrameInfo(path[k]), color_bits=color_bits)
+            pixels = np.zeros((H, W), fb.dtype)
+            r.draw_frame(pixels)
+            blended += int((hf.cmds["blend"] != 0).sum())
+            oracle_lib.reset_assert_failures()
+            surf = oracle_lib.build_surfaces(color_bits, hf.jobs, None, None, hf.cam_pos, sc.images, sc.lightmaps, sc.directional_lightmaps, hf.total_surface_pixels)
+            if hf.needs_clear:
+                oracle_lib.fill(fb, S.BACKGROUND_COLOR64 if color_bits == 64 else S.BACKGROUND_COLOR32)
+            oracle_lib.draw(color_bits, fb, hf.cmds, hf.polygon_points, None, surf, sc.images)
+            assert oracle_lib.assert_failures() == 0
+            assert_pixels_equal(r._view.read_surfaces(0, hf.total_surface_pixels), surf, f"frame {k} surfaces")
+            assert_pixels_equal(pixels, fb, f"frame {k} picture")
+        assert blended > 40  # blended world polygons really are in view
+    finally:
+        r.close()
+        sc.close()
