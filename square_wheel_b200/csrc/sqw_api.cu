@@ -13,6 +13,19 @@
 
 using namespace sqw;
 
+// NVTX ranges named after the reference's stage counters (RendererPerformanceCounters, renderer_structs.rs:7-15;
+// PostprocessorPerformanceCounters): a timeline tool shows the stages under the names the reference's debug overlay uses.
+// Header-only NVTX 3: costs nothing without a tool attached.
+#include <nvtx3/nvToolsExt.h>
+namespace
+{
+struct NvtxRange
+{
+	explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+	~NvtxRange() { nvtxRangePop(); }
+};
+} // namespace
+
 static_assert(sizeof(sqw_surface_job) == 136, "sqw_surface_job layout");
 static_assert(sizeof(sqw_light) == 80, "sqw_light layout");
 static_assert(sizeof(sqw_draw_cmd) == 64, "sqw_draw_cmd layout");
@@ -1277,6 +1290,7 @@ int sqw_frame_submit(sqw_frame* f, uint32_t stages)
 
 	if ((stages & SQW_STAGE_SHADOW_MAPS) && f->has_depth)
 	{
+		NvtxRange nvtx("shadow_maps_building");
 		if (!f->d_shadow_maps_rw || f->depth_max_end > f->shadow_maps_len)
 			return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_frame_submit: shadow map fills write outside the frame's shadow map array (set the surfaces first)");
 		DepthLaunch l{};
@@ -1378,6 +1392,7 @@ int sqw_frame_submit(sqw_frame* f, uint32_t stages)
 
 	if (do_surfaces)
 	{
+		NvtxRange nvtx("surfaces_preparation");
 		SurfaceLaunch l{};
 		l.jobs = f->d_jobs;
 		l.images = ctx->d_images;
@@ -1403,6 +1418,7 @@ int sqw_frame_submit(sqw_frame* f, uint32_t stages)
 
 	if (do_raster)
 	{
+		NvtxRange nvtx("rasterization");
 		// portal / mirror textures: wait for the views this frame samples (they may run on other streams)
 		for (uint32_t vi : f->sampled_views)
 			if (vi < ctx->views.size() && ctx->views[vi] && ctx->views[vi]->stream != s)
@@ -1419,6 +1435,7 @@ int sqw_frame_submit(sqw_frame* f, uint32_t stages)
 
 	if (do_post && !fused_tonemap)
 	{
+		NvtxRange nvtx(f->post.bloom_sigma > 0.0f ? "bloom + tonemapping" : "tonemapping");
 		const sqw_post_params& p = f->post;
 		PostLaunch l{};
 		l.hdr = static_cast<const uint64_t*>(view->d_color);
@@ -1654,6 +1671,7 @@ int sqw_models_prepare(sqw_view* view, const sqw_model_instance* instances, uint
 	l.triangles = static_cast<uint16_t*>(view->model_triangles.ptr);
 	l.counts = static_cast<uint32_t*>(view->model_counts.ptr);
 	{
+		NvtxRange nvtx("triangle_models_preparation");
 		LaunchTimer timer(ctx, SQW_KERNEL_MODELS_PREPARE, s);
 		SQW_CUDA(ctx, sqw::launch_models_prepare(l, s));
 	}
