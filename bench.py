@@ -26,7 +26,7 @@ import numpy as np  # noqa: E402
 
 FRAMES_PER_STEP = 64  # one step = one pass over the whole fixed camera path
 NUM_POSES = 64
-NUM_VIEWS = 4  # render targets in flight per GPU (independent camera views overlap on private streams)
+NUM_VIEWS = int(os.environ.get("SQW_BENCH_VIEWS", "4"))  # render targets in flight per GPU (independent camera views overlap on private streams)
 WIDTH, HEIGHT = 3840, 2160
 SCENE_KW = dict(seed=2, grid=(24, 24, 5), cell_size=(160.0, 160.0, 128.0), num_rooms=26, num_materials=24, texture_size_log2=8, max_polygon_size=64.0, material_mode=0, emissive_fraction=0.15)
 METRIC = "4k_hdr_frames_per_sec"

@@ -1268,10 +1268,11 @@ __device__ __forceinline__ void cp_async_16_zfill(void* smem_dst, const void* gm
 // Compaction of one 32-entry piece of a tile list for one warp: entries whose column range meets the warp's block, in list
 // order, slots [first_slot, first_slot + SQW_OPAQUE_STAGE_HITS) go to the stage.  Returns the number of hits (bits 0-29) and two flags.
 __device__ __forceinline__ uint32_t opaque_stage_commands(
-	OpaqueStage& st, const uint4 c0, const uint4 c1_in, const bool entry_valid, const int32_t blk_x0, const char* __restrict__ const surfaces_base, const uint32_t first_slot, const int lane)
+	OpaqueStage& st, const uint4 c0, const uint4 c1_in, const bool entry_valid, const int32_t blk_x0, const int32_t blk_w, const char* __restrict__ const surfaces_base,
+	const uint32_t first_slot, const int lane)
 {
 	const int32_t bx0 = (int16_t)(c0.y & 0xFFFF), bx1 = (int16_t)(c0.y >> 16);
-	const bool hit = entry_valid && bx0 < blk_x0 + 32 && bx1 > blk_x0; // the row range was tested by the binning CTA (block rows = band rows)
+	const bool hit = entry_valid && bx0 < blk_x0 + blk_w && bx1 > blk_x0; // the row range was tested by the binning CTA (block rows = band rows)
 	const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, hit);
 	const uint32_t slot = __popc(ballot & ((1u << lane) - 1)) - first_slot; // (wraps for slots before first_slot)
 	if (hit && slot < SQW_OPAQUE_STAGE_HITS)
@@ -1531,7 +1532,11 @@ __global__ void __launch_bounds__(SQW_OPAQUE_WARPS * 32, SQW_OPAQUE_CTAS_PER_SM)
 	typedef typename C::Raw Raw;
 	constexpr int THREADS = SQW_OPAQUE_WARPS * 32;
 	constexpr uint32_t K = SQW_OPAQUE_STAGE_HITS;
-	static_assert(SQW_OPAQUE_WARPS % 4 == 0 && SQW_TILE_W == 128 && SQW_TILE_H == 8 && (K * SQW_TILE_H) % 32 == 0, "tile geometry");
+	// A warp renders BLOCKS adjacent 32x8 blocks of its tile one after the other from ONE staged command list (hits against the
+	// 32 * BLOCKS pixel range): the per-tile work — list compaction, span staging, the prefetch steps — is paid once per BLOCKS
+	// blocks, while the registers hold one block at a time.
+	constexpr int BLOCKS = SQW_OPAQUE_BLOCKS, WPT = 4 / BLOCKS; // warps per tile
+	static_assert((BLOCKS == 1 || BLOCKS == 2 || BLOCKS == 4) && SQW_OPAQUE_WARPS % WPT == 0 && SQW_TILE_W == 128 && SQW_TILE_H == 8 && (K * SQW_TILE_H) % 32 == 0, "tile geometry");
 	__shared__ OpaqueStage s_stage_all[SQW_OPAQUE_WARPS][2];
 	__shared__ __align__(16) uint8_t s_lut[TONEMAP ? 3 * SQW_TONEMAP_LUT_SIZE : 16];
 	if (TONEMAP)
@@ -1545,12 +1550,13 @@ __global__ void __launch_bounds__(SQW_OPAQUE_WARPS * 32, SQW_OPAQUE_CTAS_PER_SM)
 	OpaqueStage(&stage)[2] = s_stage_all[warp];
 	uint32_t sb = 0, sg = 0, sr = 0;
 	const int ra = lane >> 3, rb = 4 + (lane >> 3);
-	const int32_t lane_x = (warp & 3) * 32 + (lane & 7) * 4; // first pixel of the lane relative to the tile
+	const int32_t warp_x = (warp % WPT) * 32 * BLOCKS;  // first pixel of the warp's range relative to the tile
+	const int32_t lane_x = warp_x + (lane & 7) * 4;     // first pixel of the lane in block 0
 	const bool pitch_vec = (pitch & 3) == 0; // rows start on 32-byte boundaries: the quad stores are aligned
 
-	// Tiles of this warp: the tile group (four warps) g of CTA b takes tiles (b * G + g) + n * (gridDim.x * G).
-	constexpr uint32_t G = SQW_OPAQUE_WARPS / 4;
-	const uint32_t tile_first = blockIdx.x * G + (uint32_t)(warp >> 2), tile_stride = gridDim.x * G;
+	// Tiles of this warp: the tile group (WPT warps) g of CTA b takes tiles (b * G + g) + n * (gridDim.x * G).
+	constexpr uint32_t G = SQW_OPAQUE_WARPS / WPT;
+	const uint32_t tile_first = blockIdx.x * G + (uint32_t)(warp / WPT), tile_stride = gridDim.x * G;
 
 	// ---- pipeline registers ----
 	// A tile travels through four loads, one per iteration of the loop below: descriptor -> first 32 list entries -> their
@@ -1575,8 +1581,7 @@ __global__ void __launch_bounds__(SQW_OPAQUE_WARPS * 32, SQW_OPAQUE_CTAS_PER_SM)
 		uint32_t nh = 0;
 		if (inf.y != 0xFFFFFFFFu) // (warp-uniform)
 		{
-			const int32_t blk_x0 = (int32_t)(inf.x & 0xFFFF) + (warp & 3) * 32;
-			nh = opaque_stage_commands(st, c0n, c1n, c_valid, blk_x0, surfaces_base, 0, lane);
+			nh = opaque_stage_commands(st, c0n, c1n, c_valid, (int32_t)(inf.x & 0xFFFF) + warp_x, 32 * BLOCKS, surfaces_base, 0, lane);
 			__syncwarp();
 			opaque_stage_spans(st, min(nh & 0x3FFFFFFFu, K), (int32_t)(inf.x >> 16), spans, lane);
 		}
@@ -1620,11 +1625,12 @@ __global__ void __launch_bounds__(SQW_OPAQUE_WARPS * 32, SQW_OPAQUE_CTAS_PER_SM)
 		__syncwarp();
 
 		if (inf0.y != 0xFFFFFFFFu) // (warp-uniform) a tile of this kernel's class
+		for (int blk = 0; blk < BLOCKS; ++blk)
 		{
-			const int32_t blk_x0 = (int32_t)(inf0.x & 0xFFFF) + (warp & 3) * 32;
+			const int32_t blk_x0 = (int32_t)(inf0.x & 0xFFFF) + warp_x + 32 * blk;
 			const int32_t blk_y0 = (int32_t)(inf0.x >> 16);
 			const int32_t row_a = blk_y0 + ra, row_b = blk_y0 + rb;
-			const int32_t px0 = (int32_t)(inf0.x & 0xFFFF) + lane_x;
+			const int32_t px0 = (int32_t)(inf0.x & 0xFFFF) + lane_x + 32 * blk;
 			const uint32_t pix_a = (uint32_t)row_a * (uint32_t)pitch + (uint32_t)px0;
 			const uint32_t pix_b = pix_a + 4u * (uint32_t)pitch;
 			Raw px_a[4], px_b[4];
@@ -1644,7 +1650,7 @@ __global__ void __launch_bounds__(SQW_OPAQUE_WARPS * 32, SQW_OPAQUE_CTAS_PER_SM)
 				{
 					// Rare: a list longer than one piece, or more hits than a stage holds (far, finely tessellated geometry).  The
 					// same two passes, chunk by chunk in list order (a later chunk's winners replace earlier ones), staged
-					// synchronously into this tile's stage buffer.
+					// synchronously for THIS block into the tile's stage buffer.
 					const uint32_t list_start = __ldg(&tile_desc[tile].x);
 					for (uint32_t base = 0; base < inf0.y; base += 32)
 					{
@@ -1660,7 +1666,7 @@ __global__ void __launch_bounds__(SQW_OPAQUE_WARPS * 32, SQW_OPAQUE_CTAS_PER_SM)
 						for (uint32_t first = 0; first < nh; first += K)
 						{
 							__syncwarp();
-							const uint32_t nhf = opaque_stage_commands(st, c0, c1, valid, blk_x0, surfaces_base, first, lane);
+							const uint32_t nhf = opaque_stage_commands(st, c0, c1, valid, blk_x0, 32, surfaces_base, first, lane);
 							nh = nhf & 0x3FFFFFFFu;
 							if (first >= nh)
 								break;
@@ -1673,6 +1679,7 @@ __global__ void __launch_bounds__(SQW_OPAQUE_WARPS * 32, SQW_OPAQUE_CTAS_PER_SM)
 							opaque_chunk<C>(st, n, (nhf >> 31) != 0, !((nhf >> 30) & 1), ra, rb, px0, px_a, px_b, have_a, have_b);
 						}
 					}
+					__syncwarp();
 				}
 			}
 			if (row_a < height)
@@ -1757,7 +1764,7 @@ cudaError_t launch_raster_tiles(const RasterLaunch& l, cudaStream_t stream)
 		(RAW)l.clear_color, l.tonemap_dst, l.inv_scale_bgr[0], l.inv_scale_bgr[1], l.inv_scale_bgr[2], l.color_sums, l.tonemap_lut, num_tiles
 	// Tiles of class SQW_TILE_CLASS_OPAQUE (only polygons with BlendingMode::None: all of them in a frame of plain world geometry).
 	{
-		constexpr uint32_t G = SQW_OPAQUE_WARPS / 4;
+		constexpr uint32_t G = SQW_OPAQUE_WARPS / (4 / SQW_OPAQUE_BLOCKS); // tiles a CTA renders at a time
 		const uint32_t ogrid = std::min<uint32_t>((num_tiles + G - 1) / G, (uint32_t)sm_count * SQW_OPAQUE_CTAS_PER_SM);
 		if (l.color64 && l.tonemap_dst)
 			raster_tile_opaque_kernel<Color64, 1><<<ogrid, SQW_OPAQUE_WARPS * 32, 0, stream>>>(SQW_TILE_ARGS(uint64_t));

@@ -88,6 +88,9 @@ cudaError_t launch_mix_texture(
 #define SQW_OPAQUE_WARPS 8
 #endif
 //        /* warps per CTA of the opaque tile kernel: two 128x8 tiles side by side */
+#ifndef SQW_OPAQUE_BLOCKS
+#define SQW_OPAQUE_BLOCKS 4 /* adjacent 32x8 blocks a warp of the opaque tile kernel renders from one staged command list */
+#endif
 #ifndef SQW_OPAQUE_CTAS_PER_SM
 #define SQW_OPAQUE_CTAS_PER_SM 2
 #endif
