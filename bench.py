@@ -556,6 +556,28 @@ def run_cuda(args, rank, local_rank, world):
             v.synchronize()  # every picture of the step is in host memory
         return kk, h2d
 
+    # Host-ingest ceiling of THIS box in THIS run: the same read-back calls with no rendering in between (bare cudaMemcpyAsync of
+    # the 33 MB pictures into the same page-locked buffers, all ranks at once).  e2e is bounded by it, not by PCIe's nominal rate.
+    d2h_ceiling = None
+    if not args.kernels_only:
+        def copies(n):
+            for i in range(n):
+                views[i % NUM_VIEWS].read_pixels32_async(pinned[i % NUM_VIEWS].data_ptr(), WIDTH)
+            for v in views:
+                v.synchronize()
+
+        copies(2 * NUM_VIEWS)
+        barrier()
+        n_copies = 256
+        t0 = time.perf_counter()
+        copies(n_copies)
+        torch.cuda.synchronize()
+        d2h_s = B.max_over_ranks(time.perf_counter() - t0, dist, "cuda")
+        d2h_ceiling = {
+            "pictures_per_s": world * n_copies / d2h_s,
+            "gb_per_s": world * n_copies * WIDTH * HEIGHT * 4 / d2h_s / 1e9,
+            "note": f"bare sqw_read_pixels32_async of the 33.2 MB picture, {NUM_VIEWS} in flight per GPU, {world} GPU(s) at once, no rendering (tools/d2h_ceiling.py is the stand-alone version)",
+        }
     e2e_n = 0 if args.kernels_only else args.steps
     e2e_steps(min(e2e_n, 1), 0)
     barrier()
@@ -570,6 +592,8 @@ def run_cuda(args, rank, local_rank, world):
         "unit": UNIT,
         "h2d_bytes_per_step": int(h2d_total / args.steps),
         "d2h_bytes_per_step": WIDTH * HEIGHT * 4 * FRAMES_PER_STEP,
+        "d2h_ceiling": d2h_ceiling,
+        "frac_of_d2h_ceiling": (e2e_fps / d2h_ceiling["pictures_per_s"]) if d2h_ceiling else None,
         "note": f"per frame through the C-ABI with host buffers: sqw_frame_set_surfaces + set_draw (host lists -> device) + submit + sqw_read_pixels32_async of the 33 MB picture into page-locked host memory, {NUM_VIEWS} views in flight; every picture is in host memory when the clock stops; bound by the PCIe read-back (33.2 MB/frame); host visibility/BSP traversal (stays host in the reference too) is outside",
     }
 

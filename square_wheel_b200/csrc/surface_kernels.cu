@@ -241,9 +241,12 @@ __device__ __forceinline__ void surface_band(
 		// :477-502 interpolate two lightmap rows into the line lightmap of every row of the band.
 		const uint32_t lm_cols = min(lm_w, (uint32_t)MAX_LINE_LIGHTMAP);
 		const uint32_t entries = num_rows * lm_cols;
+		// e / lm_cols by a 16-bit reciprocal: exact for e < 65536 / lm_cols (e < 32 rows x 19 columns here), instead of the
+		// generic 32-bit division sequence in every iteration
+		const uint32_t lm_cols_rcp = 65536u / lm_cols + 1u;
 		for (uint32_t e = tid; e < entries; e += SQW_SURF_THREADS)
 		{
-			const uint32_t rr = e / lm_cols, x = e - rr * lm_cols;
+			const uint32_t rr = (e * lm_cols_rcp) >> 16, x = e - rr * lm_cols;
 			const uint32_t lightmap_base_v = band.row0 + rr + j.lightmap_tc_shift[1];
 			const uint32_t lightmap_v = lightmap_base_v >> lm_scale_log2;
 			const float k = f32_mul_add((float)(lightmap_base_v & lightmap_fetch_mask), inv_lightmap_scale_f, k_shift);
