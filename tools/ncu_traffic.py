@@ -13,7 +13,7 @@ import json
 import subprocess
 import sys
 
-NAMES = {"surface_build_kernel": "surface_build", "raster_setup_kernel": "raster_setup", "raster_tile_kernel": "raster_tile", "tonemap_kernel": "tonemap"}
+NAMES = {"surface_build_kernel": "surface_build", "raster_setup_kernel": "raster_setup", "raster_tile_kernel": "raster_tile", "raster_tile_opaque_kernel": "raster_tile", "tonemap_kernel": "tonemap"}
 # issue / occupancy figures bench.py copies into `roofline` next to the traffic (the tile kernel is issue-bound, not DRAM-bound)
 EXTRA = {
     "issue_active_pct": "smsp__issue_active.avg.pct_of_peak_sustained_active",
@@ -38,7 +38,7 @@ def main():
         key = next((v for k, v in NAMES.items() if k in name), None)
         if key is None:
             continue
-        if key == "raster_tile" and "1>" in name.replace(" ", "").split("raster_tile_kernel")[1][:40]:
+        if key == "raster_tile" and "1>" in name.replace(" ", "").split("_kernel")[1][:40]:
             key = "raster_tile_tonemap"
         a = acc[key]
         for j, m in enumerate(["dram__bytes_read.sum", "dram__bytes_write.sum"]):
