@@ -1453,44 +1453,6 @@ __device__ __forceinline__ void opaque_chunk(
 	have_b |= valid >> 4;
 }
 
-#if SQW_OPAQUE_PIPELINE
-// One row quad (four consecutive pixels of block row `row`): winners among the staged commands [0, nh), then the texel addresses of
-// the pixels that have one.  Returns the mask of those pixels.  The caller issues the gathers and only consumes them one quad later.
-template <class C>
-__device__ __forceinline__ uint32_t opaque_quad_addresses(
-	const OpaqueStage& st, const uint32_t nh, const bool any_full, const bool one_step, const int row, const int32_t px0, const typename C::Raw* (&p)[4])
-{
-	uint32_t w[4];
-#pragma unroll
-	for (int i = 0; i < 4; ++i)
-		w[i] = SQW_NO_WINNER;
-	for (uint32_t h = 0; h < nh; ++h)
-	{
-		const uint32_t xs = st.span[h][row][0].x;
-		const int32_t x0 = (int16_t)(xs & 0xFFFF);
-		const uint32_t len = (uint32_t)max((int32_t)(int16_t)(xs >> 16) - x0, 0);
-		const int32_t d = px0 - x0;
-#pragma unroll
-		for (int i = 0; i < 4; ++i)
-			w[i] = (uint32_t)(d + i) < len ? h : w[i];
-	}
-	uint32_t valid = 0;
-#pragma unroll
-	for (int i = 0; i < 4; ++i)
-		valid |= (w[i] != SQW_NO_WINNER ? 1u : 0u) << i;
-	if (any_full) // (warp-uniform) some staged command is drawn with full perspective correction
-	{
-		if (one_step) // (warp-uniform)
-			opaque_resolve_quad<C, 1>(st, w, row, px0, p);
-		else
-			opaque_resolve_quad<C, 2>(st, w, row, px0, p);
-	}
-	else
-		opaque_resolve_quad<C, 0>(st, w, row, px0, p);
-	return valid;
-}
-#endif
-
 // The finished quad of one row (four consecutive pixels): one 256-bit store of the 64-bit pixels (128-bit for 32-bit ones), and
 // with TONEMAP one 128-bit store of the 32-bit picture plus the colour sums.  Same arithmetic as finish_quad.
 template <class C, int TONEMAP>
@@ -1662,59 +1624,6 @@ __global__ void __launch_bounds__(SQW_OPAQUE_WARPS * 32, SQW_OPAQUE_CTAS_PER_SM)
 		asm volatile("cp.async.wait_group 1;" ::: "memory");
 		__syncwarp();
 
-#if SQW_OPAQUE_PIPELINE
-		// Common case (the whole list fits one piece and one stage): the tile is walked as 2 * BLOCKS row quads per lane, software
-		// pipelined — the gathers of quad q are issued, then quad q - 1 is finished (tonemapped, stored) and the addresses of quad
-		// q + 1 are evaluated before anything waits for them: the texel latency (the kernel's largest stall) hides behind the
-		// warp's own arithmetic instead of needing other warps.
-		if (inf0.y != 0xFFFFFFFFu && inf0.y <= 32 && (nh0 & 0x3FFFFFFFu) <= K) // (warp-uniform)
-		{
-			const uint32_t nh = nh0 & 0x3FFFFFFFu;
-			const bool any_full = (nh0 >> 31) != 0, one_step = !((nh0 >> 30) & 1);
-			const int32_t blk_y0 = (int32_t)(inf0.x >> 16);
-			const uint32_t have_clear = clear ? 0xFu : 0u;
-			Raw tq[4];
-			uint32_t hq = 0, pixq = 0;
-			int32_t pxq = 0;
-			bool vecq = false, okq = false;
-#pragma unroll
-			for (int i = 0; i < 4; ++i)
-				tq[i] = clear_color;
-#pragma unroll 1
-			for (int q = 0; q < 2 * BLOCKS; ++q)
-			{
-				const int blk = q >> 1, row = (q & 1) ? rb : ra;
-				const int32_t blk_x0 = (int32_t)(inf0.x & 0xFFFF) + warp_x + 32 * blk;
-				const int32_t px0 = (int32_t)(inf0.x & 0xFFFF) + lane_x + 32 * blk;
-				const bool active = blk_x0 < width; // (warp-uniform)
-				const Raw* p[4];
-				uint32_t valid = 0;
-				if (active && nh)
-					valid = opaque_quad_addresses<C>(st, nh, any_full, one_step, row, px0, p);
-				Raw tn[4];
-#pragma unroll
-				for (int i = 0; i < 4; ++i)
-				{
-					tn[i] = clear_color;
-					if (valid & (1u << i))
-						tn[i] = __ldg(p[i]);
-				}
-				if (okq)
-					opaque_finish_quad<C, TONEMAP>(tq, hq, pxq, width, vecq, color_buffer + pixq, ldr + pixq, s_lut, isb, isg, isr, sb, sg, sr);
-#pragma unroll
-				for (int i = 0; i < 4; ++i)
-					tq[i] = tn[i];
-				hq = valid | have_clear;
-				pxq = px0;
-				pixq = (uint32_t)(blk_y0 + row) * (uint32_t)pitch + (uint32_t)px0;
-				vecq = (blk_x0 + 32 <= width) && pitch_vec;
-				okq = active && blk_y0 + row < height;
-			}
-			if (okq)
-				opaque_finish_quad<C, TONEMAP>(tq, hq, pxq, width, vecq, color_buffer + pixq, ldr + pixq, s_lut, isb, isg, isr, sb, sg, sr);
-		}
-		else
-#endif
 		if (inf0.y != 0xFFFFFFFFu) // (warp-uniform) a tile of this kernel's class
 		for (int blk = 0; blk < BLOCKS; ++blk)
 		{

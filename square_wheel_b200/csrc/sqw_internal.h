@@ -91,9 +91,6 @@ cudaError_t launch_mix_texture(
 #ifndef SQW_OPAQUE_BLOCKS
 #define SQW_OPAQUE_BLOCKS 4 /* adjacent 32x8 blocks a warp of the opaque tile kernel renders from one staged command list */
 #endif
-#ifndef SQW_OPAQUE_PIPELINE
-#define SQW_OPAQUE_PIPELINE 0 /* opaque tile kernel: row quads software-pipelined (gathers of quad q consumed after the addresses of quad q + 1) */
-#endif
 #ifndef SQW_OPAQUE_CTAS_PER_SM
 #define SQW_OPAQUE_CTAS_PER_SM 2
 #endif
