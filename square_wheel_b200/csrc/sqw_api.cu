@@ -279,9 +279,10 @@ struct sqw_view
 	uint64_t model_num_vertices = 0, model_num_triangles = 0;
 };
 
-struct SurfaceGroup // one kernel launch: all bands without / with dynamic lights
+struct SurfaceGroup // one kernel launch: all bands without / with dynamic lights, CTA bands first, then warp bands
 {
 	bool dynamic_lights;
+	uint32_t num_cta_bands;
 	uint32_t band_offset, num_bands;
 };
 
@@ -816,8 +817,24 @@ int sqw_frame_set_surfaces(
 			return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_frame_set_surfaces: a light's shadow map lies outside the shadow map array");
 	}
 
+	// Warp bands (small surfaces) are sized so that they fill the machine about once: a frame with few small texels (a nested
+	// portal view, the usual map at 4K) is latency-bound and wants short bands (two texels per lane like the CTA band of a small
+	// surface), a frame with more than a million of them (the stress map) is throughput-bound and wants the prologue amortised.
+	uint32_t warp_band_texels = SQW_SURF_WARP_BAND_TEXELS;
+	{
+		uint64_t small_texels = 0;
+		for (uint32_t i = 0; i < num_jobs; ++i)
+		{
+			const uint64_t texels = (uint64_t)jobs[i].surface_size[0] * jobs[i].surface_size[1];
+			if (texels <= SQW_SURF_WARP_JOB_TEXELS)
+				small_texels += texels;
+		}
+		const uint64_t resident_warps = 148ull * 4 * (SQW_SURF_THREADS / 32);
+		while (warp_band_texels > SQW_SURF_WARP_BAND_TEXELS_MIN && small_texels < resident_warps * warp_band_texels)
+			warp_band_texels /= 2;
+	}
 	// Validate and group jobs by kernel variant (the reference's const-generic dispatch, surfaces.rs:124-423).
-	std::vector<SurfaceBand> buckets[2]; // [0] no dynamic lights, [1] dynamic lights
+	std::vector<SurfaceBand> buckets[4]; // [0] no dynamic lights, [1] dynamic lights; [2], [3] the same for warp bands (small surfaces)
 	uint32_t variants_seen = 0;
 	sqw_frame_stats& st = f->stats;
 	st.surface_texels = st.emissive_texels = st.lightmap_bytes = 0;
@@ -869,9 +886,20 @@ int sqw_frame_set_surfaces(
 			continue;
 		const uint32_t vbits = variant_bits(v);
 		variants_seen |= 1u << (vbits + (v.dynamic_lights ? 12 : 0));
-		const uint32_t band_rows = std::min<uint32_t>(std::max<uint32_t>(SQW_SURF_BAND_TEXELS / j.surface_size[0], 1), SQW_SURF_MAX_BAND_ROWS);
+		const bool warp_bands = texels <= SQW_SURF_WARP_JOB_TEXELS;
+		uint32_t band_rows;
+		if (warp_bands)
+		{
+			// rows of a warp band share a pool of line-lightmap elements (the warp-band CTAs of surface_build_kernel)
+			band_rows = std::max<uint32_t>(warp_band_texels / j.surface_size[0], 1);
+			if (diffuse && j.lightmap_offset != 0)
+				band_rows = std::min<uint32_t>(band_rows, std::max<uint32_t>(SQW_SURF_WARP_LM_ELEMENTS / std::min<uint32_t>(j.lightmap_size[0], 19), 1));
+			band_rows = std::min<uint32_t>(band_rows, SQW_SURF_MAX_BAND_ROWS);
+		}
+		else
+			band_rows = std::min<uint32_t>(std::max<uint32_t>(SQW_SURF_BAND_TEXELS / j.surface_size[0], 1), SQW_SURF_MAX_BAND_ROWS);
 		for (uint32_t row0 = 0; row0 < j.surface_size[1]; row0 += band_rows)
-			buckets[v.dynamic_lights ? 1 : 0].push_back(SurfaceBand{i, row0, std::min(band_rows, j.surface_size[1] - row0), vbits});
+			buckets[(v.dynamic_lights ? 1 : 0) + (warp_bands ? 2 : 0)].push_back(SurfaceBand{i, row0, std::min(band_rows, j.surface_size[1] - row0), vbits});
 		st.surface_texels += texels;
 		if (emissive)
 			st.emissive_texels += texels;
@@ -880,15 +908,21 @@ int sqw_frame_set_surfaces(
 	f->groups.clear();
 	for (uint32_t key = 0; key < 2; ++key)
 	{
-		if (buckets[key].empty())
+		if (buckets[key].empty() && buckets[key + 2].empty())
 			continue;
-		// heaviest variants first so the tail of the grid is made of cheap bands
-		std::stable_sort(buckets[key].begin(), buckets[key].end(), [](const SurfaceBand& a, const SurfaceBand& b) { return (a.variant & 15u) > (b.variant & 15u); });
 		SurfaceGroup g{};
 		g.dynamic_lights = key == 1;
 		g.band_offset = (uint32_t)f->h_bands.size();
-		g.num_bands = (uint32_t)buckets[key].size();
-		f->h_bands.insert(f->h_bands.end(), buckets[key].begin(), buckets[key].end());
+		for (uint32_t kind = 0; kind < 2; ++kind) // CTA bands, then warp bands
+		{
+			std::vector<SurfaceBand>& b = buckets[key + 2 * kind];
+			// heaviest variants first so the tail of the grid is made of cheap bands
+			std::stable_sort(b.begin(), b.end(), [](const SurfaceBand& x, const SurfaceBand& y) { return (x.variant & 15u) > (y.variant & 15u); });
+			f->h_bands.insert(f->h_bands.end(), b.begin(), b.end());
+			if (kind == 0)
+				g.num_cta_bands = (uint32_t)b.size();
+		}
+		g.num_bands = (uint32_t)f->h_bands.size() - g.band_offset;
 		f->groups.push_back(g);
 	}
 	st.num_surface_variants = (uint32_t)__builtin_popcount(variants_seen);
@@ -1408,6 +1442,7 @@ int sqw_frame_submit(sqw_frame* f, uint32_t stages)
 		{
 			l.bands = f->d_bands + g.band_offset;
 			l.num_bands = g.num_bands;
+			l.num_cta_bands = g.num_cta_bands;
 			{
 				LaunchTimer timer(ctx, SQW_KERNEL_SURFACE_BUILD, s);
 				SQW_CUDA(ctx, (ctx->fast_surface_numerics ? launch_surface_build_fast : launch_surface_build)(view->color_bits == 64, g.dynamic_lights, l, s));

@@ -22,6 +22,19 @@ struct ImageDev
 #define SQW_SURF_BAND_TEXELS 2048
 #endif
 #define SQW_SURF_THREADS 256
+// Jobs of at most SQW_SURF_WARP_JOB_TEXELS texels are cut into WARP bands (one warp per band): about
+// SQW_SURF_WARP_BAND_TEXELS texels each (fewer, down to SQW_SURF_WARP_BAND_TEXELS_MIN, in frames with few small texels), rows x
+// lightmap columns <= SQW_SURF_WARP_LM_ELEMENTS.
+#ifndef SQW_SURF_WARP_JOB_TEXELS
+#define SQW_SURF_WARP_JOB_TEXELS 1024
+#endif
+#ifndef SQW_SURF_WARP_BAND_TEXELS
+#define SQW_SURF_WARP_BAND_TEXELS 256
+#endif
+#ifndef SQW_SURF_WARP_BAND_TEXELS_MIN
+#define SQW_SURF_WARP_BAND_TEXELS_MIN 64
+#endif
+#define SQW_SURF_WARP_LM_ELEMENTS 80
 struct SurfaceBand
 {
 	uint32_t job;
@@ -47,6 +60,7 @@ struct SurfaceLaunch
 	const sqw_surface_job* jobs;   // device
 	const SurfaceBand* bands;      // device, this variant's slice
 	uint32_t num_bands;
+	uint32_t num_cta_bands;        // the first num_cta_bands bands are CTA bands, the others warp bands (small surfaces)
 	const ImageDev* images;        // device
 	const float* lightmaps;        // device
 	const sqw_directional_lightmap_element* directional_lightmaps; // device

@@ -157,20 +157,22 @@ __device__ __forceinline__ uint32_t pow2_mask_of(uint32_t size) { return (size &
 typedef LmEl LineLightmap[MAX_LINE_LIGHTMAP + 1];
 
 // One band of one job: build_surface_impl_6_static_params (+ the emissive pass) for rows [band.row0, band.row0 + band.num_rows).
-template <class C, bool DIRECTIONAL, bool USE_DYNAMIC_LIGHTS, bool USE_NORMAL_MAP, int SPECULAR_TYPE, bool EMISSIVE_ONLY>
+// G = threads that share the band: the whole CTA (SQW_SURF_THREADS, bands of about SQW_SURF_BAND_TEXELS texels) or one warp (32:
+// small surfaces, eight independent bands per CTA and no CTA barrier).  The line lightmap is `lm_pitch` elements per band row.
+template <class C, bool DIRECTIONAL, bool USE_DYNAMIC_LIGHTS, bool USE_NORMAL_MAP, int SPECULAR_TYPE, bool EMISSIVE_ONLY, int G>
 __device__ __forceinline__ void surface_band(
-	const sqw_surface_job& j, const SurfaceBand band, LineLightmap* line_lightmap, const ImageDev* __restrict__ images, const float* __restrict__ lightmaps,
+	const sqw_surface_job& j, const SurfaceBand band, LmEl* const line_lightmap, const ImageDev* __restrict__ images, const float* __restrict__ lightmaps,
 	const sqw_directional_lightmap_element* __restrict__ directional_lightmaps, const sqw_light* __restrict__ lights, const float* __restrict__ shadow_maps,
 	float cam_x, float cam_y, float cam_z, typename C::Raw* __restrict__ surfaces)
 {
 	typedef typename C::Raw Raw;
-	const uint32_t tid = threadIdx.x;
+	const uint32_t tid = G == 32 ? (threadIdx.x & 31u) : threadIdx.x;
 	const uint32_t size_u = j.surface_size[0];
 	const uint32_t num_rows = band.num_rows;
 	const uint32_t total = num_rows * size_u;
 	Raw* const out = surfaces + j.surface_pixels_offset;
 	// (row, u) of this thread's first texel and its advance per stride of SQW_SURF_THREADS texels
-	const uint32_t step_rows = SQW_SURF_THREADS / size_u, step_u = SQW_SURF_THREADS % size_u;
+	const uint32_t step_rows = (uint32_t)G / size_u, step_u = (uint32_t)G % size_u;
 	uint32_t r = tid / size_u, dst_u = tid % size_u;
 
 	// Emissive layer (partial_renderer.rs:1801-1819): Additive over the diffuse layer, None when there is none.
@@ -194,7 +196,7 @@ __device__ __forceinline__ void surface_band(
 
 	if (EMISSIVE_ONLY)
 	{
-		for (uint32_t i = tid; i < total; i += SQW_SURF_THREADS)
+		for (uint32_t i = tid; i < total; i += G)
 		{
 			const uint32_t dst_v = band.row0 + r;
 			const uint32_t ev = wrap_coord(j.tc_start[1] + (int32_t)dst_v, (int32_t)em_h, em_h_mask);
@@ -233,18 +235,20 @@ __device__ __forceinline__ void surface_band(
 	const float k_shift = 0.5f * inv_lightmap_scale_f;
 	const uint32_t lightmap_fetch_mask = (1u << (lm_scale_log2 & 31)) - 1;
 	const uint32_t lm_w = j.lightmap_size[0];
+	const uint32_t lm_cols = min(lm_w, (uint32_t)MAX_LINE_LIGHTMAP);
+	// row pitch of the line lightmap: fixed for CTA bands, the band's own column count for warp bands (their rows share a small pool)
+	const uint32_t lm_pitch = G == 32 ? lm_cols : (uint32_t)(MAX_LINE_LIGHTMAP + 1);
 
 	const int32_t src_u0 = (int32_t)wrap_coord(j.tc_start[0], tex_w, tex_w_mask); // rem_euclid (:510)
 
 	if (has_lightmap)
 	{
 		// :477-502 interpolate two lightmap rows into the line lightmap of every row of the band.
-		const uint32_t lm_cols = min(lm_w, (uint32_t)MAX_LINE_LIGHTMAP);
 		const uint32_t entries = num_rows * lm_cols;
 		// e / lm_cols by a 16-bit reciprocal: exact for e < 65536 / lm_cols (e < 32 rows x 19 columns here), instead of the
 		// generic 32-bit division sequence in every iteration
 		const uint32_t lm_cols_rcp = 65536u / lm_cols + 1u;
-		for (uint32_t e = tid; e < entries; e += SQW_SURF_THREADS)
+		for (uint32_t e = tid; e < entries; e += G)
 		{
 			const uint32_t rr = (e * lm_cols_rcp) >> 16, x = e - rr * lm_cols;
 			const uint32_t lightmap_base_v = band.row0 + rr + j.lightmap_tc_shift[1];
@@ -252,7 +256,7 @@ __device__ __forceinline__ void surface_band(
 			const float k = f32_mul_add((float)(lightmap_base_v & lightmap_fetch_mask), inv_lightmap_scale_f, k_shift);
 			const float omk = 1.0f - k;
 			const uint32_t base = lightmap_v * lm_w;
-			float* d = reinterpret_cast<float*>(&line_lightmap[rr][x]);
+			float* d = reinterpret_cast<float*>(line_lightmap + rr * lm_pitch + x);
 			if (DIRECTIONAL)
 			{
 				const float* l0 = reinterpret_cast<const float*>(directional_lightmaps + (size_t)j.lightmap_offset + base + x);
@@ -271,9 +275,12 @@ __device__ __forceinline__ void surface_band(
 			}
 		}
 	}
-	__syncthreads();
+	if (G == 32)
+		__syncwarp();
+	else
+		__syncthreads();
 
-	for (uint32_t i = tid; i < total; i += SQW_SURF_THREADS)
+	for (uint32_t i = tid; i < total; i += G)
 	{
 		const uint32_t dst_v = band.row0 + r;
 		const uint32_t src_v = wrap_coord(j.tc_start[1] + (int32_t)dst_v, tex_h, tex_h_mask); // :507
@@ -310,8 +317,8 @@ __device__ __forceinline__ void surface_band(
 			const uint32_t lightmap_u = lightmap_base_u >> lm_scale_log2;
 			const float k = f32_mul_add((float)(lightmap_base_u & lightmap_fetch_mask), inv_lightmap_scale_f, k_shift);
 			const float omk = 1.0f - k;
-			const LmEl& l0 = line_lightmap[r][lightmap_u];
-			const LmEl& l1 = line_lightmap[r][lightmap_u + 1];
+			const LmEl& l0 = line_lightmap[r * lm_pitch + lightmap_u];
+			const LmEl& l1 = line_lightmap[r * lm_pitch + lightmap_u + 1];
 			float constant_c[3];
 #pragma unroll
 			for (int c = 0; c < 3; ++c)
@@ -467,31 +474,17 @@ __device__ __forceinline__ void surface_band(
 }
 
 // Variant byte of a band: bit0 directional lightmap, bit1 normal map, bits2-3 specular type, bit4 emissive-only.
-template <class C, bool DYN>
-__global__ void __launch_bounds__(SQW_SURF_THREADS, DYN ? 3 : 4) surface_build_kernel(
-	const sqw_surface_job* __restrict__ jobs, const SurfaceBand* __restrict__ bands, const ImageDev* __restrict__ images,
-	const float* __restrict__ lightmaps, const sqw_directional_lightmap_element* __restrict__ directional_lightmaps,
-	const sqw_light* __restrict__ lights, const float* __restrict__ shadow_maps, float cam_x, float cam_y, float cam_z,
-	typename C::Raw* __restrict__ surfaces)
-{
-	__shared__ LineLightmap s_line_lightmap[SQW_SURF_MAX_BAND_ROWS];
-	__shared__ sqw_surface_job s_job;
-
-	const SurfaceBand band = bands[blockIdx.x];
-	{
-		// Cooperative 136-byte job load into shared memory (34 words).
-		const uint32_t* src = reinterpret_cast<const uint32_t*>(jobs + band.job);
-		uint32_t* dst = reinterpret_cast<uint32_t*>(&s_job);
-		if (threadIdx.x < sizeof(sqw_surface_job) / 4)
-			dst[threadIdx.x] = src[threadIdx.x];
-	}
-	__syncthreads();
-
 #define SQW_BAND_CASE(DIR, NM, SPEC)                                                                                                                       \
 	case ((DIR) | ((NM) << 1) | ((SPEC) << 2)):                                                                                                            \
-		surface_band<C, (DIR) != 0, DYN, (NM) != 0, SPEC, false>(                                                                                          \
-			s_job, band, s_line_lightmap, images, lightmaps, directional_lightmaps, lights, shadow_maps, cam_x, cam_y, cam_z, surfaces);                   \
+		surface_band<C, (DIR) != 0, DYN, (NM) != 0, SPEC, false, G>(                                                                                       \
+			job, band, line_lightmap, images, lightmaps, directional_lightmaps, lights, shadow_maps, cam_x, cam_y, cam_z, surfaces);                       \
 		break;
+template <class C, bool DYN, int G>
+__device__ __forceinline__ void surface_band_dispatch(
+	const sqw_surface_job& job, const SurfaceBand band, LmEl* const line_lightmap, const ImageDev* __restrict__ images, const float* __restrict__ lightmaps,
+	const sqw_directional_lightmap_element* __restrict__ directional_lightmaps, const sqw_light* __restrict__ lights, const float* __restrict__ shadow_maps,
+	float cam_x, float cam_y, float cam_z, typename C::Raw* __restrict__ surfaces)
+{
 	switch (band.variant)
 	{
 		SQW_BAND_CASE(0, 0, 0)
@@ -508,11 +501,60 @@ __global__ void __launch_bounds__(SQW_SURF_THREADS, DYN ? 3 : 4) surface_build_k
 		SQW_BAND_CASE(1, 1, 2)
 	default:
 		if (!DYN)
-			surface_band<C, false, false, false, 0, true>(
-				s_job, band, s_line_lightmap, images, lightmaps, directional_lightmaps, lights, shadow_maps, cam_x, cam_y, cam_z, surfaces);
+			surface_band<C, false, false, false, 0, true, G>(
+				job, band, line_lightmap, images, lightmaps, directional_lightmaps, lights, shadow_maps, cam_x, cam_y, cam_z, surfaces);
 		break;
 	}
+}
 #undef SQW_BAND_CASE
+
+// One grid per frame and dynamic-light class.  CTAs [0, num_cta_bands) build one CTA band each (up to SQW_SURF_MAX_BAND_ROWS rows,
+// about SQW_SURF_BAND_TEXELS texels, 256 threads); the CTAs after them build eight WARP bands each — small surfaces (far or finely
+// tessellated geometry: the stress map averages 76 texels per polygon), one warp per band and no CTA barrier: a CTA band would
+// leave most of its threads idle and still pay the prologue.  A warp's line lightmap is a pool of SQW_SURF_WARP_LM_ELEMENTS
+// elements shared by the band's rows (the host sizes the band so that rows x lightmap columns fits).  Both kinds take the same
+// time per band (eight texels per thread), so they share one grid instead of two launches with a tail each.
+template <class C, bool DYN>
+__global__ void __launch_bounds__(SQW_SURF_THREADS, DYN ? 3 : 4) surface_build_kernel(
+	const sqw_surface_job* __restrict__ jobs, const SurfaceBand* __restrict__ bands, uint32_t num_cta_bands, uint32_t num_bands, const ImageDev* __restrict__ images,
+	const float* __restrict__ lightmaps, const sqw_directional_lightmap_element* __restrict__ directional_lightmaps,
+	const sqw_light* __restrict__ lights, const float* __restrict__ shadow_maps, float cam_x, float cam_y, float cam_z,
+	typename C::Raw* __restrict__ surfaces)
+{
+	constexpr int WARPS = SQW_SURF_THREADS / 32;
+	static_assert(WARPS * SQW_SURF_WARP_LM_ELEMENTS <= SQW_SURF_MAX_BAND_ROWS * (MAX_LINE_LIGHTMAP + 1), "the warp pools fit the CTA band's line lightmap");
+	__shared__ LmEl s_line_lightmap[SQW_SURF_MAX_BAND_ROWS * (MAX_LINE_LIGHTMAP + 1)];
+	__shared__ sqw_surface_job s_job[WARPS];
+
+	if (blockIdx.x < num_cta_bands) // (CTA-uniform)
+	{
+		const SurfaceBand band = bands[blockIdx.x];
+		{
+			// Cooperative 136-byte job load into shared memory (34 words).
+			const uint32_t* src = reinterpret_cast<const uint32_t*>(jobs + band.job);
+			uint32_t* dst = reinterpret_cast<uint32_t*>(&s_job[0]);
+			if (threadIdx.x < sizeof(sqw_surface_job) / 4)
+				dst[threadIdx.x] = src[threadIdx.x];
+		}
+		__syncthreads();
+		surface_band_dispatch<C, DYN, SQW_SURF_THREADS>(
+			s_job[0], band, s_line_lightmap, images, lightmaps, directional_lightmaps, lights, shadow_maps, cam_x, cam_y, cam_z, surfaces);
+		return;
+	}
+	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const uint32_t band_index = num_cta_bands + (blockIdx.x - num_cta_bands) * WARPS + warp;
+	if (band_index >= num_bands)
+		return;
+	const SurfaceBand band = bands[band_index];
+	{
+		const uint32_t* src = reinterpret_cast<const uint32_t*>(jobs + band.job);
+		uint32_t* dst = reinterpret_cast<uint32_t*>(&s_job[warp]);
+		for (uint32_t i = lane; i < sizeof(sqw_surface_job) / 4; i += 32)
+			dst[i] = src[i];
+	}
+	__syncwarp();
+	surface_band_dispatch<C, DYN, 32>(
+		s_job[warp], band, s_line_lightmap + warp * SQW_SURF_WARP_LM_ELEMENTS, images, lightmaps, directional_lightmaps, lights, shadow_maps, cam_x, cam_y, cam_z, surfaces);
 }
 
 // mix_surface_with_texture_impl (surfaces.rs:903-971) with any of the five blending modes: the overlay of a portal /
@@ -556,8 +598,9 @@ __global__ void __launch_bounds__(256) mix_texture_kernel(
 template <class C, bool DYN>
 cudaError_t launch_one(const SurfaceLaunch& l, cudaStream_t stream)
 {
-	surface_build_kernel<C, DYN><<<l.num_bands, SQW_SURF_THREADS, 0, stream>>>(
-		l.jobs, l.bands, l.images, l.lightmaps, l.directional_lightmaps, l.lights, l.shadow_maps, l.cam_pos[0], l.cam_pos[1], l.cam_pos[2],
+	const uint32_t warp_ctas = (l.num_bands - l.num_cta_bands + SQW_SURF_THREADS / 32 - 1) / (SQW_SURF_THREADS / 32);
+	surface_build_kernel<C, DYN><<<l.num_cta_bands + warp_ctas, SQW_SURF_THREADS, 0, stream>>>(
+		l.jobs, l.bands, l.num_cta_bands, l.num_bands, l.images, l.lightmaps, l.directional_lightmaps, l.lights, l.shadow_maps, l.cam_pos[0], l.cam_pos[1], l.cam_pos[2],
 		static_cast<typename C::Raw*>(l.surfaces));
 	return cudaGetLastError();
 }

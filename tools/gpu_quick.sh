@@ -1,0 +1,18 @@
+#!/bin/bash
+# Development iteration on the GPU box: parity tests, kernels-only bench of configs[1], the named configs.  usage: tools/gpu_quick.sh TAG [only]
+TAG=${1:-q}
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+timeout 300 python bench.py --steps 6 --warmup 3 --kernels-only > gpurun_out/q_$TAG.json 2> gpurun_out/q_$TAG.err || tail -5 gpurun_out/q_$TAG.err
+python - <<PY
+import json
+d=json.load(open("gpurun_out/q_$TAG.json"))
+k=d["roofline"]["kernels"]
+print("configs[1] value",round(d["value"],1), " ".join(f"{a}={round(v['ms_per_frame']*1000,2)}us" for a,v in k.items()))
+PY
+timeout 900 python tools/bench_configs.py --out gpurun_out/qc_$TAG.json ${2:+--only "$2"} > gpurun_out/qc_$TAG.log 2>&1 || tail -5 gpurun_out/qc_$TAG.log
+python - <<PY
+import json
+d=json.load(open("gpurun_out/qc_$TAG.json"))
+for n,c in d["configs"].items():
+    print(n[:60], round(c["frames_per_sec"],1), "fps", " ".join(f"{a}={round(v['us_per_frame'],1)}" for a,v in c["kernels"].items()))
+PY
