@@ -411,7 +411,8 @@ int sqw_frame_get_stats(const sqw_frame* frame, sqw_frame_stats* out);
 #define SQW_KERNEL_DEPTH_SETUP 10
 #define SQW_KERNEL_DEPTH_RESOLVE 11
 #define SQW_KERNEL_MODELS_PREPARE 12 /* model_bones + model_vertices + model_triangles kernels of one sqw_models_prepare */
-#define SQW_NUM_KERNEL_KINDS 13
+#define SQW_KERNEL_POLYGONS_PREPARE 13 /* polygons_prepare + polygons_offsets kernels of one sqw_polygons_prepare */
+#define SQW_NUM_KERNEL_KINDS 14
 typedef struct sqw_kernel_times
 {
 	double ms[SQW_NUM_KERNEL_KINDS];
@@ -477,6 +478,66 @@ int sqw_models_prepare(sqw_view* view, const sqw_model_instance* instances, uint
 /* Read the results of the last sqw_models_prepare back (parity tests; a host that still clips and emits the triangles itself).
  * Any pointer may be NULL.  counts: [num_instances]. */
 int sqw_models_read(sqw_view* view, sqw_model_vertex* vertices, uint64_t num_vertices, uint16_t* triangles, uint64_t num_triangles, uint32_t* counts, uint32_t num_instances);
+
+/* ---- world-polygon preparation on the GPU (the geometry half of the host front end) ------------------
+ * Replaces the loop body of PartialRenderer::prepare_polygons_surfaces (partial_renderer.rs:1327-1360) for the polygons of the
+ * visible leafs: prepare_polygon_surface (:1464-1638) — back-face cull, material draw flag, vertex transform, z-near and leaf
+ * octagon clipping (renderer_utils.rs:10-58, clipping.rs), sky bounds (:1511-1529), DepthEquation / TexCoordEquation
+ * (equations.rs:22-75), calculate_mip (renderer_utils.rs:201-242), the surface rectangle (:1558-1615), the running
+ * surface_pixels_offset (:1617-1618, a prefix sum in candidate order) and the shift of the texture-coordinate equation (:1629-1635).
+ * The visibility flood stays on the host (map_visibility_calculator.rs): it hands over the (polygon, leaf clip planes) pairs.
+ * The map's polygons and vertices are uploaded once (S0). */
+typedef struct sqw_map_polygon /* Polygon, bsp_map_compact.rs:58-75, 80 bytes (the .sqwm polygons lump as it is) */
+{
+	uint32_t first_vertex, num_vertices;
+	float plane[4];                 /* Plane {vec, dist} */
+	float tex_coord_equation[2][4]; /* two Plane */
+	int32_t tex_coord_min[2];
+	int32_t tex_coord_max[2];
+	uint32_t lightmap_data_offset;
+	uint32_t texture; /* material index */
+} sqw_map_polygon;
+#define SQW_MATERIAL_DRAW 1u   /* Material::draw (material.rs) */
+#define SQW_MATERIAL_SKYBOX 2u /* Material::skybox is some: the polygon only widens the sky window */
+/* vertices: [num_vertices][3] f32 (BSPMap::vertices); material_flags: [num_materials] SQW_MATERIAL_*.  The library copies. */
+int sqw_upload_map_geometry(sqw_ctx* ctx, const sqw_map_polygon* polygons, uint32_t num_polygons, const float* vertices, uint32_t num_vertices, const uint8_t* material_flags, uint32_t num_materials);
+typedef struct sqw_polygon_candidate
+{
+	uint32_t polygon;  /* index into the uploaded polygons */
+	uint32_t clip_set; /* index into clip_planes: the eight planes of the leaf's ClippingPolygon (clipping_polygon.rs:150-163) */
+} sqw_polygon_candidate;
+typedef struct sqw_polygons_frame
+{
+	float planes_matrix[16]; /* CameraMatrices::planes_matrix, column-major (matrix.rs:4-11) */
+	float view_matrix[16];   /* CameraMatrices::view_matrix */
+	float mip_bias;          /* PartialRenderer::mip_bias (:3786-3804) */
+	uint32_t reserved[3];
+} sqw_polygons_frame;
+#define SQW_PREPARED_VISIBLE 1u /* a surface is built and the polygon drawn (DrawPolygonData::visible_frame == current frame) */
+#define SQW_PREPARED_SKY 2u     /* sky polygon that passed culling and clipping: contributed to the sky bounds */
+typedef struct sqw_prepared_polygon /* the per-frame half of DrawPolygonData (renderer_structs.rs:75-91), 64 bytes */
+{
+	uint32_t flags; /* SQW_PREPARED_* */
+	uint32_t mip;
+	float depth_equation[3];
+	float tex_coord_equation[6]; /* d_tc_dx[2], d_tc_dy[2], k[2]; scaled to the mip and shifted to the surface rectangle */
+	int32_t surface_tc_min[2];
+	uint32_t surface_size[2];
+	uint32_t surface_pixels_offset;
+} sqw_prepared_polygon;
+typedef struct sqw_polygons_totals
+{
+	uint32_t num_visible;         /* current_frame_visible_polygons.len() */
+	uint32_t has_sky;             /* current_sky is some (:1336, :1511-1529) */
+	uint64_t num_surfaces_pixels; /* num_visible_surfaces_pixels (:395) */
+	float sky_bounds[8];          /* ClippingPolygon: x, y, x_plus_y, x_minus_y as {min, max} */
+	uint32_t sky_material;        /* material of the first sky polygon in candidate order */
+	uint32_t reserved;
+} sqw_polygons_totals;
+/* clip_planes: [num_clip_sets][8][3] f32.  Runs on the view's stream; results stay on the device (sqw_polygons_read). */
+int sqw_polygons_prepare(sqw_view* view, const sqw_polygons_frame* frame, const sqw_polygon_candidate* candidates, uint32_t num_candidates, const float* clip_planes, uint32_t num_clip_sets);
+/* Read the results of the last sqw_polygons_prepare back: out[num] in candidate order (NULL to skip), totals (NULL to skip). */
+int sqw_polygons_read(sqw_view* view, sqw_prepared_polygon* out, uint32_t num, sqw_polygons_totals* totals);
 
 int sqw_self_test(sqw_ctx* ctx);
 

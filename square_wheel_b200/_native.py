@@ -169,10 +169,34 @@ class FrameStats(C.Structure):
 
 
 class KernelTimes(C.Structure):
-    _fields_ = [("ms", C.c_double * 13), ("launches", C.c_uint64 * 13)]
+    _fields_ = [("ms", C.c_double * 14), ("launches", C.c_uint64 * 14)]
 
 
-KERNEL_NAMES = ["surface_build", "raster_setup", "raster_bin", "raster_tile", "tonemap", "bloom_downscale", "bloom_blur", "tonemap_bloom", "raster_tile_tonemap", "mix_texture", "depth_setup", "depth_resolve", "models_prepare"]
+KERNEL_NAMES = ["surface_build", "raster_setup", "raster_bin", "raster_tile", "tonemap", "bloom_downscale", "bloom_blur", "tonemap_bloom", "raster_tile_tonemap", "mix_texture", "depth_setup", "depth_resolve", "models_prepare", "polygons_prepare"]
+
+# world-polygon preparation (sqw_polygons_prepare)
+map_polygon_dtype = np.dtype(
+    [("first_vertex", "<u4"), ("num_vertices", "<u4"), ("plane", "<f4", 4), ("tex_coord_equation", "<f4", (2, 4)), ("tex_coord_min", "<i4", 2), ("tex_coord_max", "<i4", 2),
+     ("lightmap_data_offset", "<u4"), ("texture", "<u4")])
+polygon_candidate_dtype = np.dtype([("polygon", "<u4"), ("clip_set", "<u4")])
+prepared_polygon_dtype = np.dtype(
+    [("flags", "<u4"), ("mip", "<u4"), ("depth_equation", "<f4", 3), ("tex_coord_equation", "<f4", 6), ("surface_tc_min", "<i4", 2), ("surface_size", "<u4", 2),
+     ("surface_pixels_offset", "<u4")])
+assert map_polygon_dtype.itemsize == 80 and prepared_polygon_dtype.itemsize == 64
+MATERIAL_DRAW, MATERIAL_SKYBOX = 1, 2
+PREPARED_VISIBLE, PREPARED_SKY = 1, 2
+
+
+class PolygonsFrame(C.Structure):
+    _fields_ = [("planes_matrix", C.c_float * 16), ("view_matrix", C.c_float * 16), ("mip_bias", C.c_float), ("reserved", C.c_uint32 * 3)]
+
+
+class PolygonsTotals(C.Structure):
+    _fields_ = [("num_visible", C.c_uint32), ("has_sky", C.c_uint32), ("num_surfaces_pixels", C.c_uint64), ("sky_bounds", C.c_float * 8), ("sky_material", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
+assert C.sizeof(PolygonsFrame) == 144
 
 # Every symbol include/sqw_cuda.h declares: (name, restype, argtypes)
 _VP = C.c_void_p
@@ -217,6 +241,9 @@ CUDA_SYMBOLS = [
     ("sqw_upload_model_mesh", C.c_int, [_VP, _VP]),
     ("sqw_models_prepare", C.c_int, [_VP, _VP, C.c_uint32]),
     ("sqw_models_read", C.c_int, [_VP, _VP, C.c_uint64, _VP, C.c_uint64, _VP, C.c_uint32]),
+    ("sqw_upload_map_geometry", C.c_int, [_VP, _VP, C.c_uint32, _VP, C.c_uint32, _VP, C.c_uint32]),
+    ("sqw_polygons_prepare", C.c_int, [_VP, C.POINTER(PolygonsFrame), _VP, C.c_uint32, _VP, C.c_uint32]),
+    ("sqw_polygons_read", C.c_int, [_VP, _VP, C.c_uint32, C.POINTER(PolygonsTotals)]),
 ]
 
 _cuda_lib = None

@@ -193,6 +193,11 @@ struct sqw_ctx
 	std::vector<void*> mesh_allocations;
 	sqw::ModelMeshDev* d_meshes = nullptr;
 	size_t d_meshes_capacity = 0;
+	// map geometry for sqw_polygons_prepare (sqw_upload_map_geometry)
+	sqw_map_polygon* d_map_polygons = nullptr;
+	float* d_map_vertices = nullptr;
+	uint8_t* d_material_flags = nullptr;
+	uint32_t num_map_polygons = 0, num_map_vertices = 0, num_materials = 0;
 	std::string last_error;
 	// per-kernel timing (sqw_profile_begin / _end)
 	bool profiling = false;
@@ -277,6 +282,9 @@ struct sqw_view
 	DevBuf model_instances, model_vertices, model_triangles, model_counts, model_bones, model_sort;
 	uint32_t model_num_instances = 0;
 	uint64_t model_num_vertices = 0, model_num_triangles = 0;
+	// inputs and results of sqw_polygons_prepare
+	DevBuf polygon_candidates, polygon_clip_planes, polygon_results, polygon_totals;
+	uint32_t polygon_num_candidates = 0;
 };
 
 struct SurfaceGroup // one kernel launch: all bands without / with dynamic lights, CTA bands first, then warp bands
@@ -562,6 +570,9 @@ void sqw_destroy(sqw_ctx* ctx)
 		cudaFree(p);
 	if (ctx->d_meshes)
 		cudaFree(ctx->d_meshes);
+	for (void* p : {static_cast<void*>(ctx->d_map_polygons), static_cast<void*>(ctx->d_map_vertices), static_cast<void*>(ctx->d_material_flags)})
+		if (p)
+			cudaFree(p);
 	if (ctx->d_lightmaps)
 		cudaFree(ctx->d_lightmaps);
 	if (ctx->d_directional_lightmaps)
@@ -719,7 +730,8 @@ void sqw_view_destroy(sqw_view* view)
 		cudaFree(view->d_sums);
 	if (view->d_tonemap_lut)
 		cudaFree(view->d_tonemap_lut);
-	for (DevBuf* b : {&view->model_instances, &view->model_vertices, &view->model_triangles, &view->model_counts, &view->model_bones, &view->model_sort})
+	for (DevBuf* b : {&view->model_instances, &view->model_vertices, &view->model_triangles, &view->model_counts, &view->model_bones, &view->model_sort,
+					  &view->polygon_candidates, &view->polygon_clip_planes, &view->polygon_results, &view->polygon_totals})
 		b->release();
 	// keep indices of the other views stable: leave a hole
 	for (auto& p : ctx->views)
@@ -1729,6 +1741,119 @@ int sqw_models_read(sqw_view* view, sqw_model_vertex* vertices, uint64_t num_ver
 	if (counts && num_instances)
 		SQW_CUDA(ctx, cudaMemcpyAsync(counts, view->model_counts.ptr, (size_t)num_instances * 4, cudaMemcpyDeviceToHost, s));
 	SQW_CUDA(ctx, cudaStreamSynchronize(s));
+	return SQW_OK;
+}
+
+static_assert(sizeof(sqw_map_polygon) == 80 && sizeof(sqw_prepared_polygon) == 64 && sizeof(sqw_polygon_candidate) == 8 && sizeof(sqw_polygons_frame) == 144, "polygon preparation layouts");
+
+int sqw_upload_map_geometry(sqw_ctx* ctx, const sqw_map_polygon* polygons, uint32_t num_polygons, const float* vertices, uint32_t num_vertices, const uint8_t* material_flags, uint32_t num_materials)
+{
+	if (!ctx || !polygons || !vertices || !material_flags || num_polygons == 0 || num_vertices == 0 || num_materials == 0)
+		return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_upload_map_geometry: null or empty argument");
+	for (uint32_t i = 0; i < num_polygons; ++i)
+		if (polygons[i].num_vertices < 3 || (uint64_t)polygons[i].first_vertex + polygons[i].num_vertices > num_vertices || polygons[i].texture >= num_materials)
+			return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_upload_map_geometry: polygon refers to vertices or a material outside the map");
+	SQW_CUDA(ctx, cudaSetDevice(ctx->device));
+	SQW_CUDA(ctx, synchronize_all(ctx));
+	for (void** p : {reinterpret_cast<void**>(&ctx->d_map_polygons), reinterpret_cast<void**>(&ctx->d_map_vertices), reinterpret_cast<void**>(&ctx->d_material_flags)})
+		if (*p)
+		{
+			cudaFree(*p);
+			*p = nullptr;
+		}
+	ctx->num_map_polygons = ctx->num_map_vertices = ctx->num_materials = 0;
+	SQW_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_map_polygons), (size_t)num_polygons * sizeof(sqw_map_polygon)));
+	SQW_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_map_vertices), (size_t)num_vertices * 12));
+	SQW_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_material_flags), (size_t)num_materials));
+	SQW_CUDA(ctx, cudaMemcpy(ctx->d_map_polygons, polygons, (size_t)num_polygons * sizeof(sqw_map_polygon), cudaMemcpyHostToDevice));
+	SQW_CUDA(ctx, cudaMemcpy(ctx->d_map_vertices, vertices, (size_t)num_vertices * 12, cudaMemcpyHostToDevice));
+	SQW_CUDA(ctx, cudaMemcpy(ctx->d_material_flags, material_flags, (size_t)num_materials, cudaMemcpyHostToDevice));
+	ctx->num_map_polygons = num_polygons;
+	ctx->num_map_vertices = num_vertices;
+	ctx->num_materials = num_materials;
+	return SQW_OK;
+}
+
+int sqw_polygons_prepare(sqw_view* view, const sqw_polygons_frame* frame, const sqw_polygon_candidate* candidates, uint32_t num_candidates, const float* clip_planes, uint32_t num_clip_sets)
+{
+	if (!view || !frame || (num_candidates && (!candidates || !clip_planes || num_clip_sets == 0)))
+		return fail(view ? view->ctx : nullptr, SQW_ERR_INVALID_ARGUMENT, "sqw_polygons_prepare: null argument");
+	sqw_ctx* ctx = view->ctx;
+	if (!ctx->d_map_polygons)
+		return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_polygons_prepare: no map geometry uploaded (sqw_upload_map_geometry)");
+	for (uint32_t i = 0; i < num_candidates; ++i)
+		if (candidates[i].polygon >= ctx->num_map_polygons || candidates[i].clip_set >= num_clip_sets)
+			return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_polygons_prepare: candidate refers to a polygon or clip set that does not exist");
+	SQW_CUDA(ctx, cudaSetDevice(ctx->device));
+	cudaStream_t s = view->stream;
+	const size_t need[4] = {(size_t)num_candidates * sizeof(sqw_polygon_candidate) + 16, (size_t)num_clip_sets * 96 + 16, (size_t)num_candidates * sizeof(sqw_prepared_polygon) + 16,
+							sizeof(sqw::PolygonsTotalsDev)};
+	DevBuf* bufs[4] = {&view->polygon_candidates, &view->polygon_clip_planes, &view->polygon_results, &view->polygon_totals};
+	for (int i = 0; i < 4; ++i)
+		if (need[i] > bufs[i]->capacity)
+		{
+			SQW_CUDA(ctx, cudaStreamSynchronize(s)); // growing frees the old buffer
+			SQW_CUDA(ctx, bufs[i]->reserve(need[i]));
+		}
+	view->polygon_num_candidates = num_candidates;
+	if (num_candidates)
+	{
+		SQW_CUDA(ctx, cudaMemcpyAsync(view->polygon_candidates.ptr, candidates, (size_t)num_candidates * sizeof(sqw_polygon_candidate), cudaMemcpyHostToDevice, s));
+		SQW_CUDA(ctx, cudaMemcpyAsync(view->polygon_clip_planes.ptr, clip_planes, (size_t)num_clip_sets * 96, cudaMemcpyHostToDevice, s));
+	}
+	sqw::PolygonsLaunch l{};
+	l.polygons = ctx->d_map_polygons;
+	l.vertices = ctx->d_map_vertices;
+	l.material_flags = ctx->d_material_flags;
+	l.num_materials = ctx->num_materials;
+	l.frame = *frame;
+	l.candidates = static_cast<const sqw_polygon_candidate*>(view->polygon_candidates.ptr);
+	l.num_candidates = num_candidates;
+	l.clip_planes = static_cast<const float*>(view->polygon_clip_planes.ptr);
+	l.out = static_cast<sqw_prepared_polygon*>(view->polygon_results.ptr);
+	l.totals = static_cast<sqw::PolygonsTotalsDev*>(view->polygon_totals.ptr);
+	{
+		NvtxRange nvtx("polygons_preparation");
+		LaunchTimer timer(ctx, SQW_KERNEL_POLYGONS_PREPARE, s);
+		SQW_CUDA(ctx, sqw::launch_polygons_prepare(l, s));
+	}
+	// the lists are the caller's (pageable) memory: they must have left it before the call returns
+	SQW_CUDA(ctx, cudaStreamSynchronize(s));
+	return SQW_OK;
+}
+
+int sqw_polygons_read(sqw_view* view, sqw_prepared_polygon* out, uint32_t num, sqw_polygons_totals* totals)
+{
+	if (!view)
+		return SQW_ERR_INVALID_ARGUMENT;
+	sqw_ctx* ctx = view->ctx;
+	if (num > view->polygon_num_candidates || !view->polygon_totals.ptr)
+		return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_polygons_read: more than the last sqw_polygons_prepare produced");
+	SQW_CUDA(ctx, cudaSetDevice(ctx->device));
+	cudaStream_t s = view->stream;
+	if (out && num)
+		SQW_CUDA(ctx, cudaMemcpyAsync(out, view->polygon_results.ptr, (size_t)num * sizeof(sqw_prepared_polygon), cudaMemcpyDeviceToHost, s));
+	sqw::PolygonsTotalsDev t{};
+	uint32_t sky_material = 0;
+	if (totals)
+		SQW_CUDA(ctx, cudaMemcpyAsync(&t, view->polygon_totals.ptr, sizeof(t), cudaMemcpyDeviceToHost, s));
+	SQW_CUDA(ctx, cudaStreamSynchronize(s));
+	if (totals)
+	{
+		std::memset(totals, 0, sizeof(*totals));
+		totals->num_visible = t.num_visible;
+		totals->num_surfaces_pixels = t.num_surfaces_pixels;
+		totals->has_sky = t.first_sky_candidate != 0xFFFFFFFFu ? 1u : 0u;
+		if (totals->has_sky)
+		{
+			std::memcpy(totals->sky_bounds, t.sky_bounds, sizeof(t.sky_bounds));
+			// material of the first sky polygon in candidate order: candidate -> polygon -> texture (two small reads)
+			sqw_polygon_candidate c{};
+			SQW_CUDA(ctx, cudaMemcpy(&c, static_cast<const sqw_polygon_candidate*>(view->polygon_candidates.ptr) + t.first_sky_candidate, sizeof(c), cudaMemcpyDeviceToHost));
+			SQW_CUDA(ctx, cudaMemcpy(&sky_material, &ctx->d_map_polygons[c.polygon].texture, 4, cudaMemcpyDeviceToHost));
+			totals->sky_material = sky_material;
+		}
+	}
 	return SQW_OK;
 }
 

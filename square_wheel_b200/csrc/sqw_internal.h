@@ -205,6 +205,29 @@ struct ModelLaunch
 };
 cudaError_t launch_models_prepare(const ModelLaunch& l, cudaStream_t stream);
 
+// ---- world-polygon preparation -------------------------------------------------------------------
+struct PolygonsTotalsDev
+{
+	float sky_bounds[8]; // x, y, x_plus_y, x_minus_y as {min, max}
+	uint32_t first_sky_candidate;
+	uint32_t num_visible;
+	unsigned long long num_surfaces_pixels;
+};
+struct PolygonsLaunch
+{
+	const sqw_map_polygon* polygons; // device (uploaded map)
+	const float* vertices;           // device
+	const uint8_t* material_flags;   // device
+	uint32_t num_materials;
+	sqw_polygons_frame frame;
+	const sqw_polygon_candidate* candidates; // device
+	uint32_t num_candidates;
+	const float* clip_planes; // device, [sets][8][3]
+	sqw_prepared_polygon* out; // device
+	PolygonsTotalsDev* totals; // device
+};
+cudaError_t launch_polygons_prepare(const PolygonsLaunch& l, cudaStream_t stream);
+
 // ---- shadow maps ----------------------------------------------------------------------------------------------
 struct DepthCmdDev // per fill call, prepared by sqw_frame_set_shadow_map_draw. 16 bytes
 {

@@ -113,6 +113,13 @@ class Context:
         m.vertices, m.triangles, m.num_triangles = v.ctypes.data, tri.ctypes.data, len(tri)
         return self._check(self._lib.sqw_upload_model_mesh(self._handle, C.byref(m)), "sqw_upload_model_mesh")
 
+    def upload_map_geometry(self, polygons: np.ndarray, vertices: np.ndarray, material_flags: np.ndarray):
+        """The map's polygons (80-byte Polygon records), vertices [n, 3] f32 and per-material SQW_MATERIAL_* flags (sqw_upload_map_geometry)."""
+        pol = _as(polygons, N.map_polygon_dtype)
+        ver = np.ascontiguousarray(vertices, np.float32).reshape(-1, 3)
+        fl = np.ascontiguousarray(material_flags, np.uint8)
+        self._check(self._lib.sqw_upload_map_geometry(self._handle, N.ptr(pol), len(pol), N.ptr(ver), len(ver), N.ptr(fl), len(fl)), "sqw_upload_map_geometry")
+
     def set_fast_surface_numerics(self, enable: bool):
         """SQW_CTX_FAST_SURFACE_NUMERICS for the frames submitted from now on (sqw_set_fast_surface_numerics)."""
         self._check(self._lib.sqw_set_fast_surface_numerics(self._handle, 1 if enable else 0), "sqw_set_fast_surface_numerics")
@@ -226,6 +233,23 @@ class View:
         c = np.zeros(num_instances, np.uint32)
         self.ctx._check(self._lib.sqw_models_read(self._handle, N.ptr(v), num_vertices, N.ptr(t), num_triangles, N.ptr(c), num_instances), "sqw_models_read")
         return v, t, c
+
+    def polygons_prepare(self, planes_matrix, view_matrix, mip_bias: float, candidates: np.ndarray, clip_planes: np.ndarray):
+        """prepare_polygon_surface for every (polygon, leaf clip planes) candidate on the GPU (sqw_polygons_prepare)."""
+        fr = N.PolygonsFrame()
+        fr.planes_matrix[:] = [float(x) for x in np.asarray(planes_matrix, np.float32).reshape(16)]
+        fr.view_matrix[:] = [float(x) for x in np.asarray(view_matrix, np.float32).reshape(16)]
+        fr.mip_bias = float(mip_bias)
+        cand = _as(candidates, N.polygon_candidate_dtype)
+        planes = np.ascontiguousarray(clip_planes, np.float32).reshape(-1, 8, 3)
+        self.ctx._check(self._lib.sqw_polygons_prepare(self._handle, C.byref(fr), N.ptr(cand), len(cand), N.ptr(planes), len(planes)), "sqw_polygons_prepare")
+
+    def polygons_read(self, num: int):
+        """(records [prepared_polygon_dtype] in candidate order, totals) of the last polygons_prepare."""
+        out = np.zeros(num, N.prepared_polygon_dtype)
+        totals = N.PolygonsTotals()
+        self.ctx._check(self._lib.sqw_polygons_read(self._handle, N.ptr(out), num, C.byref(totals)), "sqw_polygons_read")
+        return out, totals
 
     def average_color(self) -> np.ndarray:
         avg = np.zeros(3, np.float32)

@@ -502,6 +502,37 @@ int sqwh_renderer_dynamic_meshes(const Renderer* r, void* records, uint32_t capa
 	return (int)count;
 }
 
+// prepare_polygons_surfaces of the frame prepared last, leaf polygons: the (polygon, clip set) candidates in preparation order, the
+// clip planes (8 x 3 floats per set), this mirror's results in the layout of sqw_prepared_polygon (64 bytes) and the frame record
+// (Renderer::PolygonsFrameExport).  NULL buffers are skipped; counts_out = {candidates, clip sets}.
+int sqwh_renderer_prepared_polygons(const Renderer* r, void* candidates, float* clip_planes, void* prepared, void* frame, uint64_t counts_out[2])
+{
+	if (!r)
+		return -1;
+	static_assert(sizeof(Renderer::PreparedPolygonExport) == 64 && sizeof(Renderer::PolygonCandidate) == 8, "export layouts");
+	const auto& c = r->polygon_candidates();
+	const auto& p = r->polygon_clip_planes();
+	if (counts_out)
+	{
+		counts_out[0] = c.size();
+		counts_out[1] = p.size() / 8;
+	}
+	if (candidates && !c.empty())
+		std::memcpy(candidates, c.data(), c.size() * sizeof(Renderer::PolygonCandidate));
+	if (clip_planes && !p.empty())
+		std::memcpy(clip_planes, p.data(), p.size() * sizeof(Vec3f));
+	r->export_prepared_polygons(static_cast<Renderer::PreparedPolygonExport*>(prepared), static_cast<Renderer::PolygonsFrameExport*>(frame));
+	return (int)c.size();
+}
+// per-material SQW_MATERIAL_* flags for sqw_upload_map_geometry
+uint32_t sqwh_scene_material_flags(const Scene* s, uint8_t* out, uint32_t capacity)
+{
+	const uint32_t n = (uint32_t)s->materials.size();
+	for (uint32_t i = 0; i < n && i < capacity; ++i)
+		out[i] = (uint8_t)((s->materials[i].draw ? 1 : 0) | (s->materials[i].is_skybox ? 2 : 0));
+	return n;
+}
+
 int sqwh_scene_model_info(const Scene* s, uint32_t index, sqwh_model_info* out)
 {
 	if (index >= s->models.size())

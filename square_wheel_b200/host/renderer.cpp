@@ -976,6 +976,9 @@ void Renderer::prepare_frame_with_matrices(uint32_t width, uint32_t height, cons
 void Renderer::prepare_polygons_surfaces() // partial_renderer.rs:1327-1449 (leaf polygons; submodels are not part of the synthetic maps)
 {
 	current_frame_visible_polygons_.clear();
+	polygon_candidates_.clear();
+	polygon_clip_planes_.clear();
+	polygon_is_sky_candidate_.clear();
 	num_visible_surfaces_pixels_ = 0;
 	has_current_sky_ = false; // :1336
 	for (size_t i = 0; i < map_.leafs.size(); ++i)
@@ -987,8 +990,13 @@ void Renderer::prepare_polygons_surfaces() // partial_renderer.rs:1327-1449 (lea
 		const BSPLeaf& leaf = map_.leafs[i];
 		Vec3f clip_planes[8];
 		bounds.get_clip_planes(clip_planes);
+		const uint32_t clip_set = (uint32_t)(polygon_clip_planes_.size() / 8);
+		polygon_clip_planes_.insert(polygon_clip_planes_.end(), clip_planes, clip_planes + 8);
 		for (uint32_t p = leaf.first_polygon; p < leaf.first_polygon + leaf.num_polygons; ++p)
-			prepare_polygon_surface(camera_matrices_, clip_planes, p);
+		{
+			polygon_candidates_.push_back(PolygonCandidate{p, clip_set});
+			polygon_is_sky_candidate_.push_back(prepare_polygon_surface(camera_matrices_, clip_planes, p) == 2 ? 1 : 0);
+		}
 	}
 	// surfaces of the submodels located in visible leafs (:1362-1447)
 	for (size_t index = 0; index < map_.submodels.size(); ++index)
@@ -1037,17 +1045,18 @@ void Renderer::prepare_polygons_surfaces() // partial_renderer.rs:1327-1449 (lea
 	stats_.num_surfaces_pixels = num_visible_surfaces_pixels_;
 }
 
-void Renderer::prepare_polygon_surface(const CameraMatrices& camera_matrices_, const Vec3f clip_planes[8], size_t polygon_index) // partial_renderer.rs:1464-1638
+// returns 0: culled or clipped away, 1: visible (surface rectangle recorded), 2: sky polygon (only widened the sky window)
+uint32_t Renderer::prepare_polygon_surface(const CameraMatrices& camera_matrices_, const Vec3f clip_planes[8], size_t polygon_index) // partial_renderer.rs:1464-1638
 {
 	DrawPolygonData& polygon_data = polygons_data_[polygon_index];
 	const Polygon& polygon = map_.polygons[polygon_index];
 
 	const Vec4f plane_transformed = camera_matrices_.planes_matrix * extend(polygon.plane.vec, -polygon.plane.dist);
 	if (plane_transformed.w <= 0.0f) // cull back faces
-		return;
+		return 0;
 	const Material& material = scene_.materials[polygon.texture];
 	if (!material.draw)
-		return;
+		return 0;
 
 	const Vec3f* polygon_vertices = &map_.vertices[polygon.first_vertex];
 	Vec3f* polygon_vertices_transformed = &vertices_transformed_[polygon.first_vertex];
@@ -1057,7 +1066,7 @@ void Renderer::prepare_polygon_surface(const CameraMatrices& camera_matrices_, c
 	Vec2f vertices_2d[MAX_VERTICES];
 	const size_t vertex_count = project_and_clip_polygon(clip_planes, polygon_vertices_transformed, polygon.num_vertices, vertices_2d);
 	if (vertex_count < 3)
-		return;
+		return 0;
 
 	if (material.is_skybox) // :1511-1529: sky polygons are not drawn, they only grow the window the sky box is seen through
 	{
@@ -1072,7 +1081,7 @@ void Renderer::prepare_polygon_surface(const CameraMatrices& camera_matrices_, c
 			current_sky_material_ = polygon.texture;
 			current_sky_bounds_ = polygon_bounds;
 		}
-		return;
+		return 2;
 	}
 
 	// DepthEquation::from_transformed_plane_equation (equations.rs:22-31)
@@ -1157,6 +1166,55 @@ void Renderer::prepare_polygon_surface(const CameraMatrices& camera_matrices_, c
 		polygon_data.tex_coord_equation[4 + i] -= tcm * depth_equation[2];
 	}
 	current_frame_visible_polygons_.push_back((uint32_t)polygon_index);
+	return 1;
+}
+
+void Renderer::export_prepared_polygons(PreparedPolygonExport* out, PolygonsFrameExport* frame) const
+{
+	if (out)
+		for (size_t i = 0; i < polygon_candidates_.size(); ++i)
+		{
+			PreparedPolygonExport& e = out[i];
+			std::memset(&e, 0, sizeof(e));
+			const DrawPolygonData& d = polygons_data_[polygon_candidates_[i].polygon];
+			// (leaf polygons only: a submodel polygon prepared later in the frame is not a candidate)
+			if (d.visible_frame == current_frame_ && d.parent_submodel == 0xFFFFFFFFu)
+			{
+				e.flags = 1;
+				e.mip = d.mip;
+				std::memcpy(e.depth_equation, d.depth_equation, sizeof(e.depth_equation));
+				std::memcpy(e.tex_coord_equation, d.tex_coord_equation, sizeof(e.tex_coord_equation));
+				e.surface_tc_min[0] = d.surface_tc_min[0];
+				e.surface_tc_min[1] = d.surface_tc_min[1];
+				e.surface_size[0] = d.surface_size[0];
+				e.surface_size[1] = d.surface_size[1];
+				e.surface_pixels_offset = (uint32_t)d.surface_pixels_offset;
+			}
+			else if (polygon_is_sky_candidate_[i])
+				e.flags = 2;
+		}
+	if (frame)
+	{
+		std::memset(frame, 0, sizeof(*frame));
+		std::memcpy(frame->planes_matrix, &camera_matrices_.planes_matrix, 64);
+		std::memcpy(frame->view_matrix, &camera_matrices_.view_matrix, 64);
+		frame->mip_bias = mip_bias_;
+		frame->has_sky = has_current_sky_ ? 1u : 0u;
+		frame->sky_material = current_sky_material_;
+		if (has_current_sky_)
+			std::memcpy(frame->sky_bounds, &current_sky_bounds_, 32);
+		frame->num_visible = 0;
+		frame->num_surfaces_pixels = 0;
+		for (size_t i = 0; i < polygon_candidates_.size(); ++i)
+		{
+			const DrawPolygonData& d = polygons_data_[polygon_candidates_[i].polygon];
+			if (d.visible_frame == current_frame_ && d.parent_submodel == 0xFFFFFFFFu)
+			{
+				++frame->num_visible;
+				frame->num_surfaces_pixels += (uint64_t)d.surface_size[0] * d.surface_size[1];
+			}
+		}
+	}
 }
 
 namespace

@@ -198,6 +198,33 @@ public:
 		uint32_t vertices_offset, num_vertices, triangles_offset, num_triangles, num_visible_triangles;
 	};
 	size_t export_dynamic_meshes(DynamicMeshExport* out, size_t capacity) const;
+	// Inputs and results of prepare_polygons_surfaces for the leaf polygons of the frame prepared last (what sqw_polygons_prepare
+	// computes on the GPU; tests compare the two): the (polygon, clip set) pairs in the order they were prepared, eight planes per set.
+	struct PolygonCandidate
+	{
+		uint32_t polygon, clip_set;
+	};
+	struct PreparedPolygonExport // layout of sqw_prepared_polygon
+	{
+		uint32_t flags, mip;
+		float depth_equation[3];
+		float tex_coord_equation[6];
+		int32_t surface_tc_min[2];
+		uint32_t surface_size[2];
+		uint32_t surface_pixels_offset;
+	};
+	struct PolygonsFrameExport
+	{
+		float planes_matrix[16], view_matrix[16];
+		float mip_bias;
+		uint32_t has_sky, sky_material;
+		float sky_bounds[8];
+		uint32_t num_visible;
+		uint64_t num_surfaces_pixels;
+	};
+	const std::vector<PolygonCandidate>& polygon_candidates() const { return polygon_candidates_; }
+	const std::vector<Vec3f>& polygon_clip_planes() const { return polygon_clip_planes_; }
+	void export_prepared_polygons(PreparedPolygonExport* out, PolygonsFrameExport* frame) const;
 	const std::vector<ModelVertex3d>& dynamic_meshes_vertices() const { return dynamic_meshes_vertices_; }
 	const std::vector<Triangle>& dynamic_meshes_triangles() const { return dynamic_meshes_triangles_; }
 
@@ -249,7 +276,7 @@ private:
 	void draw_mesh(const ClippingPolygon& clipping_polygon, const Plane* leaf_clip_planes, size_t num_leaf_clip_planes, size_t visible_mesh_index);
 	// partial_renderer.rs
 	void prepare_polygons_surfaces();
-	void prepare_polygon_surface(const CameraMatrices& camera_matrices, const Vec3f clip_planes[8], size_t polygon_index);
+	uint32_t prepare_polygon_surface(const CameraMatrices& camera_matrices, const Vec3f clip_planes[8], size_t polygon_index);
 	void build_surface_jobs();
 	void draw_skybox(const ClippingPolygon& viewport_clipping_polygon, int color_bits);
 	void draw_tree(const ClippingPolygon& viewport_clipping_polygon);
@@ -344,6 +371,9 @@ private:
 	ClippingPolygon current_sky_bounds_;
 
 	std::vector<DrawPolygonData> polygons_data_;
+	std::vector<PolygonCandidate> polygon_candidates_;
+	std::vector<Vec3f> polygon_clip_planes_;
+	std::vector<uint8_t> polygon_is_sky_candidate_; // per candidate: the polygon reached the sky branch of prepare_polygon_surface
 	std::vector<Vec3f> vertices_transformed_;
 	std::vector<uint32_t> current_frame_visible_polygons_;
 	uint64_t num_visible_surfaces_pixels_ = 0;

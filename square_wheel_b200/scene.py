@@ -159,6 +159,13 @@ class ModelInfo(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("num_frames", "num_meshes", "num_vertices", "num_triangles", "kind", "num_bones")] + [("bbox_min", C.c_float * 3), ("bbox_max", C.c_float * 3)]
 
 
+# Renderer::PolygonsFrameExport (host/renderer.hpp)
+polygons_frame_dtype = np.dtype(
+    [("planes_matrix", "<f4", 16), ("view_matrix", "<f4", 16), ("mip_bias", "<f4"), ("has_sky", "<u4"), ("sky_material", "<u4"), ("sky_bounds", "<f4", 8), ("num_visible", "<u4"),
+     ("num_surfaces_pixels", "<u8")])
+assert polygons_frame_dtype.itemsize == 184
+
+
 def build_host_library():
     subprocess.run(["make", "-C", os.path.join(os.path.dirname(N.HOST_LIB_PATH), "host")], check=True, capture_output=True)
 
@@ -232,6 +239,14 @@ def lib() -> C.CDLL:
             getattr(l, name).restype = vp
             getattr(l, name).argtypes = [vp]
         l.sqwh_default_scene_params.argtypes = [C.POINTER(SceneParams)]
+        l.sqwh_scene_polygons.restype = vp
+        l.sqwh_scene_polygons.argtypes = [vp]
+        l.sqwh_scene_vertices.restype = vp
+        l.sqwh_scene_vertices.argtypes = [vp]
+        l.sqwh_scene_material_flags.restype = C.c_uint32
+        l.sqwh_scene_material_flags.argtypes = [vp, vp, C.c_uint32]
+        l.sqwh_renderer_prepared_polygons.restype = C.c_int
+        l.sqwh_renderer_prepared_polygons.argtypes = [vp, vp, vp, vp, vp, C.POINTER(C.c_uint64)]
         _lib = l
     return _lib
 
@@ -358,6 +373,16 @@ class Scene:
         n = self._lib.sqwh_scene_camera_path(self._handle, num_frames, jitter_seed, out.ctypes.data_as(C.c_void_p))
         return out[:n]
 
+    def map_geometry(self):
+        """(polygons [map_polygon_dtype: the 80-byte Polygon records], vertices [n, 3] f32, per-material SQW_MATERIAL_* flags) for sqw_upload_map_geometry."""
+        info = self.info
+        pol = _array_from(self._lib.sqwh_scene_polygons(self._handle), int(info.num_polygons), N.map_polygon_dtype).copy()
+        ver = _array_from(self._lib.sqwh_scene_vertices(self._handle), int(info.num_vertices) * 3, np.float32).reshape(-1, 3).copy()
+        flags = np.zeros(int(info.num_materials), np.uint8)
+        n = self._lib.sqwh_scene_material_flags(self._handle, flags.ctypes.data_as(C.c_void_p), len(flags))
+        assert n == len(flags)
+        return pol, ver, flags
+
     def upload(self, ctx):
         """Upload every image in image-id order (S0 of SURVEY.md §8b)."""
         for i, (kind, px) in enumerate(self.images):
@@ -480,6 +505,20 @@ class HostRenderer:
             self._handle, rec.ctypes.data_as(C.c_void_p), len(rec), v.ctypes.data_as(C.c_void_p), len(v), t.ctypes.data_as(C.c_void_p), len(t), counts
         )
         return rec, v, t
+
+    def prepared_polygons(self):
+        """prepare_polygons_surfaces (partial_renderer.rs:1327-1360) of the frame built last, leaf polygons: (candidates
+        [polygon_candidate_dtype], clip planes [sets, 8, 3], this mirror's results [prepared_polygon_dtype], frame record) —
+        the inputs of sqw_polygons_prepare and what it must reproduce."""
+        counts = (C.c_uint64 * 2)()
+        self._lib.sqwh_renderer_prepared_polygons(self._handle, None, None, None, None, counts)
+        cand = np.zeros(int(counts[0]), N.polygon_candidate_dtype)
+        planes = np.zeros((int(counts[1]), 8, 3), np.float32)
+        res = np.zeros(int(counts[0]), N.prepared_polygon_dtype)
+        frame = np.zeros(1, polygons_frame_dtype)
+        vp = C.c_void_p
+        self._lib.sqwh_renderer_prepared_polygons(self._handle, cand.ctypes.data_as(vp), planes.ctypes.data_as(vp), res.ctypes.data_as(vp), frame.ctypes.data_as(vp), counts)
+        return cand, planes, res, frame[0]
 
     def default_submodel_entities(self) -> np.ndarray:
         """Every submodel present, at the place the map has it (position = bbox centre, identity rotation)."""

@@ -1,0 +1,88 @@
+"""World-polygon preparation on the GPU (the geometry half of the host front end): sqw_polygons_prepare against
+the host mirror of PartialRenderer::prepare_polygons_surfaces / prepare_polygon_surface (partial_renderer.rs:1327-1360, :1464-1638).
+
+The visibility flood stays on the host; it hands over the (polygon, leaf clip planes) candidates.  Kernel and mirror evaluate the same
+float expressions in the same order without fused multiply-add, so every record — visibility, mip, depth and texture-coordinate
+equations, surface rectangle, surface_pixels_offset — the frame totals and the sky window are compared BIT FOR BIT."""
+import numpy as np
+import pytest
+
+from square_wheel_b200 import _native as N
+from square_wheel_b200 import scene as S
+from square_wheel_b200.device import Context, SqwError
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare(view, hr, what):
+    cand, planes, want, fr = hr.prepared_polygons()
+    assert len(cand) > 20, what
+    view.polygons_prepare(fr["planes_matrix"], fr["view_matrix"], float(fr["mip_bias"]), cand, planes)
+    got, totals = view.polygons_read(len(cand))
+    assert got["flags"].tolist() == want["flags"].tolist(), f"{what}: visibility / sky flags"
+    for field in ("mip", "surface_tc_min", "surface_size", "surface_pixels_offset"):
+        assert np.array_equal(got[field], want[field]), f"{what}: {field}"
+    for field in ("depth_equation", "tex_coord_equation"):
+        a, b = np.ascontiguousarray(got[field]).view(np.uint32), np.ascontiguousarray(want[field]).view(np.uint32)
+        assert np.array_equal(a, b), f"{what}: {field} differs in {int((a != b).any(axis=1).sum())} records"
+    assert totals.num_visible == int(fr["num_visible"]) == int((want["flags"] == N.PREPARED_VISIBLE).sum())
+    assert totals.num_surfaces_pixels == int(fr["num_surfaces_pixels"])
+    assert totals.has_sky == int(fr["has_sky"])
+    if totals.has_sky:
+        assert totals.sky_material == int(fr["sky_material"])
+        assert np.array_equal(np.array(list(totals.sky_bounds), np.float32).view(np.uint32), np.ascontiguousarray(fr["sky_bounds"]).view(np.uint32)), f"{what}: sky window"
+    return int(totals.num_visible), int((want["flags"] == N.PREPARED_SKY).sum()), want
+
+
+@pytest.mark.parametrize("mip_bias", [0.0, -1.0, 0.6])
+def test_polygons_prepare_matches_the_host_mirror_bit_for_bit(mip_bias):
+    sc = S.Scene(seed=7, texture_size_log2=6, num_materials=8, skybox=1, sky_size_log2=6)
+    ctx = Context(sc.lightmaps, sc.directional_lightmaps, device=0)
+    hr = S.HostRenderer(sc, textures_mip_bias=mip_bias)
+    try:
+        ctx.upload_map_geometry(*sc.map_geometry())
+        view = ctx.create_view(64, 64, 64)
+        path = sc.camera_path(64)
+        visible = sky = 0
+        mips = set()
+        for k, (w, h) in zip((0, 5, 17, 30, 44, 59), ((640, 360), (1280, 720), (3840, 2160), (333, 777), (1920, 1080), (3840, 2160))):
+            hr.build_frame(w, h, path[k])
+            v, s, want = _compare(view, hr, f"pose {k} at {w}x{h}, mip bias {mip_bias}")
+            visible += v
+            sky += s
+            mips |= set(want["mip"][want["flags"] == N.PREPARED_VISIBLE].tolist())
+        assert visible > 300 and sky > 0 and len(mips) >= 2  # culled, clipped, sky and several mips all occur
+    finally:
+        hr.close()
+        ctx.close()
+        sc.close()
+
+
+def test_polygons_prepare_on_the_bench_scene_and_bad_arguments():
+    """The 4K bench map (seed 2, 13k polygons): every pose of a strided camera path; then the argument checks of the C-ABI."""
+    sc = S.Scene(seed=2, grid=(24, 24, 5), cell_size=(160.0, 160.0, 128.0), num_rooms=26, num_materials=24, texture_size_log2=5, max_polygon_size=64.0, material_mode=0, emissive_fraction=0.15)
+    ctx = Context(sc.lightmaps, sc.directional_lightmaps, device=0)
+    hr = S.HostRenderer(sc)
+    try:
+        view = ctx.create_view(64, 64, 64)
+        path = sc.camera_path(64)
+        hr.build_frame(3840, 2160, path[0])
+        cand, planes, want, fr = hr.prepared_polygons()
+        with pytest.raises(SqwError):  # no geometry uploaded yet
+            view.polygons_prepare(fr["planes_matrix"], fr["view_matrix"], 0.0, cand, planes)
+        ctx.upload_map_geometry(*sc.map_geometry())
+        for k in range(0, 64, 7):
+            hr.build_frame(3840, 2160, path[k])
+            _compare(view, hr, f"bench scene pose {k}")
+        bad = cand.copy()
+        bad["polygon"][3] = int(sc.info.num_polygons)
+        with pytest.raises(SqwError):
+            view.polygons_prepare(fr["planes_matrix"], fr["view_matrix"], 0.0, bad, planes)
+        bad = cand.copy()
+        bad["clip_set"][0] = len(planes)
+        with pytest.raises(SqwError):
+            view.polygons_prepare(fr["planes_matrix"], fr["view_matrix"], 0.0, bad, planes)
+    finally:
+        hr.close()
+        ctx.close()
+        sc.close()
