@@ -524,6 +524,7 @@ int sqwh_renderer_prepared_polygons(const Renderer* r, void* candidates, float* 
 	r->export_prepared_polygons(static_cast<Renderer::PreparedPolygonExport*>(prepared), static_cast<Renderer::PolygonsFrameExport*>(frame));
 	return (int)c.size();
 }
+double sqwh_renderer_polygons_prepare_seconds(const Renderer* r) { return r ? r->polygons_prepare_seconds() : 0.0; }
 // per-material SQW_MATERIAL_* flags for sqw_upload_map_geometry
 uint32_t sqwh_scene_material_flags(const Scene* s, uint8_t* out, uint32_t capacity)
 {

@@ -3,6 +3,7 @@
 #include <atomic>
 #include <thread>
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 
 namespace sqwh
@@ -967,7 +968,11 @@ void Renderer::prepare_frame_with_matrices(uint32_t width, uint32_t height, cons
 	prepare_decals();               // partial_renderer.rs:209
 	position_sprites();             // renderer.rs:86
 	prepare_sprites();              // partial_renderer.rs:211
-	prepare_polygons_surfaces(); // :214
+	{
+		const auto t0 = std::chrono::steady_clock::now();
+		prepare_polygons_surfaces(); // :214
+		polygons_prepare_seconds_ = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+	}
 	build_surface_jobs();        // :221
 	position_portals();              // renderer.rs:90
 	prepare_view_portals_textures(); // partial_renderer.rs:230 (the nested views themselves: prepare_portal_view)

@@ -225,6 +225,7 @@ public:
 	const std::vector<PolygonCandidate>& polygon_candidates() const { return polygon_candidates_; }
 	const std::vector<Vec3f>& polygon_clip_planes() const { return polygon_clip_planes_; }
 	void export_prepared_polygons(PreparedPolygonExport* out, PolygonsFrameExport* frame) const;
+	double polygons_prepare_seconds() const { return polygons_prepare_seconds_; } // wall time of prepare_polygons_surfaces in the last prepare_frame
 	const std::vector<ModelVertex3d>& dynamic_meshes_vertices() const { return dynamic_meshes_vertices_; }
 	const std::vector<Triangle>& dynamic_meshes_triangles() const { return dynamic_meshes_triangles_; }
 
@@ -371,6 +372,7 @@ private:
 	ClippingPolygon current_sky_bounds_;
 
 	std::vector<DrawPolygonData> polygons_data_;
+	double polygons_prepare_seconds_ = 0.0;
 	std::vector<PolygonCandidate> polygon_candidates_;
 	std::vector<Vec3f> polygon_clip_planes_;
 	std::vector<uint8_t> polygon_is_sky_candidate_; // per candidate: the polygon reached the sky branch of prepare_polygon_surface

@@ -245,6 +245,8 @@ def lib() -> C.CDLL:
         l.sqwh_scene_vertices.argtypes = [vp]
         l.sqwh_scene_material_flags.restype = C.c_uint32
         l.sqwh_scene_material_flags.argtypes = [vp, vp, C.c_uint32]
+        l.sqwh_renderer_polygons_prepare_seconds.restype = C.c_double
+        l.sqwh_renderer_polygons_prepare_seconds.argtypes = [vp]
         l.sqwh_renderer_prepared_polygons.restype = C.c_int
         l.sqwh_renderer_prepared_polygons.argtypes = [vp, vp, vp, vp, vp, C.POINTER(C.c_uint64)]
         _lib = l
@@ -519,6 +521,10 @@ class HostRenderer:
         vp = C.c_void_p
         self._lib.sqwh_renderer_prepared_polygons(self._handle, cand.ctypes.data_as(vp), planes.ctypes.data_as(vp), res.ctypes.data_as(vp), frame.ctypes.data_as(vp), counts)
         return cand, planes, res, frame[0]
+
+    def polygons_prepare_seconds(self) -> float:
+        """Wall time the host mirror spent in prepare_polygons_surfaces during the last build_frame."""
+        return float(self._lib.sqwh_renderer_polygons_prepare_seconds(self._handle))
 
     def default_submodel_entities(self) -> np.ndarray:
         """Every submodel present, at the place the map has it (position = bbox centre, identity rotation)."""

@@ -179,6 +179,7 @@ def main():
         hr = S.HostRenderer(sc, use_directional_lightmaps=cfg["directional"], textures_mip_bias=cfg.get("mip_bias", 0.0), portals_depth=cfg.get("portals_depth", 1))
         path = sc.camera_path(64)
         frames = []
+        geometry_frames = []
         for i in range(args.frames):
             k = (i * 64) // args.frames
             pose = path[k].copy()
@@ -195,6 +196,8 @@ def main():
             if cfg.get("portals"):
                 kw["portals"] = portals_for(S, N, pose, int(sc.info.num_models))
             frames.append(hr.build_frame(W, H, pose, color_bits=cfg["bits"], **kw))
+            if i % 4 == 0:  # world-polygon preparation of this pose: the mirror's lists, results and its wall time
+                geometry_frames.append(hr.prepared_polygons() + (hr.polygons_prepare_seconds(),))
         hr.close()
         ctx = Context(sc.lightmaps, sc.directional_lightmaps, device=0, stream=stream.cuda_stream, concurrent_views=True)
         sc.upload(ctx)
@@ -231,6 +234,32 @@ def main():
         ctx.profile_begin()
         run(serial=True)
         kt = ctx.profile_end()
+        # the geometry half of the host front end on the GPU (sqw_polygons_prepare) beside the host mirror, same candidates
+        import time
+
+        ctx.upload_map_geometry(*sc.map_geometry())
+        gv = views[0]
+        for cand, planes, want, fr, _ in geometry_frames[:2]:
+            gv.polygons_prepare(fr["planes_matrix"], fr["view_matrix"], float(fr["mip_bias"]), cand, planes)
+        torch.cuda.synchronize()
+        ctx.profile_begin()
+        t0 = time.perf_counter()
+        for cand, planes, want, fr, _ in geometry_frames:
+            gv.polygons_prepare(fr["planes_matrix"], fr["view_matrix"], float(fr["mip_bias"]), cand, planes)
+        call_s = time.perf_counter() - t0
+        gkt = ctx.profile_end()
+        got, totals = gv.polygons_read(len(geometry_frames[-1][0]))
+        want = geometry_frames[-1][2]
+        geometry = {
+            "candidates_per_frame": float(np.mean([len(g[0]) for g in geometry_frames])),
+            "visible_polygons_per_frame": float(np.mean([int(g[3]["num_visible"]) for g in geometry_frames])),
+            "host_mirror_us_per_frame": 1e6 * float(np.mean([g[4] for g in geometry_frames])),
+            "gpu_kernels_us_per_frame": gkt["polygons_prepare"][0] * 1e3 / len(geometry_frames),
+            "gpu_call_us_per_frame": call_s * 1e6 / len(geometry_frames),
+            "bit_exact_vs_host_mirror": bool(np.array_equal(got.view(np.uint8), want.view(np.uint8))),
+            "note": "prepare_polygons_surfaces for the leaf polygons (partial_renderer.rs:1327-1360): host mirror = one thread, wall clock; GPU kernels = polygons_prepare + "
+                    "offsets by CUDA events; GPU call = sqw_polygons_prepare wall clock including the upload of the candidate list from pageable memory and the stream synchronisation",
+        }
         st = [f.stats() for f in recorded]
         S_tex = sum(s.surface_texels for s in st) / len(st)
         Se = sum(s.emissive_texels for s in st) / len(st)
@@ -254,9 +283,11 @@ def main():
             "nested_portal_views_per_frame": float(np.mean([f.num_nested() for f in recorded])),
             "blended_world_commands_per_frame": float(np.mean([((hf.cmds["kind"] == N.CMD_POLYGON) & (hf.cmds["blend"] != 0)).sum() for hf in frames])),
             "kernels": kernels,
+            "front_end_geometry": geometry,
         }
         results[name] = res
-        print(name, json.dumps({k: (round(v, 2) if isinstance(v, float) else v) for k, v in res.items() if k != "kernels"}), flush=True)
+        print(name, json.dumps({k: (round(v, 2) if isinstance(v, float) else v) for k, v in res.items() if k not in ("kernels", "front_end_geometry")}), flush=True)
+        print("    front-end geometry:", {k: (round(v, 1) if isinstance(v, float) else v) for k, v in geometry.items() if k != "note"}, flush=True)
         for kname, kv in kernels.items():
             print("   ", kname, {a: round(b, 3) if isinstance(b, float) else b for a, b in kv.items()}, flush=True)
         for f in recorded:
