@@ -196,7 +196,8 @@ pub struct sqw_frame_stats
 	pub reserved: u32,
 }
 
-pub const SQW_NUM_KERNEL_KINDS: usize = 13;
+pub const SQW_KERNEL_POLYGONS_PREPARE: usize = 13;
+pub const SQW_NUM_KERNEL_KINDS: usize = 14;
 #[repr(C)]
 pub struct sqw_kernel_times
 {
@@ -248,6 +249,65 @@ pub struct sqw_model_vertex // ModelVertex3d (renderer_structs.rs:311-318)
 	pub pos: [f32; 3],
 	pub tc: [f32; 2],
 	pub light: [f32; 3],
+}
+
+// ---- world-polygon preparation on the GPU (prepare_polygon_surface, partial_renderer.rs:1464-1638) ----
+#[repr(C)]
+#[derive(Copy, Clone)]
+pub struct sqw_map_polygon // = Polygon (bsp_map_compact.rs:58-75): pass BSPMap::polygons.as_ptr() as it is
+{
+	pub first_vertex: u32,
+	pub num_vertices: u32,
+	pub plane: [f32; 4],
+	pub tex_coord_equation: [[f32; 4]; 2],
+	pub tex_coord_min: [i32; 2],
+	pub tex_coord_max: [i32; 2],
+	pub lightmap_data_offset: u32,
+	pub texture: u32,
+}
+pub const SQW_MATERIAL_DRAW: u8 = 1;
+pub const SQW_MATERIAL_SKYBOX: u8 = 2;
+pub const SQW_MATERIAL_BLEND_SHIFT: u8 = 4; // bits 4-6: Material::blending_mode as SQW_BLEND_*
+#[repr(C)]
+#[derive(Copy, Clone)]
+pub struct sqw_polygon_candidate
+{
+	pub polygon: u32,
+	pub clip_set: u32,
+}
+#[repr(C)]
+#[derive(Copy, Clone)]
+pub struct sqw_polygons_frame
+{
+	pub planes_matrix: [f32; 16],
+	pub view_matrix: [f32; 16],
+	pub mip_bias: f32,
+	pub reserved: [u32; 3],
+}
+pub const SQW_PREPARED_VISIBLE: u32 = 1;
+pub const SQW_PREPARED_SKY: u32 = 2;
+#[repr(C)]
+#[derive(Copy, Clone)]
+pub struct sqw_prepared_polygon // the per-frame half of DrawPolygonData (renderer_structs.rs:75-91)
+{
+	pub flags: u32,
+	pub mip: u32,
+	pub depth_equation: [f32; 3],
+	pub tex_coord_equation: [f32; 6],
+	pub surface_tc_min: [i32; 2],
+	pub surface_size: [u32; 2],
+	pub surface_pixels_offset: u32,
+}
+#[repr(C)]
+#[derive(Copy, Clone)]
+pub struct sqw_polygons_totals
+{
+	pub num_visible: u32,
+	pub has_sky: u32,
+	pub num_surfaces_pixels: u64,
+	pub sky_bounds: [f32; 8],
+	pub sky_material: u32,
+	pub reserved: u32,
 }
 
 #[link(name = "sqw_cuda")]
@@ -317,6 +377,19 @@ extern "C" {
 	pub fn sqw_models_read(
 		view: *mut sqw_view, vertices: *mut sqw_model_vertex, num_vertices: u64, triangles: *mut u16, num_triangles: u64, counts: *mut u32, num_instances: u32,
 	) -> c_int;
+	// world-polygon preparation (loop body of prepare_polygons_surfaces, partial_renderer.rs:1327-1360)
+	pub fn sqw_upload_map_geometry(
+		ctx: *mut sqw_ctx, polygons: *const sqw_map_polygon, num_polygons: u32, vertices: *const f32, num_vertices: u32, material_flags: *const u8, num_materials: u32,
+	) -> c_int;
+	pub fn sqw_polygons_prepare(
+		view: *mut sqw_view, frame: *const sqw_polygons_frame, candidates: *const sqw_polygon_candidate, num_candidates: u32, clip_planes: *const f32, num_clip_sets: u32,
+	) -> c_int;
+	pub fn sqw_polygons_read(view: *mut sqw_view, out: *mut sqw_prepared_polygon, num: u32, totals: *mut sqw_polygons_totals) -> c_int;
+	// draw_polygon (partial_renderer.rs:4011-4142) for the prepared polygons in BSP draw order
+	pub fn sqw_polygons_draw(view: *mut sqw_view, order: *const u32, num_order: u32) -> c_int;
+	pub fn sqw_polygons_draw_read(
+		view: *mut sqw_view, cmds: *mut sqw_draw_cmd, cmds_capacity: u32, points: *mut sqw_polygon_point, points_capacity: u32, counts_out: *mut u32,
+	) -> c_int;
 }
 
 /// Turns a status into the abort the reference would have had (`panic = "abort"`, Cargo.toml:8), with the library's message.
@@ -341,3 +414,6 @@ const _: [(); 32] = [(); std::mem::size_of::<sqw_depth_cmd>()];
 const _: [(); 32] = [(); std::mem::size_of::<sqw_post_params>()];
 const _: [(); 296] = [(); std::mem::size_of::<sqw_model_instance>()];
 const _: [(); 32] = [(); std::mem::size_of::<sqw_model_vertex>()];
+const _: [(); 80] = [(); std::mem::size_of::<sqw_map_polygon>()];
+const _: [(); 64] = [(); std::mem::size_of::<sqw_prepared_polygon>()];
+const _: [(); 144] = [(); std::mem::size_of::<sqw_polygons_frame>()];

@@ -411,7 +411,7 @@ int sqw_frame_get_stats(const sqw_frame* frame, sqw_frame_stats* out);
 #define SQW_KERNEL_DEPTH_SETUP 10
 #define SQW_KERNEL_DEPTH_RESOLVE 11
 #define SQW_KERNEL_MODELS_PREPARE 12 /* model_bones + model_vertices + model_triangles kernels of one sqw_models_prepare */
-#define SQW_KERNEL_POLYGONS_PREPARE 13 /* polygons_prepare + polygons_offsets kernels of one sqw_polygons_prepare */
+#define SQW_KERNEL_POLYGONS_PREPARE 13 /* the kernels of sqw_polygons_prepare and sqw_polygons_draw */
 #define SQW_NUM_KERNEL_KINDS 14
 typedef struct sqw_kernel_times
 {
@@ -499,6 +499,7 @@ typedef struct sqw_map_polygon /* Polygon, bsp_map_compact.rs:58-75, 80 bytes (t
 } sqw_map_polygon;
 #define SQW_MATERIAL_DRAW 1u   /* Material::draw (material.rs) */
 #define SQW_MATERIAL_SKYBOX 2u /* Material::skybox is some: the polygon only widens the sky window */
+#define SQW_MATERIAL_BLEND_SHIFT 4 /* bits 4-6: Material::blending_mode as SQW_BLEND_* (sqw_polygons_draw) */
 /* vertices: [num_vertices][3] f32 (BSPMap::vertices); material_flags: [num_materials] SQW_MATERIAL_*.  The library copies. */
 int sqw_upload_map_geometry(sqw_ctx* ctx, const sqw_map_polygon* polygons, uint32_t num_polygons, const float* vertices, uint32_t num_vertices, const uint8_t* material_flags, uint32_t num_materials);
 typedef struct sqw_polygon_candidate
@@ -538,6 +539,15 @@ typedef struct sqw_polygons_totals
 int sqw_polygons_prepare(sqw_view* view, const sqw_polygons_frame* frame, const sqw_polygon_candidate* candidates, uint32_t num_candidates, const float* clip_planes, uint32_t num_clip_sets);
 /* Read the results of the last sqw_polygons_prepare back: out[num] in candidate order (NULL to skip), totals (NULL to skip). */
 int sqw_polygons_read(sqw_view* view, sqw_prepared_polygon* out, uint32_t num, sqw_polygons_totals* totals);
+/* draw_polygon (partial_renderer.rs:4011-4142) for world polygons prepared by the last sqw_polygons_prepare of this view, in the
+ * order the host's BSP walk visits them (draw_tree / draw_leaf, :2450-2565; the walk itself stays on the host): `order` holds
+ * candidate indices.  Polygons that are not visible produce nothing.  For each of the others: clipping against the leaf's octagon,
+ * 16.16 vertices, the choice between affine / line-z-corrected / full-perspective interpolation (renderer_utils.rs:60-197) and the
+ * power-of-two renormalisation of the equations (:4106-4109) -> packed sqw_draw_cmd[] (tex_kind SQW_TEX_SURFACE, tex_ref =
+ * surface_pixels_offset, blend = the material's blending mode) and sqw_polygon_point[] in draw order, on the device. */
+int sqw_polygons_draw(sqw_view* view, const uint32_t* order, uint32_t num_order);
+/* Read the lists of the last sqw_polygons_draw back (NULL to skip); counts_out = {commands, vertices}. */
+int sqw_polygons_draw_read(sqw_view* view, sqw_draw_cmd* cmds, uint32_t cmds_capacity, sqw_polygon_point* points, uint32_t points_capacity, uint32_t counts_out[2]);
 
 int sqw_self_test(sqw_ctx* ctx);
 

@@ -244,6 +244,8 @@ CUDA_SYMBOLS = [
     ("sqw_upload_map_geometry", C.c_int, [_VP, _VP, C.c_uint32, _VP, C.c_uint32, _VP, C.c_uint32]),
     ("sqw_polygons_prepare", C.c_int, [_VP, C.POINTER(PolygonsFrame), _VP, C.c_uint32, _VP, C.c_uint32]),
     ("sqw_polygons_read", C.c_int, [_VP, _VP, C.c_uint32, C.POINTER(PolygonsTotals)]),
+    ("sqw_polygons_draw", C.c_int, [_VP, _VP, C.c_uint32]),
+    ("sqw_polygons_draw_read", C.c_int, [_VP, _VP, C.c_uint32, _VP, C.c_uint32, _VP]),
 ]
 
 _cuda_lib = None

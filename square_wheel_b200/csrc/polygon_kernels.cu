@@ -9,6 +9,12 @@
 //                             (equations.rs:22-75), mip (renderer_utils.rs:201-242), surface rectangle, equation shift;
 //   polygons_offsets_kernel   one CTA: the reference's running `surface_pixels_offset` (:1617-1618) is a prefix sum over the
 //                             visible polygons in candidate order; also the frame totals.
+// and draw_polygon (:4011-4142) for the same polygons in the order of the host's BSP walk (draw_tree / draw_leaf, :2450-2565):
+//   polygons_draw_kernel      one thread per polygon: clipping again (the reference clips twice too), inverse-depth extremes,
+//                             16.16 vertices, the interpolation-mode predicates (renderer_utils.rs:60-197) and the power-of-two
+//                             renormalisation of the equations -> one sqw_draw_cmd + its vertices;
+//   polygons_draw_offsets / _compact   command index and vertex offset by a prefix sum, packed lists in draw order — the
+//                             arrays sqw_draw / sqw_frame_set_draw take.
 //
 // The sky window (:1511-1529) is the min / max of four linear forms over every clipped sky vertex: min and max are exact and
 // associative, so device atomics give the bits of the host's sequential ClippingPolygon::extend.
@@ -113,6 +119,66 @@ __device__ __forceinline__ int clip_by_line(const P2* __restrict__ in, const int
 	return count;
 }
 
+// view_matrix transform of the polygon's vertices (matrix.rs:125), clip_3d_polygon_by_z_plane (clipping.rs:4-57), projection and the
+// eight half-plane clips of project_and_clip_polygon (renderer_utils.rs:10-58).  Returns the vertex count (< 3: nothing left); the
+// clipped polygon is in `va`.
+__device__ __forceinline__ int transform_clip_project(
+	const sqw_map_polygon& polygon, const float* __restrict__ vertices, const float* __restrict__ vm, const float* __restrict__ planes, P2* __restrict__ va, P2* __restrict__ vb)
+{
+	P3 zc[MAX_POLY_VERTICES];
+	int count = 0;
+	{
+		const int n = (int)min(polygon.num_vertices, (uint32_t)MAX_POLY_VERTICES);
+		const float* const vsrc = vertices + (size_t)polygon.first_vertex * 3;
+		auto transformed = [&](int i) {
+			const P4 t = mat_mul(vm, vsrc[i * 3], vsrc[i * 3 + 1], vsrc[i * 3 + 2], 1.0f);
+			return P3{t.x, t.y, t.z};
+		};
+		P3 prev = transformed(n - 1);
+		for (int i = 0; i < n; ++i)
+		{
+			const P3 v = transformed(i);
+			if (v.z > POLY_Z_NEAR)
+			{
+				if (prev.z < POLY_Z_NEAR)
+				{
+					zc[count++] = z_intersection(prev, v, POLY_Z_NEAR);
+					if (count == MAX_POLY_VERTICES)
+						break;
+				}
+				zc[count++] = v;
+				if (count == MAX_POLY_VERTICES)
+					break;
+			}
+			else if (v.z == POLY_Z_NEAR)
+			{
+				zc[count++] = v;
+				if (count == MAX_POLY_VERTICES)
+					break;
+			}
+			else if (prev.z > POLY_Z_NEAR)
+			{
+				zc[count++] = z_intersection(prev, v, POLY_Z_NEAR);
+				if (count == MAX_POLY_VERTICES)
+					break;
+			}
+			prev = v;
+		}
+	}
+	if (count < 3)
+		return count;
+	for (int i = 0; i < count; ++i)
+		va[i] = P2{zc[i].x / zc[i].z, zc[i].y / zc[i].z};
+	for (int i = 0; i < 4 && count >= 3; ++i)
+	{
+		count = clip_by_line(va, count, planes[i * 6], planes[i * 6 + 1], planes[i * 6 + 2], vb);
+		if (count < 3)
+			break;
+		count = clip_by_line(vb, count, planes[i * 6 + 3], planes[i * 6 + 4], planes[i * 6 + 5], va);
+	}
+	return count;
+}
+
 // float min / max as integer atomics on the bit pattern (non-negative floats order like ints, negative ones in reverse)
 __device__ __forceinline__ void atomic_min_f32(float* addr, float v)
 {
@@ -164,64 +230,8 @@ __global__ void __launch_bounds__(128) polygons_prepare_kernel(const PolygonsLau
 	}
 
 	// :1494-1505 transform, clip by the z-near plane, project, clip by the leaf's octagon
-	P3 zc[MAX_POLY_VERTICES];
-	int count = 0;
-	{
-		const int n = (int)min(polygon.num_vertices, (uint32_t)MAX_POLY_VERTICES);
-		const float* const vsrc = l.vertices + (size_t)polygon.first_vertex * 3;
-		auto transformed = [&](int i) {
-			const P4 t = mat_mul(vm, vsrc[i * 3], vsrc[i * 3 + 1], vsrc[i * 3 + 2], 1.0f);
-			return P3{t.x, t.y, t.z};
-		};
-		P3 prev = transformed(n - 1);
-		for (int i = 0; i < n; ++i)
-		{
-			const P3 v = transformed(i);
-			if (v.z > POLY_Z_NEAR)
-			{
-				if (prev.z < POLY_Z_NEAR)
-				{
-					zc[count++] = z_intersection(prev, v, POLY_Z_NEAR);
-					if (count == MAX_POLY_VERTICES)
-						break;
-				}
-				zc[count++] = v;
-				if (count == MAX_POLY_VERTICES)
-					break;
-			}
-			else if (v.z == POLY_Z_NEAR)
-			{
-				zc[count++] = v;
-				if (count == MAX_POLY_VERTICES)
-					break;
-			}
-			else if (prev.z > POLY_Z_NEAR)
-			{
-				zc[count++] = z_intersection(prev, v, POLY_Z_NEAR);
-				if (count == MAX_POLY_VERTICES)
-					break;
-			}
-			prev = v;
-		}
-	}
-	if (count < 3)
-	{
-		*dst = out;
-		return;
-	}
 	P2 va[MAX_POLY_VERTICES], vb[MAX_POLY_VERTICES];
-	for (int i = 0; i < count; ++i)
-		va[i] = P2{zc[i].x / zc[i].z, zc[i].y / zc[i].z};
-	{
-		const float* const planes = l.clip_planes + (size_t)cand.clip_set * 24;
-		for (int i = 0; i < 4 && count >= 3; ++i)
-		{
-			count = clip_by_line(va, count, planes[i * 6], planes[i * 6 + 1], planes[i * 6 + 2], vb);
-			if (count < 3)
-				break;
-			count = clip_by_line(vb, count, planes[i * 6 + 3], planes[i * 6 + 4], planes[i * 6 + 5], va);
-		}
-	}
+	const int count = transform_clip_project(polygon, l.vertices, vm, l.clip_planes + (size_t)cand.clip_set * 24, va, vb);
 	if (count < 3)
 	{
 		*dst = out;
@@ -443,6 +453,242 @@ __global__ void polygons_totals_init_kernel(PolygonsTotalsDev* totals)
 	totals->num_surfaces_pixels = 0;
 }
 
+
+// ---- draw_polygon (partial_renderer.rs:4011-4142) for the world polygons, in the order of the host's BSP walk ---------------------
+// renderer_utils.rs:60-132
+__device__ __forceinline__ bool affine_interpolation_may_be_used(const float* de, const float* te, const P2 min_inv_z_point, const P2 max_inv_z_point)
+{
+	const float TC_ERROR_THRESHOLD = 0.75f; // renderer_utils.rs:199
+	const P2 edge{max_inv_z_point.x - min_inv_z_point.x, max_inv_z_point.y - min_inv_z_point.y};
+	const float edge_square_len = edge.x * edge.x + edge.y * edge.y;
+	if (edge_square_len == 0.0f)
+		return true;
+	const float edge_len = sqrtf(edge_square_len);
+	const P2 en{edge.x / edge_len, edge.y / edge_len};
+	const float inv_z_clamp = 1.0f / (float)(1 << 20);
+	const float min_point_inv_z = fmaxf((de[0] * min_inv_z_point.x + de[1] * min_inv_z_point.y) + de[2], inv_z_clamp);
+	const float max_point_inv_z = fmaxf((de[0] * max_inv_z_point.x + de[1] * max_inv_z_point.y) + de[2], inv_z_clamp);
+	const float depth_a = de[0] * en.x + de[1] * en.y;
+	const float depth_b = min_point_inv_z;
+	if (fabsf(depth_a) < 1.0e-10f)
+		return true;
+	const float depth_b_div_a = depth_b / depth_a;
+	const float max_diff_point = sqrtf((0.0f + depth_b_div_a) * (edge_len + depth_b_div_a)) - depth_b_div_a;
+	const float max_diff_point_inv_z = depth_a * max_diff_point + depth_b;
+	for (int i = 0; i < 2; ++i)
+	{
+		const float min_point_tc = (te[i] * min_inv_z_point.x + te[2 + i] * min_inv_z_point.y) + te[4 + i];
+		const float max_point_tc = (te[i] * max_inv_z_point.x + te[2 + i] * max_inv_z_point.y) + te[4 + i];
+		const float tc_a = te[i] * en.x + te[2 + i] * en.y;
+		const float tc_b = min_point_tc;
+		const float min_point_tc_z_mul = min_point_tc / min_point_inv_z;
+		const float max_point_tc_z_mul = max_point_tc / max_point_inv_z;
+		const float real = (tc_a * max_diff_point + tc_b) / max_diff_point_inv_z;
+		const float approximate = min_point_tc_z_mul + (max_point_tc_z_mul - min_point_tc_z_mul) * (max_diff_point - 0.0f) / (edge_len - 0.0f);
+		if (fabsf(real - approximate) > TC_ERROR_THRESHOLD)
+			return false;
+	}
+	return true;
+}
+// renderer_utils.rs:134-197
+__device__ __forceinline__ bool line_z_corrected_interpolation_may_be_used(const float* de, const float* te, const P2 max_inv_z_point, const float min_x, const float max_x)
+{
+	const float TC_ERROR_THRESHOLD = 0.75f;
+	if (max_x - min_x < 1.0f)
+		return true;
+	const float a = de[0];
+	const float b = de[1] * max_inv_z_point.y + de[2];
+	if (fabsf(a) < 1.0e-10f)
+		return true;
+	const float depth_b_div_a = b / a;
+	const float max_diff_x = sqrtf((min_x + depth_b_div_a) * (max_x + depth_b_div_a)) - depth_b_div_a;
+	const float max_diff_point_inv_z = a * max_diff_x + b;
+	const float inv_z_at_min_x = a * min_x + b;
+	const float inv_z_at_max_x = a * max_x + b;
+	const float almost_zero = 1e-20f;
+	if (inv_z_at_min_x <= almost_zero || inv_z_at_max_x <= almost_zero || max_diff_point_inv_z <= almost_zero)
+		return false;
+	for (int i = 0; i < 2; ++i)
+	{
+		const float ta = te[i];
+		const float tb = te[2 + i] * max_inv_z_point.y + te[4 + i];
+		const float tc_at_min_x = (ta * min_x + tb) / inv_z_at_min_x;
+		const float tc_at_max_x = (ta * max_x + tb) / inv_z_at_max_x;
+		const float real = (ta * max_diff_x + tb) / max_diff_point_inv_z;
+		const float approximate = tc_at_min_x + (tc_at_max_x - tc_at_min_x) * (max_diff_x - min_x) / (max_x - min_x);
+		if (fabsf(real - approximate) > TC_ERROR_THRESHOLD)
+			return false;
+	}
+	return true;
+}
+
+// One thread per polygon of the draw order: the command (mode choice, power-of-two renormalisation of the equations, :4106-4109)
+// and its 16.16 vertices into per-item scratch; polygons_draw_compact_kernel packs them in order.
+__global__ void __launch_bounds__(128) polygons_draw_kernel(const PolygonsDrawLaunch l)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= l.num_order)
+		return;
+	sqw_draw_cmd c;
+	c.kind = SQW_CMD_POLYGON;
+	c.blend = 0;
+	c.tc_mode = 0;
+	c.tex_kind = SQW_TEX_SURFACE;
+	c.num_vertices = 0;
+	c.vertex_offset = 0;
+	c.tex_ref = 0;
+	c.tex_size[0] = c.tex_size[1] = 0;
+	c.depth_eq[0] = c.depth_eq[1] = c.depth_eq[2] = 0.0f;
+#pragma unroll
+	for (int k = 0; k < 6; ++k)
+		c.tc_eq[k] = 0.0f;
+	c.reserved = 0;
+	const uint32_t ci = l.order[i];
+	const sqw_prepared_polygon rec = l.prepared[ci];
+	if (!(rec.flags & SQW_PREPARED_VISIBLE)) // DrawPolygonData::visible_frame != current frame (:2530)
+	{
+		l.scratch_cmds[i] = c;
+		return;
+	}
+	const sqw_polygon_candidate cand = l.candidates[ci];
+	const sqw_map_polygon& polygon = l.polygons[cand.polygon];
+	P2 va[MAX_POLY_VERTICES], vb[MAX_POLY_VERTICES];
+	const int count = transform_clip_project(polygon, l.vertices, l.frame.view_matrix, l.clip_planes + (size_t)cand.clip_set * 24, va, vb);
+	if (count < 3)
+	{
+		l.scratch_cmds[i] = c;
+		return;
+	}
+	const float* const de = rec.depth_equation;
+	const float* const te = rec.tex_coord_equation;
+	float min_inv_z = 1e24f, max_inv_z = -1e24f, min_x = 1e24f, max_x = -1e24f;
+	P2 min_inv_z_point = va[0], max_inv_z_point = va[0];
+	sqw_polygon_point* const pts = l.scratch_points + (size_t)i * MAX_POLY_VERTICES;
+	for (int k = 0; k < count; ++k)
+	{
+		const P2 point = va[k];
+		const float inv_z = (de[0] * point.x + de[1] * point.y) + de[2];
+		if (inv_z < min_inv_z)
+		{
+			min_inv_z = inv_z;
+			min_inv_z_point = point;
+		}
+		if (inv_z > max_inv_z)
+		{
+			max_inv_z = inv_z;
+			max_inv_z_point = point;
+		}
+		if (point.x < min_x)
+			min_x = point.x;
+		if (point.x > max_x)
+			max_x = point.x;
+		pts[k] = sqw_polygon_point{f32_to_i32_x86(point.x * 65536.0f), f32_to_i32_x86(point.y * 65536.0f)}; // f32_to_fixed16_unchecked (fixed_math.rs:36)
+	}
+	const uint32_t material = polygon.texture;
+	c.blend = (uint8_t)((material < l.num_materials ? l.material_flags[material] : 0u) >> 4);
+	c.tex_ref = rec.surface_pixels_offset;
+	c.tex_size[0] = (int32_t)rec.surface_size[0];
+	c.tex_size[1] = (int32_t)rec.surface_size[1];
+	c.num_vertices = (uint32_t)count;
+	if (affine_interpolation_may_be_used(de, te, min_inv_z_point, max_inv_z_point))
+	{
+		c.tc_mode = SQW_TC_AFFINE;
+#pragma unroll
+		for (int k = 0; k < 3; ++k)
+			c.depth_eq[k] = de[k];
+#pragma unroll
+		for (int k = 0; k < 6; ++k)
+			c.tc_eq[k] = te[k];
+	}
+	else
+	{
+		// z_scale = 2^(-5 - ceil(log2(max inv_z))): an exact power of two
+		const float e = ceilf((float)log2((double)fmaxf(max_inv_z, 1.0f / (float)(1 << 20))));
+		const float z_scale = ldexpf(1.0f, (int)(-5.0f - e));
+#pragma unroll
+		for (int k = 0; k < 3; ++k)
+			c.depth_eq[k] = de[k] * z_scale;
+#pragma unroll
+		for (int k = 0; k < 6; ++k)
+			c.tc_eq[k] = te[k] * z_scale;
+		c.tc_mode = line_z_corrected_interpolation_may_be_used(de, te, max_inv_z_point, min_x, max_x) ? SQW_TC_LINE_Z_CORRECTION : SQW_TC_FULL_PERSPECTIVE;
+	}
+	l.scratch_cmds[i] = c;
+}
+
+// Command index and first vertex of every item = number of commands / vertices before it in draw order (one CTA), then the totals.
+__global__ void __launch_bounds__(1024) polygons_draw_offsets_kernel(const sqw_draw_cmd* __restrict__ scratch_cmds, const uint32_t n, uint2* __restrict__ offsets, uint32_t* __restrict__ totals)
+{
+	__shared__ uint32_t s_warp[2][32];
+	__shared__ uint32_t s_carry[2];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	if (threadIdx.x < 2)
+		s_carry[threadIdx.x] = 0;
+	__syncthreads();
+	for (uint32_t base = 0; base < n; base += 1024)
+	{
+		const uint32_t i = base + threadIdx.x;
+		const uint32_t nv = i < n ? scratch_cmds[i].num_vertices : 0u;
+		uint32_t incl_c = nv ? 1u : 0u, incl_v = nv;
+		const uint32_t own_c = incl_c;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			const uint32_t tc = __shfl_up_sync(0xFFFFFFFFu, incl_c, o), tv = __shfl_up_sync(0xFFFFFFFFu, incl_v, o);
+			if (lane >= o)
+			{
+				incl_c += tc;
+				incl_v += tv;
+			}
+		}
+		if (lane == 31)
+		{
+			s_warp[0][warp] = incl_c;
+			s_warp[1][warp] = incl_v;
+		}
+		__syncthreads();
+		uint32_t before_c = s_carry[0], before_v = s_carry[1], all_c = 0, all_v = 0;
+		for (int w = 0; w < 32; ++w)
+		{
+			before_c += w < warp ? s_warp[0][w] : 0u;
+			before_v += w < warp ? s_warp[1][w] : 0u;
+			all_c += s_warp[0][w];
+			all_v += s_warp[1][w];
+		}
+		if (i < n)
+			offsets[i] = make_uint2(before_c + incl_c - own_c, before_v + incl_v - nv);
+		__syncthreads();
+		if (threadIdx.x == 0)
+		{
+			s_carry[0] += all_c;
+			s_carry[1] += all_v;
+		}
+		__syncthreads();
+	}
+	if (threadIdx.x == 0)
+	{
+		totals[0] = s_carry[0];
+		totals[1] = s_carry[1];
+	}
+}
+
+__global__ void __launch_bounds__(128) polygons_draw_compact_kernel(
+	const sqw_draw_cmd* __restrict__ scratch_cmds, const sqw_polygon_point* __restrict__ scratch_points, const uint2* __restrict__ offsets, const uint32_t n,
+	sqw_draw_cmd* __restrict__ cmds, sqw_polygon_point* __restrict__ points)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n)
+		return;
+	sqw_draw_cmd c = scratch_cmds[i];
+	if (c.num_vertices == 0)
+		return;
+	const uint2 o = offsets[i];
+	c.vertex_offset = o.y;
+	cmds[o.x] = c;
+	for (uint32_t k = 0; k < c.num_vertices; ++k)
+		points[o.y + k] = scratch_points[(size_t)i * MAX_POLY_VERTICES + k];
+}
+
 } // namespace
 
 cudaError_t launch_polygons_prepare(const PolygonsLaunch& l, cudaStream_t stream)
@@ -453,6 +699,19 @@ cudaError_t launch_polygons_prepare(const PolygonsLaunch& l, cudaStream_t stream
 		polygons_prepare_kernel<<<(l.num_candidates + 127) / 128, 128, 0, stream>>>(l);
 		polygons_offsets_kernel<<<1, 1024, 0, stream>>>(l.out, l.num_candidates, l.totals);
 	}
+	return cudaGetLastError();
+}
+
+cudaError_t launch_polygons_draw(const PolygonsDrawLaunch& l, cudaStream_t stream)
+{
+	if (l.num_order == 0)
+	{
+		cudaMemsetAsync(l.totals, 0, 8, stream);
+		return cudaGetLastError();
+	}
+	polygons_draw_kernel<<<(l.num_order + 127) / 128, 128, 0, stream>>>(l);
+	polygons_draw_offsets_kernel<<<1, 1024, 0, stream>>>(l.scratch_cmds, l.num_order, l.offsets, l.totals);
+	polygons_draw_compact_kernel<<<(l.num_order + 127) / 128, 128, 0, stream>>>(l.scratch_cmds, l.scratch_points, l.offsets, l.num_order, l.cmds, l.points);
 	return cudaGetLastError();
 }
 

@@ -285,6 +285,10 @@ struct sqw_view
 	// inputs and results of sqw_polygons_prepare
 	DevBuf polygon_candidates, polygon_clip_planes, polygon_results, polygon_totals;
 	uint32_t polygon_num_candidates = 0;
+	sqw_polygons_frame polygons_frame{};
+	// scratch and results of sqw_polygons_draw
+	DevBuf polygon_order, polygon_draw_scratch_cmds, polygon_draw_scratch_points, polygon_draw_offsets, polygon_draw_cmds, polygon_draw_points, polygon_draw_totals;
+	uint32_t polygon_num_order = 0;
 };
 
 struct SurfaceGroup // one kernel launch: all bands without / with dynamic lights, CTA bands first, then warp bands
@@ -731,7 +735,9 @@ void sqw_view_destroy(sqw_view* view)
 	if (view->d_tonemap_lut)
 		cudaFree(view->d_tonemap_lut);
 	for (DevBuf* b : {&view->model_instances, &view->model_vertices, &view->model_triangles, &view->model_counts, &view->model_bones, &view->model_sort,
-					  &view->polygon_candidates, &view->polygon_clip_planes, &view->polygon_results, &view->polygon_totals})
+					  &view->polygon_candidates, &view->polygon_clip_planes, &view->polygon_results, &view->polygon_totals, &view->polygon_order,
+					  &view->polygon_draw_scratch_cmds, &view->polygon_draw_scratch_points, &view->polygon_draw_offsets, &view->polygon_draw_cmds, &view->polygon_draw_points,
+					  &view->polygon_draw_totals})
 		b->release();
 	// keep indices of the other views stable: leave a hole
 	for (auto& p : ctx->views)
@@ -1796,6 +1802,8 @@ int sqw_polygons_prepare(sqw_view* view, const sqw_polygons_frame* frame, const 
 			SQW_CUDA(ctx, bufs[i]->reserve(need[i]));
 		}
 	view->polygon_num_candidates = num_candidates;
+	view->polygons_frame = *frame;
+	view->polygon_num_order = 0;
 	if (num_candidates)
 	{
 		SQW_CUDA(ctx, cudaMemcpyAsync(view->polygon_candidates.ptr, candidates, (size_t)num_candidates * sizeof(sqw_polygon_candidate), cudaMemcpyHostToDevice, s));
@@ -1854,6 +1862,83 @@ int sqw_polygons_read(sqw_view* view, sqw_prepared_polygon* out, uint32_t num, s
 			totals->sky_material = sky_material;
 		}
 	}
+	return SQW_OK;
+}
+
+int sqw_polygons_draw(sqw_view* view, const uint32_t* order, uint32_t num_order)
+{
+	if (!view || (num_order && !order))
+		return fail(view ? view->ctx : nullptr, SQW_ERR_INVALID_ARGUMENT, "sqw_polygons_draw: null argument");
+	sqw_ctx* ctx = view->ctx;
+	if (!view->polygon_totals.ptr || !ctx->d_map_polygons)
+		return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_polygons_draw: no sqw_polygons_prepare on this view yet");
+	for (uint32_t i = 0; i < num_order; ++i)
+		if (order[i] >= view->polygon_num_candidates)
+			return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_polygons_draw: order refers to a candidate the last sqw_polygons_prepare did not have");
+	SQW_CUDA(ctx, cudaSetDevice(ctx->device));
+	cudaStream_t s = view->stream;
+	const size_t n = num_order;
+	const size_t need[7] = {n * 4 + 16, n * sizeof(sqw_draw_cmd) + 16, n * 24 * sizeof(sqw_polygon_point) + 16, n * 8 + 16, n * sizeof(sqw_draw_cmd) + 16,
+							n * 24 * sizeof(sqw_polygon_point) + 16, 16};
+	DevBuf* bufs[7] = {&view->polygon_order, &view->polygon_draw_scratch_cmds, &view->polygon_draw_scratch_points, &view->polygon_draw_offsets, &view->polygon_draw_cmds,
+					   &view->polygon_draw_points, &view->polygon_draw_totals};
+	for (int i = 0; i < 7; ++i)
+		if (need[i] > bufs[i]->capacity)
+		{
+			SQW_CUDA(ctx, cudaStreamSynchronize(s));
+			SQW_CUDA(ctx, bufs[i]->reserve(need[i]));
+		}
+	view->polygon_num_order = num_order;
+	if (num_order)
+		SQW_CUDA(ctx, cudaMemcpyAsync(view->polygon_order.ptr, order, n * 4, cudaMemcpyHostToDevice, s));
+	sqw::PolygonsDrawLaunch l{};
+	l.polygons = ctx->d_map_polygons;
+	l.vertices = ctx->d_map_vertices;
+	l.material_flags = ctx->d_material_flags;
+	l.num_materials = ctx->num_materials;
+	l.frame = view->polygons_frame;
+	l.candidates = static_cast<const sqw_polygon_candidate*>(view->polygon_candidates.ptr);
+	l.clip_planes = static_cast<const float*>(view->polygon_clip_planes.ptr);
+	l.prepared = static_cast<const sqw_prepared_polygon*>(view->polygon_results.ptr);
+	l.order = static_cast<const uint32_t*>(view->polygon_order.ptr);
+	l.num_order = num_order;
+	l.scratch_cmds = static_cast<sqw_draw_cmd*>(view->polygon_draw_scratch_cmds.ptr);
+	l.scratch_points = static_cast<sqw_polygon_point*>(view->polygon_draw_scratch_points.ptr);
+	l.offsets = static_cast<uint2*>(view->polygon_draw_offsets.ptr);
+	l.cmds = static_cast<sqw_draw_cmd*>(view->polygon_draw_cmds.ptr);
+	l.points = static_cast<sqw_polygon_point*>(view->polygon_draw_points.ptr);
+	l.totals = static_cast<uint32_t*>(view->polygon_draw_totals.ptr);
+	{
+		NvtxRange nvtx("polygons_draw_setup");
+		LaunchTimer timer(ctx, SQW_KERNEL_POLYGONS_PREPARE, s);
+		SQW_CUDA(ctx, sqw::launch_polygons_draw(l, s));
+	}
+	SQW_CUDA(ctx, cudaStreamSynchronize(s)); // `order` is the caller's pageable memory
+	return SQW_OK;
+}
+
+int sqw_polygons_draw_read(sqw_view* view, sqw_draw_cmd* cmds, uint32_t cmds_capacity, sqw_polygon_point* points, uint32_t points_capacity, uint32_t counts_out[2])
+{
+	if (!view)
+		return SQW_ERR_INVALID_ARGUMENT;
+	sqw_ctx* ctx = view->ctx;
+	if (!view->polygon_draw_totals.ptr)
+		return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_polygons_draw_read: no sqw_polygons_draw on this view yet");
+	SQW_CUDA(ctx, cudaSetDevice(ctx->device));
+	cudaStream_t s = view->stream;
+	uint32_t totals[2] = {0, 0};
+	SQW_CUDA(ctx, cudaMemcpyAsync(totals, view->polygon_draw_totals.ptr, 8, cudaMemcpyDeviceToHost, s));
+	SQW_CUDA(ctx, cudaStreamSynchronize(s));
+	if (counts_out)
+	{
+		counts_out[0] = totals[0];
+		counts_out[1] = totals[1];
+	}
+	if (cmds && std::min(totals[0], cmds_capacity))
+		SQW_CUDA(ctx, cudaMemcpyAsync(cmds, view->polygon_draw_cmds.ptr, (size_t)std::min(totals[0], cmds_capacity) * sizeof(sqw_draw_cmd), cudaMemcpyDeviceToHost, s));
+	if (points && std::min(totals[1], points_capacity))
+		SQW_CUDA(ctx, cudaMemcpyAsync(points, view->polygon_draw_points.ptr, (size_t)std::min(totals[1], points_capacity) * sizeof(sqw_polygon_point), cudaMemcpyDeviceToHost, s));
+	SQW_CUDA(ctx, cudaStreamSynchronize(s));
 	return SQW_OK;
 }
 

@@ -227,6 +227,26 @@ struct PolygonsLaunch
 	PolygonsTotalsDev* totals; // device
 };
 cudaError_t launch_polygons_prepare(const PolygonsLaunch& l, cudaStream_t stream);
+struct PolygonsDrawLaunch
+{
+	const sqw_map_polygon* polygons; // device (uploaded map)
+	const float* vertices;
+	const uint8_t* material_flags;
+	uint32_t num_materials;
+	sqw_polygons_frame frame;
+	const sqw_polygon_candidate* candidates; // device, of the last sqw_polygons_prepare
+	const float* clip_planes;
+	const sqw_prepared_polygon* prepared;    // device, results of the last sqw_polygons_prepare
+	const uint32_t* order;                   // device: candidate indices in draw order
+	uint32_t num_order;
+	sqw_draw_cmd* scratch_cmds;        // [num_order]
+	sqw_polygon_point* scratch_points; // [num_order][24]
+	uint2* offsets;                    // [num_order]
+	sqw_draw_cmd* cmds;                // out, packed
+	sqw_polygon_point* points;         // out, packed
+	uint32_t* totals;                  // out: {commands, vertices}
+};
+cudaError_t launch_polygons_draw(const PolygonsDrawLaunch& l, cudaStream_t stream);
 
 // ---- shadow maps ----------------------------------------------------------------------------------------------
 struct DepthCmdDev // per fill call, prepared by sqw_frame_set_shadow_map_draw. 16 bytes

@@ -251,6 +251,20 @@ class View:
         self.ctx._check(self._lib.sqw_polygons_read(self._handle, N.ptr(out), num, C.byref(totals)), "sqw_polygons_read")
         return out, totals
 
+    def polygons_draw(self, order: np.ndarray):
+        """draw_polygon for the prepared polygons in BSP draw order (sqw_polygons_draw); order = candidate indices."""
+        o = np.ascontiguousarray(order, np.uint32)
+        self.ctx._check(self._lib.sqw_polygons_draw(self._handle, N.ptr(o), len(o)), "sqw_polygons_draw")
+
+    def polygons_draw_read(self):
+        """(commands [draw_cmd_dtype], vertices [polygon_point_dtype]) of the last polygons_draw, in draw order."""
+        counts = np.zeros(2, np.uint32)
+        self.ctx._check(self._lib.sqw_polygons_draw_read(self._handle, None, 0, None, 0, N.ptr(counts)), "sqw_polygons_draw_read")
+        cmds = np.zeros(int(counts[0]), N.draw_cmd_dtype)
+        pts = np.zeros(int(counts[1]), N.polygon_point_dtype)
+        self.ctx._check(self._lib.sqw_polygons_draw_read(self._handle, N.ptr(cmds), len(cmds), N.ptr(pts), len(pts), N.ptr(counts)), "sqw_polygons_draw_read")
+        return cmds, pts
+
     def average_color(self) -> np.ndarray:
         avg = np.zeros(3, np.float32)
         self.ctx._check(self._lib.sqw_view_get_average_color(self._handle, N.ptr(avg)), "sqw_view_get_average_color")

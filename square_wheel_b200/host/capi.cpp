@@ -525,12 +525,20 @@ int sqwh_renderer_prepared_polygons(const Renderer* r, void* candidates, float* 
 	return (int)c.size();
 }
 double sqwh_renderer_polygons_prepare_seconds(const Renderer* r) { return r ? r->polygons_prepare_seconds() : 0.0; }
+// map polygon indices of the leaf polygons drawn by the last draw_frame, in draw order (the BSP walk); returns the count
+uint32_t sqwh_renderer_polygon_draw_order(const Renderer* r, uint32_t* out, uint32_t capacity)
+{
+	const auto& o = r->polygon_draw_order();
+	if (out)
+		std::memcpy(out, o.data(), std::min<size_t>(o.size(), capacity) * 4);
+	return (uint32_t)o.size();
+}
 // per-material SQW_MATERIAL_* flags for sqw_upload_map_geometry
 uint32_t sqwh_scene_material_flags(const Scene* s, uint8_t* out, uint32_t capacity)
 {
 	const uint32_t n = (uint32_t)s->materials.size();
 	for (uint32_t i = 0; i < n && i < capacity; ++i)
-		out[i] = (uint8_t)((s->materials[i].draw ? 1 : 0) | (s->materials[i].is_skybox ? 2 : 0));
+		out[i] = (uint8_t)((s->materials[i].draw ? 1 : 0) | (s->materials[i].is_skybox ? 2 : 0) | ((s->materials[i].blending_mode & 7) << 4));
 	return n;
 }
 

@@ -1348,6 +1348,7 @@ void Renderer::draw_frame(int color_bits) // PartialRenderer::draw_frame -> perf
 	cmds_.clear();
 	polygon_points_.clear();
 	triangle_points_.clear();
+	polygon_draw_order_.clear();
 	const ClippingPolygon viewport_clipping_polygon = ClippingPolygon::from_box(0.0f, 0.0f, (float)width_, (float)height_);
 	draw_skybox(viewport_clipping_polygon, color_bits); // perform_rasterization_for_viewport_part (:1296): sky first
 	draw_tree(viewport_clipping_polygon);
@@ -1472,6 +1473,7 @@ void Renderer::draw_leaf(const ClippingPolygon& bounds, uint32_t leaf_index) // 
 		const DrawPolygonData& polygon_data = polygons_data_[polygon_index];
 		if (polygon_data.visible_frame != current_frame_)
 			continue;
+		polygon_draw_order_.push_back(polygon_index);
 		draw_polygon(
 			clip_planes, &vertices_transformed_[polygon.first_vertex], polygon.num_vertices, polygon_data.depth_equation, polygon_data.tex_coord_equation,
 			polygon_data.surface_size, SQW_TEX_SURFACE, (uint32_t)polygon_data.surface_pixels_offset, scene_.materials[polygon.texture].blending_mode);

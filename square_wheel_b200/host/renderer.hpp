@@ -224,6 +224,7 @@ public:
 	};
 	const std::vector<PolygonCandidate>& polygon_candidates() const { return polygon_candidates_; }
 	const std::vector<Vec3f>& polygon_clip_planes() const { return polygon_clip_planes_; }
+	const std::vector<uint32_t>& polygon_draw_order() const { return polygon_draw_order_; } // leaf polygons in the order draw_leaf drew them (last draw_frame)
 	void export_prepared_polygons(PreparedPolygonExport* out, PolygonsFrameExport* frame) const;
 	double polygons_prepare_seconds() const { return polygons_prepare_seconds_; } // wall time of prepare_polygons_surfaces in the last prepare_frame
 	const std::vector<ModelVertex3d>& dynamic_meshes_vertices() const { return dynamic_meshes_vertices_; }
@@ -374,6 +375,7 @@ private:
 	std::vector<DrawPolygonData> polygons_data_;
 	double polygons_prepare_seconds_ = 0.0;
 	std::vector<PolygonCandidate> polygon_candidates_;
+	std::vector<uint32_t> polygon_draw_order_;
 	std::vector<Vec3f> polygon_clip_planes_;
 	std::vector<uint8_t> polygon_is_sky_candidate_; // per candidate: the polygon reached the sky branch of prepare_polygon_surface
 	std::vector<Vec3f> vertices_transformed_;

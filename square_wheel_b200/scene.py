@@ -247,6 +247,8 @@ def lib() -> C.CDLL:
         l.sqwh_scene_material_flags.argtypes = [vp, vp, C.c_uint32]
         l.sqwh_renderer_polygons_prepare_seconds.restype = C.c_double
         l.sqwh_renderer_polygons_prepare_seconds.argtypes = [vp]
+        l.sqwh_renderer_polygon_draw_order.restype = C.c_uint32
+        l.sqwh_renderer_polygon_draw_order.argtypes = [vp, vp, C.c_uint32]
         l.sqwh_renderer_prepared_polygons.restype = C.c_int
         l.sqwh_renderer_prepared_polygons.argtypes = [vp, vp, vp, vp, vp, C.POINTER(C.c_uint64)]
         _lib = l
@@ -521,6 +523,13 @@ class HostRenderer:
         vp = C.c_void_p
         self._lib.sqwh_renderer_prepared_polygons(self._handle, cand.ctypes.data_as(vp), planes.ctypes.data_as(vp), res.ctypes.data_as(vp), frame.ctypes.data_as(vp), counts)
         return cand, planes, res, frame[0]
+
+    def polygon_draw_order(self) -> np.ndarray:
+        """Map polygon indices of the leaf polygons the last build_frame drew, in draw order (draw_tree / draw_leaf)."""
+        n = int(self._lib.sqwh_renderer_polygon_draw_order(self._handle, None, 0))
+        out = np.zeros(n, np.uint32)
+        self._lib.sqwh_renderer_polygon_draw_order(self._handle, out.ctypes.data_as(C.c_void_p), n)
+        return out
 
     def polygons_prepare_seconds(self) -> float:
         """Wall time the host mirror spent in prepare_polygons_surfaces during the last build_frame."""

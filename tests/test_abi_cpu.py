@@ -33,6 +33,14 @@ def test_library_exports_every_declared_symbol():
     assert lib.sqw_abi_version() == int(re.search(r'#define SQW_ABI_VERSION (\d+)', header).group(1))
 
 
+def test_rust_binding_declares_every_symbol():
+    """bindings/sqw_cuda.rs (the file a maintainer drops into src/square_wheel/) names every entry point of the header."""
+    rs = open(os.path.join(ROOT, "bindings", "sqw_cuda.rs")).read()
+    bound = set(re.findall(r"pub fn (sqw_[a-z0-9_]+)\s*\(", rs))
+    missing = set(_declared_functions()) - bound
+    assert not missing, f"bindings/sqw_cuda.rs lacks {sorted(missing)}"
+
+
 def test_struct_sizes_match_header():
     text = open(os.path.join(ROOT, "square_wheel_b200", "csrc", "sqw_api.cu")).read()
     sizes = dict(re.findall(r"static_assert\(sizeof\((\w+)\) == (\d+)", text))

@@ -34,11 +34,36 @@ def _compare(view, hr, what):
     return int(totals.num_visible), int((want["flags"] == N.PREPARED_SKY).sum()), want
 
 
+def _compare_draw(view, hr, hf, what):
+    """sqw_polygons_draw against the commands the mirror's draw_polygon recorded for the same polygons (after _compare)."""
+    cand, _, _, _ = hr.prepared_polygons()
+    index_of = {int(p): i for i, p in enumerate(cand["polygon"])}
+    order = np.array([index_of[int(p)] for p in hr.polygon_draw_order()], np.uint32)
+    view.polygons_draw(order)
+    got_cmds, got_pts = view.polygons_draw_read()
+    sel = (hf.cmds["kind"] == N.CMD_POLYGON) & (hf.cmds["tex_kind"] == N.TEX_SURFACE)
+    want_cmds = hf.cmds[sel]
+    assert len(got_cmds) == len(want_cmds) == len(order) > 10, what
+    for field in ("kind", "blend", "tc_mode", "tex_kind", "num_vertices", "tex_ref", "tex_size"):
+        assert np.array_equal(got_cmds[field], want_cmds[field]), f"{what}: {field}"
+    for field in ("depth_eq", "tc_eq"):
+        a, b = np.ascontiguousarray(got_cmds[field]).view(np.uint32), np.ascontiguousarray(want_cmds[field]).view(np.uint32)
+        assert np.array_equal(a, b), f"{what}: {field} differs in {int((a != b).any(axis=1).sum())} commands"
+    # vertices: the mirror's list also holds the vertices of other commands (sky box), so compare per command
+    assert got_cmds["vertex_offset"].tolist() == np.concatenate(([0], np.cumsum(got_cmds["num_vertices"])[:-1])).tolist()
+    for g, w in zip(got_cmds, want_cmds):
+        a = got_pts[int(g["vertex_offset"]) : int(g["vertex_offset"]) + int(g["num_vertices"])]
+        b = hf.polygon_points[int(w["vertex_offset"]) : int(w["vertex_offset"]) + int(w["num_vertices"])]
+        assert np.array_equal(a.view(np.int32), b.view(np.int32)), f"{what}: vertices"
+    return set(want_cmds["tc_mode"].tolist()), set(want_cmds["blend"].tolist())
+
+
 @pytest.mark.parametrize("mip_bias", [0.0, -1.0, 0.6])
 def test_polygons_prepare_matches_the_host_mirror_bit_for_bit(mip_bias):
-    sc = S.Scene(seed=7, texture_size_log2=6, num_materials=8, skybox=1, sky_size_log2=6)
+    sc = S.Scene(seed=7, texture_size_log2=6, num_materials=8, skybox=1, sky_size_log2=6, material_mode=2)
     ctx = Context(sc.lightmaps, sc.directional_lightmaps, device=0)
     hr = S.HostRenderer(sc, textures_mip_bias=mip_bias)
+    modes, blends = set(), set()
     try:
         ctx.upload_map_geometry(*sc.map_geometry())
         view = ctx.create_view(64, 64, 64)
@@ -46,12 +71,16 @@ def test_polygons_prepare_matches_the_host_mirror_bit_for_bit(mip_bias):
         visible = sky = 0
         mips = set()
         for k, (w, h) in zip((0, 5, 17, 30, 44, 59), ((640, 360), (1280, 720), (3840, 2160), (333, 777), (1920, 1080), (3840, 2160))):
-            hr.build_frame(w, h, path[k])
+            hf = hr.build_frame(w, h, path[k])
             v, s, want = _compare(view, hr, f"pose {k} at {w}x{h}, mip bias {mip_bias}")
+            m, b = _compare_draw(view, hr, hf, f"draw, pose {k} at {w}x{h}, mip bias {mip_bias}")
+            modes |= m
+            blends |= b
             visible += v
             sky += s
             mips |= set(want["mip"][want["flags"] == N.PREPARED_VISIBLE].tolist())
         assert visible > 300 and sky > 0 and len(mips) >= 2  # culled, clipped, sky and several mips all occur
+        assert len(modes) >= 2 and len(blends) >= 2  # several interpolation modes and blended world materials
     finally:
         hr.close()
         ctx.close()
@@ -71,9 +100,12 @@ def test_polygons_prepare_on_the_bench_scene_and_bad_arguments():
         with pytest.raises(SqwError):  # no geometry uploaded yet
             view.polygons_prepare(fr["planes_matrix"], fr["view_matrix"], 0.0, cand, planes)
         ctx.upload_map_geometry(*sc.map_geometry())
+        modes = set()
         for k in range(0, 64, 7):
-            hr.build_frame(3840, 2160, path[k])
+            hf = hr.build_frame(3840, 2160, path[k])
             _compare(view, hr, f"bench scene pose {k}")
+            modes |= _compare_draw(view, hr, hf, f"draw, bench scene pose {k}")[0]
+        assert modes == {N.TC_FULL_PERSPECTIVE, N.TC_LINE_Z_CORRECTION, N.TC_AFFINE} or len(modes) >= 2
         bad = cand.copy()
         bad["polygon"][3] = int(sc.info.num_polygons)
         with pytest.raises(SqwError):
