@@ -524,6 +524,26 @@ def run_cuda(args, rank, local_rank, world):
                 roofline[k_] = tj["kernels"][dominant][k_]
     except (NameError, KeyError):
         pass
+    # SM issue-slot roofline (SURVEY 8d asks for the FP32 / issue figure beside the HBM one: the frame is issue-bound).  Warp
+    # instructions per launch come from the same ncu capture; issue slots = SMs x 4 schedulers x SM clock x the LIVE time.
+    try:
+        sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        clock_hz = 1e6 * float((clocks or {}).get("sm_mhz") or 1965.0)
+        frame_insts = 0.0
+        for name, k_ in kernels.items():
+            wi = tj["kernels"].get(name, {}).get("warp_instructions")
+            if wi:
+                k_["warp_instructions_ncu"] = wi
+                k_["issue_slot_frac"] = wi / (sm_count * 4 * clock_hz * k_["ms_per_frame"] * 1e-3)
+                frame_insts += wi
+        if frame_insts:
+            roofline["issue"] = {
+                "frame_warp_instructions": frame_insts,
+                "frame_issue_slot_frac": frame_insts / (sm_count * 4 * clock_hz * (elapsed_ms * 1e-3 / frames_timed)),
+                "note": "warp instructions of one frame's kernels (ncu capture of two frames, profiles/ncu_traffic.json) / (SMs x 4 schedulers x SM clock x measured time per frame with the views in flight): the share of all issue slots the frame uses; per kernel in kernels[*].issue_slot_frac (serial time)",
+            }
+    except (NameError, KeyError, TypeError):
+        pass
 
     # ---- BASELINE configs[4]: the batch of 8192 fly-through views at 1920x1080, sharded across the ranks (strong scaling) ----
     view_batch = None

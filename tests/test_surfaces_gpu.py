@@ -42,6 +42,42 @@ def test_surface_variants_bit_exact(assets, oracle_lib, color_bits, directional,
     assert_pixels_equal(got, want, f"surfaces c{color_bits} dir{directional} lights{with_lights}")
 
 
+@pytest.mark.parametrize("num_jobs, band", [(300, 64), (5000, 128), (11000, 256)])
+def test_small_surfaces_on_warp_bands(oracle_lib, num_jobs, band):
+    """Surfaces of at most 1024 texels are built one WARP per band (eight bands per CTA, csrc/surface_kernels.cu); the band size
+    follows the number of small texels in the frame (64 / 128 / 256 texels: sqw_frame_set_surfaces).  All three sizes, with
+    dynamic lights on a third of the jobs so that both grids carry warp bands."""
+    from common import Assets
+
+    a = Assets(seed=31, num_lightmap_elements=1600000, tex_sizes=(32,))
+    r = synth.rng(500 + num_jobs)
+    ctx = a.device_context()
+    try:
+        lights, sm = synth.make_lights(r, 5)
+        jobs, total, lm_needed = synth.make_surface_jobs(r, num_jobs, a.texture_ids, a.texture_flags, emissive_images=a.lite_ids, directional=True, lights=len(lights), max_size=32)
+        assert lm_needed <= len(a.lightmaps)
+        jobs["num_lights"][::3] = 0
+        small = int((jobs["surface_size"].astype(np.int64).prod(axis=1)).sum())
+        resident_warps = 148 * 4 * 8
+        expect = 256
+        while expect > 64 and small < resident_warps * expect:
+            expect //= 2
+        assert expect == band, f"{small} small texels give {expect}-texel bands: adjust the job count of this case"
+        cam = r.uniform(-300, 300, 3).astype(np.float32)
+        view = ctx.create_view(64, 64, 64)
+        try:
+            view.build_surfaces(jobs, lights, sm, cam, total)
+            got = view.read_surfaces(0, total)
+        finally:
+            view.close()
+        oracle_lib.reset_assert_failures()
+        want = oracle_lib.build_surfaces(64, jobs, lights, sm, cam, a.images, a.lightmaps, a.directional_lightmaps, total)
+        assert oracle_lib.assert_failures() == 0
+        assert_pixels_equal(got, want, f"{num_jobs} small surfaces, {band}-texel warp bands")
+    finally:
+        ctx.close()
+
+
 @pytest.mark.parametrize("color_bits", [32, 64])
 def test_non_power_of_two_textures(oracle_lib, color_bits):
     """Texture and emissive images whose sizes are not powers of two take the general rem_euclid wrap (surfaces.rs:507-510, :843-847;
