@@ -320,6 +320,8 @@ extern "C" {
 	pub fn sqw_upload_image(ctx: *mut sqw_ctx, kind: c_int, width: u32, height: u32, pixels: *const c_void) -> c_int;
 	pub fn sqw_update_image(ctx: *mut sqw_ctx, image_id: c_int, pixels: *const c_void) -> c_int;
 	pub fn sqw_set_fast_surface_numerics(ctx: *mut sqw_ctx, enable: c_int) -> c_int;
+	pub fn sqw_set_compressed_readback(ctx: *mut sqw_ctx, enable: c_int) -> c_int;
+	pub fn sqw_view_get_readback_stats(view: *const sqw_view, out: *mut u64) -> c_int;
 	pub fn sqw_self_test(ctx: *mut sqw_ctx) -> c_int;
 	// views (one per PartialRenderer: root + nested portal renderers, partial_renderer.rs:120-133)
 	pub fn sqw_view_create(ctx: *mut sqw_ctx, out_view: *mut *mut sqw_view, width: u32, height: u32, color_bits: c_int) -> c_int;

@@ -85,6 +85,13 @@ typedef struct sqw_map_desc
  * reference builds by no more than those builds differ from each other (north_star's +-1 LSB of the final 8-bit picture);
  * stages 2 and 3 are not affected. */
 #define SQW_CTX_FAST_SURFACE_NUMERICS 2u
+/* sqw_read_pixels32_async moves the picture as run-length rows instead of raw pixels: the alpha byte of the tonemapped picture is
+ * 255 by construction, so a run of equal pixels travels as one word B | G << 8 | R << 16 | (length - 1) << 24, written by the GPU
+ * straight into page-locked, device-mapped host memory and expanded into the caller's buffer by a small pool of host threads of the
+ * library (SQW_READBACK_THREADS, default min(8, cores / 2)).  Lossless (rows whose alpha is not 255 travel raw); the caller's buffer
+ * needs not be page-locked.  At 4K a surface texel covers several pixels, so the 33 MB picture shrinks several times and the PCIe
+ * read-back stops being the end-to-end limit.  The picture is complete after sqw_view_synchronize, like the raw asynchronous copy. */
+#define SQW_CTX_COMPRESSED_READBACK 4u
 
 /* Create a context on CUDA device `device` and upload the static map data.  Replaces the ownership half of
  * Renderer::new (renderer.rs:24).  `external_stream` may be a cudaStream_t the caller wants all work of this
@@ -314,10 +321,15 @@ int sqw_write_pixels(sqw_view* view, const void* src, size_t src_pitch);
 /* Copy the post-processed 32-bit picture of a 64-bit view. Synchronises. */
 int sqw_read_pixels32(sqw_view* view, uint32_t* dst, size_t dst_pitch);
 /* Asynchronous variants: the copy is queued behind the view's rendering and completes by the next
- * sqw_view_synchronize (or any synchronising call on the view).  dst should be page-locked memory, otherwise CUDA stages
+ * sqw_view_synchronize (raw copies also by any other synchronising call on the view).  dst should be page-locked memory, otherwise CUDA stages
  * the copy.  With SQW_CTX_CONCURRENT_VIEWS the read-back of one view overlaps the rendering of the others. */
 int sqw_read_pixels_async(sqw_view* view, void* dst, size_t dst_pitch);
 int sqw_read_pixels32_async(sqw_view* view, uint32_t* dst, size_t dst_pitch);
+/* Switch SQW_CTX_COMPRESSED_READBACK on or off for read-backs started from now on (pictures on their way are completed first). */
+int sqw_set_compressed_readback(sqw_ctx* ctx, int enable);
+/* out[0] = compressed read-backs of this view completed so far, out[1] = the bytes they moved over the bus (run words + one count
+ * word per row). */
+int sqw_view_get_readback_stats(const sqw_view* view, uint64_t out[2]);
 /* Copy `count` pixels of the surface pool starting at `offset` (both in pixels) — test/inspection hook. */
 int sqw_read_surfaces(sqw_view* view, void* dst, uint64_t offset, uint64_t count);
 /* Wait for everything issued for this view. */

@@ -28,6 +28,7 @@ STAGE_SURFACES, STAGE_RASTER, STAGE_POST, STAGE_SHADOW_MAPS, STAGE_ALL = 1, 2, 4
 DEPTH_MAP_CLEAR, DEPTH_MAP_PROJECTOR_CIRCLE = 1, 2
 CTX_CONCURRENT_VIEWS = 1
 CTX_FAST_SURFACE_NUMERICS = 2
+CTX_COMPRESSED_READBACK = 4
 
 # ---- struct layouts as numpy dtypes (sizes asserted against the static_asserts in sqw_api.cu) ---------------
 surface_job_dtype = np.dtype(
@@ -238,6 +239,8 @@ CUDA_SYMBOLS = [
     ("sqw_profile_end", C.c_int, [_VP, C.POINTER(KernelTimes)]),
     ("sqw_self_test", C.c_int, [_VP]),
     ("sqw_set_fast_surface_numerics", C.c_int, [_VP, C.c_int]),
+    ("sqw_set_compressed_readback", C.c_int, [_VP, C.c_int]),
+    ("sqw_view_get_readback_stats", C.c_int, [_VP, _VP]),
     ("sqw_upload_model_mesh", C.c_int, [_VP, _VP]),
     ("sqw_models_prepare", C.c_int, [_VP, _VP, C.c_uint32]),
     ("sqw_models_read", C.c_int, [_VP, _VP, C.c_uint64, _VP, C.c_uint64, _VP, C.c_uint32]),

@@ -294,6 +294,93 @@ inline uint32_t grid_for(uint64_t work_items, int threads, int max_ctas_per_sm =
 	return (uint32_t)(needed < cap ? (needed ? needed : 1) : cap);
 }
 
+
+// ---- compressed read-back of the 32-bit picture (host half: readback_decode.cu) --------------------------------------------------
+// One CTA per picture row.  A run of equal pixels becomes one word B | G << 8 | R << 16 | (length - 1) << 24; runs never cross a
+// 256-pixel boundary, so the length always fits the byte the constant alpha (255) leaves free.  The row's runs go to
+// `rows_out + row * row_capacity` (page-locked host memory mapped into the device: only what is written crosses PCIe) and their
+// number to row_counts[row].  A row with any alpha != 255 is copied raw (count = 0x80000000 | width): lossless in every case.
+#define SQW_RLE_THREADS 128
+#define SQW_RLE_SEGMENT (SQW_RLE_THREADS * 8)
+__global__ void __launch_bounds__(SQW_RLE_THREADS) picture_rle_kernel(
+	const uint32_t* __restrict__ ldr, uint32_t width, uint32_t pitch, uint32_t* __restrict__ rows_out, uint32_t row_capacity, uint32_t* __restrict__ row_counts)
+{
+	__shared__ uint16_t s_start[SQW_RLE_SEGMENT + 1];
+	__shared__ uint32_t s_val[SQW_RLE_SEGMENT];
+	__shared__ uint32_t s_warp[SQW_RLE_THREADS / 32];
+	const uint32_t row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const uint32_t* const src = ldr + (size_t)row * pitch;
+	uint32_t* const dst = rows_out + (size_t)row * row_capacity;
+	// alpha check of the whole row first (rare path: raw copy)
+	{
+		uint32_t bad = 0;
+		for (uint32_t x = tid; x < width; x += SQW_RLE_THREADS)
+			bad |= (~__ldg(src + x)) & 0xFF000000u;
+		if (__syncthreads_or(bad != 0))
+		{
+			for (uint32_t x = tid; x < width; x += SQW_RLE_THREADS)
+				dst[x] = __ldg(src + x);
+			if (tid == 0)
+				row_counts[row] = 0x80000000u | width;
+			return;
+		}
+	}
+	uint32_t total = 0;
+	for (uint32_t seg0 = 0; seg0 < width; seg0 += SQW_RLE_SEGMENT)
+	{
+		const uint32_t x0 = seg0 + tid * 8;
+		uint32_t p[8];
+		uint32_t prev = 0;
+		if (x0 < width && x0 > 0)
+			prev = __ldg(src + x0 - 1);
+		uint32_t flags = 0;
+#pragma unroll
+		for (int i = 0; i < 8; ++i)
+		{
+			const uint32_t x = x0 + i;
+			p[i] = x < width ? __ldg(src + x) : 0u;
+			const bool start = x < width && (((x & 255u) == 0) || p[i] != (i ? p[i - 1] : prev));
+			flags |= start ? (1u << i) : 0u;
+		}
+		const uint32_t cnt = __popc(flags);
+		uint32_t incl = cnt;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+			if ((int)lane >= o)
+				incl += t;
+		}
+		if (lane == 31)
+			s_warp[warp] = incl;
+		__syncthreads();
+		uint32_t base = incl - cnt, seg_total = 0;
+#pragma unroll
+		for (int w = 0; w < SQW_RLE_THREADS / 32; ++w)
+		{
+			base += w < (int)warp ? s_warp[w] : 0u;
+			seg_total += s_warp[w];
+		}
+#pragma unroll
+		for (int i = 0; i < 8; ++i)
+			if (flags & (1u << i))
+			{
+				s_start[base] = (uint16_t)(tid * 8 + i);
+				s_val[base] = p[i];
+				++base;
+			}
+		if (tid == 0)
+			s_start[seg_total] = (uint16_t)min((uint32_t)SQW_RLE_SEGMENT, width - seg0);
+		__syncthreads();
+		for (uint32_t r = tid; r < seg_total; r += SQW_RLE_THREADS)
+			dst[total + r] = (s_val[r] & 0x00FFFFFFu) | (((uint32_t)s_start[r + 1] - (uint32_t)s_start[r] - 1u) << 24);
+		total += seg_total;
+		__syncthreads(); // s_start / s_val / s_warp are rewritten by the next segment
+	}
+	if (tid == 0)
+		row_counts[row] = total;
+}
+
 } // namespace
 
 cudaError_t launch_tonemap(const PostLaunch& l, cudaStream_t stream)
@@ -360,6 +447,12 @@ cudaError_t launch_tonemap_bloom(const PostLaunch& l, cudaStream_t stream)
 		}
 	}
 #undef SQW_TB
+	return cudaGetLastError();
+}
+
+cudaError_t launch_picture_rle(const uint32_t* ldr, uint32_t width, uint32_t height, uint32_t pitch, uint32_t* rows_out, uint32_t row_capacity, uint32_t* row_counts, cudaStream_t stream)
+{
+	picture_rle_kernel<<<height, SQW_RLE_THREADS, 0, stream>>>(ldr, width, pitch, rows_out, row_capacity, row_counts);
 	return cudaGetLastError();
 }
 

@@ -3,7 +3,12 @@
 // when the CUDA device is unavailable.
 #include "sqw_internal.h"
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -172,6 +177,94 @@ struct ImageHost
 
 } // namespace
 
+// ---- compressed read-back: decode jobs on a small pool of host threads (readback_decode.cu) ---------------------------------
+struct ReadbackJob // one per view: a picture travelling to the caller's buffer
+{
+	const uint32_t* rle = nullptr;    // page-locked, device-mapped: row r at r * row_capacity words
+	const uint32_t* counts = nullptr; // run words per row
+	uint32_t* dst = nullptr;
+	size_t dst_pitch = 0;
+	uint32_t width = 0, height = 0, row_capacity = 0;
+	std::atomic<uint32_t> next_row{0}, rows_done{0};
+	std::atomic<uint64_t> words{0}; // run / raw words the rows held: what crossed the bus
+	int workers_inside = 0; // guarded by the pool mutex
+	bool finished = true;   // guarded by the pool mutex: every row decoded and no worker still holds the job
+};
+struct ReadbackPool
+{
+	std::vector<std::thread> threads;
+	std::deque<ReadbackJob*> queue;
+	std::mutex m;
+	std::condition_variable work, done;
+	bool stop = false;
+	static constexpr uint32_t ROWS_PER_CHUNK = 16;
+
+	void start(unsigned n)
+	{
+		for (unsigned i = 0; i < n; ++i)
+			threads.emplace_back([this] { run(); });
+	}
+	void run()
+	{
+		std::unique_lock<std::mutex> lock(m);
+		for (;;)
+		{
+			work.wait(lock, [this] { return stop || !queue.empty(); });
+			if (stop)
+				return;
+			ReadbackJob* job = queue.front();
+			++job->workers_inside;
+			lock.unlock();
+			for (;;)
+			{
+				const uint32_t r0 = job->next_row.fetch_add(ROWS_PER_CHUNK);
+				if (r0 >= job->height)
+					break;
+				const uint32_t r1 = std::min(r0 + ROWS_PER_CHUNK, job->height);
+				sqw::decode_picture_rows(job->rle, job->counts, job->row_capacity, job->width, r0, r1, job->dst, job->dst_pitch);
+				uint64_t words = 0;
+				for (uint32_t r = r0; r < r1; ++r)
+					words += job->counts[r] & 0x7FFFFFFFu;
+				job->words.fetch_add(words + (r1 - r0));
+				job->rows_done.fetch_add(r1 - r0);
+			}
+			lock.lock();
+			if (!queue.empty() && queue.front() == job)
+				queue.pop_front(); // every row has an owner: nobody else needs to pick this job up
+			--job->workers_inside;
+			if (job->workers_inside == 0 && job->rows_done.load() == job->height)
+			{
+				job->finished = true;
+				done.notify_all();
+			}
+		}
+	}
+	void push(ReadbackJob* job) // from the stream's host callback: the GPU has written the rows
+	{
+		{
+			std::lock_guard<std::mutex> lock(m);
+			queue.push_back(job);
+		}
+		work.notify_all();
+	}
+	void wait(ReadbackJob* job)
+	{
+		std::unique_lock<std::mutex> lock(m);
+		done.wait(lock, [job] { return job->finished; });
+	}
+	void shutdown()
+	{
+		{
+			std::lock_guard<std::mutex> lock(m);
+			stop = true;
+		}
+		work.notify_all();
+		for (auto& t : threads)
+			t.join();
+		threads.clear();
+	}
+};
+
 struct sqw_ctx
 {
 	int device = 0;
@@ -179,6 +272,8 @@ struct sqw_ctx
 	bool own_stream = false;
 	bool concurrent_views = false; // SQW_CTX_CONCURRENT_VIEWS: every view issues its work on a private stream
 	bool fast_surface_numerics = false; // SQW_CTX_FAST_SURFACE_NUMERICS
+	bool compressed_readback = false;   // SQW_CTX_COMPRESSED_READBACK
+	ReadbackPool* readback_pool = nullptr; // started by the first compressed read-back
 	size_t l2_persist_bytes = 0;   // > 0: the views' scratch blocks are marked L2-persisting on their streams (sqw_create)
 	cudaEvent_t batch_event = nullptr;
 	float* d_lightmaps = nullptr;
@@ -282,6 +377,12 @@ struct sqw_view
 	DevBuf model_instances, model_vertices, model_triangles, model_counts, model_bones, model_sort;
 	uint32_t model_num_instances = 0;
 	uint64_t model_num_vertices = 0, model_num_triangles = 0;
+	// compressed read-back (sqw_read_pixels32_async with SQW_CTX_COMPRESSED_READBACK)
+	uint32_t* h_rle = nullptr; // page-locked, device-mapped: height rows of row_capacity words, then height count words
+	size_t h_rle_words = 0;
+	ReadbackJob readback_job;
+	bool readback_pending = false;
+	uint64_t readback_bytes_total = 0, readback_pictures = 0; // completed compressed read-backs of this view
 	// inputs and results of sqw_polygons_prepare
 	DevBuf polygon_candidates, polygon_clip_planes, polygon_results, polygon_totals;
 	uint32_t polygon_num_candidates = 0;
@@ -471,6 +572,19 @@ uint32_t variant_bits(const SurfaceVariant& v) // SurfaceBand::variant
 extern "C"
 {
 
+// The decode job of the view's last compressed read-back, if any: call after the view's stream has been synchronised (the
+// stream's host callback has queued it by then).
+static void finish_readback(sqw_view* view)
+{
+	if (view->readback_pending)
+	{
+		view->ctx->readback_pool->wait(&view->readback_job);
+		view->readback_pending = false;
+		view->readback_bytes_total += view->readback_job.words.load() * 4;
+		++view->readback_pictures;
+	}
+}
+
 int sqw_abi_version(void) { return SQW_ABI_VERSION; }
 
 const char* sqw_last_error(const sqw_ctx* ctx) { return ctx ? ctx->last_error.c_str() : g_create_error.c_str(); }
@@ -506,6 +620,7 @@ int sqw_create(sqw_ctx** out_ctx, int device, const sqw_map_desc* map, void* ext
 	}
 	ctx->concurrent_views = (map->flags & SQW_CTX_CONCURRENT_VIEWS) != 0;
 	ctx->fast_surface_numerics = (map->flags & SQW_CTX_FAST_SURFACE_NUMERICS) != 0;
+	ctx->compressed_readback = (map->flags & SQW_CTX_COMPRESSED_READBACK) != 0;
 	{
 		// A view's scratch — surface pool, span table, tile lists — is written by one kernel of a frame and read by the next a moment
 		// later, while the other views in flight stream ~100 MB of pixels each through the 126 MB L2.  Marking the views' scratch
@@ -563,6 +678,11 @@ void sqw_destroy(sqw_ctx* ctx)
 		cudaStreamSynchronize(ctx->stream);
 	while (!ctx->views.empty())
 		sqw_view_destroy(ctx->views.back());
+	if (ctx->readback_pool)
+	{
+		ctx->readback_pool->shutdown();
+		delete ctx->readback_pool;
+	}
 	if (ctx->l2_persist_bytes)
 		cudaCtxResetPersistingL2Cache();
 	for (auto& img : ctx->images)
@@ -706,6 +826,9 @@ void sqw_view_destroy(sqw_view* view)
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(view->stream);
 	cudaStreamSynchronize(ctx->stream);
+	finish_readback(view);
+	if (view->h_rle)
+		cudaFreeHost(view->h_rle);
 	if (view->immediate)
 		sqw_frame_destroy(view->immediate);
 	if (view->done)
@@ -2130,7 +2253,79 @@ int sqw_read_pixels32_async(sqw_view* view, uint32_t* dst, size_t dst_pitch)
 		return fail(view ? view->ctx : nullptr, SQW_ERR_INVALID_ARGUMENT, "sqw_read_pixels32_async: bad argument");
 	sqw_ctx* ctx = view->ctx;
 	SQW_CUDA(ctx, cudaSetDevice(ctx->device));
+	if (ctx->compressed_readback)
+	{
+		// run-length rows written by the GPU straight into mapped host memory, expanded into dst by the pool (readback_decode.cu)
+		if (view->readback_pending) // the previous picture of this view is still travelling: its buffer is about to be reused
+		{
+			SQW_CUDA(ctx, cudaStreamSynchronize(view->stream));
+			finish_readback(view);
+		}
+		const size_t words = (size_t)view->width * view->height + view->height;
+		if (words > view->h_rle_words)
+		{
+			if (view->h_rle)
+				SQW_CUDA(ctx, cudaFreeHost(view->h_rle));
+			view->h_rle = nullptr;
+			view->h_rle_words = 0;
+			SQW_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&view->h_rle), words * 4, cudaHostAllocMapped | cudaHostAllocPortable));
+			view->h_rle_words = words;
+		}
+		if (!ctx->readback_pool)
+		{
+			unsigned n = std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));
+			if (const char* e = std::getenv("SQW_READBACK_THREADS"))
+				n = (unsigned)std::max(1, std::min(64, std::atoi(e)));
+			ctx->readback_pool = new ReadbackPool();
+			ctx->readback_pool->start(n);
+		}
+		uint32_t* const counts = view->h_rle + (size_t)view->width * view->height;
+		SQW_CUDA(ctx, sqw::launch_picture_rle(view->d_ldr, view->width, view->height, view->width, view->h_rle, view->width, counts, view->stream));
+		ReadbackJob& job = view->readback_job;
+		job.rle = view->h_rle;
+		job.counts = counts;
+		job.dst = dst;
+		job.dst_pitch = dst_pitch;
+		job.width = view->width;
+		job.height = view->height;
+		job.row_capacity = view->width;
+		job.next_row.store(0);
+		job.rows_done.store(0);
+		job.words.store(0);
+		job.workers_inside = 0;
+		job.finished = false;
+		view->readback_pending = true;
+		SQW_CUDA(ctx, cudaLaunchHostFunc(view->stream, [](void* p) {
+			sqw_view* v = static_cast<sqw_view*>(p);
+			v->ctx->readback_pool->push(&v->readback_job);
+		}, view));
+		return SQW_OK;
+	}
 	SQW_CUDA(ctx, cudaMemcpy2DAsync(dst, dst_pitch * 4, view->d_ldr, (size_t)view->width * 4, (size_t)view->width * 4, view->height, cudaMemcpyDeviceToHost, view->stream));
+	return SQW_OK;
+}
+
+int sqw_view_get_readback_stats(const sqw_view* view, uint64_t out[2])
+{
+	if (!view || !out)
+		return SQW_ERR_INVALID_ARGUMENT;
+	out[0] = view->readback_pictures;
+	out[1] = view->readback_bytes_total;
+	return SQW_OK;
+}
+
+int sqw_set_compressed_readback(sqw_ctx* ctx, int enable)
+{
+	if (!ctx)
+		return SQW_ERR_INVALID_ARGUMENT;
+	SQW_CUDA(ctx, cudaSetDevice(ctx->device));
+	for (sqw_view* v : ctx->views) // pictures on their way keep the mode they were started with
+		if (v && v->readback_pending)
+		{
+			SQW_CUDA(ctx, cudaStreamSynchronize(v->stream));
+			finish_readback(v);
+		}
+	ctx->compressed_readback = enable != 0;
 	return SQW_OK;
 }
 
@@ -2165,6 +2360,7 @@ int sqw_view_synchronize(sqw_view* view)
 		return SQW_ERR_INVALID_ARGUMENT;
 	SQW_CUDA(view->ctx, cudaSetDevice(view->ctx->device));
 	SQW_CUDA(view->ctx, cudaStreamSynchronize(view->stream));
+	finish_readback(view);
 	return SQW_OK;
 }
 

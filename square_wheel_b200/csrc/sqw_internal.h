@@ -205,6 +205,10 @@ struct ModelLaunch
 };
 cudaError_t launch_models_prepare(const ModelLaunch& l, cudaStream_t stream);
 
+// ---- compressed read-back of the 32-bit picture ----------------------------------------------------------------------
+cudaError_t launch_picture_rle(const uint32_t* ldr, uint32_t width, uint32_t height, uint32_t pitch, uint32_t* rows_out, uint32_t row_capacity, uint32_t* row_counts, cudaStream_t stream);
+void decode_picture_rows(const uint32_t* rle, const uint32_t* counts, uint32_t row_capacity, uint32_t width, uint32_t row0, uint32_t row1, uint32_t* dst, size_t dst_pitch); // readback_decode.cu
+
 // ---- world-polygon preparation -------------------------------------------------------------------
 struct PolygonsTotalsDev
 {

@@ -27,7 +27,7 @@ class Context:
 
     def __init__(
         self, lightmaps: Optional[np.ndarray], directional_lightmaps: Optional[np.ndarray], device: int = 0, stream: int = 0, max_images: int = 0, concurrent_views: bool = False,
-        fast_surface_numerics: bool = False,
+        fast_surface_numerics: bool = False, compressed_readback: bool = False,
     ):
         self._lib = N.load_cuda_library()
         self._handle = C.c_void_p()
@@ -40,7 +40,7 @@ class Context:
             if lm is not None and dlm.size != n:
                 raise ValueError("lightmap arrays must have the same element count")
             n = dlm.size
-        flags = (N.CTX_CONCURRENT_VIEWS if concurrent_views else 0) | (N.CTX_FAST_SURFACE_NUMERICS if fast_surface_numerics else 0)
+        flags = (N.CTX_CONCURRENT_VIEWS if concurrent_views else 0) | (N.CTX_FAST_SURFACE_NUMERICS if fast_surface_numerics else 0) | (N.CTX_COMPRESSED_READBACK if compressed_readback else 0)
         desc = N.MapDesc(N.ptr(lm), N.ptr(dlm), n, max_images, flags)
         rc = self._lib.sqw_create(C.byref(self._handle), device, C.byref(desc), C.c_void_p(stream) if stream else None)
         if rc != N.SQW_OK:
@@ -123,6 +123,10 @@ class Context:
     def set_fast_surface_numerics(self, enable: bool):
         """SQW_CTX_FAST_SURFACE_NUMERICS for the frames submitted from now on (sqw_set_fast_surface_numerics)."""
         self._check(self._lib.sqw_set_fast_surface_numerics(self._handle, 1 if enable else 0), "sqw_set_fast_surface_numerics")
+
+    def set_compressed_readback(self, enable: bool):
+        """SQW_CTX_COMPRESSED_READBACK for the read_pixels32_async calls made from now on (sqw_set_compressed_readback)."""
+        self._check(self._lib.sqw_set_compressed_readback(self._handle, 1 if enable else 0), "sqw_set_compressed_readback")
 
     def self_test(self):
         """Exhaustive device check of the arithmetic shortcuts of the kernels (sqw_self_test); raises SqwError on a mismatch."""
@@ -212,6 +216,12 @@ class View:
     def read_pixels32_async(self, dst_ptr: int, dst_pitch: int):
         """Queue the copy of the post-processed picture into (page-locked) host memory at dst_ptr; complete after synchronize()."""
         self.ctx._check(self._lib.sqw_read_pixels32_async(self._handle, C.c_void_p(dst_ptr), dst_pitch), "sqw_read_pixels32_async")
+
+    def readback_stats(self):
+        """(compressed read-backs completed so far, bytes they moved over the bus) (sqw_view_get_readback_stats)."""
+        out = np.zeros(2, np.uint64)
+        self.ctx._check(self._lib.sqw_view_get_readback_stats(self._handle, N.ptr(out)), "sqw_view_get_readback_stats")
+        return int(out[0]), int(out[1])
 
     def read_pixels_async(self, dst_ptr: int, dst_pitch: int):
         self.ctx._check(self._lib.sqw_read_pixels_async(self._handle, C.c_void_p(dst_ptr), dst_pitch), "sqw_read_pixels_async")

@@ -48,11 +48,28 @@ def _read_async(view):
     return buf.numpy().view(np.uint32).copy()
 
 
+def _read_async_compressed(view):
+    """The same with SQW_CTX_COMPRESSED_READBACK: run-length rows written by the GPU into mapped host memory, expanded by the
+    library's host threads into an ordinary (pageable) buffer with a pitch larger than the width."""
+    pitch = view.width + 5
+    buf = np.full((view.height, pitch), 0x5A5A5A5A, np.uint32)
+    view.ctx.set_compressed_readback(True)
+    try:
+        view.read_pixels32_async(buf.ctypes.data, pitch)
+        view.read_pixels32_async(buf.ctypes.data, pitch)  # a second picture of the same view while the first one is on its way
+        view.synchronize()
+    finally:
+        view.ctx.set_compressed_readback(False)
+    assert (buf[:, view.width :] == 0x5A5A5A5A).all(), "the decoder wrote past the end of a row"
+    return buf[:, : view.width].copy()
+
+
 def _check_fused(view, frame, fb_want, post, what, stats_launches=None):
     frame.submit(N.STAGE_ALL)
     got_hdr = view.read_pixels()
     got_ldr = view.read_pixels32()
     got_ldr_async = _read_async(view)
+    assert_pixels_equal(_read_async_compressed(view), got_ldr, f"{what}: compressed asynchronous read-back")
     got_avg = view.average_color()
     import oracle
 
@@ -254,3 +271,31 @@ def test_fused_tonemap_bench_scene_4k(oracle_lib):
             v.close()
         ctx.close()
         sc.close()
+
+
+@pytest.mark.parametrize("size", [(3840, 64), (1027, 33), (256, 5), (255, 3), (1, 1), (2049, 2)])
+def test_compressed_readback_of_flat_noisy_and_striped_pictures(assets, size):
+    """The run-length read-back on pictures that stress it: one colour (runs cut at every 256 pixels), noise (every run one pixel:
+    the compressed row is as long as the raw one), stripes whose period straddles the 256-pixel and 1024-pixel boundaries."""
+    W, H = size
+    ctx = assets.device_context()
+    view = ctx.create_view(W, H, 64)
+    r = synth.rng(W * 7 + H)
+    post = make_post_params(exposure=1.0, bloom_sigma=0.0)
+    x = np.arange(W, dtype=np.uint64)[None, :] + np.zeros((H, 1), np.uint64)
+    pictures = {
+        "flat": np.full((H, W), 0x0000012300450067, np.uint64),
+        "noise": r.integers(0, 4000, (H, W), dtype=np.uint64) | (r.integers(0, 4000, (H, W), dtype=np.uint64) << np.uint64(16)) | (r.integers(0, 4000, (H, W), dtype=np.uint64) << np.uint64(32)),
+        "stripes of 3": (x // np.uint64(3) % np.uint64(7)) * np.uint64(300),
+        "stripes of 255": (x // np.uint64(255) % np.uint64(5)) * np.uint64(500) << np.uint64(16),
+        "stripes of 257": (x // np.uint64(257) % np.uint64(5)) * np.uint64(500) << np.uint64(32),
+    }
+    try:
+        for name, px in pictures.items():
+            view.write_pixels(np.ascontiguousarray(px))
+            view.postprocess(post, read_back=False)
+            want = view.read_pixels32()
+            got = _read_async_compressed(view)
+            assert_pixels_equal(got, want, f"{W}x{H} {name}")
+    finally:
+        view.close()
