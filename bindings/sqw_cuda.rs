@@ -389,6 +389,7 @@ extern "C" {
 	pub fn sqw_polygons_read(view: *mut sqw_view, out: *mut sqw_prepared_polygon, num: u32, totals: *mut sqw_polygons_totals) -> c_int;
 	// draw_polygon (partial_renderer.rs:4011-4142) for the prepared polygons in BSP draw order
 	pub fn sqw_polygons_draw(view: *mut sqw_view, order: *const u32, num_order: u32) -> c_int;
+	pub fn sqw_frame_set_draw_from_polygons(frame: *mut sqw_frame, clear_color: *const c_void) -> c_int;
 	pub fn sqw_polygons_draw_read(
 		view: *mut sqw_view, cmds: *mut sqw_draw_cmd, cmds_capacity: u32, points: *mut sqw_polygon_point, points_capacity: u32, counts_out: *mut u32,
 	) -> c_int;

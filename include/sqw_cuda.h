@@ -558,6 +558,12 @@ int sqw_polygons_read(sqw_view* view, sqw_prepared_polygon* out, uint32_t num, s
  * power-of-two renormalisation of the equations (:4106-4109) -> packed sqw_draw_cmd[] (tex_kind SQW_TEX_SURFACE, tex_ref =
  * surface_pixels_offset, blend = the material's blending mode) and sqw_polygon_point[] in draw order, on the device. */
 int sqw_polygons_draw(sqw_view* view, const uint32_t* order, uint32_t num_order);
+/* The draw half of a recorded frame straight from the device lists of the last sqw_polygons_draw of the frame's view: what
+ * sqw_frame_set_draw derives on the host from host lists (row and column ranges, span-table offsets, 32-scan-line chunks, ordered
+ * per-band command lists) is derived by set-up kernels; the commands and vertices never visit the host, which only reads four
+ * totals back to size the view's scratch.  clear_color as in sqw_draw.  The surfaces the commands reference must have been sized
+ * (sqw_frame_set_surfaces / sqw_build_surfaces) before. */
+int sqw_frame_set_draw_from_polygons(sqw_frame* frame, const void* clear_color);
 /* Read the lists of the last sqw_polygons_draw back (NULL to skip); counts_out = {commands, vertices}. */
 int sqw_polygons_draw_read(sqw_view* view, sqw_draw_cmd* cmds, uint32_t cmds_capacity, sqw_polygon_point* points, uint32_t points_capacity, uint32_t counts_out[2]);
 

@@ -249,6 +249,7 @@ CUDA_SYMBOLS = [
     ("sqw_polygons_read", C.c_int, [_VP, _VP, C.c_uint32, C.POINTER(PolygonsTotals)]),
     ("sqw_polygons_draw", C.c_int, [_VP, _VP, C.c_uint32]),
     ("sqw_polygons_draw_read", C.c_int, [_VP, _VP, C.c_uint32, _VP, C.c_uint32, _VP]),
+    ("sqw_frame_set_draw_from_polygons", C.c_int, [_VP, _VP]),
 ]
 
 _cuda_lib = None

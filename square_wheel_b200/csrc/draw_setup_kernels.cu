@@ -1,0 +1,234 @@
+// Device-side frame set-up of the rasteriser (the commands never visit the host).
+//
+// sqw_frame_set_draw builds, on the host, what the raster kernels need besides the command list itself: per command the row /
+// column ranges, the span-table offset and the resolved texture reference (CmdDev), the list of 32-scan-line chunks the span
+// set-up warps take, and per 8-row band the ordered list of the commands touching it.  When the command list was produced on the
+// device (sqw_polygons_draw), sqw_frame_set_draw_from_polygons runs the same construction here:
+//
+//   draw_cmd_dev_kernel      one thread per command: vertex bounding box -> rows [y0, y1) and conservative columns, the one-step
+//                            division flag (the same double-precision bound as the host), rows and chunk count of the command;
+//   draw_scan_kernel         one CTA: exclusive prefix sums -> span_base of every command, first chunk of every command, totals;
+//   draw_band_count / _fill  one warp per band: the commands whose rows touch the band, IN COMMAND ORDER (ballot / popc
+//                            compaction over the command list, 32 at a time): painter's order per band, as the host builds it;
+//   draw_band_scan_kernel    one warp: band list offsets;
+//   draw_chunks_kernel       one thread per command: its chunk records.
+//
+// The host only reads four totals back (to size the span table and the tile lists of the view) and launches.
+#include "sqw_device.cuh"
+#include "sqw_internal.h"
+
+namespace sqw
+{
+namespace
+{
+
+__global__ void __launch_bounds__(128) draw_cmd_dev_kernel(const DrawSetupLaunch l)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= l.num_cmds)
+		return;
+	const sqw_draw_cmd c = l.cmds[i];
+	CmdDev d;
+	d.kind = c.kind;
+	d.blend = c.blend;
+	d.tc_mode = c.tc_mode;
+	d.tex_width = c.tex_size[0];
+	d.tex_height = c.tex_size[1];
+	int32_t min_x = INT32_MAX, max_x = INT32_MIN, min_y = INT32_MAX, max_y = INT32_MIN;
+	const sqw_polygon_point* const pts = l.points + c.vertex_offset;
+	for (uint32_t k = 0; k < c.num_vertices; ++k)
+	{
+		const sqw_polygon_point p = pts[k];
+		min_x = min(min_x, p.x);
+		max_x = max(max_x, p.x);
+		min_y = min(min_y, p.y);
+		max_y = max(max_y, p.y);
+	}
+	// the same bound as sqw_frame_set_draw: smallest inverse depth of the polygon lowered by two pixels of gradient, in the
+	// rasteriser's 2^29 scale; when half of it stays above 2^11 << 8 the opaque tile kernel may use its one-step division
+	uint8_t z_flag = 0;
+	if (c.tc_mode == SQW_TC_FULL_PERSPECTIVE)
+	{
+		double min_iz = 1e300;
+		for (uint32_t k = 0; k < c.num_vertices; ++k)
+		{
+			const sqw_polygon_point p = pts[k];
+			min_iz = fmin(min_iz, (double)c.depth_eq[0] * (p.x / 65536.0) + (double)c.depth_eq[1] * (p.y / 65536.0) + (double)c.depth_eq[2]);
+		}
+		min_iz -= 2.0 * (fabs((double)c.depth_eq[0]) + fabs((double)c.depth_eq[1]));
+		if (min_iz * 536870912.0 * 0.5 >= 2048.0 * 256.0)
+			z_flag = SQW_CMDF_Z_ONE_STEP;
+	}
+	// polygon textures have the framebuffer's colour type; the list holds surface references only (sqw_polygons_draw)
+	d.texture = reinterpret_cast<const void*>((uintptr_t)c.tex_ref * l.bytes_per_pixel);
+	d.tex_flags = (uint8_t)((l.bytes_per_pixel == 8 ? 1 : 0) | 2 | z_flag);
+	const uint64_t tex_elems = (uint64_t)c.tex_size[0] * (uint64_t)c.tex_size[1];
+	if (c.kind != SQW_CMD_POLYGON || c.tex_kind != SQW_TEX_SURFACE || c.num_vertices < 3 || c.tex_size[0] <= 0 || c.tex_size[1] <= 0 ||
+		(uint64_t)c.tex_ref + tex_elems > l.surface_pool_elements)
+		atomicOr(l.totals + 4, 1u); // a command this path cannot take: the host reports the error
+
+	// rows that can own a span: [round(min_y), round(max_y)) clipped (rasterizer.rs:316-317)
+	int32_t y0 = max(fixed16_round_to_int(min_y), 0);
+	int32_t y1 = min(fixed16_round_to_int(max_y), l.height);
+	int32_t bx0 = max((min_x >> 16) - 1, 0);
+	int32_t bx1 = min((max_x >> 16) + 2, l.width);
+	if (y0 >= y1 || bx0 >= bx1)
+		y0 = y1 = bx0 = bx1 = 0;
+	d.y0 = (int16_t)y0;
+	d.y1 = (int16_t)y1;
+	d.bx0 = (int16_t)bx0;
+	d.bx1 = (int16_t)bx1;
+	d.span_base = 0;
+	l.cmd_dev[i] = d;
+	l.rows[i] = (uint32_t)(y1 - y0);
+	if (c.blend != SQW_BLEND_NONE)
+		atomicAdd(l.totals + 3, 1u);
+}
+
+// span_base[i] = rows of the commands before i; chunk_base[i] = chunks (32 scan-lines) of the commands before i
+__global__ void __launch_bounds__(1024) draw_scan_kernel(CmdDev* __restrict__ cmd_dev, const uint32_t* __restrict__ rows, uint32_t* __restrict__ chunk_base, const uint32_t n, uint32_t* __restrict__ totals)
+{
+	__shared__ unsigned long long s_warp[32];
+	__shared__ unsigned long long s_carry;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	if (threadIdx.x == 0)
+		s_carry = 0;
+	__syncthreads();
+	for (uint32_t base = 0; base < n; base += 1024)
+	{
+		const uint32_t i = base + threadIdx.x;
+		const uint32_t r = i < n ? rows[i] : 0u;
+		// rows in the low word, chunks in the high word: one scan for both
+		const unsigned long long own = (unsigned long long)r | ((unsigned long long)((r + 31u) / 32u) << 32);
+		unsigned long long incl = own;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+			if (lane >= o)
+				incl += t;
+		}
+		if (lane == 31)
+			s_warp[warp] = incl;
+		__syncthreads();
+		unsigned long long before = s_carry, all = 0;
+		for (int w = 0; w < 32; ++w)
+		{
+			before += w < warp ? s_warp[w] : 0ull;
+			all += s_warp[w];
+		}
+		if (i < n)
+		{
+			const unsigned long long excl = before + incl - own;
+			cmd_dev[i].span_base = (uint32_t)excl;
+			chunk_base[i] = (uint32_t)(excl >> 32);
+		}
+		__syncthreads();
+		if (threadIdx.x == 0)
+			s_carry += all;
+		__syncthreads();
+	}
+	if (threadIdx.x == 0)
+	{
+		totals[0] = (uint32_t)s_carry;         // scan-lines (the host rejects frames past 2^32 before they get here: rows <= height per command)
+		totals[1] = (uint32_t)(s_carry >> 32); // chunks
+	}
+}
+
+__global__ void __launch_bounds__(128) draw_chunks_kernel(const uint32_t* __restrict__ rows, const uint32_t* __restrict__ chunk_base, const uint32_t n, uint2* __restrict__ chunks)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n)
+		return;
+	const uint32_t r = rows[i];
+	uint2* o = chunks + chunk_base[i];
+	for (uint32_t r0 = 0; r0 < r; r0 += 32)
+		*o++ = make_uint2(i, r0);
+}
+
+// One warp per 8-row band: FILL = 0 counts the commands touching the band, FILL = 1 writes them in command order.
+template <int FILL>
+__global__ void __launch_bounds__(128) draw_band_lists_kernel(const CmdDev* __restrict__ cmd_dev, const uint32_t n, const uint32_t num_bands, uint32_t* __restrict__ band_counts, const uint32_t* __restrict__ band_offsets, uint32_t* __restrict__ band_list)
+{
+	const uint32_t band = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	if (band >= num_bands)
+		return;
+	const int lane = threadIdx.x & 31;
+	const int32_t band_y0 = (int32_t)band * SQW_TILE_H, band_y1 = band_y0 + SQW_TILE_H;
+	uint32_t count = 0;
+	const uint32_t out0 = FILL ? band_offsets[band] : 0u;
+	for (uint32_t base = 0; base < n; base += 32)
+	{
+		const uint32_t i = base + (uint32_t)lane;
+		bool hit = false;
+		if (i < n)
+		{
+			const uint32_t rows = __ldg(reinterpret_cast<const uint32_t*>(cmd_dev + i)); // y0 | y1 << 16
+			const int32_t y0 = (int16_t)(rows & 0xFFFF), y1 = (int16_t)(rows >> 16);
+			hit = y0 < y1 && y0 < band_y1 && y1 > band_y0;
+		}
+		const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, hit);
+		if (FILL && hit)
+			band_list[out0 + count + __popc(ballot & ((1u << lane) - 1))] = i;
+		count += __popc(ballot);
+	}
+	if (!FILL && lane == 0)
+		band_counts[band] = count;
+}
+
+__global__ void __launch_bounds__(32) draw_band_scan_kernel(const uint32_t* __restrict__ band_counts, const uint32_t num_bands, uint32_t* __restrict__ band_offsets, uint32_t* __restrict__ totals)
+{
+	const int lane = threadIdx.x;
+	uint32_t carry = 0;
+	for (uint32_t base = 0; base < num_bands; base += 32)
+	{
+		const uint32_t b = base + (uint32_t)lane;
+		const uint32_t own = b < num_bands ? band_counts[b] : 0u;
+		uint32_t incl = own;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+			if (lane >= o)
+				incl += t;
+		}
+		if (b < num_bands)
+			band_offsets[b] = carry + incl - own;
+		carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
+	}
+	if (lane == 0)
+	{
+		band_offsets[num_bands] = carry;
+		totals[2] = carry;
+	}
+}
+
+} // namespace
+
+// Phase 1: everything whose size is known (CmdDev, rows, prefix sums, band counts and offsets); totals = {scan-lines, chunks, band
+// list entries, commands that are not opaque polygons, error flag}.
+cudaError_t launch_draw_setup_phase1(const DrawSetupLaunch& l, cudaStream_t stream)
+{
+	cudaMemsetAsync(l.totals, 0, 8 * sizeof(uint32_t), stream);
+	if (l.num_cmds)
+	{
+		draw_cmd_dev_kernel<<<(l.num_cmds + 127) / 128, 128, 0, stream>>>(l);
+		draw_scan_kernel<<<1, 1024, 0, stream>>>(l.cmd_dev, l.rows, l.chunk_base, l.num_cmds, l.totals);
+	}
+	draw_band_lists_kernel<0><<<(l.num_bands + 3) / 4, 128, 0, stream>>>(l.cmd_dev, l.num_cmds, l.num_bands, l.band_counts, nullptr, nullptr);
+	draw_band_scan_kernel<<<1, 32, 0, stream>>>(l.band_counts, l.num_bands, l.band_offsets, l.totals);
+	return cudaGetLastError();
+}
+
+// Phase 2, once the host has sized the lists: chunk records and the ordered band lists.
+cudaError_t launch_draw_setup_phase2(const DrawSetupLaunch& l, cudaStream_t stream)
+{
+	if (l.num_cmds)
+	{
+		draw_chunks_kernel<<<(l.num_cmds + 127) / 128, 128, 0, stream>>>(l.rows, l.chunk_base, l.num_cmds, l.chunks);
+		draw_band_lists_kernel<1><<<(l.num_bands + 3) / 4, 128, 0, stream>>>(l.cmd_dev, l.num_cmds, l.num_bands, nullptr, l.band_offsets, l.band_list);
+	}
+	return cudaGetLastError();
+}
+
+} // namespace sqw

@@ -443,7 +443,9 @@ struct sqw_frame
 	std::vector<CmdDev> h_cmd_dev;
 	std::vector<uint2> h_chunks, h_chunks_tri;
 	std::vector<uint32_t> h_band_offsets;
-	uint32_t num_cmds = 0, total_spans = 0, num_bands = 0, total_band_entries = 0, num_triangle_cmds = 0, num_general_cmds = 0;
+	uint32_t num_cmds = 0, total_spans = 0, num_bands = 0, total_band_entries = 0, num_triangle_cmds = 0, num_general_cmds = 0, num_chunks = 0;
+	// sqw_frame_set_draw_from_polygons: the lists live in buffers of the frame, built on the device
+	DevBuf dev_cmds, dev_points, dev_cmd_dev, dev_rows, dev_chunk_base, dev_chunks, dev_band_counts, dev_band_offsets, dev_band_list, dev_totals;
 	uint32_t draw_width = 0, draw_height = 0; // view size the command list was prepared for
 	bool clear = false;
 	uint64_t clear_color = 0;
@@ -927,6 +929,8 @@ void sqw_frame_destroy(sqw_frame* f)
 	f->depth_arena.release();
 	f->d_depth_spans.release();
 	f->d_shadow_dev.release();
+	for (DevBuf* b : {&f->dev_cmds, &f->dev_points, &f->dev_cmd_dev, &f->dev_rows, &f->dev_chunk_base, &f->dev_chunks, &f->dev_band_counts, &f->dev_band_offsets, &f->dev_band_list, &f->dev_totals})
+		b->release();
 	if (f->view->immediate == f)
 		f->view->immediate = nullptr;
 	delete f;
@@ -1257,6 +1261,7 @@ int sqw_frame_set_draw(
 				f->h_band_offsets[(size_t)b + 1]++;
 	}
 	f->h_chunks.insert(f->h_chunks.end(), f->h_chunks_tri.begin(), f->h_chunks_tri.end());
+	f->num_chunks = (uint32_t)f->h_chunks.size();
 	for (uint32_t b = 0; b < num_bands; ++b)
 		f->h_band_offsets[(size_t)b + 1] += f->h_band_offsets[b];
 	f->num_cmds = num_cmds;
@@ -1314,6 +1319,99 @@ int sqw_frame_set_draw(
 		f->d_band_list = static_cast<const uint32_t*>(a.push(f->h_band_list.data(), b_list));
 		SQW_CUDA(ctx, a.commit(view->stream));
 	}
+	f->clear = clear_color != nullptr;
+	f->clear_color = 0;
+	if (clear_color)
+		std::memcpy(&f->clear_color, clear_color, C);
+	f->has_draw = true;
+	return SQW_OK;
+}
+
+int sqw_frame_set_draw_from_polygons(sqw_frame* f, const void* clear_color)
+{
+	if (!f)
+		return SQW_ERR_INVALID_ARGUMENT;
+	sqw_view* view = f->view;
+	sqw_ctx* ctx = view->ctx;
+	if (!view->polygon_draw_totals.ptr)
+		return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_frame_set_draw_from_polygons: no sqw_polygons_draw on this view yet");
+	SQW_CUDA(ctx, cudaSetDevice(ctx->device));
+	cudaStream_t s = view->stream;
+	const int32_t W = (int32_t)view->width, H = (int32_t)view->height;
+	const size_t C = (size_t)view->color_bits / 8;
+	const uint32_t num_bands = (uint32_t)((H + SQW_TILE_H - 1) / SQW_TILE_H);
+	const uint64_t tiles_x = (uint64_t)((W + SQW_TILE_W - 1) / SQW_TILE_W);
+	// the lists of the last sqw_polygons_draw: their sizes, then a copy the frame owns (the view's buffers are reused per frame)
+	uint32_t counts[2] = {0, 0};
+	SQW_CUDA(ctx, cudaMemcpyAsync(counts, view->polygon_draw_totals.ptr, 8, cudaMemcpyDeviceToHost, s));
+	SQW_CUDA(ctx, cudaStreamSynchronize(s));
+	const uint32_t num_cmds = counts[0], num_points = counts[1];
+	const size_t need1[8] = {(size_t)num_cmds * sizeof(sqw_draw_cmd) + 16, (size_t)num_points * sizeof(sqw_polygon_point) + 16, (size_t)num_cmds * sizeof(CmdDev) + 16, (size_t)num_cmds * 4 + 16,
+							 (size_t)num_cmds * 4 + 16, (size_t)num_bands * 4 + 16, (size_t)(num_bands + 1) * 4 + 16, 64};
+	DevBuf* bufs1[8] = {&f->dev_cmds, &f->dev_points, &f->dev_cmd_dev, &f->dev_rows, &f->dev_chunk_base, &f->dev_band_counts, &f->dev_band_offsets, &f->dev_totals};
+	for (int i = 0; i < 8; ++i)
+		SQW_CUDA(ctx, bufs1[i]->reserve(need1[i])); // (the stream is idle: synchronised above)
+	if (num_cmds)
+	{
+		SQW_CUDA(ctx, cudaMemcpyAsync(f->dev_cmds.ptr, view->polygon_draw_cmds.ptr, (size_t)num_cmds * sizeof(sqw_draw_cmd), cudaMemcpyDeviceToDevice, s));
+		SQW_CUDA(ctx, cudaMemcpyAsync(f->dev_points.ptr, view->polygon_draw_points.ptr, (size_t)num_points * sizeof(sqw_polygon_point), cudaMemcpyDeviceToDevice, s));
+	}
+	sqw::DrawSetupLaunch l{};
+	l.cmds = static_cast<const sqw_draw_cmd*>(f->dev_cmds.ptr);
+	l.points = static_cast<const sqw_polygon_point*>(f->dev_points.ptr);
+	l.num_cmds = num_cmds;
+	l.width = W;
+	l.height = H;
+	l.num_bands = num_bands;
+	l.bytes_per_pixel = (uint32_t)C;
+	l.surface_pool_elements = view->surfaces.capacity / C;
+	l.cmd_dev = static_cast<CmdDev*>(f->dev_cmd_dev.ptr);
+	l.rows = static_cast<uint32_t*>(f->dev_rows.ptr);
+	l.chunk_base = static_cast<uint32_t*>(f->dev_chunk_base.ptr);
+	l.band_counts = static_cast<uint32_t*>(f->dev_band_counts.ptr);
+	l.band_offsets = static_cast<uint32_t*>(f->dev_band_offsets.ptr);
+	l.totals = static_cast<uint32_t*>(f->dev_totals.ptr);
+	SQW_CUDA(ctx, sqw::launch_draw_setup_phase1(l, s));
+	uint32_t totals[8] = {};
+	SQW_CUDA(ctx, cudaMemcpyAsync(totals, f->dev_totals.ptr, sizeof(totals), cudaMemcpyDeviceToHost, s));
+	SQW_CUDA(ctx, cudaStreamSynchronize(s));
+	if (totals[4])
+		return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_frame_set_draw_from_polygons: the device command list holds a command outside the surface pool (build surfaces first)");
+	const uint32_t span_total = totals[0], num_chunks = totals[1], band_entries = totals[2];
+	if ((uint64_t)band_entries * tiles_x > 0xFFFFFFFFull)
+		return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_frame_set_draw_from_polygons: too many commands per band");
+	SQW_CUDA(ctx, f->dev_chunks.reserve((size_t)num_chunks * sizeof(uint2) + 16));
+	SQW_CUDA(ctx, f->dev_band_list.reserve((size_t)band_entries * 4 + 16));
+	l.chunks = static_cast<uint2*>(f->dev_chunks.ptr);
+	l.band_list = static_cast<uint32_t*>(f->dev_band_list.ptr);
+	SQW_CUDA(ctx, sqw::launch_draw_setup_phase2(l, s));
+	// the view's scratch, as sqw_frame_set_draw sizes it
+	const size_t bin_bytes = bin_scratch_bytes(band_entries, (uint32_t)tiles_x, num_bands);
+	if ((size_t)span_total * sizeof(SpanRec) + 64 > view->spans.capacity || bin_bytes > view->band_lists.capacity)
+	{
+		SQW_CUDA(ctx, cudaStreamSynchronize(s));
+		SQW_CUDA(ctx, view_scratch_reserve(view, 1, (size_t)span_total * sizeof(SpanRec) + 64));
+		SQW_CUDA(ctx, view_scratch_reserve(view, 2, bin_bytes));
+	}
+	f->sampled_views.clear();
+	f->d_cmds = static_cast<const sqw_draw_cmd*>(f->dev_cmds.ptr);
+	f->d_cmd_dev = static_cast<const CmdDev*>(f->dev_cmd_dev.ptr);
+	f->d_polygon_points = static_cast<const sqw_polygon_point*>(f->dev_points.ptr);
+	f->d_triangle_points = nullptr;
+	f->d_chunks = static_cast<const uint2*>(f->dev_chunks.ptr);
+	f->d_band_offsets = static_cast<const uint32_t*>(f->dev_band_offsets.ptr);
+	f->d_band_list = static_cast<const uint32_t*>(f->dev_band_list.ptr);
+	f->num_cmds = num_cmds;
+	f->num_triangle_cmds = 0;
+	f->num_general_cmds = totals[3];
+	f->num_chunks = num_chunks;
+	f->draw_width = view->width;
+	f->draw_height = view->height;
+	f->total_spans = span_total;
+	f->num_bands = num_bands;
+	f->total_band_entries = band_entries;
+	f->stats.num_spans = span_total;
+	f->stats.num_tiles = num_bands * (uint32_t)tiles_x;
 	f->clear = clear_color != nullptr;
 	f->clear_color = 0;
 	if (clear_color)
@@ -1510,7 +1608,7 @@ int sqw_frame_submit(sqw_frame* f, uint32_t stages)
 		rl.num_general_cmds = f->num_general_cmds;
 		rl.spans = static_cast<SpanRec*>(view->spans.ptr);
 		rl.chunks = f->d_chunks;
-		rl.num_chunks = (uint32_t)f->h_chunks.size();
+		rl.num_chunks = f->num_chunks;
 		rl.total_spans = f->total_spans;
 		{
 			const uint32_t tiles_x = (view->width + SQW_TILE_W - 1) / SQW_TILE_W;

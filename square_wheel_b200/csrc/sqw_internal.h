@@ -205,6 +205,28 @@ struct ModelLaunch
 };
 cudaError_t launch_models_prepare(const ModelLaunch& l, cudaStream_t stream);
 
+// ---- device-side frame set-up of the rasteriser (draw_setup_kernels.cu) ----------------------------------------------
+struct DrawSetupLaunch
+{
+	const sqw_draw_cmd* cmds;         // device, packed, draw order
+	const sqw_polygon_point* points;  // device
+	uint32_t num_cmds;
+	int32_t width, height;
+	uint32_t num_bands;
+	uint32_t bytes_per_pixel;         // 4 or 8
+	uint64_t surface_pool_elements;   // capacity of the view's surface pool, in pixels
+	CmdDev* cmd_dev;                  // out [num_cmds]
+	uint32_t* rows;                   // out [num_cmds]: scan-lines of the command
+	uint32_t* chunk_base;             // out [num_cmds]
+	uint32_t* band_counts;            // out [num_bands]
+	uint32_t* band_offsets;           // out [num_bands + 1]
+	uint2* chunks;                    // phase 2 out
+	uint32_t* band_list;              // phase 2 out
+	uint32_t* totals;                 // [8]: scan-lines, chunks, band list entries, non-opaque commands, error flag
+};
+cudaError_t launch_draw_setup_phase1(const DrawSetupLaunch& l, cudaStream_t stream);
+cudaError_t launch_draw_setup_phase2(const DrawSetupLaunch& l, cudaStream_t stream);
+
 // ---- compressed read-back of the 32-bit picture ----------------------------------------------------------------------
 cudaError_t launch_picture_rle(const uint32_t* ldr, uint32_t width, uint32_t height, uint32_t pitch, uint32_t* rows_out, uint32_t row_capacity, uint32_t* row_counts, cudaStream_t stream);
 void decode_picture_rows(const uint32_t* rle, const uint32_t* counts, uint32_t row_capacity, uint32_t width, uint32_t row0, uint32_t row1, uint32_t* dst, size_t dst_pitch); // readback_decode.cu

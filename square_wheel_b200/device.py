@@ -328,6 +328,11 @@ class Frame:
         )
         self.h2d_bytes += cmds.nbytes + pp.nbytes + tp.nbytes
 
+    def set_draw_from_polygons(self, clear_color: Optional[int] = None):
+        """The draw half of the frame from the device lists of the view's last polygons_draw (sqw_frame_set_draw_from_polygons)."""
+        cc = np.array([clear_color], np.uint64) if clear_color is not None else None
+        self.view.ctx._check(self._lib.sqw_frame_set_draw_from_polygons(self._handle, N.ptr(cc)), "sqw_frame_set_draw_from_polygons")
+
     def set_shadow_map_draw(self, maps, cmds, polygon_points):
         """Record the shadow-map fills (DepthRasterizer::fill_polygon calls, rasterizer.rs:1314) of the frame."""
         maps = _as(maps, N.depth_map_dtype)

@@ -118,3 +118,57 @@ def test_polygons_prepare_on_the_bench_scene_and_bad_arguments():
         hr.close()
         ctx.close()
         sc.close()
+
+
+@pytest.mark.parametrize("material_mode, size", [(0, (1280, 720)), (2, (1918, 1078)), (0, (3840, 2160))])
+def test_frame_drawn_from_device_command_lists(material_mode, size):
+    """The chain of SURVEY 8 f3 for world polygons: candidates and draw order from the host's visibility flood and BSP walk, geometry
+    (sqw_polygons_prepare / _draw) and the rasteriser's frame set-up (sqw_frame_set_draw_from_polygons: CmdDev, span offsets, chunk and
+    band lists) on the device — the command list never visits the host.  The picture must equal, bit for bit, the one of the same
+    frame recorded from the host mirror's lists (which the frame tests pin against the oracle)."""
+    from square_wheel_b200.device import make_post_params
+
+    W, H = size
+    sc = S.Scene(seed=11, texture_size_log2=6, num_materials=8, material_mode=material_mode)
+    ctx = Context(sc.lightmaps, sc.directional_lightmaps, device=0)
+    hr = S.HostRenderer(sc)
+    try:
+        sc.upload(ctx)
+        ctx.upload_map_geometry(*sc.map_geometry())
+        view = ctx.create_view(W, H, 64)
+        post = make_post_params(exposure=0.9, bloom_sigma=0.0)
+        path = sc.camera_path(64)
+        blended = 0
+        for k in (2, 23, 41):
+            hf = hr.build_frame(W, H, path[k])
+            clear = S.BACKGROUND_COLOR64 if hf.needs_clear else None
+            frame = view.create_frame()
+            hf.record(frame, clear_color=clear, post=post)
+            # blended polygons read what lies below them: both pictures start from the same buffer
+            view.write_pixels(np.zeros((H, W), np.uint64))
+            frame.submit(N.STAGE_ALL)
+            want_hdr, want_ldr, want_avg = view.read_pixels(), view.read_pixels32(), view.average_color()
+            frame.close()
+            # the same frame with the draw half built on the device
+            cand, planes, want, fr = hr.prepared_polygons()
+            view.polygons_prepare(fr["planes_matrix"], fr["view_matrix"], float(fr["mip_bias"]), cand, planes)
+            index_of = {int(p): i for i, p in enumerate(cand["polygon"])}
+            view.polygons_draw(np.array([index_of[int(p)] for p in hr.polygon_draw_order()], np.uint32))
+            frame = view.create_frame()
+            frame.set_surfaces(hf.jobs, None, None, hf.cam_pos, hf.total_surface_pixels)
+            frame.set_draw_from_polygons(clear_color=clear)
+            frame.set_post(post)
+            view.write_pixels(np.zeros((H, W), np.uint64))
+            frame.submit(N.STAGE_ALL)
+            got_hdr, got_ldr, got_avg = view.read_pixels(), view.read_pixels32(), view.average_color()
+            frame.close()
+            assert len(hf.cmds) == int(((hf.cmds["kind"] == N.CMD_POLYGON) & (hf.cmds["tex_kind"] == N.TEX_SURFACE)).sum()) > 10  # a world-only frame
+            assert np.array_equal(got_hdr, want_hdr), f"pose {k}: 64-bit picture differs in {int((got_hdr != want_hdr).sum())} pixels"
+            assert np.array_equal(got_ldr, want_ldr), f"pose {k}: tonemapped picture"
+            assert np.array_equal(got_avg, want_avg)
+            blended += int((hf.cmds["blend"] != 0).sum())
+        assert (blended > 0) == (material_mode == 2)
+    finally:
+        hr.close()
+        ctx.close()
+        sc.close()
