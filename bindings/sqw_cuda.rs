@@ -284,6 +284,22 @@ pub struct sqw_polygons_frame
 	pub mip_bias: f32,
 	pub reserved: [u32; 3],
 }
+pub const SQW_MAT_LIGHT: u32 = 1;
+pub const SQW_MAT_HAS_DIFFUSE: u32 = 2;
+pub const SQW_MAT_HAS_NORMAL_MAP: u32 = 4;
+pub const SQW_MAT_HAS_NON_ONE_ROUGHNESS: u32 = 8;
+pub const SQW_MAT_IS_METAL: u32 = 16;
+pub const SQW_MAT_HAS_EMISSIVE: u32 = 32;
+#[repr(C)]
+#[derive(Copy, Clone)]
+pub struct sqw_map_material
+{
+	pub flags: u32,
+	pub texture_images: [u32; 5],
+	pub emissive_images: [u32; 5],
+	pub emissive_light: [f32; 3],
+	pub texture_shift: [i32; 2],
+}
 pub const SQW_PREPARED_VISIBLE: u32 = 1;
 pub const SQW_PREPARED_SKY: u32 = 2;
 #[repr(C)]
@@ -390,6 +406,8 @@ extern "C" {
 	// draw_polygon (partial_renderer.rs:4011-4142) for the prepared polygons in BSP draw order
 	pub fn sqw_polygons_draw(view: *mut sqw_view, order: *const u32, num_order: u32) -> c_int;
 	pub fn sqw_frame_set_draw_from_polygons(frame: *mut sqw_frame, clear_color: *const c_void) -> c_int;
+	pub fn sqw_upload_map_materials(ctx: *mut sqw_ctx, materials: *const sqw_map_material, num_materials: u32, polygon_basis: *const f32, num_polygons: u32) -> c_int;
+	pub fn sqw_frame_set_surfaces_from_polygons(frame: *mut sqw_frame, cam_pos: *const f32, use_directional_lightmaps: c_int) -> c_int;
 	pub fn sqw_polygons_draw_read(
 		view: *mut sqw_view, cmds: *mut sqw_draw_cmd, cmds_capacity: u32, points: *mut sqw_polygon_point, points_capacity: u32, counts_out: *mut u32,
 	) -> c_int;

@@ -558,6 +558,30 @@ int sqw_polygons_read(sqw_view* view, sqw_prepared_polygon* out, uint32_t num, s
  * power-of-two renormalisation of the equations (:4106-4109) -> packed sqw_draw_cmd[] (tex_kind SQW_TEX_SURFACE, tex_ref =
  * surface_pixels_offset, blend = the material's blending mode) and sqw_polygon_point[] in draw order, on the device. */
 int sqw_polygons_draw(sqw_view* view, const uint32_t* order, uint32_t num_order);
+/* Per-material and per-polygon constants of job building (the closure of build_polygons_surfaces, partial_renderer.rs:1682-1819),
+ * uploaded once per map for sqw_frame_set_surfaces_from_polygons. */
+#define SQW_MAT_LIGHT 1u                 /* Material::light */
+#define SQW_MAT_HAS_DIFFUSE 2u           /* a diffuse texture exists */
+#define SQW_MAT_HAS_NORMAL_MAP 4u        /* Texture::has_normal_map (textures.rs:14) */
+#define SQW_MAT_HAS_NON_ONE_ROUGHNESS 8u /* Texture::has_non_one_roughness */
+#define SQW_MAT_IS_METAL 16u             /* Texture::is_metal */
+#define SQW_MAT_HAS_EMISSIVE 32u         /* an emissive layer exists */
+typedef struct sqw_map_material /* 64 bytes */
+{
+	uint32_t flags;              /* SQW_MAT_* */
+	uint32_t texture_images[5];  /* image ids of the TextureElement mips */
+	uint32_t emissive_images[5]; /* image ids of the emissive mips (Color32) */
+	float emissive_light[3];
+	int32_t texture_shift[2];    /* MapMaterialsProcessor::get_texture_shift (scrolling); 0 when animations are off */
+} sqw_map_material;
+/* polygon_basis: [num uploaded polygons][12] f32 = PolygonBasisVecs {u, v, start, normal} for mip 0 (surfaces.rs:7-47), computed once
+ * per map by the host like the reference does (partial_renderer.rs:86-100).  num_materials must match sqw_upload_map_geometry. */
+int sqw_upload_map_materials(sqw_ctx* ctx, const sqw_map_material* materials, uint32_t num_materials, const float* polygon_basis, uint32_t num_polygons);
+/* The surface half of a recorded frame from the records of the last sqw_polygons_prepare of the frame's view: one sqw_surface_job
+ * per visible polygon in candidate order (texture shift, basis vectors at the polygon's mip, lightmap shift / size / scale,
+ * emissive layer — partial_renderer.rs:1682-1819 without dynamic lights: the static world) and the band lists of the surface
+ * kernel, built on the device.  The host reads the totals back to size the surface pool. */
+int sqw_frame_set_surfaces_from_polygons(sqw_frame* frame, const float cam_pos[3], int use_directional_lightmaps);
 /* The draw half of a recorded frame straight from the device lists of the last sqw_polygons_draw of the frame's view: what
  * sqw_frame_set_draw derives on the host from host lists (row and column ranges, span-table offsets, 32-scan-line chunks, ordered
  * per-band command lists) is derived by set-up kernels; the commands and vertices never visit the host, which only reads four

@@ -179,6 +179,8 @@ KERNEL_NAMES = ["surface_build", "raster_setup", "raster_bin", "raster_tile", "t
 map_polygon_dtype = np.dtype(
     [("first_vertex", "<u4"), ("num_vertices", "<u4"), ("plane", "<f4", 4), ("tex_coord_equation", "<f4", (2, 4)), ("tex_coord_min", "<i4", 2), ("tex_coord_max", "<i4", 2),
      ("lightmap_data_offset", "<u4"), ("texture", "<u4")])
+map_material_dtype = np.dtype([("flags", "<u4"), ("texture_images", "<u4", 5), ("emissive_images", "<u4", 5), ("emissive_light", "<f4", 3), ("texture_shift", "<i4", 2)])
+assert map_material_dtype.itemsize == 64
 polygon_candidate_dtype = np.dtype([("polygon", "<u4"), ("clip_set", "<u4")])
 prepared_polygon_dtype = np.dtype(
     [("flags", "<u4"), ("mip", "<u4"), ("depth_equation", "<f4", 3), ("tex_coord_equation", "<f4", 6), ("surface_tc_min", "<i4", 2), ("surface_size", "<u4", 2),
@@ -250,6 +252,8 @@ CUDA_SYMBOLS = [
     ("sqw_polygons_draw", C.c_int, [_VP, _VP, C.c_uint32]),
     ("sqw_polygons_draw_read", C.c_int, [_VP, _VP, C.c_uint32, _VP, C.c_uint32, _VP]),
     ("sqw_frame_set_draw_from_polygons", C.c_int, [_VP, _VP]),
+    ("sqw_upload_map_materials", C.c_int, [_VP, _VP, C.c_uint32, _VP, C.c_uint32]),
+    ("sqw_frame_set_surfaces_from_polygons", C.c_int, [_VP, _VP, C.c_int]),
 ]
 
 _cuda_lib = None

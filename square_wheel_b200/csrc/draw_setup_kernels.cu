@@ -203,6 +203,244 @@ __global__ void __launch_bounds__(32) draw_band_scan_kernel(const uint32_t* __re
 	}
 }
 
+
+// ---- surface jobs and bands from the prepared polygons ----------------------------------------------------------------------------
+// visible_rank[i] = visible polygons before candidate i (the job index: current_frame_visible_polygons is in candidate order)
+__global__ void __launch_bounds__(1024) surface_rank_kernel(const sqw_prepared_polygon* __restrict__ prepared, const uint32_t n, uint32_t* __restrict__ visible_rank, unsigned long long* __restrict__ totals)
+{
+	__shared__ uint32_t s_warp[32];
+	__shared__ uint32_t s_carry;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	if (threadIdx.x == 0)
+		s_carry = 0;
+	__syncthreads();
+	for (uint32_t base = 0; base < n; base += 1024)
+	{
+		const uint32_t i = base + threadIdx.x;
+		const uint32_t own = (i < n && (prepared[i].flags & SQW_PREPARED_VISIBLE)) ? 1u : 0u;
+		uint32_t incl = own;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+			if (lane >= o)
+				incl += t;
+		}
+		if (lane == 31)
+			s_warp[warp] = incl;
+		__syncthreads();
+		uint32_t before = s_carry, all = 0;
+		for (int w = 0; w < 32; ++w)
+		{
+			before += w < warp ? s_warp[w] : 0u;
+			all += s_warp[w];
+		}
+		if (i < n)
+			visible_rank[i] = before + incl - own;
+		__syncthreads();
+		if (threadIdx.x == 0)
+			s_carry += all;
+		__syncthreads();
+	}
+	if (threadIdx.x == 0)
+		totals[0] = s_carry;
+}
+
+// get_lightmap_size (common/lightmap.rs:19-27)
+__device__ __forceinline__ uint32_t lightmap_size_of(const int32_t tc_min, const int32_t tc_max) { return (uint32_t)(((tc_max + 15) >> 4) - (tc_min >> 4) + 1); }
+
+// One thread per candidate: the job of a visible polygon (the closure of build_polygons_surfaces without dynamic lights).
+__global__ void __launch_bounds__(128) surface_jobs_kernel(const SurfaceSetupLaunch l)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= l.num_candidates)
+		return;
+	const sqw_prepared_polygon rec = l.prepared[i];
+	if (!(rec.flags & SQW_PREPARED_VISIBLE))
+		return;
+	const uint32_t polygon_index = l.candidates[i].polygon;
+	const sqw_map_polygon& polygon = l.polygons[polygon_index];
+	const sqw_map_material& material = l.materials[polygon.texture];
+	const float* const basis = l.polygon_basis + (size_t)polygon_index * 12;
+	sqw_surface_job j;
+	memset(&j, 0, sizeof(j));
+	const int32_t shift0 = material.texture_shift[0] >> rec.mip, shift1 = material.texture_shift[1] >> rec.mip;
+	j.surface_size[0] = rec.surface_size[0];
+	j.surface_size[1] = rec.surface_size[1];
+	j.tc_start[0] = rec.surface_tc_min[0] + shift0;
+	j.tc_start[1] = rec.surface_tc_min[1] + shift1;
+	j.surface_pixels_offset = rec.surface_pixels_offset;
+	const unsigned long long texels = (unsigned long long)rec.surface_size[0] * rec.surface_size[1];
+	const bool diffuse = (material.flags & SQW_MAT_LIGHT) && (material.flags & SQW_MAT_HAS_DIFFUSE);
+	if (diffuse)
+	{
+		j.flags |= SQW_SURF_APPLY_DIFFUSE;
+		// get_basis_vecs_for_mip (surfaces.rs:49-63) + shift correction (partial_renderer.rs:1736-1740)
+		const float scale = (float)(1 << rec.mip);
+		float u[3], v[3];
+#pragma unroll
+		for (int k = 0; k < 3; ++k)
+		{
+			u[k] = rec.mip == 0 ? basis[k] : basis[k] * scale;
+			v[k] = rec.mip == 0 ? basis[3 + k] : basis[3 + k] * scale;
+		}
+#pragma unroll
+		for (int k = 0; k < 3; ++k)
+		{
+			j.basis_u[k] = u[k];
+			j.basis_v[k] = v[k];
+			j.basis_start[k] = basis[6 + k] - (u[k] * (float)shift0 + v[k] * (float)shift1);
+			j.basis_normal[k] = basis[9 + k];
+		}
+		j.texture_image = material.texture_images[rec.mip];
+		if (material.flags & SQW_MAT_HAS_NORMAL_MAP)
+			j.flags |= SQW_SURF_HAS_NORMAL_MAP;
+		if (material.flags & SQW_MAT_HAS_NON_ONE_ROUGHNESS)
+			j.flags |= SQW_SURF_HAS_NON_ONE_ROUGHNESS;
+		if (material.flags & SQW_MAT_IS_METAL)
+			j.flags |= SQW_SURF_IS_METAL;
+#pragma unroll
+		for (int k = 0; k < 2; ++k) // :1744-1752
+			j.lightmap_tc_shift[k] = (uint32_t)(rec.surface_tc_min[k] - ((polygon.tex_coord_min[k] & ~15) >> rec.mip));
+		j.lightmap_size[0] = lightmap_size_of(polygon.tex_coord_min[0], polygon.tex_coord_max[0]);
+		j.lightmap_size[1] = lightmap_size_of(polygon.tex_coord_min[1], polygon.tex_coord_max[1]);
+		j.lightmap_scale_log2 = 4u - rec.mip;
+		j.lightmap_offset = polygon.lightmap_data_offset;
+		if (l.use_directional)
+			j.flags |= SQW_SURF_DIRECTIONAL_LIGHTMAP;
+		if (j.lightmap_offset != 0)
+			atomicAdd(l.totals + 6, (unsigned long long)j.lightmap_size[0] * j.lightmap_size[1] * (l.use_directional ? 40ull : 12ull));
+	}
+	if (material.flags & SQW_MAT_HAS_EMISSIVE)
+	{
+		j.flags |= SQW_SURF_EMISSIVE;
+		j.emissive_image = material.emissive_images[rec.mip];
+		j.emissive_light[0] = material.emissive_light[0];
+		j.emissive_light[1] = material.emissive_light[1];
+		j.emissive_light[2] = material.emissive_light[2];
+		if (texels)
+			atomicAdd(l.totals + 5, texels);
+	}
+	l.jobs[l.visible_rank[i]] = j;
+	if ((j.flags & (SQW_SURF_APPLY_DIFFUSE | SQW_SURF_EMISSIVE)) && texels)
+	{
+		atomicAdd(l.totals + 4, texels);
+		if (texels <= SQW_SURF_WARP_JOB_TEXELS)
+			atomicAdd(l.totals + 1, texels);
+	}
+}
+
+// Band geometry of one job, as sqw_frame_set_surfaces cuts it: rows per band, and whether the job goes to warp bands.
+__device__ __forceinline__ uint32_t surface_band_rows(const sqw_surface_job& j, const uint32_t warp_band_texels, bool& warp_bands)
+{
+	const unsigned long long texels = (unsigned long long)j.surface_size[0] * j.surface_size[1];
+	warp_bands = texels <= SQW_SURF_WARP_JOB_TEXELS;
+	uint32_t band_rows;
+	if (warp_bands)
+	{
+		band_rows = max(warp_band_texels / j.surface_size[0], 1u);
+		if ((j.flags & SQW_SURF_APPLY_DIFFUSE) && j.lightmap_offset != 0)
+			band_rows = min(band_rows, max((uint32_t)SQW_SURF_WARP_LM_ELEMENTS / min(j.lightmap_size[0], 19u), 1u));
+		band_rows = min(band_rows, (uint32_t)SQW_SURF_MAX_BAND_ROWS);
+	}
+	else
+		band_rows = min(max((uint32_t)SQW_SURF_BAND_TEXELS / j.surface_size[0], 1u), (uint32_t)SQW_SURF_MAX_BAND_ROWS);
+	return band_rows;
+}
+__device__ __forceinline__ uint32_t surface_warp_band_texels(const unsigned long long small_texels)
+{
+	uint32_t t = SQW_SURF_WARP_BAND_TEXELS;
+	const unsigned long long resident_warps = 148ull * 4 * (SQW_SURF_THREADS / 32);
+	while (t > SQW_SURF_WARP_BAND_TEXELS_MIN && small_texels < resident_warps * t)
+		t /= 2;
+	return t;
+}
+__device__ __forceinline__ uint32_t surface_variant_bits(const sqw_surface_job& j)
+{
+	if (!(j.flags & SQW_SURF_APPLY_DIFFUSE))
+		return 16u; // emissive-only
+	const uint32_t spec = (j.flags & SQW_SURF_HAS_NON_ONE_ROUGHNESS) ? ((j.flags & SQW_SURF_IS_METAL) ? 2u : 1u) : 0u;
+	return ((j.flags & SQW_SURF_DIRECTIONAL_LIGHTMAP) ? 1u : 0u) | ((j.flags & SQW_SURF_HAS_NORMAL_MAP) ? 2u : 0u) | (spec << 2);
+}
+
+// FILL = 0: bands of every job (CTA kind, warp kind); FILL = 1: the band records at the scanned offsets.
+template <int FILL>
+__global__ void __launch_bounds__(128) surface_bands_kernel(const sqw_surface_job* __restrict__ jobs, const uint32_t num_jobs, const unsigned long long* __restrict__ totals, uint32_t* __restrict__ band_counts, const uint32_t* __restrict__ band_base, SurfaceBand* __restrict__ bands)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= num_jobs)
+		return;
+	const sqw_surface_job j = jobs[i];
+	const unsigned long long texels = (unsigned long long)j.surface_size[0] * j.surface_size[1];
+	uint32_t n = 0;
+	bool warp_bands = false;
+	uint32_t band_rows = 1;
+	if ((j.flags & (SQW_SURF_APPLY_DIFFUSE | SQW_SURF_EMISSIVE)) && texels)
+	{
+		band_rows = surface_band_rows(j, surface_warp_band_texels(totals[1]), warp_bands);
+		n = (j.surface_size[1] + band_rows - 1) / band_rows;
+	}
+	if (!FILL)
+	{
+		band_counts[2 * i] = warp_bands ? 0u : n;
+		band_counts[2 * i + 1] = warp_bands ? n : 0u;
+		return;
+	}
+	const uint32_t num_cta_bands = (uint32_t)totals[2];
+	SurfaceBand* o = bands + (warp_bands ? num_cta_bands + band_base[2 * i + 1] : band_base[2 * i]);
+	const uint32_t variant = surface_variant_bits(j);
+	for (uint32_t row0 = 0; row0 < j.surface_size[1]; row0 += band_rows)
+		*o++ = SurfaceBand{i, row0, min(band_rows, j.surface_size[1] - row0), variant};
+}
+
+// exclusive scans of the two band counts of every job (one CTA), totals[2] = CTA bands, totals[3] = warp bands
+__global__ void __launch_bounds__(1024) surface_band_scan_kernel(const uint32_t* __restrict__ band_counts, const uint32_t num_jobs, uint32_t* __restrict__ band_base, unsigned long long* __restrict__ totals)
+{
+	__shared__ unsigned long long s_warp[32];
+	__shared__ unsigned long long s_carry;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	if (threadIdx.x == 0)
+		s_carry = 0;
+	__syncthreads();
+	for (uint32_t base = 0; base < num_jobs; base += 1024)
+	{
+		const uint32_t i = base + threadIdx.x;
+		const unsigned long long own = i < num_jobs ? ((unsigned long long)band_counts[2 * i] | ((unsigned long long)band_counts[2 * i + 1] << 32)) : 0ull;
+		unsigned long long incl = own;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+			if (lane >= o)
+				incl += t;
+		}
+		if (lane == 31)
+			s_warp[warp] = incl;
+		__syncthreads();
+		unsigned long long before = s_carry, all = 0;
+		for (int w = 0; w < 32; ++w)
+		{
+			before += w < warp ? s_warp[w] : 0ull;
+			all += s_warp[w];
+		}
+		if (i < num_jobs)
+		{
+			const unsigned long long excl = before + incl - own;
+			band_base[2 * i] = (uint32_t)excl;
+			band_base[2 * i + 1] = (uint32_t)(excl >> 32);
+		}
+		__syncthreads();
+		if (threadIdx.x == 0)
+			s_carry += all;
+		__syncthreads();
+	}
+	if (threadIdx.x == 0)
+	{
+		totals[2] = s_carry & 0xFFFFFFFFull;
+		totals[3] = s_carry >> 32;
+	}
+}
+
 } // namespace
 
 // Phase 1: everything whose size is known (CmdDev, rows, prefix sums, band counts and offsets); totals = {scan-lines, chunks, band
@@ -228,6 +466,34 @@ cudaError_t launch_draw_setup_phase2(const DrawSetupLaunch& l, cudaStream_t stre
 		draw_chunks_kernel<<<(l.num_cmds + 127) / 128, 128, 0, stream>>>(l.rows, l.chunk_base, l.num_cmds, l.chunks);
 		draw_band_lists_kernel<1><<<(l.num_bands + 3) / 4, 128, 0, stream>>>(l.cmd_dev, l.num_cmds, l.num_bands, nullptr, l.band_offsets, l.band_list);
 	}
+	return cudaGetLastError();
+}
+
+// Surfaces, phase 1: jobs of the visible polygons and their band counts; totals = {visible polygons, small texels, CTA bands, warp bands,
+// surface texels, emissive texels, lightmap bytes}.
+cudaError_t launch_surface_setup_phase1(const SurfaceSetupLaunch& l, cudaStream_t stream)
+{
+	cudaMemsetAsync(l.totals, 0, 8 * sizeof(unsigned long long), stream);
+	if (l.num_candidates == 0)
+		return cudaGetLastError();
+	surface_rank_kernel<<<1, 1024, 0, stream>>>(l.prepared, l.num_candidates, l.visible_rank, l.totals);
+	surface_jobs_kernel<<<(l.num_candidates + 127) / 128, 128, 0, stream>>>(l);
+	// (jobs are at most num_candidates: the kernels below take the visible count from the device)
+	return cudaGetLastError();
+}
+// Surfaces, phase 1b (the host knows the number of jobs now) and phase 2 (it has sized the band list).
+cudaError_t launch_surface_bands_count(const SurfaceSetupLaunch& l, uint32_t num_jobs, cudaStream_t stream)
+{
+	if (num_jobs == 0)
+		return cudaGetLastError();
+	surface_bands_kernel<0><<<(num_jobs + 127) / 128, 128, 0, stream>>>(l.jobs, num_jobs, l.totals, l.band_counts, nullptr, nullptr);
+	surface_band_scan_kernel<<<1, 1024, 0, stream>>>(l.band_counts, num_jobs, l.band_base, l.totals);
+	return cudaGetLastError();
+}
+cudaError_t launch_surface_setup_phase2(const SurfaceSetupLaunch& l, uint32_t num_jobs, cudaStream_t stream)
+{
+	if (num_jobs)
+		surface_bands_kernel<1><<<(num_jobs + 127) / 128, 128, 0, stream>>>(l.jobs, num_jobs, l.totals, nullptr, l.band_base, l.bands);
 	return cudaGetLastError();
 }
 

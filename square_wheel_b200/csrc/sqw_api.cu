@@ -292,6 +292,8 @@ struct sqw_ctx
 	sqw_map_polygon* d_map_polygons = nullptr;
 	float* d_map_vertices = nullptr;
 	uint8_t* d_material_flags = nullptr;
+	sqw_map_material* d_map_materials = nullptr; // sqw_upload_map_materials
+	float* d_polygon_basis = nullptr;
 	uint32_t num_map_polygons = 0, num_map_vertices = 0, num_materials = 0;
 	std::string last_error;
 	// per-kernel timing (sqw_profile_begin / _end)
@@ -446,6 +448,8 @@ struct sqw_frame
 	uint32_t num_cmds = 0, total_spans = 0, num_bands = 0, total_band_entries = 0, num_triangle_cmds = 0, num_general_cmds = 0, num_chunks = 0;
 	// sqw_frame_set_draw_from_polygons: the lists live in buffers of the frame, built on the device
 	DevBuf dev_cmds, dev_points, dev_cmd_dev, dev_rows, dev_chunk_base, dev_chunks, dev_band_counts, dev_band_offsets, dev_band_list, dev_totals;
+	// sqw_frame_set_surfaces_from_polygons
+	DevBuf dev_jobs, dev_visible_rank, dev_surf_band_counts, dev_surf_band_base, dev_surf_bands, dev_surf_totals;
 	uint32_t draw_width = 0, draw_height = 0; // view size the command list was prepared for
 	bool clear = false;
 	uint64_t clear_color = 0;
@@ -696,7 +700,8 @@ void sqw_destroy(sqw_ctx* ctx)
 		cudaFree(p);
 	if (ctx->d_meshes)
 		cudaFree(ctx->d_meshes);
-	for (void* p : {static_cast<void*>(ctx->d_map_polygons), static_cast<void*>(ctx->d_map_vertices), static_cast<void*>(ctx->d_material_flags)})
+	for (void* p : {static_cast<void*>(ctx->d_map_polygons), static_cast<void*>(ctx->d_map_vertices), static_cast<void*>(ctx->d_material_flags), static_cast<void*>(ctx->d_map_materials),
+					static_cast<void*>(ctx->d_polygon_basis)})
 		if (p)
 			cudaFree(p);
 	if (ctx->d_lightmaps)
@@ -929,7 +934,8 @@ void sqw_frame_destroy(sqw_frame* f)
 	f->depth_arena.release();
 	f->d_depth_spans.release();
 	f->d_shadow_dev.release();
-	for (DevBuf* b : {&f->dev_cmds, &f->dev_points, &f->dev_cmd_dev, &f->dev_rows, &f->dev_chunk_base, &f->dev_chunks, &f->dev_band_counts, &f->dev_band_offsets, &f->dev_band_list, &f->dev_totals})
+	for (DevBuf* b : {&f->dev_cmds, &f->dev_points, &f->dev_cmd_dev, &f->dev_rows, &f->dev_chunk_base, &f->dev_chunks, &f->dev_band_counts, &f->dev_band_offsets, &f->dev_band_list, &f->dev_totals,
+					  &f->dev_jobs, &f->dev_visible_rank, &f->dev_surf_band_counts, &f->dev_surf_band_base, &f->dev_surf_bands, &f->dev_surf_totals})
 		b->release();
 	if (f->view->immediate == f)
 		f->view->immediate = nullptr;
@@ -1324,6 +1330,122 @@ int sqw_frame_set_draw(
 	if (clear_color)
 		std::memcpy(&f->clear_color, clear_color, C);
 	f->has_draw = true;
+	return SQW_OK;
+}
+
+static_assert(sizeof(sqw_map_material) == 64, "sqw_map_material layout");
+
+int sqw_upload_map_materials(sqw_ctx* ctx, const sqw_map_material* materials, uint32_t num_materials, const float* polygon_basis, uint32_t num_polygons)
+{
+	if (!ctx || !materials || !polygon_basis)
+		return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_upload_map_materials: null argument");
+	if (!ctx->d_map_polygons || num_materials != ctx->num_materials || num_polygons != ctx->num_map_polygons)
+		return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_upload_map_materials: counts must match the geometry uploaded by sqw_upload_map_geometry");
+	for (uint32_t m = 0; m < num_materials; ++m)
+		for (int k = 0; k < 5; ++k)
+		{
+			const sqw_map_material& mat = materials[m];
+			if ((mat.flags & SQW_MAT_HAS_DIFFUSE) && (mat.texture_images[k] >= ctx->images.size() || ctx->images[mat.texture_images[k]].kind != SQW_IMAGE_TEXTURE_ELEMENT))
+				return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_upload_map_materials: bad texture image");
+			if ((mat.flags & SQW_MAT_HAS_EMISSIVE) && (mat.emissive_images[k] >= ctx->images.size() || ctx->images[mat.emissive_images[k]].kind != SQW_IMAGE_COLOR32))
+				return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_upload_map_materials: bad emissive image");
+		}
+	SQW_CUDA(ctx, cudaSetDevice(ctx->device));
+	SQW_CUDA(ctx, synchronize_all(ctx));
+	for (void** p : {reinterpret_cast<void**>(&ctx->d_map_materials), reinterpret_cast<void**>(&ctx->d_polygon_basis)})
+		if (*p)
+		{
+			cudaFree(*p);
+			*p = nullptr;
+		}
+	SQW_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_map_materials), (size_t)num_materials * sizeof(sqw_map_material)));
+	SQW_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_polygon_basis), (size_t)num_polygons * 48));
+	SQW_CUDA(ctx, cudaMemcpy(ctx->d_map_materials, materials, (size_t)num_materials * sizeof(sqw_map_material), cudaMemcpyHostToDevice));
+	SQW_CUDA(ctx, cudaMemcpy(ctx->d_polygon_basis, polygon_basis, (size_t)num_polygons * 48, cudaMemcpyHostToDevice));
+	return SQW_OK;
+}
+
+int sqw_frame_set_surfaces_from_polygons(sqw_frame* f, const float cam_pos[3], int use_directional_lightmaps)
+{
+	if (!f || !cam_pos)
+		return SQW_ERR_INVALID_ARGUMENT;
+	sqw_view* view = f->view;
+	sqw_ctx* ctx = view->ctx;
+	if (!view->polygon_totals.ptr || !ctx->d_map_materials)
+		return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_frame_set_surfaces_from_polygons: needs sqw_upload_map_materials and a sqw_polygons_prepare on this view");
+	if (use_directional_lightmaps ? !ctx->d_directional_lightmaps : !ctx->d_lightmaps)
+		return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_frame_set_surfaces_from_polygons: lightmap kind not uploaded");
+	SQW_CUDA(ctx, cudaSetDevice(ctx->device));
+	cudaStream_t s = view->stream;
+	const size_t C = (size_t)view->color_bits / 8;
+	const uint32_t n = view->polygon_num_candidates;
+	const size_t need1[5] = {(size_t)n * sizeof(sqw_surface_job) + 16, (size_t)n * 4 + 16, (size_t)n * 8 + 16, (size_t)n * 8 + 16, 64};
+	DevBuf* bufs1[5] = {&f->dev_jobs, &f->dev_visible_rank, &f->dev_surf_band_counts, &f->dev_surf_band_base, &f->dev_surf_totals};
+	bool grow = false;
+	for (int i = 0; i < 5; ++i)
+		grow |= need1[i] > bufs1[i]->capacity;
+	if (grow)
+		SQW_CUDA(ctx, cudaStreamSynchronize(s)); // a queued submission of this frame may still read the old buffers
+	for (int i = 0; i < 5; ++i)
+		SQW_CUDA(ctx, bufs1[i]->reserve(need1[i]));
+	sqw::SurfaceSetupLaunch l{};
+	l.polygons = ctx->d_map_polygons;
+	l.materials = ctx->d_map_materials;
+	l.polygon_basis = ctx->d_polygon_basis;
+	l.candidates = static_cast<const sqw_polygon_candidate*>(view->polygon_candidates.ptr);
+	l.prepared = static_cast<const sqw_prepared_polygon*>(view->polygon_results.ptr);
+	l.num_candidates = n;
+	l.use_directional = use_directional_lightmaps ? 1u : 0u;
+	l.visible_rank = static_cast<uint32_t*>(f->dev_visible_rank.ptr);
+	l.jobs = static_cast<sqw_surface_job*>(f->dev_jobs.ptr);
+	l.band_counts = static_cast<uint32_t*>(f->dev_surf_band_counts.ptr);
+	l.band_base = static_cast<uint32_t*>(f->dev_surf_band_base.ptr);
+	l.totals = static_cast<unsigned long long*>(f->dev_surf_totals.ptr);
+	SQW_CUDA(ctx, sqw::launch_surface_setup_phase1(l, s));
+	unsigned long long totals[8] = {};
+	// jobs exist for the visible polygons only, but their number is at most n: count the bands of all n slots' worth by the device count
+	SQW_CUDA(ctx, cudaMemcpyAsync(totals, f->dev_surf_totals.ptr, sizeof(totals), cudaMemcpyDeviceToHost, s));
+	SQW_CUDA(ctx, cudaStreamSynchronize(s));
+	const uint32_t num_jobs = (uint32_t)totals[0];
+	SQW_CUDA(ctx, sqw::launch_surface_bands_count(l, num_jobs, s));
+	SQW_CUDA(ctx, cudaMemcpyAsync(totals, f->dev_surf_totals.ptr, sizeof(totals), cudaMemcpyDeviceToHost, s));
+	sqw::PolygonsTotalsDev pt{};
+	SQW_CUDA(ctx, cudaMemcpyAsync(&pt, view->polygon_totals.ptr, sizeof(pt), cudaMemcpyDeviceToHost, s));
+	SQW_CUDA(ctx, cudaStreamSynchronize(s));
+	const uint32_t num_cta_bands = (uint32_t)totals[2], num_warp_bands = (uint32_t)totals[3];
+	SQW_CUDA(ctx, f->dev_surf_bands.reserve((size_t)(num_cta_bands + num_warp_bands) * sizeof(SurfaceBand) + 16));
+	l.bands = static_cast<SurfaceBand*>(f->dev_surf_bands.ptr);
+	SQW_CUDA(ctx, sqw::launch_surface_setup_phase2(l, num_jobs, s));
+	const uint64_t total_surface_pixels = pt.num_surfaces_pixels;
+	if ((size_t)total_surface_pixels * C + 16 > view->surfaces.capacity)
+	{
+		SQW_CUDA(ctx, cudaStreamSynchronize(s));
+		SQW_CUDA(ctx, view_scratch_reserve(view, 0, (size_t)total_surface_pixels * C + 16));
+	}
+	f->d_jobs = static_cast<const sqw_surface_job*>(f->dev_jobs.ptr);
+	f->d_bands = static_cast<const SurfaceBand*>(f->dev_surf_bands.ptr);
+	f->d_lights = nullptr;
+	f->d_shadow_maps = nullptr;
+	f->d_shadow_maps_rw = nullptr;
+	f->shadow_maps_len = 0;
+	f->groups.clear();
+	if (num_cta_bands + num_warp_bands)
+	{
+		SurfaceGroup g{};
+		g.dynamic_lights = false;
+		g.num_cta_bands = num_cta_bands;
+		g.band_offset = 0;
+		g.num_bands = num_cta_bands + num_warp_bands;
+		f->groups.push_back(g);
+	}
+	f->stats.surface_texels = totals[4];
+	f->stats.emissive_texels = totals[5];
+	f->stats.lightmap_bytes = totals[6];
+	f->stats.num_surface_variants = 0; // (not counted on this path)
+	f->cam_pos[0] = cam_pos[0];
+	f->cam_pos[1] = cam_pos[1];
+	f->cam_pos[2] = cam_pos[2];
+	f->has_surfaces = true;
 	return SQW_OK;
 }
 

@@ -205,6 +205,27 @@ struct ModelLaunch
 };
 cudaError_t launch_models_prepare(const ModelLaunch& l, cudaStream_t stream);
 
+// ---- device-side job and band building (draw_setup_kernels.cu) ---------------------------------------------------------
+struct SurfaceSetupLaunch
+{
+	const sqw_map_polygon* polygons;         // device (uploaded map)
+	const sqw_map_material* materials;       // device
+	const float* polygon_basis;              // device, 12 floats per polygon
+	const sqw_polygon_candidate* candidates; // device, of the last sqw_polygons_prepare
+	const sqw_prepared_polygon* prepared;    // device
+	uint32_t num_candidates;
+	uint32_t use_directional;
+	uint32_t* visible_rank;  // scratch [num_candidates]
+	sqw_surface_job* jobs;   // out [num visible]
+	uint32_t* band_counts;   // scratch [num_candidates][2]: CTA bands, warp bands of the job
+	uint32_t* band_base;     // scratch [num_candidates][2]
+	SurfaceBand* bands;      // phase 2 out: CTA bands first, then warp bands
+	unsigned long long* totals; // [8]: visible, small texels, CTA bands, warp bands, surface texels, emissive texels, lightmap bytes, -
+};
+cudaError_t launch_surface_setup_phase1(const SurfaceSetupLaunch& l, cudaStream_t stream);
+cudaError_t launch_surface_bands_count(const SurfaceSetupLaunch& l, uint32_t num_jobs, cudaStream_t stream);
+cudaError_t launch_surface_setup_phase2(const SurfaceSetupLaunch& l, uint32_t num_jobs, cudaStream_t stream);
+
 // ---- device-side frame set-up of the rasteriser (draw_setup_kernels.cu) ----------------------------------------------
 struct DrawSetupLaunch
 {

@@ -120,6 +120,12 @@ class Context:
         fl = np.ascontiguousarray(material_flags, np.uint8)
         self._check(self._lib.sqw_upload_map_geometry(self._handle, N.ptr(pol), len(pol), N.ptr(ver), len(ver), N.ptr(fl), len(fl)), "sqw_upload_map_geometry")
 
+    def upload_map_materials(self, materials: np.ndarray, polygon_basis: np.ndarray):
+        """Per-material constants (map_material_dtype) and per-polygon basis vectors [n, 12] f32 of job building (sqw_upload_map_materials)."""
+        mat = _as(materials, N.map_material_dtype)
+        basis = np.ascontiguousarray(polygon_basis, np.float32).reshape(-1, 12)
+        self._check(self._lib.sqw_upload_map_materials(self._handle, N.ptr(mat), len(mat), N.ptr(basis), len(basis)), "sqw_upload_map_materials")
+
     def set_fast_surface_numerics(self, enable: bool):
         """SQW_CTX_FAST_SURFACE_NUMERICS for the frames submitted from now on (sqw_set_fast_surface_numerics)."""
         self._check(self._lib.sqw_set_fast_surface_numerics(self._handle, 1 if enable else 0), "sqw_set_fast_surface_numerics")
@@ -327,6 +333,11 @@ class Frame:
             self._lib.sqw_frame_set_draw(self._handle, N.ptr(cmds), len(cmds), N.ptr(pp), len(pp), N.ptr(tp), len(tp), N.ptr(cc)), "sqw_frame_set_draw"
         )
         self.h2d_bytes += cmds.nbytes + pp.nbytes + tp.nbytes
+
+    def set_surfaces_from_polygons(self, cam_pos, use_directional_lightmaps: bool = True):
+        """The surface half of the frame from the records of the view's last polygons_prepare (sqw_frame_set_surfaces_from_polygons)."""
+        cam = np.ascontiguousarray(cam_pos, np.float32)
+        self.view.ctx._check(self._lib.sqw_frame_set_surfaces_from_polygons(self._handle, N.ptr(cam), 1 if use_directional_lightmaps else 0), "sqw_frame_set_surfaces_from_polygons")
 
     def set_draw_from_polygons(self, clear_color: Optional[int] = None):
         """The draw half of the frame from the device lists of the view's last polygons_draw (sqw_frame_set_draw_from_polygons)."""

@@ -533,6 +533,37 @@ uint32_t sqwh_renderer_polygon_draw_order(const Renderer* r, uint32_t* out, uint
 		std::memcpy(out, o.data(), std::min<size_t>(o.size(), capacity) * 4);
 	return (uint32_t)o.size();
 }
+// sqw_map_material records (64 bytes each) for sqw_upload_map_materials
+uint32_t sqwh_scene_map_materials(const Scene* s, void* out, uint32_t capacity)
+{
+	struct Rec
+	{
+		uint32_t flags, texture_images[5], emissive_images[5];
+		float emissive_light[3];
+		int32_t texture_shift[2];
+	};
+	static_assert(sizeof(Rec) == 64, "sqw_map_material layout");
+	const uint32_t n = (uint32_t)s->materials.size();
+	Rec* o = static_cast<Rec*>(out);
+	for (uint32_t i = 0; i < n && i < capacity; ++i)
+	{
+		const Material& m = s->materials[i];
+		Rec r{};
+		r.flags = (m.light ? 1u : 0u) | (m.has_diffuse ? 2u : 0u) | (m.has_normal_map ? 4u : 0u) | (m.has_non_one_roughness ? 8u : 0u) | (m.is_metal ? 16u : 0u) | (m.has_emissive ? 32u : 0u);
+		for (int k = 0; k < 5; ++k)
+		{
+			r.texture_images[k] = m.texture_images[k];
+			r.emissive_images[k] = m.emissive_images[k];
+		}
+		std::memcpy(r.emissive_light, m.emissive_light, 12);
+		r.texture_shift[0] = m.texture_shift[0];
+		r.texture_shift[1] = m.texture_shift[1];
+		o[i] = r;
+	}
+	return n;
+}
+// PolygonBasisVecs of every map polygon for mip 0: [num_polygons][12] floats {u, v, start, normal}
+uint32_t sqwh_renderer_polygon_basis(const Renderer* r, float* out, uint32_t capacity) { return r->export_polygon_basis(out, capacity); }
 // per-material SQW_MATERIAL_* flags for sqw_upload_map_geometry
 uint32_t sqwh_scene_material_flags(const Scene* s, uint8_t* out, uint32_t capacity)
 {

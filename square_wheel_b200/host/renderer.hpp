@@ -226,6 +226,22 @@ public:
 	const std::vector<Vec3f>& polygon_clip_planes() const { return polygon_clip_planes_; }
 	const std::vector<uint32_t>& polygon_draw_order() const { return polygon_draw_order_; } // leaf polygons in the order draw_leaf drew them (last draw_frame)
 	void export_prepared_polygons(PreparedPolygonExport* out, PolygonsFrameExport* frame) const;
+	uint32_t export_polygon_basis(float* out, uint32_t capacity) const
+	{
+		const uint32_t n = (uint32_t)polygons_data_.size();
+		for (uint32_t i = 0; out && i < n && i < capacity; ++i)
+		{
+			const DrawPolygonData& d = polygons_data_[i];
+			const Vec3f v[4] = {d.basis_u, d.basis_v, d.basis_start, d.basis_normal};
+			for (int k = 0; k < 4; ++k)
+			{
+				out[i * 12 + k * 3] = v[k].x;
+				out[i * 12 + k * 3 + 1] = v[k].y;
+				out[i * 12 + k * 3 + 2] = v[k].z;
+			}
+		}
+		return n;
+	}
 	double polygons_prepare_seconds() const { return polygons_prepare_seconds_; } // wall time of prepare_polygons_surfaces in the last prepare_frame
 	const std::vector<ModelVertex3d>& dynamic_meshes_vertices() const { return dynamic_meshes_vertices_; }
 	const std::vector<Triangle>& dynamic_meshes_triangles() const { return dynamic_meshes_triangles_; }

@@ -247,6 +247,10 @@ def lib() -> C.CDLL:
         l.sqwh_scene_material_flags.argtypes = [vp, vp, C.c_uint32]
         l.sqwh_renderer_polygons_prepare_seconds.restype = C.c_double
         l.sqwh_renderer_polygons_prepare_seconds.argtypes = [vp]
+        l.sqwh_scene_map_materials.restype = C.c_uint32
+        l.sqwh_scene_map_materials.argtypes = [vp, vp, C.c_uint32]
+        l.sqwh_renderer_polygon_basis.restype = C.c_uint32
+        l.sqwh_renderer_polygon_basis.argtypes = [vp, vp, C.c_uint32]
         l.sqwh_renderer_polygon_draw_order.restype = C.c_uint32
         l.sqwh_renderer_polygon_draw_order.argtypes = [vp, vp, C.c_uint32]
         l.sqwh_renderer_prepared_polygons.restype = C.c_int
@@ -387,6 +391,13 @@ class Scene:
         assert n == len(flags)
         return pol, ver, flags
 
+    def map_materials(self) -> np.ndarray:
+        """sqw_map_material records of the scene's materials (map_material_dtype) for sqw_upload_map_materials."""
+        out = np.zeros(int(self.info.num_materials), N.map_material_dtype)
+        n = self._lib.sqwh_scene_map_materials(self._handle, out.ctypes.data_as(C.c_void_p), len(out))
+        assert n == len(out)
+        return out
+
     def upload(self, ctx):
         """Upload every image in image-id order (S0 of SURVEY.md §8b)."""
         for i, (kind, px) in enumerate(self.images):
@@ -523,6 +534,13 @@ class HostRenderer:
         vp = C.c_void_p
         self._lib.sqwh_renderer_prepared_polygons(self._handle, cand.ctypes.data_as(vp), planes.ctypes.data_as(vp), res.ctypes.data_as(vp), frame.ctypes.data_as(vp), counts)
         return cand, planes, res, frame[0]
+
+    def polygon_basis(self) -> np.ndarray:
+        """PolygonBasisVecs of every map polygon for mip 0, [num_polygons, 12] f32 {u, v, start, normal} (computed once per map)."""
+        n = int(self._lib.sqwh_renderer_polygon_basis(self._handle, None, 0))
+        out = np.zeros((n, 12), np.float32)
+        self._lib.sqwh_renderer_polygon_basis(self._handle, out.ctypes.data_as(C.c_void_p), n)
+        return out
 
     def polygon_draw_order(self) -> np.ndarray:
         """Map polygon indices of the leaf polygons the last build_frame drew, in draw order (draw_tree / draw_leaf)."""

@@ -135,6 +135,7 @@ def test_frame_drawn_from_device_command_lists(material_mode, size):
     try:
         sc.upload(ctx)
         ctx.upload_map_geometry(*sc.map_geometry())
+        ctx.upload_map_materials(sc.map_materials(), hr.polygon_basis())
         view = ctx.create_view(W, H, 64)
         post = make_post_params(exposure=0.9, bloom_sigma=0.0)
         path = sc.camera_path(64)
@@ -166,6 +167,20 @@ def test_frame_drawn_from_device_command_lists(material_mode, size):
             assert np.array_equal(got_hdr, want_hdr), f"pose {k}: 64-bit picture differs in {int((got_hdr != want_hdr).sum())} pixels"
             assert np.array_equal(got_ldr, want_ldr), f"pose {k}: tonemapped picture"
             assert np.array_equal(got_avg, want_avg)
+            # and with the surface half from the device too: jobs and band lists built from the prepared records — the host's part
+            # of the frame is the visibility flood, the BSP walk and two small index lists
+            frame = view.create_frame()
+            frame.set_surfaces_from_polygons(hf.cam_pos, use_directional_lightmaps=True)
+            frame.set_draw_from_polygons(clear_color=clear)
+            frame.set_post(post)
+            view.write_pixels(np.zeros((H, W), np.uint64))
+            frame.submit(N.STAGE_ALL)
+            got_hdr, got_ldr = view.read_pixels(), view.read_pixels32()
+            st = frame.stats()
+            frame.close()
+            assert np.array_equal(got_hdr, want_hdr), f"pose {k}, device jobs: 64-bit picture differs in {int((got_hdr != want_hdr).sum())} pixels"
+            assert np.array_equal(got_ldr, want_ldr), f"pose {k}, device jobs: tonemapped picture"
+            assert st.surface_texels == hf.total_surface_pixels
             blended += int((hf.cmds["blend"] != 0).sum())
         assert (blended > 0) == (material_mode == 2)
     finally:
