@@ -361,10 +361,15 @@ __global__ void __launch_bounds__(SQW_RLE_THREADS) picture_rle_kernel(
 			base += w < (int)warp ? s_warp[w] : 0u;
 			seg_total += s_warp[w];
 		}
+		__syncthreads(); // every warp has read the warp totals before the run records are written (and before the next segment rewrites the totals)
 #pragma unroll
 		for (int i = 0; i < 8; ++i)
 			if (flags & (1u << i))
 			{
+#ifdef SQW_DEBUG_RLE_BOUNDS
+				if (base >= SQW_RLE_SEGMENT)
+					__trap();
+#endif
 				s_start[base] = (uint16_t)(tid * 8 + i);
 				s_val[base] = p[i];
 				++base;

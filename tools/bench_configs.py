@@ -18,6 +18,7 @@ import argparse
 import json
 import os
 import sys
+import time
 
 import numpy as np
 
@@ -168,6 +169,8 @@ def main():
             look_up=0.35,
         ),
         "configs[4] view-batch unit: 1920x1080 HDR + tonemap": dict(scene=base_scene, size=(1920, 1080), bits=64, directional=True, post=dict()),
+        # the stress map's static world alone (no lights, no models): what the device-side front-end chain is for
+        "front-end chain: stress map, static world only, 4K HDR": dict(scene=dict(base_scene, max_polygon_size=7.5), size=(3840, 2160), bits=64, directional=True, post=dict(), mip_bias=-1.0, frames=8),
     }
     results = {}
     for name, cfg in configs.items():
@@ -180,8 +183,11 @@ def main():
         path = sc.camera_path(64)
         frames = []
         geometry_frames = []
-        for i in range(args.frames):
-            k = (i * 64) // args.frames
+        draw_orders = []
+        build_s = []
+        num_frames = min(args.frames, cfg.get("frames", args.frames))
+        for i in range(num_frames):
+            k = (i * 64) // num_frames
             pose = path[k].copy()
             pose[4] += cfg.get("look_up", 0.0)
             kw = {}
@@ -195,9 +201,14 @@ def main():
                 kw["decals"] = scatter_decals(S, pose, cfg["decals"], k, num_skins=int(sc.info.num_models))
             if cfg.get("portals"):
                 kw["portals"] = portals_for(S, N, pose, int(sc.info.num_models))
+            t_build = time.perf_counter()
             frames.append(hr.build_frame(W, H, pose, color_bits=cfg["bits"], **kw))
+            build_s.append(time.perf_counter() - t_build)
             if i % 4 == 0:  # world-polygon preparation of this pose: the mirror's lists, results and its wall time
                 geometry_frames.append(hr.prepared_polygons() + (hr.polygons_prepare_seconds(),))
+                index_of = {int(p): ci for ci, p in enumerate(geometry_frames[-1][0]["polygon"])}
+                order = hr.polygon_draw_order()
+                draw_orders.append(np.array([index_of[int(p)] for p in order], np.uint32) if all(int(p) in index_of for p in order) else None)
         hr.close()
         ctx = Context(sc.lightmaps, sc.directional_lightmaps, device=0, stream=stream.cuda_stream, concurrent_views=True)
         sc.upload(ctx)
@@ -235,8 +246,6 @@ def main():
         run(serial=True)
         kt = ctx.profile_end()
         # the geometry half of the host front end on the GPU (sqw_polygons_prepare) beside the host mirror, same candidates
-        import time
-
         ctx.upload_map_geometry(*sc.map_geometry())
         gv = views[0]
         for cand, planes, want, fr, _ in geometry_frames[:2]:
@@ -248,15 +257,51 @@ def main():
             gv.polygons_prepare(fr["planes_matrix"], fr["view_matrix"], float(fr["mip_bias"]), cand, planes)
         call_s = time.perf_counter() - t0
         gkt = ctx.profile_end()
+        # the whole chain for frames of static world geometry: prepare + draw + device-side job / band / frame set-up, against the
+        # host-list path (sqw_frame_set_surfaces + sqw_frame_set_draw of the mirror's lists), wall clock per frame
+        chain = None
+        world_only = all(len(frames[i * 4].cmds) == int(((frames[i * 4].cmds["kind"] == N.CMD_POLYGON) & (frames[i * 4].cmds["tex_kind"] == N.TEX_SURFACE)).sum()) and (frames[i * 4].lights is None or len(frames[i * 4].lights) == 0) for i in range(len(geometry_frames)))
+        if world_only and draw_orders and all(o is not None for o in draw_orders):
+            hr2 = S.HostRenderer(sc, use_directional_lightmaps=cfg["directional"], textures_mip_bias=cfg.get("mip_bias", 0.0))
+            ctx.upload_map_materials(sc.map_materials(), hr2.polygon_basis())
+            hr2.close()
+            fr_dev, fr_host = gv.create_frame(), gv.create_frame()
+            t_dev = t_host = 0.0
+            for rep in range(3):
+                for gi, (cand, planes, want, fr, _) in enumerate(geometry_frames):
+                    hf = frames[gi * 4]
+                    t0 = time.perf_counter()
+                    gv.polygons_prepare(fr["planes_matrix"], fr["view_matrix"], float(fr["mip_bias"]), cand, planes)
+                    gv.polygons_draw(draw_orders[gi])
+                    fr_dev.set_surfaces_from_polygons(hf.cam_pos, use_directional_lightmaps=cfg["directional"])
+                    fr_dev.set_draw_from_polygons(clear_color=None)
+                    gv.synchronize()
+                    t1 = time.perf_counter()
+                    fr_host.set_surfaces(hf.jobs, None, None, hf.cam_pos, hf.total_surface_pixels)
+                    fr_host.set_draw(hf.cmds, hf.polygon_points, None, clear_color=None)
+                    gv.synchronize()
+                    t2 = time.perf_counter()
+                    if rep:
+                        t_dev += t1 - t0
+                        t_host += t2 - t1
+            fr_dev.close()
+            fr_host.close()
+            chain = {
+                "device_chain_us_per_frame": t_dev * 1e6 / (2 * len(geometry_frames)),
+                "host_lists_us_per_frame": t_host * 1e6 / (2 * len(geometry_frames)),
+                "note": "device chain = sqw_polygons_prepare + sqw_polygons_draw + sqw_frame_set_surfaces_from_polygons + sqw_frame_set_draw_from_polygons from the candidate and draw-order lists (wall clock, five small synchronising read-backs of totals); host lists = sqw_frame_set_surfaces + sqw_frame_set_draw of the mirror's job / command / vertex lists (the mirror's own time to BUILD those lists is host_mirror_us_per_frame for the geometry alone, 0.3 ms per 4K frame for the whole front end)",
+            }
         got, totals = gv.polygons_read(len(geometry_frames[-1][0]))
         want = geometry_frames[-1][2]
         geometry = {
             "candidates_per_frame": float(np.mean([len(g[0]) for g in geometry_frames])),
             "visible_polygons_per_frame": float(np.mean([int(g[3]["num_visible"]) for g in geometry_frames])),
             "host_mirror_us_per_frame": 1e6 * float(np.mean([g[4] for g in geometry_frames])),
+            "host_mirror_whole_front_end_us_per_frame": 1e6 * float(np.mean(build_s)),
             "gpu_kernels_us_per_frame": gkt["polygons_prepare"][0] * 1e3 / len(geometry_frames),
             "gpu_call_us_per_frame": call_s * 1e6 / len(geometry_frames),
             "bit_exact_vs_host_mirror": bool(np.array_equal(got.view(np.uint8), want.view(np.uint8))),
+            "chain": chain,
             "note": "prepare_polygons_surfaces for the leaf polygons (partial_renderer.rs:1327-1360): host mirror = one thread, wall clock; GPU kernels = polygons_prepare + "
                     "offsets by CUDA events; GPU call = sqw_polygons_prepare wall clock including the upload of the candidate list from pageable memory and the stream synchronisation",
         }

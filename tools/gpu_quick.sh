@@ -15,5 +15,5 @@ import json
 d=json.load(open("gpurun_out/qc_$TAG.json"))
 for n,c in d["configs"].items():
     print(n[:60], round(c["frames_per_sec"],1), "fps", " ".join(f"{a}={round(v['us_per_frame'],1)}" for a,v in c["kernels"].items()))
-    g=c["front_end_geometry"]; print("     geometry: candidates", round(g["candidates_per_frame"]), "host us", round(g["host_mirror_us_per_frame"],1), "gpu kernels us", round(g["gpu_kernels_us_per_frame"],1), "gpu call us", round(g["gpu_call_us_per_frame"],1), "bit-exact", g["bit_exact_vs_host_mirror"])
+    g=c["front_end_geometry"]; print("     geometry: candidates", round(g["candidates_per_frame"]), "host geometry us", round(g["host_mirror_us_per_frame"],1), "host front end us", round(g["host_mirror_whole_front_end_us_per_frame"],1), "gpu kernels us", round(g["gpu_kernels_us_per_frame"],1), "gpu call us", round(g["gpu_call_us_per_frame"],1), "bit-exact", g["bit_exact_vs_host_mirror"], "chain", {k: round(v, 1) for k, v in (g.get("chain") or {}).items() if k != "note"})
 PY
