@@ -625,8 +625,12 @@ def run_cuda(args, rank, local_rank, world):
         pictures = sum(a[0] - b[0] for a, b in zip(after, before))
         moved = sum(a[1] - b[1] for a, b in zip(after, before))
         d2h_step = int(moved / max(pictures, 1) * FRAMES_PER_STEP)
+        compressed_fps = e2e_fps
+        if raw_fps > compressed_fps:  # many GPUs sharing few host cores: the plain copy wins, and a caller would pick it
+            e2e_fps, d2h_step = raw_fps, WIDTH * HEIGHT * 4 * FRAMES_PER_STEP
         readback = {
-            "mode": "run-length rows (SQW_CTX_COMPRESSED_READBACK), lossless",
+            "mode": "run-length rows (SQW_CTX_COMPRESSED_READBACK), lossless" if e2e_fps == compressed_fps else "plain copy (the compressed read-back was slower with this many GPUs per host core)",
+            "compressed_value": compressed_fps,
             "bytes_per_picture": moved / max(pictures, 1),
             "compression": WIDTH * HEIGHT * 4 / max(moved / max(pictures, 1), 1.0),
             "decode_threads": int(os.environ.get("SQW_READBACK_THREADS", "0")) or None,
