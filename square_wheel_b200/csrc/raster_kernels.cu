@@ -223,8 +223,8 @@ __device__ void setup_polygon_line(const sqw_draw_cmd& c, const CmdDev& cd, cons
 // fill_triangle (rasterizer.rs:731-982) does almost all of its work once per triangle HALF, before the row loop: edge
 // slopes, texture-coordinate and light gradients (two dozen 16.16 divisions) and the range-correction block
 // (:1018-1192).  Only `x_left/x_right += dx_dy`, `tc_left += d_tc_dy_left`, `light_left += d_light_left` and the first
-// pixel offset depend on the row.  So the set-up is split the same way: raster_triangle_setup_kernel runs ONE THREAD
-// PER TRIANGLE and stores a TriRec (both halves, corrections applied); the per-row set-up in raster_setup_kernel reads
+// pixel offset depend on the row.  So the set-up is split the same way: raster_triangle_setup_kernel runs FIVE LANES
+// PER TRIANGLE (one per interpolant) and stores a TriRec (both halves, corrections applied); the per-row set-up in raster_setup_kernel reads
 // the half that owns its row (a warp-uniform 96-byte broadcast) and evaluates the closed forms of the row loop.
 struct TriPart // 96 bytes
 {
@@ -241,123 +241,120 @@ struct TriRec
 };
 static_assert(sizeof(TriPart) == 96 && sizeof(TriRec) == SQW_TRI_REC_BYTES, "TriRec layout");
 
-// The row-independent part of fill_triangle_part (rasterizer.rs:984-1192).
-__device__ void triangle_part_setup(
-	const sqw_draw_cmd& c, Fixed16 y_start, Fixed16 y_end, PolygonSide left_side, PolygonSide right_side, const Fixed16 tc_start_left[2],
-	const Fixed16 d_tc_dy_left_in[2], const Fixed16 d_tc_dx_in[2], const Fixed16 light_start_left[3], const Fixed16 d_light_left_in[3],
-	const Fixed16 d_light_dx_in[3], int32_t clip_h, TriPart& p)
+// The row-independent part of fill_triangle_part (rasterizer.rs:984-1192), split by what it depends on so that the five
+// interpolants of a triangle (two texture coordinates, three light components) can be set up by five lanes:
+//   TriPartGeometry      rows and edges of the half, shared by every interpolant (:984-1016);
+//   tc_channel_part      range correction of ONE texture coordinate (:1018-1138);
+//   light_channel_part   underflow correction of ONE light component (:1140-1192).
+struct TriPartGeometry
 {
-	const int32_t y_start_int = max(fixed16_round_to_int(y_start), 0);
-	p.row0 = y_start_int;
-	p.row1 = min(fixed16_round_to_int(y_end), clip_h);
-	p.y_start_int = y_start_int;
-	p.pad[0] = p.pad[1] = 0;
+	int32_t y_start_int, row1;
+	Fixed16 x_left0, x_right0, dx_dy_left, dx_dy_right;
+	Fixed16 y_start_delta, y_end_delta, d_x_lower, d_x_upper;
+};
+__device__ __forceinline__ TriPartGeometry triangle_part_geometry(const Fixed16 y_start, const Fixed16 y_end, const PolygonSide left_side, const PolygonSide right_side, const int32_t clip_h)
+{
+	TriPartGeometry g;
+	g.y_start_int = max(fixed16_round_to_int(y_start), 0);
+	g.row1 = min(fixed16_round_to_int(y_end), clip_h);
+	g.y_start_delta = wsub(wadd(int_to_fixed16(g.y_start_int), SQW_FIXED16_HALF), y_start);
+	g.x_left0 = wadd(wadd(left_side.x_start, fixed16_mul(g.y_start_delta, left_side.dx_dy)), SQW_FIXED16_HALF);
+	g.x_right0 = wadd(wadd(right_side.x_start, fixed16_mul(g.y_start_delta, right_side.dx_dy)), SQW_FIXED16_HALF);
+	g.dx_dy_left = left_side.dx_dy;
+	g.dx_dy_right = right_side.dx_dy;
+	g.y_end_delta = wsub(y_end, wadd(y_start, g.y_start_delta));
+	g.d_x_lower = max(wsub(g.x_right0, g.x_left0), 0);
+	const Fixed16 x_upper_left = wadd(g.x_left0, fixed16_mul(g.y_end_delta, left_side.dx_dy));
+	const Fixed16 x_upper_right = wadd(g.x_right0, fixed16_mul(g.y_end_delta, right_side.dx_dy));
+	g.d_x_upper = max(wsub(x_upper_right, x_upper_left), 0);
+	return g;
+}
 
-	const Fixed16 y_start_delta = wsub(wadd(int_to_fixed16(y_start_int), SQW_FIXED16_HALF), y_start);
-	const Fixed16 x_left0 = wadd(wadd(left_side.x_start, fixed16_mul(y_start_delta, left_side.dx_dy)), SQW_FIXED16_HALF);
-	const Fixed16 x_right0 = wadd(wadd(right_side.x_start, fixed16_mul(y_start_delta, right_side.dx_dy)), SQW_FIXED16_HALF);
-	p.x_left0 = x_left0;
-	p.dx_dy_left = left_side.dx_dy;
-	p.x_right0 = x_right0;
-	p.dx_dy_right = right_side.dx_dy;
-
-	const Fixed16 y_end_delta = wsub(y_end, wadd(y_start, y_start_delta));
-	const Fixed16 d_x_lower = max(wsub(x_right0, x_left0), 0);
-	const Fixed16 x_upper_left = wadd(x_left0, fixed16_mul(y_end_delta, left_side.dx_dy));
-	const Fixed16 x_upper_right = wadd(x_right0, fixed16_mul(y_end_delta, right_side.dx_dy));
-	const Fixed16 d_x_upper = max(wsub(x_upper_right, x_upper_left), 0);
-
-	// :1018-1138 texture coordinate range correction
-#pragma unroll
-	for (int i = 0; i < 2; ++i)
+// :1018-1138 texture coordinate range correction of one coordinate -> {tc_left, d_tc_dy_left, d_tc_dx}
+__device__ __forceinline__ void tc_channel_part(const TriPartGeometry& g, const Fixed16 max_tc, const Fixed16 tc_start_left, Fixed16 d_tc_dy_left, Fixed16 d_tc_dx, Fixed16 (&out)[3])
+{
+	const Fixed16 y_start_delta = g.y_start_delta, y_end_delta = g.y_end_delta, d_x_lower = g.d_x_lower, d_x_upper = g.d_x_upper;
+	Fixed16 tc_left = min(max(wadd(tc_start_left, fixed16_mul(y_start_delta, d_tc_dy_left)), 0), max_tc);
 	{
-		Fixed16 d_tc_dy_left = d_tc_dy_left_in[i];
-		Fixed16 d_tc_dx = d_tc_dx_in[i];
-		const Fixed16 max_tc = wsub(int_to_fixed16(c.tex_size[i]), 1);
-		Fixed16 tc_left = min(max(wadd(tc_start_left[i], fixed16_mul(y_start_delta, d_tc_dy_left)), 0), max_tc);
+		const Fixed16 tc_lower_delta = fixed16_mul(d_tc_dx, d_x_lower);
+		if (tc_lower_delta > max_tc)
 		{
-			const Fixed16 tc_lower_delta = fixed16_mul(d_tc_dx, d_x_lower);
-			if (tc_lower_delta > max_tc)
-			{
-				tc_left = 0;
-				d_tc_dx = fixed16_div(max_tc, d_x_lower);
-			}
-			else if (tc_lower_delta < -max_tc)
-			{
-				tc_left = max_tc;
-				d_tc_dx = fixed16_div(-max_tc, d_x_lower);
-			}
-			else
-			{
-				const Fixed16 tc_lower_right = wadd(tc_left, tc_lower_delta);
-				if (tc_lower_right > max_tc)
-					tc_left = wsub(tc_left, wsub(tc_lower_right, max_tc));
-				else if (tc_lower_right < 0)
-					tc_left = wsub(tc_left, tc_lower_right);
-			}
+			tc_left = 0;
+			d_tc_dx = fixed16_div(max_tc, d_x_lower);
 		}
+		else if (tc_lower_delta < -max_tc)
 		{
-			Fixed16 tc_upper_left = min(max(wadd(tc_left, fixed16_mul(y_end_delta, d_tc_dy_left)), 0), max_tc);
-			const Fixed16 tc_upper_delta = fixed16_mul(d_tc_dx, d_x_upper);
-			if (tc_upper_delta > max_tc)
-			{
-				tc_upper_left = 0;
-				d_tc_dx = fixed16_div(max_tc, d_x_upper);
-			}
-			else if (tc_upper_delta < -max_tc)
-			{
-				tc_upper_left = max_tc;
-				d_tc_dx = fixed16_div(-max_tc, d_x_upper);
-			}
-			else
-			{
-				const Fixed16 tc_upper_right = wadd(tc_upper_left, tc_upper_delta);
-				if (tc_upper_right > max_tc)
-					tc_upper_left = wsub(tc_upper_left, wsub(tc_upper_right, max_tc));
-				else if (tc_upper_right < 0)
-					tc_upper_left = wsub(tc_upper_left, tc_upper_right);
-			}
-			d_tc_dy_left = y_end_delta > 0 ? fixed16_div(wsub(tc_upper_left, tc_left), y_end_delta) : 0;
-
-			const Fixed16 tc_upper_left2 = wadd(tc_left, fixed16_mul(y_end_delta, d_tc_dy_left));
-			const Fixed16 tc_upper_delta2 = fixed16_mul(d_tc_dx, d_x_upper);
-			const Fixed16 tc_upper_right2 = wadd(tc_upper_left2, tc_upper_delta2);
-			if (tc_upper_right2 < 0)
-				d_tc_dx = d_x_upper > 0 ? fixed16_div(-tc_upper_left2, d_x_upper) : 0;
-			else if (tc_upper_right2 > max_tc)
-				d_tc_dx = d_x_upper > 0 ? fixed16_div(wsub(max_tc, tc_upper_left2), d_x_upper) : 0;
+			tc_left = max_tc;
+			d_tc_dx = fixed16_div(-max_tc, d_x_lower);
 		}
-		p.tc_left[i] = tc_left;
-		p.d_tc_dy_left[i] = d_tc_dy_left;
-		p.d_tc_dx[i] = d_tc_dx;
+		else
+		{
+			const Fixed16 tc_lower_right = wadd(tc_left, tc_lower_delta);
+			if (tc_lower_right > max_tc)
+				tc_left = wsub(tc_left, wsub(tc_lower_right, max_tc));
+			else if (tc_lower_right < 0)
+				tc_left = wsub(tc_left, tc_lower_right);
+		}
 	}
-
-	// :1140-1192 light underflow correction
-#pragma unroll
-	for (int i = 0; i < 3; ++i)
 	{
-		Fixed16 d_light_left = d_light_left_in[i];
-		Fixed16 d_light_dx = d_light_dx_in[i];
-		Fixed16 light_left = max(wadd(light_start_left[i], fixed16_mul(y_start_delta, d_light_left)), 0);
-		const Fixed16 light_lower_right = wadd(light_left, fixed16_mul(d_x_lower, d_light_dx));
-		if (light_lower_right < 0)
-			light_left = wsub(light_left, light_lower_right);
+		Fixed16 tc_upper_left = min(max(wadd(tc_left, fixed16_mul(y_end_delta, d_tc_dy_left)), 0), max_tc);
+		const Fixed16 tc_upper_delta = fixed16_mul(d_tc_dx, d_x_upper);
+		if (tc_upper_delta > max_tc)
 		{
-			Fixed16 light_upper_left = max(wadd(light_left, fixed16_mul(y_end_delta, d_light_left)), 0);
-			const Fixed16 light_upper_right = wadd(light_upper_left, fixed16_mul(d_x_upper, d_light_dx));
-			if (light_upper_right < 0)
-				light_upper_left = wsub(light_upper_left, light_upper_right);
-			d_light_left = y_end_delta > 0 ? fixed16_div(wsub(light_upper_left, light_left), y_end_delta) : 0;
-
-			const Fixed16 light_upper_left2 = wadd(light_left, fixed16_mul(y_end_delta, d_light_left));
-			const Fixed16 light_upper_right2 = wadd(light_upper_left2, fixed16_mul(d_x_upper, d_light_dx));
-			if (light_upper_right2 < 0)
-				d_light_dx = d_x_upper > 0 ? fixed16_div(-light_upper_left2, d_x_upper) : 0;
+			tc_upper_left = 0;
+			d_tc_dx = fixed16_div(max_tc, d_x_upper);
 		}
-		p.light_left[i] = light_left;
-		p.d_light_left[i] = d_light_left;
-		p.d_light_dx[i] = d_light_dx;
+		else if (tc_upper_delta < -max_tc)
+		{
+			tc_upper_left = max_tc;
+			d_tc_dx = fixed16_div(-max_tc, d_x_upper);
+		}
+		else
+		{
+			const Fixed16 tc_upper_right = wadd(tc_upper_left, tc_upper_delta);
+			if (tc_upper_right > max_tc)
+				tc_upper_left = wsub(tc_upper_left, wsub(tc_upper_right, max_tc));
+			else if (tc_upper_right < 0)
+				tc_upper_left = wsub(tc_upper_left, tc_upper_right);
+		}
+		d_tc_dy_left = y_end_delta > 0 ? fixed16_div(wsub(tc_upper_left, tc_left), y_end_delta) : 0;
+
+		const Fixed16 tc_upper_left2 = wadd(tc_left, fixed16_mul(y_end_delta, d_tc_dy_left));
+		const Fixed16 tc_upper_delta2 = fixed16_mul(d_tc_dx, d_x_upper);
+		const Fixed16 tc_upper_right2 = wadd(tc_upper_left2, tc_upper_delta2);
+		if (tc_upper_right2 < 0)
+			d_tc_dx = d_x_upper > 0 ? fixed16_div(-tc_upper_left2, d_x_upper) : 0;
+		else if (tc_upper_right2 > max_tc)
+			d_tc_dx = d_x_upper > 0 ? fixed16_div(wsub(max_tc, tc_upper_left2), d_x_upper) : 0;
 	}
+	out[0] = tc_left;
+	out[1] = d_tc_dy_left;
+	out[2] = d_tc_dx;
+}
+
+// :1140-1192 light underflow correction of one component -> {light_left, d_light_left, d_light_dx}
+__device__ __forceinline__ void light_channel_part(const TriPartGeometry& g, const Fixed16 light_start_left, Fixed16 d_light_left, Fixed16 d_light_dx, Fixed16 (&out)[3])
+{
+	const Fixed16 y_start_delta = g.y_start_delta, y_end_delta = g.y_end_delta, d_x_lower = g.d_x_lower, d_x_upper = g.d_x_upper;
+	Fixed16 light_left = max(wadd(light_start_left, fixed16_mul(y_start_delta, d_light_left)), 0);
+	const Fixed16 light_lower_right = wadd(light_left, fixed16_mul(d_x_lower, d_light_dx));
+	if (light_lower_right < 0)
+		light_left = wsub(light_left, light_lower_right);
+	{
+		Fixed16 light_upper_left = max(wadd(light_left, fixed16_mul(y_end_delta, d_light_left)), 0);
+		const Fixed16 light_upper_right = wadd(light_upper_left, fixed16_mul(d_x_upper, d_light_dx));
+		if (light_upper_right < 0)
+			light_upper_left = wsub(light_upper_left, light_upper_right);
+		d_light_left = y_end_delta > 0 ? fixed16_div(wsub(light_upper_left, light_left), y_end_delta) : 0;
+
+		const Fixed16 light_upper_left2 = wadd(light_left, fixed16_mul(y_end_delta, d_light_left));
+		const Fixed16 light_upper_right2 = wadd(light_upper_left2, fixed16_mul(d_x_upper, d_light_dx));
+		if (light_upper_right2 < 0)
+			d_light_dx = d_x_upper > 0 ? fixed16_div(-light_upper_left2, d_x_upper) : 0;
+	}
+	out[0] = light_left;
+	out[1] = d_light_left;
+	out[2] = d_light_dx;
 }
 
 // The row loop of fill_triangle_part (rasterizer.rs:1194-1291) in closed form for the line `row` of the half `p`.
@@ -399,8 +396,11 @@ __device__ __forceinline__ void triangle_row(const TriPart& p, int32_t row, int3
 	o[2] = s[2];
 }
 
-// fill_triangle_impl (rasterizer.rs:765-966): both halves of one triangle.
-__device__ void triangle_command_setup(const sqw_draw_cmd& c, const sqw_triangle_point* __restrict__ vertices, int32_t clip_h, TriRec& rec)
+// fill_triangle_impl (rasterizer.rs:765-966) for ONE interpolant of one triangle: lane role `ch` 0-1 = texture coordinate, 2-4 = light
+// component.  The geometry (vertex order, edge slopes, the two halves' rows) is recomputed by every lane of the triangle — it is a
+// fraction of the work — so the lanes never communicate; lane 0 also stores the fields the interpolants share.  The channel only
+// selects DATA (which vertex attribute, which output slot), never code, except for the two correction routines.
+__device__ void triangle_channel_setup(const sqw_draw_cmd& c, const sqw_triangle_point* __restrict__ vertices, const int32_t clip_h, const int ch, TriRec* __restrict__ rec)
 {
 	const sqw_triangle_point v0 = vertices[0], v1 = vertices[1], v2 = vertices[2];
 	int upper_index, lower_index;
@@ -423,6 +423,9 @@ __device__ void triangle_command_setup(const sqw_draw_cmd& c, const sqw_triangle
 	const sqw_triangle_point upper_vertex = upper_index == 0 ? v0 : (upper_index == 1 ? v1 : v2);
 	const sqw_triangle_point lower_vertex = lower_index == 0 ? v0 : (lower_index == 1 ? v1 : v2);
 	const sqw_triangle_point middle_vertex = middle_index == 0 ? v0 : (middle_index == 1 ? v1 : v2);
+	// this lane's attribute at the three vertices
+	auto attribute = [ch](const sqw_triangle_point& v) -> Fixed16 { return ch == 0 ? v.tc[0] : (ch == 1 ? v.tc[1] : (ch == 2 ? v.light[0] : (ch == 3 ? v.light[1] : v.light[2]))); };
+	const Fixed16 a_upper = attribute(upper_vertex), a_lower = attribute(lower_vertex), a_middle = attribute(middle_vertex);
 
 	const Fixed16 long_edge_dy = max(wsub(upper_vertex.y, lower_vertex.y), SQW_FIXED16_HALF);
 	const Fixed16 lower_part_dy = max(wsub(middle_vertex.y, lower_vertex.y), SQW_FIXED16_HALF);
@@ -433,86 +436,100 @@ __device__ void triangle_command_setup(const sqw_draw_cmd& c, const sqw_triangle
 	const Fixed16 lower_part_dx_dy = fixed16_div(wsub(middle_vertex.x, lower_vertex.x), lower_part_dy);
 	const Fixed16 upper_part_dx_dy = fixed16_div(wsub(upper_vertex.x, middle_vertex.x), upper_part_dy);
 
-	Fixed16 long_edge_d_tc_dy[2], long_edge_tc_in_middle[2], d_tc_dy_lower[2], d_tc_dy_upper[2];
-#pragma unroll
-	for (int i = 0; i < 2; ++i)
-	{
-		long_edge_d_tc_dy[i] = fixed16_div(wsub(upper_vertex.tc[i], lower_vertex.tc[i]), long_edge_dy);
-		long_edge_tc_in_middle[i] = wadd(lower_vertex.tc[i], fixed16_mul(long_edge_d_tc_dy[i], lower_part_dy));
-		d_tc_dy_lower[i] = fixed16_div(wsub(middle_vertex.tc[i], lower_vertex.tc[i]), lower_part_dy);
-		d_tc_dy_upper[i] = fixed16_div(wsub(upper_vertex.tc[i], middle_vertex.tc[i]), upper_part_dy);
-	}
-	Fixed16 long_edge_d_light_dy[3], long_edge_light_in_middle[3], d_light_dy_lower[3], d_light_dy_upper[3];
-#pragma unroll
-	for (int i = 0; i < 3; ++i)
-	{
-		long_edge_d_light_dy[i] = fixed16_div(wsub(upper_vertex.light[i], lower_vertex.light[i]), long_edge_dy);
-		long_edge_light_in_middle[i] = wadd(lower_vertex.light[i], fixed16_mul(long_edge_d_light_dy[i], lower_part_dy));
-		d_light_dy_lower[i] = fixed16_div(wsub(middle_vertex.light[i], lower_vertex.light[i]), lower_part_dy);
-		d_light_dy_upper[i] = fixed16_div(wsub(upper_vertex.light[i], middle_vertex.light[i]), upper_part_dy);
-	}
+	const Fixed16 long_edge_d_dy = fixed16_div(wsub(a_upper, a_lower), long_edge_dy);
+	const Fixed16 long_edge_in_middle = wadd(a_lower, fixed16_mul(long_edge_d_dy, lower_part_dy));
+	const Fixed16 d_dy_lower = fixed16_div(wsub(a_middle, a_lower), lower_part_dy);
+	const Fixed16 d_dy_upper = fixed16_div(wsub(a_upper, a_middle), upper_part_dy);
 
-	Fixed16 d_tc_dx[2], d_light_dx[3];
-	PolygonSide l, r;
-	if (long_edge_x_in_middle >= middle_vertex.x)
+	// the two halves: {y range, left / right edge, start value and slope along the LEFT edge}
+	const bool long_edge_right = long_edge_x_in_middle >= middle_vertex.x;
+	Fixed16 d_dx;
+	PolygonSide l[2], r[2];
+	Fixed16 start[2], d_dy[2];
+	if (long_edge_right)
 	{
 		const Fixed16 middle_dx = max(wsub(long_edge_x_in_middle, middle_vertex.x), SQW_FIXED16_HALF);
-#pragma unroll
-		for (int i = 0; i < 2; ++i)
-			d_tc_dx[i] = fixed16_div(wsub(long_edge_tc_in_middle[i], middle_vertex.tc[i]), middle_dx);
-#pragma unroll
-		for (int i = 0; i < 3; ++i)
-			d_light_dx[i] = fixed16_div(wsub(long_edge_light_in_middle[i], middle_vertex.light[i]), middle_dx);
-		l.x_start = lower_vertex.x;
-		l.dx_dy = lower_part_dx_dy;
-		r.x_start = lower_vertex.x;
-		r.dx_dy = long_edge_dx_dy;
-		triangle_part_setup(c, lower_vertex.y, middle_vertex.y, l, r, lower_vertex.tc, d_tc_dy_lower, d_tc_dx, lower_vertex.light, d_light_dy_lower, d_light_dx, clip_h, rec.part[0]);
-		l.x_start = middle_vertex.x;
-		l.dx_dy = upper_part_dx_dy;
-		r.x_start = long_edge_x_in_middle;
-		r.dx_dy = long_edge_dx_dy;
-		triangle_part_setup(c, middle_vertex.y, upper_vertex.y, l, r, middle_vertex.tc, d_tc_dy_upper, d_tc_dx, middle_vertex.light, d_light_dy_upper, d_light_dx, clip_h, rec.part[1]);
+		d_dx = fixed16_div(wsub(long_edge_in_middle, a_middle), middle_dx);
+		l[0].x_start = lower_vertex.x;
+		l[0].dx_dy = lower_part_dx_dy;
+		r[0].x_start = lower_vertex.x;
+		r[0].dx_dy = long_edge_dx_dy;
+		start[0] = a_lower;
+		d_dy[0] = d_dy_lower;
+		l[1].x_start = middle_vertex.x;
+		l[1].dx_dy = upper_part_dx_dy;
+		r[1].x_start = long_edge_x_in_middle;
+		r[1].dx_dy = long_edge_dx_dy;
+		start[1] = a_middle;
+		d_dy[1] = d_dy_upper;
 	}
 	else
 	{
 		const Fixed16 middle_dx = max(wsub(middle_vertex.x, long_edge_x_in_middle), SQW_FIXED16_HALF);
+		d_dx = fixed16_div(wsub(a_middle, long_edge_in_middle), middle_dx);
+		l[0].x_start = lower_vertex.x;
+		l[0].dx_dy = long_edge_dx_dy;
+		r[0].x_start = lower_vertex.x;
+		r[0].dx_dy = lower_part_dx_dy;
+		start[0] = a_lower;
+		d_dy[0] = long_edge_d_dy;
+		l[1].x_start = long_edge_x_in_middle;
+		l[1].dx_dy = long_edge_dx_dy;
+		r[1].x_start = middle_vertex.x;
+		r[1].dx_dy = upper_part_dx_dy;
+		start[1] = long_edge_in_middle;
+		d_dy[1] = long_edge_d_dy;
+	}
+	const Fixed16 y_range[3] = {lower_vertex.y, middle_vertex.y, upper_vertex.y};
 #pragma unroll
-		for (int i = 0; i < 2; ++i)
-			d_tc_dx[i] = fixed16_div(wsub(middle_vertex.tc[i], long_edge_tc_in_middle[i]), middle_dx);
-#pragma unroll
-		for (int i = 0; i < 3; ++i)
-			d_light_dx[i] = fixed16_div(wsub(middle_vertex.light[i], long_edge_light_in_middle[i]), middle_dx);
-		l.x_start = lower_vertex.x;
-		l.dx_dy = long_edge_dx_dy;
-		r.x_start = lower_vertex.x;
-		r.dx_dy = lower_part_dx_dy;
-		triangle_part_setup(c, lower_vertex.y, middle_vertex.y, l, r, lower_vertex.tc, long_edge_d_tc_dy, d_tc_dx, lower_vertex.light, long_edge_d_light_dy, d_light_dx, clip_h, rec.part[0]);
-		l.x_start = long_edge_x_in_middle;
-		l.dx_dy = long_edge_dx_dy;
-		r.x_start = middle_vertex.x;
-		r.dx_dy = upper_part_dx_dy;
-		triangle_part_setup(c, middle_vertex.y, upper_vertex.y, l, r, long_edge_tc_in_middle, long_edge_d_tc_dy, d_tc_dx, long_edge_light_in_middle, long_edge_d_light_dy, d_light_dx, clip_h, rec.part[1]);
+	for (int half = 0; half < 2; ++half)
+	{
+		const TriPartGeometry g = triangle_part_geometry(y_range[half], y_range[half + 1], l[half], r[half], clip_h);
+		TriPart* const p = &rec->part[half];
+		if (ch == 0)
+		{
+			p->row0 = g.y_start_int;
+			p->row1 = g.row1;
+			p->y_start_int = g.y_start_int;
+			p->x_left0 = g.x_left0;
+			p->dx_dy_left = g.dx_dy_left;
+			p->x_right0 = g.x_right0;
+			p->dx_dy_right = g.dx_dy_right;
+			p->pad[0] = p->pad[1] = 0;
+		}
+		Fixed16 out[3];
+		if (ch < 2)
+		{
+			tc_channel_part(g, wsub(int_to_fixed16(ch == 0 ? c.tex_size[0] : c.tex_size[1]), 1), start[half], d_dy[half], d_dx, out);
+			p->tc_left[ch] = out[0];
+			p->d_tc_dy_left[ch] = out[1];
+			p->d_tc_dx[ch] = out[2];
+		}
+		else
+		{
+			light_channel_part(g, start[half], d_dy[half], d_dx, out);
+			p->light_left[ch - 2] = out[0];
+			p->d_light_left[ch - 2] = out[1];
+			p->d_light_dx[ch - 2] = out[2];
+		}
 	}
 }
 
-// One thread per command: the TriRec of every triangle command (polygon commands leave their slot untouched).
-__global__ void __launch_bounds__(32) raster_triangle_setup_kernel(
+// Eight lanes per command, five of them at work: the TriRec of every triangle command, one interpolant per lane (polygon commands
+// leave their slot untouched).  A triangle's set-up is a chain of two dozen 16.16 divisions; five lanes cut it to a third and
+// four triangles per warp put four times as many warps on the machine as one thread per triangle did.
+__global__ void __launch_bounds__(128) raster_triangle_setup_kernel(
 	const sqw_draw_cmd* __restrict__ cmds, uint32_t num_cmds, const sqw_triangle_point* __restrict__ triangle_points, int32_t clip_h, TriRec* __restrict__ tri_recs)
 {
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= num_cmds)
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t i = t >> 3;
+	const int ch = (int)(t & 7);
+	if (i >= num_cmds || ch >= 5)
 		return;
 	const sqw_draw_cmd c = cmds[i];
 	if (c.kind != SQW_CMD_TRIANGLE)
 		return;
-	TriRec rec;
-	triangle_command_setup(c, triangle_points + c.vertex_offset, clip_h, rec);
-	uint4* o = reinterpret_cast<uint4*>(tri_recs + i);
-	const uint4* s4 = reinterpret_cast<const uint4*>(&rec);
-#pragma unroll
-	for (int k = 0; k < (int)(sizeof(TriRec) / 16); ++k)
-		o[k] = s4[k];
+	triangle_channel_setup(c, triangle_points + c.vertex_offset, clip_h, ch, tri_recs + i);
 }
 
 // The line `row` of a triangle command: the half that owns the row (fill_triangle_part returns early when its clipped
@@ -1725,7 +1742,7 @@ cudaError_t launch_raster_setup(const RasterLaunch& l, cudaStream_t stream)
 	const uint32_t bin_blocks = l.num_bands; // also with an empty command list: the tile kernel reads every tile descriptor
 	const uint32_t lut_blocks = l.tonemap_dst ? (3 * SQW_TONEMAP_LUT_SIZE + SQW_SETUP_THREADS - 1) / SQW_SETUP_THREADS : 0;
 	if (l.num_triangle_cmds)
-		raster_triangle_setup_kernel<<<(l.num_cmds + 31) / 32, 32, 0, stream>>> // one warp per CTA: a few hundred long serial chains spread over all SMs
+		raster_triangle_setup_kernel<<<(l.num_cmds * 8 + 127) / 128, 128, 0, stream>>> // eight lanes per command, one interpolant per lane
 		(l.cmds, l.num_cmds, l.triangle_points, l.height, static_cast<TriRec*>(l.tri_recs));
 	raster_setup_kernel<<<setup_blocks + bin_blocks + lut_blocks, SQW_SETUP_THREADS, 0, stream>>>(
 		l.cmds, l.cmd_dev, l.num_cmds, l.polygon_points, static_cast<const TriRec*>(l.tri_recs), l.chunks, l.num_chunks, l.spans, l.width, l.height, setup_blocks, l.band_offsets,
