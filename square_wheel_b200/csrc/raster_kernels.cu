@@ -762,6 +762,7 @@ __device__ __forceinline__ typename C::Raw fetch_texel(const void* tex, uint32_t
 	return __ldg(static_cast<const typename C::Raw*>(tex) + address);
 }
 
+
 #define SQW_PX_OFS(i) (((i) & 1) + 16 * ((i) >> 1))
 #define SQW_NEED_DST(i)                       \
 	if (!(have & (1u << (i))))                \
@@ -769,6 +770,117 @@ __device__ __forceinline__ typename C::Raw fetch_texel(const void* tex, uint32_t
 		px[i] = dst[SQW_PX_OFS(i)];           \
 		have |= 1u << (i);                    \
 	}
+// fill_triangle_part pixel loop (rasterizer.rs:1223-1279) of one command on the lane's pixels [I0, I1) of one row (0-1 = the pair in
+// the left 16 pixels of the block, 2-3 = the pair in the right 16): small triangles usually touch one side only, and the
+// caller skips the other (warp-uniform), which halves the shading of a model's triangles.
+template <class C, int I0, int I1>
+__device__ __forceinline__ void shade_triangle(
+	const uint4 w0, const void* const tex, const uint32_t tex_width, const uint4 r0, const uint4 r1, const uint4 r2, const int32_t px0,
+	const typename C::Raw* __restrict__ const dst, typename C::Raw (&px)[4], uint32_t& have)
+{
+	const int32_t x0 = (int16_t)(r0.x & 0xFFFF), x1 = (int16_t)(r0.x >> 16);
+	const uint32_t blend = (w0.w >> 8) & 0xFF, tex64 = (w0.w >> 24) & 1;
+	// fill_triangle_part pixel loop (rasterizer.rs:1223-1279), in three branch-free steps like the polygon path: the four
+	// texel addresses, the four gathers in flight together, then light and blend with the (warp-uniform) blend mode
+	// decided once outside the pixel loop.
+	const int32_t tc0 = (int32_t)r0.y, tc1 = (int32_t)r0.z, dtc0 = (int32_t)r0.w, dtc1 = (int32_t)r1.x;
+	const int32_t l0 = (int32_t)r1.y, l1 = (int32_t)r1.z, l2 = (int32_t)r1.w;
+	const int32_t dl0 = (int32_t)r2.x, dl1 = (int32_t)r2.y, dl2 = (int32_t)r2.z;
+	bool in[4];
+	uint32_t address[4];
+#pragma unroll
+	for (int i = I0; i < I1; ++i)
+	{
+		const int32_t x = px0 + SQW_PX_OFS(i);
+		in[i] = x >= x0 && x < x1;
+		const int32_t k = x - x0;
+		const uint32_t u = (uint32_t)(wadd(tc0, wmul(k, dtc0)) >> 16);
+		const uint32_t v = (uint32_t)(wadd(tc1, wmul(k, dtc1)) >> 16);
+		address[i] = u + v * tex_width; // garbage for uncovered pixels, never dereferenced
+	}
+	ColorVecI texel_vec[4];
+	int32_t alpha[4];
+	bool alpha_pass[4];
+	if (tex64)
+	{
+		uint64_t t[4];
+#pragma unroll
+		for (int i = I0; i < I1; ++i)
+		{
+			t[i] = 0;
+			if (in[i])
+				t[i] = __ldg(static_cast<const uint64_t*>(tex) + address[i]);
+		}
+#pragma unroll
+		for (int i = I0; i < I1; ++i)
+		{
+			texel_vec[i] = cvi_from_color64(t[i]);
+			alpha[i] = Color64::get_alpha(t[i]);
+			alpha_pass[i] = Color64::test_alpha(t[i]);
+		}
+	}
+	else
+	{
+		uint32_t t[4];
+#pragma unroll
+		for (int i = I0; i < I1; ++i)
+		{
+			t[i] = 0;
+			if (in[i])
+				t[i] = __ldg(static_cast<const uint32_t*>(tex) + address[i]);
+		}
+#pragma unroll
+		for (int i = I0; i < I1; ++i)
+		{
+			texel_vec[i] = cvi_from_color32(t[i]);
+			alpha[i] = Color32::get_alpha(t[i]);
+			alpha_pass[i] = Color32::test_alpha(t[i]);
+		}
+	}
+	ColorVecI lighted[4];
+#pragma unroll
+	for (int i = I0; i < I1; ++i)
+	{
+		const int32_t k = px0 + SQW_PX_OFS(i) - x0;
+		// line_light = from_color_i32x3([l0,l1,l2]) -> lanes [B,G,R,A] = [l2,l1,l0,0]
+		const ColorVecI light = cvi(wadd(l2, wmul(k, dl2)), wadd(l1, wmul(k, dl1)), wadd(l0, wmul(k, dl0)), 0);
+		lighted[i] = cvi_shr<16>(cvi_mul(texel_vec[i], light));
+	}
+	if (blend == SQW_BLEND_NONE)
+	{
+#pragma unroll
+		for (int i = I0; i < I1; ++i)
+		{
+			px[i] = in[i] ? C::from_veci(lighted[i]) : px[i];
+			have |= in[i] ? (1u << i) : 0u;
+		}
+	}
+	else if (blend == SQW_BLEND_ALPHA_TEST)
+	{
+#pragma unroll
+		for (int i = I0; i < I1; ++i)
+		{
+			const bool pass = in[i] && alpha_pass[i];
+			px[i] = pass ? C::from_veci(lighted[i]) : px[i];
+			have |= pass ? (1u << i) : 0u;
+		}
+	}
+	else
+	{
+#pragma unroll
+		for (int i = I0; i < I1; ++i)
+			if (in[i])
+			{
+				SQW_NEED_DST(i)
+				if (blend == SQW_BLEND_AVERAGE)
+					px[i] = C::average(px[i], C::from_veci(lighted[i]));
+				else if (blend == SQW_BLEND_ADDITIVE)
+					px[i] = C::saturated_sum(px[i], C::from_veci(lighted[i]));
+				else
+					px[i] = C::from_veci(cvi_shr<8>(cvi_add(cvi_mul_scalar(C::to_veci(px[i]), 255 - alpha[i]), cvi_mul_scalar(lighted[i], alpha[i]))));
+			}
+	}
+}
 
 // One command on the four pixels x = px0 + {0, 1, 16, 17} of one row: the pixel loops of fill_polygon_part*
 // (rasterizer.rs:424-445, :558-572, :705-719) or fill_triangle_part (:1223-1279) and write_into_framebuffer (:1511-1536).
@@ -861,109 +973,7 @@ __device__ __forceinline__ void shade_quad(
 				}
 		}
 	}
-	else
-	{
-		// fill_triangle_part pixel loop (rasterizer.rs:1223-1279), in three branch-free steps like the polygon path: the four
-		// texel addresses, the four gathers in flight together, then light and blend with the (warp-uniform) blend mode
-		// decided once outside the pixel loop.
-		const int32_t tc0 = (int32_t)r0.y, tc1 = (int32_t)r0.z, dtc0 = (int32_t)r0.w, dtc1 = (int32_t)r1.x;
-		const int32_t l0 = (int32_t)r1.y, l1 = (int32_t)r1.z, l2 = (int32_t)r1.w;
-		const int32_t dl0 = (int32_t)r2.x, dl1 = (int32_t)r2.y, dl2 = (int32_t)r2.z;
-		bool in[4];
-		uint32_t address[4];
-#pragma unroll
-		for (int i = 0; i < 4; ++i)
-		{
-			const int32_t x = px0 + SQW_PX_OFS(i);
-			in[i] = x >= x0 && x < x1;
-			const int32_t k = x - x0;
-			const uint32_t u = (uint32_t)(wadd(tc0, wmul(k, dtc0)) >> 16);
-			const uint32_t v = (uint32_t)(wadd(tc1, wmul(k, dtc1)) >> 16);
-			address[i] = u + v * tex_width; // garbage for uncovered pixels, never dereferenced
-		}
-		ColorVecI texel_vec[4];
-		int32_t alpha[4];
-		bool alpha_pass[4];
-		if (tex64)
-		{
-			uint64_t t[4];
-#pragma unroll
-			for (int i = 0; i < 4; ++i)
-			{
-				t[i] = 0;
-				if (in[i])
-					t[i] = __ldg(static_cast<const uint64_t*>(tex) + address[i]);
-			}
-#pragma unroll
-			for (int i = 0; i < 4; ++i)
-			{
-				texel_vec[i] = cvi_from_color64(t[i]);
-				alpha[i] = Color64::get_alpha(t[i]);
-				alpha_pass[i] = Color64::test_alpha(t[i]);
-			}
-		}
-		else
-		{
-			uint32_t t[4];
-#pragma unroll
-			for (int i = 0; i < 4; ++i)
-			{
-				t[i] = 0;
-				if (in[i])
-					t[i] = __ldg(static_cast<const uint32_t*>(tex) + address[i]);
-			}
-#pragma unroll
-			for (int i = 0; i < 4; ++i)
-			{
-				texel_vec[i] = cvi_from_color32(t[i]);
-				alpha[i] = Color32::get_alpha(t[i]);
-				alpha_pass[i] = Color32::test_alpha(t[i]);
-			}
-		}
-		ColorVecI lighted[4];
-#pragma unroll
-		for (int i = 0; i < 4; ++i)
-		{
-			const int32_t k = px0 + SQW_PX_OFS(i) - x0;
-			// line_light = from_color_i32x3([l0,l1,l2]) -> lanes [B,G,R,A] = [l2,l1,l0,0]
-			const ColorVecI light = cvi(wadd(l2, wmul(k, dl2)), wadd(l1, wmul(k, dl1)), wadd(l0, wmul(k, dl0)), 0);
-			lighted[i] = cvi_shr<16>(cvi_mul(texel_vec[i], light));
-		}
-		if (blend == SQW_BLEND_NONE)
-		{
-#pragma unroll
-			for (int i = 0; i < 4; ++i)
-			{
-				px[i] = in[i] ? C::from_veci(lighted[i]) : px[i];
-				have |= in[i] ? (1u << i) : 0u;
-			}
-		}
-		else if (blend == SQW_BLEND_ALPHA_TEST)
-		{
-#pragma unroll
-			for (int i = 0; i < 4; ++i)
-			{
-				const bool pass = in[i] && alpha_pass[i];
-				px[i] = pass ? C::from_veci(lighted[i]) : px[i];
-				have |= pass ? (1u << i) : 0u;
-			}
-		}
-		else
-		{
-#pragma unroll
-			for (int i = 0; i < 4; ++i)
-				if (in[i])
-				{
-					SQW_NEED_DST(i)
-					if (blend == SQW_BLEND_AVERAGE)
-						px[i] = C::average(px[i], C::from_veci(lighted[i]));
-					else if (blend == SQW_BLEND_ADDITIVE)
-						px[i] = C::saturated_sum(px[i], C::from_veci(lighted[i]));
-					else
-						px[i] = C::from_veci(cvi_shr<8>(cvi_add(cvi_mul_scalar(C::to_veci(px[i]), 255 - alpha[i]), cvi_mul_scalar(lighted[i], alpha[i]))));
-				}
-		}
-	}
+	// (triangle commands are shaded pair by pair: shade_triangle)
 }
 
 // The finished quad of one row: one 128-bit store per pixel pair, and with TONEMAP the 32-bit picture and colour sums.
@@ -1201,17 +1211,33 @@ __global__ void __launch_bounds__(SQW_RASTER_THREADS, SQW_TILE_CTAS_PER_SM) rast
 				const uint4 ra0 = s_span[0][hh][ra], rb0 = s_span[0][hh][rb];
 				const int32_t ax0 = (int16_t)(ra0.x & 0xFFFF), ax1 = (int16_t)(ra0.x >> 16);
 				const int32_t bx0 = (int16_t)(rb0.x & 0xFFFF), bx1 = (int16_t)(rb0.x >> 16);
-				const bool cov_a = (ax0 < px0 + 2 && ax1 > px0) || (ax0 < px0 + 18 && ax1 > px0 + 16);
-				const bool cov_b = (bx0 < px0 + 2 && bx1 > px0) || (bx0 < px0 + 18 && bx1 > px0 + 16);
-				const uint32_t any_a = __ballot_sync(0xFFFFFFFFu, cov_a), any_b = __ballot_sync(0xFFFFFFFFu, cov_b);
-				if ((any_a | any_b) == 0)
+				// coverage of the lane's left pair (x = px0, px0 + 1) and right pair (x = px0 + 16, px0 + 17) of both rows
+				const bool cov_al = ax0 < px0 + 2 && ax1 > px0, cov_ar = ax0 < px0 + 18 && ax1 > px0 + 16;
+				const bool cov_bl = bx0 < px0 + 2 && bx1 > px0, cov_br = bx0 < px0 + 18 && bx1 > px0 + 16;
+				// one ballot for the four: bit groups of 8 lanes would need four ballots; a packed vote does it in one reduction
+				const uint32_t mine = (cov_al ? 1u : 0u) | (cov_ar ? 2u : 0u) | (cov_bl ? 4u : 0u) | (cov_br ? 8u : 0u);
+				const uint32_t any = __reduce_or_sync(0xFFFFFFFFu, mine);
+				if (any == 0)
 					continue;
 				const uint4 w0 = s_cmd[0][h0 + hh];
 				const uint4 w1 = s_cmd[1][h0 + hh];
 				const void* const tex = reinterpret_cast<const void*>((uint64_t)w1.x | ((uint64_t)w1.y << 32));
-				if (any_a) // (warp-uniform)
+				if ((w0.w & 0xFF) == SQW_CMD_TRIANGLE) // (warp-uniform) small triangles mostly touch one 16-pixel side of the block: shade only that pair
+				{
+					const uint4 ra1 = s_span[1][hh][ra], ra2 = s_span[2][hh][ra], rb1 = s_span[1][hh][rb], rb2 = s_span[2][hh][rb];
+					if (any & 1u)
+						shade_triangle<C, 0, 2>(w0, tex, w1.z, ra0, ra1, ra2, px0, color_buffer + pix_a, px_a, have_a);
+					if (any & 2u)
+						shade_triangle<C, 2, 4>(w0, tex, w1.z, ra0, ra1, ra2, px0, color_buffer + pix_a, px_a, have_a);
+					if (any & 4u)
+						shade_triangle<C, 0, 2>(w0, tex, w1.z, rb0, rb1, rb2, px0, color_buffer + pix_b, px_b, have_b);
+					if (any & 8u)
+						shade_triangle<C, 2, 4>(w0, tex, w1.z, rb0, rb1, rb2, px0, color_buffer + pix_b, px_b, have_b);
+					continue;
+				}
+				if (any & 3u) // (warp-uniform)
 					shade_quad<C>(w0, tex, w1.z, ra0, s_span[1][hh][ra], s_span[2][hh][ra], px0, color_buffer + pix_a, px_a, have_a);
-				if (any_b)
+				if (any & 12u)
 					shade_quad<C>(w0, tex, w1.z, rb0, s_span[1][hh][rb], s_span[2][hh][rb], px0, color_buffer + pix_b, px_b, have_b);
 			}
 			__syncwarp(); // the span stage (and, after the last group, the warp's list) is rewritten next
