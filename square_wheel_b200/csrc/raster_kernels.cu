@@ -894,7 +894,7 @@ __device__ __forceinline__ void shade_quad(
 {
 	typedef typename C::Raw Raw;
 	const int32_t x0 = (int16_t)(r0.x & 0xFFFF), x1 = (int16_t)(r0.x >> 16);
-	const uint32_t kind = w0.w & 0xFF, blend = (w0.w >> 8) & 0xFF, tc_mode = (w0.w >> 16) & 0xFF, tex64 = (w0.w >> 24) & 1;
+	const uint32_t kind = w0.w & 0xFF, blend = (w0.w >> 8) & 0xFF, tc_mode = (w0.w >> 16) & 0xFF;
 
 	if (kind == SQW_CMD_POLYGON)
 	{
