@@ -407,7 +407,10 @@ extern "C" {
 	pub fn sqw_polygons_draw(view: *mut sqw_view, order: *const u32, num_order: u32) -> c_int;
 	pub fn sqw_frame_set_draw_from_polygons(frame: *mut sqw_frame, clear_color: *const c_void) -> c_int;
 	pub fn sqw_upload_map_materials(ctx: *mut sqw_ctx, materials: *const sqw_map_material, num_materials: u32, polygon_basis: *const f32, num_polygons: u32) -> c_int;
-	pub fn sqw_frame_set_surfaces_from_polygons(frame: *mut sqw_frame, cam_pos: *const f32, use_directional_lightmaps: c_int) -> c_int;
+	pub fn sqw_frame_set_surfaces_from_polygons(
+		frame: *mut sqw_frame, cam_pos: *const f32, use_directional_lightmaps: c_int, lights: *const sqw_light, num_lights: u32, clip_set_light_offsets: *const u32,
+		clip_set_lights: *const u16, num_clip_sets: u32, shadow_maps_len: u64,
+	) -> c_int;
 	pub fn sqw_polygons_draw_read(
 		view: *mut sqw_view, cmds: *mut sqw_draw_cmd, cmds_capacity: u32, points: *mut sqw_polygon_point, points_capacity: u32, counts_out: *mut u32,
 	) -> c_int;

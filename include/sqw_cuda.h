@@ -579,9 +579,16 @@ typedef struct sqw_map_material /* 64 bytes */
 int sqw_upload_map_materials(sqw_ctx* ctx, const sqw_map_material* materials, uint32_t num_materials, const float* polygon_basis, uint32_t num_polygons);
 /* The surface half of a recorded frame from the records of the last sqw_polygons_prepare of the frame's view: one sqw_surface_job
  * per visible polygon in candidate order (texture shift, basis vectors at the polygon's mip, lightmap shift / size / scale,
- * emissive layer — partial_renderer.rs:1682-1819 without dynamic lights: the static world) and the band lists of the surface
- * kernel, built on the device.  The host reads the totals back to size the surface pool. */
-int sqw_frame_set_surfaces_from_polygons(sqw_frame* frame, const float cam_pos[3], int use_directional_lightmaps);
+ * emissive layer, and the dynamic lights that reach the polygon — the whole closure of build_polygons_surfaces,
+ * partial_renderer.rs:1682-1819) and the band lists of the surface kernel, built on the device.  Dynamic lights: `lights` as in
+ * sqw_build_surfaces, and for every clip set (= visible leaf) of the prepare call the lights located in that leaf
+ * (DynamicObjectsIndex::get_leaf_objects): clip_set_lights[clip_set_light_offsets[s] .. clip_set_light_offsets[s + 1]) are indices into
+ * lights, tested in that order by polygon_is_affected_by_light (:3877-3985), at most SQW_MAX_POLYGON_LIGHTS kept (:1705-1734).  The
+ * shadow maps live on the device (filled by the frame's shadow map stage); shadow_maps_len is their array's length in floats.
+ * num_lights = 0: the static world.  The host reads the totals back to size the surface pool. */
+int sqw_frame_set_surfaces_from_polygons(
+	sqw_frame* frame, const float cam_pos[3], int use_directional_lightmaps, const sqw_light* lights, uint32_t num_lights, const uint32_t* clip_set_light_offsets,
+	const uint16_t* clip_set_lights, uint32_t num_clip_sets, uint64_t shadow_maps_len);
 /* The draw half of a recorded frame straight from the device lists of the last sqw_polygons_draw of the frame's view: what
  * sqw_frame_set_draw derives on the host from host lists (row and column ranges, span-table offsets, 32-scan-line chunks, ordered
  * per-band command lists) is derived by set-up kernels; the commands and vertices never visit the host, which only reads four

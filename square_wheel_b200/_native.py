@@ -253,7 +253,7 @@ CUDA_SYMBOLS = [
     ("sqw_polygons_draw_read", C.c_int, [_VP, _VP, C.c_uint32, _VP, C.c_uint32, _VP]),
     ("sqw_frame_set_draw_from_polygons", C.c_int, [_VP, _VP]),
     ("sqw_upload_map_materials", C.c_int, [_VP, _VP, C.c_uint32, _VP, C.c_uint32]),
-    ("sqw_frame_set_surfaces_from_polygons", C.c_int, [_VP, _VP, C.c_int]),
+    ("sqw_frame_set_surfaces_from_polygons", C.c_int, [_VP, _VP, C.c_int, _VP, C.c_uint32, _VP, _VP, C.c_uint32, C.c_uint64]),
 ]
 
 _cuda_lib = None

@@ -249,7 +249,64 @@ __global__ void __launch_bounds__(1024) surface_rank_kernel(const sqw_prepared_p
 // get_lightmap_size (common/lightmap.rs:19-27)
 __device__ __forceinline__ uint32_t lightmap_size_of(const int32_t tc_min, const int32_t tc_max) { return (uint32_t)(((tc_max + 15) >> 4) - (tc_min >> 4) + 1); }
 
-// One thread per candidate: the job of a visible polygon (the closure of build_polygons_surfaces without dynamic lights).
+// polygon_is_affected_by_light (partial_renderer.rs:3877-3985), operand order of the host mirror: the light's sphere against the polygon's
+// plane and texture-coordinate rectangle, or, for a projector, the polygon's corners against the five planes of its pyramid.
+__device__ bool polygon_is_affected_by_light(const sqw_map_polygon& polygon, const float* __restrict__ basis, const sqw_light& light)
+{
+	const float bu[3] = {basis[0], basis[1], basis[2]}, bv[3] = {basis[3], basis[4], basis[5]}, bs[3] = {basis[6], basis[7], basis[8]}, bn[3] = {basis[9], basis[10], basis[11]};
+	const float d[3] = {light.position[0] - bs[0], light.position[1] - bs[1], light.position[2] - bs[2]};
+	auto dot3 = [](const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
+	const float signed_distance = dot3(d, bn);
+	if (signed_distance <= 0.0f)
+		return false;
+	const float square_radius_at_plane = light.radius * light.radius - signed_distance * signed_distance;
+	if (square_radius_at_plane <= 0.0f)
+		return false;
+	if (light.shadow_type == SQW_SHADOW_PROJECTOR)
+	{
+		const float tmin0 = (float)polygon.tex_coord_min[0], tmax0 = (float)polygon.tex_coord_max[0], tmin1 = (float)polygon.tex_coord_min[1], tmax1 = (float)polygon.tex_coord_max[1];
+		float vertices[4][3];
+#pragma unroll
+		for (int k = 0; k < 3; ++k)
+		{
+			const float u0 = bu[k] * tmin0, u1 = bu[k] * tmax0, v0 = bv[k] * tmin1, v1 = bv[k] * tmax1;
+			vertices[0][k] = (bs[k] + u0) + v0;
+			vertices[1][k] = (bs[k] + u0) + v1;
+			vertices[2][k] = (bs[k] + u1) + v0;
+			vertices[3][k] = (bs[k] + u1) + v1;
+		}
+		for (int p = 0; p < 5; ++p)
+		{
+			float plane_vec[3];
+#pragma unroll
+			for (int k = 0; k < 3; ++k)
+				plane_vec[k] = p == 0 ? light.basis_z[k] : (p == 1 ? light.basis_z[k] - light.basis_x[k] : (p == 2 ? light.basis_z[k] + light.basis_x[k] : (p == 3 ? light.basis_z[k] - light.basis_y[k] : light.basis_z[k] + light.basis_y[k])));
+			const float dist = dot3(plane_vec, light.position);
+			int vertices_front = 0;
+			for (int v = 0; v < 4; ++v)
+				if (dot3(plane_vec, vertices[v]) >= dist)
+					++vertices_front;
+			if (vertices_front >= 4)
+				return false;
+		}
+		return true;
+	}
+	// texture coordinates of the projection of the light onto the polygon plane: rows of inverse(cols(u, v, n))
+	const float vxn[3] = {bv[1] * bn[2] - bv[2] * bn[1], bv[2] * bn[0] - bv[0] * bn[2], bv[0] * bn[1] - bv[1] * bn[0]};
+	const float nxu[3] = {bn[1] * bu[2] - bn[2] * bu[1], bn[2] * bu[0] - bn[0] * bu[2], bn[0] * bu[1] - bn[1] * bu[0]};
+	const float det = dot3(bu, vxn);
+	if (det == 0.0f || !isfinite(det))
+		return false;
+	const float mat_x[3] = {vxn[0] / det, vxn[1] / det, vxn[2] / det}, mat_y[3] = {nxu[0] / det, nxu[1] / det, nxu[2] / det};
+	const float tc_u = dot3(d, mat_x), tc_v = dot3(d, mat_y);
+	const float radius_at_plane = sqrtf(square_radius_at_plane);
+	const float u_radius = radius_at_plane * (1.0f / sqrtf(dot3(bu, bu)));
+	const float v_radius = radius_at_plane * (1.0f / sqrtf(dot3(bv, bv)));
+	return !(tc_u + u_radius < (float)polygon.tex_coord_min[0] || tc_v + v_radius < (float)polygon.tex_coord_min[1] || tc_u - u_radius > (float)polygon.tex_coord_max[0] ||
+			 tc_v - v_radius > (float)polygon.tex_coord_max[1]);
+}
+
+// One thread per candidate: the job of a visible polygon (the closure of build_polygons_surfaces; dynamic lights when the frame has them).
 __global__ void __launch_bounds__(128) surface_jobs_kernel(const SurfaceSetupLaunch l)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -308,6 +365,21 @@ __global__ void __launch_bounds__(128) surface_jobs_kernel(const SurfaceSetupLau
 		j.lightmap_offset = polygon.lightmap_data_offset;
 		if (l.use_directional)
 			j.flags |= SQW_SURF_DIRECTIONAL_LIGHTMAP;
+		// lights of the polygon's leaf that reach it, at most SQW_MAX_POLYGON_LIGHTS, in list order (partial_renderer.rs:1705-1734)
+		if (l.lights)
+		{
+			const uint32_t set = l.candidates[i].clip_set;
+			for (uint32_t k = l.set_light_offsets[set]; k < l.set_light_offsets[set + 1]; ++k)
+			{
+				const uint32_t light_index = l.set_lights[k];
+				if (polygon_is_affected_by_light(polygon, basis, l.lights[light_index]))
+				{
+					j.lights[j.num_lights++] = (uint16_t)light_index;
+					if (j.num_lights == SQW_MAX_POLYGON_LIGHTS)
+						break;
+				}
+			}
+		}
 		if (j.lightmap_offset != 0)
 			atomicAdd(l.totals + 6, (unsigned long long)j.lightmap_size[0] * j.lightmap_size[1] * (l.use_directional ? 40ull : 12ull));
 	}
@@ -380,64 +452,88 @@ __global__ void __launch_bounds__(128) surface_bands_kernel(const sqw_surface_jo
 		band_rows = surface_band_rows(j, surface_warp_band_texels(totals[1]), warp_bands);
 		n = (j.surface_size[1] + band_rows - 1) / band_rows;
 	}
+	const uint32_t kind = (j.num_lights ? 2u : 0u) + (warp_bands ? 1u : 0u);
 	if (!FILL)
 	{
-		band_counts[2 * i] = warp_bands ? 0u : n;
-		band_counts[2 * i + 1] = warp_bands ? n : 0u;
+#pragma unroll
+		for (uint32_t k = 0; k < 4; ++k)
+			band_counts[4 * i + k] = k == kind ? n : 0u;
 		return;
 	}
-	const uint32_t num_cta_bands = (uint32_t)totals[2];
-	SurfaceBand* o = bands + (warp_bands ? num_cta_bands + band_base[2 * i + 1] : band_base[2 * i]);
+	// the four kinds one after the other: CTA, warp (no dynamic lights), CTA, warp (dynamic lights)
+	const uint32_t kind_base[4] = {0u, (uint32_t)totals[2], (uint32_t)(totals[2] + totals[3]), (uint32_t)(totals[2] + totals[3] + (totals[7] & 0xFFFFFFFFull))};
+	SurfaceBand* o = bands + kind_base[kind] + band_base[4 * i + kind];
 	const uint32_t variant = surface_variant_bits(j);
 	for (uint32_t row0 = 0; row0 < j.surface_size[1]; row0 += band_rows)
 		*o++ = SurfaceBand{i, row0, min(band_rows, j.surface_size[1] - row0), variant};
 }
 
-// exclusive scans of the two band counts of every job (one CTA), totals[2] = CTA bands, totals[3] = warp bands
+// exclusive scans of the four band counts of every job (one CTA): totals[2], [3] = CTA / warp bands without dynamic lights,
+// totals[7] = CTA | warp << 32 with
 __global__ void __launch_bounds__(1024) surface_band_scan_kernel(const uint32_t* __restrict__ band_counts, const uint32_t num_jobs, uint32_t* __restrict__ band_base, unsigned long long* __restrict__ totals)
 {
-	__shared__ unsigned long long s_warp[32];
-	__shared__ unsigned long long s_carry;
+	__shared__ unsigned long long s_warp[2][32];
+	__shared__ unsigned long long s_carry[2];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	if (threadIdx.x == 0)
-		s_carry = 0;
+	if (threadIdx.x < 2)
+		s_carry[threadIdx.x] = 0;
 	__syncthreads();
 	for (uint32_t base = 0; base < num_jobs; base += 1024)
 	{
 		const uint32_t i = base + threadIdx.x;
-		const unsigned long long own = i < num_jobs ? ((unsigned long long)band_counts[2 * i] | ((unsigned long long)band_counts[2 * i + 1] << 32)) : 0ull;
-		unsigned long long incl = own;
+		unsigned long long own[2] = {0ull, 0ull}, incl[2];
+		if (i < num_jobs)
+		{
+			own[0] = (unsigned long long)band_counts[4 * i] | ((unsigned long long)band_counts[4 * i + 1] << 32);
+			own[1] = (unsigned long long)band_counts[4 * i + 2] | ((unsigned long long)band_counts[4 * i + 3] << 32);
+		}
+		incl[0] = own[0];
+		incl[1] = own[1];
 #pragma unroll
 		for (int o = 1; o < 32; o <<= 1)
 		{
-			const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+			const unsigned long long t0 = __shfl_up_sync(0xFFFFFFFFu, incl[0], o), t1 = __shfl_up_sync(0xFFFFFFFFu, incl[1], o);
 			if (lane >= o)
-				incl += t;
+			{
+				incl[0] += t0;
+				incl[1] += t1;
+			}
 		}
 		if (lane == 31)
-			s_warp[warp] = incl;
+		{
+			s_warp[0][warp] = incl[0];
+			s_warp[1][warp] = incl[1];
+		}
 		__syncthreads();
-		unsigned long long before = s_carry, all = 0;
+		unsigned long long before[2] = {s_carry[0], s_carry[1]}, all[2] = {0ull, 0ull};
 		for (int w = 0; w < 32; ++w)
 		{
-			before += w < warp ? s_warp[w] : 0ull;
-			all += s_warp[w];
+			before[0] += w < warp ? s_warp[0][w] : 0ull;
+			before[1] += w < warp ? s_warp[1][w] : 0ull;
+			all[0] += s_warp[0][w];
+			all[1] += s_warp[1][w];
 		}
 		if (i < num_jobs)
 		{
-			const unsigned long long excl = before + incl - own;
-			band_base[2 * i] = (uint32_t)excl;
-			band_base[2 * i + 1] = (uint32_t)(excl >> 32);
+			const unsigned long long e0 = before[0] + incl[0] - own[0], e1 = before[1] + incl[1] - own[1];
+			band_base[4 * i] = (uint32_t)e0;
+			band_base[4 * i + 1] = (uint32_t)(e0 >> 32);
+			band_base[4 * i + 2] = (uint32_t)e1;
+			band_base[4 * i + 3] = (uint32_t)(e1 >> 32);
 		}
 		__syncthreads();
 		if (threadIdx.x == 0)
-			s_carry += all;
+		{
+			s_carry[0] += all[0];
+			s_carry[1] += all[1];
+		}
 		__syncthreads();
 	}
 	if (threadIdx.x == 0)
 	{
-		totals[2] = s_carry & 0xFFFFFFFFull;
-		totals[3] = s_carry >> 32;
+		totals[2] = s_carry[0] & 0xFFFFFFFFull;
+		totals[3] = s_carry[0] >> 32;
+		totals[7] = s_carry[1];
 	}
 }
 

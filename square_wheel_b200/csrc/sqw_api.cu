@@ -449,7 +449,7 @@ struct sqw_frame
 	// sqw_frame_set_draw_from_polygons: the lists live in buffers of the frame, built on the device
 	DevBuf dev_cmds, dev_points, dev_cmd_dev, dev_rows, dev_chunk_base, dev_chunks, dev_band_counts, dev_band_offsets, dev_band_list, dev_totals;
 	// sqw_frame_set_surfaces_from_polygons
-	DevBuf dev_jobs, dev_visible_rank, dev_surf_band_counts, dev_surf_band_base, dev_surf_bands, dev_surf_totals;
+	DevBuf dev_jobs, dev_visible_rank, dev_surf_band_counts, dev_surf_band_base, dev_surf_bands, dev_surf_totals, dev_lights, dev_set_light_offsets, dev_set_lights;
 	uint32_t draw_width = 0, draw_height = 0; // view size the command list was prepared for
 	bool clear = false;
 	uint64_t clear_color = 0;
@@ -935,7 +935,8 @@ void sqw_frame_destroy(sqw_frame* f)
 	f->d_depth_spans.release();
 	f->d_shadow_dev.release();
 	for (DevBuf* b : {&f->dev_cmds, &f->dev_points, &f->dev_cmd_dev, &f->dev_rows, &f->dev_chunk_base, &f->dev_chunks, &f->dev_band_counts, &f->dev_band_offsets, &f->dev_band_list, &f->dev_totals,
-					  &f->dev_jobs, &f->dev_visible_rank, &f->dev_surf_band_counts, &f->dev_surf_band_base, &f->dev_surf_bands, &f->dev_surf_totals})
+					  &f->dev_jobs, &f->dev_visible_rank, &f->dev_surf_band_counts, &f->dev_surf_band_base, &f->dev_surf_bands, &f->dev_surf_totals, &f->dev_lights,
+					  &f->dev_set_light_offsets, &f->dev_set_lights})
 		b->release();
 	if (f->view->immediate == f)
 		f->view->immediate = nullptr;
@@ -1365,9 +1366,11 @@ int sqw_upload_map_materials(sqw_ctx* ctx, const sqw_map_material* materials, ui
 	return SQW_OK;
 }
 
-int sqw_frame_set_surfaces_from_polygons(sqw_frame* f, const float cam_pos[3], int use_directional_lightmaps)
+int sqw_frame_set_surfaces_from_polygons(
+	sqw_frame* f, const float cam_pos[3], int use_directional_lightmaps, const sqw_light* lights, uint32_t num_lights, const uint32_t* clip_set_light_offsets,
+	const uint16_t* clip_set_lights, uint32_t num_clip_sets, uint64_t shadow_maps_len)
 {
-	if (!f || !cam_pos)
+	if (!f || !cam_pos || (num_lights && (!lights || !clip_set_light_offsets)))
 		return SQW_ERR_INVALID_ARGUMENT;
 	sqw_view* view = f->view;
 	sqw_ctx* ctx = view->ctx;
@@ -1375,19 +1378,56 @@ int sqw_frame_set_surfaces_from_polygons(sqw_frame* f, const float cam_pos[3], i
 		return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_frame_set_surfaces_from_polygons: needs sqw_upload_map_materials and a sqw_polygons_prepare on this view");
 	if (use_directional_lightmaps ? !ctx->d_directional_lightmaps : !ctx->d_lightmaps)
 		return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_frame_set_surfaces_from_polygons: lightmap kind not uploaded");
+	uint32_t num_set_lights = 0;
+	if (num_lights)
+	{
+		// the same checks as sqw_frame_set_surfaces: shadow maps inside the frame's array, light indices in range
+		for (uint32_t l = 0; l < num_lights; ++l)
+		{
+			const sqw_light& li = lights[l];
+			if (li.shadow_type == SQW_SHADOW_NONE)
+				continue;
+			if (li.shadow_type != SQW_SHADOW_CUBE && li.shadow_type != SQW_SHADOW_PROJECTOR)
+				return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_frame_set_surfaces_from_polygons: unknown shadow type");
+			const uint64_t sides = li.shadow_type == SQW_SHADOW_CUBE ? 6 : 1;
+			if (li.shadow_map_size == 0 || (uint64_t)li.shadow_map_offset + sides * (uint64_t)li.shadow_map_size * li.shadow_map_size > shadow_maps_len)
+				return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_frame_set_surfaces_from_polygons: a light's shadow map lies outside the shadow map array");
+		}
+		for (uint32_t i = 0; i < num_clip_sets; ++i)
+			if (clip_set_light_offsets[i] > clip_set_light_offsets[i + 1])
+				return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_frame_set_surfaces_from_polygons: light list offsets must not decrease");
+		num_set_lights = clip_set_light_offsets[num_clip_sets];
+		if (num_set_lights && !clip_set_lights)
+			return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_frame_set_surfaces_from_polygons: null light list");
+		for (uint32_t i = 0; i < num_set_lights; ++i)
+			if (clip_set_lights[i] >= num_lights)
+				return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_frame_set_surfaces_from_polygons: light index out of range");
+	}
 	SQW_CUDA(ctx, cudaSetDevice(ctx->device));
 	cudaStream_t s = view->stream;
 	const size_t C = (size_t)view->color_bits / 8;
 	const uint32_t n = view->polygon_num_candidates;
-	const size_t need1[5] = {(size_t)n * sizeof(sqw_surface_job) + 16, (size_t)n * 4 + 16, (size_t)n * 8 + 16, (size_t)n * 8 + 16, 64};
-	DevBuf* bufs1[5] = {&f->dev_jobs, &f->dev_visible_rank, &f->dev_surf_band_counts, &f->dev_surf_band_base, &f->dev_surf_totals};
-	bool grow = false;
-	for (int i = 0; i < 5; ++i)
+	// (a queued submission of this frame may still read the old buffers: growing any of them waits for the stream first)
+	const size_t need1[8] = {(size_t)n * sizeof(sqw_surface_job) + 16, (size_t)n * 4 + 16, (size_t)n * 16 + 16, (size_t)n * 16 + 16, 64, (size_t)num_lights * sizeof(sqw_light) + 16,
+							 (size_t)(num_clip_sets + 1) * 4 + 16, (size_t)num_set_lights * 2 + 16};
+	DevBuf* bufs1[8] = {&f->dev_jobs, &f->dev_visible_rank, &f->dev_surf_band_counts, &f->dev_surf_band_base, &f->dev_surf_totals, &f->dev_lights, &f->dev_set_light_offsets, &f->dev_set_lights};
+	const size_t b_sm = (size_t)shadow_maps_len * sizeof(float);
+	bool grow = num_lights && b_sm + 16 > f->d_shadow_dev.capacity;
+	for (int i = 0; i < 8; ++i)
 		grow |= need1[i] > bufs1[i]->capacity;
 	if (grow)
-		SQW_CUDA(ctx, cudaStreamSynchronize(s)); // a queued submission of this frame may still read the old buffers
-	for (int i = 0; i < 5; ++i)
+		SQW_CUDA(ctx, cudaStreamSynchronize(s));
+	for (int i = 0; i < 8; ++i)
 		SQW_CUDA(ctx, bufs1[i]->reserve(need1[i]));
+	if (num_lights && b_sm)
+		SQW_CUDA(ctx, f->d_shadow_dev.reserve(b_sm + 16));
+	if (num_lights)
+	{
+		SQW_CUDA(ctx, cudaMemcpyAsync(f->dev_lights.ptr, lights, (size_t)num_lights * sizeof(sqw_light), cudaMemcpyHostToDevice, s));
+		SQW_CUDA(ctx, cudaMemcpyAsync(f->dev_set_light_offsets.ptr, clip_set_light_offsets, (size_t)(num_clip_sets + 1) * 4, cudaMemcpyHostToDevice, s));
+		if (num_set_lights)
+			SQW_CUDA(ctx, cudaMemcpyAsync(f->dev_set_lights.ptr, clip_set_lights, (size_t)num_set_lights * 2, cudaMemcpyHostToDevice, s));
+	}
 	sqw::SurfaceSetupLaunch l{};
 	l.polygons = ctx->d_map_polygons;
 	l.materials = ctx->d_map_materials;
@@ -1396,6 +1436,10 @@ int sqw_frame_set_surfaces_from_polygons(sqw_frame* f, const float cam_pos[3], i
 	l.prepared = static_cast<const sqw_prepared_polygon*>(view->polygon_results.ptr);
 	l.num_candidates = n;
 	l.use_directional = use_directional_lightmaps ? 1u : 0u;
+	l.lights = num_lights ? static_cast<const sqw_light*>(f->dev_lights.ptr) : nullptr;
+	l.num_lights = num_lights;
+	l.set_light_offsets = static_cast<const uint32_t*>(f->dev_set_light_offsets.ptr);
+	l.set_lights = static_cast<const uint16_t*>(f->dev_set_lights.ptr);
 	l.visible_rank = static_cast<uint32_t*>(f->dev_visible_rank.ptr);
 	l.jobs = static_cast<sqw_surface_job*>(f->dev_jobs.ptr);
 	l.band_counts = static_cast<uint32_t*>(f->dev_surf_band_counts.ptr);
@@ -1403,17 +1447,17 @@ int sqw_frame_set_surfaces_from_polygons(sqw_frame* f, const float cam_pos[3], i
 	l.totals = static_cast<unsigned long long*>(f->dev_surf_totals.ptr);
 	SQW_CUDA(ctx, sqw::launch_surface_setup_phase1(l, s));
 	unsigned long long totals[8] = {};
-	// jobs exist for the visible polygons only, but their number is at most n: count the bands of all n slots' worth by the device count
 	SQW_CUDA(ctx, cudaMemcpyAsync(totals, f->dev_surf_totals.ptr, sizeof(totals), cudaMemcpyDeviceToHost, s));
-	SQW_CUDA(ctx, cudaStreamSynchronize(s));
+	SQW_CUDA(ctx, cudaStreamSynchronize(s)); // (also: the caller's light lists have left pageable memory)
 	const uint32_t num_jobs = (uint32_t)totals[0];
 	SQW_CUDA(ctx, sqw::launch_surface_bands_count(l, num_jobs, s));
 	SQW_CUDA(ctx, cudaMemcpyAsync(totals, f->dev_surf_totals.ptr, sizeof(totals), cudaMemcpyDeviceToHost, s));
 	sqw::PolygonsTotalsDev pt{};
 	SQW_CUDA(ctx, cudaMemcpyAsync(&pt, view->polygon_totals.ptr, sizeof(pt), cudaMemcpyDeviceToHost, s));
 	SQW_CUDA(ctx, cudaStreamSynchronize(s));
-	const uint32_t num_cta_bands = (uint32_t)totals[2], num_warp_bands = (uint32_t)totals[3];
-	SQW_CUDA(ctx, f->dev_surf_bands.reserve((size_t)(num_cta_bands + num_warp_bands) * sizeof(SurfaceBand) + 16));
+	const uint32_t kinds[4] = {(uint32_t)totals[2], (uint32_t)totals[3], (uint32_t)(totals[7] & 0xFFFFFFFFull), (uint32_t)(totals[7] >> 32)};
+	const uint32_t num_bands = kinds[0] + kinds[1] + kinds[2] + kinds[3];
+	SQW_CUDA(ctx, f->dev_surf_bands.reserve((size_t)num_bands * sizeof(SurfaceBand) + 16));
 	l.bands = static_cast<SurfaceBand*>(f->dev_surf_bands.ptr);
 	SQW_CUDA(ctx, sqw::launch_surface_setup_phase2(l, num_jobs, s));
 	const uint64_t total_surface_pixels = pt.num_surfaces_pixels;
@@ -1424,20 +1468,22 @@ int sqw_frame_set_surfaces_from_polygons(sqw_frame* f, const float cam_pos[3], i
 	}
 	f->d_jobs = static_cast<const sqw_surface_job*>(f->dev_jobs.ptr);
 	f->d_bands = static_cast<const SurfaceBand*>(f->dev_surf_bands.ptr);
-	f->d_lights = nullptr;
-	f->d_shadow_maps = nullptr;
-	f->d_shadow_maps_rw = nullptr;
-	f->shadow_maps_len = 0;
+	f->d_lights = num_lights ? static_cast<const sqw_light*>(f->dev_lights.ptr) : nullptr;
+	// the shadow map array lives on the device only: filled by the frame's shadow map stage (sqw_frame_set_shadow_map_draw)
+	f->d_shadow_maps_rw = (num_lights && b_sm) ? static_cast<float*>(f->d_shadow_dev.ptr) : nullptr;
+	f->d_shadow_maps = f->d_shadow_maps_rw;
+	f->shadow_maps_len = num_lights ? shadow_maps_len : 0;
 	f->groups.clear();
-	if (num_cta_bands + num_warp_bands)
-	{
-		SurfaceGroup g{};
-		g.dynamic_lights = false;
-		g.num_cta_bands = num_cta_bands;
-		g.band_offset = 0;
-		g.num_bands = num_cta_bands + num_warp_bands;
-		f->groups.push_back(g);
-	}
+	for (uint32_t key = 0; key < 2; ++key)
+		if (kinds[2 * key] + kinds[2 * key + 1])
+		{
+			SurfaceGroup g{};
+			g.dynamic_lights = key == 1;
+			g.num_cta_bands = kinds[2 * key];
+			g.band_offset = key == 0 ? 0u : kinds[0] + kinds[1];
+			g.num_bands = kinds[2 * key] + kinds[2 * key + 1];
+			f->groups.push_back(g);
+		}
 	f->stats.surface_texels = totals[4];
 	f->stats.emissive_texels = totals[5];
 	f->stats.lightmap_bytes = totals[6];

@@ -215,12 +215,16 @@ struct SurfaceSetupLaunch
 	const sqw_prepared_polygon* prepared;    // device
 	uint32_t num_candidates;
 	uint32_t use_directional;
+	const sqw_light* lights;             // device, or NULL: static world only
+	uint32_t num_lights;
+	const uint32_t* set_light_offsets;   // device [num clip sets + 1]: the lights of every clip set's leaf ...
+	const uint16_t* set_lights;          // ... as indices into lights
 	uint32_t* visible_rank;  // scratch [num_candidates]
 	sqw_surface_job* jobs;   // out [num visible]
-	uint32_t* band_counts;   // scratch [num_candidates][2]: CTA bands, warp bands of the job
-	uint32_t* band_base;     // scratch [num_candidates][2]
-	SurfaceBand* bands;      // phase 2 out: CTA bands first, then warp bands
-	unsigned long long* totals; // [8]: visible, small texels, CTA bands, warp bands, surface texels, emissive texels, lightmap bytes, -
+	uint32_t* band_counts;   // scratch [num_candidates][4]: CTA / warp bands of a job without dynamic lights, CTA / warp bands of a job with
+	uint32_t* band_base;     // scratch [num_candidates][4]
+	SurfaceBand* bands;      // phase 2 out: the four kinds one after the other
+	unsigned long long* totals; // [8]: visible, small texels, CTA bands, warp bands (no lights), surface texels, emissive texels, lightmap bytes, CTA | warp << 32 (with lights)
 };
 cudaError_t launch_surface_setup_phase1(const SurfaceSetupLaunch& l, cudaStream_t stream);
 cudaError_t launch_surface_bands_count(const SurfaceSetupLaunch& l, uint32_t num_jobs, cudaStream_t stream);

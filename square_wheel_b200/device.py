@@ -334,10 +334,18 @@ class Frame:
         )
         self.h2d_bytes += cmds.nbytes + pp.nbytes + tp.nbytes
 
-    def set_surfaces_from_polygons(self, cam_pos, use_directional_lightmaps: bool = True):
-        """The surface half of the frame from the records of the view's last polygons_prepare (sqw_frame_set_surfaces_from_polygons)."""
+    def set_surfaces_from_polygons(self, cam_pos, use_directional_lightmaps: bool = True, lights=None, clip_set_light_offsets=None, clip_set_lights=None, shadow_maps_len: int = 0):
+        """The surface half of the frame from the records of the view's last polygons_prepare (sqw_frame_set_surfaces_from_polygons);
+        lights + the per-clip-set light lists select the dynamic lights of every polygon on the device."""
         cam = np.ascontiguousarray(cam_pos, np.float32)
-        self.view.ctx._check(self._lib.sqw_frame_set_surfaces_from_polygons(self._handle, N.ptr(cam), 1 if use_directional_lightmaps else 0), "sqw_frame_set_surfaces_from_polygons")
+        li = _as(lights, N.light_dtype) if lights is not None and len(lights) else None
+        off = np.ascontiguousarray(clip_set_light_offsets, np.uint32) if li is not None else None
+        lst = np.ascontiguousarray(clip_set_lights, np.uint16) if li is not None else None
+        self.view.ctx._check(
+            self._lib.sqw_frame_set_surfaces_from_polygons(
+                self._handle, N.ptr(cam), 1 if use_directional_lightmaps else 0, N.ptr(li), len(li) if li is not None else 0, N.ptr(off), N.ptr(lst),
+                (len(off) - 1) if off is not None else 0, shadow_maps_len if li is not None else 0),
+            "sqw_frame_set_surfaces_from_polygons")
 
     def set_draw_from_polygons(self, clear_color: Optional[int] = None):
         """The draw half of the frame from the device lists of the view's last polygons_draw (sqw_frame_set_draw_from_polygons)."""

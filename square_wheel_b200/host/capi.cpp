@@ -564,6 +564,23 @@ uint32_t sqwh_scene_map_materials(const Scene* s, void* out, uint32_t capacity)
 }
 // PolygonBasisVecs of every map polygon for mip 0: [num_polygons][12] floats {u, v, start, normal}
 uint32_t sqwh_renderer_polygon_basis(const Renderer* r, float* out, uint32_t capacity) { return r->export_polygon_basis(out, capacity); }
+// the lights located in the leaf of every clip set of the last prepare_frame: offsets [sets + 1] (u32) and light indices (u16); NULL buffers: counts only
+uint32_t sqwh_renderer_clip_set_lights(const Renderer* r, uint32_t* offsets, uint16_t* list, uint32_t counts_out[2])
+{
+	std::vector<uint32_t> off;
+	std::vector<uint16_t> li;
+	r->export_clip_set_lights(off, li);
+	if (counts_out)
+	{
+		counts_out[0] = (uint32_t)off.size();
+		counts_out[1] = (uint32_t)li.size();
+	}
+	if (offsets)
+		std::memcpy(offsets, off.data(), off.size() * 4);
+	if (list && !li.empty())
+		std::memcpy(list, li.data(), li.size() * 2);
+	return (uint32_t)off.size();
+}
 // per-material SQW_MATERIAL_* flags for sqw_upload_map_geometry
 uint32_t sqwh_scene_material_flags(const Scene* s, uint8_t* out, uint32_t capacity)
 {

@@ -983,6 +983,7 @@ void Renderer::prepare_polygons_surfaces() // partial_renderer.rs:1327-1449 (lea
 	current_frame_visible_polygons_.clear();
 	polygon_candidates_.clear();
 	polygon_clip_planes_.clear();
+	polygon_clip_set_leafs_.clear();
 	polygon_is_sky_candidate_.clear();
 	num_visible_surfaces_pixels_ = 0;
 	has_current_sky_ = false; // :1336
@@ -996,6 +997,7 @@ void Renderer::prepare_polygons_surfaces() // partial_renderer.rs:1327-1449 (lea
 		Vec3f clip_planes[8];
 		bounds.get_clip_planes(clip_planes);
 		const uint32_t clip_set = (uint32_t)(polygon_clip_planes_.size() / 8);
+		polygon_clip_set_leafs_.push_back((uint32_t)i);
 		polygon_clip_planes_.insert(polygon_clip_planes_.end(), clip_planes, clip_planes + 8);
 		for (uint32_t p = leaf.first_polygon; p < leaf.first_polygon + leaf.num_polygons; ++p)
 		{

@@ -224,7 +224,19 @@ public:
 	};
 	const std::vector<PolygonCandidate>& polygon_candidates() const { return polygon_candidates_; }
 	const std::vector<Vec3f>& polygon_clip_planes() const { return polygon_clip_planes_; }
-	const std::vector<uint32_t>& polygon_draw_order() const { return polygon_draw_order_; } // leaf polygons in the order draw_leaf drew them (last draw_frame)
+	const std::vector<uint32_t>& polygon_draw_order() const { return polygon_draw_order_; }
+	// lights located in the leaf of every clip set (leaf_lights_), concatenated: offsets [sets + 1], indices into lights()
+	void export_clip_set_lights(std::vector<uint32_t>& offsets, std::vector<uint16_t>& list) const
+	{
+		offsets.assign(1, 0u);
+		list.clear();
+		for (uint32_t leaf : polygon_clip_set_leafs_)
+		{
+			for (uint32_t l : leaf_lights_[leaf])
+				list.push_back((uint16_t)l);
+			offsets.push_back((uint32_t)list.size());
+		}
+	} // leaf polygons in the order draw_leaf drew them (last draw_frame)
 	void export_prepared_polygons(PreparedPolygonExport* out, PolygonsFrameExport* frame) const;
 	uint32_t export_polygon_basis(float* out, uint32_t capacity) const
 	{
@@ -392,6 +404,7 @@ private:
 	double polygons_prepare_seconds_ = 0.0;
 	std::vector<PolygonCandidate> polygon_candidates_;
 	std::vector<uint32_t> polygon_draw_order_;
+	std::vector<uint32_t> polygon_clip_set_leafs_; // leaf of every clip set
 	std::vector<Vec3f> polygon_clip_planes_;
 	std::vector<uint8_t> polygon_is_sky_candidate_; // per candidate: the polygon reached the sky branch of prepare_polygon_surface
 	std::vector<Vec3f> vertices_transformed_;

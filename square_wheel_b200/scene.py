@@ -251,6 +251,8 @@ def lib() -> C.CDLL:
         l.sqwh_scene_map_materials.argtypes = [vp, vp, C.c_uint32]
         l.sqwh_renderer_polygon_basis.restype = C.c_uint32
         l.sqwh_renderer_polygon_basis.argtypes = [vp, vp, C.c_uint32]
+        l.sqwh_renderer_clip_set_lights.restype = C.c_uint32
+        l.sqwh_renderer_clip_set_lights.argtypes = [vp, vp, vp, vp]
         l.sqwh_renderer_polygon_draw_order.restype = C.c_uint32
         l.sqwh_renderer_polygon_draw_order.argtypes = [vp, vp, C.c_uint32]
         l.sqwh_renderer_prepared_polygons.restype = C.c_int
@@ -541,6 +543,15 @@ class HostRenderer:
         out = np.zeros((n, 12), np.float32)
         self._lib.sqwh_renderer_polygon_basis(self._handle, out.ctypes.data_as(C.c_void_p), n)
         return out
+
+    def clip_set_lights(self):
+        """(offsets [sets + 1] uint32, light indices uint16): the dynamic lights located in the leaf of every clip set of the last build_frame."""
+        counts = np.zeros(2, np.uint32)
+        self._lib.sqwh_renderer_clip_set_lights(self._handle, None, None, counts.ctypes.data_as(C.c_void_p))
+        off = np.zeros(int(counts[0]), np.uint32)
+        lst = np.zeros(max(int(counts[1]), 1), np.uint16)
+        self._lib.sqwh_renderer_clip_set_lights(self._handle, off.ctypes.data_as(C.c_void_p), lst.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p))
+        return off, lst[: int(counts[1])]
 
     def polygon_draw_order(self) -> np.ndarray:
         """Map polygon indices of the leaf polygons the last build_frame drew, in draw order (draw_tree / draw_leaf)."""

@@ -187,3 +187,60 @@ def test_frame_drawn_from_device_command_lists(material_mode, size):
         hr.close()
         ctx.close()
         sc.close()
+
+
+def test_lit_frame_with_device_side_light_selection():
+    """Dynamic lights on the device chain: the per-polygon light lists (polygon_is_affected_by_light, partial_renderer.rs:3877-3985: sphere
+    against the polygon's plane and texture-coordinate rectangle; projector pyramid against its corners; at most six per polygon, in the
+    order of the leaf's list) are selected by the job kernel from the lights of every visible leaf.  Shadow maps are rendered on the GPU
+    from the host's fill list as in every lit frame.  Picture and light counts must equal the host-recorded frame's."""
+    from square_wheel_b200.device import make_post_params
+    from test_frames_gpu import _lights_along_path
+
+    W, H = 1280, 720
+    sc = S.Scene(seed=7, texture_size_log2=6, num_materials=8)
+    ctx = Context(sc.lightmaps, sc.directional_lightmaps, device=0)
+    hr = S.HostRenderer(sc)
+    try:
+        sc.upload(ctx)
+        ctx.upload_map_geometry(*sc.map_geometry())
+        ctx.upload_map_materials(sc.map_materials(), hr.polygon_basis())
+        view = ctx.create_view(W, H, 64)
+        post = make_post_params(exposure=1.0, bloom_sigma=0.0)
+        path = sc.camera_path(64)
+        lit = 0
+        for k in (4, 30, 52):
+            lights = _lights_along_path(path, 9, 40 + k)
+            lights["position"] = path[k][:3] + np.random.default_rng(k).uniform(-120.0, 120.0, (9, 3)) * (1.0, 1.0, 0.3)
+            hf = hr.build_frame(W, H, path[k], lights=lights)
+            assert len(hf.lights) == 9 and (hf.jobs["num_lights"] > 0).sum() > 5
+            lit += int((hf.jobs["num_lights"] > 0).sum())
+            clear = S.BACKGROUND_COLOR64 if hf.needs_clear else None
+            frame = view.create_frame()
+            hf.record(frame, clear_color=clear, post=post)
+            view.write_pixels(np.zeros((H, W), np.uint64))
+            frame.submit(N.STAGE_ALL)
+            want_hdr, want_ldr = view.read_pixels(), view.read_pixels32()
+            frame.close()
+            cand, planes, want, fr = hr.prepared_polygons()
+            view.polygons_prepare(fr["planes_matrix"], fr["view_matrix"], float(fr["mip_bias"]), cand, planes)
+            index_of = {int(p): i for i, p in enumerate(cand["polygon"])}
+            view.polygons_draw(np.array([index_of[int(p)] for p in hr.polygon_draw_order()], np.uint32))
+            offsets, indices = hr.clip_set_lights()
+            assert len(offsets) == len(planes) + 1
+            frame = view.create_frame()
+            frame.set_surfaces_from_polygons(hf.cam_pos, True, lights=hf.lights, clip_set_light_offsets=offsets, clip_set_lights=indices, shadow_maps_len=hf.shadow_maps_len)
+            frame.set_shadow_map_draw(hf.depth_maps, hf.depth_cmds, hf.depth_points)
+            frame.set_draw_from_polygons(clear_color=clear)
+            frame.set_post(post)
+            view.write_pixels(np.zeros((H, W), np.uint64))
+            frame.submit(N.STAGE_ALL)
+            got_hdr, got_ldr = view.read_pixels(), view.read_pixels32()
+            frame.close()
+            assert np.array_equal(got_hdr, want_hdr), f"pose {k}: 64-bit picture differs in {int((got_hdr != want_hdr).sum())} pixels"
+            assert np.array_equal(got_ldr, want_ldr), f"pose {k}: tonemapped picture"
+        assert lit > 40
+    finally:
+        hr.close()
+        ctx.close()
+        sc.close()
