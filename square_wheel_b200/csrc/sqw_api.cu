@@ -387,7 +387,7 @@ struct sqw_view
 	uint64_t readback_bytes_total = 0, readback_pictures = 0; // completed compressed read-backs of this view
 	// inputs and results of sqw_polygons_prepare
 	DevBuf polygon_candidates, polygon_clip_planes, polygon_results, polygon_totals;
-	uint32_t polygon_num_candidates = 0;
+	uint32_t polygon_num_candidates = 0, polygon_num_clip_sets = 0;
 	sqw_polygons_frame polygons_frame{};
 	// scratch and results of sqw_polygons_draw
 	DevBuf polygon_order, polygon_draw_scratch_cmds, polygon_draw_scratch_points, polygon_draw_offsets, polygon_draw_cmds, polygon_draw_points, polygon_draw_totals;
@@ -1381,6 +1381,8 @@ int sqw_frame_set_surfaces_from_polygons(
 	uint32_t num_set_lights = 0;
 	if (num_lights)
 	{
+		if (num_clip_sets != view->polygon_num_clip_sets)
+			return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_frame_set_surfaces_from_polygons: one light list per clip set of the last sqw_polygons_prepare is needed");
 		// the same checks as sqw_frame_set_surfaces: shadow maps inside the frame's array, light indices in range
 		for (uint32_t l = 0; l < num_lights; ++l)
 		{
@@ -2191,6 +2193,7 @@ int sqw_polygons_prepare(sqw_view* view, const sqw_polygons_frame* frame, const 
 			SQW_CUDA(ctx, bufs[i]->reserve(need[i]));
 		}
 	view->polygon_num_candidates = num_candidates;
+	view->polygon_num_clip_sets = num_clip_sets;
 	view->polygons_frame = *frame;
 	view->polygon_num_order = 0;
 	if (num_candidates)

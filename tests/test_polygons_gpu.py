@@ -229,6 +229,8 @@ def test_lit_frame_with_device_side_light_selection():
             offsets, indices = hr.clip_set_lights()
             assert len(offsets) == len(planes) + 1
             frame = view.create_frame()
+            with pytest.raises(SqwError):  # one light list per clip set
+                frame.set_surfaces_from_polygons(hf.cam_pos, True, lights=hf.lights, clip_set_light_offsets=offsets[:-1], clip_set_lights=indices, shadow_maps_len=hf.shadow_maps_len)
             frame.set_surfaces_from_polygons(hf.cam_pos, True, lights=hf.lights, clip_set_light_offsets=offsets, clip_set_lights=indices, shadow_maps_len=hf.shadow_maps_len)
             frame.set_shadow_map_draw(hf.depth_maps, hf.depth_cmds, hf.depth_points)
             frame.set_draw_from_polygons(clear_color=clear)
