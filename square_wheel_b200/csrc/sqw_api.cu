@@ -392,6 +392,7 @@ struct sqw_view
 	// scratch and results of sqw_polygons_draw
 	DevBuf polygon_order, polygon_draw_scratch_cmds, polygon_draw_scratch_points, polygon_draw_offsets, polygon_draw_cmds, polygon_draw_points, polygon_draw_totals;
 	uint32_t polygon_num_order = 0;
+	bool polygon_draw_valid = false; // the draw lists belong to the records of the last sqw_polygons_prepare
 };
 
 struct SurfaceGroup // one kernel launch: all bands without / with dynamic lights, CTA bands first, then warp bands
@@ -1503,8 +1504,8 @@ int sqw_frame_set_draw_from_polygons(sqw_frame* f, const void* clear_color)
 		return SQW_ERR_INVALID_ARGUMENT;
 	sqw_view* view = f->view;
 	sqw_ctx* ctx = view->ctx;
-	if (!view->polygon_draw_totals.ptr)
-		return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_frame_set_draw_from_polygons: no sqw_polygons_draw on this view yet");
+	if (!view->polygon_draw_totals.ptr || !view->polygon_draw_valid)
+		return fail(ctx, SQW_ERR_INVALID_ARGUMENT, "sqw_frame_set_draw_from_polygons: no sqw_polygons_draw on this view since its last sqw_polygons_prepare");
 	SQW_CUDA(ctx, cudaSetDevice(ctx->device));
 	cudaStream_t s = view->stream;
 	const int32_t W = (int32_t)view->width, H = (int32_t)view->height;
@@ -2196,6 +2197,7 @@ int sqw_polygons_prepare(sqw_view* view, const sqw_polygons_frame* frame, const 
 	view->polygon_num_clip_sets = num_clip_sets;
 	view->polygons_frame = *frame;
 	view->polygon_num_order = 0;
+	view->polygon_draw_valid = false;
 	if (num_candidates)
 	{
 		SQW_CUDA(ctx, cudaMemcpyAsync(view->polygon_candidates.ptr, candidates, (size_t)num_candidates * sizeof(sqw_polygon_candidate), cudaMemcpyHostToDevice, s));
@@ -2306,6 +2308,7 @@ int sqw_polygons_draw(sqw_view* view, const uint32_t* order, uint32_t num_order)
 		SQW_CUDA(ctx, sqw::launch_polygons_draw(l, s));
 	}
 	SQW_CUDA(ctx, cudaStreamSynchronize(s)); // `order` is the caller's pageable memory
+	view->polygon_draw_valid = true;
 	return SQW_OK;
 }
 

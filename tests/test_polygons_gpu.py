@@ -153,6 +153,10 @@ def test_frame_drawn_from_device_command_lists(material_mode, size):
             # the same frame with the draw half built on the device
             cand, planes, want, fr = hr.prepared_polygons()
             view.polygons_prepare(fr["planes_matrix"], fr["view_matrix"], float(fr["mip_bias"]), cand, planes)
+            frame = view.create_frame()
+            with pytest.raises(SqwError):  # the draw lists of an earlier prepare are not this frame's
+                frame.set_draw_from_polygons(clear_color=clear)
+            frame.close()
             index_of = {int(p): i for i, p in enumerate(cand["polygon"])}
             view.polygons_draw(np.array([index_of[int(p)] for p in hr.polygon_draw_order()], np.uint32))
             frame = view.create_frame()
