@@ -2,6 +2,7 @@
 // This library contains NO pixel work: it plays the part of the reference's Rust host around the C-ABI seams
 // (scene description, visibility, surface preparation, BSP traversal).
 #include "renderer.hpp"
+#include "map_compiler.hpp"
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -745,6 +746,77 @@ int64_t sqwh_scene_model_copy(const Scene* s, uint32_t index, uint32_t mesh_inde
 	if (out && bytes <= capacity && bytes)
 		std::memcpy(out, src, bytes);
 	return (int64_t)bytes;
+}
+
+// ---- offline map tools (map_compiler.cpp, lightmapper.cpp; the reference's map_compiler / lightmapper binaries) -----------------
+// materials_table: the text form of the reference's materials/*.json that mapc::parse_material_table reads.
+// flags: bit 0 --perform-csg, bit 1 --perform-advanced-splitter-plane-selection.  stats_out: 11 x u32 (mapc::CompileStats).
+// Returns 0, 1 (i/o error writing the map) or 5 (the map text does not parse / holds no entity); the tool's messages go to log.
+int sqwh_map_compile(const char* map_text, const char* materials_table, uint32_t flags, const char* out_path, uint32_t* stats_out, char* log, uint32_t log_capacity)
+{
+	mapc::CompileOptions opt;
+	opt.perform_csg = (flags & 1u) != 0;
+	opt.advanced_splitter_plane_selection = (flags & 2u) != 0;
+	const mapc::MaterialTable table = mapc::parse_material_table(materials_table ? materials_table : "");
+	BSPMap map;
+	mapc::CompileStats st;
+	std::string messages;
+	const bool ok = mapc::compile_map(map_text ? map_text : "", table, opt, map, st, messages);
+	if (log && log_capacity)
+	{
+		const size_t n = std::min<size_t>(messages.size(), log_capacity - 1);
+		std::memcpy(log, messages.data(), n);
+		log[n] = 0;
+	}
+	if (stats_out)
+	{
+		const uint32_t v[11] = {st.initial_polygons, st.polygons_after_csg, st.leafs_initial, st.leafs_removed, st.tree_depth, st.nodes, st.leafs, st.polygons, st.portals, st.submodels, st.lightmap_texels};
+		std::memcpy(stats_out, v, sizeof(v));
+	}
+	if (!ok)
+		return 5;
+	return (int)save_map(map, out_path);
+}
+
+// lightmapper -i in_path -o out_path --sample-grid-size .. --light-scale .. --ambient-light .. [--no-directional-lightmap]
+// (direct light only: lightmapper.cpp).  stats_out: 4 x u32 (mapc::LightmapStats).  Returns a MapFileResult.
+int sqwh_map_light(const char* in_path, const char* materials_table, uint32_t sample_grid_size, float light_scale, float ambient_light, int32_t directional, float light_cutoff, const char* out_path, uint32_t* stats_out)
+{
+	BSPMap map;
+	const MapFileResult r = load_map(in_path, map);
+	if (r != MAP_FILE_OK)
+		return (int)r;
+	const mapc::MaterialTable table = mapc::parse_material_table(materials_table ? materials_table : "");
+	mapc::LightmappingSettings settings;
+	settings.sample_grid_size = sample_grid_size;
+	settings.light_scale = light_scale;
+	settings.ambient_light = ambient_light;
+	settings.build_directional_lightmap = directional != 0;
+	if (light_cutoff > 0.0f)
+		settings.light_cutoff = light_cutoff;
+	mapc::LightmapStats st;
+	mapc::build_lightmaps(settings, table, map, st);
+	if (stats_out)
+	{
+		const uint32_t v[4] = {st.point_lights, st.sun_lights, st.lightmap_texels, st.light_grid_samples};
+		std::memcpy(stats_out, v, sizeof(v));
+	}
+	return (int)save_map(map, out_path);
+}
+
+// Replace the scene by a compiled map with materials bound by texture name (bind_compiled_map).  Returns a MapFileResult, or 4
+// when the map fails validate_map (message in sqwh_last_map_error).  No Renderer may exist for the scene meanwhile.
+int sqwh_scene_load_compiled_map(Scene* s, const char* path, const char* materials_table, uint32_t texture_size_log2, uint32_t seed)
+{
+	BSPMap map;
+	const MapFileResult r = load_map(path, map);
+	if (r != MAP_FILE_OK)
+		return (int)r;
+	g_last_map_error = validate_map(map, map.textures.size());
+	if (!g_last_map_error.empty())
+		return 4;
+	bind_compiled_map(*s, std::move(map), mapc::parse_material_table(materials_table ? materials_table : ""), std::min(std::max(texture_size_log2, 4u), 10u), seed);
+	return 0;
 }
 
 } // extern "C"

@@ -6,6 +6,7 @@
 // 2 texels per map unit, one lightmap texel per 16 surface texels, simple + directional lightmaps sharing offsets
 // (offset 0 = no lightmap).  Lighting is a direct-light-only stand-in for the lightmapper with voxel shadow rays.
 #include "map.hpp"
+#include "map_compiler.hpp"
 #include <algorithm>
 #include <array>
 #include <cmath>
@@ -1036,6 +1037,248 @@ void generate_scene(const SceneParams& params, Scene& out)
 	}
 }
 
+// ---- a compiled map (map_compiler.cpp + lightmapper.cpp, or the reference's own tools) as a Scene ------------------------------
+namespace
+{
+uint32_t leaf_of_point(const BSPMap& map, Vec3f p) // bsp_map_compact.rs get_leaf_for_point
+{
+	uint32_t index = map.root_node();
+	while (index < FIRST_LEAF_INDEX)
+	{
+		const BSPNode& n = map.nodes[index];
+		index = dot(n.plane.vec, p) >= n.plane.dist ? n.children[0] : n.children[1];
+	}
+	return index - FIRST_LEAF_INDEX;
+}
+Vec3f portal_center(const BSPMap& map, const Portal& p)
+{
+	Vec3f c{0, 0, 0};
+	for (uint32_t i = 0; i < p.num_vertices; ++i)
+		c = c + map.vertices[p.first_vertex + i];
+	return c / (float)p.num_vertices;
+}
+} // namespace
+
+void bind_compiled_map(Scene& s, BSPMap&& map, const mapc::MaterialTable& table, uint32_t texture_size_log2, uint32_t seed)
+{
+	s.map = std::move(map);
+	s.materials.clear();
+	s.images.clear();
+	s.models.clear();
+	s.model_skins.clear();
+	s.params.seed = seed;
+	s.params.texture_size_log2 = texture_size_log2;
+	s.params.num_materials = (uint32_t)s.map.textures.size();
+	const uint32_t size = 1u << texture_size_log2;
+	// Materials by texture name (map_materials_processor.rs:29-120 reads the same table).  The demo's texture IMAGES are not
+	// shipped (procedural .ptex sources), so every material gets a seeded texture of the kind its definition asks for.
+	for (size_t ti = 0; ti < s.map.textures.size(); ++ti)
+	{
+		const mapc::MaterialDef* def = mapc::material_of_texture(table, s.map.textures[ti]);
+		Material mat;
+		Pcg32 rng(seed * 7919u + (uint32_t)ti * 104729u + 13u);
+		float base_roughness = 1.0f;
+		int alpha_mode = 0;
+		if (def)
+		{
+			mat.draw = def->draw;
+			mat.light = def->light;
+			mat.decals = def->decals;
+			mat.shadow = def->shadow;
+			mat.blending_mode = def->blending_mode;
+			mat.has_normal_map = def->normal_map;
+			mat.has_non_one_roughness = def->roughness_map || def->roughness < 1.0f;
+			mat.is_metal = def->is_metal;
+			base_roughness = def->roughness_map ? 0.5f : std::fmin(std::fmax(def->roughness, 1.0f / 126.0f), 1.0f);
+			alpha_mode = def->blending_mode == SQW_BLEND_ALPHA_BLEND ? 1 : (def->blending_mode == SQW_BLEND_ALPHA_TEST ? 2 : 0);
+			mat.is_skybox = def->skybox;
+		}
+		HostImage mips[NUM_MIPS];
+		make_world_texture(rng, size, mat.has_normal_map, mat.has_non_one_roughness, base_roughness, mips[0], alpha_mode);
+		for (uint32_t k = 1; k < NUM_MIPS; ++k)
+			build_texture_mip(mips[k], mips[k - 1]);
+		for (uint32_t k = 0; k < NUM_MIPS; ++k)
+		{
+			mat.texture_images[k] = (uint32_t)s.images.size();
+			s.images.push_back(std::move(mips[k]));
+		}
+		s.materials.push_back(mat);
+	}
+	for (Material& sky : s.materials)
+	{
+		if (!sky.is_skybox)
+			continue;
+		Pcg32 sky_rng(seed * 40503u + 7u);
+		const uint32_t sky_size = 1u << std::min(std::max(s.params.sky_size_log2, 5u), 10u);
+		for (uint32_t side = 0; side < 6; ++side)
+		{
+			HostImage m32[NUM_MIPS], m64[NUM_MIPS];
+			make_sky_side(sky_rng, sky_size, side, m32[0], m64[0]);
+			for (uint32_t k = 1; k < NUM_MIPS; ++k)
+			{
+				build_texture_lite_mip(m32[k], m32[k - 1]);
+				build_color64_mip(m64[k], m64[k - 1]);
+			}
+			for (uint32_t k = 0; k < NUM_MIPS; ++k)
+			{
+				sky.skybox_images[0][side][k] = (uint32_t)s.images.size();
+				s.images.push_back(std::move(m32[k]));
+				sky.skybox_images[1][side][k] = (uint32_t)s.images.size();
+				s.images.push_back(std::move(m64[k]));
+			}
+		}
+	}
+
+	// Camera path: from info_player_start through the info_teleport_destination origins, in entity order.
+	// Between two of them the path follows the leaf graph (breadth-first over portals) through the portal centres — inside a
+	// convex leaf the straight piece between two points of its boundary stays in empty space; where the graph does not connect
+	// them (areas joined only by a teleporter) the path jumps.
+	s.camera_waypoints.clear();
+	s.waypoint_breaks.clear();
+	s.polyline_path = true;
+	std::vector<Vec3f> stops;
+	{
+		const BSPMap& m = s.map;
+		std::vector<Vec3f> destinations;
+		for (const Entity& e : m.entities)
+		{
+			std::string classname;
+			Vec3f origin{0, 0, 0};
+			bool has_origin = false;
+			for (uint32_t i = 0; i < e.num_key_value_pairs; ++i)
+			{
+				const KeyValuePair& kv = m.key_value_pairs[e.first_key_value_pair + i];
+				const std::string key((const char*)m.strings_data.data() + kv.key.offset, kv.key.size), value((const char*)m.strings_data.data() + kv.value.offset, kv.value.size);
+				if (key == "classname")
+					classname = value;
+				if (key == "origin")
+					has_origin = mapc::parse_vec3(value, origin);
+			}
+			if (!has_origin)
+				continue;
+			origin.z += 40.0f; // eye above the entity's origin
+			if (classname == "info_player_start")
+				stops.insert(stops.begin(), origin);
+			else if (classname == "info_teleport_destination")
+				destinations.push_back(origin);
+		}
+		stops.insert(stops.end(), destinations.begin(), destinations.end());
+	}
+	const BSPMap& m = s.map;
+	for (size_t si = 0; si < stops.size(); ++si)
+	{
+		if (si == 0)
+		{
+			s.camera_waypoints.push_back(stops[0]);
+			s.waypoint_breaks.push_back(1);
+			continue;
+		}
+		const uint32_t from = leaf_of_point(m, stops[si - 1]), to = leaf_of_point(m, stops[si]);
+		std::vector<int32_t> via(m.leafs.size(), -1); // portal through which the leaf was reached
+		std::vector<uint32_t> prev(m.leafs.size(), ~0u), queue{from};
+		std::vector<uint8_t> seen(m.leafs.size(), 0);
+		seen[from] = 1;
+		for (size_t qi = 0; qi < queue.size() && !seen[to]; ++qi)
+		{
+			const BSPLeaf& leaf = m.leafs[queue[qi]];
+			for (uint32_t k = 0; k < leaf.num_leaf_portals; ++k)
+			{
+				const uint32_t pi = m.leafs_portals[leaf.first_leaf_portal + k];
+				const Portal& portal = m.portals[pi];
+				const uint32_t other = portal.leafs[0] == queue[qi] ? portal.leafs[1] : portal.leafs[0];
+				if (seen[other])
+					continue;
+				seen[other] = 1;
+				via[other] = (int32_t)pi;
+				prev[other] = queue[qi];
+				queue.push_back(other);
+			}
+		}
+		if (!seen[to])
+		{
+			s.camera_waypoints.push_back(stops[si]);
+			s.waypoint_breaks.push_back(1);
+			continue;
+		}
+		std::vector<Vec3f> centres;
+		for (uint32_t l = to; l != from; l = prev[l])
+			centres.push_back(portal_center(m, m.portals[(size_t)via[l]]));
+		for (size_t k = centres.size(); k-- > 0;)
+		{
+			s.camera_waypoints.push_back(centres[k]);
+			s.waypoint_breaks.push_back(0);
+		}
+		s.camera_waypoints.push_back(stops[si]);
+		s.waypoint_breaks.push_back(0);
+	}
+}
+
+namespace
+{
+// make_camera_path for Scene::polyline_path: poses at equal steps of arc length along the poly-line, looking at the point 160
+// units further along it (never across a break)
+void make_polyline_camera_path(const Scene& scene, uint32_t num_frames, uint32_t jitter_seed, std::vector<CameraPose>& out)
+{
+	const std::vector<Vec3f>& w = scene.camera_waypoints;
+	const size_t n = w.size();
+	std::vector<float> start(n, 0.0f); // arc length at waypoint i (breaks add no length)
+	for (size_t i = 1; i < n; ++i)
+		start[i] = start[i - 1] + (scene.waypoint_breaks[i] ? 0.0f : magnitude(w[i] - w[i - 1]));
+	const float total = start[n - 1];
+	Pcg32 rng(jitter_seed ? jitter_seed : 1, 0x5157);
+	auto at = [&](float t, size_t& seg) {
+		// last segment whose start is <= t
+		size_t i = (size_t)(std::upper_bound(start.begin(), start.end(), t) - start.begin());
+		i = i == 0 ? 0 : i - 1;
+		while (i + 1 < n && scene.waypoint_breaks[i + 1] && start[i + 1] <= t)
+			++i;
+		seg = i;
+		if (i + 1 >= n || scene.waypoint_breaks[i + 1])
+			return w[i];
+		const float len = start[i + 1] - start[i];
+		const float f = len > 0.0f ? std::fmin(std::fmax((t - start[i]) / len, 0.0f), 1.0f) : 0.0f;
+		return w[i] + (w[i + 1] - w[i]) * f;
+	};
+	for (uint32_t k = 0; k < num_frames; ++k)
+	{
+		const float t = total * ((float)k + 0.5f) / (float)num_frames;
+		size_t seg, seg_ahead;
+		CameraPose pose;
+		pose.position = at(t, seg);
+		Vec3f d{0, 1, 0};
+		for (float ahead : {160.0f, 64.0f, 16.0f, -64.0f})
+		{
+			const Vec3f target = at(std::fmin(std::fmax(t + ahead, 0.0f), total), seg_ahead);
+			bool crosses_break = false;
+			for (size_t i = std::min(seg, seg_ahead) + 1; i <= std::max(seg, seg_ahead); ++i)
+				crosses_break = crosses_break || scene.waypoint_breaks[i];
+			const Vec3f dd = ahead > 0.0f ? target - pose.position : pose.position - target;
+			if (!crosses_break && magnitude(dd) > 1.0f)
+			{
+				d = dd;
+				break;
+			}
+		}
+		pose.azimuth = std::atan2(d.y, d.x) - 3.14159265358979323846f * 0.5f; // azimuth 0 looks along +Y (matrix.rs:22)
+		pose.elevation = std::atan2(d.z, std::fmax(std::sqrt(d.x * d.x + d.y * d.y), 1.0f)) * 0.5f;
+		if (jitter_seed)
+		{
+			pose.position.x += rng.uniform(-6.0f, 6.0f);
+			pose.position.y += rng.uniform(-6.0f, 6.0f);
+			pose.position.z += rng.uniform(-4.0f, 4.0f);
+			pose.azimuth += rng.uniform(-0.25f, 0.25f);
+			pose.elevation += rng.uniform(-0.15f, 0.15f);
+		}
+		else
+		{
+			pose.azimuth += 0.5f * std::sin((float)k * 0.37f);
+			pose.elevation += 0.25f * std::sin((float)k * 0.23f + 1.0f);
+		}
+		out.push_back(pose);
+	}
+}
+} // namespace
+
 void make_camera_path(const Scene& scene, uint32_t num_frames, uint32_t jitter_seed, std::vector<CameraPose>& out)
 {
 	out.clear();
@@ -1043,6 +1286,11 @@ void make_camera_path(const Scene& scene, uint32_t num_frames, uint32_t jitter_s
 	const size_t n = w.size();
 	if (n == 0 || num_frames == 0)
 		return;
+	if (scene.polyline_path)
+	{
+		make_polyline_camera_path(scene, num_frames, jitter_seed, out);
+		return;
+	}
 	Pcg32 rng(jitter_seed ? jitter_seed : 1, 0x5157);
 	auto wp = [&](long i) { return w[(size_t)(((i % (long)n) + (long)n) % (long)n)]; };
 	auto position_at = [&](float t) {

@@ -184,6 +184,10 @@ struct Scene
 	std::vector<TriangleModel> models;
 	std::vector<std::array<uint32_t, NUM_MIPS>> model_skins;
 	std::vector<Vec3f> camera_waypoints; // centres of the cells the fly-through visits
+	// Compiled maps (bind_compiled_map): the waypoints are a poly-line through leaf portals that make_camera_path follows
+	// linearly; waypoint_breaks[i] != 0 = the path jumps to waypoint i (a teleport: no interpolation across it)
+	bool polyline_path = false;
+	std::vector<uint8_t> waypoint_breaks;
 	std::vector<uint8_t> solid;          // grid occupancy
 	bool is_solid(int x, int y, int z) const;
 	Vec3f cell_center(int x, int y, int z) const;

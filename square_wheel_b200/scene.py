@@ -219,6 +219,8 @@ def lib() -> C.CDLL:
         l.sqwh_scene_save_map.argtypes = [vp, C.c_char_p]
         l.sqwh_scene_load_map.restype = C.c_int
         l.sqwh_scene_load_map.argtypes = [vp, C.c_char_p]
+        l.sqwh_scene_load_compiled_map.restype = C.c_int
+        l.sqwh_scene_load_compiled_map.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_uint32, C.c_uint32]
         l.sqwh_last_map_error.restype = C.c_char_p
         l.sqwh_scene_num_light_grid_samples.restype = C.c_uint32
         l.sqwh_scene_num_light_grid_samples.argtypes = [vp]
@@ -325,6 +327,19 @@ class Scene:
             raise OSError(f"load_map({path}): {self.MAP_FILE_ERRORS.get(r, r)}")
         self._refresh()
 
+    def load_compiled_map(self, path: str, materials_table: str, texture_size_log2: int = 8, seed: int = 1):
+        """Replace the whole scene by a compiled + lit .sqwm map (tools/map_compiler.py, or the reference's map_compiler +
+        lightmapper): one material per texture name of the map, defined by `materials_table` (the text form of the reference's
+        materials/*.json, tools/map_compiler.py::materials_table) with a seeded procedural texture of the kind the definition
+        asks for; the camera path runs from info_player_start through the info_teleport_destination entities along the leaf
+        portals.  Close renderers of this scene before calling."""
+        r = self._lib.sqwh_scene_load_compiled_map(self._handle, os.fsencode(path), materials_table.encode("utf-8"), texture_size_log2, seed)
+        if r == 4:
+            raise ValueError(f"load_compiled_map({path}): {self._lib.sqwh_last_map_error().decode()}")
+        if r != 0:
+            raise OSError(f"load_compiled_map({path}): {self.MAP_FILE_ERRORS.get(r, r)}")
+        self._refresh()
+
     def texture_name(self, index: int) -> str:
         n = self._lib.sqwh_scene_texture_name(self._handle, index)
         if n is None:
@@ -410,6 +425,23 @@ class Scene:
         if self._handle:
             self._lib.sqwh_scene_destroy(self._handle)
             self._handle = None
+
+
+DEMO2_MAP_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "assets", "_ref", "demo2.sqwm")
+DEMO2_MATERIALS_PATH = os.path.join(os.path.dirname(DEMO2_MAP_PATH), "demo2_materials.txt")
+
+
+def demo2_scene(texture_size_log2: int = 8, seed: int = 1):
+    """The reference's demo map 2 (BASELINE.json north_star) as a Scene, or None where `__graft_entry__.build_demo_map` has not
+    produced it (it compiles /root/reference/demo/maps/demo2.map, which exists only in the build container).  Geometry, entities,
+    lights and material definitions are the demo's; the texture images are seeded stand-ins (the demo ships procedural sources)."""
+    if not (os.path.exists(DEMO2_MAP_PATH) and os.path.exists(DEMO2_MATERIALS_PATH)):
+        return None
+    with open(DEMO2_MATERIALS_PATH, "r", encoding="utf-8") as f:
+        table = f.read()
+    sc = Scene(num_materials=4, texture_size_log2=4, grid=(4, 4, 1), num_rooms=1)
+    sc.load_compiled_map(DEMO2_MAP_PATH, table, texture_size_log2, seed)
+    return sc
 
 
 class HostFrame:
