@@ -8,9 +8,12 @@
 //   lightmaps_builder.rs      allocate_lightmaps :299, build_primary_lightmap :467, build_polygon_diretional_lightmap :969 (primary
 //                             and sun lights), correct_sample_position :2122
 //   light_hemisphere.rs       add_point_light, extract_ambient_light, calculate_light_direction
+//   light_cube.rs             LightCube (add_light_sample, scale, convert_into_light_grid_sample)
 // Not restated: the PVS that limits the lights per leaf (pvs.rs; replaced by a contribution cut-off, LightmappingSettings::
-// light_cutoff), secondary (bounced) and emissive-surface light, the light grid (left empty: models and sprites of such a map get
-// no grid light).  Host-only, offline.  Parity with the Rust tool: UNPINNED, as for the map compiler.
+// light_cutoff), secondary (bounced) and emissive-surface light.  The light grid (prepare_light_grid :1614, calculate_light_grid :1643,
+// calculate_light_for_grid_point :1861 for primary and sun lights, correct_light_grid_sample_position :2005, compress_light_grid
+// :1772, light_cube.rs) is built from the same direct light.  Host-only, offline.  Parity with the Rust tool: UNPINNED, as for the
+// map compiler.
 #include "map_compiler.hpp"
 #include <algorithm>
 #include <atomic>
@@ -564,6 +567,231 @@ struct PolygonLighter
 		}
 	}
 };
+
+// ---- light_cube.rs -------------------------------------------------------------------------------------------------------------
+const float MIN_VEC_LEN = 0.00000001f;
+struct LightCube
+{
+	float light_cube[6][3] = {};
+	Vec3f sum_scaled_light_dirs[3] = {Vec3f{0, 0, 0}, Vec3f{0, 0, 0}, Vec3f{0, 0, 0}};
+
+	void add_light_sample(const Vec3f& direction, const float light_scaled[3]) // :20-77
+	{
+		const Vec3f n = direction / std::fmax(magnitude(direction), MIN_VEC_LEN);
+		const float comp[3] = {n.x, n.y, n.z};
+		for (int a = 0; a < 3; ++a)
+		{
+			const int side = comp[a] <= 0.0f ? 2 * a : 2 * a + 1;
+			for (int i = 0; i < 3; ++i)
+				light_cube[side][i] += light_scaled[i] * std::fabs(comp[a]);
+		}
+		for (int i = 0; i < 3; ++i)
+			sum_scaled_light_dirs[i] = sum_scaled_light_dirs[i] + n * light_scaled[i];
+	}
+	void scale(float k) // :90-103
+	{
+		for (auto& side : light_cube)
+			for (float& c : side)
+				c *= k;
+		for (Vec3f& v : sum_scaled_light_dirs)
+			v = v * k;
+	}
+	LightGridElement convert_into_light_grid_sample() const // :105-158
+	{
+		LightGridElement e;
+		const Vec3f dir = (sum_scaled_light_dirs[0] + sum_scaled_light_dirs[1] + sum_scaled_light_dirs[2]) * 0.33f;
+		const float len2 = std::fmax(magnitude2(dir), MIN_VEC_LEN);
+		float color[3];
+		for (int i = 0; i < 3; ++i)
+			color[i] = std::fmax(dot(sum_scaled_light_dirs[i], dir), 0.0f) / len2;
+		const float comp[3] = {dir.x, dir.y, dir.z};
+		for (int s = 0; s < 6; ++s)
+			for (int i = 0; i < 3; ++i)
+				e.light_cube[s][i] = light_cube[s][i];
+		for (int i = 0; i < 3; ++i)
+			for (int a = 0; a < 3; ++a)
+			{
+				const int side = comp[a] <= 0.0f ? 2 * a : 2 * a + 1;
+				e.light_cube[side][i] = std::fmax(e.light_cube[side][i] - color[i] * std::fabs(comp[a]), 0.0f);
+			}
+		e.light_direction_vector_scaled = dir;
+		for (int i = 0; i < 3; ++i)
+			e.directional_light_color[i] = color[i];
+		return e;
+	}
+};
+
+// ---- light grid (lightmaps_builder.rs:1614-2081) -------------------------------------------------------------------------------------
+uint32_t leaf_for_point(const BSPMap& map, const Vec3f& p) // bsp_map_compact.rs get_leaf_for_point
+{
+	uint32_t index = map.root_node();
+	while (index < FIRST_LEAF_INDEX)
+	{
+		const BSPNode& n = map.nodes[index];
+		index = dot(n.plane.vec, p) >= n.plane.dist ? n.children[0] : n.children[1];
+	}
+	return index - FIRST_LEAF_INDEX;
+}
+bool is_point_inside_leaf_volume(const BSPMap& map, const Vec3f& point) // :2068-2081
+{
+	const BSPLeaf& leaf = map.leafs[leaf_for_point(map, point)];
+	for (uint32_t i = 0; i < leaf.num_polygons; ++i)
+	{
+		const Polygon& p = map.polygons[leaf.first_polygon + i];
+		if (dot(point, p.plane.vec) <= p.plane.dist)
+			return false;
+	}
+	return true;
+}
+bool correct_light_grid_sample_position(const BSPMap& map, const Vec3f& pos, Vec3f& out) // :2005-2066
+{
+	if (is_point_inside_leaf_volume(map, pos))
+	{
+		out = pos;
+		return true;
+	}
+	static const float SHIFTS[26][3] = {{1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}, {1, 1, 0}, {-1, 1, 0}, {1, -1, 0}, {-1, -1, 0}, {1, 0, 1}, {-1, 0, 1}, {1, 0, -1},
+		{-1, 0, -1}, {0, 1, 1}, {0, -1, 1}, {0, 1, -1}, {0, -1, -1}, {1, 1, 1}, {-1, 1, 1}, {1, -1, 1}, {-1, -1, 1}, {1, 1, -1}, {-1, 1, -1}, {1, -1, -1}, {-1, -1, -1}};
+	const float* cell = map.light_grid_header.grid_cell_size;
+	const int max_step = 3;
+	for (int step = 1; step <= max_step; ++step)
+	{
+		const float f = (float)step / (float)max_step;
+		for (const float(&shift)[3] : SHIFTS)
+		{
+			const Vec3f shifted = pos + Vec3f{shift[0] * (cell[0] * f), shift[1] * (cell[1] * f), shift[2] * (cell[2] * f)};
+			if (is_point_inside_leaf_volume(map, shifted))
+			{
+				out = shifted;
+				return true;
+			}
+		}
+	}
+	return false;
+}
+bool light_grid_element_is_zero(const LightGridElement& e) // :1836-1859
+{
+	const float MIN_LIGHT = 1.0f / 256.0f;
+	for (const auto& side : e.light_cube)
+		for (float c : side)
+			if (c > MIN_LIGHT)
+				return false;
+	return !(magnitude2(e.light_direction_vector_scaled) > MIN_LIGHT * MIN_LIGHT);
+}
+
+uint32_t build_light_grid(const LightmappingSettings& settings, uint32_t sample_grid_size, const Tracer& tracer, const std::vector<PointLight>& lights, const std::vector<SunLight>& sun_lights,
+	const Vec3f& bbox_min, const Vec3f& bbox_max, BSPMap& map)
+{
+	LightGridHeader& h = map.light_grid_header; // prepare_light_grid :1614-1641
+	const float width = std::fmin(std::fmax(settings.light_grid_cell_width, 16.0f), 512.0f), height = std::fmin(std::fmax(settings.light_grid_cell_height, 16.0f), 512.0f);
+	h.grid_cell_size[0] = h.grid_cell_size[1] = width;
+	h.grid_cell_size[2] = height;
+	for (int i = 0; i < 3; ++i)
+	{
+		const float start = std::floor(bbox_min[i] / h.grid_cell_size[i]), end = std::ceil(bbox_max[i] / h.grid_cell_size[i]);
+		h.grid_start[i] = start * h.grid_cell_size[i];
+		h.grid_size[i] = (uint32_t)(end - start) + 1;
+	}
+	// calculate_light_grid :1643-1752
+	std::vector<Vec3f> shifts(1, Vec3f{0, 0, 0});
+	if (sample_grid_size > 1)
+	{
+		shifts.assign((size_t)sample_grid_size * sample_grid_size * sample_grid_size, Vec3f{0, 0, 0});
+		const float g = (float)sample_grid_size;
+		const Vec3f step{h.grid_cell_size[0] / g, h.grid_cell_size[1] / g, h.grid_cell_size[2] / g};
+		const Vec3f grid_start = step * (-0.5f * (g - 1.0f));
+		for (uint32_t x = 0; x < sample_grid_size; ++x)
+			for (uint32_t y = 0; y < sample_grid_size; ++y)
+				for (uint32_t z = 0; z < sample_grid_size; ++z)
+					shifts[x + y * sample_grid_size + z * sample_grid_size * sample_grid_size] = grid_start + Vec3f{(float)x * step.x, (float)y * step.y, (float)z * step.z};
+	}
+	const float min_light_dist = std::fmin(std::fmin(h.grid_cell_size[0], h.grid_cell_size[1]), h.grid_cell_size[2]) * 0.5f;
+	const float min_light_square_dist = min_light_dist * min_light_dist;
+	const size_t total = (size_t)h.grid_size[0] * h.grid_size[1] * h.grid_size[2];
+	std::vector<LightGridElement> grid(total); // address = z + (x + y * size_x) * size_z (:1754-1758)
+	std::atomic<size_t> next{0};
+	const unsigned nt = std::min(std::max(std::thread::hardware_concurrency(), 1u), 64u);
+	std::vector<std::thread> threads;
+	for (unsigned t = 0; t < nt; ++t)
+		threads.emplace_back([&] {
+			for (;;)
+			{
+				const size_t first = next.fetch_add(64);
+				if (first >= total)
+					break;
+				for (size_t address = first; address < std::min(first + 64, total); ++address)
+				{
+					const uint32_t z = (uint32_t)(address % h.grid_size[2]), layer = (uint32_t)(address / h.grid_size[2]);
+					const uint32_t x = layer % h.grid_size[0], y = layer / h.grid_size[0];
+					const Vec3f pos{h.grid_start[0] + (float)x * h.grid_cell_size[0], h.grid_start[1] + (float)y * h.grid_cell_size[1], h.grid_start[2] + (float)z * h.grid_cell_size[2]};
+					LightCube cube;
+					uint32_t valid = 0;
+					for (const Vec3f& shift : shifts)
+					{
+						Vec3f p;
+						if (!correct_light_grid_sample_position(map, pos + shift, p))
+							continue;
+						++valid;
+						for (const PointLight& light : lights) // calculate_light_for_grid_point :1861-2003 (primary and sun lights)
+						{
+							const Vec3f vec_to_light = light.pos - p;
+							const float len2 = std::fmax(magnitude2(vec_to_light), min_light_square_dist), len = std::sqrt(len2);
+							if (std::fmax(std::fmax(light.color[0], light.color[1]), light.color[2]) / len2 < settings.light_cutoff)
+								continue; // (stands in for the PVS row of the point's leaf)
+							if (light.has_direction && -dot(vec_to_light, light.direction.dir_normalized) < light.direction.half_angle_cos * len)
+								continue;
+							const float shadow_factor = tracer.get_shadow_factor(light.pos, p);
+							if (shadow_factor <= 0.0f)
+								continue;
+							const float k = shadow_factor / len2;
+							const float c[3] = {light.color[0] * k, light.color[1] * k, light.color[2] * k};
+							cube.add_light_sample(vec_to_light, c);
+						}
+						for (const SunLight& sun : sun_lights)
+						{
+							const float shadow_factor = tracer.get_sun_shadow_factor(p, sun.dir);
+							if (shadow_factor <= 0.0f)
+								continue;
+							const float c[3] = {sun.color[0] * shadow_factor, sun.color[1] * shadow_factor, sun.color[2] * shadow_factor};
+							cube.add_light_sample(sun.dir, c);
+						}
+					}
+					if (valid > 0)
+					{
+						cube.scale(1.0f / (float)valid);
+						if (settings.ambient_light > 0.0f) // LightCube::add_constant_light with the tool's ambient term (as in the lightmaps)
+							for (auto& side : cube.light_cube)
+								for (float& c : side)
+									c += settings.ambient_light;
+					}
+					grid[address] = cube.convert_into_light_grid_sample();
+				}
+			}
+		});
+	for (std::thread& th : threads)
+		th.join();
+	// compress_light_grid :1772-1834
+	map.light_grid_columns.assign((size_t)h.grid_size[0] * h.grid_size[1], LightGridColumn{});
+	map.light_grid_samples.clear();
+	auto sample = [&](uint32_t x, uint32_t y, uint32_t z) -> const LightGridElement& { return grid[z + ((size_t)x + (size_t)y * h.grid_size[0]) * h.grid_size[2]]; };
+	for (uint32_t x = 0; x < h.grid_size[0]; ++x)
+		for (uint32_t y = 0; y < h.grid_size[1]; ++y)
+		{
+			uint32_t lo = 0;
+			while (lo < h.grid_size[2] && light_grid_element_is_zero(sample(x, y, lo)))
+				++lo;
+			uint32_t hi = h.grid_size[2] - 1;
+			while (hi > lo && light_grid_element_is_zero(sample(x, y, hi)))
+				--hi;
+			LightGridColumn& col = map.light_grid_columns[x + (size_t)y * h.grid_size[0]];
+			col.first_sample = (uint32_t)map.light_grid_samples.size();
+			col.num_samples = hi + 1 - lo; // (an all-dark column: lo == size_z, hi == size_z - 1: no samples)
+			col.start_z = lo;
+			for (uint32_t z = lo; z <= hi && z < h.grid_size[2]; ++z)
+				map.light_grid_samples.push_back(sample(x, y, z));
+		}
+	return (uint32_t)map.light_grid_samples.size();
+}
 } // namespace
 
 void build_lightmaps(const LightmappingSettings& settings_in, const MaterialTable& materials, BSPMap& map, LightmapStats& stats)
@@ -638,10 +866,7 @@ void build_lightmaps(const LightmappingSettings& settings_in, const MaterialTabl
 	for (std::thread& th : threads)
 		th.join();
 
-	// no light grid (see the header comment)
-	map.light_grid_header = LightGridHeader{};
-	map.light_grid_columns.clear();
-	map.light_grid_samples.clear();
+	stats.light_grid_samples = build_light_grid(settings, sample_grid_size, tracer, lights, sun_lights, bbox_min, bbox_max, map);
 }
 
 } // namespace mapc

@@ -4,6 +4,8 @@ host pipeline -> C-ABI -> kernels, against the oracle fed with the same job and 
 Covers BASELINE.json configs[0] (1280x720, simple lightmaps, 32-bit LDR) and configs[1] (directional lightmaps + normal
 mapping + specular, 64-bit HDR + tonemapping) on the synthetic stand-in map, at sizes the oracle finishes in seconds, plus a
 full-size 4K frame checked through a size-independent property."""
+import os
+
 import numpy as np
 import pytest
 
@@ -378,6 +380,48 @@ def test_frames_from_a_loaded_sqwm_map(oracle_lib, tmp_path):
             assert oracle_lib.assert_failures() == 0
             assert_pixels_equal(r._view.read_surfaces(0, hf.total_surface_pixels), surf, f"frame {k} surfaces from the loaded map")
             assert_pixels_equal(pixels, fb, f"frame {k} picture from the loaded map")
+    finally:
+        r.close()
+        sc.close()
+
+
+@pytest.mark.skipif(not os.path.exists(S.DEMO2_MAP_PATH), reason="assets/_ref/demo2.sqwm is built by __graft_entry__.build() where /root/reference exists")
+@pytest.mark.parametrize("color_bits", [32, 64])
+def test_frames_of_the_demo_map(oracle_lib, color_bits):
+    """BASELINE.json's own map: demo2.map compiled and lit by this repository's map compiler / lightmapper (row f4).  World
+    geometry, submodels (doors, details), sky, alpha-tested / blended / twosided world materials as the demo's material table
+    defines them — frames along the path through its player start bit-exact against the oracle, surfaces and picture."""
+    W, H = 800, 450
+    sc = S.demo2_scene(texture_size_log2=6)
+    r = Renderer(sc, RendererConfig(use_directional_lightmaps=True))
+    try:
+        poses = sc.camera_path(64)
+        dtype = np.uint32 if color_bits == 32 else np.uint64
+        for k in (0, 5, 20, 47):
+            hf = r.prepare_frame(SurfaceInfo(W, H), FrameInfo(poses[k]), color_bits=color_bits)
+            pixels = np.zeros((H, W), dtype)
+            r.draw_frame(pixels)
+            assert len(hf.cmds) > 50
+            oracle_lib.reset_assert_failures()
+            surf = oracle_lib.build_surfaces(color_bits, hf.jobs, None, None, hf.cam_pos, sc.images, sc.lightmaps, sc.directional_lightmaps, hf.total_surface_pixels)
+            got_surf = r._view.read_surfaces(0, hf.total_surface_pixels)
+            # Polygons of `light: false` materials without an emissive layer (the demo's mirror / display materials, which the game
+            # covers with portal textures) get NO surface layer: neither the reference (partial_renderer.rs:1700-1819) nor the
+            # kernels nor the oracle write their texels, which keep what the pool held before.  The oracle draws from the same.
+            layers = N.SURF_APPLY_DIFFUSE | N.SURF_EMISSIVE
+            unwritten = 0
+            for j in hf.jobs[(hf.jobs["flags"] & layers) == 0]:
+                o, n = int(j["surface_pixels_offset"]), int(j["surface_size"][0]) * int(j["surface_size"][1])
+                surf[o : o + n] = got_surf[o : o + n]
+                unwritten += n
+            assert unwritten < 0.1 * hf.total_surface_pixels
+            fb = np.zeros((H, W), dtype)
+            if hf.needs_clear:
+                oracle_lib.fill(fb, S.BACKGROUND_COLOR64 if color_bits == 64 else S.BACKGROUND_COLOR32)
+            oracle_lib.draw(color_bits, fb, hf.cmds, hf.polygon_points, hf.triangle_points, surf, sc.images)
+            assert oracle_lib.assert_failures() == 0
+            assert_pixels_equal(got_surf, surf, f"demo map frame {k} surfaces")
+            assert_pixels_equal(pixels, fb, f"demo map frame {k} picture")
     finally:
         r.close()
         sc.close()

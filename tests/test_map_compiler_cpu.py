@@ -1,0 +1,308 @@
+"""Map compiler + lightmapper of the host mirror (square_wheel_b200/host/map_compiler.cpp, lightmapper.cpp,
+restating /root/reference/src/common/{map_file_q1, map_polygonizer, map_csg, bsp_builder, bsp_map_compact_conversion, map_lights,
+light_trace, lightmaps_builder}.rs).  There is no reference output to compare with (no Rust toolchain: parity UNPINNED), so the
+checks are the structural properties a compiled map must have for the renderer, closed forms of the direct-light formulas, and the
+oracle drawing gap-free frames of the result."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import map_compiler as mc  # noqa: E402
+
+from square_wheel_b200 import _native as N  # noqa: E402
+from square_wheel_b200 import scene as S  # noqa: E402
+
+
+def box_brush(lo, hi, texture="wall", textures=None):
+    """A Quake-format brush of six axis-aligned planes, three points each, wound so that (v0 - v1) x (v2 - v1) points out of the
+    brush (map_polygonizer.rs:294-306 keeps the half-space dot(vec, p) <= dist)."""
+    lo, hi = np.asarray(lo, float), np.asarray(hi, float)
+    lines = ["{"]
+    for axis in range(3):
+        for sign in (-1, 1):
+            n = np.zeros(3)
+            n[axis] = sign
+            u, v = np.zeros(3), np.zeros(3)
+            u[(axis + 1) % 3] = 1
+            v[(axis + 2) % 3] = 1
+            base = np.where(n > 0, hi, lo) * np.abs(n) + lo * (1 - np.abs(n))
+            p1 = base
+            p0, p2 = base + u * 16, base + v * 16
+            if np.dot(np.cross(p0 - p1, p2 - p1), n) < 0:
+                p0, p2 = p2, p0
+            tex = (textures or {}).get((axis, sign), texture)
+            pts = " ".join("( %g %g %g )" % tuple(p) for p in (p0, p1, p2))
+            lines.append(f"{pts} {tex} 0 0 0 1 1")
+    lines.append("}")
+    return "\n".join(lines)
+
+
+def two_rooms_map(door_entity=True):
+    """Two 256 x 256 x 128 rooms joined by a 64 x 96 doorway in the 32-unit wall between them, walls as slabs (like the demo map)."""
+    b = []
+    b.append(box_brush((-16, -16, -16), (560, 272, 0), "floor"))
+    b.append(box_brush((-16, -16, 128), (560, 272, 144), "ceiling"))
+    b.append(box_brush((-16, -16, 0), (0, 272, 128)))
+    b.append(box_brush((544, -16, 0), (560, 272, 128)))
+    b.append(box_brush((0, -16, 0), (544, 0, 128)))
+    b.append(box_brush((0, 256, 0), (544, 272, 128)))
+    b.append(box_brush((256, 0, 0), (288, 96, 128), "divider"))
+    b.append(box_brush((256, 160, 0), (288, 256, 128), "divider"))
+    b.append(box_brush((256, 96, 96), (288, 160, 128), "divider"))
+    ents = ['{\n"classname" "worldspawn"\n// a comment\n' + "\n".join(b) + "\n}"]
+    ents.append('{\n"classname" "info_player_start"\n"origin" "64 128 32"\n}')
+    ents.append('{\n"classname" "light"\n"origin" "128 128 96"\n"light" "200"\n}')
+    ents.append('{\n"classname" "info_teleport_destination"\n"origin" "416 128 32"\n}')
+    if door_entity:
+        ents.append('{\n"classname" "func_door"\n' + box_brush((400, 100, 0), (432, 132, 64), "crate") + "\n}")
+    return "// Game: Generic\n" + "\n".join(ents) + "\n"
+
+
+MATERIALS = {"floor": {}, "ceiling": {}, "wall": {}, "divider": {"normal_map": "x.png", "roughness": 0.3}, "crate": {"is_metal": True, "roughness": 0.2}}
+
+
+@pytest.fixture(scope="module")
+def compiled(tmp_path_factory):
+    d = tmp_path_factory.mktemp("mapc")
+    table = mc.materials_table(MATERIALS)
+    path = str(d / "two_rooms.sqwm")
+    stats = mc.compile_map(two_rooms_map(), table, path, perform_csg=True, advanced=True)
+    lit = str(d / "two_rooms_lit.sqwm")
+    lstats = mc.light_map(path, table, lit, sample_grid_size=2, ambient_light=0.125)
+    sc = S.Scene(num_materials=4, texture_size_log2=4, grid=(4, 4, 1), num_rooms=1)
+    sc.load_compiled_map(lit, table, 6, 3)
+    yield sc, stats, lstats, table, lit
+    sc.close()
+
+
+def _planes_ok(polys, verts, eps=1.0 / 16.0):
+    for p in polys:
+        v = verts[p["first_vertex"] : p["first_vertex"] + p["num_vertices"]]
+        n = np.array(p["plane"][:3], np.float64)
+        assert np.all(np.abs(v @ n - p["plane"][3]) <= eps * np.linalg.norm(n) + 1e-3)
+
+
+def test_parser_rejects_broken_text(tmp_path):
+    table = mc.materials_table(MATERIALS)
+    good = two_rooms_map()
+    for broken in (good.replace("(", "[", 1), good[: len(good) // 2], "hello"):
+        with pytest.raises(RuntimeError):
+            mc.compile_map(broken, table, str(tmp_path / "x.sqwm"))
+    with pytest.raises(RuntimeError):
+        mc.compile_map("", table, str(tmp_path / "x.sqwm"))  # no entities
+
+
+def test_compiled_map_structure(compiled):
+    sc, stats, _, _, _ = compiled
+    polys, verts, _flags = sc.map_geometry()
+    assert stats["initial_polygons"] == 9 * 6
+    # CSG removes what lies inside neighbouring slabs; the BSP keeps only leafs reachable from the entities (the two rooms, the doorway)
+    assert stats["polygons_after_csg"] < stats["initial_polygons"] + 20
+    assert stats["leafs"] >= 3 and stats["leafs_removed"] >= 1 and stats["portals"] >= 2 and stats["submodels"] == 1
+    assert sc.info.num_polygons == stats["polygons"] and sc.info.num_leafs == stats["leafs"]
+    _planes_ok(polys, verts)
+    # every lightmap within the splitter's limit (bsp_builder.rs:1282: 17, "actual size may be a little greater")
+    for p in polys:
+        for a in range(2):
+            size = ((int(p["tex_coord_max"][a]) + 15) >> 4) - (int(p["tex_coord_min"][a]) >> 4) + 1
+            assert 2 <= size <= 18
+    # no outward-facing polygon survives: every polygon's plane keeps the player start or the other room's centre in front ... of
+    # the faces that bound the rooms: here simply none of the outer faces of the shell (x = -16, x = 560, ...) may be left
+    n = polys["plane"][:, :3]
+    d = polys["plane"][:, 3]
+    outer = [(np.array([-1, 0, 0]), 16), (np.array([1, 0, 0]), 560), (np.array([0, -1, 0]), 16), (np.array([0, 1, 0]), 272), (np.array([0, 0, -1]), 16), (np.array([0, 0, 1]), 144)]
+    for on, od in outer:
+        unit = n / np.linalg.norm(n, axis=1, keepdims=True)
+        hit = (np.abs(unit @ on - 1.0) < 1e-6) & (np.abs(d / np.linalg.norm(n, axis=1) - od) < 1e-3)
+        assert not hit.any()
+
+
+def test_leafs_are_convex_and_portals_symmetric(compiled, tmp_path):
+    sc, _, _, _, lit = compiled
+    # read the lumps back through the .sqwm file itself (bsp_map_save_load.rs layout)
+    raw = open(lit, "rb").read()
+    assert raw[:4] == b"SqwM" and int.from_bytes(raw[4:8], "little") == 11
+    lumps = np.frombuffer(raw, np.uint32, 96, 8).reshape(32, 3)
+
+    def lump(i, dtype):
+        o, es, n = (int(x) for x in lumps[i])
+        assert es == np.dtype(dtype).itemsize
+        return np.frombuffer(raw, dtype, n, o)
+
+    leafs = lump(1, np.dtype([("first_polygon", "<u4"), ("num_polygons", "<u4"), ("first_leaf_portal", "<u4"), ("num_leaf_portals", "<u4")]))
+    polys = lump(2, N.map_polygon_dtype)
+    portals = lump(3, np.dtype([("leafs", "<u4", 2), ("plane", "<f4", 4), ("first_vertex", "<u4"), ("num_vertices", "<u4")]))
+    leafs_portals = lump(4, np.uint32)
+    verts = lump(5, np.dtype(("<f4", 3)))
+    for li, leaf in enumerate(leafs):
+        lp = polys[leaf["first_polygon"] : leaf["first_polygon"] + leaf["num_polygons"]]
+        for p in lp:  # a leaf is convex: everything in it lies in front of (or on) each of its polygons' planes
+            nrm = np.array(p["plane"][:3], np.float64)
+            for q in lp:
+                v = verts[q["first_vertex"] : q["first_vertex"] + q["num_vertices"]].astype(np.float64)
+                assert np.all(v @ nrm - p["plane"][3] >= -np.linalg.norm(nrm) / 16.0 - 1e-3)
+        mine = leafs_portals[leaf["first_leaf_portal"] : leaf["first_leaf_portal"] + leaf["num_leaf_portals"]]
+        for pi in mine:
+            assert li in portals[pi]["leafs"]
+    for pi, p in enumerate(portals):
+        assert p["num_vertices"] >= 3 and p["leafs"][0] != p["leafs"][1]
+        for l in p["leafs"]:
+            leaf = leafs[l]
+            assert pi in leafs_portals[leaf["first_leaf_portal"] : leaf["first_leaf_portal"] + leaf["num_leaf_portals"]]
+        v = verts[p["first_vertex"] : p["first_vertex"] + p["num_vertices"]].astype(np.float64)
+        nrm = np.array(p["plane"][:3], np.float64)
+        assert np.all(np.abs(v @ nrm - p["plane"][3]) <= np.linalg.norm(nrm) / 8.0)
+    # the doorway is found: some portal lies on x = 256 or x = 288 inside the 64 x 96 opening
+    door = [p for p in portals if abs(abs(p["plane"][0]) / np.linalg.norm(p["plane"][:3]) - 1) < 1e-6 and min(abs(abs(p["plane"][3] / np.linalg.norm(p["plane"][:3])) - x) for x in (256, 288)) < 1e-3]
+    assert door
+    for p in door:
+        v = verts[p["first_vertex"] : p["first_vertex"] + p["num_vertices"]]
+        assert v[:, 1].min() >= 96 - 0.1 and v[:, 1].max() <= 160 + 0.1 and v[:, 2].max() <= 96 + 0.1
+
+
+def test_direct_light_closed_forms(compiled):
+    sc, _, lstats, _, _ = compiled
+    assert lstats["point_lights"] == 1 and lstats["sun_lights"] == 0
+    polys, verts, _ = sc.map_geometry()
+    lm = sc.lightmaps
+    dlm = sc.directional_lightmaps
+    assert len(lm) == lstats["lightmap_texels"] == len(dlm)
+    ambient = 0.125
+    color = 200.0 * 32.0  # map_lights.rs: intensity * MAP_LIGHTS_SCALE
+    # floor of room A right below the light (128, 128, 96): cos = 1, distance 96 (minus the 1/16 texel shift)
+    best = 0.0
+    best_dir = None
+    for p in polys:
+        nrm = np.array(p["plane"][:3])
+        if not (nrm[2] > 0 and abs(p["plane"][3] / np.linalg.norm(nrm)) < 1e-3):
+            continue  # not a floor polygon (z = 0, facing up)
+        w = ((int(p["tex_coord_max"][0]) + 15) >> 4) - (int(p["tex_coord_min"][0]) >> 4) + 1
+        h = ((int(p["tex_coord_max"][1]) + 15) >> 4) - (int(p["tex_coord_min"][1]) >> 4) + 1
+        o = int(p["lightmap_data_offset"])
+        assert o != 0
+        block = lm[o : o + w * h]
+        k = int(np.argmax(block[:, 0]))
+        if block[k, 0] > best:
+            best = float(block[k, 0])
+            best_dir = dlm[o + k]
+    expected = ambient + color / (96.0 - 1.0 / 16.0) ** 2
+    assert abs(best - expected) / expected < 0.02  # (8-bit quantisation of the file format + the texel grid not being centred under the light)
+    # directional element of that texel: the light comes from straight above in texel space, nearly no deviation, white
+    d = np.array(best_dir["light_direction_vector_scaled"])
+    assert d[2] > 0 and abs(d[0]) < 0.15 * d[2] and abs(d[1]) < 0.15 * d[2]
+    assert best_dir["directional_light_deviation"] < 0.05
+    np.testing.assert_allclose(best_dir["directional_light_color"], [1, 1, 1], atol=0.02)
+    np.testing.assert_allclose(best_dir["ambient_light"], [ambient] * 3, atol=0.01)
+    # the divider's faces towards room B look away from the light: exactly the ambient term; so does everything the wall shadows
+    for p in polys:
+        nrm = np.array(p["plane"][:3])
+        if nrm[0] > 0 and abs(p["plane"][3] / np.linalg.norm(nrm) - 288) < 1e-3:
+            w = ((int(p["tex_coord_max"][0]) + 15) >> 4) - (int(p["tex_coord_min"][0]) >> 4) + 1
+            h = ((int(p["tex_coord_max"][1]) + 15) >> 4) - (int(p["tex_coord_min"][1]) >> 4) + 1
+            o = int(p["lightmap_data_offset"])
+            np.testing.assert_allclose(lm[o : o + w * h], ambient, atol=1.0 / 255.0)  # (the file stores 8-bit components)
+    # room B's far wall (x = 544) is lit only through the doorway: some texels lit, most in shadow
+    lit_count = total = 0
+    for p in polys:
+        nrm = np.array(p["plane"][:3])
+        if nrm[0] < 0 and abs(-p["plane"][3] / np.linalg.norm(nrm) - 544) < 1e-3:
+            w = ((int(p["tex_coord_max"][0]) + 15) >> 4) - (int(p["tex_coord_min"][0]) >> 4) + 1
+            h = ((int(p["tex_coord_max"][1]) + 15) >> 4) - (int(p["tex_coord_min"][1]) >> 4) + 1
+            o = int(p["lightmap_data_offset"])
+            block = lm[o : o + w * h, 0]
+            lit_count += int((block > ambient + 0.01).sum())
+            total += block.size
+    assert 0 < lit_count < total * 0.5
+
+
+def test_light_grid_of_the_direct_light(compiled):
+    """prepare_light_grid / calculate_light_grid / compress_light_grid (lightmaps_builder.rs:1614-1834) with the direct light: cell
+    alignment, column compression, and more light next to the lamp than behind the dividing wall."""
+    sc, _, lstats, _, lit = compiled
+    raw = open(lit, "rb").read()
+    lumps = np.frombuffer(raw, np.uint32, 96, 8).reshape(32, 3)
+    o, es, n = (int(x) for x in lumps[14])
+    assert (es, n) == (36, 1)
+    cell = np.frombuffer(raw, "<f4", 3, o)
+    start = np.frombuffer(raw, "<f4", 3, o + 12)
+    size = np.frombuffer(raw, "<u4", 3, o + 24)
+    np.testing.assert_array_equal(cell, [64, 64, 64])
+    np.testing.assert_array_equal(start % 64, 0)  # aligned to the cell size
+    assert np.all(start <= [0, 0, 0]) and np.all(start + (size - 1) * cell >= [544, 256, 128])  # the bounding box of the map's vertices (the rooms' inner faces)
+    o, es, n = (int(x) for x in lumps[15])
+    assert es == 12 and n == size[0] * size[1]
+    cols = np.frombuffer(raw, np.dtype([("start_z", "<u4"), ("first_sample", "<u4"), ("num_samples", "<u4")]), n, o)
+    o, es, n = (int(x) for x in lumps[16])
+    assert es == 32 and n == lstats["light_grid_samples"] == int(cols["num_samples"].sum()) and n == sc._lib.sqwh_scene_num_light_grid_samples(sc._handle)
+    samples = np.frombuffer(raw, np.uint8, n * 32, o).reshape(n, 32)
+
+    def cube_light(x, y, z):  # sum of the six de-quantised cube sides' first component + the directional part's length
+        gx, gy, gz = (int(round((v - s) / c)) for v, s, c in zip((x, y, z), start, cell))
+        col = cols[gx + gy * size[0]]
+        assert col["start_z"] <= gz < col["start_z"] + col["num_samples"]
+        e = samples[col["first_sample"] + gz - col["start_z"]]
+        cube = sum(float(e[4 * s]) * float(e[4 * s + 3]) / 255.0 for s in range(6))
+        vec = e[24:27].view(np.int8).astype(np.float32) * float(e[27]) / 127.0
+        return cube + float(np.linalg.norm(vec))
+
+    near, far = cube_light(128, 128, 64), cube_light(448, 64, 64)
+    assert near > 4.0 * far and far > 0.0  # the far point sees only the ambient term (the wall shadows the lamp)
+
+
+def test_oracle_draws_the_compiled_map_without_gaps(compiled, oracle_lib):
+    sc, _, _, _, _ = compiled
+    poses = sc.camera_path(6)
+    assert len(poses) == 6
+    hr = S.HostRenderer(sc, clear_background=False)
+    try:
+        for pose in poses:
+            assert 0 < pose[0] < 544 and 0 < pose[1] < 256 and 0 < pose[2] < 128  # the path stays inside the rooms (through the doorway)
+            hf = hr.build_frame(320, 200, pose, color_bits=32)
+            assert len(hf.cmds) > 0
+            oracle_lib.reset_assert_failures()
+            surf = oracle_lib.build_surfaces(32, hf.jobs, None, None, hf.cam_pos, sc.images, sc.lightmaps, sc.directional_lightmaps, hf.total_surface_pixels)
+            fb = np.zeros((200, 320), np.uint32)
+            oracle_lib.draw(32, fb, hf.cmds, hf.polygon_points, None, surf, sc.images)
+            assert oracle_lib.assert_failures() == 0
+            assert int((fb == 0).sum()) == 0  # closed rooms: every pixel is covered by some polygon
+    finally:
+        hr.close()
+
+
+def test_compile_is_deterministic_and_csg_only_removes(tmp_path):
+    table = mc.materials_table(MATERIALS)
+    a, b, c = (str(tmp_path / n) for n in ("a.sqwm", "b.sqwm", "c.sqwm"))
+    sa = mc.compile_map(two_rooms_map(), table, a, perform_csg=True, advanced=True)
+    sb = mc.compile_map(two_rooms_map(), table, b, perform_csg=True, advanced=True)
+    assert open(a, "rb").read() == open(b, "rb").read() and sa == sb
+    sc_ = mc.compile_map(two_rooms_map(), table, c, perform_csg=False, advanced=False)
+    assert sc_["polygons_after_csg"] == sc_["initial_polygons"] == sa["initial_polygons"]
+    assert sc_["leafs"] >= 3
+
+
+@pytest.mark.skipif(not os.path.exists(S.DEMO2_MAP_PATH), reason="assets/_ref/demo2.sqwm is built by __graft_entry__.build() where /root/reference exists")
+def test_demo2_map_loads_and_draws(oracle_lib):
+    sc = S.demo2_scene(texture_size_log2=6)
+    try:
+        assert sc.info.num_polygons > 10000 and sc.info.num_leafs > 2000 and sc.info.num_portals > 5000
+        names = {sc.texture_name(i) for i in range(sc.info.num_materials)}
+        assert {"bricks", "limestone_bricks", "sky"} <= names and "__TB_empty" not in names  # bsp = false faces are gone
+        poses = sc.camera_path(64)
+        hr = S.HostRenderer(sc)
+        try:
+            for k in (0, 20, 41):
+                hf = hr.build_frame(480, 270, poses[k], color_bits=32)
+                assert len(hf.cmds) > 50
+                oracle_lib.reset_assert_failures()
+                surf = oracle_lib.build_surfaces(32, hf.jobs, None, None, hf.cam_pos, sc.images, sc.lightmaps, sc.directional_lightmaps, hf.total_surface_pixels)
+                fb = np.zeros((270, 480), np.uint32)
+                oracle_lib.draw(32, fb, hf.cmds, hf.polygon_points, None, surf, sc.images)
+                assert oracle_lib.assert_failures() == 0
+        finally:
+            hr.close()
+    finally:
+        sc.close()
