@@ -33,14 +33,32 @@ METRIC = "4k_hdr_frames_per_sec"
 UNIT = "frames/s"
 
 
-def workload_config(extra=None):
+def make_workload(which=None):
+    """The headline scene: BASELINE.json configs[1] is quoted on demo map 2.  Where `__graft_entry__.build()` has compiled it
+    (assets/_ref/demo2.sqwm, SURVEY.md 8 row f4 — only a container that holds /root/reference can) that map is the workload;
+    elsewhere, or with --map standin / SQW_BENCH_MAP=standin, the seeded stand-in of the earlier rounds.  Returns (scene, is_demo)."""
+    from square_wheel_b200 import scene as S
+
+    which = which or os.environ.get("SQW_BENCH_MAP", "demo2")
+    if which != "standin":
+        sc = S.demo2_scene(texture_size_log2=8)
+        if sc is not None:
+            return sc, True
+    return S.Scene(**SCENE_KW), False
+
+
+DEMO_WORKLOAD = "configs[1]: demo map 2 (the reference's demo/maps/demo2.map compiled + lit by this repository's map compiler and direct-light lightmapper; material definitions of demo_materials.json with seeded 256^2 stand-in texture images) 3840x2160, directional lightmaps + normal maps + specular, Color64 HDR + tonemap (bloom off)"
+STANDIN_WORKLOAD = "configs[1]: demo-map stand-in (synthetic seed 2, 24x24x5 cells, 13k polygons, 24 materials 256^2) 3840x2160, directional lightmaps + normal maps + specular, Color64 HDR + tonemap (bloom off)"
+
+
+def workload_config(is_demo=False, extra=None):
     cfg = {
-        "workload": "configs[1]: demo-map stand-in (synthetic seed 2, 24x24x5 cells, 13k polygons, 24 materials 256^2) 3840x2160, directional lightmaps + normal maps + specular, Color64 HDR + tonemap (bloom off)",
+        "workload": DEMO_WORKLOAD if is_demo else STANDIN_WORKLOAD,
         "resolution": [WIDTH, HEIGHT],
         "frames_per_step": FRAMES_PER_STEP,
-        "camera_path": f"{NUM_POSES}-pose Catmull-Rom loop, fov 0.375*pi",
+        "camera_path": f"{NUM_POSES} poses from info_player_start through the info_teleport_destination origins along the leaf portals, fov 0.375*pi" if is_demo else f"{NUM_POSES}-pose Catmull-Rom loop, fov 0.375*pi",
         "l2_policy": "inputs larger than L2: each frame streams >0.4 GB (surface pool + 66 MB HDR buffer + 33 MB picture) through a 126 MB L2",
-        "map": "synthetic stand-in: demo2.sqwm cannot be produced here (no rustc for map_compiler/lightmapper, textures not shipped)",
+        "map": "assets/_ref/demo2.sqwm: 14.0k polygons, 2.8k leafs, 8.2k portals, 96 submodels, 847k lightmap texels, 126 point lights + sun (direct light + constant ambient; the demo's bounced-light passes are not restated)" if is_demo else "synthetic stand-in: assets/_ref/demo2.sqwm is absent (it is compiled from /root/reference/demo/maps/demo2.map by __graft_entry__.build(), which needs the reference checkout) or --map standin was given",
     }
     if extra:
         cfg.update(extra)
@@ -210,7 +228,7 @@ def run_reference(args, rank, world):
     from square_wheel_b200.device import make_post_params
 
     cores = os.cpu_count() or 1
-    scene = S.Scene(**SCENE_KW)
+    scene, is_demo = make_workload(args.map)
     poses = scene.camera_path(NUM_POSES)
     frames, _ = prepare_host_frames(scene, poses)
     post = make_post_params(exposure=1.0)
@@ -241,7 +259,7 @@ def run_reference(args, rank, world):
         "vs_baseline": None,
         "dtype": "f32+i32/i64 (Color64 u16x4 pixels)",
         "data": "synthetic",
-        "config": workload_config(),
+        "config": workload_config(is_demo),
         "reference_impl": cpu.describe(),
         "cpu_baseline": {
             "value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
@@ -324,21 +342,23 @@ def run_view_batch(args, ctx, scene, poses, post, rank, world, dist, stream, bar
     return out
 
 
-def run_demo_map(args, local_rank, stream, post):
-    """The same measurement as the headline on the reference's own demo map 2 (BASELINE.json north_star), where
-    `__graft_entry__.build()` has compiled it (assets/_ref/demo2.sqwm: geometry, entities, lights and material definitions of
-    demo/maps/demo2.map through this repository's map compiler + direct-light lightmapper; texture IMAGES are seeded stand-ins).
-    64 poses from the player start through the teleport destinations along the leaf portals, 3840x2160 Color64 + fused tonemap,
-    device-resident recorded frames, four views in flight.  None where the map is absent."""
+def run_other_map(args, local_rank, stream, post, headline_is_demo):
+    """The headline's measurement repeated on the OTHER map: the seeded stand-in of the earlier rounds when the headline runs on the
+    compiled demo map 2 (so that rounds compare), the demo map when the headline had to fall back to the stand-in and the map is
+    there after all (--map standin).  64 poses, 3840x2160 Color64 + fused tonemap, device-resident recorded frames, four views in
+    flight.  None where there is no other map."""
     import torch
 
     from square_wheel_b200 import _native as N
     from square_wheel_b200 import scene as S
     from square_wheel_b200.device import Context
 
-    scene = S.demo2_scene(texture_size_log2=8)
-    if scene is None:
-        return None
+    if headline_is_demo:
+        scene, workload = S.Scene(**SCENE_KW), STANDIN_WORKLOAD
+    else:
+        scene, workload = S.demo2_scene(texture_size_log2=8), DEMO_WORKLOAD
+        if scene is None:
+            return None
     poses = scene.camera_path(NUM_POSES)
     host_frames, host_ms = prepare_host_frames(scene, poses)
     ctx = Context(scene.lightmaps, scene.directional_lightmaps, device=local_rank, stream=stream.cuda_stream, concurrent_views=True)
@@ -382,7 +402,7 @@ def run_demo_map(args, local_rank, stream, post):
     dom = max(kernels, key=kernels.get) if kernels else None
     peak_gbs, _ = load_peaks()
     out = {
-        "workload": "demo map 2 (demo/maps/demo2.map compiled + lit by this repository's tools), 3840x2160, Color64 HDR, directional lightmaps + normal maps + specular per demo_materials.json, fused tonemap",
+        "workload": workload,
         "value": args.steps * NUM_POSES / (ms * 1e-3),
         "unit": UNIT,
         "us_per_frame": ms * 1e3 / (args.steps * NUM_POSES),
@@ -396,7 +416,7 @@ def run_demo_map(args, local_rank, stream, post):
         "dominant_kernel": dom,
         "fused_minimum_bytes_per_frame": S_tex * 8 + P * 8 + P * 4,
         "frame_frac_of_measured_hbm_peak": (S_tex * 8 + P * 8 + P * 4) / (ms * 1e-3 / (args.steps * NUM_POSES)) / 1e9 / peak_gbs,
-        "note": "same recording / timing method as the headline (value stays on the stand-in so that rounds compare); pictures of this map are checked bit-exactly against the oracle in tests/test_frames_gpu.py::test_frames_of_the_demo_map",
+        "note": "same recording / timing method as the headline, on the other of the two maps (rounds 1 and 2 quoted the stand-in); pictures of both maps are checked bit-exactly against the oracle (tests/test_frames_gpu.py::test_frames_of_the_demo_map, tests/test_fused_gpu.py)",
     }
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
@@ -434,7 +454,7 @@ def run_cuda(args, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     # ---- scene + host preparation (the part of the renderer that stays on the host) ----
-    scene = S.Scene(**SCENE_KW)
+    scene, is_demo = make_workload(args.map)
     poses = scene.camera_path(NUM_POSES)
     # Weak scaling of the headline: independent camera views, no exchange step — EVERY rank renders the same 64
     # poses of configs[1], so that the per-N values differ only by what the machine does when N GPUs run at once (ranks rendering
@@ -764,9 +784,9 @@ def run_cuda(args, rank, local_rank, world):
             "note": cpu.describe(),
         }
 
-    demo_map = None
-    if rank == 0 and world == 1 and not args.kernels_only and not args.no_demo_map:
-        demo_map = run_demo_map(args, local_rank, stream, post)
+    other_map = None
+    if rank == 0 and world == 1 and not args.kernels_only and not args.no_other_map:
+        other_map = run_other_map(args, local_rank, stream, post, is_demo)
 
     if rank == 0:
         line = {
@@ -782,7 +802,7 @@ def run_cuda(args, rank, local_rank, world):
             "vs_baseline": None,
             "dtype": "f32+i32/i64 (Color64 u16x4 pixels)",
             "data": "synthetic",
-            "config": workload_config(),
+            "config": workload_config(is_demo),
             "workload_stats": {
                 "parallelism": f"x{world}: every GPU renders the same {NUM_POSES} independent camera views per step (no collective on the hot path), {NUM_VIEWS} views in flight per GPU on private streams",
                 "surface_texels_per_frame": per_frame[0],
@@ -795,7 +815,7 @@ def run_cuda(args, rank, local_rank, world):
                 "numa": numa,
             },
             "view_batch": view_batch,
-            "demo_map": demo_map,
+            "other_map": other_map,
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": launches,
@@ -839,7 +859,8 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-view-batch", action="store_true", help="skip the 8192-view 1080p batch record")
-    ap.add_argument("--no-demo-map", action="store_true", help="skip the record measured on the compiled demo map 2 (assets/_ref/demo2.sqwm)")
+    ap.add_argument("--no-other-map", action="store_true", help="skip the record measured on the other map (stand-in when the headline is demo map 2, and vice versa)")
+    ap.add_argument("--map", choices=["demo2", "standin"], default=None, help="headline map: demo2 (default where assets/_ref/demo2.sqwm exists) or the seeded stand-in of rounds 1-2")
     ap.add_argument("--kernels-only", action="store_true", help="development: device-resident timing and per-kernel times only (no e2e leg, no CPU baseline)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -209,14 +209,19 @@ def test_fused_tonemap_surfaces_and_triangles(assets, oracle_lib):
         view.close()
 
 
-def test_fused_tonemap_bench_scene_4k(oracle_lib):
-    """The frames bench.py times: its scene (SCENE_KW, seed 2, 256^2 textures), its resolution, its recorded-frame replay with
-    several views in flight on private streams — every pixel of the 64-bit and the 32-bit picture against the oracle."""
+@pytest.mark.parametrize("which", ["demo2", "standin"])
+def test_fused_tonemap_bench_scene_4k(oracle_lib, which):
+    """The frames bench.py times: its scene (demo map 2 where build() compiled it, and the seeded stand-in SCENE_KW of the earlier
+    rounds), its resolution, its recorded-frame replay with several views in flight on private streams — every pixel of the 64-bit
+    and the 32-bit picture against the oracle."""
     import bench
     from square_wheel_b200.device import Context
 
     W, H = bench.WIDTH, bench.HEIGHT
-    sc = S.Scene(**bench.SCENE_KW)
+    sc, is_demo = bench.make_workload(which)
+    if which == "demo2" and not is_demo:
+        sc.close()
+        pytest.skip("assets/_ref/demo2.sqwm is built by __graft_entry__.build() where /root/reference exists")
     ctx = Context(sc.lightmaps, sc.directional_lightmaps, device=0, concurrent_views=True)
     views, frames = [], []
     try:
@@ -233,7 +238,7 @@ def test_fused_tonemap_bench_scene_4k(oracle_lib):
         for i, hf in enumerate(hfs):
             f = views[i % 2].create_frame()
             f.set_surfaces(hf.jobs, None, None, hf.cam_pos, max_surface)
-            f.set_draw(hf.cmds, hf.polygon_points, None, clear_color=S.BACKGROUND_COLOR64 if hf.needs_clear else None)
+            f.set_draw(hf.cmds, hf.polygon_points, hf.triangle_points, clear_color=S.BACKGROUND_COLOR64 if hf.needs_clear else None)
             f.set_post(post)
             frames.append(f)
         # two rounds over the recorded frames like bench.py's steps (views alternate, the later frame of a view wins)
@@ -251,19 +256,27 @@ def test_fused_tonemap_bench_scene_4k(oracle_lib):
                     if rnd == 1:
                         continue  # the second round is compared through the first one's pictures below
                     surf = oracle_lib.build_surfaces(64, hf.jobs, None, None, hf.cam_pos, sc.images, sc.lightmaps, sc.directional_lightmaps, hf.total_surface_pixels, num_threads=4)
+                    got_surf = view.read_surfaces(0, hf.total_surface_pixels)
+                    # jobs without any layer (`light: false` materials with no emissive image) are written by nobody
+                    # (partial_renderer.rs:1700-1819): the oracle draws from what the pool holds there
+                    for j in hf.jobs[(hf.jobs["flags"] & (N.SURF_APPLY_DIFFUSE | N.SURF_EMISSIVE)) == 0]:
+                        o, n = int(j["surface_pixels_offset"]), int(j["surface_size"][0]) * int(j["surface_size"][1])
+                        surf[o : o + n] = got_surf[o : o + n]
                     fb = np.zeros((H, W), np.uint64)
                     if hf.needs_clear:
                         oracle_lib.fill(fb, S.BACKGROUND_COLOR64)
-                    oracle_lib.draw(64, fb, hf.cmds, hf.polygon_points, None, surf, sc.images)
+                    oracle_lib.draw(64, fb, hf.cmds, hf.polygon_points, hf.triangle_points, surf, sc.images)
                     want_ldr, want_avg, _ = oracle_lib.postprocess(fb, post, num_threads=4)
-                    assert_pixels_equal(view.read_surfaces(0, hf.total_surface_pixels), surf, f"pose {picks[i]} surfaces")
+                    assert_pixels_equal(got_surf, surf, f"pose {picks[i]} surfaces")
                     assert_pixels_equal(got_hdr, fb, f"pose {picks[i]} 64-bit picture")
                     assert_pixels_equal(got_ldr & 0xFFFFFF, want_ldr & 0xFFFFFF, f"pose {picks[i]} tonemapped picture")
                     np.testing.assert_allclose(got_avg, want_avg, rtol=1e-5, atol=1e-3)
                     first_ldr[i] = got_ldr
                 if rnd == 1:
                     for i in pair:
-                        assert_pixels_equal(views[i % 2].read_pixels32(), first_ldr[i], f"pose {picks[i]} replay")
+                        # (a frame that shows layer-less polygons shows whatever the view's pool held: not a replay invariant)
+                        if ((hfs[i].jobs["flags"] & (N.SURF_APPLY_DIFFUSE | N.SURF_EMISSIVE)) != 0).all():
+                            assert_pixels_equal(views[i % 2].read_pixels32(), first_ldr[i], f"pose {picks[i]} replay")
     finally:
         for f in frames:
             f.close()
