@@ -154,6 +154,8 @@ def prepare_host_frames(scene, poses, use_directional=True, width=None, height=N
     from square_wheel_b200 import scene as S
 
     hr = S.HostRenderer(scene, use_directional_lightmaps=use_directional)
+    # inline models as the reference's game shows them (doors, details, ...; not triggers, not the polygons that become view portals)
+    hr.build_frame(64, 64, poses[0], submodels=hr.game_submodel_entities())
     t0 = time.perf_counter()
     frames = [hr.build_frame(width or WIDTH, height or HEIGHT, p) for p in poses]
     host_ms = (time.perf_counter() - t0) * 1e3 / max(len(poses), 1)

@@ -804,6 +804,24 @@ int sqwh_map_light(const char* in_path, const char* materials_table, uint32_t sa
 	return (int)save_map(map, out_path);
 }
 
+// classname of the map entity that owns a submodel ("" when none): the game decides by it whether the inline model is drawn
+// (test_game/world_spawn.rs: triggers are invisible, func_mirror / func_camera_portal / func_parallax_portal become view portals)
+const char* sqwh_scene_submodel_classname(const Scene* s, uint32_t submodel_index)
+{
+	static thread_local std::string name;
+	name.clear();
+	const BSPMap& m = s->map;
+	for (const Entity& e : m.entities)
+		if (e.submodel_index == submodel_index)
+			for (uint32_t i = 0; i < e.num_key_value_pairs; ++i)
+			{
+				const KeyValuePair& kv = m.key_value_pairs[e.first_key_value_pair + i];
+				if (kv.key.size == 9 && std::memcmp(m.strings_data.data() + kv.key.offset, "classname", 9) == 0)
+					name.assign((const char*)m.strings_data.data() + kv.value.offset, kv.value.size);
+			}
+	return name.c_str();
+}
+
 // Replace the scene by a compiled map with materials bound by texture name (bind_compiled_map).  Returns a MapFileResult, or 4
 // when the map fails validate_map (message in sqwh_last_map_error).  No Renderer may exist for the scene meanwhile.
 int sqwh_scene_load_compiled_map(Scene* s, const char* path, const char* materials_table, uint32_t texture_size_log2, uint32_t seed)

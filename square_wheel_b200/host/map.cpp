@@ -1102,6 +1102,21 @@ void bind_compiled_map(Scene& s, BSPMap&& map, const mapc::MaterialTable& table,
 			mat.texture_images[k] = (uint32_t)s.images.size();
 			s.images.push_back(std::move(mips[k]));
 		}
+		if (def && def->emissive_layer) // material.rs EmissiveLayer: a TextureLite mixed in with the layer's light (surfaces.rs:854)
+		{
+			mat.has_emissive = true;
+			for (int c = 0; c < 3; ++c)
+				mat.emissive_light[c] = def->emissive_layer_light[c];
+			HostImage em[NUM_MIPS];
+			make_emissive_texture(rng, size, em[0]);
+			for (uint32_t k = 1; k < NUM_MIPS; ++k)
+				build_texture_lite_mip(em[k], em[k - 1]);
+			for (uint32_t k = 0; k < NUM_MIPS; ++k)
+			{
+				mat.emissive_images[k] = (uint32_t)s.images.size();
+				s.images.push_back(std::move(em[k]));
+			}
+		}
 		s.materials.push_back(mat);
 	}
 	for (Material& sky : s.materials)

@@ -1749,7 +1749,7 @@ void build_dummy_lightmaps(const MaterialTable& materials, BSPMap& map) // light
 }
 
 // One line per material: name bsp twosided blocks_view light shadow draw decals skybox blending normal_map roughness roughness_map
-// is_metal emissive_r emissive_g emissive_b (written by tools/map_compiler.py from the reference's materials/*.json, material.rs:7-98)
+// is_metal emissive_r emissive_g emissive_b [emissive_layer layer_r layer_g layer_b] (written by tools/map_compiler.py from the reference's materials/*.json, material.rs:7-98)
 MaterialTable parse_material_table(const std::string& text)
 {
 	// (no iostreams here: the library may be linked with a static libstdc++ next to a process-wide shared one)
@@ -1794,6 +1794,12 @@ MaterialTable parse_material_table(const std::string& text)
 		m.is_metal = flag(13);
 		for (int c = 0; c < 3; ++c)
 			m.emissive_light[c] = std::strtof(tok[14 + (size_t)c].c_str(), nullptr);
+		if (tok.size() >= 21)
+		{
+			m.emissive_layer = flag(17);
+			for (int c = 0; c < 3; ++c)
+				m.emissive_layer_light[c] = std::strtof(tok[18 + (size_t)c].c_str(), nullptr);
+		}
 		table[m.name] = m;
 	}
 	return table;

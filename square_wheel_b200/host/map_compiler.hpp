@@ -46,6 +46,8 @@ struct MaterialDef
 	bool normal_map = false, roughness_map = false, is_metal = false;
 	float roughness = 1.0f;
 	float emissive_light[3] = {0, 0, 0};
+	bool emissive_layer = false; // material.rs EmissiveLayer {image, light}
+	float emissive_layer_light[3] = {0, 0, 0};
 };
 typedef std::map<std::string, MaterialDef> MaterialTable;
 MaterialTable parse_material_table(const std::string& text);

@@ -219,6 +219,8 @@ def lib() -> C.CDLL:
         l.sqwh_scene_save_map.argtypes = [vp, C.c_char_p]
         l.sqwh_scene_load_map.restype = C.c_int
         l.sqwh_scene_load_map.argtypes = [vp, C.c_char_p]
+        l.sqwh_scene_submodel_classname.restype = C.c_char_p
+        l.sqwh_scene_submodel_classname.argtypes = [vp, C.c_uint32]
         l.sqwh_scene_load_compiled_map.restype = C.c_int
         l.sqwh_scene_load_compiled_map.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_uint32, C.c_uint32]
         l.sqwh_last_map_error.restype = C.c_char_p
@@ -606,6 +608,17 @@ class HostRenderer:
             e[i]["present"] = 1
             e[i]["position"] = c
             e[i]["rotation"] = (1.0, 0.0, 0.0, 0.0)
+        return e
+
+    def game_submodel_entities(self) -> np.ndarray:
+        """default_submodel_entities with the inline models hidden that the reference's game does not draw as such
+        (test_game/world_spawn.rs:33-55, :331-434): trigger_* volumes, and func_mirror / func_camera_portal / func_parallax_portal,
+        whose polygons become view portals (not set up here: BASELINE configs[1] runs with portals_depth 0)."""
+        e = self.default_submodel_entities()
+        for i in range(len(e)):
+            name = (self._lib.sqwh_scene_submodel_classname(self.scene._handle, i) or b"").decode()
+            if name.startswith("trigger") or name in ("func_mirror", "func_camera_portal", "func_parallax_portal"):
+                e[i]["present"] = 0
         return e
 
     def close(self):

@@ -230,6 +230,7 @@ def test_fused_tonemap_bench_scene_4k(oracle_lib, which):
         picks = (0, 21, 42, 63)
         first_ldr = {}
         hr = S.HostRenderer(sc, use_directional_lightmaps=True)
+        hr.build_frame(64, 64, poses[0], submodels=hr.game_submodel_entities())  # as bench.prepare_host_frames
         hfs = [hr.build_frame(W, H, poses[k]) for k in picks]
         hr.close()
         post = make_post_params(exposure=1.0)
@@ -267,10 +268,19 @@ def test_fused_tonemap_bench_scene_4k(oracle_lib, which):
                         oracle_lib.fill(fb, S.BACKGROUND_COLOR64)
                     oracle_lib.draw(64, fb, hf.cmds, hf.polygon_points, hf.triangle_points, surf, sc.images)
                     want_ldr, want_avg, _ = oracle_lib.postprocess(fb, post, num_threads=4)
+                    # A frame drawn from inside a leaf is not cleared (partial_renderer.rs:249-256: "normally no gaps between map
+                    # geometry should be visible"); a compiled map does show a few crack pixels between polygons, and those keep
+                    # what the buffer held before on either side.  They are left out of the comparison, and there must be few.
+                    covered = fb != 0
+                    uncovered = int(fb.size - covered.sum())
+                    assert uncovered <= 1e-4 * fb.size and (is_demo or uncovered == 0)
+                    if uncovered:
+                        got_hdr = np.where(covered, got_hdr, 0)
+                        got_ldr = np.where(covered, got_ldr, want_ldr)
                     assert_pixels_equal(got_surf, surf, f"pose {picks[i]} surfaces")
                     assert_pixels_equal(got_hdr, fb, f"pose {picks[i]} 64-bit picture")
                     assert_pixels_equal(got_ldr & 0xFFFFFF, want_ldr & 0xFFFFFF, f"pose {picks[i]} tonemapped picture")
-                    np.testing.assert_allclose(got_avg, want_avg, rtol=1e-5, atol=1e-3)
+                    np.testing.assert_allclose(got_avg, want_avg, rtol=1e-5, atol=1e-3 + uncovered * 65535.0 / fb.size)
                     first_ldr[i] = got_ldr
                 if rnd == 1:
                     for i in pair:

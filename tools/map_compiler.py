@@ -43,6 +43,8 @@ def materials_table(materials: dict) -> str:
         special = m.get("special_effect", "None")
         skybox = isinstance(special, dict) and "Skybox" in special
         e = m.get("emissive_light", [0.0, 0.0, 0.0])
+        layer = m.get("emissive_layer") or {}
+        ll = layer.get("light", [0.0, 0.0, 0.0])
         lines.append(
             " ".join(
                 str(x)
@@ -64,6 +66,10 @@ def materials_table(materials: dict) -> str:
                     float(e[0]),
                     float(e[1]),
                     float(e[2]),
+                    int(bool(layer)),
+                    float(ll[0]),
+                    float(ll[1]),
+                    float(ll[2]),
                 ]
             )
         )
