@@ -1154,7 +1154,7 @@ void bind_compiled_map(Scene& s, BSPMap&& map, const mapc::MaterialTable& table,
 	std::vector<Vec3f> stops;
 	{
 		const BSPMap& m = s.map;
-		std::vector<Vec3f> destinations;
+		std::vector<Vec3f> destinations, room_points;
 		for (const Entity& e : m.entities)
 		{
 			std::string classname;
@@ -1171,11 +1171,56 @@ void bind_compiled_map(Scene& s, BSPMap&& map, const mapc::MaterialTable& table,
 			}
 			if (!has_origin)
 				continue;
+			if (classname == "light") // free-standing point lights hang in the open space of the rooms
+				room_points.push_back(origin);
 			origin.z += 40.0f; // eye above the entity's origin
 			if (classname == "info_player_start")
 				stops.insert(stops.begin(), origin);
 			else if (classname == "info_teleport_destination")
 				destinations.push_back(origin);
+		}
+		// A tour of the part of the map the player start lies in (the demo's teleport destinations are rooms of their own that
+		// the leaf graph does not connect to it): after the start, ten times the room — a free-standing `light` entity stands for
+		// one — that is farthest, in portal hops, from every stop chosen so far.  Deterministic: ties go to the earlier entity.
+		if (!stops.empty() && !m.leafs.empty())
+		{
+			const size_t nl = m.leafs.size();
+			std::vector<uint32_t> dist(nl, ~0u);
+			auto relax_from = [&](uint32_t source) {
+				std::vector<uint32_t> queue{source};
+				dist[source] = 0;
+				for (size_t qi = 0; qi < queue.size(); ++qi)
+				{
+					const BSPLeaf& leaf = m.leafs[queue[qi]];
+					for (uint32_t k = 0; k < leaf.num_leaf_portals; ++k)
+					{
+						const Portal& portal = m.portals[m.leafs_portals[leaf.first_leaf_portal + k]];
+						const uint32_t other = portal.leafs[0] == queue[qi] ? portal.leafs[1] : portal.leafs[0];
+						if (dist[other] > dist[queue[qi]] + 1)
+						{
+							dist[other] = dist[queue[qi]] + 1;
+							queue.push_back(other);
+						}
+					}
+				}
+			};
+			relax_from(leaf_of_point(m, stops[0]));
+			std::vector<uint32_t> room_leafs;
+			for (const Vec3f& p : room_points)
+				room_leafs.push_back(leaf_of_point(m, p));
+			std::vector<Vec3f> tour;
+			for (int n = 0; n < 10; ++n)
+			{
+				size_t best = (size_t)-1;
+				for (size_t r = 0; r < room_points.size(); ++r)
+					if (dist[room_leafs[r]] != ~0u && dist[room_leafs[r]] > 0 && (best == (size_t)-1 || dist[room_leafs[r]] > dist[room_leafs[best]]))
+						best = r;
+				if (best == (size_t)-1)
+					break;
+				tour.push_back(room_points[best]);
+				relax_from(room_leafs[best]);
+			}
+			stops.insert(stops.end(), tour.begin(), tour.end());
 		}
 		stops.insert(stops.end(), destinations.begin(), destinations.end());
 	}
