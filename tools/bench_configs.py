@@ -153,6 +153,9 @@ def main():
 
     base_scene = dict(seed=2, grid=(24, 24, 5), cell_size=(160.0, 160.0, 128.0), num_rooms=26, num_materials=24, texture_size_log2=8, max_polygon_size=64.0, material_mode=0, emissive_fraction=0.15)
     configs = {
+        # the reference's own demo map 2 (assets/_ref/demo2.sqwm, compiled by __graft_entry__.build(); skipped where it is absent)
+        "configs[0] demo map 2, 1280x720 simple lightmaps LDR": dict(scene="demo2", size=(1280, 720), bits=32, directional=False, post=None),
+        "configs[1] variant B: demo map 2, 4K HDR + tonemap with the default bloom": dict(scene="demo2", size=(3840, 2160), bits=64, directional=True, post=dict(bloom_sigma=1.0)),
         "configs[0] 1280x720 simple lightmaps LDR": dict(scene=base_scene, size=(1280, 720), bits=32, directional=False, post=None),
         # ~20k visible polygons per frame on average (7.5-unit polygons: 0.75 M polygons in the map), mip bias -1 => mip 0
         "configs[2] stress 4K HDR: ~20k visible polygons, mip bias -1, 16 lights, 16 models": dict(
@@ -178,9 +181,13 @@ def main():
             continue
         W, H = cfg["size"]
         C = cfg["bits"] // 8
-        sc = S.Scene(**cfg["scene"])
+        sc = S.demo2_scene(texture_size_log2=8) if cfg["scene"] == "demo2" else S.Scene(**cfg["scene"])
+        if sc is None:
+            continue
         hr = S.HostRenderer(sc, use_directional_lightmaps=cfg["directional"], textures_mip_bias=cfg.get("mip_bias", 0.0), portals_depth=cfg.get("portals_depth", 1))
         path = sc.camera_path(64)
+        if cfg["scene"] == "demo2":  # inline models as the reference's game shows them (bench.prepare_host_frames)
+            hr.build_frame(64, 64, path[0], submodels=hr.game_submodel_entities())
         frames = []
         geometry_frames = []
         draw_orders = []
