@@ -306,3 +306,48 @@ def test_demo2_map_loads_and_draws(oracle_lib):
             hr.close()
     finally:
         sc.close()
+
+
+def test_load_compiled_map_errors_and_game_submodels(compiled, tmp_path):
+    """Scene.load_compiled_map reports what bsp_map_save_load.rs::load_map reports (missing file, bad id, bad version); the inline
+    models the reference's game does not draw as such are hidden by HostRenderer.game_submodel_entities (world_spawn.rs:33-55, :331-434)."""
+    _, _, _, table, lit = compiled
+    sc = S.Scene(num_materials=4, texture_size_log2=4, grid=(4, 4, 1), num_rooms=1)
+    try:
+        with pytest.raises(OSError):
+            sc.load_compiled_map(str(tmp_path / "missing.sqwm"), table)
+        bad = tmp_path / "bad.sqwm"
+        raw = bytearray(open(lit, "rb").read())
+        bad.write_bytes(b"XXXX" + bytes(raw[4:]))
+        with pytest.raises(OSError, match="bad id"):
+            sc.load_compiled_map(str(bad), table)
+        raw[4:8] = (10).to_bytes(4, "little")
+        bad.write_bytes(bytes(raw))
+        with pytest.raises(OSError, match="version"):
+            sc.load_compiled_map(str(bad), table)
+    finally:
+        sc.close()
+    # a map with a trigger volume, a mirror and a door: only the door is shown
+    text = two_rooms_map(door_entity=True)
+    text += '{\n"classname" "trigger_teleport"\n' + box_brush((300, 40, 0), (340, 80, 64), "wall") + "\n}\n"
+    text += '{\n"classname" "func_mirror"\n' + box_brush((500, 100, 20), (504, 160, 100), "wall") + "\n}\n"
+    path = str(tmp_path / "ents.sqwm")
+    stats = mc.compile_map(text, table, path, perform_csg=True, advanced=True)
+    assert stats["submodels"] == 3
+    sc = S.Scene(num_materials=4, texture_size_log2=4, grid=(4, 4, 1), num_rooms=1)
+    try:
+        sc.load_compiled_map(path, table, 5, 1)
+        hr = S.HostRenderer(sc)
+        try:
+            names = [(hr._lib.sqwh_scene_submodel_classname(sc._handle, i) or b"").decode() for i in range(3)]
+            assert names == ["func_door", "trigger_teleport", "func_mirror"]
+            assert list(hr.default_submodel_entities()["present"]) == [1, 1, 1]
+            assert list(hr.game_submodel_entities()["present"]) == [1, 0, 0]
+            pose = sc.camera_path(4)[0]
+            shown = hr.build_frame(320, 200, pose, submodels=hr.default_submodel_entities())
+            hidden = hr.build_frame(320, 200, pose, submodels=hr.game_submodel_entities())
+            assert len(hidden.cmds) <= len(shown.cmds)
+        finally:
+            hr.close()
+    finally:
+        sc.close()
