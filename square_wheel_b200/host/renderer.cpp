@@ -1354,7 +1354,22 @@ void Renderer::draw_frame(int color_bits) // PartialRenderer::draw_frame -> perf
 	const ClippingPolygon viewport_clipping_polygon = ClippingPolygon::from_box(0.0f, 0.0f, (float)width_, (float)height_);
 	draw_skybox(viewport_clipping_polygon, color_bits); // perform_rasterization_for_viewport_part (:1296): sky first
 	draw_tree(viewport_clipping_polygon);
+	draw_view_models(viewport_clipping_polygon);
 	stats_.num_draw_commands = (uint32_t)cmds_.size();
+}
+
+// partial_renderer.rs:2284-2309: models flagged VIEW_MODEL (the player's weapon) are drawn after everything else, over the whole
+// viewport and with no leaf clip planes — they belong to no leaf (dynamic_objects_index.rs:61 skips them).
+void Renderer::draw_view_models(const ClippingPolygon& viewport_clipping_polygon)
+{
+	for (size_t dynamic_model_index = 0; dynamic_model_index < frame_models_.size(); ++dynamic_model_index)
+	{
+		if (!(frame_models_[dynamic_model_index].flags & MODEL_FLAG_VIEW_MODEL))
+			continue;
+		const DynamicModelInfo entry = dynamic_model_to_dynamic_meshes_index_[dynamic_model_index];
+		for (uint32_t m = entry.first_visible_mesh; m < entry.first_visible_mesh + entry.num_visible_meshes; ++m)
+			draw_mesh(viewport_clipping_polygon, nullptr, 0, m);
+	}
 }
 
 void Renderer::draw_skybox(const ClippingPolygon& viewport_clipping_polygon, int color_bits) // partial_renderer.rs:2311-2448 (skybox_rotation = identity)

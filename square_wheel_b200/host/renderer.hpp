@@ -310,6 +310,7 @@ private:
 	void build_surface_jobs();
 	void draw_skybox(const ClippingPolygon& viewport_clipping_polygon, int color_bits);
 	void draw_tree(const ClippingPolygon& viewport_clipping_polygon);
+	void draw_view_models(const ClippingPolygon& viewport_clipping_polygon);
 	void draw_leaf(const ClippingPolygon& bounds, uint32_t leaf_index);
 	void draw_polygon(
 		const Vec3f clip_planes[8], const Vec3f* vertices_transformed, size_t num_vertices, const float depth_equation[3], const float tex_coord_equation[6],

@@ -114,6 +114,47 @@ def test_models_behind_the_camera_or_in_hidden_leafs_draw_nothing(scene):
         hr.close()
 
 
+def test_view_models_are_drawn_last_over_the_whole_viewport(scene, oracle_lib):
+    """ModelEntityDrawFlags::VIEW_MODEL (frame_info.rs:106): such a model belongs to no leaf (dynamic_objects_index.rs:61), is always
+    prepared (partial_renderer.rs:1048) and is drawn by draw_view_models after the tree (:1324, :2284-2309) with no leaf clip planes:
+    its triangle commands come after every other command of the frame, also when the model stands inside a wall."""
+    hr = S.HostRenderer(scene)
+    try:
+        path = scene.camera_path(32)
+        pose = path[5]
+        ents = _entities(scene, pose, 5)
+        plain = hr.build_frame(480, 270, pose, models=ents)
+        n_plain = int((plain.cmds["kind"] == N.CMD_TRIANGLE).sum())
+        assert n_plain > 0
+        # the first model becomes the view model: held 40 units ahead of the eye, and left where it stood
+        for position in (pose[:3] + 40.0 * np.array([-np.sin(pose[3]), np.cos(pose[3]), 0.0], np.float32), None):
+            view = ents.copy()
+            view[0]["flags"] = 1
+            if position is not None:
+                view[0]["position"] = position
+            hf = hr.build_frame(480, 270, pose, models=view)
+            kinds = hf.cmds["kind"]
+            tri = np.flatnonzero(kinds == N.CMD_TRIANGLE)
+            assert len(tri) > 0
+            # the frame without the view model is a prefix of this one: everything the view model adds comes last
+            others = view[1:].copy()
+            base = hr.build_frame(480, 270, pose, models=np.concatenate([np.zeros(0, S.model_entity_dtype), others]))
+            hf = hr.build_frame(480, 270, pose, models=view)
+            assert len(hf.cmds) > len(base.cmds)
+            tail = hf.cmds[len(base.cmds) :]
+            assert (tail["kind"] == N.CMD_TRIANGLE).all()
+            oracle_lib.reset_assert_failures()
+            surf = oracle_lib.build_surfaces(32, hf.jobs, None, None, hf.cam_pos, scene.images, scene.lightmaps, scene.directional_lightmaps, hf.total_surface_pixels)
+            fb = np.zeros((270, 480), np.uint32)
+            oracle_lib.draw(32, fb, hf.cmds, hf.polygon_points, hf.triangle_points, surf, scene.images)
+            assert oracle_lib.assert_failures() == 0
+            fb0 = np.zeros((270, 480), np.uint32)
+            oracle_lib.draw(32, fb0, base.cmds, base.polygon_points, base.triangle_points, surf, scene.images)
+            assert int((fb != fb0).sum()) > 200  # the view model is on the picture
+    finally:
+        hr.close()
+
+
 def test_default_lighting_uses_only_shadowless_dynamic_lights(scene):
     """ModelLighting::Default without a light grid: black without lights, lit by a shadow-less light, and NOT lit by a light
     whose shadow map lives on the device (documented limitation of the host mirror)."""
