@@ -568,7 +568,7 @@ __device__ __forceinline__ void setup_triangle_line(const TriRec* __restrict__ r
 #define SQW_BIN_CACHE 1024
 __device__ void bin_band(
 	const CmdDev* __restrict__ cmd_dev, uint32_t num_cmds, const uint32_t* __restrict__ band_offsets, const uint32_t* __restrict__ band_lists, uint32_t* __restrict__ tile_lists,
-	uint4* __restrict__ tile_desc, uint32_t tiles_x, int band)
+	uint4* __restrict__ tile_desc, uint32_t* __restrict__ general_tiles, uint32_t tiles_x, int band)
 {
 	constexpr int WARPS = SQW_SETUP_THREADS / 32;
 	__shared__ uint32_t s_idx[SQW_BIN_CACHE];
@@ -627,7 +627,15 @@ __device__ void bin_band(
 		// .w: tile class.  SQW_TILE_CLASS_OPAQUE = every command of the tile is a polygon drawn with BlendingMode::None: only the LAST
 		// command covering a pixel shows, which raster_tile_opaque_kernel exploits; everything else goes to raster_tile_kernel.
 		if (lane == 0)
-			tile_desc[(uint32_t)band * tiles_x + col] = make_uint4(list_start, count, (uint32_t)col_x0 | ((uint32_t)band_y0 << 16), complex ? SQW_TILE_CLASS_GENERAL : SQW_TILE_CLASS_OPAQUE);
+		{
+			const uint32_t tile = (uint32_t)band * tiles_x + col;
+			tile_desc[tile] = make_uint4(list_start, count, (uint32_t)col_x0 | ((uint32_t)band_y0 << 16), complex ? SQW_TILE_CLASS_GENERAL : SQW_TILE_CLASS_OPAQUE);
+			// The general tiles of the frame, as a compact list for raster_tile_kernel (in a frame of world geometry they are a
+			// few per cent of the tiles: that kernel no longer scans every descriptor to find them).  general_tiles[0] = count
+			// (zeroed by launch_raster_setup), entries from [SQW_GENERAL_LIST_HEADER]; any order will do.
+			if (complex)
+				general_tiles[SQW_GENERAL_LIST_HEADER + atomicAdd(general_tiles, 1u)] = tile;
+		}
 	}
 }
 
@@ -635,14 +643,14 @@ __global__ void __launch_bounds__(SQW_SETUP_THREADS) raster_setup_kernel(
 	const sqw_draw_cmd* __restrict__ cmds, const CmdDev* __restrict__ cmd_dev, uint32_t num_cmds, const sqw_polygon_point* __restrict__ polygon_points,
 	const TriRec* __restrict__ tri_recs, const uint2* __restrict__ chunks, uint32_t num_chunks, SpanRec* __restrict__ spans,
 	int32_t clip_w, int32_t clip_h, uint32_t setup_blocks, const uint32_t* __restrict__ band_offsets, const uint32_t* __restrict__ band_lists, uint32_t* __restrict__ tile_lists,
-	uint4* __restrict__ tile_desc, uint32_t tiles_x, uint32_t num_bands,
+	uint4* __restrict__ tile_desc, uint32_t* __restrict__ general_tiles, uint32_t tiles_x, uint32_t num_bands,
 	unsigned long long* __restrict__ sums_to_zero, uint8_t* __restrict__ tonemap_lut, float isb, float isg, float isr)
 {
 	// Grid order: binning CTAs FIRST (each is one long dependent chain over the whole command list — started last they were the
 	// tail of the kernel), then the tonemapping-table CTAs, then the span set-up CTAs.
 	if (blockIdx.x < num_bands)
 	{
-		bin_band(cmd_dev, num_cmds, band_offsets, band_lists, tile_lists, tile_desc, tiles_x, (int)blockIdx.x);
+		bin_band(cmd_dev, num_cmds, band_offsets, band_lists, tile_lists, tile_desc, general_tiles, tiles_x, (int)blockIdx.x);
 		return;
 	}
 	const uint32_t lut_blocks = tonemap_lut ? (3 * SQW_TONEMAP_LUT_SIZE + SQW_SETUP_THREADS - 1) / SQW_SETUP_THREADS : 0;
@@ -1074,11 +1082,17 @@ __global__ void __launch_bounds__(SQW_RASTER_THREADS, SQW_TILE_CTAS_PER_SM) rast
 	const CmdDev* __restrict__ cmd_dev, const SpanRec* __restrict__ spans, const uint32_t* __restrict__ tile_lists, const uint4* __restrict__ tile_desc,
 	const char* __restrict__ surfaces_base, typename C::Raw* __restrict__ color_buffer, int32_t width, int32_t height, int32_t pitch, int clear,
 	typename C::Raw clear_color, uint32_t* __restrict__ ldr, float isb, float isg, float isr, unsigned long long* __restrict__ sums,
-	const uint8_t* __restrict__ tonemap_lut, uint32_t num_tiles)
+	const uint8_t* __restrict__ tonemap_lut, uint32_t num_tiles, const uint32_t* __restrict__ general_tiles)
 {
 	typedef typename C::Raw Raw;
 	constexpr int WARPS = SQW_RASTER_THREADS / 32;
 	static_assert(WARPS * 32 == SQW_TILE_W && SQW_TILE_H == 8 && SQW_TILE_STAGE_HITS * SQW_TILE_H == 32, "tile geometry");
+	// The frame's general tiles as a list written by the binning CTAs ([0] count, entries from [SQW_GENERAL_LIST_HEADER]; the count
+	// is zeroed by launch_raster_setup before every binning).  A CTA with nothing to do leaves before it pays for anything (the
+	// tonemapping table copy is 12 KB per CTA).
+	const uint32_t num_general = __ldg(general_tiles);
+	if (blockIdx.x >= num_general)
+		return;
 	__shared__ uint4 s_cmd_all[WARPS][2][32];                                // per warp: [0] CmdDev words 0-3, [1] {texture pointer, tex_width, tex_height}
 	__shared__ uint4 s_span_all[WARPS][3][SQW_TILE_STAGE_HITS][SQW_TILE_H]; // per warp: SpanRec words of (staged command, block row)
 	// Per-channel tonemapping table (exact results for channel values < SQW_TONEMAP_LUT_SIZE, built by the set-up grid of
@@ -1101,26 +1115,17 @@ __global__ void __launch_bounds__(SQW_RASTER_THREADS, SQW_TILE_CTAS_PER_SM) rast
 
 	// Persistent CTAs: the grid is sized to what the GPU holds at once and every CTA strides over the tiles, so the
 	// per-CTA costs (tonemapping table, sum reduction, launch) are paid a few hundred times per frame, not once per tile.
-	uint4 desc_next = make_uint4(0, 0, 0, 0);
+	uint4 desc_next = __ldg(tile_desc + __ldg(general_tiles + SQW_GENERAL_LIST_HEADER + blockIdx.x));
 	uint32_t idx_next = 0;
-	if (blockIdx.x < num_tiles)
-	{
-		desc_next = __ldg(tile_desc + blockIdx.x);
-		if ((uint32_t)lane < desc_next.y)
-			idx_next = __ldg(tile_lists + desc_next.x + lane);
-	}
+	if ((uint32_t)lane < desc_next.y)
+		idx_next = __ldg(tile_lists + desc_next.x + lane);
 	const int ra = lane >> 3, rb = 4 + (lane >> 3); // this lane's two rows inside the block
-	for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+	for (uint32_t tile = blockIdx.x; tile < num_general; tile += gridDim.x) // (position in the list of general tiles)
 	{
 	const uint4 desc = desc_next; // {first entry in tile_lists, number of entries, tile_x0 | band_y0 << 16, -}
 	uint32_t idx = idx_next;
-	if (tile + gridDim.x < num_tiles)
-		desc_next = __ldg(tile_desc + tile + gridDim.x);
-	if (desc.w == SQW_TILE_CLASS_OPAQUE) // (CTA-uniform) rendered by raster_tile_opaque_kernel
-	{
-		idx_next = ((uint32_t)lane < desc_next.y && tile + gridDim.x < num_tiles) ? __ldg(tile_lists + desc_next.x + lane) : 0u;
-		continue;
-	}
+	if (tile + gridDim.x < num_general)
+		desc_next = __ldg(tile_desc + __ldg(general_tiles + SQW_GENERAL_LIST_HEADER + tile + gridDim.x));
 	// this warp's block and this lane's pixels
 	const int32_t blk_x0 = (int32_t)(desc.z & 0xFFFF) + warp * 32, blk_x1 = blk_x0 + 32;
 	const int32_t blk_y0 = (int32_t)(desc.z >> 16), blk_y1 = min(blk_y0 + SQW_TILE_H, height);
@@ -1245,7 +1250,7 @@ __global__ void __launch_bounds__(SQW_RASTER_THREADS, SQW_TILE_CTAS_PER_SM) rast
 	}
 
 	// first entries of the next tile's list: the latency overlaps the epilogue below
-	idx_next = ((uint32_t)lane < desc_next.y && tile + gridDim.x < num_tiles) ? __ldg(tile_lists + desc_next.x + lane) : 0u;
+	idx_next = ((uint32_t)lane < desc_next.y && tile + gridDim.x < num_general) ? __ldg(tile_lists + desc_next.x + lane) : 0u;
 
 	if (lut_pending) // (CTA-uniform: first tile of the CTA) the only CTA-wide barrier of the kernel
 	{
@@ -1767,12 +1772,20 @@ cudaError_t launch_raster_setup(const RasterLaunch& l, cudaStream_t stream)
 	const uint32_t setup_blocks = std::max<uint32_t>((l.num_chunks + chunks_per_block - 1) / chunks_per_block, 1); // block 0 also zeroes the sums
 	const uint32_t bin_blocks = l.num_bands; // also with an empty command list: the tile kernel reads every tile descriptor
 	const uint32_t lut_blocks = l.tonemap_dst ? (3 * SQW_TONEMAP_LUT_SIZE + SQW_SETUP_THREADS - 1) / SQW_SETUP_THREADS : 0;
+	// the binning CTAs append the frame's general tiles behind this counter (no general command -> no general tile, and
+	// launch_raster_tiles does not start the kernel that reads the list: frames of plain world geometry skip the reset)
+	if (l.num_general_cmds)
+	{
+		const cudaError_t e = cudaMemsetAsync(l.general_tiles, 0, sizeof(uint32_t), stream);
+		if (e != cudaSuccess)
+			return e;
+	}
 	if (l.num_triangle_cmds)
 		raster_triangle_setup_kernel<<<(l.num_cmds * 8 + 127) / 128, 128, 0, stream>>> // eight lanes per command, one interpolant per lane
 		(l.cmds, l.num_cmds, l.triangle_points, l.height, static_cast<TriRec*>(l.tri_recs));
 	raster_setup_kernel<<<setup_blocks + bin_blocks + lut_blocks, SQW_SETUP_THREADS, 0, stream>>>(
 		l.cmds, l.cmd_dev, l.num_cmds, l.polygon_points, static_cast<const TriRec*>(l.tri_recs), l.chunks, l.num_chunks, l.spans, l.width, l.height, setup_blocks, l.band_offsets,
-		l.band_lists, l.tile_lists, l.tile_desc, (uint32_t)((l.width + SQW_TILE_W - 1) / SQW_TILE_W), bin_blocks, l.tonemap_dst ? l.color_sums : nullptr, l.tonemap_dst ? l.tonemap_lut : nullptr, l.inv_scale_bgr[0], l.inv_scale_bgr[1], l.inv_scale_bgr[2]);
+		l.band_lists, l.tile_lists, l.tile_desc, l.general_tiles, (uint32_t)((l.width + SQW_TILE_W - 1) / SQW_TILE_W), bin_blocks, l.tonemap_dst ? l.color_sums : nullptr, l.tonemap_dst ? l.tonemap_lut : nullptr, l.inv_scale_bgr[0], l.inv_scale_bgr[1], l.inv_scale_bgr[2]);
 	return cudaGetLastError();
 }
 
@@ -1820,11 +1833,11 @@ cudaError_t launch_raster_tiles(const RasterLaunch& l, cudaStream_t stream)
 	}
 	// The other tiles: triangles, blended and alpha-tested polygons (the kernel skips the opaque class).
 	if (l.color64 && l.tonemap_dst)
-		raster_tile_kernel<Color64, 1><<<grid, SQW_RASTER_THREADS, 0, stream>>>(SQW_TILE_ARGS(uint64_t));
+		raster_tile_kernel<Color64, 1><<<grid, SQW_RASTER_THREADS, 0, stream>>>(SQW_TILE_ARGS(uint64_t), l.general_tiles);
 	else if (l.color64)
-		raster_tile_kernel<Color64, 0><<<grid, SQW_RASTER_THREADS, 0, stream>>>(SQW_TILE_ARGS(uint64_t));
+		raster_tile_kernel<Color64, 0><<<grid, SQW_RASTER_THREADS, 0, stream>>>(SQW_TILE_ARGS(uint64_t), l.general_tiles);
 	else
-		raster_tile_kernel<Color32, 0><<<grid, SQW_RASTER_THREADS, 0, stream>>>(SQW_TILE_ARGS(uint32_t));
+		raster_tile_kernel<Color32, 0><<<grid, SQW_RASTER_THREADS, 0, stream>>>(SQW_TILE_ARGS(uint32_t), l.general_tiles);
 #undef SQW_TILE_ARGS
 	return cudaGetLastError();
 }

@@ -1112,7 +1112,7 @@ int sqw_frame_set_surfaces(
 	return SQW_OK;
 }
 
-// Layout of sqw_view::band_lists (scratch of the binning CTAs of one draw): [band lists][tile lists][tile descriptors].
+// Layout of sqw_view::band_lists (scratch of the binning CTAs of one draw): [band lists][tile lists][tile descriptors][general tiles].
 static size_t bin_tile_lists_offset(uint32_t band_entries)
 {
 	return ((size_t)band_entries * 4 + 63) & ~(size_t)63;
@@ -1121,9 +1121,14 @@ static size_t bin_tile_desc_offset(uint32_t band_entries, uint32_t tiles_x)
 {
 	return bin_tile_lists_offset(band_entries) + (((size_t)band_entries * tiles_x * 4 + 63) & ~(size_t)63);
 }
+static size_t bin_general_tiles_offset(uint32_t band_entries, uint32_t tiles_x, uint32_t num_bands)
+{
+	return bin_tile_desc_offset(band_entries, tiles_x) + (size_t)num_bands * tiles_x * sizeof(uint4);
+}
 static size_t bin_scratch_bytes(uint32_t band_entries, uint32_t tiles_x, uint32_t num_bands)
 {
-	return bin_tile_desc_offset(band_entries, tiles_x) + (size_t)num_bands * tiles_x * sizeof(uint4) + 64;
+	// ... [general tiles: count + one entry per tile at most]
+	return bin_general_tiles_offset(band_entries, tiles_x, num_bands) + ((size_t)num_bands * tiles_x + SQW_GENERAL_LIST_HEADER) * sizeof(uint32_t) + 64;
 }
 
 int sqw_frame_set_draw(
@@ -1787,6 +1792,7 @@ int sqw_frame_submit(sqw_frame* f, uint32_t stages)
 			rl.band_lists = f->d_band_list;
 			rl.tile_lists = reinterpret_cast<uint32_t*>(base + bin_tile_lists_offset(f->total_band_entries));
 			rl.tile_desc = reinterpret_cast<uint4*>(base + bin_tile_desc_offset(f->total_band_entries, tiles_x));
+			rl.general_tiles = reinterpret_cast<uint32_t*>(base + bin_general_tiles_offset(f->total_band_entries, tiles_x, f->num_bands));
 		}
 		rl.band_offsets = f->d_band_offsets;
 		rl.num_bands = f->num_bands;

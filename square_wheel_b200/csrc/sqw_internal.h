@@ -94,6 +94,7 @@ cudaError_t launch_mix_texture(
 // Tile classes (tile_desc.w, written by the binning CTAs): which of the two tile kernels renders the tile.
 #define SQW_TILE_CLASS_GENERAL 0u /* raster_tile_kernel: any command mix, painter's order per pixel */
 #define SQW_TILE_CLASS_OPAQUE 1u  /* raster_tile_opaque_kernel: only polygons with BlendingMode::None */
+#define SQW_GENERAL_LIST_HEADER 2u /* words before the first entry of the general-tile list */
 #ifndef SQW_OPAQUE_STAGE_HITS
 #define SQW_OPAQUE_STAGE_HITS 8
 #endif
@@ -157,6 +158,7 @@ struct RasterLaunch
 	const uint32_t* band_offsets; // device, num_bands + 1
 	uint32_t* tile_lists;         // device, ordered command indices per 128x8 tile: tile (band, col) owns the slots
 	                              // [band_offsets[band] * tiles_x + col * N, + N), N = band list length
+	uint32_t* general_tiles;      // device, per view (sqw_view::d_general_tiles): [0] number of general tiles (zeroed per frame), entries from [SQW_GENERAL_LIST_HEADER]
 	uint4* tile_desc;             // device, {first slot, count, x0 | y0 << 16, -} per tile, written by the binning CTAs
 	uint32_t num_bands;
 	int32_t width, height, pitch;
