@@ -351,3 +351,67 @@ def test_load_compiled_map_errors_and_game_submodels(compiled, tmp_path):
             hr.close()
     finally:
         sc.close()
+
+
+def _polygon_area(v):
+    v = np.asarray(v, np.float64)
+    c = np.zeros(3)
+    for i in range(1, len(v) - 1):
+        c += np.cross(v[i] - v[0], v[i + 1] - v[0])
+    return 0.5 * float(np.linalg.norm(c))
+
+
+def _order_independent_summary(path):
+    """The facts tools/rust_golden/src/bin/map_golden.rs prints for the reference's compiler, read from a .sqwm file."""
+    raw = open(path, "rb").read()
+    lumps = np.frombuffer(raw, np.uint32, 96, 8).reshape(32, 3)
+
+    def lump(i, dtype):
+        o, es, n = (int(x) for x in lumps[i])
+        return np.frombuffer(raw, dtype, n, o) if es == np.dtype(dtype).itemsize else np.zeros(0, dtype)
+
+    polys = lump(2, N.map_polygon_dtype)
+    portals = lump(3, np.dtype([("leafs", "<u4", 2), ("plane", "<f4", 4), ("first_vertex", "<u4"), ("num_vertices", "<u4")]))
+    verts = lump(5, np.dtype(("<f4", 3)))
+    areas = sorted(_polygon_area(verts[p["first_vertex"] : p["first_vertex"] + p["num_vertices"]]) for p in polys)
+    portal_areas = sorted(_polygon_area(verts[p["first_vertex"] : p["first_vertex"] + p["num_vertices"]]) for p in portals)
+    return {"nodes": int(lumps[0][2]), "leafs": int(lumps[1][2]), "polygons": len(polys), "portals": len(portals), "submodels": int(lumps[7][2]),
+            "lightmap_texels": int(lumps[12][2]), "polygon_areas_sorted": areas, "portal_areas_sorted": portal_areas}
+
+
+def test_fixture_file_is_current():
+    """tests/golden/two_rooms.map (input of the reference-side emitter) is what two_rooms_map() writes."""
+    with open(os.path.join(ROOT, "tests", "golden", "two_rooms.map"), "r", encoding="utf-8") as f:
+        assert f.read() == two_rooms_map()
+
+
+GOLDEN_MAP = os.path.join(ROOT, "tests", "golden", "reference_map_compiler.json")
+
+
+@pytest.mark.skipif(not os.path.exists(GOLDEN_MAP), reason="tests/golden/reference_map_compiler.json is emitted by tools/rust_golden (map_golden) where a Rust toolchain exists")
+def test_compiler_against_the_reference_summary(tmp_path):
+    """Pins the C++ map compiler against the reference's own (order-independent facts: counts and the sorted areas of polygons and portals)."""
+    import json
+
+    golden = json.load(open(GOLDEN_MAP))
+    table = mc.materials_table({})
+    for name, csg, adv in (("csg_advanced", True, True), ("plain", False, False)):
+        path = str(tmp_path / f"{name}.sqwm")
+        st = mc.compile_map(two_rooms_map(), table, path, perform_csg=csg, advanced=adv)
+        want, got = golden[name], _order_independent_summary(path)
+        assert st["initial_polygons"] == want["initial_polygons"] and st["polygons_after_csg"] == want["polygons_after_csg"]
+        for key in ("nodes", "leafs", "polygons", "portals", "submodels", "lightmap_texels"):
+            assert got[key] == want[key], key
+        np.testing.assert_allclose(got["polygon_areas_sorted"], want["polygon_areas_sorted"], rtol=1e-5, atol=1e-2)
+        np.testing.assert_allclose(got["portal_areas_sorted"], want["portal_areas_sorted"], rtol=1e-5, atol=1e-2)
+
+
+def test_order_independent_summary_is_self_consistent(compiled):
+    """(the reader used for the reference comparison agrees with the compiler's own statistics)"""
+    _, stats, _, _, lit = compiled
+    got = _order_independent_summary(lit)
+    assert (got["nodes"], got["leafs"], got["polygons"], got["portals"], got["submodels"]) == (stats["nodes"], stats["leafs"], stats["polygons"], stats["portals"], stats["submodels"])
+    # the rooms' inner surface: two 256 x 256 x 128 rooms + the doorway's reveals, minus the door opening on both sides
+    inner = 2 * (2 * 256 * 256 + 4 * 256 * 128) - 2 * 64 * 96 + 32 * (2 * 96 + 64)
+    world = sum(got["polygon_areas_sorted"]) - (2 * 32 * 32 + 4 * 32 * 64)  # the door submodel's six faces
+    assert abs(world - inner) / inner < 0.02
