@@ -10,6 +10,8 @@ cp gpurun_out/bench_ref_$TAG.json profiles/${NAME}_bench_reference.json
 cp gpurun_out/configs_$TAG.json profiles/${NAME}_configs.json
 cp gpurun_out/launches_$TAG.csv profiles/${NAME}_launches.csv
 python tools/ncu_traffic.py gpurun_out/prof_$TAG.ncu-rep profiles/ncu_traffic.json > /dev/null
+# the line was printed before this capture was summarised: the fields bench.py copies from ncu_traffic.json now come from the capture of the same build
+python tools/refresh_ncu_fields.py profiles/${NAME}_bench.json profiles/ncu_traffic.json > /dev/null
 {
   echo "# ${NAME}: ncu --set full --clock-control none --import-source on (gpurun_out/prof_$TAG.ncu-rep, two consecutive frames of bench.py)"
   echo
