@@ -415,3 +415,82 @@ def test_order_independent_summary_is_self_consistent(compiled):
     inner = 2 * (2 * 256 * 256 + 4 * 256 * 128) - 2 * 64 * 96 + 32 * (2 * 96 + 64)
     world = sum(got["polygon_areas_sorted"]) - (2 * 32 * 32 + 4 * 32 * 64)  # the door submodel's six faces
     assert abs(world - inner) / inner < 0.02
+
+
+def _lightmap_blocks(sc, select):
+    """(polygon, lightmap block [h, w, 3]) of the polygons `select` accepts."""
+    polys, _verts, _ = sc.map_geometry()
+    for p in polys:
+        if not select(p):
+            continue
+        w = ((int(p["tex_coord_max"][0]) + 15) >> 4) - (int(p["tex_coord_min"][0]) >> 4) + 1
+        h = ((int(p["tex_coord_max"][1]) + 15) >> 4) - (int(p["tex_coord_min"][1]) >> 4) + 1
+        o = int(p["lightmap_data_offset"])
+        if o:
+            yield p, sc.lightmaps[o : o + w * h].reshape(h, w, 3)
+
+
+def test_sun_through_a_sky_ceiling_and_a_spot_light(tmp_path):
+    """map_lights.rs: the sun of worldspawn (`_sun_mangle`, `_sunlight`, `_sunlight_color`, :160-246) reaches a texel only through a
+    sky polygon (light_trace.rs get_sun_shadow_factor :162-176) and a `light` with a `target` is a spot light with half-angle
+    `angle` / 2 (:120-140).  A courtyard with a sky ceiling and a roofed half: sunlit floor = colour x cos(angle of incidence), the
+    floor under the roof gets no sun; the spot light lights its cone on the roofed floor and nothing outside it."""
+    b = []
+    b.append(box_brush((-16, -16, -16), (528, 272, 0), "floor"))
+    b.append(box_brush((-16, -16, 256), (272, 272, 272), "sky"))        # open half: sky ceiling high up
+    b.append(box_brush((256, -16, 128), (528, 272, 272), "ceiling"))    # roofed half: solid block down to z = 128
+    b.append(box_brush((-16, -16, 0), (0, 272, 256)))
+    b.append(box_brush((512, -16, 0), (528, 272, 128)))
+    b.append(box_brush((0, -16, 0), (512, 0, 256)))
+    b.append(box_brush((0, 256, 0), (512, 272, 256)))
+    world = '{\n"classname" "worldspawn"\n"_sun_mangle" "0 -90 0"\n"_sunlight" "2"\n"_sunlight_color" "255 128 0"\n' + "\n".join(b) + "\n}"
+    ents = [world, '{\n"classname" "info_player_start"\n"origin" "64 128 32"\n}']
+    ents.append('{\n"classname" "light"\n"origin" "448 128 120"\n"light" "100"\n"target" "t1"\n"angle" "60"\n}')
+    ents.append('{\n"classname" "info_null"\n"targetname" "t1"\n"origin" "448 128 0"\n}')
+    text = "\n".join(ents) + "\n"
+    materials = dict(MATERIALS, sky={"light": False, "special_effect": {"Skybox": {}}})
+    table = mc.materials_table(materials)
+    path = str(tmp_path / "yard.sqwm")
+    mc.compile_map(text, table, path, perform_csg=True, advanced=False)
+    st = mc.light_map(path, table, path, sample_grid_size=1)
+    assert st["sun_lights"] == 1 and st["point_lights"] == 1
+    sc = S.Scene(num_materials=4, texture_size_log2=4, grid=(4, 4, 1), num_rooms=1)
+    try:
+        sc.load_compiled_map(path, table, 5, 1)
+        _polys, verts, _ = sc.map_geometry()
+        sun = np.array([2.0 * 32.0 * 1.0, 2.0 * 32.0 * 128.0 / 255.0, 0.0])  # straight down (pitch -90): cos = 1 on the floor; colour 255 128 0
+        sunlit = shaded = 0
+        spot_hit = spot_miss = False
+
+        def is_floor(p):
+            return p["plane"][2] > 0 and abs(p["plane"][3]) < 1e-3
+
+        for p, block in _lightmap_blocks(sc, is_floor):
+            # world x / y of the texel columns / rows: the floor's texture axes are the QBSP ones (u = x, v = -y, scale 1, no offset)
+            assert tuple(np.round(p["tex_coord_equation"][0][:3], 6)) == (1.0, 0.0, 0.0) and tuple(np.round(p["tex_coord_equation"][1][:3], 6)) == (0.0, -1.0, 0.0)
+            xs = ((int(p["tex_coord_min"][0]) >> 4) + np.arange(block.shape[1])) * 16.0
+            ys = -((int(p["tex_coord_min"][1]) >> 4) + np.arange(block.shape[0])) * 16.0
+            inside = (ys > 16) & (ys < 240)
+            for col, x in enumerate(xs):
+                texels = block[inside, col]
+                if len(texels) == 0:
+                    continue
+                if 16 < x < 224:  # the open half, away from the roof's edge
+                    np.testing.assert_allclose(texels, np.broadcast_to(sun, texels.shape), rtol=0.02, atol=0.3)
+                    sunlit += len(texels)
+                elif 288 < x < 496:  # under the roof: no sun (red / green stay what the white spot light gives: equal to blue)
+                    np.testing.assert_allclose(texels[:, 0], texels[:, 2], atol=0.02)
+                    shaded += len(texels)
+                    d = np.hypot(x - 448.0, ys[inside] - 128.0)
+                    if (d < 40).any():
+                        spot_hit = spot_hit or float(texels[d < 40].min()) > 0.05
+                    if (d > 100).any():  # outside the 30 degree half-angle cone (radius 120 tan 30 = 69 units on the floor)
+                        spot_miss = True
+                        assert float(texels[d > 100].max()) < 1e-3
+        assert sunlit > 0 and shaded > 0 and spot_hit and spot_miss
+        # right below the spot light: 100 * 32 / 120^2 (the blue channel sees only the white spot light)
+        under = 100.0 * 32.0 / (120.0 - 1.0 / 16.0) ** 2
+        spot_best = max(float(block[..., 2].max()) for _p, block in _lightmap_blocks(sc, is_floor))
+        assert abs(spot_best - under) / under < 0.05
+    finally:
+        sc.close()
