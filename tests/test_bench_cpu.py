@@ -37,3 +37,29 @@ def test_cuda_arm_refuses_to_run_without_a_device():
     r = _run("--steps", "1", "--warmup", "3", "--no-cpu-baseline")
     assert r.returncode != 0
     assert "no CPU fallback" in r.stderr and r.stdout.strip() == ""
+
+
+def test_headline_workload_selection():
+    """configs[1] is quoted on demo map 2: bench.make_workload picks the compiled demo map where build() produced it and the seeded
+    stand-in otherwise (or on request); the two arms describe whichever they use in config.workload / config.map."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from square_wheel_b200 import scene as S
+
+    sc, is_demo = bench.make_workload("standin")
+    try:
+        assert not is_demo and sc.info.num_polygons > 10000 and "stand-in" in bench.workload_config(False)["workload"]
+    finally:
+        sc.close()
+    sc, is_demo = bench.make_workload(None)
+    try:
+        assert is_demo == os.path.exists(S.DEMO2_MAP_PATH)
+        cfg = bench.workload_config(is_demo)
+        assert ("demo map 2" in cfg["workload"]) == is_demo and ("demo2.sqwm" in cfg["map"])
+        poses = sc.camera_path(bench.NUM_POSES)
+        assert len(poses) == bench.NUM_POSES
+        if is_demo:
+            # the path starts at the demo's info_player_start (2560 -648 -352, eye 40 above) and stays inside the map's bounds
+            assert abs(poses[0][0] - 2560) < 600 and abs(poses[0][1] + 648) < 600  # (the first pose is half a step along the path)
+    finally:
+        sc.close()
