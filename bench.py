@@ -56,7 +56,7 @@ def workload_config(is_demo=False, extra=None):
         "workload": DEMO_WORKLOAD if is_demo else STANDIN_WORKLOAD,
         "resolution": [WIDTH, HEIGHT],
         "frames_per_step": FRAMES_PER_STEP,
-        "camera_path": f"{NUM_POSES} poses from info_player_start through the info_teleport_destination origins along the leaf portals, fov 0.375*pi" if is_demo else f"{NUM_POSES}-pose Catmull-Rom loop, fov 0.375*pi",
+        "camera_path": f"{NUM_POSES} poses at equal arc-length steps from info_player_start through the farthest rooms of its part of the map and the info_teleport_destination rooms, along the leaf portals, fov 0.375*pi" if is_demo else f"{NUM_POSES}-pose Catmull-Rom loop, fov 0.375*pi",
         "l2_policy": "inputs larger than L2: each frame streams >0.4 GB (surface pool + 66 MB HDR buffer + 33 MB picture) through a 126 MB L2",
         "map": "assets/_ref/demo2.sqwm: 14.0k polygons, 2.8k leafs, 8.2k portals, 96 submodels, 847k lightmap texels, 126 point lights + sun (direct light + constant ambient; the demo's bounced-light passes are not restated)" if is_demo else "synthetic stand-in: assets/_ref/demo2.sqwm is absent (it is compiled from /root/reference/demo/maps/demo2.map by __graft_entry__.build(), which needs the reference checkout) or --map standin was given",
     }
