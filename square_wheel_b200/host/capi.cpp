@@ -754,6 +754,8 @@ int64_t sqwh_scene_model_copy(const Scene* s, uint32_t index, uint32_t mesh_inde
 // Returns 0, 1 (i/o error writing the map) or 5 (the map text does not parse / holds no entity); the tool's messages go to log.
 int sqwh_map_compile(const char* map_text, const char* materials_table, uint32_t flags, const char* out_path, uint32_t* stats_out, char* log, uint32_t log_capacity)
 {
+	if (!out_path)
+		return (int)MAP_FILE_IO_ERROR;
 	mapc::CompileOptions opt;
 	opt.perform_csg = (flags & 1u) != 0;
 	opt.advanced_splitter_plane_selection = (flags & 2u) != 0;
@@ -782,6 +784,8 @@ int sqwh_map_compile(const char* map_text, const char* materials_table, uint32_t
 // (direct light only: lightmapper.cpp).  stats_out: 4 x u32 (mapc::LightmapStats).  Returns a MapFileResult.
 int sqwh_map_light(const char* in_path, const char* materials_table, uint32_t sample_grid_size, float light_scale, float ambient_light, int32_t directional, float light_cutoff, const char* out_path, uint32_t* stats_out)
 {
+	if (!in_path || !out_path)
+		return (int)MAP_FILE_IO_ERROR;
 	BSPMap map;
 	const MapFileResult r = load_map(in_path, map);
 	if (r != MAP_FILE_OK)
@@ -826,6 +830,8 @@ const char* sqwh_scene_submodel_classname(const Scene* s, uint32_t submodel_inde
 // when the map fails validate_map (message in sqwh_last_map_error).  No Renderer may exist for the scene meanwhile.
 int sqwh_scene_load_compiled_map(Scene* s, const char* path, const char* materials_table, uint32_t texture_size_log2, uint32_t seed)
 {
+	if (!s || !path)
+		return (int)MAP_FILE_IO_ERROR;
 	BSPMap map;
 	const MapFileResult r = load_map(path, map);
 	if (r != MAP_FILE_OK)
