@@ -795,7 +795,8 @@ int sqwh_map_light(const char* in_path, const char* materials_table, uint32_t sa
 	settings.sample_grid_size = sample_grid_size;
 	settings.light_scale = light_scale;
 	settings.ambient_light = ambient_light;
-	settings.build_directional_lightmap = directional != 0;
+	settings.build_directional_lightmap = (directional & 1) != 0;
+	settings.use_pvs = (directional & 2) != 0; // bit 1 of `directional`: --use-pvs
 	if (light_cutoff > 0.0f)
 		settings.light_cutoff = light_cutoff;
 	mapc::LightmapStats st;
@@ -806,6 +807,22 @@ int sqwh_map_light(const char* in_path, const char* materials_table, uint32_t sa
 		std::memcpy(stats_out, v, sizeof(v));
 	}
 	return (int)save_map(map, out_path);
+}
+
+// Leaf-to-leaf visibility matrix of a map file (pvs.rs calculate_visibility_matrix): writes num_leafs^2 bytes when `capacity` allows
+// and returns num_leafs, or a negative MapFileResult.
+int64_t sqwh_map_pvs(const char* in_path, uint8_t* out, uint64_t capacity)
+{
+	if (!in_path)
+		return -(int64_t)MAP_FILE_IO_ERROR;
+	BSPMap map;
+	const MapFileResult r = load_map(in_path, map);
+	if (r != MAP_FILE_OK)
+		return -(int64_t)r;
+	const std::vector<uint8_t> m = mapc::calculate_leafs_visibility(map);
+	if (out && m.size() <= capacity)
+		std::memcpy(out, m.data(), m.size());
+	return (int64_t)map.leafs.size();
 }
 
 // classname of the map entity that owns a submodel ("" when none): the game decides by it whether the inline model is drawn

@@ -9,12 +9,14 @@
 //                             and sun lights), correct_sample_position :2122
 //   light_hemisphere.rs       add_point_light, extract_ambient_light, calculate_light_direction
 //   light_cube.rs             LightCube (add_light_sample, scale, convert_into_light_grid_sample)
-// Not restated: the PVS that limits the lights per leaf (pvs.rs; replaced by a contribution cut-off, LightmappingSettings::
-// light_cutoff), secondary (bounced) and emissive-surface light.  The light grid (prepare_light_grid :1614, calculate_light_grid :1643,
+// The PVS that limits the lights per leaf (pvs.rs) is restated too and used on request (LightmappingSettings::use_pvs, `--use-pvs`);
+// by default a contribution cut-off (LightmappingSettings::light_cutoff) picks the lights of a polygon, which is what the demo map
+// of the benchmark was lit with.  Not restated: secondary (bounced) and emissive-surface light.  The light grid (prepare_light_grid :1614, calculate_light_grid :1643,
 // calculate_light_for_grid_point :1861 for primary and sun lights, correct_light_grid_sample_position :2005, compress_light_grid
 // :1772, light_cube.rs) is built from the same direct light.  Host-only, offline.  Parity with the Rust tool: UNPINNED, as for the
 // map compiler.
 #include "map_compiler.hpp"
+#include "renderer.hpp" // ClippingPolygon (common/clipping_polygon.rs)
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -442,6 +444,195 @@ struct LightHemisphere
 	}
 };
 
+// ---- pvs.rs: leaf-to-leaf visibility (LightmappingSettings::use_pvs) ---------------------------------------------------------------
+// Per leaf and per portal of it: a breadth-first wave through the portal graph, every portal projected from each vertex of the
+// start portal (90 degree views along the portal's normal) and its screen bounds intersected with the bounds under which its leaf
+// was reached; a leaf that is ever reached is potentially visible.  The matrix keeps a pair only when each leaf sees the other.
+struct Pvs
+{
+	size_t num_leafs = 0;
+	std::vector<std::vector<uint8_t>> rows; // rows[a][b] != 0: b potentially visible from a (symmetrised)
+};
+
+size_t clip_polygon_by_z_plane(const Vec3f* polygon, size_t n, float z_dist, Vec3f* out, size_t out_cap) // clipping.rs:4-57
+{
+	size_t count = 0;
+	const Vec3f* prev = &polygon[n - 1];
+	for (size_t i = 0; i < n; ++i)
+	{
+		const Vec3f* v = &polygon[i];
+		if (v->z > z_dist)
+		{
+			if (prev->z < z_dist && count < out_cap)
+			{
+				const float d0 = prev->z - z_dist, d1 = v->z - z_dist, sum = v->z - prev->z;
+				out[count++] = *prev * (d1 / sum) - *v * (d0 / sum);
+			}
+			if (count < out_cap)
+				out[count++] = *v;
+		}
+		else if (v->z == z_dist)
+		{
+			if (count < out_cap)
+				out[count++] = *v;
+		}
+		else if (prev->z > z_dist && count < out_cap)
+		{
+			const float d0 = prev->z - z_dist, d1 = v->z - z_dist, sum = v->z - prev->z;
+			out[count++] = *prev * (d1 / sum) - *v * (d0 / sum);
+		}
+		prev = v;
+	}
+	return count;
+}
+
+bool project_portal(const BSPMap& map, const Portal& portal, const std::vector<Mat4f>& view_matrices, ClippingPolygon& result) // pvs.rs:250-305
+{
+	const size_t MAX_VERTICES = 24;
+	Vec3f transformed[MAX_VERTICES], clipped[MAX_VERTICES + 8];
+	bool have = false;
+	for (const Mat4f& vm : view_matrices)
+	{
+		size_t count = std::min<size_t>(portal.num_vertices, MAX_VERTICES);
+		for (size_t i = 0; i < count; ++i)
+			transformed[i] = view_matrix_transform_vertex(vm, map.vertices[portal.first_vertex + i]);
+		count = clip_polygon_by_z_plane(transformed, count, 1.0f / 4096.0f, clipped, MAX_VERTICES + 8);
+		if (count < 3)
+			continue;
+		for (size_t i = 0; i < count; ++i)
+		{
+			const Vec2f point{clipped[i].x / clipped[i].z, clipped[i].y / clipped[i].z};
+			if (have)
+				result.extend_with_point(point);
+			else
+			{
+				result = ClippingPolygon::from_point(point);
+				have = true;
+			}
+		}
+	}
+	return have;
+}
+
+void calculate_pvs_for_leaf_portal(const BSPMap& map, uint32_t start_leaf, uint32_t start_portal, std::vector<uint8_t>& visible) // pvs.rs:97-218
+{
+	const Portal& portal = map.portals[start_portal];
+	const uint32_t first = portal.leafs[0] == start_leaf ? portal.leafs[1] : portal.leafs[0];
+	struct VisLeaf
+	{
+		bool has_bounds = false;
+		ClippingPolygon bounds;
+		size_t last_push_iteration = 0;
+	};
+	std::vector<VisLeaf> data(map.leafs.size());
+	const float inf = 1e36f;
+	data[first].has_bounds = true;
+	data[first].bounds = ClippingPolygon::from_box(-inf, -inf, inf, inf);
+	// calculate_portal_view_matrices :220-248
+	Vec3f dir = portal.plane.vec;
+	if (portal.leafs[0] == start_leaf)
+		dir = -dir;
+	const float azimuth = std::atan2(-dir.x, dir.y), elevation = std::atan2(dir.z, std::sqrt(dir.x * dir.x + dir.y * dir.y));
+	std::vector<Mat4f> view_matrices;
+	for (uint32_t i = 0; i < portal.num_vertices; ++i)
+		view_matrices.push_back(build_view_matrix(map.vertices[portal.first_vertex + i], azimuth, elevation, 3.14159265358979323846f * 0.5f, 1.0f, 1.0f).view_matrix);
+	std::vector<uint32_t> cur{first}, next;
+	size_t iteration = 1;
+	while (!cur.empty())
+	{
+		for (uint32_t leaf_index : cur)
+		{
+			const ClippingPolygon prev_bounds = data[leaf_index].bounds;
+			const BSPLeaf& leaf = map.leafs[leaf_index];
+			for (uint32_t k = 0; k < leaf.num_leaf_portals; ++k)
+			{
+				const Portal& p = map.portals[map.leafs_portals[leaf.first_leaf_portal + k]];
+				const uint32_t next_leaf = p.leafs[0] == leaf_index ? p.leafs[1] : p.leafs[0];
+				ClippingPolygon bounds;
+				if (!project_portal(map, p, view_matrices, bounds))
+					continue;
+				bounds.intersect(prev_bounds);
+				if (!bounds.is_valid_and_non_empty())
+					continue;
+				VisLeaf& d = data[next_leaf];
+				if (d.has_bounds)
+				{
+					if (d.bounds.contains(bounds))
+						continue;
+					d.bounds.extend(bounds);
+				}
+				else
+				{
+					d.has_bounds = true;
+					d.bounds = bounds;
+				}
+				if (d.last_push_iteration < iteration)
+				{
+					d.last_push_iteration = iteration;
+					next.push_back(next_leaf);
+				}
+			}
+		}
+		cur.clear();
+		std::swap(cur, next);
+		if (++iteration >= 256)
+			break;
+	}
+	for (size_t i = 0; i < data.size(); ++i)
+		if (data[i].has_bounds)
+			visible[i] = 1;
+}
+
+Pvs calculate_visibility_matrix(const BSPMap& map) // pvs.rs:7-67
+{
+	Pvs pvs;
+	pvs.num_leafs = map.leafs.size();
+	std::vector<std::vector<uint8_t>> sets(pvs.num_leafs);
+	std::atomic<size_t> next{0};
+	const unsigned nt = std::min(std::max(std::thread::hardware_concurrency(), 1u), 64u);
+	std::vector<std::thread> threads;
+	for (unsigned t = 0; t < nt; ++t)
+		threads.emplace_back([&] {
+			for (;;)
+			{
+				const size_t leaf_index = next.fetch_add(1);
+				if (leaf_index >= pvs.num_leafs)
+					break;
+				std::vector<uint8_t>& set = sets[leaf_index]; // calculate_pvs_bit_set_for_leaf :71-87
+				set.assign(pvs.num_leafs, 0);
+				set[leaf_index] = 1;
+				const BSPLeaf& leaf = map.leafs[leaf_index];
+				for (uint32_t k = 0; k < leaf.num_leaf_portals; ++k)
+					calculate_pvs_for_leaf_portal(map, (uint32_t)leaf_index, map.leafs_portals[leaf.first_leaf_portal + k], set);
+			}
+		});
+	for (std::thread& th : threads)
+		th.join();
+	pvs.rows.assign(pvs.num_leafs, std::vector<uint8_t>(pvs.num_leafs, 0));
+	for (size_t x = 0; x < pvs.num_leafs; ++x)
+		for (size_t y = 0; y < pvs.num_leafs; ++y)
+			pvs.rows[y][x] = sets[x][y] & sets[y][x];
+	return pvs;
+}
+
+void collect_submodel_leafs_r(const BSPMap& map, const Vec3f (&bbox_vertices)[8], uint32_t node_index, std::vector<uint32_t>& out) // lightmaps_builder.rs:741-775
+{
+	if (node_index >= FIRST_LEAF_INDEX)
+	{
+		out.push_back(node_index - FIRST_LEAF_INDEX);
+		return;
+	}
+	const BSPNode& node = map.nodes[node_index];
+	size_t front = 0;
+	for (const Vec3f& v : bbox_vertices)
+		if (dot(node.plane.vec, v) > node.plane.dist)
+			++front;
+	if (front > 0)
+		collect_submodel_leafs_r(map, bbox_vertices, node.children[0], out);
+	if (front < 8)
+		collect_submodel_leafs_r(map, bbox_vertices, node.children[1], out);
+}
+
 struct PolygonLighter
 {
 	const BSPMap& map;
@@ -452,7 +643,9 @@ struct PolygonLighter
 	uint32_t sample_grid_size;
 
 	// lightmaps_builder.rs:467-603 (simple) and :969-1112 (directional) over the same sample positions
-	void light_polygon(const Polygon& polygon, float* simple, sqw_directional_lightmap_element* directional) const
+	// `visible_lights`: the lights of the leafs the polygon's leaf (or submodel) can see (build_primary_lightmaps :391-465), or null
+	// when the PVS is not used: then every light whose unshadowed contribution can exceed the cut-off
+	void light_polygon(const Polygon& polygon, float* simple, sqw_directional_lightmap_element* directional, const std::vector<const PointLight*>* visible_lights = nullptr) const
 	{
 		const uint32_t size[2] = {get_lightmap_size(polygon.tex_coord_min[0], polygon.tex_coord_max[0]), get_lightmap_size(polygon.tex_coord_min[1], polygon.tex_coord_max[1])};
 		const Vec3f normal = polygon.plane.vec / magnitude(polygon.plane.vec);
@@ -481,6 +674,9 @@ struct PolygonLighter
 
 		// lights that can matter for this polygon (stands in for the reference's per-leaf PVS light list)
 		std::vector<const PointLight*> near_lights;
+		if (visible_lights)
+			near_lights = *visible_lights;
+		else
 		{
 			float radius = 0;
 			for (uint32_t i = 0; i < polygon.num_vertices; ++i)
@@ -794,6 +990,15 @@ uint32_t build_light_grid(const LightmappingSettings& settings, uint32_t sample_
 }
 } // namespace
 
+std::vector<uint8_t> calculate_leafs_visibility(const BSPMap& map)
+{
+	const Pvs pvs = calculate_visibility_matrix(map);
+	std::vector<uint8_t> out(pvs.num_leafs * pvs.num_leafs);
+	for (size_t y = 0; y < pvs.num_leafs; ++y)
+		std::copy(pvs.rows[y].begin(), pvs.rows[y].end(), out.begin() + y * pvs.num_leafs);
+	return out;
+}
+
 void build_lightmaps(const LightmappingSettings& settings_in, const MaterialTable& materials, BSPMap& map, LightmapStats& stats)
 {
 	LightmappingSettings settings = settings_in;
@@ -846,6 +1051,54 @@ void build_lightmaps(const LightmappingSettings& settings_in, const MaterialTabl
 		map.lightmaps_data[i] = settings.ambient_light; // element 0 (build_lightmaps fills every element with the ambient term first)
 
 	PolygonLighter lighter{map, tracer, lights, sun_lights, settings, sample_grid_size};
+	// With the PVS (the reference's way): a polygon is lit by the lights standing in leafs its own leaf can see
+	// (group_lights_by_leafs :229-240, get_visible_leafs :683-700, get_visible_leafs_for_submodel :702-739).
+	std::vector<std::vector<const PointLight*>> polygon_lights; // per polygon, only with use_pvs
+	if (settings.use_pvs)
+	{
+		const Pvs pvs = calculate_visibility_matrix(map);
+		std::vector<std::vector<const PointLight*>> by_leaf(map.leafs.size());
+		for (const PointLight& l : lights)
+			by_leaf[leaf_for_point(map, l.pos)].push_back(&l);
+		auto lights_of_row = [&](const std::vector<uint8_t>& row) {
+			std::vector<const PointLight*> out;
+			for (size_t other = 0; other < row.size(); ++other)
+				if (row[other])
+					out.insert(out.end(), by_leaf[other].begin(), by_leaf[other].end());
+			return out;
+		};
+		polygon_lights.resize(map.polygons.size());
+		for (size_t li = 0; li < map.leafs.size(); ++li)
+		{
+			const std::vector<const PointLight*> ll = lights_of_row(pvs.rows[li]);
+			for (uint32_t k = 0; k < map.leafs[li].num_polygons; ++k)
+				polygon_lights[map.leafs[li].first_polygon + k] = ll;
+		}
+		for (const Submodel& sm : map.submodels)
+		{
+			Vec3f lo{1e24f, 1e24f, 1e24f}, hi{-1e24f, -1e24f, -1e24f}; // get_submodel_bbox (bsp_map_compact.rs:236-258)
+			for (uint32_t k = 0; k < sm.num_polygons; ++k)
+			{
+				const Polygon& p = map.polygons[sm.first_polygon + k];
+				for (uint32_t v = 0; v < p.num_vertices; ++v)
+					for (int a = 0; a < 3; ++a)
+					{
+						lo.at(a) = std::fmin(lo[a], map.vertices[p.first_vertex + v][a]);
+						hi.at(a) = std::fmax(hi[a], map.vertices[p.first_vertex + v][a]);
+					}
+			}
+			const Vec3f corners[8] = {{lo.x, lo.y, lo.z}, {lo.x, lo.y, hi.z}, {lo.x, hi.y, lo.z}, {lo.x, hi.y, hi.z}, {hi.x, lo.y, lo.z}, {hi.x, lo.y, hi.z}, {hi.x, hi.y, lo.z}, {hi.x, hi.y, hi.z}};
+			std::vector<uint32_t> leafs;
+			collect_submodel_leafs_r(map, corners, map.root_node(), leafs);
+			std::vector<uint8_t> row(map.leafs.size(), 0);
+			for (uint32_t l : leafs)
+				for (size_t other = 0; other < row.size(); ++other)
+					row[other] |= pvs.rows[l][other];
+			const std::vector<const PointLight*> ll = lights_of_row(row);
+			for (uint32_t k = 0; k < sm.num_polygons; ++k)
+				polygon_lights[sm.first_polygon + k] = ll;
+		}
+	}
 	std::atomic<size_t> next{0};
 	const unsigned nt = std::min(std::max(std::thread::hardware_concurrency(), 1u), 64u);
 	std::vector<std::thread> threads;
@@ -860,7 +1113,7 @@ void build_lightmaps(const LightmappingSettings& settings_in, const MaterialTabl
 					break;
 				for (size_t k = i; k < std::min(i + 16, map.polygons.size()); ++k)
 					if (map.polygons[k].lightmap_data_offset != 0)
-						lighter.light_polygon(map.polygons[k], simple, directional); // each polygon owns its lightmap range
+						lighter.light_polygon(map.polygons[k], simple, directional, settings.use_pvs ? &polygon_lights[k] : nullptr); // each polygon owns its lightmap range
 			}
 		});
 	for (std::thread& th : threads)

@@ -99,12 +99,15 @@ struct LightmappingSettings // lightmaps_builder.rs:8-20 (the subset of a direct
 	bool build_directional_lightmap = true;
 	float light_grid_cell_width = 64.0f, light_grid_cell_height = 64.0f;
 	float light_cutoff = 1.0f / 512.0f; // (not in the reference) a point light is skipped where its unshadowed contribution stays below this
+	bool use_pvs = false;               // the reference's way instead: lights of the leafs the polygon's leaf can see (pvs.rs)
 };
 struct LightmapStats
 {
 	uint32_t point_lights = 0, sun_lights = 0, lightmap_texels = 0, light_grid_samples = 0;
 };
 void build_lightmaps(const LightmappingSettings& settings, const MaterialTable& materials, BSPMap& map, LightmapStats& stats);
+// pvs.rs calculate_visibility_matrix: [leaf a][leaf b] != 0 when each of the two leafs can potentially see the other
+std::vector<uint8_t> calculate_leafs_visibility(const BSPMap& map);
 
 } // namespace mapc
 

@@ -494,3 +494,53 @@ def test_sun_through_a_sky_ceiling_and_a_spot_light(tmp_path):
         assert abs(spot_best - under) / under < 0.05
     finally:
         sc.close()
+
+
+def test_pvs_of_a_zig_zag_of_rooms(tmp_path):
+    """pvs.rs calculate_visibility_matrix: three rooms in a row whose doorways are at opposite ends of the dividing walls.  The
+    matrix is symmetric with a true diagonal; neighbouring rooms see each other through their doorway; the far corner of room C is
+    hidden from the far corner of room A (no straight line passes both doorways).  Lighting with --use-pvs gives the same lightmaps
+    as the contribution cut-off here (the lamp reaches every leaf it can see; what the PVS prunes is shadowed anyway)."""
+    # rooms A x in [0, 256], B [384, 640], C [768, 1024], all y in [0, 512]; the walls between them are 128 thick with 48-wide
+    # doorways (tunnels) at opposite ends: whatever passes tunnel A|B has |dy/dx| <= 48 / 128 seen from that tunnel's mouth, while
+    # tunnel B|C lies at dy/dx >= 384 / 384 from there (the PVS is conservative: it unions the views from a portal's vertices)
+    b = [box_brush((-16, -16, -16), (1040, 528, 0), "floor"), box_brush((-16, -16, 128), (1040, 528, 144), "ceiling"),
+         box_brush((-16, -16, 0), (0, 528, 128)), box_brush((1024, -16, 0), (1040, 528, 128)), box_brush((0, -16, 0), (1024, 0, 128)), box_brush((0, 512, 0), (1024, 528, 128)),
+         box_brush((256, 0, 0), (384, 16, 128), "divider"), box_brush((256, 64, 0), (384, 512, 128), "divider"), box_brush((256, 16, 96), (384, 64, 128), "divider"),
+         box_brush((640, 0, 0), (768, 448, 128), "divider"), box_brush((640, 496, 0), (768, 512, 128), "divider"), box_brush((640, 448, 96), (768, 496, 128), "divider")]
+    ents = ['{\n"classname" "worldspawn"\n' + "\n".join(b) + "\n}", '{\n"classname" "info_player_start"\n"origin" "64 128 32"\n}',
+            '{\n"classname" "light"\n"origin" "128 128 96"\n"light" "200"\n}']
+    table = mc.materials_table(MATERIALS)
+    path = str(tmp_path / "zigzag.sqwm")
+    mc.compile_map("\n".join(ents) + "\n", table, path, perform_csg=True, advanced=True)
+    vis = mc.leafs_visibility(path)
+    n = len(vis)
+    assert n >= 5 and (vis == vis.T).all() and vis.diagonal().all()
+    sc = S.Scene(num_materials=4, texture_size_log2=4, grid=(4, 4, 1), num_rooms=1)
+    try:
+        sc.load_compiled_map(path, table, 5, 1)
+        leaf_at = lambda p: _leaf_of_point(path, p)
+        a_far, b_mid, c_far = leaf_at((16, 496, 64)), leaf_at((512, 256, 64)), leaf_at((1008, 16, 64))
+        a_door, c_door = leaf_at((320, 40, 48)), leaf_at((704, 472, 48))  # inside the two tunnels
+        assert vis[a_far, a_door] and vis[a_door, b_mid] and vis[b_mid, c_door] and vis[c_door, c_far]  # through one doorway each
+        assert not vis[a_far, c_far]                               # two doorways that do not line up
+        assert vis.sum() < n * n                                   # (not everything sees everything)
+    finally:
+        sc.close()
+    lit_a, lit_b = str(tmp_path / "a.sqwm"), str(tmp_path / "b.sqwm")
+    mc.light_map(path, table, lit_a, sample_grid_size=1, ambient_light=0.125)
+    mc.light_map(path, table, lit_b, sample_grid_size=1, ambient_light=0.125, use_pvs=True)
+    assert open(lit_a, "rb").read() == open(lit_b, "rb").read()
+
+
+def _leaf_of_point(path, point):
+    """bsp_map_compact.rs get_leaf_for_point on the file's node lump."""
+    raw = open(path, "rb").read()
+    lumps = np.frombuffer(raw, np.uint32, 96, 8).reshape(32, 3)
+    o, es, cnt = (int(x) for x in lumps[0])
+    nodes = np.frombuffer(raw, np.dtype([("children", "<u4", 2), ("plane", "<f4", 4)]), cnt, o)
+    index = cnt - 1 if cnt else 1 << 31
+    while index < (1 << 31):
+        nd = nodes[index]
+        index = int(nd["children"][0] if float(np.dot(nd["plane"][:3], point)) >= float(nd["plane"][3]) else nd["children"][1])
+    return index - (1 << 31)

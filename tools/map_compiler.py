@@ -87,6 +87,21 @@ def _lib():
     return l
 
 
+def leafs_visibility(map_path: str):
+    """pvs.rs calculate_visibility_matrix of a .sqwm file as a bool array [num_leafs, num_leafs]."""
+    import numpy as np
+
+    l = _lib()
+    l.sqwh_map_pvs.restype = C.c_int64
+    l.sqwh_map_pvs.argtypes = [C.c_char_p, C.c_void_p, C.c_uint64]
+    n = l.sqwh_map_pvs(os.fsencode(map_path), None, 0)
+    if n < 0:
+        raise OSError(f"sqwh_map_pvs({map_path}): {-n}")
+    m = np.zeros((n, n), np.uint8)
+    l.sqwh_map_pvs(os.fsencode(map_path), m.ctypes.data_as(C.c_void_p), m.size)
+    return m.astype(bool)
+
+
 COMPILE_STATS = ["initial_polygons", "polygons_after_csg", "leafs_initial", "leafs_removed", "tree_depth", "nodes", "leafs", "polygons", "portals", "submodels", "lightmap_texels"]
 
 
@@ -102,9 +117,9 @@ def compile_map(map_text: str, table: str, out_path: str, perform_csg=False, adv
     return d
 
 
-def light_map(in_path: str, table: str, out_path: str, sample_grid_size=1, light_scale=1.0, ambient_light=0.0, directional=True, light_cutoff=0.0) -> dict:
+def light_map(in_path: str, table: str, out_path: str, sample_grid_size=1, light_scale=1.0, ambient_light=0.0, directional=True, light_cutoff=0.0, use_pvs=False) -> dict:
     stats = (C.c_uint32 * 4)()
-    r = _lib().sqwh_map_light(os.fsencode(in_path), table.encode("utf-8"), sample_grid_size, light_scale, ambient_light, int(directional), light_cutoff, os.fsencode(out_path), stats)
+    r = _lib().sqwh_map_light(os.fsencode(in_path), table.encode("utf-8"), sample_grid_size, light_scale, ambient_light, int(directional) | (2 if use_pvs else 0), light_cutoff, os.fsencode(out_path), stats)
     if r != 0:
         raise RuntimeError(f"lightmapper failed ({r})")
     return dict(zip(["point_lights", "sun_lights", "lightmap_texels", "light_grid_samples"], [int(x) for x in stats]))
@@ -131,6 +146,7 @@ def main():
     l.add_argument("--ambient-light", type=float, default=0.0)
     l.add_argument("--no-directional-lightmap", action="store_true")
     l.add_argument("--light-cutoff", type=float, default=0.0)
+    l.add_argument("--use-pvs", action="store_true", help="pick a polygon's lights through the leaf-to-leaf visibility matrix (pvs.rs) like the reference, not by the contribution cut-off")
     a = ap.parse_args()
     table = materials_table(load_materials(a.materials_dir))
     t0 = time.time()
@@ -143,7 +159,7 @@ def main():
             sys.stderr.write(log)
         print(json.dumps({"seconds": round(time.time() - t0, 2), **st}))
     else:
-        st = light_map(a.input, table, a.output, a.sample_grid_size, a.light_scale, a.ambient_light, not a.no_directional_lightmap, a.light_cutoff)
+        st = light_map(a.input, table, a.output, a.sample_grid_size, a.light_scale, a.ambient_light, not a.no_directional_lightmap, a.light_cutoff, a.use_pvs)
         print(json.dumps({"seconds": round(time.time() - t0, 2), **st}))
 
 
