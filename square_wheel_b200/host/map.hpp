@@ -1,6 +1,7 @@
 // In-memory map (BSPMap, src/common/bsp_map_compact.rs:7-35), materials and textures of the host-side mirror, plus the
-// seeded synthetic map generator that stands in for map_compiler + lightmapper output (the compiled demo
-// map and its textures are not shipped and the Rust tools cannot be built here).
+// seeded synthetic map generator that stood in for map_compiler + lightmapper output before those tools were restated
+// (map_compiler.hpp; SURVEY.md §0: the compiled demo map and its textures are not shipped); it remains the fixture of most tests
+// and the fallback workload of bench.py.
 #pragma once
 #include "../../include/sqw_cuda.h"
 #include "math.hpp"
