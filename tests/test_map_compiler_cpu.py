@@ -544,3 +544,37 @@ def _leaf_of_point(path, point):
         nd = nodes[index]
         index = int(nd["children"][0] if float(np.dot(nd["plane"][:3], point)) >= float(nd["plane"][3]) else nd["children"][1])
     return index - (1 << 31)
+
+
+def test_csg_cuts_holes_for_a_pillar(tmp_path, oracle_lib):
+    """map_csg.rs make_hole_in_polygon (:162-328): a pillar from floor to ceiling in the middle of a room leaves its footprint as a
+    hole in both (pieces cut along the texture axes), and its own bottom / top faces vanish.  Total surface = the closed form; the
+    oracle still draws gap-free frames (no crack around the hole)."""
+    b = [box_brush((-16, -16, -16), (272, 272, 0), "floor"), box_brush((-16, -16, 128), (272, 272, 144), "ceiling"),
+         box_brush((-16, -16, 0), (0, 272, 128)), box_brush((256, -16, 0), (272, 272, 128)), box_brush((0, -16, 0), (256, 0, 128)), box_brush((0, 256, 0), (256, 272, 128)),
+         box_brush((96, 112, 0), (144, 160, 128), "divider")]  # the pillar: 48 x 48 footprint
+    ents = ['{\n"classname" "worldspawn"\n' + "\n".join(b) + "\n}", '{\n"classname" "info_player_start"\n"origin" "32 32 32"\n}', '{\n"classname" "light"\n"origin" "200 64 100"\n"light" "150"\n}']
+    table = mc.materials_table(MATERIALS)
+    path = str(tmp_path / "pillar.sqwm")
+    st = mc.compile_map("\n".join(ents) + "\n", table, path, perform_csg=True, advanced=True)
+    assert st["polygons_after_csg"] > 6 + 4  # the floor and the ceiling are in several pieces now
+    got = _order_independent_summary(path)
+    want = 2 * (256 * 256 - 48 * 48) + 4 * 256 * 128 + 4 * 48 * 128
+    assert abs(sum(got["polygon_areas_sorted"]) - want) / want < 1e-3
+    mc.light_map(path, table, path, sample_grid_size=1, ambient_light=0.2)
+    sc = S.Scene(num_materials=4, texture_size_log2=4, grid=(4, 4, 1), num_rooms=1)
+    try:
+        sc.load_compiled_map(path, table, 5, 1)
+        hr = S.HostRenderer(sc, clear_background=False)
+        try:
+            for pose in ([32.0, 32.0, 64.0, -0.8, -0.3], [220.0, 220.0, 40.0, 2.4, 0.4], [128.0, 40.0, 100.0, 0.0, -0.9]):
+                hf = hr.build_frame(320, 200, np.array(pose, np.float32), color_bits=32)
+                oracle_lib.reset_assert_failures()
+                surf = oracle_lib.build_surfaces(32, hf.jobs, None, None, hf.cam_pos, sc.images, sc.lightmaps, sc.directional_lightmaps, hf.total_surface_pixels)
+                fb = np.zeros((200, 320), np.uint32)
+                oracle_lib.draw(32, fb, hf.cmds, hf.polygon_points, None, surf, sc.images)
+                assert oracle_lib.assert_failures() == 0 and int((fb == 0).sum()) == 0
+        finally:
+            hr.close()
+    finally:
+        sc.close()
