@@ -578,3 +578,62 @@ def test_csg_cuts_holes_for_a_pillar(tmp_path, oracle_lib):
             hr.close()
     finally:
         sc.close()
+
+
+def plane_brush(planes, texture="wall"):
+    """A brush from (outward normal, point on the plane) pairs: three points per plane wound like box_brush's."""
+    lines = ["{"]
+    for n, p in planes:
+        n, p = np.asarray(n, float), np.asarray(p, float)
+        t1 = np.cross(n, [0.0, 0.0, 1.0] if abs(n[2]) < 0.9 else [1.0, 0.0, 0.0])
+        t1 /= np.linalg.norm(t1)
+        t2 = np.cross(n, t1)
+        p0, p1, p2 = p + t1 * 32, p, p + t2 * 32
+        if np.dot(np.cross(p0 - p1, p2 - p1), n) < 0:
+            p0, p2 = p2, p0
+        lines.append(" ".join("( %.6f %.6f %.6f )" % tuple(q) for q in (p0, p1, p2)) + f" {texture} 0 0 0 1 1")
+    lines.append("}")
+    return "\n".join(lines)
+
+
+def test_sloped_brush_in_a_room(tmp_path, oracle_lib):
+    """Planes that are not axis-aligned: a ramp (wedge) against a wall.  Its slope and its two triangular sides are what remains of
+    it after CSG (bottom and back lie in the floor and the wall), the floor and the wall lose the covered rectangles; QBSP texture
+    axes pick the floor projection for the slope (map_polygonizer.rs:447-497).  Closed-form area, gap-free frames."""
+    ramp = plane_brush([((0, 0, -1), (0, 0, 0)), ((1, 0, 0), (256, 0, 0)), ((0, -1, 0), (0, 64, 0)), ((0, 1, 0), (0, 192, 0)),
+                        ((-64.0, 0.0, 128.0), (128, 0, 0))], "divider")  # rises from (128, *, 0) to (256, *, 64)
+    b = [box_brush((-16, -16, -16), (272, 272, 0), "floor"), box_brush((-16, -16, 128), (272, 272, 144), "ceiling"),
+         box_brush((-16, -16, 0), (0, 272, 128)), box_brush((256, -16, 0), (272, 272, 128)), box_brush((0, -16, 0), (256, 0, 128)), box_brush((0, 256, 0), (256, 272, 128)), ramp]
+    ents = ['{\n"classname" "worldspawn"\n' + "\n".join(b) + "\n}", '{\n"classname" "info_player_start"\n"origin" "32 32 32"\n}', '{\n"classname" "light"\n"origin" "64 128 100"\n"light" "150"\n}']
+    table = mc.materials_table(MATERIALS)
+    path = str(tmp_path / "ramp.sqwm")
+    mc.compile_map("\n".join(ents) + "\n", table, path, perform_csg=True, advanced=True)
+    got = _order_independent_summary(path)
+    slope = 128.0 * np.hypot(128.0, 64.0)
+    sides = 2 * 0.5 * 128.0 * 64.0
+    want = 2 * 256 * 256 + 4 * 256 * 128 - 128 * 128 - 128 * 64 + slope + sides  # floor and wall lose the ramp's bottom and back
+    assert abs(sum(got["polygon_areas_sorted"]) - want) / want < 2e-3
+    mc.light_map(path, table, path, sample_grid_size=1, ambient_light=0.2)
+    sc = S.Scene(num_materials=4, texture_size_log2=4, grid=(4, 4, 1), num_rooms=1)
+    try:
+        sc.load_compiled_map(path, table, 5, 1)
+        polys, _verts, _ = sc.map_geometry()
+        sloped = [p for p in polys if abs(p["plane"][0]) > 1e-3 and abs(p["plane"][2]) > 1e-3]
+        assert sloped
+        for p in sloped:  # the slope is textured like a floor: u along x, v along -y
+            assert abs(p["tex_coord_equation"][0][0] - 1.0) < 1e-6 and abs(p["tex_coord_equation"][1][1] + 1.0) < 1e-6
+            o = int(p["lightmap_data_offset"])
+            assert o != 0 and float(sc.lightmaps[o : o + 4].max()) > 0.2  # lit by the lamp it faces
+        hr = S.HostRenderer(sc, clear_background=False)
+        try:
+            for pose in ([32.0, 32.0, 64.0, -0.8, -0.3], [40.0, 128.0, 40.0, -1.57, 0.0], [200.0, 30.0, 110.0, 0.3, -0.8]):
+                hf = hr.build_frame(320, 200, np.array(pose, np.float32), color_bits=32)
+                oracle_lib.reset_assert_failures()
+                surf = oracle_lib.build_surfaces(32, hf.jobs, None, None, hf.cam_pos, sc.images, sc.lightmaps, sc.directional_lightmaps, hf.total_surface_pixels)
+                fb = np.zeros((200, 320), np.uint32)
+                oracle_lib.draw(32, fb, hf.cmds, hf.polygon_points, None, surf, sc.images)
+                assert oracle_lib.assert_failures() == 0 and int((fb == 0).sum()) == 0
+        finally:
+            hr.close()
+    finally:
+        sc.close()
