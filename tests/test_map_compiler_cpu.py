@@ -637,3 +637,59 @@ def test_sloped_brush_in_a_room(tmp_path, oracle_lib):
             hr.close()
     finally:
         sc.close()
+
+
+def test_material_flags_steer_the_compiler(tmp_path):
+    """material.rs flags read by the tools: `bsp: false` faces are dropped (bsp_builder.rs:555-582: the demo marks hidden faces with
+    __TB_empty), `twosided` polygons are doubled with the opposite winding, `blocks_view: false` brushes neither cut other brushes
+    (map_csg.rs:50-66) nor close portals (bsp_builder.rs:717-737): a fence across the doorway leaves room B reachable and visible."""
+    materials = dict(MATERIALS, fence={"twosided": True, "blocks_view": False, "blending_mode": "AlphaTest", "shadow": False}, hidden={"bsp": False})
+    table = mc.materials_table(materials)
+    base = two_rooms_map(door_entity=False)
+    fence = box_brush((268, 96, 0), (276, 160, 96), "fence", textures={(1, -1): "hidden", (1, 1): "hidden", (2, -1): "hidden", (2, 1): "hidden"})
+    text = base.replace('// a comment\n', '// a comment\n' + fence + "\n", 1)
+    assert text != base
+    a, b = str(tmp_path / "plain.sqwm"), str(tmp_path / "fence.sqwm")
+    s0 = mc.compile_map(base, table, a, perform_csg=True, advanced=True)
+    s1 = mc.compile_map(text, table, b, perform_csg=True, advanced=True)
+    g0, g1 = _order_independent_summary(a), _order_independent_summary(b)
+    # the fence adds its two 64 x 96 faces, each twice (both windings); its four `hidden` faces are gone; nothing else changes in area
+    added = sum(g1["polygon_areas_sorted"]) - sum(g0["polygon_areas_sorted"])
+    assert abs(added - 4 * 64 * 96) < 1.0
+    assert s1["leafs"] >= s0["leafs"] and g1["portals"] >= g0["portals"]
+    sc = S.Scene(num_materials=4, texture_size_log2=4, grid=(4, 4, 1), num_rooms=1)
+    try:
+        sc.load_compiled_map(b, table, 5, 1)
+        names = [sc.texture_name(i) for i in range(sc.info.num_materials)]
+        assert "fence" in names and "hidden" not in names
+        polys, verts, _ = sc.map_geometry()
+        fi = names.index("fence")
+        normals = sorted(round(float(p["plane"][0] / np.linalg.norm(p["plane"][:3]))) for p in polys if p["texture"] == fi)
+        assert normals.count(1) == normals.count(-1) and len(normals) >= 4  # every fence polygon exists with both facings
+        # room B stays reachable (the camera path still runs through the doorway) and potentially visible from room A
+        poses = sc.camera_path(8)
+        assert poses[:, 0].max() > 300
+        vis = mc.leafs_visibility(b)
+        assert vis[_leaf_of_point(b, (64, 128, 32)), _leaf_of_point(b, (416, 128, 32))]
+    finally:
+        sc.close()
+    # the fence lets light through (shadow: false -> opacity 1, light_trace.rs:15-40): room B's floor behind it is lit as without it
+    la, lb = str(tmp_path / "la.sqwm"), str(tmp_path / "lb.sqwm")
+    mc.light_map(a, table, la, sample_grid_size=1)
+    mc.light_map(b, table, lb, sample_grid_size=1)
+
+    def floor_light_in_b(path):
+        sc2 = S.Scene(num_materials=4, texture_size_log2=4, grid=(4, 4, 1), num_rooms=1)
+        try:
+            sc2.load_compiled_map(path, table, 5, 1)
+            _p, v2, _ = sc2.map_geometry()
+            total = 0.0
+            for p, block in _lightmap_blocks(sc2, lambda q: q["plane"][2] > 0 and abs(q["plane"][3]) < 1e-3):
+                if v2[p["first_vertex"] : p["first_vertex"] + p["num_vertices"]][:, 0].min() >= 288:
+                    total += float(block[..., 0].sum())
+            return total
+        finally:
+            sc2.close()
+
+    fa, fb_ = floor_light_in_b(la), floor_light_in_b(lb)
+    assert fa > 1.0 and abs(fa - fb_) / fa < 0.05
